@@ -1,0 +1,322 @@
+/* oracle/_ref harness: a plain-C, ctypes-friendly door onto the UNMODIFIED
+ * reference functions of the parse->filter path:
+ *   flb_parser_create / flb_parser_do            (src/flb_parser.c:148,1044)
+ *   flb_filter_new / _set_property / _init / flb_filter_do  (src/flb_filter.c:426,325,550,119)
+ *   plugin cb_filter callbacks                   (plugins/filter_*)
+ *   flb_regex_create / flb_regex_do              (src/flb_regex.c:160,182)
+ *   flb_pack_json                                (src/flb_pack.c)
+ *   flb_parser_time_lookup                       (src/flb_parser.c:1159)
+ * TEST INFRASTRUCTURE ONLY: nothing under fluent-bit_b200/ may link or call this. */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <fluent-bit/flb_info.h>
+#include <fluent-bit/flb_config.h>
+#include <fluent-bit/flb_env.h>
+#include <fluent-bit/flb_mem.h>
+#include <fluent-bit/flb_parser.h>
+#include <fluent-bit/flb_regex.h>
+#include <onigmo.h>
+#include <fluent-bit/flb_pack.h>
+#include <fluent-bit/flb_time.h>
+#include <fluent-bit/flb_filter.h>
+#include <fluent-bit/flb_input.h>
+#include <fluent-bit/flb_input_chunk.h>
+#include <fluent-bit/flb_mp.h>
+#include <fluent-bit/flb_sds.h>
+#include <cmetrics/cmetrics.h>
+#include <cmetrics/cmt_encode_text.h>
+#include <cmetrics/cmt_encode_msgpack.h>
+#include "filter_log_to_metrics/log_to_metrics.h"
+
+extern struct flb_filter_plugin filter_parser_plugin;
+extern struct flb_filter_plugin filter_grep_plugin;
+extern struct flb_filter_plugin filter_modify_plugin;
+extern struct flb_filter_plugin filter_record_modifier_plugin;
+extern struct flb_filter_plugin filter_log_to_metrics_plugin;
+
+struct flbref_cfg {
+    struct flb_config *config;
+    struct flb_input_instance in;
+    struct flb_filter_plugin plugins[5];
+};
+
+void *flbref_config_create(void)
+{
+    struct flbref_cfg *c = calloc(1, sizeof(*c));
+    struct flb_config *config = calloc(1, sizeof(struct flb_config));
+    int i;
+
+    c->config = config;
+    mk_list_init(&config->parsers);
+    mk_list_init(&config->filters);
+    mk_list_init(&config->filter_plugins);
+    mk_list_init(&config->inputs);
+    mk_list_init(&config->cf_parsers_list);
+    config->env = flb_env_create();
+    /* the dlopen path memcpy's the plugin struct the same way (src/flb_plugin.c:274) */
+    c->plugins[0] = filter_parser_plugin;
+    c->plugins[1] = filter_grep_plugin;
+    c->plugins[2] = filter_modify_plugin;
+    c->plugins[3] = filter_record_modifier_plugin;
+    c->plugins[4] = filter_log_to_metrics_plugin;
+    for (i = 0; i < 5; i++) {
+        mk_list_add(&c->plugins[i]._head, &config->filter_plugins);
+    }
+    mk_list_init(&c->in.properties);
+    c->in.config = config;
+    return c;
+}
+
+void *flbref_config_raw(void *cfg) { return ((struct flbref_cfg *) cfg)->config; }
+
+static int type_from_name(const char *s, int n)
+{
+    if (n == 7 && !strncasecmp(s, "integer", 7)) return FLB_PARSER_TYPE_INT;
+    if (n == 4 && !strncasecmp(s, "bool", 4)) return FLB_PARSER_TYPE_BOOL;
+    if (n == 5 && !strncasecmp(s, "float", 5)) return FLB_PARSER_TYPE_FLOAT;
+    if (n == 3 && !strncasecmp(s, "hex", 3)) return FLB_PARSER_TYPE_HEX;
+    return FLB_PARSER_TYPE_STRING;
+}
+
+/* types_spec: "key:integer key2:float" (same text as the Types option,
+ * src/flb_parser.c proc_types_str) or NULL. */
+void *flbref_parser_create(void *cfg, const char *name, const char *format, const char *regex,
+                           int skip_empty, const char *time_fmt, const char *time_key,
+                           const char *time_offset, int time_keep, int time_strict,
+                           int logfmt_no_bare_keys, const char *types_spec)
+{
+    struct flbref_cfg *c = cfg;
+    struct flb_parser_types *types = NULL;
+    int types_len = 0;
+
+    if (types_spec && *types_spec) {
+        const char *p = types_spec;
+        types = calloc(64, sizeof(*types));
+        while (*p && types_len < 63) {
+            const char *e, *colon;
+            while (*p == ' ') p++;
+            if (!*p) break;
+            e = p;
+            while (*e && *e != ' ') e++;
+            colon = memchr(p, ':', e - p);
+            if (colon) {
+                types[types_len].key = strndup(p, colon - p);
+                types[types_len].key_len = colon - p;
+                types[types_len].type = type_from_name(colon + 1, e - colon - 1);
+                types_len++;
+            }
+            p = e;
+        }
+    }
+    return flb_parser_create(name, format, regex, skip_empty, time_fmt, time_key, time_offset,
+                             time_keep, time_strict, FLB_FALSE, logfmt_no_bare_keys,
+                             types, types_len, NULL, c->config);
+}
+
+int flbref_parser_do(void *parser, const char *buf, size_t len, void **out_buf, size_t *out_size,
+                     long long *sec, long long *nsec)
+{
+    struct flb_time t;
+    int ret;
+
+    flb_time_zero(&t);
+    *out_buf = NULL;
+    *out_size = 0;
+    ret = flb_parser_do(parser, buf, len, out_buf, out_size, &t);
+    *sec = (long long) t.tm.tv_sec;
+    *nsec = (long long) t.tm.tv_nsec;
+    return ret;
+}
+
+int flbref_time_lookup(void *parser, const char *str, size_t len, long long now,
+                       long long *sec, double *ns)
+{
+    struct flb_tm tm;
+    int ret;
+
+    memset(&tm, 0, sizeof(tm));
+    *ns = 0;
+    ret = flb_parser_time_lookup(str, len, (time_t) now, parser, &tm, ns);
+    if (ret == 0) {
+        *sec = (long long) flb_parser_tm2time(&tm, FLB_FALSE);
+    }
+    return ret;
+}
+
+void flbref_free(void *p) { flb_free(p); }
+
+/* ---- regex ---- */
+void *flbref_regex_create(const char *pattern) { return flb_regex_create(pattern); }
+void flbref_regex_destroy(void *re) { flb_regex_destroy(re); }
+
+struct names_ctx { char *buf; size_t cap; size_t len; int n; };
+static void names_cb(const char *name, const char *value, size_t vlen, void *data)
+{
+    struct names_ctx *nc = data;
+    size_t l = strlen(name);
+    if (nc->len + l + 1 < nc->cap) {
+        memcpy(nc->buf + nc->len, name, l);
+        nc->len += l;
+        nc->buf[nc->len++] = '\n';
+    }
+    nc->n++;
+}
+
+/* Leftmost search over [str,str+len).  Returns flb_regex_do()'s value (number of
+ * named groups, or -1).  beg/end get the byte offsets of group 0..maxregs-1
+ * (-1 when unset); *nregs the region size. */
+int flbref_regex_search(void *re, const char *str, size_t len, int *beg, int *end, int maxregs,
+                        int *nregs)
+{
+    struct flb_regex_search res;
+    int ret, i;
+
+    memset(&res, 0, sizeof(res));
+    *nregs = 0;
+    ret = flb_regex_do(re, str, len, &res);
+    if (ret < 0) {
+        return ret;
+    }
+    *nregs = ((OnigRegion *) res.region)->num_regs;
+    for (i = 0; i < ((OnigRegion *) res.region)->num_regs && i < maxregs; i++) {
+        beg[i] = ((OnigRegion *) res.region)->beg[i];
+        end[i] = ((OnigRegion *) res.region)->end[i];
+    }
+    /* flb_regex_parse frees the region */
+    {
+        char tmp[4]; struct names_ctx nc = { tmp, 0, 0, 0 };
+        flb_regex_parse(re, &res, names_cb, &nc);
+    }
+    return ret;
+}
+
+/* names of the named groups in the order flb_regex_parse reports them, '\n' separated */
+int flbref_regex_names(void *re, const char *str, size_t len, char *out, size_t cap)
+{
+    struct flb_regex_search res;
+    struct names_ctx nc = { out, cap, 0, 0 };
+    int ret;
+
+    memset(&res, 0, sizeof(res));
+    ret = flb_regex_do(re, str, len, &res);
+    if (ret < 0) return ret;
+    flb_regex_parse(re, &res, names_cb, &nc);
+    if (nc.len < cap) out[nc.len] = '\0';
+    return nc.n;
+}
+
+int flbref_regex_match(void *re, const char *str, size_t len)
+{
+    return flb_regex_match(re, (unsigned char *) str, len);
+}
+
+/* ---- JSON -> msgpack ---- */
+int flbref_pack_json(const char *js, size_t len, void **out, size_t *out_size)
+{
+    int root_type;
+    char *buf = NULL;
+    int ret;
+    size_t consumed = 0;
+
+    ret = flb_pack_json(js, len, &buf, out_size, &root_type, &consumed);
+    *out = buf;
+    return ret;
+}
+
+/* ---- filters ---- */
+void *flbref_filter_create(void *cfg, const char *plugin)
+{
+    struct flbref_cfg *c = cfg;
+    struct flb_filter_instance *ins = flb_filter_new(c->config, plugin, NULL);
+    if (ins) {
+        flb_filter_set_property(ins, "match", "*");
+    }
+    return ins;
+}
+
+int flbref_filter_set(void *filter, const char *k, const char *v)
+{
+    return flb_filter_set_property(filter, k, v);
+}
+
+int flbref_filter_init(void *cfg, void *filter)
+{
+    struct flbref_cfg *c = cfg;
+    return flb_filter_init(c->config, filter);
+}
+
+/* one plugin callback; returns FLB_FILTER_MODIFIED(1) / FLB_FILTER_NOTOUCH(2) */
+int flbref_filter_cb(void *cfg, void *filter, const void *data, size_t bytes, const char *tag,
+                     void **out, size_t *out_size)
+{
+    struct flbref_cfg *c = cfg;
+    struct flb_filter_instance *ins = filter;
+
+    *out = NULL;
+    *out_size = 0;
+    return ins->p->cb_filter(data, bytes, tag, (int) strlen(tag), out, out_size, ins, &c->in,
+                             ins->context, c->config);
+}
+
+/* the whole configured chain through flb_filter_do() (src/flb_filter.c:119).
+ * returns 0 when the result is the caller's buffer (untouched), 1 when *out is a
+ * new heap buffer (free with flbref_free), and *out_size==0 when all dropped. */
+int flbref_filter_do(void *cfg, const void *data, size_t bytes, int records, const char *tag,
+                     void **out, size_t *out_size)
+{
+    struct flbref_cfg *c = cfg;
+    struct flb_input_chunk ic;
+
+    memset(&ic, 0, sizeof(ic));
+    ic.in = &c->in;
+    ic.added_records = records;
+    ic.total_records = records;
+    flb_filter_do(&ic, data, bytes, out, out_size, tag, (int) strlen(tag), c->config);
+    if (*out == data) {
+        return 0;
+    }
+    return 1;
+}
+
+int flbref_count_records(const void *buf, size_t size)
+{
+    return flb_mp_count_log_records(buf, size);
+}
+
+/* text dump of a filter instance's framework counters (src/flb_filter.c:574-616) */
+char *flbref_filter_cmt_text(void *filter)
+{
+    struct flb_filter_instance *ins = filter;
+    cfl_sds_t t = cmt_encode_text_create(ins->cmt);
+    char *r = strdup(t ? t : "");
+    if (t) cmt_encode_text_destroy(t);
+    return r;
+}
+
+/* text dump of filter_log_to_metrics' own cmetrics context */
+char *flbref_l2m_cmt_text(void *filter)
+{
+    struct flb_filter_instance *ins = filter;
+    struct log_to_metrics_ctx *ctx = ins->context;
+    cfl_sds_t t = cmt_encode_text_create(ctx->cmt);
+    char *r = strdup(t ? t : "");
+    if (t) cmt_encode_text_destroy(t);
+    return r;
+}
+
+int flbref_l2m_cmt_msgpack(void *filter, void **out, size_t *out_size)
+{
+    struct flb_filter_instance *ins = filter;
+    struct log_to_metrics_ctx *ctx = ins->context;
+    char *b = NULL;
+    int ret = cmt_encode_msgpack_create(ctx->cmt, &b, out_size);
+    if (ret == 0) {
+        *out = malloc(*out_size);
+        memcpy(*out, b, *out_size);
+        cmt_encode_msgpack_destroy(b);
+    }
+    return ret;
+}
+
+void flbref_cfree(void *p) { free(p); }
