@@ -175,7 +175,7 @@ int flbref_regex_search(void *re, const char *str, size_t len, int *beg, int *en
     memset(&res, 0, sizeof(res));
     *nregs = 0;
     ret = flb_regex_do(re, str, len, &res);
-    if (ret < 0) {
+    if (ret <= 0) {            /* 0: matched, but no groups -> region already freed */
         return ret;
     }
     *nregs = ((OnigRegion *) res.region)->num_regs;
@@ -200,7 +200,7 @@ int flbref_regex_names(void *re, const char *str, size_t len, char *out, size_t 
 
     memset(&res, 0, sizeof(res));
     ret = flb_regex_do(re, str, len, &res);
-    if (ret < 0) return ret;
+    if (ret <= 0) return ret;
     flb_regex_parse(re, &res, names_cb, &nc);
     if (nc.len < cap) out[nc.len] = '\0';
     return nc.n;
