@@ -1,0 +1,29 @@
+# Build recipe for the product library, the CPU-only device-code emulation used by
+# the `-m "not gpu"` tests, and the oracle.  __graft_entry__.build() drives this.
+PKG    = fluent-bit_b200
+CSRC   = $(PKG)/csrc
+NVCC  ?= nvcc
+NVFLAGS = -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC
+CFLAGS = -O2 -g -fPIC -Wall -Wno-unused-function
+
+all: product hostsim oracle
+
+product: $(PKG)/libflbgpu.so
+$(PKG)/libflbgpu.so: $(CSRC)/kernels.cu $(CSRC)/runtime.c $(CSRC)/rx_compile.c $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/flbgpu.h
+	$(NVCC) $(NVFLAGS) -c $(CSRC)/kernels.cu -o $(CSRC)/kernels.o
+	gcc $(CFLAGS) -c $(CSRC)/runtime.c -o $(CSRC)/runtime.o
+	gcc $(CFLAGS) -c $(CSRC)/rx_compile.c -o $(CSRC)/rx_compile.o
+	$(NVCC) -shared -o $@ $(CSRC)/kernels.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o -lcudart
+
+hostsim: tests/hostsim/libhostsim.so
+tests/hostsim/libhostsim.so: tests/hostsim/hostsim.cpp $(CSRC)/runtime.c $(CSRC)/rx_compile.c $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h)
+	gcc $(CFLAGS) -c $(CSRC)/runtime.c -o tests/hostsim/runtime.o
+	gcc $(CFLAGS) -c $(CSRC)/rx_compile.c -o tests/hostsim/rx_compile.o
+	g++ $(CFLAGS) -shared -o $@ tests/hostsim/hostsim.cpp tests/hostsim/runtime.o tests/hostsim/rx_compile.o
+
+oracle:
+	@if [ -d /root/reference ]; then $(MAKE) -s -C oracle/refshim; else echo "oracle/_ref: reference tree absent, using prebuilt"; fi
+
+clean:
+	rm -f $(PKG)/libflbgpu.so $(CSRC)/*.o tests/hostsim/*.so tests/hostsim/*.o
+.PHONY: all product hostsim oracle clean

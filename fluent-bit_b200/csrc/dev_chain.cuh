@@ -1,0 +1,969 @@
+/* dev_chain.cuh -- one log record through the configured filter chain (one lane = one
+ * record).  The record is held as a FIELD LIST of references into the input chunk /
+ * the program's constant pool; every filter is an operation on that list and a single
+ * encoder at the end writes msgpack.  The same function runs twice per record:
+ * EMIT=false measures (output size, keep/drop, chunk-level evidence) and EMIT=true
+ * writes at the offset the prefix sum assigned.
+ *
+ * Reference behaviour mirrored here (file:line in /root/reference):
+ *   record framing ........ src/flb_log_event_decoder.c:180-297, :309-456
+ *   record encoding ....... src/flb_log_event_encoder.c:172-218 (92 92 d7 00 sec nsec meta body)
+ *   filter_parser ......... plugins/filter_parser/filter_parser.c:174-442
+ *   regex parser .......... src/flb_parser_regex.c:44-227, src/flb_regex.c:28-58,294-316
+ *   typecast .............. src/flb_parser.c:1280-1377
+ *   filter_grep ........... plugins/filter_grep/grep.c:167-194,250-284,286-392
+ *   record accessor ....... src/flb_ra_key.c:108-134,151-240,303-340,374-435
+ *   filter_modify ......... plugins/filter_modify/modify.c:523-953 (conditions), :955-1339 (rules),
+ *                           :1341-1457 (sequential application)
+ *   filter_record_modifier  plugins/filter_record_modifier/filter_modifier.c:213-279,298-486
+ */
+#ifndef FLBGPU_DEV_CHAIN_CUH
+#define FLBGPU_DEV_CHAIN_CUH
+
+#include <stdint.h>
+#include "flbgpu_prog.h"
+#include "dev_msgpack.cuh"
+#include "dev_regex.cuh"
+#include "dev_time.cuh"
+
+#define CH_MAXF        64
+#define CH_RX_STACK    192      /* 32-bit words of backtrack stack per lane */
+#define CH_RX_BUDGET   4000000u /* VM steps per search: guards against catastrophic backtracking */
+
+#ifdef __CUDA_ARCH__
+#define CH_ATOMIC_OR(p, v)  atomicOr((unsigned int *) (p), (unsigned int) (v))
+#define CH_ATOMIC_ADD(p, v) atomicAdd((unsigned long long *) (p), (unsigned long long) (v))
+#else
+#define CH_ATOMIC_OR(p, v)  (*(p) |= (v))
+#define CH_ATOMIC_ADD(p, v) (*(p) += (v))
+#endif
+
+/* reference = kind:4 | len:28 | off:32 */
+typedef uint64_t ref_t;
+enum { RK_MP_IN = 1, RK_MP_CONST, RK_MP_SCR, RK_STR_IN, RK_INT_IN, RK_HEX_IN, RK_FLT_IN, RK_TRUE, RK_FALSE,
+       RK_STR_SCR };
+FLB_HD ref_t mkref(uint32_t kind, uint32_t off, uint32_t len) { return ((uint64_t) kind << 60) | ((uint64_t) (len & 0x0fffffffu) << 32) | off; }
+FLB_HD uint32_t r_kind(ref_t r) { return (uint32_t) (r >> 60); }
+FLB_HD uint32_t r_len(ref_t r) { return (uint32_t) (r >> 32) & 0x0fffffffu; }
+FLB_HD uint32_t r_off(ref_t r) { return (uint32_t) r; }
+
+enum { ST_CANON = 0, ST_MAP32 = 1, ST_PRESET = 2 };
+
+struct ch_env {
+    const uint8_t *in;
+    uint32_t in_len;
+    const uint8_t *blob;
+    uint8_t *scr;
+    int32_t *capcache;
+    uint32_t cap_stride;
+    int64_t now;
+    uint32_t assume;          /* bit k: filter k is chunk-level MODIFIED */
+    uint32_t *fl_flags;       /* [n_filters] CHF_* evidence (evaluation pass only) */
+    uint32_t *err;            /* FLBGPU_E_* */
+};
+
+struct ch_rec {
+    int64_t ts_sec, ts_nsec;
+    ref_t meta;
+    int nf;
+    ref_t k[CH_MAXF], v[CH_MAXF];
+    int style;
+    uint32_t preset_n;
+    int reenc;
+};
+
+FLB_HD const uint8_t *ref_ptr(const struct ch_env *e, ref_t r)
+{
+    uint32_t k = r_kind(r);
+    if (k == RK_MP_CONST) return e->blob + r_off(r);
+    if (k == RK_MP_SCR || k == RK_STR_SCR) return e->scr + r_off(r);
+    return e->in + r_off(r);
+}
+
+/* string view of a key/value: 1 STR, 2 BIN, 3 true, 4 false, 0 anything else */
+FLB_HD int ref_view(const struct ch_env *e, ref_t r, const uint8_t **p, uint32_t *n)
+{
+    uint32_t k = r_kind(r);
+    const uint8_t *b = ref_ptr(e, r);
+    if (k == RK_STR_IN || k == RK_STR_SCR) { *p = b; *n = r_len(r); return 1; }
+    if (k == RK_TRUE) return 3;
+    if (k == RK_FALSE) return 4;
+    if (k == RK_MP_IN || k == RK_MP_CONST || k == RK_MP_SCR) {
+        struct mp_tok t;
+        if (mp_token(b, b + r_len(r), &t) != 0) return 0;
+        if (t.type == MPT_STR) { *p = b + t.hdr; *n = t.len; return 1; }
+        if (t.type == MPT_BIN) { *p = b + t.hdr; *n = t.len; return 2; }
+        if (t.type == MPT_BOOL) return t.u ? 3 : 4;
+    }
+    return 0;
+}
+
+FLB_HD int bytes_eq(const uint8_t *a, const uint8_t *b, uint32_t n)
+{
+    uint32_t i;
+    for (i = 0; i < n; i++) if (a[i] != b[i]) return 0;
+    return 1;
+}
+
+/* strtoll(s, NULL, 10) on a counted string (atoll in flb_parser_typecast) */
+FLB_HD int64_t ch_atoll(const uint8_t *s, uint32_t n)
+{
+    uint32_t i = 0;
+    int neg = 0;
+    uint64_t v = 0, lim;
+    while (i < n && dt_isspace(s[i])) i++;
+    if (i < n && (s[i] == '+' || s[i] == '-')) { neg = s[i] == '-'; i++; }
+    lim = neg ? 9223372036854775808ull : 9223372036854775807ull;
+    for (; i < n && s[i] >= '0' && s[i] <= '9'; i++) {
+        uint64_t d = s[i] - '0';
+        if (v > (lim - d) / 10) { v = lim; while (i < n && s[i] >= '0' && s[i] <= '9') i++; break; }
+        v = v * 10 + d;
+    }
+    return neg ? (int64_t) (0 - v) : (int64_t) v;
+}
+
+/* strtoull(s, NULL, 16) */
+FLB_HD uint64_t ch_strtoull16(const uint8_t *s, uint32_t n)
+{
+    uint32_t i = 0;
+    int neg = 0, any = 0, ovf = 0;
+    uint64_t v = 0;
+    while (i < n && dt_isspace(s[i])) i++;
+    if (i < n && (s[i] == '+' || s[i] == '-')) { neg = s[i] == '-'; i++; }
+    if (i + 1 < n && s[i] == '0' && (s[i + 1] == 'x' || s[i + 1] == 'X')) {
+        int h = (i + 2 < n) ? s[i + 2] : 0;
+        if ((h >= '0' && h <= '9') || ((h | 0x20) >= 'a' && (h | 0x20) <= 'f')) i += 2;
+    }
+    for (; i < n; i++) {
+        int c = s[i], d;
+        if (c >= '0' && c <= '9') d = c - '0';
+        else if ((c | 0x20) >= 'a' && (c | 0x20) <= 'f') d = (c | 0x20) - 'a' + 10;
+        else break;
+        any = 1;
+        if (v >> 60) ovf = 1;
+        v = (v << 4) | (uint64_t) d;
+    }
+    (void) any;
+    if (ovf) return 0xffffffffffffffffull;
+    return neg ? (uint64_t) (0 - v) : v;
+}
+
+/* strtod() restricted to the exactly-representable fast path (Clinger): up to 19
+ * significant digits that fit 2^53 and |exp10| <= 22.  *ok=0 outside it. */
+FLB_HD double ch_strtod_fast(const uint8_t *s, uint32_t n, int *ok)
+{
+    uint32_t i = 0;
+    int neg = 0, exp10 = 0, nd = 0, seen = 0;
+    uint64_t m = 0;
+    double d;
+    const double p10[23] = { 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                             1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22 };
+    *ok = 1;
+    while (i < n && dt_isspace(s[i])) i++;
+    if (i < n && (s[i] == '+' || s[i] == '-')) { neg = s[i] == '-'; i++; }
+    for (; i < n && s[i] >= '0' && s[i] <= '9'; i++) {
+        seen = 1;
+        if (m || s[i] != '0') { if (nd < 19) { m = m * 10 + (s[i] - '0'); nd++; } else exp10++; }
+    }
+    if (i < n && s[i] == '.') {
+        i++;
+        for (; i < n && s[i] >= '0' && s[i] <= '9'; i++) {
+            seen = 1;
+            if (m || s[i] != '0') { if (nd < 19) { m = m * 10 + (s[i] - '0'); nd++; exp10--; } }
+            else exp10--;
+        }
+    }
+    if (!seen) return 0.0;                      /* no conversion: atof gives 0 */
+    if (i < n && (s[i] == 'e' || s[i] == 'E')) {
+        uint32_t j = i + 1;
+        int eneg = 0, ev = 0, ed = 0;
+        if (j < n && (s[j] == '+' || s[j] == '-')) { eneg = s[j] == '-'; j++; }
+        for (; j < n && s[j] >= '0' && s[j] <= '9'; j++) { if (ev < 100000) ev = ev * 10 + (s[j] - '0'); ed = 1; }
+        if (ed) exp10 += eneg ? -ev : ev;
+    }
+    if (m == 0) return neg ? -0.0 : 0.0;
+    if (m > (1ull << 53) || exp10 > 22 || exp10 < -22) { *ok = 0; return 0.0; }
+    d = (double) m;
+    if (exp10 >= 0) d = d * p10[exp10]; else d = d / p10[-exp10];
+    return neg ? -d : d;
+}
+
+/* ------------------------------------------------------------ emission */
+/* size (o == NULL) or bytes of one field reference */
+FLB_HD uint32_t ref_emit(const struct ch_env *e, ref_t r, uint8_t *o)
+{
+    uint32_t k = r_kind(r), n = r_len(r);
+    const uint8_t *b = ref_ptr(e, r);
+    switch (k) {
+    case RK_MP_IN:
+        return mp_canon(b, b + n, o, 0);
+    case RK_MP_CONST:
+    case RK_MP_SCR:
+        if (o) mp_copy(o, b, n);
+        return n;
+    case RK_STR_IN:
+    case RK_STR_SCR:
+        if (o) { uint32_t h = mp_put_str_hdr(o, n); mp_copy(o + h, b, n); }
+        return mp_str_hdr_size(n) + n;
+    case RK_INT_IN: {
+        int64_t v = ch_atoll(b, n);
+        if (o) mp_put_int(o, v);
+        return mp_int_size(v);
+    }
+    case RK_HEX_IN: {
+        uint64_t v = ch_strtoull16(b, n);
+        if (o) mp_put_uint(o, v);
+        return mp_uint_size(v);
+    }
+    case RK_FLT_IN: {
+        int ok;
+        double d = ch_strtod_fast(b, n, &ok);
+        if (!ok) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
+        if (o) {
+            union { double d; uint64_t u; } cv;
+            cv.d = d;
+            o[0] = 0xcb; mp_put_be64(o + 1, cv.u);
+        }
+        return 9;
+    }
+    case RK_TRUE: if (o) o[0] = 0xc3; return 1;
+    case RK_FALSE: if (o) o[0] = 0xc2; return 1;
+    }
+    return 0;
+}
+
+FLB_HD uint32_t rec_emit(const struct ch_env *e, const struct ch_rec *rc, uint8_t *o)
+{
+    uint32_t n = 0;
+    int i;
+    if (o) {
+        o[0] = 0x92; o[1] = 0x92; o[2] = 0xd7; o[3] = 0x00;
+        mp_put_be32(o + 4, (uint32_t) rc->ts_sec);
+        mp_put_be32(o + 8, (uint32_t) rc->ts_nsec);
+    }
+    n = 12;
+    n += ref_emit(e, rc->meta, o ? o + n : 0);
+    if (rc->style == ST_MAP32) {
+        if (o) { o[n] = 0xdf; mp_put_be32(o + n + 1, (uint32_t) rc->nf); }
+        n += 5;
+    }
+    else if (rc->style == ST_PRESET) {
+        /* header type chosen for preset_n (msgpack_pack_map(n)), count patched afterwards
+         * (src/flb_parser_regex.c:182-199) */
+        if (rc->preset_n < 16) { if (o) o[n] = 0x80 | (uint8_t) rc->nf; n += 1; }
+        else if (rc->preset_n < 65536) { if (o) { o[n] = 0xde; mp_put_be16(o + n + 1, (uint32_t) rc->nf); } n += 3; }
+        else { if (o) { o[n] = 0xdf; mp_put_be32(o + n + 1, (uint32_t) rc->nf); } n += 5; }
+    }
+    else {
+        if (o) mp_put_map_hdr(o + n, (uint32_t) rc->nf);
+        n += mp_cnt_hdr_size((uint32_t) rc->nf);
+    }
+    for (i = 0; i < rc->nf; i++) {
+        n += ref_emit(e, rc->k[i], o ? o + n : 0);
+        n += ref_emit(e, rc->v[i], o ? o + n : 0);
+    }
+    return n;
+}
+
+/* ------------------------------------------------------------- decoding */
+/* Frame check of ONE record starting at p: returns its end or NULL.
+ * kind: 0 normal, 1 skipped by the decoder (negative 32-bit seconds). */
+FLB_HD const uint8_t *rec_frame(const uint8_t *p, const uint8_t *end, int *kind)
+{
+    struct mp_tok t;
+    const uint8_t *q;
+    int64_t sec = 0;
+    if (end - p < 3 || p[0] != 0x92) return 0;
+    q = p + 1;
+    if (*q == 0x92) q++;                        /* [ [ts, meta], body ] */
+    else if ((*q & 0xf0) == 0x90 || *q == 0xdc || *q == 0xdd) return 0;   /* header array of another size */
+    if (q >= end || mp_token(q, end, &t) != 0) return 0;
+    if (t.type == MPT_UINT) sec = (int64_t) t.u;
+    else if (t.type == MPT_INT) { if ((int64_t) t.u < 0) return 0; sec = (int64_t) t.u; }
+    else if (t.type == MPT_F64) { union { uint64_t u; double d; } cv; cv.u = t.u; sec = (int64_t) cv.d; }
+    else if (t.type == MPT_EXT) {
+        if (t.ext_type != 0 || t.len != 8 || (size_t) (end - q) < t.hdr + 8u) return 0;
+        sec = (int64_t) (int32_t) mp_be32(q + t.hdr);
+    }
+    else return 0;
+    q += t.hdr + (t.type == MPT_EXT ? t.len : 0);
+    if (p[1] == 0x92) {                          /* metadata must be a map */
+        if (q >= end || mp_token(q, end, &t) != 0 || t.type != MPT_MAP) return 0;
+        q = mp_skip(q, end);
+        if (!q) return 0;
+    }
+    if (q >= end || mp_token(q, end, &t) != 0 || t.type != MPT_MAP) return 0;
+    q = mp_skip(q, end);
+    if (!q) return 0;
+    *kind = ((int32_t) (uint32_t) sec) < 0 ? 1 : 0;
+    return q;
+}
+
+/* A candidate at p is the HEADER ARRAY of a v2 record, not a record, when the byte
+ * before it starts a well-formed [[ts, meta], body] frame: "[ts, meta]" on its own has
+ * the shape of a legacy [ts, body] event.  (If p-1 frames as v2, then p cannot also be
+ * a record start: the outer body would have to be both a map and an array.) */
+FLB_HD int rec_is_shadowed(const uint8_t *base, const uint8_t *p, const uint8_t *end)
+{
+    int kind;
+    if (p == base || p[-1] != 0x92) return 0;
+    return rec_frame(p - 1, end, &kind) != 0;
+}
+
+/* Split a framed record into timestamp, metadata and the top-level field list.
+ * Returns 0, or -1 when it has more than CH_MAXF keys. */
+FLB_HD int rec_decode(const struct ch_env *e, uint32_t off, uint32_t len, struct ch_rec *rc, uint32_t empty_map_off)
+{
+    const uint8_t *p = e->in + off, *end = p + len, *q = p + 1, *nx;
+    struct mp_tok t;
+    uint32_t i;
+    int v2 = (*q == 0x92);
+    if (v2) q++;
+    mp_token(q, end, &t);
+    rc->ts_nsec = 0;
+    if (t.type == MPT_UINT || t.type == MPT_INT) rc->ts_sec = (int64_t) t.u;
+    else if (t.type == MPT_F64) {
+        union { uint64_t u; double d; } cv;
+        cv.u = t.u;
+        rc->ts_sec = (int64_t) cv.d;
+        rc->ts_nsec = (int64_t) ((cv.d - (double) rc->ts_sec) * 1000000000.0);
+    }
+    else {
+        rc->ts_sec = (int64_t) (int32_t) mp_be32(q + t.hdr);
+        rc->ts_nsec = (int64_t) (int32_t) mp_be32(q + t.hdr + 4);
+    }
+    q += t.hdr + (t.type == MPT_EXT ? t.len : 0);
+    if (v2) {
+        nx = mp_skip(q, end);
+        rc->meta = mkref(RK_MP_IN, (uint32_t) (q - e->in), (uint32_t) (nx - q));
+        q = nx;
+    }
+    else rc->meta = mkref(RK_MP_CONST, empty_map_off, 1);
+    mp_token(q, end, &t);
+    q += t.hdr;
+    rc->style = ST_CANON; rc->preset_n = 0; rc->reenc = 0;
+    if (t.len > CH_MAXF) { rc->nf = 0; return -1; }
+    rc->nf = (int) t.len;
+    for (i = 0; i < t.len; i++) {
+        nx = mp_skip(q, end);
+        rc->k[i] = mkref(RK_MP_IN, (uint32_t) (q - e->in), (uint32_t) (nx - q));
+        q = nx;
+        nx = mp_skip(q, end);
+        rc->v[i] = mkref(RK_MP_IN, (uint32_t) (q - e->in), (uint32_t) (nx - q));
+        q = nx;
+    }
+    return 0;
+}
+
+/* -------------------------------------------------------- record accessor */
+/* ra_key_val_id(): index of the LAST field whose key is a STR equal to name */
+FLB_HD int ra_find(const struct ch_env *e, const struct ch_rec *rc, const uint8_t *name, uint32_t nlen)
+{
+    int i;
+    for (i = rc->nf - 1; i >= 0; i--) {
+        const uint8_t *kp; uint32_t kn;
+        if (ref_view(e, rc->k[i], &kp, &kn) != 1) continue;
+        if (kn == nlen && bytes_eq(kp, name, nlen)) return i;
+    }
+    return -1;
+}
+
+/* subkey_to_object() over raw msgpack: on success *vp..*ve is the value object and
+ * *key_is_null tells whether the last step was an array index */
+FLB_HD int ra_walk_sub(const struct ch_env *e, const struct cf_ra *ra, const uint8_t *p, const uint8_t *end,
+                       const uint8_t **vp, const uint8_t **ve, int *key_is_null)
+{
+    const struct cf_ra_sub *sub = (const struct cf_ra_sub *) (e->blob + ra->sub_off);
+    uint32_t levels = ra->n_sub, matched = 0, s;
+    const uint8_t *cur = p, *cur_end = end;
+    struct mp_tok t;
+    if (levels == 0) return -1;
+    for (s = 0; s < levels; s++) {
+        if (mp_token(cur, cur_end, &t) != 0) return -1;
+        if (sub[s].is_index) {
+            const uint8_t *q;
+            uint32_t i;
+            if (t.type != MPT_ARRAY) return -1;
+            if (sub[s].index == 0x7fffffffu || sub[s].index >= t.len) return -1;
+            q = cur + t.hdr;
+            for (i = 0; i < sub[s].index; i++) q = mp_skip(q, cur_end);
+            cur = q; cur_end = mp_skip(q, cur_end);
+            *key_is_null = 1;
+            matched++;
+            if (matched == levels) break;
+            continue;
+        }
+        if (t.type != MPT_MAP) break;
+        {
+            /* last matching STR key wins */
+            const uint8_t *q = cur + t.hdr, *found = 0, *found_end = 0;
+            const uint8_t *want = e->blob + sub[s].str_off;
+            uint32_t i;
+            for (i = 0; i < t.len; i++) {
+                struct mp_tok kt;
+                const uint8_t *kq = q, *vq;
+                mp_token(q, cur_end, &kt);
+                vq = mp_skip(q, cur_end);
+                q = mp_skip(vq, cur_end);
+                if (kt.type == MPT_STR && kt.len == sub[s].str_len && bytes_eq(kq + kt.hdr, want, kt.len)) {
+                    found = vq; found_end = q;
+                }
+            }
+            if (!found) continue;               /* "try next entry" (src/flb_ra_key.c:214) */
+            cur = found; cur_end = found_end;
+            *key_is_null = 0;
+            matched++;
+            if (matched == levels) break;
+        }
+    }
+    if (matched == 0 || levels != matched) return -1;
+    *vp = cur; *ve = cur_end;
+    return 0;
+}
+
+/* flb_ra_key_value_get(): 0 found (flags: *okey_null), -1 not found.
+ * On success either *top >= 0 (the top-level field itself) or *vp/*ve (nested). */
+FLB_HD int ra_get(const struct ch_env *e, const struct ch_rec *rc, const struct cf_ra *ra, int *top,
+                  const uint8_t **vp, const uint8_t **ve, int *okey_null)
+{
+    int i = ra_find(e, rc, e->blob + ra->key_off, ra->key_len);
+    uint32_t k;
+    *top = -1; *okey_null = 0;
+    if (i < 0) return -1;
+    k = r_kind(rc->v[i]);
+    if (ra->n_sub > 0 && (k == RK_MP_IN || k == RK_MP_CONST || k == RK_MP_SCR)) {
+        const uint8_t *b = ref_ptr(e, rc->v[i]);
+        struct mp_tok t;
+        if (mp_token(b, b + r_len(rc->v[i]), &t) == 0 && (t.type == MPT_MAP || t.type == MPT_ARRAY)) {
+            return ra_walk_sub(e, ra, b, b + r_len(rc->v[i]), vp, ve, okey_null);
+        }
+    }
+    *top = i;
+    return 0;
+}
+
+/* view of a located value as STR/BIN/bool (same codes as ref_view) */
+FLB_HD int loc_view(const struct ch_env *e, const struct ch_rec *rc, int top, const uint8_t *vp, const uint8_t *ve,
+                    const uint8_t **p, uint32_t *n)
+{
+    struct mp_tok t;
+    if (top >= 0) return ref_view(e, rc->v[top], p, n);
+    if (mp_token(vp, ve, &t) != 0) return 0;
+    if (t.type == MPT_STR) { *p = vp + t.hdr; *n = t.len; return 1; }
+    if (t.type == MPT_BIN) { *p = vp + t.hdr; *n = t.len; return 2; }
+    if (t.type == MPT_BOOL) return t.u ? 3 : 4;
+    return 0;
+}
+
+FLB_HD int rx_run(const struct ch_env *e, uint32_t rx_off, const uint8_t *s, uint32_t n, int *caps, uint32_t *stk)
+{
+    uint32_t budget = CH_RX_BUDGET;
+    int r = rx_search((const struct rx_prog *) (e->blob + rx_off), s, (int) n, caps, stk, CH_RX_STACK, &budget);
+    if (r == RX_R_ESTACK) { CH_ATOMIC_OR(e->err, FLBGPU_E_RXSTACK); return 0; }
+    if (r == RX_R_EBUDGET) { CH_ATOMIC_OR(e->err, FLBGPU_E_RXBUDGET); return 0; }
+    return r == RX_R_MATCH;
+}
+
+/* flb_ra_regex_match() > 0 ? */
+FLB_HD int ra_regex_match(const struct ch_env *e, const struct ch_rec *rc, uint32_t ra_off, uint32_t rx_off,
+                          int *caps, uint32_t *stk)
+{
+    const struct cf_ra *ra = (const struct cf_ra *) (e->blob + ra_off);
+    const uint8_t *vp = 0, *ve = 0, *s;
+    uint32_t n;
+    int top, kn;
+    if (ra_get(e, rc, ra, &top, &vp, &ve, &kn) != 0) return 0;
+    if (loc_view(e, rc, top, vp, ve, &s, &n) != 1) return 0;      /* value must be a STR */
+    return rx_run(e, rx_off, s, n, caps, stk);
+}
+
+/* ---------------------------------------------------------- filter_parser */
+/* One regex parser over s[0,n): returns 1 parsed (fields appended to out_*), 0 not.
+ * Timestamp result in *t_sec/*t_nsec (0/0 when no time was resolved). */
+FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s,
+                      uint32_t n, const int *caps, ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec,
+                      int64_t *t_nsec)
+{
+    const struct cf_pname *nm = (const struct cf_pname *) (e->blob + pd->names_off);
+    uint32_t i;
+    int any_end = 0, cnt = 0;
+    int64_t lookup = 0;
+    double frac = 0;
+    if (pd->n_groups == 0) return 0;                 /* flb_parser_regex_do: n <= 0 -> -1 */
+    for (i = 0; i < pd->n_names; i++) {
+        int b = caps[2 * nm[i].group], en = caps[2 * nm[i].group + 1];
+        uint32_t vlen = (uint32_t) (en - b);
+        const uint8_t *v = s + b;
+        if (en >= 0) any_end = 1;
+        if (vlen == 0 && pd->skip_empty) continue;
+        if (pd->has_time && nm[i].is_time) {
+            struct dt_tm tm;
+            struct dt_parser tp;
+            double ns;
+            int r;
+            tm.sec = tm.min = tm.hour = tm.mday = tm.mon = tm.year = tm.wday = tm.yday = tm.isdst = 0;
+            tm.gmtoff = 0;
+            tp.fmt = (const char *) (e->blob + pd->fmt_off);
+            tp.frac_fmt = pd->has_frac ? (const char *) (e->blob + pd->frac_off) : 0;
+            tp.with_year = (int) pd->time_with_year; tp.with_tz = (int) pd->time_with_tz;
+            tp.strict = (int) pd->time_strict; tp.offset = pd->time_offset;
+            r = dt_time_lookup(vlen ? v : s, vlen, e->now, &tp, &tm, &ns);
+            if (r == -1) continue;
+            frac = ns;
+            lookup = dt_timegm(&tm) - tm.gmtoff;
+            if (!pd->time_keep) continue;
+        }
+        if (cnt >= CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
+        ok_[cnt] = mkref(RK_MP_CONST, nm[i].kmp_off, nm[i].kmp_len);
+        {
+            uint32_t kind = RK_STR_IN, voff = val_off + (uint32_t) (vlen ? b : 0);
+            if (nm[i].cast == FLBGPU_TYPE_INT) kind = RK_INT_IN;
+            else if (nm[i].cast == FLBGPU_TYPE_HEX) kind = RK_HEX_IN;
+            else if (nm[i].cast == FLBGPU_TYPE_FLOAT) kind = RK_FLT_IN;
+            else if (nm[i].cast == FLBGPU_TYPE_BOOL) {
+                if (vlen >= 4 && dt_lower(v[0]) == 't' && dt_lower(v[1]) == 'r' && dt_lower(v[2]) == 'u' && dt_lower(v[3]) == 'e') kind = RK_TRUE;
+                else if (vlen >= 5 && dt_lower(v[0]) == 'f' && dt_lower(v[1]) == 'a' && dt_lower(v[2]) == 'l' && dt_lower(v[3]) == 's' && dt_lower(v[4]) == 'e') kind = RK_FALSE;
+            }
+            ov_[cnt] = mkref(kind, voff, vlen);
+        }
+        cnt++;
+    }
+    if (!any_end) return 0;                          /* flb_regex_parse: last_pos == -1 */
+    *on = cnt;
+    *t_sec = lookup;
+#ifdef __CUDA_ARCH__
+    *t_nsec = (int64_t) __dmul_rn(frac, 1000000000.0);
+#else
+    *t_nsec = (int64_t) (frac * 1000000000.0);
+#endif
+    return 1;
+}
+
+struct ch_scratch {              /* per-lane working memory */
+    int caps[2 * (RX_MAX_GROUPS + 1)];
+    uint32_t stk[CH_RX_STACK];
+    ref_t tk[CH_MAXF], tv[CH_MAXF];
+};
+
+template <bool EMIT>
+FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct ch_rec *rc, struct ch_scratch *w,
+                     uint32_t ridx, uint32_t *cache_pos)
+{
+    uint8_t keep[CH_MAXF];
+    int i, parse_ok = 0, np = 0, preserved = -1, have_arr, pi;
+    int64_t ps = 0, pns = 0;
+    uint32_t preset = 0;
+    int style = ST_CANON;
+
+    have_arr = cf->reserve_data || cf->preserve_key;
+    for (i = 0; i < rc->nf; i++) keep[i] = cf->reserve_data ? 1 : 0;
+
+    for (i = (cf->ra_off ? -1 : 0); i < (cf->ra_off ? 0 : rc->nf); i++) {
+        const uint8_t *vp = 0; uint32_t vn = 0;
+        uint32_t val_off;
+        if (cf->ra_off) {
+            const struct cf_ra *ra = (const struct cf_ra *) (e->blob + cf->ra_off);
+            const uint8_t *np_ = 0, *ne_ = 0;
+            int top, kn, vt;
+            if (ra_get(e, rc, ra, &top, &np_, &ne_, &kn) != 0) break;
+            vt = loc_view(e, rc, top, np_, ne_, &vp, &vn);
+            if (vt != 1 && vt != 2) break;
+        }
+        else {
+            const uint8_t *kp; uint32_t kn; int kt, vt;
+            kt = ref_view(e, rc->k[i], &kp, &kn);
+            if (kt != 1 && kt != 2) continue;
+            if (kn != cf->key_len || !bytes_eq(kp, e->blob + cf->key_off, kn)) continue;
+            vt = ref_view(e, rc->v[i], &vp, &vn);
+            if (vt != 1 && vt != 2) continue;
+        }
+        val_off = (uint32_t) (vp - e->in);
+        parse_ok = 0;
+        for (pi = 0; pi < (int) cf->n_parsers; pi++) {
+            const struct cf_pdef *pd = (const struct cf_pdef *) (e->blob + cf->pdef_off[pi]);
+            int64_t ts = 0, tns = 0;
+            int got = 0, cnt = 0;
+            if (pd->type == FLBGPU_PARSER_REGEX) {
+                uint32_t need = 1 + 2 * (pd->n_groups + 1), c;
+                int32_t *slot = 0;
+                int matched;
+                if (e->capcache && *cache_pos + need <= e->cap_stride)
+                    slot = e->capcache + (size_t) ridx * e->cap_stride + *cache_pos;
+                *cache_pos += need;
+                if (EMIT && slot) {
+                    matched = slot[0];
+                    for (c = 0; c + 1 < need; c++) w->caps[c] = slot[1 + c];
+                }
+                else {
+                    matched = rx_run(e, pd->rx_off, vp, vn, w->caps, w->stk);
+                    if (!EMIT && slot) {
+                        slot[0] = matched;
+                        for (c = 0; c + 1 < need; c++) slot[1 + c] = w->caps[c];
+                    }
+                }
+                if (matched) got = pdef_regex(e, pd, val_off, vp, vn, w->caps, w->tk, w->tv, &cnt, &ts, &tns);
+                if (got) { preset = pd->n_groups; style = ST_PRESET; }
+            }
+            if (got) {
+                parse_ok = 1;
+                np = cnt;
+                if ((uint64_t) ts * 1000000000ull + (uint64_t) tns != 0) { ps = ts; pns = tns; }
+                if ((uint64_t) ts * 1000000000ull + (uint64_t) tns != 0) { rc->ts_sec = ts; rc->ts_nsec = tns; }
+                if (have_arr && !cf->ra_off) {
+                    if (!cf->preserve_key) keep[i] = 0;
+                    else if (!cf->reserve_data) preserved = i;
+                }
+                break;
+            }
+        }
+    }
+    (void) ps; (void) pns;
+    rc->reenc = 1;
+    if (!parse_ok) { rc->style = ST_CANON; return; }
+    {
+        /* parsed keys first, then the reserved originals (src/flb_pack.c:1716-1723) */
+        int extra = 0, j = np;
+        if (cf->reserve_data) { for (i = 0; i < rc->nf; i++) if (keep[i]) extra++; }
+        else if (preserved >= 0) extra = 1;
+        if (np + extra > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return; }
+        if (cf->reserve_data) {
+            for (i = 0; i < rc->nf; i++) if (keep[i]) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; j++; }
+        }
+        else if (preserved >= 0) { w->tk[j] = rc->k[preserved]; w->tv[j] = rc->v[preserved]; j++; }
+        for (i = 0; i < j; i++) { rc->k[i] = w->tk[i]; rc->v[i] = w->tv[i]; }
+        rc->nf = j;
+        if (extra > 0) rc->style = ST_CANON;
+        else { rc->style = style; rc->preset_n = preset; }
+    }
+}
+
+/* ------------------------------------------------------------ filter_grep */
+/* returns 1 keep, 0 exclude */
+FLB_HD int f_grep(const struct ch_env *e, const struct cf_grep *cf, const struct ch_rec *rc, struct ch_scratch *w)
+{
+    const struct cf_grep_rule *r = (const struct cf_grep_rule *) (e->blob + cf->rules_off);
+    uint32_t i;
+    int found = 0;
+    if (cf->op == GREP_OP_LEGACY) {
+        for (i = 0; i < cf->n_rules; i++) {
+            int m = ra_regex_match(e, rc, r[i].ra_off, r[i].rx_off, w->caps, w->stk);
+            if (!m) { if (r[i].type == GREP_REGEX) return 0; }
+            else return r[i].type == GREP_EXCLUDE ? 0 : 1;
+        }
+        return 1;
+    }
+    if (cf->n_rules == 0) return 1;
+    for (i = 0; i < cf->n_rules; i++) {
+        found = ra_regex_match(e, rc, r[i].ra_off, r[i].rx_off, w->caps, w->stk);
+        if (cf->op == GREP_OP_OR && found) break;
+        if (cf->op == GREP_OP_AND && !found) break;
+    }
+    if (i == cf->n_rules) i = cf->n_rules - 1;
+    if (r[i].type == GREP_REGEX) return found ? 1 : 0;
+    return found ? 0 : 1;
+}
+
+/* ---------------------------------------------------------- filter_modify */
+FLB_HD int key_eq(const struct ch_env *e, ref_t k, const uint8_t *s, uint32_t n)
+{
+    const uint8_t *kp; uint32_t kn;
+    int t = ref_view(e, k, &kp, &kn);
+    return (t == 1 || t == 2) && kn == n && bytes_eq(kp, s, n);
+}
+/* helper_msgpack_object_matches_wildcard(): prefix test (defined as length-guarded) */
+FLB_HD int key_prefix(const struct ch_env *e, ref_t k, const uint8_t *s, uint32_t n)
+{
+    const uint8_t *kp; uint32_t kn;
+    int t = ref_view(e, k, &kp, &kn);
+    return (t == 1 || t == 2) && kn >= n && bytes_eq(kp, s, n);
+}
+/* helper_msgpack_object_matches_regex(): STR, or BOOLEAN as "true"/"false" */
+FLB_HD int obj_rx(const struct ch_env *e, int vt, const uint8_t *p, uint32_t n, uint32_t rx_off, struct ch_scratch *w)
+{
+    const uint8_t tr[4] = { 't', 'r', 'u', 'e' }, fa[5] = { 'f', 'a', 'l', 's', 'e' };
+    if (vt == 1) return rx_run(e, rx_off, p, n, w->caps, w->stk);
+    if (vt == 3) return rx_run(e, rx_off, tr, 4, w->caps, w->stk);
+    if (vt == 4) return rx_run(e, rx_off, fa, 5, w->caps, w->stk);
+    return 0;
+}
+FLB_HD int ref_rx(const struct ch_env *e, ref_t r, uint32_t rx_off, struct ch_scratch *w)
+{
+    const uint8_t *p = 0; uint32_t n = 0;
+    int vt = ref_view(e, r, &p, &n);
+    return obj_rx(e, vt, p, n, rx_off, w);
+}
+
+FLB_HD int mod_conditions(const struct ch_env *e, const struct cf_modify *cf, const struct ch_rec *rc,
+                          struct ch_scratch *w)
+{
+    const struct cf_mod_cond *c = (const struct cf_mod_cond *) (e->blob + cf->conds_off);
+    uint32_t ci;
+    int ok = 1, i;
+    for (ci = 0; ci < cf->n_conds; ci++) {
+        const struct cf_ra *ra = c[ci].ra_off ? (const struct cf_ra *) (e->blob + c[ci].ra_off) : 0;
+        const uint8_t *vp = 0, *ve = 0, *sp = 0;
+        uint32_t sn = 0;
+        int top = -1, kn = 0, exists = 0, vt = 0, r = 0, cnt = 0;
+        if (ra) {
+            exists = (ra_get(e, rc, ra, &top, &vp, &ve, &kn) == 0) && !kn;
+            if (exists) vt = loc_view(e, rc, top, vp, ve, &sp, &sn);
+        }
+        switch (c[ci].type) {
+        case MODC_KEY_EXISTS: r = exists; break;
+        case MODC_KEY_DOES_NOT_EXIST: r = !exists; break;
+        case MODC_A_KEY_MATCHES:
+        case MODC_NO_KEY_MATCHES:
+            for (i = 0; i < rc->nf; i++) if (ref_rx(e, rc->k[i], c[ci].a_rx, w)) cnt++;
+            r = (c[ci].type == MODC_A_KEY_MATCHES) ? cnt > 0 : cnt == 0;
+            break;
+        case MODC_KEY_VALUE_EQUALS:
+            r = exists && (vt == 1 || vt == 2) && sn == c[ci].b_len && bytes_eq(sp, e->blob + c[ci].b_off, sn);
+            break;
+        case MODC_KEY_VALUE_DOES_NOT_EQUAL:
+            r = exists && !((vt == 1 || vt == 2) && sn == c[ci].b_len && bytes_eq(sp, e->blob + c[ci].b_off, sn));
+            break;
+        case MODC_KEY_VALUE_MATCHES:
+            r = exists && obj_rx(e, vt, sp, sn, c[ci].b_rx, w);
+            break;
+        case MODC_KEY_VALUE_DOES_NOT_MATCH:
+            r = exists && !obj_rx(e, vt, sp, sn, c[ci].b_rx, w);
+            break;
+        case MODC_MATCHING_KEYS_HAVE_MATCHING_VALUES:
+        case MODC_MATCHING_KEYS_DO_NOT_HAVE_MATCHING_VALUES:
+            r = 1;
+            for (i = 0; i < rc->nf; i++) {
+                if (ref_rx(e, rc->k[i], c[ci].a_rx, w) && !ref_rx(e, rc->v[i], c[ci].b_rx, w)) { r = 0; break; }
+            }
+            if (c[ci].type == MODC_MATCHING_KEYS_DO_NOT_HAVE_MATCHING_VALUES) r = !r;
+            break;
+        default: r = 0;
+        }
+        if (!r) ok = 0;
+    }
+    return ok;
+}
+
+FLB_HD int count_keys(const struct ch_env *e, const struct ch_rec *rc, const uint8_t *s, uint32_t n)
+{
+    int i, c = 0;
+    for (i = 0; i < rc->nf; i++) if (key_eq(e, rc->k[i], s, n)) c++;
+    return c;
+}
+
+/* remove fields flagged in del[] */
+FLB_HD void compact(struct ch_rec *rc, const uint8_t *del)
+{
+    int i, j = 0;
+    for (i = 0; i < rc->nf; i++) if (!del[i]) { rc->k[j] = rc->k[i]; rc->v[j] = rc->v[i]; j++; }
+    rc->nf = j;
+}
+
+/* returns 1 when the rule modified the map */
+FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct ch_rec *rc, struct ch_scratch *w)
+{
+    const uint8_t *key = e->blob + r->key_off, *val = e->blob + r->val_off;
+    ref_t kmp = mkref(RK_MP_CONST, r->kmp_off, r->kmp_len), vmp = mkref(RK_MP_CONST, r->vmp_off, r->vmp_len);
+    uint8_t del[CH_MAXF];
+    int i, j, match, conflict;
+
+    switch (r->type) {
+    case MOD_RENAME:
+    case MOD_HARD_RENAME:
+        match = count_keys(e, rc, key, r->key_len);
+        conflict = count_keys(e, rc, val, r->val_len);
+        if (match == 0) return 0;
+        if (r->type == MOD_RENAME && conflict > 0) return 0;
+        for (i = 0; i < rc->nf; i++) del[i] = (conflict > 0 && key_eq(e, rc->k[i], val, r->val_len)) ? 1 : 0;
+        for (i = 0; i < rc->nf; i++) if (!del[i] && key_eq(e, rc->k[i], key, r->key_len)) rc->k[i] = vmp;
+        compact(rc, del);
+        return 1;
+    case MOD_COPY:
+    case MOD_HARD_COPY:
+        match = count_keys(e, rc, key, r->key_len);
+        conflict = count_keys(e, rc, val, r->val_len);
+        if (match != 1) return 0;
+        if (r->type == MOD_COPY && conflict > 0) return 0;
+        if (r->type == MOD_HARD_COPY && conflict > 1) return 0;
+        if (conflict == 1) {
+            for (i = 0; i < rc->nf; i++) del[i] = key_eq(e, rc->k[i], val, r->val_len) ? 1 : 0;
+            compact(rc, del);
+        }
+        if (rc->nf + 1 > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
+        for (i = 0; i < rc->nf; i++) if (key_eq(e, rc->k[i], key, r->key_len)) break;
+        if (i == rc->nf) return 1;       /* source vanished with the conflict key (same name): map repacked */
+        for (j = rc->nf; j > i + 1; j--) { rc->k[j] = rc->k[j - 1]; rc->v[j] = rc->v[j - 1]; }
+        rc->k[i + 1] = vmp; rc->v[i + 1] = rc->v[i];
+        rc->nf++;
+        return 1;
+    case MOD_ADD:
+        if (count_keys(e, rc, key, r->key_len) != 0) return 0;
+        if (rc->nf + 1 > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
+        rc->k[rc->nf] = kmp; rc->v[rc->nf] = vmp; rc->nf++;
+        return 1;
+    case MOD_SET:
+        for (i = 0; i < rc->nf; i++) del[i] = key_eq(e, rc->k[i], key, r->key_len) ? 1 : 0;
+        compact(rc, del);
+        if (rc->nf + 1 > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 1; }
+        rc->k[rc->nf] = kmp; rc->v[rc->nf] = vmp; rc->nf++;
+        return 1;
+    case MOD_REMOVE:
+    case MOD_REMOVE_WILDCARD:
+    case MOD_REMOVE_REGEX:
+        match = 0;
+        for (i = 0; i < rc->nf; i++) {
+            if (r->type == MOD_REMOVE) del[i] = key_eq(e, rc->k[i], key, r->key_len) ? 1 : 0;
+            else if (r->type == MOD_REMOVE_WILDCARD) del[i] = key_prefix(e, rc->k[i], key, r->key_len) ? 1 : 0;
+            else del[i] = ref_rx(e, rc->k[i], r->key_rx, w) ? 1 : 0;
+            match += del[i];
+        }
+        if (match == 0) return 0;
+        compact(rc, del);
+        return 1;
+    case MOD_MOVE_TO_START:
+    case MOD_MOVE_TO_END:
+        match = 0;
+        for (i = 0; i < rc->nf; i++) { del[i] = key_prefix(e, rc->k[i], key, r->key_len) ? 1 : 0; match += del[i]; }
+        if (match == 0) return 0;
+        j = 0;
+        for (i = 0; i < rc->nf; i++) if (del[i] == (r->type == MOD_MOVE_TO_START)) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; j++; }
+        for (i = 0; i < rc->nf; i++) if (del[i] != (r->type == MOD_MOVE_TO_START)) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; j++; }
+        for (i = 0; i < rc->nf; i++) { rc->k[i] = w->tk[i]; rc->v[i] = w->tv[i]; }
+        return 1;
+    }
+    return 0;
+}
+
+/* returns 1 when the record was modified (and is re-encoded canonically) */
+FLB_HD int f_modify(const struct ch_env *e, const struct cf_modify *cf, struct ch_rec *rc, struct ch_scratch *w)
+{
+    const struct cf_mod_rule *r = (const struct cf_mod_rule *) (e->blob + cf->rules_off);
+    uint32_t i;
+    int mod = 0;
+    if (!mod_conditions(e, cf, rc, w)) return 0;
+    for (i = 0; i < cf->n_rules; i++) if (mod_rule(e, &r[i], rc, w)) mod = 1;
+    if (mod) { rc->reenc = 1; rc->style = ST_CANON; }
+    return mod;
+}
+
+/* ------------------------------------------------- filter_record_modifier */
+FLB_HD int ci_eq(const uint8_t *a, const uint8_t *b, uint32_t n)
+{
+    uint32_t i;
+    for (i = 0; i < n; i++) {
+        if (dt_lower(a[i]) != dt_lower(b[i])) return 0;
+        if (a[i] == 0) break;                 /* strncasecmp stops at NUL */
+    }
+    return 1;
+}
+
+/* returns: 0 passes untouched evidence-wise, sets *cause; *drop when no field is left */
+FLB_HD void f_recmod(const struct ch_env *e, const struct cf_recmod *cf, struct ch_rec *rc, int *cause, int *drop)
+{
+    const struct cf_rm_key *keys = 0;
+    const struct cf_rm_rec *recs = (const struct cf_rm_rec *) (e->blob + cf->records_off);
+    uint8_t del[CH_MAXF];
+    uint32_t nk = 0, q;
+    int is_delete = 0, i, remaining = rc->nf, total;
+
+    if (cf->n_remove > 0) { keys = (const struct cf_rm_key *) (e->blob + cf->remove_off); nk = cf->n_remove; is_delete = 1; }
+    else if (cf->n_allow > 0) { keys = (const struct cf_rm_key *) (e->blob + cf->allow_off); nk = cf->n_allow; is_delete = 0; }
+    for (i = 0; i < rc->nf; i++) del[i] = 0;
+    if (keys) {
+        for (i = 0; i < rc->nf; i++) {
+            const uint8_t *kp = 0; uint32_t kn = 0;
+            int kt = ref_view(e, rc->k[i], &kp, &kn), result = 0;
+            for (q = 0; q < nk && (kt == 1 || kt == 2); q++) {
+                if (!keys[q].dynamic && kn != keys[q].len) continue;
+                if (keys[q].dynamic && kn < keys[q].len) continue;
+                if (ci_eq(kp, e->blob + keys[q].off, keys[q].len)) { result = 1; break; }
+            }
+            if (result == is_delete) { del[i] = 1; remaining--; }
+        }
+    }
+    *cause = (remaining != rc->nf) || cf->n_records > 0;
+    total = remaining + (int) cf->n_records;
+    *drop = total <= 0;
+    if (*drop) return;
+    compact(rc, del);
+    if (rc->nf + (int) cf->n_records > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return; }
+    for (q = 0; q < cf->n_records; q++) {
+        rc->k[rc->nf] = mkref(RK_MP_CONST, recs[q].kmp_off, recs[q].kmp_len);
+        rc->v[rc->nf] = mkref(RK_MP_CONST, recs[q].vmp_off, recs[q].vmp_len);
+        rc->nf++;
+    }
+    rc->reenc = 1;
+    rc->style = ST_MAP32;
+}
+
+/* ------------------------------------------------------------- the chain */
+/* Runs record `ridx` (framed at off/len, kind 0) through the chain.
+ * EMIT=false: returns the output size (0 = dropped) and records evidence.
+ * EMIT=true : writes the record at `out` (the caller only calls it for size>0). */
+template <bool EMIT>
+FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off, uint32_t len, uint8_t *out)
+{
+    const struct chain_hdr *h = (const struct chain_hdr *) e->blob;
+    const struct chain_filter *f = (const struct chain_filter *) (e->blob + h->filters_off);
+    struct ch_rec rc;
+    struct ch_scratch w;
+    uint32_t k, cache_pos = 0;
+
+    if (rec_decode(e, off, len, &rc, h->empty_map_off) != 0) {
+        CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS);
+        return 0;
+    }
+    for (k = 0; k < h->n_filters; k++) {
+        const uint8_t *cfg = e->blob + f[k].cfg_off;
+        int assumed = (e->assume >> k) & 1;
+        switch (f[k].kind) {
+        case FLBGPU_F_PARSER:
+            if (!assumed) break;
+            f_parser<EMIT>(e, (const struct cf_parser *) cfg, &rc, &w, ridx, &cache_pos);
+            if (!EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_EMITTED);
+            break;
+        case FLBGPU_F_GREP:
+            if (!f_grep(e, (const struct cf_grep *) cfg, &rc, &w)) {
+                if (!EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_CAUSE);
+                if (assumed) return 0;
+            }
+            else if (!EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_EMITTED);
+            break;
+        case FLBGPU_F_MODIFY: {
+            /* evaluate on a copy when the filter is assumed NOTOUCH so the record passes unchanged */
+            if (assumed) {
+                if (f_modify(e, (const struct cf_modify *) cfg, &rc, &w) && !EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_CAUSE);
+            }
+            else if (!EMIT) {
+                struct ch_rec tmp = rc;
+                if (f_modify(e, (const struct cf_modify *) cfg, &tmp, &w)) CH_ATOMIC_OR(&e->fl_flags[k], CHF_CAUSE);
+            }
+            if (!EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_EMITTED);
+            break;
+        }
+        case FLBGPU_F_RECORD_MODIFIER: {
+            int cause = 0, drop = 0;
+            if (assumed) {
+                f_recmod(e, (const struct cf_recmod *) cfg, &rc, &cause, &drop);
+                if (!EMIT) { if (cause) CH_ATOMIC_OR(&e->fl_flags[k], CHF_CAUSE); if (!drop) CH_ATOMIC_OR(&e->fl_flags[k], CHF_EMITTED); }
+                if (drop) return 0;
+            }
+            else if (!EMIT) {
+                struct ch_rec tmp = rc;
+                f_recmod(e, (const struct cf_recmod *) cfg, &tmp, &cause, &drop);
+                if (cause) CH_ATOMIC_OR(&e->fl_flags[k], CHF_CAUSE);
+                if (!drop) CH_ATOMIC_OR(&e->fl_flags[k], CHF_EMITTED);
+            }
+            break;
+        }
+        default:
+            break;
+        }
+    }
+    if (!rc.reenc) {
+        if (EMIT) mp_copy(out, e->in + off, len);
+        return len;
+    }
+    return rec_emit(e, &rc, EMIT ? out : 0);
+}
+
+#endif

@@ -90,6 +90,105 @@ struct rx_prog {
 #define RX_R_ESTACK   -2   /* backtrack stack exhausted: rerun with a bigger stack */
 #define RX_R_EBUDGET  -3   /* step budget exhausted (catastrophic backtracking guard) */
 
+
+/* ------------------------------------------------------- chain program */
+/* All *_off fields are byte offsets from the blob base; 0 means "absent". */
+
+enum { FLBGPU_F_PARSER = 1, FLBGPU_F_GREP, FLBGPU_F_MODIFY, FLBGPU_F_RECORD_MODIFIER, FLBGPU_F_LOG_TO_METRICS };
+
+/* parser types: include/fluent-bit/flb_parser.h:30-33 */
+enum { FLBGPU_PARSER_REGEX = 1, FLBGPU_PARSER_JSON, FLBGPU_PARSER_LTSV, FLBGPU_PARSER_LOGFMT };
+/* Types casts: include/fluent-bit/flb_parser.h:70-76 */
+enum { FLBGPU_TYPE_INT = 1, FLBGPU_TYPE_FLOAT, FLBGPU_TYPE_BOOL, FLBGPU_TYPE_STRING, FLBGPU_TYPE_HEX };
+
+struct cf_ra_sub { uint32_t is_index, index, str_off, str_len; };
+struct cf_ra { uint32_t key_off, key_len, n_sub, sub_off; };
+
+struct cf_pname {              /* one (name, group) pair in onig_foreach_name order */
+    uint32_t kmp_off, kmp_len; /* the name as a msgpack str, in the constant pool */
+    uint32_t raw_off, raw_len; /* the name's bytes */
+    uint32_t group;
+    uint32_t is_time;          /* this is the Time_Key */
+    uint32_t cast;             /* FLBGPU_TYPE_* or 0 */
+    uint32_t pad;
+};
+
+struct cf_ptype { uint32_t key_off, key_len, type, pad; };
+
+struct cf_pdef {               /* device view of struct flb_parser (flb_parser.h:41-68) */
+    uint32_t type;
+    uint32_t rx_off;
+    uint32_t n_names, names_off;
+    uint32_t skip_empty, time_keep, time_strict, has_time;
+    uint32_t time_with_year, time_with_tz;
+    int32_t  time_offset;
+    uint32_t fmt_off, frac_off, has_frac;
+    uint32_t time_key_off, time_key_len;
+    uint32_t n_types, types_off;
+    uint32_t logfmt_no_bare_keys;
+    uint32_t n_groups;
+};
+
+struct cf_parser {             /* filter_parser */
+    uint32_t key_off, key_len;
+    uint32_t ra_off;
+    uint32_t reserve_data, preserve_key;
+    uint32_t n_parsers;
+    uint32_t pdef_off[8];
+};
+
+enum { GREP_REGEX = 1, GREP_EXCLUDE = 2 };
+enum { GREP_OP_LEGACY = 0, GREP_OP_OR, GREP_OP_AND };
+struct cf_grep_rule { uint32_t type, ra_off, rx_off, pad; };
+struct cf_grep { uint32_t op, n_rules, rules_off, pad; };
+
+/* plugins/filter_modify/modify.h rule / condition kinds */
+enum { MOD_RENAME = 1, MOD_HARD_RENAME, MOD_ADD, MOD_SET, MOD_REMOVE, MOD_REMOVE_WILDCARD, MOD_REMOVE_REGEX,
+       MOD_COPY, MOD_HARD_COPY, MOD_MOVE_TO_START, MOD_MOVE_TO_END };
+enum { MODC_KEY_EXISTS = 1, MODC_KEY_DOES_NOT_EXIST, MODC_A_KEY_MATCHES, MODC_NO_KEY_MATCHES,
+       MODC_KEY_VALUE_EQUALS, MODC_KEY_VALUE_DOES_NOT_EQUAL, MODC_KEY_VALUE_MATCHES,
+       MODC_KEY_VALUE_DOES_NOT_MATCH, MODC_MATCHING_KEYS_HAVE_MATCHING_VALUES,
+       MODC_MATCHING_KEYS_DO_NOT_HAVE_MATCHING_VALUES };
+struct cf_mod_cond { uint32_t type, ra_off, b_off, b_len, a_rx, b_rx, pad0, pad1; };
+struct cf_mod_rule {
+    uint32_t type;
+    uint32_t key_off, key_len;     /* raw bytes */
+    uint32_t kmp_off, kmp_len;     /* msgpack str */
+    uint32_t val_off, val_len;
+    uint32_t vmp_off, vmp_len;
+    uint32_t key_rx;
+    uint32_t pad0, pad1;
+};
+struct cf_modify { uint32_t n_conds, conds_off, n_rules, rules_off; };
+
+struct cf_rm_key { uint32_t off, len, dynamic, pad; };
+struct cf_rm_rec { uint32_t kmp_off, kmp_len, vmp_off, vmp_len; };
+struct cf_recmod { uint32_t n_records, records_off, n_remove, remove_off, n_allow, allow_off, pad0, pad1; };
+
+struct chain_filter { uint32_t kind, cfg_off; };
+
+#define FLBGPU_MAX_FILTERS 16
+struct chain_hdr {
+    uint32_t total_bytes;
+    uint32_t n_filters;
+    uint32_t filters_off;      /* struct chain_filter[] */
+    uint32_t cap_stride;       /* ints of capture cache per record (0 = none) */
+    uint32_t empty_map_off;    /* one byte 0x80 */
+    uint32_t needs_scratch;
+    uint32_t pad0, pad1;
+};
+
+/* per-filter chunk-level evidence accumulated by the evaluation pass */
+#define CHF_CAUSE   1u   /* some record made this filter "modify" the chunk */
+#define CHF_EMITTED 2u   /* some record left this filter */
+
+/* record-level problems (bit set in the per-call error word; the call fails loudly) */
+#define FLBGPU_E_FIELDS    1u   /* more top-level keys than the interpreter holds */
+#define FLBGPU_E_RXSTACK   2u   /* regex backtrack stack exhausted */
+#define FLBGPU_E_RXBUDGET  4u   /* regex step budget exhausted */
+#define FLBGPU_E_FLOAT     8u   /* decimal->double outside the exact fast path */
+#define FLBGPU_E_INDEX    16u   /* record index fast path failed */
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,333 @@
+/* kernels.cu -- sm_100a kernels and the CUDA implementation of the bk_* seam.
+ *
+ *   k_index<FILL> ..... K1 record index: every 0x92 byte is a record candidate; a
+ *                       candidate is kept when a complete, well-formed log event
+ *                       ([[ts, meta], body] or [ts, body]) starts there
+ *                       (reference framing rules: src/flb_log_event_decoder.c:214-297).
+ *                       Two passes (count -> prefix sum -> fill) keep file order.
+ *   k_index_check ..... the kept candidates must tile the chunk; the first gap ends
+ *                       the decodable prefix (the reference decoder stops there too).
+ *   k_scan_top ........ exclusive prefix sum over per-block totals (one CTA).
+ *   k_chain<EMIT> ..... one lane = one record through the filter-chain interpreter
+ *                       (dev_chain.cuh); EMIT=false sizes, EMIT=true writes.
+ *
+ * This is byte-stream work bounded by HBM traffic and instruction issue; there is no
+ * contraction here, so no tensor-core path.  Loads of chunk bytes are 128-bit and
+ * coalesced in k_index; k_chain lanes walk adjacent records (L1/L2 resident lines).
+ */
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include "flbgpu_internal.h"
+#include "dev_chain.cuh"
+
+static char g_err[256];
+static unsigned long long g_launches;
+static cudaStream_t g_stream;
+
+#define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
+    snprintf(g_err, sizeof(g_err), "%s: %s", #call, cudaGetErrorString(e_)); return -1; } } while (0)
+
+/* ---------------------------------------------------------------- helpers */
+/* exclusive scan of one value per thread over a 256-thread block */
+template <typename T>
+__device__ __forceinline__ T block_excl_scan_t(T v, T *total)
+{
+    __shared__ T wsum[8];
+    __shared__ T tot;
+    const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    T x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        T y = __shfl_up_sync(0xffffffffu, x, d);
+        if (lane >= (unsigned) d) x += y;
+    }
+    if (lane == 31) wsum[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        T s = lane < 8 ? wsum[lane] : 0;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            T y = __shfl_up_sync(0xffffffffu, s, d);
+            if (lane >= (unsigned) d) s += y;
+        }
+        if (lane < 8) wsum[lane] = s;
+        if (lane == 7) tot = s;
+    }
+    __syncthreads();
+    T base = warp ? wsum[warp - 1] : 0;
+    *total = tot;
+    __syncthreads();
+    return base + x - v;
+}
+__device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total)
+{
+    return block_excl_scan_t<uint32_t>(v, total);
+}
+
+/* ------------------------------------------------------------------ index */
+template <bool FILL>
+__global__ void __launch_bounds__(256) k_index(const uint8_t *__restrict__ in, uint32_t len,
+                                               uint32_t *__restrict__ tile, uint32_t *__restrict__ o_off,
+                                               uint32_t *__restrict__ o_len, uint8_t *__restrict__ o_kind)
+{
+    __shared__ uint16_t cand[BK_INDEX_TILE];
+    __shared__ uint32_t v2ok[BK_INDEX_TILE / 32];   /* bit per tile byte: a valid v2 frame starts here */
+    __shared__ uint32_t s_ncand;
+    const uint32_t base = blockIdx.x * BK_INDEX_TILE;
+    uint32_t ncand = 0;
+
+    /* phase 1: ordered list of candidate positions in this tile */
+    for (uint32_t it = 0; it < BK_INDEX_TILE / (256 * 16); it++) {
+        const uint32_t rel = (it * 256 + threadIdx.x) * 16;
+        const uint32_t pos = base + rel;
+        uint32_t mask = 0;
+        if (pos + 16 <= len) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(in + pos);   /* 128-bit coalesced load */
+            const uint32_t w[4] = { v.x, v.y, v.z, v.w };
+#pragma unroll
+            for (int k = 0; k < 16; k++) if (((w[k >> 2] >> (8 * (k & 3))) & 0xff) == 0x92) mask |= 1u << k;
+        }
+        else {
+            for (int k = 0; k < 16; k++) if (pos + k < len && in[pos + k] == 0x92) mask |= 1u << k;
+        }
+        uint32_t tot;
+        uint32_t at = block_excl_scan(__popc(mask), &tot) + ncand;
+        while (mask) {
+            int k = __ffs(mask) - 1;
+            mask &= mask - 1;
+            cand[at++] = (uint16_t) (rel + k);
+        }
+        ncand += tot;
+    }
+    if (threadIdx.x == 0) s_ncand = ncand;
+    v2ok[threadIdx.x] = 0;
+    __syncthreads();
+    ncand = s_ncand;
+
+    /* phase 2: validate candidates, 256 at a time, keeping order.  A candidate whose
+     * predecessor byte starts a valid v2 frame is that frame's header array, not a
+     * record (rec_is_shadowed); within a tile the predecessor's verdict is read from
+     * shared memory (it belongs to an earlier or the same round: positions ascend). */
+    uint32_t kept = 0;
+    const uint32_t tile_base = FILL ? tile[blockIdx.x] : 0;
+    for (uint32_t r = 0; r < ncand; r += 256) {
+        const uint32_t j = r + threadIdx.x;
+        uint32_t ok = 0, rlen = 0;
+        int kind = 0;
+        uint32_t pos = 0, rel = 0;
+        if (j < ncand) {
+            rel = cand[j];
+            pos = base + rel;
+            const uint8_t *e = rec_frame(in + pos, in + len, &kind);
+            if (e) {
+                ok = 1; rlen = (uint32_t) (e - (in + pos));
+                if (in[pos + 1] == 0x92) atomicOr(&v2ok[rel >> 5], 1u << (rel & 31));
+            }
+        }
+        __syncthreads();
+        if (ok && pos > 0 && in[pos - 1] == 0x92) {
+            if (rel > 0) { if ((v2ok[(rel - 1) >> 5] >> ((rel - 1) & 31)) & 1) ok = 0; }
+            else if (rec_is_shadowed(in, in + pos, in + len)) ok = 0;      /* predecessor lives in the previous tile */
+        }
+        uint32_t tot;
+        uint32_t at = block_excl_scan(ok, &tot);
+        if (FILL && ok) {
+            const uint32_t o = tile_base + kept + at;
+            o_off[o] = pos; o_len[o] = rlen; o_kind[o] = (uint8_t) kind;
+        }
+        kept += tot;
+    }
+    if (!FILL && threadIdx.x == 0) tile[blockIdx.x] = kept;
+}
+
+/* exclusive scan of a[0..n) in place, one CTA; total in *out_total */
+template <typename T>
+__global__ void __launch_bounds__(256) k_scan_top(T *a, uint32_t n, unsigned long long *out_total)
+{
+    unsigned long long carry = 0;
+    for (uint32_t b = 0; b < n; b += 256) {
+        const uint32_t i = b + threadIdx.x;
+        unsigned long long v = i < n ? (unsigned long long) a[i] : 0, tot;
+        unsigned long long ex = block_excl_scan_t<unsigned long long>(v, &tot);
+        if (i < n) a[i] = (T) (carry + ex);
+        carry += tot;
+    }
+    if (threadIdx.x == 0) *out_total = carry;
+}
+
+__global__ void k_index_check(const uint32_t *__restrict__ off, const uint32_t *__restrict__ rlen, uint32_t n,
+                              uint32_t total, uint32_t *first_break)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t next = (i + 1 < n) ? off[i + 1] : total;
+    if (off[i] + rlen[i] != next) atomicMin(first_break, i);
+    if (i == 0 && off[0] != 0) atomicMin(first_break, 0xfffffffeu);    /* marker: does not start at 0 */
+}
+
+/* ------------------------------------------------------------------ chain */
+struct k_chain_params {
+    struct ch_env env;
+    const uint32_t *off, *len;
+    const uint8_t *kind;
+    uint32_t n_rec;
+    uint32_t *size;
+    uint64_t *bsum;
+    uint8_t *out;
+};
+
+template <bool EMIT>
+__global__ void __launch_bounds__(BK_REC_BLOCK) k_chain(const k_chain_params p)
+{
+    const uint32_t i = blockIdx.x * BK_REC_BLOCK + threadIdx.x;
+    uint32_t sz = 0;
+    if (!EMIT) {
+        if (i < p.n_rec && p.kind[i] == 0) sz = chain_record<false>(&p.env, i, p.off[i], p.len[i], 0);
+        if (i < p.n_rec) p.size[i] = sz;
+        uint32_t tot;
+        block_excl_scan(sz, &tot);
+        if (threadIdx.x == 0) p.bsum[blockIdx.x] = tot;
+    }
+    else {
+        if (i < p.n_rec) sz = p.size[i];
+        uint32_t tot;
+        const uint32_t local = block_excl_scan(sz, &tot);
+        if (sz) chain_record<true>(&p.env, i, p.off[i], p.len[i], p.out + p.bsum[blockIdx.x] + local);
+    }
+}
+
+/* ------------------------------------------------------------ bk_* seam */
+extern "C" {
+
+const char *bk_name(void) { return "cuda-sm_100a"; }
+const char *bk_last_error(void) { return g_err; }
+uint64_t bk_launch_count(void) { return g_launches; }
+
+int bk_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+int bk_init(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n <= 0) {
+        snprintf(g_err, sizeof(g_err), "no CUDA device available (%s); libflbgpu has no CPU path",
+                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return -1;
+    }
+    if (device < 0 || device >= n) { snprintf(g_err, sizeof(g_err), "device %d out of range (0..%d)", device, n - 1); return -1; }
+    CK(cudaSetDevice(device));
+    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    /* the interpreter keeps its field list and backtrack stack in local memory */
+    CK(cudaFuncSetCacheConfig(k_chain<false>, cudaFuncCachePreferL1));
+    CK(cudaFuncSetCacheConfig(k_chain<true>, cudaFuncCachePreferL1));
+    return 0;
+}
+
+void *bk_alloc(size_t n) { void *p = 0; if (cudaMalloc(&p, n ? n : 16) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaMalloc(%zu) failed", n); return 0; } return p; }
+void bk_free(void *p) { if (p) cudaFree(p); }
+void *bk_alloc_host(size_t n) { void *p = 0; if (cudaMallocHost(&p, n ? n : 16) != cudaSuccess) return 0; return p; }
+void bk_free_host(void *p) { if (p) cudaFreeHost(p); }
+int bk_h2d(void *d, const void *h, size_t n) { CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, g_stream)); return 0; }
+int bk_d2h(void *h, const void *d, size_t n) { CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, g_stream)); return 0; }
+int bk_zero(void *d, size_t n) { CK(cudaMemsetAsync(d, 0, n, g_stream)); return 0; }
+int bk_sync(void) { CK(cudaStreamSynchronize(g_stream)); return 0; }
+void *bk_stream(void) { return (void *) g_stream; }
+
+static unsigned long long *g_dtotal;   /* device scratch for totals / first_break */
+static int ensure_small(void)
+{
+    if (!g_dtotal) CK(cudaMalloc((void **) &g_dtotal, 64));
+    return 0;
+}
+
+int bk_index_count(const uint8_t *d_in, uint32_t len, uint32_t *d_tile, uint32_t n_tiles, uint32_t *n_cand)
+{
+    unsigned long long tot = 0;
+    if (ensure_small()) return -1;
+    *n_cand = 0;
+    if (n_tiles == 0) return 0;
+    k_index<false><<<n_tiles, 256, 0, g_stream>>>(d_in, len, d_tile, 0, 0, 0);
+    k_scan_top<uint32_t><<<1, 256, 0, g_stream>>>(d_tile, n_tiles, g_dtotal);
+    g_launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&tot, g_dtotal, sizeof(tot), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    *n_cand = (uint32_t) tot;
+    return 0;
+}
+
+int bk_index_fill(const uint8_t *d_in, uint32_t len, const uint32_t *d_tile, uint32_t n_tiles, uint32_t n_cand,
+                  uint32_t *d_off, uint32_t *d_len, uint8_t *d_kind, uint32_t *n_valid, int *tiled)
+{
+    uint32_t fb = 0xffffffffu;
+    uint32_t *d_fb = (uint32_t *) (g_dtotal + 1);
+    *n_valid = 0; *tiled = (len == 0);
+    if (n_cand == 0) return 0;
+    k_index<true><<<n_tiles, 256, 0, g_stream>>>(d_in, len, (uint32_t *) d_tile, d_off, d_len, d_kind);
+    CK(cudaMemcpyAsync(d_fb, &fb, sizeof(fb), cudaMemcpyHostToDevice, g_stream));
+    k_index_check<<<(n_cand + 255) / 256, 256, 0, g_stream>>>(d_off, d_len, n_cand, len, d_fb);
+    g_launches += 2;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(&fb, d_fb, sizeof(fb), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    if (fb == 0xffffffffu) { *n_valid = n_cand; *tiled = 1; return 0; }
+    if (fb == 0xfffffffeu) {                      /* first candidate is not at offset 0 */
+        /* a break may ALSO exist; either way nothing before the garbage decodes */
+        *n_valid = 0; *tiled = 0; return 0;
+    }
+    if (fb == n_cand - 1) { *n_valid = n_cand; *tiled = 0; return 0; }   /* trailing bytes after the last record */
+    snprintf(g_err, sizeof(g_err), "record index: candidate chain breaks at record %u of %u "
+             "(record-shaped data nested inside a record is not supported yet)", fb, n_cand);
+    return -1;
+}
+
+static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_t *d_out)
+{
+    p->env.in = a->d_in; p->env.in_len = a->in_len; p->env.blob = a->d_blob; p->env.scr = a->d_scr;
+    p->env.capcache = a->d_capcache; p->env.cap_stride = a->cap_stride; p->env.now = a->now;
+    p->env.assume = a->assume; p->env.fl_flags = a->d_flags; p->env.err = a->d_flags + FLBGPU_MAX_FILTERS;
+    p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->n_rec = a->n_rec;
+    p->size = a->d_size; p->bsum = a->d_bsum; p->out = d_out;
+}
+
+int bk_chain_size(const struct bk_chain_args *a, uint32_t *h_flags, uint64_t *total)
+{
+    k_chain_params p;
+    unsigned long long tot = 0;
+    const uint32_t nb = (a->n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK;
+    if (ensure_small()) return -1;
+    *total = 0;
+    CK(cudaMemsetAsync(a->d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1), g_stream));
+    if (nb) {
+        fill_params(a, &p, 0);
+        k_chain<false><<<nb, BK_REC_BLOCK, 0, g_stream>>>(p);
+        k_scan_top<uint64_t><<<1, 256, 0, g_stream>>>((uint64_t *) a->d_bsum, nb, g_dtotal);
+        g_launches += 2;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&tot, g_dtotal, sizeof(tot), cudaMemcpyDeviceToHost, g_stream));
+    }
+    CK(cudaMemcpyAsync(h_flags, a->d_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    *total = tot;
+    return 0;
+}
+
+int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out)
+{
+    k_chain_params p;
+    const uint32_t nb = (a->n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK;
+    if (!nb) return 0;
+    fill_params(a, &p, d_out);
+    k_chain<true><<<nb, BK_REC_BLOCK, 0, g_stream>>>(p);
+    g_launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+}

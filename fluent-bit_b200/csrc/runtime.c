@@ -1,0 +1,1068 @@
+/* runtime.c -- host side of libflbgpu (plain C): contexts, parser definitions,
+ * filter instances (property lists, cb_init-time validation), chain compilation
+ * into the device program blob, and the per-call driver
+ *   upload -> record index -> evaluation pass (-> revise chunk-level assumptions)
+ *          -> prefix sum -> emission pass -> download.
+ *
+ * Reference behaviour mirrored here (paths in /root/reference):
+ *   flb_parser_create ............ src/flb_parser.c:148-348
+ *   flb_filter_set_property ...... src/flb_filter.c:325-410
+ *   filter_parser cb_init ........ plugins/filter_parser/filter_parser.c:60-172
+ *   filter_grep set_rules ........ plugins/filter_grep/grep.c:56-165,196-248
+ *   filter_modify setup .......... plugins/filter_modify/modify.c:141-513
+ *   record_modifier configure .... plugins/filter_record_modifier/filter_modifier.c:36-160
+ *   record accessor text ......... src/flb_record_accessor.c:64-232, src/record_accessor/ra.l,ra.y
+ *   chunk-level MODIFIED/NOTOUCH . each plugin's cb_filter epilogue (see dev_chain.cuh header)
+ */
+#define _GNU_SOURCE
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <strings.h>
+#include <ctype.h>
+#include <time.h>
+#include "../../include/flbgpu.h"
+#include "flbgpu_internal.h"
+#include "rx_compile.h"
+
+static char g_rt_err[512];
+static void set_err(const char *fmt, const char *a, const char *b)
+{
+    snprintf(g_rt_err, sizeof(g_rt_err), fmt, a ? a : "", b ? b : "");
+}
+const char *flbgpu_last_error(void)
+{
+    if (g_rt_err[0]) return g_rt_err;
+    return bk_last_error();
+}
+const char *flbgpu_backend_name(void) { return bk_name(); }
+int flbgpu_device_count(void) { return bk_device_count(); }
+
+/* ------------------------------------------------------------------ blob */
+struct blob { uint8_t *p; size_t n, cap; };
+
+static uint32_t blob_reserve(struct blob *b, size_t n, size_t align)
+{
+    size_t off = (b->n + align - 1) & ~(align - 1);
+    if (off + n > b->cap) {
+        size_t nc = b->cap ? b->cap * 2 : 4096;
+        while (nc < off + n) nc *= 2;
+        b->p = realloc(b->p, nc);
+        memset(b->p + b->cap, 0, nc - b->cap);
+        b->cap = nc;
+    }
+    memset(b->p + b->n, 0, off - b->n);
+    b->n = off + n;
+    return (uint32_t) off;
+}
+static uint32_t blob_add(struct blob *b, const void *d, size_t n, size_t align)
+{
+    uint32_t off = blob_reserve(b, n ? n : 1, align);
+    if (n) memcpy(b->p + off, d, n);
+    return off;
+}
+/* msgpack str (pack_template.h:762-780) */
+static uint32_t blob_add_mpstr(struct blob *b, const char *s, uint32_t n, uint32_t *out_len)
+{
+    uint8_t h[5];
+    uint32_t hl, off;
+    if (n < 32) { h[0] = 0xa0 | n; hl = 1; }
+    else if (n < 256) { h[0] = 0xd9; h[1] = (uint8_t) n; hl = 2; }
+    else if (n < 65536) { h[0] = 0xda; h[1] = n >> 8; h[2] = n & 0xff; hl = 3; }
+    else { h[0] = 0xdb; h[1] = n >> 24; h[2] = n >> 16; h[3] = n >> 8; h[4] = n; hl = 5; }
+    off = blob_reserve(b, hl + n, 1);
+    memcpy(b->p + off, h, hl);
+    memcpy(b->p + off + hl, s, n);
+    *out_len = hl + n;
+    return off;
+}
+
+/* --------------------------------------------------------------- objects */
+struct flbgpu_parser {
+    flbgpu_ctx *ctx;
+    char *name;
+    int type;
+    struct rx_compiled rx;
+    int has_rx;
+    int skip_empty, time_keep, time_strict, logfmt_no_bare_keys;
+    char *time_fmt;          /* format up to %L, already "%Y "-prefixed when the format has no year */
+    char *time_frac;         /* format after %L or NULL */
+    char *time_key;
+    int time_with_year, time_with_tz, time_offset, has_time;
+    struct flbgpu_parser_types *types;
+    int types_len;
+    struct flbgpu_parser *next;
+    flbgpu_chain *solo;      /* lazily built chain behind flbgpu_parser_do() */
+    flbgpu_filter *solo_filter;
+};
+
+struct kv { char *k, *v; struct kv *next; };
+
+struct flbgpu_filter {
+    flbgpu_ctx *ctx;
+    int kind;
+    struct kv *props, *props_tail;
+    int inited;
+    flbgpu_chain *solo;
+};
+
+struct flbgpu_ctx {
+    int device;
+    struct flbgpu_parser *parsers;
+};
+
+struct flbgpu_chain {
+    flbgpu_ctx *ctx;
+    flbgpu_filter *f[FLBGPU_MAX_FILTERS];
+    int nf;
+    int inited;
+    struct blob blob;
+    uint8_t *d_blob;
+    uint32_t cap_stride;
+    /* device buffers, grown on demand */
+    uint8_t *d_in;  size_t cap_in;
+    uint8_t *d_out; size_t cap_out;
+    uint32_t *d_tile; size_t cap_tile;
+    uint32_t *d_off, *d_len, *d_size; uint8_t *d_kind; size_t cap_rec;
+    uint64_t *d_bsum; size_t cap_bsum;
+    int32_t *d_cap; size_t cap_cap;
+    uint32_t *d_flags;
+    uint8_t *h_stage; size_t cap_stage;      /* pinned staging */
+    struct flbgpu_stats st;
+};
+
+/* ---------------------------------------------------------------- context */
+flbgpu_ctx *flbgpu_init(int device)
+{
+    flbgpu_ctx *c;
+    g_rt_err[0] = 0;
+    if (bk_init(device) != 0) return NULL;
+    c = calloc(1, sizeof(*c));
+    c->device = device;
+    return c;
+}
+
+void flbgpu_parser_destroy(flbgpu_parser *p);
+
+void flbgpu_shutdown(flbgpu_ctx *ctx)
+{
+    if (!ctx) return;
+    while (ctx->parsers) flbgpu_parser_destroy(ctx->parsers);
+    free(ctx);
+}
+
+void *flbgpu_dev_alloc(flbgpu_ctx *ctx, size_t n) { (void) ctx; return bk_alloc(n); }
+void  flbgpu_dev_free(flbgpu_ctx *ctx, void *p) { (void) ctx; bk_free(p); }
+int   flbgpu_dev_upload(flbgpu_ctx *ctx, void *d, const void *h, size_t n) { (void) ctx; if (bk_h2d(d, h, n)) return -1; return bk_sync(); }
+int   flbgpu_dev_download(flbgpu_ctx *ctx, void *h, const void *d, size_t n) { (void) ctx; if (bk_d2h(h, d, n)) return -1; return bk_sync(); }
+void *flbgpu_host_alloc(flbgpu_ctx *ctx, size_t n) { (void) ctx; return bk_alloc_host(n); }
+void  flbgpu_host_free(flbgpu_ctx *ctx, void *p) { (void) ctx; bk_free_host(p); }
+void *flbgpu_stream(flbgpu_ctx *ctx) { (void) ctx; return bk_stream(); }
+
+/* ---------------------------------------------------------------- parsers */
+static int tzone_offset(const char *str, int len, int *tmdiff)
+{
+    /* flb_parser_tzone_offset(), src/flb_parser.c:1069-1127 */
+    int neg;
+    long hour, min;
+    const char *end, *p = str;
+    if (*p == 'Z') { *tmdiff = 0; return 0; }
+    if (*p != '+' && *p != '-') { *tmdiff = 0; return -1; }
+    if (len < 4) { *tmdiff = 0; return -1; }
+    neg = (*p++ == '-');
+    end = str + len;
+    hour = ((p[0] - '0') * 10) + (p[1] - '0');
+    if (end - p == 5 && p[2] == ':') {
+        if (len < 5) { *tmdiff = 0; return -1; }
+        min = ((p[3] - '0') * 10) + (p[4] - '0');
+    }
+    else min = ((p[2] - '0') * 10) + (p[3] - '0');
+    if (hour < 0 || hour > 59 || min < 0 || min > 59) return -1;
+    *tmdiff = (int) ((hour * 3600) + (min * 60));
+    if (neg) *tmdiff = -*tmdiff;
+    return 0;
+}
+
+/* conversions dev_time.cuh implements */
+static int time_fmt_supported(const char *f, char *bad)
+{
+    for (; *f; f++) {
+        if (*f != '%') continue;
+        f++;
+        while (*f == 'E' || *f == 'O') f++;
+        if (!*f) return 1;
+        if (!strchr("%DRrTFAaBbhCedkHlIjMmpSsUWwugGVYyZznt", *f)) { *bad = *f; return 0; }
+    }
+    return 1;
+}
+
+flbgpu_parser *flbgpu_parser_get(flbgpu_ctx *ctx, const char *name)
+{
+    struct flbgpu_parser *p;
+    for (p = ctx->parsers; p; p = p->next) if (p->name && strcmp(p->name, name) == 0) return p;
+    return NULL;
+}
+
+flbgpu_parser *flbgpu_parser_create(flbgpu_ctx *ctx, const char *name, const char *format,
+                                    const char *p_regex, int skip_empty,
+                                    const char *time_fmt, const char *time_key,
+                                    const char *time_offset, int time_keep, int time_strict,
+                                    int time_system_timezone, int logfmt_no_bare_keys,
+                                    struct flbgpu_parser_types *types, int types_len, void *decoders)
+{
+    struct flbgpu_parser *p;
+    int i;
+    g_rt_err[0] = 0;
+    if (!ctx || !name || !format) { set_err("parser: missing argument%s%s", NULL, NULL); return NULL; }
+    if (flbgpu_parser_get(ctx, name)) { set_err("[parser] parser named '%s' already exists, skip.%s", name, NULL); return NULL; }
+    if (decoders) { set_err("[parser:%s] Decode_Field is not supported on the GPU path%s", name, NULL); return NULL; }
+    if (time_system_timezone) { set_err("[parser:%s] Time_System_Timezone is not supported on the GPU path%s", name, NULL); return NULL; }
+    p = calloc(1, sizeof(*p));
+    p->ctx = ctx;
+    if (!strcasecmp(format, "regex")) p->type = FLBGPU_PARSER_REGEX;
+    else if (!strcasecmp(format, "json")) p->type = FLBGPU_PARSER_JSON;
+    else if (!strcasecmp(format, "ltsv")) p->type = FLBGPU_PARSER_LTSV;
+    else if (!strcasecmp(format, "logfmt")) p->type = FLBGPU_PARSER_LOGFMT;
+    else { set_err("[parser:%s] Invalid format %s", name, format); free(p); return NULL; }
+    if (p->type != FLBGPU_PARSER_REGEX) {
+        set_err("[parser:%s] format %s is not implemented on the GPU path yet", name, format);
+        free(p);
+        return NULL;
+    }
+    if (p->type == FLBGPU_PARSER_REGEX) {
+        if (!p_regex) { set_err("[parser:%s] Invalid regex pattern%s", name, NULL); free(p); return NULL; }
+        if (rx_compile(p_regex, &p->rx) != 0) {
+            char tmp[300];
+            snprintf(tmp, sizeof(tmp), "%s (%s)", p_regex, p->rx.err);
+            set_err("[parser:%s] Invalid regex pattern %s", name, tmp);
+            free(p);
+            return NULL;
+        }
+        p->has_rx = 1;
+        p->skip_empty = skip_empty;
+    }
+    p->name = strdup(name);
+    if (time_fmt) {
+        char *fmt, *l;
+        char bad = 0;
+        p->has_time = 1;
+        if (strstr(time_fmt, "%Y") || strstr(time_fmt, "%y") || strstr(time_fmt, "%s")) {
+            p->time_with_year = 1;
+            fmt = strdup(time_fmt);
+        }
+        else {
+            p->time_with_year = 0;
+            fmt = malloc(strlen(time_fmt) + 4);
+            sprintf(fmt, "%%Y %s", time_fmt);
+        }
+        if (strstr(time_fmt, "%z") || strstr(time_fmt, "%Z") || strstr(time_fmt, "%SZ") || strstr(time_fmt, "%S.%LZ"))
+            p->time_with_tz = 1;
+        l = strstr(fmt, "%L");
+        if (l) { l[0] = 0; p->time_frac = strdup(l + 2); }
+        p->time_fmt = fmt;
+        if (!time_fmt_supported(p->time_fmt, &bad) || (p->time_frac && !time_fmt_supported(p->time_frac, &bad))) {
+            char b[2] = { bad, 0 };
+            set_err("[parser:%s] time conversion %%%s is not supported on the GPU path", name, b);
+            flbgpu_parser_destroy(p);
+            return NULL;
+        }
+        if (time_offset) {
+            int diff = 0;
+            if (tzone_offset(time_offset, (int) strlen(time_offset), &diff) == -1) { flbgpu_parser_destroy(p); return NULL; }
+            p->time_offset = diff;
+        }
+    }
+    if (time_key) p->time_key = strdup(time_key);
+    p->time_keep = time_keep;
+    p->time_strict = time_strict;
+    p->logfmt_no_bare_keys = logfmt_no_bare_keys;
+    if (types_len > 0) {
+        p->types = calloc(types_len, sizeof(*types));
+        for (i = 0; i < types_len; i++) {
+            p->types[i].key = types[i].key ? strndup(types[i].key, types[i].key_len) : NULL;
+            p->types[i].key_len = types[i].key_len;
+            p->types[i].type = types[i].type;
+        }
+        p->types_len = types_len;
+    }
+    p->next = ctx->parsers;
+    ctx->parsers = p;
+    return p;
+}
+
+void flbgpu_parser_destroy(flbgpu_parser *p)
+{
+    struct flbgpu_parser **pp;
+    int i;
+    if (!p) return;
+    for (pp = &p->ctx->parsers; *pp; pp = &(*pp)->next) if (*pp == p) { *pp = p->next; break; }
+    if (p->solo) flbgpu_chain_destroy(p->solo);
+    if (p->solo_filter) flbgpu_filter_destroy(p->solo_filter);
+    if (p->has_rx) rx_compiled_free(&p->rx);
+    for (i = 0; i < p->types_len; i++) free(p->types[i].key);
+    free(p->types); free(p->name); free(p->time_fmt); free(p->time_frac); free(p->time_key);
+    free(p);
+}
+
+/* emit the device view of a parser; returns its offset */
+static uint32_t emit_pdef(struct blob *b, struct flbgpu_parser *p)
+{
+    struct cf_pdef d;
+    uint32_t off, i, nn = 0;
+    memset(&d, 0, sizeof(d));
+    d.type = p->type;
+    d.skip_empty = p->skip_empty; d.time_keep = p->time_keep; d.time_strict = p->time_strict;
+    d.has_time = p->has_time; d.time_with_year = p->time_with_year; d.time_with_tz = p->time_with_tz;
+    d.time_offset = p->time_offset; d.logfmt_no_bare_keys = p->logfmt_no_bare_keys;
+    if (p->has_time) {
+        d.fmt_off = blob_add(b, p->time_fmt, strlen(p->time_fmt) + 1, 1);
+        if (p->time_frac) { d.has_frac = 1; d.frac_off = blob_add(b, p->time_frac, strlen(p->time_frac) + 1, 1); }
+    }
+    if (p->has_rx) {
+        const char *tk = p->time_key ? p->time_key : "time";
+        struct cf_pname *nm;
+        int ni, g;
+        d.rx_off = blob_add(b, p->rx.prog, p->rx.prog->total_bytes, 16);
+        d.n_groups = p->rx.prog->n_groups;
+        for (ni = 0; ni < p->rx.n_names; ni++) nn += p->rx.names[ni].n_groups;
+        nm = calloc(nn ? nn : 1, sizeof(*nm));
+        i = 0;
+        for (ni = 0; ni < p->rx.n_names; ni++) {
+            const char *name = p->rx.names[ni].name;
+            uint32_t len = (uint32_t) strlen(name);
+            for (g = 0; g < p->rx.names[ni].n_groups; g++, i++) {
+                int t;
+                nm[i].kmp_off = blob_add_mpstr(b, name, len, &nm[i].kmp_len);
+                nm[i].raw_off = blob_add(b, name, len, 1);
+                nm[i].raw_len = len;
+                nm[i].group = p->rx.names[ni].groups[g];
+                nm[i].is_time = p->has_time && strcmp(name, tk) == 0;
+                for (t = 0; t < p->types_len; t++) {
+                    if (p->types[t].key && (uint32_t) p->types[t].key_len == len && !strncmp(name, p->types[t].key, len)) {
+                        nm[i].cast = p->types[t].type;
+                        break;
+                    }
+                }
+            }
+        }
+        d.n_names = nn;
+        d.names_off = blob_add(b, nm, sizeof(*nm) * (nn ? nn : 1), 8);
+        free(nm);
+    }
+    off = blob_add(b, &d, sizeof(d), 8);
+    return off;
+}
+
+/* ----------------------------------------------------------------- filters */
+static int plugin_kind(const char *name)
+{
+    if (!strcasecmp(name, "parser")) return FLBGPU_F_PARSER;
+    if (!strcasecmp(name, "grep")) return FLBGPU_F_GREP;
+    if (!strcasecmp(name, "modify")) return FLBGPU_F_MODIFY;
+    if (!strcasecmp(name, "record_modifier")) return FLBGPU_F_RECORD_MODIFIER;
+    return 0;
+}
+
+flbgpu_filter *flbgpu_filter_new(flbgpu_ctx *ctx, const char *plugin)
+{
+    flbgpu_filter *f;
+    int kind = plugin ? plugin_kind(plugin) : 0;
+    g_rt_err[0] = 0;
+    if (!ctx || !kind) { set_err("unknown filter plugin '%s'%s", plugin, NULL); return NULL; }
+    f = calloc(1, sizeof(*f));
+    f->ctx = ctx;
+    f->kind = kind;
+    return f;
+}
+
+int flbgpu_filter_set_property(flbgpu_filter *f, const char *k, const char *v)
+{
+    struct kv *n;
+    if (!f || !k || !v) return -1;
+    /* instance-level keys are consumed by the framework, not by the plugin
+     * (src/flb_filter.c:346-395) */
+    if (!strcasecmp(k, "match") || !strcasecmp(k, "match_regex") || !strcasecmp(k, "alias") ||
+        !strcasecmp(k, "log_level") || !strcasecmp(k, "log_suppress_interval")) return 0;
+    n = calloc(1, sizeof(*n));
+    n->k = strdup(k);
+    n->v = strdup(v);
+    if (f->props_tail) f->props_tail->next = n; else f->props = n;
+    f->props_tail = n;
+    return 0;
+}
+
+void flbgpu_filter_destroy(flbgpu_filter *f)
+{
+    struct kv *n, *nx;
+    if (!f) return;
+    if (f->solo) flbgpu_chain_destroy(f->solo);
+    for (n = f->props; n; n = nx) { nx = n->next; free(n->k); free(n->v); free(n); }
+    free(f);
+}
+
+static int parse_bool(const char *v)
+{
+    /* flb_utils_bool() */
+    if (!strcasecmp(v, "true") || !strcasecmp(v, "on") || !strcasecmp(v, "yes")) return 1;
+    if (!strcasecmp(v, "false") || !strcasecmp(v, "off") || !strcasecmp(v, "no")) return 0;
+    return -1;
+}
+
+/* record accessor text -> struct cf_ra in the blob.  Supported shapes: "$key",
+ * "$key['a'][0]...", and a plain string (taken as the key name).  Returns 0 on error. */
+static uint32_t emit_ra(struct blob *b, const char *s)
+{
+    struct cf_ra ra;
+    struct cf_ra_sub subs[32];
+    uint32_t ns = 0;
+    memset(&ra, 0, sizeof(ra));
+    if (!s || !*s) return 0;
+    if (s[0] != '$') {
+        if (strchr(s, '$')) { set_err("unsupported record accessor '%s'%s", s, NULL); return 0; }
+        ra.key_off = blob_add(b, s, strlen(s), 1);
+        ra.key_len = (uint32_t) strlen(s);
+        return blob_add(b, &ra, sizeof(ra), 8);
+    }
+    {
+        const char *p = s + 1, *st = p;
+        if (!(isalpha((unsigned char) *p) || *p == '_')) { set_err("invalid record accessor? '%s'%s", s, NULL); return 0; }
+        while (isalnum((unsigned char) *p) || *p == '_' || *p == '.' || *p == '-' || *p == '/') {
+            /* src/flb_record_accessor.c:170-182: '.', ' ', ',' and '"' end the accessor text */
+            if (*p == '.') break;
+            p++;
+        }
+        ra.key_off = blob_add(b, st, (size_t) (p - st), 1);
+        ra.key_len = (uint32_t) (p - st);
+        while (*p == '[') {
+            p++;
+            if (ns >= 32) { set_err("record accessor too deep '%s'%s", s, NULL); return 0; }
+            if (*p == '\'') {
+                char *tmp = malloc(strlen(p) + 1);
+                size_t n = 0;
+                p++;
+                for (;;) {
+                    if (!*p) { free(tmp); set_err("invalid record accessor? '%s'%s", s, NULL); return 0; }
+                    if (*p == '\'') { if (p[1] == '\'') { tmp[n++] = '\''; p += 2; continue; } break; }
+                    tmp[n++] = *p++;
+                }
+                p++;
+                subs[ns].is_index = 0; subs[ns].index = 0;
+                subs[ns].str_off = blob_add(b, tmp, n, 1);
+                subs[ns].str_len = (uint32_t) n;
+                free(tmp);
+            }
+            else if (isdigit((unsigned char) *p)) {
+                subs[ns].is_index = 1; subs[ns].index = (uint32_t) atoi(p);
+                subs[ns].str_off = 0; subs[ns].str_len = 0;
+                while (isdigit((unsigned char) *p)) p++;
+            }
+            else { set_err("invalid record accessor? '%s'%s", s, NULL); return 0; }
+            if (*p != ']') { set_err("invalid record accessor? '%s'%s", s, NULL); return 0; }
+            p++;
+            ns++;
+        }
+        if (*p && *p != '.' && *p != ' ' && *p != ',' && *p != '"') { set_err("invalid record accessor? '%s'%s", s, NULL); return 0; }
+        if (*p) { set_err("unsupported record accessor '%s' (text after the key)%s", s, NULL); return 0; }
+        ra.n_sub = ns;
+        if (ns) ra.sub_off = blob_add(b, subs, sizeof(subs[0]) * ns, 8);
+        return blob_add(b, &ra, sizeof(ra), 8);
+    }
+}
+
+static uint32_t emit_rx(struct blob *b, const char *pattern, uint32_t *max_groups)
+{
+    struct rx_compiled c;
+    uint32_t off;
+    if (rx_compile(pattern, &c) != 0) {
+        set_err("could not compile regex pattern '%s' (%s)", pattern, c.err);
+        return 0;
+    }
+    off = blob_add(b, c.prog, c.prog->total_bytes, 16);
+    if (max_groups && c.prog->n_groups > *max_groups) *max_groups = c.prog->n_groups;
+    rx_compiled_free(&c);
+    return off;
+}
+
+/* flb_utils_split(line, ' ', max_split): leading separators skipped per token, at most
+ * max_split tokens then the rest verbatim (src/flb_utils.c:321-456), unquoted */
+static int split_plain(const char *line, int max_split, char **out, int max_out)
+{
+    int n = 0, i = 0, len = (int) strlen(line);
+    while (i < len && n < max_out) {
+        const char *t = line + i;
+        int tl;
+        const char *sp;
+        while (*t == ' ') t++;
+        sp = strchr(t, ' ');
+        tl = (sp && sp > t) ? (int) (sp - t) : (int) strlen(t);
+        out[n++] = strndup(t, tl);
+        i = (int) (t - line) + tl;
+        i++;
+        if (n >= max_split && max_split > 0 && i < len) {
+            if (n < max_out) out[n++] = strdup(line + i);
+            break;
+        }
+    }
+    return n;
+}
+
+/* flb_utils_split_quoted(line, ' ', max_split) */
+static int split_quoted(const char *line, int max_split, char **out, int max_out)
+{
+    int n = 0, i = 0, len = (int) strlen(line);
+    while (i < len && n < max_out) {
+        const char *t = line + i;
+        while (*t == ' ') t++;
+        if (*t != '"' && *t != '\'') {
+            const char *sp = strchr(t, ' ');
+            int tl = (sp && sp > t) ? (int) (sp - t) : (int) strlen(t);
+            out[n++] = strndup(t, tl);
+            i = (int) (t - line) + tl;
+        }
+        else {
+            char q = *t;
+            const char *p = t + 1;
+            char *tok = malloc(strlen(t) + 1);
+            int tl = 0;
+            while (*p && *p != q) {
+                if (*p == '\\' && (p[1] == q || p[1] == '\\')) p++;
+                tok[tl++] = *p++;
+            }
+            if (!*p) { free(tok); return -1; }      /* unterminated quote */
+            tok[tl] = 0;
+            out[n++] = tok;
+            i = (int) (p - line);                    /* at the closing quote */
+        }
+        i++;
+        if (n >= max_split && max_split > 0 && i < len) {
+            if (n < max_out) out[n++] = strdup(line + i);
+            break;
+        }
+    }
+    return n;
+}
+
+/* token_retrieve() loop of flb_slist_split_tokens() for SLIST_2 ("Record k v") */
+static int split_tokens(const char *str, int max_split, char **out, int max_out)
+{
+    const char *p = str;
+    int n = 0;
+    while (n < max_out) {
+        const char *start;
+        char *tok;
+        int quoted = 0, tl;
+        while (*p == ' ') p++;
+        if (!*p) break;
+        start = p;
+        if (*p == '"') {
+            quoted = 1; p++; start = p;
+            for (;;) {
+                while (*p && *p != '"') p++;
+                if (!*p) break;
+                if (p[-1] == '\\') { p++; continue; }
+                break;
+            }
+        }
+        else while (*p && *p != ' ') p++;
+        tl = (int) (p - start);
+        tok = strndup(start, tl);
+        if (quoted) {
+            char *in = tok, *o = tok;
+            while (*in) { if (in[0] == '\\' && in[1] == '"') { *o++ = '"'; in += 2; } else *o++ = *in++; }
+            *o = 0;
+            if (*p == '"') p++;
+        }
+        out[n++] = tok;
+        if (!*p) break;
+        if (n >= max_split && max_split > 0) {
+            while (*p == ' ') p++;
+            if (*p && n < max_out) out[n++] = strdup(p);
+            break;
+        }
+    }
+    return n;
+}
+
+static void free_toks(char **t, int n) { int i; for (i = 0; i < n; i++) free(t[i]); }
+
+/* ---- per-plugin configuration -> blob ---- */
+static uint32_t emit_parser_filter(flbgpu_filter *f, struct blob *b, uint32_t *cap_need)
+{
+    struct cf_parser cf;
+    struct kv *p;
+    const char *key_name = NULL;
+    memset(&cf, 0, sizeof(cf));
+    for (p = f->props; p; p = p->next) {
+        if (!strcasecmp(p->k, "key_name")) key_name = p->v;
+        else if (!strcasecmp(p->k, "parser")) {
+            struct flbgpu_parser *ps = flbgpu_parser_get(f->ctx, p->v);
+            if (!ps) { set_err("requested parser '%s' not found%s", p->v, NULL); return 0; }
+            if (cf.n_parsers >= 8) { set_err("too many parsers in one filter%s%s", NULL, NULL); return 0; }
+            cf.pdef_off[cf.n_parsers++] = emit_pdef(b, ps);
+            if (ps->has_rx) *cap_need += 1 + 2 * (ps->rx.prog->n_groups + 1);
+        }
+        else if (!strcasecmp(p->k, "preserve_key")) { int v = parse_bool(p->v); if (v < 0) { set_err("invalid boolean '%s'%s", p->v, NULL); return 0; } cf.preserve_key = v; }
+        else if (!strcasecmp(p->k, "reserve_data")) { int v = parse_bool(p->v); if (v < 0) { set_err("invalid boolean '%s'%s", p->v, NULL); return 0; } cf.reserve_data = v; }
+        else if (!strcasecmp(p->k, "unescape_key")) { /* deprecated, ignored */ }
+        else { set_err("[filter parser] unknown configuration property '%s'%s", p->k, NULL); return 0; }
+    }
+    if (!key_name) { set_err("Key name is required%s%s", NULL, NULL); return 0; }
+    if (cf.n_parsers == 0) { set_err("Invalid 'parser'%s%s", NULL, NULL); return 0; }
+    cf.key_off = blob_add(b, key_name, strlen(key_name), 1);
+    cf.key_len = (uint32_t) strlen(key_name);
+    if (key_name[0] == '$') { cf.ra_off = emit_ra(b, key_name); if (!cf.ra_off) return 0; }
+    return blob_add(b, &cf, sizeof(cf), 8);
+}
+
+static uint32_t emit_grep_filter(flbgpu_filter *f, struct blob *b)
+{
+    struct cf_grep cf;
+    struct cf_grep_rule rules[64];
+    struct kv *p;
+    int first_rule = 0;
+    memset(&cf, 0, sizeof(cf));
+    cf.op = GREP_OP_LEGACY;
+    for (p = f->props; p; p = p->next) {
+        if (!strcasecmp(p->k, "logical_op")) {
+            if (!strcasecmp(p->v, "AND")) cf.op = GREP_OP_AND;
+            else if (!strcasecmp(p->v, "OR")) cf.op = GREP_OP_OR;
+            else if (!strcasecmp(p->v, "legacy")) cf.op = GREP_OP_LEGACY;
+        }
+    }
+    for (p = f->props; p; p = p->next) {
+        char *tok[3];
+        char field[512];
+        int nt, type;
+        if (!strcasecmp(p->k, "regex")) type = GREP_REGEX;
+        else if (!strcasecmp(p->k, "exclude")) type = GREP_EXCLUDE;
+        else if (!strcasecmp(p->k, "logical_op")) continue;
+        else { set_err("[filter grep] unknown configuration property '%s'%s", p->k, NULL); return 0; }
+        if (cf.op != GREP_OP_LEGACY && first_rule != 0 && first_rule != type) { set_err("Both 'regex' and 'exclude' are set.%s%s", NULL, NULL); return 0; }
+        first_rule = type;
+        nt = split_plain(p->v, 1, tok, 3);
+        if (nt != 2) { free_toks(tok, nt); set_err("invalid regex, expected field and regular expression%s%s", NULL, NULL); return 0; }
+        if (cf.n_rules >= 64) { free_toks(tok, nt); set_err("too many grep rules%s%s", NULL, NULL); return 0; }
+        if (tok[0][0] == '$') snprintf(field, sizeof(field), "%s", tok[0]);
+        else snprintf(field, sizeof(field), "$%s", tok[0]);
+        rules[cf.n_rules].type = type;
+        rules[cf.n_rules].pad = 0;
+        rules[cf.n_rules].ra_off = emit_ra(b, field);
+        if (!rules[cf.n_rules].ra_off) { free_toks(tok, nt); return 0; }
+        rules[cf.n_rules].rx_off = emit_rx(b, tok[1], NULL);
+        free_toks(tok, nt);
+        if (!rules[cf.n_rules].rx_off) return 0;
+        cf.n_rules++;
+    }
+    cf.rules_off = blob_add(b, rules, sizeof(rules[0]) * (cf.n_rules ? cf.n_rules : 1), 8);
+    return blob_add(b, &cf, sizeof(cf), 8);
+}
+
+static uint32_t emit_modify_filter(flbgpu_filter *f, struct blob *b)
+{
+    struct cf_modify cf;
+    struct cf_mod_cond *conds = calloc(64, sizeof(*conds));
+    struct cf_mod_rule *rules = calloc(256, sizeof(*rules));
+    struct kv *p;
+    uint32_t ret = 0;
+    memset(&cf, 0, sizeof(cf));
+    for (p = f->props; p; p = p->next) {
+        char *tok[4];
+        int nt = split_quoted(p->v, 3, tok, 4);
+        if (nt <= 0 || nt > 3) { if (nt > 0) free_toks(tok, nt); set_err("Invalid config for %s%s", p->k, NULL); goto out; }
+        if (!strcasecmp(p->k, "condition")) {
+            struct cf_mod_cond *c = &conds[cf.n_conds];
+            static const struct { const char *n; int t, a_rx, b_rx; } ct[] = {
+                { "key_exists", MODC_KEY_EXISTS, 0, 0 }, { "key_does_not_exist", MODC_KEY_DOES_NOT_EXIST, 0, 0 },
+                { "a_key_matches", MODC_A_KEY_MATCHES, 1, 0 }, { "no_key_matches", MODC_NO_KEY_MATCHES, 1, 0 },
+                { "key_value_equals", MODC_KEY_VALUE_EQUALS, 0, 0 }, { "key_value_does_not_equal", MODC_KEY_VALUE_DOES_NOT_EQUAL, 0, 0 },
+                { "key_value_matches", MODC_KEY_VALUE_MATCHES, 0, 1 }, { "key_value_does_not_match", MODC_KEY_VALUE_DOES_NOT_MATCH, 0, 1 },
+                { "matching_keys_have_matching_values", MODC_MATCHING_KEYS_HAVE_MATCHING_VALUES, 1, 1 },
+                { "matching_keys_do_not_have_matching_values", MODC_MATCHING_KEYS_DO_NOT_HAVE_MATCHING_VALUES, 1, 1 } };
+            int i, found = -1;
+            if (cf.n_conds >= 64 || nt < 2) { free_toks(tok, nt); set_err("Invalid config for %s : %s", p->k, p->v); goto out; }
+            for (i = 0; i < 10; i++) if (!strcasecmp(tok[0], ct[i].n)) found = i;
+            if (found < 0) { free_toks(tok, nt); set_err("Invalid config for %s : %s", p->k, p->v); goto out; }
+            c->type = ct[found].t;
+            if (!ct[found].a_rx) {
+                c->ra_off = emit_ra(b, tok[1]);
+                if (!c->ra_off) { free_toks(tok, nt); goto out; }
+            }
+            else {
+                if (!*tok[1]) { free_toks(tok, nt); set_err("Unable to create regex for condition %s %s", p->k, p->v); goto out; }
+                c->a_rx = emit_rx(b, tok[1], NULL);
+                if (!c->a_rx) { free_toks(tok, nt); goto out; }
+            }
+            if (nt == 3) { c->b_off = blob_add(b, tok[2], strlen(tok[2]), 1); c->b_len = (uint32_t) strlen(tok[2]); }
+            if (ct[found].b_rx) {
+                if (nt < 3 || !*tok[2]) { free_toks(tok, nt); set_err("Unable to create regex for condition %s %s", p->k, p->v); goto out; }
+                c->b_rx = emit_rx(b, tok[2], NULL);
+                if (!c->b_rx) { free_toks(tok, nt); goto out; }
+            }
+            cf.n_conds++;
+        }
+        else {
+            struct cf_mod_rule *r = &rules[cf.n_rules];
+            const char *key = tok[0], *val = tok[nt - 1];
+            int type = 0;
+            if (cf.n_rules >= 256) { free_toks(tok, nt); set_err("too many modify rules%s%s", NULL, NULL); goto out; }
+            if (nt == 1) {
+                if (!strcasecmp(p->k, "remove")) type = MOD_REMOVE;
+                else if (!strcasecmp(p->k, "remove_wildcard")) type = MOD_REMOVE_WILDCARD;
+                else if (!strcasecmp(p->k, "remove_regex")) type = MOD_REMOVE_REGEX;
+                else if (!strcasecmp(p->k, "move_to_start")) type = MOD_MOVE_TO_START;
+                else if (!strcasecmp(p->k, "move_to_end")) type = MOD_MOVE_TO_END;
+            }
+            else if (nt == 2) {
+                if (!strcasecmp(p->k, "rename")) type = MOD_RENAME;
+                else if (!strcasecmp(p->k, "hard_rename")) type = MOD_HARD_RENAME;
+                else if (!strcasecmp(p->k, "add") || !strcasecmp(p->k, "add_if_not_present")) type = MOD_ADD;
+                else if (!strcasecmp(p->k, "set")) type = MOD_SET;
+                else if (!strcasecmp(p->k, "copy")) type = MOD_COPY;
+                else if (!strcasecmp(p->k, "hard_copy")) type = MOD_HARD_COPY;
+            }
+            if (!type) { free_toks(tok, nt); set_err("Invalid operation %s : %s in configuration", p->k, p->v); goto out; }
+            r->type = type;
+            r->key_off = blob_add(b, key, strlen(key), 1); r->key_len = (uint32_t) strlen(key);
+            r->kmp_off = blob_add_mpstr(b, key, (uint32_t) strlen(key), &r->kmp_len);
+            r->val_off = blob_add(b, val, strlen(val), 1); r->val_len = (uint32_t) strlen(val);
+            r->vmp_off = blob_add_mpstr(b, val, (uint32_t) strlen(val), &r->vmp_len);
+            if (type == MOD_REMOVE_REGEX) {
+                if (!*key) { free_toks(tok, nt); set_err("Unable to create regex for rule %s %s", p->k, p->v); goto out; }
+                r->key_rx = emit_rx(b, key, NULL);
+                if (!r->key_rx) { free_toks(tok, nt); goto out; }
+            }
+            cf.n_rules++;
+        }
+        free_toks(tok, nt);
+    }
+    cf.conds_off = blob_add(b, conds, sizeof(*conds) * (cf.n_conds ? cf.n_conds : 1), 8);
+    cf.rules_off = blob_add(b, rules, sizeof(*rules) * (cf.n_rules ? cf.n_rules : 1), 8);
+    ret = blob_add(b, &cf, sizeof(cf), 8);
+out:
+    free(conds);
+    free(rules);
+    return ret;
+}
+
+static uint32_t emit_recmod_filter(flbgpu_filter *f, struct blob *b)
+{
+    struct cf_recmod cf;
+    struct cf_rm_rec recs[64];
+    struct cf_rm_key rem[64], allow[64];
+    struct kv *p;
+    int pass;
+    memset(&cf, 0, sizeof(cf));
+    for (p = f->props; p; p = p->next) {
+        if (!strcasecmp(p->k, "record")) {
+            char *tok[4];
+            int nt = split_tokens(p->v, 2, tok, 4);
+            if (nt < 2) { free_toks(tok, nt); set_err("[filter record_modifier] invalid value for 'record': %s%s", p->v, NULL); return 0; }
+            if (nt != 2) { free_toks(tok, nt); continue; }          /* "invalid record parameters": entry skipped */
+            if (cf.n_records >= 64) { free_toks(tok, nt); set_err("too many Record entries%s%s", NULL, NULL); return 0; }
+            recs[cf.n_records].kmp_off = blob_add_mpstr(b, tok[0], (uint32_t) strlen(tok[0]), &recs[cf.n_records].kmp_len);
+            recs[cf.n_records].vmp_off = blob_add_mpstr(b, tok[1], (uint32_t) strlen(tok[1]), &recs[cf.n_records].vmp_len);
+            cf.n_records++;
+            free_toks(tok, nt);
+        }
+        else if (!strcasecmp(p->k, "remove_key")) {
+            uint32_t l = (uint32_t) strlen(p->v);
+            if (cf.n_remove >= 64 || l == 0) { set_err("invalid Remove_key%s%s", NULL, NULL); return 0; }
+            rem[cf.n_remove].dynamic = p->v[l - 1] == '*';
+            if (rem[cf.n_remove].dynamic) l--;
+            rem[cf.n_remove].off = blob_add(b, p->v, l, 1); rem[cf.n_remove].len = l; rem[cf.n_remove].pad = 0;
+            cf.n_remove++;
+        }
+        else if (!strcasecmp(p->k, "allowlist_key") || !strcasecmp(p->k, "whitelist_key")) { /* second pass: allowlist first, then whitelist */ }
+        else if (!strcasecmp(p->k, "uuid_key")) { set_err("Uuid_key draws random numbers and cannot be reproduced; not supported on the GPU path%s%s", NULL, NULL); return 0; }
+        else { set_err("[filter record_modifier] unknown configuration property '%s'%s", p->k, NULL); return 0; }
+    }
+    for (pass = 0; pass < 2; pass++) {
+        for (p = f->props; p; p = p->next) {
+            uint32_t l;
+            if (strcasecmp(p->k, pass == 0 ? "allowlist_key" : "whitelist_key")) continue;
+            l = (uint32_t) strlen(p->v);
+            if (cf.n_allow >= 64 || l == 0) { set_err("invalid Allowlist_key%s%s", NULL, NULL); return 0; }
+            allow[cf.n_allow].dynamic = p->v[l - 1] == '*';
+            if (allow[cf.n_allow].dynamic) l--;
+            allow[cf.n_allow].off = blob_add(b, p->v, l, 1); allow[cf.n_allow].len = l; allow[cf.n_allow].pad = 0;
+            cf.n_allow++;
+        }
+    }
+    if (cf.n_remove > 0 && cf.n_allow > 0) { set_err("remove_keys and allowlist_keys are exclusive with each other.%s%s", NULL, NULL); return 0; }
+    cf.records_off = blob_add(b, recs, sizeof(recs[0]) * (cf.n_records ? cf.n_records : 1), 8);
+    cf.remove_off = blob_add(b, rem, sizeof(rem[0]) * (cf.n_remove ? cf.n_remove : 1), 8);
+    cf.allow_off = blob_add(b, allow, sizeof(allow[0]) * (cf.n_allow ? cf.n_allow : 1), 8);
+    return blob_add(b, &cf, sizeof(cf), 8);
+}
+
+static uint32_t emit_filter(flbgpu_filter *f, struct blob *b, uint32_t *cap_need)
+{
+    switch (f->kind) {
+    case FLBGPU_F_PARSER: return emit_parser_filter(f, b, cap_need);
+    case FLBGPU_F_GREP: return emit_grep_filter(f, b);
+    case FLBGPU_F_MODIFY: return emit_modify_filter(f, b);
+    case FLBGPU_F_RECORD_MODIFIER: return emit_recmod_filter(f, b);
+    }
+    return 0;
+}
+
+int flbgpu_filter_init(flbgpu_filter *f)
+{
+    struct blob b;
+    uint32_t cap = 0, off;
+    if (!f) return -1;
+    g_rt_err[0] = 0;
+    memset(&b, 0, sizeof(b));
+    blob_reserve(&b, sizeof(struct chain_hdr), 16);
+    off = emit_filter(f, &b, &cap);         /* validation pass; the chain re-emits */
+    free(b.p);
+    if (!off) return -1;
+    f->inited = 1;
+    return 0;
+}
+
+/* ------------------------------------------------------------------ chain */
+flbgpu_chain *flbgpu_chain_new(flbgpu_ctx *ctx)
+{
+    flbgpu_chain *c;
+    if (!ctx) return NULL;
+    c = calloc(1, sizeof(*c));
+    c->ctx = ctx;
+    return c;
+}
+
+int flbgpu_chain_add(flbgpu_chain *c, flbgpu_filter *f)
+{
+    if (!c || !f || !f->inited || c->inited || c->nf >= FLBGPU_MAX_FILTERS) return -1;
+    c->f[c->nf++] = f;
+    return 0;
+}
+
+int flbgpu_chain_init(flbgpu_chain *c)
+{
+    struct chain_hdr h;
+    struct chain_filter cf[FLBGPU_MAX_FILTERS];
+    uint32_t cap = 0, i;
+    uint8_t empty = 0x80;
+    if (!c || c->inited) return -1;
+    g_rt_err[0] = 0;
+    memset(&h, 0, sizeof(h));
+    blob_reserve(&c->blob, sizeof(h), 16);
+    h.empty_map_off = blob_add(&c->blob, &empty, 1, 1);
+    for (i = 0; i < (uint32_t) c->nf; i++) {
+        cf[i].kind = c->f[i]->kind;
+        cf[i].cfg_off = emit_filter(c->f[i], &c->blob, &cap);
+        if (!cf[i].cfg_off) return -1;
+    }
+    h.n_filters = c->nf;
+    h.filters_off = blob_add(&c->blob, cf, sizeof(cf[0]) * (c->nf ? c->nf : 1), 8);
+    h.cap_stride = cap;
+    blob_reserve(&c->blob, 16, 16);
+    h.total_bytes = (uint32_t) c->blob.n;
+    memcpy(c->blob.p, &h, sizeof(h));
+    c->cap_stride = cap;
+    c->d_blob = bk_alloc(c->blob.n);
+    c->d_flags = bk_alloc(sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1));
+    if (!c->d_blob || !c->d_flags) return -1;
+    if (bk_h2d(c->d_blob, c->blob.p, c->blob.n) || bk_sync()) return -1;
+    c->inited = 1;
+    return 0;
+}
+
+void flbgpu_chain_destroy(flbgpu_chain *c)
+{
+    if (!c) return;
+    bk_free(c->d_blob); bk_free(c->d_in); bk_free(c->d_out); bk_free(c->d_tile); bk_free(c->d_off);
+    bk_free(c->d_len); bk_free(c->d_size); bk_free(c->d_kind); bk_free(c->d_bsum); bk_free(c->d_cap);
+    bk_free(c->d_flags); bk_free_host(c->h_stage);
+    free(c->blob.p);
+    free(c);
+}
+
+void flbgpu_chain_stats(flbgpu_chain *c, struct flbgpu_stats *out) { if (c && out) *out = c->st; }
+
+#define GROW(ptr, cap, need, type) do { if ((cap) < (size_t) (need)) { size_t nc_ = (size_t) (need) + (size_t) (need) / 4 + 64; \
+        bk_free(ptr); (ptr) = (type *) bk_alloc(nc_ * sizeof(type)); if (!(ptr)) { (cap) = 0; return -1; } (cap) = nc_; } } while (0)
+
+/* chunk-level verdict of filter k from the evidence word (see dev_chain.cuh) */
+static int verdict(int kind, uint32_t fl)
+{
+    switch (kind) {
+    case FLBGPU_F_PARSER: return (fl & CHF_EMITTED) != 0;
+    case FLBGPU_F_GREP: return (fl & CHF_CAUSE) != 0;
+    case FLBGPU_F_MODIFY: return (fl & CHF_CAUSE) != 0;
+    case FLBGPU_F_RECORD_MODIFIER: return (fl & CHF_CAUSE) && (fl & CHF_EMITTED);
+    }
+    return 0;
+}
+
+/* the device part of one call: d_in holds `bytes` of chunk.  On MODIFIED the result is
+ * in c->d_out (or ext_out) and *out_size is its size. */
+static int chain_run_device(flbgpu_chain *c, const uint8_t *d_in, size_t bytes, uint8_t *ext_out, size_t ext_cap,
+                            size_t *out_size)
+{
+    struct bk_chain_args a;
+    uint32_t n_tiles, n_cand = 0, n_valid = 0, h_flags[FLBGPU_MAX_FILTERS + 1];
+    uint64_t total = 0;
+    int tiled = 0, k, pass;
+
+    memset(&c->st, 0, sizeof(c->st));
+    c->st.bytes_in = bytes;
+    *out_size = 0;
+    if (bytes >= 0xfff00000ull) { set_err("chunk larger than 4 GiB: split the append%s%s", NULL, NULL); return -1; }
+    n_tiles = (uint32_t) ((bytes + BK_INDEX_TILE - 1) / BK_INDEX_TILE);
+    GROW(c->d_tile, c->cap_tile, n_tiles + 1, uint32_t);
+    if (bk_index_count(d_in, (uint32_t) bytes, c->d_tile, n_tiles, &n_cand)) return -1;
+    if (c->cap_rec < n_cand) {
+        size_t nc = (size_t) n_cand + n_cand / 4 + 64;
+        bk_free(c->d_off); bk_free(c->d_len); bk_free(c->d_size); bk_free(c->d_kind);
+        c->d_off = bk_alloc(nc * 4); c->d_len = bk_alloc(nc * 4); c->d_size = bk_alloc(nc * 4); c->d_kind = bk_alloc(nc);
+        if (!c->d_off || !c->d_len || !c->d_size || !c->d_kind) { c->cap_rec = 0; return -1; }
+        c->cap_rec = nc;
+    }
+    if (bk_index_fill(d_in, (uint32_t) bytes, c->d_tile, n_tiles, n_cand, c->d_off, c->d_len, c->d_kind, &n_valid, &tiled)) {
+        c->st.error_bits = FLBGPU_E_INDEX;
+        return -1;
+    }
+    c->st.records_in = n_valid;
+    GROW(c->d_bsum, c->cap_bsum, (n_valid + BK_REC_BLOCK - 1) / BK_REC_BLOCK + 1, uint64_t);
+    if (c->cap_stride) GROW(c->d_cap, c->cap_cap, (size_t) n_valid * c->cap_stride + 1, int32_t);
+
+    memset(&a, 0, sizeof(a));
+    a.d_in = d_in; a.in_len = (uint32_t) bytes; a.d_blob = c->d_blob; a.d_scr = NULL;
+    a.d_capcache = c->cap_stride ? c->d_cap : NULL; a.cap_stride = c->cap_stride;
+    a.now = (int64_t) time(NULL);
+    a.d_off = c->d_off; a.d_len = c->d_len; a.d_kind = c->d_kind; a.n_rec = n_valid;
+    a.d_size = c->d_size; a.d_bsum = c->d_bsum; a.d_flags = c->d_flags;
+    a.assume = (c->nf >= 32) ? 0xffffffffu : ((1u << c->nf) - 1u);
+
+    /* evaluation pass; revise chunk-level assumptions front to back until they hold */
+    for (pass = 0; pass <= c->nf; pass++) {
+        int changed = 0;
+        if (bk_chain_size(&a, h_flags, &total)) return -1;
+        c->st.passes++;
+        if (h_flags[FLBGPU_MAX_FILTERS]) {
+            c->st.error_bits = h_flags[FLBGPU_MAX_FILTERS];
+            snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
+                     "1=too many keys 2=regex stack 4=regex budget 8=float outside exact path)", h_flags[FLBGPU_MAX_FILTERS]);
+            return -1;
+        }
+        for (k = 0; k < c->nf; k++) {
+            int v = verdict(c->f[k]->kind, h_flags[k]);
+            if (v != (int) ((a.assume >> k) & 1)) {
+                a.assume = (a.assume & ~(1u << k)) | ((uint32_t) v << k);
+                changed = 1;
+                break;                   /* later filters saw the wrong input: re-evaluate */
+            }
+        }
+        if (!changed) break;
+    }
+    c->st.kernel_launches = bk_launch_count();
+    if (a.assume == 0) return FLBGPU_FILTER_NOTOUCH;
+    if (total >= 0xfff00000ull) { set_err("result larger than 4 GiB%s%s", NULL, NULL); return -1; }
+    c->st.bytes_out = total;
+    *out_size = (size_t) total;
+    if (total == 0) return FLBGPU_FILTER_MODIFIED;
+    if (ext_out) {
+        if (ext_cap < total) { set_err("device output buffer too small%s%s", NULL, NULL); return -1; }
+        if (bk_chain_emit(&a, ext_out)) return -1;
+    }
+    else {
+        GROW(c->d_out, c->cap_out, total, uint8_t);
+        if (bk_chain_emit(&a, c->d_out)) return -1;
+    }
+    c->st.kernel_launches = bk_launch_count();
+    return FLBGPU_FILTER_MODIFIED;
+}
+
+int flbgpu_chain_do_device(flbgpu_chain *c, const void *d_data, size_t bytes, void *d_out, size_t out_cap, size_t *out_size)
+{
+    int r;
+    if (!c || !c->inited) return -1;
+    g_rt_err[0] = 0;
+    r = chain_run_device(c, d_data, bytes, d_out, out_cap, out_size);
+    if (r < 0) return r;
+    if (bk_sync()) return -1;
+    return r;
+}
+
+int flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes, const char *tag, int tag_len,
+                    void **out_buf, size_t *out_size)
+{
+    int r;
+    size_t osz = 0;
+    (void) tag; (void) tag_len;
+    if (!c || !c->inited || !out_buf || !out_size) return -1;
+    g_rt_err[0] = 0;
+    *out_buf = NULL; *out_size = 0;
+    if (bytes == 0) return FLBGPU_FILTER_NOTOUCH;
+    GROW(c->d_in, c->cap_in, bytes + 64, uint8_t);
+    if (bk_h2d(c->d_in, data, bytes)) return -1;
+    r = chain_run_device(c, c->d_in, bytes, NULL, 0, &osz);
+    if (r != FLBGPU_FILTER_MODIFIED) return r;
+    *out_size = osz;
+    if (osz == 0) return FLBGPU_FILTER_MODIFIED;
+    *out_buf = malloc(osz);
+    if (!*out_buf) return -1;
+    if (bk_d2h(*out_buf, c->d_out, osz) || bk_sync()) { free(*out_buf); *out_buf = NULL; return -1; }
+    return FLBGPU_FILTER_MODIFIED;
+}
+
+int flbgpu_filter_cb(flbgpu_filter *f, const void *data, size_t bytes, const char *tag, int tag_len,
+                     void **out_buf, size_t *out_size)
+{
+    if (!f || !f->inited) return -1;
+    if (!f->solo) {
+        flbgpu_chain *c = flbgpu_chain_new(f->ctx);
+        if (flbgpu_chain_add(c, f) || flbgpu_chain_init(c)) { flbgpu_chain_destroy(c); return -1; }
+        f->solo = c;
+    }
+    return flbgpu_chain_do(f->solo, data, bytes, tag, tag_len, out_buf, out_size);
+}
+
+/* flb_parser_do() for one line: wrap it as one event {"_": line}, run filter_parser
+ * with Key_Name "_" and unwrap the body map. */
+int flbgpu_parser_do(flbgpu_parser *p, const char *buf, size_t length, void **out_buf, size_t *out_size,
+                     struct flbgpu_time *out_time)
+{
+    uint8_t *rec, *o = NULL;
+    size_t n = 0, osz = 0, i;
+    int r;
+    if (!p || !buf || !out_buf || !out_size) return -1;
+    *out_buf = NULL; *out_size = 0;
+    if (out_time) { out_time->tv_sec = 0; out_time->tv_nsec = 0; }
+    if (!p->solo) {
+        flbgpu_filter *f = flbgpu_filter_new(p->ctx, "parser");
+        flbgpu_chain *c;
+        flbgpu_filter_set_property(f, "key_name", "_");
+        flbgpu_filter_set_property(f, "parser", p->name);
+        if (flbgpu_filter_init(f)) { flbgpu_filter_destroy(f); return -1; }
+        c = flbgpu_chain_new(p->ctx);
+        if (flbgpu_chain_add(c, f) || flbgpu_chain_init(c)) { flbgpu_chain_destroy(c); flbgpu_filter_destroy(f); return -1; }
+        p->solo = c; p->solo_filter = f;
+    }
+    rec = malloc(length + 32);
+    rec[n++] = 0x92; rec[n++] = 0x92; rec[n++] = 0xd7; rec[n++] = 0x00;
+    for (i = 0; i < 8; i++) rec[n++] = 0;
+    rec[n++] = 0x80; rec[n++] = 0x81; rec[n++] = 0xa1; rec[n++] = '_';
+    if (length < 32) rec[n++] = 0xa0 | (uint8_t) length;
+    else if (length < 256) { rec[n++] = 0xd9; rec[n++] = (uint8_t) length; }
+    else if (length < 65536) { rec[n++] = 0xda; rec[n++] = (uint8_t) (length >> 8); rec[n++] = (uint8_t) length; }
+    else { rec[n++] = 0xdb; rec[n++] = (uint8_t) (length >> 24); rec[n++] = (uint8_t) (length >> 16); rec[n++] = (uint8_t) (length >> 8); rec[n++] = (uint8_t) length; }
+    memcpy(rec + n, buf, length);
+    n += length;
+    r = flbgpu_chain_do(p->solo, rec, n, "", 0, (void **) &o, &osz);
+    if (r != FLBGPU_FILTER_MODIFIED || osz < 13) { free(rec); free(o); return -1; }
+    /* an unparsed record comes back with its original body: {"_": line} */
+    if (osz == n && memcmp(o + 13, rec + 13, n - 13) == 0) { free(rec); free(o); return -1; }
+    free(rec);
+    if (out_time) {
+        out_time->tv_sec = ((int64_t) o[4] << 24) | (o[5] << 16) | (o[6] << 8) | o[7];
+        out_time->tv_nsec = ((int64_t) o[8] << 24) | (o[9] << 16) | (o[10] << 8) | o[11];
+    }
+    *out_size = osz - 13;
+    *out_buf = malloc(*out_size ? *out_size : 1);
+    memcpy(*out_buf, o + 13, *out_size);
+    free(o);
+    return (int) length;
+}

@@ -1,0 +1,137 @@
+/* flbgpu.h -- C ABI of libflbgpu.so: Fluent Bit's parse->filter hot path on B200.
+ *
+ * Plain C, plain pointers and sizes.  Each entry point names the reference
+ * interface it stands in for (paths relative to the fluent-bit source tree, v5.0.2).
+ * INTEGRATION.md shows the few lines of glue a Fluent Bit maintainer adds on the
+ * reference side (a `struct flb_filter_plugin` whose callbacks forward here).
+ *
+ * There is no CPU implementation behind this ABI: flbgpu_init() fails when no CUDA
+ * device is usable and every other call then returns an error.
+ */
+#ifndef FLBGPU_H
+#define FLBGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* include/fluent-bit/flb_filter.h:42-43 */
+#define FLBGPU_FILTER_MODIFIED 1
+#define FLBGPU_FILTER_NOTOUCH  2
+
+/* include/fluent-bit/flb_parser.h:70-76 (enum FLB_PARSER_TYPE_*) */
+#define FLBGPU_PARSER_TYPE_INT    1
+#define FLBGPU_PARSER_TYPE_FLOAT  2
+#define FLBGPU_PARSER_TYPE_BOOL   3
+#define FLBGPU_PARSER_TYPE_STRING 4
+#define FLBGPU_PARSER_TYPE_HEX    5
+
+typedef struct flbgpu_ctx    flbgpu_ctx;     /* one device context (per GPU)            */
+typedef struct flbgpu_parser flbgpu_parser;  /* struct flb_parser, flb_parser.h:41-68   */
+typedef struct flbgpu_filter flbgpu_filter;  /* struct flb_filter_instance + plugin ctx */
+typedef struct flbgpu_chain  flbgpu_chain;   /* config->filters as one fused program    */
+
+/* struct flb_parser_types, include/fluent-bit/flb_parser.h:35-39 */
+struct flbgpu_parser_types {
+    char *key;
+    int   key_len;
+    int   type;
+};
+
+/* struct flb_time { struct timespec tm; }, include/fluent-bit/flb_time.h */
+struct flbgpu_time {
+    int64_t tv_sec;
+    int64_t tv_nsec;
+};
+
+/* ---- context ---------------------------------------------------------- */
+/* Stands in for the process-wide state flb_config_init() sets up for this path
+ * (config->parsers, config->filters).  device = CUDA ordinal.  NULL on failure;
+ * flbgpu_last_error() says why (e.g. "no CUDA device available"). */
+flbgpu_ctx *flbgpu_init(int device);
+void        flbgpu_shutdown(flbgpu_ctx *ctx);
+const char *flbgpu_last_error(void);
+const char *flbgpu_backend_name(void);
+int         flbgpu_device_count(void);
+
+/* ---- parsers ---------------------------------------------------------- */
+/* flb_parser_create(), src/flb_parser.c:148-348 -- same arguments, same meaning
+ * (`decoders` must be NULL: Decode_Field is not on this path yet).  The parser is
+ * registered under `name` in the context, like config->parsers.  NULL on error. */
+flbgpu_parser *flbgpu_parser_create(flbgpu_ctx *ctx, const char *name, const char *format,
+                                    const char *p_regex, int skip_empty,
+                                    const char *time_fmt, const char *time_key,
+                                    const char *time_offset, int time_keep, int time_strict,
+                                    int time_system_timezone, int logfmt_no_bare_keys,
+                                    struct flbgpu_parser_types *types, int types_len,
+                                    void *decoders);
+/* flb_parser_get(), src/flb_parser.c:1022 */
+flbgpu_parser *flbgpu_parser_get(flbgpu_ctx *ctx, const char *name);
+/* flb_parser_do(), src/flb_parser.c:1044-1066: one line in, one msgpack map out.
+ * Returns >= 0 (last byte consumed) or -1; *out_buf is malloc()ed, caller frees. */
+int flbgpu_parser_do(flbgpu_parser *parser, const char *buf, size_t length,
+                     void **out_buf, size_t *out_size, struct flbgpu_time *out_time);
+void flbgpu_parser_destroy(flbgpu_parser *parser);
+
+/* ---- filters ---------------------------------------------------------- */
+/* flb_filter_new(), src/flb_filter.c:426: plugin = "parser" | "grep" | "modify" |
+ * "record_modifier" (the names of the reference's filter_*_plugin structs). */
+flbgpu_filter *flbgpu_filter_new(flbgpu_ctx *ctx, const char *plugin);
+/* flb_filter_set_property(), src/flb_filter.c:325: properties keep config order,
+ * keys are case-insensitive; "match"/"alias"/"log_level" are accepted and ignored. */
+int flbgpu_filter_set_property(flbgpu_filter *f, const char *k, const char *v);
+/* the plugin's cb_init (e.g. plugins/filter_grep/grep.c:196): 0 or -1 */
+int flbgpu_filter_init(flbgpu_filter *f);
+/* the plugin's cb_filter, include/fluent-bit/flb_filter.h:66-73: `data` is a chunk of
+ * msgpack log events in HOST memory, not owned; on FLBGPU_FILTER_MODIFIED *out_buf is a
+ * malloc()ed chunk owned by the caller (*out_size may be 0: everything dropped). */
+int flbgpu_filter_cb(flbgpu_filter *f, const void *data, size_t bytes,
+                     const char *tag, int tag_len, void **out_buf, size_t *out_size);
+/* the plugin's cb_exit */
+void flbgpu_filter_destroy(flbgpu_filter *f);
+
+/* ---- fused chain ------------------------------------------------------ */
+/* flb_filter_do(), src/flb_filter.c:119-323, over filters that all live on the GPU:
+ * one host->device copy, one evaluation pass, one emission pass, one copy back.
+ * Filters are applied in the order they were added (config order). */
+flbgpu_chain *flbgpu_chain_new(flbgpu_ctx *ctx);
+int  flbgpu_chain_add(flbgpu_chain *c, flbgpu_filter *f);     /* f must be initialised */
+int  flbgpu_chain_init(flbgpu_chain *c);
+/* Same contract as flbgpu_filter_cb.  Returns MODIFIED / NOTOUCH, or -1 on error. */
+int  flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes,
+                     const char *tag, int tag_len, void **out_buf, size_t *out_size);
+void flbgpu_chain_destroy(flbgpu_chain *c);
+
+/* Device-resident variant used for kernel-level measurement: the chunk is already in
+ * HBM (d_data) and the result stays in HBM (d_out, capacity out_cap).  *out_size gets
+ * the result size; returns MODIFIED / NOTOUCH / -1. */
+int flbgpu_chain_do_device(flbgpu_chain *c, const void *d_data, size_t bytes,
+                           void *d_out, size_t out_cap, size_t *out_size);
+
+/* per-call statistics of the last flbgpu_chain_do*() on this chain */
+struct flbgpu_stats {
+    uint64_t records_in;        /* decodable records in the chunk            */
+    uint64_t records_out;       /* records in the result                      */
+    uint64_t bytes_in, bytes_out;
+    uint64_t kernel_launches;   /* kernels launched by this library so far   */
+    uint32_t passes;            /* evaluation passes (1 unless a chunk-level assumption was revised) */
+    uint32_t error_bits;        /* FLBGPU_E_* (flbgpu_prog.h) when the call failed */
+};
+void flbgpu_chain_stats(flbgpu_chain *c, struct flbgpu_stats *out);
+
+/* device memory helpers for callers that keep chunks resident (bench, tests) */
+void *flbgpu_dev_alloc(flbgpu_ctx *ctx, size_t n);
+void  flbgpu_dev_free(flbgpu_ctx *ctx, void *p);
+int   flbgpu_dev_upload(flbgpu_ctx *ctx, void *d, const void *h, size_t n);
+int   flbgpu_dev_download(flbgpu_ctx *ctx, void *h, const void *d, size_t n);
+void *flbgpu_host_alloc(flbgpu_ctx *ctx, size_t n);       /* pinned */
+void  flbgpu_host_free(flbgpu_ctx *ctx, void *p);
+void *flbgpu_stream(flbgpu_ctx *ctx);                     /* cudaStream_t the library launches on */
+
+#ifdef __cplusplus
+}
+#endif
+#endif

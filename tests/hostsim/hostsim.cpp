@@ -63,3 +63,131 @@ int sim_rx_search(void *h, const char *s, int len, int *caps, int stack_words, u
 }
 
 }
+
+/* ------------------------------------------------------------------------
+ * CPU implementation of the bk_* seam (flbgpu_internal.h) so that runtime.c --
+ * the real host logic -- and dev_chain.cuh -- the real device algorithms -- can be
+ * exercised without a GPU.  Linked ONLY into tests/hostsim/libhostsim.so.
+ * ---------------------------------------------------------------------- */
+#include <stdio.h>
+#include "../../fluent-bit_b200/csrc/flbgpu_internal.h"
+#include "../../fluent-bit_b200/csrc/dev_chain.cuh"
+
+static char hs_err[256];
+static uint64_t hs_launches;
+
+extern "C" {
+
+const char *bk_name(void) { return "hostsim-cpu-emulation(TEST ONLY)"; }
+const char *bk_last_error(void) { return hs_err; }
+uint64_t bk_launch_count(void) { return hs_launches; }
+int bk_device_count(void) { return 1; }
+int bk_init(int device) { (void) device; return 0; }
+void *bk_alloc(size_t n) { return malloc(n ? n : 16); }
+void bk_free(void *p) { free(p); }
+void *bk_alloc_host(size_t n) { return malloc(n ? n : 16); }
+void bk_free_host(void *p) { free(p); }
+int bk_h2d(void *d, const void *h, size_t n) { memcpy(d, h, n); return 0; }
+int bk_d2h(void *h, const void *d, size_t n) { memcpy(h, d, n); return 0; }
+int bk_zero(void *d, size_t n) { memset(d, 0, n); return 0; }
+int bk_sync(void) { return 0; }
+void *bk_stream(void) { return 0; }
+
+int bk_index_count(const uint8_t *d_in, uint32_t len, uint32_t *d_tile, uint32_t n_tiles, uint32_t *n_cand)
+{
+    uint32_t t, run = 0;
+    for (t = 0; t < n_tiles; t++) {
+        uint32_t b = t * BK_INDEX_TILE, e = b + BK_INDEX_TILE, i, cnt = 0;
+        if (e > len) e = len;
+        for (i = b; i < e; i++) {
+            int kind;
+            if (d_in[i] == 0x92 && rec_frame(d_in + i, d_in + len, &kind) && !rec_is_shadowed(d_in, d_in + i, d_in + len)) cnt++;
+        }
+        d_tile[t] = run;
+        run += cnt;
+    }
+    *n_cand = run;
+    hs_launches += 2;
+    return 0;
+}
+
+int bk_index_fill(const uint8_t *d_in, uint32_t len, const uint32_t *d_tile, uint32_t n_tiles, uint32_t n_cand,
+                  uint32_t *d_off, uint32_t *d_len, uint8_t *d_kind, uint32_t *n_valid, int *tiled)
+{
+    uint32_t t, i, fb = 0xffffffffu;
+    *n_valid = 0; *tiled = (len == 0);
+    if (n_cand == 0) return 0;
+    for (t = 0; t < n_tiles; t++) {
+        uint32_t b = t * BK_INDEX_TILE, e = b + BK_INDEX_TILE, o = d_tile[t];
+        if (e > len) e = len;
+        for (i = b; i < e; i++) {
+            int kind = 0;
+            const uint8_t *q;
+            if (d_in[i] == 0x92 && (q = rec_frame(d_in + i, d_in + len, &kind)) && !rec_is_shadowed(d_in, d_in + i, d_in + len)) {
+                d_off[o] = i; d_len[o] = (uint32_t) (q - (d_in + i)); d_kind[o] = (uint8_t) kind; o++;
+            }
+        }
+    }
+    hs_launches += 2;
+    for (i = 0; i < n_cand; i++) {
+        uint32_t next = (i + 1 < n_cand) ? d_off[i + 1] : len;
+        if (d_off[i] + d_len[i] != next) { fb = i; break; }
+    }
+    if (d_off[0] != 0) { *n_valid = 0; *tiled = 0; return 0; }
+    if (fb == 0xffffffffu) { *n_valid = n_cand; *tiled = 1; return 0; }
+    if (fb == n_cand - 1) { *n_valid = n_cand; *tiled = 0; return 0; }
+    snprintf(hs_err, sizeof(hs_err), "record index: candidate chain breaks at record %u of %u", fb, n_cand);
+    return -1;
+}
+
+static void hs_env(const struct bk_chain_args *a, struct ch_env *e)
+{
+    e->in = a->d_in; e->in_len = a->in_len; e->blob = a->d_blob; e->scr = a->d_scr;
+    e->capcache = a->d_capcache; e->cap_stride = a->cap_stride; e->now = a->now; e->assume = a->assume;
+    e->fl_flags = a->d_flags; e->err = a->d_flags + FLBGPU_MAX_FILTERS;
+}
+
+int bk_chain_size(const struct bk_chain_args *a, uint32_t *h_flags, uint64_t *total)
+{
+    struct ch_env e;
+    uint32_t i, nb = (a->n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK, b;
+    uint64_t run = 0;
+    hs_env(a, &e);
+    memset(a->d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1));
+    for (b = 0; b < nb; b++) {
+        uint64_t bs = 0;
+        for (i = b * BK_REC_BLOCK; i < a->n_rec && i < (b + 1) * BK_REC_BLOCK; i++) {
+            uint32_t sz = 0;
+            if (a->d_kind[i] == 0) sz = chain_record<false>(&e, i, a->d_off[i], a->d_len[i], 0);
+            a->d_size[i] = sz;
+            bs += sz;
+        }
+        a->d_bsum[b] = run;
+        run += bs;
+    }
+    memcpy(h_flags, a->d_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1));
+    *total = run;
+    hs_launches += 2;
+    return 0;
+}
+
+int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out)
+{
+    struct ch_env e;
+    uint32_t i, nb = (a->n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK, b;
+    hs_env(a, &e);
+    for (b = 0; b < nb; b++) {
+        uint64_t at = a->d_bsum[b];
+        for (i = b * BK_REC_BLOCK; i < a->n_rec && i < (b + 1) * BK_REC_BLOCK; i++) {
+            if (a->d_size[i]) {
+                uint32_t w = chain_record<true>(&e, i, a->d_off[i], a->d_len[i], d_out + at);
+                if (w != a->d_size[i]) { snprintf(hs_err, sizeof(hs_err), "emit size mismatch at record %u: %u vs %u", i, w, a->d_size[i]); return -1; }
+                at += w;
+            }
+        }
+    }
+    hs_launches += 1;
+    return 0;
+}
+
+}

@@ -1,0 +1,225 @@
+"""Shared test helpers: reference harness binding (oracle/_ref), event encoding,
+synthetic line generators."""
+import ctypes as C
+import importlib
+import os
+import random
+import struct
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_SO = os.path.join(ROOT, "oracle", "_ref", "libflbref.so")
+HOSTSIM_SO = os.path.join(ROOT, "tests", "hostsim", "libhostsim.so")
+
+pkg = importlib.import_module("fluent-bit_b200")
+
+
+def have_ref():
+    return os.path.exists(REF_SO)
+
+
+class Ref:
+    """The UNMODIFIED reference code (oracle/_ref/libflbref.so)."""
+
+    def __init__(self):
+        L = C.CDLL(REF_SO)
+        vp, cp, sz = C.c_void_p, C.c_char_p, C.c_size_t
+        L.flbref_config_create.restype = vp
+        L.flbref_parser_create.restype = vp
+        L.flbref_parser_create.argtypes = [vp, cp, cp, cp, C.c_int, cp, cp, cp, C.c_int, C.c_int, C.c_int, cp]
+        L.flbref_parser_do.argtypes = [vp, cp, sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
+        L.flbref_filter_create.restype = vp; L.flbref_filter_create.argtypes = [vp, cp]
+        L.flbref_filter_set.argtypes = [vp, cp, cp]
+        L.flbref_filter_init.argtypes = [vp, vp]
+        L.flbref_filter_cb.argtypes = [vp, vp, vp, sz, cp, C.POINTER(vp), C.POINTER(sz)]
+        L.flbref_filter_do.argtypes = [vp, vp, sz, C.c_int, cp, C.POINTER(vp), C.POINTER(sz)]
+        L.flbref_count_records.argtypes = [vp, sz]
+        L.flbref_free.argtypes = [vp]
+        L.flbref_time_lookup.argtypes = [vp, cp, sz, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
+        self.L = L
+        self.cfg = L.flbref_config_create()
+
+    @staticmethod
+    def _b(s):
+        return s if s is None or isinstance(s, bytes) else s.encode()
+
+    def parser(self, name, format, regex=None, skip_empty=True, time_fmt=None, time_key=None, time_offset=None,
+               time_keep=False, time_strict=True, logfmt_no_bare_keys=False, types=None):
+        b = self._b
+        p = self.L.flbref_parser_create(self.cfg, b(name), b(format), b(regex), int(skip_empty), b(time_fmt),
+                                        b(time_key), b(time_offset), int(time_keep), int(time_strict),
+                                        int(logfmt_no_bare_keys), b(types))
+        if not p:
+            raise RuntimeError("reference rejected parser " + name)
+        return p
+
+    def parser_do(self, p, line):
+        out, n = C.c_void_p(), C.c_size_t()
+        s, ns = C.c_longlong(), C.c_longlong()
+        r = self.L.flbref_parser_do(p, line, len(line), C.byref(out), C.byref(n), C.byref(s), C.byref(ns))
+        data = C.string_at(out.value, n.value) if (r >= 0 and out.value) else None
+        if out.value:
+            self.L.flbref_free(out)
+        return r, data, (s.value, ns.value)
+
+    def filter(self, plugin, props):
+        f = self.L.flbref_filter_create(self.cfg, self._b(plugin))
+        for k, v in props:
+            self.L.flbref_filter_set(f, self._b(k), self._b(v))
+        if self.L.flbref_filter_init(self.cfg, f) != 0:
+            raise RuntimeError("reference filter init failed: %s %r" % (plugin, props))
+        return f
+
+    def filter_cb(self, f, data, tag="test"):
+        out, n = C.c_void_p(), C.c_size_t()
+        buf = C.create_string_buffer(data, len(data))
+        r = self.L.flbref_filter_cb(self.cfg, f, C.cast(buf, C.c_void_p), len(data), self._b(tag), C.byref(out), C.byref(n))
+        res = None
+        if r == 1:
+            res = C.string_at(out.value, n.value) if n.value else b""
+            if out.value:
+                self.L.flbref_free(out)
+        return r, res
+
+    def chain_do(self, data, tag="test"):
+        """flb_filter_do over every filter created on this Ref, in creation order."""
+        out, n = C.c_void_p(), C.c_size_t()
+        buf = C.create_string_buffer(data, len(data))
+        nrec = self.L.flbref_count_records(C.cast(buf, C.c_void_p), len(data))
+        r = self.L.flbref_filter_do(self.cfg, C.cast(buf, C.c_void_p), len(data), nrec, self._b(tag), C.byref(out), C.byref(n))
+        if r == 0:
+            return 2, None
+        res = C.string_at(out.value, n.value) if n.value else b""
+        if out.value:
+            self.L.flbref_free(out)
+        return 1, res
+
+
+# ---------------------------------------------------------------- msgpack bits
+def mp_str(b):
+    n = len(b)
+    if n < 32:
+        return bytes([0xa0 | n]) + b
+    if n < 256:
+        return bytes([0xd9, n]) + b
+    if n < 65536:
+        return b"\xda" + struct.pack(">H", n) + b
+    return b"\xdb" + struct.pack(">I", n) + b
+
+
+def mp_map_hdr(n):
+    if n < 16:
+        return bytes([0x80 | n])
+    if n < 65536:
+        return b"\xde" + struct.pack(">H", n)
+    return b"\xdf" + struct.pack(">I", n)
+
+
+def event(sec, nsec, body_items, meta=b"\x80"):
+    """One v2 log event; body_items: list of (key bytes, encoded value bytes)."""
+    body = mp_map_hdr(len(body_items)) + b"".join(mp_str(k) + v for k, v in body_items)
+    return b"\x92\x92\xd7\x00" + struct.pack(">II", sec & 0xffffffff, nsec & 0xffffffff) + meta + body
+
+
+def chunk_from_lines(lines, key=b"log", t0=1700000000):
+    return b"".join(event(t0 + i, i % 1000, [(key, mp_str(l))]) for i, l in enumerate(lines))
+
+
+def split_records(chunk):
+    """[(offset, length)] of the top-level objects of a chunk (pure python walker)."""
+    out, i = [], 0
+    while i < len(chunk):
+        j = _skip(chunk, i)
+        out.append((i, j - i))
+        i = j
+    return out
+
+
+def _skip(b, i):
+    owed = 1
+    while owed:
+        owed -= 1
+        c = b[i]
+        if c < 0x80 or c >= 0xe0 or c in (0xc0, 0xc2, 0xc3):
+            i += 1
+        elif c <= 0x8f:
+            owed += 2 * (c & 15); i += 1
+        elif c <= 0x9f:
+            owed += c & 15; i += 1
+        elif c <= 0xbf:
+            i += 1 + (c & 31)
+        elif c in (0xc4, 0xd9):
+            i += 2 + b[i + 1]
+        elif c in (0xc5, 0xda):
+            i += 3 + struct.unpack(">H", b[i + 1:i + 3])[0]
+        elif c in (0xc6, 0xdb):
+            i += 5 + struct.unpack(">I", b[i + 1:i + 5])[0]
+        elif c == 0xc7:
+            i += 3 + b[i + 1]
+        elif c == 0xc8:
+            i += 4 + struct.unpack(">H", b[i + 1:i + 3])[0]
+        elif c == 0xc9:
+            i += 6 + struct.unpack(">I", b[i + 1:i + 5])[0]
+        elif c in (0xca, 0xce, 0xd2):
+            i += 5
+        elif c in (0xcb, 0xcf, 0xd3):
+            i += 9
+        elif c in (0xcc, 0xd0):
+            i += 2
+        elif c in (0xcd, 0xd1):
+            i += 3
+        elif c in (0xd4, 0xd5, 0xd6, 0xd7, 0xd8):
+            i += 2 + {0xd4: 1, 0xd5: 2, 0xd6: 4, 0xd7: 8, 0xd8: 16}[c]
+        elif c == 0xdc:
+            owed += struct.unpack(">H", b[i + 1:i + 3])[0]; i += 3
+        elif c == 0xdd:
+            owed += struct.unpack(">I", b[i + 1:i + 5])[0]; i += 5
+        elif c == 0xde:
+            owed += 2 * struct.unpack(">H", b[i + 1:i + 3])[0]; i += 3
+        elif c == 0xdf:
+            owed += 2 * struct.unpack(">I", b[i + 1:i + 5])[0]; i += 5
+        else:
+            raise ValueError("bad msgpack byte %02x at %d" % (c, i))
+    return i
+
+
+# ------------------------------------------------------------- synthetic logs
+APACHE_RX = (r'^(?<host>[^ ]*) [^ ]* (?<user>[^ ]*) \[(?<time>[^\]]*)\] "(?<method>\S+)(?: +(?<path>[^\"]*?)'
+             r'(?: +\S*)?)?" (?<code>[^ ]*) (?<size>[^ ]*)(?: "(?<referer>[^\"]*)" "(?<agent>[^\"]*)")?$')
+APACHE_TIME_FMT = "%d/%b/%Y:%H:%M:%S %z"
+NGINX_RX = (r'^(?<remote>[^ ]*) (?<host>[^ ]*) (?<user>[^ ]*) \[(?<time>[^\]]*)\] "(?<method>\S+)(?: +(?<path>[^\"]*?)'
+            r'(?: +\S*)?)?" (?<code>[^ ]*) (?<size>[^ ]*)(?: "(?<referer>[^\"]*)" "(?<agent>[^\"]*)")')
+_MON = ["Jan", "Feb", "Mar", "Apr", "May", "Jun", "Jul", "Aug", "Sep", "Oct", "Nov", "Dec"]
+_REF = ["-", "http://example.com/", "https://www.google.com/search?q=fluent", "http://10.0.0.1/index.html",
+        "https://example.org/a/b/c", "-", "-", "http://intranet/login"]
+_AGENT = ["Mozilla/5.0 (X11; Linux x86_64) AppleWebKit/537.36 (KHTML, like Gecko) Chrome/118.0 Safari/537.36",
+          "curl/8.1.2", "Mozilla/5.0 (Macintosh; Intel Mac OS X 10_15_7) Gecko/20100101 Firefox/119.0",
+          "kube-probe/1.27", "Go-http-client/1.1", "python-requests/2.31.0", "-", "Prometheus/2.45.0"]
+
+
+def apache_lines(n, seed=0xF1B1 + 1, garbage=0.005, nginx=False):
+    rng = random.Random(seed)
+    out = []
+    t = 1672531200
+    for _ in range(n):
+        if rng.random() < garbage:
+            out.append(("garbage line %d without structure" % rng.randint(0, 10 ** 6)).encode())
+            continue
+        host = "%d.%d.%d.%d" % (rng.randint(1, 254), rng.randint(0, 255), rng.randint(0, 255), rng.randint(1, 254))
+        user = "-" if rng.random() < 0.9 else "".join(rng.choice("abcdefghijklmnopqrstuvwxyz") for _ in range(rng.randint(3, 8)))
+        t += rng.randint(0, 3)
+        y, mo, d = 2023, (t // 2678400) % 12, (t // 86400) % 28 + 1
+        ts = "%02d/%s/%d:%02d:%02d:%02d %s" % (d, _MON[mo], y, (t // 3600) % 24, (t // 60) % 60, t % 60,
+                                               rng.choice(["+0000", "-0300", "+0900", "+0530"]))
+        method = rng.choices(["GET", "POST", "PUT", "HEAD"], [70, 20, 5, 5])[0]
+        path = "/" + "".join(rng.choice("abcdefghijklmnopqrstuvwxyz0123456789/_-") for _ in range(rng.randint(4, 48)))
+        if rng.random() < 0.05:
+            path += "?q=" + str(rng.randint(0, 9999))
+        code = rng.choices(["200", "304", "404", "500", "301"], [80, 5, 8, 2, 5])[0]
+        size = "-" if rng.random() < 0.03 else str(int(10 ** (rng.random() * 6)))
+        line = '%s - %s [%s] "%s %s HTTP/1.1" %s %s' % (host, user, ts, method, path, code, size)
+        if nginx:
+            line = "10.0.0.%d " % rng.randint(1, 250) + line
+        if nginx or rng.random() >= 0.10:
+            line += ' "%s" "%s"' % (rng.choice(_REF), rng.choice(_AGENT))
+        out.append(line.encode())
+    return out
