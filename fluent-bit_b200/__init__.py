@@ -42,7 +42,7 @@ EXPORTS = [
     "flbgpu_filter_destroy", "flbgpu_chain_new", "flbgpu_chain_add", "flbgpu_chain_init", "flbgpu_chain_do",
     "flbgpu_chain_destroy", "flbgpu_chain_do_device", "flbgpu_chain_stats", "flbgpu_dev_alloc",
     "flbgpu_dev_free", "flbgpu_dev_upload", "flbgpu_dev_download", "flbgpu_host_alloc", "flbgpu_host_free",
-    "flbgpu_stream",
+    "flbgpu_stream", "flbgpu_kernel_ms",
 ]
 
 
@@ -83,6 +83,7 @@ def load(path=None):
     L.flbgpu_host_alloc.restype = vp; L.flbgpu_host_alloc.argtypes = [vp, sz]
     L.flbgpu_host_free.argtypes = [vp, vp]
     L.flbgpu_stream.restype = vp; L.flbgpu_stream.argtypes = [vp]
+    L.flbgpu_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     return L
 
 

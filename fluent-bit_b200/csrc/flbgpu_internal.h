@@ -50,6 +50,7 @@ int   bk_d2h(void *h, const void *d, size_t n);
 int   bk_zero(void *d, size_t n);
 int   bk_sync(void);
 void *bk_stream(void);
+int   bk_kernel_ms(float out[3]);               /* CUDA-event ms of index / evaluate / emit in the last call */
 const char *bk_last_error(void);
 
 /* Record index (K1).  Pass 1 counts validated record candidates per tile and leaves

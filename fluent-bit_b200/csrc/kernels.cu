@@ -24,6 +24,12 @@
 static char g_err[256];
 static unsigned long long g_launches;
 static cudaStream_t g_stream;
+/* CUDA-event timing of the three kernel groups of the last call (index, evaluate, emit) */
+static cudaEvent_t g_ev[6];
+static int g_ev_used[3];
+static int g_ev_ready;
+static void ev_begin(int k) { if (g_ev_ready) { cudaEventRecord(g_ev[2 * k], g_stream); } }
+static void ev_end(int k) { if (g_ev_ready) { cudaEventRecord(g_ev[2 * k + 1], g_stream); g_ev_used[k] = 1; } }
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     snprintf(g_err, sizeof(g_err), "%s: %s", #call, cudaGetErrorString(e_)); return -1; } } while (0)
@@ -223,6 +229,7 @@ int bk_init(int device)
     if (device < 0 || device >= n) { snprintf(g_err, sizeof(g_err), "device %d out of range (0..%d)", device, n - 1); return -1; }
     CK(cudaSetDevice(device));
     if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
+    if (!g_ev_ready) { for (int i = 0; i < 6; i++) CK(cudaEventCreate(&g_ev[i])); g_ev_ready = 1; }
     /* the interpreter keeps its field list and backtrack stack in local memory */
     CK(cudaFuncSetCacheConfig(k_chain<false>, cudaFuncCachePreferL1));
     CK(cudaFuncSetCacheConfig(k_chain<true>, cudaFuncCachePreferL1));
@@ -239,6 +246,16 @@ int bk_zero(void *d, size_t n) { CK(cudaMemsetAsync(d, 0, n, g_stream)); return 
 int bk_sync(void) { CK(cudaStreamSynchronize(g_stream)); return 0; }
 void *bk_stream(void) { return (void *) g_stream; }
 
+/* milliseconds of [index, evaluate (last pass), emit] of the last call; needs a prior bk_sync() */
+int bk_kernel_ms(float out[3])
+{
+    for (int k = 0; k < 3; k++) {
+        out[k] = 0.f;
+        if (g_ev_used[k] && cudaEventElapsedTime(&out[k], g_ev[2 * k], g_ev[2 * k + 1]) != cudaSuccess) out[k] = -1.f;
+    }
+    return 0;
+}
+
 static unsigned long long *g_dtotal;   /* device scratch for totals / first_break */
 static int ensure_small(void)
 {
@@ -251,7 +268,9 @@ int bk_index_count(const uint8_t *d_in, uint32_t len, uint32_t *d_tile, uint32_t
     unsigned long long tot = 0;
     if (ensure_small()) return -1;
     *n_cand = 0;
+    g_ev_used[0] = g_ev_used[1] = g_ev_used[2] = 0;
     if (n_tiles == 0) return 0;
+    ev_begin(0);
     k_index<false><<<n_tiles, 256, 0, g_stream>>>(d_in, len, d_tile, 0, 0, 0);
     k_scan_top<uint32_t><<<1, 256, 0, g_stream>>>(d_tile, n_tiles, g_dtotal);
     g_launches += 2;
@@ -272,6 +291,7 @@ int bk_index_fill(const uint8_t *d_in, uint32_t len, const uint32_t *d_tile, uin
     k_index<true><<<n_tiles, 256, 0, g_stream>>>(d_in, len, (uint32_t *) d_tile, d_off, d_len, d_kind);
     CK(cudaMemcpyAsync(d_fb, &fb, sizeof(fb), cudaMemcpyHostToDevice, g_stream));
     k_index_check<<<(n_cand + 255) / 256, 256, 0, g_stream>>>(d_off, d_len, n_cand, len, d_fb);
+    ev_end(0);
     g_launches += 2;
     CK(cudaGetLastError());
     CK(cudaMemcpyAsync(&fb, d_fb, sizeof(fb), cudaMemcpyDeviceToHost, g_stream));
@@ -306,7 +326,9 @@ int bk_chain_size(const struct bk_chain_args *a, uint32_t *h_flags, uint64_t *to
     CK(cudaMemsetAsync(a->d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1), g_stream));
     if (nb) {
         fill_params(a, &p, 0);
+        ev_begin(1);
         k_chain<false><<<nb, BK_REC_BLOCK, 0, g_stream>>>(p);
+        ev_end(1);
         k_scan_top<uint64_t><<<1, 256, 0, g_stream>>>((uint64_t *) a->d_bsum, nb, g_dtotal);
         g_launches += 2;
         CK(cudaGetLastError());
@@ -324,7 +346,9 @@ int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out)
     const uint32_t nb = (a->n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK;
     if (!nb) return 0;
     fill_params(a, &p, d_out);
+    ev_begin(2);
     k_chain<true><<<nb, BK_REC_BLOCK, 0, g_stream>>>(p);
+    ev_end(2);
     g_launches += 1;
     CK(cudaGetLastError());
     return 0;

@@ -880,17 +880,22 @@ void flbgpu_chain_destroy(flbgpu_chain *c)
 }
 
 void flbgpu_chain_stats(flbgpu_chain *c, struct flbgpu_stats *out) { if (c && out) *out = c->st; }
+int flbgpu_kernel_ms(flbgpu_ctx *ctx, float out[3]) { (void) ctx; if (bk_sync()) return -1; return bk_kernel_ms(out); }
 
 #define GROW(ptr, cap, need, type) do { if ((cap) < (size_t) (need)) { size_t nc_ = (size_t) (need) + (size_t) (need) / 4 + 64; \
         bk_free(ptr); (ptr) = (type *) bk_alloc(nc_ * sizeof(type)); if (!(ptr)) { (cap) = 0; return -1; } (cap) = nc_; } } while (0)
 
-/* chunk-level verdict of filter k from the evidence word (see dev_chain.cuh) */
-static int verdict(int kind, uint32_t fl)
+/* chunk-level verdict of filter k from the evidence word (see dev_chain.cuh).
+ * `clean`: the filter's input decodes to its very end.  grep and modify return
+ * NOTOUCH (after logging an encoder error) when the decoder stopped early
+ * (plugins/filter_grep/grep.c:355-384, plugins/filter_modify/modify.c:1547-1566);
+ * filter_parser and record_modifier hand back whatever they encoded. */
+static int verdict(int kind, uint32_t fl, int clean)
 {
     switch (kind) {
     case FLBGPU_F_PARSER: return (fl & CHF_EMITTED) != 0;
-    case FLBGPU_F_GREP: return (fl & CHF_CAUSE) != 0;
-    case FLBGPU_F_MODIFY: return (fl & CHF_CAUSE) != 0;
+    case FLBGPU_F_GREP: return (fl & CHF_CAUSE) != 0 && clean;
+    case FLBGPU_F_MODIFY: return (fl & CHF_CAUSE) != 0 && clean;
     case FLBGPU_F_RECORD_MODIFIER: return (fl & CHF_CAUSE) && (fl & CHF_EMITTED);
     }
     return 0;
@@ -947,13 +952,17 @@ static int chain_run_device(flbgpu_chain *c, const uint8_t *d_in, size_t bytes, 
                      "1=too many keys 2=regex stack 4=regex budget 8=float outside exact path)", h_flags[FLBGPU_MAX_FILTERS]);
             return -1;
         }
+        {
+        int clean = tiled;
         for (k = 0; k < c->nf; k++) {
-            int v = verdict(c->f[k]->kind, h_flags[k]);
+            int v = verdict(c->f[k]->kind, h_flags[k], clean);
+            if (v) clean = 1;                /* a MODIFIED filter hands a well-formed chunk on */
             if (v != (int) ((a.assume >> k) & 1)) {
                 a.assume = (a.assume & ~(1u << k)) | ((uint32_t) v << k);
                 changed = 1;
                 break;                   /* later filters saw the wrong input: re-evaluate */
             }
+        }
         }
         if (!changed) break;
     }

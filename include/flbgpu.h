@@ -122,6 +122,11 @@ struct flbgpu_stats {
 };
 void flbgpu_chain_stats(flbgpu_chain *c, struct flbgpu_stats *out);
 
+/* CUDA-event milliseconds of the three kernel groups of the most recent chain call on this
+ * context: out[0] record index, out[1] evaluation pass (the regex/interpreter kernel),
+ * out[2] emission pass.  Synchronises the library stream. */
+int flbgpu_kernel_ms(flbgpu_ctx *ctx, float out[3]);
+
 /* device memory helpers for callers that keep chunks resident (bench, tests) */
 void *flbgpu_dev_alloc(flbgpu_ctx *ctx, size_t n);
 void  flbgpu_dev_free(flbgpu_ctx *ctx, void *p);

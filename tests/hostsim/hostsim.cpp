@@ -92,6 +92,7 @@ int bk_d2h(void *h, const void *d, size_t n) { memcpy(h, d, n); return 0; }
 int bk_zero(void *d, size_t n) { memset(d, 0, n); return 0; }
 int bk_sync(void) { return 0; }
 void *bk_stream(void) { return 0; }
+int bk_kernel_ms(float out[3]) { out[0] = out[1] = out[2] = 0.f; return 0; }
 
 int bk_index_count(const uint8_t *d_in, uint32_t len, uint32_t *d_tile, uint32_t n_tiles, uint32_t *n_cand)
 {

@@ -1,0 +1,83 @@
+"""Byte parity of the filter chain against the UNMODIFIED reference (oracle/_ref).
+
+CPU half: the device algorithms compiled for the host (tests/hostsim).  GPU half: the
+same cases through libflbgpu.so's C ABI on a real device.  Both compare the returned
+code (MODIFIED / NOTOUCH) and every output byte."""
+import pytest
+
+import cases
+import util
+
+pkg = util.pkg
+
+
+def run_case(lib, parsers, filters, chunk, fused=True):
+    ctx = pkg.Context(0, lib=lib)
+    ref = util.Ref()
+    for kw in parsers:
+        ctx.parser(**kw)
+        ref.parser(**kw)
+    fs = [ctx.filter(p, props) for p, props in filters]
+    for p, props in filters:
+        ref.filter(p, props)
+    want = ref.chain_do(chunk)
+    if fused:
+        got = ctx.chain(fs).do(chunk)
+    else:
+        # the reference's own loop: one cb_filter per plugin, host buffers in between
+        cur, modified = chunk, False
+        for f in fs:
+            r, out = f.cb(cur)
+            if r == pkg.FILTER_MODIFIED:
+                cur, modified = out, True
+                if len(out) == 0:
+                    break
+        got = (pkg.FILTER_MODIFIED, cur) if modified else (pkg.FILTER_NOTOUCH, None)
+    assert got[0] == want[0]
+    assert got[1] == want[1]
+
+
+@pytest.mark.parametrize("case", cases.CASES, ids=[c[0] for c in cases.CASES])
+def test_fused_chain_hostsim(case, sim_lib, ref_available):
+    _, parsers, filters, mk = case
+    run_case(sim_lib, parsers, filters, mk())
+
+
+@pytest.mark.parametrize("case", cases.CASES[:6], ids=[c[0] for c in cases.CASES[:6]])
+def test_per_filter_callbacks_hostsim(case, sim_lib, ref_available):
+    _, parsers, filters, mk = case
+    run_case(sim_lib, parsers, filters, mk(), fused=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", cases.CASES, ids=[c[0] for c in cases.CASES])
+def test_fused_chain_gpu(case, gpu_lib, ref_available):
+    _, parsers, filters, mk = case
+    run_case(gpu_lib, parsers, filters, mk())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", cases.CASES[:6], ids=[c[0] for c in cases.CASES[:6]])
+def test_per_filter_callbacks_gpu(case, gpu_lib, ref_available):
+    _, parsers, filters, mk = case
+    run_case(gpu_lib, parsers, filters, mk(), fused=False)
+
+
+def test_edge_chunks_hostsim(sim_lib, ref_available):
+    chunk = cases.apache_chunk(50)
+    # empty chunk, trailing garbage, garbage at the front, group markers
+    marker = util.event(0xffffffff, 0, [(b"g", util.mp_str(b"start"))])
+    endm = util.event(0xfffffffe, 0, [])
+    for data in [chunk + b"\x01\x02\x03", b"\xc1" + chunk, marker + chunk + endm, marker + endm]:
+        for filters in ([("grep", [("Regex", "log GET")])], [cases.P], [("modify", [("Add", "a b")])]):
+            run_case(sim_lib, [cases.AP], filters, data)
+
+
+@pytest.mark.gpu
+def test_edge_chunks_gpu(gpu_lib, ref_available):
+    chunk = cases.apache_chunk(50)
+    marker = util.event(0xffffffff, 0, [(b"g", util.mp_str(b"start"))])
+    endm = util.event(0xfffffffe, 0, [])
+    for data in [chunk + b"\x01\x02\x03", b"\xc1" + chunk, marker + chunk + endm, marker + endm]:
+        for filters in ([("grep", [("Regex", "log GET")])], [cases.P], [("modify", [("Add", "a b")])]):
+            run_case(gpu_lib, [cases.AP], filters, data)
