@@ -196,20 +196,69 @@ FLB_HD int dt_find_mon(const unsigned char *bp, int *len)
     return -1;
 }
 
+/* tail of _flb_strptime(): resolve %y/%C and derive yday/wday/mon/mday when possible
+ * (src/flb_strptime.c:765-812); runs at the end of every (nested) format */
+FLB_HD void dt_finalize(struct dt_tm *tm, struct dt_state *st)
+{
+    int i;
+    if (st->relyear != -1) {
+        if (st->century == 1900) {
+            if (st->relyear <= 68) tm->year = st->relyear + 2000 - 1900;
+            else tm->year = st->relyear + 1900 - 1900;
+        }
+        else tm->year = st->relyear + st->century - 1900;
+        st->fields |= DT_F_YEAR;
+    }
+    if (st->fields & DT_F_YEAR) {
+        const int year = (int) ((unsigned) tm->year + 1900u);
+        const int ml[2][12] = { { 31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31 },
+                                { 31, 29, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31 } };
+        const int *mon_lens = ml[dt_isleap(year)];
+        if (!(st->fields & DT_F_YDAY) && (st->fields & DT_F_MON) && (st->fields & DT_F_MDAY)) {
+            tm->yday = tm->mday - 1;
+            for (i = 0; i < tm->mon; i++) tm->yday += mon_lens[i];
+            st->fields |= DT_F_YDAY;
+        }
+        if (st->fields & DT_F_YDAY) {
+            int days = tm->yday;
+            if (!(st->fields & DT_F_WDAY)) {
+                tm->wday = 4 + ((year - 1970) % 7) * (365 % 7) + dt_leaps_thru_end_of(year - 1) -
+                           dt_leaps_thru_end_of(1969) + tm->yday;
+                tm->wday %= 7;
+                if (tm->wday < 0) tm->wday += 7;
+            }
+            if (!(st->fields & DT_F_MON)) {
+                tm->mon = 0;
+                while (tm->mon < 12 && days >= mon_lens[tm->mon]) days -= mon_lens[tm->mon++];
+            }
+            if (!(st->fields & DT_F_MDAY)) tm->mday = days + 1;
+        }
+    }
+}
+
 /* _flb_strptime(): returns the position after the last consumed byte, or NULL.
- * buf must be NUL terminated.  `depth` bounds the %D/%F/%T... recursion. */
+ * buf must be NUL terminated.  The reference recurses for %D %R %r %T %F; their
+ * expansions contain no nested composite, so one saved return pointer replaces the
+ * recursion (no device call stack needed). */
 FLB_HDN const unsigned char *dt_strptime(const unsigned char *bp, const char *fmt, struct dt_tm *tm,
                                          struct dt_state *st, int initialize)
 {
     unsigned char c;
     int i, len, offs, neg;
-    const char *sub;
+    const char *sub, *ret_fmt = 0;
 
     if (initialize) {
         st->century = 1900; st->relyear = -1; st->fields = 0;
         tm->gmtoff = 0; tm->isdst = -1;
     }
-    while ((c = (unsigned char) *fmt) != '\0') {
+    for (;;) {
+        c = (unsigned char) *fmt;
+        if (c == '\0') {
+            if (!ret_fmt) break;
+            dt_finalize(tm, st);            /* end of the nested format */
+            fmt = ret_fmt; ret_fmt = 0;
+            continue;
+        }
         if (dt_isspace(c)) {
             while (dt_isspace(*bp)) bp++;
             fmt++;
@@ -228,14 +277,11 @@ literal:
         case 'D': sub = "%m/%d/%y"; goto recurse;
         case 'R': sub = "%H:%M"; goto recurse;
         case 'r': sub = "%I:%M:%S %p"; goto recurse;
-        case 'T': sub = "%H:%M:%S";
+        case 'T': sub = "%H:%M:%S"; goto recurse;
+        case 'F': sub = "%Y-%m-%d";
 recurse:
-            bp = dt_strptime(bp, sub, tm, st, 0);
-            if (!bp) return 0;
-            break;
-        case 'F':
-            bp = dt_strptime(bp, "%Y-%m-%d", tm, st, 0);
-            if (!bp) return 0;
+            if (ret_fmt) return 0;          /* cannot happen: expansions hold no composites */
+            ret_fmt = fmt; fmt = sub;
             continue;
         case 'A': case 'a':
             i = dt_find_day(bp, &len);
@@ -393,39 +439,7 @@ recurse:
             return 0;
         }
     }
-    if (st->relyear != -1) {
-        if (st->century == 1900) {
-            if (st->relyear <= 68) tm->year = st->relyear + 2000 - 1900;
-            else tm->year = st->relyear + 1900 - 1900;
-        }
-        else tm->year = st->relyear + st->century - 1900;
-        st->fields |= DT_F_YEAR;
-    }
-    if (st->fields & DT_F_YEAR) {
-        const int year = (int) ((unsigned) tm->year + 1900u);
-        const int ml[2][12] = { { 31, 28, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31 },
-                                { 31, 29, 31, 30, 31, 30, 31, 31, 30, 31, 30, 31 } };
-        const int *mon_lens = ml[dt_isleap(year)];
-        if (!(st->fields & DT_F_YDAY) && (st->fields & DT_F_MON) && (st->fields & DT_F_MDAY)) {
-            tm->yday = tm->mday - 1;
-            for (i = 0; i < tm->mon; i++) tm->yday += mon_lens[i];
-            st->fields |= DT_F_YDAY;
-        }
-        if (st->fields & DT_F_YDAY) {
-            int days = tm->yday;
-            if (!(st->fields & DT_F_WDAY)) {
-                tm->wday = 4 + ((year - 1970) % 7) * (365 % 7) + dt_leaps_thru_end_of(year - 1) -
-                           dt_leaps_thru_end_of(1969) + tm->yday;
-                tm->wday %= 7;
-                if (tm->wday < 0) tm->wday += 7;
-            }
-            if (!(st->fields & DT_F_MON)) {
-                tm->mon = 0;
-                while (tm->mon < 12 && days >= mon_lens[tm->mon]) days -= mon_lens[tm->mon++];
-            }
-            if (!(st->fields & DT_F_MDAY)) tm->mday = days + 1;
-        }
-    }
+    dt_finalize(tm, st);
     return bp;
 }
 

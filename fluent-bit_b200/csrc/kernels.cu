@@ -162,14 +162,58 @@ __global__ void __launch_bounds__(256) k_scan_top(T *a, uint32_t n, unsigned lon
     if (threadIdx.x == 0) *out_total = carry;
 }
 
+#define BK_MAX_BREAKS 8192u
+
+/* Links of the candidate list: candidate i must end where candidate i+1 starts (the
+ * last one at the end of the chunk).  Broken links are rare -- a false candidate is a
+ * byte run inside a real record that happens to frame as an event, e.g. the timestamp
+ * bytes `.. 92 ce 00 00 01 a6 | 80` read as the legacy event [422, {}] -- and are
+ * collected for k_index_repair. */
 __global__ void k_index_check(const uint32_t *__restrict__ off, const uint32_t *__restrict__ rlen, uint32_t n,
-                              uint32_t total, uint32_t *first_break)
+                              uint32_t total, uint32_t *n_breaks, uint32_t *breaks)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t next = (i + 1 < n) ? off[i + 1] : total;
-    if (off[i] + rlen[i] != next) atomicMin(first_break, i);
-    if (i == 0 && off[0] != 0) atomicMin(first_break, 0xfffffffeu);    /* marker: does not start at 0 */
+    if (off[i] + rlen[i] != next) {
+        const uint32_t at = atomicAdd(n_breaks, 1u);
+        if (at < BK_MAX_BREAKS) breaks[at] = i;
+    }
+}
+
+/* One CTA: sort the broken links, then follow the record chain across them.  At a
+ * break the chain jumps to the candidate that starts exactly where the current record
+ * ends; the candidates jumped over were false and get kind 2 (ignored by k_chain).
+ * If nothing starts there the decodable prefix ends (the reference decoder stops at
+ * the first undecodable byte too).  res[0] = records in the prefix, res[1] = tiled. */
+__global__ void __launch_bounds__(1024) k_index_repair(const uint32_t *__restrict__ off, const uint32_t *__restrict__ rlen,
+                                                        uint8_t *kind, uint32_t n, uint32_t total,
+                                                        const uint32_t *n_breaks, const uint32_t *breaks, uint32_t *res)
+{
+    __shared__ uint32_t sorted[BK_MAX_BREAKS];
+    const uint32_t m = *n_breaks;
+    for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {          /* rank sort: values are distinct */
+        const uint32_t v = breaks[i];
+        uint32_t r = 0;
+        for (uint32_t j = 0; j < m; j++) r += breaks[j] < v;
+        sorted[r] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x != 0) return;
+    uint32_t n_valid = n, tiled = 1, skip_until = 0;
+    if (off[0] != 0) { res[0] = 0; res[1] = 0; return; }
+    for (uint32_t q = 0; q < m; q++) {
+        const uint32_t b = sorted[q];
+        if (b < skip_until) continue;                                  /* a candidate already ruled out */
+        const uint32_t target = off[b] + rlen[b];
+        uint32_t k = b + 1;
+        while (k < n && off[k] < target) { kind[k] = 2; k++; }
+        if (k < n && off[k] == target) { skip_until = k; continue; }
+        if (k == n && target == total) { skip_until = n; continue; }
+        n_valid = b + 1; tiled = 0;                                    /* nothing decodable starts at `target` */
+        break;
+    }
+    res[0] = n_valid; res[1] = tiled;
 }
 
 /* ------------------------------------------------------------------ chain */
@@ -284,27 +328,28 @@ int bk_index_count(const uint8_t *d_in, uint32_t len, uint32_t *d_tile, uint32_t
 int bk_index_fill(const uint8_t *d_in, uint32_t len, const uint32_t *d_tile, uint32_t n_tiles, uint32_t n_cand,
                   uint32_t *d_off, uint32_t *d_len, uint8_t *d_kind, uint32_t *n_valid, int *tiled)
 {
-    uint32_t fb = 0xffffffffu;
-    uint32_t *d_fb = (uint32_t *) (g_dtotal + 1);
+    static uint32_t *d_breaks;
+    uint32_t h[4] = { 0, 0, 0, 0 };
+    uint32_t *d_w = (uint32_t *) (g_dtotal + 1);          /* [0] n_breaks, [1] n_valid, [2] tiled */
     *n_valid = 0; *tiled = (len == 0);
     if (n_cand == 0) return 0;
+    if (!d_breaks) CK(cudaMalloc((void **) &d_breaks, sizeof(uint32_t) * BK_MAX_BREAKS));
     k_index<true><<<n_tiles, 256, 0, g_stream>>>(d_in, len, (uint32_t *) d_tile, d_off, d_len, d_kind);
-    CK(cudaMemcpyAsync(d_fb, &fb, sizeof(fb), cudaMemcpyHostToDevice, g_stream));
-    k_index_check<<<(n_cand + 255) / 256, 256, 0, g_stream>>>(d_off, d_len, n_cand, len, d_fb);
+    CK(cudaMemsetAsync(d_w, 0, 16, g_stream));
+    k_index_check<<<(n_cand + 255) / 256, 256, 0, g_stream>>>(d_off, d_len, n_cand, len, d_w, d_breaks);
+    k_index_repair<<<1, 1024, 0, g_stream>>>(d_off, d_len, d_kind, n_cand, len, d_w, d_breaks, d_w + 1);
     ev_end(0);
-    g_launches += 2;
+    g_launches += 3;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(&fb, d_fb, sizeof(fb), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaMemcpyAsync(h, d_w, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
     CK(cudaStreamSynchronize(g_stream));
-    if (fb == 0xffffffffu) { *n_valid = n_cand; *tiled = 1; return 0; }
-    if (fb == 0xfffffffeu) {                      /* first candidate is not at offset 0 */
-        /* a break may ALSO exist; either way nothing before the garbage decodes */
-        *n_valid = 0; *tiled = 0; return 0;
+    if (h[0] > BK_MAX_BREAKS) {
+        snprintf(g_err, sizeof(g_err), "record index: %u broken candidate links in one chunk (limit %u)", h[0], BK_MAX_BREAKS);
+        return -1;
     }
-    if (fb == n_cand - 1) { *n_valid = n_cand; *tiled = 0; return 0; }   /* trailing bytes after the last record */
-    snprintf(g_err, sizeof(g_err), "record index: candidate chain breaks at record %u of %u "
-             "(record-shaped data nested inside a record is not supported yet)", fb, n_cand);
-    return -1;
+    *n_valid = h[1];
+    *tiled = (int) h[2];
+    return 0;
 }
 
 static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_t *d_out)

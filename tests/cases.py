@@ -36,6 +36,17 @@ def mixed_chunk():
     return b"".join(ev)
 
 
+def tricky_ts_chunk():
+    """Timestamps whose bytes frame as complete legacy events ([uint32, {}]) inside real records:
+    the record index has to rule those candidates out (sec = 0x655492ce -> `92 ce 00 00 xx xx 80`)."""
+    lines = util.apache_lines(400, seed=21)
+    ev = []
+    for i, l in enumerate(lines):
+        sec = 0x655492ce if i % 5 == 0 else (0x6554cc92 if i % 7 == 0 else 1700000000 + i)
+        ev.append(util.event(sec, i % 1000, [(b"log", util.mp_str(l)), (b"n", b"\x92\xcc\x05\x80") if i % 9 == 0 else (b"n", b"\x01")]))
+    return b"".join(ev)
+
+
 CASES = [
     ("apache_parser", [AP], [P], apache_chunk),
     ("apache_parser_types_keep", [AP_TYPES], [P], apache_chunk),
@@ -48,6 +59,8 @@ CASES = [
     ("parser_preserve", [AP], [("parser", [("Key_Name", "log"), ("Parser", "apache"), ("Preserve_Key", "On")])], apache_chunk),
     ("parser_reserve", [AP], [("parser", [("Key_Name", "log"), ("Parser", "apache"), ("Reserve_Data", "On")])], mixed_chunk),
     ("parser_ra_key", [AP], [("parser", [("Key_Name", "$log"), ("Parser", "apache"), ("Reserve_Data", "On")])], apache_chunk),
+    ("tricky_timestamps_parser", [AP], [P], tricky_ts_chunk),
+    ("tricky_timestamps_grep", [], [("grep", [("Regex", "log GET")])], tricky_ts_chunk),
     ("grep_regex", [], [("grep", [("Regex", "log GET")])], apache_chunk),
     ("grep_exclude", [], [("grep", [("Exclude", "log HTTP")])], apache_chunk),
     ("grep_keep_all_notouch", [], [("grep", [("Regex", "log .")])], apache_chunk),

@@ -129,16 +129,26 @@ int bk_index_fill(const uint8_t *d_in, uint32_t len, const uint32_t *d_tile, uin
             }
         }
     }
-    hs_launches += 2;
-    for (i = 0; i < n_cand; i++) {
-        uint32_t next = (i + 1 < n_cand) ? d_off[i + 1] : len;
-        if (d_off[i] + d_len[i] != next) { fb = i; break; }
+    hs_launches += 3;
+    {
+        /* same walk as k_index_repair: breaks visited in ascending order */
+        uint32_t skip_until = 0, nv = n_cand, til = 1;
+        if (d_off[0] != 0) { *n_valid = 0; *tiled = 0; return 0; }
+        for (i = 0; i < n_cand; i++) {
+            uint32_t next = (i + 1 < n_cand) ? d_off[i + 1] : len, target, k;
+            if (d_off[i] + d_len[i] == next) continue;
+            if (i < skip_until) continue;
+            target = d_off[i] + d_len[i];
+            k = i + 1;
+            while (k < n_cand && d_off[k] < target) { d_kind[k] = 2; k++; }
+            if (k < n_cand && d_off[k] == target) { skip_until = k; continue; }
+            if (k == n_cand && target == len) { skip_until = n_cand; continue; }
+            nv = i + 1; til = 0;
+            break;
+        }
+        *n_valid = nv; *tiled = (int) til;
     }
-    if (d_off[0] != 0) { *n_valid = 0; *tiled = 0; return 0; }
-    if (fb == 0xffffffffu) { *n_valid = n_cand; *tiled = 1; return 0; }
-    if (fb == n_cand - 1) { *n_valid = n_cand; *tiled = 0; return 0; }
-    snprintf(hs_err, sizeof(hs_err), "record index: candidate chain breaks at record %u of %u", fb, n_cand);
-    return -1;
+    return 0;
 }
 
 static void hs_env(const struct bk_chain_args *a, struct ch_env *e)

@@ -1,0 +1,87 @@
+"""Committed golden vectors (tests/golden/*.json, produced from the UNMODIFIED reference by
+tests/golden/make_golden.py).  These run without /root/reference and without oracle/_ref, on
+the CPU emulation of the device code here and on the real GPU on the box."""
+import ctypes as C
+import json
+import os
+
+import pytest
+
+import util
+
+pkg = util.pkg
+G = os.path.join(util.ROOT, "tests", "golden")
+TIME = json.load(open(os.path.join(G, "time_vectors.json")))
+REGEX = json.load(open(os.path.join(G, "regex_vectors.json")))
+CHAIN = json.load(open(os.path.join(G, "chain_vectors.json")))
+
+
+def test_reference_table_pins_the_oracle():
+    """The reference's own expected epochs (tests/internal/parser.c:61-105) equal what the
+    reference build under oracle/_ref produced when the fixtures were generated."""
+    n = 0
+    for v in TIME:
+        if v["table_epoch"] is not None and not v["no_year"]:
+            assert v["ref_ret"] >= 0
+            assert v["ref_sec"] == v["table_epoch"], v
+            assert v["ref_nsec"] == int(v["table_frac"] * 1000000000.0), v
+            n += 1
+    assert n >= 20
+
+
+def check_time(lib):
+    ctx = pkg.Context(0, lib=lib)
+    for i, v in enumerate(TIME):
+        p = ctx.parser("t%d" % i, "regex", r"^(?<time>.+)$", time_fmt=v["fmt"], time_key="time",
+                       time_offset=v["offset"], time_keep=True)
+        r, data, (sec, nsec) = p.do(v["str"].encode())
+        assert (r >= 0) == (v["ref_ret"] >= 0), v
+        if r < 0:
+            continue
+        assert nsec == v["ref_nsec"], v
+        if not v["no_year"]:
+            assert sec == v["ref_sec"] & 0xffffffff, v
+        assert data.hex() == v["ref_map_hex"], v
+
+
+def test_time_vectors_hostsim(sim_lib):
+    check_time(sim_lib)
+
+
+@pytest.mark.gpu
+def test_time_vectors_gpu(gpu_lib):
+    check_time(gpu_lib)
+
+
+def test_regex_vectors_hostsim():
+    import rxdiff_sim
+    for entry in REGEX:
+        h = rxdiff_sim.compile(entry["pattern"])
+        assert h, entry["pattern"]
+        for c in entry["cases"]:
+            got = rxdiff_sim.search(h, bytes.fromhex(c["s"]))
+            want = None if c["m"] is None else tuple(tuple(x) for x in c["m"])
+            if want == ("m",) or (want is not None and len(want) == 1 and want[0] == ("m",)):
+                assert got is not None
+            else:
+                assert got == want, (entry["pattern"], c)
+
+
+def check_chain(lib):
+    for v in CHAIN:
+        ctx = pkg.Context(0, lib=lib)
+        for kw in v["parsers"]:
+            ctx.parser(**kw)
+        fs = [ctx.filter(p, [tuple(x) for x in props]) for p, props in v["filters"]]
+        ret, out = ctx.chain(fs).do(bytes.fromhex(v["in_hex"]))
+        assert ret == v["ret"], v["name"]
+        assert (out.hex() if out is not None else None) == v["out_hex"], v["name"]
+
+
+def test_chain_vectors_hostsim(sim_lib):
+    check_chain(sim_lib)
+
+
+@pytest.mark.gpu
+def test_chain_vectors_gpu(gpu_lib):
+    check_chain(gpu_lib)
