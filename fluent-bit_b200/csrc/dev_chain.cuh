@@ -539,6 +539,169 @@ FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t
     return 1;
 }
 
+/* Types cast of a parsed (key, value) pair: flb_parser_typecast(), src/flb_parser.c:1280-1377 */
+FLB_HD ref_t cast_value(const struct ch_env *e, const struct cf_pdef *pd, const uint8_t *key, uint32_t klen,
+                        const uint8_t *v, uint32_t voff, uint32_t vlen)
+{
+    const struct cf_ptype *ty = (const struct cf_ptype *) (e->blob + pd->types_off);
+    uint32_t i;
+    for (i = 0; i < pd->n_types; i++) {
+        if (ty[i].key_len != klen || !bytes_eq(e->blob + ty[i].key_off, key, klen)) continue;
+        if (ty[i].type == FLBGPU_TYPE_INT) return mkref(RK_INT_IN, voff, vlen);
+        if (ty[i].type == FLBGPU_TYPE_HEX) return mkref(RK_HEX_IN, voff, vlen);
+        if (ty[i].type == FLBGPU_TYPE_FLOAT) return mkref(RK_FLT_IN, voff, vlen);
+        if (ty[i].type == FLBGPU_TYPE_BOOL) {
+            if (vlen >= 4 && dt_lower(v[0]) == 't' && dt_lower(v[1]) == 'r' && dt_lower(v[2]) == 'u' && dt_lower(v[3]) == 'e') return mkref(RK_TRUE, 0, 0);
+            if (vlen >= 5 && dt_lower(v[0]) == 'f' && dt_lower(v[1]) == 'a' && dt_lower(v[2]) == 'l' && dt_lower(v[3]) == 's' && dt_lower(v[4]) == 'e') return mkref(RK_FALSE, 0, 0);
+        }
+        break;
+    }
+    return mkref(RK_STR_IN, voff, vlen);
+}
+
+FLB_HD int pdef_time(const struct ch_env *e, const struct cf_pdef *pd, const uint8_t *v, uint32_t vlen,
+                     int64_t *lookup, double *frac)
+{
+    struct dt_tm tm;
+    struct dt_parser tp;
+    double ns;
+    tm.sec = tm.min = tm.hour = tm.mday = tm.mon = tm.year = tm.wday = tm.yday = tm.isdst = 0;
+    tm.gmtoff = 0;
+    tp.fmt = (const char *) (e->blob + pd->fmt_off);
+    tp.frac_fmt = pd->has_frac ? (const char *) (e->blob + pd->frac_off) : 0;
+    tp.with_year = (int) pd->time_with_year; tp.with_tz = (int) pd->time_with_tz;
+    tp.strict = (int) pd->time_strict; tp.offset = pd->time_offset;
+    if (dt_time_lookup(v, vlen, e->now, &tp, &tm, &ns) == -1) return -1;
+    *frac = ns;
+    *lookup = dt_timegm(&tm) - tm.gmtoff;
+    return 0;
+}
+
+FLB_HD int64_t frac_to_nsec(double frac)
+{
+#ifdef __CUDA_ARCH__
+    return (int64_t) __dmul_rn(frac, 1000000000.0);
+#else
+    return (int64_t) (frac * 1000000000.0);
+#endif
+}
+
+/* ltsv_parser(), src/flb_parser_ltsv.c:82-197.  label bytes [0-9A-Za-z_.-] (:43-60),
+ * field bytes = everything but NUL, TAB, LF, CR (:62-79). */
+FLB_HD int ltsv_label(uint32_t c) { return (c >= '0' && c <= '9') || ((c | 0x20) >= 'a' && (c | 0x20) <= 'z') || c == '_' || c == '.' || c == '-'; }
+FLB_HD int ltsv_field(uint32_t c) { return c != 0 && c != 9 && c != 10 && c != 13; }
+
+FLB_HD int pdef_ltsv(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
+                     ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec)
+{
+    uint32_t c = 0;
+    int cnt = 0;
+    int64_t lookup = 0;
+    double frac = 0;
+    while (c < n) {
+        uint32_t label = c, label_len, field, field_len;
+        while (c < n && ltsv_label(s[c])) c++;
+        label_len = c - label;
+        if (c == n) break;
+        if (s[c] != ':') break;
+        c++;
+        field = c;
+        while (c < n && ltsv_field(s[c])) c++;
+        field_len = c - field;
+        if (label_len > 0) {
+            int time_found = 0;
+            if (pd->has_time && label_len == pd->time_key_len && field_len > 0 &&
+                bytes_eq(s + label, e->blob + pd->time_key_off, label_len)) {
+                if (pdef_time(e, pd, s + field, field_len, &lookup, &frac) != 0) return 0;
+                time_found = 1;
+            }
+            if (!time_found || pd->time_keep) {
+                if (cnt >= CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
+                ok_[cnt] = mkref(RK_STR_IN, val_off + label, label_len);
+                ov_[cnt] = pd->n_types ? cast_value(e, pd, s + label, label_len, s + field, val_off + field, field_len)
+                                       : mkref(RK_STR_IN, val_off + field, field_len);
+                cnt++;
+            }
+        }
+        if (c == n) break;
+        if (s[c] == '\t') c++;
+        if (c == n) break;
+        if (s[c] == '\r' || s[c] == '\n') break;
+    }
+    if (cnt == 0) return 0;
+    *on = cnt; *t_sec = lookup; *t_nsec = frac_to_nsec(frac);
+    return 1;
+}
+
+/* logfmt_parser(), src/flb_parser_logfmt.c:63-254.  ident bytes: > ' ' and not '=' '"' (:44-61) */
+FLB_HD int logfmt_ident(uint32_t c) { return c > ' ' && c != '=' && c != '"'; }
+
+FLB_HD int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
+                       ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec)
+{
+    uint32_t c = 0;
+    int cnt = 0;
+    int64_t lookup = 0;
+    double frac = 0;
+    while (c < n) {
+        uint32_t key, key_len, value = 0, value_len = 0;
+        int value_set = 0, value_str = 0, value_escape = 0;
+        while (c < n && !logfmt_ident(s[c])) c++;
+        if (c == n) break;
+        key = c;
+        while (c < n && logfmt_ident(s[c])) c++;
+        key_len = c - key;
+        if (c < n && s[c] == '=') {
+            value_set = 1;
+            c++;
+            if (c < n) {
+                if (s[c] == '"') {
+                    c++;
+                    value = c;
+                    value_str = 1;
+                    while (c < n) {
+                        if (s[c] != '\\' && s[c] != '"') c++;
+                        else if (s[c] == '\\') { value_escape = 1; c++; if (c == n) break; c++; }
+                        else break;
+                    }
+                    value_len = c - value;
+                    if (c < n && s[c] == '"') c++;
+                }
+                else {
+                    value = c;
+                    while (c < n && logfmt_ident(s[c])) c++;
+                    value_len = c - value;
+                }
+            }
+        }
+        if (key_len > 0) {
+            int time_found = 0;
+            if (pd->logfmt_no_bare_keys && value_len == 0 && !value_set) return 0;
+            if (pd->has_time && key_len == pd->time_key_len && value_len > 0 &&
+                bytes_eq(s + key, e->blob + pd->time_key_off, key_len)) {
+                if (pdef_time(e, pd, s + value, value_len, &lookup, &frac) != 0) return 0;
+                time_found = 1;
+            }
+            if (!time_found || pd->time_keep) {
+                if (cnt >= CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
+                ok_[cnt] = mkref(RK_STR_IN, val_off + key, key_len);
+                if (pd->n_types) ov_[cnt] = cast_value(e, pd, s + key, key_len, s + value, val_off + value, value_len);
+                else if (value_len == 0) ov_[cnt] = value_str ? mkref(RK_STR_IN, val_off + value, 0) : mkref(RK_TRUE, 0, 0);
+                else {
+                    if (value_escape) CH_ATOMIC_OR(e->err, FLBGPU_E_ESCAPE);      /* flb_unescape_string_utf8 not on the device yet */
+                    ov_[cnt] = mkref(RK_STR_IN, val_off + value, value_len);
+                }
+                cnt++;
+            }
+        }
+        if (c == n) break;
+        if (s[c] == '\r' || s[c] == '\n') break;
+    }
+    if (cnt == 0) return 0;
+    *on = cnt; *t_sec = lookup; *t_nsec = frac_to_nsec(frac);
+    return 1;
+}
+
 struct ch_scratch {              /* per-lane working memory */
     int caps[2 * (RX_MAX_GROUPS + 1)];
     uint32_t stk[CH_RX_STACK];
@@ -603,6 +766,14 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                 }
                 if (matched) got = pdef_regex(e, pd, val_off, vp, vn, w->caps, w->tk, w->tv, &cnt, &ts, &tns);
                 if (got) { preset = pd->n_groups; style = ST_PRESET; }
+            }
+            else if (pd->type == FLBGPU_PARSER_LTSV) {
+                got = pdef_ltsv(e, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns);
+                if (got) style = ST_CANON;
+            }
+            else if (pd->type == FLBGPU_PARSER_LOGFMT) {
+                got = pdef_logfmt(e, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns);
+                if (got) style = ST_CANON;
             }
             if (got) {
                 parse_ok = 1;

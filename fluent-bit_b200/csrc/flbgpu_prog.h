@@ -188,6 +188,7 @@ struct chain_hdr {
 #define FLBGPU_E_RXBUDGET  4u   /* regex step budget exhausted */
 #define FLBGPU_E_FLOAT     8u   /* decimal->double outside the exact fast path */
 #define FLBGPU_E_INDEX    16u   /* record index fast path failed */
+#define FLBGPU_E_ESCAPE   32u   /* logfmt quoted value with backslash escapes */
 
 #ifdef __cplusplus
 }

@@ -224,7 +224,7 @@ flbgpu_parser *flbgpu_parser_create(flbgpu_ctx *ctx, const char *name, const cha
     else if (!strcasecmp(format, "ltsv")) p->type = FLBGPU_PARSER_LTSV;
     else if (!strcasecmp(format, "logfmt")) p->type = FLBGPU_PARSER_LOGFMT;
     else { set_err("[parser:%s] Invalid format %s", name, format); free(p); return NULL; }
-    if (p->type != FLBGPU_PARSER_REGEX) {
+    if (p->type == FLBGPU_PARSER_JSON) {
         set_err("[parser:%s] format %s is not implemented on the GPU path yet", name, format);
         free(p);
         return NULL;
@@ -348,6 +348,25 @@ static uint32_t emit_pdef(struct blob *b, struct flbgpu_parser *p)
         d.n_names = nn;
         d.names_off = blob_add(b, nm, sizeof(*nm) * (nn ? nn : 1), 8);
         free(nm);
+    }
+    {
+        const char *tk = p->time_key ? p->time_key : "time";
+        d.time_key_off = blob_add(b, tk, strlen(tk), 1);
+        d.time_key_len = (uint32_t) strlen(tk);
+    }
+    if (p->types_len > 0 && !p->has_rx) {
+        struct cf_ptype *ty = calloc(p->types_len, sizeof(*ty));
+        int t, nt = 0;
+        for (t = 0; t < p->types_len; t++) {
+            if (!p->types[t].key) continue;
+            ty[nt].key_off = blob_add(b, p->types[t].key, p->types[t].key_len, 1);
+            ty[nt].key_len = (uint32_t) p->types[t].key_len;
+            ty[nt].type = (uint32_t) p->types[t].type;
+            nt++;
+        }
+        d.n_types = nt;
+        d.types_off = blob_add(b, ty, sizeof(*ty) * (nt ? nt : 1), 8);
+        free(ty);
     }
     off = blob_add(b, &d, sizeof(d), 8);
     return off;
@@ -949,7 +968,7 @@ static int chain_run_device(flbgpu_chain *c, const uint8_t *d_in, size_t bytes, 
         if (h_flags[FLBGPU_MAX_FILTERS]) {
             c->st.error_bits = h_flags[FLBGPU_MAX_FILTERS];
             snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
-                     "1=too many keys 2=regex stack 4=regex budget 8=float outside exact path)", h_flags[FLBGPU_MAX_FILTERS]);
+                     "1=too many keys 2=regex stack 4=regex budget 8=float outside exact path 32=logfmt escapes)", h_flags[FLBGPU_MAX_FILTERS]);
             return -1;
         }
         {
