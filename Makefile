@@ -13,7 +13,7 @@ $(PKG)/libflbgpu.so: $(CSRC)/kernels.cu $(CSRC)/runtime.c $(CSRC)/rx_compile.c $
 	$(NVCC) $(NVFLAGS) -c $(CSRC)/kernels.cu -o $(CSRC)/kernels.o
 	gcc $(CFLAGS) -c $(CSRC)/runtime.c -o $(CSRC)/runtime.o
 	gcc $(CFLAGS) -c $(CSRC)/rx_compile.c -o $(CSRC)/rx_compile.o
-	$(NVCC) -shared -o $@ $(CSRC)/kernels.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o -lcudart
+	$(NVCC) -shared -o $@ $(CSRC)/kernels.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o -lcudart -lpthread
 
 hostsim: tests/hostsim/libhostsim.so
 tests/hostsim/libhostsim.so: tests/hostsim/hostsim.cpp $(CSRC)/runtime.c $(CSRC)/rx_compile.c $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h)

@@ -218,6 +218,14 @@ def run_ours(args):
     out_p = C.c_void_p()
     libc = C.CDLL(None)
     libc.free.argtypes = [C.c_void_p]
+    # Host allocator policy of the embedding process: keep freed result buffers in the heap instead of
+    # returning them to the kernel (glibc: no mmap for big blocks, no trimming) -- what Fluent Bit's
+    # default jemalloc build does with its retained extents.  Without it every step pays ~300k page
+    # faults for the fresh 1.2 GB result.
+    if os.environ.get("FLBGPU_BENCH_DEFAULT_MALLOC") != "1":
+        libc.mallopt(-4, 0)              # M_MMAP_MAX = 0
+        libc.mallopt(-1, 1 << 30)        # M_TRIM_THRESHOLD (int: capped at 1 GiB)
+        libc.mallopt(-2, 1 << 30)        # M_TOP_PAD
 
     def step_host():
         r = L.flbgpu_chain_do(chain.h, h_in, nbytes, b"bench", 5, C.byref(out_p), C.byref(osz))

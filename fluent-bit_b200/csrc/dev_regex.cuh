@@ -29,6 +29,19 @@
 #endif
 #endif
 
+/* Lanes of a warp run the same program over different subjects.  Left alone they drift
+ * apart (one lane is still stepping a lazy loop while its neighbours are three groups
+ * further) and the interpreter's switch serialises them.  On the device every iteration
+ * therefore serves only the lanes at the SMALLEST pc among the lanes currently inside the
+ * interpreter: laggards catch up, and once aligned the whole warp executes each op -- in
+ * particular each character-class run -- together. */
+#ifdef __CUDA_ARCH__
+#define RX_ALIGN_PC(pc) { const unsigned m_ = __activemask(); \
+        if ((unsigned) (pc) != __reduce_min_sync(m_, (unsigned) (pc))) continue; }
+#else
+#define RX_ALIGN_PC(pc)
+#endif
+
 #define RXT_ALT      0u
 #define RXT_RESTORE  1u
 #define RXT_BACKOFF  2u
@@ -96,6 +109,27 @@ FLB_HD int rx_class_match(const struct rx_prog *pg, const struct rx_class *cl, c
     }
 }
 
+/* cls*: advance over the longest run of class members starting at pos.  The four ASCII
+ * bitmap words live in registers for the whole run (the hot loop of every log pattern). */
+FLB_HD int rx_class_run(const struct rx_prog *pg, const struct rx_class *cl, const uint8_t *s, int pos, int len)
+{
+    const uint32_t w0 = cl->bits[0], w1 = cl->bits[1], w2 = cl->bits[2], w3 = cl->bits[3];
+    int n;
+    while (pos < len) {
+        const uint32_t b = s[pos];
+        if (b < 0x80) {
+            const uint32_t w = (b < 64) ? ((b < 32) ? w0 : w1) : ((b < 96) ? w2 : w3);
+            if (!((w >> (b & 31)) & 1)) break;
+            pos++;
+        }
+        else {
+            if (!rx_class_match(pg, cl, s, pos, len, &n)) break;
+            pos += n;
+        }
+    }
+    return pos;
+}
+
 FLB_HD int rx_is_word_at(const uint8_t *s, int pos, int len)
 {
     uint32_t b;
@@ -130,6 +164,7 @@ FLB_HD int rx_match_at(const struct rx_prog *pg, const uint8_t *s, int len, int 
 
     for (;;) {
         uint32_t w, op, arg;
+        RX_ALIGN_PC(pc)
         if (steps-- == 0) { *budget = 0; return RX_R_EBUDGET; }
         w = code[pc]; op = RX_OP(w); arg = RX_ARG(w);
         switch (op) {
@@ -170,16 +205,13 @@ FLB_HD int rx_match_at(const struct rx_prog *pg, const uint8_t *s, int len, int 
             caps[arg] = pos;
             pc++;
             continue;
-        case RX_CSTAR_POSS: {
-            const struct rx_class *cl = &cls[arg];
-            while (pos < len && rx_class_match(pg, cl, s, pos, len, &n)) pos += n;
+        case RX_CSTAR_POSS:
+            pos = rx_class_run(pg, &cls[arg], s, pos, len);
             pc++;
             continue;
-        }
         case RX_CSTAR_BT: {
-            const struct rx_class *cl = &cls[arg];
             int start = pos;
-            while (pos < len && rx_class_match(pg, cl, s, pos, len, &n)) pos += n;
+            pos = rx_class_run(pg, &cls[arg], s, pos, len);
             if (pos > start) {
                 if (sp + 3 > stk_cap) { *budget = steps; return RX_R_ESTACK; }
                 stk[sp] = (uint32_t) start; stk[sp + 1] = (uint32_t) pos;
@@ -189,10 +221,19 @@ FLB_HD int rx_match_at(const struct rx_prog *pg, const uint8_t *s, int len, int 
             pc++;
             continue;
         }
-        case RX_CSTAR_LAZY:
+        case RX_CSTAR_LAZY: {
+            /* word 2: 1 + index of the "continuation can start here" byte class (0 = unknown).
+             * Positions whose next byte cannot start the continuation would fail at once, so
+             * the lazy loop steps over them right away. */
+            const uint32_t stop = code[pc + 1];
+            if (stop) {
+                const struct rx_class *cl = &cls[arg], *sc = &cls[stop - 1];
+                while (pos < len && !((sc->bits[s[pos] >> 5] >> (s[pos] & 31)) & 1) && rx_class_match(pg, cl, s, pos, len, &n)) pos += n;
+            }
             RX_PUSH2(pos, ((uint32_t) pc << 3) | RXT_LAZY);
-            pc++;
+            pc += 2;
             continue;
+        }
         case RX_BOL:
             if (pos == 0 || (s[pos - 1] == '\n' && pos != len)) { pc++; continue; }   /* regexec.c OP_BEGIN_LINE: !ON_STR_END */
             goto fail;
@@ -293,9 +334,14 @@ fail:
             if (t == RXT_LAZY) {
                 int p0 = (int) stk[sp - 2], opc = (int) (top >> 3);
                 if (p0 < len && rx_class_match(pg, &cls[RX_ARG(code[opc])], s, p0, len, &n)) {
+                    const uint32_t stop = code[opc + 1];
                     pos = p0 + n;
+                    if (stop) {
+                        const struct rx_class *cl = &cls[RX_ARG(code[opc])], *sc = &cls[stop - 1];
+                        while (pos < len && !((sc->bits[s[pos] >> 5] >> (s[pos] & 31)) & 1) && rx_class_match(pg, cl, s, pos, len, &n)) pos += n;
+                    }
                     stk[sp - 2] = (uint32_t) pos;
-                    pc = opc + 1;
+                    pc = opc + 2;
                     break;
                 }
                 sp -= 2;

@@ -48,6 +48,8 @@ void  bk_free_host(void *p);
 int   bk_h2d(void *d, const void *h, size_t n);
 int   bk_d2h(void *h, const void *d, size_t n);
 int   bk_zero(void *d, size_t n);
+int   bk_d2h_big(void *h_dst, const void *d_src, size_t n);   /* synchronous, pipelined through pinned slices */
+int   bk_h2d_big(void *d_dst, const void *h_src, size_t n);   /* asynchronous on the library stream */
 int   bk_sync(void);
 void *bk_stream(void);
 int   bk_kernel_ms(float out[3]);               /* CUDA-event ms of index / evaluate / emit in the last call */

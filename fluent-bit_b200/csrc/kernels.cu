@@ -16,6 +16,10 @@
  * coalesced in k_index; k_chain lanes walk adjacent records (L1/L2 resident lines).
  */
 #include <cuda_runtime.h>
+#include <atomic>
+#include <thread>
+#include <string.h>
+#include <sched.h>
 #include <stdint.h>
 #include <stdio.h>
 #include "flbgpu_internal.h"
@@ -297,6 +301,83 @@ int bk_kernel_ms(float out[3])
         out[k] = 0.f;
         if (g_ev_used[k] && cudaEventElapsedTime(&out[k], g_ev[2 * k], g_ev[2 * k + 1]) != cudaSuccess) out[k] = -1.f;
     }
+    return 0;
+}
+
+
+/* ---- large device->host results -------------------------------------------------
+ * cb_filter must hand back a malloc()ed (pageable) buffer.  A plain cudaMemcpy into
+ * pageable memory is staged by the driver on one thread and pays a page fault per
+ * 4 KB of the fresh allocation.  Here the result is DMA'd in 16 MB slices into a ring
+ * of pinned buffers on a copy stream while one host thread per ring slot moves the
+ * finished slices into the destination, so the DMA and the (parallel, page-faulting)
+ * host copies overlap. */
+#define XF_SLOTS 8
+#define XF_SLICE ((size_t) 16 << 20)
+static uint8_t *xf_ring[XF_SLOTS];
+static cudaEvent_t xf_ev[XF_SLOTS], xf_evc;
+static cudaStream_t g_copy;
+static int xf_ready;
+
+static int xf_init(void)
+{
+    if (xf_ready) return 0;
+    CK(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
+    for (int i = 0; i < XF_SLOTS; i++) {
+        CK(cudaMallocHost((void **) &xf_ring[i], XF_SLICE));
+        CK(cudaEventCreateWithFlags(&xf_ev[i], cudaEventDisableTiming));
+    }
+    CK(cudaEventCreateWithFlags(&xf_evc, cudaEventDisableTiming));
+    xf_ready = 1;
+    return 0;
+}
+
+int bk_d2h_big(void *h_dst, const void *d_src, size_t n)
+{
+    if (n < (4u << 20)) {
+        CK(cudaMemcpyAsync(h_dst, d_src, n, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaStreamSynchronize(g_stream));
+        return 0;
+    }
+    if (xf_init()) return -1;
+    CK(cudaEventRecord(xf_evc, g_stream));              /* the copy stream starts after the emission kernel */
+    CK(cudaStreamWaitEvent(g_copy, xf_evc, 0));
+    const size_t n_slices = (n + XF_SLICE - 1) / XF_SLICE;
+    std::atomic<long> issued[XF_SLOTS], done[XF_SLOTS];
+    for (int s = 0; s < XF_SLOTS; s++) { issued[s].store(-1); done[s].store(-1); }
+    std::atomic<int> failed(0);
+    std::thread workers[XF_SLOTS];
+    const int nw = (int) (n_slices < XF_SLOTS ? n_slices : XF_SLOTS);
+    for (int s = 0; s < nw; s++) {
+        workers[s] = std::thread([&, s]() {
+            for (size_t i = s; i < n_slices; i += XF_SLOTS) {
+                while (issued[s].load(std::memory_order_acquire) < (long) i) { if (failed.load()) return; sched_yield(); }
+                if (cudaEventSynchronize(xf_ev[s]) != cudaSuccess) { failed.store(1); return; }
+                const size_t off = i * XF_SLICE, sz = (off + XF_SLICE <= n) ? XF_SLICE : n - off;
+                memcpy((uint8_t *) h_dst + off, xf_ring[s], sz);
+                done[s].store((long) i, std::memory_order_release);
+            }
+        });
+    }
+    int rc = 0;
+    for (size_t i = 0; i < n_slices && !failed.load(); i++) {
+        const int s = (int) (i % XF_SLOTS);
+        if (i >= XF_SLOTS) while (done[s].load(std::memory_order_acquire) < (long) (i - XF_SLOTS)) { if (failed.load()) break; sched_yield(); }
+        const size_t off = i * XF_SLICE, sz = (off + XF_SLICE <= n) ? XF_SLICE : n - off;
+        if (cudaMemcpyAsync(xf_ring[s], (const uint8_t *) d_src + off, sz, cudaMemcpyDeviceToHost, g_copy) != cudaSuccess ||
+            cudaEventRecord(xf_ev[s], g_copy) != cudaSuccess) { failed.store(1); break; }
+        issued[s].store((long) i, std::memory_order_release);
+    }
+    for (int s = 0; s < nw; s++) workers[s].join();
+    if (failed.load()) { snprintf(g_err, sizeof(g_err), "device->host transfer failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    return rc;
+}
+
+/* host->device: pinned (or registered) memory is DMA'd as is; pageable memory goes
+ * through the driver's staging path */
+int bk_h2d_big(void *d_dst, const void *h_src, size_t n)
+{
+    CK(cudaMemcpyAsync(d_dst, h_src, n, cudaMemcpyHostToDevice, g_stream));
     return 0;
 }
 

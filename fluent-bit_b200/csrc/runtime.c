@@ -21,6 +21,7 @@
 #include <strings.h>
 #include <ctype.h>
 #include <time.h>
+#include <sys/mman.h>
 #include "../../include/flbgpu.h"
 #include "flbgpu_internal.h"
 #include "rx_compile.h"
@@ -1025,14 +1026,21 @@ int flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes, const char 
     *out_buf = NULL; *out_size = 0;
     if (bytes == 0) return FLBGPU_FILTER_NOTOUCH;
     GROW(c->d_in, c->cap_in, bytes + 64, uint8_t);
-    if (bk_h2d(c->d_in, data, bytes)) return -1;
+    if (bk_h2d_big(c->d_in, data, bytes)) return -1;
     r = chain_run_device(c, c->d_in, bytes, NULL, 0, &osz);
     if (r != FLBGPU_FILTER_MODIFIED) return r;
     *out_size = osz;
     if (osz == 0) return FLBGPU_FILTER_MODIFIED;
     *out_buf = malloc(osz);
     if (!*out_buf) return -1;
-    if (bk_d2h(*out_buf, c->d_out, osz) || bk_sync()) { free(*out_buf); *out_buf = NULL; return -1; }
+#ifdef MADV_HUGEPAGE
+    if (osz >= ((size_t) 8 << 20)) {          /* fewer, larger page faults while the result is filled in */
+        uintptr_t a = ((uintptr_t) *out_buf + ((size_t) 2 << 20) - 1) & ~(((uintptr_t) 2 << 20) - 1);
+        uintptr_t e = ((uintptr_t) *out_buf + osz) & ~(((uintptr_t) 2 << 20) - 1);
+        if (e > a) madvise((void *) a, e - a, MADV_HUGEPAGE);
+    }
+#endif
+    if (bk_d2h_big(*out_buf, c->d_out, osz)) { free(*out_buf); *out_buf = NULL; return -1; }
     return FLBGPU_FILTER_MODIFIED;
 }
 

@@ -154,6 +154,8 @@ struct comp {
     int n_code, cap_code;
     int n_null;
     int depth;
+    struct { int idx; uint32_t b[8]; } *raw_sets;   /* classes given as raw byte bitmaps */
+    int n_raw;
     jmp_buf jb;
 };
 
@@ -1027,7 +1029,25 @@ static void emit_rep(struct comp *c, struct node *n, const struct follow *fo)
         if (cls >= 0) {
             struct fset cf;
             int k, disjoint = 1;
-            if (!n->greedy) { emit_word(c, RX_MK(RX_CSTAR_LAZY, cls)); return; }
+            if (!n->greedy) {
+                /* lazy cls*?: second word names the bytes that can start the continuation
+                 * (byte-level class, bits only) so the matcher can skip hopeless positions */
+                uint32_t stop = 0;
+                if (!fo->sure && !fo->f.wild) {
+                    struct cset st;
+                    int sidx;
+                    cset_init(&st);
+                    sidx = add_set(c, &st);
+                    c->raw_sets = realloc(c->raw_sets, sizeof(*c->raw_sets) * (c->n_raw + 1));
+                    c->raw_sets[c->n_raw].idx = sidx;
+                    memcpy(c->raw_sets[c->n_raw].b, fo->f.b, sizeof(fo->f.b));
+                    c->n_raw++;
+                    stop = (uint32_t) sidx + 1;
+                }
+                emit_word(c, RX_MK(RX_CSTAR_LAZY, cls));
+                emit_word(c, stop);
+                return;
+            }
             memset(&cf, 0, sizeof(cf));
             cls_first_bytes(&c->sets[cls], &cf);
             for (k = 0; k < 8; k++) if (cf.b[k] & fo->f.b[k]) disjoint = 0;
@@ -1242,6 +1262,7 @@ int rx_compile(const char *pattern, struct rx_compiled *out)
                 int k;
                 for (k = 0; k < 4; k++) cl[i].bits[k] = s->ascii[k];
                 for (k = 4; k < 8; k++) cl[i].bits[k] = s->hi ? 0xffffffffu : 0;
+                for (k = 0; k < c.n_raw; k++) if (c.raw_sets[k].idx == i) memcpy(cl[i].bits, c.raw_sets[k].b, sizeof(cl[i].bits));
                 if (s->nr == 0) cl[i].mb_mode = RX_MB_NONE;
                 else if (s->nr == 1 && s->r[0] == 0x80 && s->r[1] == 0x10FFFF) cl[i].mb_mode = RX_MB_ALL;
                 else {
@@ -1272,6 +1293,7 @@ done:
     free(c.all);
     for (i = 0; i < c.n_sets; i++) cset_free(&c.sets[i]);
     free(c.sets);
+    free(c.raw_sets);
     free(c.code);
     if (!ok) { rx_compiled_free(out); return -1; }
     return 0;

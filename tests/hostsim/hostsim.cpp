@@ -90,6 +90,8 @@ void bk_free_host(void *p) { free(p); }
 int bk_h2d(void *d, const void *h, size_t n) { memcpy(d, h, n); return 0; }
 int bk_d2h(void *h, const void *d, size_t n) { memcpy(h, d, n); return 0; }
 int bk_zero(void *d, size_t n) { memset(d, 0, n); return 0; }
+int bk_d2h_big(void *h, const void *d, size_t n) { memcpy(h, d, n); return 0; }
+int bk_h2d_big(void *d, const void *h, size_t n) { memcpy(d, h, n); return 0; }
 int bk_sync(void) { return 0; }
 void *bk_stream(void) { return 0; }
 int bk_kernel_ms(float out[3]) { out[0] = out[1] = out[2] = 0.f; return 0; }
