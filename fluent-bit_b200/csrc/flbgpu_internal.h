@@ -32,9 +32,9 @@ struct bk_chain_args {
     const uint32_t *d_off;        /* record index */
     const uint32_t *d_len;
     const uint8_t *d_kind;
-    uint32_t n_rec;               /* records in the valid prefix */
+    uint32_t n_rec;               /* records indexed so far */
     uint32_t *d_size;             /* [n_rec] output size per record */
-    uint64_t *d_bsum;             /* [ceil(n_rec/BK_REC_BLOCK)] block sums -> exclusive offsets */
+    uint64_t *d_bsum;             /* [ceil(n_rec/BK_REC_BLOCK)+1] exclusive output offset per block */
     uint32_t *d_flags;            /* [FLBGPU_MAX_FILTERS + 1]: CHF_* per filter, last = error word */
 };
 
@@ -48,29 +48,61 @@ void  bk_free_host(void *p);
 int   bk_h2d(void *d, const void *h, size_t n);
 int   bk_d2h(void *h, const void *d, size_t n);
 int   bk_zero(void *d, size_t n);
-int   bk_d2h_big(void *h_dst, const void *d_src, size_t n);   /* synchronous, pipelined through pinned slices */
-int   bk_h2d_big(void *d_dst, const void *h_src, size_t n);   /* asynchronous on the library stream */
 int   bk_sync(void);
 void *bk_stream(void);
 int   bk_kernel_ms(float out[3]);               /* CUDA-event ms of index / evaluate / emit in the last call */
 const char *bk_last_error(void);
 
-/* Record index (K1).  Pass 1 counts validated record candidates per tile and leaves
- * the exclusive tile offsets in d_tile; *n_cand gets the total (synchronises). */
-int bk_index_count(const uint8_t *d_in, uint32_t len, uint32_t *d_tile, uint32_t n_tiles, uint32_t *n_cand);
-/* Pass 2 writes (offset,length,kind) per candidate and checks that the candidates
- * tile [0,len) exactly.  *n_valid = records in the decodable prefix; *tiled = 1 when
- * the whole buffer is covered; returns -1 (FLBGPU_E_INDEX) when a candidate chain
- * breaks in the middle (nested record-shaped data), which this version refuses. */
-int bk_index_fill(const uint8_t *d_in, uint32_t len, const uint32_t *d_tile, uint32_t n_tiles,
-                  uint32_t n_cand, uint32_t *d_off, uint32_t *d_len, uint8_t *d_kind,
-                  uint32_t *n_valid, int *tiled);
+/* ---- the per-call pipeline ----------------------------------------------------
+ * A chunk is processed in SLICES (byte ranges that start at a record boundary):
+ *
+ *   upload stream :  H2D piece 0 | piece 1 | piece 2 | ...
+ *   index stream  :        index(slice 0) | index(slice 1) | ...      (waits for its pieces)
+ *   compute stream:               eval(slice 0) | eval(slice 1) | ... | sizes scan |
+ *                                  emit(range 0) | emit(range 1) | ...
+ *   download strm :                                       D2H(range 0) | D2H(range 1) ...
+ *   host threads  :                                          pinned ring -> malloc()ed result
+ *
+ * so host->device copy, evaluation, emission and device->host copy overlap. */
 
-/* Chain evaluation pass: sizes + block sums + evidence.  h_flags receives
- * FLBGPU_MAX_FILTERS+1 words; *total the output size (synchronises). */
-int bk_chain_size(const struct bk_chain_args *a, uint32_t *h_flags, uint64_t *total);
-/* Chain emission pass into d_out (d_bsum holds exclusive block offsets). */
-int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out);
+/* start the asynchronous upload of a whole chunk (pieces + one event per piece) */
+int bk_upload_start(void *d_dst, const void *h_src, size_t n);
+/* the index stream may not read beyond bytes that have arrived: wait (on the device) for [0,upto) */
+int bk_upload_wait_index(size_t upto);
+/* device-resident input: nothing to wait for */
+void bk_upload_none(void);
+
+/* Record index (K1) of one slice d_in[slice_off, slice_off+slice_len).  Pass 1 counts
+ * validated candidates per tile (exclusive tile offsets left in d_tile) and returns the
+ * total (synchronises the index stream only). */
+int bk_index_count(const uint8_t *d_in, size_t slice_off, uint32_t slice_len, uint32_t *d_tile, uint32_t n_tiles,
+                   uint32_t *n_cand);
+/* Pass 2 writes (absolute offset, length, kind) of the slice's candidates at d_off/d_len/
+ * d_kind (already advanced to the slice's first record), repairs the candidate chain and
+ * reports: *n_valid records that chain from the slice start, *end_off = absolute offset
+ * where the last of them ends, *tiled = 1 when that is the slice end. */
+int bk_index_fill(const uint8_t *d_in, size_t slice_off, uint32_t slice_len, const uint32_t *d_tile, uint32_t n_tiles,
+                  uint32_t n_cand, uint32_t *d_off, uint32_t *d_len, uint8_t *d_kind,
+                  uint32_t *n_valid, uint64_t *end_off, int *tiled);
+
+int bk_flags_clear(uint32_t *d_flags);
+/* evaluation pass over records [r0, r1): asynchronous on the compute stream */
+int bk_chain_eval(const struct bk_chain_args *a, uint32_t r0, uint32_t r1);
+/* evidence + error word (synchronises the compute stream) */
+int bk_flags_fetch(const uint32_t *d_flags, uint32_t *h_flags);
+/* per-block sums of d_size[0,n_rec) -> exclusive offsets in d_bsum, copied to h_bsum
+ * (n_blocks+1 entries, last = total).  Synchronises. */
+int bk_sizes_scan(const uint32_t *d_size, uint32_t n_rec, uint64_t *d_bsum, uint64_t *h_bsum);
+/* emission of blocks [b0, b1) into d_out: asynchronous on the compute stream */
+int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1);
+
+/* result download session: bytes [lo,hi) of d_out become valid after the emission just
+ * enqueued; they are DMA'd into a pinned ring and moved into h_dst by host threads. */
+int bk_download_begin(void *h_dst, const void *d_out);
+int bk_download_push(size_t lo, size_t hi);
+int bk_download_end(void);
+
+int bk_d2d(void *dst, const void *src, size_t n);          /* synchronous device copy (buffer growth) */
 
 /* counters for bench.py's gpu_launches claim */
 uint64_t bk_launch_count(void);

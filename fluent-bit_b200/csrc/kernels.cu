@@ -28,12 +28,30 @@
 static char g_err[256];
 static unsigned long long g_launches;
 static cudaStream_t g_stream;
-/* CUDA-event timing of the three kernel groups of the last call (index, evaluate, emit) */
-static cudaEvent_t g_ev[6];
-static int g_ev_used[3];
+/* CUDA-event timing of the kernel groups of the last call: one event pair per launch
+ * (0 = index, 1 = evaluate, 2 = emit); bk_kernel_ms() sums the pairs of a group. */
+#define EV_MAX 1024
+static cudaEvent_t g_evp[3][EV_MAX][2];
+static int g_ev_made[3], g_ev_used[3];
 static int g_ev_ready;
-static void ev_begin(int k) { if (g_ev_ready) { cudaEventRecord(g_ev[2 * k], g_stream); } }
-static void ev_end(int k) { if (g_ev_ready) { cudaEventRecord(g_ev[2 * k + 1], g_stream); g_ev_used[k] = 1; } }
+static cudaStream_t g_istream;
+static void ev_begin_on(int k, cudaStream_t st)
+{
+    if (!g_ev_ready || g_ev_used[k] >= EV_MAX) return;
+    if (g_ev_used[k] >= g_ev_made[k]) {
+        cudaEventCreate(&g_evp[k][g_ev_made[k]][0]); cudaEventCreate(&g_evp[k][g_ev_made[k]][1]);
+        g_ev_made[k]++;
+    }
+    cudaEventRecord(g_evp[k][g_ev_used[k]][0], st);
+}
+static void ev_end_on(int k, cudaStream_t st)
+{
+    if (!g_ev_ready || g_ev_used[k] >= EV_MAX) return;
+    cudaEventRecord(g_evp[k][g_ev_used[k]][1], st);
+    g_ev_used[k]++;
+}
+static void ev_begin(int k) { ev_begin_on(k, g_stream); }
+static void ev_end(int k) { ev_end_on(k, g_stream); }
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     snprintf(g_err, sizeof(g_err), "%s: %s", #call, cudaGetErrorString(e_)); return -1; } } while (0)
@@ -77,7 +95,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total)
 
 /* ------------------------------------------------------------------ index */
 template <bool FILL>
-__global__ void __launch_bounds__(256) k_index(const uint8_t *__restrict__ in, uint32_t len,
+__global__ void __launch_bounds__(256) k_index(const uint8_t *__restrict__ in, uint32_t len, uint32_t abs_base,
                                                uint32_t *__restrict__ tile, uint32_t *__restrict__ o_off,
                                                uint32_t *__restrict__ o_len, uint8_t *__restrict__ o_kind)
 {
@@ -144,7 +162,7 @@ __global__ void __launch_bounds__(256) k_index(const uint8_t *__restrict__ in, u
         uint32_t at = block_excl_scan(ok, &tot);
         if (FILL && ok) {
             const uint32_t o = tile_base + kept + at;
-            o_off[o] = pos; o_len[o] = rlen; o_kind[o] = (uint8_t) kind;
+            o_off[o] = abs_base + pos; o_len[o] = rlen; o_kind[o] = (uint8_t) kind;
         }
         kept += tot;
     }
@@ -174,7 +192,7 @@ __global__ void __launch_bounds__(256) k_scan_top(T *a, uint32_t n, unsigned lon
  * bytes `.. 92 ce 00 00 01 a6 | 80` read as the legacy event [422, {}] -- and are
  * collected for k_index_repair. */
 __global__ void k_index_check(const uint32_t *__restrict__ off, const uint32_t *__restrict__ rlen, uint32_t n,
-                              uint32_t total, uint32_t *n_breaks, uint32_t *breaks)
+                              uint32_t total /* absolute end of the slice */, uint32_t *n_breaks, uint32_t *breaks)
 {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -191,7 +209,7 @@ __global__ void k_index_check(const uint32_t *__restrict__ off, const uint32_t *
  * If nothing starts there the decodable prefix ends (the reference decoder stops at
  * the first undecodable byte too).  res[0] = records in the prefix, res[1] = tiled. */
 __global__ void __launch_bounds__(1024) k_index_repair(const uint32_t *__restrict__ off, const uint32_t *__restrict__ rlen,
-                                                        uint8_t *kind, uint32_t n, uint32_t total,
+                                                        uint8_t *kind, uint32_t n, uint32_t base, uint32_t total,
                                                         const uint32_t *n_breaks, const uint32_t *breaks, uint32_t *res)
 {
     __shared__ uint32_t sorted[BK_MAX_BREAKS];
@@ -205,7 +223,7 @@ __global__ void __launch_bounds__(1024) k_index_repair(const uint32_t *__restric
     __syncthreads();
     if (threadIdx.x != 0) return;
     uint32_t n_valid = n, tiled = 1, skip_until = 0;
-    if (off[0] != 0) { res[0] = 0; res[1] = 0; return; }
+    if (off[0] != base) { res[0] = 0; res[1] = 0; res[2] = base; return; }
     for (uint32_t q = 0; q < m; q++) {
         const uint32_t b = sorted[q];
         if (b < skip_until) continue;                                  /* a candidate already ruled out */
@@ -218,6 +236,12 @@ __global__ void __launch_bounds__(1024) k_index_repair(const uint32_t *__restric
         break;
     }
     res[0] = n_valid; res[1] = tiled;
+    /* where the chain ends: the next slice starts here */
+    {
+        uint32_t last = n_valid;
+        while (last > 0 && kind[last - 1] == 2) last--;
+        res[2] = last ? off[last - 1] + rlen[last - 1] : base;
+    }
 }
 
 /* ------------------------------------------------------------------ chain */
@@ -225,30 +249,41 @@ struct k_chain_params {
     struct ch_env env;
     const uint32_t *off, *len;
     const uint8_t *kind;
+    uint32_t r0;                 /* first record / first block of this launch */
     uint32_t n_rec;
     uint32_t *size;
     uint64_t *bsum;
     uint8_t *out;
 };
 
-template <bool EMIT>
-__global__ void __launch_bounds__(BK_REC_BLOCK) k_chain(const k_chain_params p)
+/* evaluation: record r0 + global thread id.  No barrier: a warp retires as soon as its
+ * 32 records are done (block-level reductions happen in k_bsum). */
+__global__ void __launch_bounds__(BK_REC_BLOCK) k_chain_eval(const k_chain_params p)
+{
+    const uint32_t i = p.r0 + blockIdx.x * BK_REC_BLOCK + threadIdx.x;
+    if (i >= p.n_rec) return;
+    uint32_t sz = 0;
+    if (p.kind[i] == 0) sz = chain_record<false>(&p.env, i, p.off[i], p.len[i], 0);
+    p.size[i] = sz;
+}
+
+/* per-block sums of the record sizes */
+__global__ void __launch_bounds__(BK_REC_BLOCK) k_bsum(const uint32_t *__restrict__ size, uint32_t n, uint64_t *__restrict__ bsum)
 {
     const uint32_t i = blockIdx.x * BK_REC_BLOCK + threadIdx.x;
-    uint32_t sz = 0;
-    if (!EMIT) {
-        if (i < p.n_rec && p.kind[i] == 0) sz = chain_record<false>(&p.env, i, p.off[i], p.len[i], 0);
-        if (i < p.n_rec) p.size[i] = sz;
-        uint32_t tot;
-        block_excl_scan(sz, &tot);
-        if (threadIdx.x == 0) p.bsum[blockIdx.x] = tot;
-    }
-    else {
-        if (i < p.n_rec) sz = p.size[i];
-        uint32_t tot;
-        const uint32_t local = block_excl_scan(sz, &tot);
-        if (sz) chain_record<true>(&p.env, i, p.off[i], p.len[i], p.out + p.bsum[blockIdx.x] + local);
-    }
+    uint32_t tot;
+    block_excl_scan(i < n ? size[i] : 0, &tot);
+    if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+
+/* emission of block (r0/256 + blockIdx): in-block exclusive scan + the block's offset */
+__global__ void __launch_bounds__(BK_REC_BLOCK) k_chain_emit(const k_chain_params p)
+{
+    const uint32_t blk = p.r0 / BK_REC_BLOCK + blockIdx.x;
+    const uint32_t i = blk * BK_REC_BLOCK + threadIdx.x;
+    uint32_t sz = (i < p.n_rec) ? p.size[i] : 0, tot;
+    const uint32_t local = block_excl_scan(sz, &tot);
+    if (sz) chain_record<true>(&p.env, i, p.off[i], p.len[i], p.out + p.bsum[blk] + local);
 }
 
 /* ------------------------------------------------------------ bk_* seam */
@@ -277,10 +312,10 @@ int bk_init(int device)
     if (device < 0 || device >= n) { snprintf(g_err, sizeof(g_err), "device %d out of range (0..%d)", device, n - 1); return -1; }
     CK(cudaSetDevice(device));
     if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-    if (!g_ev_ready) { for (int i = 0; i < 6; i++) CK(cudaEventCreate(&g_ev[i])); g_ev_ready = 1; }
+    g_ev_ready = 1;
     /* the interpreter keeps its field list and backtrack stack in local memory */
-    CK(cudaFuncSetCacheConfig(k_chain<false>, cudaFuncCachePreferL1));
-    CK(cudaFuncSetCacheConfig(k_chain<true>, cudaFuncCachePreferL1));
+    CK(cudaFuncSetCacheConfig(k_chain_eval, cudaFuncCachePreferL1));
+    CK(cudaFuncSetCacheConfig(k_chain_emit, cudaFuncCachePreferL1));
     return 0;
 }
 
@@ -299,30 +334,82 @@ int bk_kernel_ms(float out[3])
 {
     for (int k = 0; k < 3; k++) {
         out[k] = 0.f;
-        if (g_ev_used[k] && cudaEventElapsedTime(&out[k], g_ev[2 * k], g_ev[2 * k + 1]) != cudaSuccess) out[k] = -1.f;
+        for (int i = 0; i < g_ev_used[k]; i++) {
+            float ms = 0.f;
+            if (cudaEventSynchronize(g_evp[k][i][1]) == cudaSuccess &&
+                cudaEventElapsedTime(&ms, g_evp[k][i][0], g_evp[k][i][1]) == cudaSuccess) out[k] += ms;
+        }
     }
     return 0;
 }
 
 
-/* ---- large device->host results -------------------------------------------------
- * cb_filter must hand back a malloc()ed (pageable) buffer.  A plain cudaMemcpy into
- * pageable memory is staged by the driver on one thread and pays a page fault per
- * 4 KB of the fresh allocation.  Here the result is DMA'd in 16 MB slices into a ring
- * of pinned buffers on a copy stream while one host thread per ring slot moves the
- * finished slices into the destination, so the DMA and the (parallel, page-faulting)
- * host copies overlap. */
+static cudaStream_t g_h2d, g_copy;
+static int g_streams_ready;
+static int streams_init(void)
+{
+    if (g_streams_ready) return 0;
+    CK(cudaStreamCreateWithFlags(&g_istream, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g_h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
+    g_streams_ready = 1;
+    return 0;
+}
+
+/* ---- upload: pieces with events ---- */
+#define UP_PIECE ((size_t) 32 << 20)
+#define UP_MAX_EV 256
+static cudaEvent_t up_ev[UP_MAX_EV];
+static int up_ev_made;
+static size_t up_total, up_piece;
+static int up_active;
+
+int bk_upload_start(void *d_dst, const void *h_src, size_t n)
+{
+    if (streams_init()) return -1;
+    up_piece = UP_PIECE;
+    while ((n + up_piece - 1) / up_piece > UP_MAX_EV) up_piece *= 2;
+    const size_t np = (n + up_piece - 1) / up_piece;
+    for (; up_ev_made < (int) np; up_ev_made++) CK(cudaEventCreateWithFlags(&up_ev[up_ev_made], cudaEventDisableTiming));
+    for (size_t i = 0; i < np; i++) {
+        const size_t off = i * up_piece, sz = (off + up_piece <= n) ? up_piece : n - off;
+        CK(cudaMemcpyAsync((uint8_t *) d_dst + off, (const uint8_t *) h_src + off, sz, cudaMemcpyHostToDevice, g_h2d));
+        CK(cudaEventRecord(up_ev[i], g_h2d));
+    }
+    up_total = n; up_active = 1;
+    return 0;
+}
+void bk_upload_none(void) { up_active = 0; }
+int bk_upload_wait_index(size_t upto)
+{
+    if (streams_init()) return -1;
+    if (!up_active || upto == 0) return 0;
+    if (upto > up_total) upto = up_total;
+    CK(cudaStreamWaitEvent(g_istream, up_ev[(upto - 1) / up_piece], 0));
+    return 0;
+}
+
+/* ---- download session: pinned ring + one host thread per slot ---- */
 #define XF_SLOTS 8
 #define XF_SLICE ((size_t) 16 << 20)
 static uint8_t *xf_ring[XF_SLOTS];
 static cudaEvent_t xf_ev[XF_SLOTS], xf_evc;
-static cudaStream_t g_copy;
 static int xf_ready;
+struct xf_session {
+    uint8_t *h_dst; const uint8_t *d_src;
+    std::atomic<long> issued[XF_SLOTS], done[XF_SLOTS];
+    size_t s_off[XF_SLOTS], s_len[XF_SLOTS];
+    std::atomic<long> n_issued;          /* slices issued so far */
+    std::atomic<int> closed, failed;
+    std::thread th[XF_SLOTS];
+    int started;
+};
+static xf_session *g_xf;
 
 static int xf_init(void)
 {
     if (xf_ready) return 0;
-    CK(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
+    if (streams_init()) return -1;
     for (int i = 0; i < XF_SLOTS; i++) {
         CK(cudaMallocHost((void **) &xf_ring[i], XF_SLICE));
         CK(cudaEventCreateWithFlags(&xf_ev[i], cudaEventDisableTiming));
@@ -332,148 +419,193 @@ static int xf_init(void)
     return 0;
 }
 
-int bk_d2h_big(void *h_dst, const void *d_src, size_t n)
+static void xf_worker(xf_session *x, int s)
 {
-    if (n < (4u << 20)) {
-        CK(cudaMemcpyAsync(h_dst, d_src, n, cudaMemcpyDeviceToHost, g_stream));
-        CK(cudaStreamSynchronize(g_stream));
-        return 0;
+    for (long i = s;; i += XF_SLOTS) {
+        while (x->issued[s].load(std::memory_order_acquire) < i) {
+            if (x->failed.load()) return;
+            if (x->closed.load() && x->n_issued.load() <= i) return;
+            sched_yield();
+        }
+        if (cudaEventSynchronize(xf_ev[s]) != cudaSuccess) { x->failed.store(1); return; }
+        memcpy(x->h_dst + x->s_off[s], xf_ring[s], x->s_len[s]);
+        x->done[s].store(i, std::memory_order_release);
     }
+}
+
+int bk_download_begin(void *h_dst, const void *d_out)
+{
     if (xf_init()) return -1;
-    CK(cudaEventRecord(xf_evc, g_stream));              /* the copy stream starts after the emission kernel */
+    xf_session *x = new xf_session();
+    x->h_dst = (uint8_t *) h_dst; x->d_src = (const uint8_t *) d_out;
+    for (int s = 0; s < XF_SLOTS; s++) { x->issued[s].store(-1); x->done[s].store(-1); }
+    x->n_issued.store(0); x->closed.store(0); x->failed.store(0);
+    for (int s = 0; s < XF_SLOTS; s++) x->th[s] = std::thread(xf_worker, x, s);
+    x->started = 1;
+    g_xf = x;
+    return 0;
+}
+
+int bk_download_push(size_t lo, size_t hi)
+{
+    xf_session *x = g_xf;
+    if (!x) return -1;
+    CK(cudaEventRecord(xf_evc, g_stream));            /* bytes [lo,hi) exist once the emission enqueued so far is done */
     CK(cudaStreamWaitEvent(g_copy, xf_evc, 0));
-    const size_t n_slices = (n + XF_SLICE - 1) / XF_SLICE;
-    std::atomic<long> issued[XF_SLOTS], done[XF_SLOTS];
-    for (int s = 0; s < XF_SLOTS; s++) { issued[s].store(-1); done[s].store(-1); }
-    std::atomic<int> failed(0);
-    std::thread workers[XF_SLOTS];
-    const int nw = (int) (n_slices < XF_SLOTS ? n_slices : XF_SLOTS);
-    for (int s = 0; s < nw; s++) {
-        workers[s] = std::thread([&, s]() {
-            for (size_t i = s; i < n_slices; i += XF_SLOTS) {
-                while (issued[s].load(std::memory_order_acquire) < (long) i) { if (failed.load()) return; sched_yield(); }
-                if (cudaEventSynchronize(xf_ev[s]) != cudaSuccess) { failed.store(1); return; }
-                const size_t off = i * XF_SLICE, sz = (off + XF_SLICE <= n) ? XF_SLICE : n - off;
-                memcpy((uint8_t *) h_dst + off, xf_ring[s], sz);
-                done[s].store((long) i, std::memory_order_release);
-            }
-        });
-    }
-    int rc = 0;
-    for (size_t i = 0; i < n_slices && !failed.load(); i++) {
+    for (size_t off = lo; off < hi && !x->failed.load(); off += XF_SLICE) {
+        const long i = x->n_issued.load();
         const int s = (int) (i % XF_SLOTS);
-        if (i >= XF_SLOTS) while (done[s].load(std::memory_order_acquire) < (long) (i - XF_SLOTS)) { if (failed.load()) break; sched_yield(); }
-        const size_t off = i * XF_SLICE, sz = (off + XF_SLICE <= n) ? XF_SLICE : n - off;
-        if (cudaMemcpyAsync(xf_ring[s], (const uint8_t *) d_src + off, sz, cudaMemcpyDeviceToHost, g_copy) != cudaSuccess ||
-            cudaEventRecord(xf_ev[s], g_copy) != cudaSuccess) { failed.store(1); break; }
-        issued[s].store((long) i, std::memory_order_release);
+        const size_t sz = (off + XF_SLICE <= hi) ? XF_SLICE : hi - off;
+        if (i >= XF_SLOTS) while (x->done[s].load(std::memory_order_acquire) < i - XF_SLOTS) { if (x->failed.load()) return -1; sched_yield(); }
+        x->s_off[s] = off; x->s_len[s] = sz;
+        if (cudaMemcpyAsync(xf_ring[s], x->d_src + off, sz, cudaMemcpyDeviceToHost, g_copy) != cudaSuccess ||
+            cudaEventRecord(xf_ev[s], g_copy) != cudaSuccess) { x->failed.store(1); return -1; }
+        x->issued[s].store(i, std::memory_order_release);
+        x->n_issued.store(i + 1);
     }
-    for (int s = 0; s < nw; s++) workers[s].join();
-    if (failed.load()) { snprintf(g_err, sizeof(g_err), "device->host transfer failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    return x->failed.load() ? -1 : 0;
+}
+
+int bk_download_end(void)
+{
+    xf_session *x = g_xf;
+    int rc = 0;
+    if (!x) return -1;
+    x->closed.store(1);
+    for (int s = 0; s < XF_SLOTS; s++) x->th[s].join();
+    if (x->failed.load()) { snprintf(g_err, sizeof(g_err), "device->host transfer failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
+    delete x;
+    g_xf = 0;
     return rc;
 }
 
-/* host->device: pinned (or registered) memory is DMA'd as is; pageable memory goes
- * through the driver's staging path */
-int bk_h2d_big(void *d_dst, const void *h_src, size_t n)
+int bk_d2d(void *dst, const void *src, size_t n)
 {
-    CK(cudaMemcpyAsync(d_dst, h_src, n, cudaMemcpyHostToDevice, g_stream));
+    CK(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToDevice));
     return 0;
 }
 
-static unsigned long long *g_dtotal;   /* device scratch for totals / first_break */
+static unsigned long long *g_dtotal;   /* device scratch for totals / repair results */
+static uint32_t *g_dbreaks;
 static int ensure_small(void)
 {
-    if (!g_dtotal) CK(cudaMalloc((void **) &g_dtotal, 64));
+    if (streams_init()) return -1;
+    if (!g_dtotal) CK(cudaMalloc((void **) &g_dtotal, 128));
+    if (!g_dbreaks) CK(cudaMalloc((void **) &g_dbreaks, sizeof(uint32_t) * BK_MAX_BREAKS));
     return 0;
 }
 
-int bk_index_count(const uint8_t *d_in, uint32_t len, uint32_t *d_tile, uint32_t n_tiles, uint32_t *n_cand)
+int bk_index_count(const uint8_t *d_in, size_t slice_off, uint32_t slice_len, uint32_t *d_tile, uint32_t n_tiles,
+                   uint32_t *n_cand)
 {
     unsigned long long tot = 0;
     if (ensure_small()) return -1;
     *n_cand = 0;
-    g_ev_used[0] = g_ev_used[1] = g_ev_used[2] = 0;
     if (n_tiles == 0) return 0;
-    ev_begin(0);
-    k_index<false><<<n_tiles, 256, 0, g_stream>>>(d_in, len, d_tile, 0, 0, 0);
-    k_scan_top<uint32_t><<<1, 256, 0, g_stream>>>(d_tile, n_tiles, g_dtotal);
+    ev_begin_on(0, g_istream);
+    k_index<false><<<n_tiles, 256, 0, g_istream>>>(d_in + slice_off, slice_len, (uint32_t) slice_off, d_tile, 0, 0, 0);
+    k_scan_top<uint32_t><<<1, 256, 0, g_istream>>>(d_tile, n_tiles, g_dtotal);
+    ev_end_on(0, g_istream);
     g_launches += 2;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(&tot, g_dtotal, sizeof(tot), cudaMemcpyDeviceToHost, g_stream));
-    CK(cudaStreamSynchronize(g_stream));
+    CK(cudaMemcpyAsync(&tot, g_dtotal, sizeof(tot), cudaMemcpyDeviceToHost, g_istream));
+    CK(cudaStreamSynchronize(g_istream));
     *n_cand = (uint32_t) tot;
     return 0;
 }
 
-int bk_index_fill(const uint8_t *d_in, uint32_t len, const uint32_t *d_tile, uint32_t n_tiles, uint32_t n_cand,
-                  uint32_t *d_off, uint32_t *d_len, uint8_t *d_kind, uint32_t *n_valid, int *tiled)
+int bk_index_fill(const uint8_t *d_in, size_t slice_off, uint32_t slice_len, const uint32_t *d_tile, uint32_t n_tiles,
+                  uint32_t n_cand, uint32_t *d_off, uint32_t *d_len, uint8_t *d_kind,
+                  uint32_t *n_valid, uint64_t *end_off, int *tiled)
 {
-    static uint32_t *d_breaks;
     uint32_t h[4] = { 0, 0, 0, 0 };
-    uint32_t *d_w = (uint32_t *) (g_dtotal + 1);          /* [0] n_breaks, [1] n_valid, [2] tiled */
-    *n_valid = 0; *tiled = (len == 0);
+    uint32_t *d_w = (uint32_t *) (g_dtotal + 1);          /* [0] n_breaks, [1] n_valid, [2] tiled, [3] end offset */
+    *n_valid = 0; *tiled = (slice_len == 0); *end_off = slice_off;
     if (n_cand == 0) return 0;
-    if (!d_breaks) CK(cudaMalloc((void **) &d_breaks, sizeof(uint32_t) * BK_MAX_BREAKS));
-    k_index<true><<<n_tiles, 256, 0, g_stream>>>(d_in, len, (uint32_t *) d_tile, d_off, d_len, d_kind);
-    CK(cudaMemsetAsync(d_w, 0, 16, g_stream));
-    k_index_check<<<(n_cand + 255) / 256, 256, 0, g_stream>>>(d_off, d_len, n_cand, len, d_w, d_breaks);
-    k_index_repair<<<1, 1024, 0, g_stream>>>(d_off, d_len, d_kind, n_cand, len, d_w, d_breaks, d_w + 1);
-    ev_end(0);
+    ev_begin_on(0, g_istream);
+    k_index<true><<<n_tiles, 256, 0, g_istream>>>(d_in + slice_off, slice_len, (uint32_t) slice_off, (uint32_t *) d_tile, d_off, d_len, d_kind);
+    CK(cudaMemsetAsync(d_w, 0, 16, g_istream));
+    k_index_check<<<(n_cand + 255) / 256, 256, 0, g_istream>>>(d_off, d_len, n_cand, (uint32_t) (slice_off + slice_len), d_w, g_dbreaks);
+    k_index_repair<<<1, 1024, 0, g_istream>>>(d_off, d_len, d_kind, n_cand, (uint32_t) slice_off, (uint32_t) (slice_off + slice_len), d_w, g_dbreaks, d_w + 1);
+    ev_end_on(0, g_istream);
     g_launches += 3;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h, d_w, sizeof(h), cudaMemcpyDeviceToHost, g_stream));
-    CK(cudaStreamSynchronize(g_stream));
+    CK(cudaMemcpyAsync(h, d_w, sizeof(h), cudaMemcpyDeviceToHost, g_istream));
+    CK(cudaStreamSynchronize(g_istream));
     if (h[0] > BK_MAX_BREAKS) {
-        snprintf(g_err, sizeof(g_err), "record index: %u broken candidate links in one chunk (limit %u)", h[0], BK_MAX_BREAKS);
+        snprintf(g_err, sizeof(g_err), "record index: %u broken candidate links in one slice (limit %u)", h[0], BK_MAX_BREAKS);
         return -1;
     }
     *n_valid = h[1];
     *tiled = (int) h[2];
+    *end_off = h[3];
     return 0;
 }
 
-static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_t *d_out)
+static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_t *d_out, uint32_t r0)
 {
     p->env.in = a->d_in; p->env.in_len = a->in_len; p->env.blob = a->d_blob; p->env.scr = a->d_scr;
     p->env.capcache = a->d_capcache; p->env.cap_stride = a->cap_stride; p->env.now = a->now;
     p->env.assume = a->assume; p->env.fl_flags = a->d_flags; p->env.err = a->d_flags + FLBGPU_MAX_FILTERS;
-    p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->n_rec = a->n_rec;
+    p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->r0 = r0; p->n_rec = a->n_rec;
     p->size = a->d_size; p->bsum = a->d_bsum; p->out = d_out;
 }
 
-int bk_chain_size(const struct bk_chain_args *a, uint32_t *h_flags, uint64_t *total)
+int bk_flags_clear(uint32_t *d_flags)
 {
-    k_chain_params p;
-    unsigned long long tot = 0;
-    const uint32_t nb = (a->n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK;
-    if (ensure_small()) return -1;
-    *total = 0;
-    CK(cudaMemsetAsync(a->d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1), g_stream));
-    if (nb) {
-        fill_params(a, &p, 0);
-        ev_begin(1);
-        k_chain<false><<<nb, BK_REC_BLOCK, 0, g_stream>>>(p);
-        ev_end(1);
-        k_scan_top<uint64_t><<<1, 256, 0, g_stream>>>((uint64_t *) a->d_bsum, nb, g_dtotal);
-        g_launches += 2;
-        CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(&tot, g_dtotal, sizeof(tot), cudaMemcpyDeviceToHost, g_stream));
-    }
-    CK(cudaMemcpyAsync(h_flags, a->d_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1), cudaMemcpyDeviceToHost, g_stream));
-    CK(cudaStreamSynchronize(g_stream));
-    *total = tot;
+    if (streams_init()) return -1;
+    CK(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1), g_stream));
+    g_ev_used[0] = g_ev_used[1] = g_ev_used[2] = 0;
     return 0;
 }
 
-int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out)
+int bk_chain_eval(const struct bk_chain_args *a, uint32_t r0, uint32_t r1)
 {
     k_chain_params p;
-    const uint32_t nb = (a->n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK;
-    if (!nb) return 0;
-    fill_params(a, &p, d_out);
+    if (r1 <= r0) return 0;
+    fill_params(a, &p, 0, r0);
+    p.n_rec = r1;
+    ev_begin(1);
+    k_chain_eval<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, 0, g_stream>>>(p);
+    ev_end(1);
+    g_launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int bk_flags_fetch(const uint32_t *d_flags, uint32_t *h_flags)
+{
+    CK(cudaMemcpyAsync(h_flags, d_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1), cudaMemcpyDeviceToHost, g_stream));
+    CK(cudaStreamSynchronize(g_stream));
+    return 0;
+}
+
+int bk_sizes_scan(const uint32_t *d_size, uint32_t n_rec, uint64_t *d_bsum, uint64_t *h_bsum)
+{
+    const uint32_t nb = (n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK;
+    unsigned long long tot = 0;
+    if (ensure_small()) return -1;
+    h_bsum[0] = 0;
+    if (nb) {
+        k_bsum<<<nb, BK_REC_BLOCK, 0, g_stream>>>(d_size, n_rec, d_bsum);
+        k_scan_top<uint64_t><<<1, 256, 0, g_stream>>>(d_bsum, nb, g_dtotal);
+        g_launches += 2;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&tot, g_dtotal, sizeof(tot), cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaMemcpyAsync(h_bsum, d_bsum, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, g_stream));
+    }
+    CK(cudaStreamSynchronize(g_stream));
+    h_bsum[nb] = tot;
+    return 0;
+}
+
+int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1)
+{
+    k_chain_params p;
+    if (b1 <= b0) return 0;
+    fill_params(a, &p, d_out, b0 * BK_REC_BLOCK);
     ev_begin(2);
-    k_chain<true><<<nb, BK_REC_BLOCK, 0, g_stream>>>(p);
+    k_chain_emit<<<b1 - b0, BK_REC_BLOCK, 0, g_stream>>>(p);
     ev_end(2);
     g_launches += 1;
     CK(cudaGetLastError());

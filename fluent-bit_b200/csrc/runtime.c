@@ -128,7 +128,7 @@ struct flbgpu_chain {
     uint64_t *d_bsum; size_t cap_bsum;
     int32_t *d_cap; size_t cap_cap;
     uint32_t *d_flags;
-    uint8_t *h_stage; size_t cap_stage;      /* pinned staging */
+    uint64_t *h_bsum; size_t cap_hbsum;      /* host copy of the per-block output offsets */
     struct flbgpu_stats st;
 };
 
@@ -894,7 +894,7 @@ void flbgpu_chain_destroy(flbgpu_chain *c)
     if (!c) return;
     bk_free(c->d_blob); bk_free(c->d_in); bk_free(c->d_out); bk_free(c->d_tile); bk_free(c->d_off);
     bk_free(c->d_len); bk_free(c->d_size); bk_free(c->d_kind); bk_free(c->d_bsum); bk_free(c->d_cap);
-    bk_free(c->d_flags); bk_free_host(c->h_stage);
+    bk_free(c->d_flags); free(c->h_bsum);
     free(c->blob.p);
     free(c);
 }
@@ -921,84 +921,184 @@ static int verdict(int kind, uint32_t fl, int clean)
     return 0;
 }
 
-/* the device part of one call: d_in holds `bytes` of chunk.  On MODIFIED the result is
- * in c->d_out (or ext_out) and *out_size is its size. */
-static int chain_run_device(flbgpu_chain *c, const uint8_t *d_in, size_t bytes, uint8_t *ext_out, size_t ext_cap,
-                            size_t *out_size)
+/* grow the per-record arrays to hold `need` records, keeping the first `keep` */
+static int ensure_rec_cap(flbgpu_chain *c, size_t need, size_t keep)
+{
+    size_t nc;
+    uint32_t *o, *l, *z;
+    uint8_t *k;
+    int32_t *cp = NULL;
+    if (c->cap_rec >= need) return 0;
+    nc = need + need / 2 + 1024;
+    o = bk_alloc(nc * 4); l = bk_alloc(nc * 4); z = bk_alloc(nc * 4); k = bk_alloc(nc);
+    if (c->cap_stride) cp = bk_alloc(nc * c->cap_stride * sizeof(int32_t));
+    if (!o || !l || !z || !k || (c->cap_stride && !cp)) return -1;
+    if (keep) {
+        if (bk_sync()) return -1;                 /* running kernels still read the old arrays */
+        if (bk_d2d(o, c->d_off, keep * 4) || bk_d2d(l, c->d_len, keep * 4) || bk_d2d(z, c->d_size, keep * 4) ||
+            bk_d2d(k, c->d_kind, keep)) return -1;
+        if (cp && bk_d2d(cp, c->d_cap, keep * c->cap_stride * sizeof(int32_t))) return -1;
+    }
+    bk_free(c->d_off); bk_free(c->d_len); bk_free(c->d_size); bk_free(c->d_kind); bk_free(c->d_cap);
+    c->d_off = o; c->d_len = l; c->d_size = z; c->d_kind = k; c->d_cap = cp;
+    c->cap_rec = nc;
+    return 0;
+}
+
+static size_t slice_bytes(void)
+{
+    const char *e = getenv("FLBGPU_SLICE_MB");
+    size_t mb = e ? (size_t) atol(e) : 64;
+    if (mb < 1) mb = 1;
+    if (mb > 2048) mb = 2048;
+    return mb << 20;
+}
+
+static void fill_args(flbgpu_chain *c, struct bk_chain_args *a, const uint8_t *d_in, size_t bytes, uint32_t n_rec)
+{
+    a->d_in = d_in; a->in_len = (uint32_t) bytes; a->d_blob = c->d_blob; a->d_scr = NULL;
+    a->d_capcache = c->cap_stride ? c->d_cap : NULL; a->cap_stride = c->cap_stride;
+    a->d_off = c->d_off; a->d_len = c->d_len; a->d_kind = c->d_kind; a->n_rec = n_rec;
+    a->d_size = c->d_size; a->d_bsum = c->d_bsum; a->d_flags = c->d_flags;
+}
+
+/* One call.  Input: h_in (host, uploaded in pieces) or d_in_ext (already in HBM).
+ * Result: host_out != NULL -> malloc()ed host buffer; else ext_out (device, capacity ext_cap). */
+static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_ext, size_t bytes,
+                     uint8_t *ext_out, size_t ext_cap, void **host_out, size_t *out_size)
 {
     struct bk_chain_args a;
-    uint32_t n_tiles, n_cand = 0, n_valid = 0, h_flags[FLBGPU_MAX_FILTERS + 1];
-    uint64_t total = 0;
-    int tiled = 0, k, pass;
+    const uint8_t *d_in;
+    uint32_t n_rec = 0, h_flags[FLBGPU_MAX_FILTERS + 1], nb;
+    size_t off = 0, S = slice_bytes();
+    uint64_t total;
+    int clean, k, pass;
 
     memset(&c->st, 0, sizeof(c->st));
     c->st.bytes_in = bytes;
     *out_size = 0;
     if (bytes >= 0xfff00000ull) { set_err("chunk larger than 4 GiB: split the append%s%s", NULL, NULL); return -1; }
-    n_tiles = (uint32_t) ((bytes + BK_INDEX_TILE - 1) / BK_INDEX_TILE);
-    GROW(c->d_tile, c->cap_tile, n_tiles + 1, uint32_t);
-    if (bk_index_count(d_in, (uint32_t) bytes, c->d_tile, n_tiles, &n_cand)) return -1;
-    if (c->cap_rec < n_cand) {
-        size_t nc = (size_t) n_cand + n_cand / 4 + 64;
-        bk_free(c->d_off); bk_free(c->d_len); bk_free(c->d_size); bk_free(c->d_kind);
-        c->d_off = bk_alloc(nc * 4); c->d_len = bk_alloc(nc * 4); c->d_size = bk_alloc(nc * 4); c->d_kind = bk_alloc(nc);
-        if (!c->d_off || !c->d_len || !c->d_size || !c->d_kind) { c->cap_rec = 0; return -1; }
-        c->cap_rec = nc;
+    if (d_in_ext) { d_in = d_in_ext; bk_upload_none(); }
+    else {
+        GROW(c->d_in, c->cap_in, bytes + 64, uint8_t);
+        d_in = c->d_in;
+        if (bk_upload_start(c->d_in, h_in, bytes)) return -1;
     }
-    if (bk_index_fill(d_in, (uint32_t) bytes, c->d_tile, n_tiles, n_cand, c->d_off, c->d_len, c->d_kind, &n_valid, &tiled)) {
-        c->st.error_bits = FLBGPU_E_INDEX;
-        return -1;
-    }
-    c->st.records_in = n_valid;
-    GROW(c->d_bsum, c->cap_bsum, (n_valid + BK_REC_BLOCK - 1) / BK_REC_BLOCK + 1, uint64_t);
-    if (c->cap_stride) GROW(c->d_cap, c->cap_cap, (size_t) n_valid * c->cap_stride + 1, int32_t);
-
     memset(&a, 0, sizeof(a));
-    a.d_in = d_in; a.in_len = (uint32_t) bytes; a.d_blob = c->d_blob; a.d_scr = NULL;
-    a.d_capcache = c->cap_stride ? c->d_cap : NULL; a.cap_stride = c->cap_stride;
     a.now = (int64_t) time(NULL);
-    a.d_off = c->d_off; a.d_len = c->d_len; a.d_kind = c->d_kind; a.n_rec = n_valid;
-    a.d_size = c->d_size; a.d_bsum = c->d_bsum; a.d_flags = c->d_flags;
     a.assume = (c->nf >= 32) ? 0xffffffffu : ((1u << c->nf) - 1u);
+    if (bk_flags_clear(c->d_flags)) return -1;
 
-    /* evaluation pass; revise chunk-level assumptions front to back until they hold */
+    /* ---- index + evaluate, slice by slice, while the upload is still running ---- */
+    while (off < bytes) {
+        size_t len = bytes - off < S ? bytes - off : S;
+        uint32_t n_tiles = (uint32_t) ((len + BK_INDEX_TILE - 1) / BK_INDEX_TILE), n_cand = 0, n_valid = 0;
+        uint64_t end_off = off;
+        uint32_t assume = a.assume;
+        int64_t now = a.now;
+        int tiled = 0;
+        if (bk_upload_wait_index(off + len)) return -1;
+        GROW(c->d_tile, c->cap_tile, n_tiles + 1, uint32_t);
+        if (bk_index_count(d_in, off, (uint32_t) len, c->d_tile, n_tiles, &n_cand)) return -1;
+        if (ensure_rec_cap(c, (size_t) n_rec + n_cand, n_rec)) return -1;
+        if (bk_index_fill(d_in, off, (uint32_t) len, c->d_tile, n_tiles, n_cand, c->d_off + n_rec, c->d_len + n_rec,
+                          c->d_kind + n_rec, &n_valid, &end_off, &tiled)) {
+            c->st.error_bits = FLBGPU_E_INDEX;
+            return -1;
+        }
+        if (n_valid == 0) {
+            if (off + len < bytes) { S *= 2; continue; }       /* a record longer than the slice: widen it */
+            break;                                             /* nothing decodable from here to the end */
+        }
+        fill_args(c, &a, d_in, bytes, n_rec + n_valid);
+        a.assume = assume; a.now = now;
+        if (bk_chain_eval(&a, n_rec, n_rec + n_valid)) return -1;
+        n_rec += n_valid;
+        off = (size_t) end_off;
+    }
+    clean = (off == bytes);
+    c->st.records_in = n_rec;
+    c->st.passes = 1;
+    {
+        uint32_t assume = a.assume;
+        int64_t now = a.now;
+        fill_args(c, &a, d_in, bytes, n_rec);
+        a.assume = assume; a.now = now;
+    }
+
+    /* ---- chunk-level verdicts; revise assumptions front to back until they hold ---- */
     for (pass = 0; pass <= c->nf; pass++) {
-        int changed = 0;
-        if (bk_chain_size(&a, h_flags, &total)) return -1;
-        c->st.passes++;
+        int changed = 0, cl = clean;
+        if (bk_flags_fetch(c->d_flags, h_flags)) return -1;
         if (h_flags[FLBGPU_MAX_FILTERS]) {
             c->st.error_bits = h_flags[FLBGPU_MAX_FILTERS];
             snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
-                     "1=too many keys 2=regex stack 4=regex budget 8=float outside exact path 32=logfmt escapes)", h_flags[FLBGPU_MAX_FILTERS]);
+                     "1=too many keys 2=regex stack 4=regex budget 8=float outside exact path 32=logfmt escapes)",
+                     h_flags[FLBGPU_MAX_FILTERS]);
             return -1;
         }
-        {
-        int clean = tiled;
         for (k = 0; k < c->nf; k++) {
-            int v = verdict(c->f[k]->kind, h_flags[k], clean);
-            if (v) clean = 1;                /* a MODIFIED filter hands a well-formed chunk on */
+            int v = verdict(c->f[k]->kind, h_flags[k], cl);
+            if (v) cl = 1;                   /* a MODIFIED filter hands a well-formed chunk on */
             if (v != (int) ((a.assume >> k) & 1)) {
                 a.assume = (a.assume & ~(1u << k)) | ((uint32_t) v << k);
                 changed = 1;
-                break;                   /* later filters saw the wrong input: re-evaluate */
+                break;                       /* later filters saw the wrong input: re-evaluate */
             }
         }
-        }
         if (!changed) break;
+        if (bk_flags_clear(c->d_flags) || bk_chain_eval(&a, 0, n_rec)) return -1;
+        c->st.passes++;
     }
     c->st.kernel_launches = bk_launch_count();
     if (a.assume == 0) return FLBGPU_FILTER_NOTOUCH;
+
+    /* ---- output offsets ---- */
+    nb = (n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK;
+    GROW(c->d_bsum, c->cap_bsum, nb + 2, uint64_t);
+    if (c->cap_hbsum < (size_t) nb + 2) {
+        free(c->h_bsum);
+        c->cap_hbsum = (size_t) nb + nb / 4 + 64;
+        c->h_bsum = malloc(c->cap_hbsum * sizeof(uint64_t));
+        if (!c->h_bsum) { c->cap_hbsum = 0; return -1; }
+    }
+    a.d_bsum = c->d_bsum;
+    if (bk_sizes_scan(c->d_size, n_rec, c->d_bsum, c->h_bsum)) return -1;
+    total = c->h_bsum[nb];
     if (total >= 0xfff00000ull) { set_err("result larger than 4 GiB%s%s", NULL, NULL); return -1; }
     c->st.bytes_out = total;
     *out_size = (size_t) total;
     if (total == 0) return FLBGPU_FILTER_MODIFIED;
-    if (ext_out) {
+
+    /* ---- emit (+ download) ---- */
+    if (!host_out) {
         if (ext_cap < total) { set_err("device output buffer too small%s%s", NULL, NULL); return -1; }
-        if (bk_chain_emit(&a, ext_out)) return -1;
+        if (bk_chain_emit(&a, ext_out, 0, nb)) return -1;
     }
     else {
+        const uint32_t step = 2048;                   /* blocks per emission launch (512 K records) */
+        uint32_t b0;
+        void *out = malloc((size_t) total);
+        if (!out) return -1;
+#ifdef MADV_HUGEPAGE
+        if (total >= ((size_t) 8 << 20)) {            /* fewer, larger page faults while the result is filled in */
+            uintptr_t lo = ((uintptr_t) out + ((size_t) 2 << 20) - 1) & ~(((uintptr_t) 2 << 20) - 1);
+            uintptr_t hi = ((uintptr_t) out + (size_t) total) & ~(((uintptr_t) 2 << 20) - 1);
+            if (hi > lo) madvise((void *) lo, hi - lo, MADV_HUGEPAGE);
+        }
+#endif
         GROW(c->d_out, c->cap_out, total, uint8_t);
-        if (bk_chain_emit(&a, c->d_out)) return -1;
+        if (bk_download_begin(out, c->d_out)) { free(out); return -1; }
+        for (b0 = 0; b0 < nb; b0 += step) {
+            uint32_t b1 = b0 + step < nb ? b0 + step : nb;
+            if (bk_chain_emit(&a, c->d_out, b0, b1) || bk_download_push((size_t) c->h_bsum[b0], (size_t) c->h_bsum[b1])) {
+                bk_download_end();
+                free(out);
+                return -1;
+            }
+        }
+        if (bk_download_end()) { free(out); return -1; }
+        *host_out = out;
     }
     c->st.kernel_launches = bk_launch_count();
     return FLBGPU_FILTER_MODIFIED;
@@ -1009,7 +1109,7 @@ int flbgpu_chain_do_device(flbgpu_chain *c, const void *d_data, size_t bytes, vo
     int r;
     if (!c || !c->inited) return -1;
     g_rt_err[0] = 0;
-    r = chain_run_device(c, d_data, bytes, d_out, out_cap, out_size);
+    r = chain_run(c, NULL, d_data, bytes, d_out, out_cap, NULL, out_size);
     if (r < 0) return r;
     if (bk_sync()) return -1;
     return r;
@@ -1018,30 +1118,12 @@ int flbgpu_chain_do_device(flbgpu_chain *c, const void *d_data, size_t bytes, vo
 int flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes, const char *tag, int tag_len,
                     void **out_buf, size_t *out_size)
 {
-    int r;
-    size_t osz = 0;
     (void) tag; (void) tag_len;
     if (!c || !c->inited || !out_buf || !out_size) return -1;
     g_rt_err[0] = 0;
     *out_buf = NULL; *out_size = 0;
     if (bytes == 0) return FLBGPU_FILTER_NOTOUCH;
-    GROW(c->d_in, c->cap_in, bytes + 64, uint8_t);
-    if (bk_h2d_big(c->d_in, data, bytes)) return -1;
-    r = chain_run_device(c, c->d_in, bytes, NULL, 0, &osz);
-    if (r != FLBGPU_FILTER_MODIFIED) return r;
-    *out_size = osz;
-    if (osz == 0) return FLBGPU_FILTER_MODIFIED;
-    *out_buf = malloc(osz);
-    if (!*out_buf) return -1;
-#ifdef MADV_HUGEPAGE
-    if (osz >= ((size_t) 8 << 20)) {          /* fewer, larger page faults while the result is filled in */
-        uintptr_t a = ((uintptr_t) *out_buf + ((size_t) 2 << 20) - 1) & ~(((uintptr_t) 2 << 20) - 1);
-        uintptr_t e = ((uintptr_t) *out_buf + osz) & ~(((uintptr_t) 2 << 20) - 1);
-        if (e > a) madvise((void *) a, e - a, MADV_HUGEPAGE);
-    }
-#endif
-    if (bk_d2h_big(*out_buf, c->d_out, osz)) { free(*out_buf); *out_buf = NULL; return -1; }
-    return FLBGPU_FILTER_MODIFIED;
+    return chain_run(c, data, NULL, bytes, NULL, 0, out_buf, out_size);
 }
 
 int flbgpu_filter_cb(flbgpu_filter *f, const void *data, size_t bytes, const char *tag, int tag_len,

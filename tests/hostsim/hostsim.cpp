@@ -90,21 +90,25 @@ void bk_free_host(void *p) { free(p); }
 int bk_h2d(void *d, const void *h, size_t n) { memcpy(d, h, n); return 0; }
 int bk_d2h(void *h, const void *d, size_t n) { memcpy(h, d, n); return 0; }
 int bk_zero(void *d, size_t n) { memset(d, 0, n); return 0; }
-int bk_d2h_big(void *h, const void *d, size_t n) { memcpy(h, d, n); return 0; }
-int bk_h2d_big(void *d, const void *h, size_t n) { memcpy(d, h, n); return 0; }
 int bk_sync(void) { return 0; }
 void *bk_stream(void) { return 0; }
 int bk_kernel_ms(float out[3]) { out[0] = out[1] = out[2] = 0.f; return 0; }
 
-int bk_index_count(const uint8_t *d_in, uint32_t len, uint32_t *d_tile, uint32_t n_tiles, uint32_t *n_cand)
+int bk_d2d(void *dst, const void *src, size_t n) { memcpy(dst, src, n); return 0; }
+int bk_upload_start(void *d_dst, const void *h_src, size_t n) { memcpy(d_dst, h_src, n); return 0; }
+int bk_upload_wait_index(size_t upto) { (void) upto; return 0; }
+void bk_upload_none(void) {}
+
+int bk_index_count(const uint8_t *d_in, size_t slice_off, uint32_t len, uint32_t *d_tile, uint32_t n_tiles, uint32_t *n_cand)
 {
+    const uint8_t *in = d_in + slice_off;
     uint32_t t, run = 0;
     for (t = 0; t < n_tiles; t++) {
         uint32_t b = t * BK_INDEX_TILE, e = b + BK_INDEX_TILE, i, cnt = 0;
         if (e > len) e = len;
         for (i = b; i < e; i++) {
             int kind;
-            if (d_in[i] == 0x92 && rec_frame(d_in + i, d_in + len, &kind) && !rec_is_shadowed(d_in, d_in + i, d_in + len)) cnt++;
+            if (in[i] == 0x92 && rec_frame(in + i, in + len, &kind) && !rec_is_shadowed(in, in + i, in + len)) cnt++;
         }
         d_tile[t] = run;
         run += cnt;
@@ -114,11 +118,13 @@ int bk_index_count(const uint8_t *d_in, uint32_t len, uint32_t *d_tile, uint32_t
     return 0;
 }
 
-int bk_index_fill(const uint8_t *d_in, uint32_t len, const uint32_t *d_tile, uint32_t n_tiles, uint32_t n_cand,
-                  uint32_t *d_off, uint32_t *d_len, uint8_t *d_kind, uint32_t *n_valid, int *tiled)
+int bk_index_fill(const uint8_t *d_in, size_t slice_off, uint32_t len, const uint32_t *d_tile, uint32_t n_tiles, uint32_t n_cand,
+                  uint32_t *d_off, uint32_t *d_len, uint8_t *d_kind, uint32_t *n_valid, uint64_t *end_off, int *tiled)
 {
-    uint32_t t, i, fb = 0xffffffffu;
-    *n_valid = 0; *tiled = (len == 0);
+    const uint8_t *in = d_in + slice_off;
+    const uint32_t base = (uint32_t) slice_off, total = base + len;
+    uint32_t t, i;
+    *n_valid = 0; *tiled = (len == 0); *end_off = slice_off;
     if (n_cand == 0) return 0;
     for (t = 0; t < n_tiles; t++) {
         uint32_t b = t * BK_INDEX_TILE, e = b + BK_INDEX_TILE, o = d_tile[t];
@@ -126,28 +132,31 @@ int bk_index_fill(const uint8_t *d_in, uint32_t len, const uint32_t *d_tile, uin
         for (i = b; i < e; i++) {
             int kind = 0;
             const uint8_t *q;
-            if (d_in[i] == 0x92 && (q = rec_frame(d_in + i, d_in + len, &kind)) && !rec_is_shadowed(d_in, d_in + i, d_in + len)) {
-                d_off[o] = i; d_len[o] = (uint32_t) (q - (d_in + i)); d_kind[o] = (uint8_t) kind; o++;
+            if (in[i] == 0x92 && (q = rec_frame(in + i, in + len, &kind)) && !rec_is_shadowed(in, in + i, in + len)) {
+                d_off[o] = base + i; d_len[o] = (uint32_t) (q - (in + i)); d_kind[o] = (uint8_t) kind; o++;
             }
         }
     }
     hs_launches += 3;
     {
         /* same walk as k_index_repair: breaks visited in ascending order */
-        uint32_t skip_until = 0, nv = n_cand, til = 1;
-        if (d_off[0] != 0) { *n_valid = 0; *tiled = 0; return 0; }
+        uint32_t skip_until = 0, nv = n_cand, til = 1, last;
+        if (d_off[0] != base) { *n_valid = 0; *tiled = 0; return 0; }
         for (i = 0; i < n_cand; i++) {
-            uint32_t next = (i + 1 < n_cand) ? d_off[i + 1] : len, target, k;
+            uint32_t next = (i + 1 < n_cand) ? d_off[i + 1] : total, target, k;
             if (d_off[i] + d_len[i] == next) continue;
             if (i < skip_until) continue;
             target = d_off[i] + d_len[i];
             k = i + 1;
             while (k < n_cand && d_off[k] < target) { d_kind[k] = 2; k++; }
             if (k < n_cand && d_off[k] == target) { skip_until = k; continue; }
-            if (k == n_cand && target == len) { skip_until = n_cand; continue; }
+            if (k == n_cand && target == total) { skip_until = n_cand; continue; }
             nv = i + 1; til = 0;
             break;
         }
+        last = nv;
+        while (last > 0 && d_kind[last - 1] == 2) last--;
+        *end_off = last ? d_off[last - 1] + d_len[last - 1] : base;
         *n_valid = nv; *tiled = (int) til;
     }
     return 0;
@@ -160,36 +169,42 @@ static void hs_env(const struct bk_chain_args *a, struct ch_env *e)
     e->fl_flags = a->d_flags; e->err = a->d_flags + FLBGPU_MAX_FILTERS;
 }
 
-int bk_chain_size(const struct bk_chain_args *a, uint32_t *h_flags, uint64_t *total)
+int bk_flags_clear(uint32_t *d_flags) { memset(d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)); return 0; }
+int bk_flags_fetch(const uint32_t *d_flags, uint32_t *h_flags) { memcpy(h_flags, d_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)); return 0; }
+
+int bk_chain_eval(const struct bk_chain_args *a, uint32_t r0, uint32_t r1)
 {
     struct ch_env e;
-    uint32_t i, nb = (a->n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK, b;
-    uint64_t run = 0;
+    uint32_t i;
     hs_env(a, &e);
-    memset(a->d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1));
-    for (b = 0; b < nb; b++) {
-        uint64_t bs = 0;
-        for (i = b * BK_REC_BLOCK; i < a->n_rec && i < (b + 1) * BK_REC_BLOCK; i++) {
-            uint32_t sz = 0;
-            if (a->d_kind[i] == 0) sz = chain_record<false>(&e, i, a->d_off[i], a->d_len[i], 0);
-            a->d_size[i] = sz;
-            bs += sz;
-        }
-        a->d_bsum[b] = run;
-        run += bs;
+    for (i = r0; i < r1; i++) {
+        uint32_t sz = 0;
+        if (a->d_kind[i] == 0) sz = chain_record<false>(&e, i, a->d_off[i], a->d_len[i], 0);
+        a->d_size[i] = sz;
     }
-    memcpy(h_flags, a->d_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1));
-    *total = run;
+    hs_launches += 1;
+    return 0;
+}
+
+int bk_sizes_scan(const uint32_t *d_size, uint32_t n_rec, uint64_t *d_bsum, uint64_t *h_bsum)
+{
+    uint32_t nb = (n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK, b, i;
+    uint64_t run = 0;
+    for (b = 0; b < nb; b++) {
+        d_bsum[b] = run; h_bsum[b] = run;
+        for (i = b * BK_REC_BLOCK; i < n_rec && i < (b + 1) * BK_REC_BLOCK; i++) run += d_size[i];
+    }
+    h_bsum[nb] = run;
     hs_launches += 2;
     return 0;
 }
 
-int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out)
+int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1)
 {
     struct ch_env e;
-    uint32_t i, nb = (a->n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK, b;
+    uint32_t i, b;
     hs_env(a, &e);
-    for (b = 0; b < nb; b++) {
+    for (b = b0; b < b1; b++) {
         uint64_t at = a->d_bsum[b];
         for (i = b * BK_REC_BLOCK; i < a->n_rec && i < (b + 1) * BK_REC_BLOCK; i++) {
             if (a->d_size[i]) {
@@ -202,5 +217,10 @@ int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out)
     hs_launches += 1;
     return 0;
 }
+
+static uint8_t *hs_dl_dst; static const uint8_t *hs_dl_src;
+int bk_download_begin(void *h_dst, const void *d_out) { hs_dl_dst = (uint8_t *) h_dst; hs_dl_src = (const uint8_t *) d_out; return 0; }
+int bk_download_push(size_t lo, size_t hi) { memcpy(hs_dl_dst + lo, hs_dl_src + lo, hi - lo); return 0; }
+int bk_download_end(void) { return 0; }
 
 }

@@ -81,3 +81,34 @@ def test_edge_chunks_gpu(gpu_lib, ref_available):
     for data in [chunk + b"\x01\x02\x03", b"\xc1" + chunk, marker + chunk + endm, marker + endm]:
         for filters in ([("grep", [("Regex", "log GET")])], [cases.P], [("modify", [("Add", "a b")])]):
             run_case(gpu_lib, [cases.AP], filters, data)
+
+
+def _sliced(lib, monkeypatch, n_lines, reps, slice_mb):
+    monkeypatch.setenv("FLBGPU_SLICE_MB", str(slice_mb))
+    block = util.chunk_from_lines(util.apache_lines(n_lines, seed=33))
+    chunk = block * reps
+    for name in ("north_star_chain", "grep_regex", "parser_modify_recmod"):
+        case = [c for c in cases.CASES if c[0] == name][0]
+        run_case(lib, case[1], case[2], chunk)
+    # a chunk cut in the middle of a record, and one with garbage in the middle
+    case = [c for c in cases.CASES if c[0] == "north_star_chain"][0]
+    run_case(lib, case[1], case[2], chunk[:len(chunk) - 37])
+    run_case(lib, case[1], case[2], chunk[:len(block) * 2] + b"\xc1garbage" + chunk[len(block) * 2:])
+
+
+def test_sliced_pipeline_hostsim(sim_lib, ref_available, monkeypatch):
+    """several slices per call: slice boundaries fall inside records"""
+    _sliced(sim_lib, monkeypatch, 4000, 6, 1)
+
+
+@pytest.mark.gpu
+def test_sliced_pipeline_gpu(gpu_lib, ref_available, monkeypatch):
+    _sliced(gpu_lib, monkeypatch, 4000, 6, 1)
+
+
+@pytest.mark.gpu
+def test_large_chunk_gpu(gpu_lib, ref_available):
+    """more than one emission range (>512 K records) and more than one upload piece"""
+    block = util.chunk_from_lines(util.apache_lines(20000, seed=34))
+    case = [c for c in cases.CASES if c[0] == "north_star_chain"][0]
+    run_case(gpu_lib, case[1], case[2], block * 30)
