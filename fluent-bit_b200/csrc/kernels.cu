@@ -95,7 +95,7 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total)
 
 /* ------------------------------------------------------------------ index */
 template <bool FILL>
-__global__ void __launch_bounds__(256) k_index(const uint8_t *__restrict__ in, uint32_t len, uint32_t abs_base,
+__global__ void __launch_bounds__(256) k_index(const uint8_t *__restrict__ in, uint32_t len, uint32_t skip, uint32_t abs_base,
                                                uint32_t *__restrict__ tile, uint32_t *__restrict__ o_off,
                                                uint32_t *__restrict__ o_len, uint8_t *__restrict__ o_kind)
 {
@@ -119,6 +119,8 @@ __global__ void __launch_bounds__(256) k_index(const uint8_t *__restrict__ in, u
         else {
             for (int k = 0; k < 16; k++) if (pos + k < len && in[pos + k] == 0x92) mask |= 1u << k;
         }
+        /* `in` is the slice start rounded down to 16 bytes: bytes before `skip` belong to the previous slice */
+        if (pos < skip) mask &= (pos + 16 <= skip) ? 0u : (0xffffu << (skip - pos));
         uint32_t tot;
         uint32_t at = block_excl_scan(__popc(mask), &tot) + ncand;
         while (mask) {
@@ -503,7 +505,10 @@ int bk_index_count(const uint8_t *d_in, size_t slice_off, uint32_t slice_len, ui
     *n_cand = 0;
     if (n_tiles == 0) return 0;
     ev_begin_on(0, g_istream);
-    k_index<false><<<n_tiles, 256, 0, g_istream>>>(d_in + slice_off, slice_len, (uint32_t) slice_off, d_tile, 0, 0, 0);
+    {
+        const uint32_t skip = (uint32_t) (slice_off & 15);
+        k_index<false><<<n_tiles, 256, 0, g_istream>>>(d_in + slice_off - skip, slice_len + skip, skip, (uint32_t) (slice_off - skip), d_tile, 0, 0, 0);
+    }
     k_scan_top<uint32_t><<<1, 256, 0, g_istream>>>(d_tile, n_tiles, g_dtotal);
     ev_end_on(0, g_istream);
     g_launches += 2;
@@ -523,7 +528,10 @@ int bk_index_fill(const uint8_t *d_in, size_t slice_off, uint32_t slice_len, con
     *n_valid = 0; *tiled = (slice_len == 0); *end_off = slice_off;
     if (n_cand == 0) return 0;
     ev_begin_on(0, g_istream);
-    k_index<true><<<n_tiles, 256, 0, g_istream>>>(d_in + slice_off, slice_len, (uint32_t) slice_off, (uint32_t *) d_tile, d_off, d_len, d_kind);
+    {
+        const uint32_t skip = (uint32_t) (slice_off & 15);
+        k_index<true><<<n_tiles, 256, 0, g_istream>>>(d_in + slice_off - skip, slice_len + skip, skip, (uint32_t) (slice_off - skip), (uint32_t *) d_tile, d_off, d_len, d_kind);
+    }
     CK(cudaMemsetAsync(d_w, 0, 16, g_istream));
     k_index_check<<<(n_cand + 255) / 256, 256, 0, g_istream>>>(d_off, d_len, n_cand, (uint32_t) (slice_off + slice_len), d_w, g_dbreaks);
     k_index_repair<<<1, 1024, 0, g_istream>>>(d_off, d_len, d_kind, n_cand, (uint32_t) slice_off, (uint32_t) (slice_off + slice_len), d_w, g_dbreaks, d_w + 1);

@@ -992,7 +992,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     /* ---- index + evaluate, slice by slice, while the upload is still running ---- */
     while (off < bytes) {
         size_t len = bytes - off < S ? bytes - off : S;
-        uint32_t n_tiles = (uint32_t) ((len + BK_INDEX_TILE - 1) / BK_INDEX_TILE), n_cand = 0, n_valid = 0;
+        uint32_t n_tiles = (uint32_t) ((len + (off & 15) + BK_INDEX_TILE - 1) / BK_INDEX_TILE), n_cand = 0, n_valid = 0;   /* tiles start at off rounded down to 16 B */
         uint64_t end_off = off;
         uint32_t assume = a.assume;
         int64_t now = a.now;

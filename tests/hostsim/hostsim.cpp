@@ -102,9 +102,11 @@ void bk_upload_none(void) {}
 int bk_index_count(const uint8_t *d_in, size_t slice_off, uint32_t len, uint32_t *d_tile, uint32_t n_tiles, uint32_t *n_cand)
 {
     const uint8_t *in = d_in + slice_off;
+    const uint32_t skip = (uint32_t) (slice_off & 15);
     uint32_t t, run = 0;
     for (t = 0; t < n_tiles; t++) {
-        uint32_t b = t * BK_INDEX_TILE, e = b + BK_INDEX_TILE, i, cnt = 0;
+        /* tile t covers bytes [t*TILE - skip, (t+1)*TILE - skip) of the slice, like the CUDA kernel */
+        uint32_t b = t * BK_INDEX_TILE > skip ? t * BK_INDEX_TILE - skip : 0, e = (t + 1) * BK_INDEX_TILE - skip, i, cnt = 0;
         if (e > len) e = len;
         for (i = b; i < e; i++) {
             int kind;
@@ -122,12 +124,12 @@ int bk_index_fill(const uint8_t *d_in, size_t slice_off, uint32_t len, const uin
                   uint32_t *d_off, uint32_t *d_len, uint8_t *d_kind, uint32_t *n_valid, uint64_t *end_off, int *tiled)
 {
     const uint8_t *in = d_in + slice_off;
-    const uint32_t base = (uint32_t) slice_off, total = base + len;
+    const uint32_t base = (uint32_t) slice_off, total = base + len, skip = (uint32_t) (slice_off & 15);
     uint32_t t, i;
     *n_valid = 0; *tiled = (len == 0); *end_off = slice_off;
     if (n_cand == 0) return 0;
     for (t = 0; t < n_tiles; t++) {
-        uint32_t b = t * BK_INDEX_TILE, e = b + BK_INDEX_TILE, o = d_tile[t];
+        uint32_t b = t * BK_INDEX_TILE > skip ? t * BK_INDEX_TILE - skip : 0, e = (t + 1) * BK_INDEX_TILE - skip, o = d_tile[t];
         if (e > len) e = len;
         for (i = b; i < e; i++) {
             int kind = 0;
