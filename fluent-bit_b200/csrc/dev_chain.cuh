@@ -25,6 +25,7 @@
 #include "dev_msgpack.cuh"
 #include "dev_regex.cuh"
 #include "dev_time.cuh"
+#include "dev_json.cuh"
 
 #define CH_MAXF        64
 #define CH_RX_STACK    192      /* 32-bit words of backtrack stack per lane */
@@ -702,6 +703,70 @@ FLB_HD int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32_
     return 1;
 }
 
+/* flb_parser_json_do(), src/flb_parser_json.c:29-247.  The document is transcoded into
+ * this record's scratch region by the evaluation pass (msgpack, canonical); both passes
+ * then read the top-level map back as the field list.  Time key: first member whose key
+ * equals Time_Key; its value must be a STR; a failed lookup keeps the member and leaves
+ * the timestamp at 0 (:198-209). */
+template <bool EMIT>
+FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, const uint8_t *s, uint32_t n,
+                     ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec, uint32_t ridx,
+                     uint32_t *cache_pos)
+{
+    int32_t *slot = 0;
+    uint32_t mplen = 0, i;
+    int ok, cnt = 0, skip = -1;
+    struct mp_tok t;
+    const uint8_t *q, *end, *nx;
+    int64_t lookup = 0;
+    double frac = 0;
+
+    if (!e->scr) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
+    if (e->capcache && *cache_pos + 2 <= e->cap_stride) slot = e->capcache + (size_t) ridx * e->cap_stride + *cache_pos;
+    *cache_pos += 2;
+    if (EMIT && slot) { ok = slot[0]; mplen = (uint32_t) slot[1]; }
+    else {
+        uint32_t jerr = 0;
+        ok = dj_parse_record(s, (int) n, e->scr, &mplen, &jerr);
+        if (jerr) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
+        if (!EMIT && slot) { slot[0] = ok; slot[1] = (int32_t) mplen; }
+    }
+    if (!ok) return 0;
+    q = e->scr; end = q + mplen;
+    mp_token(q, end, &t);
+    q += t.hdr;
+    if (t.len > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
+    for (i = 0; i < t.len; i++) {
+        nx = mp_skip(q, end);
+        ok_[cnt] = mkref(RK_MP_SCR, (uint32_t) (q - e->scr), (uint32_t) (nx - q));
+        q = nx;
+        nx = mp_skip(q, end);
+        ov_[cnt] = mkref(RK_MP_SCR, (uint32_t) (q - e->scr), (uint32_t) (nx - q));
+        q = nx;
+        cnt++;
+    }
+    if (pd->has_time) {
+        for (i = 0; i < (uint32_t) cnt; i++) {
+            const uint8_t *kp; uint32_t kn;
+            if (ref_view(e, ok_[i], &kp, &kn) != 1) continue;
+            if (kn != pd->time_key_len || !bytes_eq(kp, e->blob + pd->time_key_off, kn)) continue;
+            {
+                const uint8_t *vp; uint32_t vn;
+                if (ref_view(e, ov_[i], &vp, &vn) != 1) break;            /* value is not a STR: no time */
+                if (pdef_time(e, pd, vp, vn, &lookup, &frac) != 0) { lookup = 0; frac = 0; break; }
+                if (!pd->time_keep) skip = (int) i;
+            }
+            break;
+        }
+    }
+    if (skip >= 0) {
+        for (i = (uint32_t) skip; i + 1 < (uint32_t) cnt; i++) { ok_[i] = ok_[i + 1]; ov_[i] = ov_[i + 1]; }
+        cnt--;
+    }
+    *on = cnt; *t_sec = lookup; *t_nsec = frac_to_nsec(frac);
+    return 1;
+}
+
 struct ch_scratch {              /* per-lane working memory */
     int caps[2 * (RX_MAX_GROUPS + 1)];
     uint32_t stk[CH_RX_STACK];
@@ -766,6 +831,10 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                 }
                 if (matched) got = pdef_regex(e, pd, val_off, vp, vn, w->caps, w->tk, w->tv, &cnt, &ts, &tns);
                 if (got) { preset = pd->n_groups; style = ST_PRESET; }
+            }
+            else if (pd->type == FLBGPU_PARSER_JSON) {
+                got = pdef_json<EMIT>(e, pd, vp, vn, w->tk, w->tv, &cnt, &ts, &tns, ridx, cache_pos);
+                if (got) style = ST_CANON;
             }
             else if (pd->type == FLBGPU_PARSER_LTSV) {
                 got = pdef_ltsv(e, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns);
@@ -1077,8 +1146,14 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
     const struct chain_filter *f = (const struct chain_filter *) (e->blob + h->filters_off);
     struct ch_rec rc;
     struct ch_scratch w;
+    struct ch_env le;
     uint32_t k, cache_pos = 0;
 
+    if (e->scr) {               /* this record's private scratch region: 4 bytes per record byte */
+        le = *e;
+        le.scr = e->scr + (size_t) 4 * off;
+        e = &le;
+    }
     if (rec_decode(e, off, len, &rc, h->empty_map_off) != 0) {
         CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS);
         return 0;

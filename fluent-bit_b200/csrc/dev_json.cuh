@@ -1,0 +1,377 @@
+/* dev_json.cuh -- JSON text -> msgpack on the device, one lane per document.
+ *
+ * Mirrors what the reference's default JSON back end produces
+ * (flb_pack_json_recs -> pack_json_to_msgpack_yyjson, src/flb_pack.c:389-508, with
+ * yyjson 0.12 read flags STOP_WHEN_DONE | INSITU | ALLOW_INVALID_UNICODE |
+ * REPLACE_INVALID_UNICODE, :441-442) and yyjson_val_to_msgpack (:317-373):
+ *   object -> map (count = members, duplicates kept, order kept), array -> array,
+ *   string -> str (escapes decoded as yyjson's read_str_opt / read_uni_esc do),
+ *   non-negative integer -> uint minimal, negative integer -> int minimal,
+ *   integer overflow / fraction / exponent -> float64 (correctly rounded),
+ *   true/false/null.
+ * Grammar is RFC 8259 as yyjson enforces it without extension flags: no trailing
+ * commas, no comments, no leading zeros, no NaN/Inf (an overflowing real is an error),
+ * whitespace = space \t \n \r.  Raw control characters and invalid UTF-8 inside strings
+ * are accepted and copied (ALLOW_INVALID_UNICODE); unknown escapes are errors.
+ *
+ * Decimal -> double: Clinger's exact fast path, then Eisel-Lemire with the 128-bit
+ * power-of-five table (dev_pow5_table.h).  When Eisel-Lemire cannot decide (a few
+ * halfway cases, >19 significant digits straddling a boundary) DJ_E_FLOAT is reported
+ * instead of guessing.
+ */
+#ifndef FLBGPU_DEV_JSON_CUH
+#define FLBGPU_DEV_JSON_CUH
+
+#include <stdint.h>
+#include "dev_msgpack.cuh"
+
+#ifdef __CUDA_ARCH__
+#define DJ_TABLE_QUAL __device__ static const
+#else
+#define DJ_TABLE_QUAL static const
+#endif
+#include "dev_pow5_table.h"
+
+#define DJ_MAX_DEPTH 31        /* nesting the reference's msgpack_unpack_next() still accepts */
+#define DJ_E_FLOAT   1
+
+FLB_HD int dj_ws(uint32_t c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
+FLB_HD int dj_hex(uint32_t c)
+{
+    if (c >= '0' && c <= '9') return (int) c - '0';
+    if (c >= 'a' && c <= 'f') return (int) c - 'a' + 10;
+    if (c >= 'A' && c <= 'F') return (int) c - 'A' + 10;
+    return -1;
+}
+
+FLB_HD void dj_mul64(uint64_t a, uint64_t b, uint64_t *hi, uint64_t *lo)
+{
+#ifdef __CUDA_ARCH__
+    *lo = a * b;
+    *hi = __umul64hi(a, b);
+#else
+    unsigned __int128 p = (unsigned __int128) a * b;
+    *lo = (uint64_t) p;
+    *hi = (uint64_t) (p >> 64);
+#endif
+}
+
+FLB_HD int dj_clz64(uint64_t x)
+{
+#ifdef __CUDA_ARCH__
+    return __clzll((long long) x);
+#else
+    return __builtin_clzll(x);
+#endif
+}
+
+/* w * 10^q -> IEEE double bits.  Returns 0 ok, 1 overflow (infinity), 2 undecided. */
+FLB_HD int dj_eisel_lemire(uint64_t w, int64_t q, uint64_t *bits)
+{
+    uint64_t hi, lo, mant;
+    int lz, upperbit;
+    int64_t exponent;
+    if (w == 0 || q < DJ_POW5_MIN) { *bits = 0; return 0; }
+    if (q > DJ_POW5_MAX) return 1;
+    lz = dj_clz64(w);
+    w <<= lz;
+    {
+        const uint64_t t_hi = dj_pow5[2 * (q - DJ_POW5_MIN)], t_lo = dj_pow5[2 * (q - DJ_POW5_MIN) + 1];
+        dj_mul64(w, t_hi, &hi, &lo);
+        if ((hi & 0x1FF) == 0x1FF) {
+            uint64_t shi, slo;
+            dj_mul64(w, t_lo, &shi, &slo);
+            lo += shi;
+            if (shi > lo) hi++;
+            (void) slo;        /* "the computed product is always sufficient" (Lemire 2021, section 6) */
+        }
+    }
+    upperbit = (int) (hi >> 63);
+    mant = hi >> (upperbit + 64 - 52 - 3);
+    /* power2 = power(q) + upperbit - lz - minimum_exponent, power(q) = ((217706*q) >> 16) + 63 */
+    exponent = ((((int64_t) (152170 + 65536) * q) >> 16) + 63) + upperbit - lz + 1023;
+    if (exponent <= 0) {                                               /* subnormal */
+        if (-exponent + 1 >= 64) { *bits = 0; return 0; }
+        mant >>= -exponent + 1;
+        mant += (mant & 1);
+        mant >>= 1;
+        *bits = mant;                                                  /* bit 52, when set, is exponent 1 */
+        return 0;
+    }
+    if (lo <= 1 && q >= -4 && q <= 23 && (mant & 3) == 1) {
+        if ((mant << (upperbit + 64 - 52 - 3)) == hi) mant &= ~(uint64_t) 1;
+    }
+    mant += (mant & 1);
+    mant >>= 1;
+    if (mant >= ((uint64_t) 2 << 52)) { mant = (uint64_t) 1 << 52; exponent++; }
+    mant &= ~((uint64_t) 1 << 52);
+    if (exponent >= 0x7FF) return 1;
+    *bits = mant | ((uint64_t) exponent << 52);
+    return 0;
+}
+
+/* Parse the JSON number at s[pos].  Returns the position after it or -1.
+ * kind: 0 uint (u), 1 sint (value in u as two's complement), 2 real (bits in u). */
+FLB_HD int dj_number(const uint8_t *s, int n, int pos, int *kind, uint64_t *u, uint32_t *err)
+{
+    int neg = 0, p = pos, nd = 0, dropped = 0, is_real = 0, int_overflow = 0, truncated = 0;
+    uint64_t w = 0, iw = 0;
+    int64_t exp10 = 0;
+    const double p10[23] = { 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                             1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22 };
+    if (p < n && s[p] == '-') { neg = 1; p++; }
+    if (p >= n || s[p] < '0' || s[p] > '9') return -1;
+    if (s[p] == '0') {
+        p++;
+        if (p < n && s[p] >= '0' && s[p] <= '9') return -1;           /* leading zero */
+    }
+    else {
+        while (p < n && s[p] >= '0' && s[p] <= '9') {
+            uint32_t d = s[p] - '0';
+            if (iw > (0xffffffffffffffffull - d) / 10) int_overflow = 1; else iw = iw * 10 + d;
+            if (nd < 19) { w = w * 10 + d; nd++; } else { dropped++; if (d) truncated = 1; }
+            p++;
+        }
+    }
+    if (p < n && s[p] == '.') {
+        int fd = 0;
+        p++;
+        while (p < n && s[p] >= '0' && s[p] <= '9') {
+            uint32_t d = s[p] - '0';
+            if (nd < 19) { if (w || d) { w = w * 10 + d; nd++; } exp10--; }
+            else if (d) truncated = 1;
+            fd++; p++;
+        }
+        if (fd == 0) return -1;
+        is_real = 1;
+    }
+    if (p < n && (s[p] == 'e' || s[p] == 'E')) {
+        int eneg = 0, ed = 0;
+        int64_t ev = 0;
+        p++;
+        if (p < n && (s[p] == '+' || s[p] == '-')) { eneg = s[p] == '-'; p++; }
+        while (p < n && s[p] >= '0' && s[p] <= '9') { if (ev < 100000) ev = ev * 10 + (s[p] - '0'); ed++; p++; }
+        if (ed == 0) return -1;
+        exp10 += eneg ? -ev : ev;
+        is_real = 1;
+    }
+    if (!is_real) {
+        if (!int_overflow) {
+            if (!neg) { *kind = 0; *u = iw; return p; }
+            if (iw <= 9223372036854775808ull) { *kind = 1; *u = (uint64_t) (0 - iw); return p; }
+        }
+    }
+    exp10 += dropped;
+    *kind = 2;
+    {
+        uint64_t bits = 0;
+        if (w == 0) bits = 0;
+        else if (!truncated && w <= ((uint64_t) 1 << 53) && exp10 >= -22 && exp10 <= 22) {
+            union { double d; uint64_t u; } cv;
+            cv.d = (double) w;
+            if (exp10 >= 0) cv.d = cv.d * p10[exp10]; else cv.d = cv.d / p10[-exp10];
+            bits = cv.u;
+        }
+        else {
+            int r = dj_eisel_lemire(w, exp10, &bits);
+            if (r == 1) return -1;                                     /* infinity: yyjson rejects the document */
+            if (r == 0 && truncated) {
+                uint64_t b2 = 0;
+                int r2 = dj_eisel_lemire(w + 1, exp10, &b2);
+                if (r2 != 0 || b2 != bits) r = 2;
+            }
+            if (r == 2) { *err |= DJ_E_FLOAT; bits = 0; }
+        }
+        if (neg) bits |= (uint64_t) 1 << 63;
+        *u = bits;
+    }
+    return p;
+}
+
+/* Decode the string whose opening quote is at s[pos].  Writes the decoded bytes to o
+ * (when o != NULL), returns the position after the closing quote or -1; *olen = length. */
+FLB_HD int dj_string(const uint8_t *s, int n, int pos, uint8_t *o, uint32_t *olen)
+{
+    int p = pos + 1;
+    uint32_t k = 0;
+#define DJ_PUT(b) do { if (o) o[k] = (uint8_t) (b); k++; } while (0)
+    for (;;) {
+        uint32_t c;
+        if (p >= n) return -1;                                         /* unclosed string */
+        c = s[p];
+        if (c == '"') { *olen = k; return p + 1; }
+        if (c != '\\') { DJ_PUT(c); p++; continue; }
+        if (p + 1 >= n) return -1;
+        c = s[p + 1];
+        switch (c) {
+        case '"': DJ_PUT('"'); p += 2; continue;
+        case '\\': DJ_PUT('\\'); p += 2; continue;
+        case '/': DJ_PUT('/'); p += 2; continue;
+        case 'b': DJ_PUT(8); p += 2; continue;
+        case 'f': DJ_PUT(12); p += 2; continue;
+        case 'n': DJ_PUT(10); p += 2; continue;
+        case 'r': DJ_PUT(13); p += 2; continue;
+        case 't': DJ_PUT(9); p += 2; continue;
+        case 'u': break;
+        default: return -1;                                            /* invalid escaped sequence */
+        }
+        {
+            /* read_uni_esc(), lib/yyjson-0.12.0/src/yyjson.c:4659-4820 with REPLACE_INVALID_UNICODE */
+            int q = p + 2, cnt = 0, h;
+            uint32_t hi = 0, lo = 0, uni;
+            while (cnt < 4 && q + cnt < n && (h = dj_hex(s[q + cnt])) >= 0) { hi = hi * 16 + (uint32_t) h; cnt++; }
+            if (cnt < 4) {
+                uint32_t ch = (q + cnt < n) ? s[q + cnt] : 0;
+                int i;
+                DJ_PUT('\\'); DJ_PUT('u');
+                for (i = 0; i < cnt; i++) DJ_PUT(s[q + i]);
+                p = q + cnt;
+                if (ch && ch != '"' && ch != '\'') p++;
+                continue;
+            }
+            q += 4;
+            if ((hi & 0xF800) != 0xD800) {
+                if (hi >= 0x800) { DJ_PUT(0xE0 | (hi >> 12)); DJ_PUT(0x80 | ((hi >> 6) & 0x3F)); DJ_PUT(0x80 | (hi & 0x3F)); }
+                else if (hi >= 0x80) { DJ_PUT(0xC0 | (hi >> 6)); DJ_PUT(0x80 | (hi & 0x3F)); }
+                else DJ_PUT(hi);
+                p = q;
+                continue;
+            }
+            if ((hi & 0xFC00) != 0xD800) { DJ_PUT(0xEF); DJ_PUT(0xBF); DJ_PUT(0xBD); p = q; continue; }   /* lone low surrogate */
+            if (!(q + 1 < n && s[q] == '\\' && s[q + 1] == 'u')) { DJ_PUT(0xEF); DJ_PUT(0xBF); DJ_PUT(0xBD); p = q; continue; }
+            cnt = 0;
+            while (cnt < 4 && q + 2 + cnt < n && (h = dj_hex(s[q + 2 + cnt])) >= 0) { lo = lo * 16 + (uint32_t) h; cnt++; }
+            if (cnt < 4) { DJ_PUT(0xEF); DJ_PUT(0xBF); DJ_PUT(0xBD); p = q + 2 + cnt; continue; }
+            if ((lo & 0xFC00) != 0xDC00) { DJ_PUT(0xEF); DJ_PUT(0xBF); DJ_PUT(0xBD); p = q + 6; continue; }
+            uni = (((hi - 0xD800) << 10) | (lo - 0xDC00)) + 0x10000;
+            DJ_PUT(0xF0 | (uni >> 18)); DJ_PUT(0x80 | ((uni >> 12) & 0x3F)); DJ_PUT(0x80 | ((uni >> 6) & 0x3F)); DJ_PUT(0x80 | (uni & 0x3F));
+            p = q + 6;
+        }
+    }
+#undef DJ_PUT
+}
+
+/* members of the container whose opening bracket is at s[pos] (pairs for objects);
+ * -1 when it never closes.  Purely structural: the real parse validates. */
+FLB_HD int dj_count(const uint8_t *s, int n, int pos)
+{
+    int p = pos + 1, depth = 0, count = 0, seen = 0;
+    while (p < n) {
+        uint32_t c = s[p];
+        if (c == '"') { uint32_t sl; p = dj_string(s, n, p, 0, &sl); if (p < 0) return -1; seen = 1; continue; }   /* the same lexer the real parse uses (\\u quirks) */
+        if (c == '[' || c == '{') { depth++; seen = 1; }
+        else if (c == ']' || c == '}') { if (depth == 0) return count + (seen ? 1 : 0); depth--; }
+        else if (c == ',' && depth == 0) { count++; seen = 0; }
+        else if (!dj_ws(c)) seen = 1;
+        p++;
+    }
+    return -1;
+}
+
+/* One JSON value at s[pos] -> msgpack at o (NULL = only measure and validate).
+ * Returns the position after the value, or -1 on any syntax error.  *olen = msgpack bytes. */
+FLB_HDN int dj_value(const uint8_t *s, int n, int pos, uint8_t *o, uint32_t *olen, uint32_t *err)
+{
+    uint32_t k = 0, rem[DJ_MAX_DEPTH + 1];
+    uint8_t isobj[DJ_MAX_DEPTH + 1];
+    int sp = 0, p = pos;
+
+    for (;;) {
+        /* ---- a value starts at p (whitespace already skipped by the caller of this state) ---- */
+        uint32_t c;
+        while (p < n && dj_ws(s[p])) p++;
+        if (p >= n) return -1;
+        c = s[p];
+        if (c == '{' || c == '[') {
+            int cnt = dj_count(s, n, p);
+            if (cnt < 0) return -1;
+            if (c == '{') { if (o) mp_put_map_hdr(o + k, (uint32_t) cnt); }
+            else if (o) mp_put_array_hdr(o + k, (uint32_t) cnt);
+            k += mp_cnt_hdr_size((uint32_t) cnt);
+            p++;
+            if (cnt == 0) {
+                while (p < n && dj_ws(s[p])) p++;
+                if (p >= n || s[p] != (c == '{' ? '}' : ']')) return -1;
+                p++;
+                goto value_done;
+            }
+            if (sp >= DJ_MAX_DEPTH) return -1;
+            rem[sp] = (uint32_t) cnt; isobj[sp] = (c == '{'); sp++;
+            goto next_member;
+        }
+        if (c == '"') {
+            uint32_t sl = 0;
+            int e = dj_string(s, n, p, 0, &sl);
+            if (e < 0) return -1;
+            if (o) { uint32_t h = mp_put_str_hdr(o + k, sl); dj_string(s, n, p, o + k + h, &sl); }
+            k += mp_str_hdr_size(sl) + sl;
+            p = e;
+            goto value_done;
+        }
+        if (c == '-' || (c >= '0' && c <= '9')) {
+            int kind = 0;
+            uint64_t u = 0;
+            int e = dj_number(s, n, p, &kind, &u, err);
+            if (e < 0) return -1;
+            if (kind == 0) { if (o) mp_put_uint(o + k, u); k += mp_uint_size(u); }
+            else if (kind == 1) { if (o) mp_put_int(o + k, (int64_t) u); k += mp_int_size((int64_t) u); }
+            else { if (o) { o[k] = 0xcb; mp_put_be64(o + k + 1, u); } k += 9; }
+            p = e;
+            goto value_done;
+        }
+        if (c == 't' && p + 4 <= n && s[p + 1] == 'r' && s[p + 2] == 'u' && s[p + 3] == 'e') { if (o) o[k] = 0xc3; k++; p += 4; goto value_done; }
+        if (c == 'f' && p + 5 <= n && s[p + 1] == 'a' && s[p + 2] == 'l' && s[p + 3] == 's' && s[p + 4] == 'e') { if (o) o[k] = 0xc2; k++; p += 5; goto value_done; }
+        if (c == 'n' && p + 4 <= n && s[p + 1] == 'u' && s[p + 2] == 'l' && s[p + 3] == 'l') { if (o) o[k] = 0xc0; k++; p += 4; goto value_done; }
+        return -1;
+
+value_done:
+        if (sp == 0) { *olen = k; return p; }
+        rem[sp - 1]--;
+        while (p < n && dj_ws(s[p])) p++;
+        if (p >= n) return -1;
+        if (rem[sp - 1] == 0) {
+            if (s[p] != (isobj[sp - 1] ? '}' : ']')) return -1;
+            p++;
+            sp--;
+            goto value_done;
+        }
+        if (s[p] != ',') return -1;
+        p++;
+next_member:
+        if (isobj[sp - 1]) {
+            uint32_t sl = 0;
+            int e;
+            while (p < n && dj_ws(s[p])) p++;
+            if (p >= n || s[p] != '"') return -1;
+            e = dj_string(s, n, p, 0, &sl);
+            if (e < 0) return -1;
+            if (o) { uint32_t h = mp_put_str_hdr(o + k, sl); dj_string(s, n, p, o + k + h, &sl); }
+            k += mp_str_hdr_size(sl) + sl;
+            p = e;
+            while (p < n && dj_ws(s[p])) p++;
+            if (p >= n || s[p] != ':') return -1;
+            p++;
+        }
+        /* loop: parse the member value */
+    }
+}
+
+/* flb_pack_json_recs() for one line: exactly one document, which must be an object.
+ * Returns 1 and the msgpack map at o (length *olen), or 0. */
+FLB_HD int dj_parse_record(const uint8_t *s, int n, uint8_t *o, uint32_t *olen, uint32_t *err)
+{
+    int p = 0, e;
+    uint32_t dummy = 0, derr = 0;
+    while (p < n && dj_ws(s[p])) p++;
+    if (p >= n) return 0;
+    e = dj_value(s, n, p, o, olen, err);
+    if (e < 0) return 0;
+    if (s[p] != '{') return 0;                                         /* root must be a map (src/flb_parser_json.c:70-85) */
+    /* a second parsable document means records == 2 -> rejected; trailing junk is fine */
+    p = e;
+    while (p < n && dj_ws(s[p])) p++;
+    if (p < n && dj_value(s, n, p, 0, &dummy, &derr) >= 0) return 0;
+    return 1;
+}
+
+#endif

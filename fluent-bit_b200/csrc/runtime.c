@@ -104,6 +104,7 @@ struct flbgpu_filter {
     int kind;
     struct kv *props, *props_tail;
     int inited;
+    int needs_scratch;       /* a JSON parser transcodes into per-record scratch */
     flbgpu_chain *solo;
 };
 
@@ -120,6 +121,8 @@ struct flbgpu_chain {
     struct blob blob;
     uint8_t *d_blob;
     uint32_t cap_stride;
+    int needs_scratch;
+    uint8_t *d_scr; size_t cap_scr;
     /* device buffers, grown on demand */
     uint8_t *d_in;  size_t cap_in;
     uint8_t *d_out; size_t cap_out;
@@ -225,11 +228,7 @@ flbgpu_parser *flbgpu_parser_create(flbgpu_ctx *ctx, const char *name, const cha
     else if (!strcasecmp(format, "ltsv")) p->type = FLBGPU_PARSER_LTSV;
     else if (!strcasecmp(format, "logfmt")) p->type = FLBGPU_PARSER_LOGFMT;
     else { set_err("[parser:%s] Invalid format %s", name, format); free(p); return NULL; }
-    if (p->type == FLBGPU_PARSER_JSON) {
-        set_err("[parser:%s] format %s is not implemented on the GPU path yet", name, format);
-        free(p);
-        return NULL;
-    }
+
     if (p->type == FLBGPU_PARSER_REGEX) {
         if (!p_regex) { set_err("[parser:%s] Invalid regex pattern%s", name, NULL); free(p); return NULL; }
         if (rx_compile(p_regex, &p->rx) != 0) {
@@ -620,6 +619,7 @@ static uint32_t emit_parser_filter(flbgpu_filter *f, struct blob *b, uint32_t *c
             if (cf.n_parsers >= 8) { set_err("too many parsers in one filter%s%s", NULL, NULL); return 0; }
             cf.pdef_off[cf.n_parsers++] = emit_pdef(b, ps);
             if (ps->has_rx) *cap_need += 1 + 2 * (ps->rx.prog->n_groups + 1);
+            if (ps->type == FLBGPU_PARSER_JSON) { *cap_need += 2; f->needs_scratch = 1; }
         }
         else if (!strcasecmp(p->k, "preserve_key")) { int v = parse_bool(p->v); if (v < 0) { set_err("invalid boolean '%s'%s", p->v, NULL); return 0; } cf.preserve_key = v; }
         else if (!strcasecmp(p->k, "reserve_data")) { int v = parse_bool(p->v); if (v < 0) { set_err("invalid boolean '%s'%s", p->v, NULL); return 0; } cf.reserve_data = v; }
@@ -874,6 +874,8 @@ int flbgpu_chain_init(flbgpu_chain *c)
         cf[i].cfg_off = emit_filter(c->f[i], &c->blob, &cap);
         if (!cf[i].cfg_off) return -1;
     }
+    for (i = 0; i < (uint32_t) c->nf; i++) if (c->f[i]->needs_scratch) h.needs_scratch = 1;
+    c->needs_scratch = (int) h.needs_scratch;
     h.n_filters = c->nf;
     h.filters_off = blob_add(&c->blob, cf, sizeof(cf[0]) * (c->nf ? c->nf : 1), 8);
     h.cap_stride = cap;
@@ -894,7 +896,7 @@ void flbgpu_chain_destroy(flbgpu_chain *c)
     if (!c) return;
     bk_free(c->d_blob); bk_free(c->d_in); bk_free(c->d_out); bk_free(c->d_tile); bk_free(c->d_off);
     bk_free(c->d_len); bk_free(c->d_size); bk_free(c->d_kind); bk_free(c->d_bsum); bk_free(c->d_cap);
-    bk_free(c->d_flags); free(c->h_bsum);
+    bk_free(c->d_flags); bk_free(c->d_scr); free(c->h_bsum);
     free(c->blob.p);
     free(c);
 }
@@ -948,7 +950,7 @@ static int ensure_rec_cap(flbgpu_chain *c, size_t need, size_t keep)
 static size_t slice_bytes(void)
 {
     const char *e = getenv("FLBGPU_SLICE_MB");
-    size_t mb = e ? (size_t) atol(e) : 64;
+    size_t mb = e ? (size_t) atol(e) : 256;
     if (mb < 1) mb = 1;
     if (mb > 2048) mb = 2048;
     return mb << 20;
@@ -956,7 +958,7 @@ static size_t slice_bytes(void)
 
 static void fill_args(flbgpu_chain *c, struct bk_chain_args *a, const uint8_t *d_in, size_t bytes, uint32_t n_rec)
 {
-    a->d_in = d_in; a->in_len = (uint32_t) bytes; a->d_blob = c->d_blob; a->d_scr = NULL;
+    a->d_in = d_in; a->in_len = (uint32_t) bytes; a->d_blob = c->d_blob; a->d_scr = c->needs_scratch ? c->d_scr : NULL;
     a->d_capcache = c->cap_stride ? c->d_cap : NULL; a->cap_stride = c->cap_stride;
     a->d_off = c->d_off; a->d_len = c->d_len; a->d_kind = c->d_kind; a->n_rec = n_rec;
     a->d_size = c->d_size; a->d_bsum = c->d_bsum; a->d_flags = c->d_flags;
@@ -984,6 +986,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         d_in = c->d_in;
         if (bk_upload_start(c->d_in, h_in, bytes)) return -1;
     }
+    if (c->needs_scratch) GROW(c->d_scr, c->cap_scr, 4 * bytes + 64, uint8_t);
     memset(&a, 0, sizeof(a));
     a.now = (int64_t) time(NULL);
     a.assume = (c->nf >= 32) ? 0xffffffffu : ((1u << c->nf) - 1u);

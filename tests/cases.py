@@ -36,6 +36,44 @@ def mixed_chunk():
     return b"".join(ev)
 
 
+JS = dict(name="json", format="json", time_fmt="%d/%b/%Y:%H:%M:%S %z", time_key="time")
+JS_PLAIN = dict(name="jsonp", format="json")
+LT = dict(name="ltsv", format="ltsv", time_fmt="%d/%b/%Y:%H:%M:%S %z", time_key="time", types="status:integer size:integer")
+LF = dict(name="logfmt", format="logfmt", time_fmt="%Y-%m-%dT%H:%M:%SZ", time_key="ts", time_keep=True)
+PJ = ("parser", [("Key_Name", "log"), ("Parser", "json")])
+
+JSON_EDGE = [
+    b'{"a":1,"b":"x","c":[1,2,{"d":null}],"e":true,"f":false,"g":-5,"h":1.5,"i":1e3,"time":"28/Jul/2006:10:27:10 -0300"}',
+    b'  {"k":"v"}  ', b'{"a":1} trailing', b'{"a":1} {"b":2}', b'{"a":1}5', b'[1,2]', b'"str"', b'{}', b'{"a":}', b'{"a":1,}',
+    b'{"a" 1}', b'{"big":18446744073709551615,"bigger":18446744073709551616,"neg":-9223372036854775808,"neg2":-9223372036854775809,"z":-0,"zf":-0.0}',
+    b'{"s":"esc \\" \\\\ \\/ \\b \\f \\n \\r \\t \\u0041 \\u00e9 \\u20ac \\ud83d\\ude00 end"}',
+    b'{"s":"bad \\ud83d x","t":"\\udc00","u":"\\u12","v":"\\ud83d\\u0041","w":"\\uZZ"}', b'{"s":"\\x41"}',
+    b'{"s":"ctl\x01\x1f","u":"\xff\xfe ok \xc3\xa9"}',
+    b'{"f":[0.1,0.2,0.3,3.14159,2.718281828459045,1e-7,1.7976931348623157e308,4.9e-324,5e-324,0.000001,1e22,1e23,9007199254740993,0.1e1]}',
+    b'{"inf":1e999}', b'{"a":01}', b'{"a":1.}', b'{"a":.5}', b'{"a":1e}', b'{"a":+1}', b'{"a":tru}',
+    b'{"nested":' + b'[' * 30 + b']' * 30 + b'}', b'{"nested":' + b'[' * 31 + b']' * 31 + b'}', b'{"nested":' + b'[' * 32 + b']' * 32 + b'}',
+    b'{"time":123}', b'{"time":"bogus"}', b'{"a":"x","a":"y","time":"28/Jul/2006:10:27:10 -0300","time":"dup"}', b'', b'   ',
+    b'{"a":"unterminated', b'{"a":{"b":{"c":{"d":[1,[2,[3]]]}}}}', b'\t{"tab":1}\n', b'{"a":1}\x00', b'{"a"\n:\r1 ,\t"b" : 2 }',
+    b'{"u":"\\u0000x"}', b'{"e":"\\u00"}', b'{"k\\u0041":1,"\\n":2}', b'{"x":"\\ud3d\\ude00b\\u004\\":1}',
+]
+
+
+def json_chunk(n=1200, seed=5):
+    return util.chunk_from_lines(util.json_lines(n, seed=seed))
+
+
+def json_edge_chunk():
+    return util.chunk_from_lines(JSON_EDGE)
+
+
+def ltsv_chunk():
+    return util.chunk_from_lines(util.ltsv_lines(400) + [b"a:1\tb:\t:x\tc:3", b"nolabel", b"k:v\r\nrest:1", b"time:bogus\ta:1", b"", b"a:1\t\tb:2"])
+
+
+def logfmt_chunk():
+    return util.chunk_from_lines(util.logfmt_lines(400) + [b"a=1 b c=", b'x="unterminated', b"=novalue k=v", b"  ", b'q="a b" r=s\nnext=1'])
+
+
 def tricky_ts_chunk():
     """Timestamps whose bytes frame as complete legacy events ([uint32, {}]) inside real records:
     the record index has to rule those candidates out (sec = 0x655492ce -> `92 ce 00 00 xx xx 80`)."""
@@ -61,6 +99,16 @@ CASES = [
     ("parser_ra_key", [AP], [("parser", [("Key_Name", "$log"), ("Parser", "apache"), ("Reserve_Data", "On")])], apache_chunk),
     ("tricky_timestamps_parser", [AP], [P], tricky_ts_chunk),
     ("tricky_timestamps_grep", [], [("grep", [("Regex", "log GET")])], tricky_ts_chunk),
+    ("json_parser", [JS], [PJ], json_chunk),
+    ("json_parser_edge", [JS], [PJ], json_edge_chunk),
+    ("json_parser_edge_plain_reserve", [JS_PLAIN], [("parser", [("Key_Name", "log"), ("Parser", "jsonp"), ("Reserve_Data", "On")])], json_edge_chunk),
+    ("json_chain_config1", [JS], [PJ, ("grep", [("Regex", "level ^(warn|error)$")]),
+                                 ("modify", [("Add", "env prod"), ("Rename", "msg message"), ("Remove", "debug")])], json_chunk),
+    ("json_chain_nested_grep", [JS], [PJ, ("grep", [("Regex", "$kubernetes['labels']['app'] .")]),
+                                     ("record_modifier", [("Remove_key", "trace_id"), ("Record", "cluster c1")])], json_chunk),
+    ("ltsv_parser", [LT], [("parser", [("Key_Name", "log"), ("Parser", "ltsv")])], ltsv_chunk),
+    ("logfmt_parser", [LF], [("parser", [("Key_Name", "log"), ("Parser", "logfmt")]), ("grep", [("Exclude", "level debug")])], logfmt_chunk),
+    ("multi_parser_fallthrough", [AP, JS, LF], [("parser", [("Key_Name", "log"), ("Parser", "json"), ("Parser", "apache"), ("Parser", "logfmt")])], lambda: util.chunk_from_lines(util.json_lines(100, 3) + util.apache_lines(100, 4) + util.logfmt_lines(100, 5))),
     ("grep_regex", [], [("grep", [("Regex", "log GET")])], apache_chunk),
     ("grep_exclude", [], [("grep", [("Exclude", "log HTTP")])], apache_chunk),
     ("grep_keep_all_notouch", [], [("grep", [("Regex", "log .")])], apache_chunk),

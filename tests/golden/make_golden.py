@@ -119,6 +119,10 @@ def main():
              "nginx_chunk": lambda: util.chunk_from_lines(util.apache_lines(60, seed=12, nginx=True)),
              "tricky_ts_chunk": lambda: cases.tricky_ts_chunk()[:30000 * 0 + len(b"".join(cases.tricky_ts_chunk()[o:o + l] for o, l in util.split_records(cases.tricky_ts_chunk())[:60]))],
              "mixed_chunk": lambda: cases.mixed_chunk()[:20000]}
+    small.update({"json_chunk": lambda: cases.json_chunk(60), "json_edge_chunk": cases.json_edge_chunk,
+                  "ltsv_chunk": lambda: util.chunk_from_lines(util.ltsv_lines(40) + [b"a:1\tb:\t:x\tc:3", b"nolabel"]),
+                  "logfmt_chunk": lambda: util.chunk_from_lines(util.logfmt_lines(40) + [b"a=1 b c=", b'x="unterminated']),
+                  "<lambda>": lambda: util.chunk_from_lines(util.json_lines(20, 3) + util.apache_lines(20, 4) + util.logfmt_lines(20, 5))})
     for name, parsers, filters, mk in cases.CASES:
         chunk = small[mk.__name__]()
         if mk.__name__ == "mixed_chunk":

@@ -223,3 +223,61 @@ def apache_lines(n, seed=0xF1B1 + 1, garbage=0.005, nginx=False):
             line += ' "%s" "%s"' % (rng.choice(_REF), rng.choice(_AGENT))
         out.append(line.encode())
     return out
+
+
+_LEVELS = ["debug", "info", "info", "info", "warn", "error", "info", "debug"]
+_WORDS = ["request", "completed", "failed", "timeout", "connection", "user", "cache", "miss", "hit", "retry",
+          "upstream", "queue", "flush", "chunk", "parser", "filter", "ok", "slow", "db", "auth"]
+
+
+def json_lines(n, seed=0xF1B1 + 2):
+    """6-12 keys, str/int/float/bool/null, 3 % nested map, 2 % escapes, ~150 B."""
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        level = rng.choice(_LEVELS)
+        msg = " ".join(rng.choice(_WORDS) for _ in range(rng.randint(3, 8)))
+        if rng.random() < 0.02:
+            msg += ' \\"quoted\\" caf\\u00e9 \\n tab\\t'
+        items = ['"level":"%s"' % level, '"msg":"%s"' % msg, '"status":%d' % rng.choice([200, 200, 200, 404, 500, 301]),
+                 '"latency_ms":%s' % ("%.3f" % (rng.random() * 500) if rng.random() < 0.8 else str(rng.randint(0, 5000))),
+                 '"ok":%s' % rng.choice(["true", "false"]), '"pid":%d' % rng.randint(1, 65535)]
+        if rng.random() < 0.5:
+            items.append('"debug":"%s"' % rng.choice(_WORDS))
+        if rng.random() < 0.5:
+            items.append('"trace_id":"%032x"' % rng.getrandbits(128))
+        if rng.random() < 0.3:
+            items.append('"user":null')
+        if rng.random() < 0.4:
+            items.append('"bytes":%d' % int(10 ** (rng.random() * 9)))
+        if rng.random() < 0.03:
+            items.append('"kubernetes":{"pod":"p-%d","labels":{"app":"%s"},"ports":[80,%d]}' % (i % 977, rng.choice(_WORDS), rng.randint(1000, 9999)))
+        if rng.random() < 0.2:
+            items.append('"neg":-%d' % rng.randint(1, 10 ** 6))
+        rng.shuffle(items)
+        if rng.random() < 0.005:
+            out.append(("not json at all %d" % i).encode())
+        else:
+            out.append(("{" + ",".join(items) + "}").encode())
+    return out
+
+
+def ltsv_lines(n, seed=77):
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        out.append(("host:10.0.%d.%d\tident:-\tuser:%s\ttime:%02d/Oct/2023:13:%02d:%02d +0000\treq:GET /p/%d HTTP/1.1\tstatus:%d\tsize:%d\tempty:"
+                    % (rng.randint(0, 255), rng.randint(1, 254), rng.choice(["-", "bob", "alice"]), rng.randint(1, 28), rng.randint(0, 59),
+                       rng.randint(0, 59), i, rng.choice([200, 404, 500]), rng.randint(0, 10 ** 6))).encode())
+    return out
+
+
+def logfmt_lines(n, seed=78):
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        out.append(('ts=2023-10-%02dT10:%02d:%02dZ level=%s msg="%s" dur=%.2f n=%d flag %s'
+                    % (rng.randint(1, 28), rng.randint(0, 59), rng.randint(0, 59), rng.choice(_LEVELS),
+                       " ".join(rng.choice(_WORDS) for _ in range(rng.randint(1, 5))), rng.random() * 10, i,
+                       rng.choice(["", 'empty=""', "k=v"]))).encode())
+    return out
