@@ -31,21 +31,41 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 BASE_LINES = 100_000          # distinct synthetic lines; the batch tiles this block
-AP = None
-FILTERS = [("parser", [("Key_Name", "log"), ("Parser", "apache")]),
-           ("grep", [("Regex", "method ^(GET|POST)$")]),
-           ("modify", [("Add", "env prod"), ("Rename", "code status"), ("Remove", "agent")])]
-WORKLOAD = "north-star chain: filter_parser(apache regex)+filter_grep+filter_modify over synthetic apache-combined events"
+
+# BASELINE.json configs[1]: "in_dummy 10M JSON lines -> filter_parser(json) + filter_grep + filter_modify on 1xB200"
+# (value shapes of SURVEY.md section 8d C2) -- the default workload.
+# BASELINE.json north_star: "apache-combined parser + grep + modify chain" -- reported beside it (key "north_star").
+WORKLOADS = {
+    "json": {
+        "name": "configs[1]: 10M JSON lines -> filter_parser(json)+filter_grep(level ^(warn|error)$)+filter_modify(Add,Rename,Remove)",
+        "filters": [("parser", [("Key_Name", "log"), ("Parser", "json")]),
+                    ("grep", [("Regex", "level ^(warn|error)$")]),
+                    ("modify", [("Add", "env prod"), ("Rename", "msg message"), ("Remove", "debug")])],
+    },
+    "apache": {
+        "name": "north-star chain: filter_parser(apache regex)+filter_grep(method ^(GET|POST)$)+filter_modify over apache-combined events",
+        "filters": [("parser", [("Key_Name", "log"), ("Parser", "apache")]),
+                    ("grep", [("Regex", "method ^(GET|POST)$")]),
+                    ("modify", [("Add", "env prod"), ("Rename", "code status"), ("Remove", "agent")])],
+    },
+}
+WL = "json"
 
 
-def make_block(rank=0):
+def make_block(rank=0, wl=None):
     import util
-    lines = util.apache_lines(BASE_LINES, seed=0xF1B1 + 1 + rank)
+    wl = wl or WL
+    if wl == "json":
+        lines = util.json_lines(BASE_LINES, seed=0xF1B1 + 2 + rank)
+    else:
+        lines = util.apache_lines(BASE_LINES, seed=0xF1B1 + 1 + rank)
     return util.chunk_from_lines(lines)
 
 
-def apache_parser_kw():
+def parser_kw(wl=None):
     import util
+    if (wl or WL) == "json":
+        return dict(name="json", format="json", time_fmt="%d/%b/%Y:%H:%M:%S %z", time_key="time")
     return dict(name="apache", format="regex", regex=util.APACHE_RX, time_fmt=util.APACHE_TIME_FMT, time_key="time")
 
 
@@ -54,8 +74,8 @@ def _ref_worker(args):
     block, reps = args
     import util
     ref = util.Ref()
-    ref.parser(**apache_parser_kw())
-    for p, props in FILTERS:
+    ref.parser(**parser_kw())
+    for p, props in WORKLOADS[WL]["filters"]:
         ref.filter(p, props)
     buf = C.create_string_buffer(block, len(block))
     nrec = ref.L.flbref_count_records(C.cast(buf, C.c_void_p), len(block))
@@ -105,7 +125,7 @@ def run_reference(args):
         "impl": "reference", "metric": "log lines/sec through parser+filter chain", "value": val, "unit": "lines/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "events_per_step": cores * BASE_LINES, "host_cores": cores},
+        "config": {"workload": WORKLOADS[WL]["name"], "events_per_step": cores * BASE_LINES, "host_cores": cores},
         "cpu_baseline": {"value": val, "unit": "lines/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": "lines/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -140,24 +160,13 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def run_ours(args):
-    import torch
-    import torch.distributed as dist
+def measure(args, wl, L, ctx, torch, dist, rank, world, local):
+    """value / e2e / kernel times of one workload on this rank's GPU"""
     import util
     pkg = util.pkg
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-
-    L = pkg.load()                                  # raises if the CUDA library is missing
-    ctx = pkg.Context(local, lib=L)
-    ctx.parser(**apache_parser_kw())
-    chain = ctx.chain([ctx.filter(p, props) for p, props in FILTERS])
-
-    block = make_block(rank)
+    ctx.parser(**parser_kw(wl))
+    chain = ctx.chain([ctx.filter(p, props) for p, props in WORKLOADS[wl]["filters"]])
+    block = make_block(rank, wl)
     reps = max(1, args.lines // BASE_LINES)
     n_lines = reps * BASE_LINES
     nbytes = len(block) * reps
@@ -165,12 +174,11 @@ def run_ours(args):
     for i in range(reps):
         C.memmove(h_in + i * len(block), block, len(block))
     d_in = L.flbgpu_dev_alloc(ctx.h, nbytes + 64)
-    out_cap = nbytes + 64
+    out_cap = nbytes + nbytes // 2 + 64
     d_out = L.flbgpu_dev_alloc(ctx.h, out_cap)
     assert h_in and d_in and d_out, "allocation failed"
     L.flbgpu_dev_upload(ctx.h, d_in, h_in, nbytes)
     stream = torch.cuda.ExternalStream(L.flbgpu_stream(ctx.h), device=torch.device("cuda", local))
-
     osz = C.c_size_t()
 
     def step_device():
@@ -184,7 +192,6 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- kernel-resident throughput (value)
     for _ in range(args.warmup):
         step_device()
     st0 = chain.stats()
@@ -218,14 +225,6 @@ def run_ours(args):
     out_p = C.c_void_p()
     libc = C.CDLL(None)
     libc.free.argtypes = [C.c_void_p]
-    # Host allocator policy of the embedding process: keep freed result buffers in the heap instead of
-    # returning them to the kernel (glibc: no mmap for big blocks, no trimming) -- what Fluent Bit's
-    # default jemalloc build does with its retained extents.  Without it every step pays ~300k page
-    # faults for the fresh 1.2 GB result.
-    if os.environ.get("FLBGPU_BENCH_DEFAULT_MALLOC") != "1":
-        libc.mallopt(-4, 0)              # M_MMAP_MAX = 0
-        libc.mallopt(-1, 1 << 30)        # M_TRIM_THRESHOLD (int: capped at 1 GiB)
-        libc.mallopt(-2, 1 << 30)        # M_TOP_PAD
 
     def step_host():
         r = L.flbgpu_chain_do(chain.h, h_in, nbytes, b"bench", 5, C.byref(out_p), C.byref(osz))
@@ -246,29 +245,68 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e = world * n_lines * e2e_steps / e2e_s
+    L.flbgpu_dev_free(ctx.h, d_in)
+    L.flbgpu_dev_free(ctx.h, d_out)
+    L.flbgpu_host_free(ctx.h, h_in)
+    return {"value": value, "dev_ms": dev_ms, "e2e": e2e, "e2e_steps": e2e_steps, "kms": [k / args.steps for k in kms],
+            "launches": launches, "n_lines": n_lines, "nbytes": nbytes, "out_bytes": out_bytes, "clocks": clocks}
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import util
+    pkg = util.pkg
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    L = pkg.load()                                  # raises if the CUDA library is missing
+    ctx = pkg.Context(local, lib=L)
+    # Host allocator policy of the embedding process: keep freed result buffers in the heap instead of
+    # returning them to the kernel (glibc: no mmap for big blocks, no trimming) -- what Fluent Bit's
+    # default jemalloc build does with its retained extents.  Without it every step pays ~300k page
+    # faults for the fresh result buffer.  FLBGPU_BENCH_DEFAULT_MALLOC=1 turns the tuning off.
+    if os.environ.get("FLBGPU_BENCH_DEFAULT_MALLOC") != "1":
+        libc = C.CDLL(None)
+        libc.mallopt(-4, 0)              # M_MMAP_MAX = 0
+        libc.mallopt(-1, 1 << 30)        # M_TRIM_THRESHOLD
+        libc.mallopt(-2, 1 << 30)        # M_TOP_PAD
+
+    m = measure(args, WL, L, ctx, torch, dist, rank, world, local)
+    other = "apache" if WL == "json" else "json"
+    m2 = None
+    if not args.primary_only:
+        m2 = measure(args, other, L, ctx, torch, dist, rank, world, local)
 
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
         return
 
-    # ---- roofline of the dominant kernel
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
-    eval_ms = kms[1] / args.steps
-    alg_bytes = nbytes + out_bytes
-    achieved = alg_bytes / (eval_ms / 1000.0) / 1e9 if eval_ms > 0 else None
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_chain_eval_dram_bytes_per_launch")
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_chain_eval_dram_bytes_per_launch_" + WL)
     except Exception:
         pass
 
-    # ---- CPU baseline: the reference itself, bounded sample
+    def roof(mm):
+        eval_ms = mm["kms"][1]
+        alg = mm["nbytes"] + mm["out_bytes"]
+        ach = alg / (eval_ms / 1000.0) / 1e9 if eval_ms > 0 else None
+        return eval_ms, alg, ach
+
+    eval_ms, alg_bytes, achieved = roof(m)
+
     cpu = None
     if util.have_ref():
         cores = os.cpu_count() or 1
@@ -276,25 +314,34 @@ def run_ours(args):
         cpu = {"value": v, "unit": "lines/s", "cores": cores, "kind": "reference",
                "sample": "%d cores x one %d-event block each (%.1f s wall)" % (cores, BASE_LINES, wall)}
 
-    print(json.dumps({
-        "metric": "log lines/sec through parser+filter chain", "value": value, "unit": "lines/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
+    line = {
+        "metric": "log lines/sec through parser+filter chain", "value": m["value"], "unit": "lines/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["dev_ms"] / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "events_per_gpu_per_step": n_lines, "input_bytes_per_gpu": nbytes,
-                   "output_bytes_per_gpu": out_bytes, "distinct_lines": BASE_LINES,
-                   "l2": "input (%.0f MB) and output larger than the 126 MB L2" % (nbytes / 1e6),
-                   "parallelism": "record shards, no data-path collective"},
-        "e2e": {"value": e2e, "unit": "lines/s", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": out_bytes,
-                "steps": e2e_steps, "timing": "wall clock between device-synchronising barriers"},
-        "gpu_launches": launches,
-        "kernel_ms_per_step": {"index": kms[0] / args.steps, "evaluate": eval_ms, "emit": kms[2] / args.steps},
+        "config": {"workload": WORKLOADS[WL]["name"], "events_per_gpu_per_step": m["n_lines"], "input_bytes_per_gpu": m["nbytes"],
+                   "output_bytes_per_gpu": m["out_bytes"], "distinct_lines": BASE_LINES,
+                   "l2": "input (%.0f MB) and output larger than the 126 MB L2" % (m["nbytes"] / 1e6),
+                   "parallelism": "record shards, no data-path collective",
+                   "host_malloc": "default" if os.environ.get("FLBGPU_BENCH_DEFAULT_MALLOC") == "1" else "glibc tuned to retain freed result buffers (M_MMAP_MAX=0, M_TRIM_THRESHOLD=1GiB)"},
+        "e2e": {"value": m["e2e"], "unit": "lines/s", "h2d_bytes_per_step": m["nbytes"], "d2h_bytes_per_step": m["out_bytes"],
+                "steps": m["e2e_steps"], "timing": "wall clock between device-synchronising barriers"},
+        "gpu_launches": m["launches"],
+        "kernel_ms_per_step": {"index": m["kms"][0], "evaluate": eval_ms, "emit": m["kms"][2]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
-                     "kernel": "k_chain<false> (evaluation pass)", "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel": "k_chain_eval (evaluation pass)", "algorithmic_bytes_per_launch": alg_bytes,
                      "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s"},
         "cpu_baseline": cpu,
-        "clocks": clocks,
-    }))
+        "clocks": m["clocks"],
+    }
+    if m2:
+        e2, a2, ach2 = roof(m2)
+        line["north_star" if other == "apache" else "configs1_json"] = {
+            "workload": WORKLOADS[other]["name"], "value": m2["value"], "e2e": m2["e2e"], "unit": "lines/s",
+            "events_per_gpu_per_step": m2["n_lines"], "input_bytes_per_gpu": m2["nbytes"], "output_bytes_per_gpu": m2["out_bytes"],
+            "kernel_ms_per_step": {"index": m2["kms"][0], "evaluate": e2, "emit": m2["kms"][2]},
+            "roofline_frac": (ach2 / peak) if ach2 else None, "gpu_launches": m2["launches"]}
+    print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
 
@@ -306,7 +353,11 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lines", type=int, default=10_000_000, help="events per GPU per step")
+    ap.add_argument("--workload", default="json", choices=["json", "apache"], help="primary workload (the other one is reported beside it)")
+    ap.add_argument("--primary-only", action="store_true")
     args = ap.parse_args()
+    global WL
+    WL = args.workload
     if args.impl == "reference":
         run_reference(args)
     else:
