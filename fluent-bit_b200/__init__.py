@@ -84,8 +84,16 @@ def load(path=None):
     L.flbgpu_host_free.argtypes = [vp, vp]
     L.flbgpu_stream.restype = vp; L.flbgpu_stream.argtypes = [vp]
     L.flbgpu_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    ip = C.POINTER(C.c_int); u64p = C.POINTER(C.c_uint64)
+    L.flbgpu_l2m_info.argtypes = [vp, ip, ip, ip, ip]
+    L.flbgpu_l2m_get.argtypes = [vp, C.c_int, u64p, u64p, C.POINTER(C.c_double), u64p, vp]
+    L.flbgpu_l2m_reset.argtypes = [vp]
+    L.flbgpu_l2m_put.argtypes = [vp, C.c_uint64, C.c_uint64, C.c_double, u64p, vp]
+    L.flbgpu_l2m_text.restype = vp; L.flbgpu_l2m_text.argtypes = [vp]
     return L
 
+
+L2M_LABEL_BYTES = 256
 
 _libc = C.CDLL(None)
 _libc.free.argtypes = [C.c_void_p]
@@ -188,6 +196,92 @@ class Filter:
     def cb(self, data, tag="test"):
         """cb_filter(): (FILTER_MODIFIED, bytes) or (FILTER_NOTOUCH, None)."""
         return _call_filter(self.ctx.L.flbgpu_filter_cb, self.ctx.L, self.h, data, tag)
+
+    # ---- filter_log_to_metrics state (the plugin's ctx->cmt) ----
+    def l2m_info(self):
+        m, nl, nb, ns = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+        if self.ctx.L.flbgpu_l2m_info(self.h, C.byref(m), C.byref(nl), C.byref(nb), C.byref(ns)) != 0:
+            raise FlbGpuError("not a log_to_metrics filter")
+        return m.value, nl.value, nb.value, ns.value
+
+    def l2m_sets(self):
+        """[(hash, (label, ...), count, sum, [cumulative buckets..., +Inf])] in first-seen order."""
+        _, nl, nb, ns = self.l2m_info()
+        out = []
+        for i in range(ns):
+            h, c, s = C.c_uint64(), C.c_uint64(), C.c_double()
+            bk = (C.c_uint64 * (nb + 1))()
+            lab = C.create_string_buffer(max(nl, 1) * L2M_LABEL_BYTES)
+            self.ctx.L.flbgpu_l2m_get(self.h, i, C.byref(h), C.byref(c), C.byref(s), bk, C.cast(lab, C.c_void_p))
+            raw = lab.raw
+            labels = tuple(raw[j * L2M_LABEL_BYTES + 1: j * L2M_LABEL_BYTES + 1 + raw[j * L2M_LABEL_BYTES]] for j in range(nl))
+            out.append((h.value, labels, c.value, s.value, list(bk)))
+        return out
+
+    def l2m_replace(self, sets):
+        """Replace the table (used after a cross-rank merge)."""
+        _, nl, nb, _ = self.l2m_info()
+        self.ctx.L.flbgpu_l2m_reset(self.h)
+        for h, labels, c, s, bk in sets:
+            lab = bytearray(max(nl, 1) * L2M_LABEL_BYTES)
+            for j, v in enumerate(labels):
+                lab[j * L2M_LABEL_BYTES] = len(v)
+                lab[j * L2M_LABEL_BYTES + 1: j * L2M_LABEL_BYTES + 1 + len(v)] = v
+            arr = (C.c_uint64 * (nb + 1))(*bk)
+            buf = (C.c_char * len(lab)).from_buffer(lab)
+            self.ctx.L.flbgpu_l2m_put(self.h, h, c, s, arr, C.cast(buf, C.c_void_p))
+
+    def l2m_text(self):
+        p = self.ctx.L.flbgpu_l2m_text(self.h)
+        if not p:
+            raise FlbGpuError("not a log_to_metrics filter")
+        t = C.string_at(p).decode(errors="replace")
+        _libc.free(p)
+        return t
+
+    def l2m_allreduce(self, device=None):
+        """Sum this filter's metric table over all ranks of the default process group (the one
+        exchange step of the path: cmetrics of N shards -> one table).  Keys travel with one
+        all_gather, values with ONE all_reduce (NCCL on GPUs, gloo in the CPU tests).  Label sets
+        end up in (rank, first-seen) order on every rank."""
+        import torch
+        import torch.distributed as dist
+        _, nl, nb, _ = self.l2m_info()
+        mine = self.l2m_sets()
+        world = dist.get_world_size()
+        gathered = [None] * world
+        dist.all_gather_object(gathered, [(h, labels) for h, labels, _, _, _ in mine])
+        order, seen = [], {}
+        for per_rank in gathered:
+            for h, labels in per_rank:
+                if h not in seen:
+                    seen[h] = len(order)
+                    order.append((h, labels))
+        n = len(order)
+        dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+        counts = torch.zeros((n, nb + 2), dtype=torch.int64)
+        sums = torch.zeros((n,), dtype=torch.float64)
+        for h, _, c, s, bk in mine:
+            i = seen[h]
+            counts[i, 0] = c
+            counts[i, 1:] = torch.tensor(bk, dtype=torch.int64)
+            sums[i] = s
+        if n:
+            # one collective: the float64 sums ride in the same buffer, bit-cast to int64 lanes would
+            # not add correctly, so the buffer is [counts | sums] as float64 only when exact (< 2^53)
+            counts = counts.to(dev); sums = sums.to(dev)
+            if int(counts.max()) < (1 << 52):
+                buf = torch.cat([counts.to(torch.float64).reshape(-1), sums])
+                dist.all_reduce(buf)
+                counts = buf[: n * (nb + 2)].reshape(n, nb + 2).to(torch.int64)
+                sums = buf[n * (nb + 2):]
+            else:
+                dist.all_reduce(counts); dist.all_reduce(sums)
+            counts = counts.cpu(); sums = sums.cpu()
+        merged = [(h, labels, int(counts[i, 0]), float(sums[i]), [int(x) for x in counts[i, 1:]])
+                  for i, (h, labels) in enumerate(order)]
+        self.l2m_replace(merged)
+        return merged
 
 
 class Chain:

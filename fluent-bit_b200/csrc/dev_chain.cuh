@@ -61,6 +61,7 @@ struct ch_env {
     uint32_t assume;          /* bit k: filter k is chunk-level MODIFIED */
     uint32_t *fl_flags;       /* [n_filters] CHF_* evidence (evaluation pass only) */
     uint32_t *err;            /* FLBGPU_E_* */
+    struct l2m_table l2m;     /* log_to_metrics delta table of this call (hash == NULL: none) */
 };
 
 struct ch_rec {
@@ -1135,6 +1136,159 @@ FLB_HD void f_recmod(const struct ch_env *e, const struct cf_recmod *cf, struct 
     rc->style = ST_MAP32;
 }
 
+/* ------------------------------------------------ filter_log_to_metrics */
+#ifdef __CUDA_ARCH__
+#define CH_CAS64(p, c, v)   atomicCAS((unsigned long long *) (p), (unsigned long long) (c), (unsigned long long) (v))
+#define CH_MAX32(p, v)      atomicMax((unsigned int *) (p), (unsigned int) (v))
+#define CH_ADDF64(p, v)     atomicAdd((double *) (p), (double) (v))
+#else
+static inline unsigned long long ch_cas64_host(unsigned long long *p, unsigned long long c, unsigned long long v) { unsigned long long o = *p; if (o == c) *p = v; return o; }
+#define CH_CAS64(p, c, v)   ch_cas64_host((unsigned long long *) (p), (c), (v))
+#define CH_MAX32(p, v)      do { if (*(p) < (v)) *(p) = (v); } while (0)
+#define CH_ADDF64(p, v)     (*(p) += (v))
+#endif
+
+/* flb_ra_get_value_object() as the label/value code uses it: the located msgpack token.
+ * Returns 1 and the token, 0 when the accessor finds nothing. */
+FLB_HD int l2m_lookup(const struct ch_env *e, const struct ch_rec *rc, uint32_t ra_off, struct mp_tok *t,
+                      const uint8_t **payload, int *is_raw_str, uint32_t *raw_len)
+{
+    const struct cf_ra *ra = (const struct cf_ra *) (e->blob + ra_off);
+    const uint8_t *vp = 0, *ve = 0;
+    int top, kn, i;
+    *is_raw_str = 0;
+    i = ra_find(e, rc, e->blob + ra->key_off, ra->key_len);
+    if (i < 0) return 0;
+    top = i;
+    {
+        uint32_t k = r_kind(rc->v[i]);
+        if (k == RK_STR_IN || k == RK_STR_SCR) { *is_raw_str = 1; *payload = ref_ptr(e, rc->v[i]); *raw_len = r_len(rc->v[i]); return 1; }
+        if (k == RK_TRUE || k == RK_FALSE) { t->type = MPT_BOOL; return 1; }
+        if (k == RK_INT_IN) { t->type = MPT_INT; t->u = (uint64_t) ch_atoll(ref_ptr(e, rc->v[i]), r_len(rc->v[i])); return 1; }
+        if (k == RK_HEX_IN) { t->type = MPT_UINT; t->u = ch_strtoull16(ref_ptr(e, rc->v[i]), r_len(rc->v[i])); return 1; }
+        if (k == RK_FLT_IN) {
+            union { double d; uint64_t u; } cv;
+            int okf;
+            cv.d = ch_strtod_fast(ref_ptr(e, rc->v[i]), r_len(rc->v[i]), &okf);
+            if (!okf) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
+            t->type = MPT_F64; t->u = cv.u; return 1;
+        }
+        if (k != RK_MP_IN && k != RK_MP_CONST && k != RK_MP_SCR) { t->type = MPT_NIL; CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return 1; }
+        vp = ref_ptr(e, rc->v[i]); ve = vp + r_len(rc->v[i]);
+        if (mp_token(vp, ve, t) != 0) return 0;
+        if (ra->n_sub > 0 && (t->type == MPT_MAP || t->type == MPT_ARRAY)) {
+            if (ra_walk_sub(e, ra, vp, ve, &vp, &ve, &kn) != 0) return 0;
+            if (mp_token(vp, ve, t) != 0) return 0;
+        }
+    }
+    (void) top;
+    *payload = vp + t->hdr;
+    return 1;
+}
+
+FLB_HD void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct ch_rec *rc, struct ch_scratch *w,
+                  uint32_t ridx)
+{
+    const struct l2m_table *tb = &e->l2m;
+    uint8_t *lab = (uint8_t *) w->stk;                     /* label strings: reuse the regex stack area */
+    uint32_t li, lpos = 0;
+    unsigned long long h = 1469598103934665603ull;
+    uint32_t idx, probes = 0;
+    double val = 0;
+
+    if (!tb->hash) return;
+    if (cf->grep_off && !f_grep(e, (const struct cf_grep *) (e->blob + cf->grep_off), rc, w)) return;
+
+    /* label values -> strings (log_to_metrics.c:1010-1043): STR "%s" (<= 251 bytes, stops at NUL),
+     * integers "%ld", anything else "" */
+    for (li = 0; li < cf->n_labels; li++) {
+        struct mp_tok t;
+        const uint8_t *pl = 0;
+        int raw = 0;
+        uint32_t rl = 0, n = 0, k;
+        uint8_t *dst = lab + lpos + 1;
+        if (lpos + 1 + 252 > sizeof(w->stk)) { CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return; }
+        t.type = MPT_NIL; t.len = 0; t.u = 0; t.hdr = 0;
+        if (l2m_lookup(e, rc, cf->label_ra_off[li], &t, &pl, &raw, &rl)) {
+            if (raw || t.type == MPT_STR) {
+                uint32_t sl = raw ? rl : t.len;
+                for (k = 0; k < sl && k < 251 && pl[k]; k++) dst[n++] = pl[k];
+            }
+            else if (t.type == MPT_UINT || t.type == MPT_INT) {
+                int64_t v = (int64_t) t.u;
+                uint64_t a = v < 0 ? (uint64_t) (0 - (uint64_t) v) : (uint64_t) v;
+                uint8_t tmp[24];
+                int m = 0;
+                do { tmp[m++] = (uint8_t) ('0' + a % 10); a /= 10; } while (a);
+                if (v < 0) dst[n++] = '-';
+                while (m) dst[n++] = tmp[--m];
+            }
+            else if (t.type == MPT_F32 || t.type == MPT_F64) CH_ATOMIC_OR(e->err, FLBGPU_E_L2M);   /* "%f" not on the device */
+        }
+        lab[lpos] = (uint8_t) n;
+        for (k = 0; k <= n; k++) { h ^= lab[lpos + k]; h *= 1099511628211ull; }
+        lpos += 1 + n;
+    }
+    h |= 1ull;
+
+    if (cf->mode == L2M_HISTOGRAM) {
+        struct mp_tok t;
+        const uint8_t *pl = 0;
+        int raw = 0, ok = 1;
+        uint32_t rl = 0;
+        t.type = MPT_NIL; t.len = 0; t.u = 0; t.hdr = 0;
+        if (!l2m_lookup(e, rc, cf->value_ra_off, &t, &pl, &raw, &rl)) return;    /* "value field is empty or not existent" */
+        if (raw || t.type == MPT_STR) {
+            /* sscanf("%lf"): a text that converts nothing leaves the PREVIOUS record's value in
+             * place (log_to_metrics.c:984,1105) -- order dependent, refused; so are inf/nan/hex */
+            uint32_t sl = raw ? rl : t.len, q = 0;
+            while (q < sl && dt_isspace(pl[q])) q++;
+            if (q < sl && (pl[q] == '+' || pl[q] == '-')) q++;
+            if (q < sl && pl[q] == '.') q++;
+            if (q >= sl || pl[q] < '0' || pl[q] > '9' || (pl[q] == '0' && q + 1 < sl && (pl[q + 1] | 0x20) == 'x')) {
+                CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return;
+            }
+            val = ch_strtod_fast(pl, sl, &ok);
+            if (!ok) { CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return; }
+        }
+        else if (t.type == MPT_UINT || t.type == MPT_INT) val = (double) (int64_t) t.u;
+        else if (t.type == MPT_F64) { union { uint64_t u; double d; } cv; cv.u = t.u; val = cv.d; }
+        else if (t.type == MPT_F32) { union { uint32_t u; float f; } cv; cv.u = (uint32_t) t.u; val = (double) cv.f; }
+        else return;                                                              /* "cannot convert given value to metric" */
+    }
+
+    /* find or claim the slot of this label set */
+    idx = (uint32_t) (h >> 20) & tb->mask;
+    for (;;) {
+        unsigned long long cur = CH_CAS64(&tb->hash[idx], 0ull, h);
+        if (cur == 0ull) {
+            uint8_t *d = tb->str + (size_t) idx * cf->n_labels * L2M_LABEL_BYTES;
+            uint32_t p = 0, k;
+            for (li = 0; li < cf->n_labels; li++) {
+                uint32_t n = lab[p];
+                for (k = 0; k <= n; k++) d[(size_t) li * L2M_LABEL_BYTES + k] = lab[p + k];
+                p += 1 + n;
+            }
+            break;
+        }
+        if (cur == h) break;
+        idx = (idx + 1) & tb->mask;
+        if (++probes > tb->mask) { CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return; }
+    }
+    CH_MAX32(&tb->first[idx], 0xffffffffu - ridx);
+    CH_ATOMIC_ADD(&tb->cnt[idx], 1ull);
+    if (cf->mode == L2M_HISTOGRAM) {
+        const double *ub = (const double *) (e->blob + cf->buckets_off);
+        int i;
+        for (i = (int) cf->n_buckets - 1; i >= 0; i--) {
+            if (val > ub[i]) break;
+            CH_ATOMIC_ADD(&tb->bkt[(size_t) idx * (cf->n_buckets + 1) + i], 1ull);
+        }
+        CH_ATOMIC_ADD(&tb->bkt[(size_t) idx * (cf->n_buckets + 1) + cf->n_buckets], 1ull);
+        CH_ADDF64(&tb->sum[idx], val);
+    }
+}
+
 /* ------------------------------------------------------------- the chain */
 /* Runs record `ridx` (framed at off/len, kind 0) through the chain.
  * EMIT=false: returns the output size (0 = dropped) and records evidence.
@@ -1201,6 +1355,12 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
             }
             break;
         }
+        case FLBGPU_F_LOG_TO_METRICS:
+            /* metrics are accumulated once per call, by the evaluation pass; logs pass
+             * through unless discard_logs (log_to_metrics.c:1136-1141) */
+            if (!EMIT) f_l2m(e, (const struct cf_l2m *) cfg, &rc, &w, ridx);
+            if (assumed) return 0;
+            break;
         default:
             break;
         }

@@ -252,12 +252,23 @@ FLB_HD int dj_string(const uint8_t *s, int n, int pos, uint8_t *o, uint32_t *ole
 }
 
 /* members of the container whose opening bracket is at s[pos] (pairs for objects);
- * -1 when it never closes.  Purely structural: the real parse validates. */
-FLB_HD int dj_count(const uint8_t *s, int n, int pos)
+ * -1 when it never closes.  Purely structural: the real parse validates -- a wrong count
+ * cannot survive it (the member loop expects exactly `count` values before the closing
+ * bracket).  exact=0 skips strings by looking only at backslashes, which disagrees with
+ * yyjson's lexer in its invalid-\u corner; dj_parse_record() retries with exact=1 (the
+ * real string lexer) whenever the fast attempt fails. */
+FLB_HD int dj_count(const uint8_t *s, int n, int pos, int exact)
 {
     int p = pos + 1, depth = 0, count = 0, seen = 0;
     while (p < n) {
         uint32_t c = s[p];
+        if (c == '"' && !exact) {
+            p++;
+            while (p < n && s[p] != '"') p += (s[p] == '\\') ? 2 : 1;
+            if (p >= n) return -1;
+            p++; seen = 1;
+            continue;
+        }
         if (c == '"') { uint32_t sl; p = dj_string(s, n, p, 0, &sl); if (p < 0) return -1; seen = 1; continue; }   /* the same lexer the real parse uses (\\u quirks) */
         if (c == '[' || c == '{') { depth++; seen = 1; }
         else if (c == ']' || c == '}') { if (depth == 0) return count + (seen ? 1 : 0); depth--; }
@@ -268,9 +279,30 @@ FLB_HD int dj_count(const uint8_t *s, int n, int pos)
     return -1;
 }
 
+/* string at s[pos] -> msgpack str at o+k; returns the position after it or -1.  Strings
+ * without a backslash (nearly all) are located by one scan and copied once. */
+FLB_HD int dj_emit_string(const uint8_t *s, int n, int pos, uint8_t *o, uint32_t *k)
+{
+    int p = pos + 1;
+    uint32_t sl = 0;
+    while (p < n && s[p] != '"' && s[p] != '\\') p++;
+    if (p >= n) return -1;
+    if (s[p] == '"') {
+        sl = (uint32_t) (p - pos - 1);
+        if (o) { uint32_t h = mp_put_str_hdr(o + *k, sl); mp_copy(o + *k + h, s + pos + 1, sl); }
+        *k += mp_str_hdr_size(sl) + sl;
+        return p + 1;
+    }
+    p = dj_string(s, n, pos, 0, &sl);
+    if (p < 0) return -1;
+    if (o) { uint32_t h = mp_put_str_hdr(o + *k, sl); dj_string(s, n, pos, o + *k + h, &sl); }
+    *k += mp_str_hdr_size(sl) + sl;
+    return p;
+}
+
 /* One JSON value at s[pos] -> msgpack at o (NULL = only measure and validate).
  * Returns the position after the value, or -1 on any syntax error.  *olen = msgpack bytes. */
-FLB_HDN int dj_value(const uint8_t *s, int n, int pos, uint8_t *o, uint32_t *olen, uint32_t *err)
+FLB_HDN int dj_value(const uint8_t *s, int n, int pos, uint8_t *o, uint32_t *olen, uint32_t *err, int exact)
 {
     uint32_t k = 0, rem[DJ_MAX_DEPTH + 1];
     uint8_t isobj[DJ_MAX_DEPTH + 1];
@@ -283,7 +315,7 @@ FLB_HDN int dj_value(const uint8_t *s, int n, int pos, uint8_t *o, uint32_t *ole
         if (p >= n) return -1;
         c = s[p];
         if (c == '{' || c == '[') {
-            int cnt = dj_count(s, n, p);
+            int cnt = dj_count(s, n, p, exact);
             if (cnt < 0) return -1;
             if (c == '{') { if (o) mp_put_map_hdr(o + k, (uint32_t) cnt); }
             else if (o) mp_put_array_hdr(o + k, (uint32_t) cnt);
@@ -300,12 +332,8 @@ FLB_HDN int dj_value(const uint8_t *s, int n, int pos, uint8_t *o, uint32_t *ole
             goto next_member;
         }
         if (c == '"') {
-            uint32_t sl = 0;
-            int e = dj_string(s, n, p, 0, &sl);
-            if (e < 0) return -1;
-            if (o) { uint32_t h = mp_put_str_hdr(o + k, sl); dj_string(s, n, p, o + k + h, &sl); }
-            k += mp_str_hdr_size(sl) + sl;
-            p = e;
+            p = dj_emit_string(s, n, p, o, &k);
+            if (p < 0) return -1;
             goto value_done;
         }
         if (c == '-' || (c >= '0' && c <= '9')) {
@@ -339,15 +367,10 @@ value_done:
         p++;
 next_member:
         if (isobj[sp - 1]) {
-            uint32_t sl = 0;
-            int e;
             while (p < n && dj_ws(s[p])) p++;
             if (p >= n || s[p] != '"') return -1;
-            e = dj_string(s, n, p, 0, &sl);
-            if (e < 0) return -1;
-            if (o) { uint32_t h = mp_put_str_hdr(o + k, sl); dj_string(s, n, p, o + k + h, &sl); }
-            k += mp_str_hdr_size(sl) + sl;
-            p = e;
+            p = dj_emit_string(s, n, p, o, &k);
+            if (p < 0) return -1;
             while (p < n && dj_ws(s[p])) p++;
             if (p >= n || s[p] != ':') return -1;
             p++;
@@ -364,13 +387,17 @@ FLB_HD int dj_parse_record(const uint8_t *s, int n, uint8_t *o, uint32_t *olen, 
     uint32_t dummy = 0, derr = 0;
     while (p < n && dj_ws(s[p])) p++;
     if (p >= n) return 0;
-    e = dj_value(s, n, p, o, olen, err);
+    if (s[p] != '{') {                                                 /* only objects can succeed; still must be valid to count as a record */
+        return 0;
+    }
+    e = dj_value(s, n, p, o, olen, err, 0);
+    if (e < 0) { *err = 0; e = dj_value(s, n, p, o, olen, err, 1); }
     if (e < 0) return 0;
     if (s[p] != '{') return 0;                                         /* root must be a map (src/flb_parser_json.c:70-85) */
     /* a second parsable document means records == 2 -> rejected; trailing junk is fine */
     p = e;
     while (p < n && dj_ws(s[p])) p++;
-    if (p < n && dj_value(s, n, p, 0, &dummy, &derr) >= 0) return 0;
+    if (p < n && dj_value(s, n, p, 0, &dummy, &derr, 1) >= 0) return 0;
     return 1;
 }
 

@@ -165,6 +165,34 @@ struct cf_rm_key { uint32_t off, len, dynamic, pad; };
 struct cf_rm_rec { uint32_t kmp_off, kmp_len, vmp_off, vmp_len; };
 struct cf_recmod { uint32_t n_records, records_off, n_remove, remove_off, n_allow, allow_off, pad0, pad1; };
 
+/* filter_log_to_metrics (plugins/filter_log_to_metrics/log_to_metrics.c) */
+enum { L2M_COUNTER = 0, L2M_GAUGE = 1, L2M_HISTOGRAM = 2 };
+#define L2M_MAX_LABELS 16
+#define L2M_LABEL_BYTES 256          /* MAX_LABEL_LENGTH 253 rounded up */
+#define L2M_SLOTS_LOG2 16
+struct cf_l2m {
+    uint32_t grep_off;               /* struct cf_grep (legacy semantics) for Regex / Exclude */
+    uint32_t mode;
+    uint32_t n_labels;
+    uint32_t label_ra_off[L2M_MAX_LABELS];
+    uint32_t value_ra_off;
+    uint32_t n_buckets;
+    uint32_t buckets_off;            /* double[n_buckets], ascending */
+    uint32_t discard;
+};
+
+/* per-call device table of label sets (open addressing on a 64-bit hash of the label values) */
+struct l2m_table {
+    unsigned long long *hash;        /* 0 = empty */
+    uint32_t *first;                 /* 0xffffffff - (smallest record index of the set) */
+    unsigned long long *cnt;         /* counter value / histogram count */
+    double *sum;                     /* histogram sum */
+    unsigned long long *bkt;         /* [slot][n_buckets + 1] cumulative buckets, last = +Inf */
+    uint8_t *str;                    /* [slot][n_labels][L2M_LABEL_BYTES]: length byte + bytes */
+    uint32_t mask;
+    uint32_t pad;
+};
+
 struct chain_filter { uint32_t kind, cfg_off; };
 
 #define FLBGPU_MAX_FILTERS 16
@@ -189,6 +217,7 @@ struct chain_hdr {
 #define FLBGPU_E_FLOAT     8u   /* decimal->double outside the exact fast path */
 #define FLBGPU_E_INDEX    16u   /* record index fast path failed */
 #define FLBGPU_E_ESCAPE   32u   /* logfmt quoted value with backslash escapes */
+#define FLBGPU_E_L2M      64u   /* log_to_metrics: label table full / float label / unparsable value */
 
 #ifdef __cplusplus
 }

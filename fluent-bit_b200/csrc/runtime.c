@@ -99,6 +99,24 @@ struct flbgpu_parser {
 
 struct kv { char *k, *v; struct kv *next; };
 
+/* host-side cumulative state of one filter_log_to_metrics instance: what the reference
+ * keeps in its struct cmt (lib/cmetrics): one metric per label set, first-seen order */
+struct l2m_set {
+    uint64_t hash;
+    char *labels;            /* n_labels strings, each L2M_LABEL_BYTES: length byte + bytes */
+    uint64_t count;          /* counter value / histogram _count */
+    double sum;
+    uint64_t *buckets;       /* n_buckets + 1 */
+};
+struct l2m_state {
+    int mode, n_labels, n_buckets, discard;
+    char *label_keys[L2M_MAX_LABELS];
+    double *bounds;
+    char *ns, *subsystem, *name, *desc;
+    struct l2m_set *sets;
+    int n_sets, cap_sets;
+};
+
 struct flbgpu_filter {
     flbgpu_ctx *ctx;
     int kind;
@@ -106,6 +124,7 @@ struct flbgpu_filter {
     int inited;
     int needs_scratch;       /* a JSON parser transcodes into per-record scratch */
     flbgpu_chain *solo;
+    struct l2m_state *l2m;   /* cumulative metrics of a log_to_metrics filter */
 };
 
 struct flbgpu_ctx {
@@ -123,6 +142,10 @@ struct flbgpu_chain {
     uint32_t cap_stride;
     int needs_scratch;
     uint8_t *d_scr; size_t cap_scr;
+    int l2m_index;                            /* filter index of the log_to_metrics filter, or -1 */
+    struct l2m_table l2m;                     /* device table (per-call delta) */
+    size_t l2m_slots;
+    uint64_t *h_hash, *h_cnt, *h_bkt; uint32_t *h_first; double *h_sum;    /* host mirror */
     /* device buffers, grown on demand */
     uint8_t *d_in;  size_t cap_in;
     uint8_t *d_out; size_t cap_out;
@@ -379,6 +402,7 @@ static int plugin_kind(const char *name)
     if (!strcasecmp(name, "grep")) return FLBGPU_F_GREP;
     if (!strcasecmp(name, "modify")) return FLBGPU_F_MODIFY;
     if (!strcasecmp(name, "record_modifier")) return FLBGPU_F_RECORD_MODIFIER;
+    if (!strcasecmp(name, "log_to_metrics")) return FLBGPU_F_LOG_TO_METRICS;
     return 0;
 }
 
@@ -410,11 +434,14 @@ int flbgpu_filter_set_property(flbgpu_filter *f, const char *k, const char *v)
     return 0;
 }
 
+static void l2m_state_free(struct l2m_state *st);
+
 void flbgpu_filter_destroy(flbgpu_filter *f)
 {
     struct kv *n, *nx;
     if (!f) return;
     if (f->solo) flbgpu_chain_destroy(f->solo);
+    l2m_state_free(f->l2m);
     for (n = f->props; n; n = nx) { nx = n->next; free(n->k); free(n->v); free(n); }
     free(f);
 }
@@ -815,6 +842,134 @@ static uint32_t emit_recmod_filter(flbgpu_filter *f, struct blob *b)
     return blob_add(b, &cf, sizeof(cf), 8);
 }
 
+static void l2m_state_free(struct l2m_state *st)
+{
+    int i;
+    if (!st) return;
+    for (i = 0; i < st->n_labels; i++) free(st->label_keys[i]);
+    for (i = 0; i < st->n_sets; i++) { free(st->sets[i].labels); free(st->sets[i].buckets); }
+    free(st->sets); free(st->bounds); free(st->ns); free(st->subsystem); free(st->name); free(st->desc);
+    free(st);
+}
+
+static int cmp_double(const void *a, const void *b)
+{
+    double x = *(const double *) a, y = *(const double *) b;
+    return x < y ? -1 : x > y;
+}
+
+/* cb_log_to_metrics_init(), plugins/filter_log_to_metrics/log_to_metrics.c:649-962 */
+static uint32_t emit_l2m_filter(flbgpu_filter *f, struct blob *b)
+{
+    struct cf_l2m cf;
+    struct l2m_state *st;
+    struct kv *p;
+    const char *mode = "counter", *value_field = NULL, *name = "a", *ns = "log_metric", *subsystem = NULL,
+               *desc = NULL, *tag = NULL;
+    double bounds[64];
+    static const double def_bounds[11] = { 0.005, 0.01, 0.025, 0.05, 0.1, 0.25, 0.5, 1.0, 2.5, 5.0, 10.0 };
+    int nb = 0, i;
+    flbgpu_filter g;
+
+    memset(&cf, 0, sizeof(cf));
+    st = calloc(1, sizeof(*st));
+    /* Regex / Exclude rules: same text and legacy semantics as filter_grep */
+    memset(&g, 0, sizeof(g));
+    g.ctx = f->ctx; g.kind = FLBGPU_F_GREP;
+    for (p = f->props; p; p = p->next) {
+        if (!strcasecmp(p->k, "regex") || !strcasecmp(p->k, "exclude")) {
+            struct kv *n;
+            const char *q = p->v;
+            /* log_to_metrics.c:318 creates the accessor from the field text as written (no '$' is
+             * prepended like grep.c does): identical for plain key names, which is what we accept */
+            if (*q != '$') {
+                for (; *q && *q != ' '; q++) {
+                    if (!(isalnum((unsigned char) *q) || *q == '_' || *q == '-')) {
+                        set_err("log_to_metrics rule field '%s' must be a plain key or a $accessor%s", p->v, NULL);
+                        l2m_state_free(st); return 0;
+                    }
+                }
+            }
+            n = calloc(1, sizeof(*n));
+            n->k = p->k; n->v = p->v;
+            if (g.props_tail) g.props_tail->next = n; else g.props = n;
+            g.props_tail = n;
+        }
+    }
+    if (g.props) {
+        cf.grep_off = emit_grep_filter(&g, b);
+        while (g.props) { struct kv *n = g.props->next; free(g.props); g.props = n; }
+        if (!cf.grep_off) { l2m_state_free(st); return 0; }
+    }
+    for (p = f->props; p; p = p->next) {
+        if (!strcasecmp(p->k, "regex") || !strcasecmp(p->k, "exclude")) continue;
+        else if (!strcasecmp(p->k, "metric_mode")) mode = p->v;
+        else if (!strcasecmp(p->k, "value_field")) value_field = p->v;
+        else if (!strcasecmp(p->k, "metric_name")) name = p->v;
+        else if (!strcasecmp(p->k, "metric_namespace")) ns = p->v;
+        else if (!strcasecmp(p->k, "metric_subsystem")) subsystem = p->v;
+        else if (!strcasecmp(p->k, "metric_description")) desc = p->v;
+        else if (!strcasecmp(p->k, "tag")) tag = p->v;
+        else if (!strcasecmp(p->k, "kubernetes_mode")) {
+            if (parse_bool(p->v) == 1) { set_err("kubernetes_mode is not supported on the GPU path%s%s", NULL, NULL); l2m_state_free(st); return 0; }
+        }
+        else if (!strcasecmp(p->k, "discard_logs")) { int v = parse_bool(p->v); if (v < 0) { set_err("invalid boolean '%s'%s", p->v, NULL); l2m_state_free(st); return 0; } cf.discard = v; }
+        else if (!strcasecmp(p->k, "bucket")) {
+            char *end = NULL;
+            double d = strtod(p->v, &end);
+            if (end == p->v || nb >= 64) { set_err("Setting buckets failed (%s)%s", p->v, NULL); l2m_state_free(st); return 0; }
+            bounds[nb++] = d;
+        }
+        else if (!strcasecmp(p->k, "label_field") || !strcasecmp(p->k, "add_label")) {
+            char *tok[3];
+            const char *key, *acc;
+            int nt = 0;
+            if (st->n_labels >= L2M_MAX_LABELS) { set_err("too many labels%s%s", NULL, NULL); l2m_state_free(st); return 0; }
+            if (!strcasecmp(p->k, "label_field")) { key = p->v; acc = p->v; }
+            else {
+                nt = split_plain(p->v, 1, tok, 3);
+                if (nt != 2) { free_toks(tok, nt); set_err("invalid label, expected name and key%s%s", NULL, NULL); l2m_state_free(st); return 0; }
+                key = tok[0]; acc = tok[1];
+            }
+            st->label_keys[st->n_labels] = strdup(key);
+            cf.label_ra_off[st->n_labels] = emit_ra(b, acc);
+            if (nt) free_toks(tok, nt);
+            if (!cf.label_ra_off[st->n_labels]) { st->n_labels++; l2m_state_free(st); return 0; }
+            st->n_labels++;
+        }
+        else if (!strcasecmp(p->k, "emitter_name") || !strcasecmp(p->k, "emitter_mem_buf_limit") ||
+                 !strcasecmp(p->k, "flush_interval_sec") || !strcasecmp(p->k, "flush_interval_nsec")) { /* delivery side: host concern */ }
+        else { set_err("[filter log_to_metrics] unknown configuration property '%s'%s", p->k, NULL); l2m_state_free(st); return 0; }
+    }
+    if (!tag || !*tag) { set_err("Metric tag is not set%s%s", NULL, NULL); l2m_state_free(st); return 0; }
+    if (!strcasecmp(mode, "counter")) cf.mode = L2M_COUNTER;
+    else if (!strcasecmp(mode, "histogram")) cf.mode = L2M_HISTOGRAM;
+    else if (!strcasecmp(mode, "gauge")) { set_err("metric_mode gauge is last-writer-wins (order dependent) and is not supported on the GPU path%s%s", NULL, NULL); l2m_state_free(st); return 0; }
+    else { set_err("invalid 'mode' value. Only 'counter', 'gauge' or 'histogram' types are allowed%s%s", NULL, NULL); l2m_state_free(st); return 0; }
+    if (!desc || !*desc) { set_err("metric_description is not set%s%s", NULL, NULL); l2m_state_free(st); return 0; }
+    if (cf.mode == L2M_HISTOGRAM) {
+        if (!value_field || !*value_field) { set_err("value_field is not set%s%s", NULL, NULL); l2m_state_free(st); return 0; }
+        cf.value_ra_off = emit_ra(b, value_field);
+        if (!cf.value_ra_off) { l2m_state_free(st); return 0; }
+        if (nb == 0) { memcpy(bounds, def_bounds, sizeof(def_bounds)); nb = 11; }
+        else qsort(bounds, nb, sizeof(double), cmp_double);
+        cf.n_buckets = nb;
+        cf.buckets_off = blob_add(b, bounds, sizeof(double) * nb, 8);
+        st->bounds = malloc(sizeof(double) * nb);
+        memcpy(st->bounds, bounds, sizeof(double) * nb);
+    }
+    cf.n_labels = st->n_labels;
+    st->mode = cf.mode; st->n_buckets = cf.n_buckets; st->discard = cf.discard;
+    st->ns = strdup(ns); st->name = strdup(name); st->desc = strdup(desc);
+    st->subsystem = strdup(subsystem && *subsystem ? subsystem : mode);
+    for (i = 0; i < st->n_labels; i++) (void) i;
+    if (f->l2m) {                       /* re-emission for a chain: keep accumulated values */
+        l2m_state_free(st);
+    }
+    else f->l2m = st;
+    return blob_add(b, &cf, sizeof(cf), 8);
+}
+
 static uint32_t emit_filter(flbgpu_filter *f, struct blob *b, uint32_t *cap_need)
 {
     switch (f->kind) {
@@ -822,6 +977,7 @@ static uint32_t emit_filter(flbgpu_filter *f, struct blob *b, uint32_t *cap_need
     case FLBGPU_F_GREP: return emit_grep_filter(f, b);
     case FLBGPU_F_MODIFY: return emit_modify_filter(f, b);
     case FLBGPU_F_RECORD_MODIFIER: return emit_recmod_filter(f, b);
+    case FLBGPU_F_LOG_TO_METRICS: return emit_l2m_filter(f, b);
     }
     return 0;
 }
@@ -874,6 +1030,12 @@ int flbgpu_chain_init(flbgpu_chain *c)
         cf[i].cfg_off = emit_filter(c->f[i], &c->blob, &cap);
         if (!cf[i].cfg_off) return -1;
     }
+    c->l2m_index = -1;
+    for (i = 0; i < (uint32_t) c->nf; i++) {
+        if (c->f[i]->kind != FLBGPU_F_LOG_TO_METRICS) continue;
+        if (c->l2m_index >= 0) { set_err("only one log_to_metrics filter per fused chain%s%s", NULL, NULL); return -1; }
+        c->l2m_index = (int) i;
+    }
     for (i = 0; i < (uint32_t) c->nf; i++) if (c->f[i]->needs_scratch) h.needs_scratch = 1;
     c->needs_scratch = (int) h.needs_scratch;
     h.n_filters = c->nf;
@@ -886,6 +1048,18 @@ int flbgpu_chain_init(flbgpu_chain *c)
     c->d_blob = bk_alloc(c->blob.n);
     c->d_flags = bk_alloc(sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1));
     if (!c->d_blob || !c->d_flags) return -1;
+    if (c->l2m_index >= 0) {
+        struct l2m_state *st = c->f[c->l2m_index]->l2m;
+        size_t n = (size_t) 1 << L2M_SLOTS_LOG2, nbk = (size_t) st->n_buckets + 1;
+        c->l2m_slots = n;
+        c->l2m.hash = bk_alloc(n * 8); c->l2m.first = bk_alloc(n * 4); c->l2m.cnt = bk_alloc(n * 8);
+        c->l2m.sum = bk_alloc(n * 8); c->l2m.bkt = bk_alloc(n * nbk * 8);
+        c->l2m.str = bk_alloc(n * (st->n_labels ? st->n_labels : 1) * L2M_LABEL_BYTES);
+        c->l2m.mask = (uint32_t) (n - 1);
+        c->h_hash = malloc(n * 8); c->h_first = malloc(n * 4); c->h_cnt = malloc(n * 8); c->h_sum = malloc(n * 8);
+        c->h_bkt = malloc(n * nbk * 8);
+        if (!c->l2m.hash || !c->l2m.first || !c->l2m.cnt || !c->l2m.sum || !c->l2m.bkt || !c->l2m.str) return -1;
+    }
     if (bk_h2d(c->d_blob, c->blob.p, c->blob.n) || bk_sync()) return -1;
     c->inited = 1;
     return 0;
@@ -897,6 +1071,8 @@ void flbgpu_chain_destroy(flbgpu_chain *c)
     bk_free(c->d_blob); bk_free(c->d_in); bk_free(c->d_out); bk_free(c->d_tile); bk_free(c->d_off);
     bk_free(c->d_len); bk_free(c->d_size); bk_free(c->d_kind); bk_free(c->d_bsum); bk_free(c->d_cap);
     bk_free(c->d_flags); bk_free(c->d_scr); free(c->h_bsum);
+    bk_free(c->l2m.hash); bk_free(c->l2m.first); bk_free(c->l2m.cnt); bk_free(c->l2m.sum); bk_free(c->l2m.bkt); bk_free(c->l2m.str);
+    free(c->h_hash); free(c->h_first); free(c->h_cnt); free(c->h_sum); free(c->h_bkt);
     free(c->blob.p);
     free(c);
 }
@@ -922,6 +1098,8 @@ static int verdict(int kind, uint32_t fl, int clean)
     }
     return 0;
 }
+/* log_to_metrics: MODIFIED (empty) iff discard_logs, whatever the records were */
+#define L2M_VERDICT(c, k) ((c)->f[k]->l2m->discard ? 1 : 0)
 
 /* grow the per-record arrays to hold `need` records, keeping the first `keep` */
 static int ensure_rec_cap(flbgpu_chain *c, size_t need, size_t keep)
@@ -962,6 +1140,69 @@ static void fill_args(flbgpu_chain *c, struct bk_chain_args *a, const uint8_t *d
     a->d_capcache = c->cap_stride ? c->d_cap : NULL; a->cap_stride = c->cap_stride;
     a->d_off = c->d_off; a->d_len = c->d_len; a->d_kind = c->d_kind; a->n_rec = n_rec;
     a->d_size = c->d_size; a->d_bsum = c->d_bsum; a->d_flags = c->d_flags;
+    if (c->l2m_index >= 0) a->l2m = c->l2m; else memset(&a->l2m, 0, sizeof(a->l2m));
+}
+
+/* zero the per-call metrics table (before every evaluation pass) */
+static int l2m_clear(flbgpu_chain *c)
+{
+    struct l2m_state *st;
+    size_t n = c->l2m_slots;
+    if (c->l2m_index < 0) return 0;
+    st = c->f[c->l2m_index]->l2m;
+    if (bk_zero(c->l2m.hash, n * 8) || bk_zero(c->l2m.first, n * 4) || bk_zero(c->l2m.cnt, n * 8) ||
+        bk_zero(c->l2m.sum, n * 8) || bk_zero(c->l2m.bkt, n * ((size_t) st->n_buckets + 1) * 8)) return -1;
+    return 0;
+}
+
+static int cmp_first(const void *a, const void *b, void *arg)
+{
+    const uint32_t *first = arg;
+    uint32_t x = first[*(const uint32_t *) a], y = first[*(const uint32_t *) b];
+    return x > y ? -1 : x < y;             /* stored as 0xffffffff - index: larger = seen earlier */
+}
+
+/* fold the settled per-call table into the filter's cumulative state, new label sets in
+ * first-seen (record) order -- the order cmetrics appends them (cmt_map.c:209-243) */
+static int l2m_merge(flbgpu_chain *c)
+{
+    struct l2m_state *st;
+    size_t n = c->l2m_slots, nbk, i, m = 0;
+    uint32_t *order;
+    if (c->l2m_index < 0) return 0;
+    st = c->f[c->l2m_index]->l2m;
+    nbk = (size_t) st->n_buckets + 1;
+    if (bk_d2h(c->h_hash, c->l2m.hash, n * 8) || bk_d2h(c->h_first, c->l2m.first, n * 4) || bk_d2h(c->h_cnt, c->l2m.cnt, n * 8) ||
+        bk_d2h(c->h_sum, c->l2m.sum, n * 8) || bk_d2h(c->h_bkt, c->l2m.bkt, n * nbk * 8) || bk_sync()) return -1;
+    order = malloc(sizeof(uint32_t) * n);
+    for (i = 0; i < n; i++) if (c->h_hash[i]) order[m++] = (uint32_t) i;
+    qsort_r(order, m, sizeof(uint32_t), cmp_first, c->h_first);
+    for (i = 0; i < m; i++) {
+        uint32_t slot = order[i];
+        struct l2m_set *set = NULL;
+        size_t lb = (size_t) (st->n_labels ? st->n_labels : 1) * L2M_LABEL_BYTES, k;
+        int j;
+        char *labels = NULL;
+        for (j = 0; j < st->n_sets; j++) if (st->sets[j].hash == c->h_hash[slot]) { set = &st->sets[j]; break; }
+        if (!set) {
+            labels = calloc(1, lb);
+            if (st->n_labels && (bk_d2h(labels, c->l2m.str + (size_t) slot * lb, lb) || bk_sync())) { free(labels); free(order); return -1; }
+            if (st->n_sets == st->cap_sets) {
+                st->cap_sets = st->cap_sets ? st->cap_sets * 2 : 64;
+                st->sets = realloc(st->sets, sizeof(*st->sets) * st->cap_sets);
+            }
+            set = &st->sets[st->n_sets++];
+            memset(set, 0, sizeof(*set));
+            set->hash = c->h_hash[slot];
+            set->labels = labels;
+            set->buckets = calloc(nbk, sizeof(uint64_t));
+        }
+        set->count += c->h_cnt[slot];
+        set->sum += c->h_sum[slot];
+        for (k = 0; k < nbk; k++) set->buckets[k] += c->h_bkt[slot * nbk + k];
+    }
+    free(order);
+    return 0;
 }
 
 /* One call.  Input: h_in (host, uploaded in pieces) or d_in_ext (already in HBM).
@@ -990,7 +1231,8 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     memset(&a, 0, sizeof(a));
     a.now = (int64_t) time(NULL);
     a.assume = (c->nf >= 32) ? 0xffffffffu : ((1u << c->nf) - 1u);
-    if (bk_flags_clear(c->d_flags)) return -1;
+    if (c->l2m_index >= 0 && !c->f[c->l2m_index]->l2m->discard) a.assume &= ~(1u << c->l2m_index);
+    if (bk_flags_clear(c->d_flags) || l2m_clear(c)) return -1;
 
     /* ---- index + evaluate, slice by slice, while the upload is still running ---- */
     while (off < bytes) {
@@ -1036,12 +1278,12 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         if (h_flags[FLBGPU_MAX_FILTERS]) {
             c->st.error_bits = h_flags[FLBGPU_MAX_FILTERS];
             snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
-                     "1=too many keys 2=regex stack 4=regex budget 8=float outside exact path 32=logfmt escapes)",
+                     "1=too many keys 2=regex stack 4=regex budget 8=float outside exact path 32=logfmt escapes 64=log_to_metrics value/label outside the device path)",
                      h_flags[FLBGPU_MAX_FILTERS]);
             return -1;
         }
         for (k = 0; k < c->nf; k++) {
-            int v = verdict(c->f[k]->kind, h_flags[k], cl);
+            int v = c->f[k]->kind == FLBGPU_F_LOG_TO_METRICS ? L2M_VERDICT(c, k) : verdict(c->f[k]->kind, h_flags[k], cl);
             if (v) cl = 1;                   /* a MODIFIED filter hands a well-formed chunk on */
             if (v != (int) ((a.assume >> k) & 1)) {
                 a.assume = (a.assume & ~(1u << k)) | ((uint32_t) v << k);
@@ -1050,10 +1292,11 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
             }
         }
         if (!changed) break;
-        if (bk_flags_clear(c->d_flags) || bk_chain_eval(&a, 0, n_rec)) return -1;
+        if (bk_flags_clear(c->d_flags) || l2m_clear(c) || bk_chain_eval(&a, 0, n_rec)) return -1;
         c->st.passes++;
     }
     c->st.kernel_launches = bk_launch_count();
+    if (l2m_merge(c)) return -1;
     if (a.assume == 0) return FLBGPU_FILTER_NOTOUCH;
 
     /* ---- output offsets ---- */
@@ -1127,6 +1370,86 @@ int flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes, const char 
     *out_buf = NULL; *out_size = 0;
     if (bytes == 0) return FLBGPU_FILTER_NOTOUCH;
     return chain_run(c, data, NULL, bytes, NULL, 0, out_buf, out_size);
+}
+
+
+/* ---- log_to_metrics state ------------------------------------------------------ */
+int flbgpu_l2m_info(flbgpu_filter *f, int *mode, int *n_labels, int *n_buckets, int *n_sets)
+{
+    if (!f || !f->l2m) return -1;
+    *mode = f->l2m->mode; *n_labels = f->l2m->n_labels; *n_buckets = f->l2m->n_buckets; *n_sets = f->l2m->n_sets;
+    return 0;
+}
+
+int flbgpu_l2m_get(flbgpu_filter *f, int i, uint64_t *hash, uint64_t *count, double *sum, uint64_t *buckets, char *labels)
+{
+    struct l2m_state *st = f ? f->l2m : NULL;
+    if (!st || i < 0 || i >= st->n_sets) return -1;
+    *hash = st->sets[i].hash; *count = st->sets[i].count; *sum = st->sets[i].sum;
+    if (buckets) memcpy(buckets, st->sets[i].buckets, sizeof(uint64_t) * (st->n_buckets + 1));
+    if (labels) memcpy(labels, st->sets[i].labels, (size_t) (st->n_labels ? st->n_labels : 1) * L2M_LABEL_BYTES);
+    return 0;
+}
+
+int flbgpu_l2m_reset(flbgpu_filter *f)
+{
+    struct l2m_state *st = f ? f->l2m : NULL;
+    int i;
+    if (!st) return -1;
+    for (i = 0; i < st->n_sets; i++) { free(st->sets[i].labels); free(st->sets[i].buckets); }
+    st->n_sets = 0;
+    return 0;
+}
+
+int flbgpu_l2m_put(flbgpu_filter *f, uint64_t hash, uint64_t count, double sum, const uint64_t *buckets, const char *labels)
+{
+    struct l2m_state *st = f ? f->l2m : NULL;
+    struct l2m_set *set;
+    size_t lb;
+    if (!st) return -1;
+    lb = (size_t) (st->n_labels ? st->n_labels : 1) * L2M_LABEL_BYTES;
+    if (st->n_sets == st->cap_sets) {
+        st->cap_sets = st->cap_sets ? st->cap_sets * 2 : 64;
+        st->sets = realloc(st->sets, sizeof(*st->sets) * st->cap_sets);
+    }
+    set = &st->sets[st->n_sets++];
+    set->hash = hash; set->count = count; set->sum = sum;
+    set->labels = malloc(lb); memcpy(set->labels, labels, lb);
+    set->buckets = calloc(st->n_buckets + 1, sizeof(uint64_t));
+    if (buckets) memcpy(set->buckets, buckets, sizeof(uint64_t) * (st->n_buckets + 1));
+    return 0;
+}
+
+/* Text of the metric in the format of cmt_encode_text_create() (lib/cmetrics/src/cmt_encode_text.c:
+ * 273-336, 468-600) without the leading timestamp, label sets in first-seen order; malloc()ed */
+char *flbgpu_l2m_text(flbgpu_filter *f)
+{
+    struct l2m_state *st = f ? f->l2m : NULL;
+    size_t cap = 4096, len = 0;
+    char *out;
+    int i, j, k;
+    if (!st) return NULL;
+    out = malloc(cap);
+    out[0] = 0;
+#define L2M_APPEND(...) do { for (;;) { int w_ = snprintf(out + len, cap - len, __VA_ARGS__); \
+        if ((size_t) w_ < cap - len) { len += (size_t) w_; break; } cap *= 2; out = realloc(out, cap); } } while (0)
+    for (i = 0; i < st->n_sets; i++) {
+        struct l2m_set *s = &st->sets[i];
+        L2M_APPEND("%s_%s_%s", st->ns, st->subsystem, st->name);
+        for (j = 0; j < st->n_labels; j++) {
+            const unsigned char *v = (const unsigned char *) s->labels + (size_t) j * L2M_LABEL_BYTES;
+            L2M_APPEND("%s%s=\"%.*s\"", j ? "," : "{", st->label_keys[j], (int) v[0], (const char *) v + 1);
+        }
+        if (st->n_labels) L2M_APPEND("}");
+        if (st->mode == L2M_COUNTER) L2M_APPEND(" = %.17g\n", (double) s->count);
+        else {
+            L2M_APPEND(" = { buckets = { ");
+            for (k = 0; k < st->n_buckets; k++) L2M_APPEND("%g=%llu, ", st->bounds[k], (unsigned long long) s->buckets[k]);
+            L2M_APPEND("+Inf=%llu }, sum=%g, count=%llu }\n", (unsigned long long) s->buckets[st->n_buckets], s->sum,
+                       (unsigned long long) s->count);
+        }
+    }
+    return out;
 }
 
 int flbgpu_filter_cb(flbgpu_filter *f, const void *data, size_t bytes, const char *tag, int tag_len,

@@ -78,7 +78,7 @@ void flbgpu_parser_destroy(flbgpu_parser *parser);
 
 /* ---- filters ---------------------------------------------------------- */
 /* flb_filter_new(), src/flb_filter.c:426: plugin = "parser" | "grep" | "modify" |
- * "record_modifier" (the names of the reference's filter_*_plugin structs). */
+ * "record_modifier" | "log_to_metrics" (the names of the reference's filter_*_plugin structs). */
 flbgpu_filter *flbgpu_filter_new(flbgpu_ctx *ctx, const char *plugin);
 /* flb_filter_set_property(), src/flb_filter.c:325: properties keep config order,
  * keys are case-insensitive; "match"/"alias"/"log_level" are accepted and ignored. */
@@ -121,6 +121,20 @@ struct flbgpu_stats {
     uint32_t error_bits;        /* FLBGPU_E_* (flbgpu_prog.h) when the call failed */
 };
 void flbgpu_chain_stats(flbgpu_chain *c, struct flbgpu_stats *out);
+
+/* ---- filter_log_to_metrics state ------------------------------------------------
+ * The filter ("log_to_metrics": metric_mode counter | histogram, Regex/Exclude gates, label_field /
+ * add_label, bucket, discard_logs) accumulates into a per-instance table, like ctx->cmt in
+ * plugins/filter_log_to_metrics/log_to_metrics.c:964-1148 (cmt_counter_inc / cmt_histogram_observe).
+ * Label sets keep first-seen order.  A multi-GPU deployment sums these tables with one
+ * NCCL all-reduce at flush time (bench.py / tests show the exchange with torch.distributed). */
+int   flbgpu_l2m_info(flbgpu_filter *f, int *mode, int *n_labels, int *n_buckets, int *n_sets);
+/* label set i: 64-bit key, counter value (or histogram count), histogram sum, cumulative buckets
+ * [n_buckets + 1] (last = +Inf), labels = n_labels x 256 bytes (length byte + bytes) */
+int   flbgpu_l2m_get(flbgpu_filter *f, int i, uint64_t *hash, uint64_t *count, double *sum, uint64_t *buckets, char *labels);
+int   flbgpu_l2m_reset(flbgpu_filter *f);
+int   flbgpu_l2m_put(flbgpu_filter *f, uint64_t hash, uint64_t count, double sum, const uint64_t *buckets, const char *labels);
+char *flbgpu_l2m_text(flbgpu_filter *f);       /* malloc()ed text dump, free() it */
 
 /* CUDA-event milliseconds of the three kernel groups of the most recent chain call on this
  * context: out[0] record index, out[1] evaluation pass (the regex/interpreter kernel),

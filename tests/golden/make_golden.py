@@ -141,6 +141,27 @@ def main():
     json.dump(out_chain, open(os.path.join(HERE, "chain_vectors.json"), "w"))
     print("wrote %d time, %d regex patterns, %d chain vectors" % (len(out_time), len(out_rx), len(out_chain)))
 
+    # filter_log_to_metrics: result of the chain plus the text dump of the plugin's cmetrics context
+    import ctypes as C
+    import re as _re
+    import l2m_cases
+    out_l2m = []
+    for name, parsers, filters, mk, k in l2m_cases.L2M_CASES:
+        full = mk()
+        chunk = b"".join(full[o:o + l] for o, l in util.split_records(full)[:80])
+        r = util.Ref()
+        for kw in parsers:
+            r.parser(**kw)
+        fs = [r.filter(p, props) for p, props in filters]
+        ret, out = r.chain_do(chunk)
+        r.L.flbref_l2m_cmt_text.restype = C.c_void_p
+        r.L.flbref_l2m_cmt_text.argtypes = [C.c_void_p]
+        text = _re.sub(r"^\S+Z ", "", C.string_at(r.L.flbref_l2m_cmt_text(fs[k])).decode(errors="replace"), flags=_re.M)
+        out_l2m.append({"name": name, "parsers": parsers, "filters": filters, "k": k, "in_hex": chunk.hex(), "ret": ret,
+                        "out_hex": None if out is None else out.hex(), "text": text})
+    json.dump(out_l2m, open(os.path.join(HERE, "l2m_vectors.json"), "w"))
+    print("wrote %d log_to_metrics vectors" % len(out_l2m))
+
 
 if __name__ == "__main__":
     main()

@@ -169,6 +169,7 @@ static void hs_env(const struct bk_chain_args *a, struct ch_env *e)
     e->in = a->d_in; e->in_len = a->in_len; e->blob = a->d_blob; e->scr = a->d_scr;
     e->capcache = a->d_capcache; e->cap_stride = a->cap_stride; e->now = a->now; e->assume = a->assume;
     e->fl_flags = a->d_flags; e->err = a->d_flags + FLBGPU_MAX_FILTERS;
+    e->l2m = a->l2m;
 }
 
 int bk_flags_clear(uint32_t *d_flags) { memset(d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)); return 0; }

@@ -1,0 +1,93 @@
+"""filter_log_to_metrics cases (plugins/filter_log_to_metrics/log_to_metrics.c; the reference's own
+runtime tests are tests/runtime/filter_log_to_metrics.c: counter, histogram, labels, regex gate,
+discard_logs).  Each case: (name, parsers, filters, chunk maker, index of the l2m filter)."""
+import random
+import struct
+
+import util
+
+
+def _mp(v):
+    if isinstance(v, bool):
+        return b"\xc3" if v else b"\xc2"
+    if v is None:
+        return b"\xc0"
+    if isinstance(v, int):
+        if 0 <= v < 128:
+            return bytes([v])
+        if -32 <= v < 0:
+            return struct.pack("b", v)
+        if 0 <= v < 1 << 32:
+            return b"\xce" + struct.pack(">I", v)
+        return b"\xd3" + struct.pack(">q", v)
+    if isinstance(v, float):
+        return b"\xcb" + struct.pack(">d", v)
+    if isinstance(v, bytes):
+        return util.mp_str(v)
+    if isinstance(v, dict):
+        return util.mp_map_hdr(len(v)) + b"".join(util.mp_str(k) + _mp(x) for k, x in v.items())
+    raise TypeError(v)
+
+
+def events(n, seed, extra=None):
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        rec = [
+            (b"message", rng.choice([b"ok request", b"error: disk", b"ok cached", b"warn slow", b""])),
+            (b"color", rng.choice([b"red", b"green", b"blue", b"a" * 300, b"nul\x00tail"])),
+            (b"code", rng.choice([200, 404, 500, -7, 1 << 40])),
+            (b"duration", rng.choice([0.001, 0.25, 0.5, 3, b"1.5", 12, 2.5, b"0.004", b"7"])),
+            (b"kubernetes", {b"pod_name": rng.choice([b"web-1", b"web-2"]), b"labels": {b"app": b"shop"}}),
+        ]
+        if rng.random() < 0.1:
+            rec = [kv for kv in rec if kv[0] != b"color"]                  # missing label -> ""
+        if rng.random() < 0.1:
+            rec = [kv for kv in rec if kv[0] != b"duration"]               # missing value -> no observation
+        if rng.random() < 0.05:
+            rec.append((b"code", True))                                    # unsupported type -> ""
+        if extra:
+            rec += extra(rng)
+        out.append(util.event(1700000000 + i, i % 1000, [(k, _mp(v)) for k, v in rec]))
+    return b"".join(out)
+
+
+BASE = [("metric_name", "reqs"), ("metric_description", "requests"), ("tag", "metrics")]
+
+L2M_CASES = [
+    ("counter_no_labels", [], [("log_to_metrics", BASE + [("metric_mode", "counter")])], lambda: events(500, 1), 0),
+    ("counter_labels", [], [("log_to_metrics", BASE + [("metric_mode", "counter"), ("label_field", "color"),
+                                                       ("add_label", "status $code"), ("add_label", "pod $kubernetes['pod_name']")])],
+     lambda: events(800, 2), 0),
+    ("counter_regex_gate", [], [("log_to_metrics", BASE + [("regex", "message ^ok"), ("exclude", "color blue"),
+                                                           ("label_field", "color")])], lambda: events(800, 3), 0),
+    ("counter_exclude_first", [], [("log_to_metrics", BASE + [("exclude", "message error"), ("regex", "message ^(ok|warn)"),
+                                                              ("label_field", "message")])], lambda: events(600, 4), 0),
+    ("counter_discard", [], [("log_to_metrics", BASE + [("discard_logs", "true"), ("label_field", "code")])],
+     lambda: events(300, 5), 0),
+    ("histogram_default_buckets", [], [("log_to_metrics", BASE + [("metric_mode", "histogram"), ("value_field", "duration"),
+                                                                  ("label_field", "color")])], lambda: events(900, 6), 0),
+    ("histogram_custom_buckets", [], [("log_to_metrics", BASE + [("metric_mode", "histogram"), ("value_field", "$duration"),
+                                                                 ("bucket", "5"), ("bucket", "0.3"), ("bucket", "1"),
+                                                                 ("metric_subsystem", "web"), ("metric_namespace", "shop"),
+                                                                 ("add_label", "app $kubernetes['labels']['app']")])],
+     lambda: events(900, 7), 0),
+    ("histogram_regex", [], [("log_to_metrics", BASE + [("metric_mode", "histogram"), ("value_field", "duration"),
+                                                        ("regex", "message ^ok")])], lambda: events(500, 8), 0),
+    ("after_parser_and_grep",
+     [dict(name="apache2", format="regex", regex=util.APACHE_RX, time_key="time", time_fmt="%d/%b/%Y:%H:%M:%S %z",
+           types="code:integer size:integer")],
+     [("parser", [("key_name", "log"), ("parser", "apache2"), ("reserve_data", "on")]),
+      ("grep", [("exclude", "code ^5")]),
+      ("log_to_metrics", BASE + [("label_field", "method"), ("label_field", "code")])],
+     lambda: util.chunk_from_lines(util.apache_lines(1500, seed=11)), 2),
+    ("discard_in_chain",
+     [dict(name="apache2", format="regex", regex=util.APACHE_RX, time_key="time", time_fmt="%d/%b/%Y:%H:%M:%S %z",
+           types="code:integer size:integer")],
+     [("parser", [("key_name", "log"), ("parser", "apache2")]),
+      ("log_to_metrics", BASE + [("metric_mode", "histogram"), ("value_field", "size"), ("label_field", "code"),
+                                 ("bucket", "1000"), ("bucket", "10000"), ("discard_logs", "on")])],
+     lambda: util.chunk_from_lines(util.apache_lines(1000, seed=12)), 1),
+    ("l2m_then_modify", [],
+     [("log_to_metrics", BASE + [("label_field", "color")]), ("modify", [("add", "seen yes")])], lambda: events(200, 13), 0),
+]
