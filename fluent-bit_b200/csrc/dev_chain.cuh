@@ -704,13 +704,272 @@ FLB_HD int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32_
     return 1;
 }
 
+/* ---- JSON fast path ------------------------------------------------------------------
+ * One flat token loop per lane, written so that a warp stays together: every iteration handles
+ * one token, lanes agree on the grammar state they execute (the lowest one goes first, the rest
+ * wait -- same trick as RX_ALIGN_PC), and strings are scanned eight bytes at a time.  Top-level
+ * members become field references straight into the input text (plain strings, integers) so
+ * nothing is copied in the common case; escapes, reals, null and nested containers are written to
+ * the record's scratch.  It only ever answers "valid document, here are the fields" (1) or
+ * "not an object" (0, src/flb_parser_json.c:70-85); anything unusual -- bytes >= 0x80 or < 0x20 in a
+ * string, surrogates, long numbers, trailing text, depth -- returns -1 and the exact transcoder
+ * (dj_parse_record, yyjson-identical) decides. */
+#ifdef __CUDA_ARCH__
+#define DJF_ALIGN(st) { const unsigned m_ = __activemask(); \
+        if ((unsigned) (st) != __reduce_min_sync(m_, (unsigned) (st))) continue; }
+#else
+#define DJF_ALIGN(st)
+#endif
+#define DJF_KEY   0
+#define DJF_COLON 1
+#define DJF_VAL   2
+#define DJF_AFTER 3
+#define DJF_DONE  4
+
+/* first position in [p, n) holding '"', '\\', a control byte or a byte >= 0x80; n if none.
+ * Reads whole aligned 8-byte words: the buffer behind s is padded (bk_alloc). */
+FLB_HD int djf_scan_plain(const uint8_t *s, int p, int n)
+{
+    while (p < n) {
+        const uintptr_t a = (uintptr_t) (s + p);
+        const unsigned sh = (unsigned) (a & 7) * 8;
+        uint64_t w = *(const uint64_t *) (a & ~(uintptr_t) 7), t, sp;
+        w >>= sh;
+        if (sh) w |= 0x6161616161616161ull << (64 - sh);
+        t = w ^ 0x2222222222222222ull; sp = (t - 0x0101010101010101ull) & ~t;
+        t = w ^ 0x5c5c5c5c5c5c5c5cull; sp |= (t - 0x0101010101010101ull) & ~t;
+        sp |= (w - 0x2020202020202020ull) & ~w;
+        sp |= w;
+        sp &= 0x8080808080808080ull;
+        if (sp) {
+#ifdef __CUDA_ARCH__
+            p += (__ffsll((long long) sp) - 1) >> 3;
+#else
+            p += __builtin_ctzll(sp) >> 3;
+#endif
+            return p < n ? p : n;
+        }
+        p += 8 - (int) (sh >> 3);
+    }
+    return n;
+}
+
+/* string whose opening quote is at s[p].  Plain: *raw = 1, [*b, *b + *len) are input offsets.
+ * With escapes: decoded to scr + at, *raw = 0, *len decoded bytes.  Returns the position after the
+ * closing quote or -1. */
+FLB_HD int djf_string(const uint8_t *s, int p, int n, uint8_t *scr, uint32_t at, int *raw, uint32_t *b, uint32_t *len)
+{
+    int q = djf_scan_plain(s, p + 1, n);
+    uint32_t k = 0;
+    if (q >= n) return -1;
+    if (s[q] == '"') { *raw = 1; *b = (uint32_t) (p + 1); *len = (uint32_t) (q - p - 1); return q + 1; }
+    if (s[q] != '\\') return -1;
+    *raw = 0;
+    {
+        int i;
+        for (i = p + 1; i < q; i++) scr[at + k++] = s[i];
+    }
+    for (;;) {
+        uint32_t c;
+        if (q >= n) return -1;
+        c = s[q];
+        if (c == '"') break;
+        if (c < 0x20 || c >= 0x80) return -1;
+        if (c != '\\') { scr[at + k++] = (uint8_t) c; q++; continue; }
+        if (q + 1 >= n) return -1;
+        c = s[q + 1];
+        q += 2;
+        switch (c) {
+        case '"': case '\\': case '/': break;
+        case 'b': c = 8; break;
+        case 'f': c = 12; break;
+        case 'n': c = 10; break;
+        case 'r': c = 13; break;
+        case 't': c = 9; break;
+        case 'u': {
+            int h0, h1, h2, h3;
+            if (q + 4 > n) return -1;
+            h0 = dj_hex(s[q]); h1 = dj_hex(s[q + 1]); h2 = dj_hex(s[q + 2]); h3 = dj_hex(s[q + 3]);
+            if ((h0 | h1 | h2 | h3) < 0) return -1;
+            c = (uint32_t) ((h0 << 12) | (h1 << 8) | (h2 << 4) | h3);
+            if (c == 0 || (c >= 0xd800 && c <= 0xdfff)) return -1;
+            q += 4;
+            if (c >= 0x800) { scr[at + k++] = (uint8_t) (0xe0 | (c >> 12)); scr[at + k++] = (uint8_t) (0x80 | ((c >> 6) & 63)); c = 0x80 | (c & 63); }
+            else if (c >= 0x80) { scr[at + k++] = (uint8_t) (0xc0 | (c >> 6)); c = 0x80 | (c & 63); }
+            break;
+        }
+        default: return -1;
+        }
+        scr[at + k++] = (uint8_t) c;
+    }
+    *len = k;
+    return q + 1;
+}
+
+FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t val_off, ref_t *ok_, ref_t *ov_, int *on)
+{
+    uint8_t *scr = e->scr;
+    uint32_t hpos[DJ_MAX_DEPTH + 1], ccnt[DJ_MAX_DEPTH + 1];
+    uint32_t k = 0, isobj = 2, top_start = 0;
+    int p = 0, st = DJF_KEY, depth = 1, cnt = 0, first = 1;
+    ref_t keyref = 0, valref = 0;
+
+    if (!scr) return -1;
+    while (p < n && dj_ws(s[p])) p++;
+    if (p >= n || s[p] != '{') return 0;
+    p++;
+    for (;;) {
+        uint32_t c;
+        int done = 0;                      /* 1: a value just completed, 2: a container closes */
+        DJF_ALIGN(st)
+        if (st == DJF_DONE) break;
+        while (p < n && dj_ws(s[p])) p++;
+        if (p >= n) return -1;
+        c = s[p];
+        if (st == DJF_COLON) {
+            if (c != ':') return -1;
+            p++; st = DJF_VAL;
+            continue;
+        }
+        if (st == DJF_AFTER) {
+            if (c == ',') { p++; first = 0; st = ((isobj >> depth) & 1) ? DJF_KEY : DJF_VAL; continue; }
+            if (c != (((isobj >> depth) & 1) ? '}' : ']')) return -1;
+            done = 2;
+        }
+        else if (st == DJF_KEY) {
+            if (c == '}' && first) done = 2;
+            else {
+                int raw; uint32_t b, len;
+                if (c != '"') return -1;
+                p = djf_string(s, p, n, scr, depth == 1 ? k : k + 5, &raw, &b, &len);
+                if (p < 0) return -1;
+                if (depth == 1) {
+                    if (raw) keyref = mkref(RK_STR_IN, val_off + b, len);
+                    else { keyref = mkref(RK_STR_SCR, k, len); k += len; }
+                }
+                else {
+                    uint32_t h = mp_put_str_hdr(scr + k, len), i;
+                    if (raw) for (i = 0; i < len; i++) scr[k + h + i] = s[b + i];
+                    else for (i = 0; i < len; i++) scr[k + h + i] = scr[k + 5 + i];
+                    k += h + len;
+                }
+                st = DJF_COLON;
+                continue;
+            }
+        }
+        else {                             /* DJF_VAL */
+            if (c == '"') {
+                int raw; uint32_t b, len;
+                p = djf_string(s, p, n, scr, depth == 1 ? k : k + 5, &raw, &b, &len);
+                if (p < 0) return -1;
+                if (depth == 1) {
+                    if (raw) valref = mkref(RK_STR_IN, val_off + b, len);
+                    else { valref = mkref(RK_STR_SCR, k, len); k += len; }
+                }
+                else {
+                    uint32_t h = mp_put_str_hdr(scr + k, len), i;
+                    if (raw) for (i = 0; i < len; i++) scr[k + h + i] = s[b + i];
+                    else for (i = 0; i < len; i++) scr[k + h + i] = scr[k + 5 + i];
+                    k += h + len;
+                }
+                done = 1;
+            }
+            else if (c == '{' || c == '[') {
+                if (depth >= DJ_MAX_DEPTH) return -1;
+                if (depth == 1) top_start = k;
+                depth++;
+                hpos[depth] = k; ccnt[depth] = 0;
+                scr[k++] = 0;
+                if (c == '{') { isobj |= 1u << depth; st = DJF_KEY; } else { isobj &= ~(1u << depth); st = DJF_VAL; }
+                first = 1;
+                p++;
+                continue;
+            }
+            else if (c == ']' && first && !((isobj >> depth) & 1)) done = 2;
+            else if (c == '-' || (c >= '0' && c <= '9')) {
+                int q = p, nd = 0, neg = 0, plain = 1;
+                uint64_t v = 0;
+                if (c == '-') { neg = 1; q++; }
+                if (q >= n || s[q] < '0' || s[q] > '9') return -1;
+                if (s[q] == '0') { q++; if (q < n && s[q] >= '0' && s[q] <= '9') return -1; }
+                else while (q < n && s[q] >= '0' && s[q] <= '9') { v = v * 10 + (s[q] - '0'); q++; if (++nd > 18) { plain = 0; break; } }
+                if (plain && q < n && (s[q] == '.' || s[q] == 'e' || s[q] == 'E')) plain = 0;
+                if (plain) {
+                    if (depth == 1) valref = mkref(RK_INT_IN, val_off + (uint32_t) p, (uint32_t) (q - p));
+                    else { int64_t iv = neg ? -(int64_t) v : (int64_t) v; mp_put_int(scr + k, iv); k += mp_int_size(iv); }
+                    p = q;
+                }
+                else {
+                    int kind = 0;
+                    uint64_t u = 0;
+                    uint32_t jerr = 0, sz;
+                    q = dj_number(s, n, p, &kind, &u, &jerr);
+                    if (q < 0) return -1;
+                    if (jerr) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
+                    if (kind == 0) { mp_put_uint(scr + k, u); sz = mp_uint_size(u); }
+                    else if (kind == 1) { mp_put_int(scr + k, (int64_t) u); sz = mp_int_size((int64_t) u); }
+                    else { scr[k] = 0xcb; mp_put_be64(scr + k + 1, u); sz = 9; }
+                    if (depth == 1) valref = mkref(RK_MP_SCR, k, sz);
+                    k += sz;
+                    p = q;
+                }
+                done = 1;
+            }
+            else if (c == 't' && p + 4 <= n && s[p + 1] == 'r' && s[p + 2] == 'u' && s[p + 3] == 'e') {
+                if (depth == 1) valref = mkref(RK_TRUE, 0, 0); else scr[k++] = 0xc3;
+                p += 4; done = 1;
+            }
+            else if (c == 'f' && p + 5 <= n && s[p + 1] == 'a' && s[p + 2] == 'l' && s[p + 3] == 's' && s[p + 4] == 'e') {
+                if (depth == 1) valref = mkref(RK_FALSE, 0, 0); else scr[k++] = 0xc2;
+                p += 5; done = 1;
+            }
+            else if (c == 'n' && p + 4 <= n && s[p + 1] == 'u' && s[p + 2] == 'l' && s[p + 3] == 'l') {
+                if (depth == 1) valref = mkref(RK_MP_SCR, k, 1);
+                scr[k++] = 0xc0;
+                p += 4; done = 1;
+            }
+            else return -1;
+        }
+
+        if (done == 2) {                   /* the container at `depth` closes at s[p] */
+            p++;
+            if (depth == 1) { st = DJF_DONE; continue; }
+            {
+                uint32_t cn = ccnt[depth], hp = hpos[depth], ob = (isobj >> depth) & 1;
+                if (cn < 16) scr[hp] = (uint8_t) ((ob ? 0x80 : 0x90) | cn);
+                else {
+                    uint32_t extra = cn < 65536 ? 2 : 4, i;
+                    for (i = k - 1; i > hp; i--) scr[i + extra] = scr[i];
+                    if (extra == 2) { scr[hp] = ob ? 0xde : 0xdc; mp_put_be16(scr + hp + 1, cn); }
+                    else { scr[hp] = ob ? 0xdf : 0xdd; mp_put_be32(scr + hp + 1, cn); }
+                    k += extra;
+                }
+            }
+            depth--;
+            if (depth == 1) valref = mkref(RK_MP_SCR, top_start, k - top_start);
+        }
+        /* a value completed inside the container at `depth` */
+        if (depth == 1) {
+            if (cnt >= CH_MAXF) return -1;
+            ok_[cnt] = keyref; ov_[cnt] = valref; cnt++;
+        }
+        else ccnt[depth]++;
+        first = 0;
+        st = DJF_AFTER;
+    }
+    while (p < n && dj_ws(s[p])) p++;
+    if (p < n) return -1;                  /* trailing text: a second document would reject the line */
+    *on = cnt;
+    return 1;
+}
+
 /* flb_parser_json_do(), src/flb_parser_json.c:29-247.  The document is transcoded into
  * this record's scratch region by the evaluation pass (msgpack, canonical); both passes
  * then read the top-level map back as the field list.  Time key: first member whose key
  * equals Time_Key; its value must be a STR; a failed lookup keeps the member and leaves
  * the timestamp at 0 (:198-209). */
 template <bool EMIT>
-FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, const uint8_t *s, uint32_t n,
+FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
                      ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec, uint32_t ridx,
                      uint32_t *cache_pos)
 {
@@ -725,6 +984,14 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, const uin
     if (!e->scr) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
     if (e->capcache && *cache_pos + 2 <= e->cap_stride) slot = e->capcache + (size_t) ridx * e->cap_stride + *cache_pos;
     *cache_pos += 2;
+    /* slot[0]: 0/1 = result of the exact transcoder (msgpack of slot[1] bytes in scratch),
+     * 2 = the fast path produced the fields (it is re-run by the emission pass, nothing cached) */
+    if (!(EMIT && slot && slot[0] != 2)) {
+        ok = djf_record(e, s, (int) n, val_off, ok_, ov_, &cnt);
+        if (ok == 0) { if (!EMIT && slot) { slot[0] = 0; slot[1] = 0; } return 0; }
+        if (ok == 1) { if (!EMIT && slot) { slot[0] = 2; slot[1] = 0; } goto have_fields; }
+    }
+    cnt = 0;
     if (EMIT && slot) { ok = slot[0]; mplen = (uint32_t) slot[1]; }
     else {
         uint32_t jerr = 0;
@@ -746,6 +1013,7 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, const uin
         q = nx;
         cnt++;
     }
+have_fields:
     if (pd->has_time) {
         for (i = 0; i < (uint32_t) cnt; i++) {
             const uint8_t *kp; uint32_t kn;
@@ -806,6 +1074,12 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
             vt = ref_view(e, rc->v[i], &vp, &vn);
             if (vt != 1 && vt != 2) continue;
         }
+        if (vp < e->in || vp >= e->in + e->in_len) {
+            /* the value was produced by an earlier filter (scratch / constant pool): parsed fields
+             * could not reference it by input offset -- refused loudly rather than mis-parsed */
+            CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS);
+            break;
+        }
         val_off = (uint32_t) (vp - e->in);
         parse_ok = 0;
         for (pi = 0; pi < (int) cf->n_parsers; pi++) {
@@ -834,7 +1108,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                 if (got) { preset = pd->n_groups; style = ST_PRESET; }
             }
             else if (pd->type == FLBGPU_PARSER_JSON) {
-                got = pdef_json<EMIT>(e, pd, vp, vn, w->tk, w->tv, &cnt, &ts, &tns, ridx, cache_pos);
+                got = pdef_json<EMIT>(e, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns, ridx, cache_pos);
                 if (got) style = ST_CANON;
             }
             else if (pd->type == FLBGPU_PARSER_LTSV) {

@@ -321,7 +321,8 @@ int bk_init(int device)
     return 0;
 }
 
-void *bk_alloc(size_t n) { void *p = 0; if (cudaMalloc(&p, n ? n : 16) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaMalloc(%zu) failed", n); return 0; } return p; }
+/* 64 bytes of slack: djf_scan_plain reads whole aligned 8-byte words */
+void *bk_alloc(size_t n) { void *p = 0; if (cudaMalloc(&p, n + 64) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaMalloc(%zu) failed", n); return 0; } return p; }
 void bk_free(void *p) { if (p) cudaFree(p); }
 void *bk_alloc_host(size_t n) { void *p = 0; if (cudaMallocHost(&p, n ? n : 16) != cudaSuccess) return 0; return p; }
 void bk_free_host(void *p) { if (p) cudaFreeHost(p); }
