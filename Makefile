@@ -21,9 +21,12 @@ tests/hostsim/libhostsim.so: tests/hostsim/hostsim.cpp $(CSRC)/runtime.c $(CSRC)
 	gcc $(CFLAGS) -c $(CSRC)/rx_compile.c -o tests/hostsim/rx_compile.o
 	g++ $(CFLAGS) -shared -o $@ tests/hostsim/hostsim.cpp tests/hostsim/runtime.o tests/hostsim/rx_compile.o
 
-oracle:
+ORC_SRC = oracle/flb_oracle.c oracle/orc_parsers.c oracle/orc_regex.c oracle/orc_time.c oracle/orc_msgpack.c
+oracle: oracle/liboracle.so
 	@if [ -d /root/reference ]; then $(MAKE) -s -C oracle/refshim; else echo "oracle/_ref: reference tree absent, using prebuilt"; fi
+oracle/liboracle.so: $(ORC_SRC) oracle/orc.h oracle/orc_flb.h
+	gcc $(CFLAGS) -shared -o $@ $(ORC_SRC) -lm
 
 clean:
-	rm -f $(PKG)/libflbgpu.so $(CSRC)/*.o tests/hostsim/*.so tests/hostsim/*.o
+	rm -f $(PKG)/libflbgpu.so $(CSRC)/*.o tests/hostsim/*.so tests/hostsim/*.o oracle/liboracle.so
 .PHONY: all product hostsim oracle clean

@@ -714,6 +714,17 @@ FLB_HD int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32_
  * "not an object" (0, src/flb_parser_json.c:70-85); anything unusual -- bytes >= 0x80 or < 0x20 in a
  * string, surrogates, long numbers, trailing text, depth -- returns -1 and the exact transcoder
  * (dj_parse_record, yyjson-identical) decides. */
+/* Reconvergence points.  Lanes of a warp leave data-dependent loops at different times and the
+ * hardware does not bring them back together by itself; CH_SYNC() is placed where every lane that
+ * is still running a record is guaranteed to pass (uniform, configuration-driven loop heads), so
+ * the next filter / rule / regex starts with the warp together again.  Lanes whose record was
+ * dropped have returned to the kernel and exited, which __syncwarp() tolerates. */
+#ifdef __CUDA_ARCH__
+#define CH_SYNC() __syncwarp()
+#else
+#define CH_SYNC()
+#endif
+
 #ifdef __CUDA_ARCH__
 #define DJF_ALIGN(st) { const unsigned m_ = __activemask(); \
         if ((unsigned) (st) != __reduce_min_sync(m_, (unsigned) (st))) continue; }
@@ -1160,18 +1171,28 @@ FLB_HD int f_grep(const struct ch_env *e, const struct cf_grep *cf, const struct
     uint32_t i;
     int found = 0;
     if (cf->op == GREP_OP_LEGACY) {
+        int verdict = -1;                 /* decided lanes idle through the remaining rules (CH_SYNC) */
         for (i = 0; i < cf->n_rules; i++) {
-            int m = ra_regex_match(e, rc, r[i].ra_off, r[i].rx_off, w->caps, w->stk);
-            if (!m) { if (r[i].type == GREP_REGEX) return 0; }
-            else return r[i].type == GREP_EXCLUDE ? 0 : 1;
+            CH_SYNC();
+            if (verdict < 0) {
+                int m = ra_regex_match(e, rc, r[i].ra_off, r[i].rx_off, w->caps, w->stk);
+                if (!m) { if (r[i].type == GREP_REGEX) verdict = 0; }
+                else verdict = r[i].type == GREP_EXCLUDE ? 0 : 1;
+            }
         }
-        return 1;
+        return verdict < 0 ? 1 : verdict;
     }
     if (cf->n_rules == 0) return 1;
-    for (i = 0; i < cf->n_rules; i++) {
-        found = ra_regex_match(e, rc, r[i].ra_off, r[i].rx_off, w->caps, w->stk);
-        if (cf->op == GREP_OP_OR && found) break;
-        if (cf->op == GREP_OP_AND && !found) break;
+    {
+        uint32_t stop = cf->n_rules;
+        for (i = 0; i < cf->n_rules; i++) {
+            CH_SYNC();
+            if (stop == cf->n_rules) {
+                found = ra_regex_match(e, rc, r[i].ra_off, r[i].rx_off, w->caps, w->stk);
+                if ((cf->op == GREP_OP_OR && found) || (cf->op == GREP_OP_AND && !found)) stop = i;
+            }
+        }
+        i = stop;
     }
     if (i == cf->n_rules) i = cf->n_rules - 1;
     if (r[i].type == GREP_REGEX) return found ? 1 : 0;
@@ -1215,6 +1236,7 @@ FLB_HD int mod_conditions(const struct ch_env *e, const struct cf_modify *cf, co
     uint32_t ci;
     int ok = 1, i;
     for (ci = 0; ci < cf->n_conds; ci++) {
+        CH_SYNC();
         const struct cf_ra *ra = c[ci].ra_off ? (const struct cf_ra *) (e->blob + c[ci].ra_off) : 0;
         const uint8_t *vp = 0, *ve = 0, *sp = 0;
         uint32_t sn = 0;
@@ -1354,8 +1376,11 @@ FLB_HD int f_modify(const struct ch_env *e, const struct cf_modify *cf, struct c
     const struct cf_mod_rule *r = (const struct cf_mod_rule *) (e->blob + cf->rules_off);
     uint32_t i;
     int mod = 0;
-    if (!mod_conditions(e, cf, rc, w)) return 0;
-    for (i = 0; i < cf->n_rules; i++) if (mod_rule(e, &r[i], rc, w)) mod = 1;
+    const int cond = mod_conditions(e, cf, rc, w);
+    for (i = 0; i < cf->n_rules; i++) {
+        CH_SYNC();
+        if (cond && mod_rule(e, &r[i], rc, w)) mod = 1;
+    }
     if (mod) { rc->reenc = 1; rc->style = ST_CANON; }
     return mod;
 }
@@ -1589,6 +1614,7 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
     for (k = 0; k < h->n_filters; k++) {
         const uint8_t *cfg = e->blob + f[k].cfg_off;
         int assumed = (e->assume >> k) & 1;
+        CH_SYNC();
         switch (f[k].kind) {
         case FLBGPU_F_PARSER:
             if (!assumed) break;

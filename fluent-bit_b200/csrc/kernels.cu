@@ -285,7 +285,17 @@ __global__ void __launch_bounds__(BK_REC_BLOCK) k_chain_emit(const k_chain_param
     const uint32_t i = blk * BK_REC_BLOCK + threadIdx.x;
     uint32_t sz = (i < p.n_rec) ? p.size[i] : 0, tot;
     const uint32_t local = block_excl_scan(sz, &tot);
-    if (sz) chain_record<true>(&p.env, i, p.off[i], p.len[i], p.out + p.bsum[blk] + local);
+    /* survivors are packed to the front of the block so that, after a selective grep, the warps
+     * that still have work are full instead of every warp dragging a few live lanes */
+    __shared__ uint32_t s_idx[BK_REC_BLOCK], s_loc[BK_REC_BLOCK];
+    uint32_t nsurv;
+    const uint32_t rank = block_excl_scan(sz ? 1u : 0u, &nsurv);
+    if (sz) { s_idx[rank] = i; s_loc[rank] = local; }
+    __syncthreads();
+    if (threadIdx.x < nsurv) {
+        const uint32_t r = s_idx[threadIdx.x];
+        chain_record<true>(&p.env, r, p.off[r], p.len[r], p.out + p.bsum[blk] + s_loc[threadIdx.x]);
+    }
 }
 
 /* ------------------------------------------------------------ bk_* seam */

@@ -11,7 +11,7 @@
  * load liboracle.so.  The product never does and has no CPU fallback.
  *
  * Parity of this restatement is PINNED: tests/test_oracle.py checks it against the committed golden
- * vectors (tests/golden/*.json, produced by the unmodified reference build oracle/_ref) and, when
+ * vectors (tests/golden/ JSON files, produced by the unmodified reference build oracle/_ref) and, when
  * oracle/_ref is present, live against the reference on the same seeded inputs.
  */
 #ifndef ORC_H

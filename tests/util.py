@@ -231,7 +231,8 @@ _WORDS = ["request", "completed", "failed", "timeout", "connection", "user", "ca
 
 
 def json_lines(n, seed=0xF1B1 + 2):
-    """6-12 keys, str/int/float/bool/null, 3 % nested map, 2 % escapes, ~150 B."""
+    """6-12 keys in the emitting application's field order, str/int/float/bool/null,
+    3 % nested map, 2 % escapes, ~150 B."""
     rng = random.Random(seed)
     out = []
     for i in range(n):
@@ -254,7 +255,7 @@ def json_lines(n, seed=0xF1B1 + 2):
             items.append('"kubernetes":{"pod":"p-%d","labels":{"app":"%s"},"ports":[80,%d]}' % (i % 977, rng.choice(_WORDS), rng.randint(1000, 9999)))
         if rng.random() < 0.2:
             items.append('"neg":-%d' % rng.randint(1, 10 ** 6))
-        rng.shuffle(items)
+        # one application writes its fields in one order; which optional fields are present varies
         if rng.random() < 0.005:
             out.append(("not json at all %d" % i).encode())
         else:
@@ -281,3 +282,94 @@ def logfmt_lines(n, seed=78):
                        " ".join(rng.choice(_WORDS) for _ in range(rng.randint(1, 5))), rng.random() * 10, i,
                        rng.choice(["", 'empty=""', "k=v"]))).encode())
     return out
+
+
+ORACLE_SO = os.path.join(ROOT, "oracle", "liboracle.so")
+
+
+class Oracle:
+    """The plain-C restatement under oracle/ (liboracle.so): same driving interface as Ref."""
+
+    def __init__(self, now=None):
+        L = C.CDLL(ORACLE_SO)
+        vp, cp, sz = C.c_void_p, C.c_char_p, C.c_size_t
+        ll = C.POINTER(C.c_longlong)
+        L.orc_config_create.restype = vp
+        L.orc_parser_create.restype = vp
+        L.orc_parser_create.argtypes = [vp, cp, cp, cp, C.c_int, cp, cp, cp, C.c_int, C.c_int, C.c_int, cp]
+        L.orc_parser_do_line.argtypes = [vp, cp, sz, C.POINTER(vp), C.POINTER(sz), ll, ll]
+        L.orc_time_lookup_str.argtypes = [vp, cp, sz, ll, ll]
+        L.orc_filter_create.restype = vp; L.orc_filter_create.argtypes = [vp, cp]
+        L.orc_filter_set.argtypes = [vp, cp, cp]
+        L.orc_filter_init.argtypes = [vp, vp]
+        L.orc_filter_cb.argtypes = [vp, vp, sz, C.POINTER(vp), C.POINTER(sz)]
+        L.orc_chain_do.argtypes = [vp, vp, sz, C.POINTER(vp), C.POINTER(sz)]
+        L.orc_l2m_text.restype = vp; L.orc_l2m_text.argtypes = [vp]
+        L.orc_free.argtypes = [vp]
+        L.orc_set_now.argtypes = [C.c_long]
+        L.orc_regex_create.restype = vp; L.orc_regex_create.argtypes = [cp, cp, sz]
+        L.orc_regex_search.argtypes = [vp, cp, sz, C.POINTER(C.c_int), C.c_int]
+        L.orc_regex_ngroups.argtypes = [vp]
+        L.orc_regex_nnames.argtypes = [vp]
+        L.orc_regex_name.restype = cp; L.orc_regex_name.argtypes = [vp, C.c_int, C.POINTER(C.c_int)]
+        self.L = L
+        self.cfg = L.orc_config_create()
+        L.orc_set_now(now or 0)
+
+    _b = staticmethod(Ref._b)
+
+    def parser(self, name, format, regex=None, skip_empty=True, time_fmt=None, time_key=None, time_offset=None,
+               time_keep=False, time_strict=True, logfmt_no_bare_keys=False, types=None):
+        b = self._b
+        p = self.L.orc_parser_create(self.cfg, b(name), b(format), b(regex), int(skip_empty), b(time_fmt), b(time_key),
+                                     b(time_offset), int(time_keep), int(time_strict), int(logfmt_no_bare_keys), b(types))
+        if not p:
+            raise RuntimeError("oracle rejected parser " + name)
+        return p
+
+    def parser_do(self, p, line):
+        out, n = C.c_void_p(), C.c_size_t()
+        s, ns = C.c_longlong(), C.c_longlong()
+        r = self.L.orc_parser_do_line(p, line, len(line), C.byref(out), C.byref(n), C.byref(s), C.byref(ns))
+        data = C.string_at(out.value, n.value) if (r >= 0 and out.value) else None
+        if out.value:
+            self.L.orc_free(out)
+        return r, data, (s.value, ns.value)
+
+    def filter(self, plugin, props):
+        f = self.L.orc_filter_create(self.cfg, self._b(plugin))
+        for k, v in props:
+            self.L.orc_filter_set(f, self._b(k), self._b(v))
+        if not f or self.L.orc_filter_init(self.cfg, f) != 0:
+            raise RuntimeError("oracle filter init failed: %s %r" % (plugin, props))
+        return f
+
+    def chain_do(self, data, tag="test"):
+        out, n = C.c_void_p(), C.c_size_t()
+        buf = C.create_string_buffer(data, len(data))
+        r = self.L.orc_chain_do(self.cfg, C.cast(buf, C.c_void_p), len(data), C.byref(out), C.byref(n))
+        if r != 1:
+            return 2, None
+        res = C.string_at(out.value, n.value) if n.value else b""
+        if out.value:
+            self.L.orc_free(out)
+        return 1, res
+
+    def l2m_text(self, f):
+        p = self.L.orc_l2m_text(f)
+        t = C.string_at(p).decode(errors="replace")
+        self.L.orc_free(C.c_void_p(p))
+        return t
+
+    def regex_search(self, pattern, subject):
+        """None = no match, else [(beg, end)] per group (as flbref_regex_search reports them)."""
+        err = C.create_string_buffer(128)
+        re = self.L.orc_regex_create(self._b(pattern), err, 128)
+        if not re:
+            raise RuntimeError("oracle rejects pattern: %s" % err.value.decode())
+        ng = self.L.orc_regex_ngroups(re)
+        reg = (C.c_int * (2 * ng))()
+        r = self.L.orc_regex_search(re, subject, len(subject), reg, ng)
+        if r != 1:
+            return None
+        return [(reg[2 * i], reg[2 * i + 1]) for i in range(ng)]
