@@ -904,8 +904,29 @@ FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t 
                 if (q >= n || s[q] < '0' || s[q] > '9') return -1;
                 if (s[q] == '0') { q++; if (q < n && s[q] >= '0' && s[q] <= '9') return -1; }
                 else while (q < n && s[q] >= '0' && s[q] <= '9') { v = v * 10 + (s[q] - '0'); q++; if (++nd > 18) { plain = 0; break; } }
-                if (plain && q < n && (s[q] == '.' || s[q] == 'e' || s[q] == 'E')) plain = 0;
-                if (plain) {
+                if (plain && q < n && s[q] == '.') {
+                    /* short decimal without exponent: mantissa / 10^k with both exact in binary64
+                     * (<= 15 digits) is correctly rounded -- Clinger's fast path, same result as
+                     * dj_number / yyjson */
+                    int r = q + 1, fd = 0;
+                    uint64_t m = v;
+                    while (r < n && s[r] >= '0' && s[r] <= '9' && nd + fd < 15) { m = m * 10 + (s[r] - '0'); r++; fd++; }
+                    if (fd > 0 && !(r < n && ((s[r] >= '0' && s[r] <= '9') || s[r] == 'e' || s[r] == 'E'))) {
+                        union { double d; uint64_t u; } cv;
+                        cv.d = (double) m / dj_p10[fd];
+                        if (neg) cv.u |= (uint64_t) 1 << 63;
+                        scr[k] = 0xcb; mp_put_be64(scr + k + 1, cv.u);
+                        if (depth == 1) valref = mkref(RK_MP_SCR, k, 9);
+                        k += 9;
+                        p = r;
+                        done = 1;
+                        plain = 2;
+                    }
+                    else plain = 0;
+                }
+                else if (plain && q < n && (s[q] == 'e' || s[q] == 'E')) plain = 0;
+                if (plain == 2) { }
+                else if (plain) {
                     if (depth == 1) valref = mkref(RK_INT_IN, val_off + (uint32_t) p, (uint32_t) (q - p));
                     else { int64_t iv = neg ? -(int64_t) v : (int64_t) v; mp_put_int(scr + k, iv); k += mp_int_size(iv); }
                     p = q;

@@ -112,13 +112,16 @@ FLB_HD int dj_eisel_lemire(uint64_t w, int64_t q, uint64_t *bits)
 
 /* Parse the JSON number at s[pos].  Returns the position after it or -1.
  * kind: 0 uint (u), 1 sint (value in u as two's complement), 2 real (bits in u). */
+/* exact powers of ten (Clinger fast path) */
+DJ_TABLE_QUAL double dj_p10[23] = { 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
+                                    1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22 };
+
 FLB_HD int dj_number(const uint8_t *s, int n, int pos, int *kind, uint64_t *u, uint32_t *err)
 {
     int neg = 0, p = pos, nd = 0, dropped = 0, is_real = 0, int_overflow = 0, truncated = 0;
     uint64_t w = 0, iw = 0;
     int64_t exp10 = 0;
-    const double p10[23] = { 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
-                             1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22 };
+    const double *p10 = dj_p10;
     if (p < n && s[p] == '-') { neg = 1; p++; }
     if (p >= n || s[p] < '0' || s[p] > '9') return -1;
     if (s[p] == '0') {
