@@ -245,11 +245,13 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_s = float(t.item())
     e2e = world * n_lines * e2e_steps / e2e_s
+    phases = [round(float(x), 2) for x in chain.stats().phase_ms]
     L.flbgpu_dev_free(ctx.h, d_in)
     L.flbgpu_dev_free(ctx.h, d_out)
     L.flbgpu_host_free(ctx.h, h_in)
     return {"value": value, "dev_ms": dev_ms, "e2e": e2e, "e2e_steps": e2e_steps, "kms": [k / args.steps for k in kms],
-            "launches": launches, "n_lines": n_lines, "nbytes": nbytes, "out_bytes": out_bytes, "clocks": clocks}
+            "launches": launches, "n_lines": n_lines, "nbytes": nbytes, "out_bytes": out_bytes, "clocks": clocks,
+            "phases": phases}
 
 
 def run_ours(args):
@@ -324,7 +326,8 @@ def run_ours(args):
                    "parallelism": "record shards, no data-path collective",
                    "host_malloc": "default" if os.environ.get("FLBGPU_BENCH_DEFAULT_MALLOC") == "1" else "glibc tuned to retain freed result buffers (M_MMAP_MAX=0, M_TRIM_THRESHOLD=1GiB)"},
         "e2e": {"value": m["e2e"], "unit": "lines/s", "h2d_bytes_per_step": m["nbytes"], "d2h_bytes_per_step": m["out_bytes"],
-                "steps": m["e2e_steps"], "timing": "wall clock between device-synchronising barriers"},
+                "steps": m["e2e_steps"], "timing": "wall clock between device-synchronising barriers",
+                "host_phase_ms_last_call": dict(zip(["upload+index+evaluate", "size_scan", "emit+download", "total"], m["phases"]))},
         "gpu_launches": m["launches"],
         "kernel_ms_per_step": {"index": m["kms"][0], "evaluate": eval_ms, "emit": m["kms"][2]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",

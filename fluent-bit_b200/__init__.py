@@ -32,7 +32,7 @@ class Time(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("records_in", C.c_uint64), ("records_out", C.c_uint64), ("bytes_in", C.c_uint64),
                 ("bytes_out", C.c_uint64), ("kernel_launches", C.c_uint64), ("passes", C.c_uint32),
-                ("error_bits", C.c_uint32)]
+                ("error_bits", C.c_uint32), ("phase_ms", C.c_float * 4)]
 
 
 EXPORTS = [

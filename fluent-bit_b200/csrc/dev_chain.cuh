@@ -69,6 +69,7 @@ struct ch_rec {
     ref_t meta;
     int nf;
     ref_t k[CH_MAXF], v[CH_MAXF];
+    uint32_t kh[CH_MAXF];        /* ch_khash() of each STR/BIN key (0 for other key types): key tests compare this first */
     int style;
     uint32_t preset_n;
     int reenc;
@@ -98,6 +99,20 @@ FLB_HD int ref_view(const struct ch_env *e, ref_t r, const uint8_t **p, uint32_t
         if (t.type == MPT_BOOL) return t.u ? 3 : 4;
     }
     return 0;
+}
+
+/* FNV-1a of a key's bytes, never 0 */
+FLB_HD uint32_t ch_khash(const uint8_t *s, uint32_t n)
+{
+    uint32_t h = 2166136261u, i;
+    for (i = 0; i < n; i++) { h ^= s[i]; h *= 16777619u; }
+    return h | 1u;
+}
+FLB_HD uint32_t ref_khash(const struct ch_env *e, ref_t r)
+{
+    const uint8_t *p; uint32_t n;
+    int t = ref_view(e, r, &p, &n);
+    return (t == 1 || t == 2) ? ch_khash(p, n) : 0u;
 }
 
 FLB_HD int bytes_eq(const uint8_t *a, const uint8_t *b, uint32_t n)
@@ -353,6 +368,7 @@ FLB_HD int rec_decode(const struct ch_env *e, uint32_t off, uint32_t len, struct
         nx = mp_skip(q, end);
         rc->v[i] = mkref(RK_MP_IN, (uint32_t) (q - e->in), (uint32_t) (nx - q));
         q = nx;
+        rc->kh[i] = ref_khash(e, rc->k[i]);
     }
     return 0;
 }
@@ -361,9 +377,11 @@ FLB_HD int rec_decode(const struct ch_env *e, uint32_t off, uint32_t len, struct
 /* ra_key_val_id(): index of the LAST field whose key is a STR equal to name */
 FLB_HD int ra_find(const struct ch_env *e, const struct ch_rec *rc, const uint8_t *name, uint32_t nlen)
 {
+    const uint32_t h = ch_khash(name, nlen);
     int i;
     for (i = rc->nf - 1; i >= 0; i--) {
         const uint8_t *kp; uint32_t kn;
+        if (rc->kh[i] != h) continue;
         if (ref_view(e, rc->k[i], &kp, &kn) != 1) continue;
         if (kn == nlen && bytes_eq(kp, name, nlen)) return i;
     }
@@ -834,9 +852,13 @@ FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t 
         int done = 0;                      /* 1: a value just completed, 2: a container closes */
         DJF_ALIGN(st)
         if (st == DJF_DONE) break;
-        while (p < n && dj_ws(s[p])) p++;
         if (p >= n) return -1;
         c = s[p];
+        if (c <= ' ') {                    /* whitespace between tokens is the exception in log lines */
+            while (p < n && dj_ws(s[p])) p++;
+            if (p >= n) return -1;
+            c = s[p];
+        }
         if (st == DJF_COLON) {
             if (c != ':') return -1;
             p++; st = DJF_VAL;
@@ -1084,6 +1106,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
     uint32_t preset = 0;
     int style = ST_CANON;
 
+    const uint32_t key_hash = cf->ra_off ? 0u : ch_khash(e->blob + cf->key_off, cf->key_len);
     have_arr = cf->reserve_data || cf->preserve_key;
     for (i = 0; i < rc->nf; i++) keep[i] = cf->reserve_data ? 1 : 0;
 
@@ -1100,6 +1123,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
         }
         else {
             const uint8_t *kp; uint32_t kn; int kt, vt;
+            if (rc->kh[i] != key_hash) continue;
             kt = ref_view(e, rc->k[i], &kp, &kn);
             if (kt != 1 && kt != 2) continue;
             if (kn != cf->key_len || !bytes_eq(kp, e->blob + cf->key_off, kn)) continue;
@@ -1177,7 +1201,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
             for (i = 0; i < rc->nf; i++) if (keep[i]) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; j++; }
         }
         else if (preserved >= 0) { w->tk[j] = rc->k[preserved]; w->tv[j] = rc->v[preserved]; j++; }
-        for (i = 0; i < j; i++) { rc->k[i] = w->tk[i]; rc->v[i] = w->tv[i]; }
+        for (i = 0; i < j; i++) { rc->k[i] = w->tk[i]; rc->v[i] = w->tv[i]; rc->kh[i] = ref_khash(e, w->tk[i]); }
         rc->nf = j;
         if (extra > 0) rc->style = ST_CANON;
         else { rc->style = style; rc->preset_n = preset; }
@@ -1301,10 +1325,15 @@ FLB_HD int mod_conditions(const struct ch_env *e, const struct cf_modify *cf, co
     return ok;
 }
 
-FLB_HD int count_keys(const struct ch_env *e, const struct ch_rec *rc, const uint8_t *s, uint32_t n)
+/* key i of the record equals (s, n) whose ch_khash is h */
+FLB_HD int key_is(const struct ch_env *e, const struct ch_rec *rc, int i, uint32_t h, const uint8_t *s, uint32_t n)
+{
+    return rc->kh[i] == h && key_eq(e, rc->k[i], s, n);
+}
+FLB_HD int count_keys(const struct ch_env *e, const struct ch_rec *rc, uint32_t h, const uint8_t *s, uint32_t n)
 {
     int i, c = 0;
-    for (i = 0; i < rc->nf; i++) if (key_eq(e, rc->k[i], s, n)) c++;
+    for (i = 0; i < rc->nf; i++) if (key_is(e, rc, i, h, s, n)) c++;
     return c;
 }
 
@@ -1312,7 +1341,7 @@ FLB_HD int count_keys(const struct ch_env *e, const struct ch_rec *rc, const uin
 FLB_HD void compact(struct ch_rec *rc, const uint8_t *del)
 {
     int i, j = 0;
-    for (i = 0; i < rc->nf; i++) if (!del[i]) { rc->k[j] = rc->k[i]; rc->v[j] = rc->v[i]; j++; }
+    for (i = 0; i < rc->nf; i++) if (!del[i]) { rc->k[j] = rc->k[i]; rc->v[j] = rc->v[i]; rc->kh[j] = rc->kh[i]; j++; }
     rc->nf = j;
 }
 
@@ -1322,54 +1351,55 @@ FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct 
     const uint8_t *key = e->blob + r->key_off, *val = e->blob + r->val_off;
     ref_t kmp = mkref(RK_MP_CONST, r->kmp_off, r->kmp_len), vmp = mkref(RK_MP_CONST, r->vmp_off, r->vmp_len);
     uint8_t del[CH_MAXF];
+    const uint32_t kh = r->key_hash, vh = r->val_hash;
     int i, j, match, conflict;
 
     switch (r->type) {
     case MOD_RENAME:
     case MOD_HARD_RENAME:
-        match = count_keys(e, rc, key, r->key_len);
-        conflict = count_keys(e, rc, val, r->val_len);
+        match = count_keys(e, rc, kh, key, r->key_len);
+        conflict = count_keys(e, rc, vh, val, r->val_len);
         if (match == 0) return 0;
         if (r->type == MOD_RENAME && conflict > 0) return 0;
-        for (i = 0; i < rc->nf; i++) del[i] = (conflict > 0 && key_eq(e, rc->k[i], val, r->val_len)) ? 1 : 0;
-        for (i = 0; i < rc->nf; i++) if (!del[i] && key_eq(e, rc->k[i], key, r->key_len)) rc->k[i] = vmp;
+        for (i = 0; i < rc->nf; i++) del[i] = (conflict > 0 && key_is(e, rc, i, vh, val, r->val_len)) ? 1 : 0;
+        for (i = 0; i < rc->nf; i++) if (!del[i] && key_is(e, rc, i, kh, key, r->key_len)) { rc->k[i] = vmp; rc->kh[i] = vh; }
         compact(rc, del);
         return 1;
     case MOD_COPY:
     case MOD_HARD_COPY:
-        match = count_keys(e, rc, key, r->key_len);
-        conflict = count_keys(e, rc, val, r->val_len);
+        match = count_keys(e, rc, kh, key, r->key_len);
+        conflict = count_keys(e, rc, vh, val, r->val_len);
         if (match != 1) return 0;
         if (r->type == MOD_COPY && conflict > 0) return 0;
         if (r->type == MOD_HARD_COPY && conflict > 1) return 0;
         if (conflict == 1) {
-            for (i = 0; i < rc->nf; i++) del[i] = key_eq(e, rc->k[i], val, r->val_len) ? 1 : 0;
+            for (i = 0; i < rc->nf; i++) del[i] = key_is(e, rc, i, vh, val, r->val_len) ? 1 : 0;
             compact(rc, del);
         }
         if (rc->nf + 1 > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
-        for (i = 0; i < rc->nf; i++) if (key_eq(e, rc->k[i], key, r->key_len)) break;
+        for (i = 0; i < rc->nf; i++) if (key_is(e, rc, i, kh, key, r->key_len)) break;
         if (i == rc->nf) return 1;       /* source vanished with the conflict key (same name): map repacked */
-        for (j = rc->nf; j > i + 1; j--) { rc->k[j] = rc->k[j - 1]; rc->v[j] = rc->v[j - 1]; }
-        rc->k[i + 1] = vmp; rc->v[i + 1] = rc->v[i];
+        for (j = rc->nf; j > i + 1; j--) { rc->k[j] = rc->k[j - 1]; rc->v[j] = rc->v[j - 1]; rc->kh[j] = rc->kh[j - 1]; }
+        rc->k[i + 1] = vmp; rc->v[i + 1] = rc->v[i]; rc->kh[i + 1] = vh;
         rc->nf++;
         return 1;
     case MOD_ADD:
-        if (count_keys(e, rc, key, r->key_len) != 0) return 0;
+        if (count_keys(e, rc, kh, key, r->key_len) != 0) return 0;
         if (rc->nf + 1 > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
-        rc->k[rc->nf] = kmp; rc->v[rc->nf] = vmp; rc->nf++;
+        rc->k[rc->nf] = kmp; rc->v[rc->nf] = vmp; rc->kh[rc->nf] = kh; rc->nf++;
         return 1;
     case MOD_SET:
-        for (i = 0; i < rc->nf; i++) del[i] = key_eq(e, rc->k[i], key, r->key_len) ? 1 : 0;
+        for (i = 0; i < rc->nf; i++) del[i] = key_is(e, rc, i, kh, key, r->key_len) ? 1 : 0;
         compact(rc, del);
         if (rc->nf + 1 > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 1; }
-        rc->k[rc->nf] = kmp; rc->v[rc->nf] = vmp; rc->nf++;
+        rc->k[rc->nf] = kmp; rc->v[rc->nf] = vmp; rc->kh[rc->nf] = kh; rc->nf++;
         return 1;
     case MOD_REMOVE:
     case MOD_REMOVE_WILDCARD:
     case MOD_REMOVE_REGEX:
         match = 0;
         for (i = 0; i < rc->nf; i++) {
-            if (r->type == MOD_REMOVE) del[i] = key_eq(e, rc->k[i], key, r->key_len) ? 1 : 0;
+            if (r->type == MOD_REMOVE) del[i] = key_is(e, rc, i, kh, key, r->key_len) ? 1 : 0;
             else if (r->type == MOD_REMOVE_WILDCARD) del[i] = key_prefix(e, rc->k[i], key, r->key_len) ? 1 : 0;
             else del[i] = ref_rx(e, rc->k[i], r->key_rx, w) ? 1 : 0;
             match += del[i];
@@ -1385,7 +1415,7 @@ FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct 
         j = 0;
         for (i = 0; i < rc->nf; i++) if (del[i] == (r->type == MOD_MOVE_TO_START)) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; j++; }
         for (i = 0; i < rc->nf; i++) if (del[i] != (r->type == MOD_MOVE_TO_START)) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; j++; }
-        for (i = 0; i < rc->nf; i++) { rc->k[i] = w->tk[i]; rc->v[i] = w->tv[i]; }
+        for (i = 0; i < rc->nf; i++) { rc->k[i] = w->tk[i]; rc->v[i] = w->tv[i]; rc->kh[i] = ref_khash(e, w->tk[i]); }
         return 1;
     }
     return 0;
@@ -1450,6 +1480,7 @@ FLB_HD void f_recmod(const struct ch_env *e, const struct cf_recmod *cf, struct 
     for (q = 0; q < cf->n_records; q++) {
         rc->k[rc->nf] = mkref(RK_MP_CONST, recs[q].kmp_off, recs[q].kmp_len);
         rc->v[rc->nf] = mkref(RK_MP_CONST, recs[q].vmp_off, recs[q].vmp_len);
+        rc->kh[rc->nf] = ref_khash(e, rc->k[rc->nf]);
         rc->nf++;
     }
     rc->reenc = 1;

@@ -157,7 +157,7 @@ struct cf_mod_rule {
     uint32_t val_off, val_len;
     uint32_t vmp_off, vmp_len;
     uint32_t key_rx;
-    uint32_t pad0, pad1;
+    uint32_t key_hash, val_hash;   /* ch_khash() of key / val (dev_chain.cuh) */
 };
 struct cf_modify { uint32_t n_conds, conds_off, n_rules, rules_off; };
 

@@ -704,6 +704,15 @@ static uint32_t emit_grep_filter(flbgpu_filter *f, struct blob *b)
     return blob_add(b, &cf, sizeof(cf), 8);
 }
 
+/* ch_khash() of dev_chain.cuh: FNV-1a, never 0 */
+static uint32_t key_hash(const char *s, size_t n)
+{
+    uint32_t h = 2166136261u;
+    size_t i;
+    for (i = 0; i < n; i++) { h ^= (unsigned char) s[i]; h *= 16777619u; }
+    return h | 1u;
+}
+
 static uint32_t emit_modify_filter(flbgpu_filter *f, struct blob *b)
 {
     struct cf_modify cf;
@@ -773,6 +782,7 @@ static uint32_t emit_modify_filter(flbgpu_filter *f, struct blob *b)
             r->kmp_off = blob_add_mpstr(b, key, (uint32_t) strlen(key), &r->kmp_len);
             r->val_off = blob_add(b, val, strlen(val), 1); r->val_len = (uint32_t) strlen(val);
             r->vmp_off = blob_add_mpstr(b, val, (uint32_t) strlen(val), &r->vmp_len);
+            r->key_hash = key_hash(key, strlen(key)); r->val_hash = key_hash(val, strlen(val));
             if (type == MOD_REMOVE_REGEX) {
                 if (!*key) { free_toks(tok, nt); set_err("Unable to create regex for rule %s %s", p->k, p->v); goto out; }
                 r->key_rx = emit_rx(b, key, NULL);
@@ -1217,9 +1227,13 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     uint64_t total;
     int clean, k, pass;
 
+    struct timespec t0, t1;
     memset(&c->st, 0, sizeof(c->st));
     c->st.bytes_in = bytes;
     *out_size = 0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+#define PHASE_MARK(i) do { clock_gettime(CLOCK_MONOTONIC, &t1); \
+        c->st.phase_ms[i] = (float) ((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) / 1e6); } while (0)
     if (bytes >= 0xfff00000ull) { set_err("chunk larger than 4 GiB: split the append%s%s", NULL, NULL); return -1; }
     if (d_in_ext) { d_in = d_in_ext; bk_upload_none(); }
     else {
@@ -1296,6 +1310,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         c->st.passes++;
     }
     c->st.kernel_launches = bk_launch_count();
+    PHASE_MARK(0);
     if (l2m_merge(c)) return -1;
     if (a.assume == 0) return FLBGPU_FILTER_NOTOUCH;
 
@@ -1314,6 +1329,8 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     if (total >= 0xfff00000ull) { set_err("result larger than 4 GiB%s%s", NULL, NULL); return -1; }
     c->st.bytes_out = total;
     *out_size = (size_t) total;
+    PHASE_MARK(1);
+    c->st.phase_ms[1] -= c->st.phase_ms[0];
     if (total == 0) return FLBGPU_FILTER_MODIFIED;
 
     /* ---- emit (+ download) ---- */
@@ -1347,6 +1364,8 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         *host_out = out;
     }
     c->st.kernel_launches = bk_launch_count();
+    PHASE_MARK(3);
+    c->st.phase_ms[2] = c->st.phase_ms[3] - c->st.phase_ms[1] - c->st.phase_ms[0];
     return FLBGPU_FILTER_MODIFIED;
 }
 

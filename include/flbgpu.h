@@ -119,6 +119,9 @@ struct flbgpu_stats {
     uint64_t kernel_launches;   /* kernels launched by this library so far   */
     uint32_t passes;            /* evaluation passes (1 unless a chunk-level assumption was revised) */
     uint32_t error_bits;        /* FLBGPU_E_* (flbgpu_prog.h) when the call failed */
+    /* host wall-clock milliseconds of the call's phases (diagnostic): [0] upload + index + evaluation
+     * (until the chunk-level verdicts are settled), [1] size scan, [2] emission + download, [3] total */
+    float phase_ms[4];
 };
 void flbgpu_chain_stats(flbgpu_chain *c, struct flbgpu_stats *out);
 
