@@ -84,7 +84,7 @@ FLB_HD const uint8_t *ref_ptr(const struct ch_env *e, ref_t r)
 }
 
 /* string view of a key/value: 1 STR, 2 BIN, 3 true, 4 false, 0 anything else */
-FLB_HD int ref_view(const struct ch_env *e, ref_t r, const uint8_t **p, uint32_t *n)
+FLB_HDN int ref_view(const struct ch_env *e, ref_t r, const uint8_t **p, uint32_t *n)
 {
     uint32_t k = r_kind(r);
     const uint8_t *b = ref_ptr(e, r);
@@ -167,7 +167,7 @@ FLB_HD uint64_t ch_strtoull16(const uint8_t *s, uint32_t n)
 
 /* strtod() restricted to the exactly-representable fast path (Clinger): up to 19
  * significant digits that fit 2^53 and |exp10| <= 22.  *ok=0 outside it. */
-FLB_HD double ch_strtod_fast(const uint8_t *s, uint32_t n, int *ok)
+FLB_HDN double ch_strtod_fast(const uint8_t *s, uint32_t n, int *ok)
 {
     uint32_t i = 0;
     int neg = 0, exp10 = 0, nd = 0, seen = 0;
@@ -207,7 +207,7 @@ FLB_HD double ch_strtod_fast(const uint8_t *s, uint32_t n, int *ok)
 
 /* ------------------------------------------------------------ emission */
 /* size (o == NULL) or bytes of one field reference */
-FLB_HD uint32_t ref_emit(const struct ch_env *e, ref_t r, uint8_t *o)
+FLB_HDN uint32_t ref_emit(const struct ch_env *e, ref_t r, uint8_t *o)
 {
     uint32_t k = r_kind(r), n = r_len(r);
     const uint8_t *b = ref_ptr(e, r);
@@ -249,7 +249,7 @@ FLB_HD uint32_t ref_emit(const struct ch_env *e, ref_t r, uint8_t *o)
     return 0;
 }
 
-FLB_HD uint32_t rec_emit(const struct ch_env *e, const struct ch_rec *rc, uint8_t *o)
+FLB_HDN uint32_t rec_emit(const struct ch_env *e, const struct ch_rec *rc, uint8_t *o)
 {
     uint32_t n = 0;
     int i;
@@ -329,7 +329,7 @@ FLB_HD int rec_is_shadowed(const uint8_t *base, const uint8_t *p, const uint8_t 
 
 /* Split a framed record into timestamp, metadata and the top-level field list.
  * Returns 0, or -1 when it has more than CH_MAXF keys. */
-FLB_HD int rec_decode(const struct ch_env *e, uint32_t off, uint32_t len, struct ch_rec *rc, uint32_t empty_map_off)
+FLB_HDN int rec_decode(const struct ch_env *e, uint32_t off, uint32_t len, struct ch_rec *rc, uint32_t empty_map_off)
 {
     const uint8_t *p = e->in + off, *end = p + len, *q = p + 1, *nx;
     struct mp_tok t;
@@ -390,7 +390,7 @@ FLB_HD int ra_find(const struct ch_env *e, const struct ch_rec *rc, const uint8_
 
 /* subkey_to_object() over raw msgpack: on success *vp..*ve is the value object and
  * *key_is_null tells whether the last step was an array index */
-FLB_HD int ra_walk_sub(const struct ch_env *e, const struct cf_ra *ra, const uint8_t *p, const uint8_t *end,
+FLB_HDN int ra_walk_sub(const struct ch_env *e, const struct cf_ra *ra, const uint8_t *p, const uint8_t *end,
                        const uint8_t **vp, const uint8_t **ve, int *key_is_null)
 {
     const struct cf_ra_sub *sub = (const struct cf_ra_sub *) (e->blob + ra->sub_off);
@@ -443,7 +443,7 @@ FLB_HD int ra_walk_sub(const struct ch_env *e, const struct cf_ra *ra, const uin
 
 /* flb_ra_key_value_get(): 0 found (flags: *okey_null), -1 not found.
  * On success either *top >= 0 (the top-level field itself) or *vp/*ve (nested). */
-FLB_HD int ra_get(const struct ch_env *e, const struct ch_rec *rc, const struct cf_ra *ra, int *top,
+FLB_HDN int ra_get(const struct ch_env *e, const struct ch_rec *rc, const struct cf_ra *ra, int *top,
                   const uint8_t **vp, const uint8_t **ve, int *okey_null)
 {
     int i = ra_find(e, rc, e->blob + ra->key_off, ra->key_len);
@@ -475,7 +475,7 @@ FLB_HD int loc_view(const struct ch_env *e, const struct ch_rec *rc, int top, co
     return 0;
 }
 
-FLB_HD int rx_run(const struct ch_env *e, uint32_t rx_off, const uint8_t *s, uint32_t n, int *caps, uint32_t *stk)
+FLB_HDN int rx_run(const struct ch_env *e, uint32_t rx_off, const uint8_t *s, uint32_t n, int *caps, uint32_t *stk)
 {
     uint32_t budget = CH_RX_BUDGET;
     int r = rx_search((const struct rx_prog *) (e->blob + rx_off), s, (int) n, caps, stk, CH_RX_STACK, &budget);
@@ -500,7 +500,7 @@ FLB_HD int ra_regex_match(const struct ch_env *e, const struct ch_rec *rc, uint3
 /* ---------------------------------------------------------- filter_parser */
 /* One regex parser over s[0,n): returns 1 parsed (fields appended to out_*), 0 not.
  * Timestamp result in *t_sec/*t_nsec (0/0 when no time was resolved). */
-FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s,
+FLB_HDN int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s,
                       uint32_t n, const int *caps, ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec,
                       int64_t *t_nsec)
 {
@@ -560,7 +560,7 @@ FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t
 }
 
 /* Types cast of a parsed (key, value) pair: flb_parser_typecast(), src/flb_parser.c:1280-1377 */
-FLB_HD ref_t cast_value(const struct ch_env *e, const struct cf_pdef *pd, const uint8_t *key, uint32_t klen,
+FLB_HDN ref_t cast_value(const struct ch_env *e, const struct cf_pdef *pd, const uint8_t *key, uint32_t klen,
                         const uint8_t *v, uint32_t voff, uint32_t vlen)
 {
     const struct cf_ptype *ty = (const struct cf_ptype *) (e->blob + pd->types_off);
@@ -579,7 +579,7 @@ FLB_HD ref_t cast_value(const struct ch_env *e, const struct cf_pdef *pd, const 
     return mkref(RK_STR_IN, voff, vlen);
 }
 
-FLB_HD int pdef_time(const struct ch_env *e, const struct cf_pdef *pd, const uint8_t *v, uint32_t vlen,
+FLB_HDN int pdef_time(const struct ch_env *e, const struct cf_pdef *pd, const uint8_t *v, uint32_t vlen,
                      int64_t *lookup, double *frac)
 {
     struct dt_tm tm;
@@ -611,7 +611,7 @@ FLB_HD int64_t frac_to_nsec(double frac)
 FLB_HD int ltsv_label(uint32_t c) { return (c >= '0' && c <= '9') || ((c | 0x20) >= 'a' && (c | 0x20) <= 'z') || c == '_' || c == '.' || c == '-'; }
 FLB_HD int ltsv_field(uint32_t c) { return c != 0 && c != 9 && c != 10 && c != 13; }
 
-FLB_HD int pdef_ltsv(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
+FLB_HDN int pdef_ltsv(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
                      ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec)
 {
     uint32_t c = 0;
@@ -656,7 +656,7 @@ FLB_HD int pdef_ltsv(const struct ch_env *e, const struct cf_pdef *pd, uint32_t 
 /* logfmt_parser(), src/flb_parser_logfmt.c:63-254.  ident bytes: > ' ' and not '=' '"' (:44-61) */
 FLB_HD int logfmt_ident(uint32_t c) { return c > ' ' && c != '=' && c != '"'; }
 
-FLB_HD int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
+FLB_HDN int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
                        ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec)
 {
     uint32_t c = 0;
@@ -835,7 +835,7 @@ FLB_HD int djf_string(const uint8_t *s, int p, int n, uint8_t *scr, uint32_t at,
     return q + 1;
 }
 
-FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t val_off, ref_t *ok_, ref_t *ov_, int *on)
+FLB_HDN int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t val_off, ref_t *ok_, ref_t *ov_, int *on)
 {
     uint8_t *scr = e->scr;
     uint32_t hpos[DJ_MAX_DEPTH + 1], ccnt[DJ_MAX_DEPTH + 1];
@@ -1023,7 +1023,7 @@ FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t 
  * equals Time_Key; its value must be a STR; a failed lookup keeps the member and leaves
  * the timestamp at 0 (:198-209). */
 template <bool EMIT>
-FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
+FLB_HDN int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
                      ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec, uint32_t ridx,
                      uint32_t *cache_pos)
 {
@@ -1097,7 +1097,7 @@ struct ch_scratch {              /* per-lane working memory */
 };
 
 template <bool EMIT>
-FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct ch_rec *rc, struct ch_scratch *w,
+FLB_HDN void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct ch_rec *rc, struct ch_scratch *w,
                      uint32_t ridx, uint32_t *cache_pos)
 {
     uint8_t keep[CH_MAXF];
@@ -1210,7 +1210,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
 
 /* ------------------------------------------------------------ filter_grep */
 /* returns 1 keep, 0 exclude */
-FLB_HD int f_grep(const struct ch_env *e, const struct cf_grep *cf, const struct ch_rec *rc, struct ch_scratch *w)
+FLB_HDN int f_grep(const struct ch_env *e, const struct cf_grep *cf, const struct ch_rec *rc, struct ch_scratch *w)
 {
     const struct cf_grep_rule *r = (const struct cf_grep_rule *) (e->blob + cf->rules_off);
     uint32_t i;
@@ -1274,7 +1274,7 @@ FLB_HD int ref_rx(const struct ch_env *e, ref_t r, uint32_t rx_off, struct ch_sc
     return obj_rx(e, vt, p, n, rx_off, w);
 }
 
-FLB_HD int mod_conditions(const struct ch_env *e, const struct cf_modify *cf, const struct ch_rec *rc,
+FLB_HDN int mod_conditions(const struct ch_env *e, const struct cf_modify *cf, const struct ch_rec *rc,
                           struct ch_scratch *w)
 {
     const struct cf_mod_cond *c = (const struct cf_mod_cond *) (e->blob + cf->conds_off);
@@ -1346,7 +1346,7 @@ FLB_HD void compact(struct ch_rec *rc, const uint8_t *del)
 }
 
 /* returns 1 when the rule modified the map */
-FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct ch_rec *rc, struct ch_scratch *w)
+FLB_HDN int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct ch_rec *rc, struct ch_scratch *w)
 {
     const uint8_t *key = e->blob + r->key_off, *val = e->blob + r->val_off;
     ref_t kmp = mkref(RK_MP_CONST, r->kmp_off, r->kmp_len), vmp = mkref(RK_MP_CONST, r->vmp_off, r->vmp_len);
@@ -1448,7 +1448,7 @@ FLB_HD int ci_eq(const uint8_t *a, const uint8_t *b, uint32_t n)
 }
 
 /* returns: 0 passes untouched evidence-wise, sets *cause; *drop when no field is left */
-FLB_HD void f_recmod(const struct ch_env *e, const struct cf_recmod *cf, struct ch_rec *rc, int *cause, int *drop)
+FLB_HDN void f_recmod(const struct ch_env *e, const struct cf_recmod *cf, struct ch_rec *rc, int *cause, int *drop)
 {
     const struct cf_rm_key *keys = 0;
     const struct cf_rm_rec *recs = (const struct cf_rm_rec *) (e->blob + cf->records_off);
@@ -1537,7 +1537,7 @@ FLB_HD int l2m_lookup(const struct ch_env *e, const struct ch_rec *rc, uint32_t 
     return 1;
 }
 
-FLB_HD void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct ch_rec *rc, struct ch_scratch *w,
+FLB_HDN void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct ch_rec *rc, struct ch_scratch *w,
                   uint32_t ridx)
 {
     const struct l2m_table *tb = &e->l2m;

@@ -66,7 +66,7 @@ FLB_HD int dj_clz64(uint64_t x)
 }
 
 /* w * 10^q -> IEEE double bits.  Returns 0 ok, 1 overflow (infinity), 2 undecided. */
-FLB_HD int dj_eisel_lemire(uint64_t w, int64_t q, uint64_t *bits)
+FLB_HDN int dj_eisel_lemire(uint64_t w, int64_t q, uint64_t *bits)
 {
     uint64_t hi, lo, mant;
     int lz, upperbit;
@@ -116,7 +116,7 @@ FLB_HD int dj_eisel_lemire(uint64_t w, int64_t q, uint64_t *bits)
 DJ_TABLE_QUAL double dj_p10[23] = { 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
                                     1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22 };
 
-FLB_HD int dj_number(const uint8_t *s, int n, int pos, int *kind, uint64_t *u, uint32_t *err)
+FLB_HDN int dj_number(const uint8_t *s, int n, int pos, int *kind, uint64_t *u, uint32_t *err)
 {
     int neg = 0, p = pos, nd = 0, dropped = 0, is_real = 0, int_overflow = 0, truncated = 0;
     uint64_t w = 0, iw = 0;
@@ -193,7 +193,7 @@ FLB_HD int dj_number(const uint8_t *s, int n, int pos, int *kind, uint64_t *u, u
 
 /* Decode the string whose opening quote is at s[pos].  Writes the decoded bytes to o
  * (when o != NULL), returns the position after the closing quote or -1; *olen = length. */
-FLB_HD int dj_string(const uint8_t *s, int n, int pos, uint8_t *o, uint32_t *olen)
+FLB_HDN int dj_string(const uint8_t *s, int n, int pos, uint8_t *o, uint32_t *olen)
 {
     int p = pos + 1;
     uint32_t k = 0;
@@ -384,7 +384,7 @@ next_member:
 
 /* flb_pack_json_recs() for one line: exactly one document, which must be an object.
  * Returns 1 and the msgpack map at o (length *olen), or 0. */
-FLB_HD int dj_parse_record(const uint8_t *s, int n, uint8_t *o, uint32_t *olen, uint32_t *err)
+FLB_HDN int dj_parse_record(const uint8_t *s, int n, uint8_t *o, uint32_t *olen, uint32_t *err)
 {
     int p = 0, e;
     uint32_t dummy = 0, derr = 0;

@@ -94,7 +94,7 @@ FLB_HD int mp_token(const uint8_t *p, const uint8_t *end, struct mp_tok *t)
 /* Skip one complete object starting at p.  Returns the first byte after it, or
  * NULL when the object is truncated or malformed.  Nesting needs no stack: a
  * single "objects still owed" counter is enough to find the end. */
-FLB_HD const uint8_t *mp_skip(const uint8_t *p, const uint8_t *end)
+FLB_HDN const uint8_t *mp_skip(const uint8_t *p, const uint8_t *end)
 {
     uint64_t owed = 1;
     struct mp_tok t;
@@ -208,7 +208,7 @@ FLB_HD void mp_copy(uint8_t *o, const uint8_t *s, uint32_t n)
 /* Canonical re-encoding of the complete object at p (already validated by
  * mp_skip).  When o is NULL only the size is computed.  Returns the output size;
  * *consumed gets the input size. */
-FLB_HD uint32_t mp_canon(const uint8_t *p, const uint8_t *end, uint8_t *o, uint32_t *consumed)
+FLB_HDN uint32_t mp_canon(const uint8_t *p, const uint8_t *end, uint8_t *o, uint32_t *consumed)
 {
     const uint8_t *p0 = p;
     uint64_t owed = 1;
