@@ -94,6 +94,10 @@ int bk_flags_fetch(const uint32_t *d_flags, uint32_t *h_flags);
 /* per-block sums of d_size[0,n_rec) -> exclusive offsets in d_bsum, copied to h_bsum
  * (n_blocks+1 entries, last = total).  Synchronises. */
 int bk_sizes_scan(const uint32_t *d_size, uint32_t n_rec, uint64_t *d_bsum, uint64_t *h_bsum);
+/* the same for blocks [b0, b1) only, continuing from carry_in bytes already placed; fills
+ * d_bsum[b0..b1), h_bsum[b0..b1] (h_bsum[b1] = bytes placed after these blocks).  Synchronous. */
+int bk_sizes_scan_range(const uint32_t *d_size, uint32_t n_rec, uint32_t b0, uint32_t b1, uint64_t *d_bsum, uint64_t *h_bsum,
+                        uint64_t carry_in);
 /* emission of blocks [b0, b1) into d_out: asynchronous on the compute stream */
 int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1);
 

@@ -619,6 +619,43 @@ int bk_sizes_scan(const uint32_t *d_size, uint32_t n_rec, uint64_t *d_bsum, uint
     return 0;
 }
 
+/* Offsets of blocks [b0, b1) when everything before them is already placed: block sums, exclusive
+ * scan continued from carry_in, host copy of the new entries; h_bsum[b1] = bytes placed so far. */
+__global__ void __launch_bounds__(256) k_scan_carry(uint64_t *a, uint32_t n, unsigned long long *carry_io)
+{
+    unsigned long long carry = *carry_io;
+    for (uint32_t b = 0; b < n; b += 256) {
+        const uint32_t i = b + threadIdx.x;
+        unsigned long long v = i < n ? (unsigned long long) a[i] : 0, tot;
+        unsigned long long ex = block_excl_scan_t<unsigned long long>(v, &tot);
+        if (i < n) a[i] = carry + ex;
+        carry += tot;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *carry_io = carry;
+}
+
+int bk_sizes_scan_range(const uint32_t *d_size, uint32_t n_rec, uint32_t b0, uint32_t b1, uint64_t *d_bsum, uint64_t *h_bsum,
+                        uint64_t carry_in)
+{
+    unsigned long long tot = carry_in;
+    if (ensure_small()) return -1;
+    h_bsum[b0] = carry_in;
+    if (b1 > b0) {
+        const uint32_t nb = b1 - b0;
+        CK(cudaMemcpyAsync(g_dtotal, &tot, sizeof(tot), cudaMemcpyHostToDevice, g_stream));
+        k_bsum<<<nb, BK_REC_BLOCK, 0, g_stream>>>(d_size + (size_t) b0 * BK_REC_BLOCK, n_rec - b0 * BK_REC_BLOCK, d_bsum + b0);
+        k_scan_carry<<<1, 256, 0, g_stream>>>(d_bsum + b0, nb, g_dtotal);
+        g_launches += 2;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&tot, g_dtotal, sizeof(tot), cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaMemcpyAsync(h_bsum + b0, d_bsum + b0, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, g_stream));
+    }
+    CK(cudaStreamSynchronize(g_stream));
+    h_bsum[b1] = tot;
+    return 0;
+}
+
 int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1)
 {
     k_chain_params p;

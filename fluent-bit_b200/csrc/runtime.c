@@ -155,6 +155,7 @@ struct flbgpu_chain {
     int32_t *d_cap; size_t cap_cap;
     uint32_t *d_flags;
     uint64_t *h_bsum; size_t cap_hbsum;      /* host copy of the per-block output offsets */
+    uint32_t spec_assume; int spec_valid;     /* verdict vector of the previous call: what the streaming path speculates on */
     struct flbgpu_stats st;
 };
 
@@ -1311,6 +1312,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     }
     c->st.kernel_launches = bk_launch_count();
     PHASE_MARK(0);
+    c->spec_assume = a.assume; c->spec_valid = 1;    /* what the streaming path speculates on next time */
     if (l2m_merge(c)) return -1;
     if (a.assume == 0) return FLBGPU_FILTER_NOTOUCH;
 
@@ -1369,6 +1371,162 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     return FLBGPU_FILTER_MODIFIED;
 }
 
+/* Streaming form of chain_run for host buffers.  The chunk-level verdicts are only known when the
+ * whole chunk has been evaluated, but they almost never differ from the previous call's (and from
+ * "every filter modifies" on the first call), so each slice is emitted and sent back as soon as it
+ * has been evaluated, speculating on that vector: upload of slice k+1, evaluation of slice k and
+ * emission + download of slice k-1 overlap.  If the settled verdicts differ from the speculation the
+ * speculative result is thrown away and the classic path runs (returns 1 = "use chain_run"). */
+static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, void **host_out, size_t *out_size, int *ret)
+{
+    struct bk_chain_args a;
+    uint32_t n_rec = 0, h_flags[FLBGPU_MAX_FILTERS + 1], b_done = 0, assume, nb_max;
+    size_t off = 0, S = slice_bytes(), cap_out_h = 0;
+    uint64_t placed = 0;
+    uint8_t *out = NULL;
+    int clean, k, dl_open = 0, rc = -1;
+    int64_t now = (int64_t) time(NULL);
+    struct timespec t0, t1;
+
+    memset(&c->st, 0, sizeof(c->st));
+    c->st.bytes_in = bytes;
+    *out_size = 0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    assume = (c->nf >= 32) ? 0xffffffffu : ((1u << c->nf) - 1u);
+    if (c->l2m_index >= 0 && !c->f[c->l2m_index]->l2m->discard) assume &= ~(1u << c->l2m_index);
+    if (c->spec_valid) assume = c->spec_assume;
+    if (assume == 0) return 1;                       /* nothing would be emitted: the classic path decides */
+    if (bytes >= 0xfff00000ull) { set_err("chunk larger than 4 GiB: split the append%s%s", NULL, NULL); return -1; }
+    GROW(c->d_in, c->cap_in, bytes + 64, uint8_t);
+    if (bk_upload_start(c->d_in, h_in, bytes)) return -1;
+    if (c->needs_scratch) GROW(c->d_scr, c->cap_scr, 4 * bytes + 64, uint8_t);
+    nb_max = (uint32_t) (bytes / (3 * BK_REC_BLOCK)) + 4;       /* an event is at least 3 bytes */
+    GROW(c->d_bsum, c->cap_bsum, nb_max, uint64_t);
+    if (c->cap_hbsum < (size_t) nb_max) {
+        free(c->h_bsum);
+        c->cap_hbsum = nb_max;
+        c->h_bsum = malloc(c->cap_hbsum * sizeof(uint64_t));
+        if (!c->h_bsum) { c->cap_hbsum = 0; return -1; }
+    }
+    memset(&a, 0, sizeof(a));
+    if (bk_flags_clear(c->d_flags) || l2m_clear(c)) return -1;
+
+#define STREAM_FLUSH(upto_blocks) do { \
+        uint32_t b1_ = (upto_blocks); \
+        if (b1_ > b_done) { \
+            fill_args(c, &a, c->d_in, bytes, n_rec); a.assume = assume; a.now = now; a.d_bsum = c->d_bsum; \
+            if (bk_sizes_scan_range(c->d_size, n_rec, b_done, b1_, c->d_bsum, c->h_bsum, placed)) goto fail; \
+            if (c->h_bsum[b1_] >= 0xfff00000ull) { set_err("result larger than 4 GiB%s%s", NULL, NULL); goto fail; } \
+            if (c->h_bsum[b1_] > placed) { \
+                if (c->h_bsum[b1_] > cap_out_h) { \
+                    /* first estimate from the output/input ratio so far; grown (rarely) when it was too low */ \
+                    double ratio_ = (double) c->h_bsum[b1_] / (double) (off ? off : 1); \
+                    size_t want_ = (size_t) (ratio_ * 1.15 * (double) bytes) + ((size_t) 8 << 20); \
+                    uint8_t *no_; \
+                    if (want_ < c->h_bsum[b1_]) want_ = (size_t) c->h_bsum[b1_] + ((size_t) 8 << 20); \
+                    if (dl_open) { if (bk_download_end()) { dl_open = 0; goto fail; } dl_open = 0; } \
+                    no_ = realloc(out, want_); \
+                    if (!no_) goto fail; \
+                    out = no_; cap_out_h = want_; \
+                    GROW_KEEP_OUT(want_); \
+                } \
+                if (!dl_open) { if (bk_download_begin(out, c->d_out)) goto fail; dl_open = 1; } \
+                if (bk_chain_emit(&a, c->d_out, b_done, b1_) || bk_download_push((size_t) placed, (size_t) c->h_bsum[b1_])) goto fail; \
+            } \
+            placed = c->h_bsum[b1_]; \
+            b_done = b1_; \
+        } } while (0)
+    /* the device output buffer grows with the host one; bytes already emitted stay where they are */
+#define GROW_KEEP_OUT(need) do { if (c->cap_out < (size_t) (need)) { \
+        uint8_t *nd_ = bk_alloc((size_t) (need) + 64); \
+        if (!nd_) goto fail; \
+        if (placed) { if (bk_sync() || bk_d2d(nd_, c->d_out, (size_t) placed)) { bk_free(nd_); goto fail; } } \
+        bk_free(c->d_out); c->d_out = nd_; c->cap_out = (size_t) (need); } } while (0)
+
+    while (off < bytes) {
+        size_t len = bytes - off < S ? bytes - off : S;
+        uint32_t n_tiles = (uint32_t) ((len + (off & 15) + BK_INDEX_TILE - 1) / BK_INDEX_TILE), n_cand = 0, n_valid = 0;
+        uint64_t end_off = off;
+        int tiled = 0;
+        if (bk_upload_wait_index(off + len)) goto fail;
+        GROW(c->d_tile, c->cap_tile, n_tiles + 1, uint32_t);
+        if (bk_index_count(c->d_in, off, (uint32_t) len, c->d_tile, n_tiles, &n_cand)) goto fail;
+        if (ensure_rec_cap(c, (size_t) n_rec + n_cand, n_rec)) goto fail;
+        if (bk_index_fill(c->d_in, off, (uint32_t) len, c->d_tile, n_tiles, n_cand, c->d_off + n_rec, c->d_len + n_rec,
+                          c->d_kind + n_rec, &n_valid, &end_off, &tiled)) {
+            c->st.error_bits = FLBGPU_E_INDEX;
+            goto fail;
+        }
+        if (n_valid == 0) {
+            if (off + len < bytes) { S *= 2; continue; }
+            break;
+        }
+        /* the previous slice has been evaluated by now (or is about to finish): place and send it */
+        STREAM_FLUSH(n_rec / BK_REC_BLOCK);
+        fill_args(c, &a, c->d_in, bytes, n_rec + n_valid);
+        a.assume = assume; a.now = now;
+        if (bk_chain_eval(&a, n_rec, n_rec + n_valid)) goto fail;
+        n_rec += n_valid;
+        off = (size_t) end_off;
+    }
+    clean = (off == bytes);
+    c->st.records_in = n_rec;
+    c->st.passes = 1;
+    STREAM_FLUSH((n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK);
+    c->st.phase_ms[0] = 0;
+
+    /* ---- the verdicts must be the ones speculated on ---- */
+    if (bk_flags_fetch(c->d_flags, h_flags)) goto fail;
+    if (h_flags[FLBGPU_MAX_FILTERS]) {
+        c->st.error_bits = h_flags[FLBGPU_MAX_FILTERS];
+        snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
+                 "1=too many keys 2=regex stack 4=regex budget 8=float outside exact path 32=logfmt escapes 64=log_to_metrics value/label outside the device path)",
+                 h_flags[FLBGPU_MAX_FILTERS]);
+        goto fail;
+    }
+    {
+        int cl = clean;
+        uint32_t settled = 0;
+        for (k = 0; k < c->nf; k++) {
+            int v = c->f[k]->kind == FLBGPU_F_LOG_TO_METRICS ? L2M_VERDICT(c, k) : verdict(c->f[k]->kind, h_flags[k], cl);
+            if (v) cl = 1;
+            if (v != (int) ((assume >> k) & 1)) {
+                /* evidence of the later filters was gathered under a wrong assumption: redo classically,
+                 * and speculate on "filter k as found" next time */
+                c->spec_assume = (assume & ~(1u << k)) | ((uint32_t) v << k);
+                c->spec_valid = 1;
+                if (dl_open) bk_download_end();
+                free(out);
+                return 1;
+            }
+            settled |= (uint32_t) v << k;
+        }
+        c->spec_assume = settled; c->spec_valid = 1;
+    }
+    c->st.kernel_launches = bk_launch_count();
+    if (l2m_merge(c)) goto fail;
+    if (dl_open) { dl_open = 0; if (bk_download_end()) goto fail; }
+    c->st.bytes_out = placed;
+    *out_size = (size_t) placed;
+    if (placed == 0) { free(out); out = NULL; }
+    else {
+        uint8_t *sh = realloc(out, (size_t) placed);
+        if (sh) out = sh;
+    }
+    *host_out = out;
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    c->st.phase_ms[3] = (float) ((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) / 1e6);
+    *ret = FLBGPU_FILTER_MODIFIED;
+    return 0;
+fail:
+    if (dl_open) bk_download_end();
+    free(out);
+    (void) rc;
+    return -1;
+#undef STREAM_FLUSH
+#undef GROW_KEEP_OUT
+}
+
 int flbgpu_chain_do_device(flbgpu_chain *c, const void *d_data, size_t bytes, void *d_out, size_t out_cap, size_t *out_size)
 {
     int r;
@@ -1388,6 +1546,15 @@ int flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes, const char 
     g_rt_err[0] = 0;
     *out_buf = NULL; *out_size = 0;
     if (bytes == 0) return FLBGPU_FILTER_NOTOUCH;
+    {
+        const char *sv = getenv("FLBGPU_STREAM");
+        if (!(sv && sv[0] == '0')) {
+            int ret = 0, r = chain_run_stream(c, data, bytes, out_buf, out_size, &ret);
+            if (r == 0) return ret;
+            if (r < 0) return -1;
+            *out_buf = NULL; *out_size = 0;          /* speculation did not hold: classic path */
+        }
+    }
     return chain_run(c, data, NULL, bytes, NULL, 0, out_buf, out_size);
 }
 

@@ -202,6 +202,21 @@ int bk_sizes_scan(const uint32_t *d_size, uint32_t n_rec, uint64_t *d_bsum, uint
     return 0;
 }
 
+int bk_sizes_scan_range(const uint32_t *d_size, uint32_t n_rec, uint32_t b0, uint32_t b1, uint64_t *d_bsum, uint64_t *h_bsum,
+                        uint64_t carry_in)
+{
+    uint32_t b, i;
+    uint64_t run = carry_in;
+    for (b = b0; b < b1; b++) {
+        d_bsum[b] = run; h_bsum[b] = run;
+        for (i = b * BK_REC_BLOCK; i < n_rec && i < (b + 1) * BK_REC_BLOCK; i++) run += d_size[i];
+    }
+    h_bsum[b0] = carry_in;
+    h_bsum[b1] = run;
+    hs_launches += 2;
+    return 0;
+}
+
 int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1)
 {
     struct ch_env e;

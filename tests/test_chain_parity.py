@@ -112,3 +112,51 @@ def test_large_chunk_gpu(gpu_lib, ref_available):
     block = util.chunk_from_lines(util.apache_lines(20000, seed=34))
     case = [c for c in cases.CASES if c[0] == "north_star_chain"][0]
     run_case(gpu_lib, case[1], case[2], block * 30)
+
+
+def _speculation(lib, monkeypatch):
+    """The streaming path speculates on the previous call's chunk-level verdicts: alternate chunks whose
+    verdicts differ (grep excludes something / nothing, modify changes something / nothing) on ONE
+    chain object and check every call, in both the streaming and the classic form."""
+    monkeypatch.setenv("FLBGPU_SLICE_MB", "1")
+    lines = util.apache_lines(6000, seed=35)
+    gets = [l for l in lines if b'"GET ' in l]
+    mixed = util.chunk_from_lines(lines)
+    only_get = util.chunk_from_lines(gets)
+    has_env = b"".join(util.event(1700000000 + i, 0, [(b"log", util.mp_str(l)), (b"env", util.mp_str(b"x"))]) for i, l in enumerate(gets))
+    filters = [("grep", [("Regex", "log GET")]), ("modify", [("Add", "env prod")])]
+    for stream in ("1", "0"):
+        monkeypatch.setenv("FLBGPU_STREAM", stream)
+        ctx = pkg.Context(0, lib=lib)
+        chain = ctx.chain([ctx.filter(p, props) for p, props in filters])
+        for chunk in (mixed, only_get, has_env, mixed, mixed, has_env, only_get, only_get):
+            ref = util.Ref()
+            for p, props in filters:
+                ref.filter(p, props)
+            assert chain.do(chunk) == ref.chain_do(chunk)
+
+
+def test_streaming_speculation_hostsim(sim_lib, ref_available, monkeypatch):
+    _speculation(sim_lib, monkeypatch)
+
+
+@pytest.mark.gpu
+def test_streaming_speculation_gpu(gpu_lib, ref_available, monkeypatch):
+    _speculation(gpu_lib, monkeypatch)
+
+
+def _json_sliced(lib, monkeypatch):
+    monkeypatch.setenv("FLBGPU_SLICE_MB", "1")
+    chunk = util.chunk_from_lines(util.json_lines(20000, seed=36))
+    case = [c for c in cases.CASES if c[0] == "json_chain_config1"][0]
+    run_case(lib, case[1], case[2], chunk)
+    run_case(lib, case[1], case[2], chunk[:len(chunk) - 11])
+
+
+def test_json_sliced_hostsim(sim_lib, ref_available, monkeypatch):
+    _json_sliced(sim_lib, monkeypatch)
+
+
+@pytest.mark.gpu
+def test_json_sliced_gpu(gpu_lib, ref_available, monkeypatch):
+    _json_sliced(gpu_lib, monkeypatch)
