@@ -48,7 +48,7 @@ EXPORTS = [
 
 def load(path=None):
     """dlopen the C-ABI library and declare prototypes."""
-    path = path or PRODUCT_LIB
+    path = path or os.environ.get("FLBGPU_LIB") or PRODUCT_LIB      # FLBGPU_LIB: a build variant, for experiments
     if not os.path.exists(path):
         raise FlbGpuError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(there is no CPU fallback)" % path)

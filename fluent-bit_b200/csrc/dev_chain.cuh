@@ -84,7 +84,7 @@ FLB_HD const uint8_t *ref_ptr(const struct ch_env *e, ref_t r)
 }
 
 /* string view of a key/value: 1 STR, 2 BIN, 3 true, 4 false, 0 anything else */
-FLB_HDN int ref_view(const struct ch_env *e, ref_t r, const uint8_t **p, uint32_t *n)
+FLB_HD int ref_view(const struct ch_env *e, ref_t r, const uint8_t **p, uint32_t *n)
 {
     uint32_t k = r_kind(r);
     const uint8_t *b = ref_ptr(e, r);
@@ -167,7 +167,7 @@ FLB_HD uint64_t ch_strtoull16(const uint8_t *s, uint32_t n)
 
 /* strtod() restricted to the exactly-representable fast path (Clinger): up to 19
  * significant digits that fit 2^53 and |exp10| <= 22.  *ok=0 outside it. */
-FLB_HDN double ch_strtod_fast(const uint8_t *s, uint32_t n, int *ok)
+FLB_HD double ch_strtod_fast(const uint8_t *s, uint32_t n, int *ok)
 {
     uint32_t i = 0;
     int neg = 0, exp10 = 0, nd = 0, seen = 0;
@@ -207,7 +207,7 @@ FLB_HDN double ch_strtod_fast(const uint8_t *s, uint32_t n, int *ok)
 
 /* ------------------------------------------------------------ emission */
 /* size (o == NULL) or bytes of one field reference */
-FLB_HDN uint32_t ref_emit(const struct ch_env *e, ref_t r, uint8_t *o)
+FLB_HD uint32_t ref_emit(const struct ch_env *e, ref_t r, uint8_t *o)
 {
     uint32_t k = r_kind(r), n = r_len(r);
     const uint8_t *b = ref_ptr(e, r);
@@ -249,7 +249,7 @@ FLB_HDN uint32_t ref_emit(const struct ch_env *e, ref_t r, uint8_t *o)
     return 0;
 }
 
-FLB_HDN uint32_t rec_emit(const struct ch_env *e, const struct ch_rec *rc, uint8_t *o)
+FLB_HD uint32_t rec_emit(const struct ch_env *e, const struct ch_rec *rc, uint8_t *o)
 {
     uint32_t n = 0;
     int i;
@@ -329,7 +329,7 @@ FLB_HD int rec_is_shadowed(const uint8_t *base, const uint8_t *p, const uint8_t 
 
 /* Split a framed record into timestamp, metadata and the top-level field list.
  * Returns 0, or -1 when it has more than CH_MAXF keys. */
-FLB_HDN int rec_decode(const struct ch_env *e, uint32_t off, uint32_t len, struct ch_rec *rc, uint32_t empty_map_off)
+FLB_HD int rec_decode(const struct ch_env *e, uint32_t off, uint32_t len, struct ch_rec *rc, uint32_t empty_map_off)
 {
     const uint8_t *p = e->in + off, *end = p + len, *q = p + 1, *nx;
     struct mp_tok t;
@@ -443,7 +443,7 @@ FLB_HDN int ra_walk_sub(const struct ch_env *e, const struct cf_ra *ra, const ui
 
 /* flb_ra_key_value_get(): 0 found (flags: *okey_null), -1 not found.
  * On success either *top >= 0 (the top-level field itself) or *vp/*ve (nested). */
-FLB_HDN int ra_get(const struct ch_env *e, const struct ch_rec *rc, const struct cf_ra *ra, int *top,
+FLB_HD int ra_get(const struct ch_env *e, const struct ch_rec *rc, const struct cf_ra *ra, int *top,
                   const uint8_t **vp, const uint8_t **ve, int *okey_null)
 {
     int i = ra_find(e, rc, e->blob + ra->key_off, ra->key_len);
@@ -500,14 +500,17 @@ FLB_HD int ra_regex_match(const struct ch_env *e, const struct ch_rec *rc, uint3
 /* ---------------------------------------------------------- filter_parser */
 /* One regex parser over s[0,n): returns 1 parsed (fields appended to out_*), 0 not.
  * Timestamp result in *t_sec/*t_nsec (0/0 when no time was resolved). */
-FLB_HDN int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s,
+/* tslot (4 ints of the capture cache, or NULL): the evaluation pass stores the Time_Key lookup there
+ * (state 1 ok / 2 failed, seconds lo/hi, nanoseconds) and the emission pass (use_cached) reads it
+ * instead of running strptime again */
+FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s,
                       uint32_t n, const int *caps, ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec,
-                      int64_t *t_nsec)
+                      int64_t *t_nsec, int32_t *tslot, int use_cached)
 {
     const struct cf_pname *nm = (const struct cf_pname *) (e->blob + pd->names_off);
     uint32_t i;
-    int any_end = 0, cnt = 0;
-    int64_t lookup = 0;
+    int any_end = 0, cnt = 0, have_nsec = 0;
+    int64_t lookup = 0, nsec_cached = 0;
     double frac = 0;
     if (pd->n_groups == 0) return 0;                 /* flb_parser_regex_do: n <= 0 -> -1 */
     for (i = 0; i < pd->n_names; i++) {
@@ -516,7 +519,13 @@ FLB_HDN int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_
         const uint8_t *v = s + b;
         if (en >= 0) any_end = 1;
         if (vlen == 0 && pd->skip_empty) continue;
-        if (pd->has_time && nm[i].is_time) {
+        if (pd->has_time && nm[i].is_time && use_cached && tslot && tslot[0]) {
+            if (tslot[0] == 2) continue;
+            lookup = (int64_t) (((uint64_t) (uint32_t) tslot[2] << 32) | (uint32_t) tslot[1]);
+            nsec_cached = tslot[3]; have_nsec = 1;
+            if (!pd->time_keep) continue;
+        }
+        else if (pd->has_time && nm[i].is_time) {
             struct dt_tm tm;
             struct dt_parser tp;
             double ns;
@@ -528,9 +537,17 @@ FLB_HDN int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_
             tp.with_year = (int) pd->time_with_year; tp.with_tz = (int) pd->time_with_tz;
             tp.strict = (int) pd->time_strict; tp.offset = pd->time_offset;
             r = dt_time_lookup(vlen ? v : s, vlen, e->now, &tp, &tm, &ns);
-            if (r == -1) continue;
+            if (r == -1) { if (tslot && !use_cached) tslot[0] = 2; continue; }
             frac = ns;
             lookup = dt_timegm(&tm) - tm.gmtoff;
+            if (tslot && !use_cached) {
+                tslot[0] = 1; tslot[1] = (int32_t) (uint32_t) lookup; tslot[2] = (int32_t) (uint32_t) ((uint64_t) lookup >> 32);
+#ifdef __CUDA_ARCH__
+                tslot[3] = (int32_t) (int64_t) __dmul_rn(frac, 1000000000.0);
+#else
+                tslot[3] = (int32_t) (int64_t) (frac * 1000000000.0);
+#endif
+            }
             if (!pd->time_keep) continue;
         }
         if (cnt >= CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
@@ -551,6 +568,7 @@ FLB_HDN int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_
     if (!any_end) return 0;                          /* flb_regex_parse: last_pos == -1 */
     *on = cnt;
     *t_sec = lookup;
+    if (have_nsec) { *t_nsec = nsec_cached; return 1; }
 #ifdef __CUDA_ARCH__
     *t_nsec = (int64_t) __dmul_rn(frac, 1000000000.0);
 #else
@@ -560,7 +578,7 @@ FLB_HDN int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_
 }
 
 /* Types cast of a parsed (key, value) pair: flb_parser_typecast(), src/flb_parser.c:1280-1377 */
-FLB_HDN ref_t cast_value(const struct ch_env *e, const struct cf_pdef *pd, const uint8_t *key, uint32_t klen,
+FLB_HD ref_t cast_value(const struct ch_env *e, const struct cf_pdef *pd, const uint8_t *key, uint32_t klen,
                         const uint8_t *v, uint32_t voff, uint32_t vlen)
 {
     const struct cf_ptype *ty = (const struct cf_ptype *) (e->blob + pd->types_off);
@@ -835,7 +853,7 @@ FLB_HD int djf_string(const uint8_t *s, int p, int n, uint8_t *scr, uint32_t at,
     return q + 1;
 }
 
-FLB_HDN int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t val_off, ref_t *ok_, ref_t *ov_, int *on)
+FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t val_off, ref_t *ok_, ref_t *ov_, int *on)
 {
     uint8_t *scr = e->scr;
     uint32_t hpos[DJ_MAX_DEPTH + 1], ccnt[DJ_MAX_DEPTH + 1];
@@ -1023,7 +1041,7 @@ FLB_HDN int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t
  * equals Time_Key; its value must be a STR; a failed lookup keeps the member and leaves
  * the timestamp at 0 (:198-209). */
 template <bool EMIT>
-FLB_HDN int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
+FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
                      ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec, uint32_t ridx,
                      uint32_t *cache_pos)
 {
@@ -1097,7 +1115,7 @@ struct ch_scratch {              /* per-lane working memory */
 };
 
 template <bool EMIT>
-FLB_HDN void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct ch_rec *rc, struct ch_scratch *w,
+FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct ch_rec *rc, struct ch_scratch *w,
                      uint32_t ridx, uint32_t *cache_pos)
 {
     uint8_t keep[CH_MAXF];
@@ -1143,12 +1161,13 @@ FLB_HDN void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct
             int64_t ts = 0, tns = 0;
             int got = 0, cnt = 0;
             if (pd->type == FLBGPU_PARSER_REGEX) {
-                uint32_t need = 1 + 2 * (pd->n_groups + 1), c;
+                uint32_t need = 1 + 2 * (pd->n_groups + 1), c;      /* + 4 ints of parsed time behind them */
                 int32_t *slot = 0;
                 int matched;
                 if (e->capcache && *cache_pos + need <= e->cap_stride)
                     slot = e->capcache + (size_t) ridx * e->cap_stride + *cache_pos;
-                *cache_pos += need;
+                *cache_pos += need + 4;
+                if (e->capcache && *cache_pos > e->cap_stride) slot = 0;
                 if (EMIT && slot) {
                     matched = slot[0];
                     for (c = 0; c + 1 < need; c++) w->caps[c] = slot[1 + c];
@@ -1158,9 +1177,11 @@ FLB_HDN void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct
                     if (!EMIT && slot) {
                         slot[0] = matched;
                         for (c = 0; c + 1 < need; c++) slot[1 + c] = w->caps[c];
+                        slot[need] = 0;
                     }
                 }
-                if (matched) got = pdef_regex(e, pd, val_off, vp, vn, w->caps, w->tk, w->tv, &cnt, &ts, &tns);
+                if (matched) got = pdef_regex(e, pd, val_off, vp, vn, w->caps, w->tk, w->tv, &cnt, &ts, &tns,
+                                              slot ? slot + need : 0, EMIT ? 1 : 0);
                 if (got) { preset = pd->n_groups; style = ST_PRESET; }
             }
             else if (pd->type == FLBGPU_PARSER_JSON) {
@@ -1210,7 +1231,7 @@ FLB_HDN void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct
 
 /* ------------------------------------------------------------ filter_grep */
 /* returns 1 keep, 0 exclude */
-FLB_HDN int f_grep(const struct ch_env *e, const struct cf_grep *cf, const struct ch_rec *rc, struct ch_scratch *w)
+FLB_HD int f_grep(const struct ch_env *e, const struct cf_grep *cf, const struct ch_rec *rc, struct ch_scratch *w)
 {
     const struct cf_grep_rule *r = (const struct cf_grep_rule *) (e->blob + cf->rules_off);
     uint32_t i;
@@ -1274,7 +1295,7 @@ FLB_HD int ref_rx(const struct ch_env *e, ref_t r, uint32_t rx_off, struct ch_sc
     return obj_rx(e, vt, p, n, rx_off, w);
 }
 
-FLB_HDN int mod_conditions(const struct ch_env *e, const struct cf_modify *cf, const struct ch_rec *rc,
+FLB_HD int mod_conditions(const struct ch_env *e, const struct cf_modify *cf, const struct ch_rec *rc,
                           struct ch_scratch *w)
 {
     const struct cf_mod_cond *c = (const struct cf_mod_cond *) (e->blob + cf->conds_off);
@@ -1346,7 +1367,7 @@ FLB_HD void compact(struct ch_rec *rc, const uint8_t *del)
 }
 
 /* returns 1 when the rule modified the map */
-FLB_HDN int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct ch_rec *rc, struct ch_scratch *w)
+FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct ch_rec *rc, struct ch_scratch *w)
 {
     const uint8_t *key = e->blob + r->key_off, *val = e->blob + r->val_off;
     ref_t kmp = mkref(RK_MP_CONST, r->kmp_off, r->kmp_len), vmp = mkref(RK_MP_CONST, r->vmp_off, r->vmp_len);

@@ -18,7 +18,11 @@
 #ifndef FLB_HD
 #ifdef __CUDACC__
 #define FLB_HD __host__ __device__ __forceinline__
+#ifdef FLB_INLINE_ALL
+#define FLB_HDN __host__ __device__ __forceinline__
+#else
 #define FLB_HDN __host__ __device__ __noinline__
+#endif
 #else
 #define FLB_HD static inline
 #define FLB_HDN static
@@ -94,7 +98,7 @@ FLB_HD int mp_token(const uint8_t *p, const uint8_t *end, struct mp_tok *t)
 /* Skip one complete object starting at p.  Returns the first byte after it, or
  * NULL when the object is truncated or malformed.  Nesting needs no stack: a
  * single "objects still owed" counter is enough to find the end. */
-FLB_HDN const uint8_t *mp_skip(const uint8_t *p, const uint8_t *end)
+FLB_HD const uint8_t *mp_skip(const uint8_t *p, const uint8_t *end)
 {
     uint64_t owed = 1;
     struct mp_tok t;

@@ -17,7 +17,11 @@
 #ifndef FLB_HD
 #ifdef __CUDACC__
 #define FLB_HD __host__ __device__ __forceinline__
+#ifdef FLB_INLINE_ALL
+#define FLB_HDN __host__ __device__ __forceinline__
+#else
 #define FLB_HDN __host__ __device__ __noinline__
+#endif
 #else
 #define FLB_HD static inline
 #define FLB_HDN static

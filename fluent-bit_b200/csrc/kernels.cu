@@ -56,6 +56,13 @@ static void ev_end(int k) { ev_end_on(k, g_stream); }
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     snprintf(g_err, sizeof(g_err), "%s: %s", #call, cudaGetErrorString(e_)); return -1; } } while (0)
 
+/* 4 resident blocks per SM (64 registers per lane): measured best on B200 -- the interpreter is bound
+ * by instruction fetch and load latency, which more resident warps hide better than fewer spills do
+ * (profiles/r01_variants.txt) */
+#ifndef BK_EVAL_MIN_BLOCKS
+#define BK_EVAL_MIN_BLOCKS 4
+#endif
+
 /* ---------------------------------------------------------------- helpers */
 /* exclusive scan of one value per thread over a 256-thread block */
 template <typename T>
@@ -260,7 +267,8 @@ struct k_chain_params {
 
 /* evaluation: record r0 + global thread id.  No barrier: a warp retires as soon as its
  * 32 records are done (block-level reductions happen in k_bsum). */
-__global__ void __launch_bounds__(BK_REC_BLOCK) k_chain_eval(const k_chain_params p)
+
+__global__ void __launch_bounds__(BK_REC_BLOCK, BK_EVAL_MIN_BLOCKS) k_chain_eval(const k_chain_params p)
 {
     const uint32_t i = p.r0 + blockIdx.x * BK_REC_BLOCK + threadIdx.x;
     if (i >= p.n_rec) return;
@@ -278,24 +286,42 @@ __global__ void __launch_bounds__(BK_REC_BLOCK) k_bsum(const uint32_t *__restric
     if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
 }
 
-/* emission of block (r0/256 + blockIdx): in-block exclusive scan + the block's offset */
-__global__ void __launch_bounds__(BK_REC_BLOCK) k_chain_emit(const k_chain_params p)
+/* ---- emission over a dense list of survivors ----
+ * After a selective grep most records of a block are gone; packing the survivors of the whole range
+ * (not just of one block) keeps every warp of the emission kernel full.
+ *   k_surv_count: survivors per block            k_scan_top<uint32_t>: rank base per block
+ *   k_surv_fill : (record, output offset) at its rank      k_chain_emit_list: one lane per rank */
+__global__ void __launch_bounds__(BK_REC_BLOCK) k_surv_count(const uint32_t *__restrict__ size, uint32_t n, uint32_t *__restrict__ cnt)
 {
-    const uint32_t blk = p.r0 / BK_REC_BLOCK + blockIdx.x;
-    const uint32_t i = blk * BK_REC_BLOCK + threadIdx.x;
-    uint32_t sz = (i < p.n_rec) ? p.size[i] : 0, tot;
+    const uint32_t i = blockIdx.x * BK_REC_BLOCK + threadIdx.x;
+    uint32_t tot;
+    block_excl_scan((i < n && size[i]) ? 1u : 0u, &tot);
+    if (threadIdx.x == 0) cnt[blockIdx.x] = tot;
+}
+
+__global__ void __launch_bounds__(BK_REC_BLOCK) k_surv_fill(const uint32_t *__restrict__ size, uint32_t n, uint32_t rec0,
+                                                            const uint32_t *__restrict__ base, const uint64_t *__restrict__ bsum,
+                                                            uint32_t *__restrict__ l_rec, uint64_t *__restrict__ l_off)
+{
+    const uint32_t i = blockIdx.x * BK_REC_BLOCK + threadIdx.x;
+    const uint32_t sz = i < n ? size[i] : 0;
+    uint32_t tot, nsurv;
     const uint32_t local = block_excl_scan(sz, &tot);
-    /* survivors are packed to the front of the block so that, after a selective grep, the warps
-     * that still have work are full instead of every warp dragging a few live lanes */
-    __shared__ uint32_t s_idx[BK_REC_BLOCK], s_loc[BK_REC_BLOCK];
-    uint32_t nsurv;
     const uint32_t rank = block_excl_scan(sz ? 1u : 0u, &nsurv);
-    if (sz) { s_idx[rank] = i; s_loc[rank] = local; }
-    __syncthreads();
-    if (threadIdx.x < nsurv) {
-        const uint32_t r = s_idx[threadIdx.x];
-        chain_record<true>(&p.env, r, p.off[r], p.len[r], p.out + p.bsum[blk] + s_loc[threadIdx.x]);
+    if (sz) {
+        l_rec[base[blockIdx.x] + rank] = rec0 + i;
+        l_off[base[blockIdx.x] + rank] = bsum[blockIdx.x] + local;
     }
+}
+
+__global__ void __launch_bounds__(BK_REC_BLOCK, BK_EVAL_MIN_BLOCKS) k_chain_emit_list(const k_chain_params p, const uint32_t *__restrict__ l_rec,
+                                                                                      const uint64_t *__restrict__ l_off,
+                                                                                      const unsigned long long *__restrict__ n_list)
+{
+    const uint32_t t = blockIdx.x * BK_REC_BLOCK + threadIdx.x;
+    if (t >= (uint32_t) *n_list) return;
+    const uint32_t r = l_rec[t];
+    chain_record<true>(&p.env, r, p.off[r], p.len[r], p.out + l_off[t]);
 }
 
 /* ------------------------------------------------------------ bk_* seam */
@@ -327,7 +353,7 @@ int bk_init(int device)
     g_ev_ready = 1;
     /* the interpreter keeps its field list and backtrack stack in local memory */
     CK(cudaFuncSetCacheConfig(k_chain_eval, cudaFuncCachePreferL1));
-    CK(cudaFuncSetCacheConfig(k_chain_emit, cudaFuncCachePreferL1));
+    CK(cudaFuncSetCacheConfig(k_chain_emit_list, cudaFuncCachePreferL1));
     return 0;
 }
 
@@ -405,6 +431,9 @@ int bk_upload_wait_index(size_t upto)
 /* ---- download session: pinned ring + one host thread per slot ---- */
 #define XF_SLOTS 8
 #define XF_SLICE ((size_t) 16 << 20)
+#define XF_MAX_RANGES 512
+static cudaEvent_t xf_rev[XF_MAX_RANGES];
+static int xf_rev_made;
 static uint8_t *xf_ring[XF_SLOTS];
 static cudaEvent_t xf_ev[XF_SLOTS], xf_evc;
 static int xf_ready;
@@ -416,6 +445,13 @@ struct xf_session {
     std::atomic<int> closed, failed;
     std::thread th[XF_SLOTS];
     int started;
+    /* byte ranges handed over by bk_download_push(); an issuer thread turns them into ring slices so
+     * that the caller (which also drives indexing and evaluation of the next slice) never blocks on a
+     * full ring */
+    size_t r_lo[XF_MAX_RANGES], r_hi[XF_MAX_RANGES];
+    std::atomic<long> n_pushed;
+    std::atomic<int> push_closed;
+    std::thread issuer;
 };
 static xf_session *g_xf;
 
@@ -446,6 +482,33 @@ static void xf_worker(xf_session *x, int s)
     }
 }
 
+static void xf_issuer(xf_session *x)
+{
+    for (long r = 0;; r++) {
+        while (x->n_pushed.load(std::memory_order_acquire) <= r) {
+            if (x->failed.load() || x->push_closed.load()) {
+                if (x->n_pushed.load(std::memory_order_acquire) > r) break;
+                x->closed.store(1);
+                return;
+            }
+            sched_yield();
+        }
+        /* bytes [lo,hi) exist once the emission recorded in xf_rev[r] is done */
+        if (cudaStreamWaitEvent(g_copy, xf_rev[r], 0) != cudaSuccess) { x->failed.store(1); x->closed.store(1); return; }
+        for (size_t off = x->r_lo[r]; off < x->r_hi[r] && !x->failed.load(); off += XF_SLICE) {
+            const long i = x->n_issued.load();
+            const int s = (int) (i % XF_SLOTS);
+            const size_t sz = (off + XF_SLICE <= x->r_hi[r]) ? XF_SLICE : x->r_hi[r] - off;
+            if (i >= XF_SLOTS) while (x->done[s].load(std::memory_order_acquire) < i - XF_SLOTS) { if (x->failed.load()) break; sched_yield(); }
+            x->s_off[s] = off; x->s_len[s] = sz;
+            if (cudaMemcpyAsync(xf_ring[s], x->d_src + off, sz, cudaMemcpyDeviceToHost, g_copy) != cudaSuccess ||
+                cudaEventRecord(xf_ev[s], g_copy) != cudaSuccess) { x->failed.store(1); break; }
+            x->issued[s].store(i, std::memory_order_release);
+            x->n_issued.store(i + 1);
+        }
+    }
+}
+
 int bk_download_begin(void *h_dst, const void *d_out)
 {
     if (xf_init()) return -1;
@@ -453,7 +516,9 @@ int bk_download_begin(void *h_dst, const void *d_out)
     x->h_dst = (uint8_t *) h_dst; x->d_src = (const uint8_t *) d_out;
     for (int s = 0; s < XF_SLOTS; s++) { x->issued[s].store(-1); x->done[s].store(-1); }
     x->n_issued.store(0); x->closed.store(0); x->failed.store(0);
+    x->n_pushed.store(0); x->push_closed.store(0);
     for (int s = 0; s < XF_SLOTS; s++) x->th[s] = std::thread(xf_worker, x, s);
+    x->issuer = std::thread(xf_issuer, x);
     x->started = 1;
     g_xf = x;
     return 0;
@@ -463,19 +528,13 @@ int bk_download_push(size_t lo, size_t hi)
 {
     xf_session *x = g_xf;
     if (!x) return -1;
-    CK(cudaEventRecord(xf_evc, g_stream));            /* bytes [lo,hi) exist once the emission enqueued so far is done */
-    CK(cudaStreamWaitEvent(g_copy, xf_evc, 0));
-    for (size_t off = lo; off < hi && !x->failed.load(); off += XF_SLICE) {
-        const long i = x->n_issued.load();
-        const int s = (int) (i % XF_SLOTS);
-        const size_t sz = (off + XF_SLICE <= hi) ? XF_SLICE : hi - off;
-        if (i >= XF_SLOTS) while (x->done[s].load(std::memory_order_acquire) < i - XF_SLOTS) { if (x->failed.load()) return -1; sched_yield(); }
-        x->s_off[s] = off; x->s_len[s] = sz;
-        if (cudaMemcpyAsync(xf_ring[s], x->d_src + off, sz, cudaMemcpyDeviceToHost, g_copy) != cudaSuccess ||
-            cudaEventRecord(xf_ev[s], g_copy) != cudaSuccess) { x->failed.store(1); return -1; }
-        x->issued[s].store(i, std::memory_order_release);
-        x->n_issued.store(i + 1);
-    }
+    if (hi <= lo) return 0;
+    const long r = x->n_pushed.load();
+    if (r >= XF_MAX_RANGES) { snprintf(g_err, sizeof(g_err), "too many download ranges"); return -1; }
+    for (; xf_rev_made <= (int) r; xf_rev_made++) CK(cudaEventCreateWithFlags(&xf_rev[xf_rev_made], cudaEventDisableTiming));
+    CK(cudaEventRecord(xf_rev[r], g_stream));
+    x->r_lo[r] = lo; x->r_hi[r] = hi;
+    x->n_pushed.store(r + 1, std::memory_order_release);
     return x->failed.load() ? -1 : 0;
 }
 
@@ -484,7 +543,8 @@ int bk_download_end(void)
     xf_session *x = g_xf;
     int rc = 0;
     if (!x) return -1;
-    x->closed.store(1);
+    x->push_closed.store(1);
+    x->issuer.join();
     for (int s = 0; s < XF_SLOTS; s++) x->th[s].join();
     if (x->failed.load()) { snprintf(g_err, sizeof(g_err), "device->host transfer failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
     delete x;
@@ -661,10 +721,29 @@ int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, ui
     k_chain_params p;
     if (b1 <= b0) return 0;
     fill_params(a, &p, d_out, b0 * BK_REC_BLOCK);
-    ev_begin(2);
-    k_chain_emit<<<b1 - b0, BK_REC_BLOCK, 0, g_stream>>>(p);
-    ev_end(2);
-    g_launches += 1;
+    {
+        const uint32_t nb = b1 - b0, rec0 = b0 * BK_REC_BLOCK;
+        const uint32_t n = (a->n_rec > rec0) ? ((a->n_rec - rec0 < nb * BK_REC_BLOCK) ? a->n_rec - rec0 : nb * BK_REC_BLOCK) : 0;
+        static uint32_t *d_cnt, *d_lrec; static uint64_t *d_loff; static unsigned long long *d_nlist; static size_t cap_b, cap_r;
+        if (ensure_small()) return -1;
+        if (cap_b < nb) { cudaFree(d_cnt); d_cnt = 0; cap_b = 0; CK(cudaMalloc((void **) &d_cnt, sizeof(uint32_t) * (nb + nb / 2 + 64))); cap_b = nb + nb / 2 + 64; }
+        if (cap_r < (size_t) nb * BK_REC_BLOCK) {
+            const size_t want = (size_t) (nb + nb / 2 + 64) * BK_REC_BLOCK;
+            CK(cudaStreamSynchronize(g_stream));           /* an emission still running reads the old lists */
+            cudaFree(d_lrec); cudaFree(d_loff); d_lrec = 0; d_loff = 0; cap_r = 0;
+            CK(cudaMalloc((void **) &d_lrec, sizeof(uint32_t) * want));
+            CK(cudaMalloc((void **) &d_loff, sizeof(uint64_t) * want));
+            cap_r = want;
+        }
+        if (!d_nlist) CK(cudaMalloc((void **) &d_nlist, 64));
+        ev_begin(2);
+        k_surv_count<<<nb, BK_REC_BLOCK, 0, g_stream>>>(a->d_size + rec0, n, d_cnt);
+        k_scan_top<uint32_t><<<1, 256, 0, g_stream>>>(d_cnt, nb, d_nlist);
+        k_surv_fill<<<nb, BK_REC_BLOCK, 0, g_stream>>>(a->d_size + rec0, n, rec0, d_cnt, a->d_bsum + b0, d_lrec, d_loff);
+        k_chain_emit_list<<<nb, BK_REC_BLOCK, 0, g_stream>>>(p, d_lrec, d_loff, d_nlist);
+        ev_end(2);
+        g_launches += 4;
+    }
     CK(cudaGetLastError());
     return 0;
 }

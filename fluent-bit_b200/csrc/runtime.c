@@ -646,7 +646,7 @@ static uint32_t emit_parser_filter(flbgpu_filter *f, struct blob *b, uint32_t *c
             if (!ps) { set_err("requested parser '%s' not found%s", p->v, NULL); return 0; }
             if (cf.n_parsers >= 8) { set_err("too many parsers in one filter%s%s", NULL, NULL); return 0; }
             cf.pdef_off[cf.n_parsers++] = emit_pdef(b, ps);
-            if (ps->has_rx) *cap_need += 1 + 2 * (ps->rx.prog->n_groups + 1);
+            if (ps->has_rx) *cap_need += 1 + 2 * (ps->rx.prog->n_groups + 1) + 4;   /* match flag, captures, parsed time */
             if (ps->type == FLBGPU_PARSER_JSON) { *cap_need += 2; f->needs_scratch = 1; }
         }
         else if (!strcasecmp(p->k, "preserve_key")) { int v = parse_bool(p->v); if (v < 0) { set_err("invalid boolean '%s'%s", p->v, NULL); return 0; } cf.preserve_key = v; }
@@ -1371,6 +1371,19 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     return FLBGPU_FILTER_MODIFIED;
 }
 
+static void hugepage_hint(void *p, size_t n)
+{
+#ifdef MADV_HUGEPAGE
+    if (n >= ((size_t) 8 << 20)) {                    /* fewer, larger page faults while the result is filled in */
+        uintptr_t lo = ((uintptr_t) p + ((size_t) 2 << 20) - 1) & ~(((uintptr_t) 2 << 20) - 1);
+        uintptr_t hi = ((uintptr_t) p + n) & ~(((uintptr_t) 2 << 20) - 1);
+        if (hi > lo) madvise((void *) lo, hi - lo, MADV_HUGEPAGE);
+    }
+#else
+    (void) p; (void) n;
+#endif
+}
+
 /* Streaming form of chain_run for host buffers.  The chunk-level verdicts are only known when the
  * whole chunk has been evaluated, but they almost never differ from the previous call's (and from
  * "every filter modifies" on the first call), so each slice is emitted and sent back as soon as it
@@ -1428,6 +1441,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
                     no_ = realloc(out, want_); \
                     if (!no_) goto fail; \
                     out = no_; cap_out_h = want_; \
+                    hugepage_hint(out, want_); \
                     GROW_KEEP_OUT(want_); \
                 } \
                 if (!dl_open) { if (bk_download_begin(out, c->d_out)) goto fail; dl_open = 1; } \
