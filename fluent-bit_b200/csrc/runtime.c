@@ -1523,7 +1523,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
     c->st.bytes_out = placed;
     *out_size = (size_t) placed;
     if (placed == 0) { free(out); out = NULL; }
-    else {
+    else if (cap_out_h > placed + placed / 2) {     /* badly over-estimated: give the excess back */
         uint8_t *sh = realloc(out, (size_t) placed);
         if (sh) out = sh;
     }
@@ -1662,6 +1662,132 @@ int flbgpu_filter_cb(flbgpu_filter *f, const void *data, size_t bytes, const cha
         f->solo = c;
     }
     return flbgpu_chain_do(f->solo, data, bytes, tag, tag_len, out_buf, out_size);
+}
+
+/* end of the msgpack object at p (host side, for unwrapping results), or NULL */
+static const uint8_t *host_mp_skip(const uint8_t *p, const uint8_t *end, int depth)
+{
+    uint32_t n = 0, c, i;
+    int is_map = 0;
+    if (p >= end || depth > 64) return NULL;
+    c = *p;
+    if (c <= 0x7f || c >= 0xe0 || c == 0xc0 || c == 0xc2 || c == 0xc3) return p + 1;
+    if (c >= 0xa0 && c <= 0xbf) return (size_t) (end - p) >= 1 + (c & 31) ? p + 1 + (c & 31) : NULL;
+    if (c >= 0x90 && c <= 0x9f) { n = c & 15; p += 1; goto cont; }
+    if (c >= 0x80 && c <= 0x8f) { n = c & 15; is_map = 1; p += 1; goto cont; }
+#define HM_NEED(k) do { if ((size_t) (end - p) < (size_t) (k)) return NULL; } while (0)
+#define HM_BE16(q) (((uint32_t) (q)[0] << 8) | (q)[1])
+#define HM_BE32(q) (((uint32_t) (q)[0] << 24) | ((uint32_t) (q)[1] << 16) | ((uint32_t) (q)[2] << 8) | (q)[3])
+    switch (c) {
+    case 0xcc: case 0xd0: HM_NEED(2); return p + 2;
+    case 0xcd: case 0xd1: HM_NEED(3); return p + 3;
+    case 0xce: case 0xd2: case 0xca: HM_NEED(5); return p + 5;
+    case 0xcf: case 0xd3: case 0xcb: HM_NEED(9); return p + 9;
+    case 0xd9: case 0xc4: HM_NEED(2); n = p[1]; HM_NEED(2 + n); return p + 2 + n;
+    case 0xda: case 0xc5: HM_NEED(3); n = HM_BE16(p + 1); HM_NEED(3 + (size_t) n); return p + 3 + n;
+    case 0xdb: case 0xc6: HM_NEED(5); n = HM_BE32(p + 1); HM_NEED(5 + (size_t) n); return p + 5 + n;
+    case 0xd4: HM_NEED(3); return p + 3;
+    case 0xd5: HM_NEED(4); return p + 4;
+    case 0xd6: HM_NEED(6); return p + 6;
+    case 0xd7: HM_NEED(10); return p + 10;
+    case 0xd8: HM_NEED(18); return p + 18;
+    case 0xc7: HM_NEED(3); n = p[1]; HM_NEED(3 + (size_t) n); return p + 3 + n;
+    case 0xc8: HM_NEED(4); n = HM_BE16(p + 1); HM_NEED(4 + (size_t) n); return p + 4 + n;
+    case 0xc9: HM_NEED(6); n = HM_BE32(p + 1); HM_NEED(6 + (size_t) n); return p + 6 + n;
+    case 0xdc: HM_NEED(3); n = HM_BE16(p + 1); p += 3; break;
+    case 0xdd: HM_NEED(5); n = HM_BE32(p + 1); p += 5; break;
+    case 0xde: HM_NEED(3); n = HM_BE16(p + 1); p += 3; is_map = 1; break;
+    case 0xdf: HM_NEED(5); n = HM_BE32(p + 1); p += 5; is_map = 1; break;
+    default: return NULL;
+    }
+cont:
+    for (i = 0; i < n * (is_map ? 2u : 1u); i++) {
+        p = host_mp_skip(p, end, depth + 1);
+        if (!p) return NULL;
+    }
+    return p;
+}
+
+static int parser_solo(flbgpu_parser *p)
+{
+    if (!p->solo) {
+        flbgpu_filter *f = flbgpu_filter_new(p->ctx, "parser");
+        flbgpu_chain *c;
+        flbgpu_filter_set_property(f, "key_name", "_");
+        flbgpu_filter_set_property(f, "parser", p->name);
+        if (flbgpu_filter_init(f)) { flbgpu_filter_destroy(f); return -1; }
+        c = flbgpu_chain_new(p->ctx);
+        if (flbgpu_chain_add(c, f) || flbgpu_chain_init(c)) { flbgpu_chain_destroy(c); flbgpu_filter_destroy(f); return -1; }
+        p->solo = c; p->solo_filter = f;
+    }
+    return 0;
+}
+
+static size_t put_line_event(uint8_t *rec, const char *buf, size_t length)
+{
+    size_t n = 0, i;
+    rec[n++] = 0x92; rec[n++] = 0x92; rec[n++] = 0xd7; rec[n++] = 0x00;
+    for (i = 0; i < 8; i++) rec[n++] = 0;
+    rec[n++] = 0x80; rec[n++] = 0x81; rec[n++] = 0xa1; rec[n++] = '_';
+    if (length < 32) rec[n++] = 0xa0 | (uint8_t) length;
+    else if (length < 256) { rec[n++] = 0xd9; rec[n++] = (uint8_t) length; }
+    else if (length < 65536) { rec[n++] = 0xda; rec[n++] = (uint8_t) (length >> 8); rec[n++] = (uint8_t) length; }
+    else { rec[n++] = 0xdb; rec[n++] = (uint8_t) (length >> 24); rec[n++] = (uint8_t) (length >> 16); rec[n++] = (uint8_t) (length >> 8); rec[n++] = (uint8_t) length; }
+    memcpy(rec + n, buf, length);
+    return n + length;
+}
+
+/* flb_parser_do() over n lines in ONE device pass (the entry a batched caller such as a GPU
+ * filter_parser or an input plugin uses): line i = base[off[i] .. off[i]+len[i]).  Results: the
+ * msgpack maps of the parsed lines back to back in *out_buf (malloc), map i at
+ * [out_off[i], out_off[i+1]) (empty when ret[i] < 0), its time in out_time[i], ret[i] as
+ * flb_parser_do would return it (>= 0 parsed, -1 not). */
+int flbgpu_parser_do_batch(flbgpu_parser *p, const char *base, const uint32_t *off, const uint32_t *len, uint32_t n,
+                           void **out_buf, size_t *out_size, uint64_t *out_off, struct flbgpu_time *out_time, int *ret)
+{
+    uint8_t *chunk, *o = NULL, *maps;
+    const uint8_t *q, *end, *in_q;
+    size_t total = 0, at = 0, osz = 0, mo = 0;
+    uint32_t i;
+    int r;
+    if (!p || !base || !off || !len || !out_buf || !out_size || !out_off || !ret) return -1;
+    *out_buf = NULL; *out_size = 0;
+    if (parser_solo(p)) return -1;
+    for (i = 0; i < n; i++) total += (size_t) len[i] + 22;
+    chunk = malloc(total + 1);
+    if (!chunk) return -1;
+    for (i = 0; i < n; i++) at += put_line_event(chunk + at, base + off[i], len[i]);
+    r = n ? flbgpu_chain_do(p->solo, chunk, at, "", 0, (void **) &o, &osz) : FLBGPU_FILTER_NOTOUCH;
+    if (n && r != FLBGPU_FILTER_MODIFIED) { free(chunk); free(o); return -1; }
+    maps = malloc(osz ? osz : 1);
+    q = o; end = o + osz; in_q = chunk;
+    for (i = 0; i < n; i++) {
+        /* filter_parser emits exactly one record per input record, in order */
+        const uint8_t *body, *nx;
+        size_t in_len = (size_t) len[i] + (len[i] < 32 ? 17 : len[i] < 256 ? 18 : len[i] < 65536 ? 19 : 21);
+        out_off[i] = mo;
+        if ((size_t) (end - q) < 13 || !(nx = host_mp_skip(q + 13, end, 0))) { free(chunk); free(o); free(maps); set_err("malformed parser result%s%s", NULL, NULL); return -1; }
+        body = q + 13;
+        if ((size_t) (nx - q) == in_len && memcmp(body, in_q + 13, in_len - 13) == 0) {
+            ret[i] = -1;                                     /* came back as it went in: no parser matched */
+            if (out_time) { out_time[i].tv_sec = 0; out_time[i].tv_nsec = 0; }
+        }
+        else {
+            ret[i] = (int) len[i];
+            if (out_time) {
+                out_time[i].tv_sec = ((int64_t) q[4] << 24) | (q[5] << 16) | (q[6] << 8) | q[7];
+                out_time[i].tv_nsec = ((int64_t) q[8] << 24) | (q[9] << 16) | (q[10] << 8) | q[11];
+            }
+            memcpy(maps + mo, body, (size_t) (nx - body));
+            mo += (size_t) (nx - body);
+        }
+        q = nx;
+        in_q += in_len;
+    }
+    out_off[n] = mo;
+    free(chunk); free(o);
+    *out_buf = maps; *out_size = mo;
+    return 0;
 }
 
 /* flb_parser_do() for one line: wrap it as one event {"_": line}, run filter_parser

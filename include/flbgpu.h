@@ -74,6 +74,13 @@ flbgpu_parser *flbgpu_parser_get(flbgpu_ctx *ctx, const char *name);
  * Returns >= 0 (last byte consumed) or -1; *out_buf is malloc()ed, caller frees. */
 int flbgpu_parser_do(flbgpu_parser *parser, const char *buf, size_t length,
                      void **out_buf, size_t *out_size, struct flbgpu_time *out_time);
+
+/* The batched form: n lines in one device pass.  line i = base[off[i], off[i]+len[i]).
+ * *out_buf (malloc) holds the msgpack maps of the parsed lines back to back, map i at
+ * [out_off[i], out_off[i+1]) (out_off has n+1 entries; empty range when ret[i] < 0); out_time[i]
+ * and ret[i] are what flb_parser_do() returns per line.  Returns 0, or -1 when the call failed. */
+int flbgpu_parser_do_batch(flbgpu_parser *p, const char *base, const uint32_t *off, const uint32_t *len, uint32_t n,
+                           void **out_buf, size_t *out_size, uint64_t *out_off, struct flbgpu_time *out_time, int *ret);
 void flbgpu_parser_destroy(flbgpu_parser *parser);
 
 /* ---- filters ---------------------------------------------------------- */

@@ -1,0 +1,10 @@
+# experiment helper: end-to-end throughput for several slice sizes
+for mb in ${SLICES:-64 128 256 512}; do
+  for wl in json apache; do
+    FLBGPU_SLICE_MB=$mb timeout 200 python bench.py --workload $wl --primary-only --steps 3 --warmup 3 2>/dev/null | python -c "
+import sys,json
+d=json.loads(sys.stdin.readline())
+print('slice $mb $wl value %.1f e2e %.1f total_ms %s' % (d['value']/1e6, d['e2e']['value']/1e6, d['e2e'].get('host_phase_ms_last_call',{}).get('total')))
+"
+  done
+done
