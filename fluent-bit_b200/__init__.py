@@ -37,7 +37,7 @@ class Stats(C.Structure):
 
 EXPORTS = [
     "flbgpu_init", "flbgpu_shutdown", "flbgpu_last_error", "flbgpu_backend_name", "flbgpu_device_count",
-    "flbgpu_parser_create", "flbgpu_parser_get", "flbgpu_parser_do", "flbgpu_parser_destroy",
+    "flbgpu_parser_create", "flbgpu_parser_get", "flbgpu_parser_do", "flbgpu_parser_do_batch", "flbgpu_parser_destroy",
     "flbgpu_filter_new", "flbgpu_filter_set_property", "flbgpu_filter_init", "flbgpu_filter_cb",
     "flbgpu_filter_destroy", "flbgpu_chain_new", "flbgpu_chain_add", "flbgpu_chain_init", "flbgpu_chain_do",
     "flbgpu_chain_destroy", "flbgpu_chain_do_device", "flbgpu_chain_stats", "flbgpu_dev_alloc",
@@ -63,6 +63,8 @@ def load(path=None):
                                        C.POINTER(ParserTypes), C.c_int, vp]
     L.flbgpu_parser_get.restype = vp; L.flbgpu_parser_get.argtypes = [vp, cp]
     L.flbgpu_parser_do.argtypes = [vp, cp, sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(Time)]
+    L.flbgpu_parser_do_batch.argtypes = [vp, vp, C.POINTER(C.c_uint32), C.POINTER(C.c_uint32), C.c_uint32, C.POINTER(vp),
+                                         C.POINTER(sz), C.POINTER(C.c_uint64), C.POINTER(Time), C.POINTER(C.c_int)]
     L.flbgpu_parser_destroy.argtypes = [vp]
     L.flbgpu_filter_new.restype = vp; L.flbgpu_filter_new.argtypes = [vp, cp]
     L.flbgpu_filter_set_property.argtypes = [vp, cp, cp]
@@ -172,6 +174,29 @@ class Parser:
         if out.value:
             _libc.free(out)
         return r, data, (t.tv_sec, t.tv_nsec)
+
+
+def _parser_do_batch(self, lines):
+    """flbgpu_parser_do_batch(): [(ret, msgpack map bytes or None, (sec, nsec))] for a list of lines."""
+    n = len(lines)
+    base = b"".join(lines)
+    off = (C.c_uint32 * n)(); ln = (C.c_uint32 * n)()
+    at = 0
+    for i, l in enumerate(lines):
+        off[i] = at; ln[i] = len(l); at += len(l)
+    out, osz = C.c_void_p(), C.c_size_t()
+    ooff = (C.c_uint64 * (n + 1))(); tm = (Time * n)(); ret = (C.c_int * n)()
+    buf = C.create_string_buffer(base, len(base) + 1)
+    r = self.ctx.L.flbgpu_parser_do_batch(self.h, C.cast(buf, C.c_void_p), off, ln, n, C.byref(out), C.byref(osz), ooff, tm, ret)
+    if r != 0:
+        raise FlbGpuError("parser_do_batch failed: %s" % self.ctx.err())
+    blob = C.string_at(out.value, osz.value) if osz.value else b""
+    if out.value:
+        _libc.free(out)
+    return [(ret[i], blob[ooff[i]:ooff[i + 1]] if ret[i] >= 0 else None, (tm[i].tv_sec, tm[i].tv_nsec)) for i in range(n)]
+
+
+Parser.do_batch = _parser_do_batch
 
 
 def _call_filter(fn, L, handle, data, tag):

@@ -1796,31 +1796,14 @@ int flbgpu_parser_do(flbgpu_parser *p, const char *buf, size_t length, void **ou
                      struct flbgpu_time *out_time)
 {
     uint8_t *rec, *o = NULL;
-    size_t n = 0, osz = 0, i;
+    size_t n = 0, osz = 0;
     int r;
     if (!p || !buf || !out_buf || !out_size) return -1;
     *out_buf = NULL; *out_size = 0;
     if (out_time) { out_time->tv_sec = 0; out_time->tv_nsec = 0; }
-    if (!p->solo) {
-        flbgpu_filter *f = flbgpu_filter_new(p->ctx, "parser");
-        flbgpu_chain *c;
-        flbgpu_filter_set_property(f, "key_name", "_");
-        flbgpu_filter_set_property(f, "parser", p->name);
-        if (flbgpu_filter_init(f)) { flbgpu_filter_destroy(f); return -1; }
-        c = flbgpu_chain_new(p->ctx);
-        if (flbgpu_chain_add(c, f) || flbgpu_chain_init(c)) { flbgpu_chain_destroy(c); flbgpu_filter_destroy(f); return -1; }
-        p->solo = c; p->solo_filter = f;
-    }
+    if (parser_solo(p)) return -1;
     rec = malloc(length + 32);
-    rec[n++] = 0x92; rec[n++] = 0x92; rec[n++] = 0xd7; rec[n++] = 0x00;
-    for (i = 0; i < 8; i++) rec[n++] = 0;
-    rec[n++] = 0x80; rec[n++] = 0x81; rec[n++] = 0xa1; rec[n++] = '_';
-    if (length < 32) rec[n++] = 0xa0 | (uint8_t) length;
-    else if (length < 256) { rec[n++] = 0xd9; rec[n++] = (uint8_t) length; }
-    else if (length < 65536) { rec[n++] = 0xda; rec[n++] = (uint8_t) (length >> 8); rec[n++] = (uint8_t) length; }
-    else { rec[n++] = 0xdb; rec[n++] = (uint8_t) (length >> 24); rec[n++] = (uint8_t) (length >> 16); rec[n++] = (uint8_t) (length >> 8); rec[n++] = (uint8_t) length; }
-    memcpy(rec + n, buf, length);
-    n += length;
+    n = put_line_event(rec, buf, length);
     r = flbgpu_chain_do(p->solo, rec, n, "", 0, (void **) &o, &osz);
     if (r != FLBGPU_FILTER_MODIFIED || osz < 13) { free(rec); free(o); return -1; }
     /* an unparsed record comes back with its original body: {"_": line} */

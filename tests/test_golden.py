@@ -85,3 +85,34 @@ def test_chain_vectors_hostsim(sim_lib):
 @pytest.mark.gpu
 def test_chain_vectors_gpu(gpu_lib):
     check_chain(gpu_lib)
+
+
+def check_parser_batch(lib):
+    """flbgpu_parser_do_batch: every line's (ret, map, time) equals flb_parser_do of the reference, for all
+    four formats, including lines that do not parse."""
+    import cases
+    ref = util.Ref()
+    ctx = pkg.Context(0, lib=lib)
+    sets = [(cases.AP, util.apache_lines(300, seed=5) + [b"", b"garbage line"]),
+            (dict(name="js", format="json", time_key="t", time_fmt="%s"), util.json_lines(300, seed=6) + [b"[1]", b'{"t":"1700000000","a":1}']),
+            (dict(name="lt", format="ltsv"), util.ltsv_lines(100) + [b"nolabel", b"a:1\tb:2"]),
+            (dict(name="lf", format="logfmt"), util.logfmt_lines(100) + [b"  ", b"k=v bare"])]
+    for kw, lines in sets:
+        rp = ref.parser(**kw)
+        got = ctx.parser(**kw).do_batch(lines)
+        assert len(got) == len(lines)
+        for line, (r, data, (sec, nsec)) in zip(lines, got):
+            rr, rdata, (rsec, rnsec) = ref.parser_do(rp, line)
+            assert (r >= 0) == (rr >= 0), line
+            if r >= 0:
+                assert data == rdata, line
+                assert (sec, nsec) == (rsec & 0xffffffff, rnsec), line
+
+
+def test_parser_batch_hostsim(sim_lib, ref_available):
+    check_parser_batch(sim_lib)
+
+
+@pytest.mark.gpu
+def test_parser_batch_gpu(gpu_lib, ref_available):
+    check_parser_batch(gpu_lib)
