@@ -48,6 +48,15 @@ WORKLOADS = {
                     ("grep", [("Regex", "method ^(GET|POST)$")]),
                     ("modify", [("Add", "env prod"), ("Rename", "code status"), ("Remove", "agent")])],
     },
+    # configs[3] in small: filter_log_to_metrics histogram, 32 label sets, integer-valued observations (exact
+    # fp64 sums), logs discarded; with N>1 every step ends with the NCCL all-reduce of the metric tables.
+    # Not a default bench line: `--workload l2m`.
+    "l2m": {
+        "name": "configs[3]: filter_log_to_metrics histogram(duration) by color,direction; discard_logs; table all-reduce per step",
+        "filters": [("log_to_metrics", [("metric_mode", "histogram"), ("metric_name", "duration"), ("metric_description", "d"),
+                                        ("tag", "m"), ("value_field", "duration"), ("label_field", "color"),
+                                        ("label_field", "direction"), ("discard_logs", "on")])],
+    },
 }
 WL = "json"
 
@@ -55,6 +64,14 @@ WL = "json"
 def make_block(rank=0, wl=None):
     import util
     wl = wl or WL
+    if wl == "l2m":
+        import random
+        rng = random.Random(0xF1B1 + 4 + rank)
+        colors = [b"red", b"green", b"blue", b"cyan", b"black", b"white", b"pink", b"grey"]
+        dirs = [b"north", b"south", b"east", b"west"]
+        return b"".join(util.event(1700000000 + i, 0, [(b"duration", util.mp_str(str(rng.randint(0, 9999)).encode())),
+                                                       (b"color", util.mp_str(rng.choice(colors))),
+                                                       (b"direction", util.mp_str(rng.choice(dirs)))]) for i in range(BASE_LINES))
     if wl == "json":
         lines = util.json_lines(BASE_LINES, seed=0xF1B1 + 2 + rank)
     else:
@@ -164,8 +181,10 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local):
     """value / e2e / kernel times of one workload on this rank's GPU"""
     import util
     pkg = util.pkg
-    ctx.parser(**parser_kw(wl))
-    chain = ctx.chain([ctx.filter(p, props) for p, props in WORKLOADS[wl]["filters"]])
+    if wl != "l2m":
+        ctx.parser(**parser_kw(wl))
+    filters = [ctx.filter(p, props) for p, props in WORKLOADS[wl]["filters"]]
+    chain = ctx.chain(filters)
     block = make_block(rank, wl)
     reps = max(1, args.lines // BASE_LINES)
     n_lines = reps * BASE_LINES
@@ -185,6 +204,9 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local):
         r = L.flbgpu_chain_do_device(chain.h, d_in, nbytes, d_out, out_cap, C.byref(osz))
         if r != pkg.FILTER_MODIFIED:
             raise RuntimeError("chain_do_device -> %d: %s" % (r, ctx.err()))
+        if wl == "l2m" and world > 1:
+            filters[0].l2m_allreduce()          # the one exchange of the path: metric tables over NCCL
+            L.flbgpu_l2m_reset(filters[0].h)    # "flushed": the next interval starts from zero
 
     def barrier():
         torch.cuda.synchronize()
@@ -230,6 +252,9 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local):
         r = L.flbgpu_chain_do(chain.h, h_in, nbytes, b"bench", 5, C.byref(out_p), C.byref(osz))
         if r != pkg.FILTER_MODIFIED:
             raise RuntimeError("chain_do -> %d: %s" % (r, ctx.err()))
+        if wl == "l2m" and world > 1:
+            filters[0].l2m_allreduce()
+            L.flbgpu_l2m_reset(filters[0].h)
         libc.free(out_p)
 
     e2e_steps = max(1, min(args.steps, 3))
@@ -356,7 +381,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lines", type=int, default=10_000_000, help="events per GPU per step")
-    ap.add_argument("--workload", default="json", choices=["json", "apache"], help="primary workload (the other one is reported beside it)")
+    ap.add_argument("--workload", default="json", choices=["json", "apache", "l2m"], help="primary workload (the other one is reported beside it)")
     ap.add_argument("--primary-only", action="store_true")
     args = ap.parse_args()
     global WL
