@@ -255,8 +255,11 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local):
         if wl == "l2m" and world > 1:
             filters[0].l2m_allreduce()
             L.flbgpu_l2m_reset(filters[0].h)
+        t_free = time.perf_counter()
         libc.free(out_p)
+        free_s[0] += time.perf_counter() - t_free
 
+    free_s = [0.0]
     e2e_steps = max(1, min(args.steps, 3))
     step_host()
     barrier()
@@ -265,6 +268,8 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local):
         step_host()
     barrier()
     e2e_s = time.perf_counter() - t0
+    if os.environ.get("FLBGPU_BENCH_DEBUG"):
+        sys.stderr.write("e2e %s: %.1f ms/step, of which free() of the result %.1f ms/step\n" % (wl, 1e3 * e2e_s / e2e_steps, 1e3 * free_s[0] / (e2e_steps + 1)))
     t = torch.tensor([e2e_s], device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -1139,7 +1139,7 @@ static int ensure_rec_cap(flbgpu_chain *c, size_t need, size_t keep)
 static size_t slice_bytes(void)
 {
     const char *e = getenv("FLBGPU_SLICE_MB");
-    size_t mb = e ? (size_t) atol(e) : 256;
+    size_t mb = e ? (size_t) atol(e) : 128;       /* measured best end to end on B200 (profiles/r01_variants.txt) */
     if (mb < 1) mb = 1;
     if (mb > 2048) mb = 2048;
     return mb << 20;
