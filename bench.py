@@ -306,7 +306,7 @@ def run_ours(args):
         libc = C.CDLL(None)
         libc.mallopt(-4, 0)              # M_MMAP_MAX = 0
         libc.mallopt(-1, (1 << 31) - 1)  # M_TRIM_THRESHOLD
-        libc.mallopt(-2, 1 << 30)        # M_TOP_PAD
+        libc.mallopt(-2, 64 << 20)       # M_TOP_PAD (small, so that a freed GB-size result does not push the top over the trim threshold)
 
     m = measure(args, WL, L, ctx, torch, dist, rank, world, local)
     other = "apache" if WL == "json" else "json"

@@ -505,7 +505,7 @@ FLB_HD int ra_regex_match(const struct ch_env *e, const struct ch_rec *rc, uint3
  * instead of running strptime again */
 FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s,
                       uint32_t n, const int *caps, ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec,
-                      int64_t *t_nsec, int32_t *tslot, int use_cached)
+                      int64_t *t_nsec, int32_t *tslot, int use_cached, uint32_t *th)
 {
     const struct cf_pname *nm = (const struct cf_pname *) (e->blob + pd->names_off);
     uint32_t i;
@@ -552,6 +552,7 @@ FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t
         }
         if (cnt >= CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
         ok_[cnt] = mkref(RK_MP_CONST, nm[i].kmp_off, nm[i].kmp_len);
+        th[cnt] = nm[i].hash;
         {
             uint32_t kind = RK_STR_IN, voff = val_off + (uint32_t) (vlen ? b : 0);
             if (nm[i].cast == FLBGPU_TYPE_INT) kind = RK_INT_IN;
@@ -1112,13 +1113,14 @@ struct ch_scratch {              /* per-lane working memory */
     int caps[2 * (RX_MAX_GROUPS + 1)];
     uint32_t stk[CH_RX_STACK];
     ref_t tk[CH_MAXF], tv[CH_MAXF];
+    uint32_t th[CH_MAXF];         /* ch_khash of tk[] where the producer knows it cheaply, else 0 */
 };
 
 template <bool EMIT>
 FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct ch_rec *rc, struct ch_scratch *w,
                      uint32_t ridx, uint32_t *cache_pos)
 {
-    uint8_t keep[CH_MAXF];
+    uint64_t keep;                /* bit i: original field i is appended after the parsed ones */
     int i, parse_ok = 0, np = 0, preserved = -1, have_arr, pi;
     int64_t ps = 0, pns = 0;
     uint32_t preset = 0;
@@ -1126,7 +1128,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
 
     const uint32_t key_hash = cf->ra_off ? 0u : ch_khash(e->blob + cf->key_off, cf->key_len);
     have_arr = cf->reserve_data || cf->preserve_key;
-    for (i = 0; i < rc->nf; i++) keep[i] = cf->reserve_data ? 1 : 0;
+    keep = cf->reserve_data ? ~0ull : 0ull;
 
     for (i = (cf->ra_off ? -1 : 0); i < (cf->ra_off ? 0 : rc->nf); i++) {
         const uint8_t *vp = 0; uint32_t vn = 0;
@@ -1181,7 +1183,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                     }
                 }
                 if (matched) got = pdef_regex(e, pd, val_off, vp, vn, w->caps, w->tk, w->tv, &cnt, &ts, &tns,
-                                              slot ? slot + need : 0, EMIT ? 1 : 0);
+                                              slot ? slot + need : 0, EMIT ? 1 : 0, w->th);
                 if (got) { preset = pd->n_groups; style = ST_PRESET; }
             }
             else if (pd->type == FLBGPU_PARSER_JSON) {
@@ -1197,12 +1199,13 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                 if (got) style = ST_CANON;
             }
             if (got) {
+                if (pd->type != FLBGPU_PARSER_REGEX) { int z; for (z = 0; z < cnt; z++) w->th[z] = 0; }
                 parse_ok = 1;
                 np = cnt;
                 if ((uint64_t) ts * 1000000000ull + (uint64_t) tns != 0) { ps = ts; pns = tns; }
                 if ((uint64_t) ts * 1000000000ull + (uint64_t) tns != 0) { rc->ts_sec = ts; rc->ts_nsec = tns; }
                 if (have_arr && !cf->ra_off) {
-                    if (!cf->preserve_key) keep[i] = 0;
+                    if (!cf->preserve_key) keep &= ~(1ull << i);
                     else if (!cf->reserve_data) preserved = i;
                 }
                 break;
@@ -1215,14 +1218,14 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
     {
         /* parsed keys first, then the reserved originals (src/flb_pack.c:1716-1723) */
         int extra = 0, j = np;
-        if (cf->reserve_data) { for (i = 0; i < rc->nf; i++) if (keep[i]) extra++; }
+        if (cf->reserve_data) { for (i = 0; i < rc->nf; i++) if ((keep >> i) & 1) extra++; }
         else if (preserved >= 0) extra = 1;
         if (np + extra > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return; }
         if (cf->reserve_data) {
-            for (i = 0; i < rc->nf; i++) if (keep[i]) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; j++; }
+            for (i = 0; i < rc->nf; i++) if ((keep >> i) & 1) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; w->th[j] = rc->kh[i]; j++; }
         }
-        else if (preserved >= 0) { w->tk[j] = rc->k[preserved]; w->tv[j] = rc->v[preserved]; j++; }
-        for (i = 0; i < j; i++) { rc->k[i] = w->tk[i]; rc->v[i] = w->tv[i]; rc->kh[i] = ref_khash(e, w->tk[i]); }
+        else if (preserved >= 0) { w->tk[j] = rc->k[preserved]; w->tv[j] = rc->v[preserved]; w->th[j] = rc->kh[preserved]; j++; }
+        for (i = 0; i < j; i++) { rc->k[i] = w->tk[i]; rc->v[i] = w->tv[i]; rc->kh[i] = w->th[i] ? w->th[i] : ref_khash(e, w->tk[i]); }
         rc->nf = j;
         if (extra > 0) rc->style = ST_CANON;
         else { rc->style = style; rc->preset_n = preset; }
@@ -1358,11 +1361,17 @@ FLB_HD int count_keys(const struct ch_env *e, const struct ch_rec *rc, uint32_t 
     return c;
 }
 
-/* remove fields flagged in del[] */
-FLB_HD void compact(struct ch_rec *rc, const uint8_t *del)
+/* remove the fields whose bit is set in del: everything before the first deleted field stays put */
+FLB_HD void compact(struct ch_rec *rc, uint64_t del)
 {
-    int i, j = 0;
-    for (i = 0; i < rc->nf; i++) if (!del[i]) { rc->k[j] = rc->k[i]; rc->v[j] = rc->v[i]; rc->kh[j] = rc->kh[i]; j++; }
+    int i, j;
+    if (!del) return;
+#ifdef __CUDA_ARCH__
+    j = __ffsll((long long) del) - 1;
+#else
+    j = __builtin_ctzll(del);
+#endif
+    for (i = j + 1; i < rc->nf; i++) if (!((del >> i) & 1)) { rc->k[j] = rc->k[i]; rc->v[j] = rc->v[i]; rc->kh[j] = rc->kh[i]; j++; }
     rc->nf = j;
 }
 
@@ -1371,7 +1380,7 @@ FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct 
 {
     const uint8_t *key = e->blob + r->key_off, *val = e->blob + r->val_off;
     ref_t kmp = mkref(RK_MP_CONST, r->kmp_off, r->kmp_len), vmp = mkref(RK_MP_CONST, r->vmp_off, r->vmp_len);
-    uint8_t del[CH_MAXF];
+    uint64_t del = 0;                 /* bit i: field i goes away (CH_MAXF <= 64) */
     const uint32_t kh = r->key_hash, vh = r->val_hash;
     int i, j, match, conflict;
 
@@ -1382,8 +1391,8 @@ FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct 
         conflict = count_keys(e, rc, vh, val, r->val_len);
         if (match == 0) return 0;
         if (r->type == MOD_RENAME && conflict > 0) return 0;
-        for (i = 0; i < rc->nf; i++) del[i] = (conflict > 0 && key_is(e, rc, i, vh, val, r->val_len)) ? 1 : 0;
-        for (i = 0; i < rc->nf; i++) if (!del[i] && key_is(e, rc, i, kh, key, r->key_len)) { rc->k[i] = vmp; rc->kh[i] = vh; }
+        if (conflict > 0) for (i = 0; i < rc->nf; i++) if (key_is(e, rc, i, vh, val, r->val_len)) del |= 1ull << i;
+        for (i = 0; i < rc->nf; i++) if (!((del >> i) & 1) && key_is(e, rc, i, kh, key, r->key_len)) { rc->k[i] = vmp; rc->kh[i] = vh; }
         compact(rc, del);
         return 1;
     case MOD_COPY:
@@ -1394,7 +1403,7 @@ FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct 
         if (r->type == MOD_COPY && conflict > 0) return 0;
         if (r->type == MOD_HARD_COPY && conflict > 1) return 0;
         if (conflict == 1) {
-            for (i = 0; i < rc->nf; i++) del[i] = key_is(e, rc, i, vh, val, r->val_len) ? 1 : 0;
+            for (i = 0; i < rc->nf; i++) if (key_is(e, rc, i, vh, val, r->val_len)) del |= 1ull << i;
             compact(rc, del);
         }
         if (rc->nf + 1 > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
@@ -1410,7 +1419,7 @@ FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct 
         rc->k[rc->nf] = kmp; rc->v[rc->nf] = vmp; rc->kh[rc->nf] = kh; rc->nf++;
         return 1;
     case MOD_SET:
-        for (i = 0; i < rc->nf; i++) del[i] = key_is(e, rc, i, kh, key, r->key_len) ? 1 : 0;
+        for (i = 0; i < rc->nf; i++) if (key_is(e, rc, i, kh, key, r->key_len)) del |= 1ull << i;
         compact(rc, del);
         if (rc->nf + 1 > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 1; }
         rc->k[rc->nf] = kmp; rc->v[rc->nf] = vmp; rc->kh[rc->nf] = kh; rc->nf++;
@@ -1420,10 +1429,12 @@ FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct 
     case MOD_REMOVE_REGEX:
         match = 0;
         for (i = 0; i < rc->nf; i++) {
-            if (r->type == MOD_REMOVE) del[i] = key_is(e, rc, i, kh, key, r->key_len) ? 1 : 0;
-            else if (r->type == MOD_REMOVE_WILDCARD) del[i] = key_prefix(e, rc->k[i], key, r->key_len) ? 1 : 0;
-            else del[i] = ref_rx(e, rc->k[i], r->key_rx, w) ? 1 : 0;
-            match += del[i];
+            int d;
+            if (r->type == MOD_REMOVE) d = key_is(e, rc, i, kh, key, r->key_len) ? 1 : 0;
+            else if (r->type == MOD_REMOVE_WILDCARD) d = key_prefix(e, rc->k[i], key, r->key_len) ? 1 : 0;
+            else d = ref_rx(e, rc->k[i], r->key_rx, w) ? 1 : 0;
+            if (d) del |= 1ull << i;
+            match += d;
         }
         if (match == 0) return 0;
         compact(rc, del);
@@ -1431,11 +1442,11 @@ FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct 
     case MOD_MOVE_TO_START:
     case MOD_MOVE_TO_END:
         match = 0;
-        for (i = 0; i < rc->nf; i++) { del[i] = key_prefix(e, rc->k[i], key, r->key_len) ? 1 : 0; match += del[i]; }
+        for (i = 0; i < rc->nf; i++) if (key_prefix(e, rc->k[i], key, r->key_len)) { del |= 1ull << i; match++; }
         if (match == 0) return 0;
         j = 0;
-        for (i = 0; i < rc->nf; i++) if (del[i] == (r->type == MOD_MOVE_TO_START)) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; j++; }
-        for (i = 0; i < rc->nf; i++) if (del[i] != (r->type == MOD_MOVE_TO_START)) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; j++; }
+        for (i = 0; i < rc->nf; i++) if ((int) ((del >> i) & 1) == (r->type == MOD_MOVE_TO_START)) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; j++; }
+        for (i = 0; i < rc->nf; i++) if ((int) ((del >> i) & 1) != (r->type == MOD_MOVE_TO_START)) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; j++; }
         for (i = 0; i < rc->nf; i++) { rc->k[i] = w->tk[i]; rc->v[i] = w->tv[i]; rc->kh[i] = ref_khash(e, w->tk[i]); }
         return 1;
     }
@@ -1473,13 +1484,12 @@ FLB_HDN void f_recmod(const struct ch_env *e, const struct cf_recmod *cf, struct
 {
     const struct cf_rm_key *keys = 0;
     const struct cf_rm_rec *recs = (const struct cf_rm_rec *) (e->blob + cf->records_off);
-    uint8_t del[CH_MAXF];
+    uint64_t del = 0;
     uint32_t nk = 0, q;
     int is_delete = 0, i, remaining = rc->nf, total;
 
     if (cf->n_remove > 0) { keys = (const struct cf_rm_key *) (e->blob + cf->remove_off); nk = cf->n_remove; is_delete = 1; }
     else if (cf->n_allow > 0) { keys = (const struct cf_rm_key *) (e->blob + cf->allow_off); nk = cf->n_allow; is_delete = 0; }
-    for (i = 0; i < rc->nf; i++) del[i] = 0;
     if (keys) {
         for (i = 0; i < rc->nf; i++) {
             const uint8_t *kp = 0; uint32_t kn = 0;
@@ -1489,7 +1499,7 @@ FLB_HDN void f_recmod(const struct ch_env *e, const struct cf_recmod *cf, struct
                 if (keys[q].dynamic && kn < keys[q].len) continue;
                 if (ci_eq(kp, e->blob + keys[q].off, keys[q].len)) { result = 1; break; }
             }
-            if (result == is_delete) { del[i] = 1; remaining--; }
+            if (result == is_delete) { del |= 1ull << i; remaining--; }
         }
     }
     *cause = (remaining != rc->nf) || cf->n_records > 0;
@@ -1680,6 +1690,26 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
         le.scr = e->scr + (size_t) 4 * off;
         e = &le;
     }
+    /* The evaluation pass leaves the final field list of every surviving record (<= RC_CACHE_MAXF
+     * fields) in the last RC_CACHE_INTS ints of its capture-cache row; the emission pass then only
+     * encodes -- no decoding, no filters.  Longer records are re-run through the chain. */
+    if (EMIT && e->capcache && e->cap_stride >= RC_CACHE_INTS) {
+        const int32_t *c = e->capcache + (size_t) ridx * e->cap_stride + (e->cap_stride - RC_CACHE_INTS);
+        const int32_t st = c[0];
+        if (st == RC_CACHE_RAW) { mp_copy(out, e->in + off, len); return len; }
+        if (st >= 0) {
+            int i;
+            rc.nf = st & 0xff; rc.style = (st >> 8) & 0xff; rc.reenc = 1;
+            rc.preset_n = (uint32_t) c[1];
+            rc.ts_sec = (int64_t) (uint32_t) c[2]; rc.ts_nsec = (int64_t) (uint32_t) c[3];
+            rc.meta = ((ref_t) (uint32_t) c[5] << 32) | (uint32_t) c[4];
+            for (i = 0; i < rc.nf; i++) {
+                rc.k[i] = ((ref_t) (uint32_t) c[8 + 4 * i + 1] << 32) | (uint32_t) c[8 + 4 * i];
+                rc.v[i] = ((ref_t) (uint32_t) c[8 + 4 * i + 3] << 32) | (uint32_t) c[8 + 4 * i + 2];
+            }
+            return rec_emit(e, &rc, out);
+        }
+    }
     if (rec_decode(e, off, len, &rc, h->empty_map_off) != 0) {
         CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS);
         return 0;
@@ -1736,6 +1766,22 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
             break;
         default:
             break;
+        }
+    }
+    if (!EMIT && e->capcache && e->cap_stride >= RC_CACHE_INTS) {
+        int32_t *c = e->capcache + (size_t) ridx * e->cap_stride + (e->cap_stride - RC_CACHE_INTS);
+        if (!rc.reenc) c[0] = RC_CACHE_RAW;
+        else if (rc.nf > RC_CACHE_MAXF) c[0] = RC_CACHE_NONE;
+        else {
+            int i;
+            c[0] = (int32_t) ((uint32_t) rc.nf | ((uint32_t) rc.style << 8));
+            c[1] = (int32_t) rc.preset_n;
+            c[2] = (int32_t) (uint32_t) rc.ts_sec; c[3] = (int32_t) (uint32_t) rc.ts_nsec;
+            c[4] = (int32_t) (uint32_t) rc.meta; c[5] = (int32_t) (uint32_t) (rc.meta >> 32);
+            for (i = 0; i < rc.nf; i++) {
+                c[8 + 4 * i] = (int32_t) (uint32_t) rc.k[i]; c[8 + 4 * i + 1] = (int32_t) (uint32_t) (rc.k[i] >> 32);
+                c[8 + 4 * i + 2] = (int32_t) (uint32_t) rc.v[i]; c[8 + 4 * i + 3] = (int32_t) (uint32_t) (rc.v[i] >> 32);
+            }
         }
     }
     if (!rc.reenc) {

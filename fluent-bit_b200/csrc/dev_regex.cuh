@@ -119,6 +119,37 @@ FLB_HD int rx_class_run(const struct rx_prog *pg, const struct rx_class *cl, con
 {
     const uint32_t w0 = cl->bits[0], w1 = cl->bits[1], w2 = cl->bits[2], w3 = cl->bits[3];
     int n;
+    if (cl->pad) {
+        /* the class is "every byte but <= 4 ASCII stop bytes" (rx_compile.c): find the first stop byte,
+         * eight bytes per step on aligned words (buffers are padded, see bk_alloc) */
+        const uint32_t sb = cl->ranges_off;
+        const uint64_t ones = 0x0101010101010101ull;
+        const uint64_t r0 = ones * (sb & 0xff), r1 = ones * ((sb >> 8) & 0xff), r2 = ones * ((sb >> 16) & 0xff), r3 = ones * (sb >> 24);
+        while (pos < len) {
+            const uintptr_t a = (uintptr_t) (s + pos);
+            const unsigned sh = (unsigned) (a & 7) * 8;
+            uint64_t w = *(const uint64_t *) (a & ~(uintptr_t) 7), t, hit;
+            w >>= sh;
+            if (sh) w |= 0x8080808080808080ull << (64 - sh);           /* filler that is never a stop byte */
+            t = w ^ r0; hit = (t - ones) & ~t;
+            if (cl->pad > 1) {
+                t = w ^ r1; hit |= (t - ones) & ~t;
+                t = w ^ r2; hit |= (t - ones) & ~t;
+                t = w ^ r3; hit |= (t - ones) & ~t;
+            }
+            hit &= 0x8080808080808080ull;
+            if (hit) {
+#ifdef __CUDA_ARCH__
+                pos += (__ffsll((long long) hit) - 1) >> 3;
+#else
+                pos += __builtin_ctzll(hit) >> 3;
+#endif
+                return pos < len ? pos : len;
+            }
+            pos += 8 - (int) (sh >> 3);
+        }
+        return len;
+    }
     while (pos < len) {
         const uint32_t b = s[pos];
         if (b < 0x80) {

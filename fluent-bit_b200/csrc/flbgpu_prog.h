@@ -102,6 +102,13 @@ enum { FLBGPU_PARSER_REGEX = 1, FLBGPU_PARSER_JSON, FLBGPU_PARSER_LTSV, FLBGPU_P
 enum { FLBGPU_TYPE_INT = 1, FLBGPU_TYPE_FLOAT, FLBGPU_TYPE_BOOL, FLBGPU_TYPE_STRING, FLBGPU_TYPE_HEX };
 
 struct cf_ra_sub { uint32_t is_index, index, str_off, str_len; };
+/* final field list of a surviving record, left by the evaluation pass for the emission pass in the
+ * last RC_CACHE_INTS ints of the record's capture-cache row: 8 header ints + 4 per field */
+#define RC_CACHE_MAXF 16
+#define RC_CACHE_INTS (8 + 4 * RC_CACHE_MAXF)
+#define RC_CACHE_NONE (-1)
+#define RC_CACHE_RAW  (-2)
+
 struct cf_ra { uint32_t key_off, key_len, n_sub, sub_off; };
 
 struct cf_pname {              /* one (name, group) pair in onig_foreach_name order */
@@ -110,7 +117,7 @@ struct cf_pname {              /* one (name, group) pair in onig_foreach_name or
     uint32_t group;
     uint32_t is_time;          /* this is the Time_Key */
     uint32_t cast;             /* FLBGPU_TYPE_* or 0 */
-    uint32_t pad;
+    uint32_t hash;             /* ch_khash() of the name */
 };
 
 struct cf_ptype { uint32_t key_off, key_len, type, pad; };

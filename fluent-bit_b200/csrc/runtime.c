@@ -98,6 +98,7 @@ struct flbgpu_parser {
 };
 
 struct kv { char *k, *v; struct kv *next; };
+static uint32_t key_hash(const char *s, size_t n);
 
 /* host-side cumulative state of one filter_log_to_metrics instance: what the reference
  * keeps in its struct cmt (lib/cmetrics): one metric per label set, first-seen order */
@@ -359,6 +360,7 @@ static uint32_t emit_pdef(struct blob *b, struct flbgpu_parser *p)
                 nm[i].kmp_off = blob_add_mpstr(b, name, len, &nm[i].kmp_len);
                 nm[i].raw_off = blob_add(b, name, len, 1);
                 nm[i].raw_len = len;
+                nm[i].hash = key_hash(name, len);
                 nm[i].group = p->rx.names[ni].groups[g];
                 nm[i].is_time = p->has_time && strcmp(name, tk) == 0;
                 for (t = 0; t < p->types_len; t++) {
@@ -1051,6 +1053,7 @@ int flbgpu_chain_init(flbgpu_chain *c)
     c->needs_scratch = (int) h.needs_scratch;
     h.n_filters = c->nf;
     h.filters_off = blob_add(&c->blob, cf, sizeof(cf[0]) * (c->nf ? c->nf : 1), 8);
+    cap += RC_CACHE_INTS;                 /* every chain: the final field list for the emission pass */
     h.cap_stride = cap;
     blob_reserve(&c->blob, 16, 16);
     h.total_bytes = (uint32_t) c->blob.n;

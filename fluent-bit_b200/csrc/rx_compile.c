@@ -1273,6 +1273,23 @@ int rx_compile(const char *pattern, struct rx_compiled *out)
                     memcpy(rg, s->r, sizeof(uint32_t) * 2 * s->nr);
                     off += sizeof(uint32_t) * 2 * s->nr;
                 }
+                /* "everything but a few ASCII bytes" ([^ ], [^"], [^\]] ...): the run is a search
+                 * for the first stop byte, which the device does eight bytes at a time.  pad = number
+                 * of stop bytes (1..4), ranges_off = the stop bytes (unused by RX_MB_ALL otherwise). */
+                if (cl[i].mb_mode == RX_MB_ALL) {
+                    uint32_t stops = 0, n = 0, b;
+                    int okc = 1;
+                    for (b = 0; b < 256 && okc; b++) {
+                        if (!((cl[i].bits[b >> 5] >> (b & 31)) & 1)) {
+                            if (b >= 0x80 || n >= 4) okc = 0;
+                            else stops |= b << (8 * n++);
+                        }
+                    }
+                    if (okc && n >= 1) {
+                        for (b = n; b < 4; b++) stops |= (stops & 0xff) << (8 * b);
+                        cl[i].pad = n; cl[i].ranges_off = stops;
+                    }
+                }
             }
             pg->total_bytes = (uint32_t) ((off + 15) & ~(size_t) 15);
             pg->n_groups = c.n_groups;
