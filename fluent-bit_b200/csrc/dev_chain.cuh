@@ -513,11 +513,13 @@ FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t
     int64_t lookup = 0, nsec_cached = 0;
     double frac = 0;
     if (pd->n_groups == 0) return 0;                 /* flb_parser_regex_do: n <= 0 -> -1 */
+    /* decided before anything is written: the caller may hand in the record's own field arrays */
+    for (i = 0; i < pd->n_names; i++) if (caps[2 * nm[i].group + 1] >= 0) any_end = 1;
+    if (!any_end) return 0;                          /* flb_regex_parse: last_pos == -1 */
     for (i = 0; i < pd->n_names; i++) {
         int b = caps[2 * nm[i].group], en = caps[2 * nm[i].group + 1];
         uint32_t vlen = (uint32_t) (en - b);
         const uint8_t *v = s + b;
-        if (en >= 0) any_end = 1;
         if (vlen == 0 && pd->skip_empty) continue;
         if (pd->has_time && nm[i].is_time && use_cached && tslot && tslot[0]) {
             if (tslot[0] == 2) continue;
@@ -566,7 +568,6 @@ FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t
         }
         cnt++;
     }
-    if (!any_end) return 0;                          /* flb_regex_parse: last_pos == -1 */
     *on = cnt;
     *t_sec = lookup;
     if (have_nsec) { *t_nsec = nsec_cached; return 1; }
@@ -1055,7 +1056,8 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t 
     double frac = 0;
 
     if (!e->scr) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
-    if (e->capcache && *cache_pos + 2 <= e->cap_stride) slot = e->capcache + (size_t) ridx * e->cap_stride + *cache_pos;
+    if (e->capcache && e->cap_stride >= RC_CACHE_INTS && *cache_pos + 2 <= e->cap_stride - RC_CACHE_INTS)
+        slot = e->capcache + (size_t) ridx * e->cap_stride + *cache_pos;
     *cache_pos += 2;
     /* slot[0]: 0/1 = result of the exact transcoder (msgpack of slot[1] bytes in scratch),
      * 2 = the fast path produced the fields (it is re-run by the emission pass, nothing cached) */
@@ -1121,7 +1123,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                      uint32_t ridx, uint32_t *cache_pos)
 {
     uint64_t keep;                /* bit i: original field i is appended after the parsed ones */
-    int i, parse_ok = 0, np = 0, preserved = -1, have_arr, pi;
+    int i, parse_ok = 0, np = 0, preserved = -1, have_arr, pi, in_place = 0;
     int64_t ps = 0, pns = 0;
     uint32_t preset = 0;
     int style = ST_CANON;
@@ -1166,10 +1168,13 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                 uint32_t need = 1 + 2 * (pd->n_groups + 1), c;      /* + 4 ints of parsed time behind them */
                 int32_t *slot = 0;
                 int matched;
-                if (e->capcache && *cache_pos + need <= e->cap_stride)
+                const uint32_t lim = e->cap_stride >= RC_CACHE_INTS ? e->cap_stride - RC_CACHE_INTS : 0;
+                /* the last-field case: nothing of the old list is looked at again, so the parsed fields
+                 * go straight into the record's arrays instead of through the staging lists */
+                const int direct = !have_arr && !cf->ra_off && i == rc->nf - 1;
+                if (e->capcache && *cache_pos + need + 4 <= lim)
                     slot = e->capcache + (size_t) ridx * e->cap_stride + *cache_pos;
                 *cache_pos += need + 4;
-                if (e->capcache && *cache_pos > e->cap_stride) slot = 0;
                 if (EMIT && slot) {
                     matched = slot[0];
                     for (c = 0; c + 1 < need; c++) w->caps[c] = slot[1 + c];
@@ -1182,9 +1187,9 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                         slot[need] = 0;
                     }
                 }
-                if (matched) got = pdef_regex(e, pd, val_off, vp, vn, w->caps, w->tk, w->tv, &cnt, &ts, &tns,
-                                              slot ? slot + need : 0, EMIT ? 1 : 0, w->th);
-                if (got) { preset = pd->n_groups; style = ST_PRESET; }
+                if (matched) got = pdef_regex(e, pd, val_off, vp, vn, w->caps, direct ? rc->k : w->tk, direct ? rc->v : w->tv, &cnt,
+                                              &ts, &tns, slot ? slot + need : 0, EMIT ? 1 : 0, direct ? rc->kh : w->th);
+                if (got) { preset = pd->n_groups; style = ST_PRESET; in_place = direct; }
             }
             else if (pd->type == FLBGPU_PARSER_JSON) {
                 got = pdef_json<EMIT>(e, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns, ridx, cache_pos);
@@ -1215,6 +1220,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
     (void) ps; (void) pns;
     rc->reenc = 1;
     if (!parse_ok) { rc->style = ST_CANON; return; }
+    if (in_place) { rc->nf = np; rc->style = style; rc->preset_n = preset; return; }
     {
         /* parsed keys first, then the reserved originals (src/flb_pack.c:1716-1723) */
         int extra = 0, j = np;

@@ -203,10 +203,32 @@ FLB_HD uint32_t mp_put_int(uint8_t *o, int64_t v)
     o[0] = 0xd3; mp_put_be64(o + 1, (uint64_t) v); return 9;
 }
 
+/* copy of n bytes between arbitrary alignments.  On the device: bytes until the destination is
+ * 4-aligned, then one aligned 32-bit store per word, the source word assembled from two aligned
+ * loads with a funnel shift (source buffers are padded, see bk_alloc); the emission pass is mostly
+ * this loop. */
 FLB_HD void mp_copy(uint8_t *o, const uint8_t *s, uint32_t n)
 {
-    uint32_t i;
-    for (i = 0; i < n; i++) o[i] = s[i];
+    uint32_t i = 0;
+#ifdef __CUDA_ARCH__
+    if (n >= 12) {
+        while (((uintptr_t) (o + i)) & 3) { o[i] = s[i]; i++; }
+        {
+            const uintptr_t sa = (uintptr_t) (s + i);
+            const uint32_t *sw = (const uint32_t *) (sa & ~(uintptr_t) 3);
+            const uint32_t sh = (uint32_t) (sa & 3) * 8;
+            uint32_t *ow = (uint32_t *) (o + i);
+            uint32_t lo = *sw++;
+            for (; i + 4 <= n; i += 4) {
+                uint32_t hi = sh ? *sw++ : 0, v;
+                if (sh) { v = __funnelshift_r(lo, hi, sh); lo = hi; }
+                else { v = lo; lo = *sw++; }
+                *ow++ = v;
+            }
+        }
+    }
+#endif
+    for (; i < n; i++) o[i] = s[i];
 }
 
 /* Canonical re-encoding of the complete object at p (already validated by

@@ -648,8 +648,10 @@ static uint32_t emit_parser_filter(flbgpu_filter *f, struct blob *b, uint32_t *c
             if (!ps) { set_err("requested parser '%s' not found%s", p->v, NULL); return 0; }
             if (cf.n_parsers >= 8) { set_err("too many parsers in one filter%s%s", NULL, NULL); return 0; }
             cf.pdef_off[cf.n_parsers++] = emit_pdef(b, ps);
-            if (ps->has_rx) *cap_need += 1 + 2 * (ps->rx.prog->n_groups + 1) + 4;   /* match flag, captures, parsed time */
-            if (ps->type == FLBGPU_PARSER_JSON) { *cap_need += 2; f->needs_scratch = 1; }
+            /* no per-record capture slots any more: the emission pass encodes from the cached final
+             * field list (RC_CACHE_INTS); only records with more than RC_CACHE_MAXF fields re-run the
+             * chain there, and then they re-run the parser too */
+            if (ps->type == FLBGPU_PARSER_JSON) f->needs_scratch = 1;
         }
         else if (!strcasecmp(p->k, "preserve_key")) { int v = parse_bool(p->v); if (v < 0) { set_err("invalid boolean '%s'%s", p->v, NULL); return 0; } cf.preserve_key = v; }
         else if (!strcasecmp(p->k, "reserve_data")) { int v = parse_bool(p->v); if (v < 0) { set_err("invalid boolean '%s'%s", p->v, NULL); return 0; } cf.reserve_data = v; }
