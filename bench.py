@@ -353,7 +353,7 @@ def run_ours(args):
         "config": {"workload": WORKLOADS[WL]["name"], "events_per_gpu_per_step": m["n_lines"], "input_bytes_per_gpu": m["nbytes"],
                    "output_bytes_per_gpu": m["out_bytes"], "distinct_lines": BASE_LINES,
                    "l2": "input (%.0f MB) and output larger than the 126 MB L2" % (m["nbytes"] / 1e6),
-                   "parallelism": "record shards, no data-path collective",
+                   "parallelism": ("record shards; one NCCL all-reduce of the metric table per step" if WL == "l2m" else "record shards, no data-path collective"),
                    "host_malloc": "default" if os.environ.get("FLBGPU_BENCH_DEFAULT_MALLOC") == "1" else "glibc tuned to retain freed result buffers (M_MMAP_MAX=0, M_TRIM_THRESHOLD=2GiB)"},
         "e2e": {"value": m["e2e"], "unit": "lines/s", "h2d_bytes_per_step": m["nbytes"], "d2h_bytes_per_step": m["out_bytes"],
                 "steps": m["e2e_steps"], "timing": "wall clock between device-synchronising barriers",
