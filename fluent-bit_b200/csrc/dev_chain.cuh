@@ -906,7 +906,9 @@ FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t 
                     else for (i = 0; i < len; i++) scr[k + h + i] = scr[k + 5 + i];
                     k += h + len;
                 }
-                st = DJF_COLON;
+                /* the colon normally follows at once: take it here and save a round of the loop */
+                if (p < n && s[p] == ':') { p++; st = DJF_VAL; }
+                else st = DJF_COLON;
                 continue;
             }
         }
@@ -1029,7 +1031,9 @@ FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t 
         }
         else ccnt[depth]++;
         first = 0;
-        st = DJF_AFTER;
+        /* likewise the comma */
+        if (p < n && s[p] == ',') { p++; st = ((isobj >> depth) & 1) ? DJF_KEY : DJF_VAL; }
+        else st = DJF_AFTER;
     }
     while (p < n && dj_ws(s[p])) p++;
     if (p < n) return -1;                  /* trailing text: a second document would reject the line */

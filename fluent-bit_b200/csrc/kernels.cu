@@ -388,7 +388,12 @@ static int g_streams_ready;
 static int streams_init(void)
 {
     if (g_streams_ready) return 0;
-    CK(cudaStreamCreateWithFlags(&g_istream, cudaStreamNonBlocking));
+    {   /* the index kernels of the next slice are short and the host waits for their result: let their
+         * blocks go ahead of the thousands of queued evaluation blocks of the previous slice */
+        int lo = 0, hi = 0;
+        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CK(cudaStreamCreateWithPriority(&g_istream, cudaStreamNonBlocking, hi));
+    }
     CK(cudaStreamCreateWithFlags(&g_h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
     g_streams_ready = 1;
