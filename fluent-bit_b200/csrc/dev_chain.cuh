@@ -101,11 +101,12 @@ FLB_HD int ref_view(const struct ch_env *e, ref_t r, const uint8_t **p, uint32_t
     return 0;
 }
 
-/* FNV-1a of a key's bytes, never 0 */
+/* O(1) fingerprint of a key (length, first, middle and last byte), never 0.  Only a pre-filter: a key
+ * test compares the bytes when the fingerprints agree.  key_hash() in runtime.c is the same function. */
 FLB_HD uint32_t ch_khash(const uint8_t *s, uint32_t n)
 {
-    uint32_t h = 2166136261u, i;
-    for (i = 0; i < n; i++) { h ^= s[i]; h *= 16777619u; }
+    uint32_t h = n * 2654435761u;
+    if (n) h ^= (uint32_t) s[0] ^ ((uint32_t) s[n - 1] << 8) ^ ((uint32_t) s[n >> 1] << 16);
     return h | 1u;
 }
 FLB_HD uint32_t ref_khash(const struct ch_env *e, ref_t r)
@@ -803,6 +804,30 @@ FLB_HD int djf_scan_plain(const uint8_t *s, int p, int n)
     return n;
 }
 
+/* first position in [p, n) that is not an ASCII digit (n if none); same word-at-a-time walk */
+FLB_HD int djf_scan_digits(const uint8_t *s, int p, int n)
+{
+    while (p < n) {
+        const uintptr_t a = (uintptr_t) (s + p);
+        const unsigned sh = (unsigned) (a & 7) * 8;
+        uint64_t w = *(const uint64_t *) (a & ~(uintptr_t) 7), t, nd;
+        w >>= sh;
+        if (sh) w |= 0x3030303030303030ull << (64 - sh);
+        t = w ^ 0x3030303030303030ull;                           /* digits become 0..9 */
+        nd = ((t + 0x7676767676767676ull) | t) & 0x8080808080808080ull;   /* bit 7 set where t >= 10 */
+        if (nd) {
+#ifdef __CUDA_ARCH__
+            p += (__ffsll((long long) nd) - 1) >> 3;
+#else
+            p += __builtin_ctzll(nd) >> 3;
+#endif
+            return p < n ? p : n;
+        }
+        p += 8 - (int) (sh >> 3);
+    }
+    return n;
+}
+
 /* string whose opening quote is at s[p].  Plain: *raw = 1, [*b, *b + *len) are input offsets.
  * With escapes: decoded to scr + at, *raw = 0, *len decoded bytes.  Returns the position after the
  * closing quote or -1. */
@@ -855,13 +880,15 @@ FLB_HD int djf_string(const uint8_t *s, int p, int n, uint8_t *scr, uint32_t at,
     return q + 1;
 }
 
-FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t val_off, ref_t *ok_, ref_t *ov_, int *on)
+FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t val_off, ref_t *ok_, ref_t *ov_, uint32_t *th,
+                      int *on)
 {
     uint8_t *scr = e->scr;
     uint32_t hpos[DJ_MAX_DEPTH + 1], ccnt[DJ_MAX_DEPTH + 1];
     uint32_t k = 0, isobj = 2, top_start = 0;
     int p = 0, st = DJF_KEY, depth = 1, cnt = 0, first = 1;
     ref_t keyref = 0, valref = 0;
+    uint32_t keyhash = 0;
 
     if (!scr) return -1;
     while (p < n && dj_ws(s[p])) p++;
@@ -897,8 +924,8 @@ FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t 
                 p = djf_string(s, p, n, scr, depth == 1 ? k : k + 5, &raw, &b, &len);
                 if (p < 0) return -1;
                 if (depth == 1) {
-                    if (raw) keyref = mkref(RK_STR_IN, val_off + b, len);
-                    else { keyref = mkref(RK_STR_SCR, k, len); k += len; }
+                    if (raw) { keyref = mkref(RK_STR_IN, val_off + b, len); keyhash = ch_khash(s + b, len); }
+                    else { keyref = mkref(RK_STR_SCR, k, len); keyhash = ch_khash(scr + k, len); k += len; }
                 }
                 else {
                     uint32_t h = mp_put_str_hdr(scr + k, len), i;
@@ -947,7 +974,13 @@ FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t 
                 if (c == '-') { neg = 1; q++; }
                 if (q >= n || s[q] < '0' || s[q] > '9') return -1;
                 if (s[q] == '0') { q++; if (q < n && s[q] >= '0' && s[q] <= '9') return -1; }
-                else while (q < n && s[q] >= '0' && s[q] <= '9') { v = v * 10 + (s[q] - '0'); q++; if (++nd > 18) { plain = 0; break; } }
+                else {
+                    const int q0 = q;
+                    q = djf_scan_digits(s, q, n);
+                    nd = q - q0;
+                    if (nd > 18) plain = 0;
+                    else if (depth != 1 || (q < n && s[q] == '.')) { int z; for (z = q0; z < q; z++) v = v * 10 + (s[z] - '0'); }
+                }
                 if (plain && q < n && s[q] == '.') {
                     /* short decimal without exponent: mantissa / 10^k with both exact in binary64
                      * (<= 15 digits) is correctly rounded -- Clinger's fast path, same result as
@@ -1027,7 +1060,7 @@ FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t 
         /* a value completed inside the container at `depth` */
         if (depth == 1) {
             if (cnt >= CH_MAXF) return -1;
-            ok_[cnt] = keyref; ov_[cnt] = valref; cnt++;
+            ok_[cnt] = keyref; ov_[cnt] = valref; th[cnt] = keyhash; cnt++;
         }
         else ccnt[depth]++;
         first = 0;
@@ -1048,7 +1081,7 @@ FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t 
  * the timestamp at 0 (:198-209). */
 template <bool EMIT>
 FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
-                     ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec, uint32_t ridx,
+                     ref_t *ok_, ref_t *ov_, uint32_t *th, int *on, int64_t *t_sec, int64_t *t_nsec, uint32_t ridx,
                      uint32_t *cache_pos)
 {
     int32_t *slot = 0;
@@ -1066,7 +1099,7 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t 
     /* slot[0]: 0/1 = result of the exact transcoder (msgpack of slot[1] bytes in scratch),
      * 2 = the fast path produced the fields (it is re-run by the emission pass, nothing cached) */
     if (!(EMIT && slot && slot[0] != 2)) {
-        ok = djf_record(e, s, (int) n, val_off, ok_, ov_, &cnt);
+        ok = djf_record(e, s, (int) n, val_off, ok_, ov_, th, &cnt);
         if (ok == 0) { if (!EMIT && slot) { slot[0] = 0; slot[1] = 0; } return 0; }
         if (ok == 1) { if (!EMIT && slot) { slot[0] = 2; slot[1] = 0; } goto have_fields; }
     }
@@ -1090,6 +1123,7 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t 
         nx = mp_skip(q, end);
         ov_[cnt] = mkref(RK_MP_SCR, (uint32_t) (q - e->scr), (uint32_t) (nx - q));
         q = nx;
+        th[cnt] = 0;                 /* fingerprint computed when the list is merged */
         cnt++;
     }
 have_fields:
@@ -1108,7 +1142,7 @@ have_fields:
         }
     }
     if (skip >= 0) {
-        for (i = (uint32_t) skip; i + 1 < (uint32_t) cnt; i++) { ok_[i] = ok_[i + 1]; ov_[i] = ov_[i + 1]; }
+        for (i = (uint32_t) skip; i + 1 < (uint32_t) cnt; i++) { ok_[i] = ok_[i + 1]; ov_[i] = ov_[i + 1]; th[i] = th[i + 1]; }
         cnt--;
     }
     *on = cnt; *t_sec = lookup; *t_nsec = frac_to_nsec(frac);
@@ -1196,7 +1230,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                 if (got) { preset = pd->n_groups; style = ST_PRESET; in_place = direct; }
             }
             else if (pd->type == FLBGPU_PARSER_JSON) {
-                got = pdef_json<EMIT>(e, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns, ridx, cache_pos);
+                got = pdef_json<EMIT>(e, pd, val_off, vp, vn, w->tk, w->tv, w->th, &cnt, &ts, &tns, ridx, cache_pos);
                 if (got) style = ST_CANON;
             }
             else if (pd->type == FLBGPU_PARSER_LTSV) {
@@ -1208,7 +1242,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                 if (got) style = ST_CANON;
             }
             if (got) {
-                if (pd->type != FLBGPU_PARSER_REGEX) { int z; for (z = 0; z < cnt; z++) w->th[z] = 0; }
+                if (pd->type == FLBGPU_PARSER_LTSV || pd->type == FLBGPU_PARSER_LOGFMT) { int z; for (z = 0; z < cnt; z++) w->th[z] = 0; }
                 parse_ok = 1;
                 np = cnt;
                 if ((uint64_t) ts * 1000000000ull + (uint64_t) tns != 0) { ps = ts; pns = tns; }

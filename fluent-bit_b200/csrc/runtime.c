@@ -709,12 +709,11 @@ static uint32_t emit_grep_filter(flbgpu_filter *f, struct blob *b)
     return blob_add(b, &cf, sizeof(cf), 8);
 }
 
-/* ch_khash() of dev_chain.cuh: FNV-1a, never 0 */
+/* ch_khash() of dev_chain.cuh: length, first, middle and last byte; never 0 */
 static uint32_t key_hash(const char *s, size_t n)
 {
-    uint32_t h = 2166136261u;
-    size_t i;
-    for (i = 0; i < n; i++) { h ^= (unsigned char) s[i]; h *= 16777619u; }
+    uint32_t h = (uint32_t) n * 2654435761u;
+    if (n) h ^= (uint32_t) (unsigned char) s[0] ^ ((uint32_t) (unsigned char) s[n - 1] << 8) ^ ((uint32_t) (unsigned char) s[n >> 1] << 16);
     return h | 1u;
 }
 
