@@ -448,11 +448,38 @@ recurse:
 }
 
 /* device-side view of the time part of struct flb_parser */
+/* "%d/%b/%Y:%H:%M:%S %z" (apache / nginx access logs) on a value of the canonical shape
+ * DD/Mon/YYYY:HH:MM:SS +hhmm: the same fields flb_strptime() produces for it, without the directive
+ * interpreter and the copy into a NUL-terminated buffer.  Anything else (other lengths, one-digit
+ * days, out-of-range numbers, a zone in another form) returns 0 and takes the general path. */
+FLB_HD int dt_fast_apache(const uint8_t *s, uint32_t n, struct dt_tm *tm)
+{
+    static const char mon3[] = "janfebmaraprmayjunjulaugsepoctnovdec";
+    int d[14], i, m;
+    /* digit positions of DD/Mon/YYYY:HH:MM:SS +hhmm */
+    const int pos[14] = { 0, 1, 7, 8, 9, 10, 12, 13, 15, 16, 18, 19, 22, 23 };
+    if (n != 26 || s[2] != '/' || s[6] != '/' || s[11] != ':' || s[14] != ':' || s[17] != ':' || s[20] != ' ') return 0;
+    if (s[21] != '+' && s[21] != '-') return 0;
+    for (i = 0; i < 14; i++) { d[i] = s[pos[i]] - '0'; if ((unsigned) d[i] > 9u) return 0; }
+    if ((unsigned) (s[24] - '0') > 9u || (unsigned) (s[25] - '0') > 9u) return 0;
+    for (m = 0; m < 12; m++)
+        if (dt_lower(s[3]) == mon3[3 * m] && dt_lower(s[4]) == mon3[3 * m + 1] && dt_lower(s[5]) == mon3[3 * m + 2]) break;
+    if (m == 12) return 0;
+    tm->mday = d[0] * 10 + d[1]; tm->mon = m;
+    tm->year = d[2] * 1000 + d[3] * 100 + d[4] * 10 + d[5] - 1900;
+    tm->hour = d[6] * 10 + d[7]; tm->min = d[8] * 10 + d[9]; tm->sec = d[10] * 10 + d[11];
+    if (tm->mday < 1 || tm->mday > 31 || tm->hour > 23 || tm->min > 59 || tm->sec > 60) return 0;
+    tm->gmtoff = ((d[12] * 10 + d[13]) * 3600 + ((s[24] - '0') * 10 + (s[25] - '0')) * 60) * (s[21] == '-' ? -1 : 1);
+    tm->isdst = 0;
+    return 1;
+}
+
 struct dt_parser {
     const char *fmt;        /* format up to %L (already prefixed with "%Y " when !with_year) */
     const char *frac_fmt;   /* format after %L, or NULL when the format has no %L */
     int with_year, with_tz, strict;
     int offset;             /* Time_Offset in seconds */
+    int fast_apache;        /* the format is exactly "%d/%b/%Y:%H:%M:%S %z" */
 };
 
 /* flb_parser_time_lookup(): 0 ok (tm/frac filled, maybe partially), -1 error */
@@ -465,6 +492,7 @@ FLB_HDN int dt_time_lookup(const uint8_t *s, uint32_t tsize, int64_t now, const 
     int time_len = (int) tsize, i;
 
     *ns = 0;
+    if (p->fast_apache && dt_fast_apache(s, tsize, tm)) return 0;
     if (tsize > sizeof(tmp) - 1) return -1;
     if (!p->with_year) {
         struct dt_tm tmy;

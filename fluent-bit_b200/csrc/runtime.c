@@ -338,6 +338,8 @@ static uint32_t emit_pdef(struct blob *b, struct flbgpu_parser *p)
     d.type = p->type;
     d.skip_empty = p->skip_empty; d.time_keep = p->time_keep; d.time_strict = p->time_strict;
     d.has_time = p->has_time; d.time_with_year = p->time_with_year; d.time_with_tz = p->time_with_tz;
+    /* bit 1: the access-log format, for which the device has a direct path (dt_fast_apache) */
+    if (p->has_time && p->time_fmt && !p->time_frac && !strcmp(p->time_fmt, "%d/%b/%Y:%H:%M:%S %z")) d.has_time |= 2;
     d.time_offset = p->time_offset; d.logfmt_no_bare_keys = p->logfmt_no_bare_keys;
     if (p->has_time) {
         d.fmt_off = blob_add(b, p->time_fmt, strlen(p->time_fmt) + 1, 1);

@@ -116,3 +116,33 @@ def test_parser_batch_hostsim(sim_lib, ref_available):
 @pytest.mark.gpu
 def test_parser_batch_gpu(gpu_lib, ref_available):
     check_parser_batch(gpu_lib)
+
+
+def check_apache_time_fast_path(lib):
+    """the direct path for "%d/%b/%Y:%H:%M:%S %z" agrees with the reference on canonical and odd values"""
+    ref = util.Ref()
+    ctx = pkg.Context(0, lib=lib)
+    kw = dict(name="t", format="regex", regex=r"^(?<time>.+)$", time_fmt="%d/%b/%Y:%H:%M:%S %z", time_key="time", time_keep=True)
+    vals = ["10/Oct/2000:13:55:36 -0700", "01/jan/1970:00:00:00 +0000", "31/DEC/9999:23:59:60 +1400", "29/Feb/2023:12:00:00 +0530",
+            "00/Jan/2023:00:00:00 +0000", "32/Jan/2023:00:00:00 +0000", "1/Jan/2023:00:00:00 +0000", "01/Jan/2023:24:00:00 +0000",
+            "01/Jan/2023:00:60:00 +0000", "01/Jan/2023:00:00:61 +0000", "01/Foo/2023:00:00:00 +0000", "01/Jan/2023:00:00:00 +00:00",
+            "01/Jan/2023:00:00:00 Z", "01/Jan/2023:00:00:00 +0", "01/Jan/2023:00:00:00 -0099", "01/Jan/0000:00:00:00 +0000",
+            "01/March/2023:00:00:00 +0000", "01/Jan/2023:00:00:00  +0000", "01/Jan/2023:00:00:00 +000a", " 1/Jan/2023:00:00:00 +0000",
+            "31/Apr/2024:07:08:09 -1234", "15/Sep/2038:03:14:08 +0000"]
+    rp = ref.parser(**kw)
+    got = ctx.parser(**kw).do_batch([v.encode() for v in vals])
+    for v, (r, data, (sec, nsec)) in zip(vals, got):
+        rr, rdata, (rsec, rnsec) = ref.parser_do(rp, v.encode())
+        assert (r >= 0) == (rr >= 0), v
+        assert data == rdata, v
+        if r >= 0:
+            assert (sec, nsec) == (rsec & 0xffffffff, rnsec), v
+
+
+def test_apache_time_fast_path_hostsim(sim_lib, ref_available):
+    check_apache_time_fast_path(sim_lib)
+
+
+@pytest.mark.gpu
+def test_apache_time_fast_path_gpu(gpu_lib, ref_available):
+    check_apache_time_fast_path(gpu_lib)
