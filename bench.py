@@ -197,6 +197,13 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local):
     d_out = L.flbgpu_dev_alloc(ctx.h, out_cap)
     assert h_in and d_in and d_out, "allocation failed"
     L.flbgpu_dev_upload(ctx.h, d_in, h_in, nbytes)
+    if os.environ.get("FLBGPU_BENCH_DEBUG"):
+        torch.cuda.synchronize()
+        t_up = time.perf_counter()
+        L.flbgpu_dev_upload(ctx.h, d_in, h_in, nbytes)
+        torch.cuda.synchronize()
+        t_up = time.perf_counter() - t_up
+        sys.stderr.write("plain pinned H2D of the input: %.1f ms = %.1f GB/s\n" % (1e3 * t_up, nbytes / t_up / 1e9))
     stream = torch.cuda.ExternalStream(L.flbgpu_stream(ctx.h), device=torch.device("cuda", local))
     osz = C.c_size_t()
 
