@@ -1401,6 +1401,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
     struct bk_chain_args a;
     uint32_t n_rec = 0, h_flags[FLBGPU_MAX_FILTERS + 1], b_done = 0, assume, nb_max;
     size_t off = 0, S = slice_bytes(), cap_out_h = 0, force = 0;
+    const int taper = !(getenv("FLBGPU_TAPER") && getenv("FLBGPU_TAPER")[0] == '0');
     uint64_t placed = 0;
     uint8_t *out = NULL;
     int clean, k, dl_open = 0, rc = -1;
@@ -1467,7 +1468,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
         /* slices shrink towards the end of the chunk: what is left to do after the last upload piece
          * arrives (index, evaluate, emit, download of the last slice) is proportional to its size */
         size_t rem = bytes - off, want = S, len;
-        if (rem < 3 * S) { want = rem / 3; if (want < ((size_t) 16 << 20)) want = (size_t) 16 << 20; if (want > S) want = S; }
+        if (taper && rem < 3 * S) { want = rem / 3; if (want < ((size_t) 16 << 20)) want = (size_t) 16 << 20; if (want > S) want = S; }
         if (want < force) want = force;
         len = rem < want ? rem : want;
         uint32_t n_tiles = (uint32_t) ((len + (off & 15) + BK_INDEX_TILE - 1) / BK_INDEX_TILE), n_cand = 0, n_valid = 0;
