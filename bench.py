@@ -267,7 +267,7 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local):
         free_s[0] += time.perf_counter() - t_free
 
     free_s = [0.0]
-    e2e_steps = max(1, min(args.steps, 3))
+    e2e_steps = max(1, args.steps)
     step_host()
     barrier()
     t0 = time.perf_counter()
@@ -334,7 +334,8 @@ def run_ours(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     traffic = None
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_chain_eval_dram_bytes_per_launch_" + WL)
+        per_event = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("k_chain_eval_dram_bytes_per_event_" + WL)
+        traffic = per_event * m["n_lines"] if per_event else None      # ncu dram read+write of the evaluation launches of one step
     except Exception:
         pass
 
