@@ -762,6 +762,12 @@ FLB_HDN int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32
  * the next filter / rule / regex starts with the warp together again.  Lanes whose record was
  * dropped have returned to the kernel and exited, which __syncwarp() tolerates. */
 #ifdef __CUDA_ARCH__
+#define CH_STCS(p, v) __stcs((int *) (p), (int) (v))
+#else
+#define CH_STCS(p, v) (*(p) = (v))
+#endif
+
+#ifdef __CUDA_ARCH__
 #define CH_SYNC() __syncwarp()
 #else
 #define CH_SYNC()
@@ -1816,18 +1822,20 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
         }
     }
     if (!EMIT && e->capcache && e->cap_stride >= RC_CACHE_INTS) {
+        /* streaming stores: written once, read once by the emission pass -- they should not push the
+         * lanes' local-memory lines out of L2 */
         int32_t *c = e->capcache + (size_t) ridx * e->cap_stride + (e->cap_stride - RC_CACHE_INTS);
-        if (!rc.reenc) c[0] = RC_CACHE_RAW;
-        else if (rc.nf > RC_CACHE_MAXF) c[0] = RC_CACHE_NONE;
+        if (!rc.reenc) CH_STCS(c, RC_CACHE_RAW);
+        else if (rc.nf > RC_CACHE_MAXF) CH_STCS(c, RC_CACHE_NONE);
         else {
             int i;
-            c[0] = (int32_t) ((uint32_t) rc.nf | ((uint32_t) rc.style << 8));
-            c[1] = (int32_t) rc.preset_n;
-            c[2] = (int32_t) (uint32_t) rc.ts_sec; c[3] = (int32_t) (uint32_t) rc.ts_nsec;
-            c[4] = (int32_t) (uint32_t) rc.meta; c[5] = (int32_t) (uint32_t) (rc.meta >> 32);
+            CH_STCS(c, (int32_t) ((uint32_t) rc.nf | ((uint32_t) rc.style << 8)));
+            CH_STCS(c + 1, (int32_t) rc.preset_n);
+            CH_STCS(c + 2, (int32_t) (uint32_t) rc.ts_sec); CH_STCS(c + 3, (int32_t) (uint32_t) rc.ts_nsec);
+            CH_STCS(c + 4, (int32_t) (uint32_t) rc.meta); CH_STCS(c + 5, (int32_t) (uint32_t) (rc.meta >> 32));
             for (i = 0; i < rc.nf; i++) {
-                c[8 + 4 * i] = (int32_t) (uint32_t) rc.k[i]; c[8 + 4 * i + 1] = (int32_t) (uint32_t) (rc.k[i] >> 32);
-                c[8 + 4 * i + 2] = (int32_t) (uint32_t) rc.v[i]; c[8 + 4 * i + 3] = (int32_t) (uint32_t) (rc.v[i] >> 32);
+                CH_STCS(c + 8 + 4 * i, (int32_t) (uint32_t) rc.k[i]); CH_STCS(c + 8 + 4 * i + 1, (int32_t) (uint32_t) (rc.k[i] >> 32));
+                CH_STCS(c + 8 + 4 * i + 2, (int32_t) (uint32_t) rc.v[i]); CH_STCS(c + 8 + 4 * i + 3, (int32_t) (uint32_t) (rc.v[i] >> 32));
             }
         }
     }

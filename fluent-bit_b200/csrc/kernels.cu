@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(BK_REC_BLOCK, BK_EVAL_MIN_BLOCKS) k_chain_eval
     if (i >= p.n_rec) return;
     uint32_t sz = 0;
     if (p.kind[i] == 0) sz = chain_record<false>(&p.env, i, p.off[i], p.len[i], 0);
-    p.size[i] = sz;
+    __stcs(&p.size[i], sz);
 }
 
 /* per-block sums of the record sizes */
