@@ -113,43 +113,45 @@ FLB_HD int rx_class_match(const struct rx_prog *pg, const struct rx_class *cl, c
     }
 }
 
+/* first position in [pos, len) holding one of k (1..4) ASCII bytes packed in sb (unused slots repeat
+ * the first); len if none.  Eight bytes per step on aligned words (buffers are padded, see bk_alloc). */
+FLB_HD int rx_find_first_of4(const uint8_t *s, int pos, int len, uint32_t sb, uint32_t k)
+{
+    const uint64_t ones = 0x0101010101010101ull;
+    const uint64_t r0 = ones * (sb & 0xff), r1 = ones * ((sb >> 8) & 0xff), r2 = ones * ((sb >> 16) & 0xff), r3 = ones * (sb >> 24);
+    while (pos < len) {
+        const uintptr_t a = (uintptr_t) (s + pos);
+        const unsigned sh = (unsigned) (a & 7) * 8;
+        uint64_t w = *(const uint64_t *) (a & ~(uintptr_t) 7), t, hit;
+        w >>= sh;
+        if (sh) w |= 0x8080808080808080ull << (64 - sh);           /* filler that is never a stop byte */
+        t = w ^ r0; hit = (t - ones) & ~t;
+        if (k > 1) {
+            t = w ^ r1; hit |= (t - ones) & ~t;
+            t = w ^ r2; hit |= (t - ones) & ~t;
+            t = w ^ r3; hit |= (t - ones) & ~t;
+        }
+        hit &= 0x8080808080808080ull;
+        if (hit) {
+#ifdef __CUDA_ARCH__
+            pos += (__ffsll((long long) hit) - 1) >> 3;
+#else
+            pos += __builtin_ctzll(hit) >> 3;
+#endif
+            return pos < len ? pos : len;
+        }
+        pos += 8 - (int) (sh >> 3);
+    }
+    return len;
+}
+
 /* cls*: advance over the longest run of class members starting at pos.  The four ASCII
  * bitmap words live in registers for the whole run (the hot loop of every log pattern). */
 FLB_HD int rx_class_run(const struct rx_prog *pg, const struct rx_class *cl, const uint8_t *s, int pos, int len)
 {
     const uint32_t w0 = cl->bits[0], w1 = cl->bits[1], w2 = cl->bits[2], w3 = cl->bits[3];
     int n;
-    if (cl->pad) {
-        /* the class is "every byte but <= 4 ASCII stop bytes" (rx_compile.c): find the first stop byte,
-         * eight bytes per step on aligned words (buffers are padded, see bk_alloc) */
-        const uint32_t sb = cl->ranges_off;
-        const uint64_t ones = 0x0101010101010101ull;
-        const uint64_t r0 = ones * (sb & 0xff), r1 = ones * ((sb >> 8) & 0xff), r2 = ones * ((sb >> 16) & 0xff), r3 = ones * (sb >> 24);
-        while (pos < len) {
-            const uintptr_t a = (uintptr_t) (s + pos);
-            const unsigned sh = (unsigned) (a & 7) * 8;
-            uint64_t w = *(const uint64_t *) (a & ~(uintptr_t) 7), t, hit;
-            w >>= sh;
-            if (sh) w |= 0x8080808080808080ull << (64 - sh);           /* filler that is never a stop byte */
-            t = w ^ r0; hit = (t - ones) & ~t;
-            if (cl->pad > 1) {
-                t = w ^ r1; hit |= (t - ones) & ~t;
-                t = w ^ r2; hit |= (t - ones) & ~t;
-                t = w ^ r3; hit |= (t - ones) & ~t;
-            }
-            hit &= 0x8080808080808080ull;
-            if (hit) {
-#ifdef __CUDA_ARCH__
-                pos += (__ffsll((long long) hit) - 1) >> 3;
-#else
-                pos += __builtin_ctzll(hit) >> 3;
-#endif
-                return pos < len ? pos : len;
-            }
-            pos += 8 - (int) (sh >> 3);
-        }
-        return len;
-    }
+    if (cl->pad & 0xff) return rx_find_first_of4(s, pos, len, cl->ranges_off, cl->pad & 0xff);
     while (pos < len) {
         const uint32_t b = s[pos];
         if (b < 0x80) {
@@ -263,7 +265,17 @@ FLB_HD int rx_match_at(const struct rx_prog *pg, const uint8_t *s, int len, int 
             const uint32_t stop = code[pc + 1];
             if (stop) {
                 const struct rx_class *cl = &cls[arg], *sc = &cls[stop - 1];
-                while (pos < len && !((sc->bits[s[pos] >> 5] >> (s[pos] & 31)) & 1) && rx_class_match(pg, cl, s, pos, len, &n)) pos += n;
+                const uint32_t nneg = cl->pad & 0xff, npos = (sc->pad >> 9) & 7;
+                if (nneg && (sc->pad & 0x100) && nneg + npos <= 4) {
+                    /* "every byte but a few" stepping lazily towards "one of a few bytes": the first
+                     * byte of either set is where the loop below would stop */
+                    uint32_t sb = 0, q = 0, z;
+                    for (z = 0; z < nneg; z++) sb |= ((cl->ranges_off >> (8 * z)) & 0xff) << (8 * q++);
+                    for (z = 0; z < npos; z++) sb |= ((sc->n_ranges >> (8 * z)) & 0xff) << (8 * q++);
+                    for (z = q; z < 4; z++) sb |= (sb & 0xff) << (8 * z);
+                    pos = rx_find_first_of4(s, pos, len, sb, q);
+                }
+                else while (pos < len && !((sc->bits[s[pos] >> 5] >> (s[pos] & 31)) & 1) && rx_class_match(pg, cl, s, pos, len, &n)) pos += n;
             }
             RX_PUSH2(pos, ((uint32_t) pc << 3) | RXT_LAZY);
             pc += 2;

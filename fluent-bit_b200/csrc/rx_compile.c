@@ -1276,6 +1276,19 @@ int rx_compile(const char *pattern, struct rx_compiled *out)
                 /* "everything but a few ASCII bytes" ([^ ], [^"], [^\]] ...): the run is a search
                  * for the first stop byte, which the device does eight bytes at a time.  pad = number
                  * of stop bytes (1..4), ranges_off = the stop bytes (unused by RX_MB_ALL otherwise). */
+                /* a plain set of <= 4 ASCII bytes (typically "what the continuation can start with"):
+                 * pad bit 8, count in bits 9..11, the bytes in n_ranges (unused by RX_MB_NONE) */
+                if (cl[i].mb_mode == RX_MB_NONE) {
+                    uint32_t mem = 0, n = 0, b;
+                    int okc = 1;
+                    for (b = 0; b < 256 && okc; b++) {
+                        if ((cl[i].bits[b >> 5] >> (b & 31)) & 1) {
+                            if (b >= 0x80 || n >= 4) okc = 0;
+                            else mem |= b << (8 * n++);
+                        }
+                    }
+                    if (okc && n >= 1) { cl[i].pad = 0x100 | (n << 9); cl[i].n_ranges = mem; }
+                }
                 if (cl[i].mb_mode == RX_MB_ALL) {
                     uint32_t stops = 0, n = 0, b;
                     int okc = 1;
