@@ -19,6 +19,7 @@
 #include <atomic>
 #include <thread>
 #include <string.h>
+#include <stdlib.h>
 #include <sched.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -434,21 +435,23 @@ int bk_upload_wait_index(size_t upto)
 }
 
 /* ---- download session: pinned ring + one host thread per slot ---- */
-#define XF_SLOTS 8
-#define XF_SLICE ((size_t) 16 << 20)
+#define XF_MAX_SLOTS 32
+/* ring geometry: FLBGPU_XF_SLOTS staging buffers (one copy-out thread each) of FLBGPU_XF_MB MiB */
+static int XF_SLOTS = 8;
+static size_t XF_SLICE = (size_t) 16 << 20;
 #define XF_MAX_RANGES 512
 static cudaEvent_t xf_rev[XF_MAX_RANGES];
 static int xf_rev_made;
-static uint8_t *xf_ring[XF_SLOTS];
-static cudaEvent_t xf_ev[XF_SLOTS], xf_evc;
+static uint8_t *xf_ring[XF_MAX_SLOTS];
+static cudaEvent_t xf_ev[XF_MAX_SLOTS], xf_evc;
 static int xf_ready;
 struct xf_session {
     uint8_t *h_dst; const uint8_t *d_src;
-    std::atomic<long> issued[XF_SLOTS], done[XF_SLOTS];
-    size_t s_off[XF_SLOTS], s_len[XF_SLOTS];
+    std::atomic<long> issued[XF_MAX_SLOTS], done[XF_MAX_SLOTS];
+    size_t s_off[XF_MAX_SLOTS], s_len[XF_MAX_SLOTS];
     std::atomic<long> n_issued;          /* slices issued so far */
     std::atomic<int> closed, failed;
-    std::thread th[XF_SLOTS];
+    std::thread th[XF_MAX_SLOTS];
     int started;
     /* byte ranges handed over by bk_download_push(); an issuer thread turns them into ring slices so
      * that the caller (which also drives indexing and evaluation of the next slice) never blocks on a
@@ -464,6 +467,11 @@ static int xf_init(void)
 {
     if (xf_ready) return 0;
     if (streams_init()) return -1;
+    {
+        const char *es = getenv("FLBGPU_XF_SLOTS"), *em = getenv("FLBGPU_XF_MB");
+        if (es && atoi(es) >= 2 && atoi(es) <= XF_MAX_SLOTS) XF_SLOTS = atoi(es);
+        if (em && atoi(em) >= 1 && atoi(em) <= 256) XF_SLICE = (size_t) atoi(em) << 20;
+    }
     for (int i = 0; i < XF_SLOTS; i++) {
         CK(cudaMallocHost((void **) &xf_ring[i], XF_SLICE));
         CK(cudaEventCreateWithFlags(&xf_ev[i], cudaEventDisableTiming));
