@@ -437,8 +437,8 @@ int bk_upload_wait_index(size_t upto)
 /* ---- download session: pinned ring + one host thread per slot ---- */
 #define XF_MAX_SLOTS 32
 /* ring geometry: FLBGPU_XF_SLOTS staging buffers (one copy-out thread each) of FLBGPU_XF_MB MiB */
-static int XF_SLOTS = 8;
-static size_t XF_SLICE = (size_t) 16 << 20;
+static int XF_SLOTS = 16;           /* measured best on the bench box: 16 x 8 MiB (profiles/r01_variants.txt) */
+static size_t XF_SLICE = (size_t) 8 << 20;
 #define XF_MAX_RANGES 512
 static cudaEvent_t xf_rev[XF_MAX_RANGES];
 static int xf_rev_made;
