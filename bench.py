@@ -189,7 +189,13 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local):
     reps = max(1, args.lines // BASE_LINES)
     n_lines = reps * BASE_LINES
     nbytes = len(block) * reps
-    h_in = L.flbgpu_host_alloc(ctx.h, nbytes)       # pinned
+    pageable = os.environ.get("FLBGPU_BENCH_PAGEABLE") == "1"   # experiment: ordinary malloc()ed input, staged by the library
+    if pageable:
+        libc0 = C.CDLL(None)
+        libc0.malloc.restype = C.c_void_p; libc0.malloc.argtypes = [C.c_size_t]
+        h_in = libc0.malloc(nbytes)
+    else:
+        h_in = L.flbgpu_host_alloc(ctx.h, nbytes)       # pinned
     for i in range(reps):
         C.memmove(h_in + i * len(block), block, len(block))
     d_in = L.flbgpu_dev_alloc(ctx.h, nbytes + 64)
@@ -285,7 +291,10 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local):
     phases = [round(float(x), 2) for x in chain.stats().phase_ms]
     L.flbgpu_dev_free(ctx.h, d_in)
     L.flbgpu_dev_free(ctx.h, d_out)
-    L.flbgpu_host_free(ctx.h, h_in)
+    if pageable:
+        libc.free(h_in)
+    else:
+        L.flbgpu_host_free(ctx.h, h_in)
     return {"value": value, "dev_ms": dev_ms, "e2e": e2e, "e2e_steps": e2e_steps, "kms": [k / args.steps for k in kms],
             "launches": launches, "n_lines": n_lines, "nbytes": nbytes, "out_bytes": out_bytes, "clocks": clocks,
             "phases": phases}

@@ -72,6 +72,8 @@ int bk_upload_start(void *d_dst, const void *h_src, size_t n);
 int bk_upload_wait_index(size_t upto);
 /* device-resident input: nothing to wait for */
 void bk_upload_none(void);
+/* joins the staging threads of a pageable upload: the caller's buffer is not read after this */
+void bk_upload_end(void);
 
 /* Record index (K1) of one slice d_in[slice_off, slice_off+slice_len).  Pass 1 counts
  * validated candidates per tile (exclusive tile offsets left in d_tile) and returns the

@@ -409,28 +409,96 @@ static int up_ev_made;
 static size_t up_total, up_piece;
 static int up_active;
 
+/* Pageable input (a chunk that lives in ordinary malloc()ed memory, as Fluent Bit's do): the driver
+ * would stage every cudaMemcpyAsync itself, synchronously and single-threaded.  Instead UP_THREADS host
+ * threads copy the pieces into pinned staging buffers in parallel and enqueue the H2D copies in piece
+ * order; up_recorded[i] tells the indexing side when piece i's event exists. */
+#define UP_THREADS 6
+#define UP_STAGE_SLOTS 12
+static uint8_t *up_stage[UP_STAGE_SLOTS];
+static cudaEvent_t up_stage_ev[UP_STAGE_SLOTS];
+static int up_stage_ready;
+static std::atomic<int> up_recorded[UP_MAX_EV];
+static std::atomic<long> up_next_issue;
+static std::atomic<int> up_failed;
+static std::thread up_threads[UP_THREADS];
+static int up_threads_live, up_staged;
+
+static void up_worker(int t, uint8_t *d_dst, const uint8_t *h_src, size_t n, size_t piece, size_t np)
+{
+    for (size_t i = (size_t) t; i < np; i += UP_THREADS) {
+        const int slot = (int) (i % UP_STAGE_SLOTS);
+        const size_t off = i * piece, sz = (off + piece <= n) ? piece : n - off;
+        /* the slot was last used by piece i - UP_STAGE_SLOTS: its H2D must have left the buffer */
+        if (i >= UP_STAGE_SLOTS) {
+            while (!up_recorded[i - UP_STAGE_SLOTS].load(std::memory_order_acquire)) { if (up_failed.load()) return; sched_yield(); }
+            if (cudaEventSynchronize(up_ev[i - UP_STAGE_SLOTS]) != cudaSuccess) { up_failed.store(1); return; }
+        }
+        memcpy(up_stage[slot], h_src + off, sz);
+        while (up_next_issue.load(std::memory_order_acquire) != (long) i) { if (up_failed.load()) return; sched_yield(); }
+        if (cudaMemcpyAsync(d_dst + off, up_stage[slot], sz, cudaMemcpyHostToDevice, g_h2d) != cudaSuccess ||
+            cudaEventRecord(up_ev[i], g_h2d) != cudaSuccess) { up_failed.store(1); up_next_issue.store((long) i + 1); return; }
+        up_recorded[i].store(1, std::memory_order_release);
+        up_next_issue.store((long) i + 1, std::memory_order_release);
+    }
+}
+
+void bk_upload_end(void)
+{
+    if (up_threads_live) {
+        for (int t = 0; t < UP_THREADS; t++) up_threads[t].join();
+        up_threads_live = 0;
+    }
+}
+
 int bk_upload_start(void *d_dst, const void *h_src, size_t n)
 {
     if (streams_init()) return -1;
+    bk_upload_end();
     up_piece = UP_PIECE;
     while ((n + up_piece - 1) / up_piece > UP_MAX_EV) up_piece *= 2;
     const size_t np = (n + up_piece - 1) / up_piece;
     for (; up_ev_made < (int) np; up_ev_made++) CK(cudaEventCreateWithFlags(&up_ev[up_ev_made], cudaEventDisableTiming));
+    up_total = n; up_active = 1; up_staged = 0;
+    {
+        cudaPointerAttributes at;
+        const int pinned = cudaPointerGetAttributes(&at, h_src) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
+        cudaGetLastError();
+        if (!pinned && up_piece == UP_PIECE && !getenv("FLBGPU_NO_STAGING")) {
+            if (!up_stage_ready) {
+                for (int i = 0; i < UP_STAGE_SLOTS; i++) CK(cudaMallocHost((void **) &up_stage[i], UP_PIECE));
+                up_stage_ready = 1;
+            }
+            for (size_t i = 0; i < np; i++) up_recorded[i].store(0);
+            up_next_issue.store(0); up_failed.store(0);
+            up_staged = 1;
+            for (int t = 0; t < UP_THREADS; t++)
+                up_threads[t] = std::thread(up_worker, t, (uint8_t *) d_dst, (const uint8_t *) h_src, n, up_piece, np);
+            up_threads_live = 1;
+            return 0;
+        }
+    }
     for (size_t i = 0; i < np; i++) {
         const size_t off = i * up_piece, sz = (off + up_piece <= n) ? up_piece : n - off;
         CK(cudaMemcpyAsync((uint8_t *) d_dst + off, (const uint8_t *) h_src + off, sz, cudaMemcpyHostToDevice, g_h2d));
         CK(cudaEventRecord(up_ev[i], g_h2d));
     }
-    up_total = n; up_active = 1;
     return 0;
 }
-void bk_upload_none(void) { up_active = 0; }
+void bk_upload_none(void) { bk_upload_end(); up_active = 0; }
 int bk_upload_wait_index(size_t upto)
 {
     if (streams_init()) return -1;
     if (!up_active || upto == 0) return 0;
     if (upto > up_total) upto = up_total;
-    CK(cudaStreamWaitEvent(g_istream, up_ev[(upto - 1) / up_piece], 0));
+    const size_t last = (upto - 1) / up_piece;
+    if (up_staged) {
+        while (!up_recorded[last].load(std::memory_order_acquire)) {
+            if (up_failed.load()) { snprintf(g_err, sizeof(g_err), "host->device staging failed"); return -1; }
+            sched_yield();
+        }
+    }
+    CK(cudaStreamWaitEvent(g_istream, up_ev[last], 0));
     return 0;
 }
 

@@ -1577,12 +1577,17 @@ int flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes, const char 
         const char *sv = getenv("FLBGPU_STREAM");
         if (!(sv && sv[0] == '0')) {
             int ret = 0, r = chain_run_stream(c, data, bytes, out_buf, out_size, &ret);
+            bk_upload_end();                         /* `data` is not read after this call returns */
             if (r == 0) return ret;
             if (r < 0) return -1;
             *out_buf = NULL; *out_size = 0;          /* speculation did not hold: classic path */
         }
     }
-    return chain_run(c, data, NULL, bytes, NULL, 0, out_buf, out_size);
+    {
+        int r = chain_run(c, data, NULL, bytes, NULL, 0, out_buf, out_size);
+        bk_upload_end();
+        return r;
+    }
 }
 
 

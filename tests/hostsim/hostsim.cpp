@@ -98,6 +98,7 @@ int bk_d2d(void *dst, const void *src, size_t n) { memcpy(dst, src, n); return 0
 int bk_upload_start(void *d_dst, const void *h_src, size_t n) { memcpy(d_dst, h_src, n); return 0; }
 int bk_upload_wait_index(size_t upto) { (void) upto; return 0; }
 void bk_upload_none(void) {}
+void bk_upload_end(void) {}
 
 int bk_index_count(const uint8_t *d_in, size_t slice_off, uint32_t len, uint32_t *d_tile, uint32_t n_tiles, uint32_t *n_cand)
 {
