@@ -503,7 +503,7 @@ FLB_HD int ra_regex_match(const struct ch_env *e, const struct ch_rec *rc, uint3
 
 /* ---------------------------------------------------------- filter_parser */
 /* One regex parser over s[0,n): returns 1 parsed (fields appended to out_*), 0 not.
- * Timestamp result in *t_sec/*t_nsec (0/0 when no time was resolved). */
+ * Timestamp result in *t_sec and *t_nsec (0/0 when no time was resolved). */
 /* tslot (4 ints of the capture cache, or NULL): the evaluation pass stores the Time_Key lookup there
  * (state 1 ok / 2 failed, seconds lo/hi, nanoseconds) and the emission pass (use_cached) reads it
  * instead of running strptime again */

@@ -90,6 +90,8 @@ int bk_index_fill(const uint8_t *d_in, size_t slice_off, uint32_t slice_len, con
 
 int bk_flags_clear(uint32_t *d_flags);
 /* evaluation pass over records [r0, r1): asynchronous on the compute stream */
+/* L2 hint: [base, base+bytes) is read once by the next evaluation launches */
+int bk_hint_streaming(const void *base, size_t bytes);
 int bk_chain_eval(const struct bk_chain_args *a, uint32_t r0, uint32_t r1);
 /* evidence + error word (synchronises the compute stream) */
 int bk_flags_fetch(const uint32_t *d_flags, uint32_t *h_flags);

@@ -720,6 +720,32 @@ int bk_flags_clear(uint32_t *d_flags)
     return 0;
 }
 
+/* The slice of input the next evaluation reads is touched once: mark it as streaming in L2 (access
+ * policy window of the stream) so that it does not evict the lanes' local-memory lines (field lists,
+ * regex stacks), which are re-used by every block.  FLBGPU_L2_WINDOW=0 turns the hint off. */
+int bk_hint_streaming(const void *base, size_t bytes)
+{
+    static int max_win = -1, enabled = -1;
+    cudaStreamAttrValue v;
+    if (streams_init()) return -1;
+    if (enabled < 0) { const char *e = getenv("FLBGPU_L2_WINDOW"); enabled = !(e && e[0] == '0'); }
+    if (!enabled) return 0;
+    if (max_win < 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev) != cudaSuccess) max_win = 0;
+    }
+    if (max_win <= 0 || !base || !bytes) return 0;
+    memset(&v, 0, sizeof(v));
+    v.accessPolicyWindow.base_ptr = (void *) base;
+    v.accessPolicyWindow.num_bytes = bytes < (size_t) max_win ? bytes : (size_t) max_win;
+    v.accessPolicyWindow.hitRatio = 1.0f;
+    v.accessPolicyWindow.hitProp = cudaAccessPropertyStreaming;
+    v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    if (cudaStreamSetAttribute(g_stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+    return 0;
+}
+
 int bk_chain_eval(const struct bk_chain_args *a, uint32_t r0, uint32_t r1)
 {
     k_chain_params p;

@@ -1278,6 +1278,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         }
         fill_args(c, &a, d_in, bytes, n_rec + n_valid);
         a.assume = assume; a.now = now;
+        bk_hint_streaming(a.d_in + off, (size_t) end_off - off);
         if (bk_chain_eval(&a, n_rec, n_rec + n_valid)) return -1;
         n_rec += n_valid;
         off = (size_t) end_off;
@@ -1492,6 +1493,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
         STREAM_FLUSH(n_rec / BK_REC_BLOCK);
         fill_args(c, &a, c->d_in, bytes, n_rec + n_valid);
         a.assume = assume; a.now = now;
+        bk_hint_streaming(a.d_in + off, (size_t) end_off - off);
         if (bk_chain_eval(&a, n_rec, n_rec + n_valid)) goto fail;
         n_rec += n_valid;
         off = (size_t) end_off;

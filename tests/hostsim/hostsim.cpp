@@ -99,6 +99,7 @@ int bk_upload_start(void *d_dst, const void *h_src, size_t n) { memcpy(d_dst, h_
 int bk_upload_wait_index(size_t upto) { (void) upto; return 0; }
 void bk_upload_none(void) {}
 void bk_upload_end(void) {}
+int bk_hint_streaming(const void *base, size_t bytes) { (void) base; (void) bytes; return 0; }
 
 int bk_index_count(const uint8_t *d_in, size_t slice_off, uint32_t len, uint32_t *d_tile, uint32_t n_tiles, uint32_t *n_cand)
 {
