@@ -541,7 +541,7 @@ FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t
             tp.fmt = (const char *) (e->blob + pd->fmt_off);
             tp.frac_fmt = pd->has_frac ? (const char *) (e->blob + pd->frac_off) : 0;
             tp.with_year = (int) pd->time_with_year; tp.with_tz = (int) pd->time_with_tz;
-            tp.strict = (int) pd->time_strict; tp.offset = pd->time_offset; tp.fast_apache = (pd->has_time & 2) != 0;
+            tp.strict = (int) pd->time_strict; tp.offset = pd->time_offset; tp.fast_apache = (pd->has_time & 2) != 0; tp.tfast = pd->tfast_off ? e->blob + pd->tfast_off : 0;
             r = dt_time_lookup(vlen ? v : s, vlen, e->now, &tp, &tm, &ns);
             if (r == -1) { if (tslot && !use_cached) tslot[0] = 2; continue; }
             frac = ns;
@@ -614,7 +614,7 @@ FLB_HDN int pdef_time(const struct ch_env *e, const struct cf_pdef *pd, const ui
     tp.fmt = (const char *) (e->blob + pd->fmt_off);
     tp.frac_fmt = pd->has_frac ? (const char *) (e->blob + pd->frac_off) : 0;
     tp.with_year = (int) pd->time_with_year; tp.with_tz = (int) pd->time_with_tz;
-    tp.strict = (int) pd->time_strict; tp.offset = pd->time_offset; tp.fast_apache = (pd->has_time & 2) != 0;
+    tp.strict = (int) pd->time_strict; tp.offset = pd->time_offset; tp.fast_apache = (pd->has_time & 2) != 0; tp.tfast = pd->tfast_off ? e->blob + pd->tfast_off : 0;
     if (dt_time_lookup(v, vlen, e->now, &tp, &tm, &ns) == -1) return -1;
     *frac = ns;
     *lookup = dt_timegm(&tm) - tm.gmtoff;

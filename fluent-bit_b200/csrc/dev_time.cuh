@@ -14,6 +14,7 @@
 
 #include <stdint.h>
 
+#include "flbgpu_prog.h"
 #ifndef FLB_HD
 #ifdef __CUDACC__
 #define FLB_HD __host__ __device__ __forceinline__
@@ -474,12 +475,104 @@ FLB_HD int dt_fast_apache(const uint8_t *s, uint32_t n, struct dt_tm *tm)
     return 1;
 }
 
+/* Fixed-shape time program (TF_* ops, compiled by runtime.c:time_fast_compile): 1 = tm / ns filled
+ * exactly as the general path would, 0 = not this shape, let the general path decide. */
+FLB_HD int dt_fast_prog(const uint8_t *prog, const uint8_t *s, uint32_t n, struct dt_tm *tm, double *ns)
+{
+    static const char mon3[] = "janfebmaraprmayjunjulaugsepoctnovdec";
+    uint32_t p = 0;
+    for (;;) {
+        const uint32_t op = *prog++;
+        switch (op) {
+        case TF_END:
+            return 1;
+        case TF_D2: {
+            const uint32_t f = prog[0], lo = prog[1], hi = prog[2];
+            uint32_t d0, d1, v;
+            prog += 3;
+            if (p + 2 > n) return 0;
+            d0 = (uint32_t) s[p] - '0'; d1 = (uint32_t) s[p + 1] - '0';
+            if (d0 > 9u || d1 > 9u) return 0;
+            v = d0 * 10 + d1;
+            if (v < lo || v > hi) return 0;
+            p += 2;
+            if (f == TFF_MDAY) tm->mday = (int) v; else if (f == TFF_MON) tm->mon = (int) v - 1;
+            else if (f == TFF_HOUR) tm->hour = (int) v; else if (f == TFF_MIN) tm->min = (int) v; else tm->sec = (int) v;
+            break;
+        }
+        case TF_Y4: {
+            uint32_t k, v = 0;
+            if (p + 4 > n) return 0;
+            for (k = 0; k < 4; k++) { const uint32_t d = (uint32_t) s[p + k] - '0'; if (d > 9u) return 0; v = v * 10 + d; }
+            p += 4;
+            tm->year = (int) v - 1900;
+            break;
+        }
+        case TF_LIT:
+            if (p >= n || s[p] != *prog) return 0;
+            prog++; p++;
+            break;
+        case TF_SPACE:
+            if (p >= n || s[p] != ' ') return 0;
+            p++;
+            if (p < n && dt_isspace(s[p])) return 0;
+            break;
+        case TF_MON3: {
+            int m;
+            if (p + 3 > n) return 0;
+            for (m = 0; m < 12; m++)
+                if (dt_lower(s[p]) == mon3[3 * m] && dt_lower(s[p + 1]) == mon3[3 * m + 1] && dt_lower(s[p + 2]) == mon3[3 * m + 2]) break;
+            if (m == 12) return 0;
+            p += 3;
+            if (p < n && ((s[p] | 0x20) >= 'a' && (s[p] | 0x20) <= 'z')) return 0;     /* maybe a full month name */
+            tm->mon = m;
+            break;
+        }
+        case TF_TZ: {
+            uint32_t c0 = p < n ? s[p] : 0, h0, h1, offs;
+            if (c0 == 'Z') { p++; tm->isdst = 0; tm->gmtoff = 0; break; }
+            if (c0 != '+' && c0 != '-') return 0;
+            p++;
+            h0 = (p < n ? (uint32_t) s[p] : 0u) - '0'; h1 = (p + 1 < n ? (uint32_t) s[p + 1] : 0u) - '0';
+            if (h0 > 9u || h1 > 9u) return 0;
+            offs = (h0 * 10 + h1) * 3600;
+            p += 2;
+            if (p < n && s[p] == ':') p++;
+            if (p < n && dt_isdigit(s[p])) {
+                const uint32_t m0 = (uint32_t) s[p] - '0', m1 = (p + 1 < n ? (uint32_t) s[p + 1] : 0u) - '0';
+                if (m1 > 9u) return 0;
+                offs += (m0 * 10 + m1) * 60;
+                p += 2;
+            }
+            tm->isdst = 0;
+            tm->gmtoff = c0 == '-' ? -(long) offs : (long) offs;
+            break;
+        }
+        case TF_FRAC: {
+            uint32_t avail = n - p, digits = avail < 9 ? avail : 9, nd = 0;
+            uint64_t num = 0;
+            double den = 1.0;
+            while (nd < digits && dt_isdigit(s[p + nd])) { num = num * 10 + (s[p + nd] - '0'); den *= 10.0; nd++; }
+            if (nd == 0) return 0;
+            if (nd == 9 && p + 9 < n && dt_isdigit(s[p + 9])) return 0;
+            *ns = (double) num / den;
+            p += nd;
+            tm->gmtoff = 0; tm->isdst = -1;          /* the part after %L is a fresh flb_strptime() call */
+            break;
+        }
+        default:
+            return 0;
+        }
+    }
+}
+
 struct dt_parser {
     const char *fmt;        /* format up to %L (already prefixed with "%Y " when !with_year) */
     const char *frac_fmt;   /* format after %L, or NULL when the format has no %L */
     int with_year, with_tz, strict;
     int offset;             /* Time_Offset in seconds */
     int fast_apache;        /* the format is exactly "%d/%b/%Y:%H:%M:%S %z" */
+    const uint8_t *tfast;   /* fixed-shape program for the format, or NULL */
 };
 
 /* flb_parser_time_lookup(): 0 ok (tm/frac filled, maybe partially), -1 error */
@@ -493,6 +586,15 @@ FLB_HDN int dt_time_lookup(const uint8_t *s, uint32_t tsize, int64_t now, const 
 
     *ns = 0;
     if (p->fast_apache && dt_fast_apache(s, tsize, tm)) return 0;
+    if (p->tfast && tsize <= 63) {
+        struct dt_tm t2 = *tm;
+        double ns2 = 0;
+        if (dt_fast_prog(p->tfast, s, tsize, &t2, &ns2)) {
+            *tm = t2; *ns = ns2;
+            if (!p->with_tz) tm->gmtoff = p->offset;
+            return 0;
+        }
+    }
     if (tsize > sizeof(tmp) - 1) return -1;
     if (!p->with_year) {
         struct dt_tm tmy;

@@ -134,7 +134,15 @@ struct cf_pdef {               /* device view of struct flb_parser (flb_parser.h
     uint32_t n_types, types_off;
     uint32_t logfmt_no_bare_keys;
     uint32_t n_groups;
+    uint32_t tfast_off;        /* compiled fixed-shape time program (TF_* ops), 0 = none */
+    uint32_t pad0;
 };
+
+/* Fixed-shape time program: what flb_strptime() does for the format when every numeric field has its
+ * full width, spaces are single, month names are the 3-letter forms and the zone is Z or +hh[:]mm.
+ * Any other value makes the program give up and the general interpreter decides. */
+enum { TF_END = 0, TF_D2, TF_Y4, TF_LIT, TF_SPACE, TF_MON3, TF_TZ, TF_FRAC };
+enum { TFF_MDAY = 0, TFF_MON, TFF_HOUR, TFF_MIN, TFF_SEC };
 
 struct cf_parser {             /* filter_parser */
     uint32_t key_off, key_len;

@@ -330,6 +330,50 @@ void flbgpu_parser_destroy(flbgpu_parser *p)
 }
 
 /* emit the device view of a parser; returns its offset */
+/* Compile "fmt [%L frac_fmt]" into TF_* ops (flbgpu_prog.h) when it only uses directives with a fixed
+ * shape; 0 when it does not (the general interpreter handles everything anyway). */
+static int time_fast_compile(const char *fmt, const char *frac_fmt, uint8_t *out, int cap)
+{
+    int n = 0, part;
+    int seen_year = 0;
+    for (part = 0; part < 2; part++) {
+        const char *f = part == 0 ? fmt : frac_fmt;
+        if (part == 1) {
+            if (!frac_fmt) break;
+            if (n + 1 >= cap) return 0;
+            out[n++] = TF_FRAC;
+        }
+        for (; f && *f; f++) {
+            if (n + 4 >= cap) return 0;
+            if (*f == ' ') { out[n++] = TF_SPACE; continue; }
+            if (isspace((unsigned char) *f)) return 0;
+            if (*f != '%') { out[n++] = TF_LIT; out[n++] = (uint8_t) *f; continue; }
+            f++;
+            switch (*f) {
+            case 'd': out[n++] = TF_D2; out[n++] = TFF_MDAY; out[n++] = 1; out[n++] = 31; break;
+            case 'm': out[n++] = TF_D2; out[n++] = TFF_MON; out[n++] = 1; out[n++] = 12; break;
+            case 'H': out[n++] = TF_D2; out[n++] = TFF_HOUR; out[n++] = 0; out[n++] = 23; break;
+            case 'M': out[n++] = TF_D2; out[n++] = TFF_MIN; out[n++] = 0; out[n++] = 59; break;
+            case 'S': out[n++] = TF_D2; out[n++] = TFF_SEC; out[n++] = 0; out[n++] = 60; break;
+            case 'Y': out[n++] = TF_Y4; seen_year = 1; break;
+            case 'b': case 'h': out[n++] = TF_MON3; break;
+            case 'z': out[n++] = TF_TZ; break;
+            case '%': out[n++] = TF_LIT; out[n++] = '%'; break;
+            case 'T':
+                out[n++] = TF_D2; out[n++] = TFF_HOUR; out[n++] = 0; out[n++] = 23; out[n++] = TF_LIT; out[n++] = ':';
+                if (n + 12 >= cap) return 0;
+                out[n++] = TF_D2; out[n++] = TFF_MIN; out[n++] = 0; out[n++] = 59; out[n++] = TF_LIT; out[n++] = ':';
+                out[n++] = TF_D2; out[n++] = TFF_SEC; out[n++] = 0; out[n++] = 60;
+                break;
+            default: return 0;           /* %y %e %j %s %Z %F ...: general path only */
+            }
+        }
+    }
+    if (!seen_year || n + 1 >= cap) return 0;
+    out[n++] = TF_END;
+    return n;
+}
+
 static uint32_t emit_pdef(struct blob *b, struct flbgpu_parser *p)
 {
     struct cf_pdef d;
@@ -341,6 +385,11 @@ static uint32_t emit_pdef(struct blob *b, struct flbgpu_parser *p)
     /* bit 1: the access-log format, for which the device has a direct path (dt_fast_apache) */
     if (p->has_time && p->time_fmt && !p->time_frac && !strcmp(p->time_fmt, "%d/%b/%Y:%H:%M:%S %z")) d.has_time |= 2;
     d.time_offset = p->time_offset; d.logfmt_no_bare_keys = p->logfmt_no_bare_keys;
+    if (p->has_time && p->time_with_year) {
+        uint8_t prog[128];
+        int n = time_fast_compile(p->time_fmt, p->time_frac, prog, (int) sizeof(prog));
+        if (n > 0) d.tfast_off = blob_add(b, prog, (size_t) n, 1);
+    }
     if (p->has_time) {
         d.fmt_off = blob_add(b, p->time_fmt, strlen(p->time_fmt) + 1, 1);
         if (p->time_frac) { d.has_frac = 1; d.frac_off = blob_add(b, p->time_frac, strlen(p->time_frac) + 1, 1); }

@@ -146,3 +146,47 @@ def test_apache_time_fast_path_hostsim(sim_lib, ref_available):
 @pytest.mark.gpu
 def test_apache_time_fast_path_gpu(gpu_lib, ref_available):
     check_apache_time_fast_path(gpu_lib)
+
+
+def check_time_programs(lib):
+    """formats with a compiled fixed-shape program (runtime.c:time_fast_compile) against the reference, on
+    canonical values and on values that must fall back to the general path"""
+    import random
+    rng = random.Random(77)
+    fmts = ["%Y-%m-%dT%H:%M:%S.%L%z", "%Y-%m-%dT%H:%M:%S.%LZ", "%Y-%m-%dT%H:%M:%S.%L", "%Y-%m-%d %H:%M:%S", "%Y-%m-%dT%T%z",
+            "%d/%b/%Y:%H:%M:%S %z", "%Y/%m/%d %H:%M:%S.%L %z", "%b %d %Y %H:%M:%S", "%Y%m%d%H%M%S", "%H:%M:%S %d-%m-%Y", "%z %Y-%m-%d %H:%M:%S.%L"]
+    base = ["2023-07-14T09:08:07.123456789+02:00", "2023-07-14T09:08:07.5Z", "2023-07-14T09:08:07.000001", "2023-07-14 09:08:07",
+            "2023-07-14T23:59:60-0330", "14/Jul/2023:09:08:07 +0000", "2023/07/14 09:08:07.25 +0900", "Jul 14 2023 09:08:07",
+            "20230714090807", "09:08:07 14-07-2023", "+0100 2023-07-14 09:08:07.75", "2023-7-14T9:8:7.1Z", "2023-07-14T09:08:07.1234567891Z",
+            "2023-07-14T09:08:07.+02:00", "2023-07-14T09:08:07.12 +02:00", "2023-13-14T09:08:07.1Z", "2023-07-32T09:08:07.1Z",
+            "2023-07-14T24:08:07.1Z", "2023-07-14T09:08:07.1z", "2023-07-14T09:08:07.1+2", "2023-07-14T09:08:07.1+02", "2023-07-14T09:08:07.1+02:",
+            "2023-07-14T09:08:07.1+02:3", "2023-07-14T09:08:07.1GMT", "July 14 2023 09:08:07", "jul 14 2023 09:08:07", "Jul  14 2023 09:08:07",
+            "2023-07-14  09:08:07", "2023-07-14 09:08:07 trailing", "0000-01-01 00:00:00", "9999-12-31 23:59:60", ""]
+    for fi, fmt in enumerate(fmts):
+        ref = util.Ref()
+        ctx = pkg.Context(0, lib=lib)
+        kw = dict(name="t%d" % fi, format="regex", regex=r"^(?<time>.*)$", time_fmt=fmt, time_key="time", time_keep=True, skip_empty=False)
+        rp = ref.parser(**kw)
+        vals = list(base)
+        for _ in range(20):                        # mutations of the canonical values
+            v = rng.choice(base[:11])
+            if v:
+                i = rng.randrange(len(v))
+                v = v[:i] + rng.choice("0159:-+.TZ /a") + v[i + 1:]
+            vals.append(v)
+        got = ctx.parser(**kw).do_batch([v.encode() for v in vals])
+        for v, (r, data, (sec, nsec)) in zip(vals, got):
+            rr, rdata, (rsec, rnsec) = ref.parser_do(rp, v.encode())
+            assert (r >= 0) == (rr >= 0), (fmt, v)
+            assert data == rdata, (fmt, v)
+            if r >= 0:
+                assert (sec, nsec) == (rsec & 0xffffffff, rnsec), (fmt, v)
+
+
+def test_time_programs_hostsim(sim_lib, ref_available):
+    check_time_programs(sim_lib)
+
+
+@pytest.mark.gpu
+def test_time_programs_gpu(gpu_lib, ref_available):
+    check_time_programs(gpu_lib)
