@@ -211,7 +211,7 @@ FLB_HD void mp_copy(uint8_t *o, const uint8_t *s, uint32_t n)
 {
     uint32_t i = 0;
 #ifdef __CUDA_ARCH__
-    if (n >= 12) {
+    if (n >= 8) {
         while (((uintptr_t) (o + i)) & 3) { o[i] = s[i]; i++; }
         {
             const uintptr_t sa = (uintptr_t) (s + i);

@@ -722,13 +722,14 @@ int bk_flags_clear(uint32_t *d_flags)
 
 /* The slice of input the next evaluation reads is touched once: mark it as streaming in L2 (access
  * policy window of the stream) so that it does not evict the lanes' local-memory lines (field lists,
- * regex stacks), which are re-used by every block.  FLBGPU_L2_WINDOW=0 turns the hint off. */
+ * regex stacks), which are re-used by every block.  Measured without effect (profiles/r01_variants.txt), so it
+ * is opt-in: FLBGPU_L2_WINDOW=1. */
 int bk_hint_streaming(const void *base, size_t bytes)
 {
     static int max_win = -1, enabled = -1;
     cudaStreamAttrValue v;
     if (streams_init()) return -1;
-    if (enabled < 0) { const char *e = getenv("FLBGPU_L2_WINDOW"); enabled = !(e && e[0] == '0'); }
+    if (enabled < 0) { const char *e = getenv("FLBGPU_L2_WINDOW"); enabled = (e && e[0] == '1'); }   /* off: no measurable effect on B200 */
     if (!enabled) return 0;
     if (max_win < 0) {
         int dev = 0;
