@@ -104,6 +104,8 @@ int bk_sizes_scan_range(const uint32_t *d_size, uint32_t n_rec, uint32_t b0, uin
                         uint64_t carry_in);
 /* emission of blocks [b0, b1) into d_out: asynchronous on the compute stream */
 int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1);
+/* records emitted since the last bk_flags_clear() */
+int bk_records_out(uint64_t *n);
 
 /* result download session: bytes [lo,hi) of d_out become valid after the emission just
  * enqueued; they are DMA'd into a pinned ring and moved into h_dst by host threads. */

@@ -27,6 +27,7 @@
 #include "dev_chain.cuh"
 
 static char g_err[256];
+static int g_nsurv;
 static unsigned long long g_launches;
 static cudaStream_t g_stream;
 /* CUDA-event timing of the kernel groups of the last call: one event pair per launch
@@ -717,6 +718,7 @@ int bk_flags_clear(uint32_t *d_flags)
     if (streams_init()) return -1;
     CK(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1), g_stream));
     g_ev_used[0] = g_ev_used[1] = g_ev_used[2] = 0;
+    g_nsurv = 0;
     return 0;
 }
 
@@ -824,6 +826,19 @@ int bk_sizes_scan_range(const uint32_t *d_size, uint32_t n_rec, uint32_t b0, uin
     return 0;
 }
 
+#define BK_MAX_EMITS 1024
+static unsigned long long *g_hsurv;
+
+/* records emitted since the last bk_flags_clear(); synchronises the library stream */
+int bk_records_out(uint64_t *n)
+{
+    unsigned long long t = 0;
+    CK(cudaStreamSynchronize(g_stream));
+    for (int i = 0; i < g_nsurv; i++) t += g_hsurv[i];
+    *n = t;
+    return 0;
+}
+
 int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1)
 {
     k_chain_params p;
@@ -851,6 +866,9 @@ int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, ui
         k_chain_emit_list<<<nb, BK_REC_BLOCK, 0, g_stream>>>(p, d_lrec, d_loff, d_nlist);
         ev_end(2);
         g_launches += 4;
+        /* how many records this range emitted: read back after the call's last synchronisation */
+        if (!g_hsurv) CK(cudaMallocHost((void **) &g_hsurv, sizeof(unsigned long long) * BK_MAX_EMITS));
+        if (g_nsurv < BK_MAX_EMITS) CK(cudaMemcpyAsync(&g_hsurv[g_nsurv++], d_nlist, sizeof(unsigned long long), cudaMemcpyDeviceToHost, g_stream));
     }
     CK(cudaGetLastError());
     return 0;

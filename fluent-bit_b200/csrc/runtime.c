@@ -1422,6 +1422,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         *host_out = out;
     }
     c->st.kernel_launches = bk_launch_count();
+    if (host_out) bk_records_out(&c->st.records_out);     /* (the device-output form leaves the stream running) */
     PHASE_MARK(3);
     c->st.phase_ms[2] = c->st.phase_ms[3] - c->st.phase_ms[1] - c->st.phase_ms[0];
     return FLBGPU_FILTER_MODIFIED;
@@ -1584,6 +1585,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
     c->st.kernel_launches = bk_launch_count();
     if (l2m_merge(c)) goto fail;
     if (dl_open) { dl_open = 0; if (bk_download_end()) goto fail; }
+    bk_records_out(&c->st.records_out);
     c->st.bytes_out = placed;
     *out_size = (size_t) placed;
     if (placed == 0) { free(out); out = NULL; }

@@ -174,7 +174,8 @@ static void hs_env(const struct bk_chain_args *a, struct ch_env *e)
     e->l2m = a->l2m;
 }
 
-int bk_flags_clear(uint32_t *d_flags) { memset(d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)); return 0; }
+static uint64_t hs_records_out;
+int bk_flags_clear(uint32_t *d_flags) { memset(d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)); hs_records_out = 0; return 0; }
 int bk_flags_fetch(const uint32_t *d_flags, uint32_t *h_flags) { memcpy(h_flags, d_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)); return 0; }
 
 int bk_chain_eval(const struct bk_chain_args *a, uint32_t r0, uint32_t r1)
@@ -219,6 +220,8 @@ int bk_sizes_scan_range(const uint32_t *d_size, uint32_t n_rec, uint32_t b0, uin
     return 0;
 }
 
+int bk_records_out(uint64_t *n) { *n = hs_records_out; return 0; }
+
 int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1)
 {
     struct ch_env e;
@@ -229,6 +232,7 @@ int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, ui
         for (i = b * BK_REC_BLOCK; i < a->n_rec && i < (b + 1) * BK_REC_BLOCK; i++) {
             if (a->d_size[i]) {
                 uint32_t w = chain_record<true>(&e, i, a->d_off[i], a->d_len[i], d_out + at);
+                hs_records_out++;
                 if (w != a->d_size[i]) { snprintf(hs_err, sizeof(hs_err), "emit size mismatch at record %u: %u vs %u", i, w, a->d_size[i]); return -1; }
                 at += w;
             }

@@ -50,3 +50,17 @@ def test_init_fails_loudly_without_a_device():
     with pytest.raises(util.pkg.FlbGpuError) as e:
         util.pkg.Context(0, lib=lib)
     assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_stats_after_a_call(sim_lib, ref_available):
+    """flbgpu_chain_stats: records and bytes in/out of the last call"""
+    import cases
+    ctx = util.pkg.Context(0, lib=sim_lib)
+    ctx.parser(**cases.AP)
+    chain = ctx.chain([ctx.filter(p, props) for p, props in [cases.P, ("grep", [("Regex", "method ^(GET|POST)$")])]])
+    lines = util.apache_lines(500, seed=2)
+    chunk = util.chunk_from_lines(lines)
+    r, out = chain.do(chunk)
+    st = chain.stats()
+    assert st.records_in == len(lines) and st.bytes_in == len(chunk) and st.bytes_out == len(out)
+    assert st.records_out == len(util.split_records(out)) and 0 < st.records_out < st.records_in
