@@ -62,6 +62,24 @@ def json_chunk(n=1200, seed=5):
     return util.chunk_from_lines(util.json_lines(n, seed=seed))
 
 
+def wide_apache_chunk():
+    """apache lines next to 8 more fields: parsed (11) + reserved (8) fields exceed the 16-field list the
+    evaluation pass caches for the emission pass, which then re-runs the chain for these records"""
+    lines = util.apache_lines(300, seed=9)
+    return b"".join(util.event(1700000000 + i, 0, [(b"log", util.mp_str(l))] + [(b"x%d" % j, util.mp_str(b"v%d" % j)) for j in range(8)])
+                    for i, l in enumerate(lines))
+
+
+def wide_json_chunk():
+    """JSON documents with 20 members (same reason), some with nested values and escapes"""
+    out = []
+    for i in range(200):
+        items = ['"k%02d":%s' % (j, ['"v%d"' % j, str(j * i), "true", "null", '{"a":[1,2,{"b":"c"}]}', '"esc\\n\"q\""', "%d.5" % j][(i + j) % 7]) for j in range(20)]
+        items.insert(i % 20, '"level":"%s"' % ["warn", "info", "error"][i % 3])
+        out.append(("{" + ",".join(items) + "}").encode())
+    return util.chunk_from_lines(out)
+
+
 def json_edge_chunk():
     return util.chunk_from_lines(JSON_EDGE)
 
@@ -106,6 +124,10 @@ CASES = [
                                  ("modify", [("Add", "env prod"), ("Rename", "msg message"), ("Remove", "debug")])], json_chunk),
     ("json_chain_nested_grep", [JS], [PJ, ("grep", [("Regex", "$kubernetes['labels']['app'] .")]),
                                      ("record_modifier", [("Remove_key", "trace_id"), ("Record", "cluster c1")])], json_chunk),
+    ("wide_records_apache", [AP], [("parser", [("Key_Name", "log"), ("Parser", "apache"), ("Reserve_Data", "On")]),
+                                   ("modify", [("Add", "env prod"), ("Remove", "x3"), ("Rename", "x5 y5")])], wide_apache_chunk),
+    ("wide_records_json", [JS], [PJ, ("grep", [("Regex", "level ^(warn|error)$")]), ("modify", [("Add", "env prod"), ("Remove", "k07")])],
+     wide_json_chunk),
     ("ltsv_parser", [LT], [("parser", [("Key_Name", "log"), ("Parser", "ltsv")])], ltsv_chunk),
     ("logfmt_parser", [LF], [("parser", [("Key_Name", "log"), ("Parser", "logfmt")]), ("grep", [("Exclude", "level debug")])], logfmt_chunk),
     ("multi_parser_fallthrough", [AP, JS, LF], [("parser", [("Key_Name", "log"), ("Parser", "json"), ("Parser", "apache"), ("Parser", "logfmt")])], lambda: util.chunk_from_lines(util.json_lines(100, 3) + util.apache_lines(100, 4) + util.logfmt_lines(100, 5))),
