@@ -193,7 +193,7 @@ FLB_HD int rx_match_at(const struct rx_prog *pg, const uint8_t *s, int len, int 
 {
     const uint32_t *code = (const uint32_t *) ((const char *) pg + pg->code_off);
     const struct rx_class *cls = (const struct rx_class *) ((const char *) pg + pg->class_off);
-    int pc = 0, pos = st, sp = 0, n;
+    int pc = 0, pos = st, sp = 0, n, unrestored = 0;
     uint32_t steps = *budget;
 
 #define RX_PUSH2(a, tagword) do { if (sp + 2 > stk_cap) { *budget = steps; return RX_R_ESTACK; } \
@@ -238,7 +238,10 @@ FLB_HD int rx_match_at(const struct rx_prog *pg, const uint8_t *s, int len, int 
             pc = (int) arg;
             continue;
         case RX_SAVE:
-            RX_PUSH2(caps[arg], (arg << 3) | RXT_RESTORE);
+            /* the old value only matters to whoever backtracks past this point: with nothing on the
+             * stack that can only be the end of this attempt, which then resets every capture */
+            if (sp > 0) RX_PUSH2(caps[arg], (arg << 3) | RXT_RESTORE);
+            else unrestored = 1;
             caps[arg] = pos;
             pc++;
             continue;
@@ -366,7 +369,12 @@ FLB_HD int rx_match_at(const struct rx_prog *pg, const uint8_t *s, int len, int 
 fail:
         for (;;) {
             uint32_t top, t;
-            if (sp == 0) { *budget = steps; return RX_R_NOMATCH; }
+            if (sp == 0) {
+                /* captures written without a restore record (see RX_SAVE) go back to "unset" here */
+                if (unrestored) { const int nc = 2 * ((int) pg->n_groups + 1); int z; for (z = 0; z < nc; z++) caps[z] = -1; }
+                *budget = steps;
+                return RX_R_NOMATCH;
+            }
             top = stk[sp - 1]; t = top & 7u;
             if (t == RXT_ALT) { pc = (int) (top >> 3); pos = (int) stk[sp - 2]; sp -= 2; break; }
             if (t == RXT_RESTORE) { caps[top >> 3] = (int) stk[sp - 2]; sp -= 2; continue; }
