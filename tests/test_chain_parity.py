@@ -160,3 +160,35 @@ def test_json_sliced_hostsim(sim_lib, ref_available, monkeypatch):
 @pytest.mark.gpu
 def test_json_sliced_gpu(gpu_lib, ref_available, monkeypatch):
     _json_sliced(gpu_lib, monkeypatch)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,maker", [("json_chain_config1", lambda: util.json_lines(100000, seed=0xF1B1 + 2)),
+                                        ("north_star_chain", lambda: util.apache_lines(100000, seed=0xF1B1 + 1))])
+def test_full_size_tiling_gpu(name, maker, gpu_lib, ref_available):
+    """BASELINE.json's full size (10 M events, the bench's own data): records are independent, so the
+    result of a chunk tiled k times is the block's result tiled k times -- and the block's result is
+    checked against the reference."""
+    case = [c for c in cases.CASES if c[0] == name][0]
+    block = util.chunk_from_lines(maker())
+    reps = 100
+    ctx = pkg.Context(0, lib=gpu_lib)
+    ref = util.Ref()
+    for kw in case[1]:
+        ctx.parser(**kw); ref.parser(**kw)
+    fs = [ctx.filter(p, props) for p, props in case[2]]
+    for p, props in case[2]:
+        ref.filter(p, props)
+    chain = ctx.chain(fs)
+    want = ref.chain_do(block)
+    one = chain.do(block)
+    assert one == want
+    big = block * reps
+    r, out = chain.do(big)
+    del big
+    assert r == want[0] and len(out) == len(want[1]) * reps
+    n = len(want[1])
+    for k in range(reps):
+        assert out[k * n:(k + 1) * n] == want[1], "tile %d differs" % k
+    st = chain.stats()
+    assert st.records_in == 100000 * reps
