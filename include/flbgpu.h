@@ -120,7 +120,8 @@ int flbgpu_chain_do_device(flbgpu_chain *c, const void *d_data, size_t bytes,
 
 /* per-call statistics of the last flbgpu_chain_do*() on this chain */
 struct flbgpu_stats {
-    uint64_t records_in;        /* decodable records in the chunk            */
+    uint64_t records_in;        /* entries of the record index: the decodable records, plus the rare byte runs
+                                   inside a record that frame as an event and are kept as "false candidate" */
     uint64_t records_out;       /* records in the result                      */
     uint64_t bytes_in, bytes_out;
     uint64_t kernel_launches;   /* kernels launched by this library so far   */

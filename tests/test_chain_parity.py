@@ -191,4 +191,4 @@ def test_full_size_tiling_gpu(name, maker, gpu_lib, ref_available):
     for k in range(reps):
         assert out[k * n:(k + 1) * n] == want[1], "tile %d differs" % k
     st = chain.stats()
-    assert st.records_in == 100000 * reps
+    assert 100000 * reps <= st.records_in <= 100000 * reps * 1.001      # index entries: records + the rare kept false candidates
