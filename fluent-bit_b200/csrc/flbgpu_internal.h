@@ -109,6 +109,8 @@ int bk_records_out(uint64_t *n);
 
 /* result download session: bytes [lo,hi) of d_out become valid after the emission just
  * enqueued; they are DMA'd into a pinned ring and moved into h_dst by host threads. */
+/* memcpy for write-once destinations (runtime.c): non-temporal stores where available */
+void flbgpu_stream_copy(void *dst, const void *src, size_t n);
 int bk_download_begin(void *h_dst, const void *d_out);
 int bk_download_push(size_t lo, size_t hi);
 int bk_download_end(void);

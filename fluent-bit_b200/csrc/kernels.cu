@@ -559,7 +559,7 @@ static void xf_worker(xf_session *x, int s)
             sched_yield();
         }
         if (cudaEventSynchronize(xf_ev[s]) != cudaSuccess) { x->failed.store(1); return; }
-        memcpy(x->h_dst + x->s_off[s], xf_ring[s], x->s_len[s]);
+        flbgpu_stream_copy(x->h_dst + x->s_off[s], xf_ring[s], x->s_len[s]);
         x->done[s].store(i, std::memory_order_release);
     }
 }

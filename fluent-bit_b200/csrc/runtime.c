@@ -1428,6 +1428,40 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     return FLBGPU_FILTER_MODIFIED;
 }
 
+/* Copy-out of result pieces from the pinned staging ring into the caller's malloc()ed chunk.  The
+ * destination is written once and not read again by this library, so on x86-64 with AVX2 the body
+ * goes out with non-temporal stores: no read-for-ownership of the destination lines and no cache
+ * pollution -- with several GPUs per host the copy-out traffic is what saturates host memory. */
+#if defined(__x86_64__) && defined(__GNUC__)
+#include <immintrin.h>
+__attribute__((target("avx2")))
+static void stream_copy_avx2(uint8_t *d, const uint8_t *s, size_t n)
+{
+    size_t head = ((uintptr_t) d & 31) ? 32 - ((uintptr_t) d & 31) : 0, i;
+    if (head > n) head = n;
+    memcpy(d, s, head);
+    d += head; s += head; n -= head;
+    for (i = 0; i + 128 <= n; i += 128) {
+        __m256i a = _mm256_loadu_si256((const __m256i *) (s + i)), b = _mm256_loadu_si256((const __m256i *) (s + i + 32));
+        __m256i c = _mm256_loadu_si256((const __m256i *) (s + i + 64)), e = _mm256_loadu_si256((const __m256i *) (s + i + 96));
+        _mm256_stream_si256((__m256i *) (d + i), a); _mm256_stream_si256((__m256i *) (d + i + 32), b);
+        _mm256_stream_si256((__m256i *) (d + i + 64), c); _mm256_stream_si256((__m256i *) (d + i + 96), e);
+    }
+    _mm_sfence();
+    memcpy(d + i, s + i, n - i);
+}
+#endif
+
+void flbgpu_stream_copy(void *dst, const void *src, size_t n)
+{
+#if defined(__x86_64__) && defined(__GNUC__)
+    static int have = -1;
+    if (have < 0) { const char *e = getenv("FLBGPU_NT_COPY"); have = __builtin_cpu_supports("avx2") && !(e && e[0] == '0'); }
+    if (have && n >= 4096) { stream_copy_avx2(dst, src, n); return; }
+#endif
+    memcpy(dst, src, n);
+}
+
 static void hugepage_hint(void *p, size_t n)
 {
 #ifdef MADV_HUGEPAGE
