@@ -340,6 +340,37 @@ int bk_device_count(void)
     return n;
 }
 
+/* Keep this process's host side next to its GPU: the threads that stage, copy out and allocate the
+ * pinned rings run on the CPUs local to the device's PCIe root (sysfs local_cpulist), so first-touch
+ * places those buffers on that NUMA node.  One process drives one GPU here; FLBGPU_NUMA_BIND=0 leaves
+ * the affinity alone. */
+static void bind_near_device(int device)
+{
+    char bus[32], path[128], line[1024];
+    const char *e = getenv("FLBGPU_NUMA_BIND");
+    FILE *f;
+    cpu_set_t set;
+    int any = 0;
+    if (e && e[0] == '0') return;
+    if (cudaDeviceGetPCIBusId(bus, sizeof(bus), device) != cudaSuccess) { cudaGetLastError(); return; }
+    for (char *c = bus; *c; c++) if (*c >= 'A' && *c <= 'F') *c = (char) (*c + 32);
+    snprintf(path, sizeof(path), "/sys/bus/pci/devices/%s/local_cpulist", bus);
+    f = fopen(path, "r");
+    if (!f) return;
+    if (!fgets(line, sizeof(line), f)) { fclose(f); return; }
+    fclose(f);
+    CPU_ZERO(&set);
+    for (char *p = line; *p && *p != '\n'; ) {            /* "0-31,64-95" */
+        char *end;
+        long a = strtol(p, &end, 10), b = a;
+        if (end == p) break;
+        if (*end == '-') { p = end + 1; b = strtol(p, &end, 10); }
+        for (long c = a; c <= b && c < CPU_SETSIZE; c++) { CPU_SET((int) c, &set); any = 1; }
+        p = (*end == ',') ? end + 1 : end;
+    }
+    if (any) sched_setaffinity(0, sizeof(set), &set);
+}
+
 int bk_init(int device)
 {
     int n = 0;
@@ -351,6 +382,7 @@ int bk_init(int device)
     }
     if (device < 0 || device >= n) { snprintf(g_err, sizeof(g_err), "device %d out of range (0..%d)", device, n - 1); return -1; }
     CK(cudaSetDevice(device));
+    bind_near_device(device);
     if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
     g_ev_ready = 1;
     /* the interpreter keeps its field list and backtrack stack in local memory */
