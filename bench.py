@@ -89,6 +89,10 @@ def parser_kw(wl=None):
 # ------------------------------------------------------------------ reference arm
 def _ref_worker(args):
     block, reps = args
+    try:                     # the GPU arm binds its process near its GPU; the reference gets every core
+        os.sched_setaffinity(0, range(os.cpu_count()))
+    except Exception:
+        pass
     import util
     ref = util.Ref()
     ref.parser(**parser_kw())
