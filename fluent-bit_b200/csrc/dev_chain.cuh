@@ -1167,7 +1167,7 @@ struct ch_scratch {              /* per-lane working memory */
 
 template <bool EMIT>
 FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct ch_rec *rc, struct ch_scratch *w,
-                     uint32_t ridx, uint32_t *cache_pos)
+                     uint32_t ridx, uint32_t *cache_pos, int pristine, uint32_t rec_off, uint32_t rec_len, uint32_t empty_map_off)
 {
     uint64_t keep;                /* bit i: original field i is appended after the parsed ones */
     int i, parse_ok = 0, np = 0, preserved = -1, have_arr, pi, in_place = 0;
@@ -1239,8 +1239,14 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                 if (got) { preset = pd->n_groups; style = ST_PRESET; in_place = direct; }
             }
             else if (pd->type == FLBGPU_PARSER_JSON) {
-                got = pdef_json<EMIT>(e, pd, val_off, vp, vn, w->tk, w->tv, w->th, &cnt, &ts, &tns, ridx, cache_pos);
-                if (got) style = ST_CANON;
+                /* same in-place case as for the regex parser, possible while the record is still exactly
+                 * what rec_decode() produced: a document that turns out not to parse after some fields
+                 * were written is undone by decoding the record again */
+                const int direct = pristine && !have_arr && !cf->ra_off && i == rc->nf - 1;
+                got = pdef_json<EMIT>(e, pd, val_off, vp, vn, direct ? rc->k : w->tk, direct ? rc->v : w->tv, direct ? rc->kh : w->th,
+                                      &cnt, &ts, &tns, ridx, cache_pos);
+                if (got) { style = ST_CANON; in_place = direct; }
+                else if (direct) rec_decode(e, rec_off, rec_len, rc, empty_map_off);
             }
             else if (pd->type == FLBGPU_PARSER_LTSV) {
                 got = pdef_ltsv(e, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns);
@@ -1252,6 +1258,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
             }
             if (got) {
                 if (pd->type == FLBGPU_PARSER_LTSV || pd->type == FLBGPU_PARSER_LOGFMT) { int z; for (z = 0; z < cnt; z++) w->th[z] = 0; }
+                if (in_place && pd->type == FLBGPU_PARSER_JSON) { int z; for (z = 0; z < cnt; z++) if (!rc->kh[z]) rc->kh[z] = ref_khash(e, rc->k[z]); }
                 parse_ok = 1;
                 np = cnt;
                 if ((uint64_t) ts * 1000000000ull + (uint64_t) tns != 0) { ps = ts; pns = tns; }
@@ -1774,7 +1781,7 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
         switch (f[k].kind) {
         case FLBGPU_F_PARSER:
             if (!assumed) break;
-            f_parser<EMIT>(e, (const struct cf_parser *) cfg, &rc, &w, ridx, &cache_pos);
+            f_parser<EMIT>(e, (const struct cf_parser *) cfg, &rc, &w, ridx, &cache_pos, k == 0, off, len, h->empty_map_off);
             if (!EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_EMITTED);
             break;
         case FLBGPU_F_GREP:
