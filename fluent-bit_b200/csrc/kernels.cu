@@ -261,6 +261,7 @@ struct k_chain_params {
     const uint32_t *off, *len;
     const uint8_t *kind;
     uint32_t r0;                 /* first record / first block of this launch */
+    uint32_t stage_bytes;        /* shared-memory slice per warp for input staging, 0 = none */
     uint32_t n_rec;
     uint32_t *size;
     uint64_t *bsum;
@@ -270,12 +271,37 @@ struct k_chain_params {
 /* evaluation: record r0 + global thread id.  No barrier: a warp retires as soon as its
  * 32 records are done (block-level reductions happen in k_bsum). */
 
+/* Optional staging (stage_bytes > 0, FLBGPU_STAGE_KB): the 32 records of a warp are adjacent in the
+ * chunk, so the warp first copies their bytes to its own slice of shared memory with coalesced 128-bit
+ * loads and the lanes then scan from there; `in` is rebased so that input offsets keep their meaning.
+ * A warp whose records span more than its slice reads global memory as before. */
 __global__ void __launch_bounds__(BK_REC_BLOCK, BK_EVAL_MIN_BLOCKS) k_chain_eval(const k_chain_params p)
 {
+    extern __shared__ __align__(16) uint8_t dsm[];
     const uint32_t i = p.r0 + blockIdx.x * BK_REC_BLOCK + threadIdx.x;
-    if (i >= p.n_rec) return;
+    const bool valid = i < p.n_rec;
+    const uint32_t my_off = valid ? p.off[i] : 0, my_len = valid ? p.len[i] : 0;
+    const bool live = valid && p.kind[i] == 0;
+    const uint8_t *in = p.env.in;
+    if (p.stage_bytes) {
+        const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        const uint32_t lo = __reduce_min_sync(0xffffffffu, live ? my_off : 0xffffffffu) & ~15u;
+        const uint32_t hi = __reduce_max_sync(0xffffffffu, live ? my_off + my_len : 0u);
+        if (hi > lo && hi - lo + 32 <= p.stage_bytes) {
+            uint8_t *buf = dsm + (size_t) warp * p.stage_bytes;
+            for (uint32_t o = lane * 16; o < hi - lo + 16; o += 512)
+                *reinterpret_cast<uint4 *>(buf + o) = *reinterpret_cast<const uint4 *>(in + lo + o);
+            __syncwarp();
+            in = buf - lo;
+        }
+    }
+    if (!valid) return;
     uint32_t sz = 0;
-    if (p.kind[i] == 0) sz = chain_record<false>(&p.env, i, p.off[i], p.len[i], 0);
+    if (live) {
+        struct ch_env le = p.env;
+        le.in = in;
+        sz = chain_record<false>(&le, i, my_off, my_len, 0);
+    }
     __stcs(&p.size[i], sz);
 }
 
@@ -741,7 +767,7 @@ static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_
     p->env.capcache = a->d_capcache; p->env.cap_stride = a->cap_stride; p->env.now = a->now;
     p->env.assume = a->assume; p->env.fl_flags = a->d_flags; p->env.err = a->d_flags + FLBGPU_MAX_FILTERS;
     p->env.l2m = a->l2m;
-    p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->r0 = r0; p->n_rec = a->n_rec;
+    p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->r0 = r0; p->n_rec = a->n_rec; p->stage_bytes = 0;
     p->size = a->d_size; p->bsum = a->d_bsum; p->out = d_out;
 }
 
@@ -787,8 +813,18 @@ int bk_chain_eval(const struct bk_chain_args *a, uint32_t r0, uint32_t r1)
     if (r1 <= r0) return 0;
     fill_params(a, &p, 0, r0);
     p.n_rec = r1;
+    {
+        static int stage_kb = -1;
+        if (stage_kb < 0) {
+            const char *e = getenv("FLBGPU_STAGE_KB");           /* KiB of shared memory per warp, 0 = off */
+            stage_kb = e ? atoi(e) : 0;
+            if (stage_kb < 0 || stage_kb > 24) stage_kb = 0;
+            if (stage_kb) CK(cudaFuncSetAttribute(k_chain_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_kb * 1024 * (BK_REC_BLOCK / 32)));
+        }
+        p.stage_bytes = (uint32_t) stage_kb * 1024;
+    }
     ev_begin(1);
-    k_chain_eval<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, 0, g_stream>>>(p);
+    k_chain_eval<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, (size_t) p.stage_bytes * (BK_REC_BLOCK / 32), g_stream>>>(p);
     ev_end(1);
     g_launches += 1;
     CK(cudaGetLastError());
