@@ -414,6 +414,14 @@ int bk_init(int device)
     /* the interpreter keeps its field list and backtrack stack in local memory */
     CK(cudaFuncSetCacheConfig(k_chain_eval, cudaFuncCachePreferL1));
     CK(cudaFuncSetCacheConfig(k_chain_emit_list, cudaFuncCachePreferL1));
+    {   /* and ask for the largest L1 the unified array can give (FLBGPU_MAX_L1=0: driver default) */
+        const char *e = getenv("FLBGPU_MAX_L1");
+        if (!(e && e[0] == '0')) {
+            cudaFuncSetAttribute(k_chain_eval, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+            cudaFuncSetAttribute(k_chain_emit_list, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
+            cudaGetLastError();
+        }
+    }
     return 0;
 }
 
