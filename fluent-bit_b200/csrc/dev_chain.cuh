@@ -677,13 +677,98 @@ FLB_HDN int pdef_ltsv(const struct ch_env *e, const struct cf_pdef *pd, uint32_t
     return 1;
 }
 
+/* flb_unescape_string_utf8() followed by strlen(), src/flb_unescape.c:40-271: what logfmt does to a
+ * quoted value that contains a backslash (src/flb_parser_logfmt.c:195-214).  Decodes s[0,n) to o and
+ * returns the length up to the first NUL the decoding produced. */
+FLB_HD uint32_t lf_hexv(uint32_t c)
+{
+    if (c >= '0' && c <= '9') return c - '0';
+    if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+    if (c >= 'A' && c <= 'F') return c - 'A' + 10;
+    return 0xffu;
+}
+FLB_HD uint32_t lf_sx(uint32_t b) { return (b & 0x80u) ? (b | 0xffffff00u) : b; }     /* (uint32_t)(signed char) */
+
+FLB_HD uint32_t lf_unescape(const uint8_t *s, uint32_t n, uint8_t *o)
+{
+    uint32_t in = 0, out = 0, i;
+    while (in < n && s[in]) {
+        uint32_t ch, used = 1, len;
+        if (s[in] == '\\' && in + 1 < n) {
+            const uint8_t *q = s + in + 1;
+            const uint32_t size = n - in - 1;
+            uint32_t c = q[0];
+            used = 2;
+            switch (c) {
+            case '"': case '\'': case '\\': case '/': ch = c; break;
+            case 'n': ch = 10; break;
+            case 'b': ch = 8; break;
+            case 't': ch = 9; break;
+            case 'f': ch = 12; break;
+            case 'r': ch = 13; break;
+            default: {
+                /* u8_read_escape_sequence(): returns the characters it consumed after the backslash */
+                uint32_t k = 1, dno = 0, v = 0;
+                ch = lf_sx(c);
+                if (c == 'v') ch = 11;
+                else if (c == 'a') ch = 7;
+                else if (c >= '0' && c <= '7') {
+                    k = 0;
+                    do { v = v * 8 + (q[k] - '0'); k++; dno++; } while (k < size && q[k] >= '0' && q[k] <= '7' && dno < 3);
+                    ch = v;
+                }
+                else if (c == 'x') {
+                    while (k < size && lf_hexv(q[k]) != 0xffu && dno < 2) { v = v * 16 + lf_hexv(q[k]); k++; dno++; }
+                    if (dno > 0) ch = v;
+                }
+                else if (c == 'u') {
+                    while (k < size && lf_hexv(q[k]) != 0xffu && dno < 4) { v = v * 16 + lf_hexv(q[k]); k++; dno++; }
+                    if (dno != 4 && dno > 0) ch = 0xfffd;
+                    else {
+                        ch = v;                                        /* no digit at all: strtol("") = 0 */
+                        if (ch >= 0xdc00 && ch <= 0xdfff) ch = 0xfffd;
+                        else if (ch >= 0xd800 && ch <= 0xdbff) {
+                            if (k + 2 < size && q[k] == '\\' && q[k + 1] == 'u') {
+                                uint32_t low = 0;
+                                dno = 0;
+                                k += 2;
+                                while (k < size && lf_hexv(q[k]) != 0xffu && dno < 4) { low = low * 16 + lf_hexv(q[k]); k++; dno++; }
+                                if (dno != 4 && dno > 0) ch = 0xfffd;
+                                else if (low >= 0xdc00 && low <= 0xdfff) ch = 0x10000 + (((ch - 0xd800) << 10) | (low - 0xdc00));
+                                else ch = 0xfffd;
+                            }
+                            else ch = 0xfffd;
+                        }
+                    }
+                }
+                else if (c == 'U') {
+                    while (k < size && lf_hexv(q[k]) != 0xffu && dno < 8) { v = v * 16 + lf_hexv(q[k]); k++; dno++; }
+                    if (dno > 0) ch = v;
+                }
+                used = k + 1;
+            }
+            }
+        }
+        else ch = lf_sx(s[in]);
+        in += used;
+        len = ch < 0x80 ? 1 : ch < 0x800 ? 2 : ch < 0x10000 ? 3 : ch < 0x110000 ? 4 : 0;
+        if (len > n - out) break;                                      /* "Crossing over string boundary" */
+        if (len <= 1) o[out++] = (uint8_t) ch;
+        else if (len == 2) { o[out++] = (uint8_t) ((ch >> 6) | 0xc0); o[out++] = (uint8_t) ((ch & 0x3f) | 0x80); }
+        else if (len == 3) { o[out++] = (uint8_t) ((ch >> 12) | 0xe0); o[out++] = (uint8_t) (((ch >> 6) & 0x3f) | 0x80); o[out++] = (uint8_t) ((ch & 0x3f) | 0x80); }
+        else { o[out++] = (uint8_t) ((ch >> 18) | 0xf0); o[out++] = (uint8_t) (((ch >> 12) & 0x3f) | 0x80); o[out++] = (uint8_t) (((ch >> 6) & 0x3f) | 0x80); o[out++] = (uint8_t) ((ch & 0x3f) | 0x80); }
+    }
+    for (i = 0; i < out; i++) if (!o[i]) return i;                     /* the caller's strlen() */
+    return out;
+}
+
 /* logfmt_parser(), src/flb_parser_logfmt.c:63-254.  ident bytes: > ' ' and not '=' '"' (:44-61) */
 FLB_HD int logfmt_ident(uint32_t c) { return c > ' ' && c != '=' && c != '"'; }
 
 FLB_HDN int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
                        ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec)
 {
-    uint32_t c = 0;
+    uint32_t c = 0, sk = 0;          /* sk: next free byte of the record's scratch (decoded escapes) */
     int cnt = 0;
     int64_t lookup = 0;
     double frac = 0;
@@ -731,10 +816,15 @@ FLB_HDN int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32
                 ok_[cnt] = mkref(RK_STR_IN, val_off + key, key_len);
                 if (pd->n_types) ov_[cnt] = cast_value(e, pd, s + key, key_len, s + value, val_off + value, value_len);
                 else if (value_len == 0) ov_[cnt] = value_str ? mkref(RK_STR_IN, val_off + value, 0) : mkref(RK_TRUE, 0, 0);
-                else {
-                    if (value_escape) CH_ATOMIC_OR(e->err, FLBGPU_E_ESCAPE);      /* flb_unescape_string_utf8 not on the device yet */
-                    ov_[cnt] = mkref(RK_STR_IN, val_off + value, value_len);
+                else if (value_escape) {
+                    if (!e->scr) { CH_ATOMIC_OR(e->err, FLBGPU_E_ESCAPE); ov_[cnt] = mkref(RK_STR_IN, val_off + value, value_len); }
+                    else {
+                        const uint32_t dl = lf_unescape(s + value, value_len, e->scr + sk);
+                        ov_[cnt] = mkref(RK_STR_SCR, sk, dl);
+                        sk += value_len;                               /* the decoded text is never longer */
+                    }
                 }
+                else ov_[cnt] = mkref(RK_STR_IN, val_off + value, value_len);
                 cnt++;
             }
         }

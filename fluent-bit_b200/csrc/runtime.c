@@ -702,7 +702,7 @@ static uint32_t emit_parser_filter(flbgpu_filter *f, struct blob *b, uint32_t *c
             /* no per-record capture slots any more: the emission pass encodes from the cached final
              * field list (RC_CACHE_INTS); only records with more than RC_CACHE_MAXF fields re-run the
              * chain there, and then they re-run the parser too */
-            if (ps->type == FLBGPU_PARSER_JSON) f->needs_scratch = 1;
+            if (ps->type == FLBGPU_PARSER_JSON || ps->type == FLBGPU_PARSER_LOGFMT) f->needs_scratch = 1;   /* transcoded JSON / decoded logfmt escapes */
         }
         else if (!strcasecmp(p->k, "preserve_key")) { int v = parse_bool(p->v); if (v < 0) { set_err("invalid boolean '%s'%s", p->v, NULL); return 0; } cf.preserve_key = v; }
         else if (!strcasecmp(p->k, "reserve_data")) { int v = parse_bool(p->v); if (v < 0) { set_err("invalid boolean '%s'%s", p->v, NULL); return 0; } cf.reserve_data = v; }

@@ -539,7 +539,95 @@ static int ltsv_do(const struct orc_parser *p, const char *s, size_t n, struct o
     return (int) c;
 }
 
-/* ---- logfmt (src/flb_parser_logfmt.c:63-254); escapes inside quoted values are not restated ---- */
+/* ---- logfmt (src/flb_parser_logfmt.c:63-254) ---------------------------------------------------- */
+/* src/flb_unescape.c:186-271 flb_unescape_string_utf8 with u8_read_escape_sequence (:80-184) and
+ * u8_wc_toutf8 (:40-66); the caller takes strlen() of the result (flb_parser_logfmt.c:207). */
+static int hexval(int c)
+{
+    if (c >= '0' && c <= '9') return c - '0';
+    if (c >= 'a' && c <= 'f') return c - 'a' + 10;
+    if (c >= 'A' && c <= 'F') return c - 'A' + 10;
+    return -1;
+}
+
+static size_t read_escape(const char *str, size_t size, uint32_t *dest)
+{
+    uint32_t ch = (uint32_t) (int32_t) (signed char) str[0], v = 0;
+    size_t i = 1;
+    int dno = 0;
+    switch (str[0]) {
+    case 'n': ch = 10; break;
+    case 't': ch = 9; break;
+    case 'r': ch = 13; break;
+    case 'b': ch = 8; break;
+    case 'f': ch = 12; break;
+    case 'v': ch = 11; break;
+    case 'a': ch = 7; break;
+    case 'x':
+        while (i < size && hexval((unsigned char) str[i]) >= 0 && dno < 2) { v = v * 16 + (uint32_t) hexval((unsigned char) str[i]); i++; dno++; }
+        if (dno > 0) ch = v;
+        break;
+    case 'U':
+        while (i < size && hexval((unsigned char) str[i]) >= 0 && dno < 8) { v = v * 16 + (uint32_t) hexval((unsigned char) str[i]); i++; dno++; }
+        if (dno > 0) ch = v;
+        break;
+    case 'u':
+        while (i < size && hexval((unsigned char) str[i]) >= 0 && dno < 4) { v = v * 16 + (uint32_t) hexval((unsigned char) str[i]); i++; dno++; }
+        if (dno != 4 && dno > 0) { ch = 0xfffd; break; }
+        ch = v;
+        if (ch >= 0xdc00 && ch <= 0xdfff) ch = 0xfffd;
+        else if (ch >= 0xd800 && ch <= 0xdbff) {
+            uint32_t low = 0;
+            if (!(i + 2 < size && str[i] == '\\' && str[i + 1] == 'u')) { ch = 0xfffd; break; }
+            i += 2; dno = 0;
+            while (i < size && hexval((unsigned char) str[i]) >= 0 && dno < 4) { low = low * 16 + (uint32_t) hexval((unsigned char) str[i]); i++; dno++; }
+            if (dno != 4 && dno > 0) ch = 0xfffd;
+            else if (low >= 0xdc00 && low <= 0xdfff) ch = 0x10000 + (((ch - 0xd800) << 10) | (low - 0xdc00));
+            else ch = 0xfffd;
+        }
+        break;
+    default:
+        if (str[0] >= '0' && str[0] <= '7') {
+            i = 0;
+            do { v = v * 8 + (uint32_t) (str[i] - '0'); i++; dno++; } while (i < size && str[i] >= '0' && str[i] <= '7' && dno < 3);
+            ch = v;
+        }
+    }
+    *dest = ch;
+    return i;
+}
+
+static size_t unescape_utf8(const char *in, size_t sz, char *out)
+{
+    size_t ci = 0, co = 0;
+    while (ci < sz && in[ci]) {
+        uint32_t ch;
+        size_t used = 1, len;
+        if (in[ci] == '\\' && ci + 1 < sz) {
+            used = 2;
+            switch (in[ci + 1]) {
+            case '"': case '\'': case '\\': case '/': ch = (uint32_t) in[ci + 1]; break;
+            case 'n': ch = 10; break;
+            case 'b': ch = 8; break;
+            case 't': ch = 9; break;
+            case 'f': ch = 12; break;
+            case 'r': ch = 13; break;
+            default: used = read_escape(in + ci + 1, sz - ci - 1, &ch) + 1;
+            }
+        }
+        else ch = (uint32_t) (int32_t) (signed char) in[ci];
+        ci += used;
+        len = ch < 0x80 ? 1 : ch < 0x800 ? 2 : ch < 0x10000 ? 3 : ch < 0x110000 ? 4 : 0;
+        if (len > sz - co) break;
+        if (len <= 1) out[co++] = (char) ch;
+        else if (len == 2) { out[co++] = (char) ((ch >> 6) | 0xc0); out[co++] = (char) ((ch & 0x3f) | 0x80); }
+        else if (len == 3) { out[co++] = (char) ((ch >> 12) | 0xe0); out[co++] = (char) (((ch >> 6) & 0x3f) | 0x80); out[co++] = (char) ((ch & 0x3f) | 0x80); }
+        else { out[co++] = (char) ((ch >> 18) | 0xf0); out[co++] = (char) (((ch >> 12) & 0x3f) | 0x80); out[co++] = (char) (((ch >> 6) & 0x3f) | 0x80); out[co++] = (char) ((ch & 0x3f) | 0x80); }
+    }
+    out[co] = 0;
+    return strlen(out);
+}
+
 static int logfmt_ident(int c) { return c > ' ' && c != '=' && c != '"'; }
 
 static int logfmt_do(const struct orc_parser *p, const char *s, size_t n, struct orc_buf *out, int64_t *sec, int64_t *nsec)
@@ -551,7 +639,7 @@ static int logfmt_do(const struct orc_parser *p, const char *s, size_t n, struct
     double frac = 0;
     while (c < n) {
         size_t key, key_len, value = 0, value_len = 0;
-        int value_set = 0, value_str = 0;
+        int value_set = 0, value_str = 0, value_escape = 0;
         while (c < n && !logfmt_ident((unsigned char) s[c])) c++;
         if (c == n) break;
         key = c;
@@ -565,7 +653,7 @@ static int logfmt_do(const struct orc_parser *p, const char *s, size_t n, struct
                     c++; value = c; value_str = 1;
                     while (c < n) {
                         if (s[c] != '\\' && s[c] != '"') c++;
-                        else if (s[c] == '\\') { c++; if (c == n) break; c++; }
+                        else if (s[c] == '\\') { value_escape = 1; c++; if (c == n) break; c++; }
                         else break;
                     }
                     value_len = c - value;
@@ -580,7 +668,24 @@ static int logfmt_do(const struct orc_parser *p, const char *s, size_t n, struct
         }
         if (key_len > 0) {
             if (p->logfmt_no_bare_keys && value_len == 0 && !value_set) { free(body.p); return -1; }
-            if (pack_kv_time(p, &body, &cnt, s + key, key_len, s + value, value_len,
+            if (value_escape && value_len > 0 && !p->n_types) {
+                /* the Time_Key test sees the raw text; the packed value is the unescaped one (:159-214) */
+                char *un = malloc(value_len + 1);
+                size_t ul = unescape_utf8(s + value, value_len, un);
+                const char *time_key = p->time_key ? p->time_key : "time";
+                int is_time = p->time_fmt && key_len == strlen(time_key) && !strncmp(s + key, time_key, key_len);
+                int rc = 0, time_found = 0;
+                if (is_time) {
+                    struct orc_tm tm;
+                    memset(&tm, 0, sizeof(tm));
+                    if (orc_time_lookup(p, s + value, value_len, &tm, &frac) == -1) rc = -1;
+                    else { lookup = tm2time(&tm); time_found = 1; }
+                }
+                if (!rc && (!time_found || p->time_keep)) { ov_pack_str(&body, s + key, key_len); ov_pack_str(&body, un, ul); cnt++; }
+                free(un);
+                if (rc) { free(body.p); return -1; }
+            }
+            else if (pack_kv_time(p, &body, &cnt, s + key, key_len, s + value, value_len,
                              (value_len == 0 && !value_str && !p->n_types) ? 1 : 0, &lookup, &frac)) { free(body.p); return -1; }
         }
         if (c == n) break;

@@ -92,6 +92,16 @@ def logfmt_chunk():
     return util.chunk_from_lines(util.logfmt_lines(400) + [b"a=1 b c=", b'x="unterminated', b"=novalue k=v", b"  ", b'q="a b" r=s\nnext=1'])
 
 
+def logfmt_escape_chunk():
+    """quoted logfmt values with backslash escapes: decoded like flb_unescape_string_utf8() + strlen()"""
+    bs = "\\"
+    vals = [bs + "n", bs + "t tab", "say " + bs + '"hi' + bs + '"', bs + bs, "a" + bs + "/b", bs + "x41" + bs + "x4" + bs + "xZ", bs + "u00e9" + bs + "u20ac",
+            bs + "ud83d" + bs + "ude00", bs + "ud83d alone", bs + "udc00", bs + "u12", bs + "u", bs + "U0001F600", bs + "101" + bs + "7", "cut" + bs + "0here",
+            bs + "q" + bs + "é", "é 日本", "tail" + bs, bs + "v" + bs + "a" + bs + "b" + bs + "f" + bs + "r", bs + "400"]
+    lines = [('level=info n=%d msg="%s" path=/x other="%s" flag' % (i, v, vals[(i * 7) % len(vals)])).encode("utf-8") for i, v in enumerate(vals * 5)]
+    return util.chunk_from_lines(lines)
+
+
 def tricky_ts_chunk():
     """Timestamps whose bytes frame as complete legacy events ([uint32, {}]) inside real records:
     the record index has to rule those candidates out (sec = 0x655492ce -> `92 ce 00 00 xx xx 80`)."""
@@ -131,6 +141,7 @@ CASES = [
     ("ltsv_parser", [LT], [("parser", [("Key_Name", "log"), ("Parser", "ltsv")])], ltsv_chunk),
     ("logfmt_parser", [LF], [("parser", [("Key_Name", "log"), ("Parser", "logfmt")]), ("grep", [("Exclude", "level debug")])], logfmt_chunk),
     ("multi_parser_fallthrough", [AP, JS, LF], [("parser", [("Key_Name", "log"), ("Parser", "json"), ("Parser", "apache"), ("Parser", "logfmt")])], lambda: util.chunk_from_lines(util.json_lines(100, 3) + util.apache_lines(100, 4) + util.logfmt_lines(100, 5))),
+    ("logfmt_escapes", [LF], [("parser", [("Key_Name", "log"), ("Parser", "logfmt")]), ("modify", [("Rename", "msg message")])], logfmt_escape_chunk),
     ("grep_regex", [], [("grep", [("Regex", "log GET")])], apache_chunk),
     ("grep_exclude", [], [("grep", [("Exclude", "log HTTP")])], apache_chunk),
     ("grep_keep_all_notouch", [], [("grep", [("Regex", "log .")])], apache_chunk),
