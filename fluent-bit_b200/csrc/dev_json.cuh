@@ -110,6 +110,111 @@ FLB_HDN int dj_eisel_lemire(uint64_t w, int64_t q, uint64_t *bits)
     return 0;
 }
 
+/* ---- exact decision for the rare number whose first 19 digits leave two candidate doubles ----
+ * (more than 19 significant digits and the Eisel-Lemire results for w and w+1 differ).  The decimal
+ * value D x 10^E is compared, in exact integer arithmetic, with the midpoint (2M+1) x 2^(k-1) of the two
+ * adjacent candidates M x 2^k and (M+1) x 2^k; ties go to the even mantissa, as every correctly
+ * rounding reader (yyjson included) does.  Returns 0 = lower candidate, 1 = upper, -1 = cannot tell
+ * (more digits / exponent than the 160-limb integers hold). */
+#define DJ_BIG_LIMBS 160
+#define DJ_BIG_DIGITS 780      /* every midpoint of two adjacent doubles has at most 767 significant digits */
+struct dj_big { uint32_t n; uint32_t v[DJ_BIG_LIMBS]; };
+
+FLB_HD int djb_mul_small(struct dj_big *b, uint32_t m, uint32_t add)
+{
+    uint64_t carry = add;
+    uint32_t i;
+    for (i = 0; i < b->n; i++) { carry += (uint64_t) b->v[i] * m; b->v[i] = (uint32_t) carry; carry >>= 32; }
+    if (carry) { if (b->n >= DJ_BIG_LIMBS) return -1; b->v[b->n++] = (uint32_t) carry; }
+    return 0;
+}
+FLB_HD int djb_mul_pow5(struct dj_big *b, uint32_t e)
+{
+    while (e >= 13) { if (djb_mul_small(b, 1220703125u, 0)) return -1; e -= 13; }
+    while (e--) if (djb_mul_small(b, 5u, 0)) return -1;
+    return 0;
+}
+FLB_HD int djb_shl(struct dj_big *b, uint32_t bits)
+{
+    const uint32_t words = bits >> 5, sh = bits & 31;
+    int i;
+    if (b->n == 0) return 0;
+    if (b->n + words + 1 > DJ_BIG_LIMBS) return -1;
+    if (sh) {
+        uint32_t carry = 0, k;
+        for (k = 0; k < b->n; k++) { const uint32_t x = b->v[k]; b->v[k] = (x << sh) | carry; carry = x >> (32 - sh); }
+        if (carry) b->v[b->n++] = carry;
+    }
+    if (words) {
+        for (i = (int) b->n - 1; i >= 0; i--) b->v[i + words] = b->v[i];
+        for (i = 0; i < (int) words; i++) b->v[i] = 0;
+        b->n += words;
+    }
+    return 0;
+}
+FLB_HD int djb_cmp(const struct dj_big *a, const struct dj_big *b)
+{
+    int i;
+    if (a->n != b->n) return a->n > b->n ? 1 : -1;
+    for (i = (int) a->n - 1; i >= 0; i--) if (a->v[i] != b->v[i]) return a->v[i] > b->v[i] ? 1 : -1;
+    return 0;
+}
+
+FLB_HDN int dj_big_decide(const uint8_t *s, int n, int pos, uint64_t bits_lo)
+{
+    struct dj_big L, R;
+    int p = pos, nd = 0, sticky = 0, seen_nz = 0;
+    int64_t E = 0;
+    uint64_t M;
+    int k, c;
+    L.n = 0;
+    if (p < n && s[p] == '-') p++;
+    for (; p < n && s[p] >= '0' && s[p] <= '9'; p++) {
+        const uint32_t d = s[p] - '0';
+        if (!seen_nz && !d) continue;
+        seen_nz = 1;
+        if (nd < DJ_BIG_DIGITS) { if (L.n == 0) { if (d) { L.v[0] = d; L.n = 1; } } else if (djb_mul_small(&L, 10u, d)) return -1; nd++; }
+        else { E++; if (d) sticky = 1; }
+    }
+    if (p < n && s[p] == '.') {
+        for (p++; p < n && s[p] >= '0' && s[p] <= '9'; p++) {
+            const uint32_t d = s[p] - '0';
+            if (!seen_nz && !d) { E--; continue; }
+            seen_nz = 1;
+            if (nd < DJ_BIG_DIGITS) { if (L.n == 0) { L.v[0] = d; L.n = 1; } else if (djb_mul_small(&L, 10u, d)) return -1; nd++; E--; }
+            else if (d) sticky = 1;
+        }
+    }
+    if (p < n && (s[p] == 'e' || s[p] == 'E')) {
+        int eneg = 0;
+        int64_t ev = 0;
+        p++;
+        if (p < n && (s[p] == '+' || s[p] == '-')) { eneg = s[p] == '-'; p++; }
+        for (; p < n && s[p] >= '0' && s[p] <= '9'; p++) if (ev < 100000) ev = ev * 10 + (s[p] - '0');
+        E += eneg ? -ev : ev;
+    }
+    if (L.n == 0 || E > 400 || E < -1200) return -1;
+    /* lower candidate M x 2^k */
+    {
+        const uint32_t ef = (uint32_t) ((bits_lo >> 52) & 0x7ff);
+        M = bits_lo & (((uint64_t) 1 << 52) - 1);
+        if (ef) { M |= (uint64_t) 1 << 52; k = (int) ef - 1075; } else k = -1074;
+    }
+    {
+        const uint64_t m2 = 2 * M + 1;
+        R.v[0] = (uint32_t) m2; R.v[1] = (uint32_t) (m2 >> 32); R.n = R.v[1] ? 2 : 1;
+    }
+    if (E >= 0) { if (djb_mul_pow5(&L, (uint32_t) E) || djb_shl(&L, (uint32_t) E)) return -1; }
+    else { if (djb_mul_pow5(&R, (uint32_t) -E) || djb_shl(&R, (uint32_t) -E)) return -1; }
+    if (k - 1 >= 0) { if (djb_shl(&R, (uint32_t) (k - 1))) return -1; }
+    else { if (djb_shl(&L, (uint32_t) (1 - k))) return -1; }
+    c = djb_cmp(&L, &R);
+    if (c > 0) return 1;
+    if (c < 0) return 0;
+    if (sticky) return 1;
+    return (M & 1) ? 1 : 0;                       /* exactly half way: to the even mantissa */
+}
+
 /* Parse the JSON number at s[pos].  Returns the position after it or -1.
  * kind: 0 uint (u), 1 sint (value in u as two's complement), 2 real (bits in u). */
 /* exact powers of ten (Clinger fast path) */
@@ -181,7 +286,16 @@ FLB_HDN int dj_number(const uint8_t *s, int n, int pos, int *kind, uint64_t *u, 
             if (r == 0 && truncated) {
                 uint64_t b2 = 0;
                 int r2 = dj_eisel_lemire(w + 1, exp10, &b2);
-                if (r2 != 0 || b2 != bits) r = 2;
+                if (r2 != 0 || b2 != bits || (bits >> 52) == 0) {
+                    /* the dropped digits matter (or the result is subnormal, where the 128-bit product is
+                     * rounded twice): decide exactly between the two neighbours */
+                    const int up = (r2 == 1 || b2 == bits + 1 || b2 == bits) ? dj_big_decide(s, n, pos, bits) : -1;
+                    if (up < 0) r = 2;
+                    else if (up == 1) {
+                        if (r2 == 1) return -1;                        /* rounds to infinity: rejected like any overflow */
+                        bits = bits + 1;
+                    }
+                }
             }
             if (r == 2) { *err |= DJ_E_FLOAT; bits = 0; }
         }
