@@ -966,6 +966,21 @@ static uint32_t emit_l2m_filter(flbgpu_filter *f, struct blob *b)
         while (g.props) { struct kv *n = g.props->next; free(g.props); g.props = n; }
         if (!cf.grep_off) { l2m_state_free(st); return 0; }
     }
+    /* kubernetes_mode: five fixed labels in front of the user's (log_to_metrics.c:43-50, 148-156, 422-438) */
+    for (p = f->props; p; p = p->next) {
+        if (!strcasecmp(p->k, "kubernetes_mode") && parse_bool(p->v) == 1 && st->n_labels == 0) {
+            static const char *k8s[5] = { "namespace_name", "pod_name", "container_name", "docker_id", "pod_id" };
+            int q;
+            for (q = 0; q < 5; q++) {
+                char acc[64];
+                snprintf(acc, sizeof(acc), "$kubernetes['%s']", k8s[q]);
+                st->label_keys[st->n_labels] = strdup(k8s[q]);
+                cf.label_ra_off[st->n_labels] = emit_ra(b, acc);
+                if (!cf.label_ra_off[st->n_labels]) { st->n_labels++; l2m_state_free(st); return 0; }
+                st->n_labels++;
+            }
+        }
+    }
     for (p = f->props; p; p = p->next) {
         if (!strcasecmp(p->k, "regex") || !strcasecmp(p->k, "exclude")) continue;
         else if (!strcasecmp(p->k, "metric_mode")) mode = p->v;
@@ -975,9 +990,7 @@ static uint32_t emit_l2m_filter(flbgpu_filter *f, struct blob *b)
         else if (!strcasecmp(p->k, "metric_subsystem")) subsystem = p->v;
         else if (!strcasecmp(p->k, "metric_description")) desc = p->v;
         else if (!strcasecmp(p->k, "tag")) tag = p->v;
-        else if (!strcasecmp(p->k, "kubernetes_mode")) {
-            if (parse_bool(p->v) == 1) { set_err("kubernetes_mode is not supported on the GPU path%s%s", NULL, NULL); l2m_state_free(st); return 0; }
-        }
+        else if (!strcasecmp(p->k, "kubernetes_mode")) { /* handled before the loop: its labels come first */ }
         else if (!strcasecmp(p->k, "discard_logs")) { int v = parse_bool(p->v); if (v < 0) { set_err("invalid boolean '%s'%s", p->v, NULL); l2m_state_free(st); return 0; } cf.discard = v; }
         else if (!strcasecmp(p->k, "bucket")) {
             char *end = NULL;

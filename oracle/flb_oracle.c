@@ -350,6 +350,17 @@ int orc_filter_init(struct orc_config *cfg, struct orc_filter *f)
         const char *mode = "counter", *value_field = NULL, *desc = NULL, *tag = NULL;
         static const double defb[11] = { 0.005, 0.01, 0.025, 0.05, 0.1, 0.25, 0.5, 1.0, 2.5, 5.0, 10.0 };
         f->ns = strdup("log_metric"); f->mname = strdup("a");
+        for (p = f->props; p; p = p->next) {     /* kubernetes_mode: five fixed labels first (:43-50, 148-156) */
+            if (!strcasecmp(p->k, "kubernetes_mode") && parse_bool(p->v) && f->n_labels == 0) {
+                static const char *k8s[5] = { "namespace_name", "pod_name", "container_name", "docker_id", "pod_id" };
+                int q;
+                for (q = 0; q < 5; q++) {
+                    char acc[64];
+                    snprintf(acc, sizeof(acc), "$kubernetes['%s']", k8s[q]);
+                    f->label_keys[f->n_labels] = strdup(k8s[q]); f->label_ras[f->n_labels] = ra_create(acc); f->n_labels++;
+                }
+            }
+        }
         for (p = f->props; p; p = p->next) {
             if (!strcasecmp(p->k, "regex")) { if (add_grep_rule(f, GREP_REGEX, p->v, 0)) return -1; }
             else if (!strcasecmp(p->k, "exclude")) { if (add_grep_rule(f, GREP_EXCLUDE, p->v, 0)) return -1; }

@@ -88,6 +88,10 @@ L2M_CASES = [
       ("log_to_metrics", BASE + [("metric_mode", "histogram"), ("value_field", "size"), ("label_field", "code"),
                                  ("bucket", "1000"), ("bucket", "10000"), ("discard_logs", "on")])],
      lambda: util.chunk_from_lines(util.apache_lines(1000, seed=12)), 1),
+    ("counter_kubernetes_mode", [], [("log_to_metrics", BASE + [("kubernetes_mode", "on"), ("label_field", "color")])],
+     lambda: events(400, 14, extra=lambda rng: [(b"kubernetes", {b"pod_name": rng.choice([b"web-1", b"web-2"]), b"namespace_name": b"prod",
+                                                             b"container_name": rng.choice([b"app", b"sidecar"]), b"docker_id": b"abc",
+                                                             b"pod_id": 17})] if rng.random() < 0.8 else []), 0),
     ("l2m_then_modify", [],
      [("log_to_metrics", BASE + [("label_field", "color")]), ("modify", [("add", "seen yes")])], lambda: events(200, 13), 0),
 ]

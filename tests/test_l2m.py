@@ -96,8 +96,7 @@ def test_l2m_config_errors(bad, sim_lib, ref_available):
 
 def test_l2m_not_supported_is_loud(sim_lib):
     ctx = pkg.Context(0, lib=sim_lib)
-    for props in ([("metric_mode", "gauge"), ("value_field", "x"), ("metric_description", "d"), ("tag", "t")],
-                  [("kubernetes_mode", "on"), ("metric_description", "d"), ("tag", "t")]):
+    for props in ([("metric_mode", "gauge"), ("value_field", "x"), ("metric_description", "d"), ("tag", "t")],):
         with pytest.raises(pkg.FlbGpuError):
             ctx.filter("log_to_metrics", props)
 
