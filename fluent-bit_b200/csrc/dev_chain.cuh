@@ -169,46 +169,6 @@ FLB_HD uint64_t ch_strtoull16(const uint8_t *s, uint32_t n)
     return neg ? (uint64_t) (0 - v) : v;
 }
 
-/* strtod() restricted to the exactly-representable fast path (Clinger): up to 19
- * significant digits that fit 2^53 and |exp10| <= 22.  *ok=0 outside it. */
-FLB_HD double ch_strtod_fast(const uint8_t *s, uint32_t n, int *ok)
-{
-    uint32_t i = 0;
-    int neg = 0, exp10 = 0, nd = 0, seen = 0;
-    uint64_t m = 0;
-    double d;
-    const double p10[23] = { 1e0, 1e1, 1e2, 1e3, 1e4, 1e5, 1e6, 1e7, 1e8, 1e9, 1e10, 1e11, 1e12, 1e13, 1e14, 1e15,
-                             1e16, 1e17, 1e18, 1e19, 1e20, 1e21, 1e22 };
-    *ok = 1;
-    while (i < n && dt_isspace(s[i])) i++;
-    if (i < n && (s[i] == '+' || s[i] == '-')) { neg = s[i] == '-'; i++; }
-    for (; i < n && s[i] >= '0' && s[i] <= '9'; i++) {
-        seen = 1;
-        if (m || s[i] != '0') { if (nd < 19) { m = m * 10 + (s[i] - '0'); nd++; } else exp10++; }
-    }
-    if (i < n && s[i] == '.') {
-        i++;
-        for (; i < n && s[i] >= '0' && s[i] <= '9'; i++) {
-            seen = 1;
-            if (m || s[i] != '0') { if (nd < 19) { m = m * 10 + (s[i] - '0'); nd++; exp10--; } }
-            else exp10--;
-        }
-    }
-    if (!seen) return 0.0;                      /* no conversion: atof gives 0 */
-    if (i < n && (s[i] == 'e' || s[i] == 'E')) {
-        uint32_t j = i + 1;
-        int eneg = 0, ev = 0, ed = 0;
-        if (j < n && (s[j] == '+' || s[j] == '-')) { eneg = s[j] == '-'; j++; }
-        for (; j < n && s[j] >= '0' && s[j] <= '9'; j++) { if (ev < 100000) ev = ev * 10 + (s[j] - '0'); ed = 1; }
-        if (ed) exp10 += eneg ? -ev : ev;
-    }
-    if (m == 0) return neg ? -0.0 : 0.0;
-    if (m > (1ull << 53) || exp10 > 22 || exp10 < -22) { *ok = 0; return 0.0; }
-    d = (double) m;
-    if (exp10 >= 0) d = d * p10[exp10]; else d = d / p10[-exp10];
-    return neg ? -d : d;
-}
-
 /* ------------------------------------------------------------ emission */
 /* size (o == NULL) or bytes of one field reference */
 FLB_HD uint32_t ref_emit(const struct ch_env *e, ref_t r, uint8_t *o)
@@ -237,14 +197,10 @@ FLB_HD uint32_t ref_emit(const struct ch_env *e, ref_t r, uint8_t *o)
         return mp_uint_size(v);
     }
     case RK_FLT_IN: {
-        int ok;
-        double d = ch_strtod_fast(b, n, &ok);
+        int ok;                                    /* decided in the sizing pass too: that is where refusals are read */
+        const uint64_t u = dj_strtod(b, (int) n, &ok);
         if (!ok) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
-        if (o) {
-            union { double d; uint64_t u; } cv;
-            cv.d = d;
-            o[0] = 0xcb; mp_put_be64(o + 1, cv.u);
-        }
+        if (o) { o[0] = 0xcb; mp_put_be64(o + 1, u); }
         return 9;
     }
     case RK_TRUE: if (o) o[0] = 0xc3; return 1;
@@ -1699,11 +1655,10 @@ FLB_HD int l2m_lookup(const struct ch_env *e, const struct ch_rec *rc, uint32_t 
         if (k == RK_INT_IN) { t->type = MPT_INT; t->u = (uint64_t) ch_atoll(ref_ptr(e, rc->v[i]), r_len(rc->v[i])); return 1; }
         if (k == RK_HEX_IN) { t->type = MPT_UINT; t->u = ch_strtoull16(ref_ptr(e, rc->v[i]), r_len(rc->v[i])); return 1; }
         if (k == RK_FLT_IN) {
-            union { double d; uint64_t u; } cv;
             int okf;
-            cv.d = ch_strtod_fast(ref_ptr(e, rc->v[i]), r_len(rc->v[i]), &okf);
+            t->u = dj_strtod(ref_ptr(e, rc->v[i]), (int) r_len(rc->v[i]), &okf);
             if (!okf) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
-            t->type = MPT_F64; t->u = cv.u; return 1;
+            t->type = MPT_F64; return 1;
         }
         if (k != RK_MP_IN && k != RK_MP_CONST && k != RK_MP_SCR) { t->type = MPT_NIL; CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return 1; }
         vp = ref_ptr(e, rc->v[i]); ve = vp + r_len(rc->v[i]);
@@ -1780,7 +1735,7 @@ FLB_HDN void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct
             if (q >= sl || pl[q] < '0' || pl[q] > '9' || (pl[q] == '0' && q + 1 < sl && (pl[q + 1] | 0x20) == 'x')) {
                 CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return;
             }
-            val = ch_strtod_fast(pl, sl, &ok);
+            { union { uint64_t u; double d; } cv; cv.u = dj_strtod(pl, (int) sl, &ok); val = cv.d; }
             if (!ok) { CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return; }
         }
         else if (t.type == MPT_UINT || t.type == MPT_INT) val = (double) (int64_t) t.u;

@@ -305,6 +305,75 @@ FLB_HDN int dj_number(const uint8_t *s, int n, int pos, int *kind, uint64_t *u, 
     return p;
 }
 
+/* strtod() of the C locale for the texts `Types key:float` (flb_parser.c:flb_parser_typecast -> atof)
+ * and log_to_metrics' sscanf("%lf") hand it: white space, sign, digits [. digits] [e[+-]digits], "inf" /
+ * "infinity" / "nan"; the longest valid prefix converts, nothing convertible gives +0.0.  The result is
+ * correctly rounded (nearest, ties to even) like glibc's: Clinger's exact products, Eisel-Lemire on the
+ * first 19 digits, and the big-integer comparison when the digits beyond them decide.  *ok = 0 for the
+ * forms that are not restated (hex floats, nan(payload)) and for texts beyond dj_big_decide's reach. */
+FLB_HDN uint64_t dj_strtod(const uint8_t *s, int n, int *ok)
+{
+    int p = 0, neg = 0, nd = 0, dropped = 0, truncated = 0, seen = 0, start;
+    uint64_t w = 0, bits = 0;
+    int64_t exp10 = 0;
+    const uint64_t sign = (uint64_t) 1 << 63, inf = (uint64_t) 0x7ff << 52;
+    *ok = 1;
+    while (p < n && (s[p] == ' ' || (s[p] >= 9 && s[p] <= 13))) p++;
+    if (p < n && (s[p] == '+' || s[p] == '-')) { neg = s[p] == '-'; p++; }
+    start = p;
+    if (p + 2 < n && (s[p] | 0x20) == 'i' && (s[p + 1] | 0x20) == 'n' && (s[p + 2] | 0x20) == 'f') return neg ? inf | sign : inf;
+    if (p + 2 < n && (s[p] | 0x20) == 'n' && (s[p + 1] | 0x20) == 'a' && (s[p + 2] | 0x20) == 'n') {
+        if (p + 3 < n && s[p + 3] == '(') *ok = 0;
+        return (inf | (uint64_t) 1 << 51) | (neg ? sign : 0);
+    }
+    if (p + 1 < n && s[p] == '0' && (s[p + 1] | 0x20) == 'x') { *ok = 0; return 0; }
+    for (; p < n && s[p] >= '0' && s[p] <= '9'; p++) {
+        const uint32_t d = s[p] - '0';
+        seen = 1;
+        if (w || d) { if (nd < 19) { w = w * 10 + d; nd++; } else { dropped++; if (d) truncated = 1; } }
+    }
+    if (p < n && s[p] == '.' && (seen || (p + 1 < n && s[p + 1] >= '0' && s[p + 1] <= '9'))) {
+        for (p++; p < n && s[p] >= '0' && s[p] <= '9'; p++) {
+            const uint32_t d = s[p] - '0';
+            seen = 1;
+            if (w || d) { if (nd < 19) { w = w * 10 + d; nd++; exp10--; } else if (d) truncated = 1; }
+            else exp10--;
+        }
+    }
+    if (!seen) return 0;                                               /* no conversion */
+    if (p < n && (s[p] | 0x20) == 'e') {
+        int q = p + 1, eneg = 0;
+        int64_t ev = 0;
+        if (q < n && (s[q] == '+' || s[q] == '-')) { eneg = s[q] == '-'; q++; }
+        if (q < n && s[q] >= '0' && s[q] <= '9') {
+            for (; q < n && s[q] >= '0' && s[q] <= '9'; q++) if (ev < 100000) ev = ev * 10 + (s[q] - '0');
+            exp10 += eneg ? -ev : ev;
+        }
+    }
+    exp10 += dropped;
+    if (w == 0) bits = 0;
+    else if (!truncated && w <= ((uint64_t) 1 << 53) && exp10 >= -22 && exp10 <= 22) {
+        union { double d; uint64_t u; } cv;
+        cv.d = (double) w;
+        if (exp10 >= 0) cv.d = cv.d * dj_p10[exp10]; else cv.d = cv.d / dj_p10[-exp10];
+        bits = cv.u;
+    }
+    else {
+        const int r = dj_eisel_lemire(w, exp10, &bits);
+        if (r == 1) bits = inf;                                        /* HUGE_VAL */
+        else if (truncated) {
+            uint64_t b2 = 0;
+            const int r2 = dj_eisel_lemire(w + 1, exp10, &b2);
+            if (r2 != 0 || b2 != bits || (bits >> 52) == 0) {
+                const int up = (r2 == 1 || b2 == bits + 1 || b2 == bits) ? dj_big_decide(s, n, start, bits) : -1;
+                if (up < 0) { *ok = 0; bits = 0; }
+                else if (up == 1) bits = bits + 1;                     /* the largest finite double + 1 ulp is infinity's pattern */
+            }
+        }
+    }
+    return neg ? bits | sign : bits;
+}
+
 /* Decode the string whose opening quote is at s[pos].  Writes the decoded bytes to o
  * (when o != NULL), returns the position after the closing quote or -1; *olen = length. */
 FLB_HDN int dj_string(const uint8_t *s, int n, int pos, uint8_t *o, uint32_t *olen)

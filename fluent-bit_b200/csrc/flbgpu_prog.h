@@ -229,7 +229,7 @@ struct chain_hdr {
 #define FLBGPU_E_FIELDS    1u   /* more top-level keys than the interpreter holds */
 #define FLBGPU_E_RXSTACK   2u   /* regex backtrack stack exhausted */
 #define FLBGPU_E_RXBUDGET  4u   /* regex step budget exhausted */
-#define FLBGPU_E_FLOAT     8u   /* decimal->double outside the exact fast path */
+#define FLBGPU_E_FLOAT     8u   /* strtod() text that is not restated: hex float, nan(payload) */
 #define FLBGPU_E_INDEX    16u   /* record index fast path failed */
 #define FLBGPU_E_ESCAPE   32u   /* logfmt escapes met without a scratch region (cannot happen through the C ABI) */
 #define FLBGPU_E_L2M      64u   /* log_to_metrics: label table full / float label / unparsable value */

@@ -102,6 +102,28 @@ def logfmt_escape_chunk():
     return util.chunk_from_lines(lines)
 
 
+# what atof() / glibc strtod makes of a captured text (`Types v:float`, flb_parser.c: flb_parser_typecast)
+STRTOD_TEXTS = ["", "-", "+", ".", "-.", "e5", ".e5", "5.", ".5", "+.5e1", "-5.e-1", "1e", "1e+", "1e-", "1ex", "1e+x", "1.5abc", "1..5",
+                "  12.5", "\t-3.25", "\v\f\r 7", "00012.50", "0000.0001", "-0", "-0.0", "0e999999", "1e400", "-1e400", "1e-400", "-1e-400",
+                "1e309", "1.7976931348623157e308", "1.7976931348623159e308", "4.9e-324", "2.4e-324", "2.5e-324", "2.2250738585072011e-308",
+                "2.2250738585072014e-308", "inf", "-inf", "INF", "Infinity", "infinit", "+infinityx", "nan", "-nan", "NaN", "nanx", "in", "na",
+                "1e99999999999", "1e-99999999999", "0." + "0" * 400 + "1e401", "1" + "0" * 400 + "e-400", "123456789012345678901234567890",
+                "9007199254740993", "9007199254740992.5", "9007199254740993e0", "0.1", "0.3", "1e23", "8.5e22", "1e22", "1e-22", "5e-23",
+                "3.14 15", "1,5", "1_000", "12e3.5", "- 5", "+-5", "\uff11"]
+
+
+def float_types_chunk():
+    """captures cast with `Types a:float b:float`: strtod's syntax, and decimals on / next to the midpoint of two doubles"""
+    import os
+    import random
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "tools"))
+    import floatfuzz
+    texts = STRTOD_TEXTS + [t for t in floatfuzz.cases(random.Random(77), 30) if len(t) < 240]
+    lines = [("%s|%s|%d" % (t, texts[(i * 7 + 3) % len(texts)], i)).encode("utf-8") for i, t in enumerate(texts)]
+    return util.chunk_from_lines(lines)
+
+
 def tricky_ts_chunk():
     """Timestamps whose bytes frame as complete legacy events ([uint32, {}]) inside real records:
     the record index has to rule those candidates out (sec = 0x655492ce -> `92 ce 00 00 xx xx 80`)."""
@@ -125,6 +147,8 @@ CASES = [
     ("parser_preserve", [AP], [("parser", [("Key_Name", "log"), ("Parser", "apache"), ("Preserve_Key", "On")])], apache_chunk),
     ("parser_reserve", [AP], [("parser", [("Key_Name", "log"), ("Parser", "apache"), ("Reserve_Data", "On")])], mixed_chunk),
     ("parser_ra_key", [AP], [("parser", [("Key_Name", "$log"), ("Parser", "apache"), ("Reserve_Data", "On")])], apache_chunk),
+    ("types_float_strtod", [dict(name="fl", format="regex", regex=r"^(?<a>[^|]*)\|(?<b>[^|]*)\|(?<n>\d+)$", types="a:float b:float n:integer")],
+     [("parser", [("Key_Name", "log"), ("Parser", "fl")]), ("grep", [("Exclude", "n ^7$")])], float_types_chunk),
     ("tricky_timestamps_parser", [AP], [P], tricky_ts_chunk),
     ("tricky_timestamps_grep", [], [("grep", [("Regex", "log GET")])], tricky_ts_chunk),
     ("json_parser", [JS], [PJ], json_chunk),
