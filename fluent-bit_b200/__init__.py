@@ -271,7 +271,7 @@ class Filter:
         end up in (rank, first-seen) order on every rank."""
         import torch
         import torch.distributed as dist
-        _, nl, nb, _ = self.l2m_info()
+        mode, nl, nb, _ = self.l2m_info()
         mine = self.l2m_sets()
         world = dist.get_world_size()
         gathered = [None] * world
@@ -284,6 +284,29 @@ class Filter:
                     order.append((h, labels))
         n = len(order)
         dev = device if device is not None else ("cuda" if dist.get_backend() == "nccl" else "cpu")
+        if mode == 1:
+            # gauge: the last record wins and shards are consecutive record ranges, so the value of the
+            # highest rank that saw the set stays.  Still ONE all_reduce: rank r owns column pair r of an
+            # int64 matrix (seen flag, value bits); adding zeros keeps the bits exact.
+            import struct
+            rank = dist.get_rank()
+            buf = torch.zeros((n, 2 * world + 1), dtype=torch.int64)
+            for h, _, c, s, _bk in mine:
+                i = seen[h]
+                buf[i, 0] = c
+                buf[i, 1 + 2 * rank] = 1
+                buf[i, 2 + 2 * rank] = struct.unpack("<q", struct.pack("<d", s))[0]
+            if n:
+                buf = buf.to(dev)
+                dist.all_reduce(buf)
+                buf = buf.cpu()
+            merged = []
+            for i, (h, labels) in enumerate(order):
+                last = max(r for r in range(world) if int(buf[i, 1 + 2 * r]))
+                val = struct.unpack("<d", struct.pack("<q", int(buf[i, 2 + 2 * last])))[0]
+                merged.append((h, labels, int(buf[i, 0]), val, [0] * (nb + 1)))
+            self.l2m_replace(merged)
+            return merged
         counts = torch.zeros((n, nb + 2), dtype=torch.int64)
         sums = torch.zeros((n,), dtype=torch.float64)
         for h, _, c, s, bk in mine:

@@ -1629,7 +1629,22 @@ FLB_HDN void f_recmod(const struct ch_env *e, const struct cf_recmod *cf, struct
 #define CH_CAS64(p, c, v)   atomicCAS((unsigned long long *) (p), (unsigned long long) (c), (unsigned long long) (v))
 #define CH_MAX32(p, v)      atomicMax((unsigned int *) (p), (unsigned int) (v))
 #define CH_ADDF64(p, v)     atomicAdd((double *) (p), (double) (v))
+/* gauge: the pair (record index + 1, value bits) of the LAST record of a label set wins, whatever order the
+ * lanes arrive in -- cmt_gauge_set() overwrites in record order.  One 16-byte compare-and-swap (sm_90+). */
+struct __align__(16) ch_pair16 { unsigned long long a, b; };
+static __device__ __forceinline__ void ch_gauge_set(unsigned long long *p, unsigned long long a, unsigned long long b)
+{
+    struct ch_pair16 cur, want;
+    cur.a = ((volatile unsigned long long *) p)[0]; cur.b = ((volatile unsigned long long *) p)[1];
+    want.a = a; want.b = b;
+    while (cur.a < a) {
+        const struct ch_pair16 old = atomicCAS((struct ch_pair16 *) p, cur, want);
+        if (old.a == cur.a && old.b == cur.b) break;
+        cur = old;
+    }
+}
 #else
+static inline void ch_gauge_set(unsigned long long *p, unsigned long long a, unsigned long long b) { if (p[0] < a) { p[0] = a; p[1] = b; } }
 static inline unsigned long long ch_cas64_host(unsigned long long *p, unsigned long long c, unsigned long long v) { unsigned long long o = *p; if (o == c) *p = v; return o; }
 #define CH_CAS64(p, c, v)   ch_cas64_host((unsigned long long *) (p), (c), (v))
 #define CH_MAX32(p, v)      do { if (*(p) < (v)) *(p) = (v); } while (0)
@@ -1718,7 +1733,7 @@ FLB_HDN void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct
     }
     h |= 1ull;
 
-    if (cf->mode == L2M_HISTOGRAM) {
+    if (cf->mode != L2M_COUNTER) {                 /* gauge and histogram read the value the same way (:1052-1110) */
         struct mp_tok t;
         const uint8_t *pl = 0;
         int raw = 0, ok = 1;
@@ -1773,6 +1788,11 @@ FLB_HDN void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct
         }
         CH_ATOMIC_ADD(&tb->bkt[(size_t) idx * (cf->n_buckets + 1) + cf->n_buckets], 1ull);
         CH_ADDF64(&tb->sum[idx], val);
+    }
+    else if (cf->mode == L2M_GAUGE) {              /* bkt is [slot][2] here: last record index + 1, value bits */
+        union { double d; unsigned long long u; } cv;
+        cv.d = val;
+        ch_gauge_set(&tb->bkt[(size_t) idx * 2], (unsigned long long) ridx + 1, cv.u);
     }
 }
 

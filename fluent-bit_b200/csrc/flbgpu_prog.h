@@ -202,7 +202,7 @@ struct l2m_table {
     uint32_t *first;                 /* 0xffffffff - (smallest record index of the set) */
     unsigned long long *cnt;         /* counter value / histogram count */
     double *sum;                     /* histogram sum */
-    unsigned long long *bkt;         /* [slot][n_buckets + 1] cumulative buckets, last = +Inf */
+    unsigned long long *bkt;         /* [slot][n_buckets + 1] cumulative buckets, last = +Inf; gauge: [slot][2] = last record + 1, value bits */
     uint8_t *str;                    /* [slot][n_labels][L2M_LABEL_BYTES]: length byte + bytes */
     uint32_t mask;
     uint32_t pad;

@@ -489,6 +489,8 @@ int flbgpu_filter_set_property(flbgpu_filter *f, const char *k, const char *v)
 }
 
 static void l2m_state_free(struct l2m_state *st);
+/* 64-bit words per slot of the device table's bkt array: cumulative buckets + Inf, or the gauge's (last record + 1, value bits) */
+#define L2M_NBK(st) ((st)->mode == L2M_GAUGE ? (size_t) 2 : (size_t) (st)->n_buckets + 1)
 
 void flbgpu_filter_destroy(flbgpu_filter *f)
 {
@@ -1022,13 +1024,15 @@ static uint32_t emit_l2m_filter(flbgpu_filter *f, struct blob *b)
     if (!tag || !*tag) { set_err("Metric tag is not set%s%s", NULL, NULL); l2m_state_free(st); return 0; }
     if (!strcasecmp(mode, "counter")) cf.mode = L2M_COUNTER;
     else if (!strcasecmp(mode, "histogram")) cf.mode = L2M_HISTOGRAM;
-    else if (!strcasecmp(mode, "gauge")) { set_err("metric_mode gauge is last-writer-wins (order dependent) and is not supported on the GPU path%s%s", NULL, NULL); l2m_state_free(st); return 0; }
+    else if (!strcasecmp(mode, "gauge")) cf.mode = L2M_GAUGE;
     else { set_err("invalid 'mode' value. Only 'counter', 'gauge' or 'histogram' types are allowed%s%s", NULL, NULL); l2m_state_free(st); return 0; }
     if (!desc || !*desc) { set_err("metric_description is not set%s%s", NULL, NULL); l2m_state_free(st); return 0; }
-    if (cf.mode == L2M_HISTOGRAM) {
+    if (cf.mode != L2M_COUNTER) {
         if (!value_field || !*value_field) { set_err("value_field is not set%s%s", NULL, NULL); l2m_state_free(st); return 0; }
         cf.value_ra_off = emit_ra(b, value_field);
         if (!cf.value_ra_off) { l2m_state_free(st); return 0; }
+    }
+    if (cf.mode == L2M_HISTOGRAM) {
         if (nb == 0) { memcpy(bounds, def_bounds, sizeof(def_bounds)); nb = 11; }
         else qsort(bounds, nb, sizeof(double), cmp_double);
         cf.n_buckets = nb;
@@ -1129,7 +1133,7 @@ int flbgpu_chain_init(flbgpu_chain *c)
     if (!c->d_blob || !c->d_flags) return -1;
     if (c->l2m_index >= 0) {
         struct l2m_state *st = c->f[c->l2m_index]->l2m;
-        size_t n = (size_t) 1 << L2M_SLOTS_LOG2, nbk = (size_t) st->n_buckets + 1;
+        size_t n = (size_t) 1 << L2M_SLOTS_LOG2, nbk = L2M_NBK(st);
         c->l2m_slots = n;
         c->l2m.hash = bk_alloc(n * 8); c->l2m.first = bk_alloc(n * 4); c->l2m.cnt = bk_alloc(n * 8);
         c->l2m.sum = bk_alloc(n * 8); c->l2m.bkt = bk_alloc(n * nbk * 8);
@@ -1230,7 +1234,7 @@ static int l2m_clear(flbgpu_chain *c)
     if (c->l2m_index < 0) return 0;
     st = c->f[c->l2m_index]->l2m;
     if (bk_zero(c->l2m.hash, n * 8) || bk_zero(c->l2m.first, n * 4) || bk_zero(c->l2m.cnt, n * 8) ||
-        bk_zero(c->l2m.sum, n * 8) || bk_zero(c->l2m.bkt, n * ((size_t) st->n_buckets + 1) * 8)) return -1;
+        bk_zero(c->l2m.sum, n * 8) || bk_zero(c->l2m.bkt, n * L2M_NBK(st) * 8)) return -1;
     return 0;
 }
 
@@ -1250,7 +1254,7 @@ static int l2m_merge(flbgpu_chain *c)
     uint32_t *order;
     if (c->l2m_index < 0) return 0;
     st = c->f[c->l2m_index]->l2m;
-    nbk = (size_t) st->n_buckets + 1;
+    nbk = L2M_NBK(st);
     if (bk_d2h(c->h_hash, c->l2m.hash, n * 8) || bk_d2h(c->h_first, c->l2m.first, n * 4) || bk_d2h(c->h_cnt, c->l2m.cnt, n * 8) ||
         bk_d2h(c->h_sum, c->l2m.sum, n * 8) || bk_d2h(c->h_bkt, c->l2m.bkt, n * nbk * 8) || bk_sync()) return -1;
     order = malloc(sizeof(uint32_t) * n);
@@ -1274,9 +1278,13 @@ static int l2m_merge(flbgpu_chain *c)
             memset(set, 0, sizeof(*set));
             set->hash = c->h_hash[slot];
             set->labels = labels;
-            set->buckets = calloc(nbk, sizeof(uint64_t));
+            set->buckets = calloc((size_t) st->n_buckets + 1, sizeof(uint64_t));
         }
         set->count += c->h_cnt[slot];
+        if (st->mode == L2M_GAUGE) {             /* the call's last record of this set overwrites what earlier calls left */
+            if (c->h_bkt[slot * 2]) memcpy(&set->sum, &c->h_bkt[slot * 2 + 1], 8);
+            continue;
+        }
         set->sum += c->h_sum[slot];
         for (k = 0; k < nbk; k++) set->buckets[k] += c->h_bkt[slot * nbk + k];
     }
@@ -1760,6 +1768,7 @@ char *flbgpu_l2m_text(flbgpu_filter *f)
         }
         if (st->n_labels) L2M_APPEND("}");
         if (st->mode == L2M_COUNTER) L2M_APPEND(" = %.17g\n", (double) s->count);
+        else if (st->mode == L2M_GAUGE) L2M_APPEND(" = %.17g\n", s->sum);
         else {
             L2M_APPEND(" = { buckets = { ");
             for (k = 0; k < st->n_buckets; k++) L2M_APPEND("%g=%llu, ", st->bounds[k], (unsigned long long) s->buckets[k]);

@@ -134,13 +134,13 @@ struct flbgpu_stats {
 void flbgpu_chain_stats(flbgpu_chain *c, struct flbgpu_stats *out);
 
 /* ---- filter_log_to_metrics state ------------------------------------------------
- * The filter ("log_to_metrics": metric_mode counter | histogram, Regex/Exclude gates, label_field /
- * add_label, bucket, discard_logs) accumulates into a per-instance table, like ctx->cmt in
- * plugins/filter_log_to_metrics/log_to_metrics.c:964-1148 (cmt_counter_inc / cmt_histogram_observe).
+ * The filter ("log_to_metrics": metric_mode counter | gauge | histogram, Regex/Exclude gates, label_field /
+ * add_label, kubernetes_mode, bucket, discard_logs) accumulates into a per-instance table, like ctx->cmt in
+ * plugins/filter_log_to_metrics/log_to_metrics.c:964-1148 (cmt_counter_inc / cmt_gauge_set / cmt_histogram_observe).
  * Label sets keep first-seen order.  A multi-GPU deployment sums these tables with one
  * NCCL all-reduce at flush time (bench.py / tests show the exchange with torch.distributed). */
 int   flbgpu_l2m_info(flbgpu_filter *f, int *mode, int *n_labels, int *n_buckets, int *n_sets);
-/* label set i: 64-bit key, counter value (or histogram count), histogram sum, cumulative buckets
+/* label set i: 64-bit key, counter value (or histogram count), histogram sum (gauge: the value), cumulative buckets
  * [n_buckets + 1] (last = +Inf), labels = n_labels x 256 bytes (length byte + bytes) */
 int   flbgpu_l2m_get(flbgpu_filter *f, int i, uint64_t *hash, uint64_t *count, double *sum, uint64_t *buckets, char *labels);
 int   flbgpu_l2m_reset(flbgpu_filter *f);

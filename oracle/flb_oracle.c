@@ -8,7 +8,7 @@
  *   plugins/filter_grep/grep.c:56-392
  *   plugins/filter_modify/modify.c:141-1578
  *   plugins/filter_record_modifier/filter_modifier.c:37-486
- *   plugins/filter_log_to_metrics/log_to_metrics.c:247-1148 (counter, histogram)
+ *   plugins/filter_log_to_metrics/log_to_metrics.c:247-1148 (counter, gauge, histogram)
  *   src/flb_filter.c:119-323             flb_filter_do: the chain, MODIFIED / NOTOUCH hand-over
  */
 #define _GNU_SOURCE
@@ -384,11 +384,14 @@ int orc_filter_init(struct orc_config *cfg, struct orc_filter *f)
         }
         if (!tag || !*tag || !desc || !*desc) return -1;
         if (!strcasecmp(mode, "counter")) f->mode = 0;
+        else if (!strcasecmp(mode, "gauge")) f->mode = 1;
         else if (!strcasecmp(mode, "histogram")) f->mode = 2;
         else return -1;
-        if (f->mode == 2) {
+        if (f->mode != 0) {
             if (!value_field || !*value_field) return -1;
             f->value_ra = ra_create(value_field);
+        }
+        if (f->mode == 2) {
             if (f->n_buckets == 0) { memcpy(f->buckets, defb, sizeof(defb)); f->n_buckets = 11; }
             else qsort(f->buckets, (size_t) f->n_buckets, sizeof(double), cmp_double);
         }
@@ -703,12 +706,12 @@ static int cb_l2m(struct orc_filter *f, const uint8_t *in, size_t len, struct or
     struct orc_arena a = { 0 };
     size_t off = 0;
     struct ov root;
+    double val = 0;                    /* :983-984: lives across records, so a text sscanf() cannot convert leaves the previous value */
     (void) out;
     while (ov_unpack(&a, in, len, &off, &root) == 0) {
         const struct ov *map;
         char labels[16][256];
         int i, s;
-        double val = 0;
         if (root.type != OV_ARR || root.n < 2) continue;
         map = &root.items[1];
         if (!grep_keep(f, map)) continue;
@@ -721,7 +724,7 @@ static int cb_l2m(struct orc_filter *f, const uint8_t *in, size_t len, struct or
             else if (v->type == OV_UINT) snprintf(labels[i], 253 - 1, "%ld", (long) v->u);
             else if (v->type == OV_INT) snprintf(labels[i], 253 - 1, "%ld", (long) v->i);
         }
-        if (f->mode == 2) {
+        if (f->mode != 0) {                                    /* gauge :1052-1080, histogram :1082-1110 */
             const struct ov *v = ra_get(f->value_ra, map);
             if (!v) continue;
             if (v->type == OV_STR) { char *t = strndup((const char *) v->p, v->len); sscanf(t, "%lf", &val); free(t); }
@@ -743,6 +746,7 @@ static int cb_l2m(struct orc_filter *f, const uint8_t *in, size_t len, struct or
             f->n_sets++;
         }
         f->sets[s].count++;
+        if (f->mode == 1) f->sets[s].sum = val;                /* cmt_gauge_set: the latest record's value stays */
         if (f->mode == 2) {                                    /* cmt_histogram_observe */
             for (i = f->n_buckets - 1; i >= 0; i--) { if (val > f->buckets[i]) break; f->sets[s].buckets[i]++; }
             f->sets[s].buckets[f->n_buckets]++;
@@ -768,6 +772,7 @@ char *orc_l2m_text(struct orc_filter *f)
         }
         if (f->n_labels) orc_buf_put(&b, "}", 1);
         if (f->mode == 0) { n = snprintf(tmp, sizeof(tmp), " = %.17g\n", (double) f->sets[s].count); orc_buf_put(&b, tmp, (size_t) n); }
+        else if (f->mode == 1) { n = snprintf(tmp, sizeof(tmp), " = %.17g\n", f->sets[s].sum); orc_buf_put(&b, tmp, (size_t) n); }
         else {
             orc_buf_put(&b, " = { buckets = { ", 17);
             for (i = 0; i < f->n_buckets; i++) {

@@ -92,6 +92,16 @@ L2M_CASES = [
      lambda: events(400, 14, extra=lambda rng: [(b"kubernetes", {b"pod_name": rng.choice([b"web-1", b"web-2"]), b"namespace_name": b"prod",
                                                              b"container_name": rng.choice([b"app", b"sidecar"]), b"docker_id": b"abc",
                                                              b"pod_id": 17})] if rng.random() < 0.8 else []), 0),
+    ("gauge_labels", [], [("log_to_metrics", BASE + [("metric_mode", "gauge"), ("value_field", "duration"), ("label_field", "color"),
+                                                     ("add_label", "pod $kubernetes['pod_name']")])], lambda: events(900, 15), 0),
+    ("gauge_regex_no_labels", [], [("log_to_metrics", BASE + [("metric_mode", "gauge"), ("value_field", "$code"), ("regex", "message ^ok"),
+                                                              ("metric_subsystem", "last")])], lambda: events(700, 16), 0),
+    ("gauge_after_parser",
+     [dict(name="apache2", format="regex", regex=util.APACHE_RX, time_key="time", time_fmt="%d/%b/%Y:%H:%M:%S %z",
+           types="code:integer size:integer")],
+     [("parser", [("key_name", "log"), ("parser", "apache2")]),
+      ("log_to_metrics", BASE + [("metric_mode", "gauge"), ("value_field", "size"), ("label_field", "method"), ("label_field", "code")])],
+     lambda: util.chunk_from_lines(util.apache_lines(1200, seed=17)), 1),
     ("l2m_then_modify", [],
      [("log_to_metrics", BASE + [("label_field", "color")]), ("modify", [("add", "seen yes")])], lambda: events(200, 13), 0),
 ]

@@ -95,10 +95,14 @@ def test_l2m_config_errors(bad, sim_lib, ref_available):
 
 
 def test_l2m_not_supported_is_loud(sim_lib):
+    """a value text sscanf("%lf") cannot convert leaves the previous record's value in place in the
+    reference (order dependent): refused, not guessed"""
     ctx = pkg.Context(0, lib=sim_lib)
-    for props in ([("metric_mode", "gauge"), ("value_field", "x"), ("metric_description", "d"), ("tag", "t")],):
+    for mode in ("gauge", "histogram"):
+        f = ctx.filter("log_to_metrics", [("metric_mode", mode), ("value_field", "x"), ("metric_description", "d"), ("tag", "t")])
+        chunk = util.event(1700000000, 0, [(b"x", util.mp_str(b"1.5"))]) + util.event(1700000001, 0, [(b"x", util.mp_str(b"fast"))])
         with pytest.raises(pkg.FlbGpuError):
-            ctx.filter("log_to_metrics", props)
+            f.cb(chunk)
 
 
 WORKER = r"""
@@ -126,7 +130,7 @@ dist.destroy_process_group()
 """
 
 
-@pytest.mark.parametrize("case", ["counter_labels", "histogram_default_buckets", "after_parser_and_grep"])
+@pytest.mark.parametrize("case", ["counter_labels", "histogram_default_buckets", "after_parser_and_grep", "gauge_labels"])
 def test_l2m_allreduce_world2(case, sim_lib, ref_available, tmp_path):
     """Two shards of one chunk, one table per rank, merged with the all-reduce: every rank ends
     with exactly the table the reference builds from the whole chunk (same order, same values)."""
