@@ -21,6 +21,16 @@ tests/hostsim/libhostsim.so: tests/hostsim/hostsim.cpp $(CSRC)/runtime.c $(CSRC)
 	gcc $(CFLAGS) -c $(CSRC)/rx_compile.c -o tests/hostsim/rx_compile.o
 	g++ $(CFLAGS) -shared -o $@ tests/hostsim/hostsim.cpp tests/hostsim/runtime.o tests/hostsim/rx_compile.o
 
+# the same emulation under AddressSanitizer + UBSan (host runtime and the device code as the CPU compiles it):
+#   make hostsim-asan && FLBGPU_HOSTSIM_SO=/tmp/flbgpu-asan/libhostsim.so LD_PRELOAD=$$(gcc -print-file-name=libasan.so) \
+#       ASAN_OPTIONS=detect_leaks=0 python -m pytest tests -q -s -m "not gpu"
+SAN = -O1 -g -fPIC -fsanitize=address,undefined -fno-omit-frame-pointer -Wno-unused-function
+hostsim-asan:
+	mkdir -p /tmp/flbgpu-asan
+	gcc $(SAN) -c $(CSRC)/runtime.c -o /tmp/flbgpu-asan/runtime.o
+	gcc $(SAN) -c $(CSRC)/rx_compile.c -o /tmp/flbgpu-asan/rx_compile.o
+	g++ $(SAN) -shared -o /tmp/flbgpu-asan/libhostsim.so tests/hostsim/hostsim.cpp /tmp/flbgpu-asan/runtime.o /tmp/flbgpu-asan/rx_compile.o
+
 ORC_SRC = oracle/flb_oracle.c oracle/orc_parsers.c oracle/orc_regex.c oracle/orc_time.c oracle/orc_msgpack.c
 oracle: oracle/liboracle.so
 	@if [ -d /root/reference ]; then $(MAKE) -s -C oracle/refshim; else echo "oracle/_ref: reference tree absent, using prebuilt"; fi
@@ -29,4 +39,4 @@ oracle/liboracle.so: $(ORC_SRC) oracle/orc.h oracle/orc_flb.h
 
 clean:
 	rm -f $(PKG)/libflbgpu.so $(CSRC)/*.o tests/hostsim/*.so tests/hostsim/*.o oracle/liboracle.so
-.PHONY: all product hostsim oracle clean
+.PHONY: all product hostsim hostsim-asan oracle clean

@@ -8,7 +8,7 @@ import struct
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libflbref.so")
-HOSTSIM_SO = os.path.join(ROOT, "tests", "hostsim", "libhostsim.so")
+HOSTSIM_SO = os.environ.get("FLBGPU_HOSTSIM_SO") or os.path.join(ROOT, "tests", "hostsim", "libhostsim.so")   # override: a sanitizer build
 
 pkg = importlib.import_module("fluent-bit_b200")
 
