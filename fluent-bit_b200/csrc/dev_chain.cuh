@@ -1725,7 +1725,11 @@ FLB_HDN void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct
                 if (v < 0) dst[n++] = '-';
                 while (m) dst[n++] = tmp[--m];
             }
-            else if (t.type == MPT_F32 || t.type == MPT_F64) CH_ATOMIC_OR(e->err, FLBGPU_E_L2M);   /* "%f" not on the device */
+            else if (t.type == MPT_F32 || t.type == MPT_F64) {                                       /* "%f" */
+                uint64_t fb = t.u;
+                if (t.type == MPT_F32) { union { uint32_t u; float f; } c4; union { double d; uint64_t u; } c8; c4.u = (uint32_t) t.u; c8.d = (double) c4.f; fb = c8.u; }
+                n = dj_fmt_f6(fb, dst, 251);
+            }
         }
         lab[lpos] = (uint8_t) n;
         for (k = 0; k <= n; k++) { h ^= lab[lpos + k]; h *= 1099511628211ull; }

@@ -374,6 +374,76 @@ FLB_HDN uint64_t dj_strtod(const uint8_t *s, int n, int *ok)
     return neg ? bits | sign : bits;
 }
 
+/* printf("%f") of a double, as glibc prints it: the exact binary value times 10^6 rounded to an integer
+ * (nearest, ties to even), six digits after the point, "inf" / "nan" with their sign.  At most `cap`
+ * bytes are written (snprintf's truncation); returns how many.  log_to_metrics renders FLOAT label
+ * values this way (log_to_metrics.c:1028-1031). */
+FLB_HD uint32_t djb_divmod_small(struct dj_big *b, uint32_t d)
+{
+    uint64_t rem = 0;
+    int i;
+    for (i = (int) b->n - 1; i >= 0; i--) {
+        const uint64_t cur = (rem << 32) | b->v[i];
+        b->v[i] = (uint32_t) (cur / d);
+        rem = cur % d;
+    }
+    while (b->n && b->v[b->n - 1] == 0) b->n--;
+    return (uint32_t) rem;
+}
+
+FLB_HDN uint32_t dj_fmt_f6(uint64_t bits, uint8_t *dst, uint32_t cap)
+{
+    struct dj_big N;
+    uint8_t tmp[336];                                  /* 309 integer digits + 6 + slack, least significant first */
+    uint32_t nt = 0, n = 0, i;
+    const uint32_t ef = (uint32_t) ((bits >> 52) & 0x7ff);
+    uint64_t M = bits & (((uint64_t) 1 << 52) - 1);
+    int k;
+#define DJ_FPUT(c) do { if (n < cap) dst[n++] = (uint8_t) (c); } while (0)
+    if (bits >> 63) DJ_FPUT('-');
+    if (ef == 0x7ff) {
+        if (M) { DJ_FPUT('n'); DJ_FPUT('a'); DJ_FPUT('n'); } else { DJ_FPUT('i'); DJ_FPUT('n'); DJ_FPUT('f'); }
+        return n;
+    }
+    if (ef) { M |= (uint64_t) 1 << 52; k = (int) ef - 1075; } else k = -1074;
+    N.n = 0;
+    if (M) {
+        if (k >= 0) {                                   /* an integer: M * 2^k * 10^6, exactly */
+            N.v[0] = (uint32_t) M; N.v[1] = (uint32_t) (M >> 32); N.n = N.v[1] ? 2 : 1;
+            djb_shl(&N, (uint32_t) k);
+            djb_mul_small(&N, 1000000u, 0);
+        }
+        else {                                          /* X = M * 10^6 < 2^73;  N = round(X / 2^s) */
+            const uint32_t sft = (uint32_t) -k;
+            uint64_t hi, lo, qhi = 0, qlo = 0;
+            int up = 0;
+            dj_mul64(M, 1000000ull, &hi, &lo);
+            if (sft <= 74) {
+                uint64_t rhi, rlo, hhi, hlo;            /* remainder and half of the divisor */
+                if (sft >= 64) { qlo = hi >> (sft - 64); qhi = 0; rhi = sft == 64 ? 0 : hi & (((uint64_t) 1 << (sft - 64)) - 1); rlo = lo; }
+                else { qlo = (lo >> sft) | (hi << (64 - sft)); qhi = hi >> sft; rhi = 0; rlo = lo & (((uint64_t) 1 << sft) - 1); }
+                if (sft - 1 >= 64) { hhi = (uint64_t) 1 << (sft - 1 - 64); hlo = 0; } else { hhi = 0; hlo = (uint64_t) 1 << (sft - 1); }
+                if (rhi > hhi || (rhi == hhi && rlo > hlo)) up = 1;
+                else if (rhi == hhi && rlo == hlo) up = (int) (qlo & 1);
+            }                                           /* else X < 2^73 <= half of 2^s: rounds to zero */
+            if (up) { qlo++; if (qlo == 0) qhi++; }
+            N.v[0] = (uint32_t) qlo; N.v[1] = (uint32_t) (qlo >> 32); N.v[2] = (uint32_t) qhi; N.v[3] = (uint32_t) (qhi >> 32);
+            N.n = 4;
+            while (N.n && N.v[N.n - 1] == 0) N.n--;
+        }
+    }
+    while (N.n) {                                       /* nine digits at a time */
+        uint32_t r = djb_divmod_small(&N, 1000000000u), j;
+        for (j = 0; j < 9 && (N.n || r); j++) { tmp[nt++] = (uint8_t) ('0' + r % 10); r /= 10; }
+    }
+    while (nt < 7) tmp[nt++] = '0';                     /* at least "0" before the point */
+    for (i = nt; i > 6; i--) DJ_FPUT(tmp[i - 1]);
+    DJ_FPUT('.');
+    for (i = 6; i > 0; i--) DJ_FPUT(tmp[i - 1]);
+#undef DJ_FPUT
+    return n;
+}
+
 /* Decode the string whose opening quote is at s[pos].  Writes the decoded bytes to o
  * (when o != NULL), returns the position after the closing quote or -1; *olen = length. */
 FLB_HDN int dj_string(const uint8_t *s, int n, int pos, uint8_t *o, uint32_t *olen)

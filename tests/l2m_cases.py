@@ -22,6 +22,8 @@ def _mp(v):
         return b"\xd3" + struct.pack(">q", v)
     if isinstance(v, float):
         return b"\xcb" + struct.pack(">d", v)
+    if isinstance(v, tuple) and v[0] == "f32":
+        return b"\xca" + struct.pack(">f", v[1])
     if isinstance(v, bytes):
         return util.mp_str(v)
     if isinstance(v, dict):
@@ -50,6 +52,21 @@ def events(n, seed, extra=None):
             rec += extra(rng)
         out.append(util.event(1700000000 + i, i % 1000, [(k, _mp(v)) for k, v in rec]))
     return b"".join(out)
+
+
+FLOATS = [0.5, 1 / 128, 3 / 128, 5 / 128, 2.5, 1e300, -1e-7, 5e-7, 4.9999995e-7, 5.0000005e-7, 1e22, 123456.789, -0.0, 0.0, float("inf"),
+          float("-inf"), float("nan"), 1.7976931348623157e308, 5e-324, 0.1, 1e-6, 9.9999995e-7, 0.9999995, 0.99999949999, 1.0000005,
+          9007199254740993.0, 4503599627370497.5, 2.0 ** 73, 2.0 ** -20, 2.0 ** -21, 3 * 2.0 ** -22, 1e15 + 0.3, 999999.9999995, 1e21,
+          ("f32", 0.1), ("f32", 1 / 128), ("f32", -3.4028234663852886e38), ("f32", 1e-45)]
+
+
+def float_label(rng):
+    r = rng.random()
+    if r < 0.5:
+        return [(b"ratio", rng.choice(FLOATS))]
+    if r < 0.8:
+        return [(b"ratio", struct.unpack("<d", struct.pack("<Q", rng.getrandbits(64)))[0])]     # any bit pattern
+    return [(b"ratio", rng.randrange(-(1 << 30), 1 << 30) / (1 << rng.randrange(0, 40)))]      # dyadic: exact ties happen
 
 
 BASE = [("metric_name", "reqs"), ("metric_description", "requests"), ("tag", "metrics")]
@@ -92,6 +109,8 @@ L2M_CASES = [
      lambda: events(400, 14, extra=lambda rng: [(b"kubernetes", {b"pod_name": rng.choice([b"web-1", b"web-2"]), b"namespace_name": b"prod",
                                                              b"container_name": rng.choice([b"app", b"sidecar"]), b"docker_id": b"abc",
                                                              b"pod_id": 17})] if rng.random() < 0.8 else []), 0),
+    ("counter_float_labels", [], [("log_to_metrics", BASE + [("label_field", "ratio"), ("add_label", "c $color")])],
+     lambda: events(700, 18, extra=float_label), 0),
     ("gauge_labels", [], [("log_to_metrics", BASE + [("metric_mode", "gauge"), ("value_field", "duration"), ("label_field", "color"),
                                                      ("add_label", "pod $kubernetes['pod_name']")])], lambda: events(900, 15), 0),
     ("gauge_regex_no_labels", [], [("log_to_metrics", BASE + [("metric_mode", "gauge"), ("value_field", "$code"), ("regex", "message ^ok"),
