@@ -402,7 +402,7 @@ FLB_HDN int ra_walk_sub(const struct ch_env *e, const struct cf_ra *ra, const ui
 }
 
 /* flb_ra_key_value_get(): 0 found (flags: *okey_null), -1 not found.
- * On success either *top >= 0 (the top-level field itself) or *vp/*ve (nested). */
+ * On success either *top >= 0 (the top-level field itself) or *vp and *ve (nested). */
 FLB_HD int ra_get(const struct ch_env *e, const struct ch_rec *rc, const struct cf_ra *ra, int *top,
                   const uint8_t **vp, const uint8_t **ve, int *okey_null)
 {

@@ -770,6 +770,18 @@ static uint32_t key_hash(const char *s, size_t n)
     return h | 1u;
 }
 
+/* modify.c:468-507 builds a regex from the key AND the value text of EVERY rule, regex rule or not, and refuses
+ * the configuration when Onigmo rejects either (tests/runtime/filter_modify.c issue_7368: `remove_wildcard *s3`).
+ * Nothing is emitted here; a construct this compiler merely does not cover is not a syntax error. */
+static int rule_text_is_a_regex(const char *text)
+{
+    struct rx_compiled rc;
+    memset(&rc, 0, sizeof(rc));
+    if (rx_compile(text, &rc) == 0) { rx_compiled_free(&rc); return 1; }
+    rx_compiled_free(&rc);
+    return strstr(rc.err, "not supported") != NULL;
+}
+
 static uint32_t emit_modify_filter(flbgpu_filter *f, struct blob *b)
 {
     struct cf_modify cf;
@@ -840,6 +852,8 @@ static uint32_t emit_modify_filter(flbgpu_filter *f, struct blob *b)
             r->val_off = blob_add(b, val, strlen(val), 1); r->val_len = (uint32_t) strlen(val);
             r->vmp_off = blob_add_mpstr(b, val, (uint32_t) strlen(val), &r->vmp_len);
             r->key_hash = key_hash(key, strlen(key)); r->val_hash = key_hash(val, strlen(val));
+            if (type != MOD_REMOVE_REGEX && !rule_text_is_a_regex(key)) { set_err("Unable to create regex(key) from %s%s", key, NULL); free_toks(tok, nt); goto out; }
+            if (!rule_text_is_a_regex(val)) { set_err("Unable to create regex(val) from %s%s", val, NULL); free_toks(tok, nt); goto out; }
             if (type == MOD_REMOVE_REGEX) {
                 if (!*key) { free_toks(tok, nt); set_err("Unable to create regex for rule %s %s", p->k, p->v); goto out; }
                 r->key_rx = emit_rx(b, key, NULL);

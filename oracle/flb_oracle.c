@@ -324,6 +324,12 @@ int orc_filter_init(struct orc_config *cfg, struct orc_filter *f)
                 r->key = strdup(tok[0]);
                 r->val = nt > 1 ? strdup(tok[1]) : strdup("");
                 if (t == R_REMOVE_REGEX && !(r->key_rx = orc_regex_create(tok[0], err, sizeof(err)))) return -1;
+                {   /* modify.c:468-507: key and value text of every rule must be regexes Onigmo accepts */
+                    struct orc_regex *probe;
+                    if (!(probe = orc_regex_create(tok[0], err, sizeof(err))) && !strstr(err, "not supported")) return -1;
+                    if (!(probe = orc_regex_create(tok[nt - 1], err, sizeof(err))) && !strstr(err, "not supported")) return -1;
+                    (void) probe;
+                }
                 f->n_mrules++;
             }
         }

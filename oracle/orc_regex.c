@@ -571,6 +571,8 @@ static struct node *parse_cat(struct parser *P, int depth)
         struct node *piece, *c;
         skip_extended(P);
         if (P->err || P->p >= P->end || *P->p == '|' || *P->p == ')') break;
+        /* regparse.c parse_exp, TK_OP_REPEAT with nothing before it: Ruby syntax has CONTEXT_INVALID_REPEAT_OPS */
+        if (*P->p == '*' || *P->p == '+' || *P->p == '?') { P->err = "target of repeat operator is not specified"; break; }
         piece = parse_piece(P, depth);
         if (!head) head = piece;
         else { c = mk(P, N_CAT); c->a = head; c->b = piece; head = c; }
