@@ -1245,7 +1245,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
             vt = ref_view(e, rc->v[i], &vp, &vn);
             if (vt != 1 && vt != 2) continue;
         }
-        if (vp < e->in || vp >= e->in + e->in_len) {
+        if (vp < e->in || vp + vn > e->in + e->in_len) {     /* (an empty value may sit at the very end of the chunk) */
             /* the value was produced by an earlier filter (scratch / constant pool): parsed fields
              * could not reference it by input offset -- refused loudly rather than mis-parsed */
             CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS);

@@ -282,7 +282,10 @@ int orc_filter_init(struct orc_config *cfg, struct orc_filter *f)
             if (!strcasecmp(p->k, "logical_op")) f->op = !strcasecmp(p->v, "AND") ? OP_AND : !strcasecmp(p->v, "OR") ? OP_OR : OP_LEGACY;
         for (p = f->props; p; p = p->next) {
             int type = !strcasecmp(p->k, "regex") ? GREP_REGEX : !strcasecmp(p->k, "exclude") ? GREP_EXCLUDE : 0;
-            if (!type) continue;
+            if (!type) {
+                if (!strcasecmp(p->k, "logical_op")) continue;
+                return -1;               /* flb_filter_config_map_set(): a key outside the plugin's config map stops flb_start() */
+            }
             if (f->op != OP_LEGACY && first && first != type) return -1;
             first = type;
             if (add_grep_rule(f, type, p->v, 1)) return -1;
@@ -350,6 +353,7 @@ int orc_filter_init(struct orc_config *cfg, struct orc_filter *f)
                 if (rm) f->n_remove++; else f->n_allow++;
             }
         }
+        if (f->n_remove > 0 && f->n_allow > 0) return -1;      /* filter_modifier.c: "remove_keys and allowlist_keys are exclusive" */
         return 0;
     }
     {   /* log_to_metrics.c:649-962 */
@@ -401,7 +405,7 @@ int orc_filter_init(struct orc_config *cfg, struct orc_filter *f)
             if (f->n_buckets == 0) { memcpy(f->buckets, defb, sizeof(defb)); f->n_buckets = 11; }
             else qsort(f->buckets, (size_t) f->n_buckets, sizeof(double), cmp_double);
         }
-        if (!f->subsystem) f->subsystem = strdup(mode);
+        if (!f->subsystem || !*f->subsystem) f->subsystem = strdup(mode);   /* :762-770: an empty subsystem falls back to the mode */
         return 0;
     }
 }

@@ -2,6 +2,7 @@
 (`[ts, {...}]`) to a chunk, and a chunk back to the compact JSON text out_lib's "format json" prints,
 which is what those tests search with strstr()."""
 import json
+import re
 import struct
 
 import msgpack
@@ -40,7 +41,7 @@ class Pairs(list):
 def chunk_from_json_events(texts):
     out = []
     for t in texts:
-        ts, body = json.loads(t, object_pairs_hook=Pairs)
+        ts, body = json.loads(re.sub(r",\s*}", "}", t), object_pairs_hook=Pairs)     # jsmn tolerates a trailing comma
         sec = int(ts)
         nsec = int(round((ts - sec) * 1e9)) if isinstance(ts, float) else 0
         out.append(util.event(sec, nsec, [(k.encode("utf-8"), mp_value(v)) for k, v in body]))
@@ -72,6 +73,22 @@ def records_as_json(chunk):
     u.feed(chunk)
     for rec in u:
         out.append(_json(rec[1]))
+    return out
+
+
+def records_as_lib_lines(chunk):
+    """`[<seconds with six decimals>,{...}]` per record: out_lib's "format json" line (flb_time_to_double, "%f")"""
+    out = []
+    if not chunk:
+        return out
+    u = msgpack.Unpacker(raw=True, strict_map_key=False, object_pairs_hook=Pairs)
+    u.feed(chunk)
+    for rec in u:
+        ts = rec[0][0] if isinstance(rec[0], list) else rec[0]
+        if isinstance(ts, msgpack.ExtType):
+            sec, nsec = struct.unpack(">II", ts.data)
+            ts = sec + nsec / 1e9
+        out.append("[%f,%s]" % (float(ts), _json(rec[1])))
     return out
 
 
