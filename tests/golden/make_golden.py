@@ -85,6 +85,13 @@ REGEX = [
     (r'/^(?<k>[a-z]+)=(?<v>\d+)$/i', [b"Abc=12", b"ABC=x", b"abc=7\n"]),
     (r'(?<a>a+?)(?<b>b*)(?<c>c|$)', [b"aaabbc", b"xxaab", b"b", b""]),
     (r'^(?<w>\w+)\s+(?<rest>(?:\S+\s*){1,3})', [b"alpha beta gamma delta epsilon", b"one two", b"solo"]),
+    # tests/internal/regex.c: test_basic, test_uri ("/pattern/option" must not be misread), /i, /m, /x, /ix
+    (r'/(?<str>[a-z]+) (?<num>\d+) (?<time>\d{4}/\d{2}/\d{2})/', [b"string 1234 2022/10/24"]),
+    (r'/uri/(?<middle>[a-z]+)/hoge', [b"/uri/is/hoge"]),
+    (r'/(?<str>[a-z]+)/i', [b"STRING"]),
+    (r'/(?<full_str>.+)/m', [b"string\n1234\nstring"]),
+    (r'/(?<pi>\d  \. 14)/x', [b"3.14"]),
+    (r'/(?<full_str>\d  \. 14PI)/ix', [b"3.14pi"]),
 ]
 
 
