@@ -1306,6 +1306,28 @@ static int l2m_merge(flbgpu_chain *c)
     return 0;
 }
 
+/* The record index frames events whose root and header arrays are fixarrays (0x92), which is all msgpack-c's
+ * packer ever writes for two elements.  The reference's decoder would also take the same arrays spelled as
+ * array16 / array32: when the decodable prefix stops at such a spelling the call is refused, not cut short. */
+static int stops_at_wide_array(const uint8_t *h_in, const uint8_t *d_in, size_t off, size_t bytes)
+{
+    uint8_t b[8] = { 0 };
+    size_t n = bytes - off < sizeof(b) ? bytes - off : sizeof(b), i = 0;
+    if (n == 0) return 0;
+    if (h_in) memcpy(b, h_in + off, n);
+    else if (bk_d2h(b, d_in + off, n) || bk_sync()) return 0;
+    if (b[0] == 0x92) i = 1;                                   /* [ [ts, meta], body ] with a wide header array */
+    if (b[i] == 0xdc) return b[i + 1] == 0 && b[i + 2] == 2;
+    if (b[i] == 0xdd) return b[i + 1] == 0 && b[i + 2] == 0 && b[i + 3] == 0 && b[i + 4] == 2;
+    return 0;
+}
+#define REFUSE_WIDE_ARRAYS(h_in_, d_in_, fail_stmt) do { \
+        if (off < bytes && stops_at_wide_array(h_in_, d_in_, off, bytes)) { \
+            c->st.error_bits = FLBGPU_E_INDEX; \
+            snprintf(g_rt_err, sizeof(g_rt_err), "event framed with an array16/array32 header at byte %zu: not decoded on the GPU path", off); \
+            fail_stmt; \
+        } } while (0)
+
 /* One call.  Input: h_in (host, uploaded in pieces) or d_in_ext (already in HBM).
  * Result: host_out != NULL -> malloc()ed host buffer; else ext_out (device, capacity ext_cap). */
 static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_ext, size_t bytes,
@@ -1368,6 +1390,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         off = (size_t) end_off;
     }
     clean = (off == bytes);
+    REFUSE_WIDE_ARRAYS(h_in, d_in, return -1);
     c->st.records_in = n_rec;
     c->st.passes = 1;
     {
@@ -1618,6 +1641,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
         off = (size_t) end_off;
     }
     clean = (off == bytes);
+    REFUSE_WIDE_ARRAYS(h_in, c->d_in, goto fail);
     c->st.records_in = n_rec;
     c->st.passes = 1;
     STREAM_FLUSH((n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK);

@@ -3,6 +3,8 @@
 CPU half: the device algorithms compiled for the host (tests/hostsim).  GPU half: the
 same cases through libflbgpu.so's C ABI on a real device.  Both compare the returned
 code (MODIFIED / NOTOUCH) and every output byte."""
+import struct
+
 import pytest
 
 import cases
@@ -81,6 +83,69 @@ def test_edge_chunks_gpu(gpu_lib, ref_available):
     for data in [chunk + b"\x01\x02\x03", b"\xc1" + chunk, marker + chunk + endm, marker + endm]:
         for filters in ([("grep", [("Regex", "log GET")])], [cases.P], [("modify", [("Add", "a b")])]):
             run_case(gpu_lib, [cases.AP], filters, data)
+
+
+def _decoder_forms():
+    """the event forms tests/internal/log_event_decoder.c walks through (decode_timestamp, decode_object, the group
+    tests): every timestamp spelling in forward and v2 framing with and without metadata, group markers in and out
+    of order, truncated and corrupted groups, roots that are not events"""
+    S = util.mp_str
+    lines = util.apache_lines(40, seed=3)
+
+    def body(i):
+        return util.mp_map_hdr(2) + S(b"log") + S(lines[i % 40]) + S(b"n") + bytes([i % 100])
+
+    def ext(s, n):
+        return b"\xd7\x00" + struct.pack(">II", s, n)
+    ts_forms = [b"\x05", b"\xcc\xc8", b"\xcd\x12\x34", b"\xce\x65\x54\x92\xce", b"\xcf" + struct.pack(">Q", 1700000000),
+                b"\xcb" + struct.pack(">d", 1700000000.25), b"\xca" + struct.pack(">f", 1.5), ext(1700000000, 5),
+                b"\xd7\x01" + struct.pack(">II", 1, 2), b"\xc7\x08\x00" + struct.pack(">II", 1700000001, 7), b"\xd3" + struct.pack(">q", -5),
+                b"\xd0\xfb", b"\xa3abc", b"\xc0", ext(0x80000000, 0), ext(0xfffffffd, 0), ext(0xffffffff, 0), ext(0xfffffffe, 0)]
+    out = []
+    for k, t in enumerate(ts_forms):
+        out.append(b"\x92" + t + body(1) + b"\x92\x92" + t + b"\x80" + body(2) + b"\x92\x92" + t + b"\x81" + S(b"m") + b"\x01" + body(3) +
+                   util.event(1700000000, 0, [(b"log", S(lines[k % 5]))]))
+
+    def gs():
+        return util.event(0xffffffff, 0, [(b"g", S(b"start"))])
+
+    def ge():
+        return util.event(0xfffffffe, 0, [])
+
+    def rec(i):
+        return util.event(1700000000 + i, i, [(b"log", S(lines[i % 40]))])
+    out += [gs() + rec(1) + rec(2), rec(1) + ge() + rec(2), gs() + gs() + rec(1) + ge() + ge() + rec(2), ge() + gs() + rec(1),
+            gs() + rec(1) + ge() + gs() + rec(2) + ge(), gs() + b"\xc1" + rec(1), gs() + rec(1)[:20], b"\x92\x92" + ext(0xffffffff, 0) + b"\x80\x01" + rec(3),
+            b"\x93" + ext(1, 1) + b"\x80\x80" + rec(1), b"\x92\x93" + ext(1, 1) + b"\x80\x80\x80" + rec(1), b"\x92\x92" + ext(1, 1) + b"\x90\x80" + rec(1),
+            b"\x92\x92" + ext(1, 1) + b"\x80\x90" + rec(2), b"\x91\x80" + rec(1), b"\x80" + rec(1), b"\xa1x" + rec(1)]
+    return out
+
+
+DECODER_FILTERS = ([("grep", [("Regex", "log GET")])], [cases.P], [("modify", [("Add", "a b")])], [("record_modifier", [("Record", "h n1")])],
+                   [cases.P, ("grep", [("Regex", "method ^(GET|POST)$")]), ("modify", [("Add", "a b")])])
+
+
+def _decoder(lib):
+    for data in _decoder_forms():
+        for filters in DECODER_FILTERS:
+            run_case(lib, [cases.AP], filters, data)
+    # the same framing spelled with array16 / array32 headers: decodable for the reference, refused -- loudly -- here
+    rec = util.event(1700000000, 1, [(b"log", util.mp_str(b"x"))])
+    inner = rec[2:]                                                          # ts + meta + body of a v2 event
+    for wide in (b"\xdc\x00\x02" + rec[1:], b"\xdd\x00\x00\x00\x02" + rec[1:], b"\x92\xdc\x00\x02" + inner, b"\x92\xdd\x00\x00\x00\x02" + inner):
+        for data in (wide, rec + wide + rec):
+            ctx = pkg.Context(0, lib=lib)
+            with pytest.raises(pkg.FlbGpuError, match="array16/array32"):
+                ctx.filter("grep", [("Regex", "log x")]).cb(data)
+
+
+def test_decoder_forms_hostsim(sim_lib, ref_available):
+    _decoder(sim_lib)
+
+
+@pytest.mark.gpu
+def test_decoder_forms_gpu(gpu_lib, ref_available):
+    _decoder(gpu_lib)
 
 
 def _sliced(lib, monkeypatch, n_lines, reps, slice_mb):
