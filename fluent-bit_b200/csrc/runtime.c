@@ -845,7 +845,22 @@ static uint32_t emit_modify_filter(flbgpu_filter *f, struct blob *b)
                 else if (!strcasecmp(p->k, "copy")) type = MOD_COPY;
                 else if (!strcasecmp(p->k, "hard_copy")) type = MOD_HARD_COPY;
             }
+            else if (nt == 3) {
+                /* modify.c:412-466 only names a rule type for one or two words; with three the calloc()ed rule keeps
+                 * type 0 = RENAME, key = first word, value = last word -- whatever the property was called */
+                static const char *known[] = { "set", "add", "add_if_not_present", "remove", "remove_wildcard", "remove_regex", "rename",
+                                               "hard_rename", "copy", "hard_copy", "move_to_start", "move_to_end" };
+                size_t q;
+                for (q = 0; q < sizeof(known) / sizeof(known[0]); q++) if (!strcasecmp(p->k, known[q])) type = MOD_RENAME;
+            }
             if (!type) { free_toks(tok, nt); set_err("Invalid operation %s : %s in configuration", p->k, p->v); goto out; }
+            if ((type == MOD_HARD_COPY || type == MOD_HARD_RENAME) && !strcmp(key, val)) {
+                /* modify.c:1142-1160 / :1010-1040 size the new map for "one conflicting key goes, one copy comes" and then
+                 * skip (or keep) the one key that is both: the header and the pairs that follow disagree and every
+                 * record after it is read out of step.  There is no result to be identical to. */
+                set_err("%s %s: source and target are the same key; the reference writes a malformed map for it -- refused", p->k, p->v);
+                free_toks(tok, nt); goto out;
+            }
             r->type = type;
             r->key_off = blob_add(b, key, strlen(key), 1); r->key_len = (uint32_t) strlen(key);
             r->kmp_off = blob_add_mpstr(b, key, (uint32_t) strlen(key), &r->kmp_len);

@@ -322,10 +322,17 @@ int orc_filter_init(struct orc_config *cfg, struct orc_filter *f)
                 struct mod_rule *r = &f->mrules[f->n_mrules];
                 int t = -1;
                 for (i = 0; i < 11; i++) if (!strcasecmp(p->k, rn[i])) t = i;
-                if (t < 0 || nt < 1 || f->n_mrules >= 256) return -1;
+                if (!strcasecmp(p->k, "add_if_not_present")) t = R_ADD;
+                if (t < 0 || nt < 1 || nt > 3 || f->n_mrules >= 256) return -1;
+                {   /* modify.c:412-466: one word names the removal / move rules, two words the others; three words leave
+                     * the calloc()ed type 0 = RENAME in place, with the first and the last word */
+                    int one = t == R_REMOVE || t == R_REMOVE_WILDCARD || t == R_REMOVE_REGEX || t == R_MOVE_TO_START || t == R_MOVE_TO_END;
+                    if (nt == 3) t = R_RENAME;
+                    else if ((nt == 1) != one) return -1;
+                }
                 r->type = t;
                 r->key = strdup(tok[0]);
-                r->val = nt > 1 ? strdup(tok[1]) : strdup("");
+                r->val = nt > 1 ? strdup(tok[nt - 1]) : strdup("");
                 if (t == R_REMOVE_REGEX && !(r->key_rx = orc_regex_create(tok[0], err, sizeof(err)))) return -1;
                 {   /* modify.c:468-507: key and value text of every rule must be regexes Onigmo accepts */
                     struct orc_regex *probe;

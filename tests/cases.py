@@ -184,6 +184,8 @@ CASES = [
                                            ("Condition", "Matching_keys_have_matching_values ^l [a-z]"),
                                            ("Add", "matched yes")])], mixed_chunk),
     ("modify_bool_condition", [], [("modify", [("Condition", "Key_value_matches flag true"), ("Rename", "flag FLAG")])], mixed_chunk),
+    # three words: the reference leaves the calloc()ed rule type (RENAME) in place, first word -> last word
+    ("modify_three_word_rules", [], [("modify", [("Copy", "level x renamed"), ("Remove", "log to raw"), ("Set", "n is count")])], mixed_chunk),
     ("modify_notouch", [], [("modify", [("Remove", "absent"), ("Rename", "nope x")])], mixed_chunk),
     ("recmod_remove_some", [], [("record_modifier", [("Remove_key", "agent-x"), ("Remove_key", "de*")])], mixed_chunk),
     ("recmod_allow", [], [("record_modifier", [("Allowlist_key", "LOG"), ("Whitelist_key", "lev*")])], mixed_chunk),

@@ -139,6 +139,15 @@ def _decoder(lib):
                 ctx.filter("grep", [("Regex", "log x")]).cb(data)
 
 
+def test_degenerate_modify_rules_are_refused(sim_lib, ref_available):
+    """Hard_copy X X / Hard_rename X X: the reference sizes the new map wrongly and writes a malformed record"""
+    for rule in ("Hard_copy", "Hard_rename"):
+        ctx = pkg.Context(0, lib=sim_lib)
+        with pytest.raises(pkg.FlbGpuError, match="malformed map"):
+            ctx.filter("modify", [(rule, "k2 k2")])
+        util.Ref().filter("modify", [(rule, "k2 k2")])          # accepted there
+
+
 def test_decoder_forms_hostsim(sim_lib, ref_available):
     _decoder(sim_lib)
 

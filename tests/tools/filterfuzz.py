@@ -1,0 +1,196 @@
+"""Random records (duplicate keys, non-string keys, bin / ext / nil / nested values, empty maps, metadata)
+through randomly configured grep / modify / record_modifier / parser filters and short chains of them:
+CPU emulation of the device code vs the unmodified reference.  Refusals (loud) are counted, not failures.
+usage: python tests/tools/filterfuzz.py SEED ROUNDS"""
+import os
+import random
+import struct
+import sys
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", ".."))
+import util
+
+pkg = util.pkg
+S = util.mp_str
+# no empty key: the reference's modify reads through a NULL key pointer when a second rule meets one (segfault here)
+KEYS = [b"log", b"level", b"k1", b"k2", b"a3", b"msg", b"nest", b"arr", b"n", b"flag", b"Key", b"k 1", b"LOG"]
+WORDS = [b"GET /a HTTP/1.1", b"error", b"warn", b"info", b"", b"sample1", b"z2", b"true", b"false", b"123", b"a b", b"\xc3\xa9", b"x\x00y",
+         b'{"a":1,"b":"c"}', b"k=v j=2", b"a:1\tb:2"]
+
+
+def value(rng, depth=0):
+    r = rng.random()
+    if r < 0.45:
+        return S(rng.choice(WORDS))
+    if r < 0.55:
+        return rng.choice([b"\x00", b"\x7f", b"\xff", b"\xe0", b"\xcc\x80", b"\xcd\x01\x00", b"\xce\x00\x01\x00\x00", b"\xd0\x80", b"\xd1\xff\x00",
+                           b"\xcf" + struct.pack(">Q", 2 ** 63 + 5), b"\xd3" + struct.pack(">q", -2 ** 40), b"\xcc\x05", b"\xd2\x00\x00\x00\x07"])
+    if r < 0.62:
+        return rng.choice([b"\xc2", b"\xc3", b"\xc0"])
+    if r < 0.68:
+        return rng.choice([b"\xcb" + struct.pack(">d", 0.5), b"\xca" + struct.pack(">f", 1.25), b"\xcb" + struct.pack(">d", -1e300)])
+    if r < 0.74:
+        w = rng.choice(WORDS)
+        return bytes([0xc4, len(w)]) + w
+    if r < 0.78:
+        return b"\xd4\x05\x01" if rng.random() < 0.5 else b"\xc7\x03\x07abc"
+    if depth < 2 and r < 0.9:
+        n = rng.randrange(0, 4)
+        return util.mp_map_hdr(n) + b"".join(key(rng) + value(rng, depth + 1) for _ in range(n))
+    if depth < 2:
+        n = rng.randrange(0, 4)
+        return bytes([0x90 | n]) + b"".join(value(rng, depth + 1) for _ in range(n))
+    return S(b"deep")
+
+
+def key(rng):
+    r = rng.random()
+    if r < 0.9:
+        return S(rng.choice(KEYS))
+    if r < 0.95:
+        k = rng.choice(KEYS)
+        return bytes([0xc4, len(k)]) + k
+    return rng.choice([b"\x05", b"\xc3", b"\xc0"])
+
+
+def record(rng, i):
+    n = rng.choice([0, 1, 2, 3, 4, 5, 6, 8])
+    body = util.mp_map_hdr(n) + b"".join(key(rng) + value(rng) for _ in range(n))
+    meta = b"\x80" if rng.random() < 0.8 else util.mp_map_hdr(1) + S(b"m") + value(rng)
+    return b"\x92\x92\xd7\x00" + struct.pack(">II", 1700000000 + i, i % 1000) + meta + body
+
+
+RA = ["log", "level", "k1", "$nest['k1']", "$nest['nest']['k2']", "$arr[1]", "$arr[0]['k1']", "$k1", "msg", "$nest", "$arr", "n", "flag", "$log['x']"]
+RX = ["GET", "^(warn|error)$", ".", "^$", "sample[0-9]", "^[a-z][0-9]$", "true", "a b", "1", "\\d+", "^x"]
+
+
+def grep_props(rng):
+    props = []
+    if rng.random() < 0.4:
+        props.append(("Logical_Op", rng.choice(["and", "or", "legacy"])))
+    kind = rng.choice(["Regex", "Exclude"])
+    for _ in range(rng.randrange(1, 4)):
+        k = kind if props and props[0][0] == "Logical_Op" and props[0][1] != "legacy" else rng.choice(["Regex", "Exclude"])
+        props.append((k, "%s %s" % (rng.choice(RA), rng.choice(RX))))
+    return props
+
+
+PLAIN = ["log", "level", "k1", "k2", "a3", "msg", "nest", "arr", "n", "flag", "Key", "new", "k 1"]
+
+
+def modify_props(rng):
+    props = []
+    for _ in range(rng.randrange(0, 3)):
+        c = rng.choice(["Key_exists", "Key_does_not_exist", "A_key_matches", "No_key_matches", "Key_value_equals", "Key_value_does_not_equal",
+                        "Key_value_matches", "Key_value_does_not_match", "Matching_keys_have_matching_values", "Matching_keys_do_not_have_matching_values"])
+        if c in ("Key_exists", "Key_does_not_exist"):
+            v = rng.choice(RA)
+        elif c in ("A_key_matches", "No_key_matches"):
+            v = rng.choice(RX)
+        elif c in ("Key_value_equals", "Key_value_does_not_equal"):
+            v = "%s %s" % (rng.choice(RA), rng.choice(["error", "sample1", "true", "123", "z2"]))
+        elif c in ("Key_value_matches", "Key_value_does_not_match"):
+            v = "%s %s" % (rng.choice(RA), rng.choice(RX))
+        else:
+            v = "%s %s" % (rng.choice(RX), rng.choice(RX))
+        props.append(("Condition", "%s %s" % (c, v)))
+    for _ in range(rng.randrange(1, 5)):
+        r = rng.choice(["Set", "Add", "Remove", "Remove_wildcard", "Remove_regex", "Rename", "Hard_rename", "Copy", "Hard_copy", "Move_to_start", "Move_to_end"])
+        if r in ("Remove", "Move_to_start", "Move_to_end"):
+            v = rng.choice(PLAIN)
+        elif r == "Remove_wildcard":
+            v = rng.choice(["k", "l", "a", "ne", "K", "m"])
+        elif r == "Remove_regex":
+            v = rng.choice(RX)
+        else:
+            v = "%s %s" % (rng.choice(PLAIN if r not in ("Set", "Add") else ["new", "k1", "level", "x"]), rng.choice(["v", "k2", "new", "level", "value 1"]) if r in ("Set", "Add") else rng.choice(PLAIN))
+            if "value 1" in v:
+                v = v.replace("value 1", '"value 1"')
+        props.append((r, v))
+    return props
+
+
+def recmod_props(rng):
+    props = [("Record", "%s %s" % (rng.choice(["host", "k1", "new"]), rng.choice(["n1", "v"]))) for _ in range(rng.randrange(0, 3))]
+    kind = rng.choice(["Remove_key", "Allowlist_key", "Whitelist_key", None])
+    if kind:
+        props += [(kind, rng.choice(["log", "LEVEL", "k*", "K1", "nest", "a*", "msg", "*"])) for _ in range(rng.randrange(1, 3))]
+    return props or [("Record", "a b")]
+
+
+PARSERS = [dict(name="js", format="json"), dict(name="lf", format="logfmt"), dict(name="lt", format="ltsv"),
+           dict(name="rx", format="regex", regex=r"^(?<m>[A-Z]+) (?<p>[^ ]+) (?<v>.*)$"), dict(name="kv", format="regex", regex=r"^(?<a>[a-z]+)(?<d>\d*)$", types="d:integer")]
+
+
+def parser_props(rng):
+    props = [("Key_Name", rng.choice(["log", "msg", "k1", "$nest['k1']", "level"]))]
+    props += [("Parser", p) for p in rng.sample(["js", "lf", "lt", "rx", "kv"], rng.randrange(1, 3))]
+    if rng.random() < 0.5:
+        props.append(("Reserve_Data", rng.choice(["On", "Off"])))
+    if rng.random() < 0.5:
+        props.append(("Preserve_Key", rng.choice(["On", "Off"])))
+    return props
+
+
+MAKERS = {"grep": grep_props, "modify": modify_props, "record_modifier": recmod_props, "parser": parser_props}
+
+
+def main(seed, rounds):
+    rng = random.Random(seed)
+    lib = pkg.load(util.HOSTSIM_SO)
+    bad = refused = rejected = 0
+    for rd in range(rounds):
+        chunk = b"".join(record(rng, i) for i in range(rng.choice([1, 5, 40])))
+        filters = [(k, MAKERS[k](rng)) for k in (rng.choice(list(MAKERS)) for _ in range(rng.choice([1, 1, 2, 3])))]
+        ctx, ref = pkg.Context(0, lib=lib), util.Ref()
+        for kw in PARSERS:
+            ctx.parser(**kw); ref.parser(**kw)
+        try:
+            rfs = [ref.filter(p, props) for p, props in filters]
+        except RuntimeError:
+            rfs = None
+        try:
+            fs = [ctx.filter(p, props) for p, props in filters]
+        except pkg.FlbGpuError as e:
+            if rfs is not None and "malformed map" not in str(e):
+                print("CONFIG refused here, accepted by the reference:", filters, str(e)[:100])
+                rejected += 1
+            continue
+        if rfs is None:
+            print("CONFIG accepted here, refused by the reference:", filters)
+            bad += 1
+            continue
+        if os.environ.get("FILTERFUZZ_TRACE"):
+            print("round", rd, filters, flush=True)
+        want = ref.chain_do(chunk)
+        try:
+            got = ctx.chain(fs).do(chunk)
+        except pkg.FlbGpuError as e:
+            refused += 1
+            continue
+        if got != want:
+            bad += 1
+            print("MISMATCH seed=%d round=%d filters=%r" % (seed, rd, filters))
+            for i in range(0, 1):
+                recs = util.split_records(chunk)
+                for o, l in recs:
+                    one = chunk[o:o + l]
+                    c2, r2 = pkg.Context(0, lib=lib), util.Ref()
+                    for kw in PARSERS:
+                        c2.parser(**kw); r2.parser(**kw)
+                    [r2.filter(p, props) for p, props in filters]
+                    try:
+                        g1 = c2.chain([c2.filter(p, props) for p, props in filters]).do(one)
+                    except pkg.FlbGpuError:
+                        continue
+                    w1 = r2.chain_do(one)
+                    if g1 != w1:
+                        print("   record", one.hex()); print("   got ", g1[0], g1[1].hex() if g1[1] else None); print("   want", w1[0], w1[1].hex() if w1[1] else None)
+                        break
+    print("rounds", rounds, "mismatches", bad, "loud refusals", refused, "configs refused only here", rejected)
+    return bad
+
+
+if __name__ == "__main__":
+    sys.exit(1 if main(int(sys.argv[1]), int(sys.argv[2])) else 0)
