@@ -1694,7 +1694,7 @@ FLB_HDN void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct
     const struct l2m_table *tb = &e->l2m;
     uint8_t *lab = (uint8_t *) w->stk;                     /* label strings: reuse the regex stack area */
     uint32_t li, lpos = 0;
-    unsigned long long h = 1469598103934665603ull;
+    unsigned long long h = 1469598103934665603ull, hc = 1469598103934665603ull;
     uint32_t idx, probes = 0;
     double val = 0;
 
@@ -1733,6 +1733,7 @@ FLB_HDN void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct
         }
         lab[lpos] = (uint8_t) n;
         for (k = 0; k <= n; k++) { h ^= lab[lpos + k]; h *= 1099511628211ull; }
+        for (k = 1; k <= n; k++) { hc ^= lab[lpos + k]; hc *= 1099511628211ull; }
         lpos += 1 + n;
     }
     h |= 1ull;
@@ -1781,6 +1782,7 @@ FLB_HDN void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct
         idx = (idx + 1) & tb->mask;
         if (++probes > tb->mask) { CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return; }
     }
+    tb->chash[idx] = hc | 1ull;                     /* every lane of this tuple stores the same value */
     CH_MAX32(&tb->first[idx], 0xffffffffu - ridx);
     CH_ATOMIC_ADD(&tb->cnt[idx], 1ull);
     if (cf->mode == L2M_HISTOGRAM) {

@@ -198,7 +198,9 @@ struct cf_l2m {
 
 /* per-call device table of label sets (open addressing on a 64-bit hash of the label values) */
 struct l2m_table {
-    unsigned long long *hash;        /* 0 = empty */
+    unsigned long long *hash;        /* 0 = empty; over the label values WITH their lengths: one slot per exact label tuple */
+    unsigned long long *chash;       /* over the label values run together, as cmetrics hashes them (cmt_map.c:208-222): tuples that
+                                        concatenate to the same text are ONE metric there; the host folds such slots together */
     uint32_t *first;                 /* 0xffffffff - (smallest record index of the set) */
     unsigned long long *cnt;         /* counter value / histogram count */
     double *sum;                     /* histogram sum */

@@ -108,6 +108,7 @@ struct l2m_set {
     uint64_t count;          /* counter value / histogram _count */
     double sum;
     uint64_t *buckets;       /* n_buckets + 1 */
+    uint64_t call_last;      /* gauge: last record index + 1 seen for this set in the call being folded in */
 };
 struct l2m_state {
     int mode, n_labels, n_buckets, discard;
@@ -146,7 +147,7 @@ struct flbgpu_chain {
     int l2m_index;                            /* filter index of the log_to_metrics filter, or -1 */
     struct l2m_table l2m;                     /* device table (per-call delta) */
     size_t l2m_slots;
-    uint64_t *h_hash, *h_cnt, *h_bkt; uint32_t *h_first; double *h_sum;    /* host mirror */
+    uint64_t *h_hash, *h_chash, *h_cnt, *h_bkt; uint32_t *h_first; double *h_sum;    /* host mirror */
     /* device buffers, grown on demand */
     uint8_t *d_in;  size_t cap_in;
     uint8_t *d_out; size_t cap_out;
@@ -1164,13 +1165,13 @@ int flbgpu_chain_init(flbgpu_chain *c)
         struct l2m_state *st = c->f[c->l2m_index]->l2m;
         size_t n = (size_t) 1 << L2M_SLOTS_LOG2, nbk = L2M_NBK(st);
         c->l2m_slots = n;
-        c->l2m.hash = bk_alloc(n * 8); c->l2m.first = bk_alloc(n * 4); c->l2m.cnt = bk_alloc(n * 8);
+        c->l2m.hash = bk_alloc(n * 8); c->l2m.chash = bk_alloc(n * 8); c->l2m.first = bk_alloc(n * 4); c->l2m.cnt = bk_alloc(n * 8);
         c->l2m.sum = bk_alloc(n * 8); c->l2m.bkt = bk_alloc(n * nbk * 8);
         c->l2m.str = bk_alloc(n * (st->n_labels ? st->n_labels : 1) * L2M_LABEL_BYTES);
         c->l2m.mask = (uint32_t) (n - 1);
-        c->h_hash = malloc(n * 8); c->h_first = malloc(n * 4); c->h_cnt = malloc(n * 8); c->h_sum = malloc(n * 8);
+        c->h_hash = malloc(n * 8); c->h_chash = malloc(n * 8); c->h_first = malloc(n * 4); c->h_cnt = malloc(n * 8); c->h_sum = malloc(n * 8);
         c->h_bkt = malloc(n * nbk * 8);
-        if (!c->l2m.hash || !c->l2m.first || !c->l2m.cnt || !c->l2m.sum || !c->l2m.bkt || !c->l2m.str) return -1;
+        if (!c->l2m.hash || !c->l2m.chash || !c->l2m.first || !c->l2m.cnt || !c->l2m.sum || !c->l2m.bkt || !c->l2m.str) return -1;
     }
     if (bk_h2d(c->d_blob, c->blob.p, c->blob.n) || bk_sync()) return -1;
     c->inited = 1;
@@ -1183,8 +1184,8 @@ void flbgpu_chain_destroy(flbgpu_chain *c)
     bk_free(c->d_blob); bk_free(c->d_in); bk_free(c->d_out); bk_free(c->d_tile); bk_free(c->d_off);
     bk_free(c->d_len); bk_free(c->d_size); bk_free(c->d_kind); bk_free(c->d_bsum); bk_free(c->d_cap);
     bk_free(c->d_flags); bk_free(c->d_scr); free(c->h_bsum);
-    bk_free(c->l2m.hash); bk_free(c->l2m.first); bk_free(c->l2m.cnt); bk_free(c->l2m.sum); bk_free(c->l2m.bkt); bk_free(c->l2m.str);
-    free(c->h_hash); free(c->h_first); free(c->h_cnt); free(c->h_sum); free(c->h_bkt);
+    bk_free(c->l2m.hash); bk_free(c->l2m.chash); bk_free(c->l2m.first); bk_free(c->l2m.cnt); bk_free(c->l2m.sum); bk_free(c->l2m.bkt); bk_free(c->l2m.str);
+    free(c->h_hash); free(c->h_chash); free(c->h_first); free(c->h_cnt); free(c->h_sum); free(c->h_bkt);
     free(c->blob.p);
     free(c);
 }
@@ -1284,9 +1285,10 @@ static int l2m_merge(flbgpu_chain *c)
     if (c->l2m_index < 0) return 0;
     st = c->f[c->l2m_index]->l2m;
     nbk = L2M_NBK(st);
-    if (bk_d2h(c->h_hash, c->l2m.hash, n * 8) || bk_d2h(c->h_first, c->l2m.first, n * 4) || bk_d2h(c->h_cnt, c->l2m.cnt, n * 8) ||
+    if (bk_d2h(c->h_hash, c->l2m.hash, n * 8) || bk_d2h(c->h_chash, c->l2m.chash, n * 8) || bk_d2h(c->h_first, c->l2m.first, n * 4) || bk_d2h(c->h_cnt, c->l2m.cnt, n * 8) ||
         bk_d2h(c->h_sum, c->l2m.sum, n * 8) || bk_d2h(c->h_bkt, c->l2m.bkt, n * nbk * 8) || bk_sync()) return -1;
     order = malloc(sizeof(uint32_t) * n);
+    for (i = 0; i < (size_t) st->n_sets; i++) st->sets[i].call_last = 0;
     for (i = 0; i < n; i++) if (c->h_hash[i]) order[m++] = (uint32_t) i;
     qsort_r(order, m, sizeof(uint32_t), cmp_first, c->h_first);
     for (i = 0; i < m; i++) {
@@ -1295,7 +1297,9 @@ static int l2m_merge(flbgpu_chain *c)
         size_t lb = (size_t) (st->n_labels ? st->n_labels : 1) * L2M_LABEL_BYTES, k;
         int j;
         char *labels = NULL;
-        for (j = 0; j < st->n_sets; j++) if (st->sets[j].hash == c->h_hash[slot]) { set = &st->sets[j]; break; }
+        /* cmetrics finds a metric by the hash of its label values run together: tuples that concatenate alike are one
+         * metric, shown with the labels of whichever came first (this loop runs in first-seen order) */
+        for (j = 0; j < st->n_sets; j++) if (st->sets[j].hash == c->h_chash[slot]) { set = &st->sets[j]; break; }
         if (!set) {
             labels = calloc(1, lb);
             if (st->n_labels && (bk_d2h(labels, c->l2m.str + (size_t) slot * lb, lb) || bk_sync())) { free(labels); free(order); return -1; }
@@ -1305,13 +1309,13 @@ static int l2m_merge(flbgpu_chain *c)
             }
             set = &st->sets[st->n_sets++];
             memset(set, 0, sizeof(*set));
-            set->hash = c->h_hash[slot];
+            set->hash = c->h_chash[slot];
             set->labels = labels;
             set->buckets = calloc((size_t) st->n_buckets + 1, sizeof(uint64_t));
         }
         set->count += c->h_cnt[slot];
         if (st->mode == L2M_GAUGE) {             /* the call's last record of this set overwrites what earlier calls left */
-            if (c->h_bkt[slot * 2]) memcpy(&set->sum, &c->h_bkt[slot * 2 + 1], 8);
+            if (c->h_bkt[slot * 2] > set->call_last) { set->call_last = c->h_bkt[slot * 2]; memcpy(&set->sum, &c->h_bkt[slot * 2 + 1], 8); }
             continue;
         }
         set->sum += c->h_sum[slot];
@@ -1792,6 +1796,7 @@ int flbgpu_l2m_put(flbgpu_filter *f, uint64_t hash, uint64_t count, double sum, 
         st->sets = realloc(st->sets, sizeof(*st->sets) * st->cap_sets);
     }
     set = &st->sets[st->n_sets++];
+    memset(set, 0, sizeof(*set));
     set->hash = hash; set->count = count; set->sum = sum;
     set->labels = malloc(lb); memcpy(set->labels, labels, lb);
     set->buckets = calloc(st->n_buckets + 1, sizeof(uint64_t));
@@ -1812,6 +1817,9 @@ char *flbgpu_l2m_text(flbgpu_filter *f)
     out[0] = 0;
 #define L2M_APPEND(...) do { for (;;) { int w_ = snprintf(out + len, cap - len, __VA_ARGS__); \
         if ((size_t) w_ < cap - len) { len += (size_t) w_; break; } cap *= 2; out = realloc(out, cap); } } while (0)
+    /* a metric without label keys is cmetrics' static metric: it exists, at 0, before anything was counted
+     * (cmt_map.c: metric_static; a histogram in that state has no buckets yet and is not printable) */
+    if (st->n_sets == 0 && st->n_labels == 0 && st->mode != L2M_HISTOGRAM) L2M_APPEND("%s_%s_%s = 0\n", st->ns, st->subsystem, st->name);
     for (i = 0; i < st->n_sets; i++) {
         struct l2m_set *s = &st->sets[i];
         L2M_APPEND("%s_%s_%s", st->ns, st->subsystem, st->name);

@@ -750,9 +750,16 @@ static int cb_l2m(struct orc_filter *f, const uint8_t *in, size_t len, struct or
             else if (v->type == OV_INT) val = (double) v->i;
             else continue;
         }
-        for (s = 0; s < f->n_sets; s++) {
-            for (i = 0; i < f->n_labels; i++) if (strcmp(f->sets[s].labels[i], labels[i])) break;
-            if (i == f->n_labels) break;
+        {   /* cmt_map_metric_get (cmt_map.c:208-224): the metric is found by the hash of the label values run together,
+             * so tuples that concatenate to the same text are one metric */
+            char cat[16 * 256], have[16 * 256];
+            cat[0] = 0;
+            for (i = 0; i < f->n_labels; i++) strcat(cat, labels[i]);
+            for (s = 0; s < f->n_sets; s++) {
+                have[0] = 0;
+                for (i = 0; i < f->n_labels; i++) strcat(have, f->sets[s].labels[i]);
+                if (!strcmp(have, cat)) break;
+            }
         }
         if (s == f->n_sets) {                                  /* cmetrics appends a new metric to the map (cmt_map.c:209-243) */
             f->sets = realloc(f->sets, sizeof(*f->sets) * (size_t) (f->n_sets + 1));
@@ -780,6 +787,10 @@ char *orc_l2m_text(struct orc_filter *f)
     struct orc_buf b = { 0, 0, 0 };
     char tmp[512];
     int s, i;
+    if (f->n_sets == 0 && f->n_labels == 0 && f->mode != 2) {      /* cmetrics' static metric: there, at 0, from creation */
+        int n = snprintf(tmp, sizeof(tmp), "%s_%s_%s = 0\n", f->ns, f->subsystem, f->mname);
+        orc_buf_put(&b, tmp, (size_t) n);
+    }
     for (s = 0; s < f->n_sets; s++) {
         int n = snprintf(tmp, sizeof(tmp), "%s_%s_%s", f->ns, f->subsystem, f->mname);
         orc_buf_put(&b, tmp, (size_t) n);

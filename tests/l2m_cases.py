@@ -111,6 +111,17 @@ L2M_CASES = [
                                                              b"pod_id": 17})] if rng.random() < 0.8 else []), 0),
     ("counter_float_labels", [], [("log_to_metrics", BASE + [("label_field", "ratio"), ("add_label", "c $color")])],
      lambda: events(700, 18, extra=float_label), 0),
+    # cmetrics finds a metric by the hash of its label values run together: ("ab",""), ("","ab") and ("a","b") are ONE metric,
+    # shown with the labels of the first record that had it (lib/cmetrics/src/cmt_map.c:208-224)
+    ("counter_label_boundaries", [], [("log_to_metrics", BASE + [("label_field", "p"), ("label_field", "q")])],
+     lambda: b"".join(util.event(1700000000 + i, 0, [(b"p", _mp(p)), (b"q", _mp(q))]) for i, (p, q) in enumerate(
+         [(b"", b"ab"), (b"ab", b""), (b"a", b"b"), (b"x", b"y"), (b"xy", b""), (b"a", b"b"), (12, b"3"), (1, 23), (b"", b"")] * 7)), 0),
+    ("gauge_label_boundaries", [], [("log_to_metrics", BASE + [("metric_mode", "gauge"), ("value_field", "v"), ("label_field", "p"), ("label_field", "q")])],
+     lambda: b"".join(util.event(1700000000 + i, 0, [(b"p", _mp(p)), (b"q", _mp(q)), (b"v", _mp(i))]) for i, (p, q) in enumerate(
+         [(b"", b"ab"), (b"ab", b""), (b"a", b"b"), (b"x", b"y"), (b"xy", b"")] * 5)), 0),
+    # no label keys: cmetrics' static metric is there, at 0, before anything is counted
+    ("counter_static_metric_at_zero", [], [("log_to_metrics", BASE + [("regex", "message ^nothing matches this$")])], lambda: events(50, 19), 0),
+    ("gauge_static_metric_at_zero", [], [("log_to_metrics", BASE + [("metric_mode", "gauge"), ("value_field", "absent")])], lambda: events(50, 20), 0),
     ("gauge_labels", [], [("log_to_metrics", BASE + [("metric_mode", "gauge"), ("value_field", "duration"), ("label_field", "color"),
                                                      ("add_label", "pod $kubernetes['pod_name']")])], lambda: events(900, 15), 0),
     ("gauge_regex_no_labels", [], [("log_to_metrics", BASE + [("metric_mode", "gauge"), ("value_field", "$code"), ("regex", "message ^ok"),

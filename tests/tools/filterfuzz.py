@@ -14,9 +14,14 @@ import util
 pkg = util.pkg
 S = util.mp_str
 # no empty key: the reference's modify reads through a NULL key pointer when a second rule meets one (segfault here)
-KEYS = [b"log", b"level", b"k1", b"k2", b"a3", b"msg", b"nest", b"arr", b"n", b"flag", b"Key", b"k 1", b"LOG"]
+KEYS = [b"log", b"level", b"k1", b"k2", b"a3", b"msg", b"nest", b"arr", b"n", b"n", b"flag", b"Key", b"k 1", b"LOG"]
 WORDS = [b"GET /a HTTP/1.1", b"error", b"warn", b"info", b"", b"sample1", b"z2", b"true", b"false", b"123", b"a b", b"\xc3\xa9", b"x\x00y",
-         b'{"a":1,"b":"c"}', b"k=v j=2", b"a:1\tb:2"]
+         b'{"a":1,"b":"c"}', b"k=v j=2", b"a:1\tb:2",
+         b'{"time":"2023-05-06T07:08:09.123Z","level":"warn","n":-5,"f":1.5e3,"nest":{"k1":"v"},"arr":[1,"two",null],"u":"\\u00e9\\ud83d\\ude00"}',
+         b'{"time":"not a time","level":"info"}', b'{"time":"2023-05-06T07:08:09Z"}', b'{"a":1} trailing', b'[1,2]', b'{"a":{"b":{"c":{"d":1}}},"e":[]}', b'{"dup":1,"dup":2,"":3}',
+         b'time=2023-05-06T07:08:09.5Z level=warn msg="quoted \\"text\\"" bare n=7', b"time=bad level=info", b"=x a==b c=\"\"",
+         b"time:2023-05-06T07:08:09.250Z\tlevel:warn\tn:7\tempty:\t:nolabel", b"time:xx\tlevel:info",
+         b"POST /p?q=1 took 2023-05-06T07:08:09.750Z 12ab 0x1F 3.25 TRUE", b"GET / took bad-time 7 ff 1e3 false"]
 
 
 def value(rng, depth=0):
@@ -119,13 +124,19 @@ def recmod_props(rng):
     return props or [("Record", "a b")]
 
 
+TF = "%Y-%m-%dT%H:%M:%S.%LZ"
 PARSERS = [dict(name="js", format="json"), dict(name="lf", format="logfmt"), dict(name="lt", format="ltsv"),
-           dict(name="rx", format="regex", regex=r"^(?<m>[A-Z]+) (?<p>[^ ]+) (?<v>.*)$"), dict(name="kv", format="regex", regex=r"^(?<a>[a-z]+)(?<d>\d*)$", types="d:integer")]
+           dict(name="rx", format="regex", regex=r"^(?<m>[A-Z]+) (?<p>[^ ]+) (?<v>.*)$"), dict(name="kv", format="regex", regex=r"^(?<a>[a-z]+)(?<d>\d*)$", types="d:integer"),
+           dict(name="jst", format="json", time_key="time", time_fmt=TF), dict(name="jsk", format="json", time_key="time", time_fmt=TF, time_keep=True, time_strict=False),
+           dict(name="lft", format="logfmt", time_key="time", time_fmt=TF, types="n:integer"), dict(name="ltt", format="ltsv", time_key="time", time_fmt=TF, time_keep=True, types="n:hex"),
+           dict(name="rxt", format="regex", regex=r"^(?<m>[A-Z]+) (?<p>[^ ]+) took (?<time>[^ ]+) (?<i>[^ ]+) (?<h>[^ ]+) (?<f>[^ ]+) (?<b>[^ ]+)$", time_key="time", time_fmt=TF,
+                types="i:integer h:hex f:float b:bool"),
+           dict(name="lfb", format="logfmt", logfmt_no_bare_keys=True), dict(name="jse", format="json", skip_empty=False)]
 
 
 def parser_props(rng):
     props = [("Key_Name", rng.choice(["log", "msg", "k1", "$nest['k1']", "level"]))]
-    props += [("Parser", p) for p in rng.sample(["js", "lf", "lt", "rx", "kv"], rng.randrange(1, 3))]
+    props += [("Parser", p) for p in rng.sample([kw["name"] for kw in PARSERS], rng.randrange(1, 4))]
     if rng.random() < 0.5:
         props.append(("Reserve_Data", rng.choice(["On", "Off"])))
     if rng.random() < 0.5:
@@ -133,7 +144,38 @@ def parser_props(rng):
     return props
 
 
-MAKERS = {"grep": grep_props, "modify": modify_props, "record_modifier": recmod_props, "parser": parser_props}
+def l2m_props(rng):
+    mode = rng.choice(["counter", "counter", "gauge", "histogram"])
+    props = [("metric_mode", mode), ("metric_name", "m"), ("metric_description", "d"), ("tag", "t")]
+    if mode != "counter":
+        props.append(("value_field", rng.choice(["n", "$nest['n']", "k2", "flag"])))
+    for _ in range(rng.randrange(0, 3)):
+        props.append(rng.choice([("label_field", rng.choice(["level", "k1", "flag", "n"])), ("add_label", "x %s" % rng.choice(RA))]))
+    if rng.random() < 0.4:
+        props.append((rng.choice(["regex", "exclude"]), "%s %s" % (rng.choice(RA), rng.choice(RX))))
+    if rng.random() < 0.2:
+        props.append(("kubernetes_mode", "on"))
+    if rng.random() < 0.2:
+        props.append(("discard_logs", "on"))
+    if mode == "histogram" and not any(k in ("label_field", "add_label", "kubernetes_mode") for k, _ in props):
+        props.append(("label_field", "level"))     # the reference cannot print a label-less histogram that saw nothing (crash in cmt_encode_text)
+    if mode == "histogram" and rng.random() < 0.5:
+        props += [("bucket", rng.choice(["1", "0.5", "100", "7"])) for _ in range(rng.randrange(1, 4))]
+    return props
+
+
+MAKERS = {"grep": grep_props, "modify": modify_props, "record_modifier": recmod_props, "parser": parser_props, "log_to_metrics": l2m_props}
+
+
+def l2m_ref_text(ref, f):
+    import ctypes as C
+    import re
+    ref.L.flbref_l2m_cmt_text.restype = C.c_void_p
+    ref.L.flbref_l2m_cmt_text.argtypes = [C.c_void_p]
+    p = ref.L.flbref_l2m_cmt_text(f)
+    t = C.string_at(p).decode(errors="replace")
+    ref.L.flbref_cfree(C.c_void_p(p))
+    return re.sub(r"^\S+Z ", "", t, flags=re.M)
 
 
 def main(seed, rounds):
@@ -143,6 +185,8 @@ def main(seed, rounds):
     for rd in range(rounds):
         chunk = b"".join(record(rng, i) for i in range(rng.choice([1, 5, 40])))
         filters = [(k, MAKERS[k](rng)) for k in (rng.choice(list(MAKERS)) for _ in range(rng.choice([1, 1, 2, 3])))]
+        if sum(k == "log_to_metrics" for k, _ in filters) > 1:
+            continue                                          # one metrics filter per fused chain
         ctx, ref = pkg.Context(0, lib=lib), util.Ref()
         for kw in PARSERS:
             ctx.parser(**kw); ref.parser(**kw)
@@ -168,7 +212,13 @@ def main(seed, rounds):
             got = ctx.chain(fs).do(chunk)
         except pkg.FlbGpuError as e:
             refused += 1
+            if os.environ.get("FILTERFUZZ_TRACE"):
+                print("refused:", str(e)[:160], filters, flush=True)
             continue
+        for (k, _), f, rf in zip(filters, fs, rfs):
+            if k == "log_to_metrics" and f.l2m_text() != l2m_ref_text(ref, rf):
+                bad += 1
+                print("METRICS MISMATCH seed=%d round=%d filters=%r\n got  %r\n want %r" % (seed, rd, filters, f.l2m_text()[:300], l2m_ref_text(ref, rf)[:300]))
         if got != want:
             bad += 1
             print("MISMATCH seed=%d round=%d filters=%r" % (seed, rd, filters))
