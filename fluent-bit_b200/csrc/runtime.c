@@ -1730,6 +1730,33 @@ int flbgpu_chain_do_device(flbgpu_chain *c, const void *d_data, size_t bytes, vo
     return r;
 }
 
+/* flb_filter_do() as the reference runs it (src/flb_filter.c:119-323): one filter after the other on the device, each
+ * on the chunk the previous one returned.  The fused form hands fields from filter to filter by reference and cannot
+ * parse a value an earlier filter of the same chain made (a decoded JSON string, a `Set` constant); it refuses with
+ * FLBGPU_E_FIELDS and the chain is run this way instead -- same result, one round trip per filter. */
+static int chain_do_one_by_one(flbgpu_chain *c, const void *data, size_t bytes, void **out_buf, size_t *out_size)
+{
+    const void *cur = data;
+    size_t cur_n = bytes;
+    void *owned = NULL;
+    int k;
+    for (k = 0; k < c->nf; k++) {
+        void *o = NULL;
+        size_t on = 0;
+        int r = flbgpu_filter_cb(c->f[k], cur, cur_n, "", 0, &o, &on);
+        if (r < 0) { free(owned); return -1; }
+        if (r != FLBGPU_FILTER_MODIFIED) { free(o); continue; }
+        free(owned);
+        owned = o;
+        if (on == 0) { free(owned); *out_buf = NULL; *out_size = 0; return FLBGPU_FILTER_MODIFIED; }   /* nothing left: the chain ends */
+        cur = o; cur_n = on;
+    }
+    if (!owned) return FLBGPU_FILTER_NOTOUCH;
+    *out_buf = owned; *out_size = cur_n;
+    return FLBGPU_FILTER_MODIFIED;
+}
+#define FUSED_REFUSED_A_HANDED_OVER_VALUE(c) ((c)->nf > 1 && (c)->st.error_bits == FLBGPU_E_FIELDS)
+
 int flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes, const char *tag, int tag_len,
                     void **out_buf, size_t *out_size)
 {
@@ -1744,13 +1771,17 @@ int flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes, const char 
             int ret = 0, r = chain_run_stream(c, data, bytes, out_buf, out_size, &ret);
             bk_upload_end();                         /* `data` is not read after this call returns */
             if (r == 0) return ret;
-            if (r < 0) return -1;
+            if (r < 0) {
+                if (FUSED_REFUSED_A_HANDED_OVER_VALUE(c)) return chain_do_one_by_one(c, data, bytes, out_buf, out_size);
+                return -1;
+            }
             *out_buf = NULL; *out_size = 0;          /* speculation did not hold: classic path */
         }
     }
     {
         int r = chain_run(c, data, NULL, bytes, NULL, 0, out_buf, out_size);
         bk_upload_end();
+        if (r < 0 && FUSED_REFUSED_A_HANDED_OVER_VALUE(c)) { *out_buf = NULL; *out_size = 0; return chain_do_one_by_one(c, data, bytes, out_buf, out_size); }
         return r;
     }
 }

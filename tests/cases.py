@@ -124,6 +124,16 @@ def float_types_chunk():
     return util.chunk_from_lines(lines)
 
 
+def docker_chunk():
+    """docker json-file lines whose `log` is itself JSON: the inner text only exists once the outer string is decoded"""
+    import json as _json
+    lines = []
+    for i, l in enumerate(util.json_lines(300, 23)):
+        inner = l.decode() if i % 3 else "plain text %d" % i
+        lines.append(_json.dumps({"log": inner + "\n" if i % 5 == 0 else inner, "stream": "stdout" if i % 2 else "stderr", "time": "2023-05-06T07:08:09.%03dZ" % (i % 1000)}).encode())
+    return util.chunk_from_lines(lines)
+
+
 def tricky_ts_chunk():
     """Timestamps whose bytes frame as complete legacy events ([uint32, {}]) inside real records:
     the record index has to rule those candidates out (sec = 0x655492ce -> `92 ce 00 00 xx xx 80`)."""
@@ -149,6 +159,11 @@ CASES = [
     ("parser_ra_key", [AP], [("parser", [("Key_Name", "$log"), ("Parser", "apache"), ("Reserve_Data", "On")])], apache_chunk),
     ("types_float_strtod", [dict(name="fl", format="regex", regex=r"^(?<a>[^|]*)\|(?<b>[^|]*)\|(?<n>\d+)$", types="a:float b:float n:integer")],
      [("parser", [("Key_Name", "log"), ("Parser", "fl")]), ("grep", [("Exclude", "n ^7$")])], float_types_chunk),
+    # a parser whose input was made by an earlier filter of the same chain: the fused form refuses, the chain then runs filter by filter on the device
+    ("docker_then_inner_json", [dict(name="docker", format="json", time_key="time", time_fmt="%Y-%m-%dT%H:%M:%S.%LZ"), JS],
+     [("parser", [("Key_Name", "log"), ("Parser", "docker"), ("Reserve_Data", "On")]), ("parser", [("Key_Name", "log"), ("Parser", "json"), ("Reserve_Data", "On"), ("Preserve_Key", "On")]),
+      ("grep", [("Exclude", "stream stderr")])], docker_chunk),
+    ("set_then_parse", [AP], [("modify", [("Set", "log \"GET /x HTTP/1.1\"")]), ("parser", [("Key_Name", "log"), ("Parser", "apache"), ("Reserve_Data", "On")])], mixed_chunk),
     ("tricky_timestamps_parser", [AP], [P], tricky_ts_chunk),
     ("tricky_timestamps_grep", [], [("grep", [("Regex", "log GET")])], tricky_ts_chunk),
     ("json_parser", [JS], [PJ], json_chunk),
