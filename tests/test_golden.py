@@ -190,3 +190,41 @@ def test_time_programs_hostsim(sim_lib, ref_available):
 @pytest.mark.gpu
 def test_time_programs_gpu(gpu_lib, ref_available):
     check_time_programs(gpu_lib)
+
+
+def check_parser_do_sign_and_bytes(lib):
+    """flbgpu_parser_do() / _do_batch() against flb_parser_do() over odd lines for every parser kind: the same
+    lines fail (-1), and the lines that parse give the reference's map and time.  The non-negative value itself is
+    `length` here and a position inside the line in the reference (include/flbgpu.h)."""
+    import cases
+    tf = "%Y-%m-%dT%H:%M:%S.%LZ"
+    parsers = [cases.AP, cases.JS, cases.LF, cases.LT, dict(name="jst", format="json", time_key="time", time_fmt=tf),
+               dict(name="jsk", format="json", time_key="time", time_fmt=tf, time_keep=True, time_strict=False),
+               dict(name="lft", format="logfmt", time_key="time", time_fmt=tf, types="n:integer"), dict(name="lfb", format="logfmt", logfmt_no_bare_keys=True),
+               dict(name="ltt", format="ltsv", time_key="time", time_fmt=tf, time_keep=True, types="n:hex"), dict(name="jse", format="json", skip_empty=False),
+               dict(name="opt", format="regex", regex=r"^(?<a>x)?y(?<b>.*)$"), dict(name="none", format="regex", regex=r"^(?<a>x)?(?<b>q)?y")]
+    lines = (util.apache_lines(20, seed=1) + util.json_lines(20, 2) + util.logfmt_lines(20, 3) + util.ltsv_lines(20) +
+             [b"", b" ", b"\t", b"{}", b"{", b"}", b"[]", b"null", b'""', b"a=", b"=", b":", b"a:", b"\xff\xfe", b'{"a":"\\ud800"}', b'{"a":1e999}', b'{"a":-0}',
+              b'{"a":1E+2}', b'{"a":12345678901234567890}', b'{"a":-9223372036854775809}', b' {"a":1} ', b'{"a":1}{"b":2}', b'{"a":1},', b'{"a":1} trailing',
+              b'{"a":1} 5', b'{"time":"2023-05-06T07:08:09.123Z","n":1}', b'{"time":"nonsense"}', b"time=2023-05-06T07:08:09.5Z n=7 bare", b"time=bad n=x",
+              b"time:2023-05-06T07:08:09.250Z\tn:1f\tempty:", b"a:1\n\tb:2", b"a=1\nb=2", b'a="x', b"y", b"xy tail", b"zzz", b"a\x01:1"])
+    for kw in parsers:
+        ctx, ref = pkg.Context(0, lib=lib), util.Ref()
+        p, rp = ctx.parser(**kw), ref.parser(**kw)
+        batch = p.do_batch(lines)
+        for line, b in zip(lines, batch):
+            r, data, t = p.do(line)
+            rr, rdata, rt = ref.parser_do(rp, line)
+            assert (r, data, t) == b, (kw["name"], line)
+            assert (r < 0) == (rr < 0), (kw["name"], line)
+            if rr >= 0:
+                assert r == len(line) and data == rdata and t == (rt[0] & 0xffffffff, rt[1]), (kw["name"], line)
+
+
+def test_parser_do_sign_and_bytes_hostsim(sim_lib, ref_available):
+    check_parser_do_sign_and_bytes(sim_lib)
+
+
+@pytest.mark.gpu
+def test_parser_do_sign_and_bytes_gpu(gpu_lib, ref_available):
+    check_parser_do_sign_and_bytes(gpu_lib)
