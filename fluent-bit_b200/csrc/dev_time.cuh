@@ -466,10 +466,13 @@ FLB_HD int dt_fast_apache(const uint8_t *s, uint32_t n, struct dt_tm *tm)
     for (m = 0; m < 12; m++)
         if (dt_lower(s[3]) == mon3[3 * m] && dt_lower(s[4]) == mon3[3 * m + 1] && dt_lower(s[5]) == mon3[3 * m + 2]) break;
     if (m == 12) return 0;
-    tm->mday = d[0] * 10 + d[1]; tm->mon = m;
+    {   /* nothing is written unless every field is in range: the general path starts from the caller's zeroed tm,
+         * and in non-strict mode what it leaves half-filled is what the reference reports */
+        const int mday = d[0] * 10 + d[1], hour = d[6] * 10 + d[7], min = d[8] * 10 + d[9], sec = d[10] * 10 + d[11];
+        if (mday < 1 || mday > 31 || hour > 23 || min > 59 || sec > 60) return 0;
+        tm->mday = mday; tm->mon = m; tm->hour = hour; tm->min = min; tm->sec = sec;
+    }
     tm->year = d[2] * 1000 + d[3] * 100 + d[4] * 10 + d[5] - 1900;
-    tm->hour = d[6] * 10 + d[7]; tm->min = d[8] * 10 + d[9]; tm->sec = d[10] * 10 + d[11];
-    if (tm->mday < 1 || tm->mday > 31 || tm->hour > 23 || tm->min > 59 || tm->sec > 60) return 0;
     tm->gmtoff = ((d[12] * 10 + d[13]) * 3600 + ((s[24] - '0') * 10 + (s[25] - '0')) * 60) * (s[21] == '-' ? -1 : 1);
     tm->isdst = 0;
     return 1;

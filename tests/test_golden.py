@@ -129,8 +129,17 @@ def check_apache_time_fast_path(lib):
             "01/Jan/2023:00:00:00 Z", "01/Jan/2023:00:00:00 +0", "01/Jan/2023:00:00:00 -0099", "01/Jan/0000:00:00:00 +0000",
             "01/March/2023:00:00:00 +0000", "01/Jan/2023:00:00:00  +0000", "01/Jan/2023:00:00:00 +000a", " 1/Jan/2023:00:00:00 +0000",
             "31/Apr/2024:07:08:09 -1234", "15/Sep/2038:03:14:08 +0000"]
+    # out-of-range fields: strptime stops there and, when time_strict is off, the half-filled tm is what counts
+    vals += ["28/Jul/2024:12:60:13 -0700", "01/May/1970:12:03:61 +0530", "01/Mar/2000:24:59:61 -1200", "31/Nov/0068:05:59:61 -0700", "09/May/2023:00:60:60 +9999"]
     rp = ref.parser(**kw)
     got = ctx.parser(**kw).do_batch([v.encode() for v in vals])
+    kw2 = dict(kw, name="t2", time_strict=False)
+    rp2 = ref.parser(**kw2)
+    for v, (r, data, (sec, nsec)) in zip(vals, ctx.parser(**kw2).do_batch([v.encode() for v in vals])):
+        rr, rdata, (rsec, rnsec) = ref.parser_do(rp2, v.encode())
+        assert (r >= 0) == (rr >= 0) and data == rdata, v
+        if rr >= 0:
+            assert (sec, nsec) == (rsec & 0xffffffff, rnsec), v
     for v, (r, data, (sec, nsec)) in zip(vals, got):
         rr, rdata, (rsec, rnsec) = ref.parser_do(rp, v.encode())
         assert (r >= 0) == (rr >= 0), v
