@@ -1325,6 +1325,91 @@ static int l2m_merge(flbgpu_chain *c)
     return 0;
 }
 
+
+/* msgpack-c's streaming parser (lib/msgpack-c/include/msgpack/unpack_template.h: template_execute) on the bytes
+ * behind the last whole event: it eats a header byte, then that header's fixed-size part (length field or scalar)
+ * only if all of it is there, then a payload only if all of it is there.  When the buffer runs out exactly at one
+ * of those points, inside the first unfinished object, msgpack_unpack_next() reports CONTINUE with the offset at
+ * the end of the buffer -- which flb_log_event_decoder_next() turns into INSUFFICIENT_DATA and the filters
+ * (grep.c:357-360, modify.c) accept as a clean end when `offset == bytes`.  1 = that is the case for b[0..n). */
+static int msgpack_tail_runs_out_cleanly(const uint8_t *b, size_t n)
+{
+    size_t p = 0;
+    uint64_t open[64];                  /* elements still owed per open container */
+    int depth = 0;
+    if (n == 0) return 1;
+    for (;;) {
+        uint32_t c, fixed = 0, is_len = 0, items = 0, is_container = 0;
+        uint64_t payload = 0;
+        if (p == n) return 1;                                   /* ran out between two objects of an open container */
+        c = b[p++];
+        if (c <= 0x7f || c >= 0xe0 || c == 0xc0 || c == 0xc2 || c == 0xc3) { }
+        else if (c >= 0xa0 && c <= 0xbf) payload = c & 31;
+        else if (c >= 0x90 && c <= 0x9f) { is_container = 1; items = c & 15; }
+        else if (c >= 0x80 && c <= 0x8f) { is_container = 1; items = 2 * (c & 15); }
+        else switch (c) {
+        case 0xcc: case 0xd0: fixed = 1; break;
+        case 0xcd: case 0xd1: fixed = 2; break;
+        case 0xce: case 0xd2: case 0xca: fixed = 4; break;
+        case 0xcf: case 0xd3: case 0xcb: fixed = 8; break;
+        case 0xd4: fixed = 2; break; case 0xd5: fixed = 3; break; case 0xd6: fixed = 5; break;
+        case 0xd7: fixed = 9; break; case 0xd8: fixed = 17; break;
+        case 0xd9: case 0xc4: fixed = 1; is_len = 1; break;
+        case 0xda: case 0xc5: fixed = 2; is_len = 1; break;
+        case 0xdb: case 0xc6: fixed = 4; is_len = 1; break;
+        case 0xc7: fixed = 1; is_len = 2; break;
+        case 0xc8: fixed = 2; is_len = 2; break;
+        case 0xc9: fixed = 4; is_len = 2; break;
+        case 0xdc: fixed = 2; is_len = 3; break;
+        case 0xdd: fixed = 4; is_len = 3; break;
+        case 0xde: fixed = 2; is_len = 4; break;
+        case 0xdf: fixed = 4; is_len = 4; break;
+        default: return 0;                                      /* 0xc1: a parse error, not a shortage */
+        }
+        if (fixed) {
+            uint64_t v = 0;
+            uint32_t i;
+            if (n - p < fixed) return p == n;                   /* stops behind the header byte */
+            for (i = 0; i < fixed; i++) v = (v << 8) | b[p + i];
+            p += fixed;
+            if (is_len == 1) payload = v;
+            else if (is_len == 2) payload = v + 1;              /* ext: type byte + data */
+            else if (is_len == 3) { is_container = 1; items = (uint32_t) v; if (v > 0x7fffffffu) return 0; }
+            else if (is_len == 4) { is_container = 1; if (v > 0x3fffffffu) return 0; items = (uint32_t) (2 * v); }
+        }
+        if (payload) {
+            if (n - p < payload) return p == n;                 /* stops where the payload begins */
+            p += (size_t) payload;
+        }
+        if (is_container && items) {
+            if (depth >= 64) return 0;
+            open[depth++] = items;
+            continue;
+        }
+        /* one object done: pay it to the containers it closes */
+        for (;;) {
+            if (depth == 0) return 0;                           /* a whole top-level object fits: not a shortage */
+            if (--open[depth - 1]) break;
+            depth--;
+        }
+    }
+}
+
+/* `clean`: the decodable prefix is the whole chunk, or what follows it is an event cut short at a point where the
+ * reference's decoder still reports `offset == bytes` (see above) */
+static int ends_cleanly(const uint8_t *h_in, const uint8_t *d_in, size_t off, size_t bytes)
+{
+    uint8_t *tmp;
+    int r;
+    if (off == bytes) return 1;
+    if (h_in) return msgpack_tail_runs_out_cleanly(h_in + off, bytes - off);
+    tmp = malloc(bytes - off);
+    if (!tmp) return 0;
+    r = (bk_d2h(tmp, d_in + off, bytes - off) || bk_sync()) ? 0 : msgpack_tail_runs_out_cleanly(tmp, bytes - off);
+    free(tmp);
+    return r;
+}
+
 /* The record index frames events whose root and header arrays are fixarrays (0x92), which is all msgpack-c's
  * packer ever writes for two elements.  The reference's decoder would also take the same arrays spelled as
  * array16 / array32: when the decodable prefix stops at such a spelling the call is refused, not cut short. */
@@ -1408,7 +1493,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         n_rec += n_valid;
         off = (size_t) end_off;
     }
-    clean = (off == bytes);
+    clean = ends_cleanly(h_in, d_in, off, bytes);
     REFUSE_WIDE_ARRAYS(h_in, d_in, return -1);
     c->st.records_in = n_rec;
     c->st.passes = 1;
@@ -1659,7 +1744,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
         n_rec += n_valid;
         off = (size_t) end_off;
     }
-    clean = (off == bytes);
+    clean = ends_cleanly(h_in, c->d_in, off, bytes);
     REFUSE_WIDE_ARRAYS(h_in, c->d_in, goto fail);
     c->st.records_in = n_rec;
     c->st.passes = 1;

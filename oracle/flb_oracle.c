@@ -417,6 +417,76 @@ int orc_filter_init(struct orc_config *cfg, struct orc_filter *f)
     }
 }
 
+
+/* msgpack-c's streaming parser (lib/msgpack-c/include/msgpack/unpack_template.h: template_execute) on the bytes
+ * behind the last whole event: it eats a header byte, then that header's fixed-size part (length field or scalar)
+ * only if all of it is there, then a payload only if all of it is there.  When the buffer runs out exactly at one
+ * of those points, inside the first unfinished object, msgpack_unpack_next() reports CONTINUE with the offset at
+ * the end of the buffer -- which flb_log_event_decoder_next() turns into INSUFFICIENT_DATA and the filters
+ * (grep.c:357-360, modify.c) accept as a clean end when `offset == bytes`.  1 = that is the case for b[0..n). */
+static int tail_runs_out_cleanly(const uint8_t *b, size_t n)
+{
+    size_t p = 0;
+    uint64_t open[64];                  /* elements still owed per open container */
+    int depth = 0;
+    if (n == 0) return 1;
+    for (;;) {
+        uint32_t c, fixed = 0, is_len = 0, items = 0, is_container = 0;
+        uint64_t payload = 0;
+        if (p == n) return 1;                                   /* ran out between two objects of an open container */
+        c = b[p++];
+        if (c <= 0x7f || c >= 0xe0 || c == 0xc0 || c == 0xc2 || c == 0xc3) { }
+        else if (c >= 0xa0 && c <= 0xbf) payload = c & 31;
+        else if (c >= 0x90 && c <= 0x9f) { is_container = 1; items = c & 15; }
+        else if (c >= 0x80 && c <= 0x8f) { is_container = 1; items = 2 * (c & 15); }
+        else switch (c) {
+        case 0xcc: case 0xd0: fixed = 1; break;
+        case 0xcd: case 0xd1: fixed = 2; break;
+        case 0xce: case 0xd2: case 0xca: fixed = 4; break;
+        case 0xcf: case 0xd3: case 0xcb: fixed = 8; break;
+        case 0xd4: fixed = 2; break; case 0xd5: fixed = 3; break; case 0xd6: fixed = 5; break;
+        case 0xd7: fixed = 9; break; case 0xd8: fixed = 17; break;
+        case 0xd9: case 0xc4: fixed = 1; is_len = 1; break;
+        case 0xda: case 0xc5: fixed = 2; is_len = 1; break;
+        case 0xdb: case 0xc6: fixed = 4; is_len = 1; break;
+        case 0xc7: fixed = 1; is_len = 2; break;
+        case 0xc8: fixed = 2; is_len = 2; break;
+        case 0xc9: fixed = 4; is_len = 2; break;
+        case 0xdc: fixed = 2; is_len = 3; break;
+        case 0xdd: fixed = 4; is_len = 3; break;
+        case 0xde: fixed = 2; is_len = 4; break;
+        case 0xdf: fixed = 4; is_len = 4; break;
+        default: return 0;                                      /* 0xc1: a parse error, not a shortage */
+        }
+        if (fixed) {
+            uint64_t v = 0;
+            uint32_t i;
+            if (n - p < fixed) return p == n;                   /* stops behind the header byte */
+            for (i = 0; i < fixed; i++) v = (v << 8) | b[p + i];
+            p += fixed;
+            if (is_len == 1) payload = v;
+            else if (is_len == 2) payload = v + 1;              /* ext: type byte + data */
+            else if (is_len == 3) { is_container = 1; items = (uint32_t) v; if (v > 0x7fffffffu) return 0; }
+            else if (is_len == 4) { is_container = 1; if (v > 0x3fffffffu) return 0; items = (uint32_t) (2 * v); }
+        }
+        if (payload) {
+            if (n - p < payload) return p == n;                 /* stops where the payload begins */
+            p += (size_t) payload;
+        }
+        if (is_container && items) {
+            if (depth >= 64) return 0;
+            open[depth++] = items;
+            continue;
+        }
+        /* one object done: pay it to the containers it closes */
+        for (;;) {
+            if (depth == 0) return 0;                           /* a whole top-level object fits: not a shortage */
+            if (--open[depth - 1]) break;
+            depth--;
+        }
+    }
+}
+
 /* grep.c:167-194 (legacy) and :250-284 (AND / OR) */
 static int grep_keep(const struct orc_filter *f, const struct ov *map)
 {
@@ -452,7 +522,7 @@ static int cb_grep(struct orc_filter *f, const uint8_t *in, size_t len, struct o
     }
     orc_arena_free(&a);
     if (old == kept) return ORC_NOTOUCH;
-    if (!(r == 1 && off == len)) return ORC_NOTOUCH;     /* decoder stopped early: "Log event encoder error" */
+    if (!(r == 1 && (off == len || tail_runs_out_cleanly(in + off, len - off)))) return ORC_NOTOUCH;     /* decoder stopped early: "Log event encoder error" */
     return ORC_MODIFIED;
 }
 
@@ -674,7 +744,7 @@ static int cb_modify(struct orc_filter *f, const uint8_t *in, size_t len, struct
     }
     orc_arena_free(&a);
     if (total == 0) return ORC_NOTOUCH;
-    if (!(r == 1 && off == len)) return ORC_NOTOUCH;
+    if (!(r == 1 && (off == len || tail_runs_out_cleanly(in + off, len - off)))) return ORC_NOTOUCH;
     return ORC_MODIFIED;
 }
 

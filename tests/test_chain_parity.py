@@ -148,6 +148,29 @@ def test_degenerate_modify_rules_are_refused(sim_lib, ref_available):
         util.Ref().filter("modify", [(rule, "k2 k2")])          # accepted there
 
 
+def _truncated_tails(lib):
+    """a chunk cut at every byte of its last event: grep / modify call it a clean end exactly when msgpack-c's
+    streaming parser eats the whole tail (header bytes, complete length fields, complete payloads)"""
+    S = util.mp_str
+    head = util.chunk_from_lines(util.apache_lines(6, seed=41))
+    last = util.event(1700000100, 5, [(b"log", S(b"POST /cut HTTP/1.1 " + b"x" * 40)), (b"n", b"\xcd\x12\x34"), (b"b", b"\xc4\x03abc"), (b"e", b"\xc7\x02\x05hi"),
+                                      (b"a", b"\x92\x01\xa0"), (b"m", b"\xde\x00\x01" + S(b"k") + b"\xcb" + struct.pack(">d", 1.5)), (b"s", b"\xda\x00\x04long")],
+                      meta=b"\x81" + S(b"t") + b"\xd6\x01abcd")
+    for cut in range(0, len(last) + 1):
+        data = head + last[:cut]
+        for filters in ([("grep", [("Exclude", "log GET")])], [("modify", [("Condition", "Key_value_matches log GET"), ("Add", "m 1")])], [cases.P]):
+            run_case(lib, [cases.AP], filters, data)
+
+
+def test_truncated_tails_hostsim(sim_lib, ref_available):
+    _truncated_tails(sim_lib)
+
+
+@pytest.mark.gpu
+def test_truncated_tails_gpu(gpu_lib, ref_available):
+    _truncated_tails(gpu_lib)
+
+
 def test_decoder_forms_hostsim(sim_lib, ref_available):
     _decoder(sim_lib)
 
