@@ -1802,6 +1802,30 @@ FLB_HDN void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct
     }
 }
 
+/* Events the decoder steps over (group markers, negative timestamps: kind 1 in the record index) are still
+ * objects of the chunk for log_to_metrics, which walks it with msgpack_unpack_next() and takes element 1 of
+ * every root array as the map (log_to_metrics.c:993-1003).  It sees them when no earlier filter of the chain
+ * rewrote the chunk -- a rewritten chunk holds decoded events only. */
+FLB_HDN void chain_skipped_record(const struct ch_env *e, uint32_t ridx, uint32_t off, uint32_t len)
+{
+    const struct chain_hdr *h = (const struct chain_hdr *) e->blob;
+    const struct chain_filter *f = (const struct chain_filter *) (e->blob + h->filters_off);
+    struct ch_env le;
+    uint32_t k;
+    for (k = 0; k < h->n_filters; k++) {
+        if (f[k].kind == FLBGPU_F_LOG_TO_METRICS) break;
+        if ((e->assume >> k) & 1) return;
+    }
+    if (k == h->n_filters) return;
+    {
+        struct ch_rec rc;
+        struct ch_scratch w;
+        if (e->scr) { le = *e; le.scr = e->scr + (size_t) 4 * off; e = &le; }
+        if (rec_decode(e, off, len, &rc, h->empty_map_off) != 0) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return; }
+        f_l2m(e, (const struct cf_l2m *) (e->blob + f[k].cfg_off), &rc, &w, ridx);
+    }
+}
+
 /* ------------------------------------------------------------- the chain */
 /* Runs record `ridx` (framed at off/len, kind 0) through the chain.
  * EMIT=false: returns the output size (0 = dropped) and records evidence.

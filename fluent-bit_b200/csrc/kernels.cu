@@ -305,6 +305,16 @@ __global__ void __launch_bounds__(BK_REC_BLOCK, BK_EVAL_MIN_BLOCKS) k_chain_eval
     __stcs(&p.size[i], sz);
 }
 
+/* Chains with a log_to_metrics filter only: the events the decoder steps over (kind 1: group markers, negative
+ * timestamps) are counted by that filter as long as nothing before it rewrote the chunk (chain_skipped_record).
+ * A kernel of its own so that k_chain_eval stays what it is for every other chain. */
+__global__ void __launch_bounds__(BK_REC_BLOCK) k_chain_skipped(const k_chain_params p)
+{
+    const uint32_t i = p.r0 + blockIdx.x * BK_REC_BLOCK + threadIdx.x;
+    if (i >= p.n_rec || p.kind[i] != 1) return;
+    chain_skipped_record(&p.env, i, p.off[i], p.len[i]);
+}
+
 /* per-block sums of the record sizes */
 __global__ void __launch_bounds__(BK_REC_BLOCK) k_bsum(const uint32_t *__restrict__ size, uint32_t n, uint64_t *__restrict__ bsum)
 {
@@ -833,6 +843,10 @@ int bk_chain_eval(const struct bk_chain_args *a, uint32_t r0, uint32_t r1)
     }
     ev_begin(1);
     k_chain_eval<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, (size_t) p.stage_bytes * (BK_REC_BLOCK / 32), g_stream>>>(p);
+    if (p.env.l2m.hash) {
+        k_chain_skipped<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, 0, g_stream>>>(p);
+        g_launches += 1;
+    }
     ev_end(1);
     g_launches += 1;
     CK(cudaGetLastError());

@@ -186,6 +186,7 @@ int bk_chain_eval(const struct bk_chain_args *a, uint32_t r0, uint32_t r1)
     for (i = r0; i < r1; i++) {
         uint32_t sz = 0;
         if (a->d_kind[i] == 0) sz = chain_record<false>(&e, i, a->d_off[i], a->d_len[i], 0);
+        else if (a->d_kind[i] == 1 && e.l2m.hash) chain_skipped_record(&e, i, a->d_off[i], a->d_len[i]);
         a->d_size[i] = sz;
     }
     hs_launches += 1;

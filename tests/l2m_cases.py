@@ -69,6 +69,18 @@ def float_label(rng):
     return [(b"ratio", rng.randrange(-(1 << 30), 1 << 30) / (1 << rng.randrange(0, 40)))]      # dyadic: exact ties happen
 
 
+def grouped_events(seed):
+    rng = random.Random(seed)
+    out = []
+    for g in range(6):
+        out.append(util.event(0xffffffff, 0, [(b"color", util.mp_str(b"group-%d" % (g % 2))), (b"duration", _mp(3))]))
+        out.append(events(rng.randrange(5, 40), seed * 10 + g))
+        if g % 3 == 0:
+            out.append(util.event(0x80000005, 1, [(b"color", util.mp_str(b"negative")), (b"duration", _mp(0.25))]))
+        out.append(util.event(0xfffffffe, 0, []))
+    return b"".join(out)
+
+
 BASE = [("metric_name", "reqs"), ("metric_description", "requests"), ("tag", "metrics")]
 
 L2M_CASES = [
@@ -122,6 +134,15 @@ L2M_CASES = [
     # no label keys: cmetrics' static metric is there, at 0, before anything is counted
     ("counter_static_metric_at_zero", [], [("log_to_metrics", BASE + [("regex", "message ^nothing matches this$")])], lambda: events(50, 19), 0),
     ("gauge_static_metric_at_zero", [], [("log_to_metrics", BASE + [("metric_mode", "gauge"), ("value_field", "absent")])], lambda: events(50, 20), 0),
+    # group markers and negative timestamps: skipped by the event decoder, but objects of the chunk for log_to_metrics
+    # (msgpack_unpack_next, log_to_metrics.c:993) as long as no earlier filter rewrote the chunk
+    ("counter_group_markers", [], [("log_to_metrics", BASE + [("label_field", "color")])], lambda: grouped_events(21), 0),
+    ("counter_group_markers_after_notouch_grep", [], [("grep", [("Regex", "color .")]), ("log_to_metrics", BASE + [("label_field", "color")]),
+                                                       ("modify", [("Add", "seen yes")])], lambda: grouped_events(22), 1),
+    ("counter_group_markers_after_grep", [], [("grep", [("Exclude", "color blue")]), ("log_to_metrics", BASE + [("label_field", "color")])],
+     lambda: grouped_events(23), 1),
+    ("histogram_group_markers_discard", [], [("log_to_metrics", BASE + [("metric_mode", "histogram"), ("value_field", "duration"), ("label_field", "color"),
+                                                                        ("discard_logs", "on")])], lambda: grouped_events(24), 0),
     ("gauge_labels", [], [("log_to_metrics", BASE + [("metric_mode", "gauge"), ("value_field", "duration"), ("label_field", "color"),
                                                      ("add_label", "pod $kubernetes['pod_name']")])], lambda: events(900, 15), 0),
     ("gauge_regex_no_labels", [], [("log_to_metrics", BASE + [("metric_mode", "gauge"), ("value_field", "$code"), ("regex", "message ^ok"),
