@@ -66,6 +66,13 @@ def record(rng, i):
     return b"\x92\x92\xd7\x00" + struct.pack(">II", 1700000000 + i, i % 1000) + meta + body
 
 
+def marker(rng):
+    """group start / end and other events with a negative timestamp: stepped over by the event decoder"""
+    sec = rng.choice([0xffffffff, 0xfffffffe, 0x80000001, 0xfffffffd])
+    n = rng.choice([0, 1, 2])
+    return b"\x92\x92\xd7\x00" + struct.pack(">II", sec, 0) + b"\x80" + util.mp_map_hdr(n) + b"".join(key(rng) + value(rng) for _ in range(n))
+
+
 RA = ["log", "level", "k1", "$nest['k1']", "$nest['nest']['k2']", "$arr[1]", "$arr[0]['k1']", "$k1", "msg", "$nest", "$arr", "n", "flag", "$log['x']"]
 RX = ["GET", "^(warn|error)$", ".", "^$", "sample[0-9]", "^[a-z][0-9]$", "true", "a b", "1", "\\d+", "^x"]
 
@@ -183,7 +190,7 @@ def main(seed, rounds):
     lib = pkg.load(util.HOSTSIM_SO)
     bad = refused = rejected = 0
     for rd in range(rounds):
-        chunk = b"".join(record(rng, i) for i in range(rng.choice([1, 5, 40])))
+        chunk = b"".join(record(rng, i) if rng.random() < 0.93 else marker(rng) for i in range(rng.choice([1, 5, 40])))
         filters = [(k, MAKERS[k](rng)) for k in (rng.choice(list(MAKERS)) for _ in range(rng.choice([1, 1, 2, 3])))]
         if sum(k == "log_to_metrics" for k, _ in filters) > 1:
             continue                                          # one metrics filter per fused chain
