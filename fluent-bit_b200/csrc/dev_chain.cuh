@@ -1292,7 +1292,12 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                 got = pdef_json<EMIT>(e, pd, val_off, vp, vn, direct ? rc->k : w->tk, direct ? rc->v : w->tv, direct ? rc->kh : w->th,
                                       &cnt, &ts, &tns, ridx, cache_pos);
                 if (got) { style = ST_CANON; in_place = direct; }
-                else if (direct) rec_decode(e, rec_off, rec_len, rc, empty_map_off);
+                else if (direct) {
+                    /* (the time an earlier key of the same name parsed stays: filter_parser.c:296-300 keeps the last non-zero one) */
+                    const int64_t s0 = rc->ts_sec, n0 = rc->ts_nsec;
+                    rec_decode(e, rec_off, rec_len, rc, empty_map_off);
+                    rc->ts_sec = s0; rc->ts_nsec = n0;
+                }
             }
             else if (pd->type == FLBGPU_PARSER_LTSV) {
                 got = pdef_ltsv(e, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns);

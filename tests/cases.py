@@ -134,6 +134,15 @@ def docker_chunk():
     return util.chunk_from_lines(lines)
 
 
+def dup_key_chunk():
+    S = util.mp_str
+    t1 = S(b"time=2023-05-06T07:08:09.5Z a=1")
+    recs = [[(b"k1", t1), (b"k1", S(b"v"))], [(b"k1", S(b"v")), (b"k1", t1)], [(b"k1", t1), (b"k1", S(b"{"))],
+            [(b"k1", t1), (b"x", S(b"y")), (b"k1", S(b'{"time":"2024-01-01T00:00:00.0Z","b":2}')), (b"k1", S(b"c=3"))],
+            [(b"k1", S(b'{"time":"2024-01-01T00:00:00.25Z"}')), (b"k1", S(b'{"q":1}'))]] * 4
+    return b"".join(util.event(1700000000 + i, 7, f) for i, f in enumerate(recs))
+
+
 def tricky_ts_chunk():
     """Timestamps whose bytes frame as complete legacy events ([uint32, {}]) inside real records:
     the record index has to rule those candidates out (sec = 0x655492ce -> `92 ce 00 00 xx xx 80`)."""
@@ -164,6 +173,11 @@ CASES = [
      [("parser", [("Key_Name", "log"), ("Parser", "docker"), ("Reserve_Data", "On")]), ("parser", [("Key_Name", "log"), ("Parser", "json"), ("Reserve_Data", "On"), ("Preserve_Key", "On")]),
       ("grep", [("Exclude", "stream stderr")])], docker_chunk),
     ("set_then_parse", [AP], [("modify", [("Set", "log \"GET /x HTTP/1.1\"")]), ("parser", [("Key_Name", "log"), ("Parser", "apache"), ("Reserve_Data", "On")])], mixed_chunk),
+    # several keys named like Key_Name: each is parsed in turn, the last one decides the body, the last non-zero time stays
+    ("parser_duplicate_key_names", [dict(name="jst", format="json", time_key="time", time_fmt="%Y-%m-%dT%H:%M:%S.%LZ"),
+                                    dict(name="lft", format="logfmt", time_key="time", time_fmt="%Y-%m-%dT%H:%M:%S.%LZ", types="n:integer")],
+     [("parser", [("Key_Name", "k1"), ("Parser", "jst"), ("Parser", "lft")])],
+     dup_key_chunk),
     ("tricky_timestamps_parser", [AP], [P], tricky_ts_chunk),
     ("tricky_timestamps_grep", [], [("grep", [("Regex", "log GET")])], tricky_ts_chunk),
     ("json_parser", [JS], [PJ], json_chunk),

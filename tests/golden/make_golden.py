@@ -126,7 +126,7 @@ def main():
              "nginx_chunk": lambda: util.chunk_from_lines(util.apache_lines(60, seed=12, nginx=True)),
              "tricky_ts_chunk": lambda: cases.tricky_ts_chunk()[:30000 * 0 + len(b"".join(cases.tricky_ts_chunk()[o:o + l] for o, l in util.split_records(cases.tricky_ts_chunk())[:60]))],
              "mixed_chunk": lambda: cases.mixed_chunk()[:20000]}
-    small.update({"logfmt_escape_chunk": cases.logfmt_escape_chunk, "float_types_chunk": cases.float_types_chunk,
+    small.update({"logfmt_escape_chunk": cases.logfmt_escape_chunk, "float_types_chunk": cases.float_types_chunk, "dup_key_chunk": cases.dup_key_chunk,
                   "docker_chunk": lambda: b"".join(cases.docker_chunk()[o:o + l] for o, l in util.split_records(cases.docker_chunk())[:40])})
     small.update({"wide_apache_chunk": lambda: b"".join(cases.wide_apache_chunk()[o:o + l] for o, l in util.split_records(cases.wide_apache_chunk())[:40]),
                   "wide_json_chunk": lambda: b"".join(cases.wide_json_chunk()[o:o + l] for o, l in util.split_records(cases.wide_json_chunk())[:40])})

@@ -226,6 +226,27 @@ def main(seed, rounds):
             if k == "log_to_metrics" and f.l2m_text() != l2m_ref_text(ref, rf):
                 bad += 1
                 print("METRICS MISMATCH seed=%d round=%d filters=%r\n got  %r\n want %r" % (seed, rd, filters, f.l2m_text()[:300], l2m_ref_text(ref, rf)[:300]))
+        # the same filters called one by one, as the reference's flb_filter_do() would call the shim's cb_filter
+        c3 = pkg.Context(0, lib=lib)
+        for kw in PARSERS:
+            c3.parser(**kw)
+        cur, changed, seq = chunk, False, None
+        try:
+            for p_, props in filters:
+                r3, o3 = c3.filter(p_, props).cb(cur)
+                if r3 == 1:
+                    changed = True
+                    if not o3:
+                        seq = (1, o3)                     # nothing left: the chain ends here
+                        break
+                    cur = o3
+            if seq is None:
+                seq = (1, cur) if changed else (2, None)
+            if seq != want:
+                bad += 1
+                print("PER-FILTER MISMATCH seed=%d round=%d filters=%r" % (seed, rd, filters))
+        except pkg.FlbGpuError:
+            pass
         if got != want:
             bad += 1
             print("MISMATCH seed=%d round=%d filters=%r" % (seed, rd, filters))
