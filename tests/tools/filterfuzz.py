@@ -40,6 +40,14 @@ def value(rng, depth=0):
         return bytes([0xc4, len(w)]) + w
     if r < 0.78:
         return b"\xd4\x05\x01" if rng.random() < 0.5 else b"\xc7\x03\x07abc"
+    if r < 0.82:
+        # spellings msgpack-c would not write (wider than needed): the reference re-packs them, raw copies keep them
+        w = rng.choice(WORDS)[:200]
+        return rng.choice([b"\xd9" + bytes([len(w)]) + w, b"\xda" + struct.pack(">H", len(w)) + w, b"\xdb" + struct.pack(">I", len(w)) + w,
+                           b"\xcd\x00\x05", b"\xce\x00\x00\x00\x05", b"\xcf" + struct.pack(">Q", 5), b"\xd1\xff\xfb", b"\xd2\xff\xff\xff\xfb",
+                           b"\xd3" + struct.pack(">q", -5), b"\xd3" + struct.pack(">q", 5), b"\xde\x00\x01" + S(b"k1") + b"\xcd\x00\x07",
+                           b"\xdf\x00\x00\x00\x00", b"\xdc\x00\x02\x01\xd9\x01x", b"\xdd\x00\x00\x00\x00", b"\xc5\x00\x02ab", b"\xc6\x00\x00\x00\x01z",
+                           b"\xc8\x00\x01\x09q", b"\xca" + struct.pack(">f", 0.1)])
     if depth < 2 and r < 0.9:
         n = rng.randrange(0, 4)
         return util.mp_map_hdr(n) + b"".join(key(rng) + value(rng, depth + 1) for _ in range(n))
@@ -51,8 +59,11 @@ def value(rng, depth=0):
 
 def key(rng):
     r = rng.random()
-    if r < 0.9:
+    if r < 0.85:
         return S(rng.choice(KEYS))
+    if r < 0.9:
+        k = rng.choice(KEYS)                       # a key spelled wider than needed
+        return rng.choice([b"\xd9" + bytes([len(k)]) + k, b"\xda" + struct.pack(">H", len(k)) + k, b"\xc5" + struct.pack(">H", len(k)) + k])
     if r < 0.95:
         k = rng.choice(KEYS)
         return bytes([0xc4, len(k)]) + k
