@@ -72,11 +72,19 @@ def main(seed, ndocs):
         chunk = util.chunk_from_lines(docs)
         ctx = pkg.Context(0, lib=lib)
         ref = util.Ref()
-        kw = dict(name="js", format="json", time_key="t", time_fmt="%s")
+        kw = dict(name="js", format="json", time_key="t", time_fmt="%s", time_keep=rng.random() < 0.5, skip_empty=rng.random() < 0.5,
+                  time_strict=rng.random() < 0.5)
         ctx.parser(**kw); ref.parser(**kw)
-        props = [("Key_Name", "log"), ("Parser", "js"), ("Reserve_Data", rng.choice(["On", "Off"]))]
-        f = ctx.filter("parser", props)
+        props = [("Key_Name", "log"), ("Parser", "js"), ("Reserve_Data", rng.choice(["On", "Off"])), ("Preserve_Key", rng.choice(["On", "Off"]))]
+        # what follows the parser in a fused chain works on the parsed field list: keys of every kind of value
+        tail = rng.choice([[], [("grep", [("Exclude", "a ^x")])], [("modify", [("Rename", "a b"), ("Remove_wildcard", "k"), ("Add", "z 1")])],
+                           [("record_modifier", [("Remove_key", "a"), ("Record", "h n")])], [("grep", [("Regex", "$a['b'] .")]), ("modify", [("Copy", "t t2")])]])
+        fs = [ctx.filter("parser", props)] + [ctx.filter(p_, pr) for p_, pr in tail]
         ref.filter("parser", props)
+        for p_, pr in tail:
+            ref.filter(p_, pr)
+        f = ctx.chain(fs)
+        f.cb = f.do
         want = ref.chain_do(chunk)
         try:
             got = f.cb(chunk)
@@ -89,13 +97,15 @@ def main(seed, ndocs):
             for d in docs:
                 c1 = util.chunk_from_lines([d])
                 r2 = util.Ref(); r2.parser(**kw); r2.filter("parser", props)
+                for p_, pr in tail:
+                    r2.filter(p_, pr)
                 c2 = pkg.Context(0, lib=lib); c2.parser(**kw)
                 try:
-                    g = c2.filter("parser", props).cb(c1)
+                    g = c2.chain([c2.filter("parser", props)] + [c2.filter(p_, pr) for p_, pr in tail]).do(c1)
                 except pkg.FlbGpuError:
                     continue
                 if g != r2.chain_do(c1):
-                    print("MISMATCH", d)
+                    print("MISMATCH", d, kw, props, tail)
                     break
     print("docs", ndocs, "bad batches", bad)
     return bad
