@@ -841,7 +841,7 @@ static uint32_t emit_modify_filter(flbgpu_filter *f, struct blob *b)
             else if (nt == 2) {
                 if (!strcasecmp(p->k, "rename")) type = MOD_RENAME;
                 else if (!strcasecmp(p->k, "hard_rename")) type = MOD_HARD_RENAME;
-                else if (!strcasecmp(p->k, "add") || !strcasecmp(p->k, "add_if_not_present")) type = MOD_ADD;
+                else if (!strcasecmp(p->k, "add")) type = MOD_ADD;       /* (add_if_not_present is handled in setup() but absent from the config map: flb_start() refuses it) */
                 else if (!strcasecmp(p->k, "set")) type = MOD_SET;
                 else if (!strcasecmp(p->k, "copy")) type = MOD_COPY;
                 else if (!strcasecmp(p->k, "hard_copy")) type = MOD_HARD_COPY;
@@ -849,7 +849,7 @@ static uint32_t emit_modify_filter(flbgpu_filter *f, struct blob *b)
             else if (nt == 3) {
                 /* modify.c:412-466 only names a rule type for one or two words; with three the calloc()ed rule keeps
                  * type 0 = RENAME, key = first word, value = last word -- whatever the property was called */
-                static const char *known[] = { "set", "add", "add_if_not_present", "remove", "remove_wildcard", "remove_regex", "rename",
+                static const char *known[] = { "set", "add", "remove", "remove_wildcard", "remove_regex", "rename",
                                                "hard_rename", "copy", "hard_copy", "move_to_start", "move_to_end" };
                 size_t q;
                 for (q = 0; q < sizeof(known) / sizeof(known[0]); q++) if (!strcasecmp(p->k, known[q])) type = MOD_RENAME;
@@ -910,8 +910,8 @@ static uint32_t emit_recmod_filter(flbgpu_filter *f, struct blob *b)
         }
         else if (!strcasecmp(p->k, "remove_key")) {
             uint32_t l = (uint32_t) strlen(p->v);
-            if (cf.n_remove >= 64 || l == 0) { set_err("invalid Remove_key%s%s", NULL, NULL); return 0; }
-            rem[cf.n_remove].dynamic = p->v[l - 1] == '*';
+            if (cf.n_remove >= 64) { set_err("too many Remove_key entries%s%s", NULL, NULL); return 0; }
+            rem[cf.n_remove].dynamic = l > 0 && p->v[l - 1] == '*';
             if (rem[cf.n_remove].dynamic) l--;
             rem[cf.n_remove].off = blob_add(b, p->v, l, 1); rem[cf.n_remove].len = l; rem[cf.n_remove].pad = 0;
             cf.n_remove++;
@@ -925,8 +925,8 @@ static uint32_t emit_recmod_filter(flbgpu_filter *f, struct blob *b)
             uint32_t l;
             if (strcasecmp(p->k, pass == 0 ? "allowlist_key" : "whitelist_key")) continue;
             l = (uint32_t) strlen(p->v);
-            if (cf.n_allow >= 64 || l == 0) { set_err("invalid Allowlist_key%s%s", NULL, NULL); return 0; }
-            allow[cf.n_allow].dynamic = p->v[l - 1] == '*';
+            if (cf.n_allow >= 64) { set_err("too many Allowlist_key entries%s%s", NULL, NULL); return 0; }
+            allow[cf.n_allow].dynamic = l > 0 && p->v[l - 1] == '*';
             if (allow[cf.n_allow].dynamic) l--;
             allow[cf.n_allow].off = blob_add(b, p->v, l, 1); allow[cf.n_allow].len = l; allow[cf.n_allow].pad = 0;
             cf.n_allow++;
@@ -1094,12 +1094,35 @@ static uint32_t emit_filter(flbgpu_filter *f, struct blob *b, uint32_t *cap_need
     return 0;
 }
 
+/* flb_config_map_properties_check() (src/flb_config_map.c:523-530): a property whose config map entry is not
+ * FLB_CONFIG_MAP_MULT may be set once.  The names below are the MULT entries of the five plugins' maps. */
+static int single_valued_set_twice(flbgpu_filter *f)
+{
+    static const char *mult[] = { "regex", "exclude",                                   /* grep, log_to_metrics */
+                                  "parser",                                             /* parser */
+                                  "record", "remove_key", "allowlist_key", "whitelist_key",   /* record_modifier */
+                                  "set", "add", "remove", "remove_wildcard", "remove_regex", "move_to_start", "move_to_end", "rename",
+                                  "hard_rename", "copy", "hard_copy", "condition",            /* modify */
+                                  "add_label", "label_field", "bucket" };                     /* log_to_metrics */
+    struct kv *p, *q;
+    for (p = f->props; p; p = p->next) {
+        size_t m;
+        int is_mult = 0, n = 0;
+        for (m = 0; m < sizeof(mult) / sizeof(mult[0]); m++) if (!strcasecmp(p->k, mult[m])) is_mult = 1;
+        if (is_mult) continue;
+        for (q = f->props; q; q = q->next) if (!strcasecmp(p->k, q->k)) n++;
+        if (n > 1) { set_err("configuration property '%s' is set more than once%s", p->k, NULL); return 1; }
+    }
+    return 0;
+}
+
 int flbgpu_filter_init(flbgpu_filter *f)
 {
     struct blob b;
     uint32_t cap = 0, off;
     if (!f) return -1;
     g_rt_err[0] = 0;
+    if (single_valued_set_twice(f)) return -1;
     memset(&b, 0, sizeof(b));
     blob_reserve(&b, sizeof(struct chain_hdr), 16);
     off = emit_filter(f, &b, &cap);         /* validation pass; the chain re-emits */

@@ -322,7 +322,6 @@ int orc_filter_init(struct orc_config *cfg, struct orc_filter *f)
                 struct mod_rule *r = &f->mrules[f->n_mrules];
                 int t = -1;
                 for (i = 0; i < 11; i++) if (!strcasecmp(p->k, rn[i])) t = i;
-                if (!strcasecmp(p->k, "add_if_not_present")) t = R_ADD;
                 if (t < 0 || nt < 1 || nt > 3 || f->n_mrules >= 256) return -1;
                 {   /* modify.c:412-466: one word names the removal / move rules, two words the others; three words leave
                      * the calloc()ed type 0 = RENAME in place, with the first and the last word */
