@@ -125,7 +125,7 @@ class Context:
         """flb_parser_create(); `types` is the Types option text, e.g. "code:integer size:integer"."""
         arr, n = None, 0
         if types:
-            items = [t.split(":") for t in types.split()]
+            items = [t.split(":", 1) for t in types.split() if ":" in t]     # flb_parser_conf: entries without a type are skipped
             arr = (ParserTypes * len(items))()
             for i, (k, t) in enumerate(items):
                 arr[i].key = _b(k); arr[i].key_len = len(_b(k)); arr[i].type = _TYPE_NAMES.get(t.lower(), TYPE_STRING)

@@ -221,7 +221,9 @@ static int time_fmt_supported(const char *f, char *bad)
         f++;
         while (*f == 'E' || *f == 'O') f++;
         if (!*f) return 1;
-        if (!strchr("%DRrTFAaBbhCedkHlIjMmpSsUWwugGVYyZznt", *f)) { *bad = *f; return 0; }
+        /* conversions flb_strptime() has and the device restatement has not (locale formats); a letter neither knows
+         * makes every parse fail at run time, there (src/flb_strptime.c: default -> NULL) and here (dt_strptime) */
+        if (strchr("cxX+", *f)) { *bad = *f; return 0; }
     }
     return 1;
 }

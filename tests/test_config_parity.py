@@ -46,3 +46,34 @@ def test_same_configurations_are_accepted(plugin, props, sim_lib, ref_available)
     if plugin != "log_to_metrics":
         recs = util.split_records(cases.mixed_chunk())
         run_case(sim_lib, [cases.AP], [(plugin, props)], cases.mixed_chunk()[:recs[30][0]])
+
+
+PARSERS = [dict(name="a", format="regex"), dict(name="a", format="regex", regex=""), dict(name="a", format="regex", regex="("), dict(name="a", format="nope"), dict(name="a", format="JSON"),
+           dict(name="a", format="json", time_fmt="%Y"), dict(name="a", format="json", time_key="t"), dict(name="a", format="json", time_fmt="%Q", time_key="t"),
+           dict(name="a", format="json", time_fmt="%Y-%m-%d %H:%M:%S.%L %z", time_key="t", time_offset="+0100"), dict(name="a", format="json", time_fmt="%H", time_key="t", time_offset="bad"),
+           dict(name="a", format="json", time_fmt="%H", time_key="t", time_offset="+01:00"), dict(name="a", format="json", time_fmt="%H", time_key="t", time_offset="0100"),
+           dict(name="a", format="regex", regex="^(?<x>.)$", types="x:integer y:float"), dict(name="a", format="regex", regex="^(?<x>.)$", types="x:nope"),
+           dict(name="", format="json"), dict(name="a", format="ltsv", regex="ignored"), dict(name="a", format="logfmt", time_fmt="%s", time_key="t", time_keep=True),
+           dict(name="a", format="regex", regex="^(.)$"), dict(name="a", format="regex", regex="^(?<x>.)(?<x>.)$"), dict(name="a", format="regex", regex="/^(?<x>.)$/i"),
+           dict(name="a", format="regex", regex="^(?<time>.*)$", time_fmt="%L", time_key="time"), dict(name="a", format="regex", regex="^(?<time>.*)$", time_fmt="%Y %L %L", time_key="time"),
+           dict(name="a", format="regex", regex="^(?<time>.*)$", time_fmt="%b %d %H:%M:%S", time_key="time"), dict(name="a", format="regex", regex="^(?<time>.*)$", time_fmt="%Y %q", time_key="time")]
+LINES = [b"x", b"xy", b'{"t":"2023","a":1}', b"t=5 a=1", b"t:5\ta:1", b"2023 123 456", b"Feb  3 04:05:06", b"123", b"2023 q"]
+
+
+@pytest.mark.parametrize("kw", PARSERS, ids=[str(i) for i in range(len(PARSERS))])
+def test_same_parser_definitions_are_accepted(kw, sim_lib, ref_available):
+    """flb_parser_create(): same definitions accepted; a conversion neither strptime knows is accepted and fails per line"""
+    ref, ctx = util.Ref(), pkg.Context(0, lib=sim_lib)
+    try:
+        rp = ref.parser(**kw)
+    except RuntimeError:
+        with pytest.raises(pkg.FlbGpuError):
+            ctx.parser(**kw)
+        return
+    p = ctx.parser(**kw)
+    for line in LINES:
+        r, data, t = p.do(line)
+        rr, rdata, rt = ref.parser_do(rp, line)
+        assert (r < 0) == (rr < 0), line
+        if rr >= 0:
+            assert data == rdata and t == (rt[0] & 0xffffffff, rt[1]), line
