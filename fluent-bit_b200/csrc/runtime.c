@@ -1002,6 +1002,7 @@ static uint32_t emit_l2m_filter(flbgpu_filter *f, struct blob *b)
     }
     /* kubernetes_mode: five fixed labels in front of the user's (log_to_metrics.c:43-50, 148-156, 422-438) */
     for (p = f->props; p; p = p->next) {
+        if (!strcasecmp(p->k, "kubernetes_mode") && parse_bool(p->v) < 0) { set_err("invalid boolean '%s'%s", p->v, NULL); l2m_state_free(st); return 0; }
         if (!strcasecmp(p->k, "kubernetes_mode") && parse_bool(p->v) == 1 && st->n_labels == 0) {
             static const char *k8s[5] = { "namespace_name", "pod_name", "container_name", "docker_id", "pod_id" };
             int q;
@@ -1960,10 +1961,12 @@ char *flbgpu_l2m_text(flbgpu_filter *f)
         if ((size_t) w_ < cap - len) { len += (size_t) w_; break; } cap *= 2; out = realloc(out, cap); } } while (0)
     /* a metric without label keys is cmetrics' static metric: it exists, at 0, before anything was counted
      * (cmt_map.c: metric_static; a histogram in that state has no buckets yet and is not printable) */
-    if (st->n_sets == 0 && st->n_labels == 0 && st->mode != L2M_HISTOGRAM) L2M_APPEND("%s_%s_%s = 0\n", st->ns, st->subsystem, st->name);
+    /* cmt_opts_init(): the fully qualified name joins namespace, subsystem and name, leaving out what is empty */
+#define L2M_FQNAME() do { if (*st->ns) L2M_APPEND("%s_", st->ns); if (*st->subsystem) L2M_APPEND("%s_", st->subsystem); L2M_APPEND("%s", st->name); } while (0)
+    if (st->n_sets == 0 && st->n_labels == 0 && st->mode != L2M_HISTOGRAM) { L2M_FQNAME(); L2M_APPEND(" = 0\n"); }
     for (i = 0; i < st->n_sets; i++) {
         struct l2m_set *s = &st->sets[i];
-        L2M_APPEND("%s_%s_%s", st->ns, st->subsystem, st->name);
+        L2M_FQNAME();
         for (j = 0; j < st->n_labels; j++) {
             const unsigned char *v = (const unsigned char *) s->labels + (size_t) j * L2M_LABEL_BYTES;
             L2M_APPEND("%s%s=\"%.*s\"", j ? "," : "{", st->label_keys[j], (int) v[0], (const char *) v + 1);

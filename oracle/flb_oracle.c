@@ -857,11 +857,11 @@ char *orc_l2m_text(struct orc_filter *f)
     char tmp[512];
     int s, i;
     if (f->n_sets == 0 && f->n_labels == 0 && f->mode != 2) {      /* cmetrics' static metric: there, at 0, from creation */
-        int n = snprintf(tmp, sizeof(tmp), "%s_%s_%s = 0\n", f->ns, f->subsystem, f->mname);
+        int n = snprintf(tmp, sizeof(tmp), "%s%s%s%s%s = 0\n", f->ns, *f->ns ? "_" : "", f->subsystem, *f->subsystem ? "_" : "", f->mname);
         orc_buf_put(&b, tmp, (size_t) n);
     }
     for (s = 0; s < f->n_sets; s++) {
-        int n = snprintf(tmp, sizeof(tmp), "%s_%s_%s", f->ns, f->subsystem, f->mname);
+        int n = snprintf(tmp, sizeof(tmp), "%s%s%s%s%s", f->ns, *f->ns ? "_" : "", f->subsystem, *f->subsystem ? "_" : "", f->mname);   /* cmt_opts_init: empty parts left out */
         orc_buf_put(&b, tmp, (size_t) n);
         for (i = 0; i < f->n_labels; i++) {
             n = snprintf(tmp, sizeof(tmp), "%s%s=\"%s\"", i ? "," : "{", f->label_keys[i], f->sets[s].labels[i]);

@@ -143,6 +143,7 @@ L2M_CASES = [
      lambda: grouped_events(23), 1),
     ("histogram_group_markers_discard", [], [("log_to_metrics", BASE + [("metric_mode", "histogram"), ("value_field", "duration"), ("label_field", "color"),
                                                                         ("discard_logs", "on")])], lambda: grouped_events(24), 0),
+    ("counter_empty_namespace", [], [("log_to_metrics", BASE + [("metric_namespace", ""), ("label_field", "color")])], lambda: events(100, 25), 0),
     ("gauge_labels", [], [("log_to_metrics", BASE + [("metric_mode", "gauge"), ("value_field", "duration"), ("label_field", "color"),
                                                      ("add_label", "pod $kubernetes['pod_name']")])], lambda: events(900, 15), 0),
     ("gauge_regex_no_labels", [], [("log_to_metrics", BASE + [("metric_mode", "gauge"), ("value_field", "$code"), ("regex", "message ^ok"),

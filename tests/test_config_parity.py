@@ -23,7 +23,10 @@ CONFIGS = {
                [("Set", '"a b" c')], [("Add", "level x"), ("add_if_not_present", "lvl y")], [("Condition", "key_exists level"), ("condition", "KEY_EXISTS log"), ("SET", "z 1")],
                [("Remove_regex", "[")], [("Remove_regex", "")], [("Condition", "Matching_keys_have_matching_values l"), ("Add", "a b")], [("Move_to_start", "")], [("Copy", "a b c")]],
     "log_to_metrics": [[("metric_description", "d"), ("tag", "t"), ("metric_mode", "counter"), ("metric_mode", "gauge"), ("value_field", "n")],
-                       [("metric_description", "d"), ("tag", "t"), ("tag", "u")], [("metric_description", "d"), ("tag", "t"), ("bucket", "1"), ("bucket", "1")]],
+                       [("metric_description", "d"), ("tag", "t"), ("tag", "u")], [("metric_description", "d"), ("tag", "t"), ("bucket", "1"), ("bucket", "1")],
+                       [("metric_description", "d"), ("tag", "t"), ("kubernetes_mode", "maybe")], [("metric_description", "d"), ("tag", "t"), ("discard_logs", "maybe")],
+                       [("metric_description", "d"), ("tag", "t"), ("add_label", "a b c")], [("metric_description", "d"), ("tag", "t"), ("metric_mode", "COUNTER")],
+                       [("metric_description", ""), ("tag", "t")], [("tag", "t")]],
 }
 ALL = [(plugin, props) for plugin, sets in CONFIGS.items() for props in sets]
 
