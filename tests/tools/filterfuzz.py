@@ -85,7 +85,8 @@ def marker(rng):
 
 
 RA = ["log", "level", "k1", "$nest['k1']", "$nest['nest']['k2']", "$arr[1]", "$arr[0]['k1']", "$k1", "msg", "$nest", "$arr", "n", "flag", "$log['x']"]
-RX = ["GET", "^(warn|error)$", ".", "^$", "sample[0-9]", "^[a-z][0-9]$", "true", "a b", "1", "\\d+", "^x"]
+RX = ["GET", "^(warn|error)$", ".", "^$", "sample[0-9]", "^[a-z][0-9]$", "true", "a b", "1", "\\d+", "^x", "/get/i", "(?i)WARN", "^(?<w>\\w+)\\s", "(a|b)\\1", "[[:digit:]]+",
+      "\\bGET\\b", "^.{3,5}$", "(?:ab)*c", "é", "\\x41", "[^\\x00-\\x7f]", "^\\s*$", "\\A.*\\z", "T /a H", "\\.", "^(?!GET)"]
 
 
 def grep_props(rng):
