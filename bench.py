@@ -4,16 +4,20 @@
   python bench.py --gpus N --steps K --warmup W            (ours; torchrun for N>1)
   python bench.py --impl reference --gpus N --steps K --warmup W
 
-Workload (config.workload): the north-star chain of BASELINE.json -- filter_parser with the
-apache-combined regex parser (conf/parsers.conf:1-6) + filter_grep + filter_modify -- over
-synthetic apache access-log events {"log": line} (SURVEY.md section 8d, C1 shape), 10 M events per
-GPU per step by default (weak scaling).  A step is one pass of the chain over that batch.
+Primary workload (config.workload): BASELINE.json configs[1] -- 10 M JSON lines through filter_parser(json) +
+filter_grep + filter_modify, 10 M events per GPU per step (weak scaling).  A step is one pass of the chain over
+that batch.  Reported beside it, each with the same fields: the north-star apache chain, configs[0] (10 k apache
+lines, parser only, one call), configs[2] (nginx regex parser + record_modifier) and configs[3]
+(filter_log_to_metrics histogram over 100 M records in total, metric tables all-reduced over NCCL every step).
 
   value ....... events/s with the batch resident in HBM (flbgpu_chain_do_device), CUDA events
-  e2e ......... the same batch through flbgpu_chain_do(): pinned host input, host<->device copies
-                and the malloc()ed host result inside the timed region
-  roofline .... evaluation kernel (k_chain<false>: record decode + regex + filters) timed by CUDA
-                events inside the library; algorithmic bytes = chain input + chain output
+  e2e ......... the same batch through flbgpu_chain_do() the way flb_filter_do() calls a filter: input in
+                ordinary malloc()ed (pageable) memory, default glibc malloc for the result, host<->device copies
+                and free() of the result inside the timed region
+  e2e_variants  pinned input; and the batch sweep: bytes per call in {64 KB, 2 MB, 64 MB, whole set}, one caller
+                thread and 8 caller threads (8 filter instances, what `threaded on` inputs give the engine)
+  roofline .... evaluation kernel (k_chain_eval: record decode + parser + filters) timed by CUDA events inside the
+                library; algorithmic bytes = chain input + chain output
   cpu_baseline  the UNMODIFIED reference (oracle/_ref) on this box's host cores, bounded sample
 """
 import argparse
@@ -32,38 +36,45 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 BASE_LINES = 100_000          # distinct synthetic lines; the batch tiles this block
 
-# BASELINE.json configs[1]: "in_dummy 10M JSON lines -> filter_parser(json) + filter_grep + filter_modify on 1xB200"
-# (value shapes of SURVEY.md section 8d C2) -- the default workload.
-# BASELINE.json north_star: "apache-combined parser + grep + modify chain" -- reported beside it (key "north_star").
 WORKLOADS = {
+    # BASELINE.json configs[1]
     "json": {
         "name": "configs[1]: 10M JSON lines -> filter_parser(json)+filter_grep(level ^(warn|error)$)+filter_modify(Add,Rename,Remove)",
         "filters": [("parser", [("Key_Name", "log"), ("Parser", "json")]),
                     ("grep", [("Regex", "level ^(warn|error)$")]),
                     ("modify", [("Add", "env prod"), ("Rename", "msg message"), ("Remove", "debug")])],
     },
+    # BASELINE.json north_star
     "apache": {
         "name": "north-star chain: filter_parser(apache regex)+filter_grep(method ^(GET|POST)$)+filter_modify over apache-combined events",
         "filters": [("parser", [("Key_Name", "log"), ("Parser", "apache")]),
                     ("grep", [("Regex", "method ^(GET|POST)$")]),
                     ("modify", [("Add", "env prod"), ("Rename", "code status"), ("Remove", "agent")])],
     },
-    # configs[3] in small: filter_log_to_metrics histogram, 32 label sets, integer-valued observations (exact
-    # fp64 sums), logs discarded; with N>1 every step ends with the NCCL all-reduce of the metric tables.
-    # Not a default bench line: `--workload l2m`.
+    # BASELINE.json configs[0]: the reference's own CPU-runnable case, one 10k-line batch per call
+    "c0": {
+        "name": "configs[0]: 10k-line apache batch -> parser 'apache' (conf/parsers.conf:1-6), one call per batch",
+        "filters": [("parser", [("Key_Name", "log"), ("Parser", "apache")])],
+    },
+    # BASELINE.json configs[2] (filter_rewrite_tag is added when the chain supports it: SURVEY 8f1)
+    "nginx": {
+        "name": "configs[2]: nginx access logs -> regex parser 'nginx' + filter_record_modifier(Record hostname node-1; Remove_key agent)",
+        "filters": [("parser", [("Key_Name", "log"), ("Parser", "nginx")]),
+                    ("record_modifier", [("Record", "hostname node-1"), ("Remove_key", "agent")])],
+    },
+    # BASELINE.json configs[3]: 32 label sets, integer-valued observations (exact fp64 sums), logs discarded; with N>1
+    # every step ends with the all-reduce of the metric tables (NCCL).
     "l2m": {
-        "name": "configs[3]: filter_log_to_metrics histogram(duration) by color,direction; discard_logs; table all-reduce per step",
+        "name": "configs[3]: filter_log_to_metrics histogram(duration) by color,direction over 100M records in total; discard_logs; table all-reduce per step",
         "filters": [("log_to_metrics", [("metric_mode", "histogram"), ("metric_name", "duration"), ("metric_description", "d"),
                                         ("tag", "m"), ("value_field", "duration"), ("label_field", "color"),
                                         ("label_field", "direction"), ("discard_logs", "on")])],
     },
 }
-WL = "json"
 
 
-def make_block(rank=0, wl=None):
+def make_block(wl, rank=0):
     import util
-    wl = wl or WL
     if wl == "l2m":
         import random
         rng = random.Random(0xF1B1 + 4 + rank)
@@ -74,53 +85,135 @@ def make_block(rank=0, wl=None):
                                                        (b"direction", util.mp_str(rng.choice(dirs)))]) for i in range(BASE_LINES))
     if wl == "json":
         lines = util.json_lines(BASE_LINES, seed=0xF1B1 + 2 + rank)
+    elif wl == "nginx":
+        lines = util.apache_lines(BASE_LINES, seed=0xF1B1 + 3 + rank, nginx=True)
     else:
         lines = util.apache_lines(BASE_LINES, seed=0xF1B1 + 1 + rank)
     return util.chunk_from_lines(lines)
 
 
-def parser_kw(wl=None):
+def block_offsets(block):
+    """offset of every event of a block built by util.chunk_from_lines / util.event (v2 events, 0x80 metadata)"""
     import util
-    if (wl or WL) == "json":
+    return [o for o, _ in util.split_records(block)] + [len(block)]
+
+
+def parser_kw(wl):
+    import util
+    if wl == "json":
         return dict(name="json", format="json", time_fmt="%d/%b/%Y:%H:%M:%S %z", time_key="time")
+    if wl == "nginx":
+        return dict(name="nginx", format="regex", regex=util.NGINX_RX, time_fmt=util.APACHE_TIME_FMT, time_key="time")
     return dict(name="apache", format="regex", regex=util.APACHE_RX, time_fmt=util.APACHE_TIME_FMT, time_key="time")
 
 
+def lines_for(args, wl, world=1):
+    if wl == "c0":
+        return 10_000
+    if wl == "l2m":
+        return max(BASE_LINES, args.l2m_total // world)      # 100 M records in total: strong scaling
+    return args.lines
+
+
 # ------------------------------------------------------------------ reference arm
-def _ref_worker(args):
-    block, reps = args
+_REF_STATE = {}
+_BLOCKS = {}
+
+
+def _ref_state(wl):
+    import util
+    st = _REF_STATE.get(wl)
+    if st is None:
+        ref = util.Ref()
+        if wl != "l2m":
+            ref.parser(**parser_kw(wl))
+        for p, props in WORKLOADS[wl]["filters"]:
+            ref.filter(p, props)
+        block = _BLOCKS.get(wl) or make_block(wl)
+        buf = C.create_string_buffer(block, len(block))
+        st = _REF_STATE[wl] = (ref, buf)
+    return st
+
+
+def _ref_init(workloads):
+    """every pool worker: its own reference pipeline per workload and its own copy of the block, built before timing"""
     try:                     # the GPU arm binds its process near its GPU; the reference gets every core
         os.sched_setaffinity(0, range(os.cpu_count()))
     except Exception:
         pass
-    import util
-    ref = util.Ref()
-    ref.parser(**parser_kw())
-    for p, props in WORKLOADS[WL]["filters"]:
-        ref.filter(p, props)
-    buf = C.create_string_buffer(block, len(block))
-    nrec = ref.L.flbref_count_records(C.cast(buf, C.c_void_p), len(block))
+    for wl in workloads:
+        ref, buf = _ref_state(wl)
+        cut = block_offsets_cached(wl)[200]
+        out, n = C.c_void_p(), C.c_size_t()
+        nrec = ref.L.flbref_count_records(C.cast(buf, C.c_void_p), cut)
+        if ref.L.flbref_filter_do(ref.cfg, C.cast(buf, C.c_void_p), cut, nrec, b"bench", C.byref(out), C.byref(n)) == 1 and out.value:
+            ref.L.flbref_free(out)
+
+
+_OFFS = {}
+
+
+def block_offsets_cached(wl):
+    if wl not in _OFFS:
+        _OFFS[wl] = block_offsets(_BLOCKS.get(wl) or make_block(wl))
+    return _OFFS[wl]
+
+
+def _ref_task(args):
+    """one pool task: the reference's flb_filter_do over the first `cut` bytes of this worker's block, `reps` times"""
+    wl, cut, reps = args
+    ref, buf = _ref_state(wl)
+    nrec = ref.L.flbref_count_records(C.cast(buf, C.c_void_p), cut)
     t0 = time.perf_counter()
     for _ in range(reps):
         out, n = C.c_void_p(), C.c_size_t()
-        r = ref.L.flbref_filter_do(ref.cfg, C.cast(buf, C.c_void_p), len(block), nrec, b"bench", C.byref(out), C.byref(n))
+        r = ref.L.flbref_filter_do(ref.cfg, C.cast(buf, C.c_void_p), cut, nrec, b"bench", C.byref(out), C.byref(n))
         if r == 1 and out.value:
             ref.L.flbref_free(out)
     return time.perf_counter() - t0, nrec * reps
 
 
-def reference_throughput(block, cores, reps=1):
-    """All host cores, each its own reference pipeline (filters are single-threaded per
-    pipeline in the reference) over its own copy of the block.  Returns (lines/s, seconds)."""
-    import multiprocessing as mp
-    ctx = mp.get_context("fork")
-    with ctx.Pool(cores) as pool:
+class RefPool:
+    """All host cores, each its own reference pipeline (filters are single-threaded per pipeline in the
+    reference) over its own copy of the block."""
+
+    def __init__(self, cores, workloads):
+        import multiprocessing as mp
+        self.cores = cores
+        for wl in workloads:                      # generated once; the forked workers inherit them
+            _BLOCKS[wl] = make_block(wl)
+        self.offs = {wl: block_offsets_cached(wl) for wl in workloads}
+        self.pool = mp.get_context("fork").Pool(cores, initializer=_ref_init, initargs=(list(workloads),))
+        self.pool.map(time.sleep, [0.01] * cores, chunksize=1)      # every worker is up (initialised) before anything is timed
+
+    def step(self, wl, lines):
+        """`lines` events spread over 4 tasks per core; returns (events done, wall seconds of the whole job)"""
+        offs = self.offs[wl]
+        n_tasks = self.cores * 4
+        if wl == "c0":                            # configs[0]: whole 10k-line batches, 4 per core
+            per = 10_000
+        else:
+            per = max(1, min(BASE_LINES, -(-lines // n_tasks)))
+            n_tasks = -(-lines // per)
         t0 = time.perf_counter()
-        res = pool.map(_ref_worker, [(block, reps)] * cores)
+        res = self.pool.map(_ref_task, [(wl, offs[per], 1)] * n_tasks, chunksize=1)
         wall = time.perf_counter() - t0
-    lines = sum(r[1] for r in res)
-    busy = max(r[0] for r in res)
-    return lines / busy, wall, lines
+        return sum(r[1] for r in res), wall
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def reference_workload(pool, wl, lines, steps, warmup):
+    for _ in range(max(1, warmup)):            # first touch builds each worker's pipeline and block
+        pool.step(wl, min(lines, pool.cores * 4 * 2000))
+    done, dt = 0, 0.0
+    for _ in range(steps):
+        n, wall = pool.step(wl, lines)
+        done += n
+        dt += wall
+    return done / dt, dt / steps, done // steps
 
 
 def run_reference(args):
@@ -132,24 +225,32 @@ def run_reference(args):
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libflbref.so missing"}))
         return
     cores = os.cpu_count() or 1
-    block = make_block()
-    for _ in range(args.warmup):
-        reference_throughput(block, cores, 1)
-    lines, dt = 0, 0.0
-    for _ in range(args.steps):
-        v, _, n = reference_throughput(block, cores, 1)
-        lines += n
-        dt += n / v                    # slowest worker's time inside the reference calls (pool start-up excluded)
-    val = lines / dt
-    sample = "%d cores x %d-event block per step, %d steps" % (cores, BASE_LINES, args.steps)
-    print(json.dumps({
+    wl = args.workload
+    side = [] if args.primary_only else [o for o in ("apache", "c0", "nginx") if o != wl]
+    pool = RefPool(cores, [wl] + side)
+    # bounded sample: the reference does 10-50 M lines/s on 128 cores, so a full 10 M-event step is 0.2-1 s
+    val, s_per_step, n = reference_workload(pool, wl, lines_for(args, wl), args.steps, args.warmup)
+    others = {}
+    if not args.primary_only:
+        for o in side:
+            v, sps, nn = reference_workload(pool, o, lines_for(args, o), max(1, min(args.steps, 3)), 1)
+            others[o] = {"workload": WORKLOADS[o]["name"], "value": v, "e2e": v, "unit": "lines/s", "events_per_step": nn,
+                         "ms_per_step": 1000 * sps}
+    pool.close()
+    sample = "%d cores, %d events per step in %d-event calls (4 per core), %d steps, whole-job wall clock" % (
+        cores, n, -(-n // (cores * 4)), args.steps)
+    line = {
         "impl": "reference", "metric": "log lines/sec through parser+filter chain", "value": val, "unit": "lines/s",
-        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * dt / args.steps,
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * s_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOADS[WL]["name"], "events_per_step": cores * BASE_LINES, "host_cores": cores},
+        "config": {"workload": WORKLOADS[wl]["name"], "events_per_gpu_per_step": lines_for(args, wl), "distinct_lines": BASE_LINES},
         "cpu_baseline": {"value": val, "unit": "lines/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": "lines/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    }
+    if "apache" in others:
+        line["north_star"] = others.pop("apache")
+    line["workloads"] = others
+    print(json.dumps(line))
 
 
 # ------------------------------------------------------------------------ our arm
@@ -181,49 +282,149 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def measure(args, wl, L, ctx, torch, dist, rank, world, local):
-    """value / e2e / kernel times of one workload on this rank's GPU"""
-    import util
-    pkg = util.pkg
-    if wl != "l2m":
-        ctx.parser(**parser_kw(wl))
-    filters = [ctx.filter(p, props) for p, props in WORKLOADS[wl]["filters"]]
-    chain = ctx.chain(filters)
-    block = make_block(rank, wl)
-    reps = max(1, args.lines // BASE_LINES)
-    n_lines = reps * BASE_LINES
-    nbytes = len(block) * reps
-    pageable = os.environ.get("FLBGPU_BENCH_PAGEABLE") == "1"   # experiment: ordinary malloc()ed input, staged by the library
-    if pageable:
-        libc0 = C.CDLL(None)
-        libc0.malloc.restype = C.c_void_p; libc0.malloc.argtypes = [C.c_size_t]
-        h_in = libc0.malloc(nbytes)
-    else:
-        h_in = L.flbgpu_host_alloc(ctx.h, nbytes)       # pinned
-    for i in range(reps):
-        C.memmove(h_in + i * len(block), block, len(block))
-    d_in = L.flbgpu_dev_alloc(ctx.h, nbytes + 64)
-    out_cap = nbytes + nbytes // 2 + 64
-    d_out = L.flbgpu_dev_alloc(ctx.h, out_cap)
-    assert h_in and d_in and d_out, "allocation failed"
-    L.flbgpu_dev_upload(ctx.h, d_in, h_in, nbytes)
-    if os.environ.get("FLBGPU_BENCH_DEBUG"):
-        torch.cuda.synchronize()
-        t_up = time.perf_counter()
-        L.flbgpu_dev_upload(ctx.h, d_in, h_in, nbytes)
-        torch.cuda.synchronize()
-        t_up = time.perf_counter() - t_up
-        sys.stderr.write("plain pinned H2D of the input: %.1f ms = %.1f GB/s\n" % (1e3 * t_up, nbytes / t_up / 1e9))
-    stream = torch.cuda.ExternalStream(L.flbgpu_stream(ctx.h), device=torch.device("cuda", local))
-    osz = C.c_size_t()
+_libc = C.CDLL(None)
+_libc.malloc.restype = C.c_void_p
+_libc.malloc.argtypes = [C.c_size_t]
+_libc.free.argtypes = [C.c_void_p]
+_libc.mallopt.argtypes = [C.c_int, C.c_int]
 
-    def step_device():
-        r = L.flbgpu_chain_do_device(chain.h, d_in, nbytes, d_out, out_cap, C.byref(osz))
-        if r != pkg.FILTER_MODIFIED:
-            raise RuntimeError("chain_do_device -> %d: %s" % (r, ctx.err()))
-        if wl == "l2m" and world > 1:
-            filters[0].l2m_allreduce()          # the one exchange of the path: metric tables over NCCL
-            L.flbgpu_l2m_reset(filters[0].h)    # "flushed": the next interval starts from zero
+
+def tune_malloc(on):
+    """Host allocator policy of the embedding process.  on: keep freed result buffers in the heap instead of returning
+    them to the kernel (no mmap for big blocks, no trimming) -- what Fluent Bit's default jemalloc build does with its
+    retained extents.  off: glibc's defaults (every big result is a fresh mmap)."""
+    if on:
+        _libc.mallopt(-4, 0)              # M_MMAP_MAX = 0
+        _libc.mallopt(-1, (1 << 31) - 1)  # M_TRIM_THRESHOLD
+        _libc.mallopt(-2, 64 << 20)       # M_TOP_PAD
+    else:
+        _libc.mallopt(-4, 65536)          # M_MMAP_MAX default
+        _libc.mallopt(-3, 128 * 1024)     # M_MMAP_THRESHOLD default (also re-enables the dynamic threshold off)
+        _libc.mallopt(-1, 128 * 1024)     # M_TRIM_THRESHOLD default
+        _libc.mallopt(-2, 0)              # M_TOP_PAD default
+
+
+class Workload:
+    """one workload on this rank's GPU: chain, host buffers (pageable + pinned), device buffers"""
+
+    def __init__(self, args, wl, L, ctx, rank, world):
+        import util
+        self.pkg = util.pkg
+        self.args, self.wl, self.L, self.ctx, self.rank, self.world = args, wl, L, ctx, rank, world
+        if wl != "l2m":
+            ctx.parser(**parser_kw(wl))
+        self.filters = [ctx.filter(p, props) for p, props in WORKLOADS[wl]["filters"]]
+        self.chain = ctx.chain(self.filters)
+        self.block = make_block(wl, rank)
+        self.offs = block_offsets(self.block)
+        self.n_lines = lines_for(args, wl, world)
+        reps, rem = divmod(self.n_lines, BASE_LINES)
+        self.nbytes = len(self.block) * reps + self.offs[rem]
+        self.h_page = _libc.malloc(self.nbytes)                 # what Fluent Bit hands a filter: ordinary heap memory
+        self.h_pin = None
+        for i in range(reps):
+            C.memmove(self.h_page + i * len(self.block), self.block, len(self.block))
+        if rem:
+            C.memmove(self.h_page + reps * len(self.block), self.block, self.offs[rem])
+        self.d_in = self.d_out = None
+        self.osz = C.c_size_t()
+        self.out_p = C.c_void_p()
+        # one call takes less than 4 GiB: a bigger batch is a sequence of calls over whole blocks
+        seg_blocks = max(1, (2 << 30) // len(self.block))
+        self.segs, pos = [], 0
+        while pos < self.nbytes:
+            n = min(self.nbytes - pos, seg_blocks * len(self.block))
+            self.segs.append((pos, n))
+            pos += n
+
+    def close(self):
+        L, ctx = self.L, self.ctx
+        if self.d_in:
+            L.flbgpu_dev_free(ctx.h, self.d_in); L.flbgpu_dev_free(ctx.h, self.d_out)
+        if self.h_pin:
+            L.flbgpu_host_free(ctx.h, self.h_pin)
+        _libc.free(self.h_page)
+        self.chain.close()
+
+    def exchange(self):
+        if self.wl == "l2m" and self.world > 1:
+            self.filters[0].l2m_allreduce()          # the one exchange of the path: metric tables over NCCL
+            self.L.flbgpu_l2m_reset(self.filters[0].h)    # "flushed": the next interval starts from zero
+
+    # ---- device-resident
+    def device_setup(self):
+        L, ctx = self.L, self.ctx
+        self.d_in = L.flbgpu_dev_alloc(ctx.h, self.nbytes + 64)
+        self.out_cap = self.segs[0][1] + self.segs[0][1] // 2 + 4096
+        self.d_out = L.flbgpu_dev_alloc(ctx.h, self.out_cap)
+        assert self.d_in and self.d_out, "device allocation failed"
+        L.flbgpu_dev_upload(ctx.h, self.d_in, self.h_page, self.nbytes)
+
+    def step_device(self):
+        total = 0
+        for off, n in self.segs:
+            r = self.L.flbgpu_chain_do_device(self.chain.h, self.d_in + off, n, self.d_out, self.out_cap, C.byref(self.osz))
+            if r != self.pkg.FILTER_MODIFIED:
+                raise RuntimeError("chain_do_device -> %d: %s" % (r, self.ctx.err()))
+            total += self.osz.value
+        self.out_total = total
+        self.exchange()
+
+    # ---- host buffers through the C ABI
+    def call(self, chain, ptr, n):
+        out, osz = C.c_void_p(), C.c_size_t()
+        r = self.L.flbgpu_chain_do(chain.h, ptr, n, b"bench", 5, C.byref(out), C.byref(osz))
+        if r < 0:
+            raise RuntimeError("chain_do -> %d: %s" % (r, self.ctx.err()))
+        if out.value:
+            _libc.free(out)
+        return osz.value
+
+    def step_host(self, pinned=False):
+        src = self.h_page
+        if pinned:
+            if not self.h_pin:
+                self.h_pin = self.L.flbgpu_host_alloc(self.ctx.h, self.nbytes)
+                C.memmove(self.h_pin, self.h_page, self.nbytes)
+            src = self.h_pin
+        out = sum(self.call(self.chain, src + off, n) for off, n in self.segs)
+        self.exchange()
+        return out
+
+    def batches(self, bytes_per_call, limit_bytes):
+        """[(offset, length)] of consecutive calls of about bytes_per_call, cut at event boundaries"""
+        import bisect
+        out, pos, blen = [], 0, len(self.block)
+        end = min(self.nbytes, limit_bytes)
+        while pos < end:
+            base, rel = divmod(pos, blen)
+            want = pos + bytes_per_call
+            if want >= self.nbytes:
+                nxt = self.nbytes
+            else:
+                b2, r2 = divmod(want, blen)
+                k = bisect.bisect_right(self.offs, r2) - 1
+                nxt = b2 * blen + self.offs[k]
+                if nxt <= pos:
+                    nxt = b2 * blen + self.offs[min(k + 1, len(self.offs) - 1)]
+            out.append((pos, nxt - pos))
+            pos = nxt
+        return out
+
+
+def timed(fn, barrier):
+    barrier()
+    t0 = time.perf_counter()
+    fn()
+    barrier()
+    return time.perf_counter() - t0
+
+
+def measure(args, wl, L, ctx, torch, dist, rank, world, local, full=True):
+    """value / e2e / kernel times of one workload on this rank's GPU"""
+    w = Workload(args, wl, L, ctx, rank, world)
+    n_lines, nbytes = w.n_lines, w.nbytes
+    steps = args.steps if wl not in ("c0",) else max(args.steps, 20)
 
     def barrier():
         torch.cuda.synchronize()
@@ -231,9 +432,18 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local):
             dist.barrier()
         torch.cuda.synchronize()
 
+    def allmax(x):
+        t = torch.tensor([x], device="cuda", dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- device-resident: CUDA events on the instance's stream
+    w.device_setup()
+    stream = torch.cuda.ExternalStream(w.chain.stream(), device=torch.device("cuda", local))
     for _ in range(args.warmup):
-        step_device()
-    st0 = chain.stats()
+        w.step_device()
+    st0 = w.chain.stats()
     sampler = ClockSampler(local)
     sampler.start()
     time.sleep(0.3)
@@ -242,66 +452,73 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local):
     barrier()
     ev0.record(stream)
     ms3 = (C.c_float * 3)()
-    for _ in range(args.steps):
-        step_device()
+    for _ in range(steps):
+        w.step_device()
         L.flbgpu_kernel_ms(ctx.h, ms3)
         for k in range(3):
             kms[k] += ms3[k]
     ev1.record(stream)
     barrier()
-    dev_ms = ev0.elapsed_time(ev1)
+    dev_ms = allmax(ev0.elapsed_time(ev1))
     clocks = sampler.stop()
-    st1 = chain.stats()
+    st1 = w.chain.stats()
     launches = int(st1.kernel_launches - st0.kernel_launches)
-    out_bytes = osz.value
-    t = torch.tensor([dev_ms], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    dev_ms = float(t.item())
-    value = world * n_lines * args.steps / (dev_ms / 1000.0)
+    out_bytes = w.out_total
+    value = world * n_lines * steps / (dev_ms / 1000.0)
 
-    # ---- end to end through the host-buffer C ABI
-    out_p = C.c_void_p()
-    libc = C.CDLL(None)
-    libc.free.argtypes = [C.c_void_p]
+    # ---- end to end, the way flb_filter_do() calls: pageable input, default malloc, result freed
+    tune_malloc(False)
+    w.step_host()
+    e2e_s = allmax(timed(lambda: [w.step_host() for _ in range(steps)], barrier))
+    e2e = world * n_lines * steps / e2e_s
+    phases = [round(float(x), 2) for x in w.chain.stats().phase_ms]
+    variants = {}
+    if full:
+        tune_malloc(True)
+        w.step_host(pinned=True)
+        s = allmax(timed(lambda: [w.step_host(pinned=True) for _ in range(steps)], barrier))
+        variants["pinned_input_retaining_malloc"] = {"value": world * n_lines * steps / s, "unit": "lines/s",
+                                                     "note": "input in cudaMallocHost memory; glibc tuned to retain freed result buffers (M_MMAP_MAX=0, M_TRIM_THRESHOLD=2GiB)"}
+        tune_malloc(False)
+        # batch sweep: bytes per flbgpu_chain_do() call, pageable input, default malloc; 1 caller and 8 callers
+        sweep = []
+        ncall = 8
+        extra = [ctx.chain([ctx.filter(p, props) for p, props in WORKLOADS[wl]["filters"]]) for _ in range(ncall - 1)]
+        chains = [w.chain] + extra
+        for bpc, limit in ((64 << 10, 96 << 20), (2 << 20, 512 << 20), (64 << 20, 1 << 40)):
+            if bpc >= nbytes:
+                continue
+            bl = w.batches(bpc, limit)
+            ev_per_byte = n_lines / float(nbytes)
+            for callers in (1, ncall):
+                def run_part(t, callers=callers, bl=bl):
+                    for i in range(t, len(bl), callers):
+                        w.call(chains[t], w.h_page + bl[i][0], bl[i][1])
 
-    def step_host():
-        r = L.flbgpu_chain_do(chain.h, h_in, nbytes, b"bench", 5, C.byref(out_p), C.byref(osz))
-        if r != pkg.FILTER_MODIFIED:
-            raise RuntimeError("chain_do -> %d: %s" % (r, ctx.err()))
-        if wl == "l2m" and world > 1:
-            filters[0].l2m_allreduce()
-            L.flbgpu_l2m_reset(filters[0].h)
-        t_free = time.perf_counter()
-        libc.free(out_p)
-        free_s[0] += time.perf_counter() - t_free
-
-    free_s = [0.0]
-    e2e_steps = max(1, args.steps)
-    step_host()
-    barrier()
-    t0 = time.perf_counter()
-    for _ in range(e2e_steps):
-        step_host()
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    if os.environ.get("FLBGPU_BENCH_DEBUG"):
-        sys.stderr.write("e2e %s: %.1f ms/step, of which free() of the result %.1f ms/step\n" % (wl, 1e3 * e2e_s / e2e_steps, 1e3 * free_s[0] / (e2e_steps + 1)))
-    t = torch.tensor([e2e_s], device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
-    e2e = world * n_lines * e2e_steps / e2e_s
-    phases = [round(float(x), 2) for x in chain.stats().phase_ms]
-    L.flbgpu_dev_free(ctx.h, d_in)
-    L.flbgpu_dev_free(ctx.h, d_out)
-    if pageable:
-        libc.free(h_in)
-    else:
-        L.flbgpu_host_free(ctx.h, h_in)
-    return {"value": value, "dev_ms": dev_ms, "e2e": e2e, "e2e_steps": e2e_steps, "kms": [k / args.steps for k in kms],
+                def run_all(callers=callers):
+                    if callers == 1:
+                        run_part(0)
+                    else:
+                        th = [threading.Thread(target=run_part, args=(t,)) for t in range(callers)]
+                        for x in th:
+                            x.start()
+                        for x in th:
+                            x.join()
+                run_all()                                   # warm: buffers of every instance grown
+                s = allmax(timed(run_all, barrier))
+                done = sum(b[1] for b in bl)
+                sweep.append({"bytes_per_call": bpc, "callers": callers, "calls": len(bl), "lines_per_s": world * done * ev_per_byte / s,
+                              "us_per_call": 1e6 * s * callers / len(bl),
+                              "GB_per_s_in": world * done / s / 1e9})
+        sweep.append({"bytes_per_call": nbytes, "callers": 1, "calls": 1, "lines_per_s": e2e, "us_per_call": 1e6 * e2e_s / steps,
+                      "GB_per_s_in": world * nbytes * steps / e2e_s / 1e9})
+        variants["batch_sweep"] = sweep
+        for c in extra:
+            c.close()
+    w.close()
+    return {"value": value, "dev_ms": dev_ms, "e2e": e2e, "e2e_steps": steps, "kms": [k / steps for k in kms],
             "launches": launches, "n_lines": n_lines, "nbytes": nbytes, "out_bytes": out_bytes, "clocks": clocks,
-            "phases": phases}
+            "phases": phases, "variants": variants, "steps": steps}
 
 
 def run_ours(args):
@@ -318,21 +535,14 @@ def run_ours(args):
 
     L = pkg.load()                                  # raises if the CUDA library is missing
     ctx = pkg.Context(local, lib=L)
-    # Host allocator policy of the embedding process: keep freed result buffers in the heap instead of
-    # returning them to the kernel (glibc: no mmap for big blocks, no trimming) -- what Fluent Bit's
-    # default jemalloc build does with its retained extents.  Without it every step pays ~300k page
-    # faults for the fresh result buffer.  FLBGPU_BENCH_DEFAULT_MALLOC=1 turns the tuning off.
-    if os.environ.get("FLBGPU_BENCH_DEFAULT_MALLOC") != "1":
-        libc = C.CDLL(None)
-        libc.mallopt(-4, 0)              # M_MMAP_MAX = 0
-        libc.mallopt(-1, (1 << 31) - 1)  # M_TRIM_THRESHOLD
-        libc.mallopt(-2, 64 << 20)       # M_TOP_PAD (small, so that a freed GB-size result does not push the top over the trim threshold)
-
-    m = measure(args, WL, L, ctx, torch, dist, rank, world, local)
-    other = "apache" if WL == "json" else "json"
-    m2 = None
+    WL = args.workload
+    m = measure(args, WL, L, ctx, torch, dist, rank, world, local, full=True)
+    others = {}
     if not args.primary_only:
-        m2 = measure(args, other, L, ctx, torch, dist, rank, world, local)
+        for o in ("apache", "c0", "nginx", "l2m"):
+            if o == WL:
+                continue
+            others[o] = measure(args, o, L, ctx, torch, dist, rank, world, local, full=(o == "apache"))
 
     if rank != 0:
         if world > 1:
@@ -363,24 +573,43 @@ def run_ours(args):
     cpu = None
     if util.have_ref():
         cores = os.cpu_count() or 1
-        v, wall, n = reference_throughput(make_block(), cores, 1)
+        pool = RefPool(cores, [WL])
+        sample_lines = min(m["n_lines"], 4_000_000)
+        v, sps, n = reference_workload(pool, WL, sample_lines, 2, 1)
+        pool.close()
         cpu = {"value": v, "unit": "lines/s", "cores": cores, "kind": "reference",
-               "sample": "%d cores x one %d-event block each (%.1f s wall)" % (cores, BASE_LINES, wall)}
+               "sample": "%d cores, 2 steps of %d events in %d-event calls (%.2f s per step, whole-job wall clock)" % (cores, n, -(-n // (cores * 4)), sps)}
+
+    def side(mm, name):
+        e2, a2, ach2 = roof(mm)
+        d = {"workload": WORKLOADS[name]["name"], "value": mm["value"], "e2e": mm["e2e"], "unit": "lines/s",
+             "events_per_gpu_per_step": mm["n_lines"], "input_bytes_per_gpu": mm["nbytes"], "output_bytes_per_gpu": mm["out_bytes"],
+             "steps": mm["steps"], "ms_per_step": mm["dev_ms"] / mm["steps"],
+             "kernel_ms_per_step": {"index": mm["kms"][0], "evaluate": e2, "emit": mm["kms"][2]},
+             "roofline_frac": (ach2 / peak) if ach2 else None, "gpu_launches": mm["launches"]}
+        if mm["variants"]:
+            d["e2e_variants"] = mm["variants"]
+        if name == "l2m":
+            d["scaling"] = "strong"
+            d["collective"] = "metric tables all-reduced over NCCL every step" if world > 1 else "single GPU: no exchange"
+        return d
 
     line = {
         "metric": "log lines/sec through parser+filter chain", "value": m["value"], "unit": "lines/s", "n_gpus": world,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["dev_ms"] / args.steps, "higher_is_better": True,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": m["dev_ms"] / m["steps"], "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-        "config": {"workload": WORKLOADS[WL]["name"], "events_per_gpu_per_step": m["n_lines"], "input_bytes_per_gpu": m["nbytes"],
-                   "output_bytes_per_gpu": m["out_bytes"], "distinct_lines": BASE_LINES,
-                   "l2": "input (%.0f MB) and output larger than the 126 MB L2" % (m["nbytes"] / 1e6),
-                   "parallelism": ("record shards; one NCCL all-reduce of the metric table per step" if WL == "l2m" else "record shards, no data-path collective"),
-                   "host_malloc": "default" if os.environ.get("FLBGPU_BENCH_DEFAULT_MALLOC") == "1" else "glibc tuned to retain freed result buffers (M_MMAP_MAX=0, M_TRIM_THRESHOLD=2GiB)"},
+        "config": {"workload": WORKLOADS[WL]["name"], "events_per_gpu_per_step": m["n_lines"], "distinct_lines": BASE_LINES},
+        "config_detail": {"input_bytes_per_gpu": m["nbytes"], "output_bytes_per_gpu": m["out_bytes"],
+                          "l2": "input (%.0f MB) and output larger than the 126 MB L2" % (m["nbytes"] / 1e6),
+                          "parallelism": ("record shards; one NCCL all-reduce of the metric table per step" if WL == "l2m" else "record shards, no data-path collective"),
+                          "e2e_input": "pageable malloc()ed memory", "e2e_host_malloc": "glibc defaults"},
         "e2e": {"value": m["e2e"], "unit": "lines/s", "h2d_bytes_per_step": m["nbytes"], "d2h_bytes_per_step": m["out_bytes"],
                 "steps": m["e2e_steps"], "timing": "wall clock between device-synchronising barriers",
                 "host_phase_ms_last_call": dict(zip(["upload+index+evaluate", "size_scan", "emit+download", "total"], m["phases"]))},
+        "e2e_variants": m["variants"],
         "gpu_launches": m["launches"],
-        "kernel_ms_per_step": {"index": m["kms"][0], "evaluate": eval_ms, "emit": m["kms"][2]},
+        "kernel_ms_per_step": {"index": m["kms"][0], "evaluate": eval_ms, "emit": m["kms"][2],
+                               "note": "CUDA-event pairs per launch group; index runs on its own priority stream concurrently with evaluate, so the groups are not additive"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s",
                      "frac": (achieved / peak) if achieved else None, "traffic": traffic,
                      "kernel": "k_chain_eval (evaluation pass)", "algorithmic_bytes_per_launch": alg_bytes,
@@ -388,13 +617,9 @@ def run_ours(args):
         "cpu_baseline": cpu,
         "clocks": m["clocks"],
     }
-    if m2:
-        e2, a2, ach2 = roof(m2)
-        line["north_star" if other == "apache" else "configs1_json"] = {
-            "workload": WORKLOADS[other]["name"], "value": m2["value"], "e2e": m2["e2e"], "unit": "lines/s",
-            "events_per_gpu_per_step": m2["n_lines"], "input_bytes_per_gpu": m2["nbytes"], "output_bytes_per_gpu": m2["out_bytes"],
-            "kernel_ms_per_step": {"index": m2["kms"][0], "evaluate": e2, "emit": m2["kms"][2]},
-            "roofline_frac": (ach2 / peak) if ach2 else None, "gpu_launches": m2["launches"]}
+    if "apache" in others:
+        line["north_star"] = side(others.pop("apache"), "apache")
+    line["workloads"] = {k: side(v, k) for k, v in others.items()}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
@@ -407,11 +632,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--lines", type=int, default=10_000_000, help="events per GPU per step")
-    ap.add_argument("--workload", default="json", choices=["json", "apache", "l2m"], help="primary workload (the other one is reported beside it)")
+    ap.add_argument("--l2m-total", type=int, default=100_000_000, help="records of configs[3] over all GPUs")
+    ap.add_argument("--workload", default="json", choices=list(WORKLOADS), help="primary workload (the others are reported beside it)")
     ap.add_argument("--primary-only", action="store_true")
     args = ap.parse_args()
-    global WL
-    WL = args.workload
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -42,7 +42,7 @@ EXPORTS = [
     "flbgpu_filter_destroy", "flbgpu_chain_new", "flbgpu_chain_add", "flbgpu_chain_init", "flbgpu_chain_do",
     "flbgpu_chain_destroy", "flbgpu_chain_do_device", "flbgpu_chain_stats", "flbgpu_dev_alloc",
     "flbgpu_dev_free", "flbgpu_dev_upload", "flbgpu_dev_download", "flbgpu_host_alloc", "flbgpu_host_free",
-    "flbgpu_stream", "flbgpu_kernel_ms",
+    "flbgpu_stream", "flbgpu_kernel_ms", "flbgpu_chain_stream",
 ]
 
 
@@ -86,6 +86,7 @@ def load(path=None):
     L.flbgpu_host_free.argtypes = [vp, vp]
     L.flbgpu_stream.restype = vp; L.flbgpu_stream.argtypes = [vp]
     L.flbgpu_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
+    L.flbgpu_chain_stream.restype = vp; L.flbgpu_chain_stream.argtypes = [vp]
     ip = C.POINTER(C.c_int); u64p = C.POINTER(C.c_uint64)
     L.flbgpu_l2m_info.argtypes = [vp, ip, ip, ip, ip]
     L.flbgpu_l2m_get.argtypes = [vp, C.c_int, u64p, u64p, C.POINTER(C.c_double), u64p, vp]
@@ -119,6 +120,17 @@ class Context:
     def err(self):
         e = self.L.flbgpu_last_error()
         return e.decode(errors="replace") if e else ""
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.flbgpu_shutdown(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def parser(self, name, format, regex=None, skip_empty=True, time_fmt=None, time_key=None, time_offset=None,
                time_keep=False, time_strict=True, logfmt_no_bare_keys=False, types=None):
@@ -217,6 +229,17 @@ def _call_filter(fn, L, handle, data, tag):
 class Filter:
     def __init__(self, ctx, h):
         self.ctx, self.h = ctx, h
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.L.flbgpu_filter_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
     def cb(self, data, tag="test"):
         """cb_filter(): (FILTER_MODIFIED, bytes) or (FILTER_NOTOUCH, None)."""
@@ -335,6 +358,21 @@ class Filter:
 class Chain:
     def __init__(self, ctx, h, filters):
         self.ctx, self.h, self.filters = ctx, h, filters
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.L.flbgpu_chain_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def stream(self):
+        """the cudaStream_t this instance launches on"""
+        return self.ctx.L.flbgpu_chain_stream(self.h)
 
     def do(self, data, tag="test"):
         return _call_filter(self.ctx.L.flbgpu_chain_do, self.ctx.L, self.h, data, tag)

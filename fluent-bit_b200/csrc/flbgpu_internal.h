@@ -5,6 +5,14 @@
  * point fails loudly when no CUDA device is present.  tests/hostsim provides a
  * second implementation of the same functions for CPU-only CI of the host logic
  * and of the device algorithms; it is never linked into the product.
+ *
+ * All mutable back-end state lives in a QUEUE (bk_q): the device ordinal, the
+ * streams, the timing events, the pinned staging rings with their persistent
+ * worker threads and the small device scratch.  One filter instance / fused chain
+ * owns one queue, so two instances may run on different threads (and different
+ * devices) at the same time -- what flb_processor_run() does to filters
+ * (/root/reference/src/flb_processor.c:1352-1378).  A queue itself is not
+ * re-entrant; runtime.c serialises the calls of one chain.
  */
 #ifndef FLBGPU_INTERNAL_H
 #define FLBGPU_INTERNAL_H
@@ -19,6 +27,8 @@ extern "C" {
 
 #define BK_INDEX_TILE   8192u     /* input bytes per index block */
 #define BK_REC_BLOCK    256u      /* records per chain block */
+
+typedef struct bk_q bk_q;
 
 struct bk_chain_args {
     const uint8_t *d_in;          /* input chunk (device) */
@@ -40,19 +50,24 @@ struct bk_chain_args {
 };
 
 const char *bk_name(void);
-int   bk_init(int device);                       /* 0 ok, -1 no usable device */
 int   bk_device_count(void);
-void *bk_alloc(size_t n);
-void  bk_free(void *p);
-void *bk_alloc_host(size_t n);                   /* pinned host memory */
-void  bk_free_host(void *p);
-int   bk_h2d(void *d, const void *h, size_t n);
-int   bk_d2h(void *h, const void *d, size_t n);
-int   bk_zero(void *d, size_t n);
-int   bk_sync(void);
-void *bk_stream(void);
-int   bk_kernel_ms(float out[3]);               /* CUDA-event ms of index / evaluate / emit in the last call */
-const char *bk_last_error(void);
+const char *bk_last_error(void);                 /* of the calling thread */
+uint64_t bk_launch_count(void);                  /* kernels launched by this library so far (all queues) */
+
+bk_q *bk_q_new(int device);                      /* NULL: no usable device (bk_last_error) */
+void  bk_q_free(bk_q *q);
+int   bk_q_device(bk_q *q);
+void *bk_alloc(bk_q *q, size_t n);
+void  bk_free(bk_q *q, void *p);
+void *bk_alloc_host(bk_q *q, size_t n);          /* pinned host memory */
+void  bk_free_host(bk_q *q, void *p);
+int   bk_h2d(bk_q *q, void *d, const void *h, size_t n);
+int   bk_d2h(bk_q *q, void *h, const void *d, size_t n);
+int   bk_zero(bk_q *q, void *d, size_t n);
+int   bk_sync(bk_q *q);
+void *bk_stream(bk_q *q);
+int   bk_kernel_ms(bk_q *q, float out[3]);       /* CUDA-event ms of index / evaluate / emit in the last call */
+int   bk_d2d(bk_q *q, void *dst, const void *src, size_t n);   /* synchronous device copy (buffer growth) */
 
 /* ---- the per-call pipeline ----------------------------------------------------
  * A chunk is processed in SLICES (byte ranges that start at a record boundary):
@@ -67,58 +82,73 @@ const char *bk_last_error(void);
  * so host->device copy, evaluation, emission and device->host copy overlap. */
 
 /* start the asynchronous upload of a whole chunk (pieces + one event per piece) */
-int bk_upload_start(void *d_dst, const void *h_src, size_t n);
+int bk_upload_start(bk_q *q, void *d_dst, const void *h_src, size_t n);
 /* the index stream may not read beyond bytes that have arrived: wait (on the device) for [0,upto) */
-int bk_upload_wait_index(size_t upto);
+int bk_upload_wait_index(bk_q *q, size_t upto);
 /* device-resident input: nothing to wait for */
-void bk_upload_none(void);
-/* joins the staging threads of a pageable upload: the caller's buffer is not read after this */
-void bk_upload_end(void);
+void bk_upload_none(bk_q *q);
+/* waits for the staging threads of a pageable upload: the caller's buffer is not read after this */
+void bk_upload_end(bk_q *q);
 
 /* Record index (K1) of one slice d_in[slice_off, slice_off+slice_len).  Pass 1 counts
  * validated candidates per tile (exclusive tile offsets left in d_tile) and returns the
  * total (synchronises the index stream only). */
-int bk_index_count(const uint8_t *d_in, size_t slice_off, uint32_t slice_len, uint32_t *d_tile, uint32_t n_tiles,
+int bk_index_count(bk_q *q, const uint8_t *d_in, size_t slice_off, uint32_t slice_len, uint32_t *d_tile, uint32_t n_tiles,
                    uint32_t *n_cand);
 /* Pass 2 writes (absolute offset, length, kind) of the slice's candidates at d_off/d_len/
  * d_kind (already advanced to the slice's first record), repairs the candidate chain and
  * reports: *n_valid records that chain from the slice start, *end_off = absolute offset
  * where the last of them ends, *tiled = 1 when that is the slice end. */
-int bk_index_fill(const uint8_t *d_in, size_t slice_off, uint32_t slice_len, const uint32_t *d_tile, uint32_t n_tiles,
+int bk_index_fill(bk_q *q, const uint8_t *d_in, size_t slice_off, uint32_t slice_len, const uint32_t *d_tile, uint32_t n_tiles,
                   uint32_t n_cand, uint32_t *d_off, uint32_t *d_len, uint8_t *d_kind,
                   uint32_t *n_valid, uint64_t *end_off, int *tiled);
 
-int bk_flags_clear(uint32_t *d_flags);
-/* evaluation pass over records [r0, r1): asynchronous on the compute stream */
+int bk_flags_clear(bk_q *q, uint32_t *d_flags);
 /* L2 hint: [base, base+bytes) is read once by the next evaluation launches */
-int bk_hint_streaming(const void *base, size_t bytes);
-int bk_chain_eval(const struct bk_chain_args *a, uint32_t r0, uint32_t r1);
+int bk_hint_streaming(bk_q *q, const void *base, size_t bytes);
+/* evaluation pass over records [r0, r1): asynchronous on the compute stream */
+int bk_chain_eval(bk_q *q, const struct bk_chain_args *a, uint32_t r0, uint32_t r1);
 /* evidence + error word (synchronises the compute stream) */
-int bk_flags_fetch(const uint32_t *d_flags, uint32_t *h_flags);
+int bk_flags_fetch(bk_q *q, const uint32_t *d_flags, uint32_t *h_flags);
 /* per-block sums of d_size[0,n_rec) -> exclusive offsets in d_bsum, copied to h_bsum
  * (n_blocks+1 entries, last = total).  Synchronises. */
-int bk_sizes_scan(const uint32_t *d_size, uint32_t n_rec, uint64_t *d_bsum, uint64_t *h_bsum);
+int bk_sizes_scan(bk_q *q, const uint32_t *d_size, uint32_t n_rec, uint64_t *d_bsum, uint64_t *h_bsum);
 /* the same for blocks [b0, b1) only, continuing from carry_in bytes already placed; fills
  * d_bsum[b0..b1), h_bsum[b0..b1] (h_bsum[b1] = bytes placed after these blocks).  Synchronous. */
-int bk_sizes_scan_range(const uint32_t *d_size, uint32_t n_rec, uint32_t b0, uint32_t b1, uint64_t *d_bsum, uint64_t *h_bsum,
+int bk_sizes_scan_range(bk_q *q, const uint32_t *d_size, uint32_t n_rec, uint32_t b0, uint32_t b1, uint64_t *d_bsum, uint64_t *h_bsum,
                         uint64_t carry_in);
 /* emission of blocks [b0, b1) into d_out: asynchronous on the compute stream */
-int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1);
+int bk_chain_emit(bk_q *q, const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1);
 /* records emitted since the last bk_flags_clear() */
-int bk_records_out(uint64_t *n);
+int bk_records_out(bk_q *q, uint64_t *n);
 
 /* result download session: bytes [lo,hi) of d_out become valid after the emission just
  * enqueued; they are DMA'd into a pinned ring and moved into h_dst by host threads. */
 /* memcpy for write-once destinations (runtime.c): non-temporal stores where available */
 void flbgpu_stream_copy(void *dst, const void *src, size_t n);
-int bk_download_begin(void *h_dst, const void *d_out);
-int bk_download_push(size_t lo, size_t hi);
-int bk_download_end(void);
+int bk_download_begin(bk_q *q, void *h_dst, const void *d_out);
+int bk_download_push(bk_q *q, size_t lo, size_t hi);
+int bk_download_end(bk_q *q);
 
-int bk_d2d(void *dst, const void *src, size_t n);          /* synchronous device copy (buffer growth) */
-
-/* counters for bench.py's gpu_launches claim */
-uint64_t bk_launch_count(void);
+/* ---- the small-chunk form -------------------------------------------------------
+ * What flb_filter_do() hands a filter is one append: tens of KB to a few MB.  For such a chunk the
+ * pipeline above is all overhead, so the whole call is enqueued on ONE stream without a host
+ * synchronisation in between -- upload, record index, evaluation, sizes, emission under the
+ * speculated verdict vector -- with every count the later kernels need (records, candidates, result
+ * bytes) staying in device memory; the host waits once, reads the mail below, and fetches the result.
+ * a->d_off/d_len/d_kind/d_size hold cap_rec records, a->d_bsum ceil(cap_rec/BK_REC_BLOCK)+2 entries. */
+struct bk_small_res {
+    uint32_t n_cand, n_valid, tiled, overflow;   /* overflow: more candidates than cap_rec, nothing after the index is valid */
+    uint64_t end_off;                            /* where the decodable prefix ends */
+    uint64_t total;                              /* result bytes */
+    uint64_t n_out;                              /* records in the result */
+    uint32_t emitted;                            /* 0: the result did not fit cap_out, nothing was written */
+    uint32_t flags[FLBGPU_MAX_FILTERS + 1];
+};
+int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8_t *d_in, size_t bytes, uint32_t cap_rec,
+                 uint32_t *d_tile, uint32_t n_tiles, uint8_t *d_out, size_t cap_out, struct bk_small_res *res);
+/* result bytes [0,n) of d_out into the caller's (pageable) buffer; synchronises */
+int bk_small_fetch(bk_q *q, void *h_dst, const uint8_t *d_out, size_t n);
 
 #ifdef __cplusplus
 }

@@ -7,17 +7,29 @@
  *                       Two passes (count -> prefix sum -> fill) keep file order.
  *   k_index_check ..... the kept candidates must tile the chunk; the first gap ends
  *                       the decodable prefix (the reference decoder stops there too).
+ *   k_index_repair .... walks the record chain across the (few) broken links;
+ *   k_link_* .......... the same by pointer doubling when a slice has more broken links than
+ *                       the one-CTA walk holds (records with nested [int, {map}] values).
  *   k_scan_top ........ exclusive prefix sum over per-block totals (one CTA).
- *   k_chain<EMIT> ..... one lane = one record through the filter-chain interpreter
- *                       (dev_chain.cuh); EMIT=false sizes, EMIT=true writes.
+ *   k_chain_eval ...... one lane = one record through the filter-chain interpreter
+ *                       (dev_chain.cuh): sizes, verdict evidence, final field list.
+ *   k_chain_emit_list . encodes the surviving records at their offsets.
+ *   k_small_* ......... glue of the small-chunk form: every count stays on the device.
  *
  * This is byte-stream work bounded by HBM traffic and instruction issue; there is no
  * contraction here, so no tensor-core path.  Loads of chunk bytes are 128-bit and
  * coalesced in k_index; k_chain lanes walk adjacent records (L1/L2 resident lines).
+ *
+ * Host side: all state is per queue (struct bk_q, flbgpu_internal.h); nothing here is
+ * process-global except the launch counter and the thread-local error text.
  */
 #include <cuda_runtime.h>
 #include <atomic>
 #include <thread>
+#include <mutex>
+#include <condition_variable>
+#include <vector>
+#include <new>
 #include <string.h>
 #include <stdlib.h>
 #include <sched.h>
@@ -26,34 +38,8 @@
 #include "flbgpu_internal.h"
 #include "dev_chain.cuh"
 
-static char g_err[256];
-static int g_nsurv;
-static unsigned long long g_launches;
-static cudaStream_t g_stream;
-/* CUDA-event timing of the kernel groups of the last call: one event pair per launch
- * (0 = index, 1 = evaluate, 2 = emit); bk_kernel_ms() sums the pairs of a group. */
-#define EV_MAX 1024
-static cudaEvent_t g_evp[3][EV_MAX][2];
-static int g_ev_made[3], g_ev_used[3];
-static int g_ev_ready;
-static cudaStream_t g_istream;
-static void ev_begin_on(int k, cudaStream_t st)
-{
-    if (!g_ev_ready || g_ev_used[k] >= EV_MAX) return;
-    if (g_ev_used[k] >= g_ev_made[k]) {
-        cudaEventCreate(&g_evp[k][g_ev_made[k]][0]); cudaEventCreate(&g_evp[k][g_ev_made[k]][1]);
-        g_ev_made[k]++;
-    }
-    cudaEventRecord(g_evp[k][g_ev_used[k]][0], st);
-}
-static void ev_end_on(int k, cudaStream_t st)
-{
-    if (!g_ev_ready || g_ev_used[k] >= EV_MAX) return;
-    cudaEventRecord(g_evp[k][g_ev_used[k]][1], st);
-    g_ev_used[k]++;
-}
-static void ev_begin(int k) { ev_begin_on(k, g_stream); }
-static void ev_end(int k) { ev_end_on(k, g_stream); }
+static thread_local char g_err[256];
+static std::atomic<unsigned long long> g_launches;
 
 #define CK(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { \
     snprintf(g_err, sizeof(g_err), "%s: %s", #call, cudaGetErrorString(e_)); return -1; } } while (0)
@@ -102,17 +88,31 @@ __device__ __forceinline__ uint32_t block_excl_scan(uint32_t v, uint32_t *total)
     return block_excl_scan_t<uint32_t>(v, total);
 }
 
+/* what the kernels of the small-chunk form hand each other (device memory; copied to the host once) */
+struct bk_mail {
+    unsigned long long n_cand64;     /* candidates counted (k_small_tiles) */
+    unsigned long long total;        /* result bytes */
+    unsigned long long n_out;        /* surviving records */
+    uint32_t n_breaks, n_valid, tiled, end_off;     /* k_index_check / k_index_repair (same order as the sliced form) */
+    uint32_t n_cand;                 /* candidates the arrays hold (0 on overflow) */
+    uint32_t overflow;               /* 1: more candidates than the arrays hold; 2: more broken links than the walk holds */
+    uint32_t emitted;                /* the result fits the output buffer and was written */
+    uint32_t pad;
+};
+
 /* ------------------------------------------------------------------ index */
 template <bool FILL>
 __global__ void __launch_bounds__(256) k_index(const uint8_t *__restrict__ in, uint32_t len, uint32_t skip, uint32_t abs_base,
                                                uint32_t *__restrict__ tile, uint32_t *__restrict__ o_off,
-                                               uint32_t *__restrict__ o_len, uint8_t *__restrict__ o_kind)
+                                               uint32_t *__restrict__ o_len, uint8_t *__restrict__ o_kind,
+                                               const struct bk_mail *__restrict__ mail)
 {
     __shared__ uint16_t cand[BK_INDEX_TILE];
     __shared__ uint32_t v2ok[BK_INDEX_TILE / 32];   /* bit per tile byte: a valid v2 frame starts here */
     __shared__ uint32_t s_ncand;
     const uint32_t base = blockIdx.x * BK_INDEX_TILE;
     uint32_t ncand = 0;
+    if (FILL && mail && mail->overflow) return;      /* small form: the arrays cannot hold the candidates */
 
     /* phase 1: ordered list of candidate positions in this tile */
     for (uint32_t it = 0; it < BK_INDEX_TILE / (256 * 16); it++) {
@@ -180,9 +180,9 @@ __global__ void __launch_bounds__(256) k_index(const uint8_t *__restrict__ in, u
     if (!FILL && threadIdx.x == 0) tile[blockIdx.x] = kept;
 }
 
-/* exclusive scan of a[0..n) in place, one CTA; total in *out_total */
+/* exclusive scan of a[0..n) in place, one CTA; total in *out_total (and added to *accum) */
 template <typename T>
-__global__ void __launch_bounds__(256) k_scan_top(T *a, uint32_t n, unsigned long long *out_total)
+__global__ void __launch_bounds__(256) k_scan_top(T *a, uint32_t n, unsigned long long *out_total, unsigned long long *accum)
 {
     unsigned long long carry = 0;
     for (uint32_t b = 0; b < n; b += 256) {
@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(256) k_scan_top(T *a, uint32_t n, unsigned lon
         if (i < n) a[i] = (T) (carry + ex);
         carry += tot;
     }
-    if (threadIdx.x == 0) *out_total = carry;
+    if (threadIdx.x == 0) { *out_total = carry; if (accum) *accum += carry; }
 }
 
 #define BK_MAX_BREAKS 8192u
@@ -202,9 +202,11 @@ __global__ void __launch_bounds__(256) k_scan_top(T *a, uint32_t n, unsigned lon
  * byte run inside a real record that happens to frame as an event, e.g. the timestamp
  * bytes `.. 92 ce 00 00 01 a6 | 80` read as the legacy event [422, {}] -- and are
  * collected for k_index_repair. */
-__global__ void k_index_check(const uint32_t *__restrict__ off, const uint32_t *__restrict__ rlen, uint32_t n,
+__global__ void k_index_check(const uint32_t *__restrict__ off, const uint32_t *__restrict__ rlen, uint32_t n_host,
+                              const uint32_t *__restrict__ n_dev,
                               uint32_t total /* absolute end of the slice */, uint32_t *n_breaks, uint32_t *breaks)
 {
+    const uint32_t n = n_dev ? *n_dev : n_host;
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     const uint32_t next = (i + 1 < n) ? off[i + 1] : total;
@@ -218,13 +220,25 @@ __global__ void k_index_check(const uint32_t *__restrict__ off, const uint32_t *
  * break the chain jumps to the candidate that starts exactly where the current record
  * ends; the candidates jumped over were false and get kind 2 (ignored by k_chain).
  * If nothing starts there the decodable prefix ends (the reference decoder stops at
- * the first undecodable byte too).  res[0] = records in the prefix, res[1] = tiled. */
+ * the first undecodable byte too).  res[0] = records in the prefix, res[1] = tiled,
+ * res[2] = where the chain ends.  More than BK_MAX_BREAKS broken links: *ovf = 2, nothing
+ * is touched (the pointer-doubling form below decides). */
 __global__ void __launch_bounds__(1024) k_index_repair(const uint32_t *__restrict__ off, const uint32_t *__restrict__ rlen,
-                                                        uint8_t *kind, uint32_t n, uint32_t base, uint32_t total,
-                                                        const uint32_t *n_breaks, const uint32_t *breaks, uint32_t *res)
+                                                        uint8_t *kind, uint32_t n_host, const uint32_t *__restrict__ n_dev,
+                                                        uint32_t base, uint32_t total,
+                                                        const uint32_t *n_breaks, const uint32_t *breaks, uint32_t *res, uint32_t *ovf)
 {
     __shared__ uint32_t sorted[BK_MAX_BREAKS];
+    const uint32_t n = n_dev ? *n_dev : n_host;
     const uint32_t m = *n_breaks;
+    if (m > BK_MAX_BREAKS) {
+        if (threadIdx.x == 0) { res[0] = 0; res[1] = 0; res[2] = base; if (ovf) *ovf = 2; }
+        return;
+    }
+    if (n == 0) {
+        if (threadIdx.x == 0) { res[0] = 0; res[1] = (base == total); res[2] = base; }
+        return;
+    }
     for (uint32_t i = threadIdx.x; i < m; i += blockDim.x) {          /* rank sort: values are distinct */
         const uint32_t v = breaks[i];
         uint32_t r = 0;
@@ -255,6 +269,42 @@ __global__ void __launch_bounds__(1024) k_index_repair(const uint32_t *__restric
     }
 }
 
+/* ---- the same decision by pointer doubling (any number of broken links) ----
+ * next[i] = the candidate that starts where candidate i ends (n = "the slice ends there",
+ * 0xffffffff = nothing starts there).  The records are the candidates on the path from
+ * candidate 0; after k rounds `mark` holds the first 2^k of them and jump = next^(2^k). */
+#define LINK_NONE 0xffffffffu
+__global__ void k_link_next(const uint32_t *__restrict__ off, const uint32_t *__restrict__ rlen, uint32_t n, uint32_t base,
+                            uint32_t total, uint32_t *__restrict__ next, uint8_t *__restrict__ mark)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t target = off[i] + rlen[i];
+    uint32_t lo = i + 1, hi = n;                       /* first candidate at or behind target */
+    while (lo < hi) { const uint32_t mid = lo + (hi - lo) / 2; if (off[mid] < target) lo = mid + 1; else hi = mid; }
+    next[i] = (lo < n && off[lo] == target) ? lo : (lo == n && target == total) ? n : LINK_NONE;
+    mark[i] = (i == 0 && off[0] == base) ? 1 : 0;
+}
+__global__ void k_link_step(const uint32_t *__restrict__ jump, uint32_t *__restrict__ jump2, uint8_t *mark, uint32_t n)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const uint32_t j = jump[i];
+    if (j < n) { if (mark[i]) mark[j] = 1; jump2[i] = jump[j]; }
+    else jump2[i] = j;
+}
+/* kind 2 for the candidates off the path; res as k_index_repair leaves it */
+__global__ void k_link_finish(const uint32_t *__restrict__ off, const uint32_t *__restrict__ rlen, const uint32_t *__restrict__ next,
+                              const uint8_t *__restrict__ mark, uint8_t *kind, uint32_t n, uint32_t base, uint32_t *res)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    if (!mark[i]) { kind[i] = 2; return; }
+    if (next[i] >= n) {                                /* the last record of the path: the prefix ends behind it */
+        res[0] = i + 1; res[1] = next[i] == n; res[2] = off[i] + rlen[i];
+    }
+}
+
 /* ------------------------------------------------------------------ chain */
 struct k_chain_params {
     struct ch_env env;
@@ -263,6 +313,7 @@ struct k_chain_params {
     uint32_t r0;                 /* first record / first block of this launch */
     uint32_t stage_bytes;        /* shared-memory slice per warp for input staging, 0 = none */
     uint32_t n_rec;
+    const uint32_t *n_dev;       /* small form: the record count lives on the device */
     uint32_t *size;
     uint64_t *bsum;
     uint8_t *out;
@@ -278,8 +329,9 @@ struct k_chain_params {
 __global__ void __launch_bounds__(BK_REC_BLOCK, BK_EVAL_MIN_BLOCKS) k_chain_eval(const k_chain_params p)
 {
     extern __shared__ __align__(16) uint8_t dsm[];
+    const uint32_t n_rec = p.n_dev ? *p.n_dev : p.n_rec;
     const uint32_t i = p.r0 + blockIdx.x * BK_REC_BLOCK + threadIdx.x;
-    const bool valid = i < p.n_rec;
+    const bool valid = i < n_rec;
     const uint32_t my_off = valid ? p.off[i] : 0, my_len = valid ? p.len[i] : 0;
     const bool live = valid && p.kind[i] == 0;
     const uint8_t *in = p.env.in;
@@ -310,8 +362,9 @@ __global__ void __launch_bounds__(BK_REC_BLOCK, BK_EVAL_MIN_BLOCKS) k_chain_eval
  * A kernel of its own so that k_chain_eval stays what it is for every other chain. */
 __global__ void __launch_bounds__(BK_REC_BLOCK) k_chain_skipped(const k_chain_params p)
 {
+    const uint32_t n_rec = p.n_dev ? *p.n_dev : p.n_rec;
     const uint32_t i = p.r0 + blockIdx.x * BK_REC_BLOCK + threadIdx.x;
-    if (i >= p.n_rec || p.kind[i] != 1) return;
+    if (i >= n_rec || p.kind[i] != 1) return;
     chain_skipped_record(&p.env, i, p.off[i], p.len[i]);
 }
 
@@ -337,10 +390,11 @@ __global__ void __launch_bounds__(BK_REC_BLOCK) k_surv_count(const uint32_t *__r
     if (threadIdx.x == 0) cnt[blockIdx.x] = tot;
 }
 
-__global__ void __launch_bounds__(BK_REC_BLOCK) k_surv_fill(const uint32_t *__restrict__ size, uint32_t n, uint32_t rec0,
-                                                            const uint32_t *__restrict__ base, const uint64_t *__restrict__ bsum,
+__global__ void __launch_bounds__(BK_REC_BLOCK) k_surv_fill(const uint32_t *__restrict__ size, uint32_t n_host, const uint32_t *__restrict__ n_dev,
+                                                            uint32_t rec0, const uint32_t *__restrict__ base, const uint64_t *__restrict__ bsum,
                                                             uint32_t *__restrict__ l_rec, uint64_t *__restrict__ l_off)
 {
+    const uint32_t n = n_dev ? *n_dev : n_host;
     const uint32_t i = blockIdx.x * BK_REC_BLOCK + threadIdx.x;
     const uint32_t sz = i < n ? size[i] : 0;
     uint32_t tot, nsurv;
@@ -354,20 +408,195 @@ __global__ void __launch_bounds__(BK_REC_BLOCK) k_surv_fill(const uint32_t *__re
 
 __global__ void __launch_bounds__(BK_REC_BLOCK, BK_EVAL_MIN_BLOCKS) k_chain_emit_list(const k_chain_params p, const uint32_t *__restrict__ l_rec,
                                                                                       const uint64_t *__restrict__ l_off,
-                                                                                      const unsigned long long *__restrict__ n_list)
+                                                                                      const unsigned long long *__restrict__ n_list,
+                                                                                      const uint32_t *__restrict__ go)
 {
     const uint32_t t = blockIdx.x * BK_REC_BLOCK + threadIdx.x;
+    if (go && !*go) return;
     if (t >= (uint32_t) *n_list) return;
     const uint32_t r = l_rec[t];
     chain_record<true>(&p.env, r, p.off[r], p.len[r], p.out + l_off[t]);
 }
 
+/* ---- glue of the small-chunk form ---- */
+/* exclusive scan of the tile counts; n_cand = total, or 0 + overflow when the record arrays are too small */
+__global__ void __launch_bounds__(256) k_small_tiles(uint32_t *tile, uint32_t n_tiles, uint32_t cap, struct bk_mail *mail)
+{
+    unsigned long long carry = 0;
+    for (uint32_t b = 0; b < n_tiles; b += 256) {
+        const uint32_t i = b + threadIdx.x;
+        unsigned long long v = i < n_tiles ? (unsigned long long) tile[i] : 0, tot;
+        unsigned long long ex = block_excl_scan_t<unsigned long long>(v, &tot);
+        if (i < n_tiles) tile[i] = (uint32_t) (carry + ex);
+        carry += tot;
+    }
+    if (threadIdx.x == 0) {
+        mail->n_cand64 = carry;
+        mail->overflow = carry > cap ? 1u : 0u;
+        mail->n_cand = carry > cap ? 0u : (uint32_t) carry;
+    }
+}
+
+/* per-block output bytes and survivors of size[0, n_valid) (zero for the blocks behind) */
+__global__ void __launch_bounds__(BK_REC_BLOCK) k_small_sizes(const uint32_t *__restrict__ size, const struct bk_mail *__restrict__ mail,
+                                                              uint64_t *__restrict__ bsum, uint32_t *__restrict__ cnt)
+{
+    const uint32_t n = mail->n_valid;
+    const uint32_t i = blockIdx.x * BK_REC_BLOCK + threadIdx.x;
+    const uint32_t sz = i < n ? size[i] : 0;
+    uint32_t tot, ns;
+    block_excl_scan(sz, &tot);
+    block_excl_scan(sz ? 1u : 0u, &ns);
+    if (threadIdx.x == 0) { bsum[blockIdx.x] = tot; cnt[blockIdx.x] = ns; }
+}
+
+/* exclusive scans of both; totals and the "fits the output buffer" decision into the mail */
+__global__ void __launch_bounds__(256) k_small_scan2(uint64_t *bsum, uint32_t *cnt, uint32_t nb, unsigned long long cap_out, struct bk_mail *mail)
+{
+    unsigned long long cb = 0, cc = 0;
+    for (uint32_t b = 0; b < nb; b += 256) {
+        const uint32_t i = b + threadIdx.x;
+        unsigned long long v = i < nb ? (unsigned long long) bsum[i] : 0, w = i < nb ? (unsigned long long) cnt[i] : 0, tv, tw;
+        unsigned long long ev = block_excl_scan_t<unsigned long long>(v, &tv);
+        unsigned long long ew = block_excl_scan_t<unsigned long long>(w, &tw);
+        if (i < nb) { bsum[i] = cb + ev; cnt[i] = (uint32_t) (cc + ew); }
+        cb += tv; cc += tw;
+    }
+    if (threadIdx.x == 0) { mail->total = cb; mail->n_out = cc; mail->emitted = (cb <= cap_out && !mail->overflow) ? 1u : 0u; }
+}
+
 /* ------------------------------------------------------------ bk_* seam */
+/* persistent worker threads of a queue: idle on a condition variable, woken for one job at a time */
+struct bk_pool {
+    std::mutex m;
+    std::condition_variable cv, cv_done;
+    std::vector<std::thread> th;
+    long gen = 0;
+    int running = 0;
+    bool quit = false;
+    void (*fn)(void *, int) = 0;
+    void *arg = 0;
+    int device = 0;
+
+    void loop(int t)
+    {
+        long seen = 0;
+        cudaSetDevice(device);
+        for (;;) {
+            void (*f)(void *, int); void *a;
+            {
+                std::unique_lock<std::mutex> lk(m);
+                cv.wait(lk, [&] { return quit || gen != seen; });
+                if (quit) return;
+                seen = gen; f = fn; a = arg;
+            }
+            f(a, t);
+            {
+                std::lock_guard<std::mutex> lk(m);
+                if (--running == 0) cv_done.notify_all();
+            }
+        }
+    }
+    void ensure(int n, int dev)
+    {
+        device = dev;
+        while ((int) th.size() < n) { const int t = (int) th.size(); th.emplace_back([this, t] { loop(t); }); }
+    }
+    void run(void (*f)(void *, int), void *a)        /* every thread calls f(a, t) once */
+    {
+        std::lock_guard<std::mutex> lk(m);
+        fn = f; arg = a; running = (int) th.size(); gen++;
+        cv.notify_all();
+    }
+    void wait()
+    {
+        std::unique_lock<std::mutex> lk(m);
+        cv_done.wait(lk, [&] { return running == 0; });
+    }
+    ~bk_pool()
+    {
+        { std::lock_guard<std::mutex> lk(m); quit = true; cv.notify_all(); }
+        for (auto &t : th) t.join();
+    }
+};
+
+#define EV_MAX 1024
+#define UP_PIECE ((size_t) 32 << 20)
+#define UP_MAX_EV 256
+#define UP_THREADS 6
+#define UP_STAGE_SLOTS 12
+#define XF_MAX_SLOTS 32
+#define XF_MAX_RANGES 512
+
+struct bk_q {
+    int device;
+    cudaStream_t stream, istream, h2d, copy;
+    /* CUDA-event timing of the kernel groups of the last call: one event pair per launch
+     * (0 = index, 1 = evaluate, 2 = emit); bk_kernel_ms() sums the pairs of a group. */
+    cudaEvent_t evp[3][EV_MAX][2];
+    int ev_made[3], ev_used[3];
+    /* small device scratch */
+    unsigned long long *dtotal;            /* [0] totals, [1..] index results, [8] records emitted */
+    uint32_t *dbreaks;
+    uint32_t *d_cnt, *d_lrec; uint64_t *d_loff; unsigned long long *d_nlist; size_t cap_b, cap_r;
+    uint32_t *d_link[2]; uint8_t *d_mark; size_t cap_link;
+    unsigned long long *h_word;            /* pinned: a few words read back per call */
+    struct bk_mail *d_mail, *h_mail;       /* small form */
+    uint32_t *h_flags;                     /* pinned copy of the evidence words */
+    int stage_kb;
+    /* upload */
+    cudaEvent_t up_ev[UP_MAX_EV]; int up_ev_made;
+    size_t up_total, up_piece; int up_active, up_staged;
+    uint8_t *up_stage[UP_STAGE_SLOTS]; int up_stage_ready;
+    std::atomic<int> up_recorded[UP_MAX_EV];
+    std::atomic<long> up_next_issue;
+    std::atomic<int> up_failed;
+    uint8_t *up_dst; const uint8_t *up_src; size_t up_n, up_np;
+    bk_pool *up_pool; int up_running;
+    /* download: ring geometry FLBGPU_XF_SLOTS staging buffers (one copy-out thread each) of FLBGPU_XF_MB MiB */
+    int xf_slots; size_t xf_slice;
+    cudaEvent_t xf_rev[XF_MAX_RANGES];
+    int xf_rev_made;
+    uint8_t *xf_ring[XF_MAX_SLOTS];
+    cudaEvent_t xf_ev[XF_MAX_SLOTS];
+    int xf_ready;
+    uint8_t *xf_dst; const uint8_t *xf_src;
+    std::atomic<long> xf_issued[XF_MAX_SLOTS], xf_done[XF_MAX_SLOTS];
+    size_t xf_off[XF_MAX_SLOTS], xf_len[XF_MAX_SLOTS];
+    std::atomic<long> xf_n_issued;          /* ring slices issued so far */
+    std::atomic<int> xf_closed, xf_failed;
+    /* byte ranges handed over by bk_download_push(); the issuer thread turns them into ring slices so
+     * that the caller (which also drives indexing and evaluation of the next slice) never blocks on a
+     * full ring.  The range slots are a ring themselves. */
+    size_t xf_lo[XF_MAX_RANGES], xf_hi[XF_MAX_RANGES];
+    std::atomic<long> xf_n_pushed, xf_n_taken;
+    std::atomic<int> xf_push_closed;
+    bk_pool *xf_pool; int xf_open;
+};
+
+static inline void use(bk_q *q) { cudaSetDevice(q->device); }
+
+static void ev_begin_on(bk_q *q, int k, cudaStream_t st)
+{
+    if (q->ev_used[k] >= EV_MAX) return;
+    if (q->ev_used[k] >= q->ev_made[k]) {
+        cudaEventCreate(&q->evp[k][q->ev_made[k]][0]); cudaEventCreate(&q->evp[k][q->ev_made[k]][1]);
+        q->ev_made[k]++;
+    }
+    cudaEventRecord(q->evp[k][q->ev_used[k]][0], st);
+}
+static void ev_end_on(bk_q *q, int k, cudaStream_t st)
+{
+    if (q->ev_used[k] >= EV_MAX) return;
+    cudaEventRecord(q->evp[k][q->ev_used[k]][1], st);
+    q->ev_used[k]++;
+}
+
 extern "C" {
 
 const char *bk_name(void) { return "cuda-sm_100a"; }
 const char *bk_last_error(void) { return g_err; }
-uint64_t bk_launch_count(void) { return g_launches; }
+uint64_t bk_launch_count(void) { return g_launches.load(); }
 
 int bk_device_count(void)
 {
@@ -407,20 +636,8 @@ static void bind_near_device(int device)
     if (any) sched_setaffinity(0, sizeof(set), &set);
 }
 
-int bk_init(int device)
+static int func_attrs_once(void)
 {
-    int n = 0;
-    cudaError_t e = cudaGetDeviceCount(&n);
-    if (e != cudaSuccess || n <= 0) {
-        snprintf(g_err, sizeof(g_err), "no CUDA device available (%s); libflbgpu has no CPU path",
-                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
-        return -1;
-    }
-    if (device < 0 || device >= n) { snprintf(g_err, sizeof(g_err), "device %d out of range (0..%d)", device, n - 1); return -1; }
-    CK(cudaSetDevice(device));
-    bind_near_device(device);
-    if (!g_stream) CK(cudaStreamCreateWithFlags(&g_stream, cudaStreamNonBlocking));
-    g_ev_ready = 1;
     /* the interpreter keeps its field list and backtrack stack in local memory */
     CK(cudaFuncSetCacheConfig(k_chain_eval, cudaFuncCachePreferL1));
     CK(cudaFuncSetCacheConfig(k_chain_emit_list, cudaFuncCachePreferL1));
@@ -435,343 +652,380 @@ int bk_init(int device)
     return 0;
 }
 
+void bk_q_free(bk_q *q)
+{
+    if (!q) return;
+    use(q);
+    if (q->stream) cudaStreamSynchronize(q->stream);
+    delete q->up_pool; delete q->xf_pool;
+    for (int k = 0; k < 3; k++) for (int i = 0; i < q->ev_made[k]; i++) { cudaEventDestroy(q->evp[k][i][0]); cudaEventDestroy(q->evp[k][i][1]); }
+    for (int i = 0; i < q->up_ev_made; i++) cudaEventDestroy(q->up_ev[i]);
+    for (int i = 0; i < q->xf_rev_made; i++) cudaEventDestroy(q->xf_rev[i]);
+    if (q->up_stage_ready) for (int i = 0; i < UP_STAGE_SLOTS; i++) cudaFreeHost(q->up_stage[i]);
+    if (q->xf_ready) for (int i = 0; i < q->xf_slots; i++) { cudaFreeHost(q->xf_ring[i]); cudaEventDestroy(q->xf_ev[i]); }
+    cudaFree(q->dtotal); cudaFree(q->dbreaks); cudaFree(q->d_cnt); cudaFree(q->d_lrec); cudaFree(q->d_loff); cudaFree(q->d_nlist);
+    cudaFree(q->d_link[0]); cudaFree(q->d_link[1]); cudaFree(q->d_mark); cudaFree(q->d_mail);
+    cudaFreeHost(q->h_word); cudaFreeHost(q->h_mail); cudaFreeHost(q->h_flags);
+    if (q->stream) cudaStreamDestroy(q->stream);
+    if (q->istream) cudaStreamDestroy(q->istream);
+    if (q->h2d) cudaStreamDestroy(q->h2d);
+    if (q->copy) cudaStreamDestroy(q->copy);
+    cudaGetLastError();
+    q->~bk_q();
+    free(q);
+}
+
+static int q_setup(bk_q *q)
+{
+    int lo = 0, hi = 0;
+    CK(cudaSetDevice(q->device));
+    if (func_attrs_once()) return -1;
+    CK(cudaStreamCreateWithFlags(&q->stream, cudaStreamNonBlocking));
+    /* the index kernels of the next slice are short and the host waits for their result: let their
+     * blocks go ahead of the thousands of queued evaluation blocks of the previous slice */
+    CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    CK(cudaStreamCreateWithPriority(&q->istream, cudaStreamNonBlocking, hi));
+    CK(cudaStreamCreateWithFlags(&q->h2d, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&q->copy, cudaStreamNonBlocking));
+    CK(cudaMalloc((void **) &q->dtotal, 128));
+    CK(cudaMemset(q->dtotal, 0, 128));
+    CK(cudaMalloc((void **) &q->dbreaks, sizeof(uint32_t) * BK_MAX_BREAKS));
+    CK(cudaMalloc((void **) &q->d_nlist, 64));
+    CK(cudaMalloc((void **) &q->d_mail, sizeof(struct bk_mail)));
+    CK(cudaMallocHost((void **) &q->h_word, 128));
+    CK(cudaMallocHost((void **) &q->h_mail, sizeof(struct bk_mail)));
+    CK(cudaMallocHost((void **) &q->h_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)));
+    {
+        const char *e = getenv("FLBGPU_STAGE_KB");           /* KiB of shared memory per warp, 0 = off */
+        q->stage_kb = e ? atoi(e) : 0;
+        if (q->stage_kb < 0 || q->stage_kb > 24) q->stage_kb = 0;
+        if (q->stage_kb) CK(cudaFuncSetAttribute(k_chain_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, q->stage_kb * 1024 * (BK_REC_BLOCK / 32)));
+    }
+    return 0;
+}
+
+bk_q *bk_q_new(int device)
+{
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    void *mem;
+    bk_q *q;
+    if (e != cudaSuccess || n <= 0) {
+        snprintf(g_err, sizeof(g_err), "no CUDA device available (%s); libflbgpu has no CPU path",
+                 e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+        return 0;
+    }
+    if (device < 0 || device >= n) { snprintf(g_err, sizeof(g_err), "device %d out of range (0..%d)", device, n - 1); return 0; }
+    mem = calloc(1, sizeof(bk_q));
+    if (!mem) { snprintf(g_err, sizeof(g_err), "out of memory"); return 0; }
+    q = new (mem) bk_q;
+    q->device = device;
+    q->xf_slots = 16;                 /* measured best on the bench box: 16 x 8 MiB (profiles/r01_variants.txt) */
+    q->xf_slice = (size_t) 8 << 20;
+    if (cudaSetDevice(device) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaSetDevice(%d) failed", device); q->~bk_q(); free(q); return 0; }
+    bind_near_device(device);
+    if (q_setup(q)) { bk_q_free(q); return 0; }
+    return q;
+}
+
+int bk_q_device(bk_q *q) { return q->device; }
+
 /* 64 bytes of slack: djf_scan_plain reads whole aligned 8-byte words */
-void *bk_alloc(size_t n) { void *p = 0; if (cudaMalloc(&p, n + 64) != cudaSuccess) { snprintf(g_err, sizeof(g_err), "cudaMalloc(%zu) failed", n); return 0; } return p; }
-void bk_free(void *p) { if (p) cudaFree(p); }
-void *bk_alloc_host(size_t n) { void *p = 0; if (cudaMallocHost(&p, n ? n : 16) != cudaSuccess) return 0; return p; }
-void bk_free_host(void *p) { if (p) cudaFreeHost(p); }
-int bk_h2d(void *d, const void *h, size_t n) { CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, g_stream)); return 0; }
-int bk_d2h(void *h, const void *d, size_t n) { CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, g_stream)); return 0; }
-int bk_zero(void *d, size_t n) { CK(cudaMemsetAsync(d, 0, n, g_stream)); return 0; }
-int bk_sync(void) { CK(cudaStreamSynchronize(g_stream)); return 0; }
-void *bk_stream(void) { return (void *) g_stream; }
+void *bk_alloc(bk_q *q, size_t n) { void *p = 0; use(q); if (cudaMalloc(&p, n + 64) != cudaSuccess) { cudaGetLastError(); snprintf(g_err, sizeof(g_err), "cudaMalloc(%zu) failed", n); return 0; } return p; }
+void bk_free(bk_q *q, void *p) { if (p) { use(q); cudaFree(p); } }
+void *bk_alloc_host(bk_q *q, size_t n) { void *p = 0; use(q); if (cudaMallocHost(&p, n ? n : 16) != cudaSuccess) { cudaGetLastError(); return 0; } return p; }
+void bk_free_host(bk_q *q, void *p) { if (p) { use(q); cudaFreeHost(p); } }
+int bk_h2d(bk_q *q, void *d, const void *h, size_t n) { use(q); CK(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, q->stream)); return 0; }
+int bk_d2h(bk_q *q, void *h, const void *d, size_t n) { use(q); CK(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, q->stream)); return 0; }
+int bk_zero(bk_q *q, void *d, size_t n) { use(q); CK(cudaMemsetAsync(d, 0, n, q->stream)); return 0; }
+int bk_sync(bk_q *q) { use(q); CK(cudaStreamSynchronize(q->stream)); return 0; }
+void *bk_stream(bk_q *q) { return (void *) q->stream; }
 
 /* milliseconds of [index, evaluate (last pass), emit] of the last call; needs a prior bk_sync() */
-int bk_kernel_ms(float out[3])
+int bk_kernel_ms(bk_q *q, float out[3])
 {
+    use(q);
     for (int k = 0; k < 3; k++) {
         out[k] = 0.f;
-        for (int i = 0; i < g_ev_used[k]; i++) {
+        for (int i = 0; i < q->ev_used[k]; i++) {
             float ms = 0.f;
-            if (cudaEventSynchronize(g_evp[k][i][1]) == cudaSuccess &&
-                cudaEventElapsedTime(&ms, g_evp[k][i][0], g_evp[k][i][1]) == cudaSuccess) out[k] += ms;
+            if (cudaEventSynchronize(q->evp[k][i][1]) == cudaSuccess &&
+                cudaEventElapsedTime(&ms, q->evp[k][i][0], q->evp[k][i][1]) == cudaSuccess) out[k] += ms;
         }
     }
     return 0;
 }
 
-
-static cudaStream_t g_h2d, g_copy;
-static int g_streams_ready;
-static int streams_init(void)
-{
-    if (g_streams_ready) return 0;
-    {   /* the index kernels of the next slice are short and the host waits for their result: let their
-         * blocks go ahead of the thousands of queued evaluation blocks of the previous slice */
-        int lo = 0, hi = 0;
-        CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        CK(cudaStreamCreateWithPriority(&g_istream, cudaStreamNonBlocking, hi));
-    }
-    CK(cudaStreamCreateWithFlags(&g_h2d, cudaStreamNonBlocking));
-    CK(cudaStreamCreateWithFlags(&g_copy, cudaStreamNonBlocking));
-    g_streams_ready = 1;
-    return 0;
-}
-
-/* ---- upload: pieces with events ---- */
-#define UP_PIECE ((size_t) 32 << 20)
-#define UP_MAX_EV 256
-static cudaEvent_t up_ev[UP_MAX_EV];
-static int up_ev_made;
-static size_t up_total, up_piece;
-static int up_active;
-
-/* Pageable input (a chunk that lives in ordinary malloc()ed memory, as Fluent Bit's do): the driver
+/* ---- upload: pieces with events ----
+ * Pageable input (a chunk that lives in ordinary malloc()ed memory, as Fluent Bit's do): the driver
  * would stage every cudaMemcpyAsync itself, synchronously and single-threaded.  Instead UP_THREADS host
  * threads copy the pieces into pinned staging buffers in parallel and enqueue the H2D copies in piece
  * order; up_recorded[i] tells the indexing side when piece i's event exists. */
-#define UP_THREADS 6
-#define UP_STAGE_SLOTS 12
-static uint8_t *up_stage[UP_STAGE_SLOTS];
-static cudaEvent_t up_stage_ev[UP_STAGE_SLOTS];
-static int up_stage_ready;
-static std::atomic<int> up_recorded[UP_MAX_EV];
-static std::atomic<long> up_next_issue;
-static std::atomic<int> up_failed;
-static std::thread up_threads[UP_THREADS];
-static int up_threads_live, up_staged;
-
-static void up_worker(int t, uint8_t *d_dst, const uint8_t *h_src, size_t n, size_t piece, size_t np)
+static void up_worker(void *arg, int t)
 {
+    bk_q *q = (bk_q *) arg;
+    const size_t n = q->up_n, piece = q->up_piece, np = q->up_np;
     for (size_t i = (size_t) t; i < np; i += UP_THREADS) {
         const int slot = (int) (i % UP_STAGE_SLOTS);
         const size_t off = i * piece, sz = (off + piece <= n) ? piece : n - off;
         /* the slot was last used by piece i - UP_STAGE_SLOTS: its H2D must have left the buffer */
         if (i >= UP_STAGE_SLOTS) {
-            while (!up_recorded[i - UP_STAGE_SLOTS].load(std::memory_order_acquire)) { if (up_failed.load()) return; sched_yield(); }
-            if (cudaEventSynchronize(up_ev[i - UP_STAGE_SLOTS]) != cudaSuccess) { up_failed.store(1); return; }
+            while (!q->up_recorded[i - UP_STAGE_SLOTS].load(std::memory_order_acquire)) { if (q->up_failed.load()) return; sched_yield(); }
+            if (cudaEventSynchronize(q->up_ev[i - UP_STAGE_SLOTS]) != cudaSuccess) { q->up_failed.store(1); return; }
         }
-        memcpy(up_stage[slot], h_src + off, sz);
-        while (up_next_issue.load(std::memory_order_acquire) != (long) i) { if (up_failed.load()) return; sched_yield(); }
-        if (cudaMemcpyAsync(d_dst + off, up_stage[slot], sz, cudaMemcpyHostToDevice, g_h2d) != cudaSuccess ||
-            cudaEventRecord(up_ev[i], g_h2d) != cudaSuccess) { up_failed.store(1); up_next_issue.store((long) i + 1); return; }
-        up_recorded[i].store(1, std::memory_order_release);
-        up_next_issue.store((long) i + 1, std::memory_order_release);
+        if (!q->up_stage[slot] && cudaMallocHost((void **) &q->up_stage[slot], UP_PIECE) != cudaSuccess) { q->up_failed.store(1); q->up_next_issue.store((long) i + 1); return; }
+        memcpy(q->up_stage[slot], q->up_src + off, sz);
+        while (q->up_next_issue.load(std::memory_order_acquire) != (long) i) { if (q->up_failed.load()) return; sched_yield(); }
+        if (cudaMemcpyAsync(q->up_dst + off, q->up_stage[slot], sz, cudaMemcpyHostToDevice, q->h2d) != cudaSuccess ||
+            cudaEventRecord(q->up_ev[i], q->h2d) != cudaSuccess) { q->up_failed.store(1); q->up_next_issue.store((long) i + 1); return; }
+        q->up_recorded[i].store(1, std::memory_order_release);
+        q->up_next_issue.store((long) i + 1, std::memory_order_release);
     }
 }
 
-void bk_upload_end(void)
+void bk_upload_end(bk_q *q)
 {
-    if (up_threads_live) {
-        for (int t = 0; t < UP_THREADS; t++) up_threads[t].join();
-        up_threads_live = 0;
-    }
+    if (q->up_running) { q->up_pool->wait(); q->up_running = 0; }
 }
 
-int bk_upload_start(void *d_dst, const void *h_src, size_t n)
+int bk_upload_start(bk_q *q, void *d_dst, const void *h_src, size_t n)
 {
-    if (streams_init()) return -1;
-    bk_upload_end();
-    up_piece = UP_PIECE;
-    while ((n + up_piece - 1) / up_piece > UP_MAX_EV) up_piece *= 2;
-    const size_t np = (n + up_piece - 1) / up_piece;
-    for (; up_ev_made < (int) np; up_ev_made++) CK(cudaEventCreateWithFlags(&up_ev[up_ev_made], cudaEventDisableTiming));
-    up_total = n; up_active = 1; up_staged = 0;
+    use(q);
+    bk_upload_end(q);
+    q->up_piece = UP_PIECE;
+    while ((n + q->up_piece - 1) / q->up_piece > UP_MAX_EV) q->up_piece *= 2;
+    const size_t np = (n + q->up_piece - 1) / q->up_piece;
+    for (; q->up_ev_made < (int) np; q->up_ev_made++) CK(cudaEventCreateWithFlags(&q->up_ev[q->up_ev_made], cudaEventDisableTiming));
+    q->up_total = n; q->up_active = 1; q->up_staged = 0;
     {
         cudaPointerAttributes at;
         const int pinned = cudaPointerGetAttributes(&at, h_src) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
         cudaGetLastError();
-        if (!pinned && up_piece == UP_PIECE && !getenv("FLBGPU_NO_STAGING")) {
-            if (!up_stage_ready) {
-                for (int i = 0; i < UP_STAGE_SLOTS; i++) CK(cudaMallocHost((void **) &up_stage[i], UP_PIECE));
-                up_stage_ready = 1;
-            }
-            for (size_t i = 0; i < np; i++) up_recorded[i].store(0);
-            up_next_issue.store(0); up_failed.store(0);
-            up_staged = 1;
-            for (int t = 0; t < UP_THREADS; t++)
-                up_threads[t] = std::thread(up_worker, t, (uint8_t *) d_dst, (const uint8_t *) h_src, n, up_piece, np);
-            up_threads_live = 1;
+        if (!pinned && q->up_piece == UP_PIECE && !getenv("FLBGPU_NO_STAGING")) {
+            q->up_stage_ready = 1;                 /* the pinned staging slots are allocated by the thread that first uses them */
+            if (!q->up_pool) { q->up_pool = new bk_pool; q->up_pool->ensure(UP_THREADS, q->device); }
+            for (size_t i = 0; i < np; i++) q->up_recorded[i].store(0);
+            q->up_next_issue.store(0); q->up_failed.store(0);
+            q->up_staged = 1;
+            q->up_dst = (uint8_t *) d_dst; q->up_src = (const uint8_t *) h_src; q->up_n = n; q->up_np = np;
+            q->up_pool->run(up_worker, q);
+            q->up_running = 1;
             return 0;
         }
     }
     for (size_t i = 0; i < np; i++) {
-        const size_t off = i * up_piece, sz = (off + up_piece <= n) ? up_piece : n - off;
-        CK(cudaMemcpyAsync((uint8_t *) d_dst + off, (const uint8_t *) h_src + off, sz, cudaMemcpyHostToDevice, g_h2d));
-        CK(cudaEventRecord(up_ev[i], g_h2d));
+        const size_t off = i * q->up_piece, sz = (off + q->up_piece <= n) ? q->up_piece : n - off;
+        CK(cudaMemcpyAsync((uint8_t *) d_dst + off, (const uint8_t *) h_src + off, sz, cudaMemcpyHostToDevice, q->h2d));
+        CK(cudaEventRecord(q->up_ev[i], q->h2d));
     }
     return 0;
 }
-void bk_upload_none(void) { bk_upload_end(); up_active = 0; }
-int bk_upload_wait_index(size_t upto)
+void bk_upload_none(bk_q *q) { bk_upload_end(q); q->up_active = 0; }
+int bk_upload_wait_index(bk_q *q, size_t upto)
 {
-    if (streams_init()) return -1;
-    if (!up_active || upto == 0) return 0;
-    if (upto > up_total) upto = up_total;
-    const size_t last = (upto - 1) / up_piece;
-    if (up_staged) {
-        while (!up_recorded[last].load(std::memory_order_acquire)) {
-            if (up_failed.load()) { snprintf(g_err, sizeof(g_err), "host->device staging failed"); return -1; }
+    use(q);
+    if (!q->up_active || upto == 0) return 0;
+    if (upto > q->up_total) upto = q->up_total;
+    const size_t last = (upto - 1) / q->up_piece;
+    if (q->up_staged) {
+        while (!q->up_recorded[last].load(std::memory_order_acquire)) {
+            if (q->up_failed.load()) { snprintf(g_err, sizeof(g_err), "host->device staging failed"); return -1; }
             sched_yield();
         }
     }
-    CK(cudaStreamWaitEvent(g_istream, up_ev[last], 0));
+    CK(cudaStreamWaitEvent(q->istream, q->up_ev[last], 0));
     return 0;
 }
 
-/* ---- download session: pinned ring + one host thread per slot ---- */
-#define XF_MAX_SLOTS 32
-/* ring geometry: FLBGPU_XF_SLOTS staging buffers (one copy-out thread each) of FLBGPU_XF_MB MiB */
-static int XF_SLOTS = 16;           /* measured best on the bench box: 16 x 8 MiB (profiles/r01_variants.txt) */
-static size_t XF_SLICE = (size_t) 8 << 20;
-#define XF_MAX_RANGES 512
-static cudaEvent_t xf_rev[XF_MAX_RANGES];
-static int xf_rev_made;
-static uint8_t *xf_ring[XF_MAX_SLOTS];
-static cudaEvent_t xf_ev[XF_MAX_SLOTS], xf_evc;
-static int xf_ready;
-struct xf_session {
-    uint8_t *h_dst; const uint8_t *d_src;
-    std::atomic<long> issued[XF_MAX_SLOTS], done[XF_MAX_SLOTS];
-    size_t s_off[XF_MAX_SLOTS], s_len[XF_MAX_SLOTS];
-    std::atomic<long> n_issued;          /* slices issued so far */
-    std::atomic<int> closed, failed;
-    std::thread th[XF_MAX_SLOTS];
-    int started;
-    /* byte ranges handed over by bk_download_push(); an issuer thread turns them into ring slices so
-     * that the caller (which also drives indexing and evaluation of the next slice) never blocks on a
-     * full ring */
-    size_t r_lo[XF_MAX_RANGES], r_hi[XF_MAX_RANGES];
-    std::atomic<long> n_pushed;
-    std::atomic<int> push_closed;
-    std::thread issuer;
-};
-static xf_session *g_xf;
-
-static int xf_init(void)
+/* ---- download session: pinned ring + one persistent host thread per slot + the issuer ---- */
+static int xf_init(bk_q *q)
 {
-    if (xf_ready) return 0;
-    if (streams_init()) return -1;
+    if (q->xf_ready) return 0;
     {
         const char *es = getenv("FLBGPU_XF_SLOTS"), *em = getenv("FLBGPU_XF_MB");
-        if (es && atoi(es) >= 2 && atoi(es) <= XF_MAX_SLOTS) XF_SLOTS = atoi(es);
-        if (em && atoi(em) >= 1 && atoi(em) <= 256) XF_SLICE = (size_t) atoi(em) << 20;
+        if (es && atoi(es) >= 2 && atoi(es) <= XF_MAX_SLOTS) q->xf_slots = atoi(es);
+        if (em && atoi(em) >= 1 && atoi(em) <= 256) q->xf_slice = (size_t) atoi(em) << 20;
     }
-    for (int i = 0; i < XF_SLOTS; i++) {
-        CK(cudaMallocHost((void **) &xf_ring[i], XF_SLICE));
-        CK(cudaEventCreateWithFlags(&xf_ev[i], cudaEventDisableTiming));
-    }
-    CK(cudaEventCreateWithFlags(&xf_evc, cudaEventDisableTiming));
-    xf_ready = 1;
+    for (int i = 0; i < q->xf_slots; i++) CK(cudaEventCreateWithFlags(&q->xf_ev[i], cudaEventDisableTiming));   /* ring buffers: on first use */
+    q->xf_pool = new bk_pool;
+    q->xf_pool->ensure(q->xf_slots + 1, q->device);
+    q->xf_ready = 1;
     return 0;
 }
 
-static void xf_worker(xf_session *x, int s)
+static void xf_copy_out(bk_q *q, int s)
 {
-    for (long i = s;; i += XF_SLOTS) {
-        while (x->issued[s].load(std::memory_order_acquire) < i) {
-            if (x->failed.load()) return;
-            if (x->closed.load() && x->n_issued.load() <= i) return;
+    for (long i = s;; i += q->xf_slots) {
+        while (q->xf_issued[s].load(std::memory_order_acquire) < i) {
+            if (q->xf_failed.load()) return;
+            if (q->xf_closed.load() && q->xf_n_issued.load() <= i) return;
             sched_yield();
         }
-        if (cudaEventSynchronize(xf_ev[s]) != cudaSuccess) { x->failed.store(1); return; }
-        flbgpu_stream_copy(x->h_dst + x->s_off[s], xf_ring[s], x->s_len[s]);
-        x->done[s].store(i, std::memory_order_release);
+        if (cudaEventSynchronize(q->xf_ev[s]) != cudaSuccess) { q->xf_failed.store(1); return; }
+        flbgpu_stream_copy(q->xf_dst + q->xf_off[s], q->xf_ring[s], q->xf_len[s]);
+        q->xf_done[s].store(i, std::memory_order_release);
     }
 }
 
-static void xf_issuer(xf_session *x)
+static void xf_issue(bk_q *q)
 {
     for (long r = 0;; r++) {
-        while (x->n_pushed.load(std::memory_order_acquire) <= r) {
-            if (x->failed.load() || x->push_closed.load()) {
-                if (x->n_pushed.load(std::memory_order_acquire) > r) break;
-                x->closed.store(1);
+        while (q->xf_n_pushed.load(std::memory_order_acquire) <= r) {
+            if (q->xf_failed.load() || q->xf_push_closed.load()) {
+                if (q->xf_n_pushed.load(std::memory_order_acquire) > r) break;
+                q->xf_closed.store(1);
                 return;
             }
             sched_yield();
         }
-        /* bytes [lo,hi) exist once the emission recorded in xf_rev[r] is done */
-        if (cudaStreamWaitEvent(g_copy, xf_rev[r], 0) != cudaSuccess) { x->failed.store(1); x->closed.store(1); return; }
-        for (size_t off = x->r_lo[r]; off < x->r_hi[r] && !x->failed.load(); off += XF_SLICE) {
-            const long i = x->n_issued.load();
-            const int s = (int) (i % XF_SLOTS);
-            const size_t sz = (off + XF_SLICE <= x->r_hi[r]) ? XF_SLICE : x->r_hi[r] - off;
-            if (i >= XF_SLOTS) while (x->done[s].load(std::memory_order_acquire) < i - XF_SLOTS) { if (x->failed.load()) break; sched_yield(); }
-            x->s_off[s] = off; x->s_len[s] = sz;
-            if (cudaMemcpyAsync(xf_ring[s], x->d_src + off, sz, cudaMemcpyDeviceToHost, g_copy) != cudaSuccess ||
-                cudaEventRecord(xf_ev[s], g_copy) != cudaSuccess) { x->failed.store(1); break; }
-            x->issued[s].store(i, std::memory_order_release);
-            x->n_issued.store(i + 1);
+        const int rs = (int) (r % XF_MAX_RANGES);
+        const size_t lo = q->xf_lo[rs], hi = q->xf_hi[rs];
+        /* bytes [lo,hi) exist once the emission recorded in xf_rev[rs] is done */
+        if (cudaStreamWaitEvent(q->copy, q->xf_rev[rs], 0) != cudaSuccess) { q->xf_failed.store(1); q->xf_closed.store(1); return; }
+        q->xf_n_taken.store(r + 1, std::memory_order_release);          /* the range slot may be used again */
+        for (size_t off = lo; off < hi && !q->xf_failed.load(); off += q->xf_slice) {
+            const long i = q->xf_n_issued.load();
+            const int s = (int) (i % q->xf_slots);
+            const size_t sz = (off + q->xf_slice <= hi) ? q->xf_slice : hi - off;
+            if (i >= q->xf_slots) while (q->xf_done[s].load(std::memory_order_acquire) < i - q->xf_slots) { if (q->xf_failed.load()) break; sched_yield(); }
+            q->xf_off[s] = off; q->xf_len[s] = sz;
+            if (!q->xf_ring[s] && cudaMallocHost((void **) &q->xf_ring[s], q->xf_slice) != cudaSuccess) { q->xf_failed.store(1); break; }
+            if (cudaMemcpyAsync(q->xf_ring[s], q->xf_src + off, sz, cudaMemcpyDeviceToHost, q->copy) != cudaSuccess ||
+                cudaEventRecord(q->xf_ev[s], q->copy) != cudaSuccess) { q->xf_failed.store(1); break; }
+            q->xf_issued[s].store(i, std::memory_order_release);
+            q->xf_n_issued.store(i + 1);
         }
     }
 }
 
-int bk_download_begin(void *h_dst, const void *d_out)
+static void xf_worker(void *arg, int t)
 {
-    if (xf_init()) return -1;
-    xf_session *x = new xf_session();
-    x->h_dst = (uint8_t *) h_dst; x->d_src = (const uint8_t *) d_out;
-    for (int s = 0; s < XF_SLOTS; s++) { x->issued[s].store(-1); x->done[s].store(-1); }
-    x->n_issued.store(0); x->closed.store(0); x->failed.store(0);
-    x->n_pushed.store(0); x->push_closed.store(0);
-    for (int s = 0; s < XF_SLOTS; s++) x->th[s] = std::thread(xf_worker, x, s);
-    x->issuer = std::thread(xf_issuer, x);
-    x->started = 1;
-    g_xf = x;
+    bk_q *q = (bk_q *) arg;
+    if (t == q->xf_slots) xf_issue(q); else xf_copy_out(q, t);
+}
+
+int bk_download_begin(bk_q *q, void *h_dst, const void *d_out)
+{
+    use(q);
+    if (xf_init(q)) return -1;
+    q->xf_dst = (uint8_t *) h_dst; q->xf_src = (const uint8_t *) d_out;
+    for (int s = 0; s < q->xf_slots; s++) { q->xf_issued[s].store(-1); q->xf_done[s].store(-1); }
+    q->xf_n_issued.store(0); q->xf_closed.store(0); q->xf_failed.store(0);
+    q->xf_n_pushed.store(0); q->xf_n_taken.store(0); q->xf_push_closed.store(0);
+    q->xf_pool->run(xf_worker, q);
+    q->xf_open = 1;
     return 0;
 }
 
-int bk_download_push(size_t lo, size_t hi)
+int bk_download_push(bk_q *q, size_t lo, size_t hi)
 {
-    xf_session *x = g_xf;
-    if (!x) return -1;
+    use(q);
+    if (!q->xf_open) return -1;
     if (hi <= lo) return 0;
-    const long r = x->n_pushed.load();
-    if (r >= XF_MAX_RANGES) { snprintf(g_err, sizeof(g_err), "too many download ranges"); return -1; }
-    for (; xf_rev_made <= (int) r; xf_rev_made++) CK(cudaEventCreateWithFlags(&xf_rev[xf_rev_made], cudaEventDisableTiming));
-    CK(cudaEventRecord(xf_rev[r], g_stream));
-    x->r_lo[r] = lo; x->r_hi[r] = hi;
-    x->n_pushed.store(r + 1, std::memory_order_release);
-    return x->failed.load() ? -1 : 0;
+    const long r = q->xf_n_pushed.load();
+    while (r - q->xf_n_taken.load(std::memory_order_acquire) >= XF_MAX_RANGES) { if (q->xf_failed.load()) return -1; sched_yield(); }
+    const int rs = (int) (r % XF_MAX_RANGES);
+    for (; q->xf_rev_made <= rs; q->xf_rev_made++) CK(cudaEventCreateWithFlags(&q->xf_rev[q->xf_rev_made], cudaEventDisableTiming));
+    CK(cudaEventRecord(q->xf_rev[rs], q->stream));
+    q->xf_lo[rs] = lo; q->xf_hi[rs] = hi;
+    q->xf_n_pushed.store(r + 1, std::memory_order_release);
+    return q->xf_failed.load() ? -1 : 0;
 }
 
-int bk_download_end(void)
+int bk_download_end(bk_q *q)
 {
-    xf_session *x = g_xf;
     int rc = 0;
-    if (!x) return -1;
-    x->push_closed.store(1);
-    x->issuer.join();
-    for (int s = 0; s < XF_SLOTS; s++) x->th[s].join();
-    if (x->failed.load()) { snprintf(g_err, sizeof(g_err), "device->host transfer failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
-    delete x;
-    g_xf = 0;
+    if (!q->xf_open) return -1;
+    q->xf_push_closed.store(1);
+    q->xf_pool->wait();
+    q->xf_open = 0;
+    if (q->xf_failed.load()) { use(q); snprintf(g_err, sizeof(g_err), "device->host transfer failed: %s", cudaGetErrorString(cudaGetLastError())); rc = -1; }
     return rc;
 }
 
-int bk_d2d(void *dst, const void *src, size_t n)
+int bk_d2d(bk_q *q, void *dst, const void *src, size_t n)
 {
+    use(q);
     CK(cudaMemcpy(dst, src, n, cudaMemcpyDeviceToDevice));
     return 0;
 }
 
-static unsigned long long *g_dtotal;   /* device scratch for totals / repair results */
-static uint32_t *g_dbreaks;
-static int ensure_small(void)
-{
-    if (streams_init()) return -1;
-    if (!g_dtotal) CK(cudaMalloc((void **) &g_dtotal, 128));
-    if (!g_dbreaks) CK(cudaMalloc((void **) &g_dbreaks, sizeof(uint32_t) * BK_MAX_BREAKS));
-    return 0;
-}
-
-int bk_index_count(const uint8_t *d_in, size_t slice_off, uint32_t slice_len, uint32_t *d_tile, uint32_t n_tiles,
+int bk_index_count(bk_q *q, const uint8_t *d_in, size_t slice_off, uint32_t slice_len, uint32_t *d_tile, uint32_t n_tiles,
                    uint32_t *n_cand)
 {
-    unsigned long long tot = 0;
-    if (ensure_small()) return -1;
+    use(q);
     *n_cand = 0;
     if (n_tiles == 0) return 0;
-    ev_begin_on(0, g_istream);
+    ev_begin_on(q, 0, q->istream);
     {
         const uint32_t skip = (uint32_t) (slice_off & 15);
-        k_index<false><<<n_tiles, 256, 0, g_istream>>>(d_in + slice_off - skip, slice_len + skip, skip, (uint32_t) (slice_off - skip), d_tile, 0, 0, 0);
+        k_index<false><<<n_tiles, 256, 0, q->istream>>>(d_in + slice_off - skip, slice_len + skip, skip, (uint32_t) (slice_off - skip), d_tile, 0, 0, 0, 0);
     }
-    k_scan_top<uint32_t><<<1, 256, 0, g_istream>>>(d_tile, n_tiles, g_dtotal);
-    ev_end_on(0, g_istream);
+    k_scan_top<uint32_t><<<1, 256, 0, q->istream>>>(d_tile, n_tiles, q->dtotal, 0);
+    ev_end_on(q, 0, q->istream);
     g_launches += 2;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(&tot, g_dtotal, sizeof(tot), cudaMemcpyDeviceToHost, g_istream));
-    CK(cudaStreamSynchronize(g_istream));
-    *n_cand = (uint32_t) tot;
+    CK(cudaMemcpyAsync(&q->h_word[0], q->dtotal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, q->istream));
+    CK(cudaStreamSynchronize(q->istream));
+    *n_cand = (uint32_t) q->h_word[0];
     return 0;
 }
 
-int bk_index_fill(const uint8_t *d_in, size_t slice_off, uint32_t slice_len, const uint32_t *d_tile, uint32_t n_tiles,
+int bk_index_fill(bk_q *q, const uint8_t *d_in, size_t slice_off, uint32_t slice_len, const uint32_t *d_tile, uint32_t n_tiles,
                   uint32_t n_cand, uint32_t *d_off, uint32_t *d_len, uint8_t *d_kind,
                   uint32_t *n_valid, uint64_t *end_off, int *tiled)
 {
-    uint32_t h[4] = { 0, 0, 0, 0 };
-    uint32_t *d_w = (uint32_t *) (g_dtotal + 1);          /* [0] n_breaks, [1] n_valid, [2] tiled, [3] end offset */
+    uint32_t *h = (uint32_t *) &q->h_word[2];
+    uint32_t *d_w = (uint32_t *) (q->dtotal + 1);          /* [0] n_breaks, [1] n_valid, [2] tiled, [3] end offset, [4] overflow */
+    use(q);
     *n_valid = 0; *tiled = (slice_len == 0); *end_off = slice_off;
     if (n_cand == 0) return 0;
-    ev_begin_on(0, g_istream);
+    ev_begin_on(q, 0, q->istream);
     {
         const uint32_t skip = (uint32_t) (slice_off & 15);
-        k_index<true><<<n_tiles, 256, 0, g_istream>>>(d_in + slice_off - skip, slice_len + skip, skip, (uint32_t) (slice_off - skip), (uint32_t *) d_tile, d_off, d_len, d_kind);
+        k_index<true><<<n_tiles, 256, 0, q->istream>>>(d_in + slice_off - skip, slice_len + skip, skip, (uint32_t) (slice_off - skip), (uint32_t *) d_tile, d_off, d_len, d_kind, 0);
     }
-    CK(cudaMemsetAsync(d_w, 0, 16, g_istream));
-    k_index_check<<<(n_cand + 255) / 256, 256, 0, g_istream>>>(d_off, d_len, n_cand, (uint32_t) (slice_off + slice_len), d_w, g_dbreaks);
-    k_index_repair<<<1, 1024, 0, g_istream>>>(d_off, d_len, d_kind, n_cand, (uint32_t) slice_off, (uint32_t) (slice_off + slice_len), d_w, g_dbreaks, d_w + 1);
-    ev_end_on(0, g_istream);
+    CK(cudaMemsetAsync(d_w, 0, 32, q->istream));
+    k_index_check<<<(n_cand + 255) / 256, 256, 0, q->istream>>>(d_off, d_len, n_cand, 0, (uint32_t) (slice_off + slice_len), d_w, q->dbreaks);
+    k_index_repair<<<1, 1024, 0, q->istream>>>(d_off, d_len, d_kind, n_cand, 0, (uint32_t) slice_off, (uint32_t) (slice_off + slice_len), d_w, q->dbreaks, d_w + 1, d_w + 4);
+    ev_end_on(q, 0, q->istream);
     g_launches += 3;
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(h, d_w, sizeof(h), cudaMemcpyDeviceToHost, g_istream));
-    CK(cudaStreamSynchronize(g_istream));
-    if (h[0] > BK_MAX_BREAKS) {
-        snprintf(g_err, sizeof(g_err), "record index: %u broken candidate links in one slice (limit %u)", h[0], BK_MAX_BREAKS);
-        return -1;
+    CK(cudaMemcpyAsync(h, d_w, 32, cudaMemcpyDeviceToHost, q->istream));
+    CK(cudaStreamSynchronize(q->istream));
+    if (h[4] == 2) {
+        /* more broken links than the one-CTA walk holds (e.g. every record carries a nested [int, {map}]
+         * value, which frames as a legacy event): decide the chain by pointer doubling instead */
+        const uint32_t nb = (n_cand + 255) / 256, base = (uint32_t) slice_off, total = (uint32_t) (slice_off + slice_len);
+        uint32_t steps = 1, cur = 0;
+        if (q->cap_link < n_cand) {
+            const size_t want = (size_t) n_cand + n_cand / 2 + 1024;
+            cudaFree(q->d_link[0]); cudaFree(q->d_link[1]); cudaFree(q->d_mark);
+            q->d_link[0] = q->d_link[1] = 0; q->d_mark = 0; q->cap_link = 0;
+            CK(cudaMalloc((void **) &q->d_link[0], sizeof(uint32_t) * want));
+            CK(cudaMalloc((void **) &q->d_link[1], sizeof(uint32_t) * want));
+            CK(cudaMalloc((void **) &q->d_mark, want));
+            q->cap_link = want;
+        }
+        while ((1ull << steps) < (unsigned long long) n_cand + 1) steps++;
+        {
+            const uint32_t none[3] = { 0, 0, base };    /* candidate 0 does not start the slice: nothing decodable */
+            CK(cudaMemcpyAsync(d_w + 1, none, sizeof(none), cudaMemcpyHostToDevice, q->istream));
+        }
+        ev_begin_on(q, 0, q->istream);
+        k_link_next<<<nb, 256, 0, q->istream>>>(d_off, d_len, n_cand, base, total, q->d_link[0], q->d_mark);
+        for (uint32_t s = 0; s < steps; s++) {
+            k_link_step<<<nb, 256, 0, q->istream>>>(q->d_link[cur], q->d_link[cur ^ 1], q->d_mark, n_cand);
+            cur ^= 1;
+        }
+        /* the jump arrays are spent: recompute next[] (mark untouched: a scratch byte array takes the second output) */
+        k_link_next<<<nb, 256, 0, q->istream>>>(d_off, d_len, n_cand, 0xffffffffu, total, q->d_link[0], (uint8_t *) q->d_link[1]);
+        k_link_finish<<<nb, 256, 0, q->istream>>>(d_off, d_len, q->d_link[0], q->d_mark, d_kind, n_cand, base, d_w + 1);
+        ev_end_on(q, 0, q->istream);
+        g_launches += steps + 3;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(h, d_w, 32, cudaMemcpyDeviceToHost, q->istream));
+        CK(cudaStreamSynchronize(q->istream));
     }
     *n_valid = h[1];
     *tiled = (int) h[2];
@@ -786,15 +1040,16 @@ static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_
     p->env.assume = a->assume; p->env.fl_flags = a->d_flags; p->env.err = a->d_flags + FLBGPU_MAX_FILTERS;
     p->env.l2m = a->l2m;
     p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->r0 = r0; p->n_rec = a->n_rec; p->stage_bytes = 0;
+    p->n_dev = 0;
     p->size = a->d_size; p->bsum = a->d_bsum; p->out = d_out;
 }
 
-int bk_flags_clear(uint32_t *d_flags)
+int bk_flags_clear(bk_q *q, uint32_t *d_flags)
 {
-    if (streams_init()) return -1;
-    CK(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1), g_stream));
-    g_ev_used[0] = g_ev_used[1] = g_ev_used[2] = 0;
-    g_nsurv = 0;
+    use(q);
+    CK(cudaMemsetAsync(d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1), q->stream));
+    CK(cudaMemsetAsync(q->dtotal + 8, 0, sizeof(unsigned long long), q->stream));      /* records emitted */
+    q->ev_used[0] = q->ev_used[1] = q->ev_used[2] = 0;
     return 0;
 }
 
@@ -802,17 +1057,15 @@ int bk_flags_clear(uint32_t *d_flags)
  * policy window of the stream) so that it does not evict the lanes' local-memory lines (field lists,
  * regex stacks), which are re-used by every block.  Measured without effect (profiles/r01_variants.txt), so it
  * is opt-in: FLBGPU_L2_WINDOW=1. */
-int bk_hint_streaming(const void *base, size_t bytes)
+int bk_hint_streaming(bk_q *q, const void *base, size_t bytes)
 {
     static int max_win = -1, enabled = -1;
     cudaStreamAttrValue v;
-    if (streams_init()) return -1;
     if (enabled < 0) { const char *e = getenv("FLBGPU_L2_WINDOW"); enabled = (e && e[0] == '1'); }   /* off: no measurable effect on B200 */
     if (!enabled) return 0;
+    use(q);
     if (max_win < 0) {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        if (cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, dev) != cudaSuccess) max_win = 0;
+        if (cudaDeviceGetAttribute(&max_win, cudaDevAttrMaxAccessPolicyWindowSize, q->device) != cudaSuccess) max_win = 0;
     }
     if (max_win <= 0 || !base || !bytes) return 0;
     memset(&v, 0, sizeof(v));
@@ -821,61 +1074,55 @@ int bk_hint_streaming(const void *base, size_t bytes)
     v.accessPolicyWindow.hitRatio = 1.0f;
     v.accessPolicyWindow.hitProp = cudaAccessPropertyStreaming;
     v.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
-    if (cudaStreamSetAttribute(g_stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
+    if (cudaStreamSetAttribute(q->stream, cudaStreamAttributeAccessPolicyWindow, &v) != cudaSuccess) cudaGetLastError();
     return 0;
 }
 
-int bk_chain_eval(const struct bk_chain_args *a, uint32_t r0, uint32_t r1)
+int bk_chain_eval(bk_q *q, const struct bk_chain_args *a, uint32_t r0, uint32_t r1)
 {
     k_chain_params p;
     if (r1 <= r0) return 0;
+    use(q);
     fill_params(a, &p, 0, r0);
     p.n_rec = r1;
-    {
-        static int stage_kb = -1;
-        if (stage_kb < 0) {
-            const char *e = getenv("FLBGPU_STAGE_KB");           /* KiB of shared memory per warp, 0 = off */
-            stage_kb = e ? atoi(e) : 0;
-            if (stage_kb < 0 || stage_kb > 24) stage_kb = 0;
-            if (stage_kb) CK(cudaFuncSetAttribute(k_chain_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, stage_kb * 1024 * (BK_REC_BLOCK / 32)));
-        }
-        p.stage_bytes = (uint32_t) stage_kb * 1024;
-    }
-    ev_begin(1);
-    k_chain_eval<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, (size_t) p.stage_bytes * (BK_REC_BLOCK / 32), g_stream>>>(p);
+    p.stage_bytes = (uint32_t) q->stage_kb * 1024;
+    ev_begin_on(q, 1, q->stream);
+    k_chain_eval<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, (size_t) p.stage_bytes * (BK_REC_BLOCK / 32), q->stream>>>(p);
     if (p.env.l2m.hash) {
-        k_chain_skipped<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, 0, g_stream>>>(p);
+        k_chain_skipped<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, 0, q->stream>>>(p);
         g_launches += 1;
     }
-    ev_end(1);
+    ev_end_on(q, 1, q->stream);
     g_launches += 1;
     CK(cudaGetLastError());
     return 0;
 }
 
-int bk_flags_fetch(const uint32_t *d_flags, uint32_t *h_flags)
+int bk_flags_fetch(bk_q *q, const uint32_t *d_flags, uint32_t *h_flags)
 {
-    CK(cudaMemcpyAsync(h_flags, d_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1), cudaMemcpyDeviceToHost, g_stream));
-    CK(cudaStreamSynchronize(g_stream));
+    use(q);
+    CK(cudaMemcpyAsync(q->h_flags, d_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1), cudaMemcpyDeviceToHost, q->stream));
+    CK(cudaStreamSynchronize(q->stream));
+    memcpy(h_flags, q->h_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1));
     return 0;
 }
 
-int bk_sizes_scan(const uint32_t *d_size, uint32_t n_rec, uint64_t *d_bsum, uint64_t *h_bsum)
+int bk_sizes_scan(bk_q *q, const uint32_t *d_size, uint32_t n_rec, uint64_t *d_bsum, uint64_t *h_bsum)
 {
     const uint32_t nb = (n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK;
-    unsigned long long tot = 0;
-    if (ensure_small()) return -1;
+    use(q);
     h_bsum[0] = 0;
+    q->h_word[0] = 0;
     if (nb) {
-        k_bsum<<<nb, BK_REC_BLOCK, 0, g_stream>>>(d_size, n_rec, d_bsum);
-        k_scan_top<uint64_t><<<1, 256, 0, g_stream>>>(d_bsum, nb, g_dtotal);
+        k_bsum<<<nb, BK_REC_BLOCK, 0, q->stream>>>(d_size, n_rec, d_bsum);
+        k_scan_top<uint64_t><<<1, 256, 0, q->stream>>>(d_bsum, nb, q->dtotal, 0);
         g_launches += 2;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(&tot, g_dtotal, sizeof(tot), cudaMemcpyDeviceToHost, g_stream));
-        CK(cudaMemcpyAsync(h_bsum, d_bsum, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaMemcpyAsync(&q->h_word[0], q->dtotal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, q->stream));
+        CK(cudaMemcpyAsync(h_bsum, d_bsum, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, q->stream));
     }
-    CK(cudaStreamSynchronize(g_stream));
-    h_bsum[nb] = tot;
+    CK(cudaStreamSynchronize(q->stream));
+    h_bsum[nb] = q->h_word[0];
     return 0;
 }
 
@@ -895,72 +1142,132 @@ __global__ void __launch_bounds__(256) k_scan_carry(uint64_t *a, uint32_t n, uns
     if (threadIdx.x == 0) *carry_io = carry;
 }
 
-int bk_sizes_scan_range(const uint32_t *d_size, uint32_t n_rec, uint32_t b0, uint32_t b1, uint64_t *d_bsum, uint64_t *h_bsum,
+int bk_sizes_scan_range(bk_q *q, const uint32_t *d_size, uint32_t n_rec, uint32_t b0, uint32_t b1, uint64_t *d_bsum, uint64_t *h_bsum,
                         uint64_t carry_in)
 {
-    unsigned long long tot = carry_in;
-    if (ensure_small()) return -1;
+    use(q);
     h_bsum[b0] = carry_in;
+    q->h_word[0] = carry_in;
     if (b1 > b0) {
         const uint32_t nb = b1 - b0;
-        CK(cudaMemcpyAsync(g_dtotal, &tot, sizeof(tot), cudaMemcpyHostToDevice, g_stream));
-        k_bsum<<<nb, BK_REC_BLOCK, 0, g_stream>>>(d_size + (size_t) b0 * BK_REC_BLOCK, n_rec - b0 * BK_REC_BLOCK, d_bsum + b0);
-        k_scan_carry<<<1, 256, 0, g_stream>>>(d_bsum + b0, nb, g_dtotal);
+        q->h_word[1] = carry_in;
+        CK(cudaMemcpyAsync(q->dtotal, &q->h_word[1], sizeof(unsigned long long), cudaMemcpyHostToDevice, q->stream));
+        k_bsum<<<nb, BK_REC_BLOCK, 0, q->stream>>>(d_size + (size_t) b0 * BK_REC_BLOCK, n_rec - b0 * BK_REC_BLOCK, d_bsum + b0);
+        k_scan_carry<<<1, 256, 0, q->stream>>>(d_bsum + b0, nb, q->dtotal);
         g_launches += 2;
         CK(cudaGetLastError());
-        CK(cudaMemcpyAsync(&tot, g_dtotal, sizeof(tot), cudaMemcpyDeviceToHost, g_stream));
-        CK(cudaMemcpyAsync(h_bsum + b0, d_bsum + b0, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, g_stream));
+        CK(cudaMemcpyAsync(&q->h_word[0], q->dtotal, sizeof(unsigned long long), cudaMemcpyDeviceToHost, q->stream));
+        CK(cudaMemcpyAsync(h_bsum + b0, d_bsum + b0, sizeof(uint64_t) * nb, cudaMemcpyDeviceToHost, q->stream));
     }
-    CK(cudaStreamSynchronize(g_stream));
-    h_bsum[b1] = tot;
+    CK(cudaStreamSynchronize(q->stream));
+    h_bsum[b1] = q->h_word[0];
     return 0;
 }
-
-#define BK_MAX_EMITS 1024
-static unsigned long long *g_hsurv;
 
 /* records emitted since the last bk_flags_clear(); synchronises the library stream */
-int bk_records_out(uint64_t *n)
+int bk_records_out(bk_q *q, uint64_t *n)
 {
-    unsigned long long t = 0;
-    CK(cudaStreamSynchronize(g_stream));
-    for (int i = 0; i < g_nsurv; i++) t += g_hsurv[i];
-    *n = t;
+    use(q);
+    CK(cudaMemcpyAsync(&q->h_word[0], q->dtotal + 8, sizeof(unsigned long long), cudaMemcpyDeviceToHost, q->stream));
+    CK(cudaStreamSynchronize(q->stream));
+    *n = q->h_word[0];
     return 0;
 }
 
-int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1)
+/* survivor lists for nb blocks */
+static int ensure_lists(bk_q *q, uint32_t nb)
+{
+    if (q->cap_b < nb) { cudaFree(q->d_cnt); q->d_cnt = 0; q->cap_b = 0; CK(cudaMalloc((void **) &q->d_cnt, sizeof(uint32_t) * (nb + nb / 2 + 64))); q->cap_b = nb + nb / 2 + 64; }
+    if (q->cap_r < (size_t) nb * BK_REC_BLOCK) {
+        const size_t want = (size_t) (nb + nb / 2 + 64) * BK_REC_BLOCK;
+        CK(cudaStreamSynchronize(q->stream));           /* an emission still running reads the old lists */
+        cudaFree(q->d_lrec); cudaFree(q->d_loff); q->d_lrec = 0; q->d_loff = 0; q->cap_r = 0;
+        CK(cudaMalloc((void **) &q->d_lrec, sizeof(uint32_t) * want));
+        CK(cudaMalloc((void **) &q->d_loff, sizeof(uint64_t) * want));
+        q->cap_r = want;
+    }
+    return 0;
+}
+
+int bk_chain_emit(bk_q *q, const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1)
 {
     k_chain_params p;
     if (b1 <= b0) return 0;
+    use(q);
     fill_params(a, &p, d_out, b0 * BK_REC_BLOCK);
     {
         const uint32_t nb = b1 - b0, rec0 = b0 * BK_REC_BLOCK;
         const uint32_t n = (a->n_rec > rec0) ? ((a->n_rec - rec0 < nb * BK_REC_BLOCK) ? a->n_rec - rec0 : nb * BK_REC_BLOCK) : 0;
-        static uint32_t *d_cnt, *d_lrec; static uint64_t *d_loff; static unsigned long long *d_nlist; static size_t cap_b, cap_r;
-        if (ensure_small()) return -1;
-        if (cap_b < nb) { cudaFree(d_cnt); d_cnt = 0; cap_b = 0; CK(cudaMalloc((void **) &d_cnt, sizeof(uint32_t) * (nb + nb / 2 + 64))); cap_b = nb + nb / 2 + 64; }
-        if (cap_r < (size_t) nb * BK_REC_BLOCK) {
-            const size_t want = (size_t) (nb + nb / 2 + 64) * BK_REC_BLOCK;
-            CK(cudaStreamSynchronize(g_stream));           /* an emission still running reads the old lists */
-            cudaFree(d_lrec); cudaFree(d_loff); d_lrec = 0; d_loff = 0; cap_r = 0;
-            CK(cudaMalloc((void **) &d_lrec, sizeof(uint32_t) * want));
-            CK(cudaMalloc((void **) &d_loff, sizeof(uint64_t) * want));
-            cap_r = want;
-        }
-        if (!d_nlist) CK(cudaMalloc((void **) &d_nlist, 64));
-        ev_begin(2);
-        k_surv_count<<<nb, BK_REC_BLOCK, 0, g_stream>>>(a->d_size + rec0, n, d_cnt);
-        k_scan_top<uint32_t><<<1, 256, 0, g_stream>>>(d_cnt, nb, d_nlist);
-        k_surv_fill<<<nb, BK_REC_BLOCK, 0, g_stream>>>(a->d_size + rec0, n, rec0, d_cnt, a->d_bsum + b0, d_lrec, d_loff);
-        k_chain_emit_list<<<nb, BK_REC_BLOCK, 0, g_stream>>>(p, d_lrec, d_loff, d_nlist);
-        ev_end(2);
+        if (ensure_lists(q, nb)) return -1;
+        ev_begin_on(q, 2, q->stream);
+        k_surv_count<<<nb, BK_REC_BLOCK, 0, q->stream>>>(a->d_size + rec0, n, q->d_cnt);
+        k_scan_top<uint32_t><<<1, 256, 0, q->stream>>>(q->d_cnt, nb, q->d_nlist, q->dtotal + 8);
+        k_surv_fill<<<nb, BK_REC_BLOCK, 0, q->stream>>>(a->d_size + rec0, n, 0, rec0, q->d_cnt, a->d_bsum + b0, q->d_lrec, q->d_loff);
+        k_chain_emit_list<<<nb, BK_REC_BLOCK, 0, q->stream>>>(p, q->d_lrec, q->d_loff, q->d_nlist, 0);
+        ev_end_on(q, 2, q->stream);
         g_launches += 4;
-        /* how many records this range emitted: read back after the call's last synchronisation */
-        if (!g_hsurv) CK(cudaMallocHost((void **) &g_hsurv, sizeof(unsigned long long) * BK_MAX_EMITS));
-        if (g_nsurv < BK_MAX_EMITS) CK(cudaMemcpyAsync(&g_hsurv[g_nsurv++], d_nlist, sizeof(unsigned long long), cudaMemcpyDeviceToHost, g_stream));
     }
     CK(cudaGetLastError());
+    return 0;
+}
+
+/* ---- the small-chunk form: one stream, no host synchronisation until the mail is read ---- */
+int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8_t *d_in, size_t bytes, uint32_t cap_rec,
+                 uint32_t *d_tile, uint32_t n_tiles, uint8_t *d_out, size_t cap_out, struct bk_small_res *res)
+{
+    k_chain_params p;
+    cudaStream_t st = q->stream;
+    const uint32_t nb_cap = (cap_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK;
+    struct bk_mail *m = q->d_mail;
+    use(q);
+    memset(res, 0, sizeof(*res));
+    if (ensure_lists(q, nb_cap)) return -1;
+    bk_upload_none(q);
+    if (h_in) CK(cudaMemcpyAsync(d_in, h_in, bytes, cudaMemcpyHostToDevice, st));
+    CK(cudaMemsetAsync(m, 0, sizeof(*m), st));
+    /* record index */
+    ev_begin_on(q, 0, st);
+    k_index<false><<<n_tiles, 256, 0, st>>>(d_in, (uint32_t) bytes, 0, 0, d_tile, 0, 0, 0, 0);
+    k_small_tiles<<<1, 256, 0, st>>>(d_tile, n_tiles, cap_rec, m);
+    k_index<true><<<n_tiles, 256, 0, st>>>(d_in, (uint32_t) bytes, 0, 0, d_tile, (uint32_t *) a->d_off, (uint32_t *) a->d_len, (uint8_t *) a->d_kind, m);
+    k_index_check<<<nb_cap, 256, 0, st>>>(a->d_off, a->d_len, 0, &m->n_cand, (uint32_t) bytes, &m->n_breaks, q->dbreaks);
+    k_index_repair<<<1, 1024, 0, st>>>(a->d_off, a->d_len, (uint8_t *) a->d_kind, 0, &m->n_cand, 0, (uint32_t) bytes, &m->n_breaks, q->dbreaks, &m->n_valid, &m->overflow);
+    ev_end_on(q, 0, st);
+    /* evaluation of records [0, n_valid) */
+    fill_params(a, &p, d_out, 0);
+    p.n_rec = 0; p.n_dev = &m->n_valid;
+    p.stage_bytes = (uint32_t) q->stage_kb * 1024;
+    ev_begin_on(q, 1, st);
+    k_chain_eval<<<nb_cap, BK_REC_BLOCK, (size_t) p.stage_bytes * (BK_REC_BLOCK / 32), st>>>(p);
+    if (p.env.l2m.hash) { k_chain_skipped<<<nb_cap, BK_REC_BLOCK, 0, st>>>(p); g_launches += 1; }
+    ev_end_on(q, 1, st);
+    /* sizes, survivor lists, emission under the speculated verdicts */
+    ev_begin_on(q, 2, st);
+    k_small_sizes<<<nb_cap, BK_REC_BLOCK, 0, st>>>(a->d_size, m, a->d_bsum, q->d_cnt);
+    k_small_scan2<<<1, 256, 0, st>>>(a->d_bsum, q->d_cnt, nb_cap, (unsigned long long) cap_out, m);
+    k_surv_fill<<<nb_cap, BK_REC_BLOCK, 0, st>>>(a->d_size, 0, &m->n_valid, 0, q->d_cnt, a->d_bsum, q->d_lrec, q->d_loff);
+    p.stage_bytes = 0;
+    k_chain_emit_list<<<nb_cap, BK_REC_BLOCK, 0, st>>>(p, q->d_lrec, q->d_loff, &m->n_out, &m->emitted);
+    ev_end_on(q, 2, st);
+    g_launches += 10;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(q->h_mail, m, sizeof(*m), cudaMemcpyDeviceToHost, st));
+    CK(cudaMemcpyAsync(q->h_flags, a->d_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1), cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    res->n_cand = (uint32_t) (q->h_mail->n_cand64 > 0xffffffffull ? 0xffffffffu : q->h_mail->n_cand64);
+    res->n_valid = q->h_mail->n_valid; res->tiled = q->h_mail->tiled; res->overflow = q->h_mail->overflow;
+    res->end_off = q->h_mail->end_off; res->total = q->h_mail->total; res->n_out = q->h_mail->n_out;
+    res->emitted = q->h_mail->emitted;
+    memcpy(res->flags, q->h_flags, sizeof(res->flags));
+    return 0;
+}
+
+int bk_small_fetch(bk_q *q, void *h_dst, const uint8_t *d_out, size_t n)
+{
+    use(q);
+    if (!n) return 0;
+    CK(cudaMemcpyAsync(h_dst, d_out, n, cudaMemcpyDeviceToHost, q->stream));
+    CK(cudaStreamSynchronize(q->stream));
     return 0;
 }
 

@@ -22,11 +22,12 @@
 #include <ctype.h>
 #include <time.h>
 #include <sys/mman.h>
+#include <pthread.h>
 #include "../../include/flbgpu.h"
 #include "flbgpu_internal.h"
 #include "rx_compile.h"
 
-static char g_rt_err[512];
+static __thread char g_rt_err[512];
 static void set_err(const char *fmt, const char *a, const char *b)
 {
     snprintf(g_rt_err, sizeof(g_rt_err), fmt, a ? a : "", b ? b : "");
@@ -132,10 +133,14 @@ struct flbgpu_filter {
 struct flbgpu_ctx {
     int device;
     struct flbgpu_parser *parsers;
+    bk_q *q0;                /* queue of the context-level helpers (flbgpu_dev_*, flbgpu_stream) */
+    bk_q *last_q;            /* queue of the most recent chain call: flbgpu_kernel_ms() reads its events */
 };
 
 struct flbgpu_chain {
     flbgpu_ctx *ctx;
+    bk_q *q;                                  /* this instance's device queue: streams, staging rings, worker threads */
+    pthread_mutex_t lock;                     /* one call at a time per instance (the reference never re-enters one either) */
     flbgpu_filter *f[FLBGPU_MAX_FILTERS];
     int nf;
     int inited;
@@ -158,6 +163,7 @@ struct flbgpu_chain {
     uint32_t *d_flags;
     uint64_t *h_bsum; size_t cap_hbsum;      /* host copy of the per-block output offsets */
     uint32_t spec_assume; int spec_valid;     /* verdict vector of the previous call: what the streaming path speculates on */
+    uint32_t small_cap_rec; size_t small_cap_out;   /* what the small-chunk form learnt about this instance's chunks */
     struct flbgpu_stats st;
 };
 
@@ -166,9 +172,14 @@ flbgpu_ctx *flbgpu_init(int device)
 {
     flbgpu_ctx *c;
     g_rt_err[0] = 0;
-    if (bk_init(device) != 0) return NULL;
-    c = calloc(1, sizeof(*c));
-    c->device = device;
+    {
+        bk_q *q0 = bk_q_new(device);
+        if (!q0) return NULL;
+        c = calloc(1, sizeof(*c));
+        if (!c) { bk_q_free(q0); set_err("out of memory%s%s", NULL, NULL); return NULL; }
+        c->device = device;
+        c->q0 = q0;
+    }
     return c;
 }
 
@@ -178,16 +189,17 @@ void flbgpu_shutdown(flbgpu_ctx *ctx)
 {
     if (!ctx) return;
     while (ctx->parsers) flbgpu_parser_destroy(ctx->parsers);
+    bk_q_free(ctx->q0);
     free(ctx);
 }
 
-void *flbgpu_dev_alloc(flbgpu_ctx *ctx, size_t n) { (void) ctx; return bk_alloc(n); }
-void  flbgpu_dev_free(flbgpu_ctx *ctx, void *p) { (void) ctx; bk_free(p); }
-int   flbgpu_dev_upload(flbgpu_ctx *ctx, void *d, const void *h, size_t n) { (void) ctx; if (bk_h2d(d, h, n)) return -1; return bk_sync(); }
-int   flbgpu_dev_download(flbgpu_ctx *ctx, void *h, const void *d, size_t n) { (void) ctx; if (bk_d2h(h, d, n)) return -1; return bk_sync(); }
-void *flbgpu_host_alloc(flbgpu_ctx *ctx, size_t n) { (void) ctx; return bk_alloc_host(n); }
-void  flbgpu_host_free(flbgpu_ctx *ctx, void *p) { (void) ctx; bk_free_host(p); }
-void *flbgpu_stream(flbgpu_ctx *ctx) { (void) ctx; return bk_stream(); }
+void *flbgpu_dev_alloc(flbgpu_ctx *ctx, size_t n) { return bk_alloc(ctx->q0, n); }
+void  flbgpu_dev_free(flbgpu_ctx *ctx, void *p) { bk_free(ctx->q0, p); }
+int   flbgpu_dev_upload(flbgpu_ctx *ctx, void *d, const void *h, size_t n) { if (bk_h2d(ctx->q0, d, h, n)) return -1; return bk_sync(ctx->q0); }
+int   flbgpu_dev_download(flbgpu_ctx *ctx, void *h, const void *d, size_t n) { if (bk_d2h(ctx->q0, h, d, n)) return -1; return bk_sync(ctx->q0); }
+void *flbgpu_host_alloc(flbgpu_ctx *ctx, size_t n) { return bk_alloc_host(ctx->q0, n); }
+void  flbgpu_host_free(flbgpu_ctx *ctx, void *p) { bk_free_host(ctx->q0, p); }
+void *flbgpu_stream(flbgpu_ctx *ctx) { return bk_stream(ctx->q0); }
 
 /* ---------------------------------------------------------------- parsers */
 static int tzone_offset(const char *str, int len, int *tmdiff)
@@ -1141,7 +1153,11 @@ flbgpu_chain *flbgpu_chain_new(flbgpu_ctx *ctx)
     flbgpu_chain *c;
     if (!ctx) return NULL;
     c = calloc(1, sizeof(*c));
+    if (!c) { set_err("out of memory%s%s", NULL, NULL); return NULL; }
     c->ctx = ctx;
+    c->q = bk_q_new(ctx->device);
+    if (!c->q) { free(c); return NULL; }
+    pthread_mutex_init(&c->lock, NULL);
     return c;
 }
 
@@ -1184,22 +1200,22 @@ int flbgpu_chain_init(flbgpu_chain *c)
     h.total_bytes = (uint32_t) c->blob.n;
     memcpy(c->blob.p, &h, sizeof(h));
     c->cap_stride = cap;
-    c->d_blob = bk_alloc(c->blob.n);
-    c->d_flags = bk_alloc(sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1));
+    c->d_blob = bk_alloc(c->q, c->blob.n);
+    c->d_flags = bk_alloc(c->q, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1));
     if (!c->d_blob || !c->d_flags) return -1;
     if (c->l2m_index >= 0) {
         struct l2m_state *st = c->f[c->l2m_index]->l2m;
         size_t n = (size_t) 1 << L2M_SLOTS_LOG2, nbk = L2M_NBK(st);
         c->l2m_slots = n;
-        c->l2m.hash = bk_alloc(n * 8); c->l2m.chash = bk_alloc(n * 8); c->l2m.first = bk_alloc(n * 4); c->l2m.cnt = bk_alloc(n * 8);
-        c->l2m.sum = bk_alloc(n * 8); c->l2m.bkt = bk_alloc(n * nbk * 8);
-        c->l2m.str = bk_alloc(n * (st->n_labels ? st->n_labels : 1) * L2M_LABEL_BYTES);
+        c->l2m.hash = bk_alloc(c->q, n * 8); c->l2m.chash = bk_alloc(c->q, n * 8); c->l2m.first = bk_alloc(c->q, n * 4); c->l2m.cnt = bk_alloc(c->q, n * 8);
+        c->l2m.sum = bk_alloc(c->q, n * 8); c->l2m.bkt = bk_alloc(c->q, n * nbk * 8);
+        c->l2m.str = bk_alloc(c->q, n * (st->n_labels ? st->n_labels : 1) * L2M_LABEL_BYTES);
         c->l2m.mask = (uint32_t) (n - 1);
         c->h_hash = malloc(n * 8); c->h_chash = malloc(n * 8); c->h_first = malloc(n * 4); c->h_cnt = malloc(n * 8); c->h_sum = malloc(n * 8);
         c->h_bkt = malloc(n * nbk * 8);
         if (!c->l2m.hash || !c->l2m.chash || !c->l2m.first || !c->l2m.cnt || !c->l2m.sum || !c->l2m.bkt || !c->l2m.str) return -1;
     }
-    if (bk_h2d(c->d_blob, c->blob.p, c->blob.n) || bk_sync()) return -1;
+    if (bk_h2d(c->q, c->d_blob, c->blob.p, c->blob.n) || bk_sync(c->q)) return -1;
     c->inited = 1;
     return 0;
 }
@@ -1207,20 +1223,29 @@ int flbgpu_chain_init(flbgpu_chain *c)
 void flbgpu_chain_destroy(flbgpu_chain *c)
 {
     if (!c) return;
-    bk_free(c->d_blob); bk_free(c->d_in); bk_free(c->d_out); bk_free(c->d_tile); bk_free(c->d_off);
-    bk_free(c->d_len); bk_free(c->d_size); bk_free(c->d_kind); bk_free(c->d_bsum); bk_free(c->d_cap);
-    bk_free(c->d_flags); bk_free(c->d_scr); free(c->h_bsum);
-    bk_free(c->l2m.hash); bk_free(c->l2m.chash); bk_free(c->l2m.first); bk_free(c->l2m.cnt); bk_free(c->l2m.sum); bk_free(c->l2m.bkt); bk_free(c->l2m.str);
+    bk_free(c->q, c->d_blob); bk_free(c->q, c->d_in); bk_free(c->q, c->d_out); bk_free(c->q, c->d_tile); bk_free(c->q, c->d_off);
+    bk_free(c->q, c->d_len); bk_free(c->q, c->d_size); bk_free(c->q, c->d_kind); bk_free(c->q, c->d_bsum); bk_free(c->q, c->d_cap);
+    bk_free(c->q, c->d_flags); bk_free(c->q, c->d_scr); free(c->h_bsum);
+    bk_free(c->q, c->l2m.hash); bk_free(c->q, c->l2m.chash); bk_free(c->q, c->l2m.first); bk_free(c->q, c->l2m.cnt); bk_free(c->q, c->l2m.sum); bk_free(c->q, c->l2m.bkt); bk_free(c->q, c->l2m.str);
     free(c->h_hash); free(c->h_chash); free(c->h_first); free(c->h_cnt); free(c->h_sum); free(c->h_bkt);
     free(c->blob.p);
+    if (c->ctx && c->ctx->last_q == c->q) c->ctx->last_q = NULL;
+    bk_q_free(c->q);
+    pthread_mutex_destroy(&c->lock);
     free(c);
 }
 
 void flbgpu_chain_stats(flbgpu_chain *c, struct flbgpu_stats *out) { if (c && out) *out = c->st; }
-int flbgpu_kernel_ms(flbgpu_ctx *ctx, float out[3]) { (void) ctx; if (bk_sync()) return -1; return bk_kernel_ms(out); }
+void *flbgpu_chain_stream(flbgpu_chain *c) { return c ? bk_stream(c->q) : NULL; }
+int flbgpu_kernel_ms(flbgpu_ctx *ctx, float out[3])
+{
+    bk_q *q = ctx && ctx->last_q ? ctx->last_q : (ctx ? ctx->q0 : NULL);
+    if (!q || bk_sync(q)) return -1;
+    return bk_kernel_ms(q, out);
+}
 
 #define GROW(ptr, cap, need, type) do { if ((cap) < (size_t) (need)) { size_t nc_ = (size_t) (need) + (size_t) (need) / 4 + 64; \
-        bk_free(ptr); (ptr) = (type *) bk_alloc(nc_ * sizeof(type)); if (!(ptr)) { (cap) = 0; return -1; } (cap) = nc_; } } while (0)
+        bk_free(c->q, ptr); (ptr) = (type *) bk_alloc(c->q, nc_ * sizeof(type)); if (!(ptr)) { (cap) = 0; return -1; } (cap) = nc_; } } while (0)
 
 /* chunk-level verdict of filter k from the evidence word (see dev_chain.cuh).
  * `clean`: the filter's input decodes to its very end.  grep and modify return
@@ -1249,16 +1274,16 @@ static int ensure_rec_cap(flbgpu_chain *c, size_t need, size_t keep)
     int32_t *cp = NULL;
     if (c->cap_rec >= need) return 0;
     nc = need + need / 2 + 1024;
-    o = bk_alloc(nc * 4); l = bk_alloc(nc * 4); z = bk_alloc(nc * 4); k = bk_alloc(nc);
-    if (c->cap_stride) cp = bk_alloc(nc * c->cap_stride * sizeof(int32_t));
+    o = bk_alloc(c->q, nc * 4); l = bk_alloc(c->q, nc * 4); z = bk_alloc(c->q, nc * 4); k = bk_alloc(c->q, nc);
+    if (c->cap_stride) cp = bk_alloc(c->q, nc * c->cap_stride * sizeof(int32_t));
     if (!o || !l || !z || !k || (c->cap_stride && !cp)) return -1;
     if (keep) {
-        if (bk_sync()) return -1;                 /* running kernels still read the old arrays */
-        if (bk_d2d(o, c->d_off, keep * 4) || bk_d2d(l, c->d_len, keep * 4) || bk_d2d(z, c->d_size, keep * 4) ||
-            bk_d2d(k, c->d_kind, keep)) return -1;
-        if (cp && bk_d2d(cp, c->d_cap, keep * c->cap_stride * sizeof(int32_t))) return -1;
+        if (bk_sync(c->q)) return -1;                 /* running kernels still read the old arrays */
+        if (bk_d2d(c->q, o, c->d_off, keep * 4) || bk_d2d(c->q, l, c->d_len, keep * 4) || bk_d2d(c->q, z, c->d_size, keep * 4) ||
+            bk_d2d(c->q, k, c->d_kind, keep)) return -1;
+        if (cp && bk_d2d(c->q, cp, c->d_cap, keep * c->cap_stride * sizeof(int32_t))) return -1;
     }
-    bk_free(c->d_off); bk_free(c->d_len); bk_free(c->d_size); bk_free(c->d_kind); bk_free(c->d_cap);
+    bk_free(c->q, c->d_off); bk_free(c->q, c->d_len); bk_free(c->q, c->d_size); bk_free(c->q, c->d_kind); bk_free(c->q, c->d_cap);
     c->d_off = o; c->d_len = l; c->d_size = z; c->d_kind = k; c->d_cap = cp;
     c->cap_rec = nc;
     return 0;
@@ -1289,8 +1314,8 @@ static int l2m_clear(flbgpu_chain *c)
     size_t n = c->l2m_slots;
     if (c->l2m_index < 0) return 0;
     st = c->f[c->l2m_index]->l2m;
-    if (bk_zero(c->l2m.hash, n * 8) || bk_zero(c->l2m.first, n * 4) || bk_zero(c->l2m.cnt, n * 8) ||
-        bk_zero(c->l2m.sum, n * 8) || bk_zero(c->l2m.bkt, n * L2M_NBK(st) * 8)) return -1;
+    if (bk_zero(c->q, c->l2m.hash, n * 8) || bk_zero(c->q, c->l2m.first, n * 4) || bk_zero(c->q, c->l2m.cnt, n * 8) ||
+        bk_zero(c->q, c->l2m.sum, n * 8) || bk_zero(c->q, c->l2m.bkt, n * L2M_NBK(st) * 8)) return -1;
     return 0;
 }
 
@@ -1311,8 +1336,8 @@ static int l2m_merge(flbgpu_chain *c)
     if (c->l2m_index < 0) return 0;
     st = c->f[c->l2m_index]->l2m;
     nbk = L2M_NBK(st);
-    if (bk_d2h(c->h_hash, c->l2m.hash, n * 8) || bk_d2h(c->h_chash, c->l2m.chash, n * 8) || bk_d2h(c->h_first, c->l2m.first, n * 4) || bk_d2h(c->h_cnt, c->l2m.cnt, n * 8) ||
-        bk_d2h(c->h_sum, c->l2m.sum, n * 8) || bk_d2h(c->h_bkt, c->l2m.bkt, n * nbk * 8) || bk_sync()) return -1;
+    if (bk_d2h(c->q, c->h_hash, c->l2m.hash, n * 8) || bk_d2h(c->q, c->h_chash, c->l2m.chash, n * 8) || bk_d2h(c->q, c->h_first, c->l2m.first, n * 4) || bk_d2h(c->q, c->h_cnt, c->l2m.cnt, n * 8) ||
+        bk_d2h(c->q, c->h_sum, c->l2m.sum, n * 8) || bk_d2h(c->q, c->h_bkt, c->l2m.bkt, n * nbk * 8) || bk_sync(c->q)) return -1;
     order = malloc(sizeof(uint32_t) * n);
     for (i = 0; i < (size_t) st->n_sets; i++) st->sets[i].call_last = 0;
     for (i = 0; i < n; i++) if (c->h_hash[i]) order[m++] = (uint32_t) i;
@@ -1328,7 +1353,7 @@ static int l2m_merge(flbgpu_chain *c)
         for (j = 0; j < st->n_sets; j++) if (st->sets[j].hash == c->h_chash[slot]) { set = &st->sets[j]; break; }
         if (!set) {
             labels = calloc(1, lb);
-            if (st->n_labels && (bk_d2h(labels, c->l2m.str + (size_t) slot * lb, lb) || bk_sync())) { free(labels); free(order); return -1; }
+            if (st->n_labels && (bk_d2h(c->q, labels, c->l2m.str + (size_t) slot * lb, lb) || bk_sync(c->q))) { free(labels); free(order); return -1; }
             if (st->n_sets == st->cap_sets) {
                 st->cap_sets = st->cap_sets ? st->cap_sets * 2 : 64;
                 st->sets = realloc(st->sets, sizeof(*st->sets) * st->cap_sets);
@@ -1423,7 +1448,7 @@ static int msgpack_tail_runs_out_cleanly(const uint8_t *b, size_t n)
 
 /* `clean`: the decodable prefix is the whole chunk, or what follows it is an event cut short at a point where the
  * reference's decoder still reports `offset == bytes` (see above) */
-static int ends_cleanly(const uint8_t *h_in, const uint8_t *d_in, size_t off, size_t bytes)
+static int ends_cleanly(bk_q *q, const uint8_t *h_in, const uint8_t *d_in, size_t off, size_t bytes)
 {
     uint8_t *tmp;
     int r;
@@ -1431,7 +1456,7 @@ static int ends_cleanly(const uint8_t *h_in, const uint8_t *d_in, size_t off, si
     if (h_in) return msgpack_tail_runs_out_cleanly(h_in + off, bytes - off);
     tmp = malloc(bytes - off);
     if (!tmp) return 0;
-    r = (bk_d2h(tmp, d_in + off, bytes - off) || bk_sync()) ? 0 : msgpack_tail_runs_out_cleanly(tmp, bytes - off);
+    r = (bk_d2h(q, tmp, d_in + off, bytes - off) || bk_sync(q)) ? 0 : msgpack_tail_runs_out_cleanly(tmp, bytes - off);
     free(tmp);
     return r;
 }
@@ -1439,20 +1464,20 @@ static int ends_cleanly(const uint8_t *h_in, const uint8_t *d_in, size_t off, si
 /* The record index frames events whose root and header arrays are fixarrays (0x92), which is all msgpack-c's
  * packer ever writes for two elements.  The reference's decoder would also take the same arrays spelled as
  * array16 / array32: when the decodable prefix stops at such a spelling the call is refused, not cut short. */
-static int stops_at_wide_array(const uint8_t *h_in, const uint8_t *d_in, size_t off, size_t bytes)
+static int stops_at_wide_array(bk_q *q, const uint8_t *h_in, const uint8_t *d_in, size_t off, size_t bytes)
 {
     uint8_t b[8] = { 0 };
     size_t n = bytes - off < sizeof(b) ? bytes - off : sizeof(b), i = 0;
     if (n == 0) return 0;
     if (h_in) memcpy(b, h_in + off, n);
-    else if (bk_d2h(b, d_in + off, n) || bk_sync()) return 0;
+    else if (bk_d2h(q, b, d_in + off, n) || bk_sync(q)) return 0;
     if (b[0] == 0x92) i = 1;                                   /* [ [ts, meta], body ] with a wide header array */
     if (b[i] == 0xdc) return b[i + 1] == 0 && b[i + 2] == 2;
     if (b[i] == 0xdd) return b[i + 1] == 0 && b[i + 2] == 0 && b[i + 3] == 0 && b[i + 4] == 2;
     return 0;
 }
 #define REFUSE_WIDE_ARRAYS(h_in_, d_in_, fail_stmt) do { \
-        if (off < bytes && stops_at_wide_array(h_in_, d_in_, off, bytes)) { \
+        if (off < bytes && stops_at_wide_array(c->q, h_in_, d_in_, off, bytes)) { \
             c->st.error_bits = FLBGPU_E_INDEX; \
             snprintf(g_rt_err, sizeof(g_rt_err), "event framed with an array16/array32 header at byte %zu: not decoded on the GPU path", off); \
             fail_stmt; \
@@ -1478,18 +1503,18 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
 #define PHASE_MARK(i) do { clock_gettime(CLOCK_MONOTONIC, &t1); \
         c->st.phase_ms[i] = (float) ((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) / 1e6); } while (0)
     if (bytes >= 0xfff00000ull) { set_err("chunk larger than 4 GiB: split the append%s%s", NULL, NULL); return -1; }
-    if (d_in_ext) { d_in = d_in_ext; bk_upload_none(); }
+    if (d_in_ext) { d_in = d_in_ext; bk_upload_none(c->q); }
     else {
         GROW(c->d_in, c->cap_in, bytes + 64, uint8_t);
         d_in = c->d_in;
-        if (bk_upload_start(c->d_in, h_in, bytes)) return -1;
+        if (bk_upload_start(c->q, c->d_in, h_in, bytes)) return -1;
     }
     if (c->needs_scratch) GROW(c->d_scr, c->cap_scr, 4 * bytes + 64, uint8_t);
     memset(&a, 0, sizeof(a));
     a.now = (int64_t) time(NULL);
     a.assume = (c->nf >= 32) ? 0xffffffffu : ((1u << c->nf) - 1u);
     if (c->l2m_index >= 0 && !c->f[c->l2m_index]->l2m->discard) a.assume &= ~(1u << c->l2m_index);
-    if (bk_flags_clear(c->d_flags) || l2m_clear(c)) return -1;
+    if (bk_flags_clear(c->q, c->d_flags) || l2m_clear(c)) return -1;
 
     /* ---- index + evaluate, slice by slice, while the upload is still running ---- */
     while (off < bytes) {
@@ -1499,11 +1524,11 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         uint32_t assume = a.assume;
         int64_t now = a.now;
         int tiled = 0;
-        if (bk_upload_wait_index(off + len)) return -1;
+        if (bk_upload_wait_index(c->q, off + len)) return -1;
         GROW(c->d_tile, c->cap_tile, n_tiles + 1, uint32_t);
-        if (bk_index_count(d_in, off, (uint32_t) len, c->d_tile, n_tiles, &n_cand)) return -1;
+        if (bk_index_count(c->q, d_in, off, (uint32_t) len, c->d_tile, n_tiles, &n_cand)) return -1;
         if (ensure_rec_cap(c, (size_t) n_rec + n_cand, n_rec)) return -1;
-        if (bk_index_fill(d_in, off, (uint32_t) len, c->d_tile, n_tiles, n_cand, c->d_off + n_rec, c->d_len + n_rec,
+        if (bk_index_fill(c->q, d_in, off, (uint32_t) len, c->d_tile, n_tiles, n_cand, c->d_off + n_rec, c->d_len + n_rec,
                           c->d_kind + n_rec, &n_valid, &end_off, &tiled)) {
             c->st.error_bits = FLBGPU_E_INDEX;
             return -1;
@@ -1514,12 +1539,12 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         }
         fill_args(c, &a, d_in, bytes, n_rec + n_valid);
         a.assume = assume; a.now = now;
-        bk_hint_streaming(a.d_in + off, (size_t) end_off - off);
-        if (bk_chain_eval(&a, n_rec, n_rec + n_valid)) return -1;
+        bk_hint_streaming(c->q, a.d_in + off, (size_t) end_off - off);
+        if (bk_chain_eval(c->q, &a, n_rec, n_rec + n_valid)) return -1;
         n_rec += n_valid;
         off = (size_t) end_off;
     }
-    clean = ends_cleanly(h_in, d_in, off, bytes);
+    clean = ends_cleanly(c->q, h_in, d_in, off, bytes);
     REFUSE_WIDE_ARRAYS(h_in, d_in, return -1);
     c->st.records_in = n_rec;
     c->st.passes = 1;
@@ -1533,7 +1558,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     /* ---- chunk-level verdicts; revise assumptions front to back until they hold ---- */
     for (pass = 0; pass <= c->nf; pass++) {
         int changed = 0, cl = clean;
-        if (bk_flags_fetch(c->d_flags, h_flags)) return -1;
+        if (bk_flags_fetch(c->q, c->d_flags, h_flags)) return -1;
         if (h_flags[FLBGPU_MAX_FILTERS]) {
             c->st.error_bits = h_flags[FLBGPU_MAX_FILTERS];
             snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
@@ -1551,7 +1576,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
             }
         }
         if (!changed) break;
-        if (bk_flags_clear(c->d_flags) || l2m_clear(c) || bk_chain_eval(&a, 0, n_rec)) return -1;
+        if (bk_flags_clear(c->q, c->d_flags) || l2m_clear(c) || bk_chain_eval(c->q, &a, 0, n_rec)) return -1;
         c->st.passes++;
     }
     c->st.kernel_launches = bk_launch_count();
@@ -1570,7 +1595,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         if (!c->h_bsum) { c->cap_hbsum = 0; return -1; }
     }
     a.d_bsum = c->d_bsum;
-    if (bk_sizes_scan(c->d_size, n_rec, c->d_bsum, c->h_bsum)) return -1;
+    if (bk_sizes_scan(c->q, c->d_size, n_rec, c->d_bsum, c->h_bsum)) return -1;
     total = c->h_bsum[nb];
     if (total >= 0xfff00000ull) { set_err("result larger than 4 GiB%s%s", NULL, NULL); return -1; }
     c->st.bytes_out = total;
@@ -1582,7 +1607,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     /* ---- emit (+ download) ---- */
     if (!host_out) {
         if (ext_cap < total) { set_err("device output buffer too small%s%s", NULL, NULL); return -1; }
-        if (bk_chain_emit(&a, ext_out, 0, nb)) return -1;
+        if (bk_chain_emit(c->q, &a, ext_out, 0, nb)) return -1;
     }
     else {
         const uint32_t step = 2048;                   /* blocks per emission launch (512 K records) */
@@ -1597,20 +1622,20 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         }
 #endif
         GROW(c->d_out, c->cap_out, total, uint8_t);
-        if (bk_download_begin(out, c->d_out)) { free(out); return -1; }
+        if (bk_download_begin(c->q, out, c->d_out)) { free(out); return -1; }
         for (b0 = 0; b0 < nb; b0 += step) {
             uint32_t b1 = b0 + step < nb ? b0 + step : nb;
-            if (bk_chain_emit(&a, c->d_out, b0, b1) || bk_download_push((size_t) c->h_bsum[b0], (size_t) c->h_bsum[b1])) {
-                bk_download_end();
+            if (bk_chain_emit(c->q, &a, c->d_out, b0, b1) || bk_download_push(c->q, (size_t) c->h_bsum[b0], (size_t) c->h_bsum[b1])) {
+                bk_download_end(c->q);
                 free(out);
                 return -1;
             }
         }
-        if (bk_download_end()) { free(out); return -1; }
+        if (bk_download_end(c->q)) { free(out); return -1; }
         *host_out = out;
     }
     c->st.kernel_launches = bk_launch_count();
-    if (host_out) bk_records_out(&c->st.records_out);     /* (the device-output form leaves the stream running) */
+    if (host_out) bk_records_out(c->q, &c->st.records_out);     /* (the device-output form leaves the stream running) */
     PHASE_MARK(3);
     c->st.phase_ms[2] = c->st.phase_ms[3] - c->st.phase_ms[1] - c->st.phase_ms[0];
     return FLBGPU_FILTER_MODIFIED;
@@ -1691,7 +1716,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
     if (assume == 0) return 1;                       /* nothing would be emitted: the classic path decides */
     if (bytes >= 0xfff00000ull) { set_err("chunk larger than 4 GiB: split the append%s%s", NULL, NULL); return -1; }
     GROW(c->d_in, c->cap_in, bytes + 64, uint8_t);
-    if (bk_upload_start(c->d_in, h_in, bytes)) return -1;
+    if (bk_upload_start(c->q, c->d_in, h_in, bytes)) return -1;
     if (c->needs_scratch) GROW(c->d_scr, c->cap_scr, 4 * bytes + 64, uint8_t);
     nb_max = (uint32_t) (bytes / (3 * BK_REC_BLOCK)) + 4;       /* an event is at least 3 bytes */
     GROW(c->d_bsum, c->cap_bsum, nb_max, uint64_t);
@@ -1702,13 +1727,13 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
         if (!c->h_bsum) { c->cap_hbsum = 0; return -1; }
     }
     memset(&a, 0, sizeof(a));
-    if (bk_flags_clear(c->d_flags) || l2m_clear(c)) return -1;
+    if (bk_flags_clear(c->q, c->d_flags) || l2m_clear(c)) return -1;
 
 #define STREAM_FLUSH(upto_blocks) do { \
         uint32_t b1_ = (upto_blocks); \
         if (b1_ > b_done) { \
             fill_args(c, &a, c->d_in, bytes, n_rec); a.assume = assume; a.now = now; a.d_bsum = c->d_bsum; \
-            if (bk_sizes_scan_range(c->d_size, n_rec, b_done, b1_, c->d_bsum, c->h_bsum, placed)) goto fail; \
+            if (bk_sizes_scan_range(c->q, c->d_size, n_rec, b_done, b1_, c->d_bsum, c->h_bsum, placed)) goto fail; \
             if (c->h_bsum[b1_] >= 0xfff00000ull) { set_err("result larger than 4 GiB%s%s", NULL, NULL); goto fail; } \
             if (c->h_bsum[b1_] > placed) { \
                 if (c->h_bsum[b1_] > cap_out_h) { \
@@ -1717,25 +1742,25 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
                     size_t want_ = (size_t) (ratio_ * 1.15 * (double) bytes) + ((size_t) 8 << 20); \
                     uint8_t *no_; \
                     if (want_ < c->h_bsum[b1_]) want_ = (size_t) c->h_bsum[b1_] + ((size_t) 8 << 20); \
-                    if (dl_open) { if (bk_download_end()) { dl_open = 0; goto fail; } dl_open = 0; } \
+                    if (dl_open) { if (bk_download_end(c->q)) { dl_open = 0; goto fail; } dl_open = 0; } \
                     no_ = realloc(out, want_); \
                     if (!no_) goto fail; \
                     out = no_; cap_out_h = want_; \
                     hugepage_hint(out, want_); \
                     GROW_KEEP_OUT(want_); \
                 } \
-                if (!dl_open) { if (bk_download_begin(out, c->d_out)) goto fail; dl_open = 1; } \
-                if (bk_chain_emit(&a, c->d_out, b_done, b1_) || bk_download_push((size_t) placed, (size_t) c->h_bsum[b1_])) goto fail; \
+                if (!dl_open) { if (bk_download_begin(c->q, out, c->d_out)) goto fail; dl_open = 1; } \
+                if (bk_chain_emit(c->q, &a, c->d_out, b_done, b1_) || bk_download_push(c->q, (size_t) placed, (size_t) c->h_bsum[b1_])) goto fail; \
             } \
             placed = c->h_bsum[b1_]; \
             b_done = b1_; \
         } } while (0)
     /* the device output buffer grows with the host one; bytes already emitted stay where they are */
 #define GROW_KEEP_OUT(need) do { if (c->cap_out < (size_t) (need)) { \
-        uint8_t *nd_ = bk_alloc((size_t) (need) + 64); \
+        uint8_t *nd_ = bk_alloc(c->q, (size_t) (need) + 64); \
         if (!nd_) goto fail; \
-        if (placed) { if (bk_sync() || bk_d2d(nd_, c->d_out, (size_t) placed)) { bk_free(nd_); goto fail; } } \
-        bk_free(c->d_out); c->d_out = nd_; c->cap_out = (size_t) (need); } } while (0)
+        if (placed) { if (bk_sync(c->q) || bk_d2d(c->q, nd_, c->d_out, (size_t) placed)) { bk_free(c->q, nd_); goto fail; } } \
+        bk_free(c->q, c->d_out); c->d_out = nd_; c->cap_out = (size_t) (need); } } while (0)
 
     while (off < bytes) {
         /* slices shrink towards the end of the chunk: what is left to do after the last upload piece
@@ -1747,11 +1772,11 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
         uint32_t n_tiles = (uint32_t) ((len + (off & 15) + BK_INDEX_TILE - 1) / BK_INDEX_TILE), n_cand = 0, n_valid = 0;
         uint64_t end_off = off;
         int tiled = 0;
-        if (bk_upload_wait_index(off + len)) goto fail;
+        if (bk_upload_wait_index(c->q, off + len)) goto fail;
         GROW(c->d_tile, c->cap_tile, n_tiles + 1, uint32_t);
-        if (bk_index_count(c->d_in, off, (uint32_t) len, c->d_tile, n_tiles, &n_cand)) goto fail;
+        if (bk_index_count(c->q, c->d_in, off, (uint32_t) len, c->d_tile, n_tiles, &n_cand)) goto fail;
         if (ensure_rec_cap(c, (size_t) n_rec + n_cand, n_rec)) goto fail;
-        if (bk_index_fill(c->d_in, off, (uint32_t) len, c->d_tile, n_tiles, n_cand, c->d_off + n_rec, c->d_len + n_rec,
+        if (bk_index_fill(c->q, c->d_in, off, (uint32_t) len, c->d_tile, n_tiles, n_cand, c->d_off + n_rec, c->d_len + n_rec,
                           c->d_kind + n_rec, &n_valid, &end_off, &tiled)) {
             c->st.error_bits = FLBGPU_E_INDEX;
             goto fail;
@@ -1765,12 +1790,12 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
         STREAM_FLUSH(n_rec / BK_REC_BLOCK);
         fill_args(c, &a, c->d_in, bytes, n_rec + n_valid);
         a.assume = assume; a.now = now;
-        bk_hint_streaming(a.d_in + off, (size_t) end_off - off);
-        if (bk_chain_eval(&a, n_rec, n_rec + n_valid)) goto fail;
+        bk_hint_streaming(c->q, a.d_in + off, (size_t) end_off - off);
+        if (bk_chain_eval(c->q, &a, n_rec, n_rec + n_valid)) goto fail;
         n_rec += n_valid;
         off = (size_t) end_off;
     }
-    clean = ends_cleanly(h_in, c->d_in, off, bytes);
+    clean = ends_cleanly(c->q, h_in, c->d_in, off, bytes);
     REFUSE_WIDE_ARRAYS(h_in, c->d_in, goto fail);
     c->st.records_in = n_rec;
     c->st.passes = 1;
@@ -1778,7 +1803,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
     c->st.phase_ms[0] = 0;
 
     /* ---- the verdicts must be the ones speculated on ---- */
-    if (bk_flags_fetch(c->d_flags, h_flags)) goto fail;
+    if (bk_flags_fetch(c->q, c->d_flags, h_flags)) goto fail;
     if (h_flags[FLBGPU_MAX_FILTERS]) {
         c->st.error_bits = h_flags[FLBGPU_MAX_FILTERS];
         snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
@@ -1797,7 +1822,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
                  * and speculate on "filter k as found" next time */
                 c->spec_assume = (assume & ~(1u << k)) | ((uint32_t) v << k);
                 c->spec_valid = 1;
-                if (dl_open) bk_download_end();
+                if (dl_open) bk_download_end(c->q);
                 free(out);
                 return 1;
             }
@@ -1807,8 +1832,8 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
     }
     c->st.kernel_launches = bk_launch_count();
     if (l2m_merge(c)) goto fail;
-    if (dl_open) { dl_open = 0; if (bk_download_end()) goto fail; }
-    bk_records_out(&c->st.records_out);
+    if (dl_open) { dl_open = 0; if (bk_download_end(c->q)) goto fail; }
+    bk_records_out(c->q, &c->st.records_out);
     c->st.bytes_out = placed;
     *out_size = (size_t) placed;
     if (placed == 0) { free(out); out = NULL; }
@@ -1822,7 +1847,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
     *ret = FLBGPU_FILTER_MODIFIED;
     return 0;
 fail:
-    if (dl_open) bk_download_end();
+    if (dl_open) bk_download_end(c->q);
     free(out);
     (void) rc;
     return -1;
@@ -1830,14 +1855,122 @@ fail:
 #undef GROW_KEEP_OUT
 }
 
+/* One append as flb_filter_do() hands it over (tens of KB to a few MB): the whole call is one stream of work
+ * without a host synchronisation in between (bk_small_run), under the verdict vector the previous call settled
+ * on.  Returns 0 (done, *ret set), 1 (not for this form or the speculation did not hold: use the general
+ * paths), -1 error. */
+static size_t small_bytes(void)
+{
+    const char *e = getenv("FLBGPU_SMALL_MB"), *sv = getenv("FLBGPU_STREAM");
+    long mb = e ? atol(e) : 8;
+    size_t v, s = slice_bytes();
+    if (sv && sv[0] == '0') return 0;                /* the classic two-pass form only */
+    if (mb < 0) mb = 0;
+    if (mb > 256) mb = 256;
+    v = (size_t) mb << 20;
+    return v < s ? v : s;                            /* the small form is a single slice */
+}
+
+static int chain_run_small(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, void **host_out, size_t *out_size, int *ret)
+{
+    struct bk_chain_args a;
+    struct bk_small_res res;
+    uint32_t assume, n_tiles, cap_rec, nb_cap;
+    size_t off, cap_out;
+    int clean, k;
+    struct timespec t0, t1;
+
+    assume = (c->nf >= 32) ? 0xffffffffu : ((1u << c->nf) - 1u);
+    if (c->l2m_index >= 0 && !c->f[c->l2m_index]->l2m->discard) assume &= ~(1u << c->l2m_index);
+    if (c->spec_valid) assume = c->spec_assume;
+    if (assume == 0) return 1;                       /* nothing would be emitted: the classic path decides */
+    memset(&c->st, 0, sizeof(c->st));
+    c->st.bytes_in = bytes;
+    *out_size = 0;
+    clock_gettime(CLOCK_MONOTONIC, &t0);
+    /* records of the shapes this path serves are tens of bytes at least; a chunk of tinier events overflows
+     * the arrays, which the device reports (res.overflow) and the general path then handles */
+    cap_rec = (uint32_t) (bytes / 24) + 1024;
+    if (c->small_cap_rec > cap_rec) cap_rec = c->small_cap_rec;
+    nb_cap = (cap_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK;
+    n_tiles = (uint32_t) ((bytes + BK_INDEX_TILE - 1) / BK_INDEX_TILE);
+    GROW(c->d_in, c->cap_in, bytes + 64, uint8_t);
+    if (c->needs_scratch) GROW(c->d_scr, c->cap_scr, 4 * bytes + 64, uint8_t);
+    GROW(c->d_tile, c->cap_tile, n_tiles + 1, uint32_t);
+    GROW(c->d_bsum, c->cap_bsum, nb_cap + 2, uint64_t);
+    if (ensure_rec_cap(c, cap_rec, 0)) return -1;
+    cap_out = bytes + bytes / 2 + 4096;
+    if (c->small_cap_out > cap_out) cap_out = c->small_cap_out;
+    GROW(c->d_out, c->cap_out, cap_out, uint8_t);
+    cap_out = c->cap_out;
+    fill_args(c, &a, c->d_in, bytes, 0);
+    a.assume = assume; a.now = (int64_t) time(NULL); a.d_bsum = c->d_bsum;
+    if (bk_flags_clear(c->q, c->d_flags) || l2m_clear(c)) return -1;
+    if (bk_small_run(c->q, &a, h_in, c->d_in, bytes, cap_rec, c->d_tile, n_tiles, c->d_out, cap_out, &res)) return -1;
+    c->st.kernel_launches = bk_launch_count();
+    if (res.overflow) {                              /* denser events than assumed, or a slice-sized tangle of broken links */
+        if (res.overflow == 1 && res.n_cand < 0x7fffffffu) c->small_cap_rec = res.n_cand + res.n_cand / 4 + 1024;
+        return 1;
+    }
+    off = (size_t) res.end_off;
+    clean = ends_cleanly(c->q, h_in, c->d_in, off, bytes);
+    REFUSE_WIDE_ARRAYS(h_in, c->d_in, return -1);
+    c->st.records_in = res.n_valid;
+    c->st.passes = 1;
+    if (res.flags[FLBGPU_MAX_FILTERS]) {
+        c->st.error_bits = res.flags[FLBGPU_MAX_FILTERS];
+        snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
+                 "1=too many keys 2=regex stack 4=regex budget 8=float text not restated (hex float, nan(payload)) 32=logfmt escapes 64=log_to_metrics value/label outside the device path)",
+                 res.flags[FLBGPU_MAX_FILTERS]);
+        return -1;
+    }
+    {
+        int cl = clean;
+        uint32_t settled = 0;
+        for (k = 0; k < c->nf; k++) {
+            int v = c->f[k]->kind == FLBGPU_F_LOG_TO_METRICS ? L2M_VERDICT(c, k) : verdict(c->f[k]->kind, res.flags[k], cl);
+            if (v) cl = 1;
+            if (v != (int) ((assume >> k) & 1)) {
+                c->spec_assume = (assume & ~(1u << k)) | ((uint32_t) v << k);
+                c->spec_valid = 1;
+                return 1;
+            }
+            settled |= (uint32_t) v << k;
+        }
+        c->spec_assume = settled; c->spec_valid = 1;
+    }
+    if (l2m_merge(c)) return -1;
+    if (res.total >= 0xfff00000ull) { set_err("result larger than 4 GiB%s%s", NULL, NULL); return -1; }
+    if (!res.emitted) {                              /* the result outgrew the output buffer: remember, let the general path do this call */
+        c->small_cap_out = (size_t) res.total + (size_t) res.total / 4 + 4096;
+        return 1;
+    }
+    c->st.records_out = res.n_out;
+    c->st.bytes_out = res.total;
+    *out_size = (size_t) res.total;
+    *host_out = NULL;
+    if (res.total) {
+        void *out = malloc((size_t) res.total);
+        if (!out) { set_err("out of memory%s%s", NULL, NULL); return -1; }
+        if (bk_small_fetch(c->q, out, c->d_out, (size_t) res.total)) { free(out); return -1; }
+        *host_out = out;
+    }
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    c->st.phase_ms[3] = (float) ((t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) / 1e6);
+    *ret = FLBGPU_FILTER_MODIFIED;
+    return 0;
+}
+
 int flbgpu_chain_do_device(flbgpu_chain *c, const void *d_data, size_t bytes, void *d_out, size_t out_cap, size_t *out_size)
 {
     int r;
     if (!c || !c->inited) return -1;
     g_rt_err[0] = 0;
+    pthread_mutex_lock(&c->lock);
+    c->ctx->last_q = c->q;
     r = chain_run(c, NULL, d_data, bytes, d_out, out_cap, NULL, out_size);
-    if (r < 0) return r;
-    if (bk_sync()) return -1;
+    if (r >= 0 && bk_sync(c->q)) r = -1;
+    pthread_mutex_unlock(&c->lock);
     return r;
 }
 
@@ -1868,19 +2001,22 @@ static int chain_do_one_by_one(flbgpu_chain *c, const void *data, size_t bytes, 
 }
 #define FUSED_REFUSED_A_HANDED_OVER_VALUE(c) ((c)->nf > 1 && (c)->st.error_bits == FLBGPU_E_FIELDS)
 
-int flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes, const char *tag, int tag_len,
-                    void **out_buf, size_t *out_size)
+static int chain_do_locked(flbgpu_chain *c, const void *data, size_t bytes, void **out_buf, size_t *out_size)
 {
-    (void) tag; (void) tag_len;
-    if (!c || !c->inited || !out_buf || !out_size) return -1;
-    g_rt_err[0] = 0;
-    *out_buf = NULL; *out_size = 0;
-    if (bytes == 0) return FLBGPU_FILTER_NOTOUCH;
+    if (bytes <= small_bytes()) {
+        int ret = 0, r = chain_run_small(c, data, bytes, out_buf, out_size, &ret);
+        if (r == 0) return ret;
+        if (r < 0) {
+            if (FUSED_REFUSED_A_HANDED_OVER_VALUE(c)) { *out_buf = NULL; *out_size = 0; return chain_do_one_by_one(c, data, bytes, out_buf, out_size); }
+            return -1;
+        }
+        *out_buf = NULL; *out_size = 0;
+    }
     {
         const char *sv = getenv("FLBGPU_STREAM");
-        if (!(sv && sv[0] == '0')) {
+        if (!(sv && sv[0] == '0') && bytes > small_bytes()) {
             int ret = 0, r = chain_run_stream(c, data, bytes, out_buf, out_size, &ret);
-            bk_upload_end();                         /* `data` is not read after this call returns */
+            bk_upload_end(c->q);                     /* `data` is not read after this call returns */
             if (r == 0) return ret;
             if (r < 0) {
                 if (FUSED_REFUSED_A_HANDED_OVER_VALUE(c)) return chain_do_one_by_one(c, data, bytes, out_buf, out_size);
@@ -1891,10 +2027,26 @@ int flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes, const char 
     }
     {
         int r = chain_run(c, data, NULL, bytes, NULL, 0, out_buf, out_size);
-        bk_upload_end();
+        bk_upload_end(c->q);
         if (r < 0 && FUSED_REFUSED_A_HANDED_OVER_VALUE(c)) { *out_buf = NULL; *out_size = 0; return chain_do_one_by_one(c, data, bytes, out_buf, out_size); }
         return r;
     }
+}
+
+int flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes, const char *tag, int tag_len,
+                    void **out_buf, size_t *out_size)
+{
+    int r;
+    (void) tag; (void) tag_len;
+    if (!c || !c->inited || !out_buf || !out_size) return -1;
+    g_rt_err[0] = 0;
+    *out_buf = NULL; *out_size = 0;
+    if (bytes == 0) return FLBGPU_FILTER_NOTOUCH;
+    pthread_mutex_lock(&c->lock);
+    c->ctx->last_q = c->q;
+    r = chain_do_locked(c, data, bytes, out_buf, out_size);
+    pthread_mutex_unlock(&c->lock);
+    return r;
 }
 
 

@@ -137,6 +137,11 @@ struct flbgpu_stats {
     float phase_ms[4];
 };
 void flbgpu_chain_stats(flbgpu_chain *c, struct flbgpu_stats *out);
+/* Every chain (and every filter instance behind flbgpu_filter_cb) owns its device queue -- streams, pinned staging
+ * rings, worker threads -- so instances may be called from different threads at the same time, as
+ * flb_processor_run() does (src/flb_processor.c:1352-1378); calls on ONE instance are serialised.
+ * This is the cudaStream_t the instance launches its kernels on. */
+void *flbgpu_chain_stream(flbgpu_chain *c);
 
 /* ---- filter_log_to_metrics state ------------------------------------------------
  * The filter ("log_to_metrics": metric_mode counter | gauge | histogram, Regex/Exclude gates, label_field /

@@ -73,8 +73,10 @@ int sim_rx_search(void *h, const char *s, int len, int *caps, int stack_words, u
 #include "../../fluent-bit_b200/csrc/flbgpu_internal.h"
 #include "../../fluent-bit_b200/csrc/dev_chain.cuh"
 
-static char hs_err[256];
+static thread_local char hs_err[256];
 static uint64_t hs_launches;
+
+struct bk_q { int device; uint64_t records_out; uint8_t *dl_dst; const uint8_t *dl_src; };
 
 extern "C" {
 
@@ -82,26 +84,28 @@ const char *bk_name(void) { return "hostsim-cpu-emulation(TEST ONLY)"; }
 const char *bk_last_error(void) { return hs_err; }
 uint64_t bk_launch_count(void) { return hs_launches; }
 int bk_device_count(void) { return 1; }
-int bk_init(int device) { (void) device; return 0; }
-void *bk_alloc(size_t n) { return malloc(n + 64); }
-void bk_free(void *p) { free(p); }
-void *bk_alloc_host(size_t n) { return malloc(n ? n : 16); }
-void bk_free_host(void *p) { free(p); }
-int bk_h2d(void *d, const void *h, size_t n) { memcpy(d, h, n); return 0; }
-int bk_d2h(void *h, const void *d, size_t n) { memcpy(h, d, n); return 0; }
-int bk_zero(void *d, size_t n) { memset(d, 0, n); return 0; }
-int bk_sync(void) { return 0; }
-void *bk_stream(void) { return 0; }
-int bk_kernel_ms(float out[3]) { out[0] = out[1] = out[2] = 0.f; return 0; }
+bk_q *bk_q_new(int device) { bk_q *q = (bk_q *) calloc(1, sizeof(bk_q)); q->device = device; return q; }
+void bk_q_free(bk_q *q) { free(q); }
+int bk_q_device(bk_q *q) { return q->device; }
+void *bk_alloc(bk_q *, size_t n) { return malloc(n + 64); }
+void bk_free(bk_q *, void *p) { free(p); }
+void *bk_alloc_host(bk_q *, size_t n) { return malloc(n ? n : 16); }
+void bk_free_host(bk_q *, void *p) { free(p); }
+int bk_h2d(bk_q *, void *d, const void *h, size_t n) { memcpy(d, h, n); return 0; }
+int bk_d2h(bk_q *, void *h, const void *d, size_t n) { memcpy(h, d, n); return 0; }
+int bk_zero(bk_q *, void *d, size_t n) { memset(d, 0, n); return 0; }
+int bk_sync(bk_q *) { return 0; }
+void *bk_stream(bk_q *) { return 0; }
+int bk_kernel_ms(bk_q *, float out[3]) { out[0] = out[1] = out[2] = 0.f; return 0; }
 
-int bk_d2d(void *dst, const void *src, size_t n) { memcpy(dst, src, n); return 0; }
-int bk_upload_start(void *d_dst, const void *h_src, size_t n) { memcpy(d_dst, h_src, n); return 0; }
-int bk_upload_wait_index(size_t upto) { (void) upto; return 0; }
-void bk_upload_none(void) {}
-void bk_upload_end(void) {}
-int bk_hint_streaming(const void *base, size_t bytes) { (void) base; (void) bytes; return 0; }
+int bk_d2d(bk_q *, void *dst, const void *src, size_t n) { memcpy(dst, src, n); return 0; }
+int bk_upload_start(bk_q *, void *d_dst, const void *h_src, size_t n) { memcpy(d_dst, h_src, n); return 0; }
+int bk_upload_wait_index(bk_q *, size_t upto) { (void) upto; return 0; }
+void bk_upload_none(bk_q *) {}
+void bk_upload_end(bk_q *) {}
+int bk_hint_streaming(bk_q *, const void *base, size_t bytes) { (void) base; (void) bytes; return 0; }
 
-int bk_index_count(const uint8_t *d_in, size_t slice_off, uint32_t len, uint32_t *d_tile, uint32_t n_tiles, uint32_t *n_cand)
+int bk_index_count(bk_q *, const uint8_t *d_in, size_t slice_off, uint32_t len, uint32_t *d_tile, uint32_t n_tiles, uint32_t *n_cand)
 {
     const uint8_t *in = d_in + slice_off;
     const uint32_t skip = (uint32_t) (slice_off & 15);
@@ -122,7 +126,7 @@ int bk_index_count(const uint8_t *d_in, size_t slice_off, uint32_t len, uint32_t
     return 0;
 }
 
-int bk_index_fill(const uint8_t *d_in, size_t slice_off, uint32_t len, const uint32_t *d_tile, uint32_t n_tiles, uint32_t n_cand,
+int bk_index_fill(bk_q *, const uint8_t *d_in, size_t slice_off, uint32_t len, const uint32_t *d_tile, uint32_t n_tiles, uint32_t n_cand,
                   uint32_t *d_off, uint32_t *d_len, uint8_t *d_kind, uint32_t *n_valid, uint64_t *end_off, int *tiled)
 {
     const uint8_t *in = d_in + slice_off;
@@ -174,11 +178,10 @@ static void hs_env(const struct bk_chain_args *a, struct ch_env *e)
     e->l2m = a->l2m;
 }
 
-static uint64_t hs_records_out;
-int bk_flags_clear(uint32_t *d_flags) { memset(d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)); hs_records_out = 0; return 0; }
-int bk_flags_fetch(const uint32_t *d_flags, uint32_t *h_flags) { memcpy(h_flags, d_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)); return 0; }
+int bk_flags_clear(bk_q *q, uint32_t *d_flags) { memset(d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)); q->records_out = 0; return 0; }
+int bk_flags_fetch(bk_q *, const uint32_t *d_flags, uint32_t *h_flags) { memcpy(h_flags, d_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)); return 0; }
 
-int bk_chain_eval(const struct bk_chain_args *a, uint32_t r0, uint32_t r1)
+int bk_chain_eval(bk_q *, const struct bk_chain_args *a, uint32_t r0, uint32_t r1)
 {
     struct ch_env e;
     uint32_t i;
@@ -193,7 +196,7 @@ int bk_chain_eval(const struct bk_chain_args *a, uint32_t r0, uint32_t r1)
     return 0;
 }
 
-int bk_sizes_scan(const uint32_t *d_size, uint32_t n_rec, uint64_t *d_bsum, uint64_t *h_bsum)
+int bk_sizes_scan(bk_q *, const uint32_t *d_size, uint32_t n_rec, uint64_t *d_bsum, uint64_t *h_bsum)
 {
     uint32_t nb = (n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK, b, i;
     uint64_t run = 0;
@@ -206,7 +209,7 @@ int bk_sizes_scan(const uint32_t *d_size, uint32_t n_rec, uint64_t *d_bsum, uint
     return 0;
 }
 
-int bk_sizes_scan_range(const uint32_t *d_size, uint32_t n_rec, uint32_t b0, uint32_t b1, uint64_t *d_bsum, uint64_t *h_bsum,
+int bk_sizes_scan_range(bk_q *, const uint32_t *d_size, uint32_t n_rec, uint32_t b0, uint32_t b1, uint64_t *d_bsum, uint64_t *h_bsum,
                         uint64_t carry_in)
 {
     uint32_t b, i;
@@ -221,9 +224,9 @@ int bk_sizes_scan_range(const uint32_t *d_size, uint32_t n_rec, uint32_t b0, uin
     return 0;
 }
 
-int bk_records_out(uint64_t *n) { *n = hs_records_out; return 0; }
+int bk_records_out(bk_q *q, uint64_t *n) { *n = q->records_out; return 0; }
 
-int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1)
+int bk_chain_emit(bk_q *q, const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, uint32_t b1)
 {
     struct ch_env e;
     uint32_t i, b;
@@ -233,7 +236,7 @@ int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, ui
         for (i = b * BK_REC_BLOCK; i < a->n_rec && i < (b + 1) * BK_REC_BLOCK; i++) {
             if (a->d_size[i]) {
                 uint32_t w = chain_record<true>(&e, i, a->d_off[i], a->d_len[i], d_out + at);
-                hs_records_out++;
+                q->records_out++;
                 if (w != a->d_size[i]) { snprintf(hs_err, sizeof(hs_err), "emit size mismatch at record %u: %u vs %u", i, w, a->d_size[i]); return -1; }
                 at += w;
             }
@@ -243,9 +246,41 @@ int bk_chain_emit(const struct bk_chain_args *a, uint8_t *d_out, uint32_t b0, ui
     return 0;
 }
 
-static uint8_t *hs_dl_dst; static const uint8_t *hs_dl_src;
-int bk_download_begin(void *h_dst, const void *d_out) { hs_dl_dst = (uint8_t *) h_dst; hs_dl_src = (const uint8_t *) d_out; return 0; }
-int bk_download_push(size_t lo, size_t hi) { memcpy(hs_dl_dst + lo, hs_dl_src + lo, hi - lo); return 0; }
-int bk_download_end(void) { return 0; }
+int bk_download_begin(bk_q *q, void *h_dst, const void *d_out) { q->dl_dst = (uint8_t *) h_dst; q->dl_src = (const uint8_t *) d_out; return 0; }
+int bk_download_push(bk_q *q, size_t lo, size_t hi) { memcpy(q->dl_dst + lo, q->dl_src + lo, hi - lo); return 0; }
+int bk_download_end(bk_q *) { return 0; }
+
+/* the small-chunk form: the same steps in sequence, with the same "does it fit" decisions the device takes */
+int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8_t *d_in, size_t bytes, uint32_t cap_rec,
+                 uint32_t *d_tile, uint32_t n_tiles, uint8_t *d_out, size_t cap_out, struct bk_small_res *res)
+{
+    struct bk_chain_args b = *a;
+    uint32_t n_cand = 0, n_valid = 0, nb, i;
+    uint64_t end_off = 0;
+    int tiled = 0;
+    memset(res, 0, sizeof(*res));
+    if (h_in) memcpy(d_in, h_in, bytes);
+    if (bk_index_count(q, d_in, 0, (uint32_t) bytes, d_tile, n_tiles, &n_cand)) return -1;
+    res->n_cand = n_cand;
+    if (n_cand > cap_rec) { res->overflow = 1; return 0; }
+    if (bk_index_fill(q, d_in, 0, (uint32_t) bytes, d_tile, n_tiles, n_cand, (uint32_t *) a->d_off, (uint32_t *) a->d_len, (uint8_t *) a->d_kind,
+                      &n_valid, &end_off, &tiled)) return -1;
+    res->n_valid = n_valid; res->tiled = (uint32_t) tiled; res->end_off = end_off;
+    b.n_rec = n_valid;
+    if (bk_chain_eval(q, &b, 0, n_valid)) return -1;
+    nb = (n_valid + BK_REC_BLOCK - 1) / BK_REC_BLOCK;
+    {
+        uint64_t *h_bsum = (uint64_t *) malloc(sizeof(uint64_t) * (nb + 2));
+        if (bk_sizes_scan(q, a->d_size, n_valid, a->d_bsum, h_bsum)) { free(h_bsum); return -1; }
+        res->total = h_bsum[nb];
+        free(h_bsum);
+    }
+    for (i = 0; i < n_valid; i++) if (a->d_size[i]) res->n_out++;
+    res->emitted = res->total <= cap_out;
+    if (res->emitted && bk_chain_emit(q, &b, d_out, 0, nb)) return -1;
+    memcpy(res->flags, a->d_flags, sizeof(res->flags));
+    return 0;
+}
+int bk_small_fetch(bk_q *, void *h_dst, const uint8_t *d_out, size_t n) { memcpy(h_dst, d_out, n); return 0; }
 
 }

@@ -222,8 +222,9 @@ def _speculation(lib, monkeypatch):
     only_get = util.chunk_from_lines(gets)
     has_env = b"".join(util.event(1700000000 + i, 0, [(b"log", util.mp_str(l)), (b"env", util.mp_str(b"x"))]) for i, l in enumerate(gets))
     filters = [("grep", [("Regex", "log GET")]), ("modify", [("Add", "env prod")])]
-    for stream in ("1", "0"):
+    for stream, slice_mb in (("1", "1"), ("0", "1"), ("1", "128")):          # streaming slices, classic two-pass, small-chunk form
         monkeypatch.setenv("FLBGPU_STREAM", stream)
+        monkeypatch.setenv("FLBGPU_SLICE_MB", slice_mb)
         ctx = pkg.Context(0, lib=lib)
         chain = ctx.chain([ctx.filter(p, props) for p, props in filters])
         for chunk in (mixed, only_get, has_env, mixed, mixed, has_env, only_get, only_get):

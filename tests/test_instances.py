@@ -1,0 +1,141 @@
+"""Per-instance back-end state: several filter instances called from different threads at the same time (what
+flb_processor_run() does, /root/reference/src/flb_processor.c:1352-1378), the small-chunk form against the sliced
+forms, and a slice with more broken candidate links than the one-CTA chain walk holds."""
+import threading
+
+import pytest
+
+import cases
+import util
+
+pkg = util.pkg
+
+
+def _ref_result(parsers, filters, chunk):
+    ref = util.Ref()
+    for kw in parsers:
+        ref.parser(**kw)
+    for p, props in filters:
+        ref.filter(p, props)
+    return ref.chain_do(chunk)
+
+
+def _concurrent(lib, n_threads=6, rounds=8):
+    north = [c for c in cases.CASES if c[0] == "north_star_chain"][0]
+    jsonc = [c for c in cases.CASES if c[0] == "json_chain_config1"][0]
+    work = []
+    for t in range(n_threads):
+        case = north if t % 2 == 0 else jsonc
+        lines = util.apache_lines(1500 + 100 * t, seed=100 + t) if t % 2 == 0 else util.json_lines(1500 + 100 * t, seed=100 + t)
+        chunk = util.chunk_from_lines(lines)
+        work.append((case, chunk, _ref_result(case[1], case[2], chunk)))
+    ctx = pkg.Context(0, lib=lib)
+    for kw in north[1] + jsonc[1]:
+        ctx.parser(**kw)
+    chains = [ctx.chain([ctx.filter(p, props) for p, props in w[0][2]]) for w in work]
+    errors = []
+
+    def run(t):
+        try:
+            for _ in range(rounds):
+                got = chains[t].do(work[t][1])
+                if got != work[t][2]:
+                    errors.append("thread %d: result differs from the reference" % t)
+                    return
+        except Exception as e:                      # noqa: BLE001
+            errors.append("thread %d: %r" % (t, e))
+
+    th = [threading.Thread(target=run, args=(t,)) for t in range(n_threads)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join()
+    assert not errors, errors
+
+
+def test_concurrent_instances_hostsim(sim_lib, ref_available):
+    _concurrent(sim_lib, n_threads=3, rounds=2)
+
+
+@pytest.mark.gpu
+def test_concurrent_instances_gpu(gpu_lib, ref_available):
+    _concurrent(gpu_lib)
+
+
+def _forms(lib, monkeypatch):
+    """the same chunk through the small-chunk form, the streaming slices and the classic two-pass form"""
+    for name, lines in (("north_star_chain", util.apache_lines(9000, seed=51)), ("json_chain_config1", util.json_lines(9000, seed=52)),
+                        ("parser_modify_recmod", util.apache_lines(5000, seed=53))):
+        case = [c for c in cases.CASES if c[0] == name][0]
+        chunk = util.chunk_from_lines(lines)
+        want = _ref_result(case[1], case[2], chunk)
+        for env in ({"FLBGPU_SMALL_MB": "8"}, {"FLBGPU_SMALL_MB": "0", "FLBGPU_SLICE_MB": "1"}, {"FLBGPU_STREAM": "0"}):
+            for k in ("FLBGPU_SMALL_MB", "FLBGPU_SLICE_MB", "FLBGPU_STREAM"):
+                monkeypatch.delenv(k, raising=False)
+            for k, v in env.items():
+                monkeypatch.setenv(k, v)
+            ctx = pkg.Context(0, lib=lib)
+            for kw in case[1]:
+                ctx.parser(**kw)
+            chain = ctx.chain([ctx.filter(p, props) for p, props in case[2]])
+            for cut in (len(chunk), len(chunk) - 29):
+                data = chunk[:cut]
+                w = want if cut == len(chunk) else _ref_result(case[1], case[2], data)
+                assert chain.do(data) == w, (name, env, cut)
+                assert chain.do(data) == w, (name, env, cut, "second call")
+
+
+def test_call_forms_hostsim(sim_lib, ref_available, monkeypatch):
+    _forms(sim_lib, monkeypatch)
+
+
+@pytest.mark.gpu
+def test_call_forms_gpu(gpu_lib, ref_available, monkeypatch):
+    _forms(gpu_lib, monkeypatch)
+
+
+def _nested_pairs_chunk(n):
+    """every record carries "pair": [1, {"a": 1}] -- bytes that frame as a legacy [ts, body] event, so each record
+    costs the record index one false candidate and one broken link"""
+    S = util.mp_str
+    pair = b"\x92\x01\x81" + S(b"a") + b"\x01"
+    return b"".join(util.event(1700000000 + i, i, [(b"log", S(b"GET /x%d" % i)), (b"pair", pair), (b"n", bytes([i % 100]))]) for i in range(n))
+
+
+def _many_breaks(lib, n):
+    chunk = _nested_pairs_chunk(n)
+    for filters in ([("grep", [("Regex", "log 7")])], [("modify", [("Add", "env prod")])], [("record_modifier", [("Remove_key", "pair")])]):
+        want = _ref_result([], filters, chunk)
+        ctx = pkg.Context(0, lib=lib)
+        got = ctx.chain([ctx.filter(p, props) for p, props in filters]).do(chunk)
+        assert got == want
+
+
+def test_many_broken_links_hostsim(sim_lib, ref_available):
+    _many_breaks(sim_lib, 3000)
+
+
+@pytest.mark.gpu
+def test_many_broken_links_gpu(gpu_lib, ref_available, monkeypatch):
+    """more than 8192 broken links in one slice: the chain is decided by pointer doubling (k_link_*)"""
+    _many_breaks(gpu_lib, 30000)                          # small-chunk form first, then the classic one
+    monkeypatch.setenv("FLBGPU_SMALL_MB", "0")
+    _many_breaks(gpu_lib, 30000)                          # streaming slices
+
+
+@pytest.mark.gpu
+def test_two_contexts_one_process_gpu(gpu_lib, ref_available):
+    """a second flbgpu_init() (same or another device) has its own queues"""
+    n_dev = gpu_lib.flbgpu_device_count()
+    case = [c for c in cases.CASES if c[0] == "north_star_chain"][0]
+    chunk = util.chunk_from_lines(util.apache_lines(2000, seed=77))
+    want = _ref_result(case[1], case[2], chunk)
+    ctxs = [pkg.Context(d % n_dev, lib=gpu_lib) for d in range(max(2, min(n_dev, 4)))]
+    chains = []
+    for ctx in ctxs:
+        for kw in case[1]:
+            ctx.parser(**kw)
+        chains.append(ctx.chain([ctx.filter(p, props) for p, props in case[2]]))
+    for _ in range(3):
+        for ch in chains:
+            assert ch.do(chunk) == want
