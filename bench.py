@@ -312,7 +312,11 @@ class Workload:
         self.pkg = util.pkg
         self.args, self.wl, self.L, self.ctx, self.rank, self.world = args, wl, L, ctx, rank, world
         if wl != "l2m":
-            ctx.parser(**parser_kw(wl))
+            kw = parser_kw(wl)
+            made = ctx.__dict__.setdefault("_bench_parsers", set())
+            if kw["name"] not in made:
+                ctx.parser(**kw)
+                made.add(kw["name"])
         self.filters = [ctx.filter(p, props) for p, props in WORKLOADS[wl]["filters"]]
         self.chain = ctx.chain(self.filters)
         self.block = make_block(wl, rank)

@@ -62,6 +62,7 @@ struct ch_env {
     uint32_t cap_stride;
     int64_t now;
     uint32_t assume;          /* bit k: filter k is chunk-level MODIFIED */
+    uint32_t active;          /* bit k: filter k is routed this chunk (Match / Match_Regex), else skipped like flb_filter_do() does */
     uint32_t *fl_flags;       /* [n_filters] CHF_* evidence (evaluation pass only) */
     uint32_t *err;            /* FLBGPU_E_* */
     struct l2m_table l2m;     /* log_to_metrics delta table of this call (hash == NULL: none) */
@@ -1818,6 +1819,7 @@ FLB_HDN void chain_skipped_record(const struct ch_env *e, uint32_t ridx, uint32_
     struct ch_env le;
     uint32_t k;
     for (k = 0; k < h->n_filters; k++) {
+        if (!((e->active >> k) & 1)) continue;
         if (f[k].kind == FLBGPU_F_LOG_TO_METRICS) break;
         if ((e->assume >> k) & 1) return;
     }
@@ -1877,6 +1879,7 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
     for (k = 0; k < h->n_filters; k++) {
         const uint8_t *cfg = e->blob + f[k].cfg_off;
         int assumed = (e->assume >> k) & 1;
+        if (!((e->active >> k) & 1)) continue;
         CH_SYNC();
         switch (f[k].kind) {
         case FLBGPU_F_PARSER:

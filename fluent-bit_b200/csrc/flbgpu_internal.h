@@ -39,6 +39,7 @@ struct bk_chain_args {
     uint32_t cap_stride;
     int64_t now;
     uint32_t assume;
+    uint32_t active;              /* bit k: filter k sees this call's chunk (Match routing) */
     const uint32_t *d_off;        /* record index */
     const uint32_t *d_len;
     const uint8_t *d_kind;
@@ -68,6 +69,8 @@ int   bk_sync(bk_q *q);
 void *bk_stream(bk_q *q);
 int   bk_kernel_ms(bk_q *q, float out[3]);       /* CUDA-event ms of index / evaluate / emit in the last call */
 int   bk_d2d(bk_q *q, void *dst, const void *src, size_t n);   /* synchronous device copy (buffer growth) */
+/* the regex VM on the host, for control-plane decisions on tags (Match_Regex); caps has 2 * (RX_MAX_GROUPS + 1) ints */
+int   bk_rx_search_host(const void *prog, const uint8_t *s, int n, int *caps);
 
 /* ---- the per-call pipeline ----------------------------------------------------
  * A chunk is processed in SLICES (byte ranges that start at a record boundary):

@@ -943,6 +943,12 @@ int bk_download_end(bk_q *q)
     return rc;
 }
 
+int bk_rx_search_host(const void *prog, const uint8_t *s, int n, int *caps)
+{
+    uint32_t stk[1024], budget = CH_RX_BUDGET;
+    return rx_search((const struct rx_prog *) prog, s, n, caps, stk, 1024, &budget);
+}
+
 int bk_d2d(bk_q *q, void *dst, const void *src, size_t n)
 {
     use(q);
@@ -1037,7 +1043,7 @@ static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_
 {
     p->env.in = a->d_in; p->env.in_len = a->in_len; p->env.blob = a->d_blob; p->env.scr = a->d_scr;
     p->env.capcache = a->d_capcache; p->env.cap_stride = a->cap_stride; p->env.now = a->now;
-    p->env.assume = a->assume; p->env.fl_flags = a->d_flags; p->env.err = a->d_flags + FLBGPU_MAX_FILTERS;
+    p->env.assume = a->assume; p->env.active = a->active; p->env.fl_flags = a->d_flags; p->env.err = a->d_flags + FLBGPU_MAX_FILTERS;
     p->env.l2m = a->l2m;
     p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->r0 = r0; p->n_rec = a->n_rec; p->stage_bytes = 0;
     p->n_dev = 0;

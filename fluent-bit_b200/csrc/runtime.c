@@ -128,6 +128,11 @@ struct flbgpu_filter {
     int needs_scratch;       /* a JSON parser transcodes into per-record scratch */
     flbgpu_chain *solo;
     struct l2m_state *l2m;   /* cumulative metrics of a log_to_metrics filter */
+    /* routing (struct flb_filter_instance: match, match_regex; the `active` property): consulted by the fused chain,
+     * like flb_filter_do() does per filter (src/flb_filter.c:180-190) */
+    char *match;
+    struct rx_compiled match_rx; int has_match_rx;
+    int inactive;
 };
 
 struct flbgpu_ctx {
@@ -163,6 +168,8 @@ struct flbgpu_chain {
     uint32_t *d_flags;
     uint64_t *h_bsum; size_t cap_hbsum;      /* host copy of the per-block output offsets */
     uint32_t spec_assume; int spec_valid;     /* verdict vector of the previous call: what the streaming path speculates on */
+    uint32_t active;                          /* bit k: filter k is routed this call's tag (Match / Match_Regex / active) */
+    uint32_t spec_active;                     /* the routing the speculation belongs to */
     uint32_t small_cap_rec; size_t small_cap_out;   /* what the small-chunk form learnt about this instance's chunks */
     struct flbgpu_stats st;
 };
@@ -493,8 +500,18 @@ int flbgpu_filter_set_property(flbgpu_filter *f, const char *k, const char *v)
     if (!f || !k || !v) return -1;
     /* instance-level keys are consumed by the framework, not by the plugin
      * (src/flb_filter.c:346-395) */
-    if (!strcasecmp(k, "match") || !strcasecmp(k, "match_regex") || !strcasecmp(k, "alias") ||
-        !strcasecmp(k, "log_level") || !strcasecmp(k, "log_suppress_interval")) return 0;
+    if (!strcasecmp(k, "match")) { free(f->match); f->match = strdup(v); return f->match ? 0 : -1; }
+    if (!strcasecmp(k, "match_regex")) {
+        if (f->has_match_rx) { rx_compiled_free(&f->match_rx); f->has_match_rx = 0; }
+        if (rx_compile(v, &f->match_rx) != 0) { set_err("could not compile Match_Regex '%s' (%s)", v, f->match_rx.err); return -1; }
+        f->has_match_rx = 1;
+        return 0;
+    }
+    if (!strcasecmp(k, "alias") || !strcasecmp(k, "log_level") || !strcasecmp(k, "log_suppress_interval")) return 0;
+    if (!strcasecmp(k, "active")) {                   /* is_active(), src/flb_filter.c:90-105; the property stays in the list there too */
+        if (!strcasecmp(v, "FALSE") || !strcmp(v, "0")) f->inactive = 1;
+        return 0;
+    }
     n = calloc(1, sizeof(*n));
     n->k = strdup(k);
     n->v = strdup(v);
@@ -513,6 +530,8 @@ void flbgpu_filter_destroy(flbgpu_filter *f)
     if (!f) return;
     if (f->solo) flbgpu_chain_destroy(f->solo);
     l2m_state_free(f->l2m);
+    free(f->match);
+    if (f->has_match_rx) rx_compiled_free(&f->match_rx);
     for (n = f->props; n; n = nx) { nx = n->next; free(n->k); free(n->v); free(n); }
     free(f);
 }
@@ -1304,7 +1323,8 @@ static void fill_args(flbgpu_chain *c, struct bk_chain_args *a, const uint8_t *d
     a->d_capcache = c->cap_stride ? c->d_cap : NULL; a->cap_stride = c->cap_stride;
     a->d_off = c->d_off; a->d_len = c->d_len; a->d_kind = c->d_kind; a->n_rec = n_rec;
     a->d_size = c->d_size; a->d_bsum = c->d_bsum; a->d_flags = c->d_flags;
-    if (c->l2m_index >= 0) a->l2m = c->l2m; else memset(&a->l2m, 0, sizeof(a->l2m));
+    if (c->l2m_index >= 0 && ((c->active >> c->l2m_index) & 1)) a->l2m = c->l2m; else memset(&a->l2m, 0, sizeof(a->l2m));
+    a->active = c->active;
 }
 
 /* zero the per-call metrics table (before every evaluation pass) */
@@ -1312,7 +1332,7 @@ static int l2m_clear(flbgpu_chain *c)
 {
     struct l2m_state *st;
     size_t n = c->l2m_slots;
-    if (c->l2m_index < 0) return 0;
+    if (c->l2m_index < 0 || !((c->active >> c->l2m_index) & 1)) return 0;
     st = c->f[c->l2m_index]->l2m;
     if (bk_zero(c->q, c->l2m.hash, n * 8) || bk_zero(c->q, c->l2m.first, n * 4) || bk_zero(c->q, c->l2m.cnt, n * 8) ||
         bk_zero(c->q, c->l2m.sum, n * 8) || bk_zero(c->q, c->l2m.bkt, n * L2M_NBK(st) * 8)) return -1;
@@ -1333,7 +1353,7 @@ static int l2m_merge(flbgpu_chain *c)
     struct l2m_state *st;
     size_t n = c->l2m_slots, nbk, i, m = 0;
     uint32_t *order;
-    if (c->l2m_index < 0) return 0;
+    if (c->l2m_index < 0 || !((c->active >> c->l2m_index) & 1)) return 0;
     st = c->f[c->l2m_index]->l2m;
     nbk = L2M_NBK(st);
     if (bk_d2h(c->q, c->h_hash, c->l2m.hash, n * 8) || bk_d2h(c->q, c->h_chash, c->l2m.chash, n * 8) || bk_d2h(c->q, c->h_first, c->l2m.first, n * 4) || bk_d2h(c->q, c->h_cnt, c->l2m.cnt, n * 8) ||
@@ -1483,6 +1503,55 @@ static int stops_at_wide_array(bk_q *q, const uint8_t *h_in, const uint8_t *d_in
             fail_stmt; \
         } } while (0)
 
+/* flb_router_match() (src/flb_router.c:37-128): Match_Regex first -- onig_match() at the start of the tag with a match of
+ * positive length -- then the Match pattern, where '*' stands for any run of characters. */
+static int wildcard_match(const char *tag, size_t n, const char *m)
+{
+    while (*m) {
+        if (*m == '*') {
+            while (*++m == '*') { }
+            if (!*m) return 1;
+            {
+                size_t i;
+                for (i = 0; i < n; i++) if (tag[i] == *m && wildcard_match(tag + i, n - i, m)) return 1;
+            }
+            return 0;
+        }
+        if (n == 0 || *tag != *m) return 0;
+        tag++; n--; m++;
+    }
+    return n == 0;
+}
+
+static int filter_routes(const flbgpu_filter *f, const char *tag, int tag_len)
+{
+    if (f->inactive) return 0;
+    if (tag_len < 0) return 0;
+    if (!tag) { if (tag_len) return 0; tag = ""; }
+    if (f->has_match_rx) {
+        int caps[2 * (RX_MAX_GROUPS + 1)];
+        if (bk_rx_search_host(f->match_rx.prog, (const uint8_t *) tag, tag_len, caps) == RX_R_MATCH && caps[0] == 0 && caps[1] > 0) return 1;
+    }
+    if (!f->match) return !f->has_match_rx;           /* no rule given at all: every chunk (the engine refuses such an instance) */
+    return wildcard_match(tag, (size_t) tag_len, f->match);
+}
+
+static uint32_t chain_active_mask(flbgpu_chain *c, const char *tag, int tag_len)
+{
+    uint32_t m = 0;
+    int k;
+    for (k = 0; k < c->nf; k++) if (filter_routes(c->f[k], tag, tag_len)) m |= 1u << k;
+    return m;
+}
+
+/* the verdict vector a call starts from: every routed filter modifies (log_to_metrics only when it discards) */
+static uint32_t initial_assume(flbgpu_chain *c)
+{
+    uint32_t a = c->active;
+    if (c->l2m_index >= 0 && !c->f[c->l2m_index]->l2m->discard) a &= ~(1u << c->l2m_index);
+    return a;
+}
+
 /* One call.  Input: h_in (host, uploaded in pieces) or d_in_ext (already in HBM).
  * Result: host_out != NULL -> malloc()ed host buffer; else ext_out (device, capacity ext_cap). */
 static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_ext, size_t bytes,
@@ -1512,8 +1581,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     if (c->needs_scratch) GROW(c->d_scr, c->cap_scr, 4 * bytes + 64, uint8_t);
     memset(&a, 0, sizeof(a));
     a.now = (int64_t) time(NULL);
-    a.assume = (c->nf >= 32) ? 0xffffffffu : ((1u << c->nf) - 1u);
-    if (c->l2m_index >= 0 && !c->f[c->l2m_index]->l2m->discard) a.assume &= ~(1u << c->l2m_index);
+    a.assume = initial_assume(c);
     if (bk_flags_clear(c->q, c->d_flags) || l2m_clear(c)) return -1;
 
     /* ---- index + evaluate, slice by slice, while the upload is still running ---- */
@@ -1567,7 +1635,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
             return -1;
         }
         for (k = 0; k < c->nf; k++) {
-            int v = c->f[k]->kind == FLBGPU_F_LOG_TO_METRICS ? L2M_VERDICT(c, k) : verdict(c->f[k]->kind, h_flags[k], cl);
+            int v = !((c->active >> k) & 1) ? 0 : c->f[k]->kind == FLBGPU_F_LOG_TO_METRICS ? L2M_VERDICT(c, k) : verdict(c->f[k]->kind, h_flags[k], cl);
             if (v) cl = 1;                   /* a MODIFIED filter hands a well-formed chunk on */
             if (v != (int) ((a.assume >> k) & 1)) {
                 a.assume = (a.assume & ~(1u << k)) | ((uint32_t) v << k);
@@ -1581,7 +1649,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     }
     c->st.kernel_launches = bk_launch_count();
     PHASE_MARK(0);
-    c->spec_assume = a.assume; c->spec_valid = 1;    /* what the streaming path speculates on next time */
+    c->spec_assume = a.assume; c->spec_valid = 1; c->spec_active = c->active;    /* what the streaming path speculates on next time */
     if (l2m_merge(c)) return -1;
     if (a.assume == 0) return FLBGPU_FILTER_NOTOUCH;
 
@@ -1710,9 +1778,8 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
     c->st.bytes_in = bytes;
     *out_size = 0;
     clock_gettime(CLOCK_MONOTONIC, &t0);
-    assume = (c->nf >= 32) ? 0xffffffffu : ((1u << c->nf) - 1u);
-    if (c->l2m_index >= 0 && !c->f[c->l2m_index]->l2m->discard) assume &= ~(1u << c->l2m_index);
-    if (c->spec_valid) assume = c->spec_assume;
+    assume = initial_assume(c);
+    if (c->spec_valid && c->spec_active == c->active) assume = c->spec_assume;
     if (assume == 0) return 1;                       /* nothing would be emitted: the classic path decides */
     if (bytes >= 0xfff00000ull) { set_err("chunk larger than 4 GiB: split the append%s%s", NULL, NULL); return -1; }
     GROW(c->d_in, c->cap_in, bytes + 64, uint8_t);
@@ -1815,20 +1882,20 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
         int cl = clean;
         uint32_t settled = 0;
         for (k = 0; k < c->nf; k++) {
-            int v = c->f[k]->kind == FLBGPU_F_LOG_TO_METRICS ? L2M_VERDICT(c, k) : verdict(c->f[k]->kind, h_flags[k], cl);
+            int v = !((c->active >> k) & 1) ? 0 : c->f[k]->kind == FLBGPU_F_LOG_TO_METRICS ? L2M_VERDICT(c, k) : verdict(c->f[k]->kind, h_flags[k], cl);
             if (v) cl = 1;
             if (v != (int) ((assume >> k) & 1)) {
                 /* evidence of the later filters was gathered under a wrong assumption: redo classically,
                  * and speculate on "filter k as found" next time */
                 c->spec_assume = (assume & ~(1u << k)) | ((uint32_t) v << k);
-                c->spec_valid = 1;
+                c->spec_valid = 1; c->spec_active = c->active;
                 if (dl_open) bk_download_end(c->q);
                 free(out);
                 return 1;
             }
             settled |= (uint32_t) v << k;
         }
-        c->spec_assume = settled; c->spec_valid = 1;
+        c->spec_assume = settled; c->spec_valid = 1; c->spec_active = c->active;
     }
     c->st.kernel_launches = bk_launch_count();
     if (l2m_merge(c)) goto fail;
@@ -1880,9 +1947,8 @@ static int chain_run_small(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, v
     int clean, k;
     struct timespec t0, t1;
 
-    assume = (c->nf >= 32) ? 0xffffffffu : ((1u << c->nf) - 1u);
-    if (c->l2m_index >= 0 && !c->f[c->l2m_index]->l2m->discard) assume &= ~(1u << c->l2m_index);
-    if (c->spec_valid) assume = c->spec_assume;
+    assume = initial_assume(c);
+    if (c->spec_valid && c->spec_active == c->active) assume = c->spec_assume;
     if (assume == 0) return 1;                       /* nothing would be emitted: the classic path decides */
     memset(&c->st, 0, sizeof(c->st));
     c->st.bytes_in = bytes;
@@ -1928,16 +1994,16 @@ static int chain_run_small(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, v
         int cl = clean;
         uint32_t settled = 0;
         for (k = 0; k < c->nf; k++) {
-            int v = c->f[k]->kind == FLBGPU_F_LOG_TO_METRICS ? L2M_VERDICT(c, k) : verdict(c->f[k]->kind, res.flags[k], cl);
+            int v = !((c->active >> k) & 1) ? 0 : c->f[k]->kind == FLBGPU_F_LOG_TO_METRICS ? L2M_VERDICT(c, k) : verdict(c->f[k]->kind, res.flags[k], cl);
             if (v) cl = 1;
             if (v != (int) ((assume >> k) & 1)) {
                 c->spec_assume = (assume & ~(1u << k)) | ((uint32_t) v << k);
-                c->spec_valid = 1;
+                c->spec_valid = 1; c->spec_active = c->active;
                 return 1;
             }
             settled |= (uint32_t) v << k;
         }
-        c->spec_assume = settled; c->spec_valid = 1;
+        c->spec_assume = settled; c->spec_valid = 1; c->spec_active = c->active;
     }
     if (l2m_merge(c)) return -1;
     if (res.total >= 0xfff00000ull) { set_err("result larger than 4 GiB%s%s", NULL, NULL); return -1; }
@@ -1968,6 +2034,11 @@ int flbgpu_chain_do_device(flbgpu_chain *c, const void *d_data, size_t bytes, vo
     g_rt_err[0] = 0;
     pthread_mutex_lock(&c->lock);
     c->ctx->last_q = c->q;
+    {   /* no tag here: every filter that is not switched off */
+        int k;
+        c->active = 0;
+        for (k = 0; k < c->nf; k++) if (!c->f[k]->inactive) c->active |= 1u << k;
+    }
     r = chain_run(c, NULL, d_data, bytes, d_out, out_cap, NULL, out_size);
     if (r >= 0 && bk_sync(c->q)) r = -1;
     pthread_mutex_unlock(&c->lock);
@@ -1978,7 +2049,7 @@ int flbgpu_chain_do_device(flbgpu_chain *c, const void *d_data, size_t bytes, vo
  * on the chunk the previous one returned.  The fused form hands fields from filter to filter by reference and cannot
  * parse a value an earlier filter of the same chain made (a decoded JSON string, a `Set` constant); it refuses with
  * FLBGPU_E_FIELDS and the chain is run this way instead -- same result, one round trip per filter. */
-static int chain_do_one_by_one(flbgpu_chain *c, const void *data, size_t bytes, void **out_buf, size_t *out_size)
+static int chain_do_one_by_one(flbgpu_chain *c, const void *data, size_t bytes, const char *tag, int tag_len, void **out_buf, size_t *out_size)
 {
     const void *cur = data;
     size_t cur_n = bytes;
@@ -1987,7 +2058,7 @@ static int chain_do_one_by_one(flbgpu_chain *c, const void *data, size_t bytes, 
     for (k = 0; k < c->nf; k++) {
         void *o = NULL;
         size_t on = 0;
-        int r = flbgpu_filter_cb(c->f[k], cur, cur_n, "", 0, &o, &on);
+        int r = flbgpu_filter_cb(c->f[k], cur, cur_n, tag, tag_len, &o, &on);
         if (r < 0) { free(owned); return -1; }
         if (r != FLBGPU_FILTER_MODIFIED) { free(o); continue; }
         free(owned);
@@ -2001,13 +2072,13 @@ static int chain_do_one_by_one(flbgpu_chain *c, const void *data, size_t bytes, 
 }
 #define FUSED_REFUSED_A_HANDED_OVER_VALUE(c) ((c)->nf > 1 && (c)->st.error_bits == FLBGPU_E_FIELDS)
 
-static int chain_do_locked(flbgpu_chain *c, const void *data, size_t bytes, void **out_buf, size_t *out_size)
+static int chain_do_locked(flbgpu_chain *c, const void *data, size_t bytes, const char *tag, int tag_len, void **out_buf, size_t *out_size)
 {
     if (bytes <= small_bytes()) {
         int ret = 0, r = chain_run_small(c, data, bytes, out_buf, out_size, &ret);
         if (r == 0) return ret;
         if (r < 0) {
-            if (FUSED_REFUSED_A_HANDED_OVER_VALUE(c)) { *out_buf = NULL; *out_size = 0; return chain_do_one_by_one(c, data, bytes, out_buf, out_size); }
+            if (FUSED_REFUSED_A_HANDED_OVER_VALUE(c)) { *out_buf = NULL; *out_size = 0; return chain_do_one_by_one(c, data, bytes, tag, tag_len, out_buf, out_size); }
             return -1;
         }
         *out_buf = NULL; *out_size = 0;
@@ -2019,7 +2090,7 @@ static int chain_do_locked(flbgpu_chain *c, const void *data, size_t bytes, void
             bk_upload_end(c->q);                     /* `data` is not read after this call returns */
             if (r == 0) return ret;
             if (r < 0) {
-                if (FUSED_REFUSED_A_HANDED_OVER_VALUE(c)) return chain_do_one_by_one(c, data, bytes, out_buf, out_size);
+                if (FUSED_REFUSED_A_HANDED_OVER_VALUE(c)) return chain_do_one_by_one(c, data, bytes, tag, tag_len, out_buf, out_size);
                 return -1;
             }
             *out_buf = NULL; *out_size = 0;          /* speculation did not hold: classic path */
@@ -2028,7 +2099,7 @@ static int chain_do_locked(flbgpu_chain *c, const void *data, size_t bytes, void
     {
         int r = chain_run(c, data, NULL, bytes, NULL, 0, out_buf, out_size);
         bk_upload_end(c->q);
-        if (r < 0 && FUSED_REFUSED_A_HANDED_OVER_VALUE(c)) { *out_buf = NULL; *out_size = 0; return chain_do_one_by_one(c, data, bytes, out_buf, out_size); }
+        if (r < 0 && FUSED_REFUSED_A_HANDED_OVER_VALUE(c)) { *out_buf = NULL; *out_size = 0; return chain_do_one_by_one(c, data, bytes, tag, tag_len, out_buf, out_size); }
         return r;
     }
 }
@@ -2037,14 +2108,15 @@ int flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes, const char 
                     void **out_buf, size_t *out_size)
 {
     int r;
-    (void) tag; (void) tag_len;
     if (!c || !c->inited || !out_buf || !out_size) return -1;
     g_rt_err[0] = 0;
     *out_buf = NULL; *out_size = 0;
     if (bytes == 0) return FLBGPU_FILTER_NOTOUCH;
     pthread_mutex_lock(&c->lock);
     c->ctx->last_q = c->q;
-    r = chain_do_locked(c, data, bytes, out_buf, out_size);
+    c->active = chain_active_mask(c, tag, tag_len);
+    if (c->active == 0) r = FLBGPU_FILTER_NOTOUCH;    /* no filter of the chain is routed this tag */
+    else r = chain_do_locked(c, data, bytes, tag, tag_len, out_buf, out_size);
     pthread_mutex_unlock(&c->lock);
     return r;
 }

@@ -8,6 +8,7 @@
  *   flb_parser_time_lookup                       (src/flb_parser.c:1159)
  * TEST INFRASTRUCTURE ONLY: nothing under fluent-bit_b200/ may link or call this. */
 #include <stdio.h>
+#include <dlfcn.h>
 #include <stdlib.h>
 #include <string.h>
 #include <fluent-bit/flb_info.h>
@@ -67,6 +68,25 @@ void *flbref_config_create(void)
     c->in.config = config;
     return c;
 }
+
+/* what flb_plugin_load() does for a dynamic filter plugin (src/flb_plugin.c:200-324): dlopen, look the registration
+ * struct up by name, memcpy it, link it to config->filter_plugins.  0 ok, -1 not. */
+int flbref_plugin_load(void *cfg, const char *path, const char *struct_name)
+{
+    struct flbref_cfg *c = cfg;
+    void *dso = dlopen(path, RTLD_LAZY);
+    struct flb_filter_plugin *sym, *copy;
+    if (!dso) { fprintf(stderr, "flbref_plugin_load: %s\n", dlerror()); return -1; }
+    sym = dlsym(dso, struct_name);
+    if (!sym) { fprintf(stderr, "flbref_plugin_load: %s lacks %s\n", path, struct_name); return -1; }
+    copy = flb_malloc(sizeof(*copy));
+    memcpy(copy, sym, sizeof(*copy));
+    mk_list_add(&copy->_head, &c->config->filter_plugins);
+    return 0;
+}
+
+/* parsers of the reference's own configuration text ([PARSER] sections, src/flb_parser.c flb_parser_conf_file) are
+ * not needed here: tests create them with flbref_parser_create() */
 
 void *flbref_config_raw(void *cfg) { return ((struct flbref_cfg *) cfg)->config; }
 

@@ -57,7 +57,7 @@ int flb_metrics_sum(int id, size_t val, struct flb_metrics *metrics) { return 0;
 int flb_metrics_destroy(struct flb_metrics *metrics) { free(metrics); return 0; }
 
 /* tag routing: the harness always passes a matching tag */
-int flb_router_match(const char *tag, int tag_len, const char *match, void *match_regex) { return 1; }
+
 
 /* --- log_to_metrics' hidden emitter input: recorded, not run --- */
 struct flb_input_instance *flb_input_new(struct flb_config *config, const char *input, void *data, int public_only)

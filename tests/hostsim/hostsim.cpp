@@ -98,6 +98,11 @@ int bk_sync(bk_q *) { return 0; }
 void *bk_stream(bk_q *) { return 0; }
 int bk_kernel_ms(bk_q *, float out[3]) { out[0] = out[1] = out[2] = 0.f; return 0; }
 
+int bk_rx_search_host(const void *prog, const uint8_t *s, int n, int *caps)
+{
+    uint32_t stk[1024], budget = CH_RX_BUDGET;
+    return rx_search((const struct rx_prog *) prog, s, n, caps, stk, 1024, &budget);
+}
 int bk_d2d(bk_q *, void *dst, const void *src, size_t n) { memcpy(dst, src, n); return 0; }
 int bk_upload_start(bk_q *, void *d_dst, const void *h_src, size_t n) { memcpy(d_dst, h_src, n); return 0; }
 int bk_upload_wait_index(bk_q *, size_t upto) { (void) upto; return 0; }
@@ -173,7 +178,7 @@ int bk_index_fill(bk_q *, const uint8_t *d_in, size_t slice_off, uint32_t len, c
 static void hs_env(const struct bk_chain_args *a, struct ch_env *e)
 {
     e->in = a->d_in; e->in_len = a->in_len; e->blob = a->d_blob; e->scr = a->d_scr;
-    e->capcache = a->d_capcache; e->cap_stride = a->cap_stride; e->now = a->now; e->assume = a->assume;
+    e->capcache = a->d_capcache; e->cap_stride = a->cap_stride; e->now = a->now; e->assume = a->assume; e->active = a->active;
     e->fl_flags = a->d_flags; e->err = a->d_flags + FLBGPU_MAX_FILTERS;
     e->l2m = a->l2m;
 }

@@ -139,3 +139,34 @@ def test_two_contexts_one_process_gpu(gpu_lib, ref_available):
     for _ in range(3):
         for ch in chains:
             assert ch.do(chunk) == want
+
+
+def _fused_match(lib):
+    """Match / Match_Regex / active decide per filter of the FUSED chain whether it sees the chunk, like flb_filter_do()
+    (src/flb_filter.c:180-190, flb_router_match)"""
+    chunk = cases.apache_chunk(500)
+    variants = [
+        [("parser", cases.P[1] + [("match", "app.*")]), ("grep", [("Regex", "method ^(GET|POST)$"), ("match", "*.web")]), ("modify", [("Add", "env prod"), ("match", "*")])],
+        [("parser", cases.P[1] + [("match", "never"), ("match_regex", "^app\\.(web|db)$")]), ("grep", [("Regex", "log GET"), ("match", "a*b*")]), ("modify", [("Add", "k v"), ("active", "false")])],
+        [("grep", [("Exclude", "log POST"), ("match", "sys"), ("match_regex", "^x")]), ("record_modifier", [("Record", "h n1"), ("match", "*s")])],
+    ]
+    for filters in variants:
+        for tag in ("app.web", "app.db", "sys", "axxbyy", "xs", ""):
+            ctx = pkg.Context(0, lib=lib)
+            ctx.parser(**cases.AP)
+            ref = util.Ref()
+            ref.parser(**cases.AP)
+            for p, props in filters:
+                ref.filter(p, props)
+            chain = ctx.chain([ctx.filter(p, props) for p, props in filters])
+            for _ in range(2):
+                assert chain.do(chunk, tag) == ref.chain_do(chunk, tag), (filters, tag)
+
+
+def test_fused_match_routing_hostsim(sim_lib, ref_available):
+    _fused_match(sim_lib)
+
+
+@pytest.mark.gpu
+def test_fused_match_routing_gpu(gpu_lib, ref_available):
+    _fused_match(gpu_lib)

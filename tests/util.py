@@ -8,6 +8,7 @@ import struct
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 REF_SO = os.path.join(ROOT, "oracle", "_ref", "libflbref.so")
+SHIM_SO = os.path.join(ROOT, "oracle", "_ref", "flb-filter_gpu.so")
 HOSTSIM_SO = os.environ.get("FLBGPU_HOSTSIM_SO") or os.path.join(ROOT, "tests", "hostsim", "libhostsim.so")   # override: a sanitizer build
 
 pkg = importlib.import_module("fluent-bit_b200")
@@ -35,8 +36,33 @@ class Ref:
         L.flbref_count_records.argtypes = [vp, sz]
         L.flbref_free.argtypes = [vp]
         L.flbref_time_lookup.argtypes = [vp, cp, sz, C.c_longlong, C.POINTER(C.c_longlong), C.POINTER(C.c_double)]
+        L.flbref_plugin_load.argtypes = [vp, cp, cp]
+        L.flbref_filter_cmt_text.restype = vp; L.flbref_filter_cmt_text.argtypes = [vp]
+        L.flbref_l2m_cmt_text.restype = vp; L.flbref_l2m_cmt_text.argtypes = [vp]
+        L.flbref_cfree.argtypes = [vp]
         self.L = L
         self.cfg = L.flbref_config_create()
+
+    def load_gpu_plugins(self, gpu_lib_path):
+        """register the five filter_gpu_*_plugin structs of the shim (oracle/_ref/flb-filter_gpu.so), bound to the
+        given implementation of the C ABI (libflbgpu.so, or the CPU emulation in the not-gpu tests)"""
+        os.environ["FLBGPU_SHIM_LIB"] = gpu_lib_path
+        for name in ("parser", "grep", "modify", "record_modifier", "log_to_metrics"):
+            if self.L.flbref_plugin_load(self.cfg, SHIM_SO.encode(), ("filter_gpu_%s_plugin" % name).encode()) != 0:
+                raise RuntimeError("cannot load the gpu_%s plugin from %s" % (name, SHIM_SO))
+
+    def filter_counters(self, f):
+        """the instance's framework counters (src/flb_filter.c:574-616) as {metric line without timestamp}"""
+        p = self.L.flbref_filter_cmt_text(f)
+        t = C.string_at(p).decode()
+        self.L.flbref_cfree(p)
+        return sorted(l.split(" ", 1)[1] for l in t.splitlines() if " " in l)
+
+    def l2m_text(self, f):
+        p = self.L.flbref_l2m_cmt_text(f)
+        t = C.string_at(p).decode()
+        self.L.flbref_cfree(p)
+        return t
 
     @staticmethod
     def _b(s):
