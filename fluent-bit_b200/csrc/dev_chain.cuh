@@ -66,6 +66,8 @@ struct ch_env {
     uint32_t *fl_flags;       /* [n_filters] CHF_* evidence (evaluation pass only) */
     uint32_t *err;            /* FLBGPU_E_* */
     struct l2m_table l2m;     /* log_to_metrics delta table of this call (hash == NULL: none) */
+    int32_t *prep;            /* parser report (flbgpu_parser_do): 6 ints per record -- parsed flag, position consumed,
+                                 seconds lo / hi, nanoseconds, spare -- or NULL */
 };
 
 struct ch_rec {
@@ -466,7 +468,7 @@ FLB_HD int ra_regex_match(const struct ch_env *e, const struct ch_rec *rc, uint3
  * instead of running strptime again */
 FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s,
                       uint32_t n, const int *caps, ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec,
-                      int64_t *t_nsec, int32_t *tslot, int use_cached, uint32_t *th)
+                      int64_t *t_nsec, int32_t *tslot, int use_cached, uint32_t *th, int *pos)
 {
     const struct cf_pname *nm = (const struct cf_pname *) (e->blob + pd->names_off);
     uint32_t i;
@@ -475,7 +477,7 @@ FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t
     double frac = 0;
     if (pd->n_groups == 0) return 0;                 /* flb_parser_regex_do: n <= 0 -> -1 */
     /* decided before anything is written: the caller may hand in the record's own field arrays */
-    for (i = 0; i < pd->n_names; i++) if (caps[2 * nm[i].group + 1] >= 0) any_end = 1;
+    for (i = 0; i < pd->n_names; i++) if (caps[2 * nm[i].group + 1] >= 0) { any_end = 1; *pos = caps[2 * nm[i].group + 1]; }   /* cb_onig_named: last_pos */
     if (!any_end) return 0;                          /* flb_regex_parse: last_pos == -1 */
     for (i = 0; i < pd->n_names; i++) {
         int b = caps[2 * nm[i].group], en = caps[2 * nm[i].group + 1];
@@ -593,7 +595,7 @@ FLB_HD int ltsv_label(uint32_t c) { return (c >= '0' && c <= '9') || ((c | 0x20)
 FLB_HD int ltsv_field(uint32_t c) { return c != 0 && c != 9 && c != 10 && c != 13; }
 
 FLB_HDN int pdef_ltsv(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
-                     ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec)
+                     ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec, int *pos)
 {
     uint32_t c = 0;
     int cnt = 0;
@@ -627,10 +629,13 @@ FLB_HDN int pdef_ltsv(const struct ch_env *e, const struct cf_pdef *pd, uint32_t
         if (c == n) break;
         if (s[c] == '\t') c++;
         if (c == n) break;
-        if (s[c] == '\r' || s[c] == '\n') break;
+        if (s[c] == '\r' || s[c] == '\n') {          /* the line end is consumed: CR, CR LF or LF (:180-193) */
+            if (s[c] == '\r') { c++; if (c < n && s[c] == '\n') c++; } else c++;
+            break;
+        }
     }
     if (cnt == 0) return 0;
-    *on = cnt; *t_sec = lookup; *t_nsec = frac_to_nsec(frac);
+    *on = cnt; *t_sec = lookup; *t_nsec = frac_to_nsec(frac); *pos = (int) c;      /* last_byte: where the scan stopped */
     return 1;
 }
 
@@ -723,7 +728,7 @@ FLB_HD uint32_t lf_unescape(const uint8_t *s, uint32_t n, uint8_t *o)
 FLB_HD int logfmt_ident(uint32_t c) { return c > ' ' && c != '=' && c != '"'; }
 
 FLB_HDN int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
-                       ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec)
+                       ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec, int *pos)
 {
     uint32_t c = 0, sk = 0;          /* sk: next free byte of the record's scratch (decoded escapes) */
     int cnt = 0;
@@ -786,10 +791,13 @@ FLB_HDN int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32
             }
         }
         if (c == n) break;
-        if (s[c] == '\r' || s[c] == '\n') break;
+        if (s[c] == '\r' || s[c] == '\n') {          /* src/flb_parser_logfmt.c:236-249 */
+            if (s[c] == '\r') { c++; if (c < n && s[c] == '\n') c++; } else c++;
+            break;
+        }
     }
     if (cnt == 0) return 0;
-    *on = cnt; *t_sec = lookup; *t_nsec = frac_to_nsec(frac);
+    *on = cnt; *t_sec = lookup; *t_nsec = frac_to_nsec(frac); *pos = (int) c;
     return 1;
 }
 
@@ -1138,7 +1146,7 @@ FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t 
 template <bool EMIT>
 FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
                      ref_t *ok_, ref_t *ov_, uint32_t *th, int *on, int64_t *t_sec, int64_t *t_nsec, uint32_t ridx,
-                     uint32_t *cache_pos)
+                     uint32_t *cache_pos, int *pos)
 {
     int32_t *slot = 0;
     uint32_t mplen = 0, i;
@@ -1157,13 +1165,13 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t 
     if (!(EMIT && slot && slot[0] != 2)) {
         ok = djf_record(e, s, (int) n, val_off, ok_, ov_, th, &cnt);
         if (ok == 0) { if (!EMIT && slot) { slot[0] = 0; slot[1] = 0; } return 0; }
-        if (ok == 1) { if (!EMIT && slot) { slot[0] = 2; slot[1] = 0; } goto have_fields; }
+        if (ok == 1) { if (!EMIT && slot) { slot[0] = 2; slot[1] = 0; } *pos = (int) n; goto have_fields; }   /* nothing but white space behind the document */
     }
     cnt = 0;
     if (EMIT && slot) { ok = slot[0]; mplen = (uint32_t) slot[1]; }
     else {
         uint32_t jerr = 0;
-        ok = dj_parse_record(s, (int) n, e->scr, &mplen, &jerr);
+        ok = dj_parse_record(s, (int) n, e->scr, &mplen, &jerr, pos);
         if (jerr) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
         if (!EMIT && slot) { slot[0] = ok; slot[1] = (int32_t) mplen; }
     }
@@ -1257,7 +1265,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
         for (pi = 0; pi < (int) cf->n_parsers; pi++) {
             const struct cf_pdef *pd = (const struct cf_pdef *) (e->blob + cf->pdef_off[pi]);
             int64_t ts = 0, tns = 0;
-            int got = 0, cnt = 0;
+            int got = 0, cnt = 0, pos = 0;
             if (pd->type == FLBGPU_PARSER_REGEX) {
                 uint32_t need = 1 + 2 * (pd->n_groups + 1), c;      /* + 4 ints of parsed time behind them */
                 int32_t *slot = 0;
@@ -1282,7 +1290,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                     }
                 }
                 if (matched) got = pdef_regex(e, pd, val_off, vp, vn, w->caps, direct ? rc->k : w->tk, direct ? rc->v : w->tv, &cnt,
-                                              &ts, &tns, slot ? slot + need : 0, EMIT ? 1 : 0, direct ? rc->kh : w->th);
+                                              &ts, &tns, slot ? slot + need : 0, EMIT ? 1 : 0, direct ? rc->kh : w->th, &pos);
                 if (got) { preset = pd->n_groups; style = ST_PRESET; in_place = direct; }
             }
             else if (pd->type == FLBGPU_PARSER_JSON) {
@@ -1291,7 +1299,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                  * were written is undone by decoding the record again */
                 const int direct = pristine && !have_arr && !cf->ra_off && i == rc->nf - 1;
                 got = pdef_json<EMIT>(e, pd, val_off, vp, vn, direct ? rc->k : w->tk, direct ? rc->v : w->tv, direct ? rc->kh : w->th,
-                                      &cnt, &ts, &tns, ridx, cache_pos);
+                                      &cnt, &ts, &tns, ridx, cache_pos, &pos);
                 if (got) { style = ST_CANON; in_place = direct; }
                 else if (direct) {
                     /* (the time an earlier key of the same name parsed stays: filter_parser.c:296-300 keeps the last non-zero one) */
@@ -1301,11 +1309,11 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                 }
             }
             else if (pd->type == FLBGPU_PARSER_LTSV) {
-                got = pdef_ltsv(e, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns);
+                got = pdef_ltsv(e, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns, &pos);
                 if (got) style = ST_CANON;
             }
             else if (pd->type == FLBGPU_PARSER_LOGFMT) {
-                got = pdef_logfmt(e, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns);
+                got = pdef_logfmt(e, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns, &pos);
                 if (got) style = ST_CANON;
             }
             if (got) {
@@ -1313,6 +1321,10 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                 if (in_place && pd->type == FLBGPU_PARSER_JSON) { int z; for (z = 0; z < cnt; z++) if (!rc->kh[z]) rc->kh[z] = ref_khash(e, rc->k[z]); }
                 parse_ok = 1;
                 np = cnt;
+                if (!EMIT && e->prep) {             /* what flb_parser_do() hands back beside the map: position, time as parsed */
+                    int32_t *pr = e->prep + (size_t) 6 * ridx;
+                    pr[0] = 1; pr[1] = pos; pr[2] = (int32_t) (uint32_t) ts; pr[3] = (int32_t) (uint32_t) ((uint64_t) ts >> 32); pr[4] = (int32_t) tns;
+                }
                 if ((uint64_t) ts * 1000000000ull + (uint64_t) tns != 0) { ps = ts; pns = tns; }
                 if ((uint64_t) ts * 1000000000ull + (uint64_t) tns != 0) { rc->ts_sec = ts; rc->ts_nsec = tns; }
                 if (have_arr && !cf->ra_off) {

@@ -637,7 +637,7 @@ next_member:
 
 /* flb_pack_json_recs() for one line: exactly one document, which must be an object.
  * Returns 1 and the msgpack map at o (length *olen), or 0. */
-FLB_HDN int dj_parse_record(const uint8_t *s, int n, uint8_t *o, uint32_t *olen, uint32_t *err)
+FLB_HDN int dj_parse_record(const uint8_t *s, int n, uint8_t *o, uint32_t *olen, uint32_t *err, int *consumed)
 {
     int p = 0, e;
     uint32_t dummy = 0, derr = 0;
@@ -654,6 +654,7 @@ FLB_HDN int dj_parse_record(const uint8_t *s, int n, uint8_t *o, uint32_t *olen,
     p = e;
     while (p < n && dj_ws(s[p])) p++;
     if (p < n && dj_value(s, n, p, 0, &dummy, &derr, 1) >= 0) return 0;
+    *consumed = p;                                                     /* pack_json_to_msgpack_yyjson(): start - insitu_buf when the loop ends */
     return 1;
 }
 

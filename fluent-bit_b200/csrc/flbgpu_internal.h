@@ -48,6 +48,7 @@ struct bk_chain_args {
     uint64_t *d_bsum;             /* [ceil(n_rec/BK_REC_BLOCK)+1] exclusive output offset per block */
     uint32_t *d_flags;            /* [FLBGPU_MAX_FILTERS + 1]: CHF_* per filter, last = error word */
     struct l2m_table l2m;         /* device pointers of the log_to_metrics delta table (hash NULL = none) */
+    int32_t *d_prep;              /* parser report, 6 ints per record (dev_chain.cuh: ch_env.prep), or NULL */
 };
 
 const char *bk_name(void);

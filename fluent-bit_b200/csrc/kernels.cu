@@ -1044,7 +1044,7 @@ static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_
     p->env.in = a->d_in; p->env.in_len = a->in_len; p->env.blob = a->d_blob; p->env.scr = a->d_scr;
     p->env.capcache = a->d_capcache; p->env.cap_stride = a->cap_stride; p->env.now = a->now;
     p->env.assume = a->assume; p->env.active = a->active; p->env.fl_flags = a->d_flags; p->env.err = a->d_flags + FLBGPU_MAX_FILTERS;
-    p->env.l2m = a->l2m;
+    p->env.l2m = a->l2m; p->env.prep = a->d_prep;
     p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->r0 = r0; p->n_rec = a->n_rec; p->stage_bytes = 0;
     p->n_dev = 0;
     p->size = a->d_size; p->bsum = a->d_bsum; p->out = d_out;

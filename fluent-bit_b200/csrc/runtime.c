@@ -168,6 +168,8 @@ struct flbgpu_chain {
     uint32_t *d_flags;
     uint64_t *h_bsum; size_t cap_hbsum;      /* host copy of the per-block output offsets */
     uint32_t spec_assume; int spec_valid;     /* verdict vector of the previous call: what the streaming path speculates on */
+    int want_report;                          /* the chain behind flbgpu_parser_do(): the parser also reports position and time per record */
+    int32_t *d_prep; size_t cap_prep; int32_t *h_prep; size_t cap_hprep;
     uint32_t active;                          /* bit k: filter k is routed this call's tag (Match / Match_Regex / active) */
     uint32_t spec_active;                     /* the routing the speculation belongs to */
     uint32_t small_cap_rec; size_t small_cap_out;   /* what the small-chunk form learnt about this instance's chunks */
@@ -1245,6 +1247,7 @@ void flbgpu_chain_destroy(flbgpu_chain *c)
     bk_free(c->q, c->d_blob); bk_free(c->q, c->d_in); bk_free(c->q, c->d_out); bk_free(c->q, c->d_tile); bk_free(c->q, c->d_off);
     bk_free(c->q, c->d_len); bk_free(c->q, c->d_size); bk_free(c->q, c->d_kind); bk_free(c->q, c->d_bsum); bk_free(c->q, c->d_cap);
     bk_free(c->q, c->d_flags); bk_free(c->q, c->d_scr); free(c->h_bsum);
+    bk_free(c->q, c->d_prep); free(c->h_prep);
     bk_free(c->q, c->l2m.hash); bk_free(c->q, c->l2m.chash); bk_free(c->q, c->l2m.first); bk_free(c->q, c->l2m.cnt); bk_free(c->q, c->l2m.sum); bk_free(c->q, c->l2m.bkt); bk_free(c->q, c->l2m.str);
     free(c->h_hash); free(c->h_chash); free(c->h_first); free(c->h_cnt); free(c->h_sum); free(c->h_bkt);
     free(c->blob.p);
@@ -1296,6 +1299,13 @@ static int ensure_rec_cap(flbgpu_chain *c, size_t need, size_t keep)
     o = bk_alloc(c->q, nc * 4); l = bk_alloc(c->q, nc * 4); z = bk_alloc(c->q, nc * 4); k = bk_alloc(c->q, nc);
     if (c->cap_stride) cp = bk_alloc(c->q, nc * c->cap_stride * sizeof(int32_t));
     if (!o || !l || !z || !k || (c->cap_stride && !cp)) return -1;
+    if (c->want_report) {
+        int32_t *np_ = bk_alloc(c->q, nc * 6 * sizeof(int32_t));
+        if (!np_ || bk_zero(c->q, np_, nc * 6 * sizeof(int32_t))) return -1;
+        if (keep && (bk_sync(c->q) || bk_d2d(c->q, np_, c->d_prep, keep * 6 * sizeof(int32_t)))) return -1;
+        bk_free(c->q, c->d_prep);
+        c->d_prep = np_;
+    }
     if (keep) {
         if (bk_sync(c->q)) return -1;                 /* running kernels still read the old arrays */
         if (bk_d2d(c->q, o, c->d_off, keep * 4) || bk_d2d(c->q, l, c->d_len, keep * 4) || bk_d2d(c->q, z, c->d_size, keep * 4) ||
@@ -1325,6 +1335,14 @@ static void fill_args(flbgpu_chain *c, struct bk_chain_args *a, const uint8_t *d
     a->d_size = c->d_size; a->d_bsum = c->d_bsum; a->d_flags = c->d_flags;
     if (c->l2m_index >= 0 && ((c->active >> c->l2m_index) & 1)) a->l2m = c->l2m; else memset(&a->l2m, 0, sizeof(a->l2m));
     a->active = c->active;
+    a->d_prep = c->want_report ? c->d_prep : NULL;
+}
+
+/* parser report of the previous call: flags back to "not parsed" */
+static int report_clear(flbgpu_chain *c)
+{
+    if (!c->want_report || !c->d_prep || !c->cap_rec) return 0;
+    return bk_zero(c->q, c->d_prep, c->cap_rec * 6 * sizeof(int32_t));
 }
 
 /* zero the per-call metrics table (before every evaluation pass) */
@@ -1582,7 +1600,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     memset(&a, 0, sizeof(a));
     a.now = (int64_t) time(NULL);
     a.assume = initial_assume(c);
-    if (bk_flags_clear(c->q, c->d_flags) || l2m_clear(c)) return -1;
+    if (bk_flags_clear(c->q, c->d_flags) || l2m_clear(c) || report_clear(c)) return -1;
 
     /* ---- index + evaluate, slice by slice, while the upload is still running ---- */
     while (off < bytes) {
@@ -1644,7 +1662,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
             }
         }
         if (!changed) break;
-        if (bk_flags_clear(c->q, c->d_flags) || l2m_clear(c) || bk_chain_eval(c->q, &a, 0, n_rec)) return -1;
+        if (bk_flags_clear(c->q, c->d_flags) || l2m_clear(c) || report_clear(c) || bk_chain_eval(c->q, &a, 0, n_rec)) return -1;
         c->st.passes++;
     }
     c->st.kernel_launches = bk_launch_count();
@@ -1794,7 +1812,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
         if (!c->h_bsum) { c->cap_hbsum = 0; return -1; }
     }
     memset(&a, 0, sizeof(a));
-    if (bk_flags_clear(c->q, c->d_flags) || l2m_clear(c)) return -1;
+    if (bk_flags_clear(c->q, c->d_flags) || l2m_clear(c) || report_clear(c)) return -1;
 
 #define STREAM_FLUSH(upto_blocks) do { \
         uint32_t b1_ = (upto_blocks); \
@@ -1971,7 +1989,7 @@ static int chain_run_small(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, v
     cap_out = c->cap_out;
     fill_args(c, &a, c->d_in, bytes, 0);
     a.assume = assume; a.now = (int64_t) time(NULL); a.d_bsum = c->d_bsum;
-    if (bk_flags_clear(c->q, c->d_flags) || l2m_clear(c)) return -1;
+    if (bk_flags_clear(c->q, c->d_flags) || l2m_clear(c) || report_clear(c)) return -1;
     if (bk_small_run(c->q, &a, h_in, c->d_in, bytes, cap_rec, c->d_tile, n_tiles, c->d_out, cap_out, &res)) return -1;
     c->st.kernel_launches = bk_launch_count();
     if (res.overflow) {                              /* denser events than assumed, or a slice-sized tangle of broken links */
@@ -2269,10 +2287,13 @@ static int parser_solo(flbgpu_parser *p)
     if (!p->solo) {
         flbgpu_filter *f = flbgpu_filter_new(p->ctx, "parser");
         flbgpu_chain *c;
+        if (!f) return -1;
         flbgpu_filter_set_property(f, "key_name", "_");
         flbgpu_filter_set_property(f, "parser", p->name);
         if (flbgpu_filter_init(f)) { flbgpu_filter_destroy(f); return -1; }
         c = flbgpu_chain_new(p->ctx);
+        if (!c) { flbgpu_filter_destroy(f); return -1; }
+        c->want_report = 1;
         if (flbgpu_chain_add(c, f) || flbgpu_chain_init(c)) { flbgpu_chain_destroy(c); flbgpu_filter_destroy(f); return -1; }
         p->solo = c; p->solo_filter = f;
     }
@@ -2293,53 +2314,79 @@ static size_t put_line_event(uint8_t *rec, const char *buf, size_t length)
     return n + length;
 }
 
+/* the parser's own report of the call just made on its solo chain: 6 ints per line (dev_chain.cuh: ch_env.prep) */
+static const int32_t *parser_report(flbgpu_chain *c, uint32_t n)
+{
+    if (c->st.records_in != n) { set_err("parser call: the lines did not come back one to one%s%s", NULL, NULL); return NULL; }
+    if (c->cap_hprep < (size_t) n * 6) {
+        free(c->h_prep);
+        c->cap_hprep = (size_t) n * 6 + 64;
+        c->h_prep = malloc(c->cap_hprep * sizeof(int32_t));
+        if (!c->h_prep) { c->cap_hprep = 0; set_err("out of memory%s%s", NULL, NULL); return NULL; }
+    }
+    if (bk_d2h(c->q, c->h_prep, c->d_prep, (size_t) n * 6 * sizeof(int32_t)) || bk_sync(c->q)) return NULL;
+    return c->h_prep;
+}
+
 /* flb_parser_do() over n lines in ONE device pass (the entry a batched caller such as a GPU
  * filter_parser or an input plugin uses): line i = base[off[i] .. off[i]+len[i]).  Results: the
  * msgpack maps of the parsed lines back to back in *out_buf (malloc), map i at
  * [out_off[i], out_off[i+1]) (empty when ret[i] < 0), its time in out_time[i], ret[i] as
- * flb_parser_do would return it (>= 0 parsed, -1 not). */
+ * flb_parser_do would return it: the position the parser consumed the line up to (end of the last named capture,
+ * src/flb_regex.c:50-54; end of the JSON document plus the white space behind it, src/flb_pack.c:427-499; where the
+ * LTSV / logfmt scan stopped), or -1. */
 int flbgpu_parser_do_batch(flbgpu_parser *p, const char *base, const uint32_t *off, const uint32_t *len, uint32_t n,
                            void **out_buf, size_t *out_size, uint64_t *out_off, struct flbgpu_time *out_time, int *ret)
 {
     uint8_t *chunk, *o = NULL, *maps;
-    const uint8_t *q, *end, *in_q;
+    const uint8_t *q, *end;
+    const int32_t *rep;
     size_t total = 0, at = 0, osz = 0, mo = 0;
     uint32_t i;
     int r;
     if (!p || !base || !off || !len || !out_buf || !out_size || !out_off || !ret) return -1;
     *out_buf = NULL; *out_size = 0;
     if (parser_solo(p)) return -1;
+    if (n == 0) { out_off[0] = 0; return 0; }
     for (i = 0; i < n; i++) total += (size_t) len[i] + 22;
     chunk = malloc(total + 1);
-    if (!chunk) return -1;
+    if (!chunk) { set_err("out of memory%s%s", NULL, NULL); return -1; }
     for (i = 0; i < n; i++) at += put_line_event(chunk + at, base + off[i], len[i]);
-    r = n ? flbgpu_chain_do(p->solo, chunk, at, "", 0, (void **) &o, &osz) : FLBGPU_FILTER_NOTOUCH;
-    if (n && r != FLBGPU_FILTER_MODIFIED) { free(chunk); free(o); return -1; }
+    pthread_mutex_lock(&p->solo->lock);              /* the report belongs to this call: keep the instance until it is read */
+    p->ctx->last_q = p->solo->q;
+    p->solo->active = 1;
+    r = chain_do_locked(p->solo, chunk, at, "", 0, (void **) &o, &osz);
+    rep = r == FLBGPU_FILTER_MODIFIED ? parser_report(p->solo, n) : NULL;
+    if (!rep) { pthread_mutex_unlock(&p->solo->lock); free(chunk); free(o); return -1; }
     maps = malloc(osz ? osz : 1);
-    q = o; end = o + osz; in_q = chunk;
+    if (!maps) { pthread_mutex_unlock(&p->solo->lock); free(chunk); free(o); set_err("out of memory%s%s", NULL, NULL); return -1; }
+    q = o; end = o + osz;
     for (i = 0; i < n; i++) {
         /* filter_parser emits exactly one record per input record, in order */
         const uint8_t *body, *nx;
-        size_t in_len = (size_t) len[i] + (len[i] < 32 ? 17 : len[i] < 256 ? 18 : len[i] < 65536 ? 19 : 21);
+        const int32_t *ri = rep + (size_t) 6 * i;
         out_off[i] = mo;
-        if ((size_t) (end - q) < 13 || !(nx = host_mp_skip(q + 13, end, 0))) { free(chunk); free(o); free(maps); set_err("malformed parser result%s%s", NULL, NULL); return -1; }
+        if ((size_t) (end - q) < 13 || !(nx = host_mp_skip(q + 13, end, 0))) {
+            pthread_mutex_unlock(&p->solo->lock);
+            free(chunk); free(o); free(maps); set_err("malformed parser result%s%s", NULL, NULL); return -1;
+        }
         body = q + 13;
-        if ((size_t) (nx - q) == in_len && memcmp(body, in_q + 13, in_len - 13) == 0) {
-            ret[i] = -1;                                     /* came back as it went in: no parser matched */
+        if (!ri[0]) {                                    /* no parser took the line */
+            ret[i] = -1;
             if (out_time) { out_time[i].tv_sec = 0; out_time[i].tv_nsec = 0; }
         }
         else {
-            ret[i] = (int) len[i];
+            ret[i] = ri[1];
             if (out_time) {
-                out_time[i].tv_sec = ((int64_t) q[4] << 24) | (q[5] << 16) | (q[6] << 8) | q[7];
-                out_time[i].tv_nsec = ((int64_t) q[8] << 24) | (q[9] << 16) | (q[10] << 8) | q[11];
+                out_time[i].tv_sec = (int64_t) (((uint64_t) (uint32_t) ri[3] << 32) | (uint32_t) ri[2]);
+                out_time[i].tv_nsec = (int64_t) ri[4];
             }
             memcpy(maps + mo, body, (size_t) (nx - body));
             mo += (size_t) (nx - body);
         }
         q = nx;
-        in_q += in_len;
     }
+    pthread_mutex_unlock(&p->solo->lock);
     out_off[n] = mo;
     free(chunk); free(o);
     *out_buf = maps; *out_size = mo;
@@ -2351,27 +2398,15 @@ int flbgpu_parser_do_batch(flbgpu_parser *p, const char *base, const uint32_t *o
 int flbgpu_parser_do(flbgpu_parser *p, const char *buf, size_t length, void **out_buf, size_t *out_size,
                      struct flbgpu_time *out_time)
 {
-    uint8_t *rec, *o = NULL;
-    size_t n = 0, osz = 0;
-    int r;
-    if (!p || !buf || !out_buf || !out_size) return -1;
+    uint32_t off = 0, len = (uint32_t) length;
+    uint64_t ooff[2];
+    struct flbgpu_time t;
+    int ret = -1;
+    if (!p || !buf || !out_buf || !out_size || length >= 0x7fffffffu) return -1;
     *out_buf = NULL; *out_size = 0;
     if (out_time) { out_time->tv_sec = 0; out_time->tv_nsec = 0; }
-    if (parser_solo(p)) return -1;
-    rec = malloc(length + 32);
-    n = put_line_event(rec, buf, length);
-    r = flbgpu_chain_do(p->solo, rec, n, "", 0, (void **) &o, &osz);
-    if (r != FLBGPU_FILTER_MODIFIED || osz < 13) { free(rec); free(o); return -1; }
-    /* an unparsed record comes back with its original body: {"_": line} */
-    if (osz == n && memcmp(o + 13, rec + 13, n - 13) == 0) { free(rec); free(o); return -1; }
-    free(rec);
-    if (out_time) {
-        out_time->tv_sec = ((int64_t) o[4] << 24) | (o[5] << 16) | (o[6] << 8) | o[7];
-        out_time->tv_nsec = ((int64_t) o[8] << 24) | (o[9] << 16) | (o[10] << 8) | o[11];
-    }
-    *out_size = osz - 13;
-    *out_buf = malloc(*out_size ? *out_size : 1);
-    memcpy(*out_buf, o + 13, *out_size);
-    free(o);
-    return (int) length;
+    if (flbgpu_parser_do_batch(p, buf, &off, &len, 1, out_buf, out_size, ooff, &t, &ret) != 0) return -1;
+    if (ret < 0) { free(*out_buf); *out_buf = NULL; *out_size = 0; return -1; }
+    if (out_time) *out_time = t;
+    return ret;
 }

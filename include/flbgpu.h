@@ -71,19 +71,19 @@ flbgpu_parser *flbgpu_parser_create(flbgpu_ctx *ctx, const char *name, const cha
 /* flb_parser_get(), src/flb_parser.c:1022 */
 flbgpu_parser *flbgpu_parser_get(flbgpu_ctx *ctx, const char *name);
 /* flb_parser_do(), src/flb_parser.c:1044-1066: one line in, one msgpack map out.
- * Returns -1 exactly when the reference does, else `length`; *out_buf is malloc()ed, caller frees.
- * (The reference's non-negative value is a position inside the line -- end of the last named capture
- * for regex, src/flb_regex.c:50-54; end of the JSON value plus the white space behind it,
- * src/flb_pack.c:427-499; where the LTSV / logfmt scan stopped.  Its callers on this path
- * (filter_parser.c:268-310) test the sign only; in_stdin, which advances a stream by that value, is an
- * input and outside this library.  Map and time are byte-identical.) */
+ * Returns what the reference returns: -1 when no record comes out, else the position inside the line the parser
+ * consumed it up to -- end of the last named capture for regex (src/flb_regex.c:50-54), end of the JSON document plus
+ * the white space behind it (src/flb_pack.c:427-499), where the LTSV / logfmt scan stopped (line end consumed).
+ * *out_buf is malloc()ed, caller frees; *out_time is the parsed time with 64-bit seconds (0/0 when the parser has no
+ * time key or the record none).  The device reports position, "parsed" and time per line itself; nothing is inferred
+ * from the output bytes. */
 int flbgpu_parser_do(flbgpu_parser *parser, const char *buf, size_t length,
                      void **out_buf, size_t *out_size, struct flbgpu_time *out_time);
 
 /* The batched form: n lines in one device pass.  line i = base[off[i], off[i]+len[i]).
  * *out_buf (malloc) holds the msgpack maps of the parsed lines back to back, map i at
  * [out_off[i], out_off[i+1]) (out_off has n+1 entries; empty range when ret[i] < 0); out_time[i]
- * and ret[i] are what flbgpu_parser_do() returns per line.  Returns 0, or -1 when the call failed. */
+ * and ret[i] are what flbgpu_parser_do() returns per line (position or -1).  Returns 0, or -1 when the call failed. */
 int flbgpu_parser_do_batch(flbgpu_parser *p, const char *base, const uint32_t *off, const uint32_t *len, uint32_t n,
                            void **out_buf, size_t *out_size, uint64_t *out_off, struct flbgpu_time *out_time, int *ret);
 void flbgpu_parser_destroy(flbgpu_parser *parser);

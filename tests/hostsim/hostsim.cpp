@@ -180,7 +180,7 @@ static void hs_env(const struct bk_chain_args *a, struct ch_env *e)
     e->in = a->d_in; e->in_len = a->in_len; e->blob = a->d_blob; e->scr = a->d_scr;
     e->capcache = a->d_capcache; e->cap_stride = a->cap_stride; e->now = a->now; e->assume = a->assume; e->active = a->active;
     e->fl_flags = a->d_flags; e->err = a->d_flags + FLBGPU_MAX_FILTERS;
-    e->l2m = a->l2m;
+    e->l2m = a->l2m; e->prep = a->d_prep;
 }
 
 int bk_flags_clear(bk_q *q, uint32_t *d_flags) { memset(d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)); q->records_out = 0; return 0; }

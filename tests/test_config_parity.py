@@ -79,4 +79,4 @@ def test_same_parser_definitions_are_accepted(kw, sim_lib, ref_available):
         rr, rdata, rt = ref.parser_do(rp, line)
         assert (r < 0) == (rr < 0), line
         if rr >= 0:
-            assert data == rdata and t == (rt[0] & 0xffffffff, rt[1]), line
+            assert data == rdata and t == rt, line

@@ -103,10 +103,10 @@ def check_parser_batch(lib):
         assert len(got) == len(lines)
         for line, (r, data, (sec, nsec)) in zip(lines, got):
             rr, rdata, (rsec, rnsec) = ref.parser_do(rp, line)
-            assert (r >= 0) == (rr >= 0), line
+            assert r == rr, line                       # the position flb_parser_do() returns, or -1
             if r >= 0:
                 assert data == rdata, line
-                assert (sec, nsec) == (rsec & 0xffffffff, rnsec), line
+                assert (sec, nsec) == (rsec, rnsec), line
 
 
 def test_parser_batch_hostsim(sim_lib, ref_available):
@@ -139,13 +139,13 @@ def check_apache_time_fast_path(lib):
         rr, rdata, (rsec, rnsec) = ref.parser_do(rp2, v.encode())
         assert (r >= 0) == (rr >= 0) and data == rdata, v
         if rr >= 0:
-            assert (sec, nsec) == (rsec & 0xffffffff, rnsec), v
+            assert (sec, nsec) == (rsec, rnsec), v
     for v, (r, data, (sec, nsec)) in zip(vals, got):
         rr, rdata, (rsec, rnsec) = ref.parser_do(rp, v.encode())
         assert (r >= 0) == (rr >= 0), v
         assert data == rdata, v
         if r >= 0:
-            assert (sec, nsec) == (rsec & 0xffffffff, rnsec), v
+            assert (sec, nsec) == (rsec, rnsec), v
 
 
 def test_apache_time_fast_path_hostsim(sim_lib, ref_available):
@@ -189,7 +189,7 @@ def check_time_programs(lib):
             assert (r >= 0) == (rr >= 0), (fmt, v)
             assert data == rdata, (fmt, v)
             if r >= 0:
-                assert (sec, nsec) == (rsec & 0xffffffff, rnsec), (fmt, v)
+                assert (sec, nsec) == (rsec, rnsec), (fmt, v)
 
 
 def test_time_programs_hostsim(sim_lib, ref_available):
@@ -203,20 +203,26 @@ def test_time_programs_gpu(gpu_lib, ref_available):
 
 def check_parser_do_sign_and_bytes(lib):
     """flbgpu_parser_do() / _do_batch() against flb_parser_do() over odd lines for every parser kind: the same
-    lines fail (-1), and the lines that parse give the reference's map and time.  The non-negative value itself is
-    `length` here and a position inside the line in the reference (include/flbgpu.h)."""
+    value comes back -- -1, or the position inside the line the parser consumed it up to (end of the last named capture,
+    end of the JSON document plus white space, where the LTSV / logfmt scan stopped) -- with the reference's map and time
+    (64-bit seconds: times before 1970 and after 2106 included)."""
     import cases
     tf = "%Y-%m-%dT%H:%M:%S.%LZ"
     parsers = [cases.AP, cases.JS, cases.LF, cases.LT, dict(name="jst", format="json", time_key="time", time_fmt=tf),
                dict(name="jsk", format="json", time_key="time", time_fmt=tf, time_keep=True, time_strict=False),
                dict(name="lft", format="logfmt", time_key="time", time_fmt=tf, types="n:integer"), dict(name="lfb", format="logfmt", logfmt_no_bare_keys=True),
                dict(name="ltt", format="ltsv", time_key="time", time_fmt=tf, time_keep=True, types="n:hex"), dict(name="jse", format="json", skip_empty=False),
-               dict(name="opt", format="regex", regex=r"^(?<a>x)?y(?<b>.*)$"), dict(name="none", format="regex", regex=r"^(?<a>x)?(?<b>q)?y")]
+               dict(name="opt", format="regex", regex=r"^(?<a>x)?y(?<b>.*)$"), dict(name="none", format="regex", regex=r"^(?<a>x)?(?<b>q)?y"),
+               dict(name="mid", format="regex", regex=r"(?<b>y+)(?<a>x)?"), dict(name="same", format="regex", regex=r"^(?<_>.*)$"),
+               dict(name="old", format="regex", regex=r"^(?<time>[^ ]+) (?<m>.*)$", time_key="time", time_fmt="%Y-%m-%dT%H:%M:%S"),
+               dict(name="jsold", format="json", time_key="time", time_fmt="%Y-%m-%dT%H:%M:%S")]
     lines = (util.apache_lines(20, seed=1) + util.json_lines(20, 2) + util.logfmt_lines(20, 3) + util.ltsv_lines(20) +
              [b"", b" ", b"\t", b"{}", b"{", b"}", b"[]", b"null", b'""', b"a=", b"=", b":", b"a:", b"\xff\xfe", b'{"a":"\\ud800"}', b'{"a":1e999}', b'{"a":-0}',
               b'{"a":1E+2}', b'{"a":12345678901234567890}', b'{"a":-9223372036854775809}', b' {"a":1} ', b'{"a":1}{"b":2}', b'{"a":1},', b'{"a":1} trailing',
               b'{"a":1} 5', b'{"time":"2023-05-06T07:08:09.123Z","n":1}', b'{"time":"nonsense"}', b"time=2023-05-06T07:08:09.5Z n=7 bare", b"time=bad n=x",
-              b"time:2023-05-06T07:08:09.250Z\tn:1f\tempty:", b"a:1\n\tb:2", b"a=1\nb=2", b'a="x', b"y", b"xy tail", b"zzz", b"a\x01:1"])
+              b"time:2023-05-06T07:08:09.250Z\tn:1f\tempty:", b"a:1\n\tb:2", b"a=1\nb=2", b'a="x', b"y", b"xy tail", b"zzz", b"a\x01:1",
+              b"1901-02-03T04:05:06 before the epoch", b"2200-01-02T03:04:05 after 2106", b'{"time":"1901-02-03T04:05:06","n":1}', b'{"time":"2200-01-02T03:04:05"}  ',
+              b"_:x", b"_=x", b"ayyyxx", b'{"a":1}\n\n', b'\n {"a":[1,2]} \t x'])
     for kw in parsers:
         ctx, ref = pkg.Context(0, lib=lib), util.Ref()
         p, rp = ctx.parser(**kw), ref.parser(**kw)
@@ -225,9 +231,9 @@ def check_parser_do_sign_and_bytes(lib):
             r, data, t = p.do(line)
             rr, rdata, rt = ref.parser_do(rp, line)
             assert (r, data, t) == b, (kw["name"], line)
-            assert (r < 0) == (rr < 0), (kw["name"], line)
+            assert r == rr, (kw["name"], line, r, rr)
             if rr >= 0:
-                assert r == len(line) and data == rdata and t == (rt[0] & 0xffffffff, rt[1]), (kw["name"], line)
+                assert data == rdata and t == rt, (kw["name"], line)
 
 
 def test_parser_do_sign_and_bytes_hostsim(sim_lib, ref_available):
