@@ -964,7 +964,7 @@ int bk_index_count(bk_q *q, const uint8_t *d_in, size_t slice_off, uint32_t slic
     if (n_tiles == 0) return 0;
     ev_begin_on(q, 0, q->istream);
     {
-        const uint32_t skip = (uint32_t) (slice_off & 15);
+        const uint32_t skip = (uint32_t) ((uintptr_t) (d_in + slice_off) & 15);      /* tiles start at a 16-byte boundary of the address space */
         k_index<false><<<n_tiles, 256, 0, q->istream>>>(d_in + slice_off - skip, slice_len + skip, skip, (uint32_t) (slice_off - skip), d_tile, 0, 0, 0, 0);
     }
     k_scan_top<uint32_t><<<1, 256, 0, q->istream>>>(d_tile, n_tiles, q->dtotal, 0);
@@ -988,7 +988,7 @@ int bk_index_fill(bk_q *q, const uint8_t *d_in, size_t slice_off, uint32_t slice
     if (n_cand == 0) return 0;
     ev_begin_on(q, 0, q->istream);
     {
-        const uint32_t skip = (uint32_t) (slice_off & 15);
+        const uint32_t skip = (uint32_t) ((uintptr_t) (d_in + slice_off) & 15);      /* tiles start at a 16-byte boundary of the address space */
         k_index<true><<<n_tiles, 256, 0, q->istream>>>(d_in + slice_off - skip, slice_len + skip, skip, (uint32_t) (slice_off - skip), (uint32_t *) d_tile, d_off, d_len, d_kind, 0);
     }
     CK(cudaMemsetAsync(d_w, 0, 32, q->istream));

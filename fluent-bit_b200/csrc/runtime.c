@@ -1605,7 +1605,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     /* ---- index + evaluate, slice by slice, while the upload is still running ---- */
     while (off < bytes) {
         size_t len = bytes - off < S ? bytes - off : S;
-        uint32_t n_tiles = (uint32_t) ((len + (off & 15) + BK_INDEX_TILE - 1) / BK_INDEX_TILE), n_cand = 0, n_valid = 0;   /* tiles start at off rounded down to 16 B */
+        uint32_t n_tiles = (uint32_t) ((len + ((uintptr_t) (d_in + off) & 15) + BK_INDEX_TILE - 1) / BK_INDEX_TILE), n_cand = 0, n_valid = 0;   /* tiles start at the address rounded down to 16 B */
         uint64_t end_off = off;
         uint32_t assume = a.assume;
         int64_t now = a.now;
@@ -1854,7 +1854,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
         if (taper && rem < 3 * S) { want = rem / 3; if (want < ((size_t) 16 << 20)) want = (size_t) 16 << 20; if (want > S) want = S; }
         if (want < force) want = force;
         len = rem < want ? rem : want;
-        uint32_t n_tiles = (uint32_t) ((len + (off & 15) + BK_INDEX_TILE - 1) / BK_INDEX_TILE), n_cand = 0, n_valid = 0;
+        uint32_t n_tiles = (uint32_t) ((len + ((uintptr_t) (c->d_in + off) & 15) + BK_INDEX_TILE - 1) / BK_INDEX_TILE), n_cand = 0, n_valid = 0;
         uint64_t end_off = off;
         int tiled = 0;
         if (bk_upload_wait_index(c->q, off + len)) goto fail;

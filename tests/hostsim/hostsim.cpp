@@ -113,7 +113,7 @@ int bk_hint_streaming(bk_q *, const void *base, size_t bytes) { (void) base; (vo
 int bk_index_count(bk_q *, const uint8_t *d_in, size_t slice_off, uint32_t len, uint32_t *d_tile, uint32_t n_tiles, uint32_t *n_cand)
 {
     const uint8_t *in = d_in + slice_off;
-    const uint32_t skip = (uint32_t) (slice_off & 15);
+    const uint32_t skip = (uint32_t) ((uintptr_t) (d_in + slice_off) & 15);
     uint32_t t, run = 0;
     for (t = 0; t < n_tiles; t++) {
         /* tile t covers bytes [t*TILE - skip, (t+1)*TILE - skip) of the slice, like the CUDA kernel */
@@ -135,7 +135,7 @@ int bk_index_fill(bk_q *, const uint8_t *d_in, size_t slice_off, uint32_t len, c
                   uint32_t *d_off, uint32_t *d_len, uint8_t *d_kind, uint32_t *n_valid, uint64_t *end_off, int *tiled)
 {
     const uint8_t *in = d_in + slice_off;
-    const uint32_t base = (uint32_t) slice_off, total = base + len, skip = (uint32_t) (slice_off & 15);
+    const uint32_t base = (uint32_t) slice_off, total = base + len, skip = (uint32_t) ((uintptr_t) (d_in + slice_off) & 15);
     uint32_t t, i;
     *n_valid = 0; *tiled = (len == 0); *end_off = slice_off;
     if (n_cand == 0) return 0;
