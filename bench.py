@@ -187,18 +187,17 @@ class RefPool:
         self.pool.map(time.sleep, [0.01] * cores, chunksize=1)      # every worker is up (initialised) before anything is timed
 
     def step(self, wl, lines):
-        """`lines` events spread over 4 tasks per core; returns (events done, wall seconds of the whole job)"""
+        """`lines` events spread evenly over the cores, one task each; returns (events done, seconds): the time of the
+        slowest worker inside the reference's calls -- python's pool dispatch is not the reference's cost"""
         offs = self.offs[wl]
-        n_tasks = self.cores * 4
+        n_tasks = self.cores
         if wl == "c0":                            # configs[0]: whole 10k-line batches, 4 per core
-            per = 10_000
+            per, reps = 10_000, 4
         else:
             per = max(1, min(BASE_LINES, -(-lines // n_tasks)))
-            n_tasks = -(-lines // per)
-        t0 = time.perf_counter()
-        res = self.pool.map(_ref_task, [(wl, offs[per], 1)] * n_tasks, chunksize=1)
-        wall = time.perf_counter() - t0
-        return sum(r[1] for r in res), wall
+            reps = max(1, -(-lines // (per * n_tasks)))
+        res = self.pool.map(_ref_task, [(wl, offs[per], reps)] * n_tasks, chunksize=1)
+        return sum(r[1] for r in res), max(r[0] for r in res)
 
     def close(self):
         self.pool.close()
@@ -207,7 +206,7 @@ class RefPool:
 
 def reference_workload(pool, wl, lines, steps, warmup):
     for _ in range(max(1, warmup)):            # first touch builds each worker's pipeline and block
-        pool.step(wl, min(lines, pool.cores * 4 * 2000))
+        pool.step(wl, min(lines, pool.cores * 2000))
     done, dt = 0, 0.0
     for _ in range(steps):
         n, wall = pool.step(wl, lines)
@@ -237,8 +236,8 @@ def run_reference(args):
             others[o] = {"workload": WORKLOADS[o]["name"], "value": v, "e2e": v, "unit": "lines/s", "events_per_step": nn,
                          "ms_per_step": 1000 * sps}
     pool.close()
-    sample = "%d cores, %d events per step in %d-event calls (4 per core), %d steps, whole-job wall clock" % (
-        cores, n, -(-n // (cores * 4)), args.steps)
+    sample = "%d cores, %d events per step in %d-event calls, one pipeline per core, %d steps; time = slowest worker inside the reference's calls" % (
+        cores, n, min(BASE_LINES, -(-n // cores)), args.steps)
     line = {
         "impl": "reference", "metric": "log lines/sec through parser+filter chain", "value": val, "unit": "lines/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * s_per_step,
@@ -289,19 +288,13 @@ _libc.free.argtypes = [C.c_void_p]
 _libc.mallopt.argtypes = [C.c_int, C.c_int]
 
 
-def tune_malloc(on):
-    """Host allocator policy of the embedding process.  on: keep freed result buffers in the heap instead of returning
-    them to the kernel (no mmap for big blocks, no trimming) -- what Fluent Bit's default jemalloc build does with its
-    retained extents.  off: glibc's defaults (every big result is a fresh mmap)."""
-    if on:
-        _libc.mallopt(-4, 0)              # M_MMAP_MAX = 0
-        _libc.mallopt(-1, (1 << 31) - 1)  # M_TRIM_THRESHOLD
-        _libc.mallopt(-2, 64 << 20)       # M_TOP_PAD
-    else:
-        _libc.mallopt(-4, 65536)          # M_MMAP_MAX default
-        _libc.mallopt(-3, 128 * 1024)     # M_MMAP_THRESHOLD default (also re-enables the dynamic threshold off)
-        _libc.mallopt(-1, 128 * 1024)     # M_TRIM_THRESHOLD default
-        _libc.mallopt(-2, 0)              # M_TOP_PAD default
+def tune_malloc():
+    """Host allocator policy of an embedding process that keeps freed result buffers in its heap instead of returning them
+    to the kernel (no mmap for big blocks, no trimming) -- what Fluent Bit's default jemalloc build does with its retained
+    extents.  glibc cannot be switched back afterwards, so this variant is measured last."""
+    _libc.mallopt(-4, 0)              # M_MMAP_MAX = 0
+    _libc.mallopt(-1, (1 << 31) - 1)  # M_TRIM_THRESHOLD
+    _libc.mallopt(-2, 64 << 20)       # M_TOP_PAD
 
 
 class Workload:
@@ -470,20 +463,16 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local, full=True):
     out_bytes = w.out_total
     value = world * n_lines * steps / (dev_ms / 1000.0)
 
-    # ---- end to end, the way flb_filter_do() calls: pageable input, default malloc, result freed
-    tune_malloc(False)
+    # ---- end to end, the way flb_filter_do() calls: pageable input, glibc's untouched malloc, result freed
     w.step_host()
     e2e_s = allmax(timed(lambda: [w.step_host() for _ in range(steps)], barrier))
     e2e = world * n_lines * steps / e2e_s
     phases = [round(float(x), 2) for x in w.chain.stats().phase_ms]
     variants = {}
     if full:
-        tune_malloc(True)
         w.step_host(pinned=True)
         s = allmax(timed(lambda: [w.step_host(pinned=True) for _ in range(steps)], barrier))
-        variants["pinned_input_retaining_malloc"] = {"value": world * n_lines * steps / s, "unit": "lines/s",
-                                                     "note": "input in cudaMallocHost memory; glibc tuned to retain freed result buffers (M_MMAP_MAX=0, M_TRIM_THRESHOLD=2GiB)"}
-        tune_malloc(False)
+        variants["pinned_input"] = {"value": world * n_lines * steps / s, "unit": "lines/s", "note": "input in cudaMallocHost memory, glibc's untouched malloc"}
         # batch sweep: bytes per flbgpu_chain_do() call, pageable input, default malloc; 1 caller and 8 callers
         sweep = []
         ncall = 8
@@ -548,6 +537,30 @@ def run_ours(args):
                 continue
             others[o] = measure(args, o, L, ctx, torch, dist, rank, world, local, full=(o == "apache"))
 
+    # last: the same end-to-end calls with an allocator that retains freed result buffers (and pinned input)
+    tune_malloc()
+    retained = {}
+    for o in ([WL] if args.primary_only else [WL, "apache"]):
+        if o in retained:
+            continue
+        w = Workload(args, o, L, ctx, rank, world)
+        for pinned in (False, True):
+            w.step_host(pinned=pinned)
+            t0 = time.perf_counter()
+            torch.cuda.synchronize()
+            for _ in range(args.steps):
+                w.step_host(pinned=pinned)
+            torch.cuda.synchronize()
+            dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+            if world > 1:
+                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+            retained.setdefault(o, {})["pinned_input" if pinned else "pageable_input"] = world * w.n_lines * args.steps / float(dt.item())
+        w.close()
+    for o, v in retained.items():
+        tgt = m if o == WL else others.get(o)
+        if tgt is not None:
+            tgt["variants"]["retaining_malloc"] = dict(v, unit="lines/s", note="glibc tuned to retain freed result buffers (M_MMAP_MAX=0, M_TRIM_THRESHOLD=2GiB): what a jemalloc build of the agent does")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -582,7 +595,7 @@ def run_ours(args):
         v, sps, n = reference_workload(pool, WL, sample_lines, 2, 1)
         pool.close()
         cpu = {"value": v, "unit": "lines/s", "cores": cores, "kind": "reference",
-               "sample": "%d cores, 2 steps of %d events in %d-event calls (%.2f s per step, whole-job wall clock)" % (cores, n, -(-n // (cores * 4)), sps)}
+               "sample": "%d cores, 2 steps of %d events in %d-event calls, one pipeline per core (%.2f s per step: slowest worker inside the reference's calls)" % (cores, n, min(BASE_LINES, -(-n // cores)), sps)}
 
     def side(mm, name):
         e2, a2, ach2 = roof(mm)
@@ -606,7 +619,7 @@ def run_ours(args):
         "config_detail": {"input_bytes_per_gpu": m["nbytes"], "output_bytes_per_gpu": m["out_bytes"],
                           "l2": "input (%.0f MB) and output larger than the 126 MB L2" % (m["nbytes"] / 1e6),
                           "parallelism": ("record shards; one NCCL all-reduce of the metric table per step" if WL == "l2m" else "record shards, no data-path collective"),
-                          "e2e_input": "pageable malloc()ed memory", "e2e_host_malloc": "glibc defaults"},
+                          "e2e_input": "pageable malloc()ed memory", "e2e_host_malloc": "glibc, untouched"},
         "e2e": {"value": m["e2e"], "unit": "lines/s", "h2d_bytes_per_step": m["nbytes"], "d2h_bytes_per_step": m["out_bytes"],
                 "steps": m["e2e_steps"], "timing": "wall clock between device-synchronising barriers",
                 "host_phase_ms_last_call": dict(zip(["upload+index+evaluate", "size_scan", "emit+download", "total"], m["phases"]))},

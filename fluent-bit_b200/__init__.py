@@ -29,6 +29,10 @@ class Time(C.Structure):
     _fields_ = [("tv_sec", C.c_int64), ("tv_nsec", C.c_int64)]
 
 
+class PackState(C.Structure):
+    _fields_ = [("multiple", C.c_int), ("tokens_count", C.c_int), ("last_byte", C.c_int)]
+
+
 class Stats(C.Structure):
     _fields_ = [("records_in", C.c_uint64), ("records_out", C.c_uint64), ("bytes_in", C.c_uint64),
                 ("bytes_out", C.c_uint64), ("kernel_launches", C.c_uint64), ("passes", C.c_uint32),
@@ -43,6 +47,7 @@ EXPORTS = [
     "flbgpu_chain_destroy", "flbgpu_chain_do_device", "flbgpu_chain_stats", "flbgpu_dev_alloc",
     "flbgpu_dev_free", "flbgpu_dev_upload", "flbgpu_dev_download", "flbgpu_host_alloc", "flbgpu_host_free",
     "flbgpu_stream", "flbgpu_kernel_ms", "flbgpu_chain_stream",
+    "flbgpu_pack_state_init", "flbgpu_pack_state_reset", "flbgpu_pack_json_state", "flbgpu_pack_json_state_batch",
 ]
 
 
@@ -87,6 +92,9 @@ def load(path=None):
     L.flbgpu_stream.restype = vp; L.flbgpu_stream.argtypes = [vp]
     L.flbgpu_kernel_ms.argtypes = [vp, C.POINTER(C.c_float)]
     L.flbgpu_chain_stream.restype = vp; L.flbgpu_chain_stream.argtypes = [vp]
+    L.flbgpu_pack_json_state.argtypes = [vp, cp, sz, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(PackState)]
+    L.flbgpu_pack_json_state_batch.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(sz), C.POINTER(vp), C.POINTER(C.c_int),
+                                               C.POINTER(PackState), C.POINTER(C.c_int)]
     ip = C.POINTER(C.c_int); u64p = C.POINTER(C.c_uint64)
     L.flbgpu_l2m_info.argtypes = [vp, ip, ip, ip, ip]
     L.flbgpu_l2m_get.argtypes = [vp, C.c_int, u64p, u64p, C.POINTER(C.c_double), u64p, vp]
@@ -131,6 +139,24 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def pack_json_state(self, bufs):
+        """flb_pack_json_state() over a batch of stream buffers: [(ret, msgpack bytes or None, last_byte, tokens_count)]"""
+        n = len(bufs)
+        js = (C.c_char_p * n)(*bufs)
+        ln = (C.c_size_t * n)(*[len(b) for b in bufs])
+        out = (C.c_void_p * n)(); sizes = (C.c_int * n)(); st = (PackState * n)(); rets = (C.c_int * n)()
+        if self.L.flbgpu_pack_json_state_batch(self.h, n, js, ln, out, sizes, st, rets) != 0:
+            raise FlbGpuError("pack_json_state_batch: %s" % self.err())
+        res = []
+        for i in range(n):
+            data = None
+            if rets[i] == 0:
+                data = C.string_at(out[i], sizes[i])
+            if out[i]:
+                _libc.free(out[i])
+            res.append((rets[i], data, st[i].last_byte, st[i].tokens_count))
+        return res
 
     def parser(self, name, format, regex=None, skip_empty=True, time_fmt=None, time_key=None, time_offset=None,
                time_keep=False, time_strict=True, logfmt_no_bare_keys=False, types=None):

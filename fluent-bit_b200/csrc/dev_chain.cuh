@@ -651,9 +651,10 @@ FLB_HD uint32_t lf_hexv(uint32_t c)
 }
 FLB_HD uint32_t lf_sx(uint32_t b) { return (b & 0x80u) ? (b | 0xffffff00u) : b; }     /* (uint32_t)(signed char) */
 
-FLB_HD uint32_t lf_unescape(const uint8_t *s, uint32_t n, uint8_t *o)
+/* the decoded bytes, NULs included: what flb_unescape_string_utf8() returns */
+FLB_HD uint32_t lf_unescape_raw(const uint8_t *s, uint32_t n, uint8_t *o)
 {
-    uint32_t in = 0, out = 0, i;
+    uint32_t in = 0, out = 0;
     while (in < n && s[in]) {
         uint32_t ch, used = 1, len;
         if (s[in] == '\\' && in + 1 < n) {
@@ -720,6 +721,13 @@ FLB_HD uint32_t lf_unescape(const uint8_t *s, uint32_t n, uint8_t *o)
         else if (len == 3) { o[out++] = (uint8_t) ((ch >> 12) | 0xe0); o[out++] = (uint8_t) (((ch >> 6) & 0x3f) | 0x80); o[out++] = (uint8_t) ((ch & 0x3f) | 0x80); }
         else { o[out++] = (uint8_t) ((ch >> 18) | 0xf0); o[out++] = (uint8_t) (((ch >> 12) & 0x3f) | 0x80); o[out++] = (uint8_t) (((ch >> 6) & 0x3f) | 0x80); o[out++] = (uint8_t) ((ch & 0x3f) | 0x80); }
     }
+    return out;
+}
+
+FLB_HD uint32_t lf_unescape(const uint8_t *s, uint32_t n, uint8_t *o)
+{
+    const uint32_t out = lf_unescape_raw(s, n, o);
+    uint32_t i;
     for (i = 0; i < out; i++) if (!o[i]) return i;                     /* the caller's strlen() */
     return out;
 }
@@ -1967,5 +1975,7 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
     }
     return rec_emit(e, &rc, EMIT ? out : 0);
 }
+
+#include "dev_jsmn.cuh"
 
 #endif

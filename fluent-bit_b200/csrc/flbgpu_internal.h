@@ -154,6 +154,20 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
 /* result bytes [0,n) of d_out into the caller's (pageable) buffer; synchronises */
 int bk_small_fetch(bk_q *q, void *h_dst, const uint8_t *d_out, size_t n);
 
+/* ---- streaming JSON packer (flb_pack_json_state over a batch of stream buffers): one lane per buffer ----
+ * d_js holds the buffers back to back, buffer i = d_js[d_off[i], d_off[i] + d_len[i]); its tokens live at
+ * d_tok[d_tok_off[i] .. + d_tok_cap[i]), its unescape scratch at d_tmp[d_off[i] + i ..) (d_len[i] + 1 bytes).
+ * scan: tokenise, decide what is whole, measure (d_res[i]); emit: pack buffer i at d_out + d_out_off[i].
+ * Both are asynchronous on the queue's stream. */
+struct bk_jsmn_args {
+    const uint8_t *d_js; const uint32_t *d_off, *d_len; uint32_t n;
+    struct jm_tok *d_tok; const uint32_t *d_tok_off, *d_tok_cap;
+    uint8_t *d_tmp; struct jm_result *d_res;
+    uint8_t *d_out; const uint32_t *d_out_off;
+};
+int bk_jsmn_scan(bk_q *q, const struct bk_jsmn_args *a);
+int bk_jsmn_emit(bk_q *q, const struct bk_jsmn_args *a);
+
 #ifdef __cplusplus
 }
 #endif

@@ -236,6 +236,28 @@ struct chain_hdr {
 #define FLBGPU_E_ESCAPE   32u   /* logfmt escapes met without a scratch region (cannot happen through the C ABI) */
 #define FLBGPU_E_L2M      64u   /* log_to_metrics: label table full / float label / unparsable value */
 
+/* ---------------------------------------------------- streaming JSON packer (dev_jsmn.cuh) */
+enum { JM_UNDEFINED = 0, JM_OBJECT = 1, JM_ARRAY = 2, JM_STRING = 4, JM_PRIMITIVE = 8 };     /* jsmntype_t, lib/jsmn/jsmn.h */
+struct jm_tok { int32_t type, start, end, size, parent; };
+
+#define JM_OK        0
+#define JM_INVAL   (-501)     /* FLB_ERR_JSON_INVAL, include/fluent-bit/flb_error.h:46 */
+#define JM_PART    (-502)     /* FLB_ERR_JSON_PART, :47 */
+#define JM_NOMEM   (-2)       /* token array too small (internal: the host retries with a larger one) */
+#define JM_FAIL    (-1)       /* tokens_to_msgpack() returned NULL */
+#define JM_REFUSED (-3)       /* a number text the device strtod does not restate (hex float, nan(payload)): loud, never wrong */
+
+struct jm_result {
+    int32_t status;           /* what flb_pack_json_state() returns */
+    int32_t last_byte;        /* state->last_byte */
+    int32_t tokens_count;     /* state->tokens_count */
+    int32_t records;          /* top-level values packed */
+    uint32_t out_size;        /* msgpack bytes */
+    uint32_t toknext;         /* tokens the tokeniser allocated */
+    int32_t tret;             /* the tokeniser's own verdict */
+    int32_t pad;
+};
+
 #ifdef __cplusplus
 }
 #endif

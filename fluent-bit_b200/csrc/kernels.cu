@@ -465,6 +465,31 @@ __global__ void __launch_bounds__(256) k_small_scan2(uint64_t *bsum, uint32_t *c
     if (threadIdx.x == 0) { mail->total = cb; mail->n_out = cc; mail->emitted = (cb <= cap_out && !mail->overflow) ? 1u : 0u; }
 }
 
+/* ---- streaming JSON packer: one lane per stream buffer (dev_jsmn.cuh) ---- */
+__global__ void __launch_bounds__(64) k_jsmn_scan(const struct bk_jsmn_args a)
+{
+    const uint32_t i = blockIdx.x * 64 + threadIdx.x;
+    if (i >= a.n) return;
+    const uint8_t *js = a.d_js + a.d_off[i];
+    struct jm_tok *tok = a.d_tok + a.d_tok_off[i];
+    uint32_t toknext = 0;
+    const int tret = jm_tokenise(js, a.d_len[i], tok, a.d_tok_cap[i], &toknext);
+    struct jm_result r;
+    r.tret = tret; r.pad = 0;
+    if (tret == JM_NOMEM) { r.status = JM_NOMEM; r.last_byte = 0; r.tokens_count = 0; r.records = 0; r.out_size = 0; r.toknext = toknext; }
+    else jm_pack(js, a.d_len[i], tok, toknext, tret, 0, a.d_tmp + a.d_off[i] + i, &r);
+    a.d_res[i] = r;
+}
+
+__global__ void __launch_bounds__(64) k_jsmn_emit(const struct bk_jsmn_args a)
+{
+    const uint32_t i = blockIdx.x * 64 + threadIdx.x;
+    if (i >= a.n) return;
+    struct jm_result r = a.d_res[i];
+    if (r.status != JM_OK || r.out_size == 0) return;
+    jm_pack(a.d_js + a.d_off[i], a.d_len[i], a.d_tok + a.d_tok_off[i], r.toknext, r.tret, a.d_out + a.d_out_off[i], a.d_tmp + a.d_off[i] + i, &r);
+}
+
 /* ------------------------------------------------------------ bk_* seam */
 /* persistent worker threads of a queue: idle on a condition variable, woken for one job at a time */
 struct bk_pool {
@@ -523,8 +548,9 @@ struct bk_pool {
 #define EV_MAX 1024
 #define UP_PIECE ((size_t) 32 << 20)
 #define UP_MAX_EV 256
-#define UP_THREADS 6
-#define UP_STAGE_SLOTS 12
+#define UP_THREADS_MAX 16
+#define UP_STAGE_SLOTS_MAX 32
+static int UP_THREADS = 6, UP_STAGE_SLOTS = 12;      /* FLBGPU_UP_THREADS: host threads staging a pageable chunk (slots = 2 x threads) */
 #define XF_MAX_SLOTS 32
 #define XF_MAX_RANGES 512
 
@@ -543,11 +569,13 @@ struct bk_q {
     unsigned long long *h_word;            /* pinned: a few words read back per call */
     struct bk_mail *d_mail, *h_mail;       /* small form */
     uint32_t *h_flags;                     /* pinned copy of the evidence words */
+    uint8_t *h_sin, *h_sout; size_t cap_sin, cap_sout;    /* small form: pinned staging for the chunk and its result */
+    cudaEvent_t ev_small;
     int stage_kb;
     /* upload */
     cudaEvent_t up_ev[UP_MAX_EV]; int up_ev_made;
     size_t up_total, up_piece; int up_active, up_staged;
-    uint8_t *up_stage[UP_STAGE_SLOTS]; int up_stage_ready;
+    uint8_t *up_stage[UP_STAGE_SLOTS_MAX]; int up_stage_ready;
     std::atomic<int> up_recorded[UP_MAX_EV];
     std::atomic<long> up_next_issue;
     std::atomic<int> up_failed;
@@ -661,11 +689,12 @@ void bk_q_free(bk_q *q)
     for (int k = 0; k < 3; k++) for (int i = 0; i < q->ev_made[k]; i++) { cudaEventDestroy(q->evp[k][i][0]); cudaEventDestroy(q->evp[k][i][1]); }
     for (int i = 0; i < q->up_ev_made; i++) cudaEventDestroy(q->up_ev[i]);
     for (int i = 0; i < q->xf_rev_made; i++) cudaEventDestroy(q->xf_rev[i]);
-    if (q->up_stage_ready) for (int i = 0; i < UP_STAGE_SLOTS; i++) cudaFreeHost(q->up_stage[i]);
+    for (int i = 0; i < UP_STAGE_SLOTS_MAX; i++) cudaFreeHost(q->up_stage[i]);
     if (q->xf_ready) for (int i = 0; i < q->xf_slots; i++) { cudaFreeHost(q->xf_ring[i]); cudaEventDestroy(q->xf_ev[i]); }
     cudaFree(q->dtotal); cudaFree(q->dbreaks); cudaFree(q->d_cnt); cudaFree(q->d_lrec); cudaFree(q->d_loff); cudaFree(q->d_nlist);
     cudaFree(q->d_link[0]); cudaFree(q->d_link[1]); cudaFree(q->d_mark); cudaFree(q->d_mail);
-    cudaFreeHost(q->h_word); cudaFreeHost(q->h_mail); cudaFreeHost(q->h_flags);
+    cudaFreeHost(q->h_word); cudaFreeHost(q->h_mail); cudaFreeHost(q->h_flags); cudaFreeHost(q->h_sin); cudaFreeHost(q->h_sout);
+    if (q->ev_small) cudaEventDestroy(q->ev_small);
     if (q->stream) cudaStreamDestroy(q->stream);
     if (q->istream) cudaStreamDestroy(q->istream);
     if (q->h2d) cudaStreamDestroy(q->h2d);
@@ -716,6 +745,12 @@ bk_q *bk_q_new(int device)
         return 0;
     }
     if (device < 0 || device >= n) { snprintf(g_err, sizeof(g_err), "device %d out of range (0..%d)", device, n - 1); return 0; }
+    {
+        static int once;
+        const char *e = getenv("FLBGPU_UP_THREADS");
+        if (!once && e && atoi(e) >= 1 && atoi(e) <= UP_THREADS_MAX) { UP_THREADS = atoi(e); UP_STAGE_SLOTS = 2 * UP_THREADS; }
+        once = 1;
+    }
     mem = calloc(1, sizeof(bk_q));
     if (!mem) { snprintf(g_err, sizeof(g_err), "out of memory"); return 0; }
     q = new (mem) bk_q;
@@ -1229,7 +1264,28 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     memset(res, 0, sizeof(*res));
     if (ensure_lists(q, nb_cap)) return -1;
     bk_upload_none(q);
-    if (h_in) CK(cudaMemcpyAsync(d_in, h_in, bytes, cudaMemcpyHostToDevice, st));
+    if (h_in) {
+        /* A pageable source makes cudaMemcpyAsync stage inside the driver, one copy at a time for the whole process;
+         * with several instances calling at once that is the bottleneck.  Each queue stages through its own pinned
+         * buffer instead, piece by piece so that the DMA of one piece runs while the next is being copied. */
+        cudaPointerAttributes at;
+        const int pinned = cudaPointerGetAttributes(&at, h_in) == cudaSuccess && (at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged);
+        cudaGetLastError();
+        if (pinned || bytes < 4096) CK(cudaMemcpyAsync(d_in, h_in, bytes, cudaMemcpyHostToDevice, st));
+        else {
+            const size_t piece = (size_t) 256 << 10;
+            if (q->cap_sin < bytes) {
+                cudaFreeHost(q->h_sin); q->h_sin = 0; q->cap_sin = 0;
+                CK(cudaMallocHost((void **) &q->h_sin, bytes + bytes / 4 + 65536));
+                q->cap_sin = bytes + bytes / 4 + 65536;
+            }
+            for (size_t off = 0; off < bytes; off += piece) {
+                const size_t sz = off + piece <= bytes ? piece : bytes - off;
+                memcpy(q->h_sin + off, (const uint8_t *) h_in + off, sz);
+                CK(cudaMemcpyAsync(d_in + off, q->h_sin + off, sz, cudaMemcpyHostToDevice, st));
+            }
+        }
+    }
     CK(cudaMemsetAsync(m, 0, sizeof(*m), st));
     /* record index */
     ev_begin_on(q, 0, st);
@@ -1268,12 +1324,54 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     return 0;
 }
 
+int bk_jsmn_scan(bk_q *q, const struct bk_jsmn_args *a)
+{
+    use(q);
+    if (!a->n) return 0;
+    k_jsmn_scan<<<(a->n + 63) / 64, 64, 0, q->stream>>>(*a);
+    g_launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
+int bk_jsmn_emit(bk_q *q, const struct bk_jsmn_args *a)
+{
+    use(q);
+    if (!a->n) return 0;
+    k_jsmn_emit<<<(a->n + 63) / 64, 64, 0, q->stream>>>(*a);
+    g_launches += 1;
+    CK(cudaGetLastError());
+    return 0;
+}
+
 int bk_small_fetch(bk_q *q, void *h_dst, const uint8_t *d_out, size_t n)
 {
     use(q);
     if (!n) return 0;
-    CK(cudaMemcpyAsync(h_dst, d_out, n, cudaMemcpyDeviceToHost, q->stream));
-    CK(cudaStreamSynchronize(q->stream));
+    if (n < 4096) {
+        CK(cudaMemcpyAsync(h_dst, d_out, n, cudaMemcpyDeviceToHost, q->stream));
+        CK(cudaStreamSynchronize(q->stream));
+        return 0;
+    }
+    /* through the queue's pinned buffer, in two halves: the first is copied out while the second arrives */
+    if (q->cap_sout < n) {
+        cudaFreeHost(q->h_sout); q->h_sout = 0; q->cap_sout = 0;
+        CK(cudaMallocHost((void **) &q->h_sout, n + n / 4 + 65536));
+        q->cap_sout = n + n / 4 + 65536;
+    }
+    if (!q->ev_small) CK(cudaEventCreateWithFlags(&q->ev_small, cudaEventDisableTiming));
+    {
+        const size_t half = n >= ((size_t) 512 << 10) ? (n / 2) & ~(size_t) 4095 : n;
+        CK(cudaMemcpyAsync(q->h_sout, d_out, half, cudaMemcpyDeviceToHost, q->stream));
+        CK(cudaEventRecord(q->ev_small, q->stream));
+        if (half < n) CK(cudaMemcpyAsync(q->h_sout + half, d_out + half, n - half, cudaMemcpyDeviceToHost, q->stream));
+        CK(cudaEventSynchronize(q->ev_small));
+        memcpy(h_dst, q->h_sout, half);
+        if (half < n) {
+            CK(cudaStreamSynchronize(q->stream));
+            memcpy((uint8_t *) h_dst + half, q->h_sout + half, n - half);
+        }
+    }
     return 0;
 }
 

@@ -1764,6 +1764,8 @@ void flbgpu_stream_copy(void *dst, const void *src, size_t n)
 static void hugepage_hint(void *p, size_t n)
 {
 #ifdef MADV_HUGEPAGE
+    const char *e = getenv("FLBGPU_HUGEPAGE");
+    if (e && e[0] == '0') return;
     if (n >= ((size_t) 8 << 20)) {                    /* fewer, larger page faults while the result is filled in */
         uintptr_t lo = ((uintptr_t) p + ((size_t) 2 << 20) - 1) & ~(((uintptr_t) 2 << 20) - 1);
         uintptr_t hi = ((uintptr_t) p + n) & ~(((uintptr_t) 2 << 20) - 1);
@@ -2408,5 +2410,125 @@ int flbgpu_parser_do(flbgpu_parser *p, const char *buf, size_t length, void **ou
     if (flbgpu_parser_do_batch(p, buf, &off, &len, 1, out_buf, out_size, ooff, &t, &ret) != 0) return -1;
     if (ret < 0) { free(*out_buf); *out_buf = NULL; *out_size = 0; return -1; }
     if (out_time) *out_time = t;
+    return ret;
+}
+
+/* ---- flb_pack_json_state(): the streaming JSON packer of the inputs (src/flb_pack.c:758-829) -----------------
+ * One device lane per stream buffer (dev_jsmn.cuh); a single call is a batch of one. */
+int flbgpu_pack_state_init(struct flbgpu_pack_state *s)
+{
+    if (!s) return -1;
+    memset(s, 0, sizeof(*s));
+    return 0;
+}
+void flbgpu_pack_state_reset(struct flbgpu_pack_state *s) { if (s) memset(s, 0, sizeof(*s)); }
+
+int flbgpu_pack_json_state_batch(flbgpu_ctx *ctx, int n, const char *const *js, const size_t *len,
+                                 char **buffers, int *sizes, struct flbgpu_pack_state *states, int *rets)
+{
+    bk_q *q;
+    struct bk_jsmn_args a;
+    uint32_t *h_off = NULL, *h_len = NULL, *h_tok_off = NULL, *h_tok_cap = NULL, *h_out_off = NULL;
+    struct jm_result *h_res = NULL;
+    uint8_t *h_js = NULL, *h_out = NULL, *d_js = NULL, *d_tmp = NULL, *d_out = NULL;
+    uint32_t *d_meta = NULL;
+    struct jm_tok *d_tok = NULL;
+    struct jm_result *d_res = NULL;
+    size_t total = 0, tok_total = 0, out_total = 0;
+    int i, rc = -1, pass;
+
+    if (!ctx || n < 0 || (n && (!js || !len || !buffers || !sizes || !states || !rets))) return -1;
+    g_rt_err[0] = 0;
+    if (n == 0) return 0;
+    q = ctx->q0;
+    for (i = 0; i < n; i++) {
+        buffers[i] = NULL; sizes[i] = 0; rets[i] = -1;
+        if (len[i] >= 0x7fffffffu) { set_err("stream buffer larger than 2 GiB%s%s", NULL, NULL); return -1; }
+        total += (len[i] + 15) & ~(size_t) 15;
+    }
+    if (total >= 0xfff00000ull) { set_err("batch larger than 4 GiB: split it%s%s", NULL, NULL); return -1; }
+    h_off = malloc(sizeof(uint32_t) * 5 * (size_t) n);
+    h_res = malloc(sizeof(*h_res) * (size_t) n);
+    h_js = malloc(total + 16);
+    if (!h_off || !h_res || !h_js) { set_err("out of memory%s%s", NULL, NULL); goto done; }
+    h_len = h_off + n; h_tok_off = h_len + n; h_tok_cap = h_tok_off + n; h_out_off = h_tok_cap + n;
+    {
+        size_t at = 0;
+        for (i = 0; i < n; i++) {
+            h_off[i] = (uint32_t) at; h_len[i] = (uint32_t) len[i];
+            if (len[i]) memcpy(h_js + at, js[i], len[i]);
+            at += (len[i] + 15) & ~(size_t) 15;
+            /* a token takes at least one byte of text; most documents need far fewer: start at half, retry at the bound */
+            h_tok_cap[i] = (uint32_t) (len[i] / 2 + 64);
+        }
+    }
+    d_js = bk_alloc(q, total + 64);
+    d_tmp = bk_alloc(q, total + (size_t) n + 64);
+    d_meta = bk_alloc(q, sizeof(uint32_t) * 5 * (size_t) n);
+    d_res = bk_alloc(q, sizeof(*d_res) * (size_t) n);
+    if (!d_js || !d_tmp || !d_meta || !d_res) goto done;
+    if (bk_h2d(q, d_js, h_js, total)) goto done;
+    for (pass = 0; pass < 2; pass++) {
+        int again = 0;
+        tok_total = 0;
+        for (i = 0; i < n; i++) { h_tok_off[i] = (uint32_t) tok_total; tok_total += h_tok_cap[i]; }
+        if (tok_total >= 0x7fffffffu / sizeof(struct jm_tok) * 4) { set_err("token scratch too large: split the batch%s%s", NULL, NULL); goto done; }
+        bk_free(q, d_tok);
+        d_tok = bk_alloc(q, sizeof(struct jm_tok) * tok_total);
+        if (!d_tok) goto done;
+        if (bk_h2d(q, d_meta, h_off, sizeof(uint32_t) * 5 * (size_t) n)) goto done;
+        memset(&a, 0, sizeof(a));
+        a.d_js = d_js; a.d_off = d_meta; a.d_len = d_meta + n; a.n = (uint32_t) n;
+        a.d_tok = d_tok; a.d_tok_off = d_meta + 2 * (size_t) n; a.d_tok_cap = d_meta + 3 * (size_t) n;
+        a.d_tmp = d_tmp; a.d_res = d_res; a.d_out_off = d_meta + 4 * (size_t) n;
+        if (bk_jsmn_scan(q, &a) || bk_d2h(q, h_res, d_res, sizeof(*h_res) * (size_t) n) || bk_sync(q)) goto done;
+        for (i = 0; i < n; i++) if (h_res[i].status == JM_NOMEM) { h_tok_cap[i] = (uint32_t) len[i] + 1; again = 1; }
+        if (!again) break;
+    }
+    for (i = 0; i < n; i++) {
+        if (h_res[i].status == JM_NOMEM) { set_err("token scratch exhausted%s%s", NULL, NULL); goto done; }
+        if (h_res[i].status == JM_REFUSED) {
+            set_err("a number text needs a strtod() form that is not restated on the device (hex float, nan(payload))%s%s", NULL, NULL);
+            goto done;
+        }
+        h_out_off[i] = (uint32_t) out_total;
+        if (h_res[i].status == JM_OK) out_total += h_res[i].out_size;
+    }
+    if (out_total) {
+        d_out = bk_alloc(q, out_total + 64);
+        h_out = malloc(out_total);
+        if (!d_out || !h_out) { set_err("out of memory%s%s", NULL, NULL); goto done; }
+        if (bk_h2d(q, d_meta + 4 * (size_t) n, h_out_off, sizeof(uint32_t) * (size_t) n)) goto done;
+        a.d_out = d_out;
+        if (bk_jsmn_emit(q, &a) || bk_d2h(q, h_out, d_out, out_total) || bk_sync(q)) goto done;
+    }
+    for (i = 0; i < n; i++) {
+        const struct jm_result *r = &h_res[i];
+        states[i].multiple = 1;                          /* flb_pack_json_state() sets it (src/flb_pack.c:773) */
+        rets[i] = r->status;
+        if (r->status == JM_OK) {
+            states[i].tokens_count = r->tokens_count;
+            states[i].last_byte = r->last_byte;
+            sizes[i] = (int) r->out_size;
+            buffers[i] = malloc(r->out_size ? r->out_size : 1);
+            if (!buffers[i]) { set_err("out of memory%s%s", NULL, NULL); goto done; }
+            if (r->out_size) memcpy(buffers[i], h_out + h_out_off[i], r->out_size);
+        }
+        else if (r->status == JM_INVAL && r->tret == JM_OK) states[i].last_byte = 0;      /* "tokens_count == 0": last_byte = last (0) */
+        else if (r->status == JM_FAIL) states[i].tokens_count = r->tokens_count;
+    }
+    rc = 0;
+done:
+    if (rc != 0) for (i = 0; i < n; i++) { free(buffers[i]); buffers[i] = NULL; }
+    bk_free(q, d_js); bk_free(q, d_tmp); bk_free(q, d_meta); bk_free(q, d_res); bk_free(q, d_tok); bk_free(q, d_out);
+    free(h_off); free(h_res); free(h_js); free(h_out);
+    return rc;
+}
+
+int flbgpu_pack_json_state(flbgpu_ctx *ctx, const char *js, size_t len, char **buffer, int *size, struct flbgpu_pack_state *state)
+{
+    int ret = -1;
+    if (!ctx || !js || !buffer || !size || !state) return -1;
+    if (flbgpu_pack_json_state_batch(ctx, 1, &js, &len, buffer, size, state, &ret) != 0) return -1;
     return ret;
 }

@@ -88,6 +88,27 @@ int flbgpu_parser_do_batch(flbgpu_parser *p, const char *base, const uint32_t *o
                            void **out_buf, size_t *out_size, uint64_t *out_off, struct flbgpu_time *out_time, int *ret);
 void flbgpu_parser_destroy(flbgpu_parser *parser);
 
+/* ---- streaming JSON packer ------------------------------------------------------------------------------------
+ * flb_pack_json_state(), src/flb_pack.c:758-829: what in_tcp / in_lib / in_stdin / in_mqtt call on the bytes a stream
+ * has received so far -- the jsmn tokeniser (strict mode, parent links) and tokens_to_msgpack() (:512-592): every
+ * whole top-level JSON value comes out as msgpack, state->last_byte says how much of the buffer that was, and an
+ * unfinished tail is reported as FLB_ERR_JSON_PART when nothing before it is whole.  Same return values
+ * (0, FLB_ERR_JSON_INVAL -501, FLB_ERR_JSON_PART -502, -1), same malloc()ed *buffer.
+ * struct flbgpu_pack_state mirrors the fields of struct flb_pack_state (include/fluent-bit/flb_pack.h:64-74) a caller
+ * reads; the tokeniser's own state is not kept between calls: a buffer that grew is tokenised again from its start,
+ * which is what resuming amounts to (the callers reset the state after every successful pack).
+ * The batch form packs n independent stream buffers (one connection each) in one device pass. */
+struct flbgpu_pack_state {
+    int multiple;
+    int tokens_count;
+    int last_byte;
+};
+int  flbgpu_pack_state_init(struct flbgpu_pack_state *s);
+void flbgpu_pack_state_reset(struct flbgpu_pack_state *s);
+int  flbgpu_pack_json_state(flbgpu_ctx *ctx, const char *js, size_t len, char **buffer, int *size, struct flbgpu_pack_state *state);
+int  flbgpu_pack_json_state_batch(flbgpu_ctx *ctx, int n, const char *const *js, const size_t *len,
+                                  char **buffers, int *sizes, struct flbgpu_pack_state *states, int *rets);
+
 /* ---- filters ---------------------------------------------------------- */
 /* flb_filter_new(), src/flb_filter.c:426: plugin = "parser" | "grep" | "modify" |
  * "record_modifier" | "log_to_metrics" (the names of the reference's filter_*_plugin structs). */

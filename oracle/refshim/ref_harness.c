@@ -244,6 +244,23 @@ int flbref_pack_json(const char *js, size_t len, void **out, size_t *out_size)
     return ret;
 }
 
+/* flb_pack_json_state() on a fresh state (src/flb_pack.c:758): returns its value; *last_byte / *tokens_count from the state */
+int flbref_pack_json_state(const char *js, size_t len, void **out, int *out_size, int *last_byte, int *tokens_count)
+{
+    struct flb_pack_state st;
+    char *buf = NULL;
+    int ret, size = 0;
+
+    *out = NULL; *out_size = 0;
+    flb_pack_state_init(&st);
+    ret = flb_pack_json_state(js, len, &buf, &size, &st);
+    *last_byte = st.last_byte;
+    *tokens_count = st.tokens_count;
+    if (ret == 0) { *out = buf; *out_size = size; }
+    flb_pack_state_reset(&st);
+    return ret;
+}
+
 /* ---- filters ---- */
 void *flbref_filter_create(void *cfg, const char *plugin)
 {

@@ -286,6 +286,33 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     memcpy(res->flags, a->d_flags, sizeof(res->flags));
     return 0;
 }
+int bk_jsmn_scan(bk_q *, const struct bk_jsmn_args *a)
+{
+    for (uint32_t i = 0; i < a->n; i++) {
+        const uint8_t *js = a->d_js + a->d_off[i];
+        struct jm_tok *tok = a->d_tok + a->d_tok_off[i];
+        uint32_t toknext = 0;
+        const int tret = jm_tokenise(js, a->d_len[i], tok, a->d_tok_cap[i], &toknext);
+        struct jm_result r;
+        memset(&r, 0, sizeof(r));
+        r.tret = tret;
+        if (tret == JM_NOMEM) { r.status = JM_NOMEM; r.toknext = toknext; }
+        else jm_pack(js, a->d_len[i], tok, toknext, tret, 0, a->d_tmp + a->d_off[i] + i, &r);
+        a->d_res[i] = r;
+    }
+    hs_launches += 1;
+    return 0;
+}
+int bk_jsmn_emit(bk_q *, const struct bk_jsmn_args *a)
+{
+    for (uint32_t i = 0; i < a->n; i++) {
+        struct jm_result r = a->d_res[i];
+        if (r.status != JM_OK || r.out_size == 0) continue;
+        jm_pack(a->d_js + a->d_off[i], a->d_len[i], a->d_tok + a->d_tok_off[i], r.toknext, r.tret, a->d_out + a->d_out_off[i], a->d_tmp + a->d_off[i] + i, &r);
+    }
+    hs_launches += 1;
+    return 0;
+}
 int bk_small_fetch(bk_q *, void *h_dst, const uint8_t *d_out, size_t n) { memcpy(h_dst, d_out, n); return 0; }
 
 }

@@ -40,6 +40,7 @@ class Ref:
         L.flbref_filter_cmt_text.restype = vp; L.flbref_filter_cmt_text.argtypes = [vp]
         L.flbref_l2m_cmt_text.restype = vp; L.flbref_l2m_cmt_text.argtypes = [vp]
         L.flbref_cfree.argtypes = [vp]
+        L.flbref_pack_json_state.argtypes = [cp, sz, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
         self.L = L
         self.cfg = L.flbref_config_create()
 
@@ -50,6 +51,16 @@ class Ref:
         for name in ("parser", "grep", "modify", "record_modifier", "log_to_metrics"):
             if self.L.flbref_plugin_load(self.cfg, SHIM_SO.encode(), ("filter_gpu_%s_plugin" % name).encode()) != 0:
                 raise RuntimeError("cannot load the gpu_%s plugin from %s" % (name, SHIM_SO))
+
+    def pack_json_state(self, js):
+        """flb_pack_json_state() on a fresh state: (ret, msgpack bytes or None, last_byte, tokens_count)"""
+        out, n, last, cnt = C.c_void_p(), C.c_int(), C.c_int(), C.c_int()
+        r = self.L.flbref_pack_json_state(js, len(js), C.byref(out), C.byref(n), C.byref(last), C.byref(cnt))
+        data = None
+        if r == 0:
+            data = C.string_at(out.value, n.value)
+            self.L.flbref_free(out)
+        return r, data, last.value, cnt.value
 
     def filter_counters(self, f):
         """the instance's framework counters (src/flb_filter.c:574-616) as {metric line without timestamp}"""
