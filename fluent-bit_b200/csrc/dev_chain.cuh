@@ -58,8 +58,10 @@ struct ch_env {
     uint32_t in_len;
     const uint8_t *blob;
     uint8_t *scr;
-    int32_t *capcache;
-    uint32_t cap_stride;
+    int32_t *capcache;        /* capture cache, one COLUMN per word: word w of record r at capcache[w * cap_n + r], so that the
+                                 lanes of a warp (adjacent records) touch adjacent words -- coalesced in both passes */
+    uint32_t cap_stride;      /* words per record */
+    uint32_t cap_n;           /* records per column */
     int64_t now;
     uint32_t assume;          /* bit k: filter k is chunk-level MODIFIED */
     uint32_t active;          /* bit k: filter k is routed this chunk (Match / Match_Regex), else skipped like flb_filter_do() does */
@@ -69,6 +71,8 @@ struct ch_env {
     int32_t *prep;            /* parser report (flbgpu_parser_do): 6 ints per record -- parsed flag, position consumed,
                                  seconds lo / hi, nanoseconds, spare -- or NULL */
 };
+
+#define CW(p, x) (p)[(size_t) (x) * cs]          /* word x of a record's capture-cache row (cs = e->cap_n) */
 
 struct ch_rec {
     int64_t ts_sec, ts_nsec;
@@ -473,6 +477,7 @@ FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t
     const struct cf_pname *nm = (const struct cf_pname *) (e->blob + pd->names_off);
     uint32_t i;
     int any_end = 0, cnt = 0, have_nsec = 0;
+    const size_t cs = e->cap_n;
     int64_t lookup = 0, nsec_cached = 0;
     double frac = 0;
     if (pd->n_groups == 0) return 0;                 /* flb_parser_regex_do: n <= 0 -> -1 */
@@ -484,10 +489,10 @@ FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t
         uint32_t vlen = (uint32_t) (en - b);
         const uint8_t *v = s + b;
         if (vlen == 0 && pd->skip_empty) continue;
-        if (pd->has_time && nm[i].is_time && use_cached && tslot && tslot[0]) {
-            if (tslot[0] == 2) continue;
-            lookup = (int64_t) (((uint64_t) (uint32_t) tslot[2] << 32) | (uint32_t) tslot[1]);
-            nsec_cached = tslot[3]; have_nsec = 1;
+        if (pd->has_time && nm[i].is_time && use_cached && tslot && CW(tslot, 0)) {
+            if (CW(tslot, 0) == 2) continue;
+            lookup = (int64_t) (((uint64_t) (uint32_t) CW(tslot, 2) << 32) | (uint32_t) CW(tslot, 1));
+            nsec_cached = CW(tslot, 3); have_nsec = 1;
             if (!pd->time_keep) continue;
         }
         else if (pd->has_time && nm[i].is_time) {
@@ -502,15 +507,15 @@ FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t
             tp.with_year = (int) pd->time_with_year; tp.with_tz = (int) pd->time_with_tz;
             tp.strict = (int) pd->time_strict; tp.offset = pd->time_offset; tp.fast_apache = (pd->has_time & 2) != 0; tp.tfast = pd->tfast_off ? e->blob + pd->tfast_off : 0;
             r = dt_time_lookup(vlen ? v : s, vlen, e->now, &tp, &tm, &ns);
-            if (r == -1) { if (tslot && !use_cached) tslot[0] = 2; continue; }
+            if (r == -1) { if (tslot && !use_cached) CW(tslot, 0) = 2; continue; }
             frac = ns;
             lookup = dt_timegm(&tm) - tm.gmtoff;
             if (tslot && !use_cached) {
-                tslot[0] = 1; tslot[1] = (int32_t) (uint32_t) lookup; tslot[2] = (int32_t) (uint32_t) ((uint64_t) lookup >> 32);
+                CW(tslot, 0) = 1; CW(tslot, 1) = (int32_t) (uint32_t) lookup; CW(tslot, 2) = (int32_t) (uint32_t) ((uint64_t) lookup >> 32);
 #ifdef __CUDA_ARCH__
-                tslot[3] = (int32_t) (int64_t) __dmul_rn(frac, 1000000000.0);
+                CW(tslot, 3) = (int32_t) (int64_t) __dmul_rn(frac, 1000000000.0);
 #else
-                tslot[3] = (int32_t) (int64_t) (frac * 1000000000.0);
+                CW(tslot, 3) = (int32_t) (int64_t) (frac * 1000000000.0);
 #endif
             }
             if (!pd->time_keep) continue;
@@ -1157,6 +1162,7 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t 
                      uint32_t *cache_pos, int *pos)
 {
     int32_t *slot = 0;
+    const size_t cs = e->cap_n;
     uint32_t mplen = 0, i;
     int ok, cnt = 0, skip = -1;
     struct mp_tok t;
@@ -1166,22 +1172,22 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t 
 
     if (!e->scr) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
     if (e->capcache && e->cap_stride >= RC_CACHE_INTS && *cache_pos + 2 <= e->cap_stride - RC_CACHE_INTS)
-        slot = e->capcache + (size_t) ridx * e->cap_stride + *cache_pos;
+        slot = e->capcache + (size_t) *cache_pos * cs + ridx;
     *cache_pos += 2;
     /* slot[0]: 0/1 = result of the exact transcoder (msgpack of slot[1] bytes in scratch),
      * 2 = the fast path produced the fields (it is re-run by the emission pass, nothing cached) */
-    if (!(EMIT && slot && slot[0] != 2)) {
+    if (!(EMIT && slot && CW(slot, 0) != 2)) {
         ok = djf_record(e, s, (int) n, val_off, ok_, ov_, th, &cnt);
-        if (ok == 0) { if (!EMIT && slot) { slot[0] = 0; slot[1] = 0; } return 0; }
-        if (ok == 1) { if (!EMIT && slot) { slot[0] = 2; slot[1] = 0; } *pos = (int) n; goto have_fields; }   /* nothing but white space behind the document */
+        if (ok == 0) { if (!EMIT && slot) { CW(slot, 0) = 0; CW(slot, 1) = 0; } return 0; }
+        if (ok == 1) { if (!EMIT && slot) { CW(slot, 0) = 2; CW(slot, 1) = 0; } *pos = (int) n; goto have_fields; }   /* nothing but white space behind the document */
     }
     cnt = 0;
-    if (EMIT && slot) { ok = slot[0]; mplen = (uint32_t) slot[1]; }
+    if (EMIT && slot) { ok = CW(slot, 0); mplen = (uint32_t) CW(slot, 1); }
     else {
         uint32_t jerr = 0;
         ok = dj_parse_record(s, (int) n, e->scr, &mplen, &jerr, pos);
         if (jerr) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
-        if (!EMIT && slot) { slot[0] = ok; slot[1] = (int32_t) mplen; }
+        if (!EMIT && slot) { CW(slot, 0) = ok; CW(slot, 1) = (int32_t) mplen; }
     }
     if (!ok) return 0;
     q = e->scr; end = q + mplen;
@@ -1237,6 +1243,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
     int64_t ps = 0, pns = 0;
     uint32_t preset = 0;
     int style = ST_CANON;
+    const size_t cs = e->cap_n;
 
     const uint32_t key_hash = cf->ra_off ? 0u : ch_khash(e->blob + cf->key_off, cf->key_len);
     have_arr = cf->reserve_data || cf->preserve_key;
@@ -1283,22 +1290,22 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                  * go straight into the record's arrays instead of through the staging lists */
                 const int direct = !have_arr && !cf->ra_off && i == rc->nf - 1;
                 if (e->capcache && *cache_pos + need + 4 <= lim)
-                    slot = e->capcache + (size_t) ridx * e->cap_stride + *cache_pos;
+                    slot = e->capcache + (size_t) *cache_pos * cs + ridx;
                 *cache_pos += need + 4;
                 if (EMIT && slot) {
-                    matched = slot[0];
-                    for (c = 0; c + 1 < need; c++) w->caps[c] = slot[1 + c];
+                    matched = CW(slot, 0);
+                    for (c = 0; c + 1 < need; c++) w->caps[c] = CW(slot, 1 + c);
                 }
                 else {
                     matched = rx_run(e, pd->rx_off, vp, vn, w->caps, w->stk);
                     if (!EMIT && slot) {
-                        slot[0] = matched;
-                        for (c = 0; c + 1 < need; c++) slot[1 + c] = w->caps[c];
-                        slot[need] = 0;
+                        CW(slot, 0) = matched;
+                        for (c = 0; c + 1 < need; c++) CW(slot, 1 + c) = w->caps[c];
+                        CW(slot, need) = 0;
                     }
                 }
                 if (matched) got = pdef_regex(e, pd, val_off, vp, vn, w->caps, direct ? rc->k : w->tk, direct ? rc->v : w->tv, &cnt,
-                                              &ts, &tns, slot ? slot + need : 0, EMIT ? 1 : 0, direct ? rc->kh : w->th, &pos);
+                                              &ts, &tns, slot ? slot + (size_t) need * cs : 0, EMIT ? 1 : 0, direct ? rc->kh : w->th, &pos);
                 if (got) { preset = pd->n_groups; style = ST_PRESET; in_place = direct; }
             }
             else if (pd->type == FLBGPU_PARSER_JSON) {
@@ -1876,18 +1883,19 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
      * fields) in the last RC_CACHE_INTS ints of its capture-cache row; the emission pass then only
      * encodes -- no decoding, no filters.  Longer records are re-run through the chain. */
     if (EMIT && e->capcache && e->cap_stride >= RC_CACHE_INTS) {
-        const int32_t *c = e->capcache + (size_t) ridx * e->cap_stride + (e->cap_stride - RC_CACHE_INTS);
-        const int32_t st = c[0];
+        const size_t cs = e->cap_n;
+        const int32_t *c = e->capcache + (size_t) (e->cap_stride - RC_CACHE_INTS) * cs + ridx;
+        const int32_t st = CW(c, 0);
         if (st == RC_CACHE_RAW) { mp_copy(out, e->in + off, len); return len; }
         if (st >= 0) {
             int i;
             rc.nf = st & 0xff; rc.style = (st >> 8) & 0xff; rc.reenc = 1;
-            rc.preset_n = (uint32_t) c[1];
-            rc.ts_sec = (int64_t) (uint32_t) c[2]; rc.ts_nsec = (int64_t) (uint32_t) c[3];
-            rc.meta = ((ref_t) (uint32_t) c[5] << 32) | (uint32_t) c[4];
+            rc.preset_n = (uint32_t) CW(c, 1);
+            rc.ts_sec = (int64_t) (uint32_t) CW(c, 2); rc.ts_nsec = (int64_t) (uint32_t) CW(c, 3);
+            rc.meta = ((ref_t) (uint32_t) CW(c, 5) << 32) | (uint32_t) CW(c, 4);
             for (i = 0; i < rc.nf; i++) {
-                rc.k[i] = ((ref_t) (uint32_t) c[8 + 4 * i + 1] << 32) | (uint32_t) c[8 + 4 * i];
-                rc.v[i] = ((ref_t) (uint32_t) c[8 + 4 * i + 3] << 32) | (uint32_t) c[8 + 4 * i + 2];
+                rc.k[i] = ((ref_t) (uint32_t) CW(c, 8 + 4 * i + 1) << 32) | (uint32_t) CW(c, 8 + 4 * i);
+                rc.v[i] = ((ref_t) (uint32_t) CW(c, 8 + 4 * i + 3) << 32) | (uint32_t) CW(c, 8 + 4 * i + 2);
             }
             return rec_emit(e, &rc, out);
         }
@@ -1954,18 +1962,19 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
     if (!EMIT && e->capcache && e->cap_stride >= RC_CACHE_INTS) {
         /* streaming stores: written once, read once by the emission pass -- they should not push the
          * lanes' local-memory lines out of L2 */
-        int32_t *c = e->capcache + (size_t) ridx * e->cap_stride + (e->cap_stride - RC_CACHE_INTS);
+        const size_t cs = e->cap_n;
+        int32_t *c = e->capcache + (size_t) (e->cap_stride - RC_CACHE_INTS) * cs + ridx;
         if (!rc.reenc) CH_STCS(c, RC_CACHE_RAW);
         else if (rc.nf > RC_CACHE_MAXF) CH_STCS(c, RC_CACHE_NONE);
         else {
             int i;
             CH_STCS(c, (int32_t) ((uint32_t) rc.nf | ((uint32_t) rc.style << 8)));
-            CH_STCS(c + 1, (int32_t) rc.preset_n);
-            CH_STCS(c + 2, (int32_t) (uint32_t) rc.ts_sec); CH_STCS(c + 3, (int32_t) (uint32_t) rc.ts_nsec);
-            CH_STCS(c + 4, (int32_t) (uint32_t) rc.meta); CH_STCS(c + 5, (int32_t) (uint32_t) (rc.meta >> 32));
+            CH_STCS(&CW(c, 1), (int32_t) rc.preset_n);
+            CH_STCS(&CW(c, 2), (int32_t) (uint32_t) rc.ts_sec); CH_STCS(&CW(c, 3), (int32_t) (uint32_t) rc.ts_nsec);
+            CH_STCS(&CW(c, 4), (int32_t) (uint32_t) rc.meta); CH_STCS(&CW(c, 5), (int32_t) (uint32_t) (rc.meta >> 32));
             for (i = 0; i < rc.nf; i++) {
-                CH_STCS(c + 8 + 4 * i, (int32_t) (uint32_t) rc.k[i]); CH_STCS(c + 8 + 4 * i + 1, (int32_t) (uint32_t) (rc.k[i] >> 32));
-                CH_STCS(c + 8 + 4 * i + 2, (int32_t) (uint32_t) rc.v[i]); CH_STCS(c + 8 + 4 * i + 3, (int32_t) (uint32_t) (rc.v[i] >> 32));
+                CH_STCS(&CW(c, 8 + 4 * i), (int32_t) (uint32_t) rc.k[i]); CH_STCS(&CW(c, 8 + 4 * i + 1), (int32_t) (uint32_t) (rc.k[i] >> 32));
+                CH_STCS(&CW(c, 8 + 4 * i + 2), (int32_t) (uint32_t) rc.v[i]); CH_STCS(&CW(c, 8 + 4 * i + 3), (int32_t) (uint32_t) (rc.v[i] >> 32));
             }
         }
     }

@@ -35,8 +35,9 @@ struct bk_chain_args {
     uint32_t in_len;
     const uint8_t *d_blob;        /* chain program (device) */
     uint8_t *d_scr;               /* scratch or NULL */
-    int32_t *d_capcache;          /* capture cache or NULL */
+    int32_t *d_capcache;          /* capture cache or NULL: word w of record r at [w * cap_n + r] */
     uint32_t cap_stride;
+    uint32_t cap_n;               /* records per column of the capture cache (= capacity of the record arrays) */
     int64_t now;
     uint32_t assume;
     uint32_t active;              /* bit k: filter k sees this call's chunk (Match routing) */
@@ -70,6 +71,8 @@ int   bk_sync(bk_q *q);
 void *bk_stream(bk_q *q);
 int   bk_kernel_ms(bk_q *q, float out[3]);       /* CUDA-event ms of index / evaluate / emit in the last call */
 int   bk_d2d(bk_q *q, void *dst, const void *src, size_t n);   /* synchronous device copy (buffer growth) */
+/* the same for `rows` rows of `width` bytes with different pitches (re-laying the capture-cache columns) */
+int   bk_d2d_2d(bk_q *q, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows);
 /* the regex VM on the host, for control-plane decisions on tags (Match_Regex); caps has 2 * (RX_MAX_GROUPS + 1) ints */
 int   bk_rx_search_host(const void *prog, const uint8_t *s, int n, int *caps);
 

@@ -406,16 +406,52 @@ __global__ void __launch_bounds__(BK_REC_BLOCK) k_surv_fill(const uint32_t *__re
     }
 }
 
-__global__ void __launch_bounds__(BK_REC_BLOCK, BK_EVAL_MIN_BLOCKS) k_chain_emit_list(const k_chain_params p, const uint32_t *__restrict__ l_rec,
-                                                                                      const uint64_t *__restrict__ l_off,
-                                                                                      const unsigned long long *__restrict__ n_list,
-                                                                                      const uint32_t *__restrict__ go)
+/* One lane encodes one surviving record.  The survivors of a warp are consecutive in the result (the list is in
+ * record order and the offsets are a running sum), so the warp first encodes its 32 records into a slice of shared
+ * memory laid out like the result, then copies the whole range out with coalesced 16-byte stores: the result leaves
+ * the SM in full sectors instead of byte-sized partial writes (profiles/: DRAM write bytes per result byte 3.7 -> ~1).
+ * A warp whose range does not fit its slice writes directly, as before. */
+#define EMIT_BLOCK 128u
+#define EMIT_STAGE 8192u          /* bytes of result per warp that can be staged (+16 of alignment slack) */
+__global__ void __launch_bounds__(EMIT_BLOCK, 6) k_chain_emit_list(const k_chain_params p, const uint32_t *__restrict__ l_rec,
+                                                                   const uint64_t *__restrict__ l_off,
+                                                                   const unsigned long long *__restrict__ n_list,
+                                                                   const uint32_t *__restrict__ go)
 {
-    const uint32_t t = blockIdx.x * BK_REC_BLOCK + threadIdx.x;
+    extern __shared__ __align__(16) uint8_t emit_stage[];
+    const uint32_t t = blockIdx.x * EMIT_BLOCK + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (go && !*go) return;
-    if (t >= (uint32_t) *n_list) return;
-    const uint32_t r = l_rec[t];
-    chain_record<true>(&p.env, r, p.off[r], p.len[r], p.out + l_off[t]);
+    const bool valid = t < (uint32_t) *n_list;
+    const uint32_t r = valid ? l_rec[t] : 0;
+    const unsigned long long off = valid ? l_off[t] : 0ull;
+    const uint32_t sz = valid ? p.size[r] : 0u;
+    const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+    if (!vmask) return;
+    /* valid lanes are a prefix of the warp: lane 0 holds the start of the range, the last valid lane its end */
+    const int last = 31 - __clz((int) vmask);
+    const unsigned long long base = __shfl_sync(0xffffffffu, off, 0);
+    const unsigned long long end = __shfl_sync(0xffffffffu, off + sz, last);
+    const uint32_t total = (uint32_t) (end - base), mis = (uint32_t) ((uintptr_t) (p.out + base) & 15u);
+    if (total + mis <= EMIT_STAGE) {
+        uint8_t *sb = emit_stage + (size_t) warp * (EMIT_STAGE + 16);
+        if (valid) chain_record<true>(&p.env, r, p.off[r], p.len[r], sb + mis + (uint32_t) (off - base));
+        __syncwarp();
+        {
+            /* shared byte i corresponds to result byte (base - mis + i): 16-byte chunks are aligned on both sides */
+            uint8_t *g = p.out + base - mis;
+            const uint32_t lo = mis, hi = mis + total;
+            const uint32_t body_lo = (lo + 15u) & ~15u, body_hi = hi & ~15u;
+            if (body_lo >= body_hi) { for (uint32_t i = lo + lane; i < hi; i += 32) g[i] = sb[i]; }
+            else {
+                for (uint32_t i = lo + lane; i < body_lo; i += 32) g[i] = sb[i];
+                for (uint32_t i = body_lo + lane * 16; i < body_hi; i += 512) __stcs(reinterpret_cast<uint4 *>(g + i), *reinterpret_cast<const uint4 *>(sb + i));
+                for (uint32_t i = body_hi + lane; i < hi; i += 32) g[i] = sb[i];
+            }
+        }
+        return;
+    }
+    if (valid) chain_record<true>(&p.env, r, p.off[r], p.len[r], p.out + off);
 }
 
 /* ---- glue of the small-chunk form ---- */
@@ -668,12 +704,12 @@ static int func_attrs_once(void)
 {
     /* the interpreter keeps its field list and backtrack stack in local memory */
     CK(cudaFuncSetCacheConfig(k_chain_eval, cudaFuncCachePreferL1));
-    CK(cudaFuncSetCacheConfig(k_chain_emit_list, cudaFuncCachePreferL1));
+    /* the emission kernel stages a warp's result range in shared memory (6 blocks x 32 KB per SM) */
+    CK(cudaFuncSetAttribute(k_chain_emit_list, cudaFuncAttributePreferredSharedMemoryCarveout, 80));
     {   /* and ask for the largest L1 the unified array can give (FLBGPU_MAX_L1=0: driver default) */
         const char *e = getenv("FLBGPU_MAX_L1");
         if (!(e && e[0] == '0')) {
             cudaFuncSetAttribute(k_chain_eval, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-            cudaFuncSetAttribute(k_chain_emit_list, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
             cudaGetLastError();
         }
     }
@@ -978,6 +1014,13 @@ int bk_download_end(bk_q *q)
     return rc;
 }
 
+int bk_d2d_2d(bk_q *q, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows)
+{
+    use(q);
+    CK(cudaMemcpy2D(dst, dpitch, src, spitch, width, rows, cudaMemcpyDeviceToDevice));
+    return 0;
+}
+
 int bk_rx_search_host(const void *prog, const uint8_t *s, int n, int *caps)
 {
     uint32_t stk[1024], budget = CH_RX_BUDGET;
@@ -1077,7 +1120,7 @@ int bk_index_fill(bk_q *q, const uint8_t *d_in, size_t slice_off, uint32_t slice
 static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_t *d_out, uint32_t r0)
 {
     p->env.in = a->d_in; p->env.in_len = a->in_len; p->env.blob = a->d_blob; p->env.scr = a->d_scr;
-    p->env.capcache = a->d_capcache; p->env.cap_stride = a->cap_stride; p->env.now = a->now;
+    p->env.capcache = a->d_capcache; p->env.cap_stride = a->cap_stride; p->env.cap_n = a->cap_n; p->env.now = a->now;
     p->env.assume = a->assume; p->env.active = a->active; p->env.fl_flags = a->d_flags; p->env.err = a->d_flags + FLBGPU_MAX_FILTERS;
     p->env.l2m = a->l2m; p->env.prep = a->d_prep;
     p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->r0 = r0; p->n_rec = a->n_rec; p->stage_bytes = 0;
@@ -1244,7 +1287,7 @@ int bk_chain_emit(bk_q *q, const struct bk_chain_args *a, uint8_t *d_out, uint32
         k_surv_count<<<nb, BK_REC_BLOCK, 0, q->stream>>>(a->d_size + rec0, n, q->d_cnt);
         k_scan_top<uint32_t><<<1, 256, 0, q->stream>>>(q->d_cnt, nb, q->d_nlist, q->dtotal + 8);
         k_surv_fill<<<nb, BK_REC_BLOCK, 0, q->stream>>>(a->d_size + rec0, n, 0, rec0, q->d_cnt, a->d_bsum + b0, q->d_lrec, q->d_loff);
-        k_chain_emit_list<<<nb, BK_REC_BLOCK, 0, q->stream>>>(p, q->d_lrec, q->d_loff, q->d_nlist, 0);
+        k_chain_emit_list<<<nb * (BK_REC_BLOCK / EMIT_BLOCK), EMIT_BLOCK, (EMIT_BLOCK / 32) * (EMIT_STAGE + 16), q->stream>>>(p, q->d_lrec, q->d_loff, q->d_nlist, 0);
         ev_end_on(q, 2, q->stream);
         g_launches += 4;
     }
@@ -1309,7 +1352,7 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     k_small_scan2<<<1, 256, 0, st>>>(a->d_bsum, q->d_cnt, nb_cap, (unsigned long long) cap_out, m);
     k_surv_fill<<<nb_cap, BK_REC_BLOCK, 0, st>>>(a->d_size, 0, &m->n_valid, 0, q->d_cnt, a->d_bsum, q->d_lrec, q->d_loff);
     p.stage_bytes = 0;
-    k_chain_emit_list<<<nb_cap, BK_REC_BLOCK, 0, st>>>(p, q->d_lrec, q->d_loff, &m->n_out, &m->emitted);
+    k_chain_emit_list<<<nb_cap * (BK_REC_BLOCK / EMIT_BLOCK), EMIT_BLOCK, (EMIT_BLOCK / 32) * (EMIT_STAGE + 16), st>>>(p, q->d_lrec, q->d_loff, &m->n_out, &m->emitted);
     ev_end_on(q, 2, st);
     g_launches += 10;
     CK(cudaGetLastError());

@@ -1310,7 +1310,8 @@ static int ensure_rec_cap(flbgpu_chain *c, size_t need, size_t keep)
         if (bk_sync(c->q)) return -1;                 /* running kernels still read the old arrays */
         if (bk_d2d(c->q, o, c->d_off, keep * 4) || bk_d2d(c->q, l, c->d_len, keep * 4) || bk_d2d(c->q, z, c->d_size, keep * 4) ||
             bk_d2d(c->q, k, c->d_kind, keep)) return -1;
-        if (cp && bk_d2d(c->q, cp, c->d_cap, keep * c->cap_stride * sizeof(int32_t))) return -1;
+        /* the capture cache is laid out in columns of cap_rec records: every column moves to its new pitch */
+        if (cp && bk_d2d_2d(c->q, cp, nc * sizeof(int32_t), c->d_cap, c->cap_rec * sizeof(int32_t), keep * sizeof(int32_t), c->cap_stride)) return -1;
     }
     bk_free(c->q, c->d_off); bk_free(c->q, c->d_len); bk_free(c->q, c->d_size); bk_free(c->q, c->d_kind); bk_free(c->q, c->d_cap);
     c->d_off = o; c->d_len = l; c->d_size = z; c->d_kind = k; c->d_cap = cp;
@@ -1330,7 +1331,7 @@ static size_t slice_bytes(void)
 static void fill_args(flbgpu_chain *c, struct bk_chain_args *a, const uint8_t *d_in, size_t bytes, uint32_t n_rec)
 {
     a->d_in = d_in; a->in_len = (uint32_t) bytes; a->d_blob = c->d_blob; a->d_scr = c->needs_scratch ? c->d_scr : NULL;
-    a->d_capcache = c->cap_stride ? c->d_cap : NULL; a->cap_stride = c->cap_stride;
+    a->d_capcache = c->cap_stride ? c->d_cap : NULL; a->cap_stride = c->cap_stride; a->cap_n = (uint32_t) c->cap_rec;
     a->d_off = c->d_off; a->d_len = c->d_len; a->d_kind = c->d_kind; a->n_rec = n_rec;
     a->d_size = c->d_size; a->d_bsum = c->d_bsum; a->d_flags = c->d_flags;
     if (c->l2m_index >= 0 && ((c->active >> c->l2m_index) & 1)) a->l2m = c->l2m; else memset(&a->l2m, 0, sizeof(a->l2m));

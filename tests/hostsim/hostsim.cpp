@@ -98,6 +98,11 @@ int bk_sync(bk_q *) { return 0; }
 void *bk_stream(bk_q *) { return 0; }
 int bk_kernel_ms(bk_q *, float out[3]) { out[0] = out[1] = out[2] = 0.f; return 0; }
 
+int bk_d2d_2d(bk_q *, void *dst, size_t dpitch, const void *src, size_t spitch, size_t width, size_t rows)
+{
+    for (size_t r = 0; r < rows; r++) memcpy((uint8_t *) dst + r * dpitch, (const uint8_t *) src + r * spitch, width);
+    return 0;
+}
 int bk_rx_search_host(const void *prog, const uint8_t *s, int n, int *caps)
 {
     uint32_t stk[1024], budget = CH_RX_BUDGET;
@@ -178,7 +183,7 @@ int bk_index_fill(bk_q *, const uint8_t *d_in, size_t slice_off, uint32_t len, c
 static void hs_env(const struct bk_chain_args *a, struct ch_env *e)
 {
     e->in = a->d_in; e->in_len = a->in_len; e->blob = a->d_blob; e->scr = a->d_scr;
-    e->capcache = a->d_capcache; e->cap_stride = a->cap_stride; e->now = a->now; e->assume = a->assume; e->active = a->active;
+    e->capcache = a->d_capcache; e->cap_stride = a->cap_stride; e->cap_n = a->cap_n; e->now = a->now; e->assume = a->assume; e->active = a->active;
     e->fl_flags = a->d_flags; e->err = a->d_flags + FLBGPU_MAX_FILTERS;
     e->l2m = a->l2m; e->prep = a->d_prep;
 }
