@@ -13,13 +13,13 @@ $(PKG)/libflbgpu.so: $(CSRC)/kernels.cu $(CSRC)/runtime.c $(CSRC)/rx_compile.c $
 	$(NVCC) $(NVFLAGS) -c $(CSRC)/kernels.cu -o $(CSRC)/kernels.o
 	gcc $(CFLAGS) -c $(CSRC)/runtime.c -o $(CSRC)/runtime.o
 	gcc $(CFLAGS) -c $(CSRC)/rx_compile.c -o $(CSRC)/rx_compile.o
-	$(NVCC) -shared -o $@ $(CSRC)/kernels.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o -lcudart -lpthread
+	$(NVCC) -shared -o $@ $(CSRC)/kernels.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o -lcudart -lpthread -ldl
 
 hostsim: tests/hostsim/libhostsim.so
 tests/hostsim/libhostsim.so: tests/hostsim/hostsim.cpp $(CSRC)/runtime.c $(CSRC)/rx_compile.c $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h)
 	gcc $(CFLAGS) -c $(CSRC)/runtime.c -o tests/hostsim/runtime.o
 	gcc $(CFLAGS) -c $(CSRC)/rx_compile.c -o tests/hostsim/rx_compile.o
-	g++ $(CFLAGS) -shared -o $@ tests/hostsim/hostsim.cpp tests/hostsim/runtime.o tests/hostsim/rx_compile.o
+	g++ $(CFLAGS) -shared -o $@ tests/hostsim/hostsim.cpp tests/hostsim/runtime.o tests/hostsim/rx_compile.o -lrt -lpthread
 
 # the same emulation under AddressSanitizer + UBSan (host runtime and the device code as the CPU compiles it):
 #   make hostsim-asan && FLBGPU_HOSTSIM_SO=/tmp/flbgpu-asan/libhostsim.so LD_PRELOAD=$$(gcc -print-file-name=libasan.so) \

@@ -115,6 +115,32 @@ def lines_for(args, wl, world=1):
     return args.lines
 
 
+def host_cores():
+    """(usable cores, note): os.cpu_count() capped by the container's CPU quota (cgroup v2 cpu.max / v1 cfs quota) --
+    a quota of 16 CPUs makes 128 busy processes run at an eighth of their speed, so the reference gets one pipeline per
+    core it can actually have"""
+    n = os.cpu_count() or 1
+    note = "%d logical CPUs" % n
+    try:
+        try:
+            q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        except OSError:
+            q = open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read().strip()
+            per = open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read().strip()
+        if q != "max" and int(q) > 0:
+            lim = max(1, int(int(q) / float(per) + 0.5))
+            if lim < n:
+                note = "%d logical CPUs, CPU quota of the container %s/%s = %d" % (n, q, per, lim)
+                n = lim
+    except Exception:
+        pass
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    return n, note
+
+
 # ------------------------------------------------------------------ reference arm
 _REF_STATE = {}
 _BLOCKS = {}
@@ -137,10 +163,6 @@ def _ref_state(wl):
 
 def _ref_init(workloads):
     """every pool worker: its own reference pipeline per workload and its own copy of the block, built before timing"""
-    try:                     # the GPU arm binds its process near its GPU; the reference gets every core
-        os.sched_setaffinity(0, range(os.cpu_count()))
-    except Exception:
-        pass
     for wl in workloads:
         ref, buf = _ref_state(wl)
         cut = block_offsets_cached(wl)[200]
@@ -223,7 +245,7 @@ def run_reference(args):
     if not util.have_ref():
         print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libflbref.so missing"}))
         return
-    cores = os.cpu_count() or 1
+    cores, cores_note = host_cores()
     wl = args.workload
     side = [] if args.primary_only else [o for o in ("apache", "c0", "nginx") if o != wl]
     pool = RefPool(cores, [wl] + side)
@@ -236,13 +258,14 @@ def run_reference(args):
             others[o] = {"workload": WORKLOADS[o]["name"], "value": v, "e2e": v, "unit": "lines/s", "events_per_step": nn,
                          "ms_per_step": 1000 * sps}
     pool.close()
-    sample = "%d cores, %d events per step in %d-event calls, one pipeline per core, %d steps; time = slowest worker inside the reference's calls" % (
-        cores, n, min(BASE_LINES, -(-n // cores)), args.steps)
+    sample = "%d cores (%s), %d events per step in %d-event calls, one pipeline per core, %d steps; time = slowest worker inside the reference's calls" % (
+        cores, cores_note, n, min(BASE_LINES, -(-n // cores)), args.steps)
     line = {
         "impl": "reference", "metric": "log lines/sec through parser+filter chain", "value": val, "unit": "lines/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000 * s_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
         "config": {"workload": WORKLOADS[wl]["name"], "events_per_gpu_per_step": lines_for(args, wl), "distinct_lines": BASE_LINES},
+        "host": cores_note,
         "cpu_baseline": {"value": val, "unit": "lines/s", "cores": cores, "kind": "reference", "sample": sample},
         "e2e": {"value": val, "unit": "lines/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -589,13 +612,13 @@ def run_ours(args):
 
     cpu = None
     if util.have_ref():
-        cores = os.cpu_count() or 1
+        cores, cores_note = host_cores()
         pool = RefPool(cores, [WL])
         sample_lines = min(m["n_lines"], 4_000_000)
         v, sps, n = reference_workload(pool, WL, sample_lines, 2, 1)
         pool.close()
         cpu = {"value": v, "unit": "lines/s", "cores": cores, "kind": "reference",
-               "sample": "%d cores, 2 steps of %d events in %d-event calls, one pipeline per core (%.2f s per step: slowest worker inside the reference's calls)" % (cores, n, min(BASE_LINES, -(-n // cores)), sps)}
+               "sample": "%d cores (%s), 2 steps of %d events in %d-event calls, one pipeline per core (%.2f s per step: slowest worker inside the reference's calls)" % (cores, cores_note, n, min(BASE_LINES, -(-n // cores)), sps)}
 
     def side(mm, name):
         e2, a2, ach2 = roof(mm)

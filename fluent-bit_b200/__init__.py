@@ -47,6 +47,7 @@ EXPORTS = [
     "flbgpu_chain_destroy", "flbgpu_chain_do_device", "flbgpu_chain_stats", "flbgpu_dev_alloc",
     "flbgpu_dev_free", "flbgpu_dev_upload", "flbgpu_dev_download", "flbgpu_host_alloc", "flbgpu_host_free",
     "flbgpu_stream", "flbgpu_kernel_ms", "flbgpu_chain_stream",
+    "flbgpu_comm_unique_id", "flbgpu_comm_init", "flbgpu_l2m_allreduce",
     "flbgpu_pack_state_init", "flbgpu_pack_state_reset", "flbgpu_pack_json_state", "flbgpu_pack_json_state_batch",
 ]
 
@@ -95,6 +96,9 @@ def load(path=None):
     L.flbgpu_pack_json_state.argtypes = [vp, cp, sz, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(PackState)]
     L.flbgpu_pack_json_state_batch.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(sz), C.POINTER(vp), C.POINTER(C.c_int),
                                                C.POINTER(PackState), C.POINTER(C.c_int)]
+    L.flbgpu_comm_unique_id.argtypes = [vp]
+    L.flbgpu_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.flbgpu_l2m_allreduce.argtypes = [vp]
     ip = C.POINTER(C.c_int); u64p = C.POINTER(C.c_uint64)
     L.flbgpu_l2m_info.argtypes = [vp, ip, ip, ip, ip]
     L.flbgpu_l2m_get.argtypes = [vp, C.c_int, u64p, u64p, C.POINTER(C.c_double), u64p, vp]
@@ -139,6 +143,17 @@ class Context:
             self.close()
         except Exception:
             pass
+
+    def comm_unique_id(self):
+        buf = C.create_string_buffer(128)
+        if self.L.flbgpu_comm_unique_id(C.cast(buf, C.c_void_p)) != 0:
+            raise FlbGpuError("comm_unique_id: %s" % self.err())
+        return buf.raw
+
+    def comm_init(self, nranks, rank, uid):
+        buf = C.create_string_buffer(uid, 128)
+        if self.L.flbgpu_comm_init(self.h, nranks, rank, C.cast(buf, C.c_void_p)) != 0:
+            raise FlbGpuError("comm_init: %s" % self.err())
 
     def pack_json_state(self, bufs):
         """flb_pack_json_state() over a batch of stream buffers: [(ret, msgpack bytes or None, last_byte, tokens_count)]"""
@@ -313,8 +328,14 @@ class Filter:
         _libc.free(p)
         return t
 
+    def l2m_allreduce_lib(self):
+        """flbgpu_l2m_allreduce(): the library's own exchange (NCCL; the context needs comm_init first)"""
+        if self.ctx.L.flbgpu_l2m_allreduce(self.h) != 0:
+            raise FlbGpuError("l2m_allreduce: %s" % self.ctx.err())
+
     def l2m_allreduce(self, device=None):
-        """Sum this filter's metric table over all ranks of the default process group (the one
+        """The same merge spelled with torch.distributed (kept as an independent check of the library's exchange).
+        Sum this filter's metric table over all ranks of the default process group (the one
         exchange step of the path: cmetrics of N shards -> one table).  Keys travel with one
         all_gather, values with ONE all_reduce (NCCL on GPUs, gloo in the CPU tests).  Label sets
         end up in (rank, first-seen) order on every rank."""

@@ -157,6 +157,16 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
 /* result bytes [0,n) of d_out into the caller's (pageable) buffer; synchronises */
 int bk_small_fetch(bk_q *q, void *h_dst, const uint8_t *d_out, size_t n);
 
+/* ---- the one exchange of the path: metric tables of filter_log_to_metrics over NCCL (NVLink / NVSwitch) ----
+ * One communicator per context (its default queue).  libnccl is opened at run time, so a single-GPU deployment needs
+ * no NCCL at all.  d_* are device buffers; the calls are synchronous (the tables are a few KB). */
+int bk_comm_unique_id(uint8_t id[128]);
+int bk_comm_init(bk_q *q, int nranks, int rank, const uint8_t id[128]);
+int bk_comm_info(bk_q *q, int *nranks, int *rank);          /* 0 when a communicator exists */
+int bk_comm_allgather(bk_q *q, const void *d_send, void *d_recv, size_t bytes_per_rank);
+int bk_comm_allreduce_u64(bk_q *q, void *d_buf, size_t count);            /* sum */
+int bk_comm_allreduce_f64(bk_q *q, void *d_buf, size_t count);            /* sum */
+
 /* ---- streaming JSON packer (flb_pack_json_state over a batch of stream buffers): one lane per buffer ----
  * d_js holds the buffers back to back, buffer i = d_js[d_off[i], d_off[i] + d_len[i]); its tokens live at
  * d_tok[d_tok_off[i] .. + d_tok_cap[i]), its unescape scratch at d_tmp[d_off[i] + i ..) (d_len[i] + 1 bytes).

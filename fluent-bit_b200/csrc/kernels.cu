@@ -35,6 +35,8 @@
 #include <sched.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <dlfcn.h>
+#include <nccl.h>
 #include "flbgpu_internal.h"
 #include "dev_chain.cuh"
 
@@ -433,9 +435,13 @@ __global__ void __launch_bounds__(EMIT_BLOCK, 6) k_chain_emit_list(const k_chain
     const unsigned long long base = __shfl_sync(0xffffffffu, off, 0);
     const unsigned long long end = __shfl_sync(0xffffffffu, off + sz, last);
     const uint32_t total = (uint32_t) (end - base), mis = (uint32_t) ((uintptr_t) (p.out + base) & 15u);
-    if (total + mis <= EMIT_STAGE) {
+    /* A record whose field list did not fit the cache row is re-run through the whole chain, reconvergence points
+     * (full-mask __syncwarp) included: those pair up only among lanes that all take that path or have exited.  A warp
+     * holding such a record therefore emits the old way -- finished lanes exit, nothing waits at a warp barrier. */
+    const bool rerun = valid && p.env.capcache[(size_t) (p.env.cap_stride - RC_CACHE_INTS) * p.env.cap_n + r] == RC_CACHE_NONE;
+    if (!__any_sync(0xffffffffu, rerun) && total + mis <= EMIT_STAGE) {
         uint8_t *sb = emit_stage + (size_t) warp * (EMIT_STAGE + 16);
-        if (valid) chain_record<true>(&p.env, r, p.off[r], p.len[r], sb + mis + (uint32_t) (off - base));
+        if (valid) chain_record<true>(&p.env, r, p.off[r], p.len[r], sb + mis + (uint32_t) (off - base));   /* cached field list: encode only */
         __syncwarp();
         {
             /* shared byte i corresponds to result byte (base - mis + i): 16-byte chunks are aligned on both sides */
@@ -451,6 +457,7 @@ __global__ void __launch_bounds__(EMIT_BLOCK, 6) k_chain_emit_list(const k_chain
         }
         return;
     }
+    if (!valid) return;
     if (valid) chain_record<true>(&p.env, r, p.off[r], p.len[r], p.out + off);
 }
 
@@ -636,9 +643,50 @@ struct bk_q {
     std::atomic<long> xf_n_pushed, xf_n_taken;
     std::atomic<int> xf_push_closed;
     bk_pool *xf_pool; int xf_open;
+    /* metric-table exchange */
+    ncclComm_t comm; int comm_ranks, comm_rank;
 };
 
 static inline void use(bk_q *q) { cudaSetDevice(q->device); }
+
+/* Waiting for another thread: a few yields, then short sleeps.  A thread that spins through a whole staging wait burns
+ * a core for nothing -- and an agent running under a CPU quota (cgroup cpu.max) pays for that with throttling of the
+ * threads that do have work.  The hand-offs here are milliseconds apart; 50 us of extra latency is nothing. */
+#include <time.h>
+struct bk_backoff {
+    int n = 0;
+    void wait() { if (n++ < 32) sched_yield(); else { struct timespec ts = { 0, 50000 }; nanosleep(&ts, 0); } }
+};
+
+/* ---- NCCL, resolved at run time ---- */
+static struct {
+    void *dso;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId *);
+    ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int);
+    ncclResult_t (*CommDestroy)(ncclComm_t);
+    ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t);
+    ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t);
+    const char *(*GetErrorString)(ncclResult_t);
+} N;
+static std::mutex g_nccl_lock;
+
+static int nccl_load(void)
+{
+    std::lock_guard<std::mutex> lk(g_nccl_lock);
+    if (N.dso) return 0;
+    const char *path = getenv("FLBGPU_NCCL_LIB");
+    void *h = dlopen(path && *path ? path : "libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) { snprintf(g_err, sizeof(g_err), "cannot open libnccl.so.2 (%s): the metric-table exchange needs NCCL", dlerror()); return -1; }
+#define NSYM(f) do { *(void **) &N.f = dlsym(h, "nccl" #f); if (!N.f) { snprintf(g_err, sizeof(g_err), "libnccl lacks nccl" #f); dlclose(h); return -1; } } while (0)
+    NSYM(GetUniqueId); NSYM(CommInitRank); NSYM(CommDestroy); NSYM(AllGather); NSYM(AllReduce); NSYM(GetErrorString);
+#undef NSYM
+    N.dso = h;
+    return 0;
+}
+#define NK(call) do { ncclResult_t r_ = (call); if (r_ != ncclSuccess) { \
+    snprintf(g_err, sizeof(g_err), "%s: %s", #call, N.GetErrorString(r_)); return -1; } } while (0)
+
+
 
 static void ev_begin_on(bk_q *q, int k, cudaStream_t st)
 {
@@ -721,6 +769,7 @@ void bk_q_free(bk_q *q)
     if (!q) return;
     use(q);
     if (q->stream) cudaStreamSynchronize(q->stream);
+    if (q->comm && N.CommDestroy) N.CommDestroy(q->comm);
     delete q->up_pool; delete q->xf_pool;
     for (int k = 0; k < 3; k++) for (int i = 0; i < q->ev_made[k]; i++) { cudaEventDestroy(q->evp[k][i][0]); cudaEventDestroy(q->evp[k][i][1]); }
     for (int i = 0; i < q->up_ev_made; i++) cudaEventDestroy(q->up_ev[i]);
@@ -841,12 +890,12 @@ static void up_worker(void *arg, int t)
         const size_t off = i * piece, sz = (off + piece <= n) ? piece : n - off;
         /* the slot was last used by piece i - UP_STAGE_SLOTS: its H2D must have left the buffer */
         if (i >= UP_STAGE_SLOTS) {
-            while (!q->up_recorded[i - UP_STAGE_SLOTS].load(std::memory_order_acquire)) { if (q->up_failed.load()) return; sched_yield(); }
+            for (bk_backoff b; !q->up_recorded[i - UP_STAGE_SLOTS].load(std::memory_order_acquire); b.wait()) if (q->up_failed.load()) return;
             if (cudaEventSynchronize(q->up_ev[i - UP_STAGE_SLOTS]) != cudaSuccess) { q->up_failed.store(1); return; }
         }
         if (!q->up_stage[slot] && cudaMallocHost((void **) &q->up_stage[slot], UP_PIECE) != cudaSuccess) { q->up_failed.store(1); q->up_next_issue.store((long) i + 1); return; }
         memcpy(q->up_stage[slot], q->up_src + off, sz);
-        while (q->up_next_issue.load(std::memory_order_acquire) != (long) i) { if (q->up_failed.load()) return; sched_yield(); }
+        for (bk_backoff b; q->up_next_issue.load(std::memory_order_acquire) != (long) i; b.wait()) if (q->up_failed.load()) return;
         if (cudaMemcpyAsync(q->up_dst + off, q->up_stage[slot], sz, cudaMemcpyHostToDevice, q->h2d) != cudaSuccess ||
             cudaEventRecord(q->up_ev[i], q->h2d) != cudaSuccess) { q->up_failed.store(1); q->up_next_issue.store((long) i + 1); return; }
         q->up_recorded[i].store(1, std::memory_order_release);
@@ -866,7 +915,7 @@ int bk_upload_start(bk_q *q, void *d_dst, const void *h_src, size_t n)
     q->up_piece = UP_PIECE;
     while ((n + q->up_piece - 1) / q->up_piece > UP_MAX_EV) q->up_piece *= 2;
     const size_t np = (n + q->up_piece - 1) / q->up_piece;
-    for (; q->up_ev_made < (int) np; q->up_ev_made++) CK(cudaEventCreateWithFlags(&q->up_ev[q->up_ev_made], cudaEventDisableTiming));
+    for (; q->up_ev_made < (int) np; q->up_ev_made++) CK(cudaEventCreateWithFlags(&q->up_ev[q->up_ev_made], cudaEventDisableTiming | cudaEventBlockingSync));
     q->up_total = n; q->up_active = 1; q->up_staged = 0;
     {
         cudaPointerAttributes at;
@@ -899,10 +948,8 @@ int bk_upload_wait_index(bk_q *q, size_t upto)
     if (upto > q->up_total) upto = q->up_total;
     const size_t last = (upto - 1) / q->up_piece;
     if (q->up_staged) {
-        while (!q->up_recorded[last].load(std::memory_order_acquire)) {
+        for (bk_backoff b; !q->up_recorded[last].load(std::memory_order_acquire); b.wait())
             if (q->up_failed.load()) { snprintf(g_err, sizeof(g_err), "host->device staging failed"); return -1; }
-            sched_yield();
-        }
     }
     CK(cudaStreamWaitEvent(q->istream, q->up_ev[last], 0));
     return 0;
@@ -917,7 +964,7 @@ static int xf_init(bk_q *q)
         if (es && atoi(es) >= 2 && atoi(es) <= XF_MAX_SLOTS) q->xf_slots = atoi(es);
         if (em && atoi(em) >= 1 && atoi(em) <= 256) q->xf_slice = (size_t) atoi(em) << 20;
     }
-    for (int i = 0; i < q->xf_slots; i++) CK(cudaEventCreateWithFlags(&q->xf_ev[i], cudaEventDisableTiming));   /* ring buffers: on first use */
+    for (int i = 0; i < q->xf_slots; i++) CK(cudaEventCreateWithFlags(&q->xf_ev[i], cudaEventDisableTiming | cudaEventBlockingSync));   /* ring buffers: on first use */
     q->xf_pool = new bk_pool;
     q->xf_pool->ensure(q->xf_slots + 1, q->device);
     q->xf_ready = 1;
@@ -927,10 +974,9 @@ static int xf_init(bk_q *q)
 static void xf_copy_out(bk_q *q, int s)
 {
     for (long i = s;; i += q->xf_slots) {
-        while (q->xf_issued[s].load(std::memory_order_acquire) < i) {
+        for (bk_backoff b; q->xf_issued[s].load(std::memory_order_acquire) < i; b.wait()) {
             if (q->xf_failed.load()) return;
             if (q->xf_closed.load() && q->xf_n_issued.load() <= i) return;
-            sched_yield();
         }
         if (cudaEventSynchronize(q->xf_ev[s]) != cudaSuccess) { q->xf_failed.store(1); return; }
         flbgpu_stream_copy(q->xf_dst + q->xf_off[s], q->xf_ring[s], q->xf_len[s]);
@@ -941,13 +987,12 @@ static void xf_copy_out(bk_q *q, int s)
 static void xf_issue(bk_q *q)
 {
     for (long r = 0;; r++) {
-        while (q->xf_n_pushed.load(std::memory_order_acquire) <= r) {
+        for (bk_backoff b; q->xf_n_pushed.load(std::memory_order_acquire) <= r; b.wait()) {
             if (q->xf_failed.load() || q->xf_push_closed.load()) {
                 if (q->xf_n_pushed.load(std::memory_order_acquire) > r) break;
                 q->xf_closed.store(1);
                 return;
             }
-            sched_yield();
         }
         const int rs = (int) (r % XF_MAX_RANGES);
         const size_t lo = q->xf_lo[rs], hi = q->xf_hi[rs];
@@ -958,7 +1003,7 @@ static void xf_issue(bk_q *q)
             const long i = q->xf_n_issued.load();
             const int s = (int) (i % q->xf_slots);
             const size_t sz = (off + q->xf_slice <= hi) ? q->xf_slice : hi - off;
-            if (i >= q->xf_slots) while (q->xf_done[s].load(std::memory_order_acquire) < i - q->xf_slots) { if (q->xf_failed.load()) break; sched_yield(); }
+            if (i >= q->xf_slots) for (bk_backoff b; q->xf_done[s].load(std::memory_order_acquire) < i - q->xf_slots; b.wait()) if (q->xf_failed.load()) break;
             q->xf_off[s] = off; q->xf_len[s] = sz;
             if (!q->xf_ring[s] && cudaMallocHost((void **) &q->xf_ring[s], q->xf_slice) != cudaSuccess) { q->xf_failed.store(1); break; }
             if (cudaMemcpyAsync(q->xf_ring[s], q->xf_src + off, sz, cudaMemcpyDeviceToHost, q->copy) != cudaSuccess ||
@@ -994,7 +1039,7 @@ int bk_download_push(bk_q *q, size_t lo, size_t hi)
     if (!q->xf_open) return -1;
     if (hi <= lo) return 0;
     const long r = q->xf_n_pushed.load();
-    while (r - q->xf_n_taken.load(std::memory_order_acquire) >= XF_MAX_RANGES) { if (q->xf_failed.load()) return -1; sched_yield(); }
+    for (bk_backoff b; r - q->xf_n_taken.load(std::memory_order_acquire) >= XF_MAX_RANGES; b.wait()) if (q->xf_failed.load()) return -1;
     const int rs = (int) (r % XF_MAX_RANGES);
     for (; q->xf_rev_made <= rs; q->xf_rev_made++) CK(cudaEventCreateWithFlags(&q->xf_rev[q->xf_rev_made], cudaEventDisableTiming));
     CK(cudaEventRecord(q->xf_rev[rs], q->stream));
@@ -1364,6 +1409,61 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     res->end_off = q->h_mail->end_off; res->total = q->h_mail->total; res->n_out = q->h_mail->n_out;
     res->emitted = q->h_mail->emitted;
     memcpy(res->flags, q->h_flags, sizeof(res->flags));
+    return 0;
+}
+
+int bk_comm_unique_id(uint8_t id[128])
+{
+    ncclUniqueId u;
+    if (nccl_load()) return -1;
+    NK(N.GetUniqueId(&u));
+    memcpy(id, u.internal, 128);
+    return 0;
+}
+
+int bk_comm_init(bk_q *q, int nranks, int rank, const uint8_t id[128])
+{
+    ncclUniqueId u;
+    if (nccl_load()) return -1;
+    use(q);
+    if (q->comm) { N.CommDestroy(q->comm); q->comm = 0; }
+    memcpy(u.internal, id, 128);
+    NK(N.CommInitRank(&q->comm, nranks, u, rank));
+    q->comm_ranks = nranks; q->comm_rank = rank;
+    return 0;
+}
+
+int bk_comm_info(bk_q *q, int *nranks, int *rank)
+{
+    if (!q->comm) return -1;
+    *nranks = q->comm_ranks; *rank = q->comm_rank;
+    return 0;
+}
+
+int bk_comm_allgather(bk_q *q, const void *d_send, void *d_recv, size_t bytes_per_rank)
+{
+    use(q);
+    if (!q->comm) { snprintf(g_err, sizeof(g_err), "no communicator: call flbgpu_comm_init first"); return -1; }
+    NK(N.AllGather(d_send, d_recv, bytes_per_rank, ncclUint8, q->comm, q->stream));
+    CK(cudaStreamSynchronize(q->stream));
+    return 0;
+}
+
+int bk_comm_allreduce_u64(bk_q *q, void *d_buf, size_t count)
+{
+    use(q);
+    if (!q->comm) { snprintf(g_err, sizeof(g_err), "no communicator: call flbgpu_comm_init first"); return -1; }
+    NK(N.AllReduce(d_buf, d_buf, count, ncclUint64, ncclSum, q->comm, q->stream));
+    CK(cudaStreamSynchronize(q->stream));
+    return 0;
+}
+
+int bk_comm_allreduce_f64(bk_q *q, void *d_buf, size_t count)
+{
+    use(q);
+    if (!q->comm) { snprintf(g_err, sizeof(g_err), "no communicator: call flbgpu_comm_init first"); return -1; }
+    NK(N.AllReduce(d_buf, d_buf, count, ncclFloat64, ncclSum, q->comm, q->stream));
+    CK(cudaStreamSynchronize(q->stream));
     return 0;
 }
 

@@ -2533,3 +2533,123 @@ int flbgpu_pack_json_state(flbgpu_ctx *ctx, const char *js, size_t len, char **b
     if (flbgpu_pack_json_state_batch(ctx, 1, &js, &len, buffer, size, state, &ret) != 0) return -1;
     return ret;
 }
+
+/* ---- the exchange step of the path: filter_log_to_metrics tables of N shards -> one table ------------
+ * Every rank holds the table of its record range.  The merged table is what the reference's single cmetrics context
+ * would hold for the whole chunk: label sets in first-seen order -- rank-major, since the ranges are consecutive --
+ * counts and cumulative buckets summed (uint64, exact), histogram sums added in double (exact for integer-valued
+ * observations; the order of a floating-point reduction is not the record order), gauges last-writer-wins = the
+ * value of the highest rank that saw the set.  Three collectives over NVLink: an all-gather of the per-rank set
+ * counts, an all-gather of the label keys, ONE all-reduce of the value matrix (two for histograms: uint64 + double). */
+int flbgpu_comm_unique_id(uint8_t id[128]) { g_rt_err[0] = 0; return id ? bk_comm_unique_id(id) : -1; }
+
+int flbgpu_comm_init(flbgpu_ctx *ctx, int nranks, int rank, const uint8_t id[128])
+{
+    g_rt_err[0] = 0;
+    if (!ctx || !id || nranks < 1 || rank < 0 || rank >= nranks) return -1;
+    return bk_comm_init(ctx->q0, nranks, rank, id);
+}
+
+int flbgpu_l2m_allreduce(flbgpu_filter *f)
+{
+    struct l2m_state *st = f ? f->l2m : NULL;
+    bk_q *q;
+    int nranks = 0, rank = 0, r, i, rc = -1;
+    size_t lb, K, maxn = 0, nu = 0, cols, j;
+    uint64_t *h_cnt = NULL, *h_mat = NULL, *d_cnt = NULL, *d_mat = NULL;
+    uint8_t *h_keys = NULL, *h_all = NULL, *d_keys = NULL, *d_all = NULL;
+    double *h_sum = NULL, *d_sum = NULL;
+    struct l2m_set *merged = NULL;
+    size_t *map = NULL;                                   /* local set -> row of the union */
+
+    if (!st) { set_err("not a log_to_metrics filter%s%s", NULL, NULL); return -1; }
+    g_rt_err[0] = 0;
+    q = f->ctx->q0;
+    if (bk_comm_info(q, &nranks, &rank) != 0) { set_err("no communicator: call flbgpu_comm_init first%s%s", NULL, NULL); return -1; }
+    lb = (size_t) (st->n_labels ? st->n_labels : 1) * L2M_LABEL_BYTES;
+    K = 8 + lb;
+    /* 1: how many label sets every rank holds */
+    h_cnt = calloc((size_t) nranks + 1, 8);
+    d_cnt = bk_alloc(q, ((size_t) nranks + 1) * 8);
+    if (!h_cnt || !d_cnt) goto done;
+    h_cnt[nranks] = (uint64_t) st->n_sets;
+    if (bk_h2d(q, d_cnt + nranks, h_cnt + nranks, 8) || bk_sync(q) || bk_comm_allgather(q, d_cnt + nranks, d_cnt, 8) ||
+        bk_d2h(q, h_cnt, d_cnt, (size_t) nranks * 8) || bk_sync(q)) goto done;
+    for (r = 0; r < nranks; r++) if (h_cnt[r] > maxn) maxn = (size_t) h_cnt[r];
+    if (maxn == 0) { rc = 0; goto done; }
+    /* 2: the label keys of every rank, in its first-seen order */
+    h_keys = calloc(maxn, K);
+    h_all = malloc((size_t) nranks * maxn * K);
+    d_keys = bk_alloc(q, maxn * K);
+    d_all = bk_alloc(q, (size_t) nranks * maxn * K);
+    if (!h_keys || !h_all || !d_keys || !d_all) goto done;
+    for (i = 0; i < st->n_sets; i++) { memcpy(h_keys + (size_t) i * K, &st->sets[i].hash, 8); memcpy(h_keys + (size_t) i * K + 8, st->sets[i].labels, lb); }
+    if (bk_h2d(q, d_keys, h_keys, maxn * K) || bk_sync(q) || bk_comm_allgather(q, d_keys, d_all, maxn * K) ||
+        bk_d2h(q, h_all, d_all, (size_t) nranks * maxn * K) || bk_sync(q)) goto done;
+    /* 3: the union, rank-major */
+    merged = calloc((size_t) nranks * maxn, sizeof(*merged));
+    map = calloc((size_t) st->n_sets + 1, sizeof(*map));
+    if (!merged || !map) goto done;
+    for (r = 0; r < nranks; r++) {
+        for (j = 0; j < (size_t) h_cnt[r]; j++) {
+            const uint8_t *k = h_all + ((size_t) r * maxn + j) * K;
+            uint64_t h;
+            size_t u;
+            memcpy(&h, k, 8);
+            for (u = 0; u < nu; u++) if (merged[u].hash == h) break;
+            if (u == nu) {
+                merged[nu].hash = h;
+                merged[nu].labels = malloc(lb);
+                merged[nu].buckets = calloc((size_t) st->n_buckets + 1, sizeof(uint64_t));
+                if (!merged[nu].labels || !merged[nu].buckets) goto done;
+                memcpy(merged[nu].labels, k + 8, lb);
+                nu++;
+            }
+            if (r == rank) map[j] = u;
+        }
+    }
+    /* 4: the values */
+    cols = st->mode == L2M_GAUGE ? 1 + 2 * (size_t) nranks : 1 + (size_t) st->n_buckets + 1;
+    h_mat = calloc(nu * cols, 8);
+    d_mat = bk_alloc(q, nu * cols * 8);
+    if (!h_mat || !d_mat) goto done;
+    for (i = 0; i < st->n_sets; i++) {
+        uint64_t *row = h_mat + map[i] * cols;
+        row[0] = st->sets[i].count;
+        if (st->mode == L2M_GAUGE) { row[1 + 2 * (size_t) rank] = 1; memcpy(&row[2 + 2 * (size_t) rank], &st->sets[i].sum, 8); }
+        else memcpy(row + 1, st->sets[i].buckets, ((size_t) st->n_buckets + 1) * 8);
+    }
+    if (bk_h2d(q, d_mat, h_mat, nu * cols * 8) || bk_sync(q) || bk_comm_allreduce_u64(q, d_mat, nu * cols) ||
+        bk_d2h(q, h_mat, d_mat, nu * cols * 8) || bk_sync(q)) goto done;
+    if (st->mode != L2M_GAUGE) {
+        h_sum = calloc(nu, 8);
+        d_sum = bk_alloc(q, nu * 8);
+        if (!h_sum || !d_sum) goto done;
+        for (i = 0; i < st->n_sets; i++) h_sum[map[i]] = st->sets[i].sum;
+        if (bk_h2d(q, d_sum, h_sum, nu * 8) || bk_sync(q) || bk_comm_allreduce_f64(q, d_sum, nu) ||
+            bk_d2h(q, h_sum, d_sum, nu * 8) || bk_sync(q)) goto done;
+    }
+    /* 5: this rank's table becomes the merged one */
+    for (j = 0; j < nu; j++) {
+        const uint64_t *row = h_mat + j * cols;
+        merged[j].count = row[0];
+        if (st->mode == L2M_GAUGE) {
+            for (r = nranks - 1; r >= 0; r--) if (row[1 + 2 * (size_t) r]) { memcpy(&merged[j].sum, &row[2 + 2 * (size_t) r], 8); break; }
+        }
+        else {
+            memcpy(merged[j].buckets, row + 1, ((size_t) st->n_buckets + 1) * 8);
+            merged[j].sum = h_sum[j];
+        }
+    }
+    for (i = 0; i < st->n_sets; i++) { free(st->sets[i].labels); free(st->sets[i].buckets); }
+    free(st->sets);
+    st->sets = merged; st->n_sets = (int) nu; st->cap_sets = (int) ((size_t) nranks * maxn);
+    merged = NULL;
+    rc = 0;
+done:
+    if (merged) { for (j = 0; j < nu + 1 && j < (size_t) nranks * maxn; j++) { free(merged[j].labels); free(merged[j].buckets); } free(merged); }
+    if (rc != 0 && !g_rt_err[0]) set_err("metric-table exchange failed: %s%s", bk_last_error(), NULL);
+    bk_free(q, d_cnt); bk_free(q, d_mat); bk_free(q, d_keys); bk_free(q, d_all); bk_free(q, d_sum);
+    free(h_cnt); free(h_mat); free(h_keys); free(h_all); free(h_sum); free(map);
+    return rc;
+}

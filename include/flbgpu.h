@@ -168,8 +168,7 @@ void *flbgpu_chain_stream(flbgpu_chain *c);
  * The filter ("log_to_metrics": metric_mode counter | gauge | histogram, Regex/Exclude gates, label_field /
  * add_label, kubernetes_mode, bucket, discard_logs) accumulates into a per-instance table, like ctx->cmt in
  * plugins/filter_log_to_metrics/log_to_metrics.c:964-1148 (cmt_counter_inc / cmt_gauge_set / cmt_histogram_observe).
- * Label sets keep first-seen order.  A multi-GPU deployment sums these tables with one
- * NCCL all-reduce at flush time (bench.py / tests show the exchange with torch.distributed). */
+ * Label sets keep first-seen order.  A multi-GPU deployment merges these tables with flbgpu_l2m_allreduce() below. */
 int   flbgpu_l2m_info(flbgpu_filter *f, int *mode, int *n_labels, int *n_buckets, int *n_sets);
 /* label set i: 64-bit key, counter value (or histogram count), histogram sum (gauge: the value), cumulative buckets
  * [n_buckets + 1] (last = +Inf), labels = n_labels x 256 bytes (length byte + bytes) */
@@ -177,6 +176,17 @@ int   flbgpu_l2m_get(flbgpu_filter *f, int i, uint64_t *hash, uint64_t *count, d
 int   flbgpu_l2m_reset(flbgpu_filter *f);
 int   flbgpu_l2m_put(flbgpu_filter *f, uint64_t hash, uint64_t count, double sum, const uint64_t *buckets, const char *labels);
 char *flbgpu_l2m_text(flbgpu_filter *f);       /* malloc()ed text dump, free() it */
+
+/* The one exchange step of the path: with one process per GPU, every rank's filter instance holds the table of
+ * its record range; flbgpu_l2m_allreduce() leaves on every rank the table cmetrics would hold for the whole input --
+ * label sets in first-seen (rank-major) order, counts and buckets summed, gauges from the highest rank that saw the set
+ * (lib/cmetrics/src/cmt_cat.c:1032 is the reference's own merge of two contexts).  NCCL over NVLink: an all-gather of the
+ * set counts, an all-gather of the label keys, one all-reduce of the value matrix.  The communicator belongs to the context:
+ * rank 0 makes the id (ncclGetUniqueId), the embedding process carries the 128 bytes to the other ranks (the engine's
+ * own control channel; bench.py uses torch.distributed), every rank calls flbgpu_comm_init.  libnccl is opened at run time. */
+int flbgpu_comm_unique_id(uint8_t id[128]);
+int flbgpu_comm_init(flbgpu_ctx *ctx, int nranks, int rank, const uint8_t id[128]);
+int flbgpu_l2m_allreduce(flbgpu_filter *f);
 
 /* CUDA-event milliseconds of the three kernel groups of the most recent chain call on this
  * context: out[0] record index, out[1] evaluation pass (the regex/interpreter kernel),

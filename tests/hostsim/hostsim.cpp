@@ -76,7 +76,8 @@ int sim_rx_search(void *h, const char *s, int len, int *caps, int stack_words, u
 static thread_local char hs_err[256];
 static uint64_t hs_launches;
 
-struct bk_q { int device; uint64_t records_out; uint8_t *dl_dst; const uint8_t *dl_src; };
+struct sim_comm;
+struct bk_q { int device; uint64_t records_out; uint8_t *dl_dst; const uint8_t *dl_src; struct sim_comm *comm; int comm_ranks, comm_rank; };
 
 extern "C" {
 
@@ -291,6 +292,75 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     memcpy(res->flags, a->d_flags, sizeof(res->flags));
     return 0;
 }
+/* ---- the collectives of the metric-table exchange between PROCESSES on this host, through a POSIX shared-memory
+ * segment named by the "unique id" (test infrastructure for the world-size-2 CPU tests of the product's merge logic) ---- */
+}
+#include <atomic>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <unistd.h>
+#include <sched.h>
+#define SIM_SLOT ((size_t) 8 << 20)
+struct sim_comm { std::atomic<int> arrived; std::atomic<int> phase; char pad[56]; };
+static void sim_barrier(bk_q *q)
+{
+    struct sim_comm *c = q->comm;
+    const int ph = c->phase.load();
+    if (c->arrived.fetch_add(1) + 1 == q->comm_ranks) { c->arrived.store(0); c->phase.store(ph + 1); }
+    else while (c->phase.load() == ph) sched_yield();
+}
+static uint8_t *sim_slot(bk_q *q, int r) { return (uint8_t *) q->comm + 4096 + (size_t) r * SIM_SLOT; }
+extern "C" {
+int bk_comm_unique_id(uint8_t id[128])
+{
+    static int n;
+    memset(id, 0, 128);
+    snprintf((char *) id, 128, "/flbgpu_sim_%d_%d", (int) getpid(), n++);
+    return 0;
+}
+int bk_comm_init(bk_q *q, int nranks, int rank, const uint8_t id[128])
+{
+    const size_t size = 4096 + (size_t) nranks * SIM_SLOT;
+    int fd = shm_open((const char *) id, O_CREAT | O_RDWR, 0600);
+    void *m;
+    if (fd < 0 || ftruncate(fd, (off_t) size) != 0) { snprintf(hs_err, sizeof(hs_err), "shm_open(%s) failed", (const char *) id); return -1; }
+    m = mmap(0, size, PROT_READ | PROT_WRITE, MAP_SHARED, fd, 0);
+    close(fd);
+    if (m == MAP_FAILED) return -1;
+    q->comm = (struct sim_comm *) m; q->comm_ranks = nranks; q->comm_rank = rank;
+    sim_barrier(q);
+    if (rank == 0) shm_unlink((const char *) id);
+    return 0;
+}
+int bk_comm_info(bk_q *q, int *nranks, int *rank) { if (!q->comm) return -1; *nranks = q->comm_ranks; *rank = q->comm_rank; return 0; }
+int bk_comm_allgather(bk_q *q, const void *d_send, void *d_recv, size_t n)
+{
+    if (!q->comm || n > SIM_SLOT) return -1;
+    memcpy(sim_slot(q, q->comm_rank), d_send, n);
+    sim_barrier(q);
+    for (int r = 0; r < q->comm_ranks; r++) memcpy((uint8_t *) d_recv + (size_t) r * n, sim_slot(q, r), n);
+    sim_barrier(q);
+    return 0;
+}
+int bk_comm_allreduce_u64(bk_q *q, void *d_buf, size_t count)
+{
+    if (!q->comm || count * 8 > SIM_SLOT) return -1;
+    memcpy(sim_slot(q, q->comm_rank), d_buf, count * 8);
+    sim_barrier(q);
+    for (size_t i = 0; i < count; i++) { uint64_t v = 0; for (int r = 0; r < q->comm_ranks; r++) v += ((const uint64_t *) sim_slot(q, r))[i]; ((uint64_t *) d_buf)[i] = v; }
+    sim_barrier(q);
+    return 0;
+}
+int bk_comm_allreduce_f64(bk_q *q, void *d_buf, size_t count)
+{
+    if (!q->comm || count * 8 > SIM_SLOT) return -1;
+    memcpy(sim_slot(q, q->comm_rank), d_buf, count * 8);
+    sim_barrier(q);
+    for (size_t i = 0; i < count; i++) { double v = 0; for (int r = 0; r < q->comm_ranks; r++) v += ((const double *) sim_slot(q, r))[i]; ((double *) d_buf)[i] = v; }
+    sim_barrier(q);
+    return 0;
+}
+
 int bk_jsmn_scan(bk_q *, const struct bk_jsmn_args *a)
 {
     for (uint32_t i = 0; i < a->n; i++) {
