@@ -368,7 +368,7 @@ class Workload:
 
     def exchange(self):
         if self.wl == "l2m" and self.world > 1:
-            self.filters[0].l2m_allreduce()          # the one exchange of the path: metric tables over NCCL
+            self.filters[0].l2m_allreduce_lib()      # the one exchange of the path: flbgpu_l2m_allreduce(), NCCL inside the library
             self.L.flbgpu_l2m_reset(self.filters[0].h)    # "flushed": the next interval starts from zero
 
     # ---- device-resident
@@ -551,6 +551,12 @@ def run_ours(args):
 
     L = pkg.load()                                  # raises if the CUDA library is missing
     ctx = pkg.Context(local, lib=L)
+    if world > 1:
+        # the library's own communicator for the metric-table exchange: rank 0 makes the id, torch.distributed (the
+        # embedding process's control channel) carries the 128 bytes
+        box = [ctx.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        ctx.comm_init(world, rank, box[0])
     WL = args.workload
     m = measure(args, WL, L, ctx, torch, dist, rank, world, local, full=True)
     others = {}
@@ -631,7 +637,7 @@ def run_ours(args):
             d["e2e_variants"] = mm["variants"]
         if name == "l2m":
             d["scaling"] = "strong"
-            d["collective"] = "metric tables all-reduced over NCCL every step" if world > 1 else "single GPU: no exchange"
+            d["collective"] = "flbgpu_l2m_allreduce(): the library's own NCCL exchange of the metric tables, every step" if world > 1 else "single GPU: no exchange"
         return d
 
     line = {

@@ -150,3 +150,73 @@ def test_l2m_allreduce_world2(case, sim_lib, ref_available, tmp_path):
         assert p.wait(timeout=300) == 0
     for r in range(2):
         assert open(out + str(r)).read() == want
+
+
+LIB_WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r}); sys.path.insert(0, os.path.join({root!r}, "tests"))
+import util, l2m_cases
+pkg = util.pkg
+rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+gpu = {gpu!r}
+name, parsers, filters, mk, k = [c for c in l2m_cases.L2M_CASES if c[0] == {case!r}][0]
+chunk = mk()
+recs = util.split_records(chunk)
+per = (len(recs) + world - 1) // world
+mine = recs[rank * per:(rank + 1) * per]
+shard = chunk[mine[0][0]: mine[-1][0] + mine[-1][1]]
+lib = pkg.load() if gpu else pkg.load(util.HOSTSIM_SO)
+ctx = pkg.Context(rank if gpu else 0, lib=lib)
+# the 128-byte communicator id travels over the embedding process's own channel: here a file
+idf = {out!r} + ".id"
+if rank == 0:
+    uid = ctx.comm_unique_id()
+    open(idf + ".tmp", "wb").write(uid); os.rename(idf + ".tmp", idf)
+else:
+    import time
+    while not os.path.exists(idf):
+        time.sleep(0.01)
+    uid = open(idf, "rb").read()
+ctx.comm_init(world, rank, uid)
+for kw in parsers:
+    ctx.parser(**kw)
+fs = [ctx.filter(p, props) for p, props in filters]
+ctx.chain(fs).do(shard)
+fs[k].l2m_allreduce_lib()              # flbgpu_l2m_allreduce(): the library's own exchange
+open({out!r} + str(rank), "w").write(fs[k].l2m_text())
+"""
+
+
+def _lib_allreduce(case, tmp_path, gpu):
+    name, parsers, filters, mk, k = [c for c in l2m_cases.L2M_CASES if c[0] == case][0]
+    ref = util.Ref()
+    for kw in parsers:
+        ref.parser(**kw)
+    rfs = [ref.filter(p, props) for p, props in filters]
+    ref.chain_do(mk())
+    want = ref_text(ref, rfs[k])
+    out = str(tmp_path / "t")
+    script = tmp_path / "w.py"
+    script.write_text(LIB_WORKER.format(root=util.ROOT, case=case, out=out, gpu=gpu))
+    env = dict(os.environ, WORLD_SIZE="2")
+    procs = [subprocess.Popen([sys.executable, str(script)], env=dict(env, RANK=str(r))) for r in range(2)]
+    for p in procs:
+        assert p.wait(timeout=300) == 0
+    for r in range(2):
+        assert open(out + str(r)).read() == want
+
+
+@pytest.mark.parametrize("case", ["counter_labels", "histogram_default_buckets", "after_parser_and_grep", "gauge_labels", "counter_no_labels"])
+def test_l2m_library_allreduce_world2(case, sim_lib, ref_available, tmp_path):
+    """flbgpu_l2m_allreduce() -- the merge logic of the PRODUCT library (runtime.c), two processes; the collectives
+    underneath are the CPU emulation's (shared memory) here and NCCL on the GPU box"""
+    _lib_allreduce(case, tmp_path, gpu=False)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", ["counter_labels", "histogram_default_buckets", "gauge_labels"])
+def test_l2m_library_allreduce_nccl(case, gpu_lib, ref_available, tmp_path):
+    """the same over NCCL: needs two GPUs"""
+    if gpu_lib.flbgpu_device_count() < 2:
+        pytest.skip("one GPU: the NCCL exchange needs two")
+    _lib_allreduce(case, tmp_path, gpu=True)
