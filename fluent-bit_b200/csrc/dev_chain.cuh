@@ -64,6 +64,8 @@ struct ch_env {
     uint32_t cap_n;           /* records per column */
     int64_t now;
     uint32_t assume;          /* bit k: filter k is chunk-level MODIFIED */
+    uint32_t bsync;           /* evaluation pass: block-wide barrier at every filter boundary, so that the warps of a block run the
+                                 same phase of the interpreter at the same time (instruction-cache working set = one phase) */
     uint32_t active;          /* bit k: filter k is routed this chunk (Match / Match_Regex), else skipped like flb_filter_do() does */
     uint32_t *fl_flags;       /* [n_filters] CHF_* evidence (evaluation pass only) */
     uint32_t *err;            /* FLBGPU_E_* */
@@ -448,6 +450,7 @@ FLB_HDN int rx_run(const struct ch_env *e, uint32_t rx_off, const uint8_t *s, ui
     int r = rx_search((const struct rx_prog *) (e->blob + rx_off), s, (int) n, caps, stk, CH_RX_STACK, &budget);
     if (r == RX_R_ESTACK) { CH_ATOMIC_OR(e->err, FLBGPU_E_RXSTACK); return 0; }
     if (r == RX_R_EBUDGET) { CH_ATOMIC_OR(e->err, FLBGPU_E_RXBUDGET); return 0; }
+    if (r == RX_R_EUNICODE) { CH_ATOMIC_OR(e->err, FLBGPU_E_RXUNICODE); return 0; }
     return r == RX_R_MATCH;
 }
 
@@ -837,8 +840,10 @@ FLB_HDN int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32
 
 #ifdef __CUDA_ARCH__
 #define CH_SYNC() __syncwarp()
+#define CH_BSYNC(e) do { if (!EMIT && (e)->bsync) __syncthreads(); } while (0)
 #else
 #define CH_SYNC()
+#define CH_BSYNC(e)
 #endif
 
 #ifdef __CUDA_ARCH__
@@ -1908,6 +1913,7 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
         const uint8_t *cfg = e->blob + f[k].cfg_off;
         int assumed = (e->assume >> k) & 1;
         if (!((e->active >> k) & 1)) continue;
+        CH_BSYNC(e);
         CH_SYNC();
         switch (f[k].kind) {
         case FLBGPU_F_PARSER:

@@ -415,6 +415,7 @@ FLB_HD int rx_search(const struct rx_prog *pg, const uint8_t *s, int len, int *c
 {
     int st = 0, ncap = 2 * ((int) pg->n_groups + 1), i, r;
     for (i = 0; i < ncap; i++) caps[i] = -1;
+    if (pg->flags & RX_F_ASCII_ONLY) { for (i = 0; i < len; i++) if (s[i] >= 0x80) return RX_R_EUNICODE; }
     for (;;) {
         int ok = 1;
         if ((pg->flags & RX_F_ANCHOR_BUF) && st > 0) return RX_R_NOMATCH;

@@ -71,6 +71,9 @@ struct rx_class {
 #define RX_F_ANCHOR_BUF   2u   /* every match starts at offset 0       */
 #define RX_F_HAS_FIRSTSET 4u   /* first[] is a sound first-byte filter */
 #define RX_F_NULLABLE     8u   /* the pattern can match the empty string */
+#define RX_F_ASCII_ONLY  16u   /* the pattern uses a construct whose non-ASCII behaviour is not restated (POSIX bracket, \b \B,
+                                  case-insensitive matching: Onigmo consults its Unicode tables there): a subject with a byte >= 0x80
+                                  is refused loudly (RX_R_EUNICODE), never matched approximately */
 
 struct rx_prog {
     uint32_t total_bytes;  /* size of this program incl. header, code, classes, ranges */
@@ -89,6 +92,7 @@ struct rx_prog {
 #define RX_R_MATCH     1
 #define RX_R_ESTACK   -2   /* backtrack stack exhausted: rerun with a bigger stack */
 #define RX_R_EBUDGET  -3   /* step budget exhausted (catastrophic backtracking guard) */
+#define RX_R_EUNICODE -4   /* RX_F_ASCII_ONLY pattern met a non-ASCII subject */
 
 
 /* ------------------------------------------------------- chain program */
@@ -235,6 +239,7 @@ struct chain_hdr {
 #define FLBGPU_E_INDEX    16u   /* record index fast path failed */
 #define FLBGPU_E_ESCAPE   32u   /* logfmt escapes met without a scratch region (cannot happen through the C ABI) */
 #define FLBGPU_E_L2M      64u   /* log_to_metrics: label table full / float label / unparsable value */
+#define FLBGPU_E_RXUNICODE 128u /* a pattern with POSIX brackets / \b / case-insensitivity met a non-ASCII subject */
 
 /* ---------------------------------------------------- streaming JSON packer (dev_jsmn.cuh) */
 enum { JM_UNDEFINED = 0, JM_OBJECT = 1, JM_ARRAY = 2, JM_STRING = 4, JM_PRIMITIVE = 8 };     /* jsmntype_t, lib/jsmn/jsmn.h */

@@ -328,11 +328,11 @@ struct k_chain_params {
  * chunk, so the warp first copies their bytes to its own slice of shared memory with coalesced 128-bit
  * loads and the lanes then scan from there; `in` is rebased so that input offsets keep their meaning.
  * A warp whose records span more than its slice reads global memory as before. */
-__global__ void __launch_bounds__(BK_REC_BLOCK, BK_EVAL_MIN_BLOCKS) k_chain_eval(const k_chain_params p)
+__global__ void __launch_bounds__(1024, 1) k_chain_eval(const k_chain_params p)       /* 64 registers per lane; block size chosen at launch */
 {
     extern __shared__ __align__(16) uint8_t dsm[];
     const uint32_t n_rec = p.n_dev ? *p.n_dev : p.n_rec;
-    const uint32_t i = p.r0 + blockIdx.x * BK_REC_BLOCK + threadIdx.x;
+    const uint32_t i = p.r0 + blockIdx.x * blockDim.x + threadIdx.x;
     const bool valid = i < n_rec;
     const uint32_t my_off = valid ? p.off[i] : 0, my_len = valid ? p.len[i] : 0;
     const bool live = valid && p.kind[i] == 0;
@@ -615,6 +615,7 @@ struct bk_q {
     uint8_t *h_sin, *h_sout; size_t cap_sin, cap_sout;    /* small form: pinned staging for the chunk and its result */
     cudaEvent_t ev_small;
     int stage_kb;
+    int eval_block, eval_bsync;            /* FLBGPU_EVAL_BLOCK (threads per evaluation block), FLBGPU_EVAL_BSYNC (block-wide phase barriers) */
     /* upload */
     cudaEvent_t up_ev[UP_MAX_EV]; int up_ev_made;
     size_t up_total, up_piece; int up_active, up_staged;
@@ -810,10 +811,16 @@ static int q_setup(bk_q *q)
     CK(cudaMallocHost((void **) &q->h_mail, sizeof(struct bk_mail)));
     CK(cudaMallocHost((void **) &q->h_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)));
     {
+        const char *eb = getenv("FLBGPU_EVAL_BLOCK"), *es = getenv("FLBGPU_EVAL_BSYNC");
+        q->eval_block = eb ? atoi(eb) : (int) BK_REC_BLOCK;
+        if (q->eval_block != 128 && q->eval_block != 256 && q->eval_block != 512 && q->eval_block != 1024) q->eval_block = (int) BK_REC_BLOCK;
+        q->eval_bsync = es && es[0] == '1';
+    }
+    {
         const char *e = getenv("FLBGPU_STAGE_KB");           /* KiB of shared memory per warp, 0 = off */
         q->stage_kb = e ? atoi(e) : 0;
         if (q->stage_kb < 0 || q->stage_kb > 24) q->stage_kb = 0;
-        if (q->stage_kb) CK(cudaFuncSetAttribute(k_chain_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, q->stage_kb * 1024 * (BK_REC_BLOCK / 32)));
+        if (q->stage_kb) CK(cudaFuncSetAttribute(k_chain_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, q->stage_kb * 1024 * (q->eval_block / 32)));
     }
     return 0;
 }
@@ -1169,7 +1176,7 @@ static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_
     p->env.assume = a->assume; p->env.active = a->active; p->env.fl_flags = a->d_flags; p->env.err = a->d_flags + FLBGPU_MAX_FILTERS;
     p->env.l2m = a->l2m; p->env.prep = a->d_prep;
     p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->r0 = r0; p->n_rec = a->n_rec; p->stage_bytes = 0;
-    p->n_dev = 0;
+    p->n_dev = 0; p->env.bsync = 0;
     p->size = a->d_size; p->bsum = a->d_bsum; p->out = d_out;
 }
 
@@ -1215,8 +1222,9 @@ int bk_chain_eval(bk_q *q, const struct bk_chain_args *a, uint32_t r0, uint32_t 
     fill_params(a, &p, 0, r0);
     p.n_rec = r1;
     p.stage_bytes = (uint32_t) q->stage_kb * 1024;
+    p.env.bsync = (uint32_t) q->eval_bsync;
     ev_begin_on(q, 1, q->stream);
-    k_chain_eval<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, (size_t) p.stage_bytes * (BK_REC_BLOCK / 32), q->stream>>>(p);
+    k_chain_eval<<<(r1 - r0 + q->eval_block - 1) / q->eval_block, q->eval_block, (size_t) p.stage_bytes * (q->eval_block / 32), q->stream>>>(p);
     if (p.env.l2m.hash) {
         k_chain_skipped<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, 0, q->stream>>>(p);
         g_launches += 1;
@@ -1388,7 +1396,7 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     p.n_rec = 0; p.n_dev = &m->n_valid;
     p.stage_bytes = (uint32_t) q->stage_kb * 1024;
     ev_begin_on(q, 1, st);
-    k_chain_eval<<<nb_cap, BK_REC_BLOCK, (size_t) p.stage_bytes * (BK_REC_BLOCK / 32), st>>>(p);
+    k_chain_eval<<<nb_cap, BK_REC_BLOCK, (size_t) p.stage_bytes * (BK_REC_BLOCK / 32), st>>>(p);     /* (no block barriers in the small form) */
     if (p.env.l2m.hash) { k_chain_skipped<<<nb_cap, BK_REC_BLOCK, 0, st>>>(p); g_launches += 1; }
     ev_end_on(q, 1, st);
     /* sizes, survivor lists, emission under the speculated verdicts */

@@ -1649,7 +1649,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         if (h_flags[FLBGPU_MAX_FILTERS]) {
             c->st.error_bits = h_flags[FLBGPU_MAX_FILTERS];
             snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
-                     "1=too many keys 2=regex stack 4=regex budget 8=float text not restated (hex float, nan(payload)) 32=logfmt escapes 64=log_to_metrics value/label outside the device path)",
+                     "1=too many keys 2=regex stack 4=regex budget 8=float text not restated (hex float, nan(payload)) 32=logfmt escapes 64=log_to_metrics value/label outside the device path 128=a pattern with POSIX brackets, \\b or case-insensitivity met a non-ASCII value)",
                      h_flags[FLBGPU_MAX_FILTERS]);
             return -1;
         }
@@ -1895,7 +1895,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
     if (h_flags[FLBGPU_MAX_FILTERS]) {
         c->st.error_bits = h_flags[FLBGPU_MAX_FILTERS];
         snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
-                 "1=too many keys 2=regex stack 4=regex budget 8=float text not restated (hex float, nan(payload)) 32=logfmt escapes 64=log_to_metrics value/label outside the device path)",
+                 "1=too many keys 2=regex stack 4=regex budget 8=float text not restated (hex float, nan(payload)) 32=logfmt escapes 64=log_to_metrics value/label outside the device path 128=a pattern with POSIX brackets, \\b or case-insensitivity met a non-ASCII value)",
                  h_flags[FLBGPU_MAX_FILTERS]);
         goto fail;
     }
@@ -2007,7 +2007,7 @@ static int chain_run_small(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, v
     if (res.flags[FLBGPU_MAX_FILTERS]) {
         c->st.error_bits = res.flags[FLBGPU_MAX_FILTERS];
         snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
-                 "1=too many keys 2=regex stack 4=regex budget 8=float text not restated (hex float, nan(payload)) 32=logfmt escapes 64=log_to_metrics value/label outside the device path)",
+                 "1=too many keys 2=regex stack 4=regex budget 8=float text not restated (hex float, nan(payload)) 32=logfmt escapes 64=log_to_metrics value/label outside the device path 128=a pattern with POSIX brackets, \\b or case-insensitivity met a non-ASCII value)",
                  res.flags[FLBGPU_MAX_FILTERS]);
         return -1;
     }

@@ -140,6 +140,7 @@ struct node {
 struct comp {
     const unsigned char *p, *end;
     int icase, dotall, extend;
+    int ascii_only;         /* a construct whose non-ASCII behaviour is approximated was used */
     int has_named;
     int n_groups;
     struct rx_compiled *out;
@@ -252,6 +253,7 @@ static void add_ctype(struct cset *dst, int esc)
 
 static int posix_bracket(struct comp *c, struct cset *dst)
 {
+    c->ascii_only = 1;
     /* at "[:" ; returns 1 if consumed */
     static const char *names[] = { "alnum", "alpha", "ascii", "blank", "cntrl", "digit", "graph",
                                    "lower", "print", "punct", "space", "upper", "xdigit", "word", NULL };
@@ -364,6 +366,7 @@ static void add_cp_icase(struct comp *c, struct cset *s, uint32_t lo, uint32_t h
     uint32_t ch;
     cset_add_range(s, lo, hi);
     if (!c->icase) return;
+    c->ascii_only = 1;            /* Onigmo folds through its Unicode tables (multi-character folds included): ASCII subjects only */
     for (ch = lo; ch <= hi && ch < 128; ch++) {
         if (ch >= 'a' && ch <= 'z') cset_add_range(s, ch - 32, ch - 32);
         if (ch >= 'A' && ch <= 'Z') cset_add_range(s, ch + 32, ch + 32);
@@ -467,6 +470,7 @@ static struct node *lit_node(struct comp *c, uint32_t cp)
         n->cls = add_set(c, &s);
         return n;
     }
+    if (c->icase && cp >= 0x80) c->ascii_only = 1;      /* its case partners are not restated */
     n = mk(c, N_LIT);
     n->cp = cp;
     return n;
@@ -676,8 +680,8 @@ static struct node *parse_atom(struct comp *c)
         case 'A': c->p++; n = mk(c, N_ANCHOR); n->anchor = RX_BEGIN_BUF; return n;
         case 'z': c->p++; n = mk(c, N_ANCHOR); n->anchor = RX_END_BUF; return n;
         case 'Z': c->p++; n = mk(c, N_ANCHOR); n->anchor = RX_SEMI_END_BUF; return n;
-        case 'b': c->p++; n = mk(c, N_ANCHOR); n->anchor = RX_WORD_B; return n;
-        case 'B': c->p++; n = mk(c, N_ANCHOR); n->anchor = RX_NOT_WORD_B; return n;
+        case 'b': c->p++; n = mk(c, N_ANCHOR); n->anchor = RX_WORD_B; c->ascii_only = 1; return n;
+        case 'B': c->p++; n = mk(c, N_ANCHOR); n->anchor = RX_NOT_WORD_B; c->ascii_only = 1; return n;
         case 'G': fail(c, "\\G is not supported");
         case 'K': fail(c, "\\K is not supported");
         case 'R': fail(c, "\\R is not supported");
@@ -1311,6 +1315,7 @@ int rx_compile(const char *pattern, struct rx_compiled *out)
             r = first_of(&c, root, &ff, 0);
             if (r & 1) pg->flags |= RX_F_NULLABLE;
             else { pg->flags |= RX_F_HAS_FIRSTSET; memcpy(pg->first, ff.b, sizeof(ff.b)); }
+            if (c.ascii_only) pg->flags |= RX_F_ASCII_ONLY;
             la = leading_anchor(root);
             if (la == RX_BOL) pg->flags |= RX_F_ANCHOR_BOL;
             if (la == RX_BEGIN_BUF) pg->flags |= RX_F_ANCHOR_BUF;

@@ -170,3 +170,30 @@ def test_fused_match_routing_hostsim(sim_lib, ref_available):
 @pytest.mark.gpu
 def test_fused_match_routing_gpu(gpu_lib, ref_available):
     _fused_match(gpu_lib)
+
+
+def _ascii_only_patterns(lib):
+    """POSIX brackets, \\b / \\B and case-insensitive matching consult Onigmo's Unicode tables for non-ASCII subjects; those are
+    not restated, so such a pattern meeting a non-ASCII value fails the call loudly instead of matching approximately"""
+    ascii_chunk = util.chunk_from_lines([b"GET /a cafe", b"post /b CAFE", b"x"])
+    uni_chunk = util.chunk_from_lines([b"GET /a caf\xc3\xa9", b"post /b CAF\xc3\x89"])
+    for rule in ("log /caf/i", "log \\bGET\\b", "log [[:alpha:]]+ /", "log (?i)post"):
+        filters = [("grep", [("Regex", rule)])]
+        ctx = pkg.Context(0, lib=lib)
+        chain = ctx.chain([ctx.filter(p, props) for p, props in filters])
+        assert chain.do(ascii_chunk) == _ref_result([], filters, ascii_chunk), rule
+        with pytest.raises(pkg.FlbGpuError, match="non-ASCII"):
+            chain.do(uni_chunk)
+    # a pattern without such constructs takes non-ASCII subjects as before
+    filters = [("grep", [("Regex", "log caf.$")])]
+    ctx = pkg.Context(0, lib=lib)
+    assert ctx.chain([ctx.filter(p, props) for p, props in filters]).do(uni_chunk) == _ref_result([], filters, uni_chunk)
+
+
+def test_ascii_only_patterns_hostsim(sim_lib, ref_available):
+    _ascii_only_patterns(sim_lib)
+
+
+@pytest.mark.gpu
+def test_ascii_only_patterns_gpu(gpu_lib, ref_available):
+    _ascii_only_patterns(gpu_lib)
