@@ -672,6 +672,8 @@ def run_ours(args):
 
 
 def main():
+    # whatever NCCL has to say (a version banner under NCCL_DEBUG=VERSION, its INFO log) goes to stderr: stdout carries the one JSON line
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)

@@ -70,6 +70,12 @@ struct ch_env {
     uint32_t *fl_flags;       /* [n_filters] CHF_* evidence (evaluation pass only) */
     uint32_t *err;            /* FLBGPU_E_* */
     struct l2m_table l2m;     /* log_to_metrics delta table of this call (hash == NULL: none) */
+    /* Stage 1 of the JSON tokenizer (k_chain_eval): one bit per input byte of the warp's byte range, set where a string
+     * scan has to look -- '"', '\\', a control byte or a byte >= 0x80.  Built cooperatively by the warp with coalesced
+     * 128-bit loads into shared memory; the per-lane walker (djf_record_bm) then finds the end of a plain string with a
+     * bit scan instead of a byte loop.  NULL: no bitmap (emission pass, ranges that do not fit, other parsers). */
+    const uint32_t *bm;
+    uint32_t bm_base, bm_end; /* input offsets covered: [bm_base, bm_end) */
     int32_t *prep;            /* parser report (flbgpu_parser_do): 6 ints per record -- parsed flag, position consumed,
                                  seconds lo / hi, nanoseconds, spare -- or NULL */
 };
@@ -1156,6 +1162,118 @@ FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t 
     return 1;
 }
 
+/* first input offset >= p_abs inside the bitmap's range whose byte is '"', '\\', < 0x20 or >= 0x80; bm_end if none */
+FLB_HD uint32_t djf_bm_next(const struct ch_env *e, uint32_t p_abs)
+{
+    uint32_t rel = p_abs - e->bm_base, w = rel >> 5;
+    const uint32_t nw = (e->bm_end - e->bm_base + 31u) >> 5;
+    uint32_t m;
+    if (p_abs >= e->bm_end) return e->bm_end;
+    m = e->bm[w] & (0xffffffffu << (rel & 31u));
+    while (!m) { if (++w >= nw) return e->bm_end; m = e->bm[w]; }
+#ifdef __CUDA_ARCH__
+    rel = (w << 5) + (uint32_t) (__ffs((int) m) - 1);
+#else
+    rel = (w << 5) + (uint32_t) __builtin_ctz(m);
+#endif
+    return e->bm_base + rel;
+}
+
+/* Stage 2 over the stage-1 bitmap: the flat object of a log line -- string keys, values that are plain strings, integers of
+ * up to 18 digits, short decimals, true / false / null -- one O(1) step per token.  Same answers as djf_record() on what it
+ * accepts (1 + fields, or 0 "not an object"); -2 = something else is in the line (escapes, non-ASCII, nesting, exponents, white
+ * space in odd places ...): djf_record() decides.  val_off is the input offset of s[0]. */
+FLB_HD int djf_record_bm(const struct ch_env *e, const uint8_t *s, int n, uint32_t val_off, ref_t *ok_, ref_t *ov_, uint32_t *th, int *on)
+{
+    uint8_t *scr = e->scr;
+    uint32_t k = 0;
+    int p = 0, cnt = 0, state = 0;             /* 0 running, 1 finished, <0 verdict */
+    if (!scr || val_off < e->bm_base || val_off + (uint32_t) n > e->bm_end) return -2;
+    while (p < n && dj_ws(s[p])) p++;
+    if (p >= n || s[p] != '{') return 0;
+    p++;
+    if (p < n && s[p] == '}') { p++; state = 1; }
+#ifdef __CUDA_ARCH__
+    const unsigned wm = __activemask();
+#endif
+    for (;;) {
+#ifdef __CUDA_ARCH__
+        if (!__any_sync(wm, state == 0)) break;    /* the lanes that came in together leave together: one member per round */
+        if (state != 0) continue;
+#else
+        if (state != 0) break;
+#endif
+        {
+            ref_t keyref, valref;
+            uint32_t keyhash, c, q;
+            /* key */
+            if (p >= n || s[p] != '"') { state = -2; continue; }
+            q = djf_bm_next(e, val_off + (uint32_t) p + 1) - val_off;
+            if (q >= (uint32_t) n || s[q] != '"') { state = -2; continue; }
+            keyref = mkref(RK_STR_IN, val_off + (uint32_t) p + 1, q - (uint32_t) p - 1);
+            keyhash = ch_khash(s + p + 1, q - (uint32_t) p - 1);
+            p = (int) q + 1;
+            if (p >= n || s[p] != ':') { state = -2; continue; }
+            p++;
+            if (p >= n) { state = -2; continue; }
+            /* value */
+            c = s[p];
+            if (c == '"') {
+                q = djf_bm_next(e, val_off + (uint32_t) p + 1) - val_off;
+                if (q >= (uint32_t) n || s[q] != '"') { state = -2; continue; }
+                valref = mkref(RK_STR_IN, val_off + (uint32_t) p + 1, q - (uint32_t) p - 1);
+                p = (int) q + 1;
+            }
+            else if (c == '-' || (c >= '0' && c <= '9')) {
+                int z = p, nd = 0, neg = 0, z0;
+                uint64_t v = 0;
+                if (c == '-') { neg = 1; z++; }
+                if (z >= n || s[z] < '0' || s[z] > '9') { state = -2; continue; }
+                if (s[z] == '0') { z++; if (z < n && s[z] >= '0' && s[z] <= '9') { state = -2; continue; } }
+                else {
+                    z0 = z;
+                    z = djf_scan_digits(s, z, n);
+                    nd = z - z0;
+                    if (nd > 18) { state = -2; continue; }
+                    if (z < n && s[z] == '.') { int y; for (y = z0; y < z; y++) v = v * 10 + (s[y] - '0'); }
+                }
+                if (z < n && s[z] == '.') {
+                    /* short decimal without exponent (Clinger's exact case), as in djf_record() */
+                    int r = z + 1, fd = 0;
+                    uint64_t m = v;
+                    while (r < n && s[r] >= '0' && s[r] <= '9' && nd + fd < 15) { m = m * 10 + (s[r] - '0'); r++; fd++; }
+                    if (fd > 0 && !(r < n && ((s[r] >= '0' && s[r] <= '9') || s[r] == 'e' || s[r] == 'E'))) {
+                        union { double d; uint64_t u; } cv;
+                        cv.d = (double) m / dj_p10[fd];
+                        if (neg) cv.u |= (uint64_t) 1 << 63;
+                        scr[k] = 0xcb; mp_put_be64(scr + k + 1, cv.u);
+                        valref = mkref(RK_MP_SCR, k, 9);
+                        k += 9;
+                        p = r;
+                    }
+                    else { state = -2; continue; }
+                }
+                else if (z < n && (s[z] == 'e' || s[z] == 'E')) { state = -2; continue; }
+                else { valref = mkref(RK_INT_IN, val_off + (uint32_t) p, (uint32_t) (z - p)); p = z; }
+            }
+            else if (c == 't' && p + 4 <= n && s[p + 1] == 'r' && s[p + 2] == 'u' && s[p + 3] == 'e') { valref = mkref(RK_TRUE, 0, 0); p += 4; }
+            else if (c == 'f' && p + 5 <= n && s[p + 1] == 'a' && s[p + 2] == 'l' && s[p + 3] == 's' && s[p + 4] == 'e') { valref = mkref(RK_FALSE, 0, 0); p += 5; }
+            else if (c == 'n' && p + 4 <= n && s[p + 1] == 'u' && s[p + 2] == 'l' && s[p + 3] == 'l') { valref = mkref(RK_MP_SCR, k, 1); scr[k++] = 0xc0; p += 4; }
+            else { state = -2; continue; }
+            if (cnt >= CH_MAXF) { state = -2; continue; }
+            ok_[cnt] = keyref; ov_[cnt] = valref; th[cnt] = keyhash; cnt++;
+            if (p < n && s[p] == ',') { p++; continue; }
+            if (p < n && s[p] == '}') { p++; state = 1; continue; }
+            state = -2;
+        }
+    }
+    if (state != 1) return -2;
+    while (p < n && dj_ws(s[p])) p++;
+    if (p < n) return -2;
+    *on = cnt;
+    return 1;
+}
+
 /* flb_parser_json_do(), src/flb_parser_json.c:29-247.  The document is transcoded into
  * this record's scratch region by the evaluation pass (msgpack, canonical); both passes
  * then read the top-level map back as the field list.  Time key: first member whose key
@@ -1182,7 +1300,8 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t 
     /* slot[0]: 0/1 = result of the exact transcoder (msgpack of slot[1] bytes in scratch),
      * 2 = the fast path produced the fields (it is re-run by the emission pass, nothing cached) */
     if (!(EMIT && slot && CW(slot, 0) != 2)) {
-        ok = djf_record(e, s, (int) n, val_off, ok_, ov_, th, &cnt);
+        ok = e->bm ? djf_record_bm(e, s, (int) n, val_off, ok_, ov_, th, &cnt) : -2;
+        if (ok == -2) { cnt = 0; ok = djf_record(e, s, (int) n, val_off, ok_, ov_, th, &cnt); }
         if (ok == 0) { if (!EMIT && slot) { CW(slot, 0) = 0; CW(slot, 1) = 0; } return 0; }
         if (ok == 1) { if (!EMIT && slot) { CW(slot, 0) = 2; CW(slot, 1) = 0; } *pos = (int) n; goto have_fields; }   /* nothing but white space behind the document */
     }

@@ -313,7 +313,7 @@ struct k_chain_params {
     const uint32_t *off, *len;
     const uint8_t *kind;
     uint32_t r0;                 /* first record / first block of this launch */
-    uint32_t stage_bytes;        /* shared-memory slice per warp for input staging, 0 = none */
+    uint32_t bm_words;           /* JSON stage 1: 32-bit words of string-event bitmap per warp in shared memory, 0 = none */
     uint32_t n_rec;
     const uint32_t *n_dev;       /* small form: the record count lives on the device */
     uint32_t *size;
@@ -328,6 +328,23 @@ struct k_chain_params {
  * chunk, so the warp first copies their bytes to its own slice of shared memory with coalesced 128-bit
  * loads and the lanes then scan from there; `in` is rebased so that input offsets keep their meaning.
  * A warp whose records span more than its slice reads global memory as before. */
+/* Stage 1 of the JSON tokenizer (chains with a JSON parser): the warp's 32 records are adjacent in the chunk, so the
+ * warp reads their whole byte range once with coalesced 128-bit loads and leaves one bit per byte in shared memory --
+ * set where a string scan has to stop and look ('"', '\\', control, >= 0x80).  Stage 2 (djf_record_bm, one lane per record)
+ * then finds the end of a plain string with a bit scan.  A range longer than BM_BYTES is scanned the old way. */
+#define BM_BYTES 8192u                               /* per warp: 256 words = 1 KB of shared memory */
+__device__ __forceinline__ uint32_t bm_mask4(uint32_t w)
+{
+    /* bit 7 of each byte of the result: byte is '"', '\\', < 0x20 or >= 0x80 */
+    uint32_t t, m;
+    t = w ^ 0x22222222u; m = (t - 0x01010101u) & ~t;
+    t = w ^ 0x5c5c5c5cu; m |= (t - 0x01010101u) & ~t;
+    m |= (w - 0x20202020u) & ~w;
+    m |= w;
+    m &= 0x80808080u;
+    return ((m >> 7) * 0x00204081u) >> 21 & 0xfu;        /* gather the four flags into bits 0..3 */
+}
+
 __global__ void __launch_bounds__(1024, 1) k_chain_eval(const k_chain_params p)       /* 64 registers per lane; block size chosen at launch */
 {
     extern __shared__ __align__(16) uint8_t dsm[];
@@ -337,23 +354,32 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval(const k_chain_params p) 
     const uint32_t my_off = valid ? p.off[i] : 0, my_len = valid ? p.len[i] : 0;
     const bool live = valid && p.kind[i] == 0;
     const uint8_t *in = p.env.in;
-    if (p.stage_bytes) {
+    const uint32_t *bm = 0;
+    uint32_t bm_base = 0, bm_end = 0;
+    if (p.bm_words) {
         const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        const uint32_t lo = __reduce_min_sync(0xffffffffu, live ? my_off : 0xffffffffu) & ~15u;
+        uint32_t lo = __reduce_min_sync(0xffffffffu, live ? my_off : 0xffffffffu);
         const uint32_t hi = __reduce_max_sync(0xffffffffu, live ? my_off + my_len : 0u);
-        if (hi > lo && hi - lo + 32 <= p.stage_bytes) {
-            uint8_t *buf = dsm + (size_t) warp * p.stage_bytes;
-            for (uint32_t o = lane * 16; o < hi - lo + 16; o += 512)
-                *reinterpret_cast<uint4 *>(buf + o) = *reinterpret_cast<const uint4 *>(in + lo + o);
-            __syncwarp();
-            in = buf - lo;
+        if (hi > lo) {
+            lo -= (uint32_t) ((uintptr_t) (in + lo) & 15u);           /* 16-byte aligned in the address space */
+            if (hi - lo <= BM_BYTES) {
+                uint32_t *w = reinterpret_cast<uint32_t *>(dsm) + (size_t) warp * p.bm_words;
+                for (uint32_t o = lane * 16; o < hi - lo; o += 512) {
+                    const uint4 v = *reinterpret_cast<const uint4 *>(in + lo + o);      /* reads past `hi` stay inside the padded buffer */
+                    const uint32_t m16 = bm_mask4(v.x) | (bm_mask4(v.y) << 4) | (bm_mask4(v.z) << 8) | (bm_mask4(v.w) << 12);
+                    const uint32_t other = __shfl_xor_sync(0xffffffffu, m16, 1);
+                    if (!(lane & 1)) w[o >> 5] = m16 | (other << 16);
+                }
+                __syncwarp();
+                bm = w; bm_base = lo; bm_end = hi;
+            }
         }
     }
     if (!valid) return;
     uint32_t sz = 0;
     if (live) {
         struct ch_env le = p.env;
-        le.in = in;
+        le.bm = bm; le.bm_base = bm_base; le.bm_end = bm_end;
         sz = chain_record<false>(&le, i, my_off, my_len, 0);
     }
     __stcs(&p.size[i], sz);
@@ -614,7 +640,7 @@ struct bk_q {
     uint32_t *h_flags;                     /* pinned copy of the evidence words */
     uint8_t *h_sin, *h_sout; size_t cap_sin, cap_sout;    /* small form: pinned staging for the chunk and its result */
     cudaEvent_t ev_small;
-    int stage_kb;
+    int json_bm;                           /* FLBGPU_JSON_BM=0 turns the stage-1 bitmap off (measurement) */
     int eval_block, eval_bsync;            /* FLBGPU_EVAL_BLOCK (threads per evaluation block), FLBGPU_EVAL_BSYNC (block-wide phase barriers) */
     /* upload */
     cudaEvent_t up_ev[UP_MAX_EV]; int up_ev_made;
@@ -817,10 +843,8 @@ static int q_setup(bk_q *q)
         q->eval_bsync = es && es[0] == '1';
     }
     {
-        const char *e = getenv("FLBGPU_STAGE_KB");           /* KiB of shared memory per warp, 0 = off */
-        q->stage_kb = e ? atoi(e) : 0;
-        if (q->stage_kb < 0 || q->stage_kb > 24) q->stage_kb = 0;
-        if (q->stage_kb) CK(cudaFuncSetAttribute(k_chain_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, q->stage_kb * 1024 * (q->eval_block / 32)));
+        const char *e = getenv("FLBGPU_JSON_BM");
+        q->json_bm = !(e && e[0] == '0');
     }
     return 0;
 }
@@ -1175,7 +1199,7 @@ static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_
     p->env.capcache = a->d_capcache; p->env.cap_stride = a->cap_stride; p->env.cap_n = a->cap_n; p->env.now = a->now;
     p->env.assume = a->assume; p->env.active = a->active; p->env.fl_flags = a->d_flags; p->env.err = a->d_flags + FLBGPU_MAX_FILTERS;
     p->env.l2m = a->l2m; p->env.prep = a->d_prep;
-    p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->r0 = r0; p->n_rec = a->n_rec; p->stage_bytes = 0;
+    p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->r0 = r0; p->n_rec = a->n_rec; p->bm_words = 0;
     p->n_dev = 0; p->env.bsync = 0;
     p->size = a->d_size; p->bsum = a->d_bsum; p->out = d_out;
 }
@@ -1221,10 +1245,10 @@ int bk_chain_eval(bk_q *q, const struct bk_chain_args *a, uint32_t r0, uint32_t 
     use(q);
     fill_params(a, &p, 0, r0);
     p.n_rec = r1;
-    p.stage_bytes = (uint32_t) q->stage_kb * 1024;
+    p.bm_words = (a->d_scr && q->json_bm) ? BM_BYTES / 32 : 0;          /* a JSON parser is in the chain */
     p.env.bsync = (uint32_t) q->eval_bsync;
     ev_begin_on(q, 1, q->stream);
-    k_chain_eval<<<(r1 - r0 + q->eval_block - 1) / q->eval_block, q->eval_block, (size_t) p.stage_bytes * (q->eval_block / 32), q->stream>>>(p);
+    k_chain_eval<<<(r1 - r0 + q->eval_block - 1) / q->eval_block, q->eval_block, (size_t) p.bm_words * 4 * (q->eval_block / 32), q->stream>>>(p);
     if (p.env.l2m.hash) {
         k_chain_skipped<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, 0, q->stream>>>(p);
         g_launches += 1;
@@ -1394,9 +1418,9 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     /* evaluation of records [0, n_valid) */
     fill_params(a, &p, d_out, 0);
     p.n_rec = 0; p.n_dev = &m->n_valid;
-    p.stage_bytes = (uint32_t) q->stage_kb * 1024;
+    p.bm_words = (a->d_scr && q->json_bm) ? BM_BYTES / 32 : 0;
     ev_begin_on(q, 1, st);
-    k_chain_eval<<<nb_cap, BK_REC_BLOCK, (size_t) p.stage_bytes * (BK_REC_BLOCK / 32), st>>>(p);     /* (no block barriers in the small form) */
+    k_chain_eval<<<nb_cap, BK_REC_BLOCK, (size_t) p.bm_words * 4 * (BK_REC_BLOCK / 32), st>>>(p);     /* (no block barriers in the small form) */
     if (p.env.l2m.hash) { k_chain_skipped<<<nb_cap, BK_REC_BLOCK, 0, st>>>(p); g_launches += 1; }
     ev_end_on(q, 1, st);
     /* sizes, survivor lists, emission under the speculated verdicts */
@@ -1404,7 +1428,7 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     k_small_sizes<<<nb_cap, BK_REC_BLOCK, 0, st>>>(a->d_size, m, a->d_bsum, q->d_cnt);
     k_small_scan2<<<1, 256, 0, st>>>(a->d_bsum, q->d_cnt, nb_cap, (unsigned long long) cap_out, m);
     k_surv_fill<<<nb_cap, BK_REC_BLOCK, 0, st>>>(a->d_size, 0, &m->n_valid, 0, q->d_cnt, a->d_bsum, q->d_lrec, q->d_loff);
-    p.stage_bytes = 0;
+    p.bm_words = 0;
     k_chain_emit_list<<<nb_cap * (BK_REC_BLOCK / EMIT_BLOCK), EMIT_BLOCK, (EMIT_BLOCK / 32) * (EMIT_STAGE + 16), st>>>(p, q->d_lrec, q->d_loff, &m->n_out, &m->emitted);
     ev_end_on(q, 2, st);
     g_launches += 10;

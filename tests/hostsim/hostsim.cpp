@@ -184,7 +184,7 @@ int bk_index_fill(bk_q *, const uint8_t *d_in, size_t slice_off, uint32_t len, c
 static void hs_env(const struct bk_chain_args *a, struct ch_env *e)
 {
     e->in = a->d_in; e->in_len = a->in_len; e->blob = a->d_blob; e->scr = a->d_scr;
-    e->capcache = a->d_capcache; e->cap_stride = a->cap_stride; e->cap_n = a->cap_n; e->now = a->now; e->assume = a->assume; e->active = a->active; e->bsync = 0;
+    e->capcache = a->d_capcache; e->cap_stride = a->cap_stride; e->cap_n = a->cap_n; e->now = a->now; e->assume = a->assume; e->active = a->active; e->bsync = 0; e->bm = 0; e->bm_base = e->bm_end = 0;
     e->fl_flags = a->d_flags; e->err = a->d_flags + FLBGPU_MAX_FILTERS;
     e->l2m = a->l2m; e->prep = a->d_prep;
 }
@@ -196,13 +196,26 @@ int bk_chain_eval(bk_q *, const struct bk_chain_args *a, uint32_t r0, uint32_t r
 {
     struct ch_env e;
     uint32_t i;
+    uint32_t *bm = 0;
     hs_env(a, &e);
+    if (a->d_scr && r1 > r0 && !getenv("FLBGPU_JSON_BM_OFF")) {
+        /* stage 1 of the JSON tokenizer as the CUDA kernel leaves it: one bit per byte that a string scan has to look at.
+         * (Here over the records' whole byte range at once; the kernel does it per warp.) */
+        const uint32_t lo = a->d_off[r0], hi = a->d_off[r1 - 1] + a->d_len[r1 - 1];
+        bm = (uint32_t *) calloc((hi - lo + 31) / 32 + 1, 4);
+        for (uint32_t b = lo; b < hi; b++) {
+            const uint8_t c = a->d_in[b];
+            if (c == '"' || c == 0x5c || c < 0x20 || c >= 0x80) bm[(b - lo) >> 5] |= 1u << ((b - lo) & 31);
+        }
+        e.bm = bm; e.bm_base = lo; e.bm_end = hi;
+    }
     for (i = r0; i < r1; i++) {
         uint32_t sz = 0;
         if (a->d_kind[i] == 0) sz = chain_record<false>(&e, i, a->d_off[i], a->d_len[i], 0);
         else if (a->d_kind[i] == 1 && e.l2m.hash) chain_skipped_record(&e, i, a->d_off[i], a->d_len[i]);
         a->d_size[i] = sz;
     }
+    free(bm);
     hs_launches += 1;
     return 0;
 }
