@@ -25,6 +25,10 @@ class ParserTypes(C.Structure):
     _fields_ = [("key", C.c_char_p), ("key_len", C.c_int), ("type", C.c_int)]
 
 
+class ParserDecoder(C.Structure):
+    _fields_ = [("property", C.c_char_p), ("value", C.c_char_p)]
+
+
 class Time(C.Structure):
     _fields_ = [("tv_sec", C.c_int64), ("tv_nsec", C.c_int64)]
 
@@ -174,9 +178,15 @@ class Context:
         return res
 
     def parser(self, name, format, regex=None, skip_empty=True, time_fmt=None, time_key=None, time_offset=None,
-               time_keep=False, time_strict=True, logfmt_no_bare_keys=False, types=None):
-        """flb_parser_create(); `types` is the Types option text, e.g. "code:integer size:integer"."""
+               time_keep=False, time_strict=True, logfmt_no_bare_keys=False, types=None, decoders=None):
+        """flb_parser_create(); `types` is the Types option text, e.g. "code:integer size:integer"; `decoders` a list of
+        (property, value) pairs such as ("Decode_Field_As", "escaped_utf8 log do_next")."""
         arr, n = None, 0
+        dec = None
+        if decoders:
+            dec = (ParserDecoder * (len(decoders) + 1))()
+            for i, (k, v) in enumerate(decoders):
+                dec[i].property = _b(k); dec[i].value = _b(v)
         if types:
             items = [t.split(":", 1) for t in types.split() if ":" in t]     # flb_parser_conf: entries without a type are skipped
             arr = (ParserTypes * len(items))()
@@ -185,7 +195,7 @@ class Context:
             n = len(items)
         p = self.L.flbgpu_parser_create(self.h, _b(name), _b(format), _b(regex), int(skip_empty), _b(time_fmt),
                                         _b(time_key), _b(time_offset), int(time_keep), int(time_strict), 0,
-                                        int(logfmt_no_bare_keys), arr, n, None)
+                                        int(logfmt_no_bare_keys), arr, n, C.cast(dec, C.c_void_p) if dec is not None else None)
         if not p:
             raise FlbGpuError("parser_create(%s): %s" % (name, self.err()))
         return Parser(self, p)

@@ -58,6 +58,8 @@ struct ch_env {
     uint32_t in_len;
     const uint8_t *blob;
     uint8_t *scr;
+    uint32_t scr_mul;         /* scratch bytes per record byte (the record's region starts at scr + scr_mul * record offset) */
+    uint32_t dec_at;          /* where the field decoders write inside the record's region (behind the parser's part) */
     int32_t *capcache;        /* capture cache, one COLUMN per word: word w of record r at capcache[w * cap_n + r], so that the
                                  lanes of a warp (adjacent records) touch adjacent words -- coalesced in both passes */
     uint32_t cap_stride;      /* words per record */
@@ -1162,6 +1164,167 @@ FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t 
     return 1;
 }
 
+/* ---- field decoders: flb_parser_decoder_do(), src/flb_parser_decoder.c:215-535 -------------------------------------
+ * Applied to the map a parser produced (regex / LTSV / logfmt: after the map is complete; JSON: before the time key is
+ * looked up, src/flb_parser_json.c:101-117).  Decoded texts and objects go to the decoders' half of the record's scratch. */
+/* flb_unescape_string(), src/flb_unescape.c:279-334 */
+FLB_HD uint32_t pdec_unescape(const uint8_t *b, uint32_t n, uint8_t *o)
+{
+    uint32_t i = 0, j = 0;
+    while (i < n) {
+        if (b[i] == 0x5c) {
+            if (i + 1 < n) {
+                const uint32_t c = b[i + 1];
+                if (c == 'n') { o[j++] = 10; i++; }
+                else if (c == 'a') { o[j++] = 7; i++; }
+                else if (c == 'b') { o[j++] = 8; i++; }
+                else if (c == 't') { o[j++] = 9; i++; }
+                else if (c == 'v') { o[j++] = 11; i++; }
+                else if (c == 'f') { o[j++] = 12; i++; }
+                else if (c == 'r') { o[j++] = 13; i++; }
+                else if (c == 0x5c) { o[j++] = 0x5c; i++; }
+                i++;
+                continue;
+            }
+            /* a backslash at the very end: the reference steps over it and then copies the byte behind the text -- the
+             * terminator of its sds buffer -- so a NUL comes out */
+            o[j++] = 0;
+            break;
+        }
+        o[j++] = b[i++];
+    }
+    return j;
+}
+
+/* flb_mysql_unquote_string(), src/flb_unescape.c:338-391 */
+FLB_HD uint32_t pdec_mysql_unquote(const uint8_t *b, uint32_t n, uint8_t *o)
+{
+    uint32_t i = 0, j = 0;
+    while (i < n) {
+        uint32_t c = b[i++];
+        if (c != 0x5c) o[j++] = (uint8_t) c;
+        else if (i >= n) o[j++] = (uint8_t) c;
+        else {
+            c = b[i++];
+            switch (c) {
+            case 'n': o[j++] = 10; break;
+            case 'r': o[j++] = 13; break;
+            case 't': o[j++] = 9; break;
+            case 0x5c: o[j++] = 0x5c; break;
+            case 0x27: o[j++] = 0x27; break;
+            case '"': o[j++] = '"'; break;
+            case '0': o[j++] = 0; break;
+            case 'Z': o[j++] = 0x1a; break;
+            default: o[j++] = 0x5c; o[j++] = (uint8_t) c; break;
+            }
+        }
+    }
+    return j;
+}
+
+#define PDEC_OUT_STRING 0
+#define PDEC_OUT_OBJECT 1
+/* one backend over text[0,n): result at scr + *at (advanced), *out_len bytes, *out_type; -1 = the decoder failed */
+FLB_HDN int pdec_backend(const struct ch_env *e, uint32_t backend, const uint8_t *text, uint32_t n, uint32_t *at, uint32_t *out_off,
+                         uint32_t *out_len, int *out_type)
+{
+    uint8_t *o = e->scr + *at;
+    *out_off = *at;
+    if (backend == PDEC_JSON) {
+        /* decode_json(): leading blanks skipped, a map or array must start there, exactly one document, and it must be a map */
+        uint32_t p = 0, mplen = 0, jerr = 0;
+        int consumed = 0;
+        while (p < n && text[p] == ' ') p++;
+        if (p >= n || (text[p] != '{' && text[p] != '[')) return -1;
+        if (!dj_parse_record(text + p, (int) (n - p), o, &mplen, &jerr, &consumed)) return -1;
+        if (jerr) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
+        *out_len = mplen; *out_type = PDEC_OUT_OBJECT;
+    }
+    else if (backend == PDEC_ESCAPED) { *out_len = pdec_unescape(text, n, o); *out_type = PDEC_OUT_STRING; }
+    else if (backend == PDEC_ESCAPED_UTF8) { *out_len = lf_unescape_raw(text, n, o); *out_type = PDEC_OUT_STRING; }
+    else {                                             /* decode_mysql_quoted() */
+        if (n < 2) { uint32_t i; for (i = 0; i < n; i++) o[i] = text[i]; *out_len = n; }
+        else if ((text[0] == 0x27 && text[n - 1] == 0x27) || (text[0] == '"' && text[n - 1] == '"')) *out_len = pdec_mysql_unquote(text + 1, n - 2, o);
+        else { uint32_t i; for (i = 0; i < n; i++) o[i] = text[i]; *out_len = n; }
+        *out_type = PDEC_OUT_STRING;
+    }
+    *at += *out_len + 1;
+    return 0;
+}
+
+/* returns 1 when some key had a decoder (the reference then re-packs the map: canonical header), 0 when none, -1 when the
+ * field list overflowed */
+FLB_HDN int apply_decoders(const struct ch_env *e, const struct cf_pdef *pd, ref_t *K, ref_t *V, uint32_t *TH, int *cnt_io)
+{
+    const struct cf_pdec *decs = (const struct cf_pdec *) (e->blob + pd->dec_off);
+    int cnt = *cnt_io, i, matched = -1, extra_keys = 0, extra_has = 0;
+    uint32_t at = e->dec_at, extra_off = 0, extra_len = 0, d;
+    if (!e->scr || !pd->n_dec) return 0;
+    /* the first STR key some decoder is registered for: nothing happens before it (and nothing at all without one) */
+    for (i = 0; i < cnt && matched < 0; i++) {
+        const uint8_t *kp; uint32_t kn;
+        if (ref_view(e, K[i], &kp, &kn) != 1) continue;
+        for (d = 0; d < pd->n_dec; d++) if (decs[d].key_len == kn && bytes_eq(kp, e->blob + decs[d].key_off, kn)) { matched = i; break; }
+    }
+    if (matched < 0) return 0;
+    for (i = matched; i < cnt; i++) {
+        const uint8_t *kp, *vp, *data;
+        uint32_t kn, vn, data_n, r;
+        const struct cf_pdec *dec = 0;
+        const struct cf_pdec_rule *rules;
+        int is_decoded = 0, is_decoded_as = 0, in_type = PDEC_OUT_STRING, out_type = PDEC_OUT_STRING;
+        uint32_t in_off = 0, in_len = 0, out_off = 0, out_len = 0;
+        if (ref_view(e, K[i], &kp, &kn) != 1 || ref_view(e, V[i], &vp, &vn) != 1) continue;
+        for (d = 0; d < pd->n_dec; d++) if (decs[d].key_len == kn && bytes_eq(kp, e->blob + decs[d].key_off, kn)) { dec = &decs[d]; break; }
+        if (!dec) continue;
+        data = vp; data_n = vn;
+        if (dec->add_extra_keys) { extra_keys = 1; extra_has = 0; }      /* the extra-keys buffer starts over with every such key */
+        rules = (const struct cf_pdec_rule *) (e->blob + dec->rules_off);
+        for (r = 0; r < dec->n_rules; r++) {
+            uint32_t o_off = 0, o_len = 0;
+            int o_type = 0, ret;
+            if (rules[r].type == PDEC_DEFAULT && rules[r].action == PDEC_ACT_DO_NEXT && is_decoded) continue;
+            if (is_decoded_as && in_type != PDEC_OUT_STRING) continue;
+            ret = pdec_backend(e, rules[r].backend, data, data_n, &at, &o_off, &o_len, &o_type);
+            if (ret == -1) {
+                if (rules[r].action == PDEC_ACT_TRY_NEXT || rules[r].action == PDEC_ACT_DO_NEXT) continue;
+                break;
+            }
+            if (rules[r].type == PDEC_AS) {
+                in_off = o_off; in_len = o_len; in_type = o_type; is_decoded_as = 1;
+                data = e->scr + o_off; data_n = o_len;               /* the next rule decodes what this one made */
+            }
+            else { out_off = o_off; out_len = o_len; out_type = o_type; is_decoded = 1; }
+            if (rules[r].action == PDEC_ACT_DO_NEXT) continue;
+            break;
+        }
+        if (is_decoded_as) V[i] = mkref(in_type == PDEC_OUT_STRING ? RK_STR_SCR : RK_MP_SCR, in_off, in_len);
+        if (is_decoded && out_type == PDEC_OUT_OBJECT) { extra_has = 1; extra_off = out_off; extra_len = out_len; }
+    }
+    /* merge_record_and_extra_keys(): the members of the (last) decoded object follow the record's own */
+    if (extra_keys && extra_has) {
+        const uint8_t *q = e->scr + extra_off, *end = q + extra_len, *nx;
+        struct mp_tok t;
+        uint32_t m;
+        if (mp_token(q, end, &t) == 0 && t.type == MPT_MAP) {
+            q += t.hdr;
+            for (m = 0; m < t.len; m++) {
+                if (cnt >= CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return -1; }
+                nx = mp_skip(q, end);
+                K[cnt] = mkref(RK_MP_SCR, (uint32_t) (q - e->scr), (uint32_t) (nx - q));
+                q = nx;
+                nx = mp_skip(q, end);
+                V[cnt] = mkref(RK_MP_SCR, (uint32_t) (q - e->scr), (uint32_t) (nx - q));
+                q = nx;
+                TH[cnt] = 0;
+                cnt++;
+            }
+        }
+    }
+    *cnt_io = cnt;
+    return 1;
+}
+
 /* first input offset >= p_abs inside the bitmap's range whose byte is '"', '\\', < 0x20 or >= 0x80; bm_end if none */
 FLB_HD uint32_t djf_bm_next(const struct ch_env *e, uint32_t p_abs)
 {
@@ -1329,6 +1492,7 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t 
         cnt++;
     }
 have_fields:
+    if (pd->n_dec) apply_decoders(e, pd, ok_, ov_, th, &cnt);
     if (pd->has_time) {
         for (i = 0; i < (uint32_t) cnt; i++) {
             const uint8_t *kp; uint32_t kn;
@@ -1457,6 +1621,11 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
             }
             if (got) {
                 if (pd->type == FLBGPU_PARSER_LTSV || pd->type == FLBGPU_PARSER_LOGFMT) { int z; for (z = 0; z < cnt; z++) w->th[z] = 0; }
+                if (pd->n_dec && pd->type != FLBGPU_PARSER_JSON) {
+                    /* (the JSON parser decodes before it looks for the time key: pdef_json) */
+                    const int r = apply_decoders(e, pd, in_place ? rc->k : w->tk, in_place ? rc->v : w->tv, in_place ? rc->kh : w->th, &cnt);
+                    if (r > 0) style = ST_CANON;                   /* flb_parser_decoder_do() packs a map of its own */
+                }
                 if (in_place && pd->type == FLBGPU_PARSER_JSON) { int z; for (z = 0; z < cnt; z++) if (!rc->kh[z]) rc->kh[z] = ref_khash(e, rc->k[z]); }
                 parse_ok = 1;
                 np = cnt;
@@ -1978,7 +2147,7 @@ FLB_HDN void chain_skipped_record(const struct ch_env *e, uint32_t ridx, uint32_
     {
         struct ch_rec rc;
         struct ch_scratch w;
-        if (e->scr) { le = *e; le.scr = e->scr + (size_t) 4 * off; e = &le; }
+        if (e->scr) { le = *e; le.scr = e->scr + (size_t) e->scr_mul * off; le.dec_at = 4u * len; e = &le; }
         if (rec_decode(e, off, len, &rc, h->empty_map_off) != 0) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return; }
         f_l2m(e, (const struct cf_l2m *) (e->blob + f[k].cfg_off), &rc, &w, ridx);
     }
@@ -2000,7 +2169,8 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
 
     if (e->scr) {               /* this record's private scratch region: 4 bytes per record byte */
         le = *e;
-        le.scr = e->scr + (size_t) 4 * off;
+        le.scr = e->scr + (size_t) e->scr_mul * off;
+        le.dec_at = 4u * len;
         e = &le;
     }
     /* The evaluation pass leaves the final field list of every surviving record (<= RC_CACHE_MAXF

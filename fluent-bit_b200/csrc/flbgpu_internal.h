@@ -35,6 +35,7 @@ struct bk_chain_args {
     uint32_t in_len;
     const uint8_t *d_blob;        /* chain program (device) */
     uint8_t *d_scr;               /* scratch or NULL */
+    uint32_t scr_mul;             /* scratch bytes per record byte: 4, or 8 when a parser has field decoders */
     int32_t *d_capcache;          /* capture cache or NULL: word w of record r at [w * cap_n + r] */
     uint32_t cap_stride;
     uint32_t cap_n;               /* records per column of the capture cache (= capacity of the record arrays) */

@@ -139,8 +139,16 @@ struct cf_pdef {               /* device view of struct flb_parser (flb_parser.h
     uint32_t logfmt_no_bare_keys;
     uint32_t n_groups;
     uint32_t tfast_off;        /* compiled fixed-shape time program (TF_* ops), 0 = none */
-    uint32_t pad0;
+    uint32_t n_dec;            /* field decoders (Decode_Field / Decode_Field_As): struct cf_pdec[n_dec] at dec_off */
+    uint32_t dec_off, pad0;
 };
+
+/* struct flb_parser_dec / flb_parser_dec_rule, include/fluent-bit/flb_parser_decoder.h:27-59 */
+enum { PDEC_DEFAULT = 0, PDEC_AS = 1 };                                        /* rule type */
+enum { PDEC_JSON = 0, PDEC_ESCAPED = 1, PDEC_ESCAPED_UTF8 = 2, PDEC_MYSQL_QUOTED = 3 };   /* backend */
+enum { PDEC_ACT_NONE = 0, PDEC_ACT_TRY_NEXT = 1, PDEC_ACT_DO_NEXT = 2 };
+struct cf_pdec_rule { uint32_t type, backend, action, pad; };
+struct cf_pdec { uint32_t key_off, key_len, add_extra_keys, n_rules, rules_off, pad0, pad1, pad2; };
 
 /* Fixed-shape time program: what flb_strptime() does for the format when every numeric field has its
  * full width, spaces are single, month names are the 3-letter forms and the zone is Z or +hh[:]mm.

@@ -94,9 +94,13 @@ struct flbgpu_parser {
     struct flbgpu_parser_types *types;
     int types_len;
     struct flbgpu_parser *next;
+    struct pdec *decs; int n_decs;     /* field decoders, one entry per decoded key in order of first appearance */
     flbgpu_chain *solo;      /* lazily built chain behind flbgpu_parser_do() */
     flbgpu_filter *solo_filter;
 };
+
+struct pdec_rule { int type, backend, action; };
+struct pdec { char *key; int add_extra_keys; struct pdec_rule *rules; int n_rules; };
 
 struct kv { char *k, *v; struct kv *next; };
 static uint32_t key_hash(const char *s, size_t n);
@@ -153,6 +157,7 @@ struct flbgpu_chain {
     uint8_t *d_blob;
     uint32_t cap_stride;
     int needs_scratch;
+    uint32_t scr_mul;
     uint8_t *d_scr; size_t cap_scr;
     int l2m_index;                            /* filter index of the log_to_metrics filter, or -1 */
     struct l2m_table l2m;                     /* device table (per-call delta) */
@@ -256,6 +261,52 @@ flbgpu_parser *flbgpu_parser_get(flbgpu_ctx *ctx, const char *name)
     return NULL;
 }
 
+static int split_tokens(const char *str, int max_split, char **out, int max_out);
+static void free_toks(char **t, int n);
+
+/* flb_parser_decoder_list_create(), src/flb_parser_decoder.c:594-745 */
+static int parser_decoders(struct flbgpu_parser *p, const struct flbgpu_parser_decoder *d)
+{
+    for (; d->property; d++) {
+        char *tok[4];
+        int nt, type, backend, action = PDEC_ACT_NONE, i;
+        struct pdec *dec = NULL;
+        if (!strcasecmp(d->property, "decode_field")) type = PDEC_DEFAULT;
+        else if (!strcasecmp(d->property, "decode_field_as")) type = PDEC_AS;
+        else continue;
+        nt = split_tokens(d->value ? d->value : "", 3, tok, 4);
+        if (nt < 2) { free_toks(tok, nt); set_err("[parser] invalid number of parameters in decoder%s%s", NULL, NULL); return -1; }
+        if (!strcasecmp(tok[0], "json")) backend = PDEC_JSON;
+        else if (!strcasecmp(tok[0], "escaped")) backend = PDEC_ESCAPED;
+        else if (!strcasecmp(tok[0], "escaped_utf8")) backend = PDEC_ESCAPED_UTF8;
+        else if (!strcasecmp(tok[0], "mysql_quoted")) backend = PDEC_MYSQL_QUOTED;
+        else { set_err("[parser] field decoder '%s' unknown%s", tok[0], NULL); free_toks(tok, nt); return -1; }
+        if (nt >= 3) {
+            if (!strcasecmp(tok[2], "try_next")) action = PDEC_ACT_TRY_NEXT;
+            else if (!strcasecmp(tok[2], "do_next")) action = PDEC_ACT_DO_NEXT;
+        }
+        for (i = 0; i < p->n_decs; i++) if (!strcmp(p->decs[i].key, tok[1])) { dec = &p->decs[i]; break; }
+        if (!dec) {
+            struct pdec *nd = realloc(p->decs, sizeof(*nd) * (size_t) (p->n_decs + 1));
+            if (!nd) { free_toks(tok, nt); set_err("out of memory%s%s", NULL, NULL); return -1; }
+            p->decs = nd;
+            dec = &p->decs[p->n_decs++];
+            memset(dec, 0, sizeof(*dec));
+            dec->key = strdup(tok[1]);
+        }
+        {
+            struct pdec_rule *nr = realloc(dec->rules, sizeof(*nr) * (size_t) (dec->n_rules + 1));
+            if (!nr) { free_toks(tok, nt); set_err("out of memory%s%s", NULL, NULL); return -1; }
+            dec->rules = nr;
+            nr[dec->n_rules].type = type; nr[dec->n_rules].backend = backend; nr[dec->n_rules].action = action;
+            dec->n_rules++;
+        }
+        if (type == PDEC_DEFAULT) dec->add_extra_keys = 1;
+        free_toks(tok, nt);
+    }
+    return 0;
+}
+
 flbgpu_parser *flbgpu_parser_create(flbgpu_ctx *ctx, const char *name, const char *format,
                                     const char *p_regex, int skip_empty,
                                     const char *time_fmt, const char *time_key,
@@ -268,7 +319,6 @@ flbgpu_parser *flbgpu_parser_create(flbgpu_ctx *ctx, const char *name, const cha
     g_rt_err[0] = 0;
     if (!ctx || !name || !format) { set_err("parser: missing argument%s%s", NULL, NULL); return NULL; }
     if (flbgpu_parser_get(ctx, name)) { set_err("[parser] parser named '%s' already exists, skip.%s", name, NULL); return NULL; }
-    if (decoders) { set_err("[parser:%s] Decode_Field is not supported on the GPU path%s", name, NULL); return NULL; }
     if (time_system_timezone) { set_err("[parser:%s] Time_System_Timezone is not supported on the GPU path%s", name, NULL); return NULL; }
     p = calloc(1, sizeof(*p));
     p->ctx = ctx;
@@ -334,6 +384,7 @@ flbgpu_parser *flbgpu_parser_create(flbgpu_ctx *ctx, const char *name, const cha
         }
         p->types_len = types_len;
     }
+    if (decoders && parser_decoders(p, (const struct flbgpu_parser_decoder *) decoders) != 0) { flbgpu_parser_destroy(p); return NULL; }
     p->next = ctx->parsers;
     ctx->parsers = p;
     return p;
@@ -348,6 +399,8 @@ void flbgpu_parser_destroy(flbgpu_parser *p)
     if (p->solo) flbgpu_chain_destroy(p->solo);
     if (p->solo_filter) flbgpu_filter_destroy(p->solo_filter);
     if (p->has_rx) rx_compiled_free(&p->rx);
+    for (i = 0; i < p->n_decs; i++) { free(p->decs[i].key); free(p->decs[i].rules); }
+    free(p->decs);
     for (i = 0; i < p->types_len; i++) free(p->types[i].key);
     free(p->types); free(p->name); free(p->time_fmt); free(p->time_frac); free(p->time_key);
     free(p);
@@ -468,6 +521,27 @@ static uint32_t emit_pdef(struct blob *b, struct flbgpu_parser *p)
         d.n_types = nt;
         d.types_off = blob_add(b, ty, sizeof(*ty) * (nt ? nt : 1), 8);
         free(ty);
+    }
+    if (p->n_decs > 0) {
+        struct cf_pdec *dc = calloc((size_t) p->n_decs, sizeof(*dc));
+        int k;
+        for (k = 0; k < p->n_decs; k++) {
+            struct cf_pdec_rule *rl = calloc((size_t) p->decs[k].n_rules, sizeof(*rl));
+            int r;
+            for (r = 0; r < p->decs[k].n_rules; r++) {
+                rl[r].type = (uint32_t) p->decs[k].rules[r].type; rl[r].backend = (uint32_t) p->decs[k].rules[r].backend;
+                rl[r].action = (uint32_t) p->decs[k].rules[r].action;
+            }
+            dc[k].key_off = blob_add(b, p->decs[k].key, strlen(p->decs[k].key), 1);
+            dc[k].key_len = (uint32_t) strlen(p->decs[k].key);
+            dc[k].add_extra_keys = (uint32_t) p->decs[k].add_extra_keys;
+            dc[k].n_rules = (uint32_t) p->decs[k].n_rules;
+            dc[k].rules_off = blob_add(b, rl, sizeof(*rl) * (size_t) p->decs[k].n_rules, 8);
+            free(rl);
+        }
+        d.n_dec = (uint32_t) p->n_decs;
+        d.dec_off = blob_add(b, dc, sizeof(*dc) * (size_t) p->n_decs, 8);
+        free(dc);
     }
     off = blob_add(b, &d, sizeof(d), 8);
     return off;
@@ -740,7 +814,8 @@ static uint32_t emit_parser_filter(flbgpu_filter *f, struct blob *b, uint32_t *c
             /* no per-record capture slots any more: the emission pass encodes from the cached final
              * field list (RC_CACHE_INTS); only records with more than RC_CACHE_MAXF fields re-run the
              * chain there, and then they re-run the parser too */
-            if (ps->type == FLBGPU_PARSER_JSON || ps->type == FLBGPU_PARSER_LOGFMT) f->needs_scratch = 1;   /* transcoded JSON / decoded logfmt escapes */
+            if (ps->type == FLBGPU_PARSER_JSON || ps->type == FLBGPU_PARSER_LOGFMT) f->needs_scratch |= 1;   /* transcoded JSON / decoded logfmt escapes */
+            if (ps->n_decs) f->needs_scratch |= 3;                                                        /* + the decoders' own half of the region */
         }
         else if (!strcasecmp(p->k, "preserve_key")) { int v = parse_bool(p->v); if (v < 0) { set_err("invalid boolean '%s'%s", p->v, NULL); return 0; } cf.preserve_key = v; }
         else if (!strcasecmp(p->k, "reserve_data")) { int v = parse_bool(p->v); if (v < 0) { set_err("invalid boolean '%s'%s", p->v, NULL); return 0; } cf.reserve_data = v; }
@@ -1211,8 +1286,9 @@ int flbgpu_chain_init(flbgpu_chain *c)
         if (c->l2m_index >= 0) { set_err("only one log_to_metrics filter per fused chain%s%s", NULL, NULL); return -1; }
         c->l2m_index = (int) i;
     }
-    for (i = 0; i < (uint32_t) c->nf; i++) if (c->f[i]->needs_scratch) h.needs_scratch = 1;
+    for (i = 0; i < (uint32_t) c->nf; i++) h.needs_scratch |= (uint32_t) c->f[i]->needs_scratch;
     c->needs_scratch = (int) h.needs_scratch;
+    c->scr_mul = (h.needs_scratch & 2) ? 8 : 4;           /* scratch bytes per record byte */
     h.n_filters = c->nf;
     h.filters_off = blob_add(&c->blob, cf, sizeof(cf[0]) * (c->nf ? c->nf : 1), 8);
     cap += RC_CACHE_INTS;                 /* every chain: the final field list for the emission pass */
@@ -1336,6 +1412,7 @@ static void fill_args(flbgpu_chain *c, struct bk_chain_args *a, const uint8_t *d
     a->d_size = c->d_size; a->d_bsum = c->d_bsum; a->d_flags = c->d_flags;
     if (c->l2m_index >= 0 && ((c->active >> c->l2m_index) & 1)) a->l2m = c->l2m; else memset(&a->l2m, 0, sizeof(a->l2m));
     a->active = c->active;
+    a->scr_mul = c->scr_mul ? c->scr_mul : 4;
     a->d_prep = c->want_report ? c->d_prep : NULL;
 }
 
@@ -1597,7 +1674,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         d_in = c->d_in;
         if (bk_upload_start(c->q, c->d_in, h_in, bytes)) return -1;
     }
-    if (c->needs_scratch) GROW(c->d_scr, c->cap_scr, 4 * bytes + 64, uint8_t);
+    if (c->needs_scratch) GROW(c->d_scr, c->cap_scr, (size_t) c->scr_mul * bytes + 64, uint8_t);
     memset(&a, 0, sizeof(a));
     a.now = (int64_t) time(NULL);
     a.assume = initial_assume(c);
@@ -1805,7 +1882,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
     if (bytes >= 0xfff00000ull) { set_err("chunk larger than 4 GiB: split the append%s%s", NULL, NULL); return -1; }
     GROW(c->d_in, c->cap_in, bytes + 64, uint8_t);
     if (bk_upload_start(c->q, c->d_in, h_in, bytes)) return -1;
-    if (c->needs_scratch) GROW(c->d_scr, c->cap_scr, 4 * bytes + 64, uint8_t);
+    if (c->needs_scratch) GROW(c->d_scr, c->cap_scr, (size_t) c->scr_mul * bytes + 64, uint8_t);
     nb_max = (uint32_t) (bytes / (3 * BK_REC_BLOCK)) + 4;       /* an event is at least 3 bytes */
     GROW(c->d_bsum, c->cap_bsum, nb_max, uint64_t);
     if (c->cap_hbsum < (size_t) nb_max) {
@@ -1982,7 +2059,7 @@ static int chain_run_small(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, v
     nb_cap = (cap_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK;
     n_tiles = (uint32_t) ((bytes + BK_INDEX_TILE - 1) / BK_INDEX_TILE);
     GROW(c->d_in, c->cap_in, bytes + 64, uint8_t);
-    if (c->needs_scratch) GROW(c->d_scr, c->cap_scr, 4 * bytes + 64, uint8_t);
+    if (c->needs_scratch) GROW(c->d_scr, c->cap_scr, (size_t) c->scr_mul * bytes + 64, uint8_t);
     GROW(c->d_tile, c->cap_tile, n_tiles + 1, uint32_t);
     GROW(c->d_bsum, c->cap_bsum, nb_cap + 2, uint64_t);
     if (ensure_rec_cap(c, cap_rec, 0)) return -1;

@@ -41,6 +41,15 @@ struct flbgpu_parser_types {
     int   type;
 };
 
+/* The field decoders of a parser definition (`Decode_Field json log`, `Decode_Field_As escaped_utf8 log do_next`, ...):
+ * the properties as the [PARSER] section spells them, in order, ended by an entry whose property is NULL.  This is what
+ * flb_parser_decoder_list_create() (src/flb_parser_decoder.c:594) reads from the section; flbgpu_parser_create() takes
+ * the array where flb_parser_create() takes the struct mk_list that function built. */
+struct flbgpu_parser_decoder {
+    const char *property;      /* "decode_field" | "decode_field_as" (any case) */
+    const char *value;         /* "<json|escaped|escaped_utf8|mysql_quoted> <field> [try_next|do_next]" */
+};
+
 /* struct flb_time { struct timespec tm; }, include/fluent-bit/flb_time.h */
 struct flbgpu_time {
     int64_t tv_sec;
@@ -58,16 +67,16 @@ const char *flbgpu_backend_name(void);
 int         flbgpu_device_count(void);
 
 /* ---- parsers ---------------------------------------------------------- */
-/* flb_parser_create(), src/flb_parser.c:148-348 -- same arguments, same meaning
- * (`decoders` must be NULL: Decode_Field is not on this path yet).  The parser is
- * registered under `name` in the context, like config->parsers.  NULL on error. */
+/* flb_parser_create(), src/flb_parser.c:148-348 -- same arguments, same meaning; `decoders` is NULL or an array of
+ * struct flbgpu_parser_decoder (above).  The parser is registered under `name` in the context, like config->parsers.
+ * NULL on error. */
 flbgpu_parser *flbgpu_parser_create(flbgpu_ctx *ctx, const char *name, const char *format,
                                     const char *p_regex, int skip_empty,
                                     const char *time_fmt, const char *time_key,
                                     const char *time_offset, int time_keep, int time_strict,
                                     int time_system_timezone, int logfmt_no_bare_keys,
                                     struct flbgpu_parser_types *types, int types_len,
-                                    void *decoders);
+                                    void *decoders /* struct flbgpu_parser_decoder[] or NULL */);
 /* flb_parser_get(), src/flb_parser.c:1022 */
 flbgpu_parser *flbgpu_parser_get(flbgpu_ctx *ctx, const char *name);
 /* flb_parser_do(), src/flb_parser.c:1044-1066: one line in, one msgpack map out.

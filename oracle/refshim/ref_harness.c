@@ -134,6 +134,63 @@ void *flbref_parser_create(void *cfg, const char *name, const char *format, cons
                              types, types_len, NULL, c->config);
 }
 
+/* the same with field decoders: `decoders` holds "property\tvalue\n" lines (Decode_Field / Decode_Field_As entries of a
+ * [PARSER] section), handed to the reference's own flb_parser_decoder_list_create() through a section made of them */
+#include <fluent-bit/flb_config_format.h>
+#include <fluent-bit/flb_parser_decoder.h>
+#include <cfl/cfl_kvlist.h>
+void *flbref_parser_create_dec(void *cfg, const char *name, const char *format, const char *regex,
+                               int skip_empty, const char *time_fmt, const char *time_key,
+                               const char *time_offset, int time_keep, int time_strict,
+                               int logfmt_no_bare_keys, const char *types_spec, const char *decoders)
+{
+    struct flbref_cfg *c = cfg;
+    struct flb_parser_types *types = NULL;
+    struct mk_list *dec_list = NULL;
+    int types_len = 0;
+
+    if (types_spec && *types_spec) {
+        const char *p = types_spec;
+        types = calloc(64, sizeof(*types));
+        while (*p && types_len < 63) {
+            const char *e, *colon;
+            while (*p == ' ') p++;
+            if (!*p) break;
+            e = p;
+            while (*e && *e != ' ') e++;
+            colon = memchr(p, ':', e - p);
+            if (colon) {
+                types[types_len].key = strndup(p, colon - p);
+                types[types_len].key_len = colon - p;
+                types[types_len].type = type_from_name(colon + 1, e - colon - 1);
+                types_len++;
+            }
+            p = e;
+        }
+    }
+    if (decoders && *decoders) {
+        struct flb_cf_section sec;
+        const char *p = decoders;
+        memset(&sec, 0, sizeof(sec));
+        sec.properties = cfl_kvlist_create();
+        while (*p) {
+            const char *tab = strchr(p, '\t'), *nl = strchr(p, '\n');
+            char *k, *v;
+            if (!tab || !nl || tab > nl) break;
+            k = strndup(p, tab - p); v = strndup(tab + 1, nl - tab - 1);
+            cfl_kvlist_insert_string(sec.properties, k, v);
+            free(k); free(v);
+            p = nl + 1;
+        }
+        dec_list = flb_parser_decoder_list_create(&sec);
+        cfl_kvlist_destroy(sec.properties);
+        if (!dec_list) return NULL;
+    }
+    return flb_parser_create(name, format, regex, skip_empty, time_fmt, time_key, time_offset,
+                             time_keep, time_strict, FLB_FALSE, logfmt_no_bare_keys,
+                             types, types_len, dec_list, c->config);
+}
+
 int flbref_parser_do(void *parser, const char *buf, size_t len, void **out_buf, size_t *out_size,
                      long long *sec, long long *nsec)
 {

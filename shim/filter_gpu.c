@@ -35,6 +35,7 @@
 #include <fluent-bit/flb_kv.h>
 #include <fluent-bit/flb_mem.h>
 #include <fluent-bit/flb_parser.h>
+#include <fluent-bit/flb_parser_decoder.h>
 #include <fluent-bit/flb_utils.h>
 #include "../include/flbgpu.h"
 
@@ -110,11 +111,39 @@ static int mirror_parser(struct flb_filter_instance *ins, struct flb_config *con
         snprintf(off, sizeof(off), "%c%02d%02d", p->time_offset < 0 ? '-' : '+', v / 3600, (v % 3600) / 60);
         offp = off;
     }
-    if (!G.parser_create(g_ctx, p->name, format, p->p_regex, p->skip_empty, p->time_fmt_full, p->time_key, offp,
-                         p->time_keep, p->time_strict, p->time_system_timezone, p->logfmt_no_bare_keys,
-                         (struct flbgpu_parser_types *) p->types, p->types_len, p->decoders)) {
-        SHIM_ERROR(ins, "parser '%s': %s", name, G.last_error());
-        return -1;
+    {
+        /* the decoders as flb_parser_decoder_list_create() built them (one struct flb_parser_dec per key, its rules in order),
+         * spelled back as the [PARSER] properties they came from */
+        static const char *backend[] = { "json", "escaped", "escaped_utf8", "mysql_quoted" };
+        static const char *action[] = { "", " try_next", " do_next" };
+        struct flbgpu_parser_decoder dec[65];
+        char text[64][320];
+        struct mk_list *head, *r_head;
+        int n = 0, ok;
+        if (p->decoders) {
+            mk_list_foreach(head, p->decoders) {
+                struct flb_parser_dec *d = mk_list_entry(head, struct flb_parser_dec, _head);
+                mk_list_foreach(r_head, &d->rules) {
+                    struct flb_parser_dec_rule *r = mk_list_entry(r_head, struct flb_parser_dec_rule, _head);
+                    if (n >= 64 || r->backend < 0 || r->backend > 3 || r->action < 0 || r->action > 2) {
+                        SHIM_ERROR(ins, "parser '%s': decoder rule outside what the GPU path takes", name);
+                        return -1;
+                    }
+                    snprintf(text[n], sizeof(text[n]), "%s %s%s", backend[r->backend], d->key, action[r->action]);
+                    dec[n].property = r->type == FLB_PARSER_DEC_AS ? "decode_field_as" : "decode_field";
+                    dec[n].value = text[n];
+                    n++;
+                }
+            }
+        }
+        dec[n].property = NULL; dec[n].value = NULL;
+        ok = G.parser_create(g_ctx, p->name, format, p->p_regex, p->skip_empty, p->time_fmt_full, p->time_key, offp,
+                             p->time_keep, p->time_strict, p->time_system_timezone, p->logfmt_no_bare_keys,
+                             (struct flbgpu_parser_types *) p->types, p->types_len, n ? dec : NULL) != NULL;
+        if (!ok) {
+            SHIM_ERROR(ins, "parser '%s': %s", name, G.last_error());
+            return -1;
+        }
     }
     return 0;
 }

@@ -74,6 +74,15 @@ def _chains(lib_path):
     same_behaviour(lib_path, [], [("grep", [("Exclude", "log NOSUCHTEXT")]), ("modify", [("Remove", "nosuchkey")])], [cases.apache_chunk(300)])
 
 
+def _docker_decoders(lib_path):
+    """the docker parser with its Decode_Field_As rules: the shim mirrors struct flb_parser, decoders included"""
+    import test_decoders as T
+    lines = [(b'{"log":"{\\"a\\":%d,\\"b\\":\\"x\\"}\\n","stream":"stdout","time":"2023-05-06T07:08:09.%dZ"}' % (i, i)) for i in range(200)]
+    lines += [b'{"log":"plain %d\\n","stream":"stderr","time":"2023-05-06T07:08:10.5Z"}' % i for i in range(50)]
+    same_behaviour(lib_path, [T.DOCKER], [("parser", [("Key_Name", "log"), ("Parser", "docker"), ("Reserve_Data", "On")]),
+                                          ("grep", [("Regex", "stream stdout")])], [util.chunk_from_lines(lines)])
+
+
 def _match_routing(lib_path):
     """Match decides per filter whether it sees the chunk (flb_router_match, src/flb_router.c)"""
     filters = [cases.P, ("grep", [("Regex", "method ^(GET|POST)$")]), ("modify", [("Add", "env prod")])]
@@ -101,6 +110,17 @@ def test_shim_exports(ref_available):
 def test_shim_chains_hostsim(ref_available):
     need_shim()
     _chains(util.HOSTSIM_SO)
+
+
+def test_shim_docker_decoders_hostsim(ref_available):
+    need_shim()
+    _docker_decoders(util.HOSTSIM_SO)
+
+
+@pytest.mark.gpu
+def test_shim_docker_decoders_gpu(gpu_lib, ref_available):
+    need_shim()
+    _docker_decoders(GPU_LIB)
 
 
 def test_shim_match_routing_hostsim(ref_available):

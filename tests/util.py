@@ -27,6 +27,8 @@ class Ref:
         L.flbref_config_create.restype = vp
         L.flbref_parser_create.restype = vp
         L.flbref_parser_create.argtypes = [vp, cp, cp, cp, C.c_int, cp, cp, cp, C.c_int, C.c_int, C.c_int, cp]
+        L.flbref_parser_create_dec.restype = vp
+        L.flbref_parser_create_dec.argtypes = [vp, cp, cp, cp, C.c_int, cp, cp, cp, C.c_int, C.c_int, C.c_int, cp, cp]
         L.flbref_parser_do.argtypes = [vp, cp, sz, C.POINTER(vp), C.POINTER(sz), C.POINTER(C.c_longlong), C.POINTER(C.c_longlong)]
         L.flbref_filter_create.restype = vp; L.flbref_filter_create.argtypes = [vp, cp]
         L.flbref_filter_set.argtypes = [vp, cp, cp]
@@ -80,8 +82,16 @@ class Ref:
         return s if s is None or isinstance(s, bytes) else s.encode()
 
     def parser(self, name, format, regex=None, skip_empty=True, time_fmt=None, time_key=None, time_offset=None,
-               time_keep=False, time_strict=True, logfmt_no_bare_keys=False, types=None):
+               time_keep=False, time_strict=True, logfmt_no_bare_keys=False, types=None, decoders=None):
         b = self._b
+        if decoders:
+            text = "".join("%s\t%s\n" % (k, v) for k, v in decoders)
+            p = self.L.flbref_parser_create_dec(self.cfg, b(name), b(format), b(regex), int(skip_empty), b(time_fmt),
+                                                b(time_key), b(time_offset), int(time_keep), int(time_strict),
+                                                int(logfmt_no_bare_keys), b(types), b(text))
+            if not p:
+                raise RuntimeError("reference rejected parser " + name)
+            return p
         p = self.L.flbref_parser_create(self.cfg, b(name), b(format), b(regex), int(skip_empty), b(time_fmt),
                                         b(time_key), b(time_offset), int(time_keep), int(time_strict),
                                         int(logfmt_no_bare_keys), b(types))
