@@ -66,8 +66,9 @@ struct ch_env {
     uint32_t cap_n;           /* records per column */
     int64_t now;
     uint32_t assume;          /* bit k: filter k is chunk-level MODIFIED */
-    uint32_t bsync;           /* evaluation pass: block-wide barrier at every filter boundary, so that the warps of a block run the
-                                 same phase of the interpreter at the same time (instruction-cache working set = one phase) */
+    uint32_t defer_ok;        /* evaluation pass: a record the stage-2 JSON walker cannot take is not scanned the slow way inside
+                                 this warp (the other 31 lanes would wait): chain_record() returns CH_DEFER and the record is
+                                 evaluated by the follow-up launch over the list of such records */
     uint32_t active;          /* bit k: filter k is routed this chunk (Match / Match_Regex), else skipped like flb_filter_do() does */
     uint32_t *fl_flags;       /* [n_filters] CHF_* evidence (evaluation pass only) */
     uint32_t *err;            /* FLBGPU_E_* */
@@ -848,10 +849,8 @@ FLB_HDN int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32
 
 #ifdef __CUDA_ARCH__
 #define CH_SYNC() __syncwarp()
-#define CH_BSYNC(e) do { if (!EMIT && (e)->bsync) __syncthreads(); } while (0)
 #else
 #define CH_SYNC()
-#define CH_BSYNC(e)
 #endif
 
 #ifdef __CUDA_ARCH__
@@ -1383,9 +1382,17 @@ FLB_HD int djf_record_bm(const struct ch_env *e, const uint8_t *s, int n, uint32
             c = s[p];
             if (c == '"') {
                 q = djf_bm_next(e, val_off + (uint32_t) p + 1) - val_off;
-                if (q >= (uint32_t) n || s[q] != '"') { state = -2; continue; }
-                valref = mkref(RK_STR_IN, val_off + (uint32_t) p + 1, q - (uint32_t) p - 1);
-                p = (int) q + 1;
+                if (q >= (uint32_t) n) { state = -2; continue; }
+                if (s[q] == '"') { valref = mkref(RK_STR_IN, val_off + (uint32_t) p + 1, q - (uint32_t) p - 1); p = (int) q + 1; }
+                else if (s[q] == 0x5c) {
+                    /* a string value with escapes: decoded into scratch exactly as djf_record() does */
+                    int raw; uint32_t b, len;
+                    const int np = djf_string(s, p, n, scr, k, &raw, &b, &len);
+                    if (np < 0 || raw) { state = -2; continue; }
+                    valref = mkref(RK_STR_SCR, k, len); k += len;
+                    p = np;
+                }
+                else { state = -2; continue; }
             }
             else if (c == '-' || (c >= '0' && c <= '9')) {
                 int z = p, nd = 0, neg = 0, z0;
@@ -1464,7 +1471,10 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t 
      * 2 = the fast path produced the fields (it is re-run by the emission pass, nothing cached) */
     if (!(EMIT && slot && CW(slot, 0) != 2)) {
         ok = e->bm ? djf_record_bm(e, s, (int) n, val_off, ok_, ov_, th, &cnt) : -2;
-        if (ok == -2) { cnt = 0; ok = djf_record(e, s, (int) n, val_off, ok_, ov_, th, &cnt); }
+        if (ok == -2) {
+            if (!EMIT && e->bm && e->defer_ok) return -2;         /* put off to the follow-up launch (CH_DEFER) */
+            cnt = 0; ok = djf_record(e, s, (int) n, val_off, ok_, ov_, th, &cnt);
+        }
         if (ok == 0) { if (!EMIT && slot) { CW(slot, 0) = 0; CW(slot, 1) = 0; } return 0; }
         if (ok == 1) { if (!EMIT && slot) { CW(slot, 0) = 2; CW(slot, 1) = 0; } *pos = (int) n; goto have_fields; }   /* nothing but white space behind the document */
     }
@@ -1520,7 +1530,9 @@ struct ch_scratch {              /* per-lane working memory */
     uint32_t stk[CH_RX_STACK];
     ref_t tk[CH_MAXF], tv[CH_MAXF];
     uint32_t th[CH_MAXF];         /* ch_khash of tk[] where the producer knows it cheaply, else 0 */
+    int defer;                    /* set by f_parser: this record goes to the follow-up launch */
 };
+#define CH_DEFER 0xffffffffu
 
 template <bool EMIT>
 FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct ch_rec *rc, struct ch_scratch *w,
@@ -1603,6 +1615,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                 const int direct = pristine && !have_arr && !cf->ra_off && i == rc->nf - 1;
                 got = pdef_json<EMIT>(e, pd, val_off, vp, vn, direct ? rc->k : w->tk, direct ? rc->v : w->tv, direct ? rc->kh : w->th,
                                       &cnt, &ts, &tns, ridx, cache_pos, &pos);
+                if (got == -2) { w->defer = 1; return; }
                 if (got) { style = ST_CANON; in_place = direct; }
                 else if (direct) {
                     /* (the time an earlier key of the same name parsed stays: filter_parser.c:296-300 keeps the last non-zero one) */
@@ -2166,6 +2179,7 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
     struct ch_scratch w;
     struct ch_env le;
     uint32_t k, cache_pos = 0;
+    w.defer = 0;
 
     if (e->scr) {               /* this record's private scratch region: 4 bytes per record byte */
         le = *e;
@@ -2202,12 +2216,12 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
         const uint8_t *cfg = e->blob + f[k].cfg_off;
         int assumed = (e->assume >> k) & 1;
         if (!((e->active >> k) & 1)) continue;
-        CH_BSYNC(e);
         CH_SYNC();
         switch (f[k].kind) {
         case FLBGPU_F_PARSER:
             if (!assumed) break;
             f_parser<EMIT>(e, (const struct cf_parser *) cfg, &rc, &w, ridx, &cache_pos, k == 0, off, len, h->empty_map_off);
+            if (!EMIT && w.defer) return CH_DEFER;
             if (!EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_EMITTED);
             break;
         case FLBGPU_F_GREP:

@@ -42,6 +42,8 @@ struct bk_chain_args {
     int64_t now;
     uint32_t assume;
     uint32_t active;              /* bit k: filter k sees this call's chunk (Match routing) */
+    uint32_t defer_ok;            /* a record may be put off to the follow-up launch before the first JSON parser runs (nothing
+                                     with side effects -- log_to_metrics -- comes earlier in the chain) */
     const uint32_t *d_off;        /* record index */
     const uint32_t *d_len;
     const uint8_t *d_kind;

@@ -314,6 +314,8 @@ struct k_chain_params {
     const uint8_t *kind;
     uint32_t r0;                 /* first record / first block of this launch */
     uint32_t bm_words;           /* JSON stage 1: 32-bit words of string-event bitmap per warp in shared memory, 0 = none */
+    uint32_t *defer_list;        /* records put off by the stage-2 walker (CH_DEFER), and how many */
+    unsigned long long *defer_cnt;
     uint32_t n_rec;
     const uint32_t *n_dev;       /* small form: the record count lives on the device */
     uint32_t *size;
@@ -380,9 +382,27 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval(const k_chain_params p) 
     if (live) {
         struct ch_env le = p.env;
         le.bm = bm; le.bm_base = bm_base; le.bm_end = bm_end;
+        le.defer_ok = (bm && p.defer_list) ? 1u : 0u;
         sz = chain_record<false>(&le, i, my_off, my_len, 0);
+        if (sz == CH_DEFER) {                          /* the follow-up launch evaluates it with the byte scanner */
+            p.defer_list[atomicAdd(p.defer_cnt, 1ull)] = i;
+            return;
+        }
     }
     __stcs(&p.size[i], sz);
+}
+
+/* The records the stage-2 walker put off (nested values, odd spacing, lines that are not JSON ...: a few per cent): dense,
+ * so that the byte scanner and the exact transcoder run with full warps instead of inside warps whose other lanes wait. */
+__global__ void __launch_bounds__(1024, 1) k_chain_eval_deferred(const k_chain_params p)
+{
+    const unsigned long long n = *p.defer_cnt;
+    for (unsigned long long t = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long) gridDim.x * blockDim.x) {
+        const uint32_t i = p.defer_list[t];
+        struct ch_env le = p.env;
+        le.bm = 0; le.defer_ok = 0;
+        __stcs(&p.size[i], chain_record<false>(&le, i, p.off[i], p.len[i], 0));
+    }
 }
 
 /* Chains with a log_to_metrics filter only: the events the decoder steps over (kind 1: group markers, negative
@@ -641,7 +661,8 @@ struct bk_q {
     uint8_t *h_sin, *h_sout; size_t cap_sin, cap_sout;    /* small form: pinned staging for the chunk and its result */
     cudaEvent_t ev_small;
     int json_bm;                           /* FLBGPU_JSON_BM=0 turns the stage-1 bitmap off (measurement) */
-    int eval_block, eval_bsync;            /* FLBGPU_EVAL_BLOCK (threads per evaluation block), FLBGPU_EVAL_BSYNC (block-wide phase barriers) */
+    int eval_block;                        /* FLBGPU_EVAL_BLOCK: threads per evaluation block */
+    uint32_t *d_defer; size_t cap_defer;   /* records the JSON stage-2 walker put off to the follow-up launch */
     /* upload */
     cudaEvent_t up_ev[UP_MAX_EV]; int up_ev_made;
     size_t up_total, up_piece; int up_active, up_staged;
@@ -804,7 +825,7 @@ void bk_q_free(bk_q *q)
     for (int i = 0; i < UP_STAGE_SLOTS_MAX; i++) cudaFreeHost(q->up_stage[i]);
     if (q->xf_ready) for (int i = 0; i < q->xf_slots; i++) { cudaFreeHost(q->xf_ring[i]); cudaEventDestroy(q->xf_ev[i]); }
     cudaFree(q->dtotal); cudaFree(q->dbreaks); cudaFree(q->d_cnt); cudaFree(q->d_lrec); cudaFree(q->d_loff); cudaFree(q->d_nlist);
-    cudaFree(q->d_link[0]); cudaFree(q->d_link[1]); cudaFree(q->d_mark); cudaFree(q->d_mail);
+    cudaFree(q->d_link[0]); cudaFree(q->d_link[1]); cudaFree(q->d_mark); cudaFree(q->d_mail); cudaFree(q->d_defer);
     cudaFreeHost(q->h_word); cudaFreeHost(q->h_mail); cudaFreeHost(q->h_flags); cudaFreeHost(q->h_sin); cudaFreeHost(q->h_sout);
     if (q->ev_small) cudaEventDestroy(q->ev_small);
     if (q->stream) cudaStreamDestroy(q->stream);
@@ -837,10 +858,9 @@ static int q_setup(bk_q *q)
     CK(cudaMallocHost((void **) &q->h_mail, sizeof(struct bk_mail)));
     CK(cudaMallocHost((void **) &q->h_flags, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)));
     {
-        const char *eb = getenv("FLBGPU_EVAL_BLOCK"), *es = getenv("FLBGPU_EVAL_BSYNC");
+        const char *eb = getenv("FLBGPU_EVAL_BLOCK");
         q->eval_block = eb ? atoi(eb) : (int) BK_REC_BLOCK;
         if (q->eval_block != 128 && q->eval_block != 256 && q->eval_block != 512 && q->eval_block != 1024) q->eval_block = (int) BK_REC_BLOCK;
-        q->eval_bsync = es && es[0] == '1';
     }
     {
         const char *e = getenv("FLBGPU_JSON_BM");
@@ -1200,7 +1220,7 @@ static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_
     p->env.assume = a->assume; p->env.active = a->active; p->env.fl_flags = a->d_flags; p->env.err = a->d_flags + FLBGPU_MAX_FILTERS;
     p->env.l2m = a->l2m; p->env.prep = a->d_prep;
     p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->r0 = r0; p->n_rec = a->n_rec; p->bm_words = 0;
-    p->n_dev = 0; p->env.bsync = 0;
+    p->n_dev = 0; p->env.defer_ok = 0; p->defer_list = 0; p->defer_cnt = 0;
     p->size = a->d_size; p->bsum = a->d_bsum; p->out = d_out;
 }
 
@@ -1238,6 +1258,22 @@ int bk_hint_streaming(bk_q *q, const void *base, size_t bytes)
     return 0;
 }
 
+/* deferral list for up to n records; the counter lives in dtotal[9] and is zeroed on `st` */
+static int defer_setup(bk_q *q, k_chain_params *p, const struct bk_chain_args *a, size_t n, cudaStream_t st)
+{
+    p->defer_list = 0; p->defer_cnt = 0;
+    if (!p->bm_words || !a->defer_ok) return 0;
+    if (q->cap_defer < n) {
+        CK(cudaStreamSynchronize(q->stream));           /* a follow-up launch still running reads the old list */
+        cudaFree(q->d_defer); q->d_defer = 0; q->cap_defer = 0;
+        CK(cudaMalloc((void **) &q->d_defer, sizeof(uint32_t) * (n + n / 4 + 1024)));
+        q->cap_defer = n + n / 4 + 1024;
+    }
+    CK(cudaMemsetAsync(q->dtotal + 9, 0, sizeof(unsigned long long), st));
+    p->defer_list = q->d_defer; p->defer_cnt = q->dtotal + 9;
+    return 0;
+}
+
 int bk_chain_eval(bk_q *q, const struct bk_chain_args *a, uint32_t r0, uint32_t r1)
 {
     k_chain_params p;
@@ -1246,9 +1282,10 @@ int bk_chain_eval(bk_q *q, const struct bk_chain_args *a, uint32_t r0, uint32_t 
     fill_params(a, &p, 0, r0);
     p.n_rec = r1;
     p.bm_words = (a->d_scr && q->json_bm) ? BM_BYTES / 32 : 0;          /* a JSON parser is in the chain */
-    p.env.bsync = (uint32_t) q->eval_bsync;
+    if (defer_setup(q, &p, a, r1 - r0, q->stream)) return -1;
     ev_begin_on(q, 1, q->stream);
     k_chain_eval<<<(r1 - r0 + q->eval_block - 1) / q->eval_block, q->eval_block, (size_t) p.bm_words * 4 * (q->eval_block / 32), q->stream>>>(p);
+    if (p.defer_list) { k_chain_eval_deferred<<<148 * 4, BK_REC_BLOCK, 0, q->stream>>>(p); g_launches += 1; }
     if (p.env.l2m.hash) {
         k_chain_skipped<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, 0, q->stream>>>(p);
         g_launches += 1;
@@ -1419,8 +1456,10 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     fill_params(a, &p, d_out, 0);
     p.n_rec = 0; p.n_dev = &m->n_valid;
     p.bm_words = (a->d_scr && q->json_bm) ? BM_BYTES / 32 : 0;
+    if (defer_setup(q, &p, a, cap_rec, st)) return -1;
     ev_begin_on(q, 1, st);
-    k_chain_eval<<<nb_cap, BK_REC_BLOCK, (size_t) p.bm_words * 4 * (BK_REC_BLOCK / 32), st>>>(p);     /* (no block barriers in the small form) */
+    k_chain_eval<<<nb_cap, BK_REC_BLOCK, (size_t) p.bm_words * 4 * (BK_REC_BLOCK / 32), st>>>(p);
+    if (p.defer_list) { k_chain_eval_deferred<<<148, BK_REC_BLOCK, 0, st>>>(p); g_launches += 1; }
     if (p.env.l2m.hash) { k_chain_skipped<<<nb_cap, BK_REC_BLOCK, 0, st>>>(p); g_launches += 1; }
     ev_end_on(q, 1, st);
     /* sizes, survivor lists, emission under the speculated verdicts */

@@ -158,6 +158,7 @@ struct flbgpu_chain {
     uint32_t cap_stride;
     int needs_scratch;
     uint32_t scr_mul;
+    int defer_ok;                             /* no log_to_metrics filter in front of a parser filter: records may be re-evaluated from scratch */
     uint8_t *d_scr; size_t cap_scr;
     int l2m_index;                            /* filter index of the log_to_metrics filter, or -1 */
     struct l2m_table l2m;                     /* device table (per-call delta) */
@@ -1289,6 +1290,12 @@ int flbgpu_chain_init(flbgpu_chain *c)
     for (i = 0; i < (uint32_t) c->nf; i++) h.needs_scratch |= (uint32_t) c->f[i]->needs_scratch;
     c->needs_scratch = (int) h.needs_scratch;
     c->scr_mul = (h.needs_scratch & 2) ? 8 : 4;           /* scratch bytes per record byte */
+    {
+        int last_parser = -1, k2;
+        c->defer_ok = 1;
+        for (k2 = 0; k2 < c->nf; k2++) if (c->f[k2]->kind == FLBGPU_F_PARSER) last_parser = k2;
+        for (k2 = 0; k2 < last_parser; k2++) if (c->f[k2]->kind == FLBGPU_F_LOG_TO_METRICS) c->defer_ok = 0;
+    }
     h.n_filters = c->nf;
     h.filters_off = blob_add(&c->blob, cf, sizeof(cf[0]) * (c->nf ? c->nf : 1), 8);
     cap += RC_CACHE_INTS;                 /* every chain: the final field list for the emission pass */
@@ -1413,6 +1420,7 @@ static void fill_args(flbgpu_chain *c, struct bk_chain_args *a, const uint8_t *d
     if (c->l2m_index >= 0 && ((c->active >> c->l2m_index) & 1)) a->l2m = c->l2m; else memset(&a->l2m, 0, sizeof(a->l2m));
     a->active = c->active;
     a->scr_mul = c->scr_mul ? c->scr_mul : 4;
+    a->defer_ok = (uint32_t) c->defer_ok;
     a->d_prep = c->want_report ? c->d_prep : NULL;
 }
 

@@ -184,7 +184,7 @@ int bk_index_fill(bk_q *, const uint8_t *d_in, size_t slice_off, uint32_t len, c
 static void hs_env(const struct bk_chain_args *a, struct ch_env *e)
 {
     e->in = a->d_in; e->in_len = a->in_len; e->blob = a->d_blob; e->scr = a->d_scr; e->scr_mul = a->scr_mul ? a->scr_mul : 4; e->dec_at = 0;
-    e->capcache = a->d_capcache; e->cap_stride = a->cap_stride; e->cap_n = a->cap_n; e->now = a->now; e->assume = a->assume; e->active = a->active; e->bsync = 0; e->bm = 0; e->bm_base = e->bm_end = 0;
+    e->capcache = a->d_capcache; e->cap_stride = a->cap_stride; e->cap_n = a->cap_n; e->now = a->now; e->assume = a->assume; e->active = a->active; e->defer_ok = 0; e->bm = 0; e->bm_base = e->bm_end = 0;
     e->fl_flags = a->d_flags; e->err = a->d_flags + FLBGPU_MAX_FILTERS;
     e->l2m = a->l2m; e->prep = a->d_prep;
 }
