@@ -798,17 +798,18 @@ static void bind_near_device(int device)
 
 static int func_attrs_once(void)
 {
-    /* the interpreter keeps its field list and backtrack stack in local memory */
-    CK(cudaFuncSetCacheConfig(k_chain_eval, cudaFuncCachePreferL1));
+    /* The interpreter keeps its field list and backtrack stack in local memory: as much L1 as possible -- but the JSON
+     * stage-1 bitmaps need 9 KB of shared memory per 256-lane block, and four blocks have to stay resident per SM (a
+     * carve-out sized for one block would cost three quarters of the occupancy): 20 % of the unified array. */
+    const char *e = getenv("FLBGPU_EVAL_CARVEOUT");
+    int pct = e ? atoi(e) : 20;
+    if (pct < 0 || pct > 100) pct = 20;
+    CK(cudaFuncSetAttribute(k_chain_eval, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    CK(cudaFuncSetCacheConfig(k_chain_eval_deferred, cudaFuncCachePreferL1));
+    cudaFuncSetAttribute(k_chain_eval_deferred, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     /* the emission kernel stages a warp's result range in shared memory (6 blocks x 32 KB per SM) */
     CK(cudaFuncSetAttribute(k_chain_emit_list, cudaFuncAttributePreferredSharedMemoryCarveout, 80));
-    {   /* and ask for the largest L1 the unified array can give (FLBGPU_MAX_L1=0: driver default) */
-        const char *e = getenv("FLBGPU_MAX_L1");
-        if (!(e && e[0] == '0')) {
-            cudaFuncSetAttribute(k_chain_eval, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
-            cudaGetLastError();
-        }
-    }
+    cudaGetLastError();
     return 0;
 }
 
