@@ -59,28 +59,28 @@ struct ch_env {
     const uint8_t *blob;
     uint8_t *scr;
     uint32_t scr_mul;         /* scratch bytes per record byte (the record's region starts at scr + scr_mul * record offset) */
-    uint32_t dec_at;          /* where the field decoders write inside the record's region (behind the parser's part) */
     int32_t *capcache;        /* capture cache, one COLUMN per word: word w of record r at capcache[w * cap_n + r], so that the
                                  lanes of a warp (adjacent records) touch adjacent words -- coalesced in both passes */
     uint32_t cap_stride;      /* words per record */
     uint32_t cap_n;           /* records per column */
     int64_t now;
     uint32_t assume;          /* bit k: filter k is chunk-level MODIFIED */
-    uint32_t defer_ok;        /* evaluation pass: a record the stage-2 JSON walker cannot take is not scanned the slow way inside
-                                 this warp (the other 31 lanes would wait): chain_record() returns CH_DEFER and the record is
-                                 evaluated by the follow-up launch over the list of such records */
     uint32_t active;          /* bit k: filter k is routed this chunk (Match / Match_Regex), else skipped like flb_filter_do() does */
     uint32_t *fl_flags;       /* [n_filters] CHF_* evidence (evaluation pass only) */
     uint32_t *err;            /* FLBGPU_E_* */
     struct l2m_table l2m;     /* log_to_metrics delta table of this call (hash == NULL: none) */
-    /* Stage 1 of the JSON tokenizer (k_chain_eval): one bit per input byte of the warp's byte range, set where a string
-     * scan has to look -- '"', '\\', a control byte or a byte >= 0x80.  Built cooperatively by the warp with coalesced
-     * 128-bit loads into shared memory; the per-lane walker (djf_record_bm) then finds the end of a plain string with a
-     * bit scan instead of a byte loop.  NULL: no bitmap (emission pass, ranges that do not fit, other parsers). */
-    const uint32_t *bm;
-    uint32_t bm_base, bm_end; /* input offsets covered: [bm_base, bm_end) */
     int32_t *prep;            /* parser report (flbgpu_parser_do): 6 ints per record -- parsed flag, position consumed,
                                  seconds lo / hi, nanoseconds, spare -- or NULL */
+};
+
+/* What differs from lane to lane.  struct ch_env itself is the same for every record of a launch and is read where the
+ * kernel parameters live (constant bank); only these few words sit in the lane's registers / local memory. */
+struct ch_lane {
+    uint8_t *scr;             /* this record's scratch region (ch_env.scr + scr_mul * record offset), or NULL */
+    uint32_t dec_at;          /* where the field decoders write inside it (behind the parser's part) */
+    const uint32_t *bm;       /* JSON stage-1 bitmap of the warp's byte range (shared memory), or NULL */
+    uint32_t bm_base, bm_end; /* input offsets it covers */
+    uint32_t defer_ok;        /* a record the stage-2 walker cannot take returns CH_DEFER instead of being scanned in place */
 };
 
 #define CW(p, x) (p)[(size_t) (x) * cs]          /* word x of a record's capture-cache row (cs = e->cap_n) */
@@ -96,19 +96,19 @@ struct ch_rec {
     int reenc;
 };
 
-FLB_HD const uint8_t *ref_ptr(const struct ch_env *e, ref_t r)
+FLB_HD const uint8_t *ref_ptr(const struct ch_env *e, const struct ch_lane *ln, ref_t r)
 {
     uint32_t k = r_kind(r);
     if (k == RK_MP_CONST) return e->blob + r_off(r);
-    if (k == RK_MP_SCR || k == RK_STR_SCR) return e->scr + r_off(r);
+    if (k == RK_MP_SCR || k == RK_STR_SCR) return ln->scr + r_off(r);
     return e->in + r_off(r);
 }
 
 /* string view of a key/value: 1 STR, 2 BIN, 3 true, 4 false, 0 anything else */
-FLB_HD int ref_view(const struct ch_env *e, ref_t r, const uint8_t **p, uint32_t *n)
+FLB_HD int ref_view(const struct ch_env *e, const struct ch_lane *ln, ref_t r, const uint8_t **p, uint32_t *n)
 {
     uint32_t k = r_kind(r);
-    const uint8_t *b = ref_ptr(e, r);
+    const uint8_t *b = ref_ptr(e, ln, r);
     if (k == RK_STR_IN || k == RK_STR_SCR) { *p = b; *n = r_len(r); return 1; }
     if (k == RK_TRUE) return 3;
     if (k == RK_FALSE) return 4;
@@ -130,10 +130,10 @@ FLB_HD uint32_t ch_khash(const uint8_t *s, uint32_t n)
     if (n) h ^= (uint32_t) s[0] ^ ((uint32_t) s[n - 1] << 8) ^ ((uint32_t) s[n >> 1] << 16);
     return h | 1u;
 }
-FLB_HD uint32_t ref_khash(const struct ch_env *e, ref_t r)
+FLB_HD uint32_t ref_khash(const struct ch_env *e, const struct ch_lane *ln, ref_t r)
 {
     const uint8_t *p; uint32_t n;
-    int t = ref_view(e, r, &p, &n);
+    int t = ref_view(e, ln, r, &p, &n);
     return (t == 1 || t == 2) ? ch_khash(p, n) : 0u;
 }
 
@@ -189,10 +189,10 @@ FLB_HD uint64_t ch_strtoull16(const uint8_t *s, uint32_t n)
 
 /* ------------------------------------------------------------ emission */
 /* size (o == NULL) or bytes of one field reference */
-FLB_HD uint32_t ref_emit(const struct ch_env *e, ref_t r, uint8_t *o)
+FLB_HD uint32_t ref_emit(const struct ch_env *e, const struct ch_lane *ln, ref_t r, uint8_t *o)
 {
     uint32_t k = r_kind(r), n = r_len(r);
-    const uint8_t *b = ref_ptr(e, r);
+    const uint8_t *b = ref_ptr(e, ln, r);
     switch (k) {
     case RK_MP_IN:
         return mp_canon(b, b + n, o, 0);
@@ -227,7 +227,7 @@ FLB_HD uint32_t ref_emit(const struct ch_env *e, ref_t r, uint8_t *o)
     return 0;
 }
 
-FLB_HD uint32_t rec_emit(const struct ch_env *e, const struct ch_rec *rc, uint8_t *o)
+FLB_HD uint32_t rec_emit(const struct ch_env *e, const struct ch_lane *ln, const struct ch_rec *rc, uint8_t *o)
 {
     uint32_t n = 0;
     int i;
@@ -237,7 +237,7 @@ FLB_HD uint32_t rec_emit(const struct ch_env *e, const struct ch_rec *rc, uint8_
         mp_put_be32(o + 8, (uint32_t) rc->ts_nsec);
     }
     n = 12;
-    n += ref_emit(e, rc->meta, o ? o + n : 0);
+    n += ref_emit(e, ln, rc->meta, o ? o + n : 0);
     if (rc->style == ST_MAP32) {
         if (o) { o[n] = 0xdf; mp_put_be32(o + n + 1, (uint32_t) rc->nf); }
         n += 5;
@@ -254,8 +254,8 @@ FLB_HD uint32_t rec_emit(const struct ch_env *e, const struct ch_rec *rc, uint8_
         n += mp_cnt_hdr_size((uint32_t) rc->nf);
     }
     for (i = 0; i < rc->nf; i++) {
-        n += ref_emit(e, rc->k[i], o ? o + n : 0);
-        n += ref_emit(e, rc->v[i], o ? o + n : 0);
+        n += ref_emit(e, ln, rc->k[i], o ? o + n : 0);
+        n += ref_emit(e, ln, rc->v[i], o ? o + n : 0);
     }
     return n;
 }
@@ -307,7 +307,7 @@ FLB_HD int rec_is_shadowed(const uint8_t *base, const uint8_t *p, const uint8_t 
 
 /* Split a framed record into timestamp, metadata and the top-level field list.
  * Returns 0, or -1 when it has more than CH_MAXF keys. */
-FLB_HD int rec_decode(const struct ch_env *e, uint32_t off, uint32_t len, struct ch_rec *rc, uint32_t empty_map_off)
+FLB_HD int rec_decode(const struct ch_env *e, const struct ch_lane *ln, uint32_t off, uint32_t len, struct ch_rec *rc, uint32_t empty_map_off)
 {
     const uint8_t *p = e->in + off, *end = p + len, *q = p + 1, *nx;
     struct mp_tok t;
@@ -346,21 +346,21 @@ FLB_HD int rec_decode(const struct ch_env *e, uint32_t off, uint32_t len, struct
         nx = mp_skip(q, end);
         rc->v[i] = mkref(RK_MP_IN, (uint32_t) (q - e->in), (uint32_t) (nx - q));
         q = nx;
-        rc->kh[i] = ref_khash(e, rc->k[i]);
+        rc->kh[i] = ref_khash(e, ln, rc->k[i]);
     }
     return 0;
 }
 
 /* -------------------------------------------------------- record accessor */
 /* ra_key_val_id(): index of the LAST field whose key is a STR equal to name */
-FLB_HD int ra_find(const struct ch_env *e, const struct ch_rec *rc, const uint8_t *name, uint32_t nlen)
+FLB_HD int ra_find(const struct ch_env *e, const struct ch_lane *ln, const struct ch_rec *rc, const uint8_t *name, uint32_t nlen)
 {
     const uint32_t h = ch_khash(name, nlen);
     int i;
     for (i = rc->nf - 1; i >= 0; i--) {
         const uint8_t *kp; uint32_t kn;
         if (rc->kh[i] != h) continue;
-        if (ref_view(e, rc->k[i], &kp, &kn) != 1) continue;
+        if (ref_view(e, ln, rc->k[i], &kp, &kn) != 1) continue;
         if (kn == nlen && bytes_eq(kp, name, nlen)) return i;
     }
     return -1;
@@ -368,7 +368,7 @@ FLB_HD int ra_find(const struct ch_env *e, const struct ch_rec *rc, const uint8_
 
 /* subkey_to_object() over raw msgpack: on success *vp..*ve is the value object and
  * *key_is_null tells whether the last step was an array index */
-FLB_HDN int ra_walk_sub(const struct ch_env *e, const struct cf_ra *ra, const uint8_t *p, const uint8_t *end,
+FLB_HDN int ra_walk_sub(const struct ch_env *e, const struct ch_lane *ln, const struct cf_ra *ra, const uint8_t *p, const uint8_t *end,
                        const uint8_t **vp, const uint8_t **ve, int *key_is_null)
 {
     const struct cf_ra_sub *sub = (const struct cf_ra_sub *) (e->blob + ra->sub_off);
@@ -421,19 +421,19 @@ FLB_HDN int ra_walk_sub(const struct ch_env *e, const struct cf_ra *ra, const ui
 
 /* flb_ra_key_value_get(): 0 found (flags: *okey_null), -1 not found.
  * On success either *top >= 0 (the top-level field itself) or *vp and *ve (nested). */
-FLB_HD int ra_get(const struct ch_env *e, const struct ch_rec *rc, const struct cf_ra *ra, int *top,
+FLB_HD int ra_get(const struct ch_env *e, const struct ch_lane *ln, const struct ch_rec *rc, const struct cf_ra *ra, int *top,
                   const uint8_t **vp, const uint8_t **ve, int *okey_null)
 {
-    int i = ra_find(e, rc, e->blob + ra->key_off, ra->key_len);
+    int i = ra_find(e, ln, rc, e->blob + ra->key_off, ra->key_len);
     uint32_t k;
     *top = -1; *okey_null = 0;
     if (i < 0) return -1;
     k = r_kind(rc->v[i]);
     if (ra->n_sub > 0 && (k == RK_MP_IN || k == RK_MP_CONST || k == RK_MP_SCR)) {
-        const uint8_t *b = ref_ptr(e, rc->v[i]);
+        const uint8_t *b = ref_ptr(e, ln, rc->v[i]);
         struct mp_tok t;
         if (mp_token(b, b + r_len(rc->v[i]), &t) == 0 && (t.type == MPT_MAP || t.type == MPT_ARRAY)) {
-            return ra_walk_sub(e, ra, b, b + r_len(rc->v[i]), vp, ve, okey_null);
+            return ra_walk_sub(e, ln, ra, b, b + r_len(rc->v[i]), vp, ve, okey_null);
         }
     }
     *top = i;
@@ -441,11 +441,11 @@ FLB_HD int ra_get(const struct ch_env *e, const struct ch_rec *rc, const struct 
 }
 
 /* view of a located value as STR/BIN/bool (same codes as ref_view) */
-FLB_HD int loc_view(const struct ch_env *e, const struct ch_rec *rc, int top, const uint8_t *vp, const uint8_t *ve,
+FLB_HD int loc_view(const struct ch_env *e, const struct ch_lane *ln, const struct ch_rec *rc, int top, const uint8_t *vp, const uint8_t *ve,
                     const uint8_t **p, uint32_t *n)
 {
     struct mp_tok t;
-    if (top >= 0) return ref_view(e, rc->v[top], p, n);
+    if (top >= 0) return ref_view(e, ln, rc->v[top], p, n);
     if (mp_token(vp, ve, &t) != 0) return 0;
     if (t.type == MPT_STR) { *p = vp + t.hdr; *n = t.len; return 1; }
     if (t.type == MPT_BIN) { *p = vp + t.hdr; *n = t.len; return 2; }
@@ -453,7 +453,7 @@ FLB_HD int loc_view(const struct ch_env *e, const struct ch_rec *rc, int top, co
     return 0;
 }
 
-FLB_HDN int rx_run(const struct ch_env *e, uint32_t rx_off, const uint8_t *s, uint32_t n, int *caps, uint32_t *stk)
+FLB_HDN int rx_run(const struct ch_env *e, const struct ch_lane *ln, uint32_t rx_off, const uint8_t *s, uint32_t n, int *caps, uint32_t *stk)
 {
     uint32_t budget = CH_RX_BUDGET;
     int r = rx_search((const struct rx_prog *) (e->blob + rx_off), s, (int) n, caps, stk, CH_RX_STACK, &budget);
@@ -464,16 +464,16 @@ FLB_HDN int rx_run(const struct ch_env *e, uint32_t rx_off, const uint8_t *s, ui
 }
 
 /* flb_ra_regex_match() > 0 ? */
-FLB_HD int ra_regex_match(const struct ch_env *e, const struct ch_rec *rc, uint32_t ra_off, uint32_t rx_off,
+FLB_HD int ra_regex_match(const struct ch_env *e, const struct ch_lane *ln, const struct ch_rec *rc, uint32_t ra_off, uint32_t rx_off,
                           int *caps, uint32_t *stk)
 {
     const struct cf_ra *ra = (const struct cf_ra *) (e->blob + ra_off);
     const uint8_t *vp = 0, *ve = 0, *s;
     uint32_t n;
     int top, kn;
-    if (ra_get(e, rc, ra, &top, &vp, &ve, &kn) != 0) return 0;
-    if (loc_view(e, rc, top, vp, ve, &s, &n) != 1) return 0;      /* value must be a STR */
-    return rx_run(e, rx_off, s, n, caps, stk);
+    if (ra_get(e, ln, rc, ra, &top, &vp, &ve, &kn) != 0) return 0;
+    if (loc_view(e, ln, rc, top, vp, ve, &s, &n) != 1) return 0;      /* value must be a STR */
+    return rx_run(e, ln, rx_off, s, n, caps, stk);
 }
 
 /* ---------------------------------------------------------- filter_parser */
@@ -482,7 +482,7 @@ FLB_HD int ra_regex_match(const struct ch_env *e, const struct ch_rec *rc, uint3
 /* tslot (4 ints of the capture cache, or NULL): the evaluation pass stores the Time_Key lookup there
  * (state 1 ok / 2 failed, seconds lo/hi, nanoseconds) and the emission pass (use_cached) reads it
  * instead of running strptime again */
-FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s,
+FLB_HD int pdef_regex(const struct ch_env *e, const struct ch_lane *ln, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s,
                       uint32_t n, const int *caps, ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec,
                       int64_t *t_nsec, int32_t *tslot, int use_cached, uint32_t *th, int *pos)
 {
@@ -560,7 +560,7 @@ FLB_HD int pdef_regex(const struct ch_env *e, const struct cf_pdef *pd, uint32_t
 }
 
 /* Types cast of a parsed (key, value) pair: flb_parser_typecast(), src/flb_parser.c:1280-1377 */
-FLB_HD ref_t cast_value(const struct ch_env *e, const struct cf_pdef *pd, const uint8_t *key, uint32_t klen,
+FLB_HD ref_t cast_value(const struct ch_env *e, const struct ch_lane *ln, const struct cf_pdef *pd, const uint8_t *key, uint32_t klen,
                         const uint8_t *v, uint32_t voff, uint32_t vlen)
 {
     const struct cf_ptype *ty = (const struct cf_ptype *) (e->blob + pd->types_off);
@@ -579,7 +579,7 @@ FLB_HD ref_t cast_value(const struct ch_env *e, const struct cf_pdef *pd, const 
     return mkref(RK_STR_IN, voff, vlen);
 }
 
-FLB_HDN int pdef_time(const struct ch_env *e, const struct cf_pdef *pd, const uint8_t *v, uint32_t vlen,
+FLB_HDN int pdef_time(const struct ch_env *e, const struct ch_lane *ln, const struct cf_pdef *pd, const uint8_t *v, uint32_t vlen,
                      int64_t *lookup, double *frac)
 {
     struct dt_tm tm;
@@ -611,7 +611,7 @@ FLB_HD int64_t frac_to_nsec(double frac)
 FLB_HD int ltsv_label(uint32_t c) { return (c >= '0' && c <= '9') || ((c | 0x20) >= 'a' && (c | 0x20) <= 'z') || c == '_' || c == '.' || c == '-'; }
 FLB_HD int ltsv_field(uint32_t c) { return c != 0 && c != 9 && c != 10 && c != 13; }
 
-FLB_HDN int pdef_ltsv(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
+FLB_HDN int pdef_ltsv(const struct ch_env *e, const struct ch_lane *ln, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
                      ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec, int *pos)
 {
     uint32_t c = 0;
@@ -632,13 +632,13 @@ FLB_HDN int pdef_ltsv(const struct ch_env *e, const struct cf_pdef *pd, uint32_t
             int time_found = 0;
             if (pd->has_time && label_len == pd->time_key_len && field_len > 0 &&
                 bytes_eq(s + label, e->blob + pd->time_key_off, label_len)) {
-                if (pdef_time(e, pd, s + field, field_len, &lookup, &frac) != 0) return 0;
+                if (pdef_time(e, ln, pd, s + field, field_len, &lookup, &frac) != 0) return 0;
                 time_found = 1;
             }
             if (!time_found || pd->time_keep) {
                 if (cnt >= CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
                 ok_[cnt] = mkref(RK_STR_IN, val_off + label, label_len);
-                ov_[cnt] = pd->n_types ? cast_value(e, pd, s + label, label_len, s + field, val_off + field, field_len)
+                ov_[cnt] = pd->n_types ? cast_value(e, ln, pd, s + label, label_len, s + field, val_off + field, field_len)
                                        : mkref(RK_STR_IN, val_off + field, field_len);
                 cnt++;
             }
@@ -752,7 +752,7 @@ FLB_HD uint32_t lf_unescape(const uint8_t *s, uint32_t n, uint8_t *o)
 /* logfmt_parser(), src/flb_parser_logfmt.c:63-254.  ident bytes: > ' ' and not '=' '"' (:44-61) */
 FLB_HD int logfmt_ident(uint32_t c) { return c > ' ' && c != '=' && c != '"'; }
 
-FLB_HDN int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
+FLB_HDN int pdef_logfmt(const struct ch_env *e, const struct ch_lane *ln, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
                        ref_t *ok_, ref_t *ov_, int *on, int64_t *t_sec, int64_t *t_nsec, int *pos)
 {
     uint32_t c = 0, sk = 0;          /* sk: next free byte of the record's scratch (decoded escapes) */
@@ -795,18 +795,18 @@ FLB_HDN int pdef_logfmt(const struct ch_env *e, const struct cf_pdef *pd, uint32
             if (pd->logfmt_no_bare_keys && value_len == 0 && !value_set) return 0;
             if (pd->has_time && key_len == pd->time_key_len && value_len > 0 &&
                 bytes_eq(s + key, e->blob + pd->time_key_off, key_len)) {
-                if (pdef_time(e, pd, s + value, value_len, &lookup, &frac) != 0) return 0;
+                if (pdef_time(e, ln, pd, s + value, value_len, &lookup, &frac) != 0) return 0;
                 time_found = 1;
             }
             if (!time_found || pd->time_keep) {
                 if (cnt >= CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
                 ok_[cnt] = mkref(RK_STR_IN, val_off + key, key_len);
-                if (pd->n_types) ov_[cnt] = cast_value(e, pd, s + key, key_len, s + value, val_off + value, value_len);
+                if (pd->n_types) ov_[cnt] = cast_value(e, ln, pd, s + key, key_len, s + value, val_off + value, value_len);
                 else if (value_len == 0) ov_[cnt] = value_str ? mkref(RK_STR_IN, val_off + value, 0) : mkref(RK_TRUE, 0, 0);
                 else if (value_escape) {
-                    if (!e->scr) { CH_ATOMIC_OR(e->err, FLBGPU_E_ESCAPE); ov_[cnt] = mkref(RK_STR_IN, val_off + value, value_len); }
+                    if (!ln->scr) { CH_ATOMIC_OR(e->err, FLBGPU_E_ESCAPE); ov_[cnt] = mkref(RK_STR_IN, val_off + value, value_len); }
                     else {
-                        const uint32_t dl = lf_unescape(s + value, value_len, e->scr + sk);
+                        const uint32_t dl = lf_unescape(s + value, value_len, ln->scr + sk);
                         ov_[cnt] = mkref(RK_STR_SCR, sk, dl);
                         sk += value_len;                               /* the decoded text is never longer */
                     }
@@ -969,10 +969,10 @@ FLB_HD int djf_string(const uint8_t *s, int p, int n, uint8_t *scr, uint32_t at,
     return q + 1;
 }
 
-FLB_HD int djf_record(const struct ch_env *e, const uint8_t *s, int n, uint32_t val_off, ref_t *ok_, ref_t *ov_, uint32_t *th,
+FLB_HD int djf_record(const struct ch_env *e, const struct ch_lane *ln, const uint8_t *s, int n, uint32_t val_off, ref_t *ok_, ref_t *ov_, uint32_t *th,
                       int *on)
 {
-    uint8_t *scr = e->scr;
+    uint8_t *scr = ln->scr;
     uint32_t hpos[DJ_MAX_DEPTH + 1], ccnt[DJ_MAX_DEPTH + 1];
     uint32_t k = 0, isobj = 2, top_start = 0;
     int p = 0, st = DJF_KEY, depth = 1, cnt = 0, first = 1;
@@ -1224,10 +1224,10 @@ FLB_HD uint32_t pdec_mysql_unquote(const uint8_t *b, uint32_t n, uint8_t *o)
 #define PDEC_OUT_STRING 0
 #define PDEC_OUT_OBJECT 1
 /* one backend over text[0,n): result at scr + *at (advanced), *out_len bytes, *out_type; -1 = the decoder failed */
-FLB_HDN int pdec_backend(const struct ch_env *e, uint32_t backend, const uint8_t *text, uint32_t n, uint32_t *at, uint32_t *out_off,
+FLB_HDN int pdec_backend(const struct ch_env *e, const struct ch_lane *ln, uint32_t backend, const uint8_t *text, uint32_t n, uint32_t *at, uint32_t *out_off,
                          uint32_t *out_len, int *out_type)
 {
-    uint8_t *o = e->scr + *at;
+    uint8_t *o = ln->scr + *at;
     *out_off = *at;
     if (backend == PDEC_JSON) {
         /* decode_json(): leading blanks skipped, a map or array must start there, exactly one document, and it must be a map */
@@ -1253,16 +1253,16 @@ FLB_HDN int pdec_backend(const struct ch_env *e, uint32_t backend, const uint8_t
 
 /* returns 1 when some key had a decoder (the reference then re-packs the map: canonical header), 0 when none, -1 when the
  * field list overflowed */
-FLB_HDN int apply_decoders(const struct ch_env *e, const struct cf_pdef *pd, ref_t *K, ref_t *V, uint32_t *TH, int *cnt_io)
+FLB_HDN int apply_decoders(const struct ch_env *e, const struct ch_lane *ln, const struct cf_pdef *pd, ref_t *K, ref_t *V, uint32_t *TH, int *cnt_io)
 {
     const struct cf_pdec *decs = (const struct cf_pdec *) (e->blob + pd->dec_off);
     int cnt = *cnt_io, i, matched = -1, extra_keys = 0, extra_has = 0;
-    uint32_t at = e->dec_at, extra_off = 0, extra_len = 0, d;
-    if (!e->scr || !pd->n_dec) return 0;
+    uint32_t at = ln->dec_at, extra_off = 0, extra_len = 0, d;
+    if (!ln->scr || !pd->n_dec) return 0;
     /* the first STR key some decoder is registered for: nothing happens before it (and nothing at all without one) */
     for (i = 0; i < cnt && matched < 0; i++) {
         const uint8_t *kp; uint32_t kn;
-        if (ref_view(e, K[i], &kp, &kn) != 1) continue;
+        if (ref_view(e, ln, K[i], &kp, &kn) != 1) continue;
         for (d = 0; d < pd->n_dec; d++) if (decs[d].key_len == kn && bytes_eq(kp, e->blob + decs[d].key_off, kn)) { matched = i; break; }
     }
     if (matched < 0) return 0;
@@ -1273,7 +1273,7 @@ FLB_HDN int apply_decoders(const struct ch_env *e, const struct cf_pdef *pd, ref
         const struct cf_pdec_rule *rules;
         int is_decoded = 0, is_decoded_as = 0, in_type = PDEC_OUT_STRING, out_type = PDEC_OUT_STRING;
         uint32_t in_off = 0, in_len = 0, out_off = 0, out_len = 0;
-        if (ref_view(e, K[i], &kp, &kn) != 1 || ref_view(e, V[i], &vp, &vn) != 1) continue;
+        if (ref_view(e, ln, K[i], &kp, &kn) != 1 || ref_view(e, ln, V[i], &vp, &vn) != 1) continue;
         for (d = 0; d < pd->n_dec; d++) if (decs[d].key_len == kn && bytes_eq(kp, e->blob + decs[d].key_off, kn)) { dec = &decs[d]; break; }
         if (!dec) continue;
         data = vp; data_n = vn;
@@ -1284,14 +1284,14 @@ FLB_HDN int apply_decoders(const struct ch_env *e, const struct cf_pdef *pd, ref
             int o_type = 0, ret;
             if (rules[r].type == PDEC_DEFAULT && rules[r].action == PDEC_ACT_DO_NEXT && is_decoded) continue;
             if (is_decoded_as && in_type != PDEC_OUT_STRING) continue;
-            ret = pdec_backend(e, rules[r].backend, data, data_n, &at, &o_off, &o_len, &o_type);
+            ret = pdec_backend(e, ln, rules[r].backend, data, data_n, &at, &o_off, &o_len, &o_type);
             if (ret == -1) {
                 if (rules[r].action == PDEC_ACT_TRY_NEXT || rules[r].action == PDEC_ACT_DO_NEXT) continue;
                 break;
             }
             if (rules[r].type == PDEC_AS) {
                 in_off = o_off; in_len = o_len; in_type = o_type; is_decoded_as = 1;
-                data = e->scr + o_off; data_n = o_len;               /* the next rule decodes what this one made */
+                data = ln->scr + o_off; data_n = o_len;               /* the next rule decodes what this one made */
             }
             else { out_off = o_off; out_len = o_len; out_type = o_type; is_decoded = 1; }
             if (rules[r].action == PDEC_ACT_DO_NEXT) continue;
@@ -1302,7 +1302,7 @@ FLB_HDN int apply_decoders(const struct ch_env *e, const struct cf_pdef *pd, ref
     }
     /* merge_record_and_extra_keys(): the members of the (last) decoded object follow the record's own */
     if (extra_keys && extra_has) {
-        const uint8_t *q = e->scr + extra_off, *end = q + extra_len, *nx;
+        const uint8_t *q = ln->scr + extra_off, *end = q + extra_len, *nx;
         struct mp_tok t;
         uint32_t m;
         if (mp_token(q, end, &t) == 0 && t.type == MPT_MAP) {
@@ -1310,10 +1310,10 @@ FLB_HDN int apply_decoders(const struct ch_env *e, const struct cf_pdef *pd, ref
             for (m = 0; m < t.len; m++) {
                 if (cnt >= CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return -1; }
                 nx = mp_skip(q, end);
-                K[cnt] = mkref(RK_MP_SCR, (uint32_t) (q - e->scr), (uint32_t) (nx - q));
+                K[cnt] = mkref(RK_MP_SCR, (uint32_t) (q - ln->scr), (uint32_t) (nx - q));
                 q = nx;
                 nx = mp_skip(q, end);
-                V[cnt] = mkref(RK_MP_SCR, (uint32_t) (q - e->scr), (uint32_t) (nx - q));
+                V[cnt] = mkref(RK_MP_SCR, (uint32_t) (q - ln->scr), (uint32_t) (nx - q));
                 q = nx;
                 TH[cnt] = 0;
                 cnt++;
@@ -1325,32 +1325,32 @@ FLB_HDN int apply_decoders(const struct ch_env *e, const struct cf_pdef *pd, ref
 }
 
 /* first input offset >= p_abs inside the bitmap's range whose byte is '"', '\\', < 0x20 or >= 0x80; bm_end if none */
-FLB_HD uint32_t djf_bm_next(const struct ch_env *e, uint32_t p_abs)
+FLB_HD uint32_t djf_bm_next(const struct ch_env *e, const struct ch_lane *ln, uint32_t p_abs)
 {
-    uint32_t rel = p_abs - e->bm_base, w = rel >> 5;
-    const uint32_t nw = (e->bm_end - e->bm_base + 31u) >> 5;
+    uint32_t rel = p_abs - ln->bm_base, w = rel >> 5;
+    const uint32_t nw = (ln->bm_end - ln->bm_base + 31u) >> 5;
     uint32_t m;
-    if (p_abs >= e->bm_end) return e->bm_end;
-    m = e->bm[w] & (0xffffffffu << (rel & 31u));
-    while (!m) { if (++w >= nw) return e->bm_end; m = e->bm[w]; }
+    if (p_abs >= ln->bm_end) return ln->bm_end;
+    m = ln->bm[w] & (0xffffffffu << (rel & 31u));
+    while (!m) { if (++w >= nw) return ln->bm_end; m = ln->bm[w]; }
 #ifdef __CUDA_ARCH__
     rel = (w << 5) + (uint32_t) (__ffs((int) m) - 1);
 #else
     rel = (w << 5) + (uint32_t) __builtin_ctz(m);
 #endif
-    return e->bm_base + rel;
+    return ln->bm_base + rel;
 }
 
 /* Stage 2 over the stage-1 bitmap: the flat object of a log line -- string keys, values that are plain strings, integers of
  * up to 18 digits, short decimals, true / false / null -- one O(1) step per token.  Same answers as djf_record() on what it
  * accepts (1 + fields, or 0 "not an object"); -2 = something else is in the line (escapes, non-ASCII, nesting, exponents, white
  * space in odd places ...): djf_record() decides.  val_off is the input offset of s[0]. */
-FLB_HD int djf_record_bm(const struct ch_env *e, const uint8_t *s, int n, uint32_t val_off, ref_t *ok_, ref_t *ov_, uint32_t *th, int *on)
+FLB_HD int djf_record_bm(const struct ch_env *e, const struct ch_lane *ln, const uint8_t *s, int n, uint32_t val_off, ref_t *ok_, ref_t *ov_, uint32_t *th, int *on)
 {
-    uint8_t *scr = e->scr;
+    uint8_t *scr = ln->scr;
     uint32_t k = 0;
     int p = 0, cnt = 0, state = 0;             /* 0 running, 1 finished, <0 verdict */
-    if (!scr || val_off < e->bm_base || val_off + (uint32_t) n > e->bm_end) return -2;
+    if (!scr || val_off < ln->bm_base || val_off + (uint32_t) n > ln->bm_end) return -2;
     while (p < n && dj_ws(s[p])) p++;
     if (p >= n || s[p] != '{') return 0;
     p++;
@@ -1370,7 +1370,7 @@ FLB_HD int djf_record_bm(const struct ch_env *e, const uint8_t *s, int n, uint32
             uint32_t keyhash, c, q;
             /* key */
             if (p >= n || s[p] != '"') { state = -2; continue; }
-            q = djf_bm_next(e, val_off + (uint32_t) p + 1) - val_off;
+            q = djf_bm_next(e, ln, val_off + (uint32_t) p + 1) - val_off;
             if (q >= (uint32_t) n || s[q] != '"') { state = -2; continue; }
             keyref = mkref(RK_STR_IN, val_off + (uint32_t) p + 1, q - (uint32_t) p - 1);
             keyhash = ch_khash(s + p + 1, q - (uint32_t) p - 1);
@@ -1381,7 +1381,7 @@ FLB_HD int djf_record_bm(const struct ch_env *e, const uint8_t *s, int n, uint32
             /* value */
             c = s[p];
             if (c == '"') {
-                q = djf_bm_next(e, val_off + (uint32_t) p + 1) - val_off;
+                q = djf_bm_next(e, ln, val_off + (uint32_t) p + 1) - val_off;
                 if (q >= (uint32_t) n) { state = -2; continue; }
                 if (s[q] == '"') { valref = mkref(RK_STR_IN, val_off + (uint32_t) p + 1, q - (uint32_t) p - 1); p = (int) q + 1; }
                 else if (s[q] == 0x5c) {
@@ -1450,7 +1450,7 @@ FLB_HD int djf_record_bm(const struct ch_env *e, const uint8_t *s, int n, uint32
  * equals Time_Key; its value must be a STR; a failed lookup keeps the member and leaves
  * the timestamp at 0 (:198-209). */
 template <bool EMIT>
-FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
+FLB_HD int pdef_json(const struct ch_env *e, const struct ch_lane *ln, const struct cf_pdef *pd, uint32_t val_off, const uint8_t *s, uint32_t n,
                      ref_t *ok_, ref_t *ov_, uint32_t *th, int *on, int64_t *t_sec, int64_t *t_nsec, uint32_t ridx,
                      uint32_t *cache_pos, int *pos)
 {
@@ -1463,17 +1463,17 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t 
     int64_t lookup = 0;
     double frac = 0;
 
-    if (!e->scr) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
+    if (!ln->scr) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
     if (e->capcache && e->cap_stride >= RC_CACHE_INTS && *cache_pos + 2 <= e->cap_stride - RC_CACHE_INTS)
         slot = e->capcache + (size_t) *cache_pos * cs + ridx;
     *cache_pos += 2;
     /* slot[0]: 0/1 = result of the exact transcoder (msgpack of slot[1] bytes in scratch),
      * 2 = the fast path produced the fields (it is re-run by the emission pass, nothing cached) */
     if (!(EMIT && slot && CW(slot, 0) != 2)) {
-        ok = e->bm ? djf_record_bm(e, s, (int) n, val_off, ok_, ov_, th, &cnt) : -2;
+        ok = ln->bm ? djf_record_bm(e, ln, s, (int) n, val_off, ok_, ov_, th, &cnt) : -2;
         if (ok == -2) {
-            if (!EMIT && e->bm && e->defer_ok) return -2;         /* put off to the follow-up launch (CH_DEFER) */
-            cnt = 0; ok = djf_record(e, s, (int) n, val_off, ok_, ov_, th, &cnt);
+            if (!EMIT && ln->bm && ln->defer_ok) return -2;         /* put off to the follow-up launch (CH_DEFER) */
+            cnt = 0; ok = djf_record(e, ln, s, (int) n, val_off, ok_, ov_, th, &cnt);
         }
         if (ok == 0) { if (!EMIT && slot) { CW(slot, 0) = 0; CW(slot, 1) = 0; } return 0; }
         if (ok == 1) { if (!EMIT && slot) { CW(slot, 0) = 2; CW(slot, 1) = 0; } *pos = (int) n; goto have_fields; }   /* nothing but white space behind the document */
@@ -1482,36 +1482,36 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct cf_pdef *pd, uint32_t 
     if (EMIT && slot) { ok = CW(slot, 0); mplen = (uint32_t) CW(slot, 1); }
     else {
         uint32_t jerr = 0;
-        ok = dj_parse_record(s, (int) n, e->scr, &mplen, &jerr, pos);
+        ok = dj_parse_record(s, (int) n, ln->scr, &mplen, &jerr, pos);
         if (jerr) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
         if (!EMIT && slot) { CW(slot, 0) = ok; CW(slot, 1) = (int32_t) mplen; }
     }
     if (!ok) return 0;
-    q = e->scr; end = q + mplen;
+    q = ln->scr; end = q + mplen;
     mp_token(q, end, &t);
     q += t.hdr;
     if (t.len > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
     for (i = 0; i < t.len; i++) {
         nx = mp_skip(q, end);
-        ok_[cnt] = mkref(RK_MP_SCR, (uint32_t) (q - e->scr), (uint32_t) (nx - q));
+        ok_[cnt] = mkref(RK_MP_SCR, (uint32_t) (q - ln->scr), (uint32_t) (nx - q));
         q = nx;
         nx = mp_skip(q, end);
-        ov_[cnt] = mkref(RK_MP_SCR, (uint32_t) (q - e->scr), (uint32_t) (nx - q));
+        ov_[cnt] = mkref(RK_MP_SCR, (uint32_t) (q - ln->scr), (uint32_t) (nx - q));
         q = nx;
         th[cnt] = 0;                 /* fingerprint computed when the list is merged */
         cnt++;
     }
 have_fields:
-    if (pd->n_dec) apply_decoders(e, pd, ok_, ov_, th, &cnt);
+    if (pd->n_dec) apply_decoders(e, ln, pd, ok_, ov_, th, &cnt);
     if (pd->has_time) {
         for (i = 0; i < (uint32_t) cnt; i++) {
             const uint8_t *kp; uint32_t kn;
-            if (ref_view(e, ok_[i], &kp, &kn) != 1) continue;
+            if (ref_view(e, ln, ok_[i], &kp, &kn) != 1) continue;
             if (kn != pd->time_key_len || !bytes_eq(kp, e->blob + pd->time_key_off, kn)) continue;
             {
                 const uint8_t *vp; uint32_t vn;
-                if (ref_view(e, ov_[i], &vp, &vn) != 1) break;            /* value is not a STR: no time */
-                if (pdef_time(e, pd, vp, vn, &lookup, &frac) != 0) { lookup = 0; frac = 0; break; }
+                if (ref_view(e, ln, ov_[i], &vp, &vn) != 1) break;            /* value is not a STR: no time */
+                if (pdef_time(e, ln, pd, vp, vn, &lookup, &frac) != 0) { lookup = 0; frac = 0; break; }
                 if (!pd->time_keep) skip = (int) i;
             }
             break;
@@ -1535,7 +1535,7 @@ struct ch_scratch {              /* per-lane working memory */
 #define CH_DEFER 0xffffffffu
 
 template <bool EMIT>
-FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct ch_rec *rc, struct ch_scratch *w,
+FLB_HD void f_parser(const struct ch_env *e, const struct ch_lane *ln, const struct cf_parser *cf, struct ch_rec *rc, struct ch_scratch *w,
                      uint32_t ridx, uint32_t *cache_pos, int pristine, uint32_t rec_off, uint32_t rec_len, uint32_t empty_map_off)
 {
     uint64_t keep;                /* bit i: original field i is appended after the parsed ones */
@@ -1556,17 +1556,17 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
             const struct cf_ra *ra = (const struct cf_ra *) (e->blob + cf->ra_off);
             const uint8_t *np_ = 0, *ne_ = 0;
             int top, kn, vt;
-            if (ra_get(e, rc, ra, &top, &np_, &ne_, &kn) != 0) break;
-            vt = loc_view(e, rc, top, np_, ne_, &vp, &vn);
+            if (ra_get(e, ln, rc, ra, &top, &np_, &ne_, &kn) != 0) break;
+            vt = loc_view(e, ln, rc, top, np_, ne_, &vp, &vn);
             if (vt != 1 && vt != 2) break;
         }
         else {
             const uint8_t *kp; uint32_t kn; int kt, vt;
             if (rc->kh[i] != key_hash) continue;
-            kt = ref_view(e, rc->k[i], &kp, &kn);
+            kt = ref_view(e, ln, rc->k[i], &kp, &kn);
             if (kt != 1 && kt != 2) continue;
             if (kn != cf->key_len || !bytes_eq(kp, e->blob + cf->key_off, kn)) continue;
-            vt = ref_view(e, rc->v[i], &vp, &vn);
+            vt = ref_view(e, ln, rc->v[i], &vp, &vn);
             if (vt != 1 && vt != 2) continue;
         }
         if (vp < e->in || vp + vn > e->in + e->in_len) {     /* (an empty value may sit at the very end of the chunk) */
@@ -1597,14 +1597,14 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                     for (c = 0; c + 1 < need; c++) w->caps[c] = CW(slot, 1 + c);
                 }
                 else {
-                    matched = rx_run(e, pd->rx_off, vp, vn, w->caps, w->stk);
+                    matched = rx_run(e, ln, pd->rx_off, vp, vn, w->caps, w->stk);
                     if (!EMIT && slot) {
                         CW(slot, 0) = matched;
                         for (c = 0; c + 1 < need; c++) CW(slot, 1 + c) = w->caps[c];
                         CW(slot, need) = 0;
                     }
                 }
-                if (matched) got = pdef_regex(e, pd, val_off, vp, vn, w->caps, direct ? rc->k : w->tk, direct ? rc->v : w->tv, &cnt,
+                if (matched) got = pdef_regex(e, ln, pd, val_off, vp, vn, w->caps, direct ? rc->k : w->tk, direct ? rc->v : w->tv, &cnt,
                                               &ts, &tns, slot ? slot + (size_t) need * cs : 0, EMIT ? 1 : 0, direct ? rc->kh : w->th, &pos);
                 if (got) { preset = pd->n_groups; style = ST_PRESET; in_place = direct; }
             }
@@ -1613,33 +1613,33 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
                  * what rec_decode() produced: a document that turns out not to parse after some fields
                  * were written is undone by decoding the record again */
                 const int direct = pristine && !have_arr && !cf->ra_off && i == rc->nf - 1;
-                got = pdef_json<EMIT>(e, pd, val_off, vp, vn, direct ? rc->k : w->tk, direct ? rc->v : w->tv, direct ? rc->kh : w->th,
+                got = pdef_json<EMIT>(e, ln, pd, val_off, vp, vn, direct ? rc->k : w->tk, direct ? rc->v : w->tv, direct ? rc->kh : w->th,
                                       &cnt, &ts, &tns, ridx, cache_pos, &pos);
                 if (got == -2) { w->defer = 1; return; }
                 if (got) { style = ST_CANON; in_place = direct; }
                 else if (direct) {
                     /* (the time an earlier key of the same name parsed stays: filter_parser.c:296-300 keeps the last non-zero one) */
                     const int64_t s0 = rc->ts_sec, n0 = rc->ts_nsec;
-                    rec_decode(e, rec_off, rec_len, rc, empty_map_off);
+                    rec_decode(e, ln, rec_off, rec_len, rc, empty_map_off);
                     rc->ts_sec = s0; rc->ts_nsec = n0;
                 }
             }
             else if (pd->type == FLBGPU_PARSER_LTSV) {
-                got = pdef_ltsv(e, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns, &pos);
+                got = pdef_ltsv(e, ln, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns, &pos);
                 if (got) style = ST_CANON;
             }
             else if (pd->type == FLBGPU_PARSER_LOGFMT) {
-                got = pdef_logfmt(e, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns, &pos);
+                got = pdef_logfmt(e, ln, pd, val_off, vp, vn, w->tk, w->tv, &cnt, &ts, &tns, &pos);
                 if (got) style = ST_CANON;
             }
             if (got) {
                 if (pd->type == FLBGPU_PARSER_LTSV || pd->type == FLBGPU_PARSER_LOGFMT) { int z; for (z = 0; z < cnt; z++) w->th[z] = 0; }
                 if (pd->n_dec && pd->type != FLBGPU_PARSER_JSON) {
                     /* (the JSON parser decodes before it looks for the time key: pdef_json) */
-                    const int r = apply_decoders(e, pd, in_place ? rc->k : w->tk, in_place ? rc->v : w->tv, in_place ? rc->kh : w->th, &cnt);
+                    const int r = apply_decoders(e, ln, pd, in_place ? rc->k : w->tk, in_place ? rc->v : w->tv, in_place ? rc->kh : w->th, &cnt);
                     if (r > 0) style = ST_CANON;                   /* flb_parser_decoder_do() packs a map of its own */
                 }
-                if (in_place && pd->type == FLBGPU_PARSER_JSON) { int z; for (z = 0; z < cnt; z++) if (!rc->kh[z]) rc->kh[z] = ref_khash(e, rc->k[z]); }
+                if (in_place && pd->type == FLBGPU_PARSER_JSON) { int z; for (z = 0; z < cnt; z++) if (!rc->kh[z]) rc->kh[z] = ref_khash(e, ln, rc->k[z]); }
                 parse_ok = 1;
                 np = cnt;
                 if (!EMIT && e->prep) {             /* what flb_parser_do() hands back beside the map: position, time as parsed */
@@ -1670,7 +1670,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
             for (i = 0; i < rc->nf; i++) if ((keep >> i) & 1) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; w->th[j] = rc->kh[i]; j++; }
         }
         else if (preserved >= 0) { w->tk[j] = rc->k[preserved]; w->tv[j] = rc->v[preserved]; w->th[j] = rc->kh[preserved]; j++; }
-        for (i = 0; i < j; i++) { rc->k[i] = w->tk[i]; rc->v[i] = w->tv[i]; rc->kh[i] = w->th[i] ? w->th[i] : ref_khash(e, w->tk[i]); }
+        for (i = 0; i < j; i++) { rc->k[i] = w->tk[i]; rc->v[i] = w->tv[i]; rc->kh[i] = w->th[i] ? w->th[i] : ref_khash(e, ln, w->tk[i]); }
         rc->nf = j;
         if (extra > 0) rc->style = ST_CANON;
         else { rc->style = style; rc->preset_n = preset; }
@@ -1679,7 +1679,7 @@ FLB_HD void f_parser(const struct ch_env *e, const struct cf_parser *cf, struct 
 
 /* ------------------------------------------------------------ filter_grep */
 /* returns 1 keep, 0 exclude */
-FLB_HD int f_grep(const struct ch_env *e, const struct cf_grep *cf, const struct ch_rec *rc, struct ch_scratch *w)
+FLB_HD int f_grep(const struct ch_env *e, const struct ch_lane *ln, const struct cf_grep *cf, const struct ch_rec *rc, struct ch_scratch *w)
 {
     const struct cf_grep_rule *r = (const struct cf_grep_rule *) (e->blob + cf->rules_off);
     uint32_t i;
@@ -1689,7 +1689,7 @@ FLB_HD int f_grep(const struct ch_env *e, const struct cf_grep *cf, const struct
         for (i = 0; i < cf->n_rules; i++) {
             CH_SYNC();
             if (verdict < 0) {
-                int m = ra_regex_match(e, rc, r[i].ra_off, r[i].rx_off, w->caps, w->stk);
+                int m = ra_regex_match(e, ln, rc, r[i].ra_off, r[i].rx_off, w->caps, w->stk);
                 if (!m) { if (r[i].type == GREP_REGEX) verdict = 0; }
                 else verdict = r[i].type == GREP_EXCLUDE ? 0 : 1;
             }
@@ -1702,7 +1702,7 @@ FLB_HD int f_grep(const struct ch_env *e, const struct cf_grep *cf, const struct
         for (i = 0; i < cf->n_rules; i++) {
             CH_SYNC();
             if (stop == cf->n_rules) {
-                found = ra_regex_match(e, rc, r[i].ra_off, r[i].rx_off, w->caps, w->stk);
+                found = ra_regex_match(e, ln, rc, r[i].ra_off, r[i].rx_off, w->caps, w->stk);
                 if ((cf->op == GREP_OP_OR && found) || (cf->op == GREP_OP_AND && !found)) stop = i;
             }
         }
@@ -1714,36 +1714,36 @@ FLB_HD int f_grep(const struct ch_env *e, const struct cf_grep *cf, const struct
 }
 
 /* ---------------------------------------------------------- filter_modify */
-FLB_HD int key_eq(const struct ch_env *e, ref_t k, const uint8_t *s, uint32_t n)
+FLB_HD int key_eq(const struct ch_env *e, const struct ch_lane *ln, ref_t k, const uint8_t *s, uint32_t n)
 {
     const uint8_t *kp; uint32_t kn;
-    int t = ref_view(e, k, &kp, &kn);
+    int t = ref_view(e, ln, k, &kp, &kn);
     return (t == 1 || t == 2) && kn == n && bytes_eq(kp, s, n);
 }
 /* helper_msgpack_object_matches_wildcard(): prefix test (defined as length-guarded) */
-FLB_HD int key_prefix(const struct ch_env *e, ref_t k, const uint8_t *s, uint32_t n)
+FLB_HD int key_prefix(const struct ch_env *e, const struct ch_lane *ln, ref_t k, const uint8_t *s, uint32_t n)
 {
     const uint8_t *kp; uint32_t kn;
-    int t = ref_view(e, k, &kp, &kn);
+    int t = ref_view(e, ln, k, &kp, &kn);
     return (t == 1 || t == 2) && kn >= n && bytes_eq(kp, s, n);
 }
 /* helper_msgpack_object_matches_regex(): STR, or BOOLEAN as "true"/"false" */
-FLB_HD int obj_rx(const struct ch_env *e, int vt, const uint8_t *p, uint32_t n, uint32_t rx_off, struct ch_scratch *w)
+FLB_HD int obj_rx(const struct ch_env *e, const struct ch_lane *ln, int vt, const uint8_t *p, uint32_t n, uint32_t rx_off, struct ch_scratch *w)
 {
     const uint8_t tr[4] = { 't', 'r', 'u', 'e' }, fa[5] = { 'f', 'a', 'l', 's', 'e' };
-    if (vt == 1) return rx_run(e, rx_off, p, n, w->caps, w->stk);
-    if (vt == 3) return rx_run(e, rx_off, tr, 4, w->caps, w->stk);
-    if (vt == 4) return rx_run(e, rx_off, fa, 5, w->caps, w->stk);
+    if (vt == 1) return rx_run(e, ln, rx_off, p, n, w->caps, w->stk);
+    if (vt == 3) return rx_run(e, ln, rx_off, tr, 4, w->caps, w->stk);
+    if (vt == 4) return rx_run(e, ln, rx_off, fa, 5, w->caps, w->stk);
     return 0;
 }
-FLB_HD int ref_rx(const struct ch_env *e, ref_t r, uint32_t rx_off, struct ch_scratch *w)
+FLB_HD int ref_rx(const struct ch_env *e, const struct ch_lane *ln, ref_t r, uint32_t rx_off, struct ch_scratch *w)
 {
     const uint8_t *p = 0; uint32_t n = 0;
-    int vt = ref_view(e, r, &p, &n);
-    return obj_rx(e, vt, p, n, rx_off, w);
+    int vt = ref_view(e, ln, r, &p, &n);
+    return obj_rx(e, ln, vt, p, n, rx_off, w);
 }
 
-FLB_HD int mod_conditions(const struct ch_env *e, const struct cf_modify *cf, const struct ch_rec *rc,
+FLB_HD int mod_conditions(const struct ch_env *e, const struct ch_lane *ln, const struct cf_modify *cf, const struct ch_rec *rc,
                           struct ch_scratch *w)
 {
     const struct cf_mod_cond *c = (const struct cf_mod_cond *) (e->blob + cf->conds_off);
@@ -1756,15 +1756,15 @@ FLB_HD int mod_conditions(const struct ch_env *e, const struct cf_modify *cf, co
         uint32_t sn = 0;
         int top = -1, kn = 0, exists = 0, vt = 0, r = 0, cnt = 0;
         if (ra) {
-            exists = (ra_get(e, rc, ra, &top, &vp, &ve, &kn) == 0) && !kn;
-            if (exists) vt = loc_view(e, rc, top, vp, ve, &sp, &sn);
+            exists = (ra_get(e, ln, rc, ra, &top, &vp, &ve, &kn) == 0) && !kn;
+            if (exists) vt = loc_view(e, ln, rc, top, vp, ve, &sp, &sn);
         }
         switch (c[ci].type) {
         case MODC_KEY_EXISTS: r = exists; break;
         case MODC_KEY_DOES_NOT_EXIST: r = !exists; break;
         case MODC_A_KEY_MATCHES:
         case MODC_NO_KEY_MATCHES:
-            for (i = 0; i < rc->nf; i++) if (ref_rx(e, rc->k[i], c[ci].a_rx, w)) cnt++;
+            for (i = 0; i < rc->nf; i++) if (ref_rx(e, ln, rc->k[i], c[ci].a_rx, w)) cnt++;
             r = (c[ci].type == MODC_A_KEY_MATCHES) ? cnt > 0 : cnt == 0;
             break;
         case MODC_KEY_VALUE_EQUALS:
@@ -1774,16 +1774,16 @@ FLB_HD int mod_conditions(const struct ch_env *e, const struct cf_modify *cf, co
             r = exists && !((vt == 1 || vt == 2) && sn == c[ci].b_len && bytes_eq(sp, e->blob + c[ci].b_off, sn));
             break;
         case MODC_KEY_VALUE_MATCHES:
-            r = exists && obj_rx(e, vt, sp, sn, c[ci].b_rx, w);
+            r = exists && obj_rx(e, ln, vt, sp, sn, c[ci].b_rx, w);
             break;
         case MODC_KEY_VALUE_DOES_NOT_MATCH:
-            r = exists && !obj_rx(e, vt, sp, sn, c[ci].b_rx, w);
+            r = exists && !obj_rx(e, ln, vt, sp, sn, c[ci].b_rx, w);
             break;
         case MODC_MATCHING_KEYS_HAVE_MATCHING_VALUES:
         case MODC_MATCHING_KEYS_DO_NOT_HAVE_MATCHING_VALUES:
             r = 1;
             for (i = 0; i < rc->nf; i++) {
-                if (ref_rx(e, rc->k[i], c[ci].a_rx, w) && !ref_rx(e, rc->v[i], c[ci].b_rx, w)) { r = 0; break; }
+                if (ref_rx(e, ln, rc->k[i], c[ci].a_rx, w) && !ref_rx(e, ln, rc->v[i], c[ci].b_rx, w)) { r = 0; break; }
             }
             if (c[ci].type == MODC_MATCHING_KEYS_DO_NOT_HAVE_MATCHING_VALUES) r = !r;
             break;
@@ -1795,14 +1795,14 @@ FLB_HD int mod_conditions(const struct ch_env *e, const struct cf_modify *cf, co
 }
 
 /* key i of the record equals (s, n) whose ch_khash is h */
-FLB_HD int key_is(const struct ch_env *e, const struct ch_rec *rc, int i, uint32_t h, const uint8_t *s, uint32_t n)
+FLB_HD int key_is(const struct ch_env *e, const struct ch_lane *ln, const struct ch_rec *rc, int i, uint32_t h, const uint8_t *s, uint32_t n)
 {
-    return rc->kh[i] == h && key_eq(e, rc->k[i], s, n);
+    return rc->kh[i] == h && key_eq(e, ln, rc->k[i], s, n);
 }
-FLB_HD int count_keys(const struct ch_env *e, const struct ch_rec *rc, uint32_t h, const uint8_t *s, uint32_t n)
+FLB_HD int count_keys(const struct ch_env *e, const struct ch_lane *ln, const struct ch_rec *rc, uint32_t h, const uint8_t *s, uint32_t n)
 {
     int i, c = 0;
-    for (i = 0; i < rc->nf; i++) if (key_is(e, rc, i, h, s, n)) c++;
+    for (i = 0; i < rc->nf; i++) if (key_is(e, ln, rc, i, h, s, n)) c++;
     return c;
 }
 
@@ -1821,7 +1821,7 @@ FLB_HD void compact(struct ch_rec *rc, uint64_t del)
 }
 
 /* returns 1 when the rule modified the map */
-FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct ch_rec *rc, struct ch_scratch *w)
+FLB_HD int mod_rule(const struct ch_env *e, const struct ch_lane *ln, const struct cf_mod_rule *r, struct ch_rec *rc, struct ch_scratch *w)
 {
     const uint8_t *key = e->blob + r->key_off, *val = e->blob + r->val_off;
     ref_t kmp = mkref(RK_MP_CONST, r->kmp_off, r->kmp_len), vmp = mkref(RK_MP_CONST, r->vmp_off, r->vmp_len);
@@ -1832,39 +1832,39 @@ FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct 
     switch (r->type) {
     case MOD_RENAME:
     case MOD_HARD_RENAME:
-        match = count_keys(e, rc, kh, key, r->key_len);
-        conflict = count_keys(e, rc, vh, val, r->val_len);
+        match = count_keys(e, ln, rc, kh, key, r->key_len);
+        conflict = count_keys(e, ln, rc, vh, val, r->val_len);
         if (match == 0) return 0;
         if (r->type == MOD_RENAME && conflict > 0) return 0;
-        if (conflict > 0) for (i = 0; i < rc->nf; i++) if (key_is(e, rc, i, vh, val, r->val_len)) del |= 1ull << i;
-        for (i = 0; i < rc->nf; i++) if (!((del >> i) & 1) && key_is(e, rc, i, kh, key, r->key_len)) { rc->k[i] = vmp; rc->kh[i] = vh; }
+        if (conflict > 0) for (i = 0; i < rc->nf; i++) if (key_is(e, ln, rc, i, vh, val, r->val_len)) del |= 1ull << i;
+        for (i = 0; i < rc->nf; i++) if (!((del >> i) & 1) && key_is(e, ln, rc, i, kh, key, r->key_len)) { rc->k[i] = vmp; rc->kh[i] = vh; }
         compact(rc, del);
         return 1;
     case MOD_COPY:
     case MOD_HARD_COPY:
-        match = count_keys(e, rc, kh, key, r->key_len);
-        conflict = count_keys(e, rc, vh, val, r->val_len);
+        match = count_keys(e, ln, rc, kh, key, r->key_len);
+        conflict = count_keys(e, ln, rc, vh, val, r->val_len);
         if (match != 1) return 0;
         if (r->type == MOD_COPY && conflict > 0) return 0;
         if (r->type == MOD_HARD_COPY && conflict > 1) return 0;
         if (conflict == 1) {
-            for (i = 0; i < rc->nf; i++) if (key_is(e, rc, i, vh, val, r->val_len)) del |= 1ull << i;
+            for (i = 0; i < rc->nf; i++) if (key_is(e, ln, rc, i, vh, val, r->val_len)) del |= 1ull << i;
             compact(rc, del);
         }
         if (rc->nf + 1 > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
-        for (i = 0; i < rc->nf; i++) if (key_is(e, rc, i, kh, key, r->key_len)) break;
+        for (i = 0; i < rc->nf; i++) if (key_is(e, ln, rc, i, kh, key, r->key_len)) break;
         if (i == rc->nf) return 1;       /* source vanished with the conflict key (same name): map repacked */
         for (j = rc->nf; j > i + 1; j--) { rc->k[j] = rc->k[j - 1]; rc->v[j] = rc->v[j - 1]; rc->kh[j] = rc->kh[j - 1]; }
         rc->k[i + 1] = vmp; rc->v[i + 1] = rc->v[i]; rc->kh[i + 1] = vh;
         rc->nf++;
         return 1;
     case MOD_ADD:
-        if (count_keys(e, rc, kh, key, r->key_len) != 0) return 0;
+        if (count_keys(e, ln, rc, kh, key, r->key_len) != 0) return 0;
         if (rc->nf + 1 > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 0; }
         rc->k[rc->nf] = kmp; rc->v[rc->nf] = vmp; rc->kh[rc->nf] = kh; rc->nf++;
         return 1;
     case MOD_SET:
-        for (i = 0; i < rc->nf; i++) if (key_is(e, rc, i, kh, key, r->key_len)) del |= 1ull << i;
+        for (i = 0; i < rc->nf; i++) if (key_is(e, ln, rc, i, kh, key, r->key_len)) del |= 1ull << i;
         compact(rc, del);
         if (rc->nf + 1 > CH_MAXF) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return 1; }
         rc->k[rc->nf] = kmp; rc->v[rc->nf] = vmp; rc->kh[rc->nf] = kh; rc->nf++;
@@ -1875,9 +1875,9 @@ FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct 
         match = 0;
         for (i = 0; i < rc->nf; i++) {
             int d;
-            if (r->type == MOD_REMOVE) d = key_is(e, rc, i, kh, key, r->key_len) ? 1 : 0;
-            else if (r->type == MOD_REMOVE_WILDCARD) d = key_prefix(e, rc->k[i], key, r->key_len) ? 1 : 0;
-            else d = ref_rx(e, rc->k[i], r->key_rx, w) ? 1 : 0;
+            if (r->type == MOD_REMOVE) d = key_is(e, ln, rc, i, kh, key, r->key_len) ? 1 : 0;
+            else if (r->type == MOD_REMOVE_WILDCARD) d = key_prefix(e, ln, rc->k[i], key, r->key_len) ? 1 : 0;
+            else d = ref_rx(e, ln, rc->k[i], r->key_rx, w) ? 1 : 0;
             if (d) del |= 1ull << i;
             match += d;
         }
@@ -1887,27 +1887,27 @@ FLB_HD int mod_rule(const struct ch_env *e, const struct cf_mod_rule *r, struct 
     case MOD_MOVE_TO_START:
     case MOD_MOVE_TO_END:
         match = 0;
-        for (i = 0; i < rc->nf; i++) if (key_prefix(e, rc->k[i], key, r->key_len)) { del |= 1ull << i; match++; }
+        for (i = 0; i < rc->nf; i++) if (key_prefix(e, ln, rc->k[i], key, r->key_len)) { del |= 1ull << i; match++; }
         if (match == 0) return 0;
         j = 0;
         for (i = 0; i < rc->nf; i++) if ((int) ((del >> i) & 1) == (r->type == MOD_MOVE_TO_START)) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; j++; }
         for (i = 0; i < rc->nf; i++) if ((int) ((del >> i) & 1) != (r->type == MOD_MOVE_TO_START)) { w->tk[j] = rc->k[i]; w->tv[j] = rc->v[i]; j++; }
-        for (i = 0; i < rc->nf; i++) { rc->k[i] = w->tk[i]; rc->v[i] = w->tv[i]; rc->kh[i] = ref_khash(e, w->tk[i]); }
+        for (i = 0; i < rc->nf; i++) { rc->k[i] = w->tk[i]; rc->v[i] = w->tv[i]; rc->kh[i] = ref_khash(e, ln, w->tk[i]); }
         return 1;
     }
     return 0;
 }
 
 /* returns 1 when the record was modified (and is re-encoded canonically) */
-FLB_HD int f_modify(const struct ch_env *e, const struct cf_modify *cf, struct ch_rec *rc, struct ch_scratch *w)
+FLB_HD int f_modify(const struct ch_env *e, const struct ch_lane *ln, const struct cf_modify *cf, struct ch_rec *rc, struct ch_scratch *w)
 {
     const struct cf_mod_rule *r = (const struct cf_mod_rule *) (e->blob + cf->rules_off);
     uint32_t i;
     int mod = 0;
-    const int cond = mod_conditions(e, cf, rc, w);
+    const int cond = mod_conditions(e, ln, cf, rc, w);
     for (i = 0; i < cf->n_rules; i++) {
         CH_SYNC();
-        if (cond && mod_rule(e, &r[i], rc, w)) mod = 1;
+        if (cond && mod_rule(e, ln, &r[i], rc, w)) mod = 1;
     }
     if (mod) { rc->reenc = 1; rc->style = ST_CANON; }
     return mod;
@@ -1925,7 +1925,7 @@ FLB_HD int ci_eq(const uint8_t *a, const uint8_t *b, uint32_t n)
 }
 
 /* returns: 0 passes untouched evidence-wise, sets *cause; *drop when no field is left */
-FLB_HDN void f_recmod(const struct ch_env *e, const struct cf_recmod *cf, struct ch_rec *rc, int *cause, int *drop)
+FLB_HDN void f_recmod(const struct ch_env *e, const struct ch_lane *ln, const struct cf_recmod *cf, struct ch_rec *rc, int *cause, int *drop)
 {
     const struct cf_rm_key *keys = 0;
     const struct cf_rm_rec *recs = (const struct cf_rm_rec *) (e->blob + cf->records_off);
@@ -1938,7 +1938,7 @@ FLB_HDN void f_recmod(const struct ch_env *e, const struct cf_recmod *cf, struct
     if (keys) {
         for (i = 0; i < rc->nf; i++) {
             const uint8_t *kp = 0; uint32_t kn = 0;
-            int kt = ref_view(e, rc->k[i], &kp, &kn), result = 0;
+            int kt = ref_view(e, ln, rc->k[i], &kp, &kn), result = 0;
             for (q = 0; q < nk && (kt == 1 || kt == 2); q++) {
                 if (!keys[q].dynamic && kn != keys[q].len) continue;
                 if (keys[q].dynamic && kn < keys[q].len) continue;
@@ -1956,7 +1956,7 @@ FLB_HDN void f_recmod(const struct ch_env *e, const struct cf_recmod *cf, struct
     for (q = 0; q < cf->n_records; q++) {
         rc->k[rc->nf] = mkref(RK_MP_CONST, recs[q].kmp_off, recs[q].kmp_len);
         rc->v[rc->nf] = mkref(RK_MP_CONST, recs[q].vmp_off, recs[q].vmp_len);
-        rc->kh[rc->nf] = ref_khash(e, rc->k[rc->nf]);
+        rc->kh[rc->nf] = ref_khash(e, ln, rc->k[rc->nf]);
         rc->nf++;
     }
     rc->reenc = 1;
@@ -1992,33 +1992,33 @@ static inline unsigned long long ch_cas64_host(unsigned long long *p, unsigned l
 
 /* flb_ra_get_value_object() as the label/value code uses it: the located msgpack token.
  * Returns 1 and the token, 0 when the accessor finds nothing. */
-FLB_HD int l2m_lookup(const struct ch_env *e, const struct ch_rec *rc, uint32_t ra_off, struct mp_tok *t,
+FLB_HD int l2m_lookup(const struct ch_env *e, const struct ch_lane *ln, const struct ch_rec *rc, uint32_t ra_off, struct mp_tok *t,
                       const uint8_t **payload, int *is_raw_str, uint32_t *raw_len)
 {
     const struct cf_ra *ra = (const struct cf_ra *) (e->blob + ra_off);
     const uint8_t *vp = 0, *ve = 0;
     int top, kn, i;
     *is_raw_str = 0;
-    i = ra_find(e, rc, e->blob + ra->key_off, ra->key_len);
+    i = ra_find(e, ln, rc, e->blob + ra->key_off, ra->key_len);
     if (i < 0) return 0;
     top = i;
     {
         uint32_t k = r_kind(rc->v[i]);
-        if (k == RK_STR_IN || k == RK_STR_SCR) { *is_raw_str = 1; *payload = ref_ptr(e, rc->v[i]); *raw_len = r_len(rc->v[i]); return 1; }
+        if (k == RK_STR_IN || k == RK_STR_SCR) { *is_raw_str = 1; *payload = ref_ptr(e, ln, rc->v[i]); *raw_len = r_len(rc->v[i]); return 1; }
         if (k == RK_TRUE || k == RK_FALSE) { t->type = MPT_BOOL; return 1; }
-        if (k == RK_INT_IN) { t->type = MPT_INT; t->u = (uint64_t) ch_atoll(ref_ptr(e, rc->v[i]), r_len(rc->v[i])); return 1; }
-        if (k == RK_HEX_IN) { t->type = MPT_UINT; t->u = ch_strtoull16(ref_ptr(e, rc->v[i]), r_len(rc->v[i])); return 1; }
+        if (k == RK_INT_IN) { t->type = MPT_INT; t->u = (uint64_t) ch_atoll(ref_ptr(e, ln, rc->v[i]), r_len(rc->v[i])); return 1; }
+        if (k == RK_HEX_IN) { t->type = MPT_UINT; t->u = ch_strtoull16(ref_ptr(e, ln, rc->v[i]), r_len(rc->v[i])); return 1; }
         if (k == RK_FLT_IN) {
             int okf;
-            t->u = dj_strtod(ref_ptr(e, rc->v[i]), (int) r_len(rc->v[i]), &okf);
+            t->u = dj_strtod(ref_ptr(e, ln, rc->v[i]), (int) r_len(rc->v[i]), &okf);
             if (!okf) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
             t->type = MPT_F64; return 1;
         }
         if (k != RK_MP_IN && k != RK_MP_CONST && k != RK_MP_SCR) { t->type = MPT_NIL; CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return 1; }
-        vp = ref_ptr(e, rc->v[i]); ve = vp + r_len(rc->v[i]);
+        vp = ref_ptr(e, ln, rc->v[i]); ve = vp + r_len(rc->v[i]);
         if (mp_token(vp, ve, t) != 0) return 0;
         if (ra->n_sub > 0 && (t->type == MPT_MAP || t->type == MPT_ARRAY)) {
-            if (ra_walk_sub(e, ra, vp, ve, &vp, &ve, &kn) != 0) return 0;
+            if (ra_walk_sub(e, ln, ra, vp, ve, &vp, &ve, &kn) != 0) return 0;
             if (mp_token(vp, ve, t) != 0) return 0;
         }
     }
@@ -2027,7 +2027,7 @@ FLB_HD int l2m_lookup(const struct ch_env *e, const struct ch_rec *rc, uint32_t 
     return 1;
 }
 
-FLB_HDN void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct ch_rec *rc, struct ch_scratch *w,
+FLB_HDN void f_l2m(const struct ch_env *e, const struct ch_lane *ln, const struct cf_l2m *cf, const struct ch_rec *rc, struct ch_scratch *w,
                   uint32_t ridx)
 {
     const struct l2m_table *tb = &e->l2m;
@@ -2038,7 +2038,7 @@ FLB_HDN void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct
     double val = 0;
 
     if (!tb->hash) return;
-    if (cf->grep_off && !f_grep(e, (const struct cf_grep *) (e->blob + cf->grep_off), rc, w)) return;
+    if (cf->grep_off && !f_grep(e, ln, (const struct cf_grep *) (e->blob + cf->grep_off), rc, w)) return;
 
     /* label values -> strings (log_to_metrics.c:1010-1043): STR "%s" (<= 251 bytes, stops at NUL),
      * integers "%ld", anything else "" */
@@ -2050,7 +2050,7 @@ FLB_HDN void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct
         uint8_t *dst = lab + lpos + 1;
         if (lpos + 1 + 252 > sizeof(w->stk)) { CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return; }
         t.type = MPT_NIL; t.len = 0; t.u = 0; t.hdr = 0;
-        if (l2m_lookup(e, rc, cf->label_ra_off[li], &t, &pl, &raw, &rl)) {
+        if (l2m_lookup(e, ln, rc, cf->label_ra_off[li], &t, &pl, &raw, &rl)) {
             if (raw || t.type == MPT_STR) {
                 uint32_t sl = raw ? rl : t.len;
                 for (k = 0; k < sl && k < 251 && pl[k]; k++) dst[n++] = pl[k];
@@ -2083,7 +2083,7 @@ FLB_HDN void f_l2m(const struct ch_env *e, const struct cf_l2m *cf, const struct
         int raw = 0, ok = 1;
         uint32_t rl = 0;
         t.type = MPT_NIL; t.len = 0; t.u = 0; t.hdr = 0;
-        if (!l2m_lookup(e, rc, cf->value_ra_off, &t, &pl, &raw, &rl)) return;    /* "value field is empty or not existent" */
+        if (!l2m_lookup(e, ln, rc, cf->value_ra_off, &t, &pl, &raw, &rl)) return;    /* "value field is empty or not existent" */
         if (raw || t.type == MPT_STR) {
             /* sscanf("%lf"): a text that converts nothing leaves the PREVIOUS record's value in
              * place (log_to_metrics.c:984,1105) -- order dependent, refused; so are inf/nan/hex */
@@ -2149,7 +2149,7 @@ FLB_HDN void chain_skipped_record(const struct ch_env *e, uint32_t ridx, uint32_
 {
     const struct chain_hdr *h = (const struct chain_hdr *) e->blob;
     const struct chain_filter *f = (const struct chain_filter *) (e->blob + h->filters_off);
-    struct ch_env le;
+    struct ch_lane lane, *ln = &lane;
     uint32_t k;
     for (k = 0; k < h->n_filters; k++) {
         if (!((e->active >> k) & 1)) continue;
@@ -2160,9 +2160,10 @@ FLB_HDN void chain_skipped_record(const struct ch_env *e, uint32_t ridx, uint32_
     {
         struct ch_rec rc;
         struct ch_scratch w;
-        if (e->scr) { le = *e; le.scr = e->scr + (size_t) e->scr_mul * off; le.dec_at = 4u * len; e = &le; }
-        if (rec_decode(e, off, len, &rc, h->empty_map_off) != 0) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return; }
-        f_l2m(e, (const struct cf_l2m *) (e->blob + f[k].cfg_off), &rc, &w, ridx);
+        lane.scr = e->scr ? e->scr + (size_t) e->scr_mul * off : 0; lane.dec_at = 4u * len;
+        lane.bm = 0; lane.bm_base = lane.bm_end = 0; lane.defer_ok = 0;
+        if (rec_decode(e, ln, off, len, &rc, h->empty_map_off) != 0) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return; }
+        f_l2m(e, ln, (const struct cf_l2m *) (e->blob + f[k].cfg_off), &rc, &w, ridx);
     }
 }
 
@@ -2171,22 +2172,17 @@ FLB_HDN void chain_skipped_record(const struct ch_env *e, uint32_t ridx, uint32_
  * EMIT=false: returns the output size (0 = dropped) and records evidence.
  * EMIT=true : writes the record at `out` (the caller only calls it for size>0). */
 template <bool EMIT>
-FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off, uint32_t len, uint8_t *out)
+FLB_HD uint32_t chain_record(const struct ch_env *e, struct ch_lane *ln, uint32_t ridx, uint32_t off, uint32_t len, uint8_t *out)
 {
     const struct chain_hdr *h = (const struct chain_hdr *) e->blob;
     const struct chain_filter *f = (const struct chain_filter *) (e->blob + h->filters_off);
     struct ch_rec rc;
     struct ch_scratch w;
-    struct ch_env le;
     uint32_t k, cache_pos = 0;
     w.defer = 0;
-
-    if (e->scr) {               /* this record's private scratch region: 4 bytes per record byte */
-        le = *e;
-        le.scr = e->scr + (size_t) e->scr_mul * off;
-        le.dec_at = 4u * len;
-        e = &le;
-    }
+    /* this record's private scratch region: scr_mul bytes per record byte, the decoders' part behind the parser's */
+    ln->scr = e->scr ? e->scr + (size_t) e->scr_mul * off : 0;
+    ln->dec_at = 4u * len;
     /* The evaluation pass leaves the final field list of every surviving record (<= RC_CACHE_MAXF
      * fields) in the last RC_CACHE_INTS ints of its capture-cache row; the emission pass then only
      * encodes -- no decoding, no filters.  Longer records are re-run through the chain. */
@@ -2205,10 +2201,10 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
                 rc.k[i] = ((ref_t) (uint32_t) CW(c, 8 + 4 * i + 1) << 32) | (uint32_t) CW(c, 8 + 4 * i);
                 rc.v[i] = ((ref_t) (uint32_t) CW(c, 8 + 4 * i + 3) << 32) | (uint32_t) CW(c, 8 + 4 * i + 2);
             }
-            return rec_emit(e, &rc, out);
+            return rec_emit(e, ln, &rc, out);
         }
     }
-    if (rec_decode(e, off, len, &rc, h->empty_map_off) != 0) {
+    if (rec_decode(e, ln, off, len, &rc, h->empty_map_off) != 0) {
         CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS);
         return 0;
     }
@@ -2220,12 +2216,12 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
         switch (f[k].kind) {
         case FLBGPU_F_PARSER:
             if (!assumed) break;
-            f_parser<EMIT>(e, (const struct cf_parser *) cfg, &rc, &w, ridx, &cache_pos, k == 0, off, len, h->empty_map_off);
+            f_parser<EMIT>(e, ln, (const struct cf_parser *) cfg, &rc, &w, ridx, &cache_pos, k == 0, off, len, h->empty_map_off);
             if (!EMIT && w.defer) return CH_DEFER;
             if (!EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_EMITTED);
             break;
         case FLBGPU_F_GREP:
-            if (!f_grep(e, (const struct cf_grep *) cfg, &rc, &w)) {
+            if (!f_grep(e, ln, (const struct cf_grep *) cfg, &rc, &w)) {
                 if (!EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_CAUSE);
                 if (assumed) return 0;
             }
@@ -2234,11 +2230,11 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
         case FLBGPU_F_MODIFY: {
             /* evaluate on a copy when the filter is assumed NOTOUCH so the record passes unchanged */
             if (assumed) {
-                if (f_modify(e, (const struct cf_modify *) cfg, &rc, &w) && !EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_CAUSE);
+                if (f_modify(e, ln, (const struct cf_modify *) cfg, &rc, &w) && !EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_CAUSE);
             }
             else if (!EMIT) {
                 struct ch_rec tmp = rc;
-                if (f_modify(e, (const struct cf_modify *) cfg, &tmp, &w)) CH_ATOMIC_OR(&e->fl_flags[k], CHF_CAUSE);
+                if (f_modify(e, ln, (const struct cf_modify *) cfg, &tmp, &w)) CH_ATOMIC_OR(&e->fl_flags[k], CHF_CAUSE);
             }
             if (!EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_EMITTED);
             break;
@@ -2246,13 +2242,13 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
         case FLBGPU_F_RECORD_MODIFIER: {
             int cause = 0, drop = 0;
             if (assumed) {
-                f_recmod(e, (const struct cf_recmod *) cfg, &rc, &cause, &drop);
+                f_recmod(e, ln, (const struct cf_recmod *) cfg, &rc, &cause, &drop);
                 if (!EMIT) { if (cause) CH_ATOMIC_OR(&e->fl_flags[k], CHF_CAUSE); if (!drop) CH_ATOMIC_OR(&e->fl_flags[k], CHF_EMITTED); }
                 if (drop) return 0;
             }
             else if (!EMIT) {
                 struct ch_rec tmp = rc;
-                f_recmod(e, (const struct cf_recmod *) cfg, &tmp, &cause, &drop);
+                f_recmod(e, ln, (const struct cf_recmod *) cfg, &tmp, &cause, &drop);
                 if (cause) CH_ATOMIC_OR(&e->fl_flags[k], CHF_CAUSE);
                 if (!drop) CH_ATOMIC_OR(&e->fl_flags[k], CHF_EMITTED);
             }
@@ -2261,7 +2257,7 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
         case FLBGPU_F_LOG_TO_METRICS:
             /* metrics are accumulated once per call, by the evaluation pass; logs pass
              * through unless discard_logs (log_to_metrics.c:1136-1141) */
-            if (!EMIT) f_l2m(e, (const struct cf_l2m *) cfg, &rc, &w, ridx);
+            if (!EMIT) f_l2m(e, ln, (const struct cf_l2m *) cfg, &rc, &w, ridx);
             if (assumed) return 0;
             break;
         default:
@@ -2291,7 +2287,7 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, uint32_t ridx, uint32_t off
         if (EMIT) mp_copy(out, e->in + off, len);
         return len;
     }
-    return rec_emit(e, &rc, EMIT ? out : 0);
+    return rec_emit(e, ln, &rc, EMIT ? out : 0);
 }
 
 #include "dev_jsmn.cuh"

@@ -347,7 +347,7 @@ __device__ __forceinline__ uint32_t bm_mask4(uint32_t w)
     return ((m >> 7) * 0x00204081u) >> 21 & 0xfu;        /* gather the four flags into bits 0..3 */
 }
 
-__global__ void __launch_bounds__(1024, 1) k_chain_eval(const k_chain_params p)       /* 64 registers per lane; block size chosen at launch */
+__global__ void __launch_bounds__(1024, 1) k_chain_eval(const __grid_constant__ k_chain_params p)       /* 64 registers per lane; block size chosen at launch */
 {
     extern __shared__ __align__(16) uint8_t dsm[];
     const uint32_t n_rec = p.n_dev ? *p.n_dev : p.n_rec;
@@ -380,10 +380,12 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval(const k_chain_params p) 
     if (!valid) return;
     uint32_t sz = 0;
     if (live) {
-        struct ch_env le = p.env;
-        le.bm = bm; le.bm_base = bm_base; le.bm_end = bm_end;
-        le.defer_ok = (bm && p.defer_list) ? 1u : 0u;
-        sz = chain_record<false>(&le, i, my_off, my_len, 0);
+        /* the environment is read where the kernel parameters live (__grid_constant__: no per-lane copy); what differs per
+         * lane travels in a few words */
+        struct ch_lane ln;
+        ln.bm = bm; ln.bm_base = bm_base; ln.bm_end = bm_end;
+        ln.defer_ok = (bm && p.defer_list) ? 1u : 0u;
+        sz = chain_record<false>(&p.env, &ln, i, my_off, my_len, 0);
         if (sz == CH_DEFER) {                          /* the follow-up launch evaluates it with the byte scanner */
             p.defer_list[atomicAdd(p.defer_cnt, 1ull)] = i;
             return;
@@ -394,21 +396,21 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval(const k_chain_params p) 
 
 /* The records the stage-2 walker put off (nested values, odd spacing, lines that are not JSON ...: a few per cent): dense,
  * so that the byte scanner and the exact transcoder run with full warps instead of inside warps whose other lanes wait. */
-__global__ void __launch_bounds__(1024, 1) k_chain_eval_deferred(const k_chain_params p)
+__global__ void __launch_bounds__(1024, 1) k_chain_eval_deferred(const __grid_constant__ k_chain_params p)
 {
     const unsigned long long n = *p.defer_cnt;
     for (unsigned long long t = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long) gridDim.x * blockDim.x) {
         const uint32_t i = p.defer_list[t];
-        struct ch_env le = p.env;
-        le.bm = 0; le.defer_ok = 0;
-        __stcs(&p.size[i], chain_record<false>(&le, i, p.off[i], p.len[i], 0));
+        struct ch_lane ln;
+        ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0;
+        __stcs(&p.size[i], chain_record<false>(&p.env, &ln, i, p.off[i], p.len[i], 0));
     }
 }
 
 /* Chains with a log_to_metrics filter only: the events the decoder steps over (kind 1: group markers, negative
  * timestamps) are counted by that filter as long as nothing before it rewrote the chunk (chain_skipped_record).
  * A kernel of its own so that k_chain_eval stays what it is for every other chain. */
-__global__ void __launch_bounds__(BK_REC_BLOCK) k_chain_skipped(const k_chain_params p)
+__global__ void __launch_bounds__(BK_REC_BLOCK) k_chain_skipped(const __grid_constant__ k_chain_params p)
 {
     const uint32_t n_rec = p.n_dev ? *p.n_dev : p.n_rec;
     const uint32_t i = p.r0 + blockIdx.x * BK_REC_BLOCK + threadIdx.x;
@@ -461,7 +463,7 @@ __global__ void __launch_bounds__(BK_REC_BLOCK) k_surv_fill(const uint32_t *__re
  * A warp whose range does not fit its slice writes directly, as before. */
 #define EMIT_BLOCK 128u
 #define EMIT_STAGE 8192u          /* bytes of result per warp that can be staged (+16 of alignment slack) */
-__global__ void __launch_bounds__(EMIT_BLOCK, 6) k_chain_emit_list(const k_chain_params p, const uint32_t *__restrict__ l_rec,
+__global__ void __launch_bounds__(EMIT_BLOCK, 6) k_chain_emit_list(const __grid_constant__ k_chain_params p, const uint32_t *__restrict__ l_rec,
                                                                    const uint64_t *__restrict__ l_off,
                                                                    const unsigned long long *__restrict__ n_list,
                                                                    const uint32_t *__restrict__ go)
@@ -487,7 +489,7 @@ __global__ void __launch_bounds__(EMIT_BLOCK, 6) k_chain_emit_list(const k_chain
     const bool rerun = valid && p.env.capcache[(size_t) (p.env.cap_stride - RC_CACHE_INTS) * p.env.cap_n + r] == RC_CACHE_NONE;
     if (!__any_sync(0xffffffffu, rerun) && total + mis <= EMIT_STAGE) {
         uint8_t *sb = emit_stage + (size_t) warp * (EMIT_STAGE + 16);
-        if (valid) chain_record<true>(&p.env, r, p.off[r], p.len[r], sb + mis + (uint32_t) (off - base));   /* cached field list: encode only */
+        if (valid) { struct ch_lane ln; ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0; chain_record<true>(&p.env, &ln, r, p.off[r], p.len[r], sb + mis + (uint32_t) (off - base)); }   /* cached field list: encode only */
         __syncwarp();
         {
             /* shared byte i corresponds to result byte (base - mis + i): 16-byte chunks are aligned on both sides */
@@ -504,7 +506,7 @@ __global__ void __launch_bounds__(EMIT_BLOCK, 6) k_chain_emit_list(const k_chain
         return;
     }
     if (!valid) return;
-    if (valid) chain_record<true>(&p.env, r, p.off[r], p.len[r], p.out + off);
+    { struct ch_lane ln; ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0; chain_record<true>(&p.env, &ln, r, p.off[r], p.len[r], p.out + off); }
 }
 
 /* ---- glue of the small-chunk form ---- */
@@ -1216,12 +1218,12 @@ int bk_index_fill(bk_q *q, const uint8_t *d_in, size_t slice_off, uint32_t slice
 
 static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_t *d_out, uint32_t r0)
 {
-    p->env.in = a->d_in; p->env.in_len = a->in_len; p->env.blob = a->d_blob; p->env.scr = a->d_scr; p->env.scr_mul = a->scr_mul ? a->scr_mul : 4; p->env.dec_at = 0;
+    p->env.in = a->d_in; p->env.in_len = a->in_len; p->env.blob = a->d_blob; p->env.scr = a->d_scr; p->env.scr_mul = a->scr_mul ? a->scr_mul : 4;
     p->env.capcache = a->d_capcache; p->env.cap_stride = a->cap_stride; p->env.cap_n = a->cap_n; p->env.now = a->now;
     p->env.assume = a->assume; p->env.active = a->active; p->env.fl_flags = a->d_flags; p->env.err = a->d_flags + FLBGPU_MAX_FILTERS;
     p->env.l2m = a->l2m; p->env.prep = a->d_prep;
     p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->r0 = r0; p->n_rec = a->n_rec; p->bm_words = 0;
-    p->n_dev = 0; p->env.defer_ok = 0; p->defer_list = 0; p->defer_cnt = 0;
+    p->n_dev = 0; p->defer_list = 0; p->defer_cnt = 0;
     p->size = a->d_size; p->bsum = a->d_bsum; p->out = d_out;
 }
 

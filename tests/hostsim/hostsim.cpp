@@ -183,8 +183,8 @@ int bk_index_fill(bk_q *, const uint8_t *d_in, size_t slice_off, uint32_t len, c
 
 static void hs_env(const struct bk_chain_args *a, struct ch_env *e)
 {
-    e->in = a->d_in; e->in_len = a->in_len; e->blob = a->d_blob; e->scr = a->d_scr; e->scr_mul = a->scr_mul ? a->scr_mul : 4; e->dec_at = 0;
-    e->capcache = a->d_capcache; e->cap_stride = a->cap_stride; e->cap_n = a->cap_n; e->now = a->now; e->assume = a->assume; e->active = a->active; e->defer_ok = 0; e->bm = 0; e->bm_base = e->bm_end = 0;
+    e->in = a->d_in; e->in_len = a->in_len; e->blob = a->d_blob; e->scr = a->d_scr; e->scr_mul = a->scr_mul ? a->scr_mul : 4;
+    e->capcache = a->d_capcache; e->cap_stride = a->cap_stride; e->cap_n = a->cap_n; e->now = a->now; e->assume = a->assume; e->active = a->active;
     e->fl_flags = a->d_flags; e->err = a->d_flags + FLBGPU_MAX_FILTERS;
     e->l2m = a->l2m; e->prep = a->d_prep;
 }
@@ -197,6 +197,8 @@ int bk_chain_eval(bk_q *, const struct bk_chain_args *a, uint32_t r0, uint32_t r
     struct ch_env e;
     uint32_t i;
     uint32_t *bm = 0;
+    struct ch_lane ln;
+    memset(&ln, 0, sizeof(ln));
     hs_env(a, &e);
     if (a->d_scr && r1 > r0 && !getenv("FLBGPU_JSON_BM_OFF")) {
         /* stage 1 of the JSON tokenizer as the CUDA kernel leaves it: one bit per byte that a string scan has to look at.
@@ -207,11 +209,11 @@ int bk_chain_eval(bk_q *, const struct bk_chain_args *a, uint32_t r0, uint32_t r
             const uint8_t c = a->d_in[b];
             if (c == '"' || c == 0x5c || c < 0x20 || c >= 0x80) bm[(b - lo) >> 5] |= 1u << ((b - lo) & 31);
         }
-        e.bm = bm; e.bm_base = lo; e.bm_end = hi;
+        ln.bm = bm; ln.bm_base = lo; ln.bm_end = hi;
     }
     for (i = r0; i < r1; i++) {
         uint32_t sz = 0;
-        if (a->d_kind[i] == 0) sz = chain_record<false>(&e, i, a->d_off[i], a->d_len[i], 0);
+        if (a->d_kind[i] == 0) sz = chain_record<false>(&e, &ln, i, a->d_off[i], a->d_len[i], 0);
         else if (a->d_kind[i] == 1 && e.l2m.hash) chain_skipped_record(&e, i, a->d_off[i], a->d_len[i]);
         a->d_size[i] = sz;
     }
@@ -259,7 +261,9 @@ int bk_chain_emit(bk_q *q, const struct bk_chain_args *a, uint8_t *d_out, uint32
         uint64_t at = a->d_bsum[b];
         for (i = b * BK_REC_BLOCK; i < a->n_rec && i < (b + 1) * BK_REC_BLOCK; i++) {
             if (a->d_size[i]) {
-                uint32_t w = chain_record<true>(&e, i, a->d_off[i], a->d_len[i], d_out + at);
+                struct ch_lane ln;
+                memset(&ln, 0, sizeof(ln));
+                uint32_t w = chain_record<true>(&e, &ln, i, a->d_off[i], a->d_len[i], d_out + at);
                 q->records_out++;
                 if (w != a->d_size[i]) { snprintf(hs_err, sizeof(hs_err), "emit size mismatch at record %u: %u vs %u", i, w, a->d_size[i]); return -1; }
                 at += w;
