@@ -662,7 +662,9 @@ struct bk_q {
     uint32_t *h_flags;                     /* pinned copy of the evidence words */
     uint8_t *h_sin, *h_sout; size_t cap_sin, cap_sout;    /* small form: pinned staging for the chunk and its result */
     cudaEvent_t ev_small;
-    int json_bm;                           /* FLBGPU_JSON_BM=0 turns the stage-1 bitmap off (measurement) */
+    int json_bm;                           /* FLBGPU_JSON_BM=1: two-stage JSON tokenizer (stage-1 bitmap + bit-scan walker + deferral).
+                                              Off by default: measured 20 % slower than the byte scanner on configs[1]
+                                              (profiles/r02_variants.txt) -- the walker's lanes diverge on the value type */
     int eval_block;                        /* FLBGPU_EVAL_BLOCK: threads per evaluation block */
     uint32_t *d_defer; size_t cap_defer;   /* records the JSON stage-2 walker put off to the follow-up launch */
     /* upload */
@@ -867,7 +869,7 @@ static int q_setup(bk_q *q)
     }
     {
         const char *e = getenv("FLBGPU_JSON_BM");
-        q->json_bm = !(e && e[0] == '0');
+        q->json_bm = e && e[0] == '1';
     }
     return 0;
 }
