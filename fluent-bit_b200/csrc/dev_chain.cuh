@@ -284,11 +284,11 @@ FLB_HD const uint8_t *rec_frame(const uint8_t *p, const uint8_t *end, int *kind)
     q += t.hdr + (t.type == MPT_EXT ? t.len : 0);
     if (p[1] == 0x92) {                          /* metadata must be a map */
         if (q >= end || mp_token(q, end, &t) != 0 || t.type != MPT_MAP) return 0;
-        q = mp_skip(q, end);
+        q = mp_skip_lim(q, end, 2);              /* open around it: the event array and the header array */
         if (!q) return 0;
     }
     if (q >= end || mp_token(q, end, &t) != 0 || t.type != MPT_MAP) return 0;
-    q = mp_skip(q, end);
+    q = mp_skip_lim(q, end, 1);
     if (!q) return 0;
     *kind = ((int32_t) (uint32_t) sec) < 0 ? 1 : 0;
     return q;
@@ -1046,7 +1046,7 @@ FLB_HD int djf_record(const struct ch_env *e, const struct ch_lane *ln, const ui
                 done = 1;
             }
             else if (c == '{' || c == '[') {
-                if (depth >= DJ_MAX_DEPTH) return -1;
+                if (depth >= DJ_DEEP_HINT) return -1;         /* nesting near the unpacker's limit: the exact transcoder decides and reports it */
                 if (depth == 1) top_start = k;
                 depth++;
                 hpos[depth] = k; ccnt[depth] = 0;
@@ -1236,7 +1236,8 @@ FLB_HDN int pdec_backend(const struct ch_env *e, const struct ch_lane *ln, uint3
         while (p < n && text[p] == ' ') p++;
         if (p >= n || (text[p] != '{' && text[p] != '[')) return -1;
         if (!dj_parse_record(text + p, (int) (n - p), o, &mplen, &jerr, &consumed)) return -1;
-        if (jerr) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
+        if (jerr & DJ_E_FLOAT) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
+        if (jerr & DJ_E_DEEP) CH_ATOMIC_OR(e->err, FLBGPU_E_DEEP);
         *out_len = mplen; *out_type = PDEC_OUT_OBJECT;
     }
     else if (backend == PDEC_ESCAPED) { *out_len = pdec_unescape(text, n, o); *out_type = PDEC_OUT_STRING; }
@@ -1483,7 +1484,8 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct ch_lane *ln, const str
     else {
         uint32_t jerr = 0;
         ok = dj_parse_record(s, (int) n, ln->scr, &mplen, &jerr, pos);
-        if (jerr) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
+        if (jerr & DJ_E_FLOAT) CH_ATOMIC_OR(e->err, FLBGPU_E_FLOAT);
+        if (ok && (jerr & DJ_E_DEEP)) CH_ATOMIC_OR(e->err, FLBGPU_E_DEEP);
         if (!EMIT && slot) { CW(slot, 0) = ok; CW(slot, 1) = (int32_t) mplen; }
     }
     if (!ok) return 0;
@@ -2170,8 +2172,16 @@ FLB_HDN void chain_skipped_record(const struct ch_env *e, uint32_t ridx, uint32_
 /* ------------------------------------------------------------- the chain */
 /* Runs record `ridx` (framed at off/len, kind 0) through the chain.
  * EMIT=false: returns the output size (0 = dropped) and records evidence.
- * EMIT=true : writes the record at `out` (the caller only calls it for size>0). */
-template <bool EMIT>
+ * EMIT=true : writes the record at `out` (the caller only calls it for size>0).
+ * PH (evaluation pass only) splits the chain into two launches whose code each fits the instruction cache better than
+ * the whole interpreter does: CH_PH_HEAD = decode the record and run filter 0 (the parser), then leave the field list in the
+ * record's capture-cache row and return 1 (alive) / 0 (dropped) / CH_DEFER (more fields than the row holds: the whole chain
+ * is run for this record by the follow-up launch); CH_PH_TAIL = pick the field list up again and run filters 1..n-1. */
+#define CH_PH_ALL  0
+#define CH_PH_HEAD 1
+#define CH_PH_TAIL 2
+#define RC_STATE_KH RC_CACHE_MAXF            /* split mode: the key fingerprints, in columns behind the row (cap_stride ..) */
+template <bool EMIT, int PH = CH_PH_ALL>
 FLB_HD uint32_t chain_record(const struct ch_env *e, struct ch_lane *ln, uint32_t ridx, uint32_t off, uint32_t len, uint8_t *out)
 {
     const struct chain_hdr *h = (const struct chain_hdr *) e->blob;
@@ -2204,11 +2214,28 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, struct ch_lane *ln, uint32_
             return rec_emit(e, ln, &rc, out);
         }
     }
-    if (rec_decode(e, ln, off, len, &rc, h->empty_map_off) != 0) {
+    if (PH == CH_PH_TAIL) {
+        /* the head launch left the state here: field list, key fingerprints, style, time */
+        const size_t cs = e->cap_n;
+        const int32_t *c = e->capcache + (size_t) (e->cap_stride - RC_CACHE_INTS) * cs + ridx;
+        const int32_t *kh = e->capcache + (size_t) e->cap_stride * cs + ridx;
+        const int32_t st = CW(c, 0);
+        int i;
+        rc.nf = st & 0xff; rc.style = (st >> 8) & 0xff; rc.reenc = (st >> 16) & 1;
+        rc.preset_n = (uint32_t) CW(c, 1);
+        rc.ts_sec = (int64_t) (((uint64_t) (uint32_t) CW(c, 6) << 32) | (uint32_t) CW(c, 2)); rc.ts_nsec = (int64_t) (uint32_t) CW(c, 3);
+        rc.meta = ((ref_t) (uint32_t) CW(c, 5) << 32) | (uint32_t) CW(c, 4);
+        for (i = 0; i < rc.nf; i++) {
+            rc.k[i] = ((ref_t) (uint32_t) CW(c, 8 + 4 * i + 1) << 32) | (uint32_t) CW(c, 8 + 4 * i);
+            rc.v[i] = ((ref_t) (uint32_t) CW(c, 8 + 4 * i + 3) << 32) | (uint32_t) CW(c, 8 + 4 * i + 2);
+            rc.kh[i] = (uint32_t) CW(kh, i);
+        }
+    }
+    else if (rec_decode(e, ln, off, len, &rc, h->empty_map_off) != 0) {
         CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS);
         return 0;
     }
-    for (k = 0; k < h->n_filters; k++) {
+    for (k = (PH == CH_PH_TAIL ? 1u : 0u); k < (PH == CH_PH_HEAD ? 1u : h->n_filters); k++) {
         const uint8_t *cfg = e->blob + f[k].cfg_off;
         int assumed = (e->assume >> k) & 1;
         if (!((e->active >> k) & 1)) continue;
@@ -2263,6 +2290,25 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, struct ch_lane *ln, uint32_
         default:
             break;
         }
+    }
+    if (PH == CH_PH_HEAD) {
+        /* hand the record over to the tail launch */
+        const size_t cs = e->cap_n;
+        int32_t *c = e->capcache + (size_t) (e->cap_stride - RC_CACHE_INTS) * cs + ridx;
+        int32_t *kh = e->capcache + (size_t) e->cap_stride * cs + ridx;
+        int i;
+        if (rc.nf > RC_CACHE_MAXF) return CH_DEFER;
+        CH_STCS(&CW(c, 6), (int32_t) (uint32_t) ((uint64_t) rc.ts_sec >> 32));
+        CH_STCS(c, (int32_t) ((uint32_t) rc.nf | ((uint32_t) rc.style << 8) | ((uint32_t) (rc.reenc ? 1 : 0) << 16)));
+        CH_STCS(&CW(c, 1), (int32_t) rc.preset_n);
+        CH_STCS(&CW(c, 2), (int32_t) (uint32_t) rc.ts_sec); CH_STCS(&CW(c, 3), (int32_t) (uint32_t) rc.ts_nsec);
+        CH_STCS(&CW(c, 4), (int32_t) (uint32_t) rc.meta); CH_STCS(&CW(c, 5), (int32_t) (uint32_t) (rc.meta >> 32));
+        for (i = 0; i < rc.nf; i++) {
+            CH_STCS(&CW(c, 8 + 4 * i), (int32_t) (uint32_t) rc.k[i]); CH_STCS(&CW(c, 8 + 4 * i + 1), (int32_t) (uint32_t) (rc.k[i] >> 32));
+            CH_STCS(&CW(c, 8 + 4 * i + 2), (int32_t) (uint32_t) rc.v[i]); CH_STCS(&CW(c, 8 + 4 * i + 3), (int32_t) (uint32_t) (rc.v[i] >> 32));
+            CH_STCS(&CW(kh, i), (int32_t) rc.kh[i]);
+        }
+        return 1;
     }
     if (!EMIT && e->capcache && e->cap_stride >= RC_CACHE_INTS) {
         /* streaming stores: written once, read once by the emission pass -- they should not push the

@@ -34,6 +34,12 @@
 
 #define DJ_MAX_DEPTH 31        /* nesting the reference's msgpack_unpack_next() still accepts */
 #define DJ_E_FLOAT   1
+/* A value nested this deep still parses, but as part of a record body -- one or two containers further down -- it is at or
+ * near the depth where msgpack-c's unpacker gives up (MSGPACK_EMBED_STACK_SIZE, dev_msgpack.cuh: mp_skip_lim): every filter
+ * that decodes the parser's result then stops at this record.  A chain that hands fields from filter to filter cannot show that,
+ * so the transcoder reports it and the chain is run filter by filter for this call (runtime.c: chain_do_one_by_one). */
+#define DJ_E_DEEP    2
+#define DJ_DEEP_HINT 28
 
 FLB_HD int dj_ws(uint32_t c) { return c == ' ' || c == '\t' || c == '\n' || c == '\r'; }
 FLB_HD int dj_hex(uint32_t c)
@@ -573,6 +579,8 @@ FLB_HDN int dj_value(const uint8_t *s, int n, int pos, uint8_t *o, uint32_t *ole
         if (c == '{' || c == '[') {
             int cnt = dj_count(s, n, p, exact);
             if (cnt < 0) return -1;
+            if (sp > DJ_MAX_DEPTH) return -1;              /* a 33rd open container, empty or not (unpack_template.h:140-144) */
+            if (sp >= DJ_DEEP_HINT) *err |= DJ_E_DEEP;
             if (c == '{') { if (o) mp_put_map_hdr(o + k, (uint32_t) cnt); }
             else if (o) mp_put_array_hdr(o + k, (uint32_t) cnt);
             k += mp_cnt_hdr_size((uint32_t) cnt);
@@ -583,7 +591,6 @@ FLB_HDN int dj_value(const uint8_t *s, int n, int pos, uint8_t *o, uint32_t *ole
                 p++;
                 goto value_done;
             }
-            if (sp >= DJ_MAX_DEPTH) return -1;
             rem[sp] = (uint32_t) cnt; isobj[sp] = (c == '{'); sp++;
             goto next_member;
         }

@@ -117,6 +117,67 @@ FLB_HD const uint8_t *mp_skip(const uint8_t *p, const uint8_t *end)
     return p;
 }
 
+/* msgpack-c's unpacker keeps its open containers on a stack of MSGPACK_EMBED_STACK_SIZE (32) entries and fails with
+ * MSGPACK_UNPACK_NOMEM_ERROR when a container header -- empty or not -- arrives while `top` is already 32
+ * (lib/msgpack-c/include/msgpack/unpack_template.h:140-144, start_container): to flb_log_event_decoder_next() such an event
+ * is a deserialization failure like any malformed byte.  mp_skip_lim() is mp_skip() with that rule: `top0` containers are open
+ * around the object at p.  The exact walk needs the count owed to every open container, so it runs only for objects that hold
+ * enough container headers to reach the limit at all. */
+#define MP_UNPACK_STACK 32
+FLB_HD
+#ifdef __CUDACC__
+__noinline__
+#endif
+const uint8_t *mp_skip_exact(const uint8_t *p, const uint8_t *end, uint32_t top0)
+{
+    uint32_t owed[MP_UNPACK_STACK];
+    uint32_t d = 0;                        /* containers of this object that are open */
+    struct mp_tok t;
+    for (;;) {
+        uint32_t items = 0;
+        int container = 0;
+        if (p >= end) return 0;
+        if (mp_token(p, end, &t) != 0) return 0;
+        p += t.hdr;
+        if (t.type == MPT_STR || t.type == MPT_BIN || t.type == MPT_EXT) {
+            if ((size_t) (end - p) < t.len) return 0;
+            p += t.len;
+        }
+        else if (t.type == MPT_ARRAY) { container = 1; items = t.len; }
+        else if (t.type == MPT_MAP) { container = 1; if (t.len > 0x7fffffffu) return 0; items = 2 * t.len; }
+        if (container) {
+            if (top0 + d >= MP_UNPACK_STACK) return 0;
+            if (items) { owed[d++] = items; continue; }
+        }
+        for (;;) {                         /* one object done: pay it to the containers it closes */
+            if (d == 0) return p;
+            if (--owed[d - 1]) break;
+            d--;
+        }
+    }
+}
+FLB_HD const uint8_t *mp_skip_lim(const uint8_t *p, const uint8_t *end, uint32_t top0)
+{
+    const uint8_t *p0 = p;
+    uint64_t owed = 1;
+    uint32_t containers = 0;
+    struct mp_tok t;
+    while (owed) {
+        if (p >= end) return 0;
+        if (mp_token(p, end, &t) != 0) return 0;
+        owed--;
+        p += t.hdr;
+        if (t.type == MPT_STR || t.type == MPT_BIN || t.type == MPT_EXT) {
+            if ((size_t) (end - p) < t.len) return 0;
+            p += t.len;
+        }
+        else if (t.type == MPT_ARRAY) { owed += t.len; containers++; }
+        else if (t.type == MPT_MAP) { owed += 2 * (uint64_t) t.len; containers++; }
+    }
+    if (top0 + containers <= MP_UNPACK_STACK) return p;          /* even nested one inside the other they fit */
+    return mp_skip_exact(p0, end, top0);
+}
+
 /* ---- sizes of canonical headers ---- */
 FLB_HD uint32_t mp_str_hdr_size(uint32_t n) { return n < 32 ? 1 : n < 256 ? 2 : n < 65536 ? 3 : 5; }
 FLB_HD uint32_t mp_bin_hdr_size(uint32_t n) { return n < 256 ? 2 : n < 65536 ? 3 : 5; }

@@ -247,6 +247,8 @@ struct chain_hdr {
 #define FLBGPU_E_INDEX    16u   /* record index fast path failed */
 #define FLBGPU_E_ESCAPE   32u   /* logfmt escapes met without a scratch region (cannot happen through the C ABI) */
 #define FLBGPU_E_L2M      64u   /* log_to_metrics: label table full / float label / unparsable value */
+#define FLBGPU_E_DEEP    256u   /* a parser made a value nested near msgpack-c's unpack limit: the filters behind it must see it as the
+                                   reference's decoder does -- the call is run filter by filter */
 #define FLBGPU_E_RXUNICODE 128u /* a pattern with POSIX brackets / \b / case-insensitivity met a non-ASCII subject */
 
 /* ---------------------------------------------------- streaming JSON packer (dev_jsmn.cuh) */

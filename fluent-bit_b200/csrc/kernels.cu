@@ -347,7 +347,12 @@ __device__ __forceinline__ uint32_t bm_mask4(uint32_t w)
     return ((m >> 7) * 0x00204081u) >> 21 & 0xfu;        /* gather the four flags into bits 0..3 */
 }
 
-__global__ void __launch_bounds__(1024, 1) k_chain_eval(const __grid_constant__ k_chain_params p)       /* 64 registers per lane; block size chosen at launch */
+/* PH: CH_PH_ALL = the whole chain in one launch.  Split form (chains `parser, then other filters`): a CH_PH_HEAD launch
+ * decodes and parses and leaves the field lists in the capture cache, a CH_PH_TAIL launch runs the other filters from there.
+ * Each half has roughly half the interpreter's code, which is what the single launch is bound by (instruction cache misses,
+ * profiles/r02_ncu_eval_json.txt). */
+template <int PH>
+__global__ void __launch_bounds__(1024, 1) k_chain_eval_t(const __grid_constant__ k_chain_params p)       /* 64 registers per lane; block size chosen at launch */
 {
     extern __shared__ __align__(16) uint8_t dsm[];
     const uint32_t n_rec = p.n_dev ? *p.n_dev : p.n_rec;
@@ -358,7 +363,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval(const __grid_constant__ 
     const uint8_t *in = p.env.in;
     const uint32_t *bm = 0;
     uint32_t bm_base = 0, bm_end = 0;
-    if (p.bm_words) {
+    if (PH != CH_PH_TAIL && p.bm_words) {
         const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         uint32_t lo = __reduce_min_sync(0xffffffffu, live ? my_off : 0xffffffffu);
         const uint32_t hi = __reduce_max_sync(0xffffffffu, live ? my_off + my_len : 0u);
@@ -366,11 +371,13 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval(const __grid_constant__ 
             lo -= (uint32_t) ((uintptr_t) (in + lo) & 15u);           /* 16-byte aligned in the address space */
             if (hi - lo <= BM_BYTES) {
                 uint32_t *w = reinterpret_cast<uint32_t *>(dsm) + (size_t) warp * p.bm_words;
-                for (uint32_t o = lane * 16; o < hi - lo; o += 512) {
-                    const uint4 v = *reinterpret_cast<const uint4 *>(in + lo + o);      /* reads past `hi` stay inside the padded buffer */
+                for (uint32_t o0 = 0; o0 < hi - lo; o0 += 512) {                         /* the same trip count in every lane: the shuffle below pairs them */
+                    const uint32_t o = o0 + lane * 16;
+                    uint4 v = make_uint4(0, 0, 0, 0);
+                    if (o < hi - lo) v = *reinterpret_cast<const uint4 *>(in + lo + o);   /* reads past `hi` stay inside the padded buffer */
                     const uint32_t m16 = bm_mask4(v.x) | (bm_mask4(v.y) << 4) | (bm_mask4(v.z) << 8) | (bm_mask4(v.w) << 12);
                     const uint32_t other = __shfl_xor_sync(0xffffffffu, m16, 1);
-                    if (!(lane & 1)) w[o >> 5] = m16 | (other << 16);
+                    if (!(lane & 1) && o < hi - lo) w[o >> 5] = m16 | (other << 16);
                 }
                 __syncwarp();
                 bm = w; bm_base = lo; bm_end = hi;
@@ -379,20 +386,25 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval(const __grid_constant__ 
     }
     if (!valid) return;
     uint32_t sz = 0;
+    if (PH == CH_PH_TAIL) {
+        if (!live || p.size[i] == 0) return;           /* dropped by the head launch, or handed to the follow-up launch */
+    }
     if (live) {
         /* the environment is read where the kernel parameters live (__grid_constant__: no per-lane copy); what differs per
          * lane travels in a few words */
         struct ch_lane ln;
         ln.bm = bm; ln.bm_base = bm_base; ln.bm_end = bm_end;
         ln.defer_ok = (bm && p.defer_list) ? 1u : 0u;
-        sz = chain_record<false>(&p.env, &ln, i, my_off, my_len, 0);
-        if (sz == CH_DEFER) {                          /* the follow-up launch evaluates it with the byte scanner */
+        sz = chain_record<false, PH>(&p.env, &ln, i, my_off, my_len, 0);
+        if (sz == CH_DEFER) {                          /* the follow-up launch evaluates it whole, with the byte scanner */
             p.defer_list[atomicAdd(p.defer_cnt, 1ull)] = i;
-            return;
+            if (PH != CH_PH_HEAD) return;
+            sz = 0;                                    /* the tail launch steps over it */
         }
     }
     __stcs(&p.size[i], sz);
 }
+#define k_chain_eval k_chain_eval_t<CH_PH_ALL>
 
 /* The records the stage-2 walker put off (nested values, odd spacing, lines that are not JSON ...: a few per cent): dense,
  * so that the byte scanner and the exact transcoder run with full warps instead of inside warps whose other lanes wait. */
@@ -809,6 +821,8 @@ static int func_attrs_once(void)
     int pct = e ? atoi(e) : 20;
     if (pct < 0 || pct > 100) pct = 20;
     CK(cudaFuncSetAttribute(k_chain_eval, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    CK(cudaFuncSetAttribute(k_chain_eval_t<CH_PH_HEAD>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+    CK(cudaFuncSetAttribute(k_chain_eval_t<CH_PH_TAIL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
     CK(cudaFuncSetCacheConfig(k_chain_eval_deferred, cudaFuncCachePreferL1));
     cudaFuncSetAttribute(k_chain_eval_deferred, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     /* the emission kernel stages a warp's result range in shared memory (6 blocks x 32 KB per SM) */
@@ -1267,7 +1281,7 @@ int bk_hint_streaming(bk_q *q, const void *base, size_t bytes)
 static int defer_setup(bk_q *q, k_chain_params *p, const struct bk_chain_args *a, size_t n, cudaStream_t st)
 {
     p->defer_list = 0; p->defer_cnt = 0;
-    if (!p->bm_words || !a->defer_ok) return 0;
+    if (!(p->bm_words && a->defer_ok) && !a->split) return 0;
     if (q->cap_defer < n) {
         CK(cudaStreamSynchronize(q->stream));           /* a follow-up launch still running reads the old list */
         cudaFree(q->d_defer); q->d_defer = 0; q->cap_defer = 0;
@@ -1289,7 +1303,13 @@ int bk_chain_eval(bk_q *q, const struct bk_chain_args *a, uint32_t r0, uint32_t 
     p.bm_words = (a->d_scr && q->json_bm) ? BM_BYTES / 32 : 0;          /* a JSON parser is in the chain */
     if (defer_setup(q, &p, a, r1 - r0, q->stream)) return -1;
     ev_begin_on(q, 1, q->stream);
-    k_chain_eval<<<(r1 - r0 + q->eval_block - 1) / q->eval_block, q->eval_block, (size_t) p.bm_words * 4 * (q->eval_block / 32), q->stream>>>(p);
+    if (a->split) {
+        k_chain_eval_t<CH_PH_HEAD><<<(r1 - r0 + q->eval_block - 1) / q->eval_block, q->eval_block, (size_t) p.bm_words * 4 * (q->eval_block / 32), q->stream>>>(p);
+        k_chain_eval_t<CH_PH_TAIL><<<(r1 - r0 + q->eval_block - 1) / q->eval_block, q->eval_block, 0, q->stream>>>(p);
+        g_launches += 1;
+    }
+    else
+        k_chain_eval<<<(r1 - r0 + q->eval_block - 1) / q->eval_block, q->eval_block, (size_t) p.bm_words * 4 * (q->eval_block / 32), q->stream>>>(p);
     if (p.defer_list) { k_chain_eval_deferred<<<148 * 4, BK_REC_BLOCK, 0, q->stream>>>(p); g_launches += 1; }
     if (p.env.l2m.hash) {
         k_chain_skipped<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, 0, q->stream>>>(p);
@@ -1463,7 +1483,13 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     p.bm_words = (a->d_scr && q->json_bm) ? BM_BYTES / 32 : 0;
     if (defer_setup(q, &p, a, cap_rec, st)) return -1;
     ev_begin_on(q, 1, st);
-    k_chain_eval<<<nb_cap, BK_REC_BLOCK, (size_t) p.bm_words * 4 * (BK_REC_BLOCK / 32), st>>>(p);
+    if (a->split) {
+        k_chain_eval_t<CH_PH_HEAD><<<nb_cap, BK_REC_BLOCK, (size_t) p.bm_words * 4 * (BK_REC_BLOCK / 32), st>>>(p);
+        k_chain_eval_t<CH_PH_TAIL><<<nb_cap, BK_REC_BLOCK, 0, st>>>(p);
+        g_launches += 1;
+    }
+    else
+        k_chain_eval<<<nb_cap, BK_REC_BLOCK, (size_t) p.bm_words * 4 * (BK_REC_BLOCK / 32), st>>>(p);
     if (p.defer_list) { k_chain_eval_deferred<<<148, BK_REC_BLOCK, 0, st>>>(p); g_launches += 1; }
     if (p.env.l2m.hash) { k_chain_skipped<<<nb_cap, BK_REC_BLOCK, 0, st>>>(p); g_launches += 1; }
     ev_end_on(q, 1, st);

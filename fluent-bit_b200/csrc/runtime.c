@@ -158,6 +158,7 @@ struct flbgpu_chain {
     uint32_t cap_stride;
     int needs_scratch;
     uint32_t scr_mul;
+    int split;                                /* evaluation in two launches: the parser (filter 0), then the other filters */
     int defer_ok;                             /* no log_to_metrics filter in front of a parser filter: records may be re-evaluated from scratch */
     uint8_t *d_scr; size_t cap_scr;
     int l2m_index;                            /* filter index of the log_to_metrics filter, or -1 */
@@ -1295,6 +1296,11 @@ int flbgpu_chain_init(flbgpu_chain *c)
         c->defer_ok = 1;
         for (k2 = 0; k2 < c->nf; k2++) if (c->f[k2]->kind == FLBGPU_F_PARSER) last_parser = k2;
         for (k2 = 0; k2 < last_parser; k2++) if (c->f[k2]->kind == FLBGPU_F_LOG_TO_METRICS) c->defer_ok = 0;
+        /* `parser, then filters that are not parsers`: the evaluation runs as two launches (kernels.cu: k_chain_eval_t) */
+        {
+            const char *e = getenv("FLBGPU_EVAL_SPLIT");
+            c->split = c->nf >= 2 && last_parser == 0 && !(e && e[0] == '0');
+        }
     }
     h.n_filters = c->nf;
     h.filters_off = blob_add(&c->blob, cf, sizeof(cf[0]) * (c->nf ? c->nf : 1), 8);
@@ -1380,7 +1386,8 @@ static int ensure_rec_cap(flbgpu_chain *c, size_t need, size_t keep)
     if (c->cap_rec >= need) return 0;
     nc = need + need / 2 + 1024;
     o = bk_alloc(c->q, nc * 4); l = bk_alloc(c->q, nc * 4); z = bk_alloc(c->q, nc * 4); k = bk_alloc(c->q, nc);
-    if (c->cap_stride) cp = bk_alloc(c->q, nc * c->cap_stride * sizeof(int32_t));
+    /* split evaluation: RC_CACHE_MAXF more columns behind the rows carry the key fingerprints from the head to the tail launch */
+    if (c->cap_stride) cp = bk_alloc(c->q, nc * (c->cap_stride + (c->split ? RC_CACHE_MAXF : 0)) * sizeof(int32_t));
     if (!o || !l || !z || !k || (c->cap_stride && !cp)) return -1;
     if (c->want_report) {
         int32_t *np_ = bk_alloc(c->q, nc * 6 * sizeof(int32_t));
@@ -1421,7 +1428,21 @@ static void fill_args(flbgpu_chain *c, struct bk_chain_args *a, const uint8_t *d
     a->active = c->active;
     a->scr_mul = c->scr_mul ? c->scr_mul : 4;
     a->defer_ok = (uint32_t) c->defer_ok;
+    a->split = (uint32_t) c->split;
     a->d_prep = c->want_report ? c->d_prep : NULL;
+}
+
+/* the interpreter's error word of a call: 0 = nothing that stops the call */
+static int refused(flbgpu_chain *c, uint32_t bits)
+{
+    if (c->nf == 1) bits &= ~FLBGPU_E_DEEP;          /* nothing behind the parser decodes its result in this call */
+    if (!bits) return 0;
+    c->st.error_bits = bits;
+    snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
+             "1=too many keys 2=regex stack 4=regex budget 8=float text not restated (hex float, nan(payload)) 32=logfmt escapes "
+             "64=log_to_metrics value/label outside the device path 128=a pattern with POSIX brackets, \\b or case-insensitivity met a non-ASCII value "
+             "256=a parsed value nested to msgpack-c's unpack limit inside a fused chain)", bits);
+    return 1;
 }
 
 /* parser report of the previous call: flags back to "not parsed" */
@@ -1556,10 +1577,9 @@ static int msgpack_tail_runs_out_cleanly(const uint8_t *b, size_t n)
             if (n - p < payload) return p == n;                 /* stops where the payload begins */
             p += (size_t) payload;
         }
-        if (is_container && items) {
-            if (depth >= 64) return 0;
-            open[depth++] = items;
-            continue;
+        if (is_container) {
+            if (depth >= 32) return 0;                          /* MSGPACK_EMBED_STACK_SIZE: a failure, not a shortage (dev_msgpack.cuh: mp_skip_lim) */
+            if (items) { open[depth++] = items; continue; }
         }
         /* one object done: pay it to the containers it closes */
         for (;;) {
@@ -1731,13 +1751,7 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     for (pass = 0; pass <= c->nf; pass++) {
         int changed = 0, cl = clean;
         if (bk_flags_fetch(c->q, c->d_flags, h_flags)) return -1;
-        if (h_flags[FLBGPU_MAX_FILTERS]) {
-            c->st.error_bits = h_flags[FLBGPU_MAX_FILTERS];
-            snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
-                     "1=too many keys 2=regex stack 4=regex budget 8=float text not restated (hex float, nan(payload)) 32=logfmt escapes 64=log_to_metrics value/label outside the device path 128=a pattern with POSIX brackets, \\b or case-insensitivity met a non-ASCII value)",
-                     h_flags[FLBGPU_MAX_FILTERS]);
-            return -1;
-        }
+        if (refused(c, h_flags[FLBGPU_MAX_FILTERS])) return -1;
         for (k = 0; k < c->nf; k++) {
             int v = !((c->active >> k) & 1) ? 0 : c->f[k]->kind == FLBGPU_F_LOG_TO_METRICS ? L2M_VERDICT(c, k) : verdict(c->f[k]->kind, h_flags[k], cl);
             if (v) cl = 1;                   /* a MODIFIED filter hands a well-formed chunk on */
@@ -1977,13 +1991,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
 
     /* ---- the verdicts must be the ones speculated on ---- */
     if (bk_flags_fetch(c->q, c->d_flags, h_flags)) goto fail;
-    if (h_flags[FLBGPU_MAX_FILTERS]) {
-        c->st.error_bits = h_flags[FLBGPU_MAX_FILTERS];
-        snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
-                 "1=too many keys 2=regex stack 4=regex budget 8=float text not restated (hex float, nan(payload)) 32=logfmt escapes 64=log_to_metrics value/label outside the device path 128=a pattern with POSIX brackets, \\b or case-insensitivity met a non-ASCII value)",
-                 h_flags[FLBGPU_MAX_FILTERS]);
-        goto fail;
-    }
+    if (refused(c, h_flags[FLBGPU_MAX_FILTERS])) goto fail;
     {
         int cl = clean;
         uint32_t settled = 0;
@@ -2089,13 +2097,7 @@ static int chain_run_small(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, v
     REFUSE_WIDE_ARRAYS(h_in, c->d_in, return -1);
     c->st.records_in = res.n_valid;
     c->st.passes = 1;
-    if (res.flags[FLBGPU_MAX_FILTERS]) {
-        c->st.error_bits = res.flags[FLBGPU_MAX_FILTERS];
-        snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
-                 "1=too many keys 2=regex stack 4=regex budget 8=float text not restated (hex float, nan(payload)) 32=logfmt escapes 64=log_to_metrics value/label outside the device path 128=a pattern with POSIX brackets, \\b or case-insensitivity met a non-ASCII value)",
-                 res.flags[FLBGPU_MAX_FILTERS]);
-        return -1;
-    }
+    if (refused(c, res.flags[FLBGPU_MAX_FILTERS])) return -1;
     {
         int cl = clean;
         uint32_t settled = 0;
@@ -2176,7 +2178,7 @@ static int chain_do_one_by_one(flbgpu_chain *c, const void *data, size_t bytes, 
     *out_buf = owned; *out_size = cur_n;
     return FLBGPU_FILTER_MODIFIED;
 }
-#define FUSED_REFUSED_A_HANDED_OVER_VALUE(c) ((c)->nf > 1 && (c)->st.error_bits == FLBGPU_E_FIELDS)
+#define FUSED_REFUSED_A_HANDED_OVER_VALUE(c) ((c)->nf > 1 && (c)->st.error_bits && !((c)->st.error_bits & ~(FLBGPU_E_FIELDS | FLBGPU_E_DEEP)))
 
 static int chain_do_locked(flbgpu_chain *c, const void *data, size_t bytes, const char *tag, int tag_len, void **out_buf, size_t *out_size)
 {

@@ -210,12 +210,41 @@ int bk_chain_eval(bk_q *, const struct bk_chain_args *a, uint32_t r0, uint32_t r
             if (c == '"' || c == 0x5c || c < 0x20 || c >= 0x80) bm[(b - lo) >> 5] |= 1u << ((b - lo) & 31);
         }
         ln.bm = bm; ln.bm_base = lo; ln.bm_end = hi;
+        ln.defer_ok = a->defer_ok && !getenv("FLBGPU_SIM_NODEFER");     /* as the kernel: records the walker cannot take go to a follow-up pass */
     }
-    for (i = r0; i < r1; i++) {
-        uint32_t sz = 0;
-        if (a->d_kind[i] == 0) sz = chain_record<false>(&e, &ln, i, a->d_off[i], a->d_len[i], 0);
-        else if (a->d_kind[i] == 1 && e.l2m.hash) chain_skipped_record(&e, i, a->d_off[i], a->d_len[i]);
-        a->d_size[i] = sz;
+    if (a->split) {
+        /* the three launches of the split form, in the kernel's order: head over all records, tail, then the records the
+         * head put off, whole */
+        uint8_t *put_off = (uint8_t *) calloc(r1 - r0 + 1, 1);
+        for (i = r0; i < r1; i++) {
+            uint32_t sz = 0;
+            if (a->d_kind[i] == 0) sz = chain_record<false, CH_PH_HEAD>(&e, &ln, i, a->d_off[i], a->d_len[i], 0);
+            if (sz == CH_DEFER) { put_off[i - r0] = 1; sz = 0; }
+            a->d_size[i] = sz;
+        }
+        for (i = r0; i < r1; i++)
+            if (a->d_kind[i] == 0 && a->d_size[i]) a->d_size[i] = chain_record<false, CH_PH_TAIL>(&e, &ln, i, a->d_off[i], a->d_len[i], 0);
+        for (i = r0; i < r1; i++)
+            if (put_off[i - r0]) { struct ch_lane plain; memset(&plain, 0, sizeof(plain)); a->d_size[i] = chain_record<false>(&e, &plain, i, a->d_off[i], a->d_len[i], 0); }
+        for (i = r0; i < r1; i++)
+            if (a->d_kind[i] == 1 && e.l2m.hash) chain_skipped_record(&e, i, a->d_off[i], a->d_len[i]);
+        free(put_off);
+        hs_launches += 1;
+    }
+    else {
+        uint8_t *put_off = (uint8_t *) calloc(r1 - r0 + 1, 1);
+        struct ch_lane plain;
+        memset(&plain, 0, sizeof(plain));
+        for (i = r0; i < r1; i++) {
+            uint32_t sz = 0;
+            if (a->d_kind[i] == 0) sz = chain_record<false>(&e, &ln, i, a->d_off[i], a->d_len[i], 0);
+            else if (a->d_kind[i] == 1 && e.l2m.hash) chain_skipped_record(&e, i, a->d_off[i], a->d_len[i]);
+            if (sz == CH_DEFER) { put_off[i - r0] = 1; sz = 0; }
+            a->d_size[i] = sz;
+        }
+        for (i = r0; i < r1; i++)
+            if (put_off[i - r0]) a->d_size[i] = chain_record<false>(&e, &plain, i, a->d_off[i], a->d_len[i], 0);
+        free(put_off);
     }
     free(bm);
     hs_launches += 1;

@@ -290,3 +290,53 @@ def test_full_size_tiling_gpu(name, maker, gpu_lib, ref_available):
         assert out[k * n:(k + 1) * n] == want[1], "tile %d differs" % k
     st = chain.stats()
     assert 100000 * reps <= st.records_in <= 100000 * reps * 1.001      # index entries: records + the rare kept false candidates
+
+
+def _deep_nesting(lib):
+    """msgpack-c's unpacker holds 32 open containers (MSGPACK_EMBED_STACK_SIZE): an event nested deeper ends the decodable part of
+    a chunk for every filter like a malformed byte does -- whether it came in with the chunk or a parser of the same chain made it."""
+    S = util.mp_str
+    def deep(n, inner=b"\x90"):
+        return b"\x91" * n + inner
+    # in the input chunk, at every position, for every plugin
+    for filt in [("grep", [("Regex", "a x")]), ("grep", [("Exclude", "a y")]), ("modify", [("Add", "env prod")]), ("record_modifier", [("Record", "c d")]),
+                 ("parser", [("Key_Name", "a"), ("Parser", "json")])]:
+        for depth in (29, 30, 31):
+            for pos in (0, 1, 3):
+                for inner in (b"\x90", b"\x80", b"\x01"):
+                    evs = [util.event(1700000000 + i, 0, [(b"a", S(b"x" if i % 2 else b"y"))]) for i in range(3)]
+                    evs.insert(pos, util.event(1700000100, 0, [(b"a", S(b"x")), (b"n", deep(depth, inner))]))
+                    chunk = b"".join(evs)
+                    ref = util.Ref(); ref.parser(**cases.JS); ref.filter(*filt)
+                    ctx = pkg.Context(0, lib=lib); ctx.parser(**cases.JS)
+                    assert ctx.chain([ctx.filter(*filt)]).do(chunk) == ref.chain_do(chunk), (filt, depth, pos, inner)
+    # metadata nests one level further down
+    for depth in (28, 29, 30):
+        evs = [util.event(1700000000 + i, 0, [(b"a", S(b"x"))]) for i in range(2)]
+        evs.insert(1, util.event(1700000100, 0, [(b"a", S(b"x"))], meta=b"\x81" + S(b"m") + deep(depth)))
+        chunk = b"".join(evs)
+        ref = util.Ref(); ref.filter("modify", [("Add", "env prod")])
+        ctx = pkg.Context(0, lib=lib)
+        assert ctx.chain([ctx.filter("modify", [("Add", "env prod")])]).do(chunk) == ref.chain_do(chunk), depth
+    # made by the JSON parser of the chain: the parser takes one level more than the filters behind it decode
+    for levels in (28, 29, 30, 31, 32):
+        for inner in (b"", b"1", b"{}"):
+            line = b'{"level":"warn","nested":' + b"[" * levels + inner + b"]" * levels + b"}"
+            lines = util.json_lines(40, seed=3) + [line] + util.json_lines(40, seed=4)
+            chunk = util.chunk_from_lines(lines)
+            for filters in ([cases.PJ, ("grep", [("Regex", "level ^(warn|error)$")]), ("modify", [("Add", "env prod")])],
+                            [cases.PJ, ("record_modifier", [("Record", "c d")])], [cases.PJ]):
+                ref = util.Ref(); ref.parser(**cases.JS)
+                ctx = pkg.Context(0, lib=lib); ctx.parser(**cases.JS)
+                for p, props in filters:
+                    ref.filter(p, props)
+                assert ctx.chain([ctx.filter(p, props) for p, props in filters]).do(chunk) == ref.chain_do(chunk), (levels, inner, filters)
+
+
+def test_deep_nesting_hostsim(sim_lib, ref_available):
+    _deep_nesting(sim_lib)
+
+
+@pytest.mark.gpu
+def test_deep_nesting_gpu(gpu_lib, ref_available):
+    _deep_nesting(gpu_lib)

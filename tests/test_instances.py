@@ -199,25 +199,39 @@ def test_ascii_only_patterns_gpu(gpu_lib, ref_available):
     _ascii_only_patterns(gpu_lib)
 
 
-@pytest.mark.gpu
-def test_two_stage_json_tokenizer_gpu(gpu_lib, ref_available, monkeypatch):
-    """FLBGPU_JSON_BM=1: the warp-cooperative stage-1 bitmap, the bit-scan walker and the follow-up launch over the records it
-    puts off give the bytes of the default byte scanner (= the reference's)"""
-    monkeypatch.setenv("FLBGPU_JSON_BM", "1")
+def _two_stage(lib, monkeypatch):
     lines = util.json_lines(20000, seed=61) + [c for c in cases.JSON_EDGE] * 20
     chunk = util.chunk_from_lines(lines)
     for name in ("json_chain_config1",):
         case = [c for c in cases.CASES if c[0] == name][0]
         want = _ref_result(case[1], case[2], chunk)
-        for env in ({}, {"FLBGPU_SMALL_MB": "0", "FLBGPU_SLICE_MB": "1"}):
+        for env in ({}, {"FLBGPU_SMALL_MB": "0", "FLBGPU_SLICE_MB": "1"}, {"FLBGPU_EVAL_SPLIT": "0"}):
             for k, v in env.items():
                 monkeypatch.setenv(k, v)
-            ctx = pkg.Context(0, lib=gpu_lib)
+            ctx = pkg.Context(0, lib=lib)
             for kw in case[1]:
                 ctx.parser(**kw)
-            assert ctx.chain([ctx.filter(p, props) for p, props in case[2]]).do(chunk) == want
+            got = ctx.chain([ctx.filter(p, props) for p, props in case[2]]).do(chunk)
+            assert got[0] == want[0] and len(got[1]) == len(want[1]), (env, got[0], want[0], len(got[1]), len(want[1]))
+            if got[1] != want[1]:
+                at = next(i for i in range(len(want[1])) if got[1][i] != want[1][i])
+                raise AssertionError((env, "first difference at byte", at, got[1][max(0, at - 60):at + 40], want[1][max(0, at - 60):at + 40]))
     # parser only, with Reserve_Data and a record accessor key: every shape the walker meets
     filters = [("parser", [("Key_Name", "log"), ("Parser", "json"), ("Reserve_Data", "On")])]
-    ctx = pkg.Context(0, lib=gpu_lib)
+    ctx = pkg.Context(0, lib=lib)
     ctx.parser(**cases.JS)
     assert ctx.chain([ctx.filter(p, props) for p, props in filters]).do(chunk) == _ref_result([cases.JS], filters, chunk)
+
+
+def test_two_stage_json_tokenizer_sim(sim_lib, ref_available, monkeypatch):
+    """FLBGPU_JSON_BM=1 as the emulation runs it: stage-1 bitmap, bit-scan walker, follow-up pass over the records put off"""
+    monkeypatch.setenv("FLBGPU_JSON_BM", "1")
+    _two_stage(sim_lib, monkeypatch)
+
+
+@pytest.mark.gpu
+def test_two_stage_json_tokenizer_gpu(gpu_lib, ref_available, monkeypatch):
+    """FLBGPU_JSON_BM=1: the warp-cooperative stage-1 bitmap, the bit-scan walker and the follow-up launch over the records it
+    puts off give the bytes of the default byte scanner (= the reference's)"""
+    monkeypatch.setenv("FLBGPU_JSON_BM", "1")
+    _two_stage(gpu_lib, monkeypatch)
