@@ -140,7 +140,8 @@ struct cf_pdef {               /* device view of struct flb_parser (flb_parser.h
     uint32_t n_groups;
     uint32_t tfast_off;        /* compiled fixed-shape time program (TF_* ops), 0 = none */
     uint32_t n_dec;            /* field decoders (Decode_Field / Decode_Field_As): struct cf_pdec[n_dec] at dec_off */
-    uint32_t dec_off, pad0;
+    uint32_t dec_off;
+    uint32_t time_key_hash;    /* ch_khash() of the Time_Key */
 };
 
 /* struct flb_parser_dec / flb_parser_dec_rule, include/fluent-bit/flb_parser_decoder.h:27-59 */

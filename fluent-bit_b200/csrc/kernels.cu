@@ -883,7 +883,7 @@ static int q_setup(bk_q *q)
     }
     {
         const char *e = getenv("FLBGPU_JSON_BM");
-        q->json_bm = e && e[0] == '1';
+        q->json_bm = e ? (e[0] == '1') : -1;           /* unset: with the split evaluation only (measured: faster there, slower in the single launch) */
     }
     return 0;
 }
@@ -1300,7 +1300,7 @@ int bk_chain_eval(bk_q *q, const struct bk_chain_args *a, uint32_t r0, uint32_t 
     use(q);
     fill_params(a, &p, 0, r0);
     p.n_rec = r1;
-    p.bm_words = (a->d_scr && q->json_bm) ? BM_BYTES / 32 : 0;          /* a JSON parser is in the chain */
+    p.bm_words = (a->d_scr && (q->json_bm > 0 || (q->json_bm < 0 && a->split))) ? BM_BYTES / 32 : 0;          /* a JSON parser is in the chain */
     if (defer_setup(q, &p, a, r1 - r0, q->stream)) return -1;
     ev_begin_on(q, 1, q->stream);
     if (a->split) {
@@ -1480,7 +1480,7 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     /* evaluation of records [0, n_valid) */
     fill_params(a, &p, d_out, 0);
     p.n_rec = 0; p.n_dev = &m->n_valid;
-    p.bm_words = (a->d_scr && q->json_bm) ? BM_BYTES / 32 : 0;
+    p.bm_words = (a->d_scr && (q->json_bm > 0 || (q->json_bm < 0 && a->split))) ? BM_BYTES / 32 : 0;
     if (defer_setup(q, &p, a, cap_rec, st)) return -1;
     ev_begin_on(q, 1, st);
     if (a->split) {

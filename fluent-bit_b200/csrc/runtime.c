@@ -508,6 +508,7 @@ static uint32_t emit_pdef(struct blob *b, struct flbgpu_parser *p)
     {
         const char *tk = p->time_key ? p->time_key : "time";
         d.time_key_off = blob_add(b, tk, strlen(tk), 1);
+        d.time_key_hash = key_hash(tk, strlen(tk));
         d.time_key_len = (uint32_t) strlen(tk);
     }
     if (p->types_len > 0 && !p->has_rx) {
@@ -1298,8 +1299,11 @@ int flbgpu_chain_init(flbgpu_chain *c)
         for (k2 = 0; k2 < last_parser; k2++) if (c->f[k2]->kind == FLBGPU_F_LOG_TO_METRICS) c->defer_ok = 0;
         /* `parser, then filters that are not parsers`: the evaluation runs as two launches (kernels.cu: k_chain_eval_t) */
         {
+            /* Measured (profiles/r02_variants.txt): -31 % evaluation time when the parser is the JSON transcoder (the largest piece
+             * of code), +5 % when it is a regex parser -- so by default only the former.  FLBGPU_EVAL_SPLIT=1 / 0 forces it. */
             const char *e = getenv("FLBGPU_EVAL_SPLIT");
-            c->split = c->nf >= 2 && last_parser == 0 && !(e && e[0] == '0');
+            const int want = e ? e[0] != '0' : (c->f[0]->needs_scratch & 1);
+            c->split = c->nf >= 2 && last_parser == 0 && want;
         }
     }
     h.n_filters = c->nf;
