@@ -81,6 +81,7 @@ def load(path=None):
     L.flbgpu_filter_init.argtypes = [vp]
     L.flbgpu_filter_cb.argtypes = [vp, vp, sz, cp, C.c_int, C.POINTER(vp), C.POINTER(sz)]
     L.flbgpu_filter_destroy.argtypes = [vp]
+    L.flbgpu_filter_emitted.argtypes = [vp, vp, C.POINTER(sz)]
     L.flbgpu_chain_new.restype = vp; L.flbgpu_chain_new.argtypes = [vp]
     L.flbgpu_chain_add.argtypes = [vp, vp]
     L.flbgpu_chain_init.argtypes = [vp]
@@ -277,6 +278,11 @@ def _call_filter(fn, L, handle, data, tag):
     return r, res
 
 
+class EmitGroup(C.Structure):
+    """struct flbgpu_emit_group (include/flbgpu.h)"""
+    _fields_ = [("tag", C.c_void_p), ("tag_len", C.c_size_t), ("data", C.c_void_p), ("size", C.c_size_t), ("records", C.c_size_t)]
+
+
 class Filter:
     def __init__(self, ctx, h):
         self.ctx, self.h = ctx, h
@@ -295,6 +301,15 @@ class Filter:
     def cb(self, data, tag="test"):
         """cb_filter(): (FILTER_MODIFIED, bytes) or (FILTER_NOTOUCH, None)."""
         return _call_filter(self.ctx.L.flbgpu_filter_cb, self.ctx.L, self.h, data, tag)
+
+    # ---- filter_rewrite_tag: what the last call handed to the emitter ----
+    def emitted(self):
+        """[(new tag, records bytes, record count)]: tags in order of first appearance, records of a tag in chunk order"""
+        groups, n = C.POINTER(EmitGroup)(), C.c_size_t()
+        if self.ctx.L.flbgpu_filter_emitted(self.h, C.byref(groups), C.byref(n)) != 0:
+            raise FlbGpuError("not a rewrite_tag filter")
+        return [(C.string_at(groups[i].tag, groups[i].tag_len), C.string_at(groups[i].data, groups[i].size), groups[i].records)
+                for i in range(n.value)]
 
     # ---- filter_log_to_metrics state (the plugin's ctx->cmt) ----
     def l2m_info(self):

@@ -71,6 +71,9 @@ struct ch_env {
     struct l2m_table l2m;     /* log_to_metrics delta table of this call (hash == NULL: none) */
     int32_t *prep;            /* parser report (flbgpu_parser_do): 6 ints per record -- parsed flag, position consumed,
                                  seconds lo / hi, nanoseconds, spare -- or NULL */
+    uint32_t *esize;          /* chains with a rewrite_tag filter: bytes of the record's entry in the re-tagged stream (0 = none) */
+    const uint8_t *tag;       /* the tag of this call (rewrite_tag templates: $TAG, $TAG[n]) */
+    uint32_t tag_len;
 };
 
 /* What differs from lane to lane.  struct ch_env itself is the same for every record of a launch and is read where the
@@ -81,6 +84,8 @@ struct ch_lane {
     const uint32_t *bm;       /* JSON stage-1 bitmap of the warp's byte range (shared memory), or NULL */
     uint32_t bm_base, bm_end; /* input offsets it covers */
     uint32_t defer_ok;        /* a record the stage-2 walker cannot take returns CH_DEFER instead of being scanned in place */
+    uint32_t raw_lo;          /* chains with a rewrite_tag filter: where the bytes the reference's decoder consumed for this record begin
+                                 (the end of the previous decoded record: events the decoder steps over in between belong to it) */
 };
 
 #define CW(p, x) (p)[(size_t) (x) * cs]          /* word x of a record's capture-cache row (cs = e->cap_n) */
@@ -2189,6 +2194,123 @@ FLB_HDN void chain_skipped_record(const struct ch_env *e, uint32_t ridx, uint32_
     }
 }
 
+/* ------------------------------------------------------ filter_rewrite_tag */
+/* plugins/filter_rewrite_tag/rewrite_tag.c:356-426 (process_record) + src/flb_record_accessor.c:483-690 (flb_ra_translate):
+ * the first rule whose key holds a string its regex matches decides; the new tag is the rule's template with $TAG, $TAG[n],
+ * $0..$9 and $key['sub'] filled in.  o == NULL: only the length. */
+FLB_HD uint32_t rt_put(uint8_t *o, uint32_t k, const uint8_t *b, uint32_t n)
+{
+    if (o) { uint32_t i; for (i = 0; i < n; i++) o[k + i] = b[i]; }
+    return n;
+}
+FLB_HD uint32_t rt_put_i64(uint8_t *o, uint32_t k, int64_t v)        /* snprintf("%" PRId64) */
+{
+    uint8_t tmp[20];
+    int n = 0;
+    uint32_t w = 0;
+    uint64_t u = v < 0 ? 0 - (uint64_t) v : (uint64_t) v;
+    do { tmp[n++] = (uint8_t) ('0' + (int) (u % 10)); u /= 10; } while (u);
+    if (v < 0) { if (o) o[k] = '-'; w++; }
+    while (n) { n--; if (o) o[k + w] = tmp[n]; w++; }
+    return w;
+}
+/* one msgpack value as ra_translate_keymap() prints it; anything it prints nothing for returns 0 */
+FLB_HD uint32_t rt_put_mp(const struct ch_env *e, const uint8_t *b, const uint8_t *end, uint8_t *o, uint32_t k)
+{
+    struct mp_tok t;
+    if (mp_token(b, end, &t) != 0) return 0;
+    switch (t.type) {
+    case MPT_STR: return rt_put(o, k, b + t.hdr, t.len);
+    case MPT_BIN: {                                  /* "%02x" per byte */
+        uint32_t i;
+        if (o) for (i = 0; i < t.len; i++) { const uint8_t c = b[t.hdr + i]; o[k + 2 * i] = "0123456789abcdef"[c >> 4]; o[k + 2 * i + 1] = "0123456789abcdef"[c & 15]; }
+        return 2 * t.len;
+    }
+    case MPT_UINT: case MPT_INT: return rt_put_i64(o, k, (int64_t) t.u);
+    case MPT_BOOL: return t.u ? rt_put(o, k, (const uint8_t *) "true", 4) : rt_put(o, k, (const uint8_t *) "false", 5);
+    case MPT_NIL: return rt_put(o, k, (const uint8_t *) "null", 4);
+    case MPT_F32: case MPT_F64: case MPT_MAP:        /* snprintf("%f") / flb_msgpack_to_json_str(): not restated -- refused, loudly */
+        CH_ATOMIC_OR(e->err, FLBGPU_E_TAGVALUE);
+        return 0;
+    default: return 0;                               /* arrays, ext: flb_ra_key_to_value_ext() has no value for them */
+    }
+}
+FLB_HD uint32_t rt_translate(const struct ch_env *e, const struct ch_lane *ln, const struct ch_rec *rc, const struct cf_rt_rule *rule,
+                             const uint8_t *subj, const int *caps, uint8_t *o)
+{
+    const struct cf_rt_part *pt = (const struct cf_rt_part *) (e->blob + rule->parts_off);
+    const struct rx_prog *pg = (const struct rx_prog *) (e->blob + rule->rx_off);
+    uint32_t k = 0, i;
+    for (i = 0; i < rule->n_parts; i++) {
+        switch (pt[i].type) {
+        case RT_STRING: k += rt_put(o, k, e->blob + pt[i].a, pt[i].b); break;
+        case RT_TAG: k += rt_put(o, k, e->tag, e->tag_len); break;
+        case RT_TAG_PART: {                          /* ra_translate_tag_part() */
+            uint32_t at = 0;
+            int id = -1, done = 0;
+            while (at < e->tag_len) {
+                uint32_t end = 0;
+                int dot = 0;
+                while (at + end < e->tag_len) { if (e->tag[at + end] == '.') { dot = 1; break; } end++; }
+                if (!dot) { if (at == 0) break; end = e->tag_len - at; }
+                id++;
+                if ((int) pt[i].a == id) { k += rt_put(o, k, e->tag + at, end); done = 1; break; }
+                at += end + 1;
+            }
+            if (!done && pt[i].a == 0 && id == -1 && at < e->tag_len) k += rt_put(o, k, e->tag, e->tag_len);      /* no dots in the tag */
+            break;
+        }
+        case RT_REGEX_ID:                            /* flb_regex_do() keeps no region for a pattern without groups: not even $0 */
+            if (pg->n_groups > 0 && pt[i].a <= pg->n_groups && caps[2 * pt[i].a] >= 0)
+                k += rt_put(o, k, subj + caps[2 * pt[i].a], (uint32_t) (caps[2 * pt[i].a + 1] - caps[2 * pt[i].a]));
+            break;
+        case RT_KEYMAP: {
+            const struct cf_ra *ra = (const struct cf_ra *) (e->blob + pt[i].a);
+            const uint8_t *vp = 0, *ve = 0;
+            int top, kn;
+            if (ra_get(e, ln, rc, ra, &top, &vp, &ve, &kn) != 0) break;
+            if (top < 0) { k += rt_put_mp(e, vp, ve, o, k); break; }
+            {
+                const ref_t r = rc->v[top];
+                const uint32_t rk = r_kind(r);
+                const uint8_t *b = ref_ptr(e, ln, r);
+                if (rk == RK_STR_IN || rk == RK_STR_SCR) k += rt_put(o, k, b, r_len(r));
+                else if (rk == RK_INT_IN) k += rt_put_i64(o, k, ch_atoll(b, r_len(r)));
+                else if (rk == RK_HEX_IN) k += rt_put_i64(o, k, (int64_t) ch_strtoull16(b, r_len(r)));
+                else if (rk == RK_TRUE) k += rt_put(o, k, (const uint8_t *) "true", 4);
+                else if (rk == RK_FALSE) k += rt_put(o, k, (const uint8_t *) "false", 5);
+                else if (rk == RK_FLT_IN) CH_ATOMIC_OR(e->err, FLBGPU_E_TAGVALUE);
+                else k += rt_put_mp(e, b, b + r_len(r), o, k);
+            }
+            break;
+        }
+        default: break;
+        }
+    }
+    return k;
+}
+/* the rule that takes the record: its index, or -1.  *subj / caps: what its regex matched on. */
+FLB_HD int f_rtag_rule(const struct ch_env *e, const struct ch_lane *ln, const struct cf_rtag *cf, const struct ch_rec *rc, struct ch_scratch *w,
+                       const uint8_t **subj)
+{
+    const struct cf_rt_rule *r = (const struct cf_rt_rule *) (e->blob + cf->rules_off);
+    uint32_t i;
+    int hit = -1;
+    for (i = 0; i < cf->n_rules; i++) {
+        CH_SYNC();
+        if (hit < 0) {
+            const struct cf_ra *ra = (const struct cf_ra *) (e->blob + r[i].ra_off);
+            const uint8_t *vp = 0, *ve = 0, *s;
+            uint32_t n;
+            int top, kn;
+            if (ra_get(e, ln, rc, ra, &top, &vp, &ve, &kn) != 0) continue;
+            if (loc_view(e, ln, rc, top, vp, ve, &s, &n) != 1) continue;        /* the value must be a STR (flb_ra_key_regex_match) */
+            if (rx_run(e, ln, r[i].rx_off, s, n, w->caps, w->stk)) { hit = (int) i; *subj = s; }
+        }
+    }
+    return hit;
+}
+
 /* ------------------------------------------------------------- the chain */
 /* Runs record `ridx` (framed at off/len, kind 0) through the chain.
  * EMIT=false: returns the output size (0 = dropped) and records evidence.
@@ -2200,6 +2322,7 @@ FLB_HDN void chain_skipped_record(const struct ch_env *e, uint32_t ridx, uint32_
 #define CH_PH_ALL  0
 #define CH_PH_HEAD 1
 #define CH_PH_TAIL 2
+#define CH_PH_RTAG 3                        /* EMIT only: stop at the rewrite_tag filter and write the record's entry of the re-tagged stream */
 #define RC_STATE_KH RC_CACHE_MAXF            /* split mode: the key fingerprints, in columns behind the row (cap_stride ..) */
 template <bool EMIT, int PH = CH_PH_ALL>
 FLB_HD uint32_t chain_record(const struct ch_env *e, struct ch_lane *ln, uint32_t ridx, uint32_t off, uint32_t len, uint8_t *out)
@@ -2210,13 +2333,14 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, struct ch_lane *ln, uint32_
     struct ch_scratch w;
     uint32_t k, cache_pos = 0;
     w.defer = 0;
+    if (!EMIT && PH != CH_PH_TAIL && e->esize) e->esize[ridx] = 0;
     /* this record's private scratch region: scr_mul bytes per record byte, the decoders' part behind the parser's */
     ln->scr = e->scr ? e->scr + (size_t) e->scr_mul * off : 0;
     ln->dec_at = 4u * len;
     /* The evaluation pass leaves the final field list of every surviving record (<= RC_CACHE_MAXF
      * fields) in the last RC_CACHE_INTS ints of its capture-cache row; the emission pass then only
      * encodes -- no decoding, no filters.  Longer records are re-run through the chain. */
-    if (EMIT && e->capcache && e->cap_stride >= RC_CACHE_INTS) {
+    if (EMIT && PH != CH_PH_RTAG && e->capcache && e->cap_stride >= RC_CACHE_INTS) {
         const size_t cs = e->cap_n;
         const int32_t *c = e->capcache + (size_t) (e->cap_stride - RC_CACHE_INTS) * cs + ridx;
         const int32_t st = CW(c, 0);
@@ -2301,6 +2425,38 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, struct ch_lane *ln, uint32_
             }
             break;
         }
+        case FLBGPU_F_REWRITE_TAG: {
+            /* rewrite_tag.c:468-497: a matched record goes to the emitter under its new tag -- as this filter sees it --
+             * and stays in the chunk only when the rule says keep */
+            const struct cf_rtag *cf = (const struct cf_rtag *) cfg;
+            const uint8_t *subj = 0;
+            const int hit = f_rtag_rule(e, ln, cf, &rc, &w, &subj);
+            if (hit >= 0) {
+                const struct cf_rt_rule *rule = (const struct cf_rt_rule *) (e->blob + cf->rules_off) + hit;
+                /* untouched so far: the bytes are the decoder's `data + pre .. off`, events it stepped over included */
+                const uint32_t lo = (!rc.reenc && (e->assume & e->active & ((1u << k) - 1u)) == 0) ? ln->raw_lo : off;
+                if (PH == CH_PH_RTAG) {
+                    const uint32_t tl = rt_translate(e, ln, &rc, rule, subj, w.caps, out + RT_ENTRY_HDR);
+                    uint32_t rl;
+                    if (!rc.reenc) { rl = off + len - lo; mp_copy(out + RT_ENTRY_HDR + tl, e->in + lo, rl); }
+                    else rl = rec_emit(e, ln, &rc, out + RT_ENTRY_HDR + tl);
+                    out[0] = (uint8_t) tl; out[1] = (uint8_t) (tl >> 8); out[2] = (uint8_t) (tl >> 16); out[3] = (uint8_t) (tl >> 24);
+                    out[4] = (uint8_t) rl; out[5] = (uint8_t) (rl >> 8); out[6] = (uint8_t) (rl >> 16); out[7] = (uint8_t) (rl >> 24);
+                    return RT_ENTRY_HDR + tl + rl;
+                }
+                if (!EMIT) {
+                    CH_ATOMIC_OR(&e->fl_flags[k], CHF_CAUSE);
+                    if (e->esize) e->esize[ridx] = RT_ENTRY_HDR + rt_translate(e, ln, &rc, rule, subj, w.caps, 0) + (rc.reenc ? rec_emit(e, ln, &rc, 0) : off + len - lo);
+                }
+                if (!rule->keep) { if (assumed) return 0; }
+                else if (!EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_EMITTED);
+            }
+            else {
+                if (PH == CH_PH_RTAG) return 0;
+                if (!EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_EMITTED);
+            }
+            break;
+        }
         case FLBGPU_F_LOG_TO_METRICS:
             /* metrics are accumulated once per call, by the evaluation pass; logs pass
              * through unless discard_logs (log_to_metrics.c:1136-1141) */
@@ -2311,6 +2467,7 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, struct ch_lane *ln, uint32_
             break;
         }
     }
+    if (PH == CH_PH_RTAG) return 0;          /* (not reached for a record the evaluation pass sized an entry for) */
     if (PH == CH_PH_HEAD) {
         /* hand the record over to the tail launch */
         const size_t cs = e->cap_n;

@@ -55,8 +55,14 @@ struct bk_chain_args {
     uint32_t *d_flags;            /* [FLBGPU_MAX_FILTERS + 1]: CHF_* per filter, last = error word */
     struct l2m_table l2m;         /* device pointers of the log_to_metrics delta table (hash NULL = none) */
     int32_t *d_prep;              /* parser report, 6 ints per record (dev_chain.cuh: ch_env.prep), or NULL */
+    uint32_t *d_esize;            /* chains with a rewrite_tag filter: [n_rec] bytes of each record's entry in the re-tagged stream */
+    const uint8_t *d_tag;         /* the tag of the call on the device (bk_tag_upload) */
+    uint32_t tag_len;
 };
 
+int   bk_tag_upload(bk_q *q, const char *tag, uint32_t tag_len, const uint8_t **d_tag);
+/* the re-tagged stream of records [0, n_rec) (sizes in a->d_esize): *h_out = malloc()ed, *bytes long, NULL when empty */
+int   bk_rtag_emit(bk_q *q, const struct bk_chain_args *a, uint32_t n_rec, uint64_t *d_bsum, uint64_t *h_bsum, void **h_out, size_t *bytes);
 const char *bk_name(void);
 int   bk_device_count(void);
 const char *bk_last_error(void);                 /* of the calling thread */

@@ -98,7 +98,7 @@ struct rx_prog {
 /* ------------------------------------------------------- chain program */
 /* All *_off fields are byte offsets from the blob base; 0 means "absent". */
 
-enum { FLBGPU_F_PARSER = 1, FLBGPU_F_GREP, FLBGPU_F_MODIFY, FLBGPU_F_RECORD_MODIFIER, FLBGPU_F_LOG_TO_METRICS };
+enum { FLBGPU_F_PARSER = 1, FLBGPU_F_GREP, FLBGPU_F_MODIFY, FLBGPU_F_RECORD_MODIFIER, FLBGPU_F_LOG_TO_METRICS, FLBGPU_F_REWRITE_TAG };
 
 /* parser types: include/fluent-bit/flb_parser.h:30-33 */
 enum { FLBGPU_PARSER_REGEX = 1, FLBGPU_PARSER_JSON, FLBGPU_PARSER_LTSV, FLBGPU_PARSER_LOGFMT };
@@ -169,6 +169,16 @@ enum { GREP_REGEX = 1, GREP_EXCLUDE = 2 };
 enum { GREP_OP_LEGACY = 0, GREP_OP_OR, GREP_OP_AND };
 struct cf_grep_rule { uint32_t type, ra_off, rx_off, pad; };
 struct cf_grep { uint32_t op, n_rules, rules_off, pad; };
+
+/* plugins/filter_rewrite_tag/rewrite_tag.h: struct rewrite_rule, and the parts of its tag template as
+ * ra_parse_buffer() (src/flb_record_accessor.c:75-214) cuts them */
+enum { RT_STRING = 1, RT_KEYMAP, RT_REGEX_ID, RT_TAG, RT_TAG_PART };
+struct cf_rt_part { uint32_t type, a, b, pad; };     /* STRING: a = offset, b = length; KEYMAP: a = struct cf_ra; REGEX_ID / TAG_PART: a = id */
+struct cf_rt_rule { uint32_t ra_off, rx_off, keep, n_parts, parts_off, pad0, pad1, pad2; };
+struct cf_rtag { uint32_t n_rules, rules_off, pad0, pad1; };
+/* one entry of the re-tagged stream a rewrite_tag filter leaves beside its result: u32 tag length, u32 record bytes,
+ * the tag, the record as the filter saw it (what the reference hands to in_emitter_add_record()) */
+#define RT_ENTRY_HDR 8u
 
 /* plugins/filter_modify/modify.h rule / condition kinds */
 enum { MOD_RENAME = 1, MOD_HARD_RENAME, MOD_ADD, MOD_SET, MOD_REMOVE, MOD_REMOVE_WILDCARD, MOD_REMOVE_REGEX,
@@ -250,6 +260,7 @@ struct chain_hdr {
 #define FLBGPU_E_L2M      64u   /* log_to_metrics: label table full / float label / unparsable value */
 #define FLBGPU_E_DEEP    256u   /* a parser made a value nested near msgpack-c's unpack limit: the filters behind it must see it as the
                                    reference's decoder does -- the call is run filter by filter */
+#define FLBGPU_E_TAGVALUE 512u   /* rewrite_tag: a tag template names a float or a map (snprintf("%f") / JSON text are not restated) */
 #define FLBGPU_E_RXUNICODE 128u /* a pattern with POSIX brackets / \b / case-insensitivity met a non-ASCII subject */
 
 /* ---------------------------------------------------- streaming JSON packer (dev_jsmn.cuh) */

@@ -323,6 +323,15 @@ struct k_chain_params {
     uint8_t *out;
 };
 
+/* chains with a rewrite_tag filter: where the bytes the reference's decoder consumed for record i begin -- behind the previous
+ * decoded record (the events it steps over in between, kind 1, are handed to the emitter with the record: rewrite_tag.c:462-470) */
+__device__ __forceinline__ uint32_t raw_lo_of(const k_chain_params &p, uint32_t i)
+{
+    uint32_t j = i;
+    while (j > 0 && p.kind[j - 1] != 0) j--;
+    return j ? p.off[j - 1] + p.len[j - 1] : 0u;
+}
+
 /* evaluation: record r0 + global thread id.  No barrier: a warp retires as soon as its
  * 32 records are done (block-level reductions happen in k_bsum). */
 
@@ -352,7 +361,8 @@ __device__ __forceinline__ uint32_t bm_mask4(uint32_t w)
  * Each half has roughly half the interpreter's code, which is what the single launch is bound by (instruction cache misses,
  * profiles/r02_ncu_eval_json.txt). */
 template <int PH>
-__global__ void __launch_bounds__(1024, 1) k_chain_eval_t(const __grid_constant__ k_chain_params p)       /* 64 registers per lane; block size chosen at launch */
+__global__ void __launch_bounds__(1024, 1) k_chain_eval_t(const __grid_constant__ k_chain_params p)       /* 64 registers per lane; block size chosen at launch.
+                                                                                                             (5 or 6 resident blocks of 256 lanes with 48 / 40 registers: slower, profiles/r02_variants.txt) */
 {
     extern __shared__ __align__(16) uint8_t dsm[];
     const uint32_t n_rec = p.n_dev ? *p.n_dev : p.n_rec;
@@ -386,6 +396,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval_t(const __grid_constant_
     }
     if (!valid) return;
     uint32_t sz = 0;
+    if (PH != CH_PH_TAIL && !live && p.env.esize) p.env.esize[i] = 0;      /* an event the decoder steps over has no entry of its own */
     if (PH == CH_PH_TAIL) {
         if (!live || p.size[i] == 0) return;           /* dropped by the head launch, or handed to the follow-up launch */
     }
@@ -395,6 +406,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval_t(const __grid_constant_
         struct ch_lane ln;
         ln.bm = bm; ln.bm_base = bm_base; ln.bm_end = bm_end;
         ln.defer_ok = (bm && p.defer_list) ? 1u : 0u;
+        ln.raw_lo = p.env.esize ? raw_lo_of(p, i) : my_off;
         sz = chain_record<false, PH>(&p.env, &ln, i, my_off, my_len, 0);
         if (sz == CH_DEFER) {                          /* the follow-up launch evaluates it whole, with the byte scanner */
             p.defer_list[atomicAdd(p.defer_cnt, 1ull)] = i;
@@ -415,6 +427,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval_deferred(const __grid_co
         const uint32_t i = p.defer_list[t];
         struct ch_lane ln;
         ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0;
+        ln.raw_lo = p.env.esize ? raw_lo_of(p, i) : p.off[i];
         __stcs(&p.size[i], chain_record<false>(&p.env, &ln, i, p.off[i], p.len[i], 0));
     }
 }
@@ -428,6 +441,21 @@ __global__ void __launch_bounds__(BK_REC_BLOCK) k_chain_skipped(const __grid_con
     const uint32_t i = p.r0 + blockIdx.x * BK_REC_BLOCK + threadIdx.x;
     if (i >= n_rec || p.kind[i] != 1) return;
     chain_skipped_record(&p.env, i, p.off[i], p.len[i]);
+}
+
+/* The re-tagged stream of a rewrite_tag filter: one entry per matched record (RT_ENTRY_HDR, tag, record as the filter saw it),
+ * in record order.  p.size = the entry sizes of the evaluation pass, p.bsum = exclusive offset per block, p.out = the stream. */
+__global__ void __launch_bounds__(BK_REC_BLOCK) k_rtag_emit(const __grid_constant__ k_chain_params p)
+{
+    const uint32_t i = p.r0 + blockIdx.x * BK_REC_BLOCK + threadIdx.x;
+    const uint32_t sz = i < p.n_rec ? p.size[i] : 0;
+    uint32_t tot;
+    const uint32_t ex = block_excl_scan(sz, &tot);
+    if (!sz) return;
+    struct ch_lane ln;
+    ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0;
+    ln.raw_lo = raw_lo_of(p, i);
+    chain_record<true, CH_PH_RTAG>(&p.env, &ln, i, p.off[i], p.len[i], p.out + p.bsum[blockIdx.x] + ex);
 }
 
 /* per-block sums of the record sizes */
@@ -501,7 +529,7 @@ __global__ void __launch_bounds__(EMIT_BLOCK, 6) k_chain_emit_list(const __grid_
     const bool rerun = valid && p.env.capcache[(size_t) (p.env.cap_stride - RC_CACHE_INTS) * p.env.cap_n + r] == RC_CACHE_NONE;
     if (!__any_sync(0xffffffffu, rerun) && total + mis <= EMIT_STAGE) {
         uint8_t *sb = emit_stage + (size_t) warp * (EMIT_STAGE + 16);
-        if (valid) { struct ch_lane ln; ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0; chain_record<true>(&p.env, &ln, r, p.off[r], p.len[r], sb + mis + (uint32_t) (off - base)); }   /* cached field list: encode only */
+        if (valid) { struct ch_lane ln; ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0; ln.raw_lo = p.off[r]; chain_record<true>(&p.env, &ln, r, p.off[r], p.len[r], sb + mis + (uint32_t) (off - base)); }   /* cached field list: encode only */
         __syncwarp();
         {
             /* shared byte i corresponds to result byte (base - mis + i): 16-byte chunks are aligned on both sides */
@@ -518,7 +546,7 @@ __global__ void __launch_bounds__(EMIT_BLOCK, 6) k_chain_emit_list(const __grid_
         return;
     }
     if (!valid) return;
-    { struct ch_lane ln; ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0; chain_record<true>(&p.env, &ln, r, p.off[r], p.len[r], p.out + off); }
+    { struct ch_lane ln; ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0; ln.raw_lo = p.off[r]; chain_record<true>(&p.env, &ln, r, p.off[r], p.len[r], p.out + off); }
 }
 
 /* ---- glue of the small-chunk form ---- */
@@ -678,6 +706,8 @@ struct bk_q {
                                               Off by default: measured 20 % slower than the byte scanner on configs[1]
                                               (profiles/r02_variants.txt) -- the walker's lanes diverge on the value type */
     int eval_block;                        /* FLBGPU_EVAL_BLOCK: threads per evaluation block */
+    uint8_t *d_tag; size_t cap_tag;        /* rewrite_tag: the tag of the call; the re-tagged stream before it goes to the host */
+    uint8_t *d_eout; size_t cap_eout;
     uint32_t *d_defer; size_t cap_defer;   /* records the JSON stage-2 walker put off to the follow-up launch */
     /* upload */
     cudaEvent_t up_ev[UP_MAX_EV]; int up_ev_made;
@@ -844,7 +874,7 @@ void bk_q_free(bk_q *q)
     for (int i = 0; i < UP_STAGE_SLOTS_MAX; i++) cudaFreeHost(q->up_stage[i]);
     if (q->xf_ready) for (int i = 0; i < q->xf_slots; i++) { cudaFreeHost(q->xf_ring[i]); cudaEventDestroy(q->xf_ev[i]); }
     cudaFree(q->dtotal); cudaFree(q->dbreaks); cudaFree(q->d_cnt); cudaFree(q->d_lrec); cudaFree(q->d_loff); cudaFree(q->d_nlist);
-    cudaFree(q->d_link[0]); cudaFree(q->d_link[1]); cudaFree(q->d_mark); cudaFree(q->d_mail); cudaFree(q->d_defer);
+    cudaFree(q->d_link[0]); cudaFree(q->d_link[1]); cudaFree(q->d_mark); cudaFree(q->d_mail); cudaFree(q->d_defer); cudaFree(q->d_tag); cudaFree(q->d_eout);
     cudaFreeHost(q->h_word); cudaFreeHost(q->h_mail); cudaFreeHost(q->h_flags); cudaFreeHost(q->h_sin); cudaFreeHost(q->h_sout);
     if (q->ev_small) cudaEventDestroy(q->ev_small);
     if (q->stream) cudaStreamDestroy(q->stream);
@@ -1238,6 +1268,7 @@ static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_
     p->env.capcache = a->d_capcache; p->env.cap_stride = a->cap_stride; p->env.cap_n = a->cap_n; p->env.now = a->now;
     p->env.assume = a->assume; p->env.active = a->active; p->env.fl_flags = a->d_flags; p->env.err = a->d_flags + FLBGPU_MAX_FILTERS;
     p->env.l2m = a->l2m; p->env.prep = a->d_prep;
+    p->env.esize = a->d_esize; p->env.tag = a->d_tag; p->env.tag_len = a->tag_len;
     p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->r0 = r0; p->n_rec = a->n_rec; p->bm_words = 0;
     p->n_dev = 0; p->defer_list = 0; p->defer_cnt = 0;
     p->size = a->d_size; p->bsum = a->d_bsum; p->out = d_out;
@@ -1346,6 +1377,53 @@ int bk_sizes_scan(bk_q *q, const uint32_t *d_size, uint32_t n_rec, uint64_t *d_b
     }
     CK(cudaStreamSynchronize(q->stream));
     h_bsum[nb] = q->h_word[0];
+    return 0;
+}
+
+/* ---- rewrite_tag: the tag of the call on the device, and the re-tagged stream ---- */
+int bk_tag_upload(bk_q *q, const char *tag, uint32_t tag_len, const uint8_t **d_tag)
+{
+    use(q);
+    if (q->cap_tag < (size_t) tag_len + 1) {
+        CK(cudaStreamSynchronize(q->stream));
+        cudaFree(q->d_tag); q->d_tag = 0; q->cap_tag = 0;
+        CK(cudaMalloc((void **) &q->d_tag, (size_t) tag_len + 256));
+        q->cap_tag = (size_t) tag_len + 256;
+    }
+    if (tag_len) CK(cudaMemcpyAsync(q->d_tag, tag, tag_len, cudaMemcpyHostToDevice, q->stream));     /* pageable source: staged before the call returns */
+    *d_tag = q->d_tag;
+    return 0;
+}
+
+/* entries of records [0, n_rec): a->d_esize holds their sizes; *h_out = malloc()ed stream of *bytes bytes (NULL when empty) */
+int bk_rtag_emit(bk_q *q, const struct bk_chain_args *a, uint32_t n_rec, uint64_t *d_bsum, uint64_t *h_bsum, void **h_out, size_t *bytes)
+{
+    const uint32_t nb = (n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK;
+    k_chain_params p;
+    uint64_t total;
+    void *out;
+    *h_out = 0; *bytes = 0;
+    if (!nb) return 0;
+    if (bk_sizes_scan(q, a->d_esize, n_rec, d_bsum, h_bsum)) return -1;
+    total = h_bsum[nb];
+    if (!total) return 0;
+    if (total >= 0xfff00000ull) { snprintf(g_err, sizeof(g_err), "re-tagged records larger than 4 GiB"); return -1; }
+    if (q->cap_eout < total) {
+        cudaFree(q->d_eout); q->d_eout = 0; q->cap_eout = 0;
+        CK(cudaMalloc((void **) &q->d_eout, (size_t) total + (size_t) total / 4 + 4096));
+        q->cap_eout = (size_t) total + (size_t) total / 4 + 4096;
+    }
+    fill_params(a, &p, q->d_eout, 0);
+    p.n_rec = n_rec; p.size = a->d_esize; p.bsum = d_bsum;
+    p.env.esize = 0;                                   /* (the entry sizes are read as p.size; nothing is sized here) */
+    k_rtag_emit<<<nb, BK_REC_BLOCK, 0, q->stream>>>(p);
+    g_launches += 1;
+    CK(cudaGetLastError());
+    out = malloc((size_t) total);
+    if (!out) { snprintf(g_err, sizeof(g_err), "out of memory"); return -1; }
+    if (cudaMemcpyAsync(out, q->d_eout, (size_t) total, cudaMemcpyDeviceToHost, q->stream) != cudaSuccess ||
+        cudaStreamSynchronize(q->stream) != cudaSuccess) { free(out); CK(cudaGetLastError()); snprintf(g_err, sizeof(g_err), "copy of the re-tagged records failed"); return -1; }
+    *h_out = out; *bytes = (size_t) total;
     return 0;
 }
 

@@ -103,6 +103,7 @@ struct pdec_rule { int type, backend, action; };
 struct pdec { char *key; int add_extra_keys; struct pdec_rule *rules; int n_rules; };
 
 struct kv { char *k, *v; struct kv *next; };
+static void rtag_release(flbgpu_filter *f);
 static uint32_t key_hash(const char *s, size_t n);
 
 /* host-side cumulative state of one filter_log_to_metrics instance: what the reference
@@ -137,6 +138,11 @@ struct flbgpu_filter {
     char *match;
     struct rx_compiled match_rx; int has_match_rx;
     int inactive;
+    /* rewrite_tag: what the last call handed to the emitter, grouped by new tag (flbgpu_filter_emitted) */
+    struct flbgpu_emit_group *rt_groups;
+    size_t rt_n;
+    void *rt_stream;         /* the entries as the device left them: the tags of rt_groups point in here */
+    void **rt_bufs;          /* one record buffer per group */
 };
 
 struct flbgpu_ctx {
@@ -162,6 +168,9 @@ struct flbgpu_chain {
     int defer_ok;                             /* no log_to_metrics filter in front of a parser filter: records may be re-evaluated from scratch */
     uint8_t *d_scr; size_t cap_scr;
     int l2m_index;                            /* filter index of the log_to_metrics filter, or -1 */
+    int rtag_index;                           /* filter index of the rewrite_tag filter, or -1; -2 = several: the chain runs filter by filter */
+    uint32_t *d_esize;                        /* rewrite_tag: bytes of each record's entry in the re-tagged stream */
+    const uint8_t *d_tag; uint32_t tag_len;   /* the tag of the call on the device */
     struct l2m_table l2m;                     /* device table (per-call delta) */
     size_t l2m_slots;
     uint64_t *h_hash, *h_chash, *h_cnt, *h_bkt; uint32_t *h_first; double *h_sum;    /* host mirror */
@@ -558,6 +567,7 @@ static int plugin_kind(const char *name)
     if (!strcasecmp(name, "modify")) return FLBGPU_F_MODIFY;
     if (!strcasecmp(name, "record_modifier")) return FLBGPU_F_RECORD_MODIFIER;
     if (!strcasecmp(name, "log_to_metrics")) return FLBGPU_F_LOG_TO_METRICS;
+    if (!strcasecmp(name, "rewrite_tag")) return FLBGPU_F_REWRITE_TAG;
     return 0;
 }
 
@@ -609,10 +619,19 @@ void flbgpu_filter_destroy(flbgpu_filter *f)
     if (!f) return;
     if (f->solo) flbgpu_chain_destroy(f->solo);
     l2m_state_free(f->l2m);
+    rtag_release(f);
     free(f->match);
     if (f->has_match_rx) rx_compiled_free(&f->match_rx);
     for (n = f->props; n; n = nx) { nx = n->next; free(n->k); free(n->v); free(n); }
     free(f);
+}
+
+static void rtag_release(flbgpu_filter *f)
+{
+    size_t i;
+    for (i = 0; i < f->rt_n; i++) free(f->rt_bufs[i]);
+    free(f->rt_bufs); free(f->rt_groups); free(f->rt_stream);
+    f->rt_bufs = NULL; f->rt_groups = NULL; f->rt_stream = NULL; f->rt_n = 0;
 }
 
 static int parse_bool(const char *v)
@@ -1196,6 +1215,133 @@ static uint32_t emit_l2m_filter(flbgpu_filter *f, struct blob *b)
     return blob_add(b, &cf, sizeof(cf), 8);
 }
 
+/* ---- filter_rewrite_tag ---- */
+/* ra_parse_buffer() (src/flb_record_accessor.c:75-214) on a tag template: the text is cut at every '$' into literal text,
+ * $0..$9, $TAG, $TAG[n] and $key['sub'] parts -- with the cutting rules of that loop, oddities included (the character behind
+ * `$TAG` or behind a key is never looked at as a '$'; a one-character tail behind a key is dropped; a '$' at the very end too). */
+struct rt_parts { struct cf_rt_part p[64]; int n; };
+static int rt_add(struct rt_parts *ps, uint32_t type, uint32_t a, uint32_t b2)
+{
+    if (ps->n >= 64) { set_err("[filter rewrite_tag] tag template with too many parts%s%s", NULL, NULL); return -1; }
+    ps->p[ps->n].type = type; ps->p[ps->n].a = a; ps->p[ps->n].b = b2; ps->p[ps->n].pad = 0;
+    ps->n++;
+    return 0;
+}
+static int rt_add_string(struct rt_parts *ps, struct blob *b, const char *s, int len)
+{
+    return rt_add(ps, RT_STRING, len > 0 ? blob_add(b, s, (size_t) len, 1) : 0, (uint32_t) (len > 0 ? len : 0));
+}
+static int rt_parse_template(struct blob *b, const char *buf, struct rt_parts *ps)
+{
+    const int len = (int) strlen(buf);
+    int i, n, pre = 0, end = 0;
+    ps->n = 0;
+    for (i = 0; i < len; i++) {
+        if (buf[i] != '$') continue;
+        if (i > pre && rt_add_string(ps, b, buf + pre, i - pre)) return -1;
+        pre = i;
+        n = i + 1;
+        if (n >= len) break;
+        if (isdigit((unsigned char) buf[n])) {
+            if (rt_add(ps, RT_REGEX_ID, (uint32_t) atoi(buf + n), 0)) return -1;
+            i++;
+            pre = i + 1;
+            continue;
+        }
+        if (n + 2 < len && strncmp(buf + n, "TAG", 3) == 0) {
+            if (n + 4 < len) {
+                end = -1;
+                if (buf[n + 3] == '[') {
+                    const int t = n + 3;
+                    const char *br = memchr(buf + t, ']', (size_t) (len - t));
+                    end = br ? (int) (br - (buf + t)) : -1;
+                    if (end == 0) end = -1;
+                    if (rt_add(ps, RT_TAG_PART, (uint32_t) atoi(buf + t + 1), 0)) return -1;
+                    i = t + end + 1;
+                    pre = i;
+                    continue;
+                }
+            }
+            if (rt_add(ps, RT_TAG, 0, 0)) return -1;
+            i = n + 3;
+            pre = n + 3;
+            continue;
+        }
+        {
+            int quote_cnt = 0;
+            char *key;
+            uint32_t ra;
+            for (end = i + 1; end < len; end++) {
+                if (buf[end] == '\'') ++quote_cnt;
+                else if (buf[end] == '.' && (quote_cnt & 1)) continue;
+                else if (buf[end] == '.' || buf[end] == ' ' || buf[end] == ',' || buf[end] == '"') break;
+            }
+            key = strndup(buf + i, (size_t) (end - i));
+            if (!key) return -1;
+            ra = emit_ra(b, key);
+            free(key);
+            if (!ra) return -1;
+            if (rt_add(ps, RT_KEYMAP, ra, 0)) return -1;
+            pre = end;
+            i = end;
+        }
+    }
+    if ((i - 1 > end && pre < i) || i == 1) {
+        if (pre <= len && rt_add_string(ps, b, buf + (pre < len ? pre : len), pre < len ? len - pre : 0)) return -1;
+    }
+    return 0;
+}
+
+static uint32_t emit_rtag_filter(flbgpu_filter *f, struct blob *b)
+{
+    struct cf_rtag cf;
+    struct cf_rt_rule rules[32];
+    struct kv *p;
+    memset(&cf, 0, sizeof(cf));
+    memset(rules, 0, sizeof(rules));
+    for (p = f->props; p; p = p->next) {
+        char *tok[6];
+        struct rt_parts parts;
+        struct cf_rt_rule *r;
+        int nt;
+        if (!strcasecmp(p->k, "emitter_name") || !strcasecmp(p->k, "emitter_mem_buf_limit")) continue;      /* the emitter is the caller's */
+        if (!strcasecmp(p->k, "emitter_storage.type")) {
+            if (strcasecmp(p->v, "memory") && strcasecmp(p->v, "filesystem")) {
+                set_err("invalid 'emitter_storage.type' value. Only 'memory' or 'filesystem' types are allowed%s%s", NULL, NULL);
+                return 0;
+            }
+            continue;
+        }
+        if (strcasecmp(p->k, "rule")) { set_err("[filter rewrite_tag] unknown configuration property '%s'%s", p->k, NULL); return 0; }
+        nt = split_tokens(p->v, 4, tok, 6);                        /* FLB_CONFIG_MAP_SLIST_4: at least four entries (flb_config_map.c:51-55) */
+        if (nt < 4) { free_toks(tok, nt); set_err("[config map] rule: four values expected (key, regex, tag, keep): '%s'%s", p->v, NULL); return 0; }
+        if (cf.n_rules >= 32) { free_toks(tok, nt); set_err("[filter rewrite_tag] too many rules%s%s", NULL, NULL); return 0; }
+        r = &rules[cf.n_rules];
+        /* the key: the FIRST part of the accessor text decides (flb_ra_regex_match: mk_list_entry_first) -- a key name with or
+         * without '$'; a part without a key ($TAG, $0) never matches */
+        if (rt_parse_template(b, tok[0], &parts)) { free_toks(tok, nt); if (!g_rt_err[0]) set_err("invalid record accessor key ? '%s'%s", tok[0], NULL); return 0; }
+        if (parts.n == 0) { free_toks(tok, nt); set_err("invalid record accessor key ? '%s'%s", tok[0], NULL); return 0; }
+        if (parts.p[0].type == RT_KEYMAP) r->ra_off = parts.p[0].a;
+        else if (parts.p[0].type == RT_STRING && parts.p[0].b) {
+            char *name = strndup((const char *) b->p + parts.p[0].a, parts.p[0].b);
+            r->ra_off = name ? emit_ra(b, name) : 0;
+            free(name);
+            if (!r->ra_off) { free_toks(tok, nt); return 0; }
+        }
+        else r->ra_off = 0;
+        r->rx_off = emit_rx(b, tok[1], NULL);
+        if (!r->rx_off) { free_toks(tok, nt); return 0; }
+        if (rt_parse_template(b, tok[2], &parts)) { free_toks(tok, nt); if (!g_rt_err[0]) set_err("could not compose tag: %s%s", tok[2], NULL); return 0; }
+        r->n_parts = (uint32_t) parts.n;
+        r->parts_off = blob_add(b, parts.p, sizeof(parts.p[0]) * (size_t) (parts.n ? parts.n : 1), 8);
+        r->keep = parse_bool(tok[3]) == 1;                          /* flb_utils_bool(): anything that is not true keeps nothing */
+        free_toks(tok, nt);
+        cf.n_rules++;
+    }
+    cf.rules_off = blob_add(b, rules, sizeof(rules[0]) * (cf.n_rules ? cf.n_rules : 1), 8);
+    return blob_add(b, &cf, sizeof(cf), 8);
+}
+
 static uint32_t emit_filter(flbgpu_filter *f, struct blob *b, uint32_t *cap_need)
 {
     switch (f->kind) {
@@ -1204,6 +1350,7 @@ static uint32_t emit_filter(flbgpu_filter *f, struct blob *b, uint32_t *cap_need
     case FLBGPU_F_MODIFY: return emit_modify_filter(f, b);
     case FLBGPU_F_RECORD_MODIFIER: return emit_recmod_filter(f, b);
     case FLBGPU_F_LOG_TO_METRICS: return emit_l2m_filter(f, b);
+    case FLBGPU_F_REWRITE_TAG: return emit_rtag_filter(f, b);
     }
     return 0;
 }
@@ -1217,7 +1364,8 @@ static int single_valued_set_twice(flbgpu_filter *f)
                                   "record", "remove_key", "allowlist_key", "whitelist_key",   /* record_modifier */
                                   "set", "add", "remove", "remove_wildcard", "remove_regex", "move_to_start", "move_to_end", "rename",
                                   "hard_rename", "copy", "hard_copy", "condition",            /* modify */
-                                  "add_label", "label_field", "bucket" };                     /* log_to_metrics */
+                                  "add_label", "label_field", "bucket",                       /* log_to_metrics */
+                                  "rule" };                                                   /* rewrite_tag */
     struct kv *p, *q;
     for (p = f->props; p; p = p->next) {
         size_t m;
@@ -1289,6 +1437,11 @@ int flbgpu_chain_init(flbgpu_chain *c)
         if (c->l2m_index >= 0) { set_err("only one log_to_metrics filter per fused chain%s%s", NULL, NULL); return -1; }
         c->l2m_index = (int) i;
     }
+    c->rtag_index = -1;
+    for (i = 0; i < (uint32_t) c->nf; i++) {
+        if (c->f[i]->kind != FLBGPU_F_REWRITE_TAG) continue;
+        c->rtag_index = c->rtag_index == -1 ? (int) i : -2;
+    }
     for (i = 0; i < (uint32_t) c->nf; i++) h.needs_scratch |= (uint32_t) c->f[i]->needs_scratch;
     c->needs_scratch = (int) h.needs_scratch;
     c->scr_mul = (h.needs_scratch & 2) ? 8 : 4;           /* scratch bytes per record byte */
@@ -1341,6 +1494,7 @@ void flbgpu_chain_destroy(flbgpu_chain *c)
     bk_free(c->q, c->d_len); bk_free(c->q, c->d_size); bk_free(c->q, c->d_kind); bk_free(c->q, c->d_bsum); bk_free(c->q, c->d_cap);
     bk_free(c->q, c->d_flags); bk_free(c->q, c->d_scr); free(c->h_bsum);
     bk_free(c->q, c->d_prep); free(c->h_prep);
+    bk_free(c->q, c->d_esize);
     bk_free(c->q, c->l2m.hash); bk_free(c->q, c->l2m.chash); bk_free(c->q, c->l2m.first); bk_free(c->q, c->l2m.cnt); bk_free(c->q, c->l2m.sum); bk_free(c->q, c->l2m.bkt); bk_free(c->q, c->l2m.str);
     free(c->h_hash); free(c->h_chash); free(c->h_first); free(c->h_cnt); free(c->h_sum); free(c->h_bkt);
     free(c->blob.p);
@@ -1374,6 +1528,7 @@ static int verdict(int kind, uint32_t fl, int clean)
     case FLBGPU_F_GREP: return (fl & CHF_CAUSE) != 0 && clean;
     case FLBGPU_F_MODIFY: return (fl & CHF_CAUSE) != 0 && clean;
     case FLBGPU_F_RECORD_MODIFIER: return (fl & CHF_CAUSE) && (fl & CHF_EMITTED);
+    case FLBGPU_F_REWRITE_TAG: return (fl & CHF_CAUSE) != 0 && clean;       /* emitted_num > 0 (rewrite_tag.c:500-531) */
     }
     return 0;
 }
@@ -1393,6 +1548,13 @@ static int ensure_rec_cap(flbgpu_chain *c, size_t need, size_t keep)
     /* split evaluation: RC_CACHE_MAXF more columns behind the rows carry the key fingerprints from the head to the tail launch */
     if (c->cap_stride) cp = bk_alloc(c->q, nc * (c->cap_stride + (c->split ? RC_CACHE_MAXF : 0)) * sizeof(int32_t));
     if (!o || !l || !z || !k || (c->cap_stride && !cp)) return -1;
+    if (c->rtag_index >= 0) {                          /* sized anew by every evaluation: nothing to keep */
+        uint32_t *ne = bk_alloc(c->q, nc * 4);
+        if (!ne) return -1;
+        if (keep && (bk_sync(c->q) || bk_d2d(c->q, ne, c->d_esize, keep * 4))) return -1;
+        bk_free(c->q, c->d_esize);
+        c->d_esize = ne;
+    }
     if (c->want_report) {
         int32_t *np_ = bk_alloc(c->q, nc * 6 * sizeof(int32_t));
         if (!np_ || bk_zero(c->q, np_, nc * 6 * sizeof(int32_t))) return -1;
@@ -1433,6 +1595,8 @@ static void fill_args(flbgpu_chain *c, struct bk_chain_args *a, const uint8_t *d
     a->scr_mul = c->scr_mul ? c->scr_mul : 4;
     a->defer_ok = (uint32_t) c->defer_ok;
     a->split = (uint32_t) c->split;
+    a->d_esize = (c->rtag_index >= 0 && ((c->active >> c->rtag_index) & 1)) ? c->d_esize : NULL;
+    a->d_tag = c->d_tag; a->tag_len = c->tag_len;
     a->d_prep = c->want_report ? c->d_prep : NULL;
 }
 
@@ -1682,6 +1846,61 @@ static uint32_t initial_assume(flbgpu_chain *c)
 
 /* One call.  Input: h_in (host, uploaded in pieces) or d_in_ext (already in HBM).
  * Result: host_out != NULL -> malloc()ed host buffer; else ext_out (device, capacity ext_cap). */
+/* rewrite_tag: fetch the re-tagged stream of this call and group it by new tag, in order of first appearance -- what the
+ * reference's per-record in_emitter_add_record() calls leave in the emitter (one chunk per tag, records in order). */
+static int rtag_collect(flbgpu_chain *c, const struct bk_chain_args *a, uint32_t n_rec, int any)
+{
+    flbgpu_filter *f = c->f[c->rtag_index];
+    uint8_t *stream = NULL;
+    size_t bytes = 0, at, g, ng = 0, cap = 0;
+    struct flbgpu_emit_group *gr = NULL;
+    size_t *fill = NULL;
+    rtag_release(f);
+    if (!any) return 0;
+    if (bk_rtag_emit(c->q, a, n_rec, c->d_bsum, c->h_bsum, (void **) &stream, &bytes)) { set_err("%s%s", bk_last_error(), NULL); return -1; }
+    if (!stream) return 0;
+    /* pass 1: the groups and their sizes */
+    for (at = 0; at + RT_ENTRY_HDR <= bytes; ) {
+        uint32_t tl, rl;
+        memcpy(&tl, stream + at, 4); memcpy(&rl, stream + at + 4, 4);
+        if (at + RT_ENTRY_HDR + tl + rl > bytes) break;
+        for (g = 0; g < ng; g++) if (gr[g].tag_len == tl && !memcmp(gr[g].tag, stream + at + RT_ENTRY_HDR, tl)) break;
+        if (g == ng) {
+            if (ng == cap) {
+                struct flbgpu_emit_group *n2 = realloc(gr, sizeof(*gr) * (cap ? cap * 2 : 16));
+                if (!n2) { free(gr); free(stream); set_err("out of memory%s%s", NULL, NULL); return -1; }
+                gr = n2; cap = cap ? cap * 2 : 16;
+            }
+            memset(&gr[ng], 0, sizeof(gr[ng]));
+            gr[ng].tag = (const char *) stream + at + RT_ENTRY_HDR; gr[ng].tag_len = tl;
+            ng++;
+        }
+        gr[g].size += rl; gr[g].records++;
+        at += RT_ENTRY_HDR + tl + rl;
+    }
+    if (at != bytes) { free(gr); free(stream); set_err("malformed re-tagged stream%s%s", NULL, NULL); return -1; }
+    f->rt_bufs = calloc(ng ? ng : 1, sizeof(void *));
+    fill = calloc(ng ? ng : 1, sizeof(size_t));
+    if (!f->rt_bufs || !fill) { free(fill); free(f->rt_bufs); f->rt_bufs = NULL; free(gr); free(stream); set_err("out of memory%s%s", NULL, NULL); return -1; }
+    f->rt_groups = gr; f->rt_n = ng; f->rt_stream = stream;
+    for (g = 0; g < ng; g++) {
+        f->rt_bufs[g] = malloc(gr[g].size ? gr[g].size : 1);
+        if (!f->rt_bufs[g]) { free(fill); rtag_release(f); set_err("out of memory%s%s", NULL, NULL); return -1; }
+        gr[g].data = f->rt_bufs[g];
+    }
+    /* pass 2: the records, in order, behind one another per group */
+    for (at = 0; at < bytes; ) {
+        uint32_t tl, rl;
+        memcpy(&tl, stream + at, 4); memcpy(&rl, stream + at + 4, 4);
+        for (g = 0; g < ng; g++) if (gr[g].tag_len == tl && !memcmp(gr[g].tag, stream + at + RT_ENTRY_HDR, tl)) break;
+        memcpy((uint8_t *) f->rt_bufs[g] + fill[g], stream + at + RT_ENTRY_HDR + tl, rl);
+        fill[g] += rl;
+        at += RT_ENTRY_HDR + tl + rl;
+    }
+    free(fill);
+    return 0;
+}
+
 static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_ext, size_t bytes,
                      uint8_t *ext_out, size_t ext_cap, void **host_out, size_t *out_size)
 {
@@ -1773,9 +1992,6 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     PHASE_MARK(0);
     c->spec_assume = a.assume; c->spec_valid = 1; c->spec_active = c->active;    /* what the streaming path speculates on next time */
     if (l2m_merge(c)) return -1;
-    if (a.assume == 0) return FLBGPU_FILTER_NOTOUCH;
-
-    /* ---- output offsets ---- */
     nb = (n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK;
     GROW(c->d_bsum, c->cap_bsum, nb + 2, uint64_t);
     if (c->cap_hbsum < (size_t) nb + 2) {
@@ -1785,6 +2001,12 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
         if (!c->h_bsum) { c->cap_hbsum = 0; return -1; }
     }
     a.d_bsum = c->d_bsum;
+    /* the records a rewrite_tag filter matched go to its emitter whatever the filter's own verdict is (a chunk that does not
+     * decode to its end makes it NOTOUCH after the fact, rewrite_tag.c:500-546) */
+    if (a.d_esize && rtag_collect(c, &a, n_rec, (h_flags[c->rtag_index] & CHF_CAUSE) != 0)) return -1;
+    if (a.assume == 0) return FLBGPU_FILTER_NOTOUCH;
+
+    /* ---- output offsets ---- */
     if (bk_sizes_scan(c->q, c->d_size, n_rec, c->d_bsum, c->h_bsum)) return -1;
     total = c->h_bsum[nb];
     if (total >= 0xfff00000ull) { set_err("result larger than 4 GiB%s%s", NULL, NULL); return -1; }
@@ -2186,6 +2408,17 @@ static int chain_do_one_by_one(flbgpu_chain *c, const void *data, size_t bytes, 
 
 static int chain_do_locked(flbgpu_chain *c, const void *data, size_t bytes, const char *tag, int tag_len, void **out_buf, size_t *out_size)
 {
+    if (c->rtag_index == -2) return chain_do_one_by_one(c, data, bytes, tag, tag_len, out_buf, out_size);     /* one re-tagged stream per chain */
+    if (c->rtag_index >= 0) {
+        /* a chain with a rewrite_tag filter takes the whole-chunk form: the re-tagged stream is cut from the same evaluation */
+        int r;
+        c->tag_len = (uint32_t) (tag && tag_len > 0 ? tag_len : 0);
+        if (bk_tag_upload(c->q, tag, c->tag_len, &c->d_tag)) { set_err("%s%s", bk_last_error(), NULL); return -1; }
+        r = chain_run(c, data, NULL, bytes, NULL, 0, out_buf, out_size);
+        bk_upload_end(c->q);
+        if (r < 0 && FUSED_REFUSED_A_HANDED_OVER_VALUE(c)) { *out_buf = NULL; *out_size = 0; return chain_do_one_by_one(c, data, bytes, tag, tag_len, out_buf, out_size); }
+        return r;
+    }
     if (bytes <= small_bytes()) {
         int ret = 0, r = chain_run_small(c, data, bytes, out_buf, out_size, &ret);
         if (r == 0) return ret;
@@ -2233,6 +2466,14 @@ int flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes, const char 
     return r;
 }
 
+
+/* ---- rewrite_tag: what the last call re-tagged ---------------------------------- */
+int flbgpu_filter_emitted(flbgpu_filter *f, const struct flbgpu_emit_group **groups, size_t *n_groups)
+{
+    if (!f || f->kind != FLBGPU_F_REWRITE_TAG || !groups || !n_groups) return -1;
+    *groups = f->rt_groups; *n_groups = f->rt_n;
+    return 0;
+}
 
 /* ---- log_to_metrics state ------------------------------------------------------ */
 int flbgpu_l2m_info(flbgpu_filter *f, int *mode, int *n_labels, int *n_buckets, int *n_sets)

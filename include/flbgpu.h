@@ -120,7 +120,7 @@ int  flbgpu_pack_json_state_batch(flbgpu_ctx *ctx, int n, const char *const *js,
 
 /* ---- filters ---------------------------------------------------------- */
 /* flb_filter_new(), src/flb_filter.c:426: plugin = "parser" | "grep" | "modify" |
- * "record_modifier" | "log_to_metrics" (the names of the reference's filter_*_plugin structs). */
+ * "record_modifier" | "log_to_metrics" | "rewrite_tag" (the names of the reference's filter_*_plugin structs). */
 flbgpu_filter *flbgpu_filter_new(flbgpu_ctx *ctx, const char *plugin);
 /* flb_filter_set_property(), src/flb_filter.c:325: properties keep config order,
  * keys are case-insensitive; "match"/"alias"/"log_level" are accepted and ignored. */
@@ -134,6 +134,25 @@ int flbgpu_filter_cb(flbgpu_filter *f, const void *data, size_t bytes,
                      const char *tag, int tag_len, void **out_buf, size_t *out_size);
 /* the plugin's cb_exit */
 void flbgpu_filter_destroy(flbgpu_filter *f);
+
+/* ---- filter "rewrite_tag" (plugins/filter_rewrite_tag/rewrite_tag.c) ---- */
+/* Properties: Rule <key> <regex> <new tag> <keep> (several), Emitter_Name, Emitter_Storage.type, Emitter_Mem_Buf_Limit (the
+ * emitter itself is the caller's: an input instance of the host pipeline).  The device matches the rules, expands the tag
+ * templates ($TAG, $TAG[n], $0..$9, $key['sub'], src/flb_record_accessor.c:483-690) and cuts the matched records out of the
+ * chunk; what the reference hands to in_emitter_add_record() one record at a time (rewrite_tag.c:404-413) is returned here
+ * grouped by new tag, tags in order of first appearance, records of a tag in chunk order -- the state those calls leave in
+ * the emitter (plugins/in_emitter/emitter.c:124: one chunk per tag).  The caller passes each group to its emitter once.
+ * The groups belong to the filter and stay valid until its next call (alone or inside a chain) or its destruction.
+ * The filter's return value follows the reference: MODIFIED iff at least one record was re-tagged (and the chunk decodes
+ * to its end), the result holding the records whose rule says keep plus the ones no rule matched. */
+struct flbgpu_emit_group {
+    const char *tag;        /* not NUL-terminated */
+    size_t tag_len;
+    const void *data;       /* the records as the filter saw them, one behind the other */
+    size_t size;
+    size_t records;
+};
+int flbgpu_filter_emitted(flbgpu_filter *f, const struct flbgpu_emit_group **groups, size_t *n_groups);
 
 /* ---- fused chain ------------------------------------------------------ */
 /* flb_filter_do(), src/flb_filter.c:119-323, over filters that all live on the GPU:

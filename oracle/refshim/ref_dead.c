@@ -16,3 +16,7 @@ int mk_print() { return 0; }
  * refers to these */
 int flb_router_apply_config(void *config) { (void) config; return 0; }
 void flb_routes_empty_mask_destroy(void *config) { (void) config; }
+/* filter_rewrite_tag's emitter set-up and its processor-stage shortcut (ingest_inline needs parent_processor, which a
+ * filter instance never has) */
+int flb_metrics_title(const char *title, void *metrics) { (void) title; (void) metrics; return 0; }
+DEAD(flb_input_instance_exit) DEAD(flb_input_instance_destroy) DEAD(flb_input_log_append_skip_processor_stages)

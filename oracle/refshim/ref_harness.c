@@ -35,11 +35,12 @@ extern struct flb_filter_plugin filter_grep_plugin;
 extern struct flb_filter_plugin filter_modify_plugin;
 extern struct flb_filter_plugin filter_record_modifier_plugin;
 extern struct flb_filter_plugin filter_log_to_metrics_plugin;
+extern struct flb_filter_plugin filter_rewrite_tag_plugin;
 
 struct flbref_cfg {
     struct flb_config *config;
     struct flb_input_instance in;
-    struct flb_filter_plugin plugins[5];
+    struct flb_filter_plugin plugins[6];
 };
 
 void *flbref_config_create(void)
@@ -61,7 +62,8 @@ void *flbref_config_create(void)
     c->plugins[2] = filter_modify_plugin;
     c->plugins[3] = filter_record_modifier_plugin;
     c->plugins[4] = filter_log_to_metrics_plugin;
-    for (i = 0; i < 5; i++) {
+    c->plugins[5] = filter_rewrite_tag_plugin;
+    for (i = 0; i < 6; i++) {
         mk_list_add(&c->plugins[i]._head, &config->filter_plugins);
     }
     mk_list_init(&c->in.properties);
@@ -414,3 +416,28 @@ int flbref_l2m_cmt_msgpack(void *filter, void **out, size_t *out_size)
 }
 
 void flbref_cfree(void *p) { free(p); }
+
+/* ---- filter_rewrite_tag's emitter: in_emitter_add_record() (plugins/in_emitter/emitter.c:124) is the one function of the
+ * emitter input the filter calls per re-tagged record.  Here it appends (tag, record bytes) to a log the tests read:
+ * u32 tag_len, u32 size, tag, bytes -- one entry per call, in call order. ---- */
+static char *g_emit_log;
+static size_t g_emit_len, g_emit_cap;
+static int g_emit_fail_after = -1;       /* >= 0: calls from this one on return -1 (a paused / full emitter) */
+static int g_emit_calls;
+int in_emitter_add_record(const char *tag, int tag_len, const char *buf_data, size_t buf_size,
+                          struct flb_input_instance *in, struct flb_input_instance *i_ins)
+{
+    uint32_t h[2];
+    size_t need = g_emit_len + 8 + (size_t) tag_len + buf_size;
+    if (g_emit_fail_after >= 0 && g_emit_calls++ >= g_emit_fail_after) return -1;
+    if (need > g_emit_cap) { g_emit_cap = need * 2 + 4096; g_emit_log = realloc(g_emit_log, g_emit_cap); }
+    h[0] = (uint32_t) tag_len; h[1] = (uint32_t) buf_size;
+    memcpy(g_emit_log + g_emit_len, h, 8);
+    memcpy(g_emit_log + g_emit_len + 8, tag, tag_len);
+    memcpy(g_emit_log + g_emit_len + 8 + tag_len, buf_data, buf_size);
+    g_emit_len = need;
+    return 0;
+}
+int in_emitter_get_collector_id(struct flb_input_instance *in) { return 0; }
+void flbref_emit_log(const void **log, size_t *len) { *log = g_emit_log; *len = g_emit_len; }
+void flbref_emit_reset(int fail_after) { g_emit_len = 0; g_emit_calls = 0; g_emit_fail_after = fail_after; }

@@ -37,6 +37,12 @@
 #include <fluent-bit/flb_parser.h>
 #include <fluent-bit/flb_parser_decoder.h>
 #include <fluent-bit/flb_utils.h>
+#include <fluent-bit/flb_input.h>
+#include <fluent-bit/flb_storage.h>
+#include <fluent-bit/flb_metrics.h>
+#include <cmetrics/cmetrics.h>
+#include <cmetrics/cmt_counter.h>
+#include <cfl/cfl_time.h>
 #include "../include/flbgpu.h"
 
 /* ---- the C ABI, resolved from the library at run time ---- */
@@ -53,6 +59,7 @@ static struct gpu_api {
     int (*filter_cb)(flbgpu_filter *, const void *, size_t, const char *, int, void **, size_t *);
     void (*filter_destroy)(flbgpu_filter *);
     char *(*l2m_text)(flbgpu_filter *);
+    int (*filter_emitted)(flbgpu_filter *, const struct flbgpu_emit_group **, size_t *);
 } G;
 static flbgpu_ctx *g_ctx;                         /* one context per process and device */
 static pthread_mutex_t g_lock = PTHREAD_MUTEX_INITIALIZER;
@@ -70,6 +77,7 @@ static int api_load(void)
     SYM(parser_get, "flbgpu_parser_get"); SYM(filter_new, "flbgpu_filter_new");
     SYM(filter_set_property, "flbgpu_filter_set_property"); SYM(filter_init, "flbgpu_filter_init");
     SYM(filter_cb, "flbgpu_filter_cb"); SYM(filter_destroy, "flbgpu_filter_destroy"); SYM(l2m_text, "flbgpu_l2m_text");
+    SYM(filter_emitted, "flbgpu_filter_emitted");
 #undef SYM
     return 0;
 }
@@ -148,7 +156,15 @@ static int mirror_parser(struct flb_filter_instance *ins, struct flb_config *con
     return 0;
 }
 
+static int gpu_init_filter(struct flb_filter_instance *ins, struct flb_config *config, const char *plugin, flbgpu_filter **out);
 static int gpu_init(struct flb_filter_instance *ins, struct flb_config *config, const char *plugin)
+{
+    flbgpu_filter *f;
+    if (gpu_init_filter(ins, config, plugin, &f) != 0) return -1;
+    flb_filter_set_context(ins, f);
+    return 0;
+}
+static int gpu_init_filter(struct flb_filter_instance *ins, struct flb_config *config, const char *plugin, flbgpu_filter **out)
 {
     struct mk_list *head;
     struct flb_kv *kv;
@@ -169,7 +185,7 @@ static int gpu_init(struct flb_filter_instance *ins, struct flb_config *config, 
         G.filter_destroy(f);
         return -1;
     }
-    flb_filter_set_context(ins, f);
+    *out = f;
     return 0;
 }
 
@@ -191,6 +207,111 @@ static int cb_gpu_exit(void *data, struct flb_config *config)
     if (data && G.filter_destroy) G.filter_destroy(data);
     return 0;
 }
+
+/* ---- gpu_rewrite_tag: the device matches the rules, expands the tags and cuts the records out; the emitter -- an input
+ * instance of this pipeline -- is created and fed here, the way plugins/filter_rewrite_tag/rewrite_tag.c does it
+ * (emitter_create: 38-110, process_record: 404-413), once per new tag instead of once per record ---- */
+int in_emitter_add_record(const char *tag, int tag_len, const char *buf_data, size_t buf_size,
+                          struct flb_input_instance *in, struct flb_input_instance *i_ins);
+struct gpu_rtag {
+    flbgpu_filter *f;
+    struct flb_input_instance *ins_emitter;
+#ifdef FLB_HAVE_METRICS
+    struct cmt_counter *cmt_emitted;          /* fluentbit_filter_emit_records_total{name} (rewrite_tag.c:301-311) */
+#endif
+};
+#define GPU_RTAG_METRIC_EMITTED 200             /* FLB_RTAG_METRIC_EMITTED */
+
+static int cb_init_rewrite_tag(struct flb_filter_instance *ins, struct flb_config *config, void *data)
+{
+    struct gpu_rtag *ctx;
+    struct flb_input_instance *em;
+    const char *name, *storage, *limit;
+    char fallback[128];
+    (void) data;
+    ctx = flb_calloc(1, sizeof(*ctx));
+    if (!ctx) return -1;
+    if (gpu_init_filter(ins, config, "rewrite_tag", &ctx->f) != 0) { flb_free(ctx); return -1; }
+    name = flb_filter_get_property("emitter_name", ins);
+    if (!name) { snprintf(fallback, sizeof(fallback), "emitter_for_%s", flb_filter_name(ins)); name = fallback; }
+    storage = flb_filter_get_property("emitter_storage.type", ins);
+    limit = flb_filter_get_property("emitter_mem_buf_limit", ins);
+    if (flb_input_name_exists(name, config) == FLB_TRUE) {
+        SHIM_ERROR(ins, "emitter_name '%s' already exists", name);
+        goto fail;
+    }
+    em = flb_input_new(config, "emitter", NULL, FLB_FALSE);
+    if (!em) { SHIM_ERROR(ins, "cannot create emitter instance"); goto fail; }
+    if (flb_input_set_property(em, "alias", name) == -1) {
+        flb_plg_warn(ins, "cannot set emitter_name, using fallback name '%s'", em->name);
+    }
+    em->mem_buf_limit = flb_utils_size_to_bytes(limit ? limit : "10M");
+    if (flb_input_set_property(em, "storage.type", storage ? storage : "memory") == -1) {
+        flb_plg_error(ins, "cannot set storage.type");
+    }
+    if (flb_input_instance_init(em, config) == -1) { SHIM_ERROR(ins, "cannot initialize emitter instance '%s'", em->name); goto fail; }
+    if (flb_storage_input_create(config->cio, em) == -1) { SHIM_ERROR(ins, "cannot initialize storage for stream '%s'", name); goto fail; }
+    ctx->ins_emitter = em;
+#ifdef FLB_HAVE_METRICS
+    ctx->cmt_emitted = cmt_counter_create(ins->cmt, "fluentbit", "filter", "emit_records_total", "Total number of emitted records",
+                                          1, (char *[]) {"name"});
+    flb_metrics_add(GPU_RTAG_METRIC_EMITTED, "emit_records", ins->metrics);
+#endif
+    flb_filter_set_context(ins, ctx);
+    return 0;
+fail:
+    G.filter_destroy(ctx->f);
+    flb_free(ctx);
+    return -1;
+}
+
+static int cb_filter_rewrite_tag(const void *data, size_t bytes, const char *tag, int tag_len, void **out_buf, size_t *out_size,
+                                 struct flb_filter_instance *ins, struct flb_input_instance *i_ins, void *context, struct flb_config *config)
+{
+    struct gpu_rtag *ctx = context;
+    const struct flbgpu_emit_group *groups = NULL;
+    size_t n = 0, i;
+    int ret = G.filter_cb(ctx->f, data, bytes, tag, tag_len, out_buf, out_size);
+    (void) config;
+    if (ret < 0) {
+        SHIM_ERROR(ins, "%s", G.last_error());
+        return FLB_FILTER_NOTOUCH;
+    }
+    if (G.filter_emitted(ctx->f, &groups, &n) == 0) {
+        size_t emitted = 0;
+        for (i = 0; i < n; i++) {
+            if (in_emitter_add_record(groups[i].tag, (int) groups[i].tag_len, groups[i].data, groups[i].size, ctx->ins_emitter, i_ins) == -1) {
+                flb_plg_warn(ins, "emitter refused %zu records re-tagged '%.*s'", groups[i].records, (int) groups[i].tag_len, groups[i].tag);
+            }
+            else {
+                emitted += groups[i].records;
+            }
+        }
+#ifdef FLB_HAVE_METRICS
+        if (emitted > 0) {
+            char *name = (char *) flb_filter_name(ins);
+            cmt_counter_add(ctx->cmt_emitted, cfl_time_now(), (double) emitted, 1, (char *[]) {name});
+            flb_metrics_sum(GPU_RTAG_METRIC_EMITTED, emitted, ins->metrics);
+        }
+#endif
+    }
+    return ret;
+}
+
+static int cb_exit_rewrite_tag(void *data, struct flb_config *config)
+{
+    struct gpu_rtag *ctx = data;
+    (void) config;
+    if (!ctx) return 0;
+    if (ctx->f && G.filter_destroy) G.filter_destroy(ctx->f);
+    flb_free(ctx);
+    return 0;
+}
+
+extern struct flb_filter_plugin filter_rewrite_tag_plugin;
+struct flb_filter_plugin filter_gpu_rewrite_tag_plugin = {
+    .name = "gpu_rewrite_tag", .description = "B200: rewrite_tag on the GPU (libflbgpu)",
+    .cb_init = cb_init_rewrite_tag, .cb_filter = cb_filter_rewrite_tag, .cb_exit = cb_exit_rewrite_tag, .flags = 0 };
 
 /* the metric table of a gpu_log_to_metrics instance in cmetrics' text form (what the stock plugin appends to its
  * hidden input from cb_filter / its flush timer, log_to_metrics.c:560-621,1117-1125); free() the result */
@@ -224,6 +345,8 @@ __attribute__((constructor)) static void gpu_plugins_adopt_config_maps(void)
     filter_gpu_modify_plugin.config_map = filter_modify_plugin.config_map;
     filter_gpu_record_modifier_plugin.config_map = filter_record_modifier_plugin.config_map;
     filter_gpu_log_to_metrics_plugin.config_map = filter_log_to_metrics_plugin.config_map;
+    filter_gpu_rewrite_tag_plugin.config_map = filter_rewrite_tag_plugin.config_map;
+    filter_gpu_rewrite_tag_plugin.event_type = filter_rewrite_tag_plugin.event_type;
     filter_gpu_parser_plugin.event_type = filter_parser_plugin.event_type;
     filter_gpu_grep_plugin.event_type = filter_grep_plugin.event_type;
     filter_gpu_modify_plugin.event_type = filter_modify_plugin.event_type;

@@ -77,7 +77,7 @@ static thread_local char hs_err[256];
 static uint64_t hs_launches;
 
 struct sim_comm;
-struct bk_q { int device; uint64_t records_out; uint8_t *dl_dst; const uint8_t *dl_src; struct sim_comm *comm; int comm_ranks, comm_rank; };
+struct bk_q { int device; uint64_t records_out; uint8_t *dl_dst; const uint8_t *dl_src; struct sim_comm *comm; int comm_ranks, comm_rank; uint8_t *tag; };
 
 extern "C" {
 
@@ -86,7 +86,7 @@ const char *bk_last_error(void) { return hs_err; }
 uint64_t bk_launch_count(void) { return hs_launches; }
 int bk_device_count(void) { return 1; }
 bk_q *bk_q_new(int device) { bk_q *q = (bk_q *) calloc(1, sizeof(bk_q)); q->device = device; return q; }
-void bk_q_free(bk_q *q) { free(q); }
+void bk_q_free(bk_q *q) { if (q) free(q->tag); free(q); }
 int bk_q_device(bk_q *q) { return q->device; }
 void *bk_alloc(bk_q *, size_t n) { return malloc(n + 64); }
 void bk_free(bk_q *, void *p) { free(p); }
@@ -187,6 +187,14 @@ static void hs_env(const struct bk_chain_args *a, struct ch_env *e)
     e->capcache = a->d_capcache; e->cap_stride = a->cap_stride; e->cap_n = a->cap_n; e->now = a->now; e->assume = a->assume; e->active = a->active;
     e->fl_flags = a->d_flags; e->err = a->d_flags + FLBGPU_MAX_FILTERS;
     e->l2m = a->l2m; e->prep = a->d_prep;
+    e->esize = a->d_esize; e->tag = a->d_tag; e->tag_len = a->tag_len;
+}
+/* where the bytes the reference's decoder consumed for record i begin (kernels.cu: raw_lo_of) */
+static uint32_t hs_raw_lo(const struct bk_chain_args *a, uint32_t i)
+{
+    uint32_t j = i;
+    while (j > 0 && a->d_kind[j - 1] != 0) j--;
+    return j ? a->d_off[j - 1] + a->d_len[j - 1] : 0u;
 }
 
 int bk_flags_clear(bk_q *q, uint32_t *d_flags) { memset(d_flags, 0, sizeof(uint32_t) * (FLBGPU_MAX_FILTERS + 1)); q->records_out = 0; return 0; }
@@ -212,20 +220,21 @@ int bk_chain_eval(bk_q *, const struct bk_chain_args *a, uint32_t r0, uint32_t r
         ln.bm = bm; ln.bm_base = lo; ln.bm_end = hi;
         ln.defer_ok = a->defer_ok && !getenv("FLBGPU_SIM_NODEFER");     /* as the kernel: records the walker cannot take go to a follow-up pass */
     }
+    if (a->d_esize) for (i = r0; i < r1; i++) if (a->d_kind[i] != 0) a->d_esize[i] = 0;
     if (a->split) {
         /* the three launches of the split form, in the kernel's order: head over all records, tail, then the records the
          * head put off, whole */
         uint8_t *put_off = (uint8_t *) calloc(r1 - r0 + 1, 1);
         for (i = r0; i < r1; i++) {
             uint32_t sz = 0;
-            if (a->d_kind[i] == 0) sz = chain_record<false, CH_PH_HEAD>(&e, &ln, i, a->d_off[i], a->d_len[i], 0);
+            if (a->d_kind[i] == 0) ln.raw_lo = hs_raw_lo(a, i), sz = chain_record<false, CH_PH_HEAD>(&e, &ln, i, a->d_off[i], a->d_len[i], 0);
             if (sz == CH_DEFER) { put_off[i - r0] = 1; sz = 0; }
             a->d_size[i] = sz;
         }
         for (i = r0; i < r1; i++)
             if (a->d_kind[i] == 0 && a->d_size[i]) a->d_size[i] = chain_record<false, CH_PH_TAIL>(&e, &ln, i, a->d_off[i], a->d_len[i], 0);
         for (i = r0; i < r1; i++)
-            if (put_off[i - r0]) { struct ch_lane plain; memset(&plain, 0, sizeof(plain)); a->d_size[i] = chain_record<false>(&e, &plain, i, a->d_off[i], a->d_len[i], 0); }
+            if (put_off[i - r0]) { struct ch_lane plain; memset(&plain, 0, sizeof(plain)); plain.raw_lo = hs_raw_lo(a, i); a->d_size[i] = chain_record<false>(&e, &plain, i, a->d_off[i], a->d_len[i], 0); }
         for (i = r0; i < r1; i++)
             if (a->d_kind[i] == 1 && e.l2m.hash) chain_skipped_record(&e, i, a->d_off[i], a->d_len[i]);
         free(put_off);
@@ -237,13 +246,13 @@ int bk_chain_eval(bk_q *, const struct bk_chain_args *a, uint32_t r0, uint32_t r
         memset(&plain, 0, sizeof(plain));
         for (i = r0; i < r1; i++) {
             uint32_t sz = 0;
-            if (a->d_kind[i] == 0) sz = chain_record<false>(&e, &ln, i, a->d_off[i], a->d_len[i], 0);
+            if (a->d_kind[i] == 0) ln.raw_lo = hs_raw_lo(a, i), sz = chain_record<false>(&e, &ln, i, a->d_off[i], a->d_len[i], 0);
             else if (a->d_kind[i] == 1 && e.l2m.hash) chain_skipped_record(&e, i, a->d_off[i], a->d_len[i]);
             if (sz == CH_DEFER) { put_off[i - r0] = 1; sz = 0; }
             a->d_size[i] = sz;
         }
         for (i = r0; i < r1; i++)
-            if (put_off[i - r0]) a->d_size[i] = chain_record<false>(&e, &plain, i, a->d_off[i], a->d_len[i], 0);
+            if (put_off[i - r0]) { plain.raw_lo = hs_raw_lo(a, i); a->d_size[i] = chain_record<false>(&e, &plain, i, a->d_off[i], a->d_len[i], 0); }
         free(put_off);
     }
     free(bm);
@@ -300,6 +309,43 @@ int bk_chain_emit(bk_q *q, const struct bk_chain_args *a, uint8_t *d_out, uint32
         }
     }
     hs_launches += 1;
+    return 0;
+}
+
+/* ---- rewrite_tag ---- */
+int bk_tag_upload(bk_q *q, const char *tag, uint32_t tag_len, const uint8_t **d_tag)
+{
+    free(q->tag);
+    q->tag = (uint8_t *) malloc(tag_len + 1);
+    if (tag_len) memcpy(q->tag, tag, tag_len);
+    *d_tag = q->tag;
+    return 0;
+}
+int bk_rtag_emit(bk_q *q, const struct bk_chain_args *a, uint32_t n_rec, uint64_t *, uint64_t *, void **h_out, size_t *bytes)
+{
+    struct ch_env e;
+    size_t total = 0, at = 0;
+    uint32_t i;
+    uint8_t *out;
+    *h_out = 0; *bytes = 0;
+    for (i = 0; i < n_rec; i++) total += a->d_esize[i];
+    if (!total) return 0;
+    out = (uint8_t *) malloc(total);
+    hs_env(a, &e);
+    e.esize = 0;
+    for (i = 0; i < n_rec; i++) {
+        struct ch_lane ln;
+        uint32_t w;
+        if (!a->d_esize[i]) continue;
+        memset(&ln, 0, sizeof(ln));
+        ln.raw_lo = hs_raw_lo(a, i);
+        w = chain_record<true, CH_PH_RTAG>(&e, &ln, i, a->d_off[i], a->d_len[i], out + at);
+        if (w != a->d_esize[i]) { snprintf(hs_err, sizeof(hs_err), "re-tagged entry size mismatch at record %u: %u vs %u", i, w, a->d_esize[i]); free(out); return -1; }
+        at += w;
+    }
+    hs_launches += 1;
+    (void) q;
+    *h_out = out; *bytes = total;
     return 0;
 }
 

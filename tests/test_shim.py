@@ -103,8 +103,44 @@ def _l2m(lib_path):
 def test_shim_exports(ref_available):
     need_shim()
     L = C.CDLL(util.SHIM_SO)
-    for name in ("parser", "grep", "modify", "record_modifier", "log_to_metrics"):
+    for name in ("parser", "grep", "modify", "record_modifier", "log_to_metrics", "rewrite_tag"):
         assert getattr(L, "filter_gpu_%s_plugin" % name)
+
+
+def _rewrite_tag(lib_path):
+    """BASELINE configs[3]: nginx parser + record_modifier + rewrite_tag -- the chunk that stays, the framework counters, and
+    what reaches the emitter (in_emitter_add_record: per record there, per new tag here; the same bytes per tag)"""
+    def per_tag(ref):
+        d = {}
+        for t, b in ref.emitted():
+            d[t] = d.get(t, b"") + b
+        return list(d.items())
+    filters = [("parser", [("Key_Name", "log"), ("Parser", "nginx"), ("Reserve_Data", "On")]),
+               ("record_modifier", [("Record", "hostname node-1"), ("Remove_key", "agent")]),
+               ("rewrite_tag", [("Rule", "$code ^5 errors.$TAG[1].$method false"), ("Rule", "$method ^(PUT|HEAD)$ audit.$1.$TAG true"), ("Emitter_Name", "re_emitted")])]
+    (ref, rins), (gpu, gins) = pipelines(lib_path, [cases.NG], filters)
+    for seed in (1, 2):
+        chunk = util.chunk_from_lines(util.apache_lines(400, seed=seed, nginx=True) + [b"not nginx"] * 2)
+        ref.emit_reset()
+        want = ref.chain_do(chunk, "web.front.access")
+        want_emit = per_tag(ref)
+        gpu.emit_reset()
+        got = gpu.chain_do(chunk, "web.front.access")
+        assert got == want
+        assert per_tag(gpu) == want_emit and want_emit
+        for a, b in zip(rins, gins):
+            assert gpu.filter_counters(b) == ref.filter_counters(a)
+
+
+def test_shim_rewrite_tag_hostsim(ref_available):
+    need_shim()
+    _rewrite_tag(util.HOSTSIM_SO)
+
+
+@pytest.mark.gpu
+def test_shim_rewrite_tag_gpu(gpu_lib, ref_available):
+    need_shim()
+    _rewrite_tag(GPU_LIB)
 
 
 def test_shim_chains_hostsim(ref_available):

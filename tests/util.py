@@ -50,7 +50,7 @@ class Ref:
         """register the five filter_gpu_*_plugin structs of the shim (oracle/_ref/flb-filter_gpu.so), bound to the
         given implementation of the C ABI (libflbgpu.so, or the CPU emulation in the not-gpu tests)"""
         os.environ["FLBGPU_SHIM_LIB"] = gpu_lib_path
-        for name in ("parser", "grep", "modify", "record_modifier", "log_to_metrics"):
+        for name in ("parser", "grep", "modify", "record_modifier", "log_to_metrics", "rewrite_tag"):
             if self.L.flbref_plugin_load(self.cfg, SHIM_SO.encode(), ("filter_gpu_%s_plugin" % name).encode()) != 0:
                 raise RuntimeError("cannot load the gpu_%s plugin from %s" % (name, SHIM_SO))
 
@@ -63,6 +63,22 @@ class Ref:
             data = C.string_at(out.value, n.value)
             self.L.flbref_free(out)
         return r, data, last.value, cnt.value
+
+    def emit_reset(self, fail_after=-1):
+        """forget what filter_rewrite_tag handed to its emitter so far; fail_after >= 0: the emitter refuses from that call on"""
+        self.L.flbref_emit_reset(fail_after)
+
+    def emitted(self):
+        """[(tag, record bytes)] in the order filter_rewrite_tag called in_emitter_add_record()"""
+        log, n = C.c_void_p(), C.c_size_t()
+        self.L.flbref_emit_log(C.byref(log), C.byref(n))
+        raw = C.string_at(log.value, n.value) if n.value else b""
+        out, at = [], 0
+        while at < len(raw):
+            tl, sz = struct.unpack_from("<II", raw, at)
+            out.append((raw[at + 8:at + 8 + tl], raw[at + 8 + tl:at + 8 + tl + sz]))
+            at += 8 + tl + sz
+        return out
 
     def filter_counters(self, f):
         """the instance's framework counters (src/flb_filter.c:574-616) as {metric line without timestamp}"""
@@ -264,8 +280,8 @@ def apache_lines(n, seed=0xF1B1 + 1, garbage=0.005, nginx=False):
         code = rng.choices(["200", "304", "404", "500", "301"], [80, 5, 8, 2, 5])[0]
         size = "-" if rng.random() < 0.03 else str(int(10 ** (rng.random() * 6)))
         line = '%s - %s [%s] "%s %s HTTP/1.1" %s %s' % (host, user, ts, method, path, code, size)
-        if nginx:
-            line = "10.0.0.%d " % rng.randint(1, 250) + line
+        # (an nginx access line is `$remote_addr - $remote_user [...]`: the parser's `host` group takes the "-";
+        #  what differs from the apache lines is that referer and agent are always there)
         if nginx or rng.random() >= 0.10:
             line += ' "%s" "%s"' % (rng.choice(_REF), rng.choice(_AGENT))
         out.append(line.encode())
