@@ -1757,10 +1757,9 @@ FLB_HD int key_prefix(const struct ch_env *e, const struct ch_lane *ln, ref_t k,
 /* helper_msgpack_object_matches_regex(): STR, or BOOLEAN as "true"/"false" */
 FLB_HD int obj_rx(const struct ch_env *e, const struct ch_lane *ln, int vt, const uint8_t *p, uint32_t n, uint32_t rx_off, struct ch_scratch *w)
 {
-    const uint8_t tr[4] = { 't', 'r', 'u', 'e' }, fa[5] = { 'f', 'a', 'l', 's', 'e' };
     if (vt == 1) return rx_run(e, ln, rx_off, p, n, w->caps, w->stk);
-    if (vt == 3) return rx_run(e, ln, rx_off, tr, 4, w->caps, w->stk);
-    if (vt == 4) return rx_run(e, ln, rx_off, fa, 5, w->caps, w->stk);
+    if (vt == 3) return rx_run(e, ln, rx_off, (const uint8_t *) "true", 4, w->caps, w->stk);
+    if (vt == 4) return rx_run(e, ln, rx_off, (const uint8_t *) "false", 5, w->caps, w->stk);
     return 0;
 }
 FLB_HD int ref_rx(const struct ch_env *e, const struct ch_lane *ln, ref_t r, uint32_t rx_off, struct ch_scratch *w)
@@ -2379,7 +2378,7 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, struct ch_lane *ln, uint32_
         CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS);
         return 0;
     }
-    for (k = (PH == CH_PH_TAIL ? 1u : 0u); k < (PH == CH_PH_HEAD ? 1u : h->n_filters); k++) {
+    for (k = (PH == CH_PH_TAIL ? h->split_at : 0u); k < (PH == CH_PH_HEAD ? h->split_at : h->n_filters); k++) {
         const uint8_t *cfg = e->blob + f[k].cfg_off;
         int assumed = (e->assume >> k) & 1;
         if (!((e->active >> k) & 1)) continue;
@@ -2389,6 +2388,7 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, struct ch_lane *ln, uint32_
             if (!assumed) break;
             f_parser<EMIT>(e, ln, (const struct cf_parser *) cfg, &rc, &w, ridx, &cache_pos, k == 0, off, len, h->empty_map_off);
             if (!EMIT && w.defer) return CH_DEFER;
+            if (PH == CH_PH_HEAD && rc.nf > RC_CACHE_MAXF) return CH_DEFER;      /* more fields than the hand-over row holds: before any filter behind it leaves evidence */
             if (!EMIT) CH_ATOMIC_OR(&e->fl_flags[k], CHF_EMITTED);
             break;
         case FLBGPU_F_GREP:

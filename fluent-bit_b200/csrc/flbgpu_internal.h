@@ -46,6 +46,7 @@ struct bk_chain_args {
                                      with side effects -- log_to_metrics -- comes earlier in the chain) */
     uint32_t split;               /* evaluate as two launches: filter 0 (the parser), then the rest (the capture cache has
                                      RC_CACHE_MAXF columns more than cap_stride) */
+    uint32_t split_list;          /* ... and the head launch holds grep filters too: the tail launch runs over the list of records it left */
     const uint32_t *d_off;        /* record index */
     const uint32_t *d_len;
     const uint8_t *d_kind;

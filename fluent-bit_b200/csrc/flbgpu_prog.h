@@ -243,7 +243,9 @@ struct chain_hdr {
     uint32_t cap_stride;       /* ints of capture cache per record (0 = none) */
     uint32_t empty_map_off;    /* one byte 0x80 */
     uint32_t needs_scratch;
-    uint32_t pad0, pad1;
+    uint32_t split_at;         /* split evaluation: the head launch runs filters [0, split_at) -- the parser and the grep filters right
+                                  behind it, which only look --, the tail launch the rest, over the records that are still there */
+    uint32_t pad1;
 };
 
 /* per-filter chunk-level evidence accumulated by the evaluation pass */

@@ -316,6 +316,7 @@ struct k_chain_params {
     uint32_t bm_words;           /* JSON stage 1: 32-bit words of string-event bitmap per warp in shared memory, 0 = none */
     uint32_t *defer_list;        /* records put off by the stage-2 walker (CH_DEFER), and how many */
     unsigned long long *defer_cnt;
+    uint32_t *tlist, *tn;        /* split evaluation with grep filters in the head launch: the records that are still there, for the tail launch */
     uint32_t n_rec;
     const uint32_t *n_dev;       /* small form: the record count lives on the device */
     uint32_t *size;
@@ -366,8 +367,13 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval_t(const __grid_constant_
 {
     extern __shared__ __align__(16) uint8_t dsm[];
     const uint32_t n_rec = p.n_dev ? *p.n_dev : p.n_rec;
-    const uint32_t i = p.r0 + blockIdx.x * blockDim.x + threadIdx.x;
-    const bool valid = i < n_rec;
+    uint32_t i = p.r0 + blockIdx.x * blockDim.x + threadIdx.x;
+    bool valid = i < n_rec;
+    if (PH == CH_PH_TAIL && p.tlist) {               /* dense: lane t takes the t-th record the head launch left */
+        const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+        valid = t < *p.tn;
+        i = valid ? p.tlist[t] : 0;
+    }
     const uint32_t my_off = valid ? p.off[i] : 0, my_len = valid ? p.len[i] : 0;
     const bool live = valid && p.kind[i] == 0;
     const uint8_t *in = p.env.in;
@@ -412,6 +418,19 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval_t(const __grid_constant_
             p.defer_list[atomicAdd(p.defer_cnt, 1ull)] = i;
             if (PH != CH_PH_HEAD) return;
             sz = 0;                                    /* the tail launch steps over it */
+        }
+    }
+    if (PH == CH_PH_HEAD && p.tlist) {
+        /* the survivors of the warp go to the tail launch's list side by side (one atomic per warp; the order of the warps in
+         * the list does not matter: every record owns its slots) */
+        const unsigned lanes = __activemask();
+        const unsigned alive = __ballot_sync(lanes, sz != 0);
+        if (sz) {
+            const unsigned lane = threadIdx.x & 31u, leader = (unsigned) __ffs((int) alive) - 1u;
+            uint32_t base = 0;
+            if (lane == leader) base = atomicAdd(p.tn, (uint32_t) __popc(alive));
+            base = __shfl_sync(alive, base, (int) leader);
+            p.tlist[base + (uint32_t) __popc(alive & ((1u << lane) - 1u))] = i;
         }
     }
     __stcs(&p.size[i], sz);
@@ -688,6 +707,8 @@ static int UP_THREADS = 6, UP_STAGE_SLOTS = 12;      /* FLBGPU_UP_THREADS: host 
 struct bk_q {
     int device;
     cudaStream_t stream, istream, h2d, copy;
+    cudaStream_t dstream;                  /* split evaluation: the follow-up launch over the records put off runs beside the tail launch */
+    cudaEvent_t d_ev[2];
     /* CUDA-event timing of the kernel groups of the last call: one event pair per launch
      * (0 = index, 1 = evaluate, 2 = emit); bk_kernel_ms() sums the pairs of a group. */
     cudaEvent_t evp[3][EV_MAX][2];
@@ -708,6 +729,7 @@ struct bk_q {
     int eval_block;                        /* FLBGPU_EVAL_BLOCK: threads per evaluation block */
     uint8_t *d_tag; size_t cap_tag;        /* rewrite_tag: the tag of the call; the re-tagged stream before it goes to the host */
     uint8_t *d_eout; size_t cap_eout;
+    uint32_t *d_tlist; size_t cap_tlist;   /* split evaluation: the records the head launch left for the tail launch */
     uint32_t *d_defer; size_t cap_defer;   /* records the JSON stage-2 walker put off to the follow-up launch */
     /* upload */
     cudaEvent_t up_ev[UP_MAX_EV]; int up_ev_made;
@@ -853,8 +875,6 @@ static int func_attrs_once(void)
     CK(cudaFuncSetAttribute(k_chain_eval, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     CK(cudaFuncSetAttribute(k_chain_eval_t<CH_PH_HEAD>, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
     CK(cudaFuncSetAttribute(k_chain_eval_t<CH_PH_TAIL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1));
-    CK(cudaFuncSetCacheConfig(k_chain_eval_deferred, cudaFuncCachePreferL1));
-    cudaFuncSetAttribute(k_chain_eval_deferred, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxL1);
     /* the emission kernel stages a warp's result range in shared memory (6 blocks x 32 KB per SM) */
     CK(cudaFuncSetAttribute(k_chain_emit_list, cudaFuncAttributePreferredSharedMemoryCarveout, 80));
     cudaGetLastError();
@@ -874,13 +894,16 @@ void bk_q_free(bk_q *q)
     for (int i = 0; i < UP_STAGE_SLOTS_MAX; i++) cudaFreeHost(q->up_stage[i]);
     if (q->xf_ready) for (int i = 0; i < q->xf_slots; i++) { cudaFreeHost(q->xf_ring[i]); cudaEventDestroy(q->xf_ev[i]); }
     cudaFree(q->dtotal); cudaFree(q->dbreaks); cudaFree(q->d_cnt); cudaFree(q->d_lrec); cudaFree(q->d_loff); cudaFree(q->d_nlist);
-    cudaFree(q->d_link[0]); cudaFree(q->d_link[1]); cudaFree(q->d_mark); cudaFree(q->d_mail); cudaFree(q->d_defer); cudaFree(q->d_tag); cudaFree(q->d_eout);
+    cudaFree(q->d_link[0]); cudaFree(q->d_link[1]); cudaFree(q->d_mark); cudaFree(q->d_mail); cudaFree(q->d_defer); cudaFree(q->d_tlist); cudaFree(q->d_tag); cudaFree(q->d_eout);
     cudaFreeHost(q->h_word); cudaFreeHost(q->h_mail); cudaFreeHost(q->h_flags); cudaFreeHost(q->h_sin); cudaFreeHost(q->h_sout);
     if (q->ev_small) cudaEventDestroy(q->ev_small);
     if (q->stream) cudaStreamDestroy(q->stream);
     if (q->istream) cudaStreamDestroy(q->istream);
     if (q->h2d) cudaStreamDestroy(q->h2d);
     if (q->copy) cudaStreamDestroy(q->copy);
+    if (q->dstream) cudaStreamDestroy(q->dstream);
+    if (q->d_ev[0]) cudaEventDestroy(q->d_ev[0]);
+    if (q->d_ev[1]) cudaEventDestroy(q->d_ev[1]);
     cudaGetLastError();
     q->~bk_q();
     free(q);
@@ -898,6 +921,9 @@ static int q_setup(bk_q *q)
     CK(cudaStreamCreateWithPriority(&q->istream, cudaStreamNonBlocking, hi));
     CK(cudaStreamCreateWithFlags(&q->h2d, cudaStreamNonBlocking));
     CK(cudaStreamCreateWithFlags(&q->copy, cudaStreamNonBlocking));
+    CK(cudaStreamCreateWithFlags(&q->dstream, cudaStreamNonBlocking));
+    CK(cudaEventCreateWithFlags(&q->d_ev[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&q->d_ev[1], cudaEventDisableTiming));
     CK(cudaMalloc((void **) &q->dtotal, 128));
     CK(cudaMemset(q->dtotal, 0, 128));
     CK(cudaMalloc((void **) &q->dbreaks, sizeof(uint32_t) * BK_MAX_BREAKS));
@@ -1270,7 +1296,7 @@ static void fill_params(const struct bk_chain_args *a, k_chain_params *p, uint8_
     p->env.l2m = a->l2m; p->env.prep = a->d_prep;
     p->env.esize = a->d_esize; p->env.tag = a->d_tag; p->env.tag_len = a->tag_len;
     p->off = a->d_off; p->len = a->d_len; p->kind = a->d_kind; p->r0 = r0; p->n_rec = a->n_rec; p->bm_words = 0;
-    p->n_dev = 0; p->defer_list = 0; p->defer_cnt = 0;
+    p->n_dev = 0; p->defer_list = 0; p->defer_cnt = 0; p->tlist = 0; p->tn = 0;
     p->size = a->d_size; p->bsum = a->d_bsum; p->out = d_out;
 }
 
@@ -1319,8 +1345,17 @@ static int defer_setup(bk_q *q, k_chain_params *p, const struct bk_chain_args *a
         CK(cudaMalloc((void **) &q->d_defer, sizeof(uint32_t) * (n + n / 4 + 1024)));
         q->cap_defer = n + n / 4 + 1024;
     }
-    CK(cudaMemsetAsync(q->dtotal + 9, 0, sizeof(unsigned long long), st));
+    CK(cudaMemsetAsync(q->dtotal + 9, 0, sizeof(unsigned long long) * 2, st));       /* [9] records put off, [10] records left for the tail launch */
     p->defer_list = q->d_defer; p->defer_cnt = q->dtotal + 9;
+    if (a->split && a->split_list) {
+        if (q->cap_tlist < n) {
+            CK(cudaStreamSynchronize(q->stream));
+            cudaFree(q->d_tlist); q->d_tlist = 0; q->cap_tlist = 0;
+            CK(cudaMalloc((void **) &q->d_tlist, sizeof(uint32_t) * (n + n / 4 + 1024)));
+            q->cap_tlist = n + n / 4 + 1024;
+        }
+        p->tlist = q->d_tlist; p->tn = (uint32_t *) (q->dtotal + 10);
+    }
     return 0;
 }
 
@@ -1335,13 +1370,22 @@ int bk_chain_eval(bk_q *q, const struct bk_chain_args *a, uint32_t r0, uint32_t 
     if (defer_setup(q, &p, a, r1 - r0, q->stream)) return -1;
     ev_begin_on(q, 1, q->stream);
     if (a->split) {
-        k_chain_eval_t<CH_PH_HEAD><<<(r1 - r0 + q->eval_block - 1) / q->eval_block, q->eval_block, (size_t) p.bm_words * 4 * (q->eval_block / 32), q->stream>>>(p);
-        k_chain_eval_t<CH_PH_TAIL><<<(r1 - r0 + q->eval_block - 1) / q->eval_block, q->eval_block, 0, q->stream>>>(p);
-        g_launches += 1;
+        const unsigned grid = (r1 - r0 + q->eval_block - 1) / q->eval_block;
+        k_chain_eval_t<CH_PH_HEAD><<<grid, q->eval_block, (size_t) p.bm_words * 4 * (q->eval_block / 32), q->stream>>>(p);
+        /* the records the head put off (a few per cent, one long lane each: ~200 us per slice with most of the GPU idle) are
+         * evaluated BESIDE the tail launch -- the two touch different records */
+        CK(cudaEventRecord(q->d_ev[0], q->stream));
+        CK(cudaStreamWaitEvent(q->dstream, q->d_ev[0], 0));
+        k_chain_eval_deferred<<<148 * 4, BK_REC_BLOCK, 0, q->dstream>>>(p);
+        CK(cudaEventRecord(q->d_ev[1], q->dstream));
+        k_chain_eval_t<CH_PH_TAIL><<<grid, q->eval_block, 0, q->stream>>>(p);
+        CK(cudaStreamWaitEvent(q->stream, q->d_ev[1], 0));
+        g_launches += 2;
     }
-    else
+    else {
         k_chain_eval<<<(r1 - r0 + q->eval_block - 1) / q->eval_block, q->eval_block, (size_t) p.bm_words * 4 * (q->eval_block / 32), q->stream>>>(p);
-    if (p.defer_list) { k_chain_eval_deferred<<<148 * 4, BK_REC_BLOCK, 0, q->stream>>>(p); g_launches += 1; }
+        if (p.defer_list) { k_chain_eval_deferred<<<148 * 4, BK_REC_BLOCK, 0, q->stream>>>(p); g_launches += 1; }
+    }
     if (p.env.l2m.hash) {
         k_chain_skipped<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, 0, q->stream>>>(p);
         g_launches += 1;
@@ -1556,6 +1600,12 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     k_index_repair<<<1, 1024, 0, st>>>(a->d_off, a->d_len, (uint8_t *) a->d_kind, 0, &m->n_cand, 0, (uint32_t) bytes, &m->n_breaks, q->dbreaks, &m->n_valid, &m->overflow);
     ev_end_on(q, 0, st);
     /* evaluation of records [0, n_valid) */
+    /* A call this small is the latency of its launches one behind the other: the split evaluation and the follow-up launch of the
+     * two-stage tokenizer, which pay off per byte, cost a serial pass each here (64 KB JSON calls: 330 us against 260 us).
+     * They start where a call is about throughput. */
+    struct bk_chain_args a_small = *a;
+    if (bytes < ((size_t) 3 << 20)) a_small.split = 0;
+    a = &a_small;
     fill_params(a, &p, d_out, 0);
     p.n_rec = 0; p.n_dev = &m->n_valid;
     p.bm_words = (a->d_scr && (q->json_bm > 0 || (q->json_bm < 0 && a->split))) ? BM_BYTES / 32 : 0;

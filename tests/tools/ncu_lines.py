@@ -35,6 +35,11 @@ for r in rows:
     a = byfile.setdefault(r[1], [0.0, 0.0]); a[0] += r[0]; a[1] += r[3]
 for f, (s, i) in sorted(byfile.items(), key=lambda x: -x[1][0]):
     print("  %-22s %5.1f %% of samples  %5.1f %% of instructions" % (f, 100 * s / tot_s, 100 * i / tot_i))
+tot_l = sum(r[11] for r in rows) or 1.0
+print("local-memory sectors to L2 (theoretical): %.3g; the lines that make them:" % tot_l)
+for r in sorted(rows, key=lambda x: -x[11])[:25]:
+    if r[11] <= 0: break
+    print("  %-26s %5.1f %%  lanes %4.1f | %s" % ("%s:%s" % (r[1], r[2]), 100 * r[11] / tot_l, r[4] / r[3] if r[3] else 0, r[12]))
 print("%-26s %6s %6s %8s %5s | %5s %5s %5s %5s %5s %5s | %s" % ("line", "smp%", "cum%", "inst%", "lanes", "lsb", "noin", "wait", "brch", "ssb", "sel", "source"))
 cum = 0.0
 for r in sorted(rows, key=lambda x: -x[0])[:top_n]:
