@@ -103,11 +103,17 @@ struct bk_mail {
 };
 
 /* ------------------------------------------------------------------ index */
+/* The counting pass leaves what it validated in a staging row per tile -- word 0: records kept, then one word per record
+ * (position in the tile, kind, length) -- so that the filling pass, which runs once the offsets are known, only copies: it does
+ * not read the chunk again and does not frame a record twice.  A tile with more records than a row holds (events of a few
+ * bytes) is validated again by the filling pass, as before. */
+#define BK_STAGE_ROW 256u                           /* 64-bit words per tile: 2 KB for 8 KB of input */
+#define BK_STAGE_PACK(rel, kind, rlen) (((unsigned long long) (rel) << 48) | ((unsigned long long) (kind) << 40) | (unsigned long long) (rlen))
 template <bool FILL>
 __global__ void __launch_bounds__(256) k_index(const uint8_t *__restrict__ in, uint32_t len, uint32_t skip, uint32_t abs_base,
                                                uint32_t *__restrict__ tile, uint32_t *__restrict__ o_off,
                                                uint32_t *__restrict__ o_len, uint8_t *__restrict__ o_kind,
-                                               const struct bk_mail *__restrict__ mail)
+                                               const struct bk_mail *__restrict__ mail, unsigned long long *__restrict__ stage)
 {
     __shared__ uint16_t cand[BK_INDEX_TILE];
     __shared__ uint32_t v2ok[BK_INDEX_TILE / 32];   /* bit per tile byte: a valid v2 frame starts here */
@@ -115,6 +121,20 @@ __global__ void __launch_bounds__(256) k_index(const uint8_t *__restrict__ in, u
     const uint32_t base = blockIdx.x * BK_INDEX_TILE;
     uint32_t ncand = 0;
     if (FILL && mail && mail->overflow) return;      /* small form: the arrays cannot hold the candidates */
+    if (FILL && stage) {
+        const unsigned long long *row = stage + (size_t) blockIdx.x * BK_STAGE_ROW;
+        const uint32_t n = (uint32_t) row[0];
+        if (n < BK_STAGE_ROW) {
+            const uint32_t tb = tile[blockIdx.x];
+            for (uint32_t j = threadIdx.x; j < n; j += 256) {
+                const unsigned long long e = row[1 + j];
+                o_off[tb + j] = abs_base + base + (uint32_t) (e >> 48);
+                o_len[tb + j] = (uint32_t) (e & 0xffffffffull);
+                o_kind[tb + j] = (uint8_t) ((e >> 40) & 0xff);
+            }
+            return;
+        }
+    }
 
     /* phase 1: ordered list of candidate positions in this tile */
     for (uint32_t it = 0; it < BK_INDEX_TILE / (256 * 16); it++) {
@@ -177,9 +197,14 @@ __global__ void __launch_bounds__(256) k_index(const uint8_t *__restrict__ in, u
             const uint32_t o = tile_base + kept + at;
             o_off[o] = abs_base + pos; o_len[o] = rlen; o_kind[o] = (uint8_t) kind;
         }
+        if (!FILL && ok && stage && kept + at + 1 < BK_STAGE_ROW)
+            stage[(size_t) blockIdx.x * BK_STAGE_ROW + 1 + kept + at] = BK_STAGE_PACK(rel, kind, rlen);
         kept += tot;
     }
-    if (!FILL && threadIdx.x == 0) tile[blockIdx.x] = kept;
+    if (!FILL && threadIdx.x == 0) {
+        tile[blockIdx.x] = kept;
+        if (stage) stage[(size_t) blockIdx.x * BK_STAGE_ROW] = kept;
+    }
 }
 
 /* exclusive scan of a[0..n) in place, one CTA; total in *out_total (and added to *accum) */
@@ -729,6 +754,7 @@ struct bk_q {
     int eval_block;                        /* FLBGPU_EVAL_BLOCK: threads per evaluation block */
     uint8_t *d_tag; size_t cap_tag;        /* rewrite_tag: the tag of the call; the re-tagged stream before it goes to the host */
     uint8_t *d_eout; size_t cap_eout;
+    unsigned long long *d_stage; size_t cap_stage;   /* index: what the counting pass validated, one row per tile */
     uint32_t *d_tlist; size_t cap_tlist;   /* split evaluation: the records the head launch left for the tail launch */
     uint32_t *d_defer; size_t cap_defer;   /* records the JSON stage-2 walker put off to the follow-up launch */
     /* upload */
@@ -894,7 +920,7 @@ void bk_q_free(bk_q *q)
     for (int i = 0; i < UP_STAGE_SLOTS_MAX; i++) cudaFreeHost(q->up_stage[i]);
     if (q->xf_ready) for (int i = 0; i < q->xf_slots; i++) { cudaFreeHost(q->xf_ring[i]); cudaEventDestroy(q->xf_ev[i]); }
     cudaFree(q->dtotal); cudaFree(q->dbreaks); cudaFree(q->d_cnt); cudaFree(q->d_lrec); cudaFree(q->d_loff); cudaFree(q->d_nlist);
-    cudaFree(q->d_link[0]); cudaFree(q->d_link[1]); cudaFree(q->d_mark); cudaFree(q->d_mail); cudaFree(q->d_defer); cudaFree(q->d_tlist); cudaFree(q->d_tag); cudaFree(q->d_eout);
+    cudaFree(q->d_link[0]); cudaFree(q->d_link[1]); cudaFree(q->d_mark); cudaFree(q->d_mail); cudaFree(q->d_defer); cudaFree(q->d_tlist); cudaFree(q->d_stage); cudaFree(q->d_tag); cudaFree(q->d_eout);
     cudaFreeHost(q->h_word); cudaFreeHost(q->h_mail); cudaFreeHost(q->h_flags); cudaFreeHost(q->h_sin); cudaFreeHost(q->h_sout);
     if (q->ev_small) cudaEventDestroy(q->ev_small);
     if (q->stream) cudaStreamDestroy(q->stream);
@@ -1205,6 +1231,18 @@ int bk_d2d(bk_q *q, void *dst, const void *src, size_t n)
     return 0;
 }
 
+/* staging rows of the index for n_tiles tiles (k_index) */
+static int stage_setup(bk_q *q, uint32_t n_tiles)
+{
+    if (q->cap_stage >= (size_t) n_tiles) return 0;
+    CK(cudaStreamSynchronize(q->istream));
+    CK(cudaStreamSynchronize(q->stream));
+    cudaFree(q->d_stage); q->d_stage = 0; q->cap_stage = 0;
+    CK(cudaMalloc((void **) &q->d_stage, sizeof(unsigned long long) * BK_STAGE_ROW * ((size_t) n_tiles + n_tiles / 4 + 16)));
+    q->cap_stage = (size_t) n_tiles + n_tiles / 4 + 16;
+    return 0;
+}
+
 int bk_index_count(bk_q *q, const uint8_t *d_in, size_t slice_off, uint32_t slice_len, uint32_t *d_tile, uint32_t n_tiles,
                    uint32_t *n_cand)
 {
@@ -1214,7 +1252,8 @@ int bk_index_count(bk_q *q, const uint8_t *d_in, size_t slice_off, uint32_t slic
     ev_begin_on(q, 0, q->istream);
     {
         const uint32_t skip = (uint32_t) ((uintptr_t) (d_in + slice_off) & 15);      /* tiles start at a 16-byte boundary of the address space */
-        k_index<false><<<n_tiles, 256, 0, q->istream>>>(d_in + slice_off - skip, slice_len + skip, skip, (uint32_t) (slice_off - skip), d_tile, 0, 0, 0, 0);
+        if (stage_setup(q, n_tiles)) return -1;
+        k_index<false><<<n_tiles, 256, 0, q->istream>>>(d_in + slice_off - skip, slice_len + skip, skip, (uint32_t) (slice_off - skip), d_tile, 0, 0, 0, 0, q->d_stage);
     }
     k_scan_top<uint32_t><<<1, 256, 0, q->istream>>>(d_tile, n_tiles, q->dtotal, 0);
     ev_end_on(q, 0, q->istream);
@@ -1238,7 +1277,8 @@ int bk_index_fill(bk_q *q, const uint8_t *d_in, size_t slice_off, uint32_t slice
     ev_begin_on(q, 0, q->istream);
     {
         const uint32_t skip = (uint32_t) ((uintptr_t) (d_in + slice_off) & 15);      /* tiles start at a 16-byte boundary of the address space */
-        k_index<true><<<n_tiles, 256, 0, q->istream>>>(d_in + slice_off - skip, slice_len + skip, skip, (uint32_t) (slice_off - skip), (uint32_t *) d_tile, d_off, d_len, d_kind, 0);
+        k_index<true><<<n_tiles, 256, 0, q->istream>>>(d_in + slice_off - skip, slice_len + skip, skip, (uint32_t) (slice_off - skip), (uint32_t *) d_tile, d_off, d_len, d_kind, 0,
+                                                       q->cap_stage >= (size_t) n_tiles ? q->d_stage : 0);
     }
     CK(cudaMemsetAsync(d_w, 0, 32, q->istream));
     k_index_check<<<(n_cand + 255) / 256, 256, 0, q->istream>>>(d_off, d_len, n_cand, 0, (uint32_t) (slice_off + slice_len), d_w, q->dbreaks);
@@ -1593,9 +1633,10 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     CK(cudaMemsetAsync(m, 0, sizeof(*m), st));
     /* record index */
     ev_begin_on(q, 0, st);
-    k_index<false><<<n_tiles, 256, 0, st>>>(d_in, (uint32_t) bytes, 0, 0, d_tile, 0, 0, 0, 0);
+    if (stage_setup(q, n_tiles)) return -1;
+    k_index<false><<<n_tiles, 256, 0, st>>>(d_in, (uint32_t) bytes, 0, 0, d_tile, 0, 0, 0, 0, q->d_stage);
     k_small_tiles<<<1, 256, 0, st>>>(d_tile, n_tiles, cap_rec, m);
-    k_index<true><<<n_tiles, 256, 0, st>>>(d_in, (uint32_t) bytes, 0, 0, d_tile, (uint32_t *) a->d_off, (uint32_t *) a->d_len, (uint8_t *) a->d_kind, m);
+    k_index<true><<<n_tiles, 256, 0, st>>>(d_in, (uint32_t) bytes, 0, 0, d_tile, (uint32_t *) a->d_off, (uint32_t *) a->d_len, (uint8_t *) a->d_kind, m, q->d_stage);
     k_index_check<<<nb_cap, 256, 0, st>>>(a->d_off, a->d_len, 0, &m->n_cand, (uint32_t) bytes, &m->n_breaks, q->dbreaks);
     k_index_repair<<<1, 1024, 0, st>>>(a->d_off, a->d_len, (uint8_t *) a->d_kind, 0, &m->n_cand, 0, (uint32_t) bytes, &m->n_breaks, q->dbreaks, &m->n_valid, &m->overflow);
     ev_end_on(q, 0, st);

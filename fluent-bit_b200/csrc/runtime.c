@@ -49,7 +49,11 @@ static uint32_t blob_reserve(struct blob *b, size_t n, size_t align)
     if (off + n > b->cap) {
         size_t nc = b->cap ? b->cap * 2 : 4096;
         while (nc < off + n) nc *= 2;
-        b->p = realloc(b->p, nc);
+        {
+            uint8_t *np_ = realloc(b->p, nc);
+            if (!np_) { fprintf(stderr, "libflbgpu: out of memory while building a chain program\n"); abort(); }   /* (configuration time, a few KB) */
+            b->p = np_;
+        }
         memset(b->p + b->cap, 0, nc - b->cap);
         b->cap = nc;
     }
@@ -333,6 +337,7 @@ flbgpu_parser *flbgpu_parser_create(flbgpu_ctx *ctx, const char *name, const cha
     if (flbgpu_parser_get(ctx, name)) { set_err("[parser] parser named '%s' already exists, skip.%s", name, NULL); return NULL; }
     if (time_system_timezone) { set_err("[parser:%s] Time_System_Timezone is not supported on the GPU path%s", name, NULL); return NULL; }
     p = calloc(1, sizeof(*p));
+    if (!p) { set_err("out of memory%s%s", NULL, NULL); return NULL; }
     p->ctx = ctx;
     if (!strcasecmp(format, "regex")) p->type = FLBGPU_PARSER_REGEX;
     else if (!strcasecmp(format, "json")) p->type = FLBGPU_PARSER_JSON;
@@ -379,7 +384,11 @@ flbgpu_parser *flbgpu_parser_create(flbgpu_ctx *ctx, const char *name, const cha
         }
         if (time_offset) {
             int diff = 0;
-            if (tzone_offset(time_offset, (int) strlen(time_offset), &diff) == -1) { flbgpu_parser_destroy(p); return NULL; }
+            if (tzone_offset(time_offset, (int) strlen(time_offset), &diff) == -1) {
+                set_err("[parser:%s] invalid Time_Offset '%s'", name, time_offset);
+                flbgpu_parser_destroy(p);
+                return NULL;
+            }
             p->time_offset = diff;
         }
     }
@@ -579,6 +588,7 @@ flbgpu_filter *flbgpu_filter_new(flbgpu_ctx *ctx, const char *plugin)
     g_rt_err[0] = 0;
     if (!ctx || !kind) { set_err("unknown filter plugin '%s'%s", plugin, NULL); return NULL; }
     f = calloc(1, sizeof(*f));
+    if (!f) { set_err("out of memory%s%s", NULL, NULL); return NULL; }
     f->ctx = ctx;
     f->kind = kind;
     return f;
@@ -603,8 +613,10 @@ int flbgpu_filter_set_property(flbgpu_filter *f, const char *k, const char *v)
         return 0;
     }
     n = calloc(1, sizeof(*n));
+    if (!n) { set_err("out of memory%s%s", NULL, NULL); return -1; }
     n->k = strdup(k);
     n->v = strdup(v);
+    if (!n->k || !n->v) { free(n->k); free(n->v); free(n); set_err("out of memory%s%s", NULL, NULL); return -1; }
     if (f->props_tail) f->props_tail->next = n; else f->props = n;
     f->props_tail = n;
     return 0;
@@ -1658,7 +1670,8 @@ static int l2m_merge(flbgpu_chain *c)
     nbk = L2M_NBK(st);
     if (bk_d2h(c->q, c->h_hash, c->l2m.hash, n * 8) || bk_d2h(c->q, c->h_chash, c->l2m.chash, n * 8) || bk_d2h(c->q, c->h_first, c->l2m.first, n * 4) || bk_d2h(c->q, c->h_cnt, c->l2m.cnt, n * 8) ||
         bk_d2h(c->q, c->h_sum, c->l2m.sum, n * 8) || bk_d2h(c->q, c->h_bkt, c->l2m.bkt, n * nbk * 8) || bk_sync(c->q)) return -1;
-    order = malloc(sizeof(uint32_t) * n);
+    order = malloc(sizeof(uint32_t) * (n ? n : 1));
+    if (!order) { set_err("out of memory%s%s", NULL, NULL); return -1; }
     for (i = 0; i < (size_t) st->n_sets; i++) st->sets[i].call_last = 0;
     for (i = 0; i < n; i++) if (c->h_hash[i]) order[m++] = (uint32_t) i;
     qsort_r(order, m, sizeof(uint32_t), cmp_first, c->h_first);
@@ -1673,16 +1686,20 @@ static int l2m_merge(flbgpu_chain *c)
         for (j = 0; j < st->n_sets; j++) if (st->sets[j].hash == c->h_chash[slot]) { set = &st->sets[j]; break; }
         if (!set) {
             labels = calloc(1, lb);
+            if (!labels) { free(order); set_err("out of memory%s%s", NULL, NULL); return -1; }
             if (st->n_labels && (bk_d2h(c->q, labels, c->l2m.str + (size_t) slot * lb, lb) || bk_sync(c->q))) { free(labels); free(order); return -1; }
             if (st->n_sets == st->cap_sets) {
+                struct l2m_set *ns_ = realloc(st->sets, sizeof(*st->sets) * (size_t) (st->cap_sets ? st->cap_sets * 2 : 64));
+                if (!ns_) { free(labels); free(order); set_err("out of memory%s%s", NULL, NULL); return -1; }
+                st->sets = ns_;
                 st->cap_sets = st->cap_sets ? st->cap_sets * 2 : 64;
-                st->sets = realloc(st->sets, sizeof(*st->sets) * st->cap_sets);
             }
             set = &st->sets[st->n_sets++];
             memset(set, 0, sizeof(*set));
             set->hash = c->h_chash[slot];
             set->labels = labels;
             set->buckets = calloc((size_t) st->n_buckets + 1, sizeof(uint64_t));
+            if (!set->buckets) { st->n_sets--; free(labels); free(order); set_err("out of memory%s%s", NULL, NULL); return -1; }
         }
         set->count += c->h_cnt[slot];
         if (st->mode == L2M_GAUGE) {             /* the call's last record of this set overwrites what earlier calls left */
@@ -2518,8 +2535,10 @@ int flbgpu_l2m_put(flbgpu_filter *f, uint64_t hash, uint64_t count, double sum, 
     if (!st) return -1;
     lb = (size_t) (st->n_labels ? st->n_labels : 1) * L2M_LABEL_BYTES;
     if (st->n_sets == st->cap_sets) {
+        struct l2m_set *ns_ = realloc(st->sets, sizeof(*st->sets) * (size_t) (st->cap_sets ? st->cap_sets * 2 : 64));
+        if (!ns_) return -1;
+        st->sets = ns_;
         st->cap_sets = st->cap_sets ? st->cap_sets * 2 : 64;
-        st->sets = realloc(st->sets, sizeof(*st->sets) * st->cap_sets);
     }
     set = &st->sets[st->n_sets++];
     memset(set, 0, sizeof(*set));
