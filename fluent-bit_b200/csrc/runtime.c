@@ -175,6 +175,7 @@ struct flbgpu_chain {
     int l2m_index;                            /* filter index of the log_to_metrics filter, or -1 */
     int rtag_index;                           /* filter index of the rewrite_tag filter, or -1; -2 = several: the chain runs filter by filter */
     uint32_t *d_esize;                        /* rewrite_tag: bytes of each record's entry in the re-tagged stream */
+    uint64_t *d_ebsum, *h_ebsum; size_t cap_ebsum;   /* ... and the scan over them */
     const uint8_t *d_tag; uint32_t tag_len;   /* the tag of the call on the device */
     struct l2m_table l2m;                     /* device table (per-call delta) */
     size_t l2m_slots;
@@ -1512,7 +1513,7 @@ void flbgpu_chain_destroy(flbgpu_chain *c)
     bk_free(c->q, c->d_len); bk_free(c->q, c->d_size); bk_free(c->q, c->d_kind); bk_free(c->q, c->d_bsum); bk_free(c->q, c->d_cap);
     bk_free(c->q, c->d_flags); bk_free(c->q, c->d_scr); free(c->h_bsum);
     bk_free(c->q, c->d_prep); free(c->h_prep);
-    bk_free(c->q, c->d_esize);
+    bk_free(c->q, c->d_esize); bk_free(c->q, c->d_ebsum); free(c->h_ebsum);
     bk_free(c->q, c->l2m.hash); bk_free(c->q, c->l2m.chash); bk_free(c->q, c->l2m.first); bk_free(c->q, c->l2m.cnt); bk_free(c->q, c->l2m.sum); bk_free(c->q, c->l2m.bkt); bk_free(c->q, c->l2m.str);
     free(c->h_hash); free(c->h_chash); free(c->h_first); free(c->h_cnt); free(c->h_sum); free(c->h_bkt);
     free(c->blob.p);
@@ -1881,7 +1882,18 @@ static int rtag_collect(flbgpu_chain *c, const struct bk_chain_args *a, uint32_t
     size_t *fill = NULL;
     rtag_release(f);
     if (!any) return 0;
-    if (bk_rtag_emit(c->q, a, n_rec, c->d_bsum, c->h_bsum, (void **) &stream, &bytes)) { set_err("%s%s", bk_last_error(), NULL); return -1; }
+    {
+        const size_t nb = ((size_t) n_rec + BK_REC_BLOCK - 1) / BK_REC_BLOCK + 2;
+        if (c->cap_ebsum < nb) {
+            bk_free(c->q, c->d_ebsum); free(c->h_ebsum);
+            c->cap_ebsum = 0;
+            c->d_ebsum = bk_alloc(c->q, (nb + nb / 4 + 64) * sizeof(uint64_t));
+            c->h_ebsum = malloc((nb + nb / 4 + 64) * sizeof(uint64_t));
+            if (!c->d_ebsum || !c->h_ebsum) { set_err("out of memory%s%s", NULL, NULL); return -1; }
+            c->cap_ebsum = nb + nb / 4 + 64;
+        }
+    }
+    if (bk_rtag_emit(c->q, a, n_rec, c->d_ebsum, c->h_ebsum, (void **) &stream, &bytes)) { set_err("%s%s", bk_last_error(), NULL); return -1; }
     if (!stream) return 0;
     /* pass 1: the groups and their sizes */
     for (at = 0; at + RT_ENTRY_HDR <= bytes; ) {
@@ -2264,6 +2276,10 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
     c->st.kernel_launches = bk_launch_count();
     if (l2m_merge(c)) goto fail;
     if (dl_open) { dl_open = 0; if (bk_download_end(c->q)) goto fail; }
+    if (c->rtag_index >= 0 && ((c->active >> c->rtag_index) & 1)) {      /* every record of the call is still indexed: one re-tagged stream */
+        fill_args(c, &a, c->d_in, bytes, n_rec); a.assume = assume; a.now = now;
+        if (rtag_collect(c, &a, n_rec, (h_flags[c->rtag_index] & CHF_CAUSE) != 0)) goto fail;
+    }
     bk_records_out(c->q, &c->st.records_out);
     c->st.bytes_out = placed;
     *out_size = (size_t) placed;
@@ -2365,6 +2381,10 @@ static int chain_run_small(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, v
     }
     if (l2m_merge(c)) return -1;
     if (res.total >= 0xfff00000ull) { set_err("result larger than 4 GiB%s%s", NULL, NULL); return -1; }
+    if (res.emitted && c->rtag_index >= 0 && ((c->active >> c->rtag_index) & 1)) {
+        fill_args(c, &a, c->d_in, bytes, res.n_valid); a.assume = assume;
+        if (rtag_collect(c, &a, res.n_valid, (res.flags[c->rtag_index] & CHF_CAUSE) != 0)) return -1;
+    }
     if (!res.emitted) {                              /* the result outgrew the output buffer: remember, let the general path do this call */
         c->small_cap_out = (size_t) res.total + (size_t) res.total / 4 + 4096;
         return 1;
@@ -2433,15 +2453,9 @@ static int chain_do_one_by_one(flbgpu_chain *c, const void *data, size_t bytes, 
 static int chain_do_locked(flbgpu_chain *c, const void *data, size_t bytes, const char *tag, int tag_len, void **out_buf, size_t *out_size)
 {
     if (c->rtag_index == -2) return chain_do_one_by_one(c, data, bytes, tag, tag_len, out_buf, out_size);     /* one re-tagged stream per chain */
-    if (c->rtag_index >= 0) {
-        /* a chain with a rewrite_tag filter takes the whole-chunk form: the re-tagged stream is cut from the same evaluation */
-        int r;
+    if (c->rtag_index >= 0) {                        /* the templates of a rewrite_tag filter may name the tag of the call */
         c->tag_len = (uint32_t) (tag && tag_len > 0 ? tag_len : 0);
         if (bk_tag_upload(c->q, tag, c->tag_len, &c->d_tag)) { set_err("%s%s", bk_last_error(), NULL); return -1; }
-        r = chain_run(c, data, NULL, bytes, NULL, 0, out_buf, out_size);
-        bk_upload_end(c->q);
-        if (r < 0 && FUSED_REFUSED_A_HANDED_OVER_VALUE(c)) { *out_buf = NULL; *out_size = 0; return chain_do_one_by_one(c, data, bytes, tag, tag_len, out_buf, out_size); }
-        return r;
     }
     if (bytes <= small_bytes()) {
         int ret = 0, r = chain_run_small(c, data, bytes, out_buf, out_size, &ret);

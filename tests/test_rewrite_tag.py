@@ -153,6 +153,28 @@ def _config(lib):
     util.Ref().filter("rewrite_tag", [("Rule", "$log x y false extra words"), ("Emitter_Name", "e"), ("Emitter_Mem_Buf_Limit", "5M"), ("Emitter_Storage.type", "filesystem")])
 
 
+def _forms(lib, monkeypatch):
+    """the three call forms (small chunk, streaming slices, whole chunk) cut the same re-tagged stream"""
+    chunk = util.chunk_from_lines(util.apache_lines(30000, seed=21, nginx=True) + [b"junk"] * 5)
+    pf = ("parser", [("Key_Name", "log"), ("Parser", "nginx")])
+    rules = [("Rule", "$code ^5 errors.$method false"), ("Rule", "$method ^(PUT|HEAD)$ audit.$1.$TAG[1] true")]
+    for env in ({}, {"FLBGPU_SMALL_MB": "0", "FLBGPU_SLICE_MB": "1"}, {"FLBGPU_SMALL_MB": "0", "FLBGPU_STREAM": "0"}):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        for rep in range(2):                     # the second call speculates on the verdicts of the first
+            got, ge, want, we = run(lib, rules, chunk, parsers=[cases.NG], before=[pf], after=[("record_modifier", [("Record", "h n1")])])
+            assert got == want and ge == we, (env, rep)
+        got, ge, want, we = run(lib, [("Rule", "$code ^9 never false")], chunk, parsers=[cases.NG], before=[pf])
+        assert got == want and ge == we == [], env
+
+
+def test_forms_hostsim(sim_lib, ref_available, monkeypatch): _forms(sim_lib, monkeypatch)
+
+
+@pytest.mark.gpu
+def test_forms_gpu(gpu_lib, ref_available, monkeypatch): _forms(gpu_lib, monkeypatch)
+
+
 def test_rules_hostsim(sim_lib, ref_available): _rules(sim_lib)
 def test_values_hostsim(sim_lib, ref_available): _values(sim_lib)
 def test_in_chains_hostsim(sim_lib, ref_available): _in_chains(sim_lib)
