@@ -84,6 +84,10 @@ struct ch_lane {
     const uint32_t *bm;       /* JSON stage-1 bitmap of the warp's byte range (shared memory), or NULL */
     uint32_t bm_base, bm_end; /* input offsets it covers */
     uint32_t defer_ok;        /* a record the stage-2 walker cannot take returns CH_DEFER instead of being scanned in place */
+    /* log_to_metrics follow-up (k_l2m_fixup): probe != NULL: report whether this record assigns a metric value (probe[0] = 1,
+     * the value's bits in probe[1]) and touch nothing; forced != NULL: the value to observe for a record whose text does not convert */
+    unsigned long long *l2m_probe;
+    const double *l2m_forced;
     uint32_t raw_lo;          /* chains with a rewrite_tag filter: where the bytes the reference's decoder consumed for this record begin
                                  (the end of the previous decoded record: events the decoder steps over in between belong to it) */
 };
@@ -1525,7 +1529,11 @@ FLB_HD int pdef_json(const struct ch_env *e, const struct ch_lane *ln, const str
 have_fields:
     if (pd->n_dec) apply_decoders(e, ln, pd, ok_, ov_, th, &cnt);
     if (pd->has_time) {
-        for (i = 0; i < (uint32_t) cnt; i++) {
+        /* the first field whose fingerprint is the key's, or unknown: found without a branch per field, so that the loads of the
+         * fingerprints are in flight together (most records do not carry the key at all) */
+        uint32_t first = (uint32_t) cnt;
+        for (i = (uint32_t) cnt; i-- > 0; ) { const uint32_t h_ = th[i]; if (h_ == 0 || h_ == pd->time_key_hash) first = i; }
+        for (i = first; i < (uint32_t) cnt; i++) {
             const uint8_t *kp; uint32_t kn;
             if (th[i] && th[i] != pd->time_key_hash) continue;      /* a known fingerprint that differs: not the key */
             if (ref_view(e, ln, ok_[i], &kp, &kn) != 1) continue;
@@ -1994,6 +2002,7 @@ FLB_HDN void f_recmod(const struct ch_env *e, const struct ch_lane *ln, const st
 #define CH_CAS64(p, c, v)   atomicCAS((unsigned long long *) (p), (unsigned long long) (c), (unsigned long long) (v))
 #define CH_MAX32(p, v)      atomicMax((unsigned int *) (p), (unsigned int) (v))
 #define CH_ADDF64(p, v)     atomicAdd((double *) (p), (double) (v))
+#define CH_ADD64(p, v)      atomicAdd((unsigned long long *) (p), (unsigned long long) (v))
 /* gauge: the pair (record index + 1, value bits) of the LAST record of a label set wins, whatever order the
  * lanes arrive in -- cmt_gauge_set() overwrites in record order.  One 16-byte compare-and-swap (sm_90+). */
 struct __align__(16) ch_pair16 { unsigned long long a, b; };
@@ -2014,6 +2023,8 @@ static inline unsigned long long ch_cas64_host(unsigned long long *p, unsigned l
 #define CH_CAS64(p, c, v)   ch_cas64_host((unsigned long long *) (p), (c), (v))
 #define CH_MAX32(p, v)      do { if (*(p) < (v)) *(p) = (v); } while (0)
 #define CH_ADDF64(p, v)     (*(p) += (v))
+static inline unsigned long long ch_add64_host(unsigned long long *p, unsigned long long v) { unsigned long long o = *p; *p = o + v; return o; }
+#define CH_ADD64(p, v)      ch_add64_host((unsigned long long *) (p), (v))
 #endif
 
 /* flb_ra_get_value_object() as the label/value code uses it: the located msgpack token.
@@ -2117,17 +2128,31 @@ FLB_HDN void f_l2m(const struct ch_env *e, const struct ch_lane *ln, const struc
             while (q < sl && dt_isspace(pl[q])) q++;
             if (q < sl && (pl[q] == '+' || pl[q] == '-')) q++;
             if (q < sl && pl[q] == '.') q++;
-            if (q >= sl || pl[q] < '0' || pl[q] > '9' || (pl[q] == '0' && q + 1 < sl && (pl[q + 1] | 0x20) == 'x')) {
-                CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return;
+            if (q < sl && pl[q] == '0' && q + 1 < sl && (pl[q + 1] | 0x20) == 'x') { CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return; }   /* hex float: not restated */
+            if (q >= sl || pl[q] < '0' || pl[q] > '9') {
+                /* "inf" / "nan" would convert: refused.  Anything else converts nothing: the value of the previous converting record */
+                const uint32_t c0 = q < sl ? (uint32_t) (pl[q] | 0x20) : 0u;
+                if (c0 == 'i' || c0 == 'n') { CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return; }
+                if (ln->l2m_forced) val = *ln->l2m_forced;
+                else if (ln->l2m_probe) return;                                     /* assigns nothing */
+                else {
+                    const unsigned long long at = tb->pending ? CH_ADD64(&tb->pending_n[0], 1ull) : (unsigned long long) L2M_PENDING_CAP;
+                    if (at < tb->pending_cap) tb->pending[at] = ridx; else CH_ATOMIC_OR(e->err, FLBGPU_E_L2M);
+                    return;
+                }
             }
-            { union { uint64_t u; double d; } cv; cv.u = dj_strtod(pl, (int) sl, &ok); val = cv.d; }
-            if (!ok) { CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return; }
+            else {
+                union { uint64_t u; double d; } cv; cv.u = dj_strtod(pl, (int) sl, &ok); val = cv.d;
+                if (!ok) { CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return; }
+            }
         }
         else if (t.type == MPT_UINT || t.type == MPT_INT) val = (double) (int64_t) t.u;
         else if (t.type == MPT_F64) { union { uint64_t u; double d; } cv; cv.u = t.u; val = cv.d; }
         else if (t.type == MPT_F32) { union { uint32_t u; float f; } cv; cv.u = (uint32_t) t.u; val = (double) cv.f; }
         else return;                                                              /* "cannot convert given value to metric" */
+        if (ln->l2m_probe) { union { uint64_t u; double d; } cv; cv.d = val; ln->l2m_probe[0] = 1ull; ln->l2m_probe[1] = cv.u; return; }
     }
+    else if (ln->l2m_probe) return;
 
     /* find or claim the slot of this label set */
     idx = (uint32_t) (h >> 20) & tb->mask;
@@ -2187,7 +2212,7 @@ FLB_HDN void chain_skipped_record(const struct ch_env *e, uint32_t ridx, uint32_
         struct ch_rec rc;
         struct ch_scratch w;
         lane.scr = e->scr ? e->scr + (size_t) e->scr_mul * off : 0; lane.dec_at = 4u * len;
-        lane.bm = 0; lane.bm_base = lane.bm_end = 0; lane.defer_ok = 0;
+        lane.bm = 0; lane.bm_base = lane.bm_end = 0; lane.defer_ok = 0; lane.l2m_probe = 0; lane.l2m_forced = 0;
         if (rec_decode(e, ln, off, len, &rc, h->empty_map_off) != 0) { CH_ATOMIC_OR(e->err, FLBGPU_E_FIELDS); return; }
         f_l2m(e, ln, (const struct cf_l2m *) (e->blob + f[k].cfg_off), &rc, &w, ridx);
     }
@@ -2511,6 +2536,30 @@ FLB_HD uint32_t chain_record(const struct ch_env *e, struct ch_lane *ln, uint32_
         return len;
     }
     return rec_emit(e, ln, &rc, EMIT ? out : 0);
+}
+
+/* log_to_metrics: observe pending record `ridx` (its value text converts nothing) with the value the nearest earlier record of
+ * the call assigned -- 0.0 when there is none (the reference's local starts at 0 in every cb_filter call).  Looking a record up
+ * means running it through the chain in front of the filter again, without side effects (ln.l2m_probe). */
+#define L2M_LOOKBACK_MAX 100000u
+FLB_HD void l2m_fixup_record(const struct ch_env *e, uint32_t ridx, const uint32_t *off, const uint32_t *len, const uint8_t *kind)
+{
+    struct ch_lane ln;
+    unsigned long long pr[2];
+    double val = 0.0;
+    uint32_t j = ridx, steps = 0;
+    ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0; ln.l2m_forced = 0; ln.scr = 0; ln.dec_at = 0;
+    while (j > 0) {
+        j--;
+        if (kind[j] != 0) continue;
+        if (++steps > L2M_LOOKBACK_MAX) { CH_ATOMIC_OR(e->err, FLBGPU_E_L2M); return; }
+        pr[0] = 0; pr[1] = 0;
+        ln.l2m_probe = pr; ln.raw_lo = off[j];
+        (void) chain_record<false>(e, &ln, j, off[j], len[j], 0);
+        if (pr[0]) { union { uint64_t u; double d; } cv; cv.u = pr[1]; val = cv.d; break; }
+    }
+    ln.l2m_probe = 0; ln.l2m_forced = &val; ln.raw_lo = off[ridx];
+    (void) chain_record<false>(e, &ln, ridx, off[ridx], len[ridx], 0);
 }
 
 #include "dev_jsmn.cuh"

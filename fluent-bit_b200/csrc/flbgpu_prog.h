@@ -230,8 +230,15 @@ struct l2m_table {
     unsigned long long *bkt;         /* [slot][n_buckets + 1] cumulative buckets, last = +Inf; gauge: [slot][2] = last record + 1, value bits */
     uint8_t *str;                    /* [slot][n_labels][L2M_LABEL_BYTES]: length byte + bytes */
     uint32_t mask;
-    uint32_t pad;
+    uint32_t pending_cap;
+    /* gauge / histogram: records whose value text sscanf("%lf") cannot convert -- the reference then observes the value the
+     * previous converting record of the call left in its local variable (log_to_metrics.c:983-984,1060,1090).  They are listed
+     * here by the evaluation launch and observed by a follow-up launch that looks that value up (k_l2m_fixup).
+     * pending_n[0] = listed, [1] = done. */
+    uint32_t *pending;
+    unsigned long long *pending_n;
 };
+#define L2M_PENDING_CAP 65536u
 
 struct chain_filter { uint32_t kind, cfg_off; };
 

@@ -412,13 +412,21 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval_t(const __grid_constant_
             lo -= (uint32_t) ((uintptr_t) (in + lo) & 15u);           /* 16-byte aligned in the address space */
             if (hi - lo <= BM_BYTES) {
                 uint32_t *w = reinterpret_cast<uint32_t *>(dsm) + (size_t) warp * p.bm_words;
-                for (uint32_t o0 = 0; o0 < hi - lo; o0 += 512) {                         /* the same trip count in every lane: the shuffle below pairs them */
-                    const uint32_t o = o0 + lane * 16;
-                    uint4 v = make_uint4(0, 0, 0, 0);
-                    if (o < hi - lo) v = *reinterpret_cast<const uint4 *>(in + lo + o);   /* reads past `hi` stay inside the padded buffer */
-                    const uint32_t m16 = bm_mask4(v.x) | (bm_mask4(v.y) << 4) | (bm_mask4(v.z) << 8) | (bm_mask4(v.w) << 12);
-                    const uint32_t other = __shfl_xor_sync(0xffffffffu, m16, 1);
-                    if (!(lane & 1) && o < hi - lo) w[o >> 5] = m16 | (other << 16);
+                for (uint32_t o0 = 0; o0 < hi - lo; o0 += 2048) {                        /* the same trip count in every lane: the shuffle below pairs them */
+                    uint4 v[4];
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {                                        /* four 512-byte rows in flight: the range is read once, from DRAM */
+                        const uint32_t o = o0 + (uint32_t) u * 512 + lane * 16;
+                        v[u] = make_uint4(0, 0, 0, 0);
+                        if (o < hi - lo) v[u] = *reinterpret_cast<const uint4 *>(in + lo + o);   /* reads past `hi` stay inside the padded buffer */
+                    }
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const uint32_t o = o0 + (uint32_t) u * 512 + lane * 16;
+                        const uint32_t m16 = bm_mask4(v[u].x) | (bm_mask4(v[u].y) << 4) | (bm_mask4(v[u].z) << 8) | (bm_mask4(v[u].w) << 12);
+                        const uint32_t other = __shfl_xor_sync(0xffffffffu, m16, 1);
+                        if (!(lane & 1) && o < hi - lo) w[o >> 5] = m16 | (other << 16);
+                    }
                 }
                 __syncwarp();
                 bm = w; bm_base = lo; bm_end = hi;
@@ -436,7 +444,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval_t(const __grid_constant_
          * lane travels in a few words */
         struct ch_lane ln;
         ln.bm = bm; ln.bm_base = bm_base; ln.bm_end = bm_end;
-        ln.defer_ok = (bm && p.defer_list) ? 1u : 0u;
+        ln.defer_ok = (bm && p.defer_list) ? 1u : 0u; ln.l2m_probe = 0; ln.l2m_forced = 0;
         ln.raw_lo = p.env.esize ? raw_lo_of(p, i) : my_off;
         sz = chain_record<false, PH>(&p.env, &ln, i, my_off, my_len, 0);
         if (sz == CH_DEFER) {                          /* the follow-up launch evaluates it whole, with the byte scanner */
@@ -470,7 +478,7 @@ __global__ void __launch_bounds__(1024, 1) k_chain_eval_deferred(const __grid_co
     for (unsigned long long t = (unsigned long long) blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (unsigned long long) gridDim.x * blockDim.x) {
         const uint32_t i = p.defer_list[t];
         struct ch_lane ln;
-        ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0;
+        ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0; ln.l2m_probe = 0; ln.l2m_forced = 0;
         ln.raw_lo = p.env.esize ? raw_lo_of(p, i) : p.off[i];
         __stcs(&p.size[i], chain_record<false>(&p.env, &ln, i, p.off[i], p.len[i], 0));
     }
@@ -497,9 +505,21 @@ __global__ void __launch_bounds__(BK_REC_BLOCK) k_rtag_emit(const __grid_constan
     const uint32_t ex = block_excl_scan(sz, &tot);
     if (!sz) return;
     struct ch_lane ln;
-    ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0;
+    ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0; ln.l2m_probe = 0; ln.l2m_forced = 0;
     ln.raw_lo = raw_lo_of(p, i);
     chain_record<true, CH_PH_RTAG>(&p.env, &ln, i, p.off[i], p.len[i], p.out + p.bsum[blockIdx.x] + ex);
+}
+
+/* log_to_metrics, gauge / histogram: the records the evaluation listed because their value text converts nothing
+ * (dev_chain.cuh: l2m_fixup_record).  A handful per call at most; entries [done, listed) are new since the last launch. */
+__global__ void __launch_bounds__(256) k_l2m_fixup(const __grid_constant__ k_chain_params p)
+{
+    const unsigned long long n = p.env.l2m.pending_n[0], d = p.env.l2m.pending_n[1];
+    const unsigned long long lim = n < p.env.l2m.pending_cap ? n : p.env.l2m.pending_cap;
+    for (unsigned long long t = d + threadIdx.x; t < lim; t += blockDim.x)
+        l2m_fixup_record(&p.env, p.env.l2m.pending[t], p.off, p.len, p.kind);
+    __syncthreads();
+    if (threadIdx.x == 0) p.env.l2m.pending_n[1] = n;
 }
 
 /* per-block sums of the record sizes */
@@ -573,7 +593,7 @@ __global__ void __launch_bounds__(EMIT_BLOCK, 6) k_chain_emit_list(const __grid_
     const bool rerun = valid && p.env.capcache[(size_t) (p.env.cap_stride - RC_CACHE_INTS) * p.env.cap_n + r] == RC_CACHE_NONE;
     if (!__any_sync(0xffffffffu, rerun) && total + mis <= EMIT_STAGE) {
         uint8_t *sb = emit_stage + (size_t) warp * (EMIT_STAGE + 16);
-        if (valid) { struct ch_lane ln; ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0; ln.raw_lo = p.off[r]; chain_record<true>(&p.env, &ln, r, p.off[r], p.len[r], sb + mis + (uint32_t) (off - base)); }   /* cached field list: encode only */
+        if (valid) { struct ch_lane ln; ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0; ln.l2m_probe = 0; ln.l2m_forced = 0; ln.raw_lo = p.off[r]; chain_record<true>(&p.env, &ln, r, p.off[r], p.len[r], sb + mis + (uint32_t) (off - base)); }   /* cached field list: encode only */
         __syncwarp();
         {
             /* shared byte i corresponds to result byte (base - mis + i): 16-byte chunks are aligned on both sides */
@@ -590,7 +610,7 @@ __global__ void __launch_bounds__(EMIT_BLOCK, 6) k_chain_emit_list(const __grid_
         return;
     }
     if (!valid) return;
-    { struct ch_lane ln; ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0; ln.raw_lo = p.off[r]; chain_record<true>(&p.env, &ln, r, p.off[r], p.len[r], p.out + off); }
+    { struct ch_lane ln; ln.bm = 0; ln.bm_base = ln.bm_end = 0; ln.defer_ok = 0; ln.l2m_probe = 0; ln.l2m_forced = 0; ln.raw_lo = p.off[r]; chain_record<true>(&p.env, &ln, r, p.off[r], p.len[r], p.out + off); }
 }
 
 /* ---- glue of the small-chunk form ---- */
@@ -1429,6 +1449,7 @@ int bk_chain_eval(bk_q *q, const struct bk_chain_args *a, uint32_t r0, uint32_t 
     if (p.env.l2m.hash) {
         k_chain_skipped<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, 0, q->stream>>>(p);
         g_launches += 1;
+        if (p.env.l2m.pending) { k_l2m_fixup<<<1, 256, 0, q->stream>>>(p); g_launches += 1; }
     }
     ev_end_on(q, 1, q->stream);
     g_launches += 1;
@@ -1660,7 +1681,10 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     else
         k_chain_eval<<<nb_cap, BK_REC_BLOCK, (size_t) p.bm_words * 4 * (BK_REC_BLOCK / 32), st>>>(p);
     if (p.defer_list) { k_chain_eval_deferred<<<148, BK_REC_BLOCK, 0, st>>>(p); g_launches += 1; }
-    if (p.env.l2m.hash) { k_chain_skipped<<<nb_cap, BK_REC_BLOCK, 0, st>>>(p); g_launches += 1; }
+    if (p.env.l2m.hash) {
+        k_chain_skipped<<<nb_cap, BK_REC_BLOCK, 0, st>>>(p); g_launches += 1;
+        if (p.env.l2m.pending) { k_l2m_fixup<<<1, 256, 0, st>>>(p); g_launches += 1; }
+    }
     ev_end_on(q, 1, st);
     /* sizes, survivor lists, emission under the speculated verdicts */
     ev_begin_on(q, 2, st);

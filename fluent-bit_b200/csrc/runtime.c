@@ -1497,6 +1497,12 @@ int flbgpu_chain_init(flbgpu_chain *c)
         c->l2m.sum = bk_alloc(c->q, n * 8); c->l2m.bkt = bk_alloc(c->q, n * nbk * 8);
         c->l2m.str = bk_alloc(c->q, n * (st->n_labels ? st->n_labels : 1) * L2M_LABEL_BYTES);
         c->l2m.mask = (uint32_t) (n - 1);
+        if (st->mode != L2M_COUNTER) {               /* the list of records whose value text converts nothing (flbgpu_prog.h: struct l2m_table) */
+            c->l2m.pending = bk_alloc(c->q, sizeof(uint32_t) * L2M_PENDING_CAP);
+            c->l2m.pending_n = bk_alloc(c->q, 16);
+            c->l2m.pending_cap = L2M_PENDING_CAP;
+            if (!c->l2m.pending || !c->l2m.pending_n) return -1;
+        }
         c->h_hash = malloc(n * 8); c->h_chash = malloc(n * 8); c->h_first = malloc(n * 4); c->h_cnt = malloc(n * 8); c->h_sum = malloc(n * 8);
         c->h_bkt = malloc(n * nbk * 8);
         if (!c->l2m.hash || !c->l2m.chash || !c->l2m.first || !c->l2m.cnt || !c->l2m.sum || !c->l2m.bkt || !c->l2m.str) return -1;
@@ -1514,7 +1520,7 @@ void flbgpu_chain_destroy(flbgpu_chain *c)
     bk_free(c->q, c->d_flags); bk_free(c->q, c->d_scr); free(c->h_bsum);
     bk_free(c->q, c->d_prep); free(c->h_prep);
     bk_free(c->q, c->d_esize); bk_free(c->q, c->d_ebsum); free(c->h_ebsum);
-    bk_free(c->q, c->l2m.hash); bk_free(c->q, c->l2m.chash); bk_free(c->q, c->l2m.first); bk_free(c->q, c->l2m.cnt); bk_free(c->q, c->l2m.sum); bk_free(c->q, c->l2m.bkt); bk_free(c->q, c->l2m.str);
+    bk_free(c->q, c->l2m.hash); bk_free(c->q, c->l2m.chash); bk_free(c->q, c->l2m.first); bk_free(c->q, c->l2m.cnt); bk_free(c->q, c->l2m.sum); bk_free(c->q, c->l2m.bkt); bk_free(c->q, c->l2m.str); bk_free(c->q, c->l2m.pending); bk_free(c->q, c->l2m.pending_n);
     free(c->h_hash); free(c->h_chash); free(c->h_first); free(c->h_cnt); free(c->h_sum); free(c->h_bkt);
     free(c->blob.p);
     if (c->ctx && c->ctx->last_q == c->q) c->ctx->last_q = NULL;
@@ -1649,6 +1655,7 @@ static int l2m_clear(flbgpu_chain *c)
     st = c->f[c->l2m_index]->l2m;
     if (bk_zero(c->q, c->l2m.hash, n * 8) || bk_zero(c->q, c->l2m.first, n * 4) || bk_zero(c->q, c->l2m.cnt, n * 8) ||
         bk_zero(c->q, c->l2m.sum, n * 8) || bk_zero(c->q, c->l2m.bkt, n * L2M_NBK(st) * 8)) return -1;
+    if (c->l2m.pending_n && bk_zero(c->q, c->l2m.pending_n, 16)) return -1;
     return 0;
 }
 

@@ -256,6 +256,13 @@ int bk_chain_eval(bk_q *, const struct bk_chain_args *a, uint32_t r0, uint32_t r
         free(put_off);
     }
     free(bm);
+    if (e.l2m.hash && e.l2m.pending) {             /* k_l2m_fixup: the records whose value text converts nothing */
+        unsigned long long n = e.l2m.pending_n[0], d = e.l2m.pending_n[1], t;
+        if (n > e.l2m.pending_cap) n = e.l2m.pending_cap;
+        for (t = d; t < n; t++) l2m_fixup_record(&e, e.l2m.pending[t], a->d_off, a->d_len, a->d_kind);
+        e.l2m.pending_n[1] = e.l2m.pending_n[0];
+        hs_launches += 1;
+    }
     hs_launches += 1;
     return 0;
 }

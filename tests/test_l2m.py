@@ -94,15 +94,57 @@ def test_l2m_config_errors(bad, sim_lib, ref_available):
         util.Ref().filter("log_to_metrics", bad)
 
 
-def test_l2m_not_supported_is_loud(sim_lib):
-    """a value text sscanf("%lf") cannot convert leaves the previous record's value in place in the
-    reference (order dependent): refused, not guessed"""
-    ctx = pkg.Context(0, lib=sim_lib)
+def _previous_value(lib):
+    """a value text sscanf("%lf") cannot convert leaves the value of the previous converting record of the call in the
+    reference's local variable (log_to_metrics.c:983-984,1060,1090), 0 when there is none: same table, record for record"""
+    import random
+    S = util.mp_str
+    rng = random.Random(5)
     for mode in ("gauge", "histogram"):
-        f = ctx.filter("log_to_metrics", [("metric_mode", mode), ("value_field", "x"), ("metric_description", "d"), ("tag", "t")])
-        chunk = util.event(1700000000, 0, [(b"x", util.mp_str(b"1.5"))]) + util.event(1700000001, 0, [(b"x", util.mp_str(b"fast"))])
+        props = [("metric_mode", mode), ("metric_name", "m"), ("value_field", "x"), ("label_field", "c"), ("metric_description", "d"), ("tag", "t"),
+                 ("regex", "keep yes")]
+        for trial in range(6):
+            evs = []
+            for i in range(300):
+                r = rng.random()
+                if trial == 0 and i < 5:
+                    v = S(b"fast")                                   # nothing converts before: the local's initial 0
+                elif r < 0.15:
+                    v = S(rng.choice([b"fast", b"", b"-", b".", b"x1", b"+.e3", b" \t"]))
+                elif r < 0.25:
+                    v = bytes([rng.randint(0, 100)])                 # integer value
+                elif r < 0.30:
+                    v = b"\xc3"                                      # a type the filter cannot convert: assigns nothing
+                else:
+                    v = S(str(rng.randint(0, 999)).encode() + rng.choice([b"", b".5", b"e1", b" tail"]))
+                fields = [(b"x", v), (b"c", S(rng.choice([b"red", b"green", b"blue"]))), (b"keep", S(b"yes" if rng.random() < 0.8 else b"no"))]
+                if rng.random() < 0.05:
+                    fields = fields[1:]                              # no value field at all
+                evs.append(util.event(1700000000 + i, 0, fields))
+            chunk = b"".join(evs)
+            ref = util.Ref()
+            rf = ref.filter("log_to_metrics", props)
+            want = ref.chain_do(chunk)
+            ctx = pkg.Context(0, lib=lib)
+            f = ctx.filter("log_to_metrics", props)
+            assert ctx.chain([f]).do(chunk) == want
+            ts = __import__("re").compile(r"^\S+Z ", __import__("re").M)
+            assert f.l2m_text() == ts.sub("", ref.l2m_text(rf)), (mode, trial)
+    # what would convert to inf / nan, and hex floats, stay refused (not restated), loudly
+    ctx = pkg.Context(0, lib=lib)
+    f = ctx.filter("log_to_metrics", [("metric_mode", "gauge"), ("value_field", "x"), ("metric_description", "d"), ("tag", "t")])
+    for bad in (b"inf", b"nan", b"0x1p3"):
         with pytest.raises(pkg.FlbGpuError):
-            f.cb(chunk)
+            f.cb(util.event(1700000000, 0, [(b"x", S(b"1.5"))]) + util.event(1700000001, 0, [(b"x", S(bad))]))
+
+
+def test_l2m_previous_value_hostsim(sim_lib, ref_available):
+    _previous_value(sim_lib)
+
+
+@pytest.mark.gpu
+def test_l2m_previous_value_gpu(gpu_lib, ref_available):
+    _previous_value(gpu_lib)
 
 
 WORKER = r"""
