@@ -9,11 +9,18 @@ CFLAGS = -O2 -g -fPIC -Wall -Wno-unused-function
 all: product hostsim oracle
 
 product: $(PKG)/libflbgpu.so
-$(PKG)/libflbgpu.so: $(CSRC)/kernels.cu $(CSRC)/runtime.c $(CSRC)/rx_compile.c $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/flbgpu.h
-	$(NVCC) $(NVFLAGS) -c $(CSRC)/kernels.cu -o $(CSRC)/kernels.o
-	gcc $(CFLAGS) -c $(CSRC)/runtime.c -o $(CSRC)/runtime.o
-	gcc $(CFLAGS) -c $(CSRC)/rx_compile.c -o $(CSRC)/rx_compile.o
-	$(NVCC) -shared -o $@ $(CSRC)/kernels.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o -lcudart -lpthread -ldl
+HDRS = $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/flbgpu.h
+# one object per translation unit, so that `make -j` compiles the two .cu files side by side (kernels.cu alone takes minutes)
+$(CSRC)/kernels.o: $(CSRC)/kernels.cu $(HDRS)
+	$(NVCC) $(NVFLAGS) -c $(CSRC)/kernels.cu -o $@
+$(CSRC)/kernels_ml.o: $(CSRC)/kernels_ml.cu $(HDRS)
+	$(NVCC) $(NVFLAGS) -c $(CSRC)/kernels_ml.cu -o $@
+$(CSRC)/runtime.o: $(CSRC)/runtime.c $(HDRS)
+	gcc $(CFLAGS) -c $(CSRC)/runtime.c -o $@
+$(CSRC)/rx_compile.o: $(CSRC)/rx_compile.c $(HDRS)
+	gcc $(CFLAGS) -c $(CSRC)/rx_compile.c -o $@
+$(PKG)/libflbgpu.so: $(CSRC)/kernels.o $(CSRC)/kernels_ml.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o
+	$(NVCC) -shared -o $@ $(CSRC)/kernels.o $(CSRC)/kernels_ml.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o -lcudart -lpthread -ldl
 
 hostsim: tests/hostsim/libhostsim.so
 tests/hostsim/libhostsim.so: tests/hostsim/hostsim.cpp $(CSRC)/runtime.c $(CSRC)/rx_compile.c $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h)

@@ -71,11 +71,50 @@ WORKLOADS = {
                                         ("tag", "m"), ("value_field", "duration"), ("label_field", "color"),
                                         ("label_field", "direction"), ("discard_logs", "on")])],
     },
+    # BASELINE.json configs[4] (first step): container logs with Java stack traces -> filter_multiline (built-in java parser,
+    # `buffer off`: the lines of a chunk are concatenated inside the call)
+    "ml": {
+        "name": "configs[4] (multiline stage): application logs with Java stack traces -> filter_multiline(multiline.parser java, key_content log, buffer off)",
+        "filters": [("multiline", [("multiline.parser", "java"), ("multiline.key_content", "log"), ("buffer", "off")])],
+    },
 }
+NO_PARSER = ("l2m", "ml")
+
+
+def java_lines(n, seed):
+    """application log lines, about one in eight followed by a Java stack trace of 3-12 frames (some with a cause)"""
+    import random
+    rng = random.Random(seed)
+    pk = ["com.example.app", "org.acme.billing", "io.svc.gateway", "net.corp.auth"]
+    cl = ["OrderService", "HttpHandler", "TokenCache", "DbPool", "RetryPolicy", "JsonCodec"]
+    ex = ["java.lang.IllegalStateException", "java.io.IOException", "java.lang.NullPointerException", "java.util.concurrent.TimeoutException",
+          "org.acme.billing.PaymentError"]
+    out = []
+    t = 1700000000
+    while len(out) < n:
+        t += rng.randint(0, 2)
+        ts = "2023-11-14 %02d:%02d:%02d.%03d" % ((t // 3600) % 24, (t // 60) % 60, t % 60, rng.randint(0, 999))
+        if rng.random() < 0.125:
+            out.append(("%s ERROR [%s] request %d failed" % (ts, rng.choice(cl), rng.randint(0, 10 ** 6))).encode())
+            out.append(("%s: %s" % (rng.choice(ex), rng.choice(["connection reset", "state is CLOSED", "timed out after 30000 ms", "null"]))).encode())
+            for _ in range(rng.randint(3, 12)):
+                out.append(("\tat %s.%s.%s(%s.java:%d)" % (rng.choice(pk), rng.choice(cl), rng.choice(["run", "call", "handle", "get", "apply"]),
+                                                          rng.choice(cl), rng.randint(1, 900))).encode())
+            if rng.random() < 0.4:
+                out.append(("Caused by: %s: %s" % (rng.choice(ex), "inner")).encode())
+                for _ in range(rng.randint(2, 6)):
+                    out.append(("\tat %s.%s.%s(%s.java:%d)" % (rng.choice(pk), rng.choice(cl), "invoke", rng.choice(cl), rng.randint(1, 900))).encode())
+                out.append(("\t... %d more" % rng.randint(1, 30)).encode())
+        else:
+            out.append(("%s INFO [%s] %s in %d ms path=/api/v1/%s/%d" % (ts, rng.choice(cl), rng.choice(["handled", "served", "cached"]),
+                                                                        rng.randint(1, 900), rng.choice(["orders", "users", "items"]), rng.randint(1, 99999))).encode())
+    return out[:n]
 
 
 def make_block(wl, rank=0):
     import util
+    if wl == "ml":
+        return util.chunk_from_lines(java_lines(BASE_LINES, 0xF1B1 + 5 + rank))
     if wl == "l2m":
         import random
         rng = random.Random(0xF1B1 + 4 + rank)
@@ -152,7 +191,7 @@ def _ref_state(wl):
     st = _REF_STATE.get(wl)
     if st is None:
         ref = util.Ref()
-        if wl != "l2m":
+        if wl not in NO_PARSER:
             ref.parser(**parser_kw(wl))
         for p, props in WORKLOADS[wl]["filters"]:
             ref.filter(p, props)
@@ -250,7 +289,7 @@ def run_reference(args):
         return
     cores, cores_note = host_cores()
     wl = args.workload
-    side = [] if args.primary_only else [o for o in ("apache", "c0", "nginx") if o != wl]
+    side = [] if args.primary_only else [o for o in ("apache", "c0", "nginx", "ml") if o != wl]
     pool = RefPool(cores, [wl] + side)
     # bounded sample: the reference does 10-50 M lines/s on 128 cores, so a full 10 M-event step is 0.2-1 s
     val, s_per_step, n = reference_workload(pool, wl, lines_for(args, wl), args.steps, args.warmup)
@@ -330,7 +369,7 @@ class Workload:
         import util
         self.pkg = util.pkg
         self.args, self.wl, self.L, self.ctx, self.rank, self.world = args, wl, L, ctx, rank, world
-        if wl != "l2m":
+        if wl not in NO_PARSER:
             kw = parser_kw(wl)
             made = ctx.__dict__.setdefault("_bench_parsers", set())
             if kw["name"] not in made:
@@ -564,10 +603,15 @@ def run_ours(args):
     m = measure(args, WL, L, ctx, torch, dist, rank, world, local, full=True)
     others = {}
     if not args.primary_only:
-        for o in ("apache", "c0", "nginx", "l2m"):
+        for o in ("apache", "c0", "nginx", "l2m", "ml"):
             if o == WL:
                 continue
-            others[o] = measure(args, o, L, ctx, torch, dist, rank, world, local, full=(o == "apache"))
+            try:
+                others[o] = measure(args, o, L, ctx, torch, dist, rank, world, local, full=(o == "apache"))
+            except Exception as ex:                       # a side workload never costs the line its primary numbers
+                if o == "apache":
+                    raise
+                others[o] = {"error": "%s: %s" % (type(ex).__name__, ex)}
 
     # last: the same end-to-end calls with an allocator that retains freed result buffers (and pinned input)
     tune_malloc()
@@ -630,6 +674,8 @@ def run_ours(args):
                "sample": "%d cores (%s), 2 steps of %d events in %d-event calls, one pipeline per core (%.2f s per step: slowest worker inside the reference's calls)" % (cores, cores_note, n, min(BASE_LINES, -(-n // cores)), sps)}
 
     def side(mm, name):
+        if "error" in mm:
+            return {"workload": WORKLOADS[name]["name"], "error": mm["error"]}
         e2, a2, ach2 = roof(mm)
         d = {"workload": WORKLOADS[name]["name"], "value": mm["value"], "e2e": mm["e2e"], "unit": "lines/s",
              "events_per_gpu_per_step": mm["n_lines"], "input_bytes_per_gpu": mm["nbytes"], "output_bytes_per_gpu": mm["out_bytes"],

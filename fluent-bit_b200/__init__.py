@@ -53,6 +53,7 @@ EXPORTS = [
     "flbgpu_stream", "flbgpu_kernel_ms", "flbgpu_chain_stream",
     "flbgpu_comm_unique_id", "flbgpu_comm_init", "flbgpu_l2m_allreduce",
     "flbgpu_pack_state_init", "flbgpu_pack_state_reset", "flbgpu_pack_json_state", "flbgpu_pack_json_state_batch",
+    "flbgpu_ml_parser_create", "flbgpu_ml_parser_rule", "flbgpu_ml_parser_init", "flbgpu_ml_set_buffer_limit",
 ]
 
 
@@ -101,6 +102,11 @@ def load(path=None):
     L.flbgpu_pack_json_state.argtypes = [vp, cp, sz, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(PackState)]
     L.flbgpu_pack_json_state_batch.argtypes = [vp, C.c_int, C.POINTER(cp), C.POINTER(sz), C.POINTER(vp), C.POINTER(C.c_int),
                                                C.POINTER(PackState), C.POINTER(C.c_int)]
+    L.flbgpu_ml_parser_create.restype = vp
+    L.flbgpu_ml_parser_create.argtypes = [vp, cp, cp, cp, C.c_int, C.c_int, cp, cp, cp, cp]
+    L.flbgpu_ml_parser_rule.argtypes = [vp, cp, cp, cp]
+    L.flbgpu_ml_parser_init.argtypes = [vp]
+    L.flbgpu_ml_set_buffer_limit.argtypes = [vp, sz]
     L.flbgpu_comm_unique_id.argtypes = [vp]
     L.flbgpu_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.flbgpu_l2m_allreduce.argtypes = [vp]
@@ -200,6 +206,21 @@ class Context:
         if not p:
             raise FlbGpuError("parser_create(%s): %s" % (name, self.err()))
         return Parser(self, p)
+
+    def ml_parser(self, name, type="regex", rules=(), match_string=None, negate=False, flush_ms=0, key_content=None,
+                  key_group=None, key_pattern=None, parser=None):
+        """a [MULTILINE_PARSER] section: flb_ml_parser_create + one flb_ml_rule_create per (from_states, regex, to_state) +
+        flb_ml_parser_init"""
+        m = self.L.flbgpu_ml_parser_create(self.h, _b(name), _b(type), _b(match_string), int(negate), flush_ms, _b(key_content),
+                                           _b(key_group), _b(key_pattern), _b(parser))
+        if not m:
+            raise FlbGpuError("ml_parser_create(%s): %s" % (name, self.err()))
+        for frm, rx, to in rules:
+            if self.L.flbgpu_ml_parser_rule(m, _b(frm), _b(rx), _b(to)) != 0:
+                raise FlbGpuError("ml_parser_rule(%s): %s" % (name, self.err()))
+        if type == "regex" and self.L.flbgpu_ml_parser_init(m) != 0:
+            raise FlbGpuError("ml_parser_init(%s): %s" % (name, self.err()))
+        return m
 
     def filter(self, plugin, props):
         """flb_filter_new + set_property (props: ordered list of (key, value)) + cb_init."""

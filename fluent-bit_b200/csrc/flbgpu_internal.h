@@ -68,6 +68,10 @@ const char *bk_name(void);
 int   bk_device_count(void);
 const char *bk_last_error(void);                 /* of the calling thread */
 uint64_t bk_launch_count(void);                  /* kernels launched by this library so far (all queues) */
+void bk_note_launches(unsigned n);               /* (between the translation units of a back end) */
+void bk_note_error(const char *what, const char *detail);
+void bk_ev_begin(bk_q *q, int k);                /* CUDA-event pair of kernel group k (0 index, 1 evaluate, 2 emit) on the queue's stream */
+void bk_ev_end(bk_q *q, int k);
 
 bk_q *bk_q_new(int device);                      /* NULL: no usable device (bk_last_error) */
 void  bk_q_free(bk_q *q);
@@ -192,6 +196,13 @@ struct bk_jsmn_args {
 };
 int bk_jsmn_scan(bk_q *q, const struct bk_jsmn_args *a);
 int bk_jsmn_emit(bk_q *q, const struct bk_jsmn_args *a);
+
+/* filter_multiline (dev_ml.cuh), asynchronous on the queue's stream.  plan: per-record pass, automaton tree, action and
+ * event lists (e->res: events, final state, the group's time); sizes: ev_size[] of the n_ev events; emit: event j at
+ * d_out + d_bsum[j / BK_REC_BLOCK] + (sum of the sizes before it in its block). */
+int bk_ml_plan(bk_q *q, const struct ml_env *e);
+int bk_ml_sizes(bk_q *q, const struct ml_env *e, uint32_t n_ev);
+int bk_ml_emit(bk_q *q, const struct ml_env *e, uint32_t n_ev, const uint64_t *d_bsum, uint8_t *d_out);
 
 #ifdef __cplusplus
 }

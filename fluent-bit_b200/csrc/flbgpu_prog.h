@@ -98,7 +98,8 @@ struct rx_prog {
 /* ------------------------------------------------------- chain program */
 /* All *_off fields are byte offsets from the blob base; 0 means "absent". */
 
-enum { FLBGPU_F_PARSER = 1, FLBGPU_F_GREP, FLBGPU_F_MODIFY, FLBGPU_F_RECORD_MODIFIER, FLBGPU_F_LOG_TO_METRICS, FLBGPU_F_REWRITE_TAG };
+enum { FLBGPU_F_PARSER = 1, FLBGPU_F_GREP, FLBGPU_F_MODIFY, FLBGPU_F_RECORD_MODIFIER, FLBGPU_F_LOG_TO_METRICS, FLBGPU_F_REWRITE_TAG,
+       FLBGPU_F_MULTILINE };
 
 /* parser types: include/fluent-bit/flb_parser.h:30-33 */
 enum { FLBGPU_PARSER_REGEX = 1, FLBGPU_PARSER_JSON, FLBGPU_PARSER_LTSV, FLBGPU_PARSER_LOGFMT };
@@ -271,6 +272,72 @@ struct chain_hdr {
                                    reference's decoder does -- the call is run filter by filter */
 #define FLBGPU_E_TAGVALUE 512u   /* rewrite_tag: a tag template names a float or a map (snprintf("%f") / JSON text are not restated) */
 #define FLBGPU_E_RXUNICODE 128u /* a pattern with POSIX brackets / \b / case-insensitivity met a non-ASCII subject */
+
+#define FLBGPU_E_MLLIMIT 1024u  /* multiline: a concatenated message reached the buffer limit (the reference truncates it and marks the record) */
+#define FLBGPU_E_MLMETA  2048u  /* multiline: an event with non-empty metadata (the merge of the lines' metadata is not restated) */
+
+/* ---------------------------------------------------- filter_multiline (dev_ml.cuh) */
+/* One multiline parser instance as the filter runs it in `buffer off` mode (plugins/filter_multiline/ml.c:792-892,
+ * src/multiline/flb_ml.c, flb_ml_rule.c).  The per-line work (find key_content, which rules' regexes match) is one lane per
+ * record; what is sequential in the reference -- the rule state, "is the buffer empty", "is there a first-line context" -- is a
+ * finite automaton over the records, composed over blocks of records and scanned (dev_ml.cuh). */
+#define ML_MAX_RULES 15
+enum { ML_T_REGEX = 0, ML_T_ENDSWITH = 1, ML_T_EQ = 2 };
+struct cf_ml_rule {
+    uint32_t rx_off;           /* regex program */
+    uint32_t start;            /* from_states names start_state */
+    uint32_t next_start;       /* some rule of to_state_map is a start state: the buffer is flushed right after this rule matched */
+    uint32_t n_to;             /* to_state_map without its start-state rules, in list order */
+    uint8_t to[16];
+};
+struct cf_ml {
+    uint32_t type, negate, n_rules, rules_off;
+    uint32_t key_off, key_len;        /* key_content; key_len 0xffffffff: none (every record passes through on its own) */
+    uint32_t match_off, match_len;    /* ENDSWITH / EQ */
+    uint32_t limit;                   /* multiline buffer limit in bytes, 0 = none */
+    uint32_t pad[3];
+};
+/* per record, after the parallel pass */
+#define MLF_MASK   0x7fffu     /* bit j: rule j matches the content (ENDSWITH / EQ: bit 0 = the match, negate applied) */
+#define MLF_HAS    0x10000u    /* key_content found with a string value */
+#define MLF_LENOK  0x20000u    /* ENDSWITH: the content is at least as long as the match string */
+#define MLF_LIVE   0x40000u    /* an event the decoder yields */
+struct ml_feat { uint32_t coff, clen, bits; };
+/* per record, after the automaton ran over it */
+#define MLA_FB      1u   /* the pending message is flushed (and comes out) before this record is looked at */
+#define MLA_APP     2u   /* the record appends to the buffer */
+#define MLA_NL      4u   /* ... a line feed only (a continuation line whose content is empty) */
+#define MLA_SEP     8u   /* ... behind a line feed when the buffer does not end in one */
+#define MLA_CTXMAP  16u  /* its map becomes the first-line context */
+#define MLA_CTXTIME 32u  /* its timestamp becomes the message's */
+#define MLA_FA      64u  /* the message is flushed (and comes out) right after this record */
+#define ML_F1 64u        /* records per automaton block, blocks per super-block */
+#define ML_F2 128u
+#define ML_MAX_STATES ((ML_MAX_RULES + 1) * 4)
+/* everything one call of the multiline filter works on (device pointers; dev_ml.cuh) */
+struct ml_env {
+    const uint8_t *in;
+    const uint8_t *blob;
+    uint32_t cfg_off;                 /* struct cf_ml */
+    const uint32_t *off, *len; const uint8_t *kind;
+    uint32_t n_rec;
+    uint32_t *err;                    /* FLBGPU_E_* */
+    /* per record */
+    struct ml_feat *feat;
+    uint8_t *act;
+    uint32_t *tl;                     /* 1 + index of the last record at or before this one that registered its time, 0 = none yet */
+    /* automaton tree */
+    uint8_t *T1, *T2, *in1, *in2;     /* [nt1][S], [nt2][S], [nt1], [nt2] */
+    uint32_t *cnt1, *lt1, *cnt2, *lt2, *base1, *tl1, *base2, *tl2;
+    uint32_t nt1, nt2, S;
+    uint32_t state_in;                /* the automaton's state when the call begins (rule carried over from the previous chunk) */
+    int64_t time_in[2];               /* the group's mp_time when the call begins */
+    int64_t now[2];                   /* what stands in for flb_time_get() when a message has no time */
+    /* results of the plan: [0] events, [1] final state, [2] seconds, [3] nanoseconds of the group's mp_time afterwards */
+    unsigned long long *res;
+    /* per event (flush) */
+    uint32_t *ev_slot, *ev_size, *ev_buflen, *ev_ctx;
+};
 
 /* ---------------------------------------------------- streaming JSON packer (dev_jsmn.cuh) */
 enum { JM_UNDEFINED = 0, JM_OBJECT = 1, JM_ARRAY = 2, JM_STRING = 4, JM_PRIMITIVE = 8 };     /* jsmntype_t, lib/jsmn/jsmn.h */

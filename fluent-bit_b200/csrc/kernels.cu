@@ -511,15 +511,22 @@ __global__ void __launch_bounds__(BK_REC_BLOCK) k_rtag_emit(const __grid_constan
 }
 
 /* log_to_metrics, gauge / histogram: the records the evaluation listed because their value text converts nothing
- * (dev_chain.cuh: l2m_fixup_record).  A handful per call at most; entries [done, listed) are new since the last launch. */
-__global__ void __launch_bounds__(256) k_l2m_fixup(const __grid_constant__ k_chain_params p)
+ * (dev_chain.cuh: l2m_fixup_record).  A handful per call at most; entries [done, listed) are new since the last launch.
+ * ONE entry per warp, worked on by lane 0 while the other lanes have left: the interpreter's reconvergence points (full-mask
+ * __syncwarp) pair up only among lanes that are in step or gone, and the entries of a warp would neither start together nor
+ * walk back equally far (a launch that gave every lane an entry and met at a block barrier afterwards hung on the device). */
+__global__ void __launch_bounds__(1024) k_l2m_fixup(const __grid_constant__ k_chain_params p)
 {
+    if (threadIdx.x & 31u) return;
     const unsigned long long n = p.env.l2m.pending_n[0], d = p.env.l2m.pending_n[1];
     const unsigned long long lim = n < p.env.l2m.pending_cap ? n : p.env.l2m.pending_cap;
-    for (unsigned long long t = d + threadIdx.x; t < lim; t += blockDim.x)
+    for (unsigned long long t = d + (threadIdx.x >> 5); t < lim; t += blockDim.x >> 5)
         l2m_fixup_record(&p.env, p.env.l2m.pending[t], p.off, p.len, p.kind);
-    __syncthreads();
-    if (threadIdx.x == 0) p.env.l2m.pending_n[1] = n;
+}
+/* ... and, behind it in the stream, what has been observed so far */
+__global__ void k_l2m_fixup_done(const __grid_constant__ k_chain_params p)
+{
+    p.env.l2m.pending_n[1] = p.env.l2m.pending_n[0];
 }
 
 /* per-block sums of the record sizes */
@@ -871,6 +878,11 @@ extern "C" {
 const char *bk_name(void) { return "cuda-sm_100a"; }
 const char *bk_last_error(void) { return g_err; }
 uint64_t bk_launch_count(void) { return g_launches.load(); }
+/* for the other translation units of the back end (kernels_ml.cu): the launch counter and the calling thread's error text */
+void bk_note_launches(unsigned n) { g_launches += n; }
+void bk_note_error(const char *what, const char *detail) { snprintf(g_err, sizeof(g_err), "%s: %s", what, detail); }
+void bk_ev_begin(bk_q *q, int k) { ev_begin_on(q, k, q->stream); }
+void bk_ev_end(bk_q *q, int k) { ev_end_on(q, k, q->stream); }
 
 int bk_device_count(void)
 {
@@ -1449,7 +1461,7 @@ int bk_chain_eval(bk_q *q, const struct bk_chain_args *a, uint32_t r0, uint32_t 
     if (p.env.l2m.hash) {
         k_chain_skipped<<<(r1 - r0 + BK_REC_BLOCK - 1) / BK_REC_BLOCK, BK_REC_BLOCK, 0, q->stream>>>(p);
         g_launches += 1;
-        if (p.env.l2m.pending) { k_l2m_fixup<<<1, 256, 0, q->stream>>>(p); g_launches += 1; }
+        if (p.env.l2m.pending) { k_l2m_fixup<<<1, 1024, 0, q->stream>>>(p); k_l2m_fixup_done<<<1, 1, 0, q->stream>>>(p); g_launches += 2; }
     }
     ev_end_on(q, 1, q->stream);
     g_launches += 1;
@@ -1683,7 +1695,7 @@ int bk_small_run(bk_q *q, const struct bk_chain_args *a, const void *h_in, uint8
     if (p.defer_list) { k_chain_eval_deferred<<<148, BK_REC_BLOCK, 0, st>>>(p); g_launches += 1; }
     if (p.env.l2m.hash) {
         k_chain_skipped<<<nb_cap, BK_REC_BLOCK, 0, st>>>(p); g_launches += 1;
-        if (p.env.l2m.pending) { k_l2m_fixup<<<1, 256, 0, st>>>(p); g_launches += 1; }
+        if (p.env.l2m.pending) { k_l2m_fixup<<<1, 1024, 0, st>>>(p); k_l2m_fixup_done<<<1, 1, 0, st>>>(p); g_launches += 2; }
     }
     ev_end_on(q, 1, st);
     /* sizes, survivor lists, emission under the speculated verdicts */

@@ -147,6 +147,10 @@ struct flbgpu_filter {
     size_t rt_n;
     void *rt_stream;         /* the entries as the device left them: the tags of rt_groups point in here */
     void **rt_bufs;          /* one record buffer per group */
+    /* multiline: what the parser instance keeps from chunk to chunk (everything pending is flushed at the end of a call):
+     * the rule the group is in (struct flb_ml_stream_group: rule_to_state) and its mp_time */
+    uint32_t ml_state;
+    int64_t ml_time[2];
 };
 
 struct flbgpu_ctx {
@@ -154,7 +158,10 @@ struct flbgpu_ctx {
     struct flbgpu_parser *parsers;
     bk_q *q0;                /* queue of the context-level helpers (flbgpu_dev_*, flbgpu_stream) */
     bk_q *last_q;            /* queue of the most recent chain call: flbgpu_kernel_ms() reads its events */
+    struct flbgpu_ml_parser *ml_parsers;      /* multiline parser definitions (config->multiline_parsers) */
+    size_t ml_limit; int ml_limit_set;        /* config->multiline_buffer_limit */
 };
+static void ml_parsers_free(flbgpu_ctx *ctx);
 
 struct flbgpu_chain {
     flbgpu_ctx *ctx;
@@ -173,6 +180,9 @@ struct flbgpu_chain {
     int defer_ok;                             /* no log_to_metrics filter in front of a parser filter: records may be re-evaluated from scratch */
     uint8_t *d_scr; size_t cap_scr;
     int l2m_index;                            /* filter index of the log_to_metrics filter, or -1 */
+    int ml_index;                             /* filter index of the multiline filter, or -1 (it runs on its own: ml_run) */
+    uint32_t ml_cfg_off;
+    uint8_t *d_mlw; size_t cap_mlw;           /* multiline: work arrays of a call */
     int rtag_index;                           /* filter index of the rewrite_tag filter, or -1; -2 = several: the chain runs filter by filter */
     uint32_t *d_esize;                        /* rewrite_tag: bytes of each record's entry in the re-tagged stream */
     uint64_t *d_ebsum, *h_ebsum; size_t cap_ebsum;   /* ... and the scan over them */
@@ -220,6 +230,7 @@ void flbgpu_shutdown(flbgpu_ctx *ctx)
 {
     if (!ctx) return;
     while (ctx->parsers) flbgpu_parser_destroy(ctx->parsers);
+    ml_parsers_free(ctx);
     bk_q_free(ctx->q0);
     free(ctx);
 }
@@ -579,6 +590,7 @@ static int plugin_kind(const char *name)
     if (!strcasecmp(name, "record_modifier")) return FLBGPU_F_RECORD_MODIFIER;
     if (!strcasecmp(name, "log_to_metrics")) return FLBGPU_F_LOG_TO_METRICS;
     if (!strcasecmp(name, "rewrite_tag")) return FLBGPU_F_REWRITE_TAG;
+    if (!strcasecmp(name, "multiline")) return FLBGPU_F_MULTILINE;
     return 0;
 }
 
@@ -1356,6 +1368,7 @@ static uint32_t emit_rtag_filter(flbgpu_filter *f, struct blob *b)
     return blob_add(b, &cf, sizeof(cf), 8);
 }
 
+static uint32_t emit_ml_filter(flbgpu_filter *f, struct blob *b);
 static uint32_t emit_filter(flbgpu_filter *f, struct blob *b, uint32_t *cap_need)
 {
     switch (f->kind) {
@@ -1365,6 +1378,7 @@ static uint32_t emit_filter(flbgpu_filter *f, struct blob *b, uint32_t *cap_need
     case FLBGPU_F_RECORD_MODIFIER: return emit_recmod_filter(f, b);
     case FLBGPU_F_LOG_TO_METRICS: return emit_l2m_filter(f, b);
     case FLBGPU_F_REWRITE_TAG: return emit_rtag_filter(f, b);
+    case FLBGPU_F_MULTILINE: return emit_ml_filter(f, b);
     }
     return 0;
 }
@@ -1379,7 +1393,8 @@ static int single_valued_set_twice(flbgpu_filter *f)
                                   "set", "add", "remove", "remove_wildcard", "remove_regex", "move_to_start", "move_to_end", "rename",
                                   "hard_rename", "copy", "hard_copy", "condition",            /* modify */
                                   "add_label", "label_field", "bucket",                       /* log_to_metrics */
-                                  "rule" };                                                   /* rewrite_tag */
+                                  "rule",                                                     /* rewrite_tag */
+                                  "multiline.parser" };                                       /* multiline */
     struct kv *p, *q;
     for (p = f->props; p; p = p->next) {
         size_t m;
@@ -1451,6 +1466,8 @@ int flbgpu_chain_init(flbgpu_chain *c)
         if (c->l2m_index >= 0) { set_err("only one log_to_metrics filter per fused chain%s%s", NULL, NULL); return -1; }
         c->l2m_index = (int) i;
     }
+    c->ml_index = -1;
+    for (i = 0; i < (uint32_t) c->nf; i++) if (c->f[i]->kind == FLBGPU_F_MULTILINE) { c->ml_index = (int) i; c->ml_cfg_off = cf[i].cfg_off; }
     c->rtag_index = -1;
     for (i = 0; i < (uint32_t) c->nf; i++) {
         if (c->f[i]->kind != FLBGPU_F_REWRITE_TAG) continue;
@@ -1517,7 +1534,7 @@ void flbgpu_chain_destroy(flbgpu_chain *c)
     if (!c) return;
     bk_free(c->q, c->d_blob); bk_free(c->q, c->d_in); bk_free(c->q, c->d_out); bk_free(c->q, c->d_tile); bk_free(c->q, c->d_off);
     bk_free(c->q, c->d_len); bk_free(c->q, c->d_size); bk_free(c->q, c->d_kind); bk_free(c->q, c->d_bsum); bk_free(c->q, c->d_cap);
-    bk_free(c->q, c->d_flags); bk_free(c->q, c->d_scr); free(c->h_bsum);
+    bk_free(c->q, c->d_flags); bk_free(c->q, c->d_scr); free(c->h_bsum); bk_free(c->q, c->d_mlw);
     bk_free(c->q, c->d_prep); free(c->h_prep);
     bk_free(c->q, c->d_esize); bk_free(c->q, c->d_ebsum); free(c->h_ebsum);
     bk_free(c->q, c->l2m.hash); bk_free(c->q, c->l2m.chash); bk_free(c->q, c->l2m.first); bk_free(c->q, c->l2m.cnt); bk_free(c->q, c->l2m.sum); bk_free(c->q, c->l2m.bkt); bk_free(c->q, c->l2m.str); bk_free(c->q, c->l2m.pending); bk_free(c->q, c->l2m.pending_n);
@@ -1635,7 +1652,8 @@ static int refused(flbgpu_chain *c, uint32_t bits)
     snprintf(g_rt_err, sizeof(g_rt_err), "device interpreter refused some records (error bits 0x%x: "
              "1=too many keys 2=regex stack 4=regex budget 8=float text not restated (hex float, nan(payload)) 32=logfmt escapes "
              "64=log_to_metrics value/label outside the device path 128=a pattern with POSIX brackets, \\b or case-insensitivity met a non-ASCII value "
-             "256=a parsed value nested to msgpack-c's unpack limit inside a fused chain)", bits);
+             "256=a parsed value nested to msgpack-c's unpack limit inside a fused chain "
+             "1024=a multiline message reached the buffer limit 2048=multiline: an event with non-empty metadata)", bits);
     return 1;
 }
 
@@ -1826,6 +1844,8 @@ static int stops_at_wide_array(bk_q *q, const uint8_t *h_in, const uint8_t *d_in
             snprintf(g_rt_err, sizeof(g_rt_err), "event framed with an array16/array32 header at byte %zu: not decoded on the GPU path", off); \
             fail_stmt; \
         } } while (0)
+
+#include "runtime_ml.h"
 
 /* flb_router_match() (src/flb_router.c:37-128): Match_Regex first -- onig_match() at the start of the tag with a match of
  * positive length -- then the Match pattern, where '*' stands for any run of characters. */
@@ -2424,7 +2444,9 @@ int flbgpu_chain_do_device(flbgpu_chain *c, const void *d_data, size_t bytes, vo
         c->active = 0;
         for (k = 0; k < c->nf; k++) if (!c->f[k]->inactive) c->active |= 1u << k;
     }
-    r = chain_run(c, NULL, d_data, bytes, d_out, out_cap, NULL, out_size);
+    if (c->ml_index >= 0 && c->nf > 1) { set_err("a multiline filter inside a longer chain runs filter by filter: host buffers only%s%s", NULL, NULL); r = -1; }
+    else if (c->ml_index >= 0) r = ml_run(c, NULL, d_data, bytes, d_out, out_cap, NULL, out_size);
+    else r = chain_run(c, NULL, d_data, bytes, d_out, out_cap, NULL, out_size);
     if (r >= 0 && bk_sync(c->q)) r = -1;
     pthread_mutex_unlock(&c->lock);
     return r;
@@ -2460,6 +2482,14 @@ static int chain_do_one_by_one(flbgpu_chain *c, const void *data, size_t bytes, 
 static int chain_do_locked(flbgpu_chain *c, const void *data, size_t bytes, const char *tag, int tag_len, void **out_buf, size_t *out_size)
 {
     if (c->rtag_index == -2) return chain_do_one_by_one(c, data, bytes, tag, tag_len, out_buf, out_size);     /* one re-tagged stream per chain */
+    if (c->ml_index >= 0) {
+        /* a multiline filter makes new records out of runs of records: it runs on its own, the filters around it on what it made */
+        int r;
+        if (c->nf > 1) return chain_do_one_by_one(c, data, bytes, tag, tag_len, out_buf, out_size);
+        r = ml_run(c, data, NULL, bytes, NULL, 0, out_buf, out_size);
+        bk_upload_end(c->q);
+        return r;
+    }
     if (c->rtag_index >= 0) {                        /* the templates of a rewrite_tag filter may name the tag of the call */
         c->tag_len = (uint32_t) (tag && tag_len > 0 ? tag_len : 0);
         if (bk_tag_upload(c->q, tag, c->tag_len, &c->d_tag)) { set_err("%s%s", bk_last_error(), NULL); return -1; }

@@ -118,9 +118,28 @@ int  flbgpu_pack_json_state(flbgpu_ctx *ctx, const char *js, size_t len, char **
 int  flbgpu_pack_json_state_batch(flbgpu_ctx *ctx, int n, const char *const *js, const size_t *len,
                                   char **buffers, int *sizes, struct flbgpu_pack_state *states, int *rets);
 
+/* ---- multiline parser definitions ----------------------------------------------------------------------------
+ * What a [MULTILINE_PARSER] section becomes (src/flb_parser.c:815-935): flb_ml_parser_create()
+ * (src/multiline/flb_ml_parser.c:199-230; type = "regex" | "endswith" | "equal" | "eq", flb_ml_type_lookup()),
+ * one flb_ml_rule_create() per `rule "from_state[, from_state]" "/regex/" "to_state"` (src/multiline/flb_ml_rule.c:48-112;
+ * the first rule must name start_state) and flb_ml_parser_init() (every to_state must be some rule's from_state).
+ * The built-in rule-based parsers java, go, python and ruby exist without being created.  Not built on the device:
+ * key_group, a sub-parser (`parser`), and therefore the built-in docker and cri parsers. */
+typedef struct flbgpu_ml_parser flbgpu_ml_parser;
+flbgpu_ml_parser *flbgpu_ml_parser_create(flbgpu_ctx *ctx, const char *name, const char *type, const char *match_string, int negate,
+                                          int flush_ms, const char *key_content, const char *key_group, const char *key_pattern,
+                                          const char *parser_name);
+int flbgpu_ml_parser_rule(flbgpu_ml_parser *mlp, const char *from_states, const char *regex, const char *to_state);
+int flbgpu_ml_parser_init(flbgpu_ml_parser *mlp);
+/* config->multiline_buffer_limit (FLB_ML_BUFFER_LIMIT_DEFAULT: 2 MiB), in bytes; read when a multiline filter is initialised.
+ * A message that reaches it fails the call (FLBGPU_E_MLLIMIT): the reference truncates it and marks the record. */
+int flbgpu_ml_set_buffer_limit(flbgpu_ctx *ctx, size_t bytes);
+
 /* ---- filters ---------------------------------------------------------- */
 /* flb_filter_new(), src/flb_filter.c:426: plugin = "parser" | "grep" | "modify" |
- * "record_modifier" | "log_to_metrics" | "rewrite_tag" (the names of the reference's filter_*_plugin structs). */
+ * "record_modifier" | "log_to_metrics" | "rewrite_tag" | "multiline" (the names of the reference's filter_*_plugin structs).
+ * "multiline" is plugins/filter_multiline/ml.c in parser mode with `buffer off` (the chunk's lines are concatenated inside
+ * the call, cb_ml_filter :833-892); `multiline.parser` names ONE multiline parser, `multiline.key_content` the key. */
 flbgpu_filter *flbgpu_filter_new(flbgpu_ctx *ctx, const char *plugin);
 /* flb_filter_set_property(), src/flb_filter.c:325: properties keep config order,
  * keys are case-insensitive; "match"/"alias"/"log_level" are accepted and ignored. */

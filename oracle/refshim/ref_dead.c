@@ -5,8 +5,6 @@
 #include <stdio.h>
 #include <stdlib.h>
 #define DEAD(name) void *name() { fprintf(stderr, "oracle/_ref: unexpected call to " #name "\n"); abort(); return NULL; }
-DEAD(flb_ml_rule_create) DEAD(flb_ml_type_lookup) DEAD(flb_ml_parser_init) DEAD(flb_ml_parser_destroy)
-DEAD(flb_ml_parser_create) DEAD(flb_ml_exit)
 DEAD(flb_cf_section_property_get_string) DEAD(flb_cf_destroy) DEAD(flb_cf_create_from_file)
 DEAD(flb_file_read) DEAD(flb_condition_evaluate)
 

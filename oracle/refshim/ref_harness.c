@@ -29,6 +29,9 @@
 #include <cmetrics/cmt_encode_text.h>
 #include <cmetrics/cmt_encode_msgpack.h>
 #include "filter_log_to_metrics/log_to_metrics.h"
+#include <fluent-bit/multiline/flb_ml.h>
+#include <fluent-bit/multiline/flb_ml_parser.h>
+#include <fluent-bit/multiline/flb_ml_rule.h>
 
 extern struct flb_filter_plugin filter_parser_plugin;
 extern struct flb_filter_plugin filter_grep_plugin;
@@ -36,11 +39,12 @@ extern struct flb_filter_plugin filter_modify_plugin;
 extern struct flb_filter_plugin filter_record_modifier_plugin;
 extern struct flb_filter_plugin filter_log_to_metrics_plugin;
 extern struct flb_filter_plugin filter_rewrite_tag_plugin;
+extern struct flb_filter_plugin filter_multiline_plugin;
 
 struct flbref_cfg {
     struct flb_config *config;
     struct flb_input_instance in;
-    struct flb_filter_plugin plugins[6];
+    struct flb_filter_plugin plugins[7];
 };
 
 void *flbref_config_create(void)
@@ -63,7 +67,13 @@ void *flbref_config_create(void)
     c->plugins[3] = filter_record_modifier_plugin;
     c->plugins[4] = filter_log_to_metrics_plugin;
     c->plugins[5] = filter_rewrite_tag_plugin;
-    for (i = 0; i < 6; i++) {
+    c->plugins[6] = filter_multiline_plugin;
+    /* what flb_config_init() does for the multiline core (src/flb_config.c:424-455): the parser list, the buffer limit,
+     * the built-in multiline parsers */
+    mk_list_init(&config->multiline_parsers);
+    config->multiline_buffer_limit = flb_strdup(FLB_ML_BUFFER_LIMIT_DEFAULT_STR);
+    flb_ml_parser_builtin_create(config);
+    for (i = 0; i < 7; i++) {
         mk_list_add(&c->plugins[i]._head, &config->filter_plugins);
     }
     mk_list_init(&c->in.properties);
@@ -416,6 +426,31 @@ int flbref_l2m_cmt_msgpack(void *filter, void **out, size_t *out_size)
 }
 
 void flbref_cfree(void *p) { free(p); }
+
+/* ---- multiline parser definitions: what a [MULTILINE_PARSER] section becomes (src/flb_parser.c:815-935):
+ * flb_ml_parser_create(), one flb_ml_rule_create() per `rule`, flb_ml_parser_init() ---- */
+void *flbref_ml_parser_create(void *cfg, const char *name, const char *type, const char *match_string, int negate,
+                              int flush_ms, const char *key_content, const char *key_group, const char *key_pattern,
+                              const char *parser_name)
+{
+    struct flbref_cfg *c = cfg;
+    struct flb_parser *pctx = parser_name ? flb_parser_get(parser_name, c->config) : NULL;
+    int t = flb_ml_type_lookup((char *) type);
+    if (t == -1) return NULL;
+    return flb_ml_parser_create(c->config, (char *) name, t, (char *) match_string, negate, flush_ms, (char *) key_content,
+                                (char *) key_group, (char *) key_pattern, pctx, (char *) parser_name);
+}
+int flbref_ml_parser_rule(void *mlp, const char *from_states, const char *regex, const char *to_state)
+{
+    return flb_ml_rule_create(mlp, (char *) from_states, (char *) regex, (char *) to_state, NULL);
+}
+int flbref_ml_parser_init(void *mlp) { return flb_ml_parser_init(mlp); }
+void flbref_set_ml_buffer_limit(void *cfg, const char *limit)
+{
+    struct flbref_cfg *c = cfg;
+    flb_free(c->config->multiline_buffer_limit);
+    c->config->multiline_buffer_limit = flb_strdup(limit);
+}
 
 /* ---- filter_rewrite_tag's emitter: in_emitter_add_record() (plugins/in_emitter/emitter.c:124) is the one function of the
  * emitter input the filter calls per re-tagged record.  Here it appends (tag, record bytes) to a log the tests read:

@@ -1,7 +1,8 @@
-/* shim/filter_gpu.c -- the reference-side binding of libflbgpu.so: five Fluent Bit filter plugins
+/* shim/filter_gpu.c -- the reference-side binding of libflbgpu.so: seven Fluent Bit filter plugins
  *
  *     filter_gpu_parser_plugin   filter_gpu_grep_plugin   filter_gpu_modify_plugin
  *     filter_gpu_record_modifier_plugin   filter_gpu_log_to_metrics_plugin
+ *     filter_gpu_rewrite_tag_plugin   filter_gpu_multiline_plugin
  *
  * written against Fluent Bit's own headers (struct flb_filter_plugin,
  * include/fluent-bit/flb_filter.h:57-81) and registered exactly like a dynamic plugin: the engine
@@ -321,7 +322,7 @@ char *filter_gpu_l2m_text(struct flb_filter_instance *ins)
 }
 
 extern struct flb_filter_plugin filter_parser_plugin, filter_grep_plugin, filter_modify_plugin,
-                                filter_record_modifier_plugin, filter_log_to_metrics_plugin;
+                                filter_record_modifier_plugin, filter_log_to_metrics_plugin, filter_multiline_plugin;
 
 #define GPU_PLUGIN(sym, short_name, gpu_name, stock)                                                        \
     static int cb_init_##sym(struct flb_filter_instance *ins, struct flb_config *config, void *data)         \
@@ -335,6 +336,13 @@ GPU_PLUGIN(grep, "grep", "gpu_grep", filter_grep_plugin)
 GPU_PLUGIN(modify, "modify", "gpu_modify", filter_modify_plugin)
 GPU_PLUGIN(record_modifier, "record_modifier", "gpu_record_modifier", filter_record_modifier_plugin)
 GPU_PLUGIN(log_to_metrics, "log_to_metrics", "gpu_log_to_metrics", filter_log_to_metrics_plugin)
+/* gpu_multiline: plugins/filter_multiline/ml.c in parser mode with `buffer off` (the one mode whose result is the call's own
+ * return value: cb_ml_filter :833-892).  The built-in rule-based multiline parsers (java, go, python, ruby) exist on the
+ * device side by name.  A parser of a [MULTILINE_PARSER] section is registered by whoever embeds the library with
+ * flbgpu_ml_parser_create() / _rule() / _init() -- struct flb_ml_rule keeps the compiled regex, not its text
+ * (include/fluent-bit/multiline/flb_ml.h:71-94), so config->multiline_parsers cannot be mirrored from here the way
+ * config->parsers is. */
+GPU_PLUGIN(multiline, "multiline", "gpu_multiline", filter_multiline_plugin)
 
 /* static initialisers cannot take another object's member: the stock config maps and event types are copied when the
  * library is loaded, before anyone looks the structs up */
@@ -346,6 +354,8 @@ __attribute__((constructor)) static void gpu_plugins_adopt_config_maps(void)
     filter_gpu_record_modifier_plugin.config_map = filter_record_modifier_plugin.config_map;
     filter_gpu_log_to_metrics_plugin.config_map = filter_log_to_metrics_plugin.config_map;
     filter_gpu_rewrite_tag_plugin.config_map = filter_rewrite_tag_plugin.config_map;
+    filter_gpu_multiline_plugin.config_map = filter_multiline_plugin.config_map;
+    filter_gpu_multiline_plugin.event_type = filter_multiline_plugin.event_type;
     filter_gpu_rewrite_tag_plugin.event_type = filter_rewrite_tag_plugin.event_type;
     filter_gpu_parser_plugin.event_type = filter_parser_plugin.event_type;
     filter_gpu_grep_plugin.event_type = filter_grep_plugin.event_type;

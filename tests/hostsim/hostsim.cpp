@@ -72,6 +72,7 @@ int sim_rx_search(void *h, const char *s, int len, int *caps, int stack_words, u
 #include <stdio.h>
 #include "../../fluent-bit_b200/csrc/flbgpu_internal.h"
 #include "../../fluent-bit_b200/csrc/dev_chain.cuh"
+#include "../../fluent-bit_b200/csrc/dev_ml.cuh"
 
 static thread_local char hs_err[256];
 static uint64_t hs_launches;
@@ -488,5 +489,40 @@ int bk_jsmn_emit(bk_q *, const struct bk_jsmn_args *a)
     return 0;
 }
 int bk_small_fetch(bk_q *, void *h_dst, const uint8_t *d_out, size_t n) { memcpy(h_dst, d_out, n); return 0; }
+
+/* filter_multiline: the launches of kernels_ml.cu as loops over the same per-thread functions (dev_ml.cuh) */
+int bk_ml_plan(bk_q *, const struct ml_env *e)
+{
+    uint32_t i;
+    for (i = 0; i < e->n_rec; i++) ml_feat_record(e, i);
+    for (i = 0; i < e->nt1; i++) ml_up1(e, i);
+    for (i = 0; i < e->nt2; i++) ml_up2(e, i);
+    ml_top(e);
+    for (i = 0; i < e->nt2; i++) ml_down2(e, i);
+    for (i = 0; i < e->nt1; i++) ml_apply(e, i);
+    for (i = 0; i < e->nt2; i++) ml_cnt_up2(e, i);
+    ml_cnt_top(e);
+    for (i = 0; i < e->nt2; i++) ml_cnt_down2(e, i);
+    for (i = 0; i < e->nt1; i++) ml_fill(e, i);
+    hs_launches += 10;
+    return 0;
+}
+int bk_ml_sizes(bk_q *, const struct ml_env *e, uint32_t n_ev)
+{
+    for (uint32_t j = 0; j < n_ev; j++) e->ev_size[j] = ml_event(e, j, 0);
+    hs_launches += 1;
+    return 0;
+}
+int bk_ml_emit(bk_q *, const struct ml_env *e, uint32_t n_ev, const uint64_t *d_bsum, uint8_t *d_out)
+{
+    uint64_t at = 0;
+    for (uint32_t j = 0; j < n_ev; j++) {
+        if (j % BK_REC_BLOCK == 0) at = d_bsum[j / BK_REC_BLOCK];
+        if (e->ev_size[j]) ml_event(e, j, d_out + at);
+        at += e->ev_size[j];
+    }
+    hs_launches += 1;
+    return 0;
+}
 
 }

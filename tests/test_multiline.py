@@ -1,0 +1,265 @@
+"""f2: filter_multiline in parser mode with `buffer off` (plugins/filter_multiline/ml.c:833-892, src/multiline/flb_ml.c,
+flb_ml_rule.c) against the reference's own plugin, chunk after chunk on one filter instance (the rule a group is in and its
+time survive from call to call)."""
+import random
+
+import pytest
+
+import util
+
+pkg = util.pkg
+S = util.mp_str
+
+EXC = [("start_state", r"/(Dec \d+ \d+\:\d+\:\d+)(.*)/", "cont"), ("cont", r"/^\s+at.*/", "cont")]        # conf/parsers_multiline.conf
+# a rule whose to_state is a start state flushes right after it matched (try_flushing_buffer); a start rule that also
+# continues; an empty-matching start rule; rules sharing a from_state (first in list order wins)
+ODD = [("start_state, more", r"/^A/", "more"), ("more", r"/^b/", "more"), ("more", r"/^c/", "start_state"), ("more", r"/^b2/", "more")]
+EMPTY = [("start_state", r"/^(S.*)?$/", "c1"), ("c1", r"/^$/", "c1"), ("c1", r"/^ +\S/", "c1")]
+RULESETS = {"exc": EXC, "odd": ODD, "empty": EMPTY}
+
+VOCAB = {
+    "exc": [b"Dec 14 06:41:08 Exception in thread main", b"Dec 15 01:01:01 again\n", b"    at foo(Foo.java:1)", b"  at x\n", b"\tat tab",
+            b"plain line", b"", b"    at orphan", b" ", b"Dec 1 1:1:1"],
+    "odd": [b"A start", b"b cont", b"c close", b"b2 never", b"x", b"", b"A", b"b\n", b"cA"],
+    "empty": [b"S one", b"", b"  indented", b"S", b"other", b" x\n", b"\n"],
+}
+
+
+def make_chunk(rng, vocab, n, t0, key=b"log"):
+    evs = []
+    for i in range(n):
+        r = rng.random()
+        line = rng.choice(vocab)
+        if r < 0.04:
+            fields = [(b"other", S(line))]                                   # no key_content at all
+        elif r < 0.08:
+            fields = [(key, bytes([rng.randint(0, 100)]))]                   # key_content is not a string
+        elif r < 0.12:
+            fields = [(key, bytes([7])), (key, S(line)), (b"z", b"\xc3")]    # the first STR key WITH a STR value counts
+        elif r < 0.16:
+            fields = [(b"a", S(b"x" * rng.randint(0, 40))), (key, S(line)), (key, S(b"second")), (b"n", b"\xcd\x01\x00")]   # duplicate key
+        elif r < 0.20:
+            fields = [(b"stream", S(b"stdout")), (key, b"\xd9" + bytes([len(line)]) + line), (b"m", b"\x81\xa1k\xcc\x05")]   # str8 spelling, nested map
+        else:
+            fields = [(key, S(line))]
+        if rng.random() < 0.03:
+            evs.append(b"\x92\x92\xd7\x00\xff\xff\xff\xff\x00\x00\x00\x00\x80\x80")     # a group marker: the decoder steps over it
+        if rng.random() < 0.03:
+            evs.append(b"\x92\xce" + (t0 + i).to_bytes(4, "big") + util.mp_map_hdr(1) + S(key) + S(line))     # legacy [ts, body]
+        else:
+            evs.append(util.event(t0 + i, (i * 7) % 1000, fields))
+    return b"".join(evs)
+
+
+def diff(lib, rules, props, chunks, name="p", **kw):
+    ref = util.Ref()
+    ctx = pkg.Context(0, lib=lib)
+    if rules is not None:
+        ref.ml_parser(name, rules=rules, **kw)
+        ctx.ml_parser(name, rules=rules, **kw)
+    rf = ref.filter("multiline", props)
+    ch = ctx.chain([ctx.filter("multiline", props)])
+    for i, c in enumerate(chunks):
+        want, got = ref.filter_cb(rf, c), ch.do(c)
+        if want != got:
+            w = [want[1][o:o + l] for o, l in util.split_records(want[1] or b"")]
+            g = [got[1][o:o + l] for o, l in util.split_records(got[1] or b"")]
+            k = next((k for k in range(max(len(w), len(g))) if (w[k:k + 1] != g[k:k + 1])), -1)
+            raise AssertionError("chunk %d: ret %s / %s, %d / %d events, first difference at event %d:\n want %r\n got  %r" %
+                                 (i, want[0], got[0], len(w), len(g), k, w[k:k + 1], g[k:k + 1]))
+
+
+def _regex_rulesets(lib, rounds, n):
+    rng = random.Random(11)
+    for name, rules in RULESETS.items():
+        for key in ("log", "message"):
+            props = [("multiline.parser", name), ("multiline.key_content", key), ("buffer", "off")]
+            for _ in range(rounds):
+                chunks = [make_chunk(rng, VOCAB[name], rng.choice([1, 2, 7, n]), 1700000000 + 1000 * k, key.encode()) for k in range(4)]
+                diff(lib, rules, props, chunks, name=name)
+
+
+def _match_types(lib):
+    rng = random.Random(12)
+    vocab = [b"one, ", b"two, ", b"three\n", b"\n", b"", b"end", b"x end", b"nd", b"three\n\n"]
+    for typ, ms in (("endswith", "\n"), ("endswith", "end"), ("equal", "end"), ("eq", "\n")):
+        for neg in (False, True):
+            props = [("multiline.parser", "m"), ("multiline.key_content", "log"), ("buffer", "off")]
+            chunks = [make_chunk(rng, vocab, 60, 1700000000 + 1000 * k) for k in range(3)]
+            diff(lib, [], props, chunks, name="m", type=typ, match_string=ms, negate=neg)
+
+
+JAVA = b"""2023-01-01 12:00:00 ERROR request failed
+java.lang.RuntimeException: outer problem
+\tat com.example.App.run(App.java:10)
+\tat com.example.App.main(App.java:5)
+Caused by: java.lang.IllegalStateException: inner
+\tat com.example.Svc.call(Svc.java:99)
+\t... 2 more
+2023-01-01 12:00:01 INFO next request
+Exception in thread "main" java.lang.Error: boom
+    at a.b.C.d(C.java:1)
+ nested exception is:
+org.x.Y: why
+    at q.r(S.java:2)
+
+--- End of stack trace from previous location where exception was thrown ---
+Suppressed: z.Q: s
+    at eval at foo
+done""".split(b"\n")
+GO = b"""starting
+panic: runtime error: index out of range
+
+goroutine 1 [running]:
+main.main()
+\t/tmp/x.go:8 +0x1d
+created by main.start
+\t/tmp/x.go:3 +0x11
+exit status 2
+2023/01/01 http: panic serving 10.0.0.1:5: oops
+goroutine 7 [running]:
+net/http.(*conn).serve.func1(0xc0)
+\t/usr/lib/go/src/net/http/server.go:1 +0x1
+[signal SIGSEGV: segmentation violation]
+ok""".split(b"\n")
+PY = b"""INFO start
+Traceback (most recent call last):
+  File "/app/main.py", line 3, in <module>
+    run()
+  File "/app/main.py", line 1, in run
+    raise ValueError("bad")
+ValueError: bad
+INFO after
+Traceback (most recent call last):
+  File "x.py", line 1
+mod.sub.Err: nope
+tail""".split(b"\n")
+RUBY = b"""I, [2023] INFO -- : ok
+/app/lib/a.rb:12:in `foo': undefined method (NoMethodError)
+\tfrom /app/lib/b.rb:3:in `bar'
+\tfrom /app/bin/run:1:in `<main>'
+next line
+x.rb:1:in `y'
+  from z.rb:2:in `w'""".split(b"\n")
+
+
+def _builtins(lib):
+    rng = random.Random(13)
+    for name, text in (("java", JAVA), ("go", GO), ("python", PY), ("ruby", RUBY)):
+        props = [("multiline.parser", name), ("multiline.key_content", "log"), ("buffer", "off")]
+        lines = list(text) * 3
+        cut = rng.randint(3, len(lines) - 3)
+        diff(lib, None, props, [util.chunk_from_lines(lines[:cut]), util.chunk_from_lines(lines[cut:], t0=1700001000),
+                                make_chunk(rng, list(text), 50, 1700002000)])
+        # no multiline.key_content and none in the parser: every record passes through on its own, re-encoded
+        diff(lib, None, [("multiline.parser", name), ("buffer", "off")], [util.chunk_from_lines(lines[:20])])
+
+
+def _refusals(lib):
+    ctx = pkg.Context(0, lib=lib)
+    ctx.ml_parser("exc", rules=EXC)
+    for bad in ([("multiline.parser", "exc"), ("multiline.key_content", "log")],                         # buffered mode (the default)
+                [("multiline.parser", "exc, java"), ("buffer", "off")],                                  # several parsers
+                [("multiline.parser", "docker"), ("buffer", "off")], [("multiline.parser", "cri"), ("buffer", "off")],
+                [("multiline.parser", "nope"), ("buffer", "off")], [("buffer", "off")],
+                [("multiline.parser", "exc"), ("buffer", "off"), ("mode", "partial_message")],
+                [("multiline.parser", "exc"), ("buffer", "off"), ("bogus", "1")]):
+        with pytest.raises(pkg.FlbGpuError):
+            ctx.filter("multiline", bad)
+    with pytest.raises(pkg.FlbGpuError):
+        ctx.ml_parser("r1", rules=[("cont", "/x/", "cont")])                     # the first rule must name start_state
+    with pytest.raises(pkg.FlbGpuError):
+        ctx.ml_parser("r2", rules=[("start_state", "/x/", "nowhere")])           # to_state nobody comes from
+    with pytest.raises(RuntimeError):
+        util.Ref().ml_parser("r2", rules=[("start_state", "/x/", "nowhere")])
+    # loud, never approximated: non-empty metadata, a message at the buffer limit
+    f = ctx.filter("multiline", [("multiline.parser", "exc"), ("multiline.key_content", "log"), ("buffer", "off")])
+    ch = ctx.chain([f])
+    with pytest.raises(pkg.FlbGpuError):
+        ch.do(util.event(1700000000, 0, [(b"log", S(b"Dec 1 1:1:1 x"))], meta=b"\x81\xa1a\x01"))
+    ctx2 = pkg.Context(0, lib=lib)
+    ctx2.L.flbgpu_ml_set_buffer_limit(ctx2.h, 64)
+    ctx2.ml_parser("exc", rules=EXC)
+    ch2 = ctx2.chain([ctx2.filter("multiline", [("multiline.parser", "exc"), ("multiline.key_content", "log"), ("buffer", "off")])])
+    assert ch2.do(util.chunk_from_lines([b"Dec 1 1:1:1 x", b"  at " + b"y" * 20]))[0] == pkg.FILTER_MODIFIED
+    with pytest.raises(pkg.FlbGpuError):
+        ch2.do(util.chunk_from_lines([b"Dec 1 1:1:1 x", b"  at " + b"y" * 30, b"  at " + b"z" * 30]))
+
+
+def _in_a_chain(lib):
+    """multiline, then the filters behind it on what it made (the k8s shape of BASELINE configs[4])"""
+    lines = list(JAVA) * 4
+    ref = util.Ref()
+    ctx = pkg.Context(0, lib=lib)
+    chain = [("multiline", [("multiline.parser", "java"), ("multiline.key_content", "log"), ("buffer", "off")]),
+             ("grep", [("Regex", "log Exception")]),
+             ("modify", [("Add", "multiline yes")])]
+    fs = []
+    for p, props in chain:
+        ref.filter(p, props)
+        fs.append(ctx.filter(p, props))
+    ch = ctx.chain(fs)
+    for t0 in (1700000000, 1700005000):
+        c = util.chunk_from_lines(lines, t0=t0)
+        assert ch.do(c) == ref.chain_do(c)
+
+
+def _large(lib, n):
+    """many automaton blocks and super-blocks: states cross every boundary"""
+    rng = random.Random(14)
+    props = [("multiline.parser", "exc"), ("multiline.key_content", "log"), ("buffer", "off")]
+    diff(lib, EXC, props, [make_chunk(rng, VOCAB["exc"], n, 1700000000), make_chunk(rng, VOCAB["exc"][2:5], n // 4, 1700100000)], name="exc")
+
+
+def test_multiline_rulesets_hostsim(sim_lib, ref_available):
+    _regex_rulesets(sim_lib, 6, 300)
+
+
+def test_multiline_match_types_hostsim(sim_lib, ref_available):
+    _match_types(sim_lib)
+
+
+def test_multiline_builtins_hostsim(sim_lib, ref_available):
+    _builtins(sim_lib)
+
+
+def test_multiline_refusals_hostsim(sim_lib, ref_available):
+    _refusals(sim_lib)
+
+
+def test_multiline_in_a_chain_hostsim(sim_lib, ref_available):
+    _in_a_chain(sim_lib)
+
+
+def test_multiline_large_hostsim(sim_lib, ref_available):
+    _large(sim_lib, 40000)
+
+
+@pytest.mark.gpu
+def test_multiline_rulesets_gpu(gpu_lib, ref_available):
+    _regex_rulesets(gpu_lib, 2, 300)
+
+
+@pytest.mark.gpu
+def test_multiline_match_types_gpu(gpu_lib, ref_available):
+    _match_types(gpu_lib)
+
+
+@pytest.mark.gpu
+def test_multiline_builtins_gpu(gpu_lib, ref_available):
+    _builtins(gpu_lib)
+
+
+@pytest.mark.gpu
+def test_multiline_refusals_gpu(gpu_lib, ref_available):
+    _refusals(gpu_lib)
+
+
+@pytest.mark.gpu
+def test_multiline_in_a_chain_gpu(gpu_lib, ref_available):
+    _in_a_chain(gpu_lib)
+
+
+@pytest.mark.gpu
+def test_multiline_large_gpu(gpu_lib, ref_available):
+    _large(gpu_lib, 40000)

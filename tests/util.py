@@ -43,6 +43,11 @@ class Ref:
         L.flbref_l2m_cmt_text.restype = vp; L.flbref_l2m_cmt_text.argtypes = [vp]
         L.flbref_cfree.argtypes = [vp]
         L.flbref_pack_json_state.argtypes = [cp, sz, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.flbref_ml_parser_create.restype = vp
+        L.flbref_ml_parser_create.argtypes = [vp, cp, cp, cp, C.c_int, C.c_int, cp, cp, cp, cp]
+        L.flbref_ml_parser_rule.argtypes = [vp, cp, cp, cp]
+        L.flbref_ml_parser_init.argtypes = [vp]
+        L.flbref_set_ml_buffer_limit.argtypes = [vp, cp]
         self.L = L
         self.cfg = L.flbref_config_create()
 
@@ -50,7 +55,7 @@ class Ref:
         """register the five filter_gpu_*_plugin structs of the shim (oracle/_ref/flb-filter_gpu.so), bound to the
         given implementation of the C ABI (libflbgpu.so, or the CPU emulation in the not-gpu tests)"""
         os.environ["FLBGPU_SHIM_LIB"] = gpu_lib_path
-        for name in ("parser", "grep", "modify", "record_modifier", "log_to_metrics", "rewrite_tag"):
+        for name in ("parser", "grep", "modify", "record_modifier", "log_to_metrics", "rewrite_tag", "multiline"):
             if self.L.flbref_plugin_load(self.cfg, SHIM_SO.encode(), ("filter_gpu_%s_plugin" % name).encode()) != 0:
                 raise RuntimeError("cannot load the gpu_%s plugin from %s" % (name, SHIM_SO))
 
@@ -123,6 +128,21 @@ class Ref:
         if out.value:
             self.L.flbref_free(out)
         return r, data, (s.value, ns.value)
+
+    def ml_parser(self, name, type="regex", rules=(), match_string=None, negate=False, flush_ms=0, key_content=None,
+                  key_group=None, key_pattern=None, parser=None):
+        """a [MULTILINE_PARSER] section: flb_ml_parser_create() + one flb_ml_rule_create() per rule + flb_ml_parser_init()"""
+        b = self._b
+        m = self.L.flbref_ml_parser_create(self.cfg, b(name), b(type), b(match_string), int(negate), flush_ms, b(key_content),
+                                           b(key_group), b(key_pattern), b(parser))
+        if not m:
+            raise RuntimeError("reference rejected multiline parser " + name)
+        for frm, rx, to in rules:
+            if self.L.flbref_ml_parser_rule(m, b(frm), b(rx), b(to)) != 0:
+                raise RuntimeError("reference rejected rule %r of multiline parser %s" % ((frm, rx, to), name))
+        if type == "regex" and self.L.flbref_ml_parser_init(m) != 0:
+            raise RuntimeError("reference rejected the states of multiline parser " + name)
+        return m
 
     def filter(self, plugin, props):
         f = self.L.flbref_filter_create(self.cfg, self._b(plugin))
