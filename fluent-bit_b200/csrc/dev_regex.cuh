@@ -424,6 +424,10 @@ FLB_HD int rx_search(const struct rx_prog *pg, const uint8_t *s, int len, int *c
             if (st >= len) return RX_R_NOMATCH;
             ok = (pg->first[s[st] >> 5] >> (s[st] & 31)) & 1;
         }
+        if (ok && (pg->flags & RX_F_HAS_SECONDSET) && st < len && s[st] < 0x80) {
+            /* the first character is this one byte; something has to follow it */
+            ok = st + 1 < len && ((pg->second[s[st + 1] >> 5] >> (s[st + 1] & 31)) & 1);
+        }
         if (ok) {
             r = rx_match_at(pg, s, len, st, caps, stk, stk_cap, budget);
             if (r != RX_R_NOMATCH) return r;

@@ -71,6 +71,7 @@ struct rx_class {
 #define RX_F_ANCHOR_BUF   2u   /* every match starts at offset 0       */
 #define RX_F_HAS_FIRSTSET 4u   /* first[] is a sound first-byte filter */
 #define RX_F_NULLABLE     8u   /* the pattern can match the empty string */
+#define RX_F_HAS_SECONDSET 32u /* second[] is a sound filter on the byte behind an ASCII first byte */
 #define RX_F_ASCII_ONLY  16u   /* the pattern uses a construct whose non-ASCII behaviour is not restated (POSIX bracket, \b \B,
                                   case-insensitive matching: Onigmo consults its Unicode tables there): a subject with a byte >= 0x80
                                   is refused loudly (RX_R_EUNICODE), never matched approximately */
@@ -85,6 +86,9 @@ struct rx_prog {
     uint32_t flags;
     uint32_t n_null;       /* number of null-check loop ids */
     uint32_t first[8];     /* first-byte filter (valid when RX_F_HAS_FIRSTSET) */
+    uint32_t second[8];    /* RX_F_HAS_SECONDSET: the pattern begins with exactly one character and cannot end right behind it --
+                              the bytes that can follow that character.  A start whose first byte is ASCII (one byte wide) and whose
+                              next byte is not in the set cannot match: `(.)(?:Exception|Error)` tries 3 starts per line, not 100 */
 };
 
 /* run-time status of one match attempt */

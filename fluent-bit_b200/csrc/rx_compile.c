@@ -884,6 +884,28 @@ static int first_of(struct comp *c, struct node *n, struct fset *f, int look)
     return 0;
 }
 
+/* the pattern as "exactly one character, then something that consumes at least one more byte": the bytes that something can
+ * begin with (rx_prog.second).  Returns 1 and fills f, or 0 when the pattern does not have that shape. */
+static int second_of(struct comp *c, struct node *root, struct fset *f)
+{
+    struct node *n = root, *e0;
+    int i, r, acc = 3;
+    while ((n->type == N_GROUP || n->type == N_ATOMIC) && n->n == 1) n = n->kid[0];
+    if (n->type != N_CAT || n->n < 2) return 0;
+    e0 = n->kid[0];
+    while ((e0->type == N_GROUP || e0->type == N_ATOMIC) && e0->n == 1) e0 = e0->kid[0];
+    if (e0->type != N_CLASS && e0->type != N_LIT) return 0;
+    memset(f, 0, sizeof(*f));
+    for (i = 1; i < n->n; i++) {
+        r = first_of(c, n->kid[i], f, 0);
+        acc &= r;
+        if (!(r & 1)) break;
+    }
+    if (i == n->n && (acc & 1)) return 0;          /* the rest can be empty: a match may end right behind the first character */
+    if (f->wild) return 0;
+    return 1;
+}
+
 static int contains_capture(struct node *n)
 {
     int i;
@@ -1316,6 +1338,8 @@ int rx_compile(const char *pattern, struct rx_compiled *out)
             if (r & 1) pg->flags |= RX_F_NULLABLE;
             else { pg->flags |= RX_F_HAS_FIRSTSET; memcpy(pg->first, ff.b, sizeof(ff.b)); }
             if (c.ascii_only) pg->flags |= RX_F_ASCII_ONLY;
+            /* (not for patterns with case folding: a folded first character may stand for two subject bytes) */
+            if (!c.ascii_only && second_of(&c, root, &ff)) { pg->flags |= RX_F_HAS_SECONDSET; memcpy(pg->second, ff.b, sizeof(ff.b)); }
             la = leading_anchor(root);
             if (la == RX_BOL) pg->flags |= RX_F_ANCHOR_BOL;
             if (la == RX_BEGIN_BUF) pg->flags |= RX_F_ANCHOR_BUF;
