@@ -10,17 +10,19 @@ all: product hostsim oracle
 
 product: $(PKG)/libflbgpu.so
 HDRS = $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h) include/flbgpu.h
-# one object per translation unit, so that `make -j` compiles the two .cu files side by side (kernels.cu alone takes minutes)
+# one object per translation unit, so that `make -j` compiles the .cu files side by side (kernels.cu alone takes minutes)
 $(CSRC)/kernels.o: $(CSRC)/kernels.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $(CSRC)/kernels.cu -o $@
 $(CSRC)/kernels_ml.o: $(CSRC)/kernels_ml.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $(CSRC)/kernels_ml.cu -o $@
+$(CSRC)/kernels_tojson.o: $(CSRC)/kernels_tojson.cu $(HDRS)
+	$(NVCC) $(NVFLAGS) -c $(CSRC)/kernels_tojson.cu -o $@
 $(CSRC)/runtime.o: $(CSRC)/runtime.c $(HDRS)
 	gcc $(CFLAGS) -c $(CSRC)/runtime.c -o $@
 $(CSRC)/rx_compile.o: $(CSRC)/rx_compile.c $(HDRS)
 	gcc $(CFLAGS) -c $(CSRC)/rx_compile.c -o $@
-$(PKG)/libflbgpu.so: $(CSRC)/kernels.o $(CSRC)/kernels_ml.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o
-	$(NVCC) -shared -o $@ $(CSRC)/kernels.o $(CSRC)/kernels_ml.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o -lcudart -lpthread -ldl
+$(PKG)/libflbgpu.so: $(CSRC)/kernels.o $(CSRC)/kernels_ml.o $(CSRC)/kernels_tojson.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o
+	$(NVCC) -shared -o $@ $(CSRC)/kernels.o $(CSRC)/kernels_ml.o $(CSRC)/kernels_tojson.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o -lcudart -lpthread -ldl
 
 hostsim: tests/hostsim/libhostsim.so
 tests/hostsim/libhostsim.so: tests/hostsim/hostsim.cpp $(CSRC)/runtime.c $(CSRC)/rx_compile.c $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h)

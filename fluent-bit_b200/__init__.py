@@ -54,6 +54,7 @@ EXPORTS = [
     "flbgpu_comm_unique_id", "flbgpu_comm_init", "flbgpu_l2m_allreduce",
     "flbgpu_pack_state_init", "flbgpu_pack_state_reset", "flbgpu_pack_json_state", "flbgpu_pack_json_state_batch",
     "flbgpu_ml_parser_create", "flbgpu_ml_parser_rule", "flbgpu_ml_parser_init", "flbgpu_ml_set_buffer_limit",
+    "flbgpu_msgpack_to_json_format",
 ]
 
 
@@ -107,6 +108,7 @@ def load(path=None):
     L.flbgpu_ml_parser_rule.argtypes = [vp, cp, cp, cp]
     L.flbgpu_ml_parser_init.argtypes = [vp]
     L.flbgpu_ml_set_buffer_limit.argtypes = [vp, sz]
+    L.flbgpu_msgpack_to_json_format.argtypes = [vp, vp, sz, C.c_int, C.c_int, cp, C.c_int, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
     L.flbgpu_comm_unique_id.argtypes = [vp]
     L.flbgpu_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.flbgpu_l2m_allreduce.argtypes = [vp]
@@ -206,6 +208,20 @@ class Context:
         if not p:
             raise FlbGpuError("parser_create(%s): %s" % (name, self.err()))
         return Parser(self, p)
+
+    def to_json(self, data, json_format=3, date_format=0, date_key="date", escape_unicode=True):
+        """flb_pack_msgpack_to_json_format(): (text bytes or None, strings whose text is undefined in the reference)"""
+        out, n, und = C.c_void_p(), C.c_size_t(), C.c_size_t()
+        buf = C.create_string_buffer(data, len(data))
+        r = self.L.flbgpu_msgpack_to_json_format(self.h, C.cast(buf, C.c_void_p), len(data), json_format, date_format, _b(date_key),
+                                                 int(escape_unicode), C.byref(out), C.byref(n), C.byref(und))
+        if r < 0:
+            raise FlbGpuError("msgpack_to_json_format: %s" % self.err())
+        if r == 1:
+            return None, und.value
+        text = C.string_at(out.value, n.value)
+        _libc.free(out)
+        return text, und.value
 
     def ml_parser(self, name, type="regex", rules=(), match_string=None, negate=False, flush_ms=0, key_content=None,
                   key_group=None, key_pattern=None, parser=None):

@@ -433,7 +433,14 @@ FLB_HD int rx_search(const struct rx_prog *pg, const uint8_t *s, int len, int *c
             if (r != RX_R_NOMATCH) return r;
         }
         if (st >= len) return RX_R_NOMATCH;
-        st += rx_u8len(s, st, len);
+        if (pg->flags & RX_F_ANCHOR_BOL) {
+            /* every match starts at a line start: the next candidate is the position behind the next line feed (never a
+             * continuation byte, so also a character boundary) -- a line without one is done after its first position */
+            st = rx_find_first_of4(s, st, len, 0x0a0a0a0au, 1);
+            if (st >= len) return RX_R_NOMATCH;
+            st++;
+        }
+        else st += rx_u8len(s, st, len);
     }
 }
 

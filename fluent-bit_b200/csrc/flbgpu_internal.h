@@ -204,6 +204,11 @@ int bk_ml_plan(bk_q *q, const struct ml_env *e);
 int bk_ml_sizes(bk_q *q, const struct ml_env *e, uint32_t n_ev);
 int bk_ml_emit(bk_q *q, const struct ml_env *e, uint32_t n_ev, const uint64_t *d_bsum, uint8_t *d_out);
 
+/* chunk -> JSON text (dev_tojson.cuh), asynchronous on the queue's stream.  sizes: every event packed as one map in its scratch
+ * slice, e->size[i] = bytes of its text; emit: event i at d_out + d_bsum[i / BK_REC_BLOCK] + (sizes before it in its block). */
+int bk_tj_sizes(bk_q *q, const struct tj_env *e);
+int bk_tj_emit(bk_q *q, const struct tj_env *e, const uint64_t *d_bsum, uint8_t *d_out);
+
 #ifdef __cplusplus
 }
 #endif

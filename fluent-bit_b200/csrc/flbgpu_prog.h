@@ -343,6 +343,34 @@ struct ml_env {
     uint32_t *ev_slot, *ev_size, *ev_buflen, *ev_ctx;
 };
 
+#define FLBGPU_E_JSONGROUP 8192u /* to-JSON: a group start marker -- the events behind it carry its attributes (`__internal__.group_attributes`): not built */
+#define FLBGPU_E_JSONDATE 4096u /* to-JSON: a date that does not fit the reference's 38-byte buffer (it returns NULL for the chunk) */
+
+/* ---------------------------------------------------- chunk -> JSON text (dev_tojson.cuh) */
+struct tj_env {
+    const uint8_t *in;
+    const uint32_t *off, *len; const uint8_t *kind;
+    uint32_t n_rec;
+    uint8_t *scr;                     /* event i packs its map at scr + off[i] + i * scr_pad */
+    uint32_t scr_pad;
+    uint32_t *plen;                   /* bytes of that map */
+    uint32_t *size;                   /* bytes of text per event (separator included) */
+    uint32_t json_format, date_format, escape_unicode;
+    uint32_t key_len;                 /* 0xffffffff: no date key */
+    uint8_t key[128];
+    uint32_t *err;
+    unsigned long long *undefined;    /* strings whose text depends, in the reference, on memory behind the event's buffer */
+};
+#define TJ_FORMAT_JSON 1u
+#define TJ_FORMAT_STREAM 2u
+#define TJ_FORMAT_LINES 3u
+#define TJ_DATE_DOUBLE 0u
+#define TJ_DATE_ISO8601 1u
+#define TJ_DATE_EPOCH 2u
+#define TJ_DATE_JAVA_SQL 3u
+#define TJ_DATE_EPOCH_MS 4u
+#define TJ_SCR_PAD(key_len) ((key_len) + 128u)
+
 /* ---------------------------------------------------- streaming JSON packer (dev_jsmn.cuh) */
 enum { JM_UNDEFINED = 0, JM_OBJECT = 1, JM_ARRAY = 2, JM_STRING = 4, JM_PRIMITIVE = 8 };     /* jsmntype_t, lib/jsmn/jsmn.h */
 struct jm_tok { int32_t type, start, end, size, parent; };

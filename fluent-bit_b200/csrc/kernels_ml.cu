@@ -3,8 +3,8 @@
  * All the work is in dev_ml.cuh (the same functions the CPU emulation of the tests loops over); a kernel here gives every
  * piece its thread:
  *   k_ml_feat ......... one lane per record: key_content, which rules' regexes match (the regex VM of dev_regex.cuh)
- *   k_ml_up1 .......... one lane per block of ML_F1 records: the block as a function on automaton states (S bytes)
- *   k_ml_up2 .......... one lane per ML_F2 blocks: composition
+ *   k_ml_up1 .......... one lane per (block of ML_F1 records, state): the block as a function on automaton states (S bytes)
+ *   k_ml_up2 .......... one lane per (ML_F2 blocks, state): composition
  *   k_ml_top .......... one lane: incoming state of every super-block (a few thousand dependent byte loads for 10 M records)
  *   k_ml_down2 ........ incoming state of every block
  *   k_ml_apply ........ the automaton over the records with the state known: actions, events and time marks per block
@@ -33,8 +33,8 @@ namespace {
     __global__ void __launch_bounds__(ML_BLOCK) name(const __grid_constant__ ml_env e) \
     { const uint32_t t = blockIdx.x * ML_BLOCK + threadIdx.x; if (t < (count)) fn(&e, t); }
 ML_KERNEL(k_ml_feat, ml_feat_record, e.n_rec)
-ML_KERNEL(k_ml_up1, ml_up1, e.nt1)
-ML_KERNEL(k_ml_up2, ml_up2, e.nt2)
+ML_KERNEL(k_ml_up1, ml_up1, e.nt1 * e.S)
+ML_KERNEL(k_ml_up2, ml_up2, e.nt2 * e.S)
 ML_KERNEL(k_ml_down2, ml_down2, e.nt2)
 ML_KERNEL(k_ml_apply, ml_apply, e.nt1)
 ML_KERNEL(k_ml_cnt_up2, ml_cnt_up2, e.nt2)
@@ -79,8 +79,8 @@ int bk_ml_plan(bk_q *q, const struct ml_env *e)
     CKM(cudaSetDevice(bk_q_device(q)));
     bk_ev_begin(q, 1);
     k_ml_feat<<<GRID(e->n_rec), ML_BLOCK, 0, st>>>(*e);
-    k_ml_up1<<<GRID(e->nt1), ML_BLOCK, 0, st>>>(*e);
-    k_ml_up2<<<GRID(e->nt2), ML_BLOCK, 0, st>>>(*e);
+    k_ml_up1<<<GRID(e->nt1 * e->S), ML_BLOCK, 0, st>>>(*e);
+    k_ml_up2<<<GRID(e->nt2 * e->S), ML_BLOCK, 0, st>>>(*e);
     k_ml_top<<<1, 1, 0, st>>>(*e);
     k_ml_down2<<<GRID(e->nt2), ML_BLOCK, 0, st>>>(*e);
     k_ml_apply<<<GRID(e->nt1), ML_BLOCK, 0, st>>>(*e);

@@ -27,7 +27,7 @@
 #include "flbgpu_internal.h"
 #include "rx_compile.h"
 
-static __thread char g_rt_err[512];
+static __thread char g_rt_err[1024];
 static void set_err(const char *fmt, const char *a, const char *b)
 {
     snprintf(g_rt_err, sizeof(g_rt_err), fmt, a ? a : "", b ? b : "");
@@ -160,6 +160,7 @@ struct flbgpu_ctx {
     bk_q *last_q;            /* queue of the most recent chain call: flbgpu_kernel_ms() reads its events */
     struct flbgpu_ml_parser *ml_parsers;      /* multiline parser definitions (config->multiline_parsers) */
     size_t ml_limit; int ml_limit_set;        /* config->multiline_buffer_limit */
+    flbgpu_chain *util;                       /* queue and buffers of the context-level conversions (flbgpu_msgpack_to_json_format) */
 };
 static void ml_parsers_free(flbgpu_ctx *ctx);
 
@@ -231,6 +232,7 @@ void flbgpu_shutdown(flbgpu_ctx *ctx)
     if (!ctx) return;
     while (ctx->parsers) flbgpu_parser_destroy(ctx->parsers);
     ml_parsers_free(ctx);
+    if (ctx->util) flbgpu_chain_destroy(ctx->util);
     bk_q_free(ctx->q0);
     free(ctx);
 }
@@ -1653,7 +1655,8 @@ static int refused(flbgpu_chain *c, uint32_t bits)
              "1=too many keys 2=regex stack 4=regex budget 8=float text not restated (hex float, nan(payload)) 32=logfmt escapes "
              "64=log_to_metrics value/label outside the device path 128=a pattern with POSIX brackets, \\b or case-insensitivity met a non-ASCII value "
              "256=a parsed value nested to msgpack-c's unpack limit inside a fused chain "
-             "1024=a multiline message reached the buffer limit 2048=multiline: an event with non-empty metadata)", bits);
+             "1024=a multiline message reached the buffer limit 2048=multiline: an event with non-empty metadata "
+             "8192=to-JSON: a group start marker)", bits);
     return 1;
 }
 
@@ -1846,6 +1849,7 @@ static int stops_at_wide_array(bk_q *q, const uint8_t *h_in, const uint8_t *d_in
         } } while (0)
 
 #include "runtime_ml.h"
+#include "runtime_tojson.h"
 
 /* flb_router_match() (src/flb_router.c:37-128): Match_Regex first -- onig_match() at the start of the tag with a match of
  * positive length -- then the Match pattern, where '*' stands for any run of characters. */

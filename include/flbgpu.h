@@ -118,6 +118,19 @@ int  flbgpu_pack_json_state(flbgpu_ctx *ctx, const char *js, size_t len, char **
 int  flbgpu_pack_json_state_batch(flbgpu_ctx *ctx, int n, const char *const *js, const size_t *len,
                                   char **buffers, int *sizes, struct flbgpu_pack_state *states, int *rets);
 
+/* ---- output side: a chunk as JSON text -----------------------------------------------------------------------------
+ * flb_pack_msgpack_to_json_format(), src/flb_pack.c:1320-1602 -- what out_stdout, out_http, out_file, out_kafka ... call on
+ * the chunk they flush.  json_format: 1 FLB_PACK_JSON_FORMAT_JSON (one array), 2 _STREAM (maps back to back), 3 _LINES (one
+ * map per line); date_format: 0 double, 1 iso8601, 2 epoch, 3 java_sql_timestamp, 4 epoch_ms (FLB_PACK_JSON_DATE_*,
+ * include/fluent-bit/flb_pack.h:38-42); date_key NULL: no date member; escape_unicode: config->json_escape_unicode.
+ * Returns 0 with *out = malloc()ed NUL-terminated text of *out_size bytes (the reference returns an flb_sds_t), 1 when the
+ * reference returns NULL for this input (nothing to convert; a date that overflows its 38-byte buffer), -1 on failure.
+ * *undefined_strings (may be NULL) counts strings whose text in the reference depends on memory behind the event: its string
+ * writers test 16 bytes at a time and, out of step after a multi-byte character, read past the end of the last strings of an
+ * event (src/flb_utils.c:920-935, 1255-1268); here such a window counts as "not plain". */
+int flbgpu_msgpack_to_json_format(flbgpu_ctx *ctx, const void *data, size_t bytes, int json_format, int date_format,
+                                  const char *date_key, int escape_unicode, char **out, size_t *out_size, size_t *undefined_strings);
+
 /* ---- multiline parser definitions ----------------------------------------------------------------------------
  * What a [MULTILINE_PARSER] section becomes (src/flb_parser.c:815-935): flb_ml_parser_create()
  * (src/multiline/flb_ml_parser.c:199-230; type = "regex" | "endswith" | "equal" | "eq", flb_ml_type_lookup()),

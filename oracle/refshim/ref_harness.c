@@ -427,6 +427,26 @@ int flbref_l2m_cmt_msgpack(void *filter, void **out, size_t *out_size)
 
 void flbref_cfree(void *p) { free(p); }
 
+/* ---- output side: flb_pack_msgpack_to_json_format() (src/flb_pack.c:1320-1602), what out_stdout / out_http / out_file ...
+ * call on a chunk.  Returns a malloc()ed copy of the sds (free with flbref_cfree) or NULL. */
+char *flbref_to_json_format(const void *data, size_t bytes, int json_format, int date_format, const char *date_key,
+                            int escape_unicode, size_t *out_len)
+{
+    flb_sds_t key = date_key ? flb_sds_create(date_key) : NULL;
+    flb_sds_t js = flb_pack_msgpack_to_json_format(data, bytes, json_format, date_format, key, escape_unicode);
+    char *r = NULL;
+    *out_len = 0;
+    if (js) {
+        *out_len = flb_sds_len(js);
+        r = malloc(*out_len + 1);
+        memcpy(r, js, *out_len);
+        r[*out_len] = 0;
+        flb_sds_destroy(js);
+    }
+    if (key) flb_sds_destroy(key);
+    return r;
+}
+
 /* ---- multiline parser definitions: what a [MULTILINE_PARSER] section becomes (src/flb_parser.c:815-935):
  * flb_ml_parser_create(), one flb_ml_rule_create() per `rule`, flb_ml_parser_init() ---- */
 void *flbref_ml_parser_create(void *cfg, const char *name, const char *type, const char *match_string, int negate,

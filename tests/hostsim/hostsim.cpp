@@ -73,6 +73,7 @@ int sim_rx_search(void *h, const char *s, int len, int *caps, int stack_words, u
 #include "../../fluent-bit_b200/csrc/flbgpu_internal.h"
 #include "../../fluent-bit_b200/csrc/dev_chain.cuh"
 #include "../../fluent-bit_b200/csrc/dev_ml.cuh"
+#include "../../fluent-bit_b200/csrc/dev_tojson.cuh"
 
 static thread_local char hs_err[256];
 static uint64_t hs_launches;
@@ -490,13 +491,32 @@ int bk_jsmn_emit(bk_q *, const struct bk_jsmn_args *a)
 }
 int bk_small_fetch(bk_q *, void *h_dst, const uint8_t *d_out, size_t n) { memcpy(h_dst, d_out, n); return 0; }
 
+/* chunk -> JSON text: the launches of kernels_tojson.cu as loops */
+int bk_tj_sizes(bk_q *, const struct tj_env *e)
+{
+    for (uint32_t i = 0; i < e->n_rec; i++) e->size[i] = tj_event(e, i, 0);
+    hs_launches += 1;
+    return 0;
+}
+int bk_tj_emit(bk_q *, const struct tj_env *e, const uint64_t *d_bsum, uint8_t *d_out)
+{
+    uint64_t at = 0;
+    for (uint32_t i = 0; i < e->n_rec; i++) {
+        if (i % BK_REC_BLOCK == 0) at = d_bsum[i / BK_REC_BLOCK];
+        if (e->size[i]) tj_event(e, i, d_out + at);
+        at += e->size[i];
+    }
+    hs_launches += 1;
+    return 0;
+}
+
 /* filter_multiline: the launches of kernels_ml.cu as loops over the same per-thread functions (dev_ml.cuh) */
 int bk_ml_plan(bk_q *, const struct ml_env *e)
 {
     uint32_t i;
     for (i = 0; i < e->n_rec; i++) ml_feat_record(e, i);
-    for (i = 0; i < e->nt1; i++) ml_up1(e, i);
-    for (i = 0; i < e->nt2; i++) ml_up2(e, i);
+    for (i = 0; i < e->nt1 * e->S; i++) ml_up1(e, i);
+    for (i = 0; i < e->nt2 * e->S; i++) ml_up2(e, i);
     ml_top(e);
     for (i = 0; i < e->nt2; i++) ml_down2(e, i);
     for (i = 0; i < e->nt1; i++) ml_apply(e, i);

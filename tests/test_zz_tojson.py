@@ -1,0 +1,198 @@
+"""f4 (output side): a chunk as JSON text -- flb_pack_msgpack_to_json_format() (src/flb_pack.c:1320-1602) against the reference's
+own function: the three layouts, the five date formats, both string writers, numbers, duplicate keys, nested values."""
+import random
+import struct
+
+import pytest
+
+import util
+
+pkg = util.pkg
+S = util.mp_str
+
+
+def mp_f64(x):
+    return b"\xcb" + struct.pack(">d", x)
+
+
+def mp_int(v):
+    if 0 <= v < 128:
+        return bytes([v])
+    if -32 <= v < 0:
+        return bytes([v & 0xff])
+    if 0 <= v < 2 ** 32:
+        return b"\xce" + struct.pack(">I", v)
+    if v >= 0:
+        return b"\xcf" + struct.pack(">Q", v)
+    return b"\xd3" + struct.pack(">q", v)
+
+
+TEXT = [b"plain", b"", b"with \"quotes\" and \\ backslash", b"tab\there", b"nl\nhere\r", b"ctl\x01\x02\x1f\x7f", b"\x7f" * 3,
+        b"0123456789abcde\x7f" + b"x" * 16, b"x" * 15 + b"\x7f" + b"y" * 16 + b"\x01", "héllo wörld".encode(), "日本語".encode(),
+        "\U0001f600 smile".encode(), b"bad \xff\xfe bytes", b"trunc \xe6\x97", b"\xc3(", b"\xed\xa0\x80 surrogate", b"\xc0\x80 overlong",
+        b"\xf4\x90\x80\x80 too big", b"\xf8\x88\x80\x80\x80 five", b"a" * 40, b"slash / and ' and <>&", b"\x08\x0c", b"\x00zero"]
+REALS = [0.0, -0.0, 1.0, -1.5, 0.1, 3.141592653589793, 1e15, 1e16, 1.5e16, 123456789012345678.0, 1e-4, 1e-5, 1.2345e-7, 5e-324, 1.7976931348623157e308,
+         2.0 ** 62, 2.0 ** 63, -(2.0 ** 63), 2.0 ** 64, 9007199254740993.0, 0.30000000000000004, 2.5, 1e21, 1e22, 123.456, float("inf"), float("-inf"),
+         1700000000.123457, 4.35, 0.000123456789012345678, 99999999999999990.0, 9999999999999999.0, 0.5, 1e100, 1.0000000000000002]
+
+
+def value(rng, depth=0):
+    r = rng.random()
+    if r < 0.30:
+        return S(rng.choice(TEXT))
+    if r < 0.40:
+        return mp_int(rng.choice([0, 1, -1, 127, 128, 255, 65535, 2 ** 31, 2 ** 32, 2 ** 63, 2 ** 64 - 1, -32, -33, -2 ** 31, -2 ** 63, 42]))
+    if r < 0.55:
+        x = rng.choice(REALS) if rng.random() < 0.6 else struct.unpack(">d", struct.pack(">Q", rng.getrandbits(64)))[0]
+        return mp_f64(x)
+    if r < 0.60:
+        return b"\xca" + struct.pack(">f", rng.choice([1.0, 0.1, 3.5, 1e-3, 16777217.0, -2.75]))
+    if r < 0.68:
+        return rng.choice([b"\xc0", b"\xc2", b"\xc3"])
+    if r < 0.73:
+        body = rng.choice(TEXT)[:20]
+        return b"\xc4" + bytes([len(body)]) + body                            # bin
+    if r < 0.77:
+        return b"\xd6\x05\x01\x80\xff\x7f" if rng.random() < 0.5 else b"\xc7\x03\x02abc"     # ext
+    if depth < 3 and r < 0.87:
+        n = rng.randint(0, 3)
+        return bytes([0x90 | n]) + b"".join(value(rng, depth + 1) for _ in range(n))
+    if depth < 3:
+        n = rng.randint(0, 3)
+        keys = [rng.choice([b"k", b"k2", b"dup", "clé".encode()]) for _ in range(n)]
+        return bytes([0x80 | n]) + b"".join(S(k) + value(rng, depth + 1) for k in keys)
+    return S(b"deep")
+
+
+def chunk(rng, n, with_meta=True):
+    evs = []
+    for i in range(n):
+        nk = rng.randint(0, 6)
+        fields = []
+        for _ in range(nk):
+            k = rng.choice([b"log", b"level", b"date", b"dup", b"dup", b"n", "clé".encode(), b"__internal__", b"q\"k"])
+            fields.append((k, value(rng)))
+        if rng.random() < 0.1:
+            fields.append((b"\x05", b"\x07"))                                # an integer key (the caller packs key bytes itself below)
+        body = util.mp_map_hdr(len(fields)) + b"".join((k if k == b"\x05" else S(k)) + v for k, v in fields)
+        meta = b"\x80"
+        if with_meta and rng.random() < 0.15:
+            meta = b"\x82" + S(b"src") + S(b"tail") + S(b"n") + mp_int(rng.randint(0, 9))
+        sec = rng.choice([0, 1, 1700000000, 1700000000 + i, 2 ** 31 - 1, 951782400, 1709164800])
+        nsec = rng.choice([0, 1, 999, 1000, 123456789, 999999999, 500000000])
+        r = rng.random()
+        if r < 0.05:
+            evs.append(b"\x92\x92\xd7\x00\xff\xff\xff\xfe\x00\x00\x00\x00\x80\x80")          # an event the decoder steps over
+        if r < 0.1:
+            evs.append(b"\x92\xce" + struct.pack(">I", sec) + body)                              # legacy [ts, body]
+        elif r < 0.15:
+            evs.append(b"\x92\x92\xcb" + struct.pack(">d", sec + 0.25) + meta + body)            # float timestamp
+        else:
+            evs.append(b"\x92\x92\xd7\x00" + struct.pack(">II", sec, nsec) + meta + body)
+    return b"".join(evs)
+
+
+def _diff(lib, rounds, n):
+    rng = random.Random(21)
+    ref = util.Ref()
+    ctx = pkg.Context(0, lib=lib)
+    checked = undefined = 0
+    for _ in range(rounds):
+        c = chunk(rng, rng.choice([0, 1, 3, n]))
+        for jf in (1, 2, 3):
+            df = rng.randint(0, 4)
+            key = rng.choice(["date", "@timestamp", None, "dup"])
+            esc = rng.random() < 0.5
+            got, und = ctx.to_json(c, jf, df, key, esc)
+            if und:                       # the reference's text depends on memory behind the event here: nothing to compare with
+                undefined += 1
+                continue
+            want = ref.to_json(c, jf, df, key, esc)
+            assert got == want, (jf, df, key, esc, c)
+            checked += 1
+    assert checked > rounds
+
+
+def _numbers(lib):
+    """every real of the table and a few thousand random bit patterns, one event each: "%.1f" / "%.16g" as glibc prints them"""
+    rng = random.Random(22)
+    ref = util.Ref()
+    ctx = pkg.Context(0, lib=lib)
+    xs = list(REALS) + [struct.unpack(">d", struct.pack(">Q", rng.getrandbits(64)))[0] for _ in range(3000)]
+    xs += [rng.random() * 10 ** rng.randint(-30, 30) for _ in range(2000)] + [float(rng.randint(-10 ** 18, 10 ** 18)) for _ in range(500)]
+    xs += [round(rng.random() * 1000, rng.randint(0, 6)) for _ in range(1500)]
+    c = b"".join(util.event(1700000000, 0, [(b"x", mp_f64(x))]) for x in xs)
+    assert ctx.to_json(c, 3, 2, "t", True)[0] == ref.to_json(c, 3, 2, "t", True)
+
+
+def _strings(lib):
+    """both writers over every text of the table at every offset of a 16-byte window, a plain key behind it (so that what the
+    reference reads past the string is the next key's header: defined)"""
+    ref = util.Ref()
+    ctx = pkg.Context(0, lib=lib)
+    evs = []
+    for t in TEXT:
+        for pad in range(0, 34, 3):
+            evs.append(util.event(1700000000, 0, [(b"s", S(b"p" * pad + t + b"q" * (pad % 5))), (b"tail", S(b"end of the event, long enough"))]))
+    c = b"".join(evs)
+    for esc in (True, False):
+        got, und = ctx.to_json(c, 3, 1, "ts", esc)
+        assert und == 0
+        assert got == ref.to_json(c, 3, 1, "ts", esc)
+
+
+def _edges(lib):
+    ref = util.Ref()
+    ctx = pkg.Context(0, lib=lib)
+    assert ctx.to_json(b"", 3)[0] is None and ref.to_json(b"", 3) is None
+    assert ctx.to_json(b"", 1)[0] == ref.to_json(b"", 1) == b"[]"
+    only_skipped = b"\x92\x92\xd7\x00\xff\xff\xff\xfe\x00\x00\x00\x00\x80\x80"
+    assert ctx.to_json(only_skipped, 2)[0] is None and ref.to_json(only_skipped, 2) is None
+    e = util.event(1700000000, 5, [(b"a", b"\x01")])
+    for jf in (1, 2, 3):
+        for df in range(5):
+            assert ctx.to_json(e * 3, jf, df, "d", True)[0] == ref.to_json(e * 3, jf, df, "d", True)
+    # garbage behind the events: what decodes is converted
+    assert ctx.to_json(e + e + b"\xc1\xc1", 3)[0] == ref.to_json(e + e + b"\xc1\xc1", 3)
+    # a group start marker: the events behind it would carry its body as group_attributes -- refused, loudly
+    with pytest.raises(pkg.FlbGpuError):
+        ctx.to_json(b"\x92\x92\xd7\x00\xff\xff\xff\xff\x00\x00\x00\x00\x80\x81\xa1g\x01" + e, 3)
+    # a string as the event's last value, out of step after multi-byte characters: counted, not compared
+    odd = util.event(1700000000, 0, [(b"m", S(("é" * 15).encode() + b"abc"))])
+    assert ctx.to_json(odd, 3, 0, "date", False)[1] == 1
+
+
+def test_tojson_diff_hostsim(sim_lib, ref_available):
+    _diff(sim_lib, 150, 40)
+
+
+def test_tojson_numbers_hostsim(sim_lib, ref_available):
+    _numbers(sim_lib)
+
+
+def test_tojson_strings_hostsim(sim_lib, ref_available):
+    _strings(sim_lib)
+
+
+def test_tojson_edges_hostsim(sim_lib, ref_available):
+    _edges(sim_lib)
+
+
+@pytest.mark.gpu
+def test_tojson_diff_gpu(gpu_lib, ref_available):
+    _diff(gpu_lib, 40, 40)
+
+
+@pytest.mark.gpu
+def test_tojson_numbers_gpu(gpu_lib, ref_available):
+    _numbers(gpu_lib)
+
+
+@pytest.mark.gpu
+def test_tojson_strings_gpu(gpu_lib, ref_available):
+    _strings(gpu_lib)
+
+
+@pytest.mark.gpu
+def test_tojson_edges_gpu(gpu_lib, ref_available):
+    _edges(gpu_lib)

@@ -43,6 +43,8 @@ class Ref:
         L.flbref_l2m_cmt_text.restype = vp; L.flbref_l2m_cmt_text.argtypes = [vp]
         L.flbref_cfree.argtypes = [vp]
         L.flbref_pack_json_state.argtypes = [cp, sz, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.flbref_to_json_format.restype = vp
+        L.flbref_to_json_format.argtypes = [vp, sz, C.c_int, C.c_int, cp, C.c_int, C.POINTER(sz)]
         L.flbref_ml_parser_create.restype = vp
         L.flbref_ml_parser_create.argtypes = [vp, cp, cp, cp, C.c_int, C.c_int, cp, cp, cp, cp]
         L.flbref_ml_parser_rule.argtypes = [vp, cp, cp, cp]
@@ -128,6 +130,18 @@ class Ref:
         if out.value:
             self.L.flbref_free(out)
         return r, data, (s.value, ns.value)
+
+    def to_json(self, data, json_format=3, date_format=0, date_key="date", escape_unicode=True):
+        """flb_pack_msgpack_to_json_format(): bytes or None.  json_format 1 json / 2 stream / 3 lines; date_format 0 double /
+        1 iso8601 / 2 epoch / 3 java_sql_timestamp / 4 epoch_ms"""
+        n = C.c_size_t()
+        buf = C.create_string_buffer(data, len(data))
+        p = self.L.flbref_to_json_format(C.cast(buf, C.c_void_p), len(data), json_format, date_format, self._b(date_key), int(escape_unicode), C.byref(n))
+        if not p:
+            return None
+        out = C.string_at(p, n.value)
+        self.L.flbref_cfree(p)
+        return out
 
     def ml_parser(self, name, type="regex", rules=(), match_string=None, negate=False, flush_ms=0, key_content=None,
                   key_group=None, key_pattern=None, parser=None):
