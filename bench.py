@@ -189,6 +189,14 @@ _BLOCKS = {}
 def _ref_state(wl):
     import util
     st = _REF_STATE.get(wl)
+    if st is None and wl == "tojson":
+        ref = util.Ref()                              # the parsed events: the reference's own parser filter over the apache block
+        ref.parser(**parser_kw("apache"))
+        for p, props in WORKLOADS["c0"]["filters"]:
+            ref.filter(p, props)
+        ret, out = ref.chain_do(_BLOCKS.get("apache") or make_block("apache"), "bench")
+        st = _REF_STATE[wl] = (util.Ref(), C.create_string_buffer(out, len(out)))
+        return st
     if st is None:
         ref = util.Ref()
         if wl not in NO_PARSER:
@@ -219,6 +227,19 @@ def block_offsets_cached(wl):
     if wl not in _OFFS:
         _OFFS[wl] = block_offsets(_BLOCKS.get(wl) or make_block(wl))
     return _OFFS[wl]
+
+
+def _ref_tojson_task(args):
+    """one pool task: the reference's flb_pack_msgpack_to_json_format() over this worker's copy of the parsed events, `reps` times"""
+    reps = args
+    ref, buf = _ref_state("tojson")
+    n = C.c_size_t()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        p = ref.L.flbref_to_json_format(C.cast(buf, C.c_void_p), len(buf), 3, 1, b"date", 1, C.byref(n))
+        if p:
+            ref.L.flbref_cfree(p)
+    return time.perf_counter() - t0, BASE_LINES * reps
 
 
 def _ref_task(args):
@@ -299,6 +320,14 @@ def run_reference(args):
             v, sps, nn = reference_workload(pool, o, lines_for(args, o), max(1, min(args.steps, 3)), 1)
             others[o] = {"workload": WORKLOADS[o]["name"], "value": v, "e2e": v, "unit": "lines/s", "events_per_step": nn,
                          "ms_per_step": 1000 * sps}
+    if not args.primary_only:
+        try:
+            pool.pool.map(_ref_tojson_task, [1] * cores, chunksize=1)                 # builds every worker's input
+            res = pool.pool.map(_ref_tojson_task, [3] * cores, chunksize=1)
+            v = sum(r[1] for r in res) / max(r[0] for r in res)
+            others["tojson"] = {"workload": TOJSON_NAME, "value": v, "e2e": v, "unit": "lines/s", "events_per_step": sum(r[1] for r in res)}
+        except Exception as ex:
+            others["tojson"] = {"workload": TOJSON_NAME, "error": "%s: %s" % (type(ex).__name__, ex)}
     pool.close()
     sample = "%d cores (%s), %d events per step in %d-event calls, one pipeline per core, %d steps; time = slowest worker inside the reference's calls" % (
         cores, cores_note, n, min(BASE_LINES, -(-n // cores)), args.steps)
@@ -579,6 +608,60 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local, full=True):
             "phases": phases, "variants": variants, "steps": steps}
 
 
+TOJSON_NAME = ("output side: the parsed apache events of configs[0] as json_lines text -- flb_pack_msgpack_to_json_format(date_key "
+               "'date', iso8601, escape_unicode on), what out_stdout / out_http call on the chunk they flush")
+
+
+def tojson_input(ctx):
+    """the events the apache parser makes of the block (our own chain; byte-identical to the reference's by the parity tests)"""
+    import util
+    made = ctx.__dict__.setdefault("_bench_parsers", set())
+    if "apache" not in made:
+        ctx.parser(**parser_kw("apache"))
+        made.add("apache")
+    ch = ctx.chain([ctx.filter(p, props) for p, props in WORKLOADS["c0"]["filters"]])
+    ret, out = ch.do(make_block("apache"))
+    ch.close()
+    assert ret == util.pkg.FILTER_MODIFIED and out
+    return out
+
+
+def measure_tojson(args, L, ctx, torch, world):
+    """end to end only (host chunk in, malloc()ed text out): lines/s over `reps` calls on a 100 k-event chunk"""
+    chunk = tojson_input(ctx)
+    n_ev = BASE_LINES
+    buf = C.create_string_buffer(chunk, len(chunk))
+    out, n, und = C.c_void_p(), C.c_size_t(), C.c_size_t()
+    ms3 = (C.c_float * 3)()
+
+    def call():
+        r = L.flbgpu_msgpack_to_json_format(ctx.h, C.cast(buf, C.c_void_p), len(chunk), 3, 1, b"date", 1, C.byref(out), C.byref(n), C.byref(und))
+        if r != 0:
+            raise RuntimeError("msgpack_to_json_format -> %d: %s" % (r, ctx.err()))
+        _libc.free(out)
+        return n.value
+    for _ in range(max(3, args.warmup)):
+        text_bytes = call()
+    reps = max(10, args.steps * 4)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    kms = [0.0, 0.0, 0.0]
+    for _ in range(reps):
+        call()
+        L.flbgpu_kernel_ms(ctx.h, ms3)
+        for k in range(3):
+            kms[k] += ms3[k]
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    kern = (kms[1] + kms[2]) / reps
+    return {"workload": TOJSON_NAME, "e2e": world * n_ev * reps / dt, "unit": "lines/s", "events_per_call": n_ev, "input_bytes_per_call": len(chunk),
+            "text_bytes_per_call": text_bytes, "calls": reps, "ms_per_call": 1000 * dt / reps,
+            "kernel_ms_per_call": {"index": kms[0] / reps, "size": kms[1] / reps, "emit": kms[2] / reps},
+            "value": (n_ev / (kern / 1000.0)) if kern > 0 else None,
+            "value_note": "events / (sizing + emission kernel time): the conversion kernels alone, input resident",
+            "gpu_launches_per_call": 2, "undefined_strings": und.value}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -612,6 +695,13 @@ def run_ours(args):
                 if o == "apache":
                     raise
                 others[o] = {"error": "%s: %s" % (type(ex).__name__, ex)}
+
+    tojson = None
+    if not args.primary_only:
+        try:
+            tojson = measure_tojson(args, L, ctx, torch, world)
+        except Exception as ex:
+            tojson = {"workload": TOJSON_NAME, "error": "%s: %s" % (type(ex).__name__, ex)}
 
     # last: the same end-to-end calls with an allocator that retains freed result buffers (and pinned input)
     tune_malloc()
@@ -715,6 +805,8 @@ def run_ours(args):
     if "apache" in others:
         line["north_star"] = side(others.pop("apache"), "apache")
     line["workloads"] = {k: side(v, k) for k, v in others.items()}
+    if tojson is not None:
+        line["workloads"]["tojson"] = tojson
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
