@@ -71,14 +71,19 @@ WORKLOADS = {
                                         ("tag", "m"), ("value_field", "duration"), ("label_field", "color"),
                                         ("label_field", "direction"), ("discard_logs", "on")])],
     },
-    # BASELINE.json configs[4] (first step): container logs with Java stack traces -> filter_multiline (built-in java parser,
-    # `buffer off`: the lines of a chunk are concatenated inside the call)
+    # BASELINE.json configs[4]: application logs with Java stack traces -> multiline + parser + grep.  filter_multiline (built-in
+    # java parser, `buffer off`: the lines of a chunk are concatenated inside the call) leaves its result on the device, the
+    # parser (timestamp / level / class of the first line; a stack trace does not match and stays as it is) and the grep
+    # (INFO and DEBUG lines go) run on it as one fused chain.
     "ml": {
-        "name": "configs[4] (multiline stage): application logs with Java stack traces -> filter_multiline(multiline.parser java, key_content log, buffer off)",
-        "filters": [("multiline", [("multiline.parser", "java"), ("multiline.key_content", "log"), ("buffer", "off")])],
+        "name": "configs[4]: application logs with Java stack traces -> filter_multiline(java, key_content log, buffer off) + filter_parser(regex: time level [class] msg, Reserve_Data) + filter_grep(Exclude level ^(INFO|DEBUG)$)",
+        "filters": [("multiline", [("multiline.parser", "java"), ("multiline.key_content", "log"), ("buffer", "off")]),
+                    ("parser", [("Key_Name", "log"), ("Parser", "applog"), ("Reserve_Data", "On")]),
+                    ("grep", [("Exclude", "level ^(INFO|DEBUG)$")])],
     },
 }
-NO_PARSER = ("l2m", "ml")
+NO_PARSER = ("l2m",)
+APPLOG_RX = r"^(?<time>\d{4}-\d{2}-\d{2} \d{2}:\d{2}:\d{2}\.\d{3}) (?<level>[A-Z]+) \[(?<class>[^\]]+)\] (?<msg>.*)$"
 
 
 def java_lines(n, seed):
@@ -144,6 +149,8 @@ def parser_kw(wl):
         return dict(name="json", format="json", time_fmt="%d/%b/%Y:%H:%M:%S %z", time_key="time")
     if wl == "nginx":
         return dict(name="nginx", format="regex", regex=util.NGINX_RX, time_fmt=util.APACHE_TIME_FMT, time_key="time")
+    if wl == "ml":
+        return dict(name="applog", format="regex", regex=APPLOG_RX, time_fmt="%Y-%m-%d %H:%M:%S.%L", time_key="time")
     return dict(name="apache", format="regex", regex=util.APACHE_RX, time_fmt=util.APACHE_TIME_FMT, time_key="time")
 
 

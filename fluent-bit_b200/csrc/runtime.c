@@ -184,6 +184,9 @@ struct flbgpu_chain {
     int ml_index;                             /* filter index of the multiline filter, or -1 (it runs on its own: ml_run) */
     uint32_t ml_cfg_off;
     uint8_t *d_mlw; size_t cap_mlw;           /* multiline: work arrays of a call */
+    /* `multiline, then other filters` (the shape of BASELINE configs[4]): the multiline filter runs as a chain of its own and
+     * hands its result to a chain of the filters behind it on the device -- no trip through host memory in between */
+    flbgpu_chain *ml_solo, *ml_post;
     int rtag_index;                           /* filter index of the rewrite_tag filter, or -1; -2 = several: the chain runs filter by filter */
     uint32_t *d_esize;                        /* rewrite_tag: bytes of each record's entry in the re-tagged stream */
     uint64_t *d_ebsum, *h_ebsum; size_t cap_ebsum;   /* ... and the scan over them */
@@ -1527,6 +1530,17 @@ int flbgpu_chain_init(flbgpu_chain *c)
         if (!c->l2m.hash || !c->l2m.chash || !c->l2m.first || !c->l2m.cnt || !c->l2m.sum || !c->l2m.bkt || !c->l2m.str) return -1;
     }
     if (bk_h2d(c->q, c->d_blob, c->blob.p, c->blob.n) || bk_sync(c->q)) return -1;
+    if (c->ml_index == 0 && c->nf > 1) {
+        int has_special = 0, k2;
+        for (k2 = 1; k2 < c->nf; k2++) if (c->f[k2]->kind == FLBGPU_F_REWRITE_TAG || c->f[k2]->kind == FLBGPU_F_MULTILINE) has_special = 1;
+        if (!has_special) {                       /* (a re-tagged stream or a second multiline filter: filter by filter) */
+            c->ml_solo = flbgpu_chain_new(c->ctx);
+            c->ml_post = flbgpu_chain_new(c->ctx);
+            if (!c->ml_solo || !c->ml_post || flbgpu_chain_add(c->ml_solo, c->f[0]) || flbgpu_chain_init(c->ml_solo)) return -1;
+            for (k2 = 1; k2 < c->nf; k2++) if (flbgpu_chain_add(c->ml_post, c->f[k2])) return -1;
+            if (flbgpu_chain_init(c->ml_post)) return -1;
+        }
+    }
     c->inited = 1;
     return 0;
 }
@@ -1534,6 +1548,7 @@ int flbgpu_chain_init(flbgpu_chain *c)
 void flbgpu_chain_destroy(flbgpu_chain *c)
 {
     if (!c) return;
+    flbgpu_chain_destroy(c->ml_solo); flbgpu_chain_destroy(c->ml_post);
     bk_free(c->q, c->d_blob); bk_free(c->q, c->d_in); bk_free(c->q, c->d_out); bk_free(c->q, c->d_tile); bk_free(c->q, c->d_off);
     bk_free(c->q, c->d_len); bk_free(c->q, c->d_size); bk_free(c->q, c->d_kind); bk_free(c->q, c->d_bsum); bk_free(c->q, c->d_cap);
     bk_free(c->q, c->d_flags); bk_free(c->q, c->d_scr); free(c->h_bsum); bk_free(c->q, c->d_mlw);
@@ -2448,7 +2463,8 @@ int flbgpu_chain_do_device(flbgpu_chain *c, const void *d_data, size_t bytes, vo
         c->active = 0;
         for (k = 0; k < c->nf; k++) if (!c->f[k]->inactive) c->active |= 1u << k;
     }
-    if (c->ml_index >= 0 && c->nf > 1) { set_err("a multiline filter inside a longer chain runs filter by filter: host buffers only%s%s", NULL, NULL); r = -1; }
+    if (c->ml_post) r = ml_then_rest(c, NULL, d_data, bytes, d_out, out_cap, NULL, out_size);
+    else if (c->ml_index >= 0 && c->nf > 1) { set_err("a multiline filter inside a longer chain runs filter by filter: host buffers only%s%s", NULL, NULL); r = -1; }
     else if (c->ml_index >= 0) r = ml_run(c, NULL, d_data, bytes, d_out, out_cap, NULL, out_size);
     else r = chain_run(c, NULL, d_data, bytes, d_out, out_cap, NULL, out_size);
     if (r >= 0 && bk_sync(c->q)) r = -1;
@@ -2489,6 +2505,12 @@ static int chain_do_locked(flbgpu_chain *c, const void *data, size_t bytes, cons
     if (c->ml_index >= 0) {
         /* a multiline filter makes new records out of runs of records: it runs on its own, the filters around it on what it made */
         int r;
+        if (c->ml_post) {
+            r = ml_then_rest(c, data, NULL, bytes, NULL, 0, out_buf, out_size);
+            /* (a record the fused rest refuses -- a value an earlier filter of it made -- takes the filter-by-filter form) */
+            if (r < 0 && c->st.error_bits && !(c->st.error_bits & ~(FLBGPU_E_FIELDS | FLBGPU_E_DEEP))) { *out_buf = NULL; *out_size = 0; return chain_do_one_by_one(c, data, bytes, tag, tag_len, out_buf, out_size); }
+            return r;
+        }
         if (c->nf > 1) return chain_do_one_by_one(c, data, bytes, tag, tag_len, out_buf, out_size);
         r = ml_run(c, data, NULL, bytes, NULL, 0, out_buf, out_size);
         bk_upload_end(c->q);

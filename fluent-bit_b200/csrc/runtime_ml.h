@@ -377,7 +377,11 @@ static int ml_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_ext,
     f->ml_state = (uint32_t) res[1]; f->ml_time[0] = (int64_t) res[2]; f->ml_time[1] = (int64_t) res[3];
     if (total == 0) return FLBGPU_FILTER_NOTOUCH;
     /* ---- emit ---- */
-    if (!host_out) {
+    if (!host_out && !ext_out) {                         /* the result stays in this chain's own device buffer (ml_then_rest) */
+        GROW(c->d_out, c->cap_out, total, uint8_t);
+        if (bk_ml_emit(c->q, &e, n_ev, c->d_bsum, c->d_out) || bk_sync(c->q)) return -1;
+    }
+    else if (!host_out) {
         if (ext_cap < total) { set_err("device output buffer too small%s%s", NULL, NULL); return -1; }
         if (bk_ml_emit(c->q, &e, n_ev, c->d_bsum, ext_out)) return -1;
     }
@@ -389,5 +393,57 @@ static int ml_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_ext,
         *host_out = out;
     }
     c->st.kernel_launches = bk_launch_count();
+    return FLBGPU_FILTER_MODIFIED;
+}
+
+/* `multiline, then other filters`: the multiline chain leaves its result on the device, the chain of the other filters takes it
+ * from there.  h_in or d_in_ext is the input; the result goes to host_out (malloc()ed) or to ext_out on the device.
+ * flb_filter_do() semantics between the two: NOTOUCH hands the input on unchanged, MODIFIED with nothing left ends the chain. */
+static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_ext, size_t bytes,
+                     uint8_t *ext_out, size_t ext_cap, void **host_out, size_t *out_size);
+static int ml_then_rest(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_ext, size_t bytes,
+                        uint8_t *ext_out, size_t ext_cap, void **host_out, size_t *out_size)
+{
+    flbgpu_chain *m = c->ml_solo, *p = c->ml_post;
+    size_t n_mid = 0;
+    int r = FLBGPU_FILTER_NOTOUCH, k;
+    p->active = 0;
+    for (k = 1; k < c->nf; k++) if ((c->active >> k) & 1) p->active |= 1u << (k - 1);
+    if (c->active & 1u) {
+        m->active = 1;
+        r = ml_run(m, h_in, d_in_ext, bytes, NULL, 0, NULL, &n_mid);
+        if (!d_in_ext) bk_upload_end(m->q);
+        c->st = m->st;
+        if (r < 0) return -1;
+    }
+    if (r == FLBGPU_FILTER_MODIFIED && n_mid == 0) { *out_size = 0; return FLBGPU_FILTER_MODIFIED; }      /* nothing left: the chain ends */
+    if (r != FLBGPU_FILTER_MODIFIED) {
+        /* the filters behind it see the chunk as it came */
+        if (!p->active) return FLBGPU_FILTER_NOTOUCH;
+        r = chain_run(p, h_in, d_in_ext, bytes, ext_out, ext_cap, host_out, out_size);
+        if (!d_in_ext) bk_upload_end(p->q);
+        if (r >= 0) c->st = p->st;
+        return r;
+    }
+    if (p->active) {
+        r = chain_run(p, NULL, m->d_out, n_mid, ext_out, ext_cap, host_out, out_size);
+        if (r < 0) { c->st.error_bits = p->st.error_bits; return -1; }
+        if (r == FLBGPU_FILTER_MODIFIED) {
+            c->st.bytes_out = p->st.bytes_out; c->st.records_out = p->st.records_out; c->st.kernel_launches = p->st.kernel_launches;
+            return r;
+        }
+    }
+    /* what the multiline filter made is the result */
+    *out_size = n_mid;
+    if (host_out) {
+        void *out = malloc(n_mid);
+        if (!out) return -1;
+        if (bk_d2h(m->q, out, m->d_out, n_mid) || bk_sync(m->q)) { free(out); return -1; }
+        *host_out = out;
+    }
+    else {
+        if (ext_cap < n_mid) { set_err("device output buffer too small%s%s", NULL, NULL); return -1; }
+        if (bk_d2d(m->q, ext_out, m->d_out, n_mid) || bk_sync(m->q)) return -1;
+    }
     return FLBGPU_FILTER_MODIFIED;
 }

@@ -204,6 +204,53 @@ def _in_a_chain(lib):
         assert ch.do(c) == ref.chain_do(c)
 
 
+def _chain_shapes(lib):
+    """`multiline, then other filters` runs as two chains with the intermediate chunk on the device: every way the two halves can
+    answer (MODIFIED / NOTOUCH / nothing left), Match routing of either half, and the device-resident form of the call"""
+    import ctypes as C
+    lines = list(JAVA) * 3
+    c1 = util.chunk_from_lines(lines)
+    no_key = b"".join(util.event(1700000000 + i, 0, [(b"other", S(b"x%d" % i))]) for i in range(20))     # multiline: every record on its own
+    ml = ("multiline", [("multiline.parser", "java"), ("multiline.key_content", "log"), ("buffer", "off")])
+    shapes = [
+        [ml, ("grep", [("Regex", "log Exception")]), ("modify", [("Add", "k v")])],
+        [ml, ("grep", [("Regex", "log .")])],                                        # the rest keeps everything: NOTOUCH, the multiline result stands
+        [ml, ("grep", [("Regex", "log no_such_text_anywhere")])],                    # the rest drops everything
+        [ml, ("modify", [("Add", "k v")]), ("record_modifier", [("Record", "h n1")]), ("grep", [("Exclude", "log INFO")])],
+        [ml + ([("match", "other.*")],), ("modify", [("Add", "k v")])],              # the multiline filter is not routed this tag
+        [ml, ("modify", [("Add", "k v"), ("match", "other.*")])],                    # ... the rest is not
+    ]
+    for shape in shapes:
+        ref = util.Ref()
+        ctx = pkg.Context(0, lib=lib)
+        fs = []
+        for item in shape:
+            p, props = item[0], list(item[1]) + (list(item[2]) if len(item) > 2 else [])
+            ref.filter(p, props)
+            fs.append(ctx.filter(p, props))
+        ch = ctx.chain(fs)
+        for c in (c1, no_key, c1[:len(c1) // 2]):
+            assert ch.do(c, tag="test") == ref.chain_do(c, "test"), shape
+    # device-resident: flbgpu_chain_do_device() on the first shape
+    ref = util.Ref()
+    ctx = pkg.Context(0, lib=lib)
+    fs = []
+    for p, props in shapes[0]:
+        ref.filter(p, props)
+        fs.append(ctx.filter(p, props))
+    ch = ctx.chain(fs)
+    L = ctx.L
+    d_in, d_out = L.flbgpu_dev_alloc(ctx.h, len(c1) + 64), L.flbgpu_dev_alloc(ctx.h, 2 * len(c1) + 4096)
+    buf = C.create_string_buffer(c1, len(c1))
+    L.flbgpu_dev_upload(ctx.h, d_in, C.cast(buf, C.c_void_p), len(c1))
+    n = C.c_size_t()
+    r = L.flbgpu_chain_do_device(ch.h, d_in, len(c1), d_out, 2 * len(c1) + 4096, C.byref(n))
+    got = C.create_string_buffer(n.value)
+    L.flbgpu_dev_download(ctx.h, C.cast(got, C.c_void_p), d_out, n.value)
+    assert (r, got.raw[:n.value]) == ref.chain_do(c1, "test")
+    L.flbgpu_dev_free(ctx.h, d_in); L.flbgpu_dev_free(ctx.h, d_out)
+
+
 def _large(lib, n):
     """many automaton blocks and super-blocks: states cross every boundary"""
     rng = random.Random(14)
@@ -229,6 +276,10 @@ def test_multiline_refusals_hostsim(sim_lib, ref_available):
 
 def test_multiline_in_a_chain_hostsim(sim_lib, ref_available):
     _in_a_chain(sim_lib)
+
+
+def test_multiline_chain_shapes_hostsim(sim_lib, ref_available):
+    _chain_shapes(sim_lib)
 
 
 def test_multiline_large_hostsim(sim_lib, ref_available):
@@ -258,6 +309,11 @@ def test_multiline_refusals_gpu(gpu_lib, ref_available):
 @pytest.mark.gpu
 def test_multiline_in_a_chain_gpu(gpu_lib, ref_available):
     _in_a_chain(gpu_lib)
+
+
+@pytest.mark.gpu
+def test_multiline_chain_shapes_gpu(gpu_lib, ref_available):
+    _chain_shapes(gpu_lib)
 
 
 @pytest.mark.gpu
