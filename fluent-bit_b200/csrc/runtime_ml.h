@@ -407,6 +407,7 @@ static int ml_then_rest(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_i
     flbgpu_chain *m = c->ml_solo, *p = c->ml_post;
     size_t n_mid = 0;
     int r = FLBGPU_FILTER_NOTOUCH, k;
+    c->ctx->last_q = m->q;                               /* flbgpu_kernel_ms(): the multiline stage's launches */
     p->active = 0;
     for (k = 1; k < c->nf; k++) if ((c->active >> k) & 1) p->active |= 1u << (k - 1);
     if (c->active & 1u) {
@@ -422,12 +423,14 @@ static int ml_then_rest(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_i
         if (!p->active) return FLBGPU_FILTER_NOTOUCH;
         r = chain_run(p, h_in, d_in_ext, bytes, ext_out, ext_cap, host_out, out_size);
         if (!d_in_ext) bk_upload_end(p->q);
+        if (r >= 0 && !host_out && bk_sync(p->q)) return -1;         /* (the caller waits on the outer chain's queue, not on this one) */
         if (r >= 0) c->st = p->st;
         return r;
     }
     if (p->active) {
         r = chain_run(p, NULL, m->d_out, n_mid, ext_out, ext_cap, host_out, out_size);
         if (r < 0) { c->st.error_bits = p->st.error_bits; return -1; }
+        if (!host_out && bk_sync(p->q)) return -1;
         if (r == FLBGPU_FILTER_MODIFIED) {
             c->st.bytes_out = p->st.bytes_out; c->st.records_out = p->st.records_out; c->st.kernel_launches = p->st.kernel_launches;
             return r;
