@@ -83,7 +83,7 @@ def main(seed, n):
                 vals = [v for v in vals if b"\n" not in v]
                 for v, (r, data, t) in zip(vals, p.do_batch(vals)):
                     rr, rdata, rt = ref.parser_do(rp, v)
-                    if (r < 0) != (rr < 0) or (rr >= 0 and (data != rdata or t != (rt[0] & 0xffffffff, rt[1]))):
+                    if (r < 0) != (rr < 0) or (rr >= 0 and (data != rdata or t != (rt[0], rt[1]))):
                         bad += 1
                         if bad <= 25:
                             print("MISMATCH fmt=%r strict=%s offset=%s value=%r got=%s want=%s" % (fmt, strict, offset, v, (r, t), (rr, rt)))
