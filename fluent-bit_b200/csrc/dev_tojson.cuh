@@ -268,6 +268,9 @@ FLB_HDN uint32_t tj_write_str(const uint8_t *str, uint32_t len, const uint8_t *l
 
 /* ---- one event ---- */
 
+/* (mp_copy() reads whole aligned words around its source, which buffers from bk_alloc() are padded for -- a string literal is not) */
+FLB_HD uint32_t tj_put_lit(uint8_t *o, const char *s, uint32_t n) { uint32_t i; for (i = 0; i < n; i++) o[i] = (uint8_t) s[i]; return n; }
+
 FLB_HD uint32_t tj_put2(uint32_t v, uint8_t *o) { o[0] = (uint8_t) ('0' + v / 10 % 10); o[1] = (uint8_t) ('0' + v % 10); return 2; }
 
 /* strftime("%Y-%m-%d?%H:%M:%S") of gmtime_r(sec) + ".%06lu" of the microseconds (+ 'Z'); returns the length (<= 37) */
@@ -332,7 +335,8 @@ FLB_HDN uint32_t tj_pack_event(const struct tj_env *e, uint32_t i, uint8_t *b)
     if (v2) { meta = q; q = mp_skip(q, end); meta_end = q; }
     if (e->key_len != 0xffffffffu) {
         n += mp_put_str_hdr(b + n, e->key_len);
-        mp_copy(b + n, e->key, e->key_len); n += e->key_len;
+        for (k = 0; k < e->key_len; k++) b[n + k] = e->key[k];
+        n += e->key_len;
         switch (e->date_format) {
         case TJ_DATE_DOUBLE: {
             union { uint64_t u; double d; } cv;
@@ -356,9 +360,9 @@ FLB_HDN uint32_t tj_pack_event(const struct tj_env *e, uint32_t i, uint8_t *b)
     if (meta) {
         mp_token(meta, meta_end, &t);
         if (t.len > 0) {                                 /* "__internal__": { "log_metadata": metadata } */
-            n += mp_put_str_hdr(b + n, 12); mp_copy(b + n, (const uint8_t *) "__internal__", 12); n += 12;
+            n += mp_put_str_hdr(b + n, 12); n += tj_put_lit(b + n, "__internal__", 12);
             b[n] = 0xdf; mp_put_be32(b + n + 1, 1); n += 5;
-            n += mp_put_str_hdr(b + n, 12); mp_copy(b + n, (const uint8_t *) "log_metadata", 12); n += 12;
+            n += mp_put_str_hdr(b + n, 12); n += tj_put_lit(b + n, "log_metadata", 12);
             n += mp_canon(meta, meta_end, b + n, 0);
             entries++;
         }
