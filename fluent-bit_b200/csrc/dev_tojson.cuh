@@ -357,13 +357,35 @@ FLB_HDN uint32_t tj_pack_event(const struct tj_env *e, uint32_t i, uint8_t *b)
         }
         entries++;
     }
-    if (meta) {
-        mp_token(meta, meta_end, &t);
-        if (t.len > 0) {                                 /* "__internal__": { "log_metadata": metadata } */
+    {
+        /* "__internal__": { "group_attributes": the governing group start's body, "log_metadata": metadata } when either holds
+         * something (flb_pack.c:1432-1474; a legacy event's metadata is the decoder's empty map) */
+        const uint8_t *ga = 0, *ga_end = 0;
+        uint32_t meta_n = 0, ga_n = 0;
+        if (meta) { mp_token(meta, meta_end, &t); meta_n = t.len; }
+        if (e->n_groups) {
+            uint32_t lo = 0, hi = e->n_groups;           /* the last marker in front of event i */
+            while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if ((e->groups[mid] >> 1) < i) lo = mid + 1; else hi = mid; }
+            if (lo && (e->groups[lo - 1] & 1u)) {
+                const uint32_t g = e->groups[lo - 1] >> 1;
+                const uint8_t *gp = e->in + e->off[g], *gend = gp + e->len[g], *gq = gp + 1;
+                struct mp_tok tg;
+                if (*gq == 0x92) { gq++; mp_token(gq, gend, &tg); gq += tg.hdr + (tg.type == MPT_EXT ? tg.len : 0); gq = mp_skip(gq, gend); }
+                else { mp_token(gq, gend, &tg); gq += tg.hdr + (tg.type == MPT_EXT ? tg.len : 0); }
+                ga = gq; ga_end = gend;
+                mp_token(ga, ga_end, &tg);
+                ga_n = tg.len;
+            }
+        }
+        if (meta_n > 0 || ga_n > 0) {
             n += mp_put_str_hdr(b + n, 12); n += tj_put_lit(b + n, "__internal__", 12);
-            b[n] = 0xdf; mp_put_be32(b + n + 1, 1); n += 5;
+            b[n] = 0xdf; mp_put_be32(b + n + 1, ga ? 2u : 1u); n += 5;
+            if (ga) {
+                n += mp_put_str_hdr(b + n, 16); n += tj_put_lit(b + n, "group_attributes", 16);
+                n += mp_canon(ga, ga_end, b + n, 0);
+            }
             n += mp_put_str_hdr(b + n, 12); n += tj_put_lit(b + n, "log_metadata", 12);
-            n += mp_canon(meta, meta_end, b + n, 0);
+            if (meta) n += mp_canon(meta, meta_end, b + n, 0); else b[n++] = 0x80;
             entries++;
         }
     }
@@ -490,15 +512,25 @@ FLB_HDN uint32_t tj_event(const struct tj_env *e, uint32_t i, uint8_t *o)
     uint8_t *b = e->scr + e->off[i] + (size_t) i * e->scr_pad;
     uint32_t n = 0, undef = 0, pl;
     if (e->kind[i] != 0) {
-        /* an event the decoder steps over; a group start (seconds -1, flb_log_event_decoder.c:393-447) would hand its body to the
-         * events behind it as group_attributes */
-        if (!o && e->kind[i] == 1) {
+        /* an event the decoder steps over; group markers (seconds -1: start, -2: end) are listed for the host */
+        if (!o && e->kind[i] == 1 && !e->groups) {
             const uint8_t *p = e->in + e->off[i], *q = p + 1;
             struct mp_tok t;
+            long long sec = 0;
             if (*q == 0x92) q++;
             mp_token(q, p + e->len[i], &t);
-            if ((t.type == MPT_EXT && (int32_t) mp_be32(q + t.hdr) == -1) || (t.type == MPT_INT && (int64_t) t.u == -1))
-                CH_ATOMIC_OR(e->err, FLBGPU_E_JSONGROUP);
+            if (t.type == MPT_EXT) sec = (long long) (int32_t) mp_be32(q + t.hdr);
+            else if (t.type == MPT_INT || t.type == MPT_UINT) sec = (long long) (int32_t) (uint32_t) t.u;
+            else if (t.type == MPT_F64) { union { uint64_t u; double d; } cv; cv.u = t.u; sec = (long long) (int32_t) (uint32_t) (int64_t) cv.d; }
+            if (sec == -1 || sec == -2) {
+#ifdef __CUDA_ARCH__
+                const unsigned long long at = atomicAdd(e->n_marks, 1ull);
+#else
+                const unsigned long long at = (*e->n_marks)++;
+#endif
+                if (at < e->marks_cap) { e->marks[2 * at] = i * 2u + (sec == -1 ? 1u : 0u); e->marks[2 * at + 1] = e->len[i]; }
+                else CH_ATOMIC_OR(e->err, FLBGPU_E_JSONGROUP);
+            }
         }
         return 0;
     }

@@ -343,7 +343,7 @@ struct ml_env {
     uint32_t *ev_slot, *ev_size, *ev_buflen, *ev_ctx;
 };
 
-#define FLBGPU_E_JSONGROUP 8192u /* to-JSON: a group start marker -- the events behind it carry its attributes (`__internal__.group_attributes`): not built */
+#define FLBGPU_E_JSONGROUP 8192u /* to-JSON: more group markers in one chunk than the list holds */
 #define FLBGPU_E_JSONDATE 4096u /* to-JSON: a date that does not fit the reference's 38-byte buffer (it returns NULL for the chunk) */
 
 /* ---------------------------------------------------- chunk -> JSON text (dev_tojson.cuh) */
@@ -360,6 +360,12 @@ struct tj_env {
     uint8_t key[128];
     uint32_t *err;
     unsigned long long *undefined;    /* strings whose text depends, in the reference, on memory behind the event's buffer */
+    /* group markers (events with seconds -1 / -2, flb_log_event_decoder.c:393-447): the sizing pass lists them in marks[]
+     * (two words each: record index * 2 + is_start, record length; any order, n_marks[0] of them); when there are any, the host sorts the list and the passes
+     * run again with it as groups[0, n_groups): an event's group_attributes are the body of the last marker in front of it,
+     * if that is a start */
+    uint32_t *marks; unsigned long long *n_marks; uint32_t marks_cap;
+    const uint32_t *groups; uint32_t n_groups;
 };
 #define TJ_FORMAT_JSON 1u
 #define TJ_FORMAT_STREAM 2u

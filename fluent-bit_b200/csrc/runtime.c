@@ -1671,7 +1671,7 @@ static int refused(flbgpu_chain *c, uint32_t bits)
              "64=log_to_metrics value/label outside the device path 128=a pattern with POSIX brackets, \\b or case-insensitivity met a non-ASCII value "
              "256=a parsed value nested to msgpack-c's unpack limit inside a fused chain "
              "1024=a multiline message reached the buffer limit 2048=multiline: an event with non-empty metadata "
-             "8192=to-JSON: a group start marker)", bits);
+             "8192=to-JSON: more group markers than the list holds)", bits);
     return 1;
 }
 

@@ -1,6 +1,8 @@
 /* runtime_tojson.h -- host side of the chunk -> JSON text conversion (part of runtime.c, included there).
  * flb_pack_msgpack_to_json_format(), src/flb_pack.c:1320-1602. */
 
+#define TJ_MARKS_CAP 65536u      /* group markers per chunk */
+
 static flbgpu_chain *tj_chain(flbgpu_ctx *ctx)
 {
     flbgpu_chain *c = ctx->util;
@@ -22,7 +24,8 @@ static int tj_run(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, int json_f
     const uint8_t *d_in;
     uint32_t n_rec = 0, nb, h_flags[FLBGPU_MAX_FILTERS + 1];
     size_t off = 0, S = slice_bytes(), at, need;
-    unsigned long long undef = 0;
+    unsigned long long undef = 0, cnt[2] = { 0, 0 };
+    uint32_t *d_groups = NULL;
     uint64_t total;
     char *res;
 
@@ -74,13 +77,17 @@ static int tj_run(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, int json_f
         e.err = c->d_flags + FLBGPU_MAX_FILTERS;
         e.scr_pad = TJ_SCR_PAD(e.key_len == 0xffffffffu ? 0u : e.key_len);
         e.size = c->d_size;
-        /* work memory: the undefined-string counter, the packed lengths, the scratch slices */
-        need = 16 + sizeof(uint32_t) * (size_t) n_rec + 16 + bytes + (size_t) n_rec * e.scr_pad + 64;
+        /* work memory: the counters (undefined strings, group markers), the marker lists, the packed lengths, the scratch slices */
+        e.marks_cap = TJ_MARKS_CAP;
+        need = 16 + 3 * sizeof(uint32_t) * (size_t) TJ_MARKS_CAP + sizeof(uint32_t) * (size_t) n_rec + 64;
         GROW(c->d_mlw, c->cap_mlw, need, uint8_t);
         at = 0;
-        e.undefined = (unsigned long long *) (c->d_mlw + at); at += 16;
-        e.plen = (uint32_t *) (c->d_mlw + at); at += sizeof(uint32_t) * (size_t) n_rec; at = (at + 15) & ~(size_t) 15;
-        e.scr = c->d_mlw + at;
+        e.undefined = (unsigned long long *) (c->d_mlw + at); e.n_marks = e.undefined + 1; at += 16;
+        e.marks = (uint32_t *) (c->d_mlw + at); at += 2 * sizeof(uint32_t) * (size_t) TJ_MARKS_CAP;
+        d_groups = (uint32_t *) (c->d_mlw + at); at += sizeof(uint32_t) * (size_t) TJ_MARKS_CAP;
+        e.plen = (uint32_t *) (c->d_mlw + at);
+        GROW(c->d_scr, c->cap_scr, bytes + (size_t) n_rec * e.scr_pad + 64, uint8_t);
+        e.scr = c->d_scr;
         if (bk_zero(c->q, e.undefined, 16)) return -1;
         GROW(c->d_bsum, c->cap_bsum, nb + 2, uint64_t);
         if (c->cap_hbsum < (size_t) nb + 2) {
@@ -95,7 +102,36 @@ static int tj_run(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, int json_f
         if (refused(c, h_flags[FLBGPU_MAX_FILTERS])) return -1;
         total = c->h_bsum[nb];
         if (total >= 0xfff00000ull) { set_err("result larger than 4 GiB%s%s", NULL, NULL); return -1; }
-        if (bk_d2h(c->q, &undef, e.undefined, sizeof(undef)) || bk_sync(c->q)) return -1;
+        if (bk_d2h(c->q, cnt, e.undefined, sizeof(cnt)) || bk_sync(c->q)) return -1;
+        if (cnt[1]) {
+            /* group markers in the chunk: the events behind a start carry its body as group_attributes -- the list in record
+             * order, and the sizing pass again with it */
+            uint32_t *h = malloc(2 * sizeof(uint32_t) * (size_t) cnt[1]), maxlen = 0;
+            size_t a, b2;
+            if (!h) return -1;
+            if (bk_d2h(c->q, h, e.marks, 2 * sizeof(uint32_t) * (size_t) cnt[1]) || bk_sync(c->q)) { free(h); return -1; }
+            for (a = 0; a < (size_t) cnt[1]; a++) { if (h[2 * a + 1] > maxlen) maxlen = h[2 * a + 1]; h[a] = h[2 * a]; }
+            for (a = 1; a < (size_t) cnt[1]; a++) {      /* a handful: insertion sort */
+                const uint32_t v = h[a];
+                for (b2 = a; b2 > 0 && h[b2 - 1] > v; b2--) h[b2] = h[b2 - 1];
+                h[b2] = v;
+            }
+            if (bk_h2d(c->q, d_groups, h, sizeof(uint32_t) * (size_t) cnt[1]) || bk_sync(c->q)) { free(h); return -1; }
+            free(h);
+            e.groups = d_groups; e.n_groups = (uint32_t) cnt[1];
+            e.scr_pad += maxlen + 32;                   /* an event's packed map now holds a marker's body too */
+            GROW(c->d_scr, c->cap_scr, bytes + (size_t) n_rec * e.scr_pad + 64, uint8_t);
+            e.scr = c->d_scr;
+            if (bk_zero(c->q, e.undefined, 8)) return -1;
+            if (bk_tj_sizes(c->q, &e) || bk_sizes_scan(c->q, c->d_size, n_rec, c->d_bsum, c->h_bsum)) return -1;
+            if (bk_flags_fetch(c->q, c->d_flags, h_flags)) return -1;
+            if (h_flags[FLBGPU_MAX_FILTERS] & FLBGPU_E_JSONDATE) return 1;
+            if (refused(c, h_flags[FLBGPU_MAX_FILTERS])) return -1;
+            total = c->h_bsum[nb];
+            if (total >= 0xfff00000ull) { set_err("result larger than 4 GiB%s%s", NULL, NULL); return -1; }
+            if (bk_d2h(c->q, cnt, e.undefined, sizeof(cnt)) || bk_sync(c->q)) return -1;
+        }
+        undef = cnt[0];
     }
     bk_upload_end(c->q);
     c->st.kernel_launches = bk_launch_count();

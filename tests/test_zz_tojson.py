@@ -81,8 +81,10 @@ def chunk(rng, n, with_meta=True):
         sec = rng.choice([0, 1, 1700000000, 1700000000 + i, 2 ** 31 - 1, 951782400, 1709164800])
         nsec = rng.choice([0, 1, 999, 1000, 123456789, 999999999, 500000000])
         r = rng.random()
-        if r < 0.05:
-            evs.append(b"\x92\x92\xd7\x00\xff\xff\xff\xfe\x00\x00\x00\x00\x80\x80")          # an event the decoder steps over
+        if r < 0.03:
+            evs.append(b"\x92\x92\xd7\x00\xff\xff\xff\xfe\x00\x00\x00\x00\x80\x80")          # a group end marker (the decoder steps over it)
+        elif r < 0.07:                                                                               # a group start marker with attributes
+            evs.append(b"\x92\x92\xd7\x00\xff\xff\xff\xff\x00\x00\x00\x00\x80" + rng.choice([b"\x80", b"\x81" + S(b"res") + value(rng, 2)]))
         if r < 0.1:
             evs.append(b"\x92\xce" + struct.pack(">I", sec) + body)                              # legacy [ts, body]
         elif r < 0.15:
@@ -154,9 +156,17 @@ def _edges(lib):
             assert ctx.to_json(e * 3, jf, df, "d", True)[0] == ref.to_json(e * 3, jf, df, "d", True)
     # garbage behind the events: what decodes is converted
     assert ctx.to_json(e + e + b"\xc1\xc1", 3)[0] == ref.to_json(e + e + b"\xc1\xc1", 3)
-    # a group start marker: the events behind it would carry its body as group_attributes -- refused, loudly
-    with pytest.raises(pkg.FlbGpuError):
-        ctx.to_json(b"\x92\x92\xd7\x00\xff\xff\xff\xff\x00\x00\x00\x00\x80\x81\xa1g\x01" + e, 3)
+    # group markers: the events between a start (seconds -1) and an end (-2) carry the start's body as group_attributes
+    def marker(sec, body, meta=b"\x80"):
+        return b"\x92\x92\xd7\x00" + struct.pack(">iI", sec, 0) + meta + body
+    attrs = b"\x82" + S(b"resource") + b"\x81" + S(b"svc") + S(b"api") + S(b"n") + b"\x05"
+    with_meta = b"\x92\x92\xd7\x00" + struct.pack(">II", 1700000001, 7) + b"\x81" + S(b"m") + b"\x01" + b"\x81" + S(b"a") + b"\x02"
+    grouped = (e + marker(-1, attrs, b"\x81" + S(b"schema") + S(b"otlp")) + e + with_meta + marker(-2, b"\x80") + e + with_meta +
+               marker(-1, b"\x80") + e + with_meta + marker(-1, attrs) + e + marker(-3, attrs) + e)
+    for jf in (1, 2, 3):
+        for esc in (True, False):
+            got, und = ctx.to_json(grouped, jf, 1, "date", esc)
+            assert und == 0 and got == ref.to_json(grouped, jf, 1, "date", esc)
     # a string as the event's last value, out of step after multi-byte characters: counted, not compared
     odd = util.event(1700000000, 0, [(b"m", S(("é" * 15).encode() + b"abc"))])
     assert ctx.to_json(odd, 3, 0, "date", False)[1] == 1
