@@ -71,11 +71,6 @@ FLB_HDN void ml_feat_record(const struct ml_env *e, uint32_t i)
         const uint8_t *q, *end;
         f.bits = MLF_LIVE;
         ml_rec_open(e, e->off[i], e->len[i], &r);
-        if (r.meta) {                                   /* only the empty map is carried (see FLBGPU_E_MLMETA) */
-            struct mp_tok t;
-            mp_token(r.meta, r.meta_end, &t);
-            if (t.len != 0) CH_ATOMIC_OR(e->err, FLBGPU_E_MLMETA);
-        }
         q = r.kv; end = r.body_end;
         if (m->key_len != 0xffffffffu) {
             const uint8_t *key = e->blob + m->key_off;
@@ -174,7 +169,7 @@ FLB_HD uint32_t ml_step(const struct cf_ml *m, const struct cf_ml_rule *R, uint3
     if (!processed) {
         /* flb_ml_append_object(): nothing took the line -- what is pending goes out, then the record on its own */
         if (b | c) act |= MLA_FB;
-        act |= MLA_FA | MLA_CTXMAP | MLA_CTXTIME;
+        act |= MLA_FA | MLA_CTXMAP | MLA_CTXTIME | MLA_ALONE;
         b = 0; c = 0;
     }
     return (rc << 2) | (b << 1) | c | (act << 8);
@@ -285,6 +280,125 @@ FLB_HD void ml_event_range(const struct ml_env *e, uint32_t j, uint32_t *first, 
     *tl = hi ? e->tl[hi - 1] : 0;
 }
 
+/* ---- the metadata of a message: the members of its lines' metadata maps in the order the lines came, a member dropped when an
+ * earlier one of the message has the same hash (flb_ml_flush_metadata_buffer(), flb_ml.c:1501-1583).  The hash
+ * (flb_hash_msgpack_object_list, :1013-1135) is taken over key and value FLATTENED: scalars in document order, nil as eight
+ * zero bytes, integers and reals as their eight bytes, strings / bins / ext bodies as their bytes, containers as nothing but
+ * their members -- so {"a": "bc"} and {"ab": "c"} are the same member to it.  Bins have become lower-case hex strings before
+ * (flb_ml_msgpack_object_deep_copy_convert(), :1286-1443).  Two independent 64-bit hashes over the same flattened bytes stand
+ * in for cfl_hash_64bits here: equal bytes give equal hashes in both, different bytes collide in neither (2^-128). */
+FLB_HD void ml_md_hash_bytes(uint64_t h[2], const uint8_t *p, uint32_t n)
+{
+    uint32_t i;
+    for (i = 0; i < n; i++) {
+        h[0] = (h[0] ^ p[i]) * 0x100000001b3ull;
+        h[1] = (h[1] + p[i] + 1u) * 0x9e3779b97f4a7c15ull; h[1] ^= h[1] >> 29;
+    }
+}
+FLB_HD void ml_md_hash(const uint8_t *p, const uint8_t *end, uint64_t h[2])      /* [p, end): a key and its value */
+{
+    struct mp_tok t;
+    h[0] = 0xcbf29ce484222325ull; h[1] = 0x243f6a8885a308d3ull;
+    while (p < end && mp_token(p, end, &t) == 0) {
+        uint8_t w[8];
+        uint64_t v = 0;
+        uint32_t i;
+        switch (t.type) {
+        case MPT_NIL: for (i = 0; i < 8; i++) w[i] = 0; ml_md_hash_bytes(h, w, 8); break;
+        case MPT_BOOL: w[0] = (uint8_t) t.u; ml_md_hash_bytes(h, w, 1); break;
+        case MPT_UINT: case MPT_INT: case MPT_F64: case MPT_F32:
+            v = t.u;
+            if (t.type == MPT_F32) { union { uint32_t u; float f; } a; union { uint64_t u; double d; } c; a.u = (uint32_t) t.u; c.d = (double) a.f; v = c.u; }
+            for (i = 0; i < 8; i++) w[i] = (uint8_t) (v >> (8 * i));
+            ml_md_hash_bytes(h, w, 8);
+            break;
+        case MPT_STR: ml_md_hash_bytes(h, p + t.hdr, t.len); break;
+        case MPT_BIN:
+            for (i = 0; i < t.len; i++) { w[0] = "0123456789abcdef"[p[t.hdr + i] >> 4]; w[1] = "0123456789abcdef"[p[t.hdr + i] & 15]; ml_md_hash_bytes(h, w, 2); }
+            break;
+        case MPT_EXT: w[0] = (uint8_t) t.ext_type; ml_md_hash_bytes(h, w, 1); ml_md_hash_bytes(h, p + t.hdr, t.len); break;
+        default: break;                                  /* array / map headers */
+        }
+        p += t.hdr;
+        if (t.type == MPT_STR || t.type == MPT_BIN || t.type == MPT_EXT) p += t.len;
+    }
+}
+/* msgpack_pack_object() of the converted copy: mp_canon() with bins as hex strings */
+FLB_HD uint32_t ml_md_pack(const uint8_t *p, const uint8_t *end, uint8_t *o)
+{
+    struct mp_tok t;
+    uint32_t n = 0, i;
+    while (p < end && mp_token(p, end, &t) == 0) {
+        if (t.type == MPT_BIN) {
+            if (o) { mp_put_str_hdr(o + n, 2 * t.len); }
+            n += mp_str_hdr_size(2 * t.len);
+            for (i = 0; i < t.len; i++) {
+                if (o) { o[n] = "0123456789abcdef"[p[t.hdr + i] >> 4]; o[n + 1] = "0123456789abcdef"[p[t.hdr + i] & 15]; }
+                n += 2;
+            }
+            p += t.hdr + t.len;
+        }
+        else if (t.type == MPT_ARRAY || t.type == MPT_MAP) {
+            if (o) { if (t.type == MPT_MAP) mp_put_map_hdr(o + n, t.len); else mp_put_array_hdr(o + n, t.len); }
+            n += mp_cnt_hdr_size(t.len);
+            p += t.hdr;
+        }
+        else {
+            const uint8_t *nx = p + t.hdr + ((t.type == MPT_STR || t.type == MPT_EXT) ? t.len : 0);
+            n += mp_canon(p, nx, o ? o + n : 0, 0);
+            p = nx;
+        }
+    }
+    return n;
+}
+/* the metadata map of the message flush j carries: `df` + count + the surviving members; returns its size */
+FLB_HDN uint32_t ml_event_metadata(const struct ml_env *e, uint32_t j, uint32_t lo, uint32_t hi, uint8_t *o)
+{
+    const uint32_t slot = e->ev_slot[j];
+    uint64_t hs[ML_MD_MAX][2];
+    uint32_t n_seen = 0, kept = 0, n = 5, i, first, last1;
+    const int alone = (slot & 1u) && slot < 2u * e->n_rec && (e->act[slot >> 1] & MLA_ALONE);
+    if (alone) { first = slot >> 1; last1 = first + 1; }            /* everything older was purged when the line found no taker */
+    else {
+        /* the lines whose metadata was added since the previous flush: a line's goes in AFTER the rule ran on it, so the line a
+         * flush-after belongs to hands its metadata to the NEXT message */
+        const uint32_t p = j ? e->ev_slot[j - 1] : 0u;
+        first = j ? p >> 1 : 0u;
+        last1 = slot >> 1;                                           /* lines i with 2i + 1.5 < slot */
+        if (last1 > e->n_rec) last1 = e->n_rec;
+        (void) lo; (void) hi;
+    }
+    for (i = first; i < last1; i++) {
+        struct ml_rec r;
+        struct mp_tok t;
+        const uint8_t *q;
+        uint32_t k;
+        if (!(e->feat[i].bits & MLF_LIVE)) continue;
+        if (!alone && (e->act[i] & MLA_ALONE)) continue;             /* went out with its own */
+        ml_rec_open(e, e->off[i], e->len[i], &r);
+        if (!r.meta) continue;                                       /* a legacy event: the decoder's empty map */
+        mp_token(r.meta, r.meta_end, &t);
+        q = r.meta + t.hdr;
+        for (k = 0; k < t.len; k++) {
+            const uint8_t *vp = mp_skip(q, r.meta_end), *nx = mp_skip(vp, r.meta_end);
+            uint64_t h[2];
+            uint32_t x;
+            int dup = 0;
+            ml_md_hash(q, nx, h);
+            for (x = 0; x < n_seen && !dup; x++) if (hs[x][0] == h[0] && hs[x][1] == h[1]) dup = 1;
+            if (!dup) {
+                if (n_seen >= ML_MD_MAX) { CH_ATOMIC_OR(e->err, FLBGPU_E_MLMETA); return 5; }
+                hs[n_seen][0] = h[0]; hs[n_seen][1] = h[1]; n_seen++;
+                n += ml_md_pack(q, nx, o ? o + n : 0);
+                kept++;
+            }
+            q = nx;
+        }
+    }
+    if (o) { o[0] = 0xdf; mp_put_be32(o + 1, kept); }
+    return n;
+}
+
 /* size of the event (out == NULL) or its bytes.  The sizing pass leaves buffer length and context record for the emission. */
 FLB_HDN uint32_t ml_event(const struct ml_env *e, uint32_t j, uint8_t *out)
 {
@@ -321,9 +435,9 @@ FLB_HDN uint32_t ml_event(const struct ml_env *e, uint32_t j, uint8_t *out)
     if (out) {
         out[0] = 0x92; out[1] = 0x92; out[2] = 0xd7; out[3] = 0x00;
         mp_put_be32(out + 4, (uint32_t) sec); mp_put_be32(out + 8, (uint32_t) nsec);
-        out[12] = 0xdf; out[13] = out[14] = out[15] = out[16] = 0;
     }
-    n = 17;
+    n = 12;
+    n += ml_event_metadata(e, j, lo, hi, out ? out + n : 0);
     if (ctx) {
         struct ml_rec r;
         ml_rec_open(e, e->off[ctx - 1], e->len[ctx - 1], &r);

@@ -278,7 +278,7 @@ struct chain_hdr {
 #define FLBGPU_E_RXUNICODE 128u /* a pattern with POSIX brackets / \b / case-insensitivity met a non-ASCII subject */
 
 #define FLBGPU_E_MLLIMIT 1024u  /* multiline: a concatenated message reached the buffer limit (the reference truncates it and marks the record) */
-#define FLBGPU_E_MLMETA  2048u  /* multiline: an event with non-empty metadata (the merge of the lines' metadata is not restated) */
+#define FLBGPU_E_MLMETA  2048u  /* multiline: more metadata members in one message than the merge holds (ML_MD_MAX) */
 
 /* ---------------------------------------------------- filter_multiline (dev_ml.cuh) */
 /* One multiline parser instance as the filter runs it in `buffer off` mode (plugins/filter_multiline/ml.c:792-892,
@@ -315,6 +315,8 @@ struct ml_feat { uint32_t coff, clen, bits; };
 #define MLA_CTXMAP  16u  /* its map becomes the first-line context */
 #define MLA_CTXTIME 32u  /* its timestamp becomes the message's */
 #define MLA_FA      64u  /* the message is flushed (and comes out) right after this record */
+#define MLA_ALONE   128u /* nothing took the line: what was pending went out, the record goes out on its own */
+#define ML_MD_MAX 48u    /* metadata members of the lines of one message (before the duplicates go) */
 #define ML_F1 64u        /* records per automaton block, blocks per super-block */
 #define ML_F2 128u
 #define ML_MAX_STATES ((ML_MAX_RULES + 1) * 4)

@@ -30,7 +30,7 @@ def multiline():
         rf = ref.filter("multiline", props)
         calls = []
         for k in range(3):
-            c = TM.make_chunk(rng, voc, 60, 1700000000 + 1000 * k)
+            c = TM.make_chunk(rng, voc, 60, 1700000000 + 1000 * k, with_meta=0.3 * (k % 2))
             ret, res = ref.filter_cb(rf, c)
             calls.append({"in": B(c), "ret": ret, "out": B(res) if res is not None else None})
         out.append({"name": name, "type": typ, "match_string": ms, "negate": neg, "rules": rules, "props": props, "calls": calls})

@@ -38,7 +38,8 @@ def main():
     for k in range(rounds):
         rs = rules(rng)
         props = [("multiline.parser", "f"), ("multiline.key_content", "log"), ("buffer", "off")]
-        chunks = [T.make_chunk(rng, WORDS, rng.choice([1, 3, 20, 150]), 1700000000 + 1000 * c) for c in range(rng.randint(1, 4))]
+        wm = rng.choice([0.0, 0.2, 1.0])
+        chunks = [T.make_chunk(rng, WORDS, rng.choice([1, 3, 20, 150]), 1700000000 + 1000 * c, with_meta=wm) for c in range(rng.randint(1, 4))]
         try:
             T.diff(lib, rs, props, chunks, name="f")
         except AssertionError as e:
