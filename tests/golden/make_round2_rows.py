@@ -12,7 +12,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import util
-import test_multiline as TM
+import test_zy_multiline as TM
 import test_zz_tojson as TJ
 
 B = lambda b: base64.b64encode(b).decode()

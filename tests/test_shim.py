@@ -107,28 +107,6 @@ def test_shim_exports(ref_available):
         assert getattr(L, "filter_gpu_%s_plugin" % name)
 
 
-def _multiline(lib_path):
-    """gpu_multiline (built-in java parser, buffer off) in front of gpu_grep and gpu_modify, driven by the reference's own
-    flb_filter_do(): the chunks and the per-filter framework counters of the stock chain"""
-    import test_multiline
-    filters = [("multiline", [("multiline.parser", "java"), ("multiline.key_content", "log"), ("buffer", "off")]),
-               ("grep", [("Regex", "log Exception")]),
-               ("modify", [("Add", "multiline yes")])]
-    lines = list(test_multiline.JAVA) * 5
-    same_behaviour(lib_path, [], filters, [util.chunk_from_lines(lines[:37]), util.chunk_from_lines(lines[37:], t0=1700009000)])
-
-
-def test_shim_multiline_hostsim(ref_available):
-    need_shim()
-    _multiline(util.HOSTSIM_SO)
-
-
-@pytest.mark.gpu
-def test_shim_multiline_gpu(gpu_lib, ref_available):
-    need_shim()
-    _multiline(GPU_LIB)
-
-
 def _rewrite_tag(lib_path):
     """BASELINE configs[3]: nginx parser + record_modifier + rewrite_tag -- the chunk that stays, the framework counters, and
     what reaches the emitter (in_emitter_add_record: per record there, per new tag here; the same bytes per tag)"""

@@ -5,6 +5,7 @@ import random
 
 import pytest
 
+import test_shim
 import util
 
 pkg = util.pkg
@@ -329,3 +330,26 @@ def test_multiline_chain_shapes_gpu(gpu_lib, ref_available):
 @pytest.mark.gpu
 def test_multiline_large_gpu(gpu_lib, ref_available):
     _large(gpu_lib, 40000)
+
+
+def _shim_multiline(lib_path):
+    """gpu_multiline (built-in java parser, buffer off) in front of gpu_grep and gpu_modify, driven by the reference's own
+    flb_filter_do(): the chunks and the per-filter framework counters of the stock chain"""
+    filters = [("multiline", [("multiline.parser", "java"), ("multiline.key_content", "log"), ("buffer", "off")]),
+               ("grep", [("Regex", "log Exception")]),
+               ("modify", [("Add", "multiline yes")])]
+    lines = list(JAVA) * 5
+    test_shim.same_behaviour(lib_path, [], filters, [util.chunk_from_lines(lines[:37]), util.chunk_from_lines(lines[37:], t0=1700009000)])
+
+
+def test_shim_multiline_hostsim(ref_available):
+    test_shim.need_shim()
+    _shim_multiline(util.HOSTSIM_SO)
+
+
+@pytest.mark.gpu
+def test_shim_multiline_gpu(gpu_lib, ref_available):
+    test_shim.need_shim()
+    _shim_multiline(test_shim.GPU_LIB)
+
+

@@ -8,7 +8,7 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
 import util
-import test_multiline as T
+import test_zy_multiline as T
 
 pkg = util.pkg
 PATS = [r"/^A/", r"/^B/", r"/^\s+at/", r"/^$/", r"/x/", r"/^[a-c]+$/", r"/./", r"/^(E|F).*:$/", r"/\d+/", r"/^ /", r"/\n$/"]
