@@ -17,12 +17,14 @@ $(CSRC)/kernels_ml.o: $(CSRC)/kernels_ml.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $(CSRC)/kernels_ml.cu -o $@
 $(CSRC)/kernels_tojson.o: $(CSRC)/kernels_tojson.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $(CSRC)/kernels_tojson.cu -o $@
+$(CSRC)/kernels_lines.o: $(CSRC)/kernels_lines.cu $(HDRS)
+	$(NVCC) $(NVFLAGS) -c $(CSRC)/kernels_lines.cu -o $@
 $(CSRC)/runtime.o: $(CSRC)/runtime.c $(HDRS)
 	gcc $(CFLAGS) -c $(CSRC)/runtime.c -o $@
 $(CSRC)/rx_compile.o: $(CSRC)/rx_compile.c $(HDRS)
 	gcc $(CFLAGS) -c $(CSRC)/rx_compile.c -o $@
-$(PKG)/libflbgpu.so: $(CSRC)/kernels.o $(CSRC)/kernels_ml.o $(CSRC)/kernels_tojson.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o
-	$(NVCC) -shared -o $@ $(CSRC)/kernels.o $(CSRC)/kernels_ml.o $(CSRC)/kernels_tojson.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o -lcudart -lpthread -ldl
+$(PKG)/libflbgpu.so: $(CSRC)/kernels.o $(CSRC)/kernels_ml.o $(CSRC)/kernels_tojson.o $(CSRC)/kernels_lines.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o
+	$(NVCC) -shared -o $@ $(CSRC)/kernels.o $(CSRC)/kernels_ml.o $(CSRC)/kernels_tojson.o $(CSRC)/kernels_lines.o $(CSRC)/runtime.o $(CSRC)/rx_compile.o -lcudart -lpthread -ldl
 
 hostsim: tests/hostsim/libhostsim.so
 tests/hostsim/libhostsim.so: tests/hostsim/hostsim.cpp $(CSRC)/runtime.c $(CSRC)/rx_compile.c $(wildcard $(CSRC)/*.cuh) $(wildcard $(CSRC)/*.h)

@@ -209,6 +209,14 @@ int bk_ml_emit(bk_q *q, const struct ml_env *e, uint32_t n_ev, const uint64_t *d
 int bk_tj_sizes(bk_q *q, const struct tj_env *e);
 int bk_tj_emit(bk_q *q, const struct tj_env *e, const uint64_t *d_bsum, uint8_t *d_out);
 
+/* raw text -> log events (dev_lines.cuh), asynchronous on the queue's stream.  count: e->cnt[t] per tile; fill: e->nl[] from the
+ * tile offsets (d_bsum per BK_REC_BLOCK tiles); sizes: e->size[k] per line; emit: line k's event at d_out + d_bsum[k / BK_REC_BLOCK]
+ * + (sizes before it in its block). */
+int bk_ln_count(bk_q *q, const struct ln_env *e);
+int bk_ln_fill(bk_q *q, const struct ln_env *e, const uint64_t *d_bsum);
+int bk_ln_sizes(bk_q *q, const struct ln_env *e);
+int bk_ln_emit(bk_q *q, const struct ln_env *e, const uint64_t *d_bsum, uint8_t *d_out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -379,6 +379,22 @@ struct tj_env {
 #define TJ_DATE_EPOCH_MS 4u
 #define TJ_SCR_PAD(key_len) ((key_len) + 128u)
 
+/* ---------------------------------------------------- raw text -> log events (dev_lines.cuh) */
+#define LN_TILE 256u
+struct ln_env {
+    const uint8_t *text; size_t bytes;
+    uint32_t n_tiles, n_lines;
+    uint32_t *cnt;                    /* line feeds per tile */
+    uint32_t *nl;                     /* position of line feed k */
+    uint32_t *size;                   /* bytes of the event of line k */
+    unsigned long long *n_events;     /* lines that became events */
+    int64_t sec, nsec;                /* the timestamp of the call (the reference stamps every line with "now") */
+    uint32_t skip_empty_lines;
+    uint64_t stream_offset;
+    const uint8_t *strs;              /* key, path_key, path, offset_key, back to back */
+    uint32_t key_off, key_len, path_key_off, path_key_len, path_off, path_len, offset_key_off, offset_key_len;   /* _len 0xffffffff: absent */
+};
+
 /* ---------------------------------------------------- streaming JSON packer (dev_jsmn.cuh) */
 enum { JM_UNDEFINED = 0, JM_OBJECT = 1, JM_ARRAY = 2, JM_STRING = 4, JM_PRIMITIVE = 8 };     /* jsmntype_t, lib/jsmn/jsmn.h */
 struct jm_tok { int32_t type, start, end, size, parent; };

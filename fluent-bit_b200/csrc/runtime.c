@@ -1865,6 +1865,7 @@ static int stops_at_wide_array(bk_q *q, const uint8_t *h_in, const uint8_t *d_in
 
 #include "runtime_ml.h"
 #include "runtime_tojson.h"
+#include "runtime_lines.h"
 
 /* flb_router_match() (src/flb_router.c:37-128): Match_Regex first -- onig_match() at the start of the tag with a match of
  * positive length -- then the Match pattern, where '*' stands for any run of characters. */

@@ -131,6 +131,19 @@ int  flbgpu_pack_json_state_batch(flbgpu_ctx *ctx, int n, const char *const *js,
 int flbgpu_msgpack_to_json_format(flbgpu_ctx *ctx, const void *data, size_t bytes, int json_format, int date_format,
                                   const char *date_key, int escape_unicode, char **out, size_t *out_size, size_t *undefined_strings);
 
+/* ---- input side: raw text as log events -------------------------------------------------------------------------
+ * The line loop of in_tail, plugins/in_tail/tail_file.c process_content() :629-700 and flb_tail_file_pack_line() :338-391, for
+ * the plain case (no parser, no docker mode, none of the tail's own multiline modes): the text is cut at '\n'; with
+ * skip_empty_lines an empty line and a lone "\r" are stepped over; a line of two bytes or more loses a trailing '\r'; every
+ * line becomes one event `[[time, {}], {[path_key: path,] [offset_key: stream_offset + offset of the line,] key: line}]`.
+ * The reference stamps each line with the current time; here the caller gives the time of the call.  *consumed = the bytes up
+ * to and including the last '\n' (what in_tail's processed_bytes comes to: the rest of the buffer is an unfinished line and
+ * stays with the caller), *lines = the lines that became events.  path_key / offset_key may be NULL.  Returns 0 with *out_buf a malloc()ed
+ * chunk (NULL when no event came out), -1 on failure. */
+int flbgpu_lines_to_events(flbgpu_ctx *ctx, const char *text, size_t bytes, const char *key, int skip_empty_lines,
+                           int64_t sec, int64_t nsec, const char *path_key, const char *path, const char *offset_key,
+                           uint64_t stream_offset, void **out_buf, size_t *out_size, size_t *consumed, size_t *lines);
+
 /* ---- multiline parser definitions ----------------------------------------------------------------------------
  * What a [MULTILINE_PARSER] section becomes (src/flb_parser.c:815-935): flb_ml_parser_create()
  * (src/multiline/flb_ml_parser.c:199-230; type = "regex" | "endswith" | "equal" | "eq", flb_ml_type_lookup()),

@@ -447,6 +447,55 @@ char *flbref_to_json_format(const void *data, size_t bytes, int json_format, int
     return r;
 }
 
+/* ---- ingest side: the line loop of in_tail (plugins/in_tail/tail_file.c process_content() :629-700 + go_next, and
+ * flb_tail_file_pack_line() :338-391) without a file behind it.  The loop -- cut at '\n', the skip_empty_lines rule, the
+ * trailing '\r' of lines of two bytes and more -- is RESTATED here line for line (the original is a static function over
+ * struct flb_tail_file); every event is encoded by the reference's own flb_log_event_encoder calls, the ones pack_line makes,
+ * with the timestamp given instead of "now".  *consumed = processed_bytes.  Returns a malloc()ed chunk (flbref_cfree). */
+#include <fluent-bit/flb_log_event_encoder.h>
+char *flbref_lines_to_events(const char *text, size_t bytes, const char *key, int skip_empty_lines, long long sec, long long nsec,
+                             const char *path_key, const char *path, const char *offset_key, unsigned long long stream_offset,
+                             size_t *out_len, size_t *consumed, size_t *lines)
+{
+    struct flb_log_event_encoder *enc = flb_log_event_encoder_create(FLB_LOG_EVENT_FORMAT_DEFAULT);
+    const char *data = text, *end = text + bytes, *p;
+    size_t processed_bytes = 0, n_lines = 0;
+    struct flb_time tm;
+    char *out;
+
+    tm.tm.tv_sec = (time_t) sec; tm.tm.tv_nsec = (long) nsec;
+    while (data < end && (p = memchr(data, '\n', end - data))) {
+        size_t len = (size_t) (p - data);
+        int crlf = 0, result;
+        if (skip_empty_lines) {
+            if (len == 0) { data++; processed_bytes++; continue; }
+            else if (len == 1 && data[0] == '\r') { data += 2; processed_bytes += 2; continue; }
+        }
+        if (len >= 2) crlf = (data[len - 1] == '\r');
+        result = flb_log_event_encoder_begin_record(enc);
+        if (result == FLB_EVENT_ENCODER_SUCCESS) result = flb_log_event_encoder_set_timestamp(enc, &tm);
+        if (path_key && result == FLB_EVENT_ENCODER_SUCCESS)
+            result = flb_log_event_encoder_append_body_values(enc, FLB_LOG_EVENT_CSTRING_VALUE(path_key),
+                                                              FLB_LOG_EVENT_STRING_VALUE(path, strlen(path)));
+        if (offset_key && result == FLB_EVENT_ENCODER_SUCCESS)
+            result = flb_log_event_encoder_append_body_values(enc, FLB_LOG_EVENT_CSTRING_VALUE(offset_key),
+                                                              FLB_LOG_EVENT_UINT64_VALUE(stream_offset + processed_bytes));
+        if (result == FLB_EVENT_ENCODER_SUCCESS)
+            result = flb_log_event_encoder_append_body_values(enc, FLB_LOG_EVENT_CSTRING_VALUE(key),
+                                                              FLB_LOG_EVENT_STRING_VALUE(data, len - crlf));
+        if (result == FLB_EVENT_ENCODER_SUCCESS) result = flb_log_event_encoder_commit_record(enc);
+        n_lines++;
+        data += len + 1;
+        processed_bytes += len + 1;
+    }
+    *out_len = enc->output_length;
+    out = malloc(enc->output_length + 1);
+    memcpy(out, enc->output_buffer, enc->output_length);
+    *consumed = processed_bytes; *lines = n_lines;
+    flb_log_event_encoder_destroy(enc);
+    return out;
+}
+
 /* ---- multiline parser definitions: what a [MULTILINE_PARSER] section becomes (src/flb_parser.c:815-935):
  * flb_ml_parser_create(), one flb_ml_rule_create() per `rule`, flb_ml_parser_init() ---- */
 void *flbref_ml_parser_create(void *cfg, const char *name, const char *type, const char *match_string, int negate,

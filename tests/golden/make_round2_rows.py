@@ -1,6 +1,7 @@
 """Golden vectors of the rows added late in round 2, produced from the UNMODIFIED reference (oracle/_ref):
   multiline_vectors.json -- filter_multiline (buffer off): parser definition, filter properties, chunks in, (ret, chunk) out per call
   tojson_vectors.json ---- flb_pack_msgpack_to_json_format(): arguments, chunk in, text out
+  lines_vectors.json ----- in_tail's line loop (restated in the harness) + the reference's encoder: text in, chunk / consumed / lines out
     python tests/golden/make_round2_rows.py
 The tests that read them (tests/test_golden.py) need neither /root/reference nor oracle/_ref."""
 import base64
@@ -62,8 +63,26 @@ def tojson():
     return out
 
 
+def lines():
+    import test_zz_lines as TL
+    rng = random.Random(33)
+    ref = util.Ref()
+    out = []
+    for r in range(30):
+        t = TL.text(rng, rng.choice([0, 1, 3, 12, 40]))
+        kw = dict(key=rng.choice(["log", "message"]), skip_empty_lines=bool(r % 2), sec=1700000000 + r, nsec=r * 1000)
+        if r % 3 == 0:
+            kw.update(path_key="file", path="/var/log/x-%d.log" % r)
+        if r % 4 == 0:
+            kw.update(offset_key="offset", stream_offset=2 ** 31 * (r % 8))
+        chunk, used, n = ref.lines_to_events(t, **kw)
+        out.append({"text": B(t), "kw": kw, "out": B(chunk) if chunk is not None else None, "consumed": used, "lines": n})
+    return out
+
+
 if __name__ == "__main__":
     g = os.path.join(ROOT, "tests", "golden")
     json.dump(multiline(), open(os.path.join(g, "multiline_vectors.json"), "w"), indent=0)
     json.dump(tojson(), open(os.path.join(g, "tojson_vectors.json"), "w"), indent=0)
+    json.dump(lines(), open(os.path.join(g, "lines_vectors.json"), "w"), indent=0)
     print("written")

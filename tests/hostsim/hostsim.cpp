@@ -74,6 +74,7 @@ int sim_rx_search(void *h, const char *s, int len, int *caps, int stack_words, u
 #include "../../fluent-bit_b200/csrc/dev_chain.cuh"
 #include "../../fluent-bit_b200/csrc/dev_ml.cuh"
 #include "../../fluent-bit_b200/csrc/dev_tojson.cuh"
+#include "../../fluent-bit_b200/csrc/dev_lines.cuh"
 
 static thread_local char hs_err[256];
 static uint64_t hs_launches;
@@ -490,6 +491,42 @@ int bk_jsmn_emit(bk_q *, const struct bk_jsmn_args *a)
     return 0;
 }
 int bk_small_fetch(bk_q *, void *h_dst, const uint8_t *d_out, size_t n) { memcpy(h_dst, d_out, n); return 0; }
+
+/* raw text -> log events: the launches of kernels_lines.cu as loops */
+int bk_ln_count(bk_q *, const struct ln_env *e)
+{
+    for (uint32_t t = 0; t < e->n_tiles; t++) e->cnt[t] = ln_count(e, t);
+    hs_launches += 1;
+    return 0;
+}
+int bk_ln_fill(bk_q *, const struct ln_env *e, const uint64_t *d_bsum)
+{
+    uint64_t at = 0;
+    for (uint32_t t = 0; t < e->n_tiles; t++) {
+        if (t % BK_REC_BLOCK == 0) at = d_bsum[t / BK_REC_BLOCK];
+        ln_fill(e, t, at);
+        at += e->cnt[t];
+    }
+    hs_launches += 1;
+    return 0;
+}
+int bk_ln_sizes(bk_q *, const struct ln_env *e)
+{
+    for (uint32_t k = 0; k < e->n_lines; k++) { uint32_t a, b; e->size[k] = ln_line(e, k, &a, &b); if (e->size[k]) e->n_events[0]++; }
+    hs_launches += 1;
+    return 0;
+}
+int bk_ln_emit(bk_q *, const struct ln_env *e, const uint64_t *d_bsum, uint8_t *d_out)
+{
+    uint64_t at = 0;
+    for (uint32_t k = 0; k < e->n_lines; k++) {
+        if (k % BK_REC_BLOCK == 0) at = d_bsum[k / BK_REC_BLOCK];
+        if (e->size[k]) ln_emit(e, k, d_out + at);
+        at += e->size[k];
+    }
+    hs_launches += 1;
+    return 0;
+}
 
 /* chunk -> JSON text: the launches of kernels_tojson.cu as loops */
 int bk_tj_sizes(bk_q *, const struct tj_env *e)

@@ -43,6 +43,8 @@ class Ref:
         L.flbref_l2m_cmt_text.restype = vp; L.flbref_l2m_cmt_text.argtypes = [vp]
         L.flbref_cfree.argtypes = [vp]
         L.flbref_pack_json_state.argtypes = [cp, sz, C.POINTER(vp), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]
+        L.flbref_lines_to_events.restype = vp
+        L.flbref_lines_to_events.argtypes = [cp, sz, cp, C.c_int, C.c_longlong, C.c_longlong, cp, cp, cp, C.c_ulonglong, C.POINTER(sz), C.POINTER(sz), C.POINTER(sz)]
         L.flbref_to_json_format.restype = vp
         L.flbref_to_json_format.argtypes = [vp, sz, C.c_int, C.c_int, cp, C.c_int, C.POINTER(sz)]
         L.flbref_ml_parser_create.restype = vp
@@ -130,6 +132,16 @@ class Ref:
         if out.value:
             self.L.flbref_free(out)
         return r, data, (s.value, ns.value)
+
+    def lines_to_events(self, text, key="log", skip_empty_lines=True, sec=0, nsec=0, path_key=None, path=None, offset_key=None, stream_offset=0):
+        """in_tail's line loop with the reference's encoder: (chunk bytes or None, bytes consumed, lines seen)"""
+        n, used, lines = C.c_size_t(), C.c_size_t(), C.c_size_t()
+        b = self._b
+        p = self.L.flbref_lines_to_events(text, len(text), b(key), int(skip_empty_lines), sec, nsec, b(path_key), b(path), b(offset_key),
+                                          stream_offset, C.byref(n), C.byref(used), C.byref(lines))
+        out = C.string_at(p, n.value) if n.value else None
+        self.L.flbref_cfree(p)
+        return out, used.value, lines.value
 
     def to_json(self, data, json_format=3, date_format=0, date_key="date", escape_unicode=True):
         """flb_pack_msgpack_to_json_format(): bytes or None.  json_format 1 json / 2 stream / 3 lines; date_format 0 double /
