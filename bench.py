@@ -196,6 +196,13 @@ _BLOCKS = {}
 def _ref_state(wl):
     import util
     st = _REF_STATE.get(wl)
+    if st is None and wl == "textpath":
+        ref = util.Ref()
+        ref.parser(**parser_kw("apache"))
+        for p, props in WORKLOADS["apache"]["filters"]:
+            ref.filter(p, props)
+        st = _REF_STATE[wl] = (ref, textpath_input())
+        return st
     if st is None and wl == "tojson":
         ref = util.Ref()                              # the parsed events: the reference's own parser filter over the apache block
         ref.parser(**parser_kw("apache"))
@@ -247,6 +254,18 @@ def _ref_tojson_task(args):
         if p:
             ref.L.flbref_cfree(p)
     return time.perf_counter() - t0, BASE_LINES * reps
+
+
+def _ref_textpath_task(reps):
+    """one pool task: line loop + flb_filter_do + flb_pack_msgpack_to_json_format of the reference over this worker's text"""
+    ref, text = _ref_state("textpath")
+    t0 = time.perf_counter()
+    n = 0
+    for _ in range(reps):
+        ev, used, n = ref.lines_to_events(text, "log", True, 1700000000, 0)
+        ret, out = ref.chain_do(ev, "bench")
+        ref.to_json(out, 3, 1, "date", True)
+    return time.perf_counter() - t0, n * reps
 
 
 def _ref_task(args):
@@ -335,6 +354,14 @@ def run_reference(args):
             others["tojson"] = {"workload": TOJSON_NAME, "value": v, "e2e": v, "unit": "lines/s", "events_per_step": sum(r[1] for r in res)}
         except Exception as ex:
             others["tojson"] = {"workload": TOJSON_NAME, "error": "%s: %s" % (type(ex).__name__, ex)}
+        try:
+            pool.pool.map(_ref_textpath_task, [1] * cores, chunksize=1)
+            res = pool.pool.map(_ref_textpath_task, [2] * cores, chunksize=1)
+            v = sum(r[1] for r in res) / max(r[0] for r in res)
+            others["textpath"] = {"workload": TEXTPATH_NAME, "value": v, "e2e": v, "unit": "lines/s", "events_per_step": sum(r[1] for r in res),
+                                  "note": "the line loop restated in the harness around the reference's encoder; python ctypes wrappers on this side too"}
+        except Exception as ex:
+            others["textpath"] = {"workload": TEXTPATH_NAME, "error": "%s: %s" % (type(ex).__name__, ex)}
     pool.close()
     sample = "%d cores (%s), %d events per step in %d-event calls, one pipeline per core, %d steps; time = slowest worker inside the reference's calls" % (
         cores, cores_note, n, min(BASE_LINES, -(-n // cores)), args.steps)
@@ -669,6 +696,45 @@ def measure_tojson(args, L, ctx, torch, world):
             "gpu_launches_per_call": 2, "undefined_strings": und.value}
 
 
+TEXTPATH_NAME = ("text in, text out: apache access log text -> in_tail's line loop (events) -> filter_parser(apache) + filter_grep(method) + "
+                 "filter_modify -> json_lines text; three library calls per 100 k-line buffer, host memory on both ends")
+
+
+def textpath_input():
+    import util
+    return b"\n".join(util.apache_lines(BASE_LINES, seed=0xF1B1 + 1)) + b"\n"
+
+
+def measure_textpath(args, L, ctx, torch, world):
+    """the whole path around the filters through the C ABI: flbgpu_lines_to_events + flbgpu_chain_do + flbgpu_msgpack_to_json_format"""
+    import util
+    text = textpath_input()
+    made = ctx.__dict__.setdefault("_bench_parsers", set())
+    if "apache" not in made:
+        ctx.parser(**parser_kw("apache"))
+        made.add("apache")
+    ch = ctx.chain([ctx.filter(p, props) for p, props in WORKLOADS["apache"]["filters"]])
+
+    def call():
+        ev, used, n = ctx.lines_to_events(text, "log", True, 1700000000, 0)
+        ret, out = ch.do(ev, tag="bench")
+        js, und = ctx.to_json(out, 3, 1, "date", True)
+        return n, len(js)
+    for _ in range(max(3, args.warmup)):
+        n, nbytes = call()
+    reps = max(5, args.steps * 2)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        call()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    ch.close()
+    return {"workload": TEXTPATH_NAME, "e2e": world * n * reps / dt, "unit": "lines/s", "lines_per_call": n, "text_in_bytes": len(text),
+            "text_out_bytes": nbytes, "calls": reps, "ms_per_call": 1000 * dt / reps,
+            "note": "python ctypes wrappers copy every buffer once more than a C caller would"}
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -709,6 +775,13 @@ def run_ours(args):
             tojson = measure_tojson(args, L, ctx, torch, world)
         except Exception as ex:
             tojson = {"workload": TOJSON_NAME, "error": "%s: %s" % (type(ex).__name__, ex)}
+
+    textpath = None
+    if not args.primary_only:
+        try:
+            textpath = measure_textpath(args, L, ctx, torch, world)
+        except Exception as ex:
+            textpath = {"workload": TEXTPATH_NAME, "error": "%s: %s" % (type(ex).__name__, ex)}
 
     # last: the same end-to-end calls with an allocator that retains freed result buffers (and pinned input)
     tune_malloc()
@@ -814,6 +887,8 @@ def run_ours(args):
     line["workloads"] = {k: side(v, k) for k, v in others.items()}
     if tojson is not None:
         line["workloads"]["tojson"] = tojson
+    if textpath is not None:
+        line["workloads"]["textpath"] = textpath
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
