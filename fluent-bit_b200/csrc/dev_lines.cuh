@@ -17,11 +17,39 @@
 #define FLBGPU_DEV_LINES_CUH
 #include "dev_msgpack.cuh"
 
+/* 0x80 in every byte of x that is a line feed (exact: no borrow between bytes) */
+FLB_HD uint64_t ln_nl_mask(uint64_t x)
+{
+    const uint64_t m = x ^ 0x0a0a0a0a0a0a0a0aull, k = 0x7f7f7f7f7f7f7f7full;
+    return ~(((m & k) + k) | m | k);
+}
+FLB_HD int ln_popc64(uint64_t v)
+{
+#ifdef __CUDA_ARCH__
+    return __popcll(v);
+#else
+    return __builtin_popcountll(v);
+#endif
+}
+FLB_HD int ln_ctz64(uint64_t v)
+{
+#ifdef __CUDA_ARCH__
+    return __ffsll((long long) v) - 1;
+#else
+    return __builtin_ctzll(v);
+#endif
+}
+/* a whole tile is read as 64-bit words (the text starts at an allocation, tiles at multiples of LN_TILE); the last one by bytes */
 FLB_HD uint32_t ln_count(const struct ln_env *e, uint32_t t)
 {
     const size_t lo = (size_t) t * LN_TILE, hi = lo + LN_TILE < e->bytes ? lo + LN_TILE : e->bytes;
     uint32_t n = 0;
     size_t i;
+    if (hi - lo == LN_TILE && (((uintptr_t) (e->text + lo)) & 7u) == 0) {
+        const uint64_t *w = (const uint64_t *) (e->text + lo);
+        for (i = 0; i < LN_TILE / 8; i++) n += (uint32_t) ln_popc64(ln_nl_mask(w[i]));
+        return n;
+    }
     for (i = lo; i < hi; i++) n += e->text[i] == '\n';
     return n;
 }
@@ -29,6 +57,14 @@ FLB_HD void ln_fill(const struct ln_env *e, uint32_t t, uint64_t at)
 {
     const size_t lo = (size_t) t * LN_TILE, hi = lo + LN_TILE < e->bytes ? lo + LN_TILE : e->bytes;
     size_t i;
+    if (hi - lo == LN_TILE && (((uintptr_t) (e->text + lo)) & 7u) == 0) {
+        const uint64_t *w = (const uint64_t *) (e->text + lo);
+        for (i = 0; i < LN_TILE / 8; i++) {
+            uint64_t m = ln_nl_mask(w[i]);                /* little-endian: byte j of the word is bits 8j .. 8j + 7 */
+            while (m) { e->nl[at++] = (uint32_t) (lo + 8 * i + (size_t) (ln_ctz64(m) >> 3)); m &= m - 1; }
+        }
+        return;
+    }
     for (i = lo; i < hi; i++) if (e->text[i] == '\n') e->nl[at++] = (uint32_t) i;
 }
 /* line k: [start, start + keep) is what the event carries; returns the event's size, 0 when the line is stepped over */
