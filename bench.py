@@ -501,7 +501,7 @@ class Workload:
         r = self.L.flbgpu_chain_do(chain.h, ptr, n, b"bench", 5, C.byref(out), C.byref(osz))
         if r < 0:
             raise RuntimeError("chain_do -> %d: %s" % (r, self.ctx.err()))
-        if out.value:
+        if out.value and out.value != getattr(self, "keep", None):
             _libc.free(out)
         return osz.value
 
@@ -598,6 +598,27 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local, full=True):
     phases = [round(float(x), 2) for x in w.chain.stats().phase_ms]
     variants = {}
     if full:
+        # the same calls with the result written into a buffer the caller keeps (flbgpu_chain_set_result_buffer): no fresh pages
+        # per call; an ordinary reused heap buffer, then a pinned one
+        try:
+            cap = int(out_bytes * 1.05) + (1 << 20)
+            for name, alloc, release in (("reused_heap_buffer", lambda n: _libc.malloc(n), lambda p: _libc.free(p)),
+                                         ("reused_pinned_buffer", lambda n: L.flbgpu_host_alloc(ctx.h, n), lambda p: L.flbgpu_host_free(ctx.h, p))):
+                rb = alloc(cap)
+                if not rb:
+                    continue
+                L.flbgpu_chain_set_result_buffer(w.chain.h, rb, cap)
+                w.keep = rb
+                w.step_host()
+                s = allmax(timed(lambda: [w.step_host() for _ in range(steps)], barrier))
+                variants[name] = {"value": world * n_lines * steps / s, "unit": "lines/s",
+                                  "note": "pageable input; the result goes into a buffer of the caller registered with flbgpu_chain_set_result_buffer()"}
+                L.flbgpu_chain_set_result_buffer(w.chain.h, None, 0)
+                w.keep = None
+                release(rb)
+        except Exception as ex:
+            variants["reused_result_buffer_error"] = "%s: %s" % (type(ex).__name__, ex)
+            w.keep = None
         w.step_host(pinned=True)
         s = allmax(timed(lambda: [w.step_host(pinned=True) for _ in range(steps)], barrier))
         variants["pinned_input"] = {"value": world * n_lines * steps / s, "unit": "lines/s", "note": "input in cudaMallocHost memory, glibc's untouched malloc"}

@@ -54,7 +54,7 @@ EXPORTS = [
     "flbgpu_comm_unique_id", "flbgpu_comm_init", "flbgpu_l2m_allreduce",
     "flbgpu_pack_state_init", "flbgpu_pack_state_reset", "flbgpu_pack_json_state", "flbgpu_pack_json_state_batch",
     "flbgpu_ml_parser_create", "flbgpu_ml_parser_rule", "flbgpu_ml_parser_init", "flbgpu_ml_set_buffer_limit",
-    "flbgpu_msgpack_to_json_format", "flbgpu_lines_to_events",
+    "flbgpu_msgpack_to_json_format", "flbgpu_lines_to_events", "flbgpu_chain_set_result_buffer",
 ]
 
 
@@ -111,6 +111,7 @@ def load(path=None):
     L.flbgpu_msgpack_to_json_format.argtypes = [vp, vp, sz, C.c_int, C.c_int, cp, C.c_int, C.POINTER(vp), C.POINTER(sz), C.POINTER(sz)]
     L.flbgpu_lines_to_events.argtypes = [vp, vp, sz, cp, C.c_int, C.c_int64, C.c_int64, cp, cp, cp, C.c_uint64, C.POINTER(vp), C.POINTER(sz),
                                          C.POINTER(sz), C.POINTER(sz)]
+    L.flbgpu_chain_set_result_buffer.argtypes = [vp, vp, sz]
     L.flbgpu_comm_unique_id.argtypes = [vp]
     L.flbgpu_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.flbgpu_l2m_allreduce.argtypes = [vp]
@@ -317,7 +318,8 @@ def _parser_do_batch(self, lines):
 Parser.do_batch = _parser_do_batch
 
 
-def _call_filter(fn, L, handle, data, tag):
+def _call_filter(fn, L, handle, data, tag, keep=None):
+    """keep: address of a result buffer registered with flbgpu_chain_set_result_buffer (not freed here)"""
     out, n = C.c_void_p(), C.c_size_t()
     buf = C.create_string_buffer(data, len(data)) if not isinstance(data, C.Array) else data
     r = fn(handle, C.cast(buf, C.c_void_p), len(data), _b(tag), len(_b(tag)), C.byref(out), C.byref(n))
@@ -327,7 +329,7 @@ def _call_filter(fn, L, handle, data, tag):
     res = None
     if r == FILTER_MODIFIED:
         res = C.string_at(out.value, n.value) if n.value else b""
-    if out.value:
+    if out.value and out.value != keep:
         _libc.free(out)
     return r, res
 
@@ -501,7 +503,13 @@ class Chain:
         return self.ctx.L.flbgpu_chain_stream(self.h)
 
     def do(self, data, tag="test"):
-        return _call_filter(self.ctx.L.flbgpu_chain_do, self.ctx.L, self.h, data, tag)
+        return _call_filter(self.ctx.L.flbgpu_chain_do, self.ctx.L, self.h, data, tag, keep=getattr(self, "_res_addr", None))
+
+    def set_result_buffer(self, nbytes):
+        """flbgpu_chain_set_result_buffer() with a buffer of nbytes owned by this object (0: back to malloc only)"""
+        self._res = C.create_string_buffer(nbytes) if nbytes else None
+        self._res_addr = C.addressof(self._res) if nbytes else None
+        self.ctx.L.flbgpu_chain_set_result_buffer(self.h, C.cast(self._res, C.c_void_p) if nbytes else None, nbytes)
 
     def stats(self):
         s = Stats()

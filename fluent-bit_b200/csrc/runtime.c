@@ -187,6 +187,8 @@ struct flbgpu_chain {
     /* `multiline, then other filters` (the shape of BASELINE configs[4]): the multiline filter runs as a chain of its own and
      * hands its result to a chain of the filters behind it on the device -- no trip through host memory in between */
     flbgpu_chain *ml_solo, *ml_post;
+    /* flbgpu_chain_set_result_buffer(): results that fit go here instead of into a fresh malloc() */
+    uint8_t *res_buf; size_t res_cap;
     int rtag_index;                           /* filter index of the rewrite_tag filter, or -1; -2 = several: the chain runs filter by filter */
     uint32_t *d_esize;                        /* rewrite_tag: bytes of each record's entry in the re-tagged stream */
     uint64_t *d_ebsum, *h_ebsum; size_t cap_ebsum;   /* ... and the scan over them */
@@ -1564,6 +1566,14 @@ void flbgpu_chain_destroy(flbgpu_chain *c)
 }
 
 void flbgpu_chain_stats(flbgpu_chain *c, struct flbgpu_stats *out) { if (c && out) *out = c->st; }
+int flbgpu_chain_set_result_buffer(flbgpu_chain *c, void *buf, size_t cap)
+{
+    if (!c) return -1;
+    pthread_mutex_lock(&c->lock);
+    c->res_buf = buf; c->res_cap = buf ? cap : 0;
+    pthread_mutex_unlock(&c->lock);
+    return 0;
+}
 void *flbgpu_chain_stream(flbgpu_chain *c) { return c ? bk_stream(c->q) : NULL; }
 int flbgpu_kernel_ms(flbgpu_ctx *ctx, float out[3])
 {
@@ -2107,26 +2117,27 @@ static int chain_run(flbgpu_chain *c, const uint8_t *h_in, const uint8_t *d_in_e
     else {
         const uint32_t step = 2048;                   /* blocks per emission launch (512 K records) */
         uint32_t b0;
-        void *out = malloc((size_t) total);
+        void *out = (c->res_buf && c->res_cap >= total) ? (void *) c->res_buf : malloc((size_t) total);
         if (!out) return -1;
+#define RES_FREE(p_) do { if ((uint8_t *) (p_) != c->res_buf) free(p_); } while (0)
 #ifdef MADV_HUGEPAGE
-        if (total >= ((size_t) 8 << 20)) {            /* fewer, larger page faults while the result is filled in */
+        if ((uint8_t *) out != c->res_buf && total >= ((size_t) 8 << 20)) {            /* fewer, larger page faults while the result is filled in */
             uintptr_t lo = ((uintptr_t) out + ((size_t) 2 << 20) - 1) & ~(((uintptr_t) 2 << 20) - 1);
             uintptr_t hi = ((uintptr_t) out + (size_t) total) & ~(((uintptr_t) 2 << 20) - 1);
             if (hi > lo) madvise((void *) lo, hi - lo, MADV_HUGEPAGE);
         }
 #endif
         GROW(c->d_out, c->cap_out, total, uint8_t);
-        if (bk_download_begin(c->q, out, c->d_out)) { free(out); return -1; }
+        if (bk_download_begin(c->q, out, c->d_out)) { RES_FREE(out); return -1; }
         for (b0 = 0; b0 < nb; b0 += step) {
             uint32_t b1 = b0 + step < nb ? b0 + step : nb;
             if (bk_chain_emit(c->q, &a, c->d_out, b0, b1) || bk_download_push(c->q, (size_t) c->h_bsum[b0], (size_t) c->h_bsum[b1])) {
                 bk_download_end(c->q);
-                free(out);
+                RES_FREE(out);
                 return -1;
             }
         }
-        if (bk_download_end(c->q)) { free(out); return -1; }
+        if (bk_download_end(c->q)) { RES_FREE(out); return -1; }
         *host_out = out;
     }
     c->st.kernel_launches = bk_launch_count();
@@ -2239,10 +2250,12 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
                     uint8_t *no_; \
                     if (want_ < c->h_bsum[b1_]) want_ = (size_t) c->h_bsum[b1_] + ((size_t) 8 << 20); \
                     if (dl_open) { if (bk_download_end(c->q)) { dl_open = 0; goto fail; } dl_open = 0; } \
-                    no_ = realloc(out, want_); \
+                    if (!out && c->res_buf && c->res_cap >= c->h_bsum[b1_]) { no_ = c->res_buf; want_ = c->res_cap; }   /* the caller's buffer, while the result fits */ \
+                    else if (out == c->res_buf && out) { no_ = malloc(want_); if (no_) memcpy(no_, out, (size_t) placed); }           /* outgrown: what has arrived moves */ \
+                    else no_ = realloc(out, want_); \
                     if (!no_) goto fail; \
                     out = no_; cap_out_h = want_; \
-                    hugepage_hint(out, want_); \
+                    if (out != c->res_buf) hugepage_hint(out, want_); \
                     GROW_KEEP_OUT(want_); \
                 } \
                 if (!dl_open) { if (bk_download_begin(c->q, out, c->d_out)) goto fail; dl_open = 1; } \
@@ -2330,8 +2343,8 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
     bk_records_out(c->q, &c->st.records_out);
     c->st.bytes_out = placed;
     *out_size = (size_t) placed;
-    if (placed == 0) { free(out); out = NULL; }
-    else if (cap_out_h > placed + placed / 2) {     /* badly over-estimated: give the excess back */
+    if (placed == 0) { RES_FREE(out); out = NULL; }
+    else if (out != c->res_buf && cap_out_h > placed + placed / 2) {     /* badly over-estimated: give the excess back */
         uint8_t *sh = realloc(out, (size_t) placed);
         if (sh) out = sh;
     }
@@ -2342,7 +2355,7 @@ static int chain_run_stream(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, 
     return 0;
 fail:
     if (dl_open) bk_download_end(c->q);
-    free(out);
+    RES_FREE(out);
     (void) rc;
     return -1;
 #undef STREAM_FLUSH
@@ -2441,9 +2454,9 @@ static int chain_run_small(flbgpu_chain *c, const uint8_t *h_in, size_t bytes, v
     *out_size = (size_t) res.total;
     *host_out = NULL;
     if (res.total) {
-        void *out = malloc((size_t) res.total);
+        void *out = (c->res_buf && c->res_cap >= res.total) ? (void *) c->res_buf : malloc((size_t) res.total);
         if (!out) { set_err("out of memory%s%s", NULL, NULL); return -1; }
-        if (bk_small_fetch(c->q, out, c->d_out, (size_t) res.total)) { free(out); return -1; }
+        if (bk_small_fetch(c->q, out, c->d_out, (size_t) res.total)) { RES_FREE(out); return -1; }
         *host_out = out;
     }
     clock_gettime(CLOCK_MONOTONIC, &t1);

@@ -230,6 +230,12 @@ struct flbgpu_stats {
      * (until the chunk-level verdicts are settled), [1] size scan, [2] emission + download, [3] total */
     float phase_ms[4];
 };
+/* Not part of the reference's contract (a filter returns a buffer the engine frees): an embedding that keeps its own result
+ * memory -- reused from call to call, or pinned with flbgpu_host_alloc() -- registers it here.  A result that fits is written
+ * there and *out_buf of flbgpu_chain_do() IS that buffer (do not free it); a larger one comes back malloc()ed as before.  With
+ * glibc's default malloc a fresh result buffer is fresh pages from the kernel on every call: on the bench's whole-set calls their
+ * page faults cost more than the device work.  buf NULL: back to malloc() only. */
+int flbgpu_chain_set_result_buffer(flbgpu_chain *c, void *buf, size_t cap);
 void flbgpu_chain_stats(flbgpu_chain *c, struct flbgpu_stats *out);
 /* Every chain (and every filter instance behind flbgpu_filter_cb) owns its device queue -- streams, pinned staging
  * rings, worker threads -- so instances may be called from different threads at the same time, as
