@@ -269,6 +269,42 @@ def _large(lib, n):
     diff(lib, EXC, props, [make_chunk(rng, VOCAB["exc"], n, 1700000000), make_chunk(rng, VOCAB["exc"][2:5], n // 4, 1700100000)], name="exc")
 
 
+GO_PUSHES = [b"panic: my panic", b"\n", b"goroutine 4 [running]:", b"panic(0x45cb40, 0x47ad70)",
+             b"  /usr/local/go/src/runtime/panic.go:542 +0x46c fp=0xc42003f7b8 sp=0xc42003f710 pc=0x422f7c", b"main.main.func1(0xc420024120)"]
+
+
+def _reference_runtime_unbuffered(lib):
+    """tests/runtime/filter_multiline.c:345-417 flb_test_multiline_unbuffered: the go parser with `buffer off`, six pushes of one
+    record each (timestamp 0: the message's time is "now") -- six records come out, no concatenation, the first holds "panic".
+    Compared with the reference's plugin record for record, the eight timestamp bytes apart; then the same six lines in ONE chunk
+    (and with real timestamps): one message."""
+    props = [("multiline.key_content", "log"), ("multiline.parser", "go"), ("buffer", "off"), ("debug_flush", "off")]
+    ref = util.Ref()
+    rf = ref.filter("multiline", props)
+    ctx = pkg.Context(0, lib=lib)
+    ch = ctx.chain([ctx.filter("multiline", props)])
+    outs = []
+    for line in GO_PUSHES:
+        c = util.event(0, 0, [(b"log", S(line))])
+        want, got = ref.filter_cb(rf, c), ch.do(c)
+        assert want[0] == got[0] == pkg.FILTER_MODIFIED
+        assert len(util.split_records(got[1])) == 1 and got[1][:4] == want[1][:4] and got[1][12:] == want[1][12:]
+        outs.append(got[1])
+    assert len(outs) == 6 and b"panic" in outs[0]
+    one = util.chunk_from_lines(GO_PUSHES)
+    want, got = ref.filter_cb(rf, one), ch.do(one)
+    assert want == got and len(util.split_records(got[1])) < 6
+
+
+def test_reference_runtime_unbuffered_hostsim(sim_lib, ref_available):
+    _reference_runtime_unbuffered(sim_lib)
+
+
+@pytest.mark.gpu
+def test_reference_runtime_unbuffered_gpu(gpu_lib, ref_available):
+    _reference_runtime_unbuffered(gpu_lib)
+
+
 def test_multiline_rulesets_hostsim(sim_lib, ref_available):
     _regex_rulesets(sim_lib, 6, 300)
 
