@@ -39,6 +39,45 @@ def _tojson(lib):
     assert n >= 30
 
 
+def _ml_reference_tables(lib):
+    """tests/internal/multiline.c: the input / expected-output tables of the java, ruby, python, go, elastic and endswith tests
+    (tests/golden/ml_scenarios.json, read from the C file by make_ml_scenarios.py).  The inputs as one chunk of {"log": line}
+    events: byte for byte what the reference's filter_multiline makes of them, and -- where that path and the test's own
+    (flb_ml_append_text, which puts a line feed behind a message when it flushes) agree -- the messages of the test's table."""
+    vec = json.load(open(os.path.join(G, "ml_scenarios.json")))
+    assert [v["name"] for v in vec] == ["java", "ruby", "python", "go", "elastic", "endswith"]
+    for v in vec:
+        ctx = pkg.Context(0, lib=lib)
+        if "rules" in v:
+            ctx.ml_parser(v["parser"], rules=[tuple(r) for r in v["rules"]])
+        if v["name"] == "endswith":
+            ctx.ml_parser(v["parser"], type=v["type"], match_string=v["match_string"], negate=v["negate"])
+        ch = ctx.chain([ctx.filter("multiline", [("multiline.parser", v["parser"]), ("multiline.key_content", "log"), ("buffer", "off")])])
+        chunk = util.chunk_from_lines([D(x) for x in v["input"]])
+        ret, out = ch.do(chunk)
+        assert (ret, out) == (v["ret"], D(v["out"])), v["name"]
+        msgs = []
+        for o, l in util.split_records(out):
+            rec = out[o:o + l]
+            k = rec.index(b"\xa3log") + 4
+            h = rec[k]
+            n, hl = (h & 31, 1) if h < 0xc0 else (rec[k + 1], 2) if h == 0xd9 else (int.from_bytes(rec[k + 1:k + 3], "big"), 3) if h == 0xda else (int.from_bytes(rec[k + 1:k + 5], "big"), 5)
+            msgs.append(rec[k + hl:k + hl + n])
+        exp = [D(x) for x in v["expected"]]
+        assert len(msgs) == len(exp), v["name"]
+        if v["name"] in ("java", "python", "elastic"):
+            assert msgs == exp, v["name"]
+
+
+def test_multiline_reference_tables_hostsim(sim_lib):
+    _ml_reference_tables(sim_lib)
+
+
+@pytest.mark.gpu
+def test_multiline_reference_tables_gpu(gpu_lib):
+    _ml_reference_tables(gpu_lib)
+
+
 def test_multiline_golden_hostsim(sim_lib):
     _multiline(sim_lib)
 
