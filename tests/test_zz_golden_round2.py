@@ -78,6 +78,28 @@ def test_multiline_reference_tables_gpu(gpu_lib):
     _ml_reference_tables(gpu_lib)
 
 
+def _write_str_cases(lib):
+    """tests/internal/utils.c: the reference's own cases for flb_utils_write_str() (escaped and raw; invalid leading / trailing
+    bytes, special bytes, edge cases), each as the value of a string member: the text between its quotes is the test's
+    expected output"""
+    vec = json.load(open(os.path.join(G, "write_str_cases.json")))
+    assert len(vec) >= 20
+    ctx = pkg.Context(0, lib=lib)
+    for c in vec:
+        ev = util.event(1700000000, 0, [(b"s", util.mp_str(D(c["input"]))), (b"tail", util.mp_str(b"a plain key behind it"))])
+        got, und = ctx.to_json(ev, 3, 2, "d", c["escape_unicode"])
+        assert und == 0 and got == b'{"d":1700000000,"s":"' + D(c["expected"]) + b'","tail":"a plain key behind it"}\n', c["test"]
+
+
+def test_write_str_cases_hostsim(sim_lib):
+    _write_str_cases(sim_lib)
+
+
+@pytest.mark.gpu
+def test_write_str_cases_gpu(gpu_lib):
+    _write_str_cases(gpu_lib)
+
+
 def test_multiline_golden_hostsim(sim_lib):
     _multiline(sim_lib)
 
