@@ -103,3 +103,12 @@ if __name__ == "__main__":
     ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     json.dump(out, open(os.path.join(ROOT, "tests", "golden", "write_str_cases.json"), "w"), indent=0)
     print(len(out), "cases from", sorted({c["test"] for c in out}))
+
+    # tests/internal/pack.c test_utf8_to_json: data/pack/*.mp (a msgpack string each) -> the JSON text of the .json beside it
+    import glob
+    pk = []
+    for mp in sorted(glob.glob("/root/reference/tests/internal/data/pack/*.mp")):
+        js = open(mp[:-3] + ".json", "rb").read()
+        pk.append({"name": os.path.basename(mp), "msgpack": base64.b64encode(open(mp, "rb").read()).decode(), "json": base64.b64encode(js.rstrip(b"\n")).decode()})
+    json.dump(pk, open(os.path.join(ROOT, "tests", "golden", "pack_to_json_cases.json"), "w"), indent=0)
+    print(len(pk), "pack fixtures")

@@ -91,6 +91,32 @@ def _write_str_cases(lib):
         assert und == 0 and got == b'{"d":1700000000,"s":"' + D(c["expected"]) + b'","tail":"a plain key behind it"}\n', c["test"]
 
 
+def _pack_fixtures(lib):
+    """tests/internal/pack.c: test_utf8_to_json (data/pack/*.mp, each a msgpack string, against the .json beside it) and
+    test_json_date_* (one legacy event, the date key in every format)"""
+    ctx = pkg.Context(0, lib=lib)
+    vec = json.load(open(os.path.join(G, "pack_to_json_cases.json")))
+    assert len(vec) >= 7
+    for v in vec:
+        ev = util.event(1700000000, 0, [(b"s", D(v["msgpack"])), (b"tail", util.mp_str(b"a plain key behind it"))])
+        got, und = ctx.to_json(ev, 3, 2, "d", True)
+        assert und == 0 and got == b'{"d":1700000000,"s":' + D(v["json"]) + b',"tail":"a plain key behind it"}\n', v["name"]
+    legacy = bytes([0x92, 0xd7, 0x00, 0x07, 0x5b, 0xcd, 0x15, 0x07, 0x5b, 0xcd, 0x15, 0x81, 0xa2, 0x61, 0x61, 0xa2, 0x62, 0x62])
+    for fmt, want in ((1, b"1973-11-29T21:33:09.123456Z"), (0, b"123456789.123456"), (3, b"1973-11-29 21:33:09.123456"), (2, b'"date":123456789,'),
+                      (4, b'"date":123456789123,')):
+        got, und = ctx.to_json(legacy, 1, fmt, "date", True)
+        assert want in got and got.startswith(b"[{") and got.endswith(b'"aa":"bb"}]'), (fmt, got)
+
+
+def test_pack_fixtures_hostsim(sim_lib):
+    _pack_fixtures(sim_lib)
+
+
+@pytest.mark.gpu
+def test_pack_fixtures_gpu(gpu_lib):
+    _pack_fixtures(gpu_lib)
+
+
 def test_write_str_cases_hostsim(sim_lib):
     _write_str_cases(sim_lib)
 
