@@ -305,6 +305,33 @@ def test_reference_runtime_unbuffered_gpu(gpu_lib, ref_available):
     _reference_runtime_unbuffered(gpu_lib)
 
 
+def _edge_chunks(lib):
+    """nothing decodable, only events the decoder steps over, garbage behind the events, a record without key_content and with a
+    zero timestamp (its time is "now": the eight timestamp bytes are left out of the comparison)"""
+    mk = b"\x92\x92\xd7\x00\xff\xff\xff\xff\x00\x00\x00\x00\x80\x80"
+    props = [("multiline.parser", "java"), ("multiline.key_content", "log"), ("buffer", "off")]
+    one = util.event(5, 0, [(b"log", S(b"x"))])
+    for c in (mk, mk * 3, mk + one + mk, b"\xc1garbage", one + b"\xc1\xc1", util.event(0, 0, [(b"other", b"\x01")])):
+        ref = util.Ref()
+        rf = ref.filter("multiline", props)
+        ctx = pkg.Context(0, lib=lib)
+        got, want = ctx.chain([ctx.filter("multiline", props)]).do(c), ref.filter_cb(rf, c)
+        assert got[0] == want[0]
+        if want[1]:
+            assert got[1][:4] == want[1][:4] and got[1][12:] == want[1][12:]
+        else:
+            assert got[1] == want[1]
+
+
+def test_multiline_edge_chunks_hostsim(sim_lib, ref_available):
+    _edge_chunks(sim_lib)
+
+
+@pytest.mark.gpu
+def test_multiline_edge_chunks_gpu(gpu_lib, ref_available):
+    _edge_chunks(gpu_lib)
+
+
 def test_multiline_rulesets_hostsim(sim_lib, ref_available):
     _regex_rulesets(sim_lib, 6, 300)
 
