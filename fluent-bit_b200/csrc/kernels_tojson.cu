@@ -19,14 +19,15 @@ namespace {                     /* the device headers' out-of-line functions get
 #define CKT(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess) { bk_note_error(#call, cudaGetErrorString(e_)); return -1; } } while (0)
 #define TJ_BLOCK 128u
 
-__global__ void __launch_bounds__(TJ_BLOCK) k_tj_size(const __grid_constant__ tj_env e)
+/* (left alone the converter takes 228 registers per lane, one block of 256 lanes per SM: bounded to 128 so that two to four blocks fit) */
+__global__ void __launch_bounds__(TJ_BLOCK, 4) k_tj_size(const __grid_constant__ tj_env e)
 {
     const uint32_t i = blockIdx.x * TJ_BLOCK + threadIdx.x;
     if (i < e.n_rec) e.size[i] = tj_event(&e, i, 0);
 }
 
 /* event i at bsum[its block of BK_REC_BLOCK events] + the sizes before it in the block */
-__global__ void __launch_bounds__(BK_REC_BLOCK) k_tj_emit(const __grid_constant__ tj_env e, const uint64_t *__restrict__ bsum, uint8_t *__restrict__ out)
+__global__ void __launch_bounds__(BK_REC_BLOCK, 2) k_tj_emit(const __grid_constant__ tj_env e, const uint64_t *__restrict__ bsum, uint8_t *__restrict__ out)
 {
     __shared__ uint32_t wsum[BK_REC_BLOCK / 32];
     const uint32_t i = blockIdx.x * BK_REC_BLOCK + threadIdx.x, lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
