@@ -55,6 +55,7 @@ EXPORTS = [
     "flbgpu_pack_state_init", "flbgpu_pack_state_reset", "flbgpu_pack_json_state", "flbgpu_pack_json_state_batch",
     "flbgpu_ml_parser_create", "flbgpu_ml_parser_rule", "flbgpu_ml_parser_init", "flbgpu_ml_set_buffer_limit",
     "flbgpu_msgpack_to_json_format", "flbgpu_lines_to_events", "flbgpu_chain_set_result_buffer",
+    "flbgpu_pool_new", "flbgpu_pool_do", "flbgpu_pool_destroy",
 ]
 
 
@@ -112,6 +113,9 @@ def load(path=None):
     L.flbgpu_lines_to_events.argtypes = [vp, vp, sz, cp, C.c_int, C.c_int64, C.c_int64, cp, cp, cp, C.c_uint64, C.POINTER(vp), C.POINTER(sz),
                                          C.POINTER(sz), C.POINTER(sz)]
     L.flbgpu_chain_set_result_buffer.argtypes = [vp, vp, sz]
+    L.flbgpu_pool_new.restype = vp; L.flbgpu_pool_new.argtypes = [C.POINTER(vp), C.c_int]
+    L.flbgpu_pool_do.argtypes = [vp, C.c_int, C.POINTER(vp), C.POINTER(sz), cp, C.c_int, C.POINTER(vp), C.POINTER(sz), C.POINTER(C.c_int)]
+    L.flbgpu_pool_destroy.argtypes = [vp]
     L.flbgpu_comm_unique_id.argtypes = [vp]
     L.flbgpu_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.flbgpu_l2m_allreduce.argtypes = [vp]

@@ -2582,6 +2582,8 @@ int flbgpu_chain_do(flbgpu_chain *c, const void *data, size_t bytes, const char 
 }
 
 
+#include "runtime_pool.h"
+
 /* ---- rewrite_tag: what the last call re-tagged ---------------------------------- */
 int flbgpu_filter_emitted(flbgpu_filter *f, const struct flbgpu_emit_group **groups, size_t *n_groups)
 {

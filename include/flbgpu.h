@@ -230,6 +230,18 @@ struct flbgpu_stats {
      * (until the chunk-level verdicts are settled), [1] size scan, [2] emission + download, [3] total */
     float phase_ms[4];
 };
+/* ---- several devices in one process ----------------------------------------------------------------------------
+ * The path shards by chunk with nothing to agree on (the filters' MODIFIED / NOTOUCH verdicts are per chunk).  A pool is n
+ * chains of the same configuration -- one per context / device -- with a worker thread each; flbgpu_pool_do() hands the chunks
+ * of a batch to whichever chain is free and returns every chunk's result in its slot: rets[i] as flbgpu_chain_do() returns it,
+ * out_bufs[i] malloc()ed on FLBGPU_FILTER_MODIFIED.  The chains stay the caller's (destroy the pool first).  Filters with state
+ * across chunks (multiline) keep it per chain; log_to_metrics tables stay per chain until flbgpu_l2m_allreduce(). */
+typedef struct flbgpu_pool flbgpu_pool;
+flbgpu_pool *flbgpu_pool_new(flbgpu_chain *const *chains, int n);
+int flbgpu_pool_do(flbgpu_pool *p, int n_chunks, const void *const *data, const size_t *bytes, const char *tag, int tag_len,
+                   void **out_bufs, size_t *out_sizes, int *rets);
+void flbgpu_pool_destroy(flbgpu_pool *p);
+
 /* Not part of the reference's contract (a filter returns a buffer the engine frees): an embedding that keeps its own result
  * memory -- reused from call to call, or pinned with flbgpu_host_alloc() -- registers it here.  A result that fits is written
  * there and *out_buf of flbgpu_chain_do() IS that buffer (do not free it); a larger one comes back malloc()ed as before.  With
