@@ -601,6 +601,8 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local, full=True):
         # the same calls with the result written into a buffer the caller keeps (flbgpu_chain_set_result_buffer): no fresh pages
         # per call; an ordinary reused heap buffer, then a pinned one
         try:
+            if world > 1:
+                raise RuntimeError("single-GPU runs only")      # (a failure on one rank between collectives would stall the others)
             cap = int(out_bytes * 1.05) + (1 << 20)
             for name, alloc, release in (("reused_heap_buffer", lambda n: _libc.malloc(n), lambda p: _libc.free(p)),
                                          ("reused_pinned_buffer", lambda n: L.flbgpu_host_alloc(ctx.h, n), lambda p: L.flbgpu_host_free(ctx.h, p))):
@@ -617,7 +619,8 @@ def measure(args, wl, L, ctx, torch, dist, rank, world, local, full=True):
                 w.keep = None
                 release(rb)
         except Exception as ex:
-            variants["reused_result_buffer_error"] = "%s: %s" % (type(ex).__name__, ex)
+            if world == 1:
+                variants["reused_result_buffer_error"] = "%s: %s" % (type(ex).__name__, ex)
             w.keep = None
         w.step_host(pinned=True)
         s = allmax(timed(lambda: [w.step_host(pinned=True) for _ in range(steps)], barrier))
