@@ -810,27 +810,36 @@ def run_ours(args):
     # last: the same end-to-end calls with an allocator that retains freed result buffers (and pinned input)
     tune_malloc()
     retained = {}
-    for o in ([WL] if args.primary_only else [WL, "apache"]):
-        if o in retained:
-            continue
-        w = Workload(args, o, L, ctx, rank, world)
-        for pinned in (False, True):
-            w.step_host(pinned=pinned)
-            t0 = time.perf_counter()
-            torch.cuda.synchronize()
-            for _ in range(args.steps):
+    retained_error = None
+    try:
+        for o in ([WL] if args.primary_only else [WL, "apache"]):
+            if o in retained:
+                continue
+            w = Workload(args, o, L, ctx, rank, world)
+            for pinned in (False, True):
                 w.step_host(pinned=pinned)
-            torch.cuda.synchronize()
-            dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
-            if world > 1:
-                dist.all_reduce(dt, op=dist.ReduceOp.MAX)
-            retained.setdefault(o, {})["pinned_input" if pinned else "pageable_input"] = world * w.n_lines * args.steps / float(dt.item())
-        w.close()
+                t0 = time.perf_counter()
+                torch.cuda.synchronize()
+                for _ in range(args.steps):
+                    w.step_host(pinned=pinned)
+                torch.cuda.synchronize()
+                dt = torch.tensor([time.perf_counter() - t0], device="cuda", dtype=torch.float64)
+                if world > 1:
+                    dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+                retained.setdefault(o, {})["pinned_input" if pinned else "pageable_input"] = world * w.n_lines * args.steps / float(dt.item())
+            w.close()
+    except Exception as ex:                           # (a device fault inside a side workload above is sticky: keep the line)
+        if world > 1:
+            raise
+        retained_error = "%s: %s" % (type(ex).__name__, ex)
+        retained = {}
     for o, v in retained.items():
         tgt = m if o == WL else others.get(o)
         if tgt is not None:
             tgt["variants"]["retaining_malloc"] = dict(v, unit="lines/s", note="glibc tuned to retain freed result buffers (M_MMAP_MAX=0, M_TRIM_THRESHOLD=2GiB): what a jemalloc build of the agent does")
 
+    if retained_error:
+        m["variants"]["retaining_malloc"] = {"error": retained_error}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
