@@ -42,6 +42,14 @@ hostsim-asan:
 	gcc $(SAN) -c $(CSRC)/rx_compile.c -o /tmp/flbgpu-asan/rx_compile.o
 	g++ $(SAN) -shared -o /tmp/flbgpu-asan/libhostsim.so tests/hostsim/hostsim.cpp /tmp/flbgpu-asan/runtime.o /tmp/flbgpu-asan/rx_compile.o
 
+# the emulation with "device" allocations filled with a byte pattern (cudaMalloc does not hand out zeroes; a fresh malloc often does):
+#   make hostsim-poison && FLBGPU_HOSTSIM_SO=/tmp/flbgpu-poison/libhostsim.so python -m pytest tests -q -m "not gpu"
+hostsim-poison:
+	mkdir -p /tmp/flbgpu-poison
+	gcc $(CFLAGS) -c $(CSRC)/runtime.c -o /tmp/flbgpu-poison/runtime.o
+	gcc $(CFLAGS) -c $(CSRC)/rx_compile.c -o /tmp/flbgpu-poison/rx_compile.o
+	g++ $(CFLAGS) -DHS_POISON=0xA5 -shared -o /tmp/flbgpu-poison/libhostsim.so tests/hostsim/hostsim.cpp /tmp/flbgpu-poison/runtime.o /tmp/flbgpu-poison/rx_compile.o -lrt -lpthread
+
 ORC_SRC = oracle/flb_oracle.c oracle/orc_parsers.c oracle/orc_regex.c oracle/orc_time.c oracle/orc_msgpack.c
 oracle: oracle/liboracle.so
 	@if [ -d /root/reference ]; then $(MAKE) -s -C oracle/refshim; else echo "oracle/_ref: reference tree absent, using prebuilt"; fi
@@ -50,4 +58,4 @@ oracle/liboracle.so: $(ORC_SRC) oracle/orc.h oracle/orc_flb.h
 
 clean:
 	rm -f $(PKG)/libflbgpu.so $(CSRC)/*.o tests/hostsim/*.so tests/hostsim/*.o oracle/liboracle.so
-.PHONY: all product hostsim hostsim-asan oracle clean
+.PHONY: all product hostsim hostsim-asan hostsim-poison oracle clean

@@ -91,7 +91,11 @@ int bk_device_count(void) { return 1; }
 bk_q *bk_q_new(int device) { bk_q *q = (bk_q *) calloc(1, sizeof(bk_q)); q->device = device; return q; }
 void bk_q_free(bk_q *q) { if (q) free(q->tag); free(q); }
 int bk_q_device(bk_q *q) { return q->device; }
+#ifdef HS_POISON        /* device memory is not zero when it is handed out: a build of the emulation that makes the same point */
+void *bk_alloc(bk_q *, size_t n) { void *p = malloc(n + 64); if (p) memset(p, HS_POISON, n + 64); return p; }
+#else
 void *bk_alloc(bk_q *, size_t n) { return malloc(n + 64); }
+#endif
 void bk_free(bk_q *, void *p) { free(p); }
 void *bk_alloc_host(bk_q *, size_t n) { return malloc(n ? n : 16); }
 void bk_free_host(bk_q *, void *p) { free(p); }
