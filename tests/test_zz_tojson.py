@@ -167,6 +167,20 @@ def _edges(lib):
         for esc in (True, False):
             got, und = ctx.to_json(grouped, jf, 1, "date", esc)
             assert und == 0 and got == ref.to_json(grouped, jf, 1, "date", esc)
+    # timestamps spelled as float64 (out of range and NaN convert as the x86-64 build converts them) and ext timestamps with
+    # negative halves: flb_time_to_millisec() divides the nanoseconds as a signed long
+    def f64ev(d):
+        return b"\x92\x92\xcb" + struct.pack(">d", d) + b"\x80\x81\xa1a\x01"
+    def extev(sec, nsec):
+        return b"\x92\x92\xd7\x00" + struct.pack(">iI", sec, nsec & 0xffffffff) + b"\x80\x81\xa1a\x01"
+    odd_times = [f64ev(1.5) * 2, f64ev(-1.5) * 2, f64ev(-0.25), f64ev(-1700000000.75), f64ev(1700000000.123456), extev(5, 0x80000001),
+                 extev(-7, 0xfffffff0), extev(-1, 999999999), extev(0x7fffffff, 0x7fffffff)]
+    for c in odd_times:
+        for df in range(5):
+            assert ctx.to_json(c, 3, df, "date", True)[0] == ref.to_json(c, 3, df, "date", True), (c, df)
+    for d in (1e300, -1e300, float("nan"), 9.3e18, -9.3e18):
+        for df in (0, 2, 4):              # (the calendar formats of such a time are gmtime_r()'s failure path)
+            assert ctx.to_json(f64ev(d) * 2, 3, df, "date", True)[0] == ref.to_json(f64ev(d) * 2, 3, df, "date", True), (d, df)
     # a string as the event's last value, out of step after multi-byte characters: counted, not compared
     odd = util.event(1700000000, 0, [(b"m", S(("é" * 15).encode() + b"abc"))])
     assert ctx.to_json(odd, 3, 0, "date", False)[1] == 1
