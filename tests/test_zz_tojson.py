@@ -80,6 +80,9 @@ def chunk(rng, n, with_meta=True):
             meta = b"\x82" + S(b"src") + S(b"tail") + S(b"n") + mp_int(rng.randint(0, 9))
         sec = rng.choice([0, 1, 1700000000, 1700000000 + i, 2 ** 31 - 1, 951782400, 1709164800])
         nsec = rng.choice([0, 1, 999, 1000, 123456789, 999999999, 500000000])
+        if rng.random() < 0.08:                                                                      # halves the decoder reads as negative, nanoseconds past a second
+            sec = rng.choice([2 ** 31 + 5, 2 ** 32 - 10, 2 ** 32 - 86400 * 400, sec])
+            nsec = rng.choice([2 ** 31 + 1, 2 ** 32 - 16, 10 ** 9 + 5, 4 * 10 ** 9, nsec])
         r = rng.random()
         if r < 0.03:
             evs.append(b"\x92\x92\xd7\x00\xff\xff\xff\xfe\x00\x00\x00\x00\x80\x80")          # a group end marker (the decoder steps over it)
@@ -88,7 +91,7 @@ def chunk(rng, n, with_meta=True):
         if r < 0.1:
             evs.append(b"\x92\xce" + struct.pack(">I", sec) + body)                              # legacy [ts, body]
         elif r < 0.15:
-            evs.append(b"\x92\x92\xcb" + struct.pack(">d", sec + 0.25) + meta + body)            # float timestamp
+            evs.append(b"\x92\x92\xcb" + struct.pack(">d", rng.choice([sec + 0.25, sec + 0.999999999, -(sec % 2 ** 31) - 0.75, float(sec)])) + meta + body)            # float timestamp
         else:
             evs.append(b"\x92\x92\xd7\x00" + struct.pack(">II", sec, nsec) + meta + body)
     return b"".join(evs)
