@@ -189,6 +189,66 @@ def _edges(lib):
     assert ctx.to_json(odd, 3, 0, "date", False)[1] == 1
 
 
+def _extremes(lib):
+    """every header width of strings, bins, keys, maps, arrays and exts, containers nested past msgpack-c's limit, keys that are
+    not strings, a body that is not a map: the text, or `nothing`, as the reference gives it"""
+    ref = util.Ref()
+    ctx = pkg.Context(0, lib=lib)
+
+    def SS(b):
+        n = len(b)
+        return S(b) if n < 256 else (b"\xda" + struct.pack(">H", n) + b if n < 65536 else b"\xdb" + struct.pack(">I", n) + b)
+
+    def ev(body):
+        return b"\x92\x92\xd7\x00" + struct.pack(">II", 1700000000, 5) + b"\x80" + body
+
+    def m(n):
+        return bytes([0x80 | n]) if n < 16 else (b"\xde" + struct.pack(">H", n) if n < 65536 else b"\xdf" + struct.pack(">I", n))
+
+    def a(n):
+        return bytes([0x90 | n]) if n < 16 else (b"\xdc" + struct.pack(">H", n) if n < 65536 else b"\xdd" + struct.pack(">I", n))
+
+    def binhdr(n):
+        return b"\xc4" + bytes([n]) if n < 256 else (b"\xc5" + struct.pack(">H", n) if n < 65536 else b"\xc6" + struct.pack(">I", n))
+    tail = S(b"z") + S(b"end of the event, long enough")
+    cases = {}
+    for n in (31, 32, 255, 256, 65535, 65536, 70000):
+        cases["str%d" % n] = ev(m(2) + S(b"s") + SS(b"x" * n) + tail)
+        cases["bin%d" % n] = ev(m(2) + S(b"s") + binhdr(n) + b"\x01" * n + tail)
+        cases["key%d" % n] = ev(m(2) + SS(b"k" * n) + b"\x01" + tail)
+    for n in (15, 16, 17, 300, 2000):                   # (the duplicate-key rule is quadratic in the members, there as here)
+        cases["map%d" % n] = ev(m(n + 1) + b"".join(S(b"k%d" % i) + b"\x01" for i in range(n)) + tail)
+        cases["arr%d" % n] = ev(m(2) + S(b"a") + a(n) + b"\x02" * n + tail)
+        cases["dup%d" % n] = ev(m(n + 1) + b"".join(S(b"k%d" % (i % 7)) + bytes([i % 100]) for i in range(n)) + tail)
+    cases["arr70000"] = ev(m(2) + S(b"a") + a(70000) + b"\x02" * 70000 + tail)
+    # the wide headers on small containers (msgpack-c never writes them; the unpacker takes them)
+    cases["map32_of_3"] = ev(b"\xdf" + struct.pack(">I", 3) + S(b"a") + b"\x01" + S(b"b") + b"\xdd" + struct.pack(">I", 2) + b"\x01\x02" + tail)
+    cases["map16_of_2"] = ev(b"\xde" + struct.pack(">H", 2) + S(b"a") + b"\xdc" + struct.pack(">H", 1) + b"\x07" + tail)
+    for d in (1, 5, 16, 31, 32, 33, 40, 100):
+        cases["nestmap%d" % d] = ev(m(2) + S(b"n") + (m(1) + S(b"k")) * d + b"\x01" + tail)
+        cases["nestarr%d" % d] = ev(m(2) + S(b"n") + a(1) * d + b"\x01" + tail)
+    for t, nb in ((0xd4, 1), (0xd5, 2), (0xd6, 4), (0xd7, 8), (0xd8, 16)):
+        cases["fixext%d" % nb] = ev(m(2) + S(b"e") + bytes([t, 5]) + bytes(range(0x78, 0x78 + nb)) + tail)
+    for n in (0, 1, 17, 255):
+        cases["ext8_%d" % n] = ev(m(2) + S(b"e") + b"\xc7" + bytes([n, 0x85]) + b"\x81" * n + tail)
+    cases["ext16"] = ev(m(2) + S(b"e") + b"\xc8" + struct.pack(">H", 300) + b"\x01" + b"\xfe" * 300 + tail)
+    cases["nil_true_false"] = ev(m(4) + S(b"a") + b"\xc0" + S(b"b") + b"\xc2" + S(b"c") + b"\xc3" + tail)
+    ints = [b"\xcc\xff", b"\xcd\xff\xff", b"\xce\xff\xff\xff\xff", b"\xcf" + b"\xff" * 8, b"\xd0\x80", b"\xd1\x80\x00", b"\xd2\x80\x00\x00\x00",
+            b"\xd3\x80" + b"\x00" * 7]
+    cases["ints"] = ev(m(9) + b"".join(S(b"i%d" % i) + v for i, v in enumerate(ints)) + tail)
+    cases["keys_not_strings"] = ev(m(6) + b"\x01\x02" + b"\xc0\x03" + b"\xc3\x04" + b"\xcb" + struct.pack(">d", 1.5) + b"\x05" + b"\x91\x01\x06" + tail)
+    cases["body_not_a_map"] = b"\x92\x92\xd7\x00" + struct.pack(">II", 1, 1) + b"\x80" + b"\x93\x01\x02\x03"
+    cases["empty_body"] = ev(m(0))
+    texts = 0
+    for name, c in cases.items():
+        for jf in (1, 3):
+            for esc in (True, False):
+                got, und = ctx.to_json(c, jf, 1, "date", esc)
+                assert und == 0 and got == ref.to_json(c, jf, 1, "date", esc), (name, jf, esc)
+                texts += got is not None
+    assert texts > 3 * len(cases)
+
+
 def test_tojson_diff_hostsim(sim_lib, ref_available):
     _diff(sim_lib, 150, 40)
 
@@ -203,6 +263,10 @@ def test_tojson_strings_hostsim(sim_lib, ref_available):
 
 def test_tojson_edges_hostsim(sim_lib, ref_available):
     _edges(sim_lib)
+
+
+def test_tojson_extremes_hostsim(sim_lib, ref_available):
+    _extremes(sim_lib)
 
 
 @pytest.mark.gpu
@@ -223,3 +287,8 @@ def test_tojson_strings_gpu(gpu_lib, ref_available):
 @pytest.mark.gpu
 def test_tojson_edges_gpu(gpu_lib, ref_available):
     _edges(gpu_lib)
+
+
+@pytest.mark.gpu
+def test_tojson_extremes_gpu(gpu_lib, ref_available):
+    _extremes(gpu_lib)
