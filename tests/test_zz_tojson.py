@@ -181,6 +181,16 @@ def _edges(lib):
     for c in odd_times:
         for df in range(5):
             assert ctx.to_json(c, 3, df, "date", True)[0] == ref.to_json(c, 3, df, "date", True), (c, df)
+    # 64-bit seconds up to the last value gmtime_r() takes (the decoder steps over the ones behind it, up to 2^56)
+    good = b"\x92\xcf" + struct.pack(">Q", 1700000000) + b"\x81\xa1a\x01"
+    for sec in (253402300799, 253402300800, 2 ** 40, 2 ** 50, 2 ** 55, 67767976233532799, 67767976233532800, 2 ** 56 - 2 ** 20):
+        forms = [b"\x92\xcf" + struct.pack(">Q", sec) + b"\x81\xa1a\x01", b"\x92\x92\xcf" + struct.pack(">Q", sec) + b"\x80\x81\xa1a\x01", f64ev(float(sec))]
+        if sec <= 2 ** 55:              # (negative seconds are not stepped over: past gmtime_r()'s range the reference formats a stale struct tm)
+            forms += [b"\x92\x92\xd3" + struct.pack(">q", -sec) + b"\x80\x81\xa1a\x01", f64ev(-float(sec) - 0.5)]
+        for c in forms:
+            for df in range(5):
+                for key in ("date", "d" * 40):
+                    assert ctx.to_json(good + c + good, 3, df, key, True)[0] == ref.to_json(good + c + good, 3, df, key, True), (sec, c, df)
     for d in (1e300, -1e300, float("nan"), 9.3e18, -9.3e18):
         for df in (0, 2, 4):              # (the calendar formats of such a time are gmtime_r()'s failure path)
             assert ctx.to_json(f64ev(d) * 2, 3, df, "date", True)[0] == ref.to_json(f64ev(d) * 2, 3, df, "date", True), (d, df)
